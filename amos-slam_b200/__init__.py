@@ -1,0 +1,278 @@
+"""amos-slam_b200 -- B200-native (sm_100a) drop-in for the ORB feature front-end of Amos-SLAM / ORB-SLAM2.
+
+Python face of the C-ABI shared library ``liborbx_b200.so`` (declared in include/orbx_b200.h).  The classes
+mirror the reference's C++ interface for this path -- same names, argument meaning and error behaviour:
+
+* :class:`ORBextractor`  <- ORB_SLAM2::ORBextractor   (/root/reference/include/ORBextractor.h:93-168)
+* :class:`ORBmatcher`    <- ORB_SLAM2::ORBmatcher     (/root/reference/include/ORBmatcher.h:57-215)
+
+There is NO CPU fallback: importing works anywhere, but creating an extractor / matcher requires the CUDA
+library and a B200; a missing library raises immediately.  (The directory name has a hyphen, so import it
+with ``importlib.import_module("amos-slam_b200")``.)
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "liborbx_b200.so")
+CSRC = os.path.join(HERE, "csrc")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177"]
+SOURCES = ["orbx_extractor.cu", "orbx_matcher.cu"]
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+
+OK, E_INVALID, E_CUDA, E_CAPACITY, E_STATE, E_OVERFLOW = 0, -1, -2, -3, -4, -5
+TH_HIGH, TH_LOW, HISTO_LENGTH = 100, 50, 30
+FRAME_GRID_COLS, FRAME_GRID_ROWS = 64, 48
+
+
+class OrbxError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("orbx error %d: %s" % (code, msg))
+        self.code = code
+
+
+def build(force=False, verbose=False):
+    """Compile every CUDA source for sm_100a into the in-tree liborbx_b200.so (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "orbx_b200.h")]
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + srcs
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """Load the C-ABI library.  Raises if it has not been built: the product has no fallback path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise OrbxError(E_CUDA, "liborbx_b200.so is missing (run __graft_entry__.build()); there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, ci, cf, sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+    L.orbx_last_error.restype = C.c_char_p
+    L.orbx_create.argtypes = [ci, cf, ci, ci, ci, ci, C.POINTER(vp)]
+    L.orbx_destroy.argtypes = [vp]; L.orbx_destroy.restype = None
+    L.orbx_get_levels.argtypes = [vp]
+    L.orbx_get_scale_factor.argtypes = [vp]; L.orbx_get_scale_factor.restype = cf
+    for name in ("orbx_get_scale_factors", "orbx_get_inverse_scale_factors", "orbx_get_scale_sigma_squares",
+                 "orbx_get_inverse_scale_sigma_squares", "orbx_get_features_per_level"):
+        getattr(L, name).argtypes = [vp, vp]
+    L.orbx_max_keypoints.argtypes = [vp, ci, ci]
+    L.orbx_stream.argtypes = [vp]; L.orbx_stream.restype = vp
+    L.orbx_launch_count.argtypes = [vp]; L.orbx_launch_count.restype = C.c_longlong
+    L.orbx_check_overflow.argtypes = [vp]
+    L.orbx_extract.argtypes = [vp, vp, ci, ci, sz, vp, vp, ci, C.POINTER(ci)]
+    L.orbx_detect.argtypes = [vp, vp, ci, ci, sz, vp, vp, ci, C.POINTER(ci)]
+    L.orbx_cull.argtypes = [vp, vp, sz, vp, sz, ci, ci, vp, ci, vp, ci, vp, vp, vp, C.POINTER(ci)]
+    L.orbx_describe.argtypes = [vp, vp, vp, vp, vp, ci, C.POINTER(ci)]
+    L.orbx_pyramid_level.argtypes = [vp, ci, ci, vp, sz, C.POINTER(ci), C.POINTER(ci)]
+    L.orbx_extract_batch.argtypes = [vp, vp, ci, ci, ci, sz, sz, vp, vp, ci, vp]
+    L.orbx_extract_batch_device.argtypes = [vp, vp, ci, ci, ci, sz, sz, vp, vp, ci, vp]
+    L.orbx_debug_level_candidates.argtypes = [vp, ci, ci, vp, ci, C.POINTER(ci)]
+    L.orbx_debug_blurred_level.argtypes = [vp, ci, ci, vp, sz]
+    L.orbx_debug_pyramid_level.argtypes = [vp, ci, ci, vp, sz]
+    L.orbx_debug_distribute.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, vp, ci, C.POINTER(ci)]
+    if hasattr(L, "orbx_matcher_create"):
+        L.orbx_matcher_create.argtypes = [cf, ci, ci, C.POINTER(vp)]
+        L.orbx_matcher_destroy.argtypes = [vp]; L.orbx_matcher_destroy.restype = None
+        L.orbx_matcher_stream.argtypes = [vp]; L.orbx_matcher_stream.restype = vp
+        L.orbx_matcher_launch_count.argtypes = [vp]; L.orbx_matcher_launch_count.restype = C.c_longlong
+        L.orbx_descriptor_distance.argtypes = [vp, vp, vp, ci, vp]
+        L.orbx_search_for_initialization.argtypes = [vp, vp, vp, vp, vp, ci, C.POINTER(ci)]
+        L.orbx_search_by_projection_frame.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp, vp, vp, cf, ci, ci, cf, vp, C.POINTER(ci)]
+        L.orbx_search_by_projection_points.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp, vp, cf, vp, C.POINTER(ci)]
+        L.orbx_compute_stereo_matches.argtypes = [vp, vp, vp, vp, vp, ci, vp, vp, ci, cf, cf, vp, vp]
+        L.orbx_match_bruteforce_device.argtypes = [vp, vp, ci, vp, ci, vp, vp, vp]
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != OK:
+        raise OrbxError(rc, lib().orbx_last_error().decode("utf-8", "replace"))
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class ORBextractor:
+    """ORB_SLAM2::ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST) on one B200.
+
+    ``extractor(image, mask=None)`` mirrors ``operator()(image, mask, keypoints, descriptors)`` and returns
+    ``(keypoints, descriptors)`` (structured array with cv::KeyPoint's layout, N x 32 uint8); the mask is
+    ignored exactly as in the reference (/root/reference/src/ORBextractor.cc:1544-1668).
+    """
+
+    def __init__(self, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, device=0):
+        self._lib = lib()
+        h = C.c_void_p()
+        _check(self._lib.orbx_create(int(nfeatures), float(scaleFactor), int(nlevels), int(iniThFAST), int(minThFAST), int(device), C.byref(h)))
+        self._h = h
+        self.nfeatures, self.nlevels, self.device = int(nfeatures), int(nlevels), int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.orbx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- getters (include/ORBextractor.h:117-165) ----
+    def GetLevels(self):
+        return self._lib.orbx_get_levels(self._h)
+
+    def GetScaleFactor(self):
+        return self._lib.orbx_get_scale_factor(self._h)
+
+    def _vec(self, fn, dtype=np.float32):
+        out = np.zeros(self.nlevels, dtype)
+        _check(getattr(self._lib, fn)(self._h, _ptr(out)))
+        return out
+
+    def GetScaleFactors(self):
+        return self._vec("orbx_get_scale_factors")
+
+    def GetInverseScaleFactors(self):
+        return self._vec("orbx_get_inverse_scale_factors")
+
+    def GetScaleSigmaSquares(self):
+        return self._vec("orbx_get_scale_sigma_squares")
+
+    def GetInverseScaleSigmaSquares(self):
+        return self._vec("orbx_get_inverse_scale_sigma_squares")
+
+    def features_per_level(self):
+        return self._vec("orbx_get_features_per_level", np.int32)
+
+    def max_keypoints(self, rows, cols):
+        rc = self._lib.orbx_max_keypoints(self._h, int(rows), int(cols))
+        if rc < 0:
+            _check(rc)
+        return rc
+
+    @property
+    def stream(self):
+        """cudaStream_t (int) all of this handle's work is ordered on."""
+        return self._lib.orbx_stream(self._h)
+
+    @property
+    def launch_count(self):
+        return self._lib.orbx_launch_count(self._h)
+
+    def check_overflow(self):
+        return self._lib.orbx_check_overflow(self._h)
+
+    # ---- operator()(image, mask, keypoints, descriptors) ----
+    def __call__(self, image, mask=None):
+        if image is None or image.size == 0:
+            return np.zeros(0, KP_DTYPE), np.zeros((0, 32), np.uint8)
+        image = self._img(image)
+        cap = self.max_keypoints(image.shape[0], image.shape[1])
+        kp = np.zeros(cap, KP_DTYPE); desc = np.zeros((cap, 32), np.uint8); n = C.c_int()
+        _check(self._lib.orbx_extract(self._h, _ptr(image), image.shape[0], image.shape[1], image.strides[0], _ptr(kp), _ptr(desc), cap, C.byref(n)))
+        return kp[:n.value].copy(), desc[:n.value].copy()
+
+    @staticmethod
+    def _img(image):
+        if image.dtype != np.uint8 or image.ndim != 2:
+            raise OrbxError(E_INVALID, "image must be CV_8UC1 (2-D uint8)")     # assert(image.type()==CV_8UC1) :1559
+        if image.strides[1] != 1:
+            image = np.ascontiguousarray(image)
+        return image
+
+    # ---- operator()(image, mask, vector<vector<KeyPoint>>&): keypoints only, level coordinates ----
+    def detect(self, image, mask=None):
+        image = self._img(image)
+        cap = self.max_keypoints(image.shape[0], image.shape[1])
+        kp = np.zeros(cap, KP_DTYPE); counts = np.zeros(self.nlevels, np.int32); n = C.c_int()
+        _check(self._lib.orbx_detect(self._h, _ptr(image), image.shape[0], image.shape[1], image.strides[0], _ptr(kp), _ptr(counts), cap, C.byref(n)))
+        return kp[:n.value].copy(), counts
+
+    # ---- MovingKeyPoints(imGray, imS, imLS, centers, rm_vector, DynaFlag, mvKeysT) ----
+    def MovingKeyPoints(self, imS, imLS, centers_id, rm_vector, keypoints, level_counts):
+        imS = np.ascontiguousarray(imS, np.uint8); imLS = np.ascontiguousarray(imLS, np.float64)
+        centers_id = np.ascontiguousarray(centers_id, np.int32); rm_vector = np.ascontiguousarray(rm_vector, np.int32)
+        kp = np.ascontiguousarray(keypoints, KP_DTYPE).copy(); counts = np.ascontiguousarray(level_counts, np.int32).copy()
+        culled = np.zeros(max(len(kp), 1), KP_DTYPE); nc = C.c_int()
+        _check(self._lib.orbx_cull(self._h, _ptr(imS), imS.strides[0], _ptr(imLS), imLS.strides[0], imS.shape[0], imS.shape[1],
+                                   _ptr(centers_id), len(centers_id), _ptr(rm_vector), len(rm_vector), _ptr(kp), _ptr(counts), _ptr(culled), C.byref(nc)))
+        return kp[:int(counts.sum())].copy(), counts, culled[:nc.value].copy()
+
+    # ---- ProcessDesp(image, mask, allKeypoints, mKeypoints, descriptors) ----
+    def ProcessDesp(self, keypoints, level_counts):
+        kp = np.ascontiguousarray(keypoints, KP_DTYPE); counts = np.ascontiguousarray(level_counts, np.int32)
+        cap = max(len(kp), 1)
+        out = np.zeros(cap, KP_DTYPE); desc = np.zeros((cap, 32), np.uint8); n = C.c_int()
+        _check(self._lib.orbx_describe(self._h, _ptr(kp), _ptr(counts), _ptr(out), _ptr(desc), cap, C.byref(n)))
+        return out[:n.value].copy(), desc[:n.value].copy()
+
+    # ---- mvImagePyramid[level] ----
+    def pyramid_level(self, level, border=0):
+        r, c = C.c_int(), C.c_int()
+        _check(self._lib.orbx_pyramid_level(self._h, level, border, None, 0, C.byref(r), C.byref(c)))
+        out = np.zeros((r.value, c.value), np.uint8)
+        _check(self._lib.orbx_pyramid_level(self._h, level, border, _ptr(out), out.strides[0], C.byref(r), C.byref(c)))
+        return out
+
+    # ---- batched operator() ----
+    def extract_batch(self, images, cap=None):
+        """images: (B, rows, cols) uint8 host array.  Returns (kp[B,cap], desc[B,cap,32], counts[B])."""
+        if images.dtype != np.uint8 or images.ndim != 3:
+            raise OrbxError(E_INVALID, "images must be (B, rows, cols) uint8")
+        images = np.ascontiguousarray(images)
+        B, rows, cols = images.shape
+        cap = cap or self.max_keypoints(rows, cols)
+        kp = np.zeros((B, cap), KP_DTYPE); desc = np.zeros((B, cap, 32), np.uint8); counts = np.zeros(B, np.int32)
+        _check(self._lib.orbx_extract_batch(self._h, _ptr(images), B, rows, cols, images.strides[1], images.strides[0], _ptr(kp), _ptr(desc), cap, _ptr(counts)))
+        return kp, desc, counts
+
+    def extract_batch_raw(self, images_ptr, B, rows, cols, step, frame_stride, kp_ptr, desc_ptr, cap, counts_ptr, device=False):
+        """Raw-pointer form (ints): host pointers (synchronous) or device pointers (asynchronous on .stream)."""
+        fn = self._lib.orbx_extract_batch_device if device else self._lib.orbx_extract_batch
+        _check(fn(self._h, C.c_void_p(images_ptr), B, rows, cols, step, frame_stride, C.c_void_p(kp_ptr), C.c_void_p(desc_ptr), cap, C.c_void_p(counts_ptr)))
+
+    # ---- stage taps (tests) ----
+    def debug_level_candidates(self, b, level):
+        n = C.c_int()
+        cap = 1 << 20
+        out = np.zeros(cap, KP_DTYPE)
+        _check(self._lib.orbx_debug_level_candidates(self._h, b, level, _ptr(out), cap, C.byref(n)))
+        return out[:n.value].copy()
+
+    def debug_pyramid_level(self, b, level, shape):
+        out = np.zeros(shape, np.uint8)
+        _check(self._lib.orbx_debug_pyramid_level(self._h, b, level, _ptr(out), out.strides[0]))
+        return out
+
+    def debug_blurred_level(self, b, level, shape):
+        out = np.zeros(shape, np.uint8)
+        _check(self._lib.orbx_debug_blurred_level(self._h, b, level, _ptr(out), out.strides[0]))
+        return out
+
+    def debug_distribute(self, cand, minX, maxX, minY, maxY, N):
+        cand = np.ascontiguousarray(cand, KP_DTYPE)
+        cap = max(4 * N + 64, 256)
+        out = np.zeros(cap, KP_DTYPE); n = C.c_int()
+        _check(self._lib.orbx_debug_distribute(self._h, _ptr(cand), len(cand), minX, maxX, minY, maxY, N, _ptr(out), cap, C.byref(n)))
+        return out[:n.value].copy()
+
+
+from ._matcher import ORBmatcher, FrameView  # noqa: E402,F401

@@ -1,0 +1,311 @@
+// k_octree.cuh -- DistributeOctTree on the device (/root/reference/src/ORBextractor.cc:635-1049).
+//
+// Formulation.  DivideNode splits a node's x-interval and y-interval independently at
+// lo + ceil((hi-lo)/2) and sends each key left/right by `pt < mid`; so every key has a fixed path
+// through the quadtree that depends only on its coordinates and the root geometry.  We give each key a
+// PATH CODE  root | d1 | d2 | ... | d13  (2 bits per depth: ybit*2 + xbit = child index n1..n4) and sort
+// the level's keys by (code, original index) once.  Every node the reference can ever create is then a
+// contiguous range of the sorted array, its children are the four sub-ranges split on the next digit,
+// and "vKeys.size()" is the range length -- no key is ever moved again.
+//   K3 k_octree_sort : one CTA per (level, frame): gather the cell slots in cell order (= the
+//                      reference's vToDistributeKeys order), compute codes, bitonic-sort 64-bit
+//                      (code<<32 | index) keys in shared memory (global memory for oversized levels).
+//   K4 k_octree_tree : one warp per (level, frame) replays the reference's list surgery exactly
+//                      (std::list push_front / erase order, the full pass, the "largest first" pass)
+//                      on node records in shared memory; lanes cooperate on range searches and on the
+//                      arg-max selection that replaces the sort at :948.  Tie-break for equal sizes is
+//                      the canonical "newest node first" (creation id), see DESIGN.md.
+// Output order = final std::list order, one keypoint per node: max response, first in original order.
+#pragma once
+#include "orbx_common.cuh"
+
+// path code of a key; x,y are the integer coordinates relative to (minBorderX, minBorderY)
+__device__ __forceinline__ uint32_t octree_code(int x, int y, const LevelGeom& g) {
+    // root: vpIniNodes[kp.pt.x / hX]   (float division, truncation)        :766
+    const int root = (int)__fdiv_rn((float)x, g.hX);
+    // root geometry: UL.x = (int)(hX*i), UR.x = (int)(hX*(i+1)), y in [0, maxY-minY)   :741-745
+    int xlo = (int)__fmul_rn(g.hX, (float)root), xhi = (int)__fmul_rn(g.hX, (float)(root + 1));
+    int ylo = 0, yhi = g.maxBY - g.minBY;
+    uint32_t code = (uint32_t)root;
+#pragma unroll
+    for (int d = 0; d < ORBX_MAXD; ++d) {
+        const int xm = xlo + ((xhi - xlo + 1) >> 1);     // UL.x + ceil((UR.x-UL.x)/2)   :641
+        const int ym = ylo + ((yhi - ylo + 1) >> 1);     // UL.y + ceil((BR.y-UL.y)/2)   :642
+        const uint32_t xb = x >= xm, yb = y >= ym;        // kp.pt.x < n1.UR.x ... :680-690
+        if (xb) xlo = xm; else xhi = xm;
+        if (yb) ylo = ym; else yhi = ym;
+        code = (code << 2) | (yb << 1) | xb;
+    }
+    return code;
+}
+
+#define SORT_THREADS 256
+
+__global__ void __launch_bounds__(SORT_THREADS)
+k_octree_sort(const LevelGeom* __restrict__ levels, const CellDesc* __restrict__ cells, int ncells,
+              int slots_per_frame, int cand_per_frame, int nlevels, int smem_keys,
+              const uint32_t* __restrict__ cand_slots, const uint16_t* __restrict__ cell_counts,
+              uint32_t* __restrict__ ocand,          // [B][cand_per_frame] candidates in reference order
+              unsigned long long* __restrict__ skey, // [B][cand_per_frame] sorted (code<<32 | index)
+              uint32_t* __restrict__ spk,            // [B][cand_per_frame] packed candidate per sorted position
+              int* __restrict__ ncand) {             // [B][nlevels]
+    extern __shared__ __align__(16) unsigned long long skeys_sm[];
+    __shared__ int warp_sums[SORT_THREADS / 32];
+    __shared__ int total_sm;
+    const int level = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const LevelGeom& g = levels[level];
+    const uint16_t* counts = cell_counts + (long long)b * ncells + g.cell_begin;
+    const uint32_t* slots = cand_slots + (long long)b * slots_per_frame;
+    uint32_t* oc = ocand + (long long)b * cand_per_frame + g.cand_off;
+    unsigned long long* sk_g = skey + (long long)b * cand_per_frame + g.cand_off;
+    uint32_t* sp = spk + (long long)b * cand_per_frame + g.cand_off;
+
+    // ---- ordered gather: exclusive scan of the per-cell counts, each thread owns a run of cells ----
+    const int per = (g.cell_count + SORT_THREADS - 1) / SORT_THREADS;
+    const int c0 = min(tid * per, g.cell_count), c1 = min(c0 + per, g.cell_count);
+    int mine = 0;
+    for (int c = c0; c < c1; ++c) mine += counts[c];
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += v; }
+    if ((tid & 31) == 31) warp_sums[tid >> 5] = incl;
+    __syncthreads();
+    if (tid < 32) {
+        int w = tid < SORT_THREADS / 32 ? warp_sums[tid] : 0;
+        int wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, wi, o); if (tid >= o) wi += v; }
+        if (tid < SORT_THREADS / 32) warp_sums[tid] = wi - w;
+        if (tid == SORT_THREADS / 32 - 1) total_sm = wi;
+    }
+    __syncthreads();
+    const int n = total_sm;
+    const bool in_smem = n <= smem_keys;
+    unsigned long long* sk = in_smem ? skeys_sm : sk_g;
+    if (n > g.cand_cap) { if (tid == 0) ncand[b * nlevels + level] = -1; return; }   // cannot happen (cap is the worst case)
+    int pos = warp_sums[tid >> 5] + incl - mine;
+    for (int c = c0; c < c1; ++c) {
+        const int cnt = counts[c];
+        const uint32_t* src = slots + cells[g.cell_begin + c].slot;
+        for (int k = 0; k < cnt; ++k, ++pos) {
+            const uint32_t p = src[k];
+            oc[pos] = p;
+            const uint32_t code = octree_code((int)(p & 0xFFF), (int)((p >> 12) & 0xFFF), g);
+            sk[pos] = ((unsigned long long)code << 32) | (unsigned)pos;
+        }
+    }
+    __syncthreads();
+
+    // ---- bitonic sort, all-ascending formulation (works for any n, no padding) ----
+    for (int k = 2; (k >> 1) < n; k <<= 1) {
+        for (int i = tid; i < n; i += SORT_THREADS) {          // first substage: mirror partner
+            const int j = i ^ (k - 1);
+            if (j > i && j < n) { unsigned long long a = sk[i], c = sk[j]; if (a > c) { sk[i] = c; sk[j] = a; } }
+        }
+        __syncthreads();
+        for (int s = k >> 2; s > 0; s >>= 1) {
+            for (int i = tid; i < n; i += SORT_THREADS) {
+                const int j = i ^ s;
+                if (j > i && j < n) { unsigned long long a = sk[i], c = sk[j]; if (a > c) { sk[i] = c; sk[j] = a; } }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = tid; i < n; i += SORT_THREADS) {
+        const unsigned long long v = sk[i];
+        if (in_smem) sk_g[i] = v;
+        sp[i] = oc[(unsigned)(v & 0xFFFFFFFFull)];
+    }
+    if (tid == 0) ncand[b * nlevels + level] = n;
+}
+
+// ---- warp-cooperative lower bound on the sorted keys: first index in [lo,hi) with key >= T ----
+__device__ __forceinline__ int warp_lower_bound(const unsigned long long* __restrict__ key, int lo, int hi,
+                                                unsigned long long T, int lane) {
+    while (hi - lo > 32) {
+        const int step = (hi - lo + 31) >> 5;
+        const int pos = lo + lane * step;
+        const bool pred = pos < hi && key[pos] < T;
+        const int c = __popc(__ballot_sync(0xffffffffu, pred));
+        if (c == 0) return lo;
+        const int nlo = lo + (c - 1) * step + 1;
+        hi = min(lo + c * step, hi);
+        lo = nlo;
+    }
+    const int pos = lo + lane;
+    const bool pred = pos < hi && key[pos] < T;
+    return lo + __popc(__ballot_sync(0xffffffffu, pred));
+}
+
+struct TreeSmem {
+    int* lo; int* hi; unsigned* cid; short* nxt; short* prv; unsigned char* dep; short* freeStack;
+    unsigned long long* vcur; unsigned long long* vprev;
+};
+
+__global__ void __launch_bounds__(32)
+k_octree_tree(const LevelGeom* __restrict__ levels, int nlevels, int cand_per_frame, int kp_per_frame, int cap_max,
+              const unsigned long long* __restrict__ skey, const uint32_t* __restrict__ spk, const int* __restrict__ ncand,
+              uint32_t* __restrict__ kp_level,      // [B][kp_per_frame] packed x:12|y:12|resp:8 (relative to minBorder)
+              int* __restrict__ kp_count,           // [B][nlevels]
+              int* __restrict__ overflow) {
+    extern __shared__ __align__(16) uint8_t tree_sm[];
+    const int level = blockIdx.x, b = blockIdx.y, lane = threadIdx.x;
+    const LevelGeom& g = levels[level];
+    const int n = ncand[b * nlevels + level];
+    const unsigned long long* key = skey + (long long)b * cand_per_frame + g.cand_off;
+    const uint32_t* pk = spk + (long long)b * cand_per_frame + g.cand_off;
+    uint32_t* out = kp_level + (long long)b * kp_per_frame + g.kp_off;
+    if (n <= 0) { if (lane == 0) { kp_count[b * nlevels + level] = 0; if (n < 0) atomicOr(overflow, ORBX_OVF_SORT); } return; }
+
+    const int cap = cap_max;     // node slots available (>= kp_cap + 8 for every level)
+    unsigned long long* vcur = reinterpret_cast<unsigned long long*>(tree_sm);
+    unsigned long long* vprev = vcur + cap;
+    int* nlo = reinterpret_cast<int*>(vprev + cap);
+    int* nhi = nlo + cap;
+    unsigned* ncid = reinterpret_cast<unsigned*>(nhi + cap);
+    short* nnxt = reinterpret_cast<short*>(ncid + cap);
+    short* nprv = nnxt + cap;
+    short* freeStack = nprv + cap;
+    unsigned char* ndep = reinterpret_cast<unsigned char*>(freeStack + cap);
+
+    const int N = g.N;
+    int head = -1, tail = -1, count = 0, nfree = cap;
+    unsigned nextCid = 0;
+    bool ovf = false;
+    for (int i = lane; i < cap; i += 32) freeStack[i] = (short)(cap - 1 - i);
+    __syncwarp();
+
+    // all lanes run the same scalar control flow; lane 0 performs the shared-memory writes
+#define NODE_ALLOC(slot) do { if (nfree == 0) { ovf = true; slot = -1; } else { slot = freeStack[--nfree]; } } while (0)
+#define NODE_FREE(slot) do { if (lane == 0) freeStack[nfree] = (short)(slot); ++nfree; } while (0)
+
+    // ---- initial nodes (:733-788): nIni roots in order (push_back), empty ones erased ----
+    for (int i = 0; i < g.nIni; ++i) {
+        const int rlo = warp_lower_bound(key, 0, n, (unsigned long long)i << (32 + ORBX_ROOT_SHIFT), lane);
+        const int rhi = warp_lower_bound(key, rlo, n, (unsigned long long)(i + 1) << (32 + ORBX_ROOT_SHIFT), lane);
+        ++nextCid;
+        if (rhi > rlo) {
+            int s; NODE_ALLOC(s);
+            if (s < 0) break;
+            if (lane == 0) { nlo[s] = rlo; nhi[s] = rhi; ncid[s] = nextCid - 1; ndep[s] = 0; nnxt[s] = -1; nprv[s] = (short)tail; if (tail >= 0) nnxt[tail] = (short)s; }
+            if (head < 0) head = s;
+            tail = s; ++count;
+            __syncwarp();
+        }
+    }
+
+    int nv = 0;   // entries in vcur
+    // divide node `slot`: push its non-empty children to the FRONT in order n1..n4, record children with
+    // more than one key in vcur (size<<40 | cid<<16 | slot), erase the node.   (:839-895 / :952-998)
+    auto divide = [&](int slot, int& nToExpand) {
+        const int lo = nlo[slot], hi = nhi[slot], d = ndep[slot];
+        const int shift = 2 * (ORBX_MAXD - d - 1);
+        int bnd[5];
+        bnd[0] = lo; bnd[4] = hi;
+        if (hi - lo <= 32) {
+            const int pos = lo + lane;
+            const unsigned digit = pos < hi ? (unsigned)((key[pos] >> (32 + shift)) & 3ull) : 4u;
+            bnd[1] = lo + __popc(__ballot_sync(0xffffffffu, digit < 1u));
+            bnd[2] = lo + __popc(__ballot_sync(0xffffffffu, digit < 2u));
+            bnd[3] = lo + __popc(__ballot_sync(0xffffffffu, digit < 3u));
+        } else {
+            const unsigned long long prefix = key[lo] >> (32 + shift + 2);
+            bnd[1] = warp_lower_bound(key, lo, hi, ((prefix << 2) | 1ull) << (32 + shift), lane);
+            bnd[2] = warp_lower_bound(key, bnd[1], hi, ((prefix << 2) | 2ull) << (32 + shift), lane);
+            bnd[3] = warp_lower_bound(key, bnd[2], hi, ((prefix << 2) | 3ull) << (32 + shift), lane);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int sz = bnd[k + 1] - bnd[k];
+            if (sz > 0) {
+                int s; NODE_ALLOC(s);
+                if (s < 0) return;
+                const unsigned id = nextCid++;
+                if (lane == 0) {
+                    nlo[s] = bnd[k]; nhi[s] = bnd[k + 1]; ncid[s] = id; ndep[s] = (unsigned char)(d + 1);
+                    nprv[s] = -1; nnxt[s] = (short)head; if (head >= 0) nprv[head] = (short)s;
+                    if (sz > 1) vcur[nv] = ((unsigned long long)sz << 40) | ((unsigned long long)(id & 0xFFFFFFu) << 16) | (unsigned)s;
+                }
+                head = s; if (tail < 0) tail = s;
+                ++count;
+                if (sz > 1) { ++nToExpand; ++nv; }
+                __syncwarp();
+            }
+        }
+        // erase(slot)
+        const int p = nprv[slot], q = nnxt[slot];
+        if (lane == 0) { if (p >= 0) nnxt[p] = (short)q; if (q >= 0) nprv[q] = (short)p; }
+        if (p < 0) head = q;
+        if (q < 0) tail = p;
+        --count;
+        NODE_FREE(slot);
+        __syncwarp();
+    };
+
+    bool bFinish = false;
+    while (!bFinish && !ovf) {
+        const int prevSize = count;
+        int nToExpand = 0;
+        nv = 0;
+        int cur = head;
+        while (cur >= 0 && !ovf) {                                   // full pass (:824-899)
+            const int nx = nnxt[cur];
+            const int sz = nhi[cur] - nlo[cur];
+            if (sz != 1 && ndep[cur] < ORBX_MAXD) divide(cur, nToExpand);   // bNoMore <=> one key
+            else if (sz != 1) ovf = true;
+            cur = nx;
+        }
+        if (count >= N || count == prevSize) bFinish = true;          // :907
+        else if (count + nToExpand * 3 > N) {                          // :929
+            while (!bFinish && !ovf) {
+                const int prevSize2 = count;
+                unsigned long long* t = vprev; vprev = vcur; vcur = t;
+                const int np = nv; nv = 0;
+                for (int it = 0; it < np; ++it) {
+                    // largest size first, newest first among equals (:948-950, canonical tie-break)
+                    unsigned long long best = 0; int bi = -1;
+                    for (int e = lane; e < np; e += 32) { const unsigned long long v = vprev[e]; if (v > best) { best = v; bi = e; } }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const unsigned long long ov = __shfl_xor_sync(0xffffffffu, best, o);
+                        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                        if (ov > best) { best = ov; bi = oi; }
+                    }
+                    if (lane == 0) vprev[bi] = 0ull;
+                    __syncwarp();
+                    const int slot = (int)(best & 0xFFFFull);
+                    if (ndep[slot] >= ORBX_MAXD) { ovf = true; break; }
+                    int dummy = 0;
+                    divide(slot, dummy);
+                    if (count >= N || ovf) break;                      // :1003
+                }
+                if (count >= N || count == prevSize2) bFinish = true; // :1009
+            }
+        }
+    }
+
+    // ---- result: one keypoint per node in list order (:1018-1048) ----
+    short* order = reinterpret_cast<short*>(vprev);
+    if (lane == 0) { int k = 0; for (int c = head; c >= 0 && k < cap; c = nnxt[c]) order[k++] = (short)c; }
+    __syncwarp();
+    const int nout = min(count, g.kp_cap);
+    if (count > g.kp_cap) ovf = true;
+    for (int k = lane; k < nout; k += 32) {
+        const int s = order[k];
+        const int lo = nlo[s], hi = nhi[s];
+        uint32_t bestp = 0; int bestr = -1; unsigned besti = 0xFFFFFFFFu;
+        for (int i = lo; i < hi; ++i) {
+            const uint32_t p = pk[i];
+            const int r = (int)(p >> 24);
+            const unsigned oi = (unsigned)(key[i] & 0xFFFFFFFFull);
+            if (r > bestr || (r == bestr && oi < besti)) { bestr = r; besti = oi; bestp = p; }   // max response, first wins
+        }
+        out[k] = bestp;
+    }
+    if (lane == 0) {
+        kp_count[b * nlevels + level] = nout;
+        if (ovf) atomicOr(overflow, ORBX_OVF_TREE);
+    }
+#undef NODE_ALLOC
+#undef NODE_FREE
+}

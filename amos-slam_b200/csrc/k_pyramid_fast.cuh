@@ -1,0 +1,193 @@
+// k_pyramid_fast.cuh -- image pyramid (bilinear, fixed point) and per-cell FAST-9 detection kernels.
+#pragma once
+#include "orbx_common.cuh"
+
+// =================================================================================================
+// K1  pyr_resize: level l from level l-1 (chained, /root/reference/src/ORBextractor.cc:1826-1886),
+// cv::resize(INTER_LINEAR) 8UC1 fixed-point arithmetic:
+//   H[d]  = src[y][sx]*w0 + src[y][min(sx+1,sw-1)]*w1          (11-bit weights, int)
+//   out   = (((b0*(H0>>4))>>16) + ((b1*(H1>>4))>>16) + 2) >> 2
+// Tables (offset + weight pairs per destination column / row) are built on the host with OpenCV's
+// float arithmetic and are padded to the destination pitch, so the kernel needs no edge branches.
+// One thread produces 4 horizontally adjacent pixels and stores them as one uchar4; a CTA of 32x8
+// threads covers a 128x8 destination tile; grid.z walks the batch.  HBM-bound stencil: reads
+// P(l-1) once (L1/L2 absorb the 2x2 footprint overlap), writes P(l) once.
+// =================================================================================================
+struct ResizeTabs { const int* xofs; const short2* xw; const int* yofs; const short2* yw; };
+
+__global__ void __launch_bounds__(256)
+k_pyr_resize(const uint8_t* __restrict__ src, long long src_fstride, int spitch, int sw, int sh,
+             uint8_t* __restrict__ dst, long long dst_fstride, int dpitch, int dw, int dh, ResizeTabs t) {
+    const int x = (blockIdx.x * 32 + threadIdx.x) * 4;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= dw || y >= dh) return;
+    const uint8_t* s = src + (long long)blockIdx.z * src_fstride;
+    const int sy0 = __ldg(t.yofs + y);
+    const int sy1 = min(sy0 + 1, sh - 1);
+    const short2 b = __ldg(t.yw + y);
+    const uint8_t* r0 = s + (long long)sy0 * spitch;
+    const uint8_t* r1 = s + (long long)sy1 * spitch;
+    const int4 xo = __ldg(reinterpret_cast<const int4*>(t.xofs + x));
+    const int xs[4] = {xo.x, xo.y, xo.z, xo.w};
+    uint32_t out = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int sx0 = xs[k], sx1 = min(sx0 + 1, sw - 1);
+        const short2 a = __ldg(t.xw + x + k);
+        const int h0 = (int)__ldg(r0 + sx0) * a.x + (int)__ldg(r0 + sx1) * a.y;
+        const int h1 = (int)__ldg(r1 + sx0) * a.x + (int)__ldg(r1 + sx1) * a.y;
+        const int v = ((((int)b.x * (h0 >> 4)) >> 16) + (((int)b.y * (h1 >> 4)) >> 16) + 2) >> 2;
+        out |= (uint32_t)(v & 0xFF) << (8 * k);
+    }
+    // pitch is a multiple of 128 and tables are padded: the (up to 3) bytes past dw land in row padding
+    *reinterpret_cast<uint32_t*>(dst + (long long)blockIdx.z * dst_fstride + (long long)y * dpitch + x) = out;
+}
+
+// =================================================================================================
+// K2  fast_cells: per-cell FAST-9/16 with the iniThFAST / minThFAST retry and 3x3 non-max suppression
+// (ORBextractor.cc:1089-1157 + cv::FAST semantics), in score-map form:
+//   S(p) = max over the 16 arcs of 9 contiguous ring pixels of min(v - p_k)  or  min(p_k - v);
+//   corner at threshold t <=> S > t;  response = S - 1;
+//   a cell's keypoints at threshold t = strict 3x3 local maxima of S inside the cell's zone with S > t
+//   (neighbours outside the zone count as 0), in raster order; if the cell yields none at iniTh, the
+//   same set at minTh is used.
+// One warp per cell, 4 cells per CTA.  The cell's ROI (zone + 3-px ring) is staged in shared memory
+// with aligned 32-bit loads; S is computed only where two adjacent compass points pass the minTh test
+// (any 9-arc contains two adjacent compass points) and a 9-run exists (bit tricks on 16-bit masks).
+// Candidates are written to the cell's fixed slot range (capacity = max possible local maxima), so
+// there are no atomics and the layout is deterministic; the octree stage gathers them in cell order,
+// which reproduces vToDistributeKeys' order exactly.
+// =================================================================================================
+__device__ __forceinline__ int fast_sliding_min9_max(const int (&a)[16]) {
+    // max over k of min(a[k..k+8]) on the circular ring (log-step sliding minimum)
+    int m2[16], m4[16], m8[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) m2[k] = min(a[k], a[(k + 1) & 15]);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) m4[k] = min(m2[k], m2[(k + 2) & 15]);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) m8[k] = min(m4[k], m4[(k + 4) & 15]);
+    int best = -256;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) best = max(best, min(m8[k], a[(k + 8) & 15]));
+    return best;
+}
+
+__device__ __forceinline__ bool has_run9(uint32_t m16) {
+    // 9 contiguous set bits on a 16-bit circular mask
+    uint32_t m = m16 | (m16 << 16);
+    uint32_t r2 = m & (m >> 1);
+    uint32_t r4 = r2 & (r2 >> 2);
+    uint32_t r8 = r4 & (r4 >> 4);
+    uint32_t r9 = r8 & (m >> 8);
+    return (r9 & 0xFFFFu) != 0;
+}
+
+// FAST score of the pixel at p (shared-memory patch, row stride ps), 0 if S <= minTh
+__device__ __forceinline__ int fast_score(const uint8_t* p, int ps, int minTh) {
+    const int v = p[0];
+    const int hi = v + minTh, lo = v - minTh;
+    // compass points k = 0 (0,+3), 4 (+3,0), 8 (0,-3), 12 (-3,0)
+    const int c0 = p[3 * ps], c4 = p[3], c8 = p[-3 * ps], c12 = p[-3];
+    const uint32_t bq = (c0 > hi) | ((c4 > hi) << 1) | ((c8 > hi) << 2) | ((c12 > hi) << 3);
+    const uint32_t dq = (c0 < lo) | ((c4 < lo) << 1) | ((c8 < lo) << 2) | ((c12 < lo) << 3);
+    const uint32_t adjb = bq & ((bq >> 1) | (bq << 3)), adjd = dq & ((dq >> 1) | (dq << 3));
+    if (((adjb | adjd) & 0xF) == 0) return 0;
+    int d[16];   // v - p_k ; ring order (dx,dy): (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
+    d[0] = v - c0;               d[1] = v - p[3 * ps + 1];   d[2] = v - p[2 * ps + 2];   d[3] = v - p[ps + 3];
+    d[4] = v - c4;               d[5] = v - p[-ps + 3];      d[6] = v - p[-2 * ps + 2];  d[7] = v - p[-3 * ps + 1];
+    d[8] = v - c8;               d[9] = v - p[-3 * ps - 1];  d[10] = v - p[-2 * ps - 2]; d[11] = v - p[-ps - 3];
+    d[12] = v - c12;             d[13] = v - p[ps - 3];      d[14] = v - p[2 * ps - 2];  d[15] = v - p[3 * ps - 1];
+    uint32_t mb = 0, md = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { mb |= (uint32_t)(d[k] < -minTh) << k; md |= (uint32_t)(d[k] > minTh) << k; }
+    if (has_run9(md)) return fast_sliding_min9_max(d);          // dark arc: min(v - p_k)
+    if (has_run9(mb)) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) d[k] = -d[k];
+        return fast_sliding_min9_max(d);                        // bright arc: min(p_k - v)
+    }
+    return 0;
+}
+
+#define FAST_WARPS 4
+
+__global__ void __launch_bounds__(FAST_WARPS * 32)
+k_fast_cells(PyrView pv, const LevelGeom* __restrict__ levels, const CellDesc* __restrict__ cells, int ncells,
+             int slots_per_frame, int smem_per_warp, int iniTh, int minTh,
+             uint32_t* __restrict__ cand_slots,      // [B][slots_per_frame]  packed x:12|y:12|resp:8 (x,y relative to minBorder)
+             uint16_t* __restrict__ cell_counts) {   // [B][ncells]
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cell = blockIdx.x * FAST_WARPS + warp;
+    const int b = blockIdx.y;
+    if (cell >= ncells) return;
+    const CellDesc c = cells[cell];
+    const LevelGeom& g = levels[c.level];
+    int pitch;
+    const uint8_t* img = level_ptr(pv, g, c.level, b, pitch);
+
+    uint8_t* sm = smem_raw + (size_t)warp * smem_per_warp;
+    const int zw = c.cw - 6, zh = c.ch - 6;
+    const int xs = c.x0 & ~3, shift = c.x0 & 3;
+    const int wpr = ((c.x0 + c.cw + 3) >> 2) - (xs >> 2);      // 32-bit words per patch row
+    const int ps = wpr * 4;                                    // patch row stride (bytes)
+    uint32_t* patch32 = reinterpret_cast<uint32_t*>(sm);
+    const int patch_bytes = ps * c.ch;
+    const int sst = zw + 2;                                    // S row stride; 1-px zero ring
+    const int s_bytes = (sst * (zh + 2) + 3) & ~3;
+    uint8_t* S = sm + patch_bytes;
+    uint8_t* F = S + s_bytes;                                  // zw*zh: S where strict local max, else 0
+
+    // stage the ROI (aligned words; level pitch and base are 4-byte aligned)
+    const int nwords = wpr * c.ch;
+    for (int w = lane; w < nwords; w += 32) {
+        const int r = w / wpr, col = w - r * wpr;
+        patch32[w] = __ldg(reinterpret_cast<const uint32_t*>(img + (long long)(c.y0 + r) * pitch + xs) + col);
+    }
+    for (int w = lane; w < (s_bytes >> 2); w += 32) reinterpret_cast<uint32_t*>(S)[w] = 0u;
+    __syncwarp();
+
+    const uint8_t* patch = sm + shift;
+    const int npx = zw * zh;
+    const uint32_t inv = ((1u << 20) + zw - 1) / zw;           // exact i / zw for i < 3600 (zw < 64)
+    for (int i = lane; i < npx; i += 32) {
+        const int y = (int)(((uint32_t)i * inv) >> 20), x = i - y * zw;
+        const int s = fast_score(patch + (y + 3) * ps + (x + 3), ps, minTh);
+        if (s) S[(y + 1) * sst + x + 1] = (uint8_t)s;
+    }
+    __syncwarp();
+
+    // strict 3x3 local maxima; count those above iniTh
+    int n_ini = 0;
+    for (int i0 = 0; i0 < npx; i0 += 32) {
+        const int i = i0 + lane;
+        int f = 0;
+        if (i < npx) {
+            const int y = (int)(((uint32_t)i * inv) >> 20), x = i - y * zw;
+            const uint8_t* q = S + (y + 1) * sst + x + 1;
+            const int s = q[0];
+            if (s && s > q[-1] && s > q[1] && s > q[-sst - 1] && s > q[-sst] && s > q[-sst + 1] &&
+                s > q[sst - 1] && s > q[sst] && s > q[sst + 1]) f = s;
+            F[i] = (uint8_t)f;
+        }
+        n_ini += __popc(__ballot_sync(0xffffffffu, f > iniTh));
+    }
+    __syncwarp();
+    const int th = n_ini > 0 ? iniTh : minTh;                  // retry at minTh iff the cell came back empty
+    uint32_t* out = cand_slots + (long long)b * slots_per_frame + c.slot;
+    int n = 0;
+    for (int i0 = 0; i0 < npx; i0 += 32) {
+        const int i = i0 + lane;
+        const int f = i < npx ? F[i] : 0;
+        const bool keep = f > th;
+        const uint32_t m = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const int y = (int)(((uint32_t)i * inv) >> 20), x = i - y * zw;
+            const int k = n + __popc(m & ((1u << lane) - 1u));
+            out[k] = (uint32_t)(x + 3 + c.sx) | ((uint32_t)(y + 3 + c.sy) << 12) | ((uint32_t)(f - 1) << 24);
+        }
+        n += __popc(m);
+    }
+    if (lane == 0) cell_counts[(long long)b * ncells + cell] = (uint16_t)n;
+}

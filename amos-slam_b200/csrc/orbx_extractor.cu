@@ -1,0 +1,581 @@
+// orbx_extractor.cu -- host side of the B200-native ORBextractor: geometry plan, device buffers,
+// kernel orchestration and the C ABI declared in include/orbx_b200.h.
+//
+// Mirrors ORB_SLAM2::ORBextractor (/root/reference/include/ORBextractor.h:93-168,
+// /root/reference/src/ORBextractor.cc).  There is no CPU path here: every stage is a CUDA kernel
+// (k_pyramid_fast.cuh, k_octree.cuh, k_describe.cuh, k_cull.cuh); the host only computes the small
+// per-geometry tables exactly as the reference's constructor / ComputePyramid / cell loop do.
+#include "../../include/orbx_b200.h"
+#include "orbx_common.cuh"
+#include "k_pyramid_fast.cuh"
+#include "k_octree.cuh"
+#include "k_describe.cuh"
+#include "k_cull.cuh"
+#include "brief_pattern.inc"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+static_assert(sizeof(orbx_keypoint) == 28, "orbx_keypoint must match cv::KeyPoint");
+static_assert(sizeof(KpOut) == 28, "KpOut must match cv::KeyPoint");
+
+static thread_local std::string g_last_error;
+extern "C" const char* orbx_last_error(void) { return g_last_error.c_str(); }
+extern "C" int orbx_version(void) { return 100; }
+void orbx_set_error(const std::string& s) { g_last_error = s; }
+
+#define CU_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { \
+    orbx_set_error(std::string(#expr) + ": " + cudaGetErrorString(_e)); return ORBX_E_CUDA; } } while (0)
+#define FAIL(code, msg) do { orbx_set_error(msg); return (code); } while (0)
+
+static inline int cv_round_f(float v) { return (int)lrintf(v); }      // cvRound: round half to even
+static inline int cv_floor_f(float v) { int i = (int)v; return i - (i > v); }
+static inline int cv_ceil_f(float v) { int i = (int)v; return i + (i < v); }
+static inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+template <typename T> struct DevBuf {
+    T* p = nullptr; size_t n = 0;
+    int ensure(size_t count) {
+        if (count <= n) return ORBX_OK;
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+        CU_TRY(cudaMalloc((void**)&p, count * sizeof(T)));
+        n = count; return ORBX_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+struct orbx_extractor {
+    // ---- parameters and tables of ORBextractor::ORBextractor (ORBextractor.cc:492-609) ----
+    int nfeatures; double scaleFactor; int nlevels, iniThFAST, minThFAST, device;
+    std::vector<float> mvScaleFactor, mvInvScaleFactor, mvLevelSigma2, mvInvLevelSigma2;
+    std::vector<int> mnFeaturesPerLevel, umax;
+    cudaStream_t stream = nullptr;
+    long long launches = 0;
+
+    // ---- geometry plan for (rows, cols) ----
+    int rows = 0, cols = 0;
+    std::vector<LevelGeom> levels; std::vector<CellDesc> cells; std::vector<BlurTile> tiles;
+    long long pyr_fstride = 0; int cand_per_frame = 0, kp_per_frame = 0, max_kp = 0;
+    int fast_smem_per_warp = 0, tree_cap = 0, sort_smem_keys = 4096;
+    DevBuf<LevelGeom> d_levels; DevBuf<CellDesc> d_cells; DevBuf<BlurTile> d_tiles; DevBuf<int> d_tabs;
+    std::vector<ResizeTabs> resize_tabs;
+
+    // ---- per-batch device state (the "stateful extractor": pyramid stays resident) ----
+    int Bcap = 0, lastB = 0;
+    DevBuf<uint8_t> d_pyr, d_blur;
+    DevBuf<uint32_t> d_slots, d_ocand, d_spk, d_kp_level;
+    DevBuf<unsigned long long> d_skey;
+    DevBuf<uint16_t> d_cell_counts;
+    DevBuf<int> d_ncand, d_kp_count, d_counts, d_level_counts, d_overflow;
+    DevBuf<KpOut> d_kp_out; DevBuf<uint8_t> d_desc_out; int out_cap = 0;
+    PyrView view{}; bool have_pyramid = false, blur_valid = false;
+    // small staging buffers for the single-frame calls
+    DevBuf<KpOut> d_kp_tmp; DevBuf<uint8_t> d_desc_tmp; DevBuf<uint8_t> d_mask, d_mask2; DevBuf<double> d_label; DevBuf<int> d_ids;
+};
+
+// -------------------------------------------------------------------------------------------------
+// cv::resize(INTER_LINEAR) coefficient tables, padded to `padded` entries
+// -------------------------------------------------------------------------------------------------
+static void linear_coefs(int ssize, int dsize, int padded, std::vector<int>& ofs, std::vector<short>& w) {
+    ofs.assign(padded, 0); w.assign((size_t)padded * 2, 0);
+    const double inv_scale = (double)dsize / ssize, scale = 1.0 / inv_scale;
+    for (int d = 0; d < padded; ++d) {
+        const int dd = std::min(d, dsize - 1);
+        float f = (float)((dd + 0.5) * scale - 0.5);
+        int s = cv_floor_f(f);
+        f -= s;
+        if (s < 0) { s = 0; f = 0.f; }
+        if (s >= ssize - 1) { s = ssize - 1; f = 0.f; }
+        ofs[d] = s;
+        w[2 * d] = (short)cv_round_f((1.f - f) * 2048.f);
+        w[2 * d + 1] = (short)cv_round_f(f * 2048.f);
+    }
+}
+
+static int build_plan(orbx_extractor* h, int rows, int cols) {
+    if (h->rows == rows && h->cols == cols) return ORBX_OK;
+    const int L = h->nlevels;
+    std::vector<LevelGeom> lv(L);
+    std::vector<CellDesc> cells; std::vector<BlurTile> tiles;
+    long long off = 0; int cand_off = 0, kp_off = 0, smem_pw = 0, tree_cap = 0;
+    for (int l = 0; l < L; ++l) {
+        LevelGeom& g = lv[l];
+        std::memset(&g, 0, sizeof(g));
+        const float inv = h->mvInvScaleFactor[l];
+        g.w = cv_round_f((float)cols * inv); g.h = cv_round_f((float)rows * inv);     // ORBextractor.cc:1834
+        if (g.w > ORBX_MAX_DIM || g.h > ORBX_MAX_DIM) FAIL(ORBX_E_INVALID, "image larger than 4095 px is not supported");
+        g.pitch = align_up(g.w, 128);
+        g.off = off; off += (long long)g.pitch * g.h;
+        g.scale = h->mvScaleFactor[l];
+        g.kp_size = (float)(int)(31 * h->mvScaleFactor[l]);                             // :1175
+        g.N = h->mnFeaturesPerLevel[l];
+        // cell grid :1067-1086
+        g.minBX = ORBX_EDGE - 3; g.minBY = g.minBX; g.maxBX = g.w - ORBX_EDGE + 3; g.maxBY = g.h - ORBX_EDGE + 3;
+        const float W = 30;
+        const float width = (float)(g.maxBX - g.minBX), height = (float)(g.maxBY - g.minBY);
+        const int nCols = (int)(width / W), nRows = (int)(height / W);
+        if (nCols <= 0 || nRows <= 0) FAIL(ORBX_E_INVALID, "image too small for the pyramid (a level has no 30-px FAST cell)");
+        const int wCell = (int)std::ceil(width / nCols), hCell = (int)std::ceil(height / nRows);
+        g.cell_begin = (int)cells.size(); g.slot_off = cand_off; g.cand_off = cand_off;
+        int slot = cand_off;
+        for (int i = 0; i < nRows; i++) {
+            const float iniY = (float)(g.minBY + i * hCell);
+            float maxY = iniY + hCell + 6;
+            if (iniY >= g.maxBY - 3) continue;                                          // :1099
+            if (maxY > g.maxBY) maxY = (float)g.maxBY;
+            for (int j = 0; j < nCols; j++) {
+                const float iniX = (float)(g.minBX + j * wCell);
+                float maxX = iniX + wCell + 6;
+                if (iniX >= g.maxBX - 6) continue;                                      // :1116
+                if (maxX > g.maxBX) maxX = (float)g.maxBX;
+                CellDesc c; std::memset(&c, 0, sizeof(c));
+                c.x0 = (short)iniX; c.y0 = (short)iniY; c.cw = (short)((int)maxX - (int)iniX); c.ch = (short)((int)maxY - (int)iniY);
+                if (c.cw < 7 || c.ch < 7) continue;                                     // cv::FAST returns nothing
+                if (c.cw - 6 >= 64) FAIL(ORBX_E_INVALID, "unsupported cell width");
+                c.sx = (short)(j * wCell); c.sy = (short)(i * hCell); c.level = (short)l;
+                const int zw = c.cw - 6, zh = c.ch - 6;
+                c.cap = (short)(((zw + 1) / 2) * ((zh + 1) / 2));
+                c.slot = slot; slot += c.cap;
+                cells.push_back(c);
+                const int wpr = ((c.x0 + c.cw + 3) >> 2) - (c.x0 >> 2);
+                const int need = wpr * 4 * c.ch + (((zw + 2) * (zh + 2) + 3) & ~3) + ((zw * zh + 3) & ~3);
+                smem_pw = std::max(smem_pw, need);
+            }
+        }
+        g.cell_count = (int)cells.size() - g.cell_begin;
+        g.cand_cap = slot - cand_off; cand_off = slot;
+        if (g.cand_cap >= (1 << 20)) FAIL(ORBX_E_INVALID, "level too large");
+        // quadtree roots :719-722
+        if (g.maxBY - g.minBY <= 0) FAIL(ORBX_E_INVALID, "image too small");
+        g.nIni = (int)std::round(static_cast<float>(g.maxBX - g.minBX) / (g.maxBY - g.minBY));
+        if (g.nIni < 1 || g.nIni > 15) FAIL(ORBX_E_INVALID, "unsupported aspect ratio (nIni must be 1..15)");
+        g.hX = static_cast<float>(g.maxBX - g.minBX) / g.nIni;
+        g.kp_off = kp_off; g.kp_cap = std::max(g.N + 2, 4 * g.nIni) + 2; kp_off += g.kp_cap;
+        tree_cap = std::max(tree_cap, g.kp_cap + 8);
+        for (int ty = 0; ty < (g.h + BLUR_TH - 1) / BLUR_TH; ++ty)
+            for (int tx = 0; tx < (g.w + BLUR_TW - 1) / BLUR_TW; ++tx) { BlurTile t; t.level = (short)l; t.tx = (short)tx; t.ty = (short)ty; t.pad = 0; tiles.push_back(t); }
+    }
+    if (tree_cap > 32000) FAIL(ORBX_E_INVALID, "too many features per level");
+    // resize tables for levels >= 1
+    std::vector<int> tabs; std::vector<size_t> tab_off((size_t)L * 4, 0);
+    for (int l = 1; l < L; ++l) {
+        std::vector<int> xo, yo; std::vector<short> xw, yw;
+        linear_coefs(lv[l - 1].w, lv[l].w, lv[l].pitch, xo, xw);
+        linear_coefs(lv[l - 1].h, lv[l].h, align_up(lv[l].h, 8), yo, yw);
+        auto push = [&](const void* p, size_t bytes) { size_t o = tabs.size(); tabs.resize(o + (bytes + 15) / 16 * 4); std::memcpy(&tabs[o], p, bytes); return o; };
+        tab_off[l * 4 + 0] = push(xo.data(), xo.size() * 4); tab_off[l * 4 + 1] = push(xw.data(), xw.size() * 2);
+        tab_off[l * 4 + 2] = push(yo.data(), yo.size() * 4); tab_off[l * 4 + 3] = push(yw.data(), yw.size() * 2);
+    }
+    if (h->d_levels.ensure(L)) return ORBX_E_CUDA;
+    if (h->d_cells.ensure(cells.size())) return ORBX_E_CUDA;
+    if (h->d_tiles.ensure(tiles.size())) return ORBX_E_CUDA;
+    if (h->d_tabs.ensure(std::max<size_t>(tabs.size(), 4))) return ORBX_E_CUDA;
+    CU_TRY(cudaMemcpyAsync(h->d_levels.p, lv.data(), sizeof(LevelGeom) * L, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(cudaMemcpyAsync(h->d_cells.p, cells.data(), sizeof(CellDesc) * cells.size(), cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(cudaMemcpyAsync(h->d_tiles.p, tiles.data(), sizeof(BlurTile) * tiles.size(), cudaMemcpyHostToDevice, h->stream));
+    if (!tabs.empty()) CU_TRY(cudaMemcpyAsync(h->d_tabs.p, tabs.data(), tabs.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));   // host vectors go out of scope below
+    h->resize_tabs.assign(L, ResizeTabs());
+    for (int l = 1; l < L; ++l) {
+        h->resize_tabs[l].xofs = h->d_tabs.p + tab_off[l * 4 + 0];
+        h->resize_tabs[l].xw = reinterpret_cast<const short2*>(h->d_tabs.p + tab_off[l * 4 + 1]);
+        h->resize_tabs[l].yofs = h->d_tabs.p + tab_off[l * 4 + 2];
+        h->resize_tabs[l].yw = reinterpret_cast<const short2*>(h->d_tabs.p + tab_off[l * 4 + 3]);
+    }
+    h->levels.swap(lv); h->cells.swap(cells); h->tiles.swap(tiles);
+    h->pyr_fstride = (off + 255) / 256 * 256;
+    h->cand_per_frame = cand_off; h->kp_per_frame = kp_off;
+    h->max_kp = 0; for (int l = 0; l < L; ++l) h->max_kp += h->levels[l].kp_cap;
+    h->fast_smem_per_warp = align_up(smem_pw, 16);
+    h->tree_cap = tree_cap;
+    h->rows = rows; h->cols = cols; h->Bcap = 0; h->have_pyramid = false;
+    return ORBX_OK;
+}
+
+static int ensure_capacity(orbx_extractor* h, int B, int out_cap) {
+    if (B > h->Bcap) {
+        const size_t b = (size_t)B;
+        if (h->d_pyr.ensure(b * h->pyr_fstride) || h->d_blur.ensure(b * h->pyr_fstride) ||
+            h->d_slots.ensure(b * h->cand_per_frame) || h->d_ocand.ensure(b * h->cand_per_frame) ||
+            h->d_spk.ensure(b * h->cand_per_frame) || h->d_skey.ensure(b * h->cand_per_frame) ||
+            h->d_cell_counts.ensure(b * h->cells.size()) || h->d_ncand.ensure(b * h->nlevels) ||
+            h->d_kp_level.ensure(b * h->kp_per_frame) || h->d_kp_count.ensure(b * h->nlevels) ||
+            h->d_counts.ensure(b) || h->d_level_counts.ensure(b * h->nlevels) || h->d_overflow.ensure(4))
+            return ORBX_E_CUDA;
+        CU_TRY(cudaMemsetAsync(h->d_overflow.p, 0, 16, h->stream));
+        h->Bcap = B;
+    }
+    if (out_cap > 0 && ((size_t)B * out_cap > h->d_kp_out.n)) {
+        if (h->d_kp_out.ensure((size_t)B * out_cap) || h->d_desc_out.ensure((size_t)B * out_cap * 32)) return ORBX_E_CUDA;
+    }
+    return ORBX_OK;
+}
+
+#define LAUNCH_CHECK() do { cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) { \
+    orbx_set_error(std::string("kernel launch: ") + cudaGetErrorString(_e)); return ORBX_E_CUDA; } ++h->launches; } while (0)
+
+// pyramid (levels >= 1) + FAST cells + quadtree; leaves per-level keypoints in d_kp_level / d_kp_count
+static int run_detect(orbx_extractor* h, int B) {
+    cudaStream_t s = h->stream;
+    const int L = h->nlevels;
+    for (int l = 1; l < L; ++l) {
+        const LevelGeom& g = h->levels[l]; const LevelGeom& gp = h->levels[l - 1];
+        const uint8_t* src; long long sfs; int sp;
+        if (l == 1) { src = h->view.l0; sfs = h->view.l0_fstride; sp = h->view.l0_pitch; }
+        else { src = h->d_pyr.p + gp.off; sfs = h->pyr_fstride; sp = gp.pitch; }
+        dim3 grid((g.w + 127) / 128, (g.h + 7) / 8, B), block(32, 8);
+        k_pyr_resize<<<grid, block, 0, s>>>(src, sfs, sp, gp.w, gp.h, h->d_pyr.p + g.off, h->pyr_fstride, g.pitch, g.w, g.h, h->resize_tabs[l]);
+        LAUNCH_CHECK();
+    }
+    const int ncells = (int)h->cells.size();
+    {
+        dim3 grid((ncells + FAST_WARPS - 1) / FAST_WARPS, B);
+        const int smem = h->fast_smem_per_warp * FAST_WARPS;
+        k_fast_cells<<<grid, FAST_WARPS * 32, smem, s>>>(h->view, h->d_levels.p, h->d_cells.p, ncells, h->cand_per_frame,
+                                                          h->fast_smem_per_warp, h->iniThFAST, h->minThFAST, h->d_slots.p, h->d_cell_counts.p);
+        LAUNCH_CHECK();
+    }
+    {
+        dim3 grid(L, B);
+        k_octree_sort<<<grid, SORT_THREADS, (size_t)h->sort_smem_keys * 8, s>>>(h->d_levels.p, h->d_cells.p, ncells, h->cand_per_frame, h->cand_per_frame, L,
+                                                                                 h->sort_smem_keys, h->d_slots.p, h->d_cell_counts.p, h->d_ocand.p, h->d_skey.p, h->d_spk.p, h->d_ncand.p);
+        LAUNCH_CHECK();
+        const size_t tsm = (size_t)h->tree_cap * (8 + 8 + 4 + 4 + 4 + 2 + 2 + 2 + 1) + 16;
+        k_octree_tree<<<grid, 32, tsm, s>>>(h->d_levels.p, L, h->cand_per_frame, h->kp_per_frame, h->tree_cap, h->d_skey.p, h->d_spk.p, h->d_ncand.p,
+                                            h->d_kp_level.p, h->d_kp_count.p, h->d_overflow.p);
+        LAUNCH_CHECK();
+    }
+    h->lastB = B; h->have_pyramid = true; h->blur_valid = false;
+    return ORBX_OK;
+}
+
+static int run_blur(orbx_extractor* h, int B) {
+    if (h->blur_valid) return ORBX_OK;
+    dim3 grid((unsigned)h->tiles.size(), B);
+    k_gauss7<<<grid, 256, 0, h->stream>>>(h->view, h->d_levels.p, h->d_tiles.p, h->d_blur.p, h->pyr_fstride);
+    LAUNCH_CHECK();
+    h->blur_valid = true;
+    return ORBX_OK;
+}
+
+static int run_orient(orbx_extractor* h, int B, bool describe, KpOut* d_kp, uint8_t* d_desc, int cap, int* d_counts, int* d_level_counts) {
+    dim3 grid((h->kp_per_frame + 3) / 4, B);
+    if (describe)
+        k_orient_describe<true><<<grid, 128, 0, h->stream>>>(h->view, h->d_levels.p, h->nlevels, h->kp_per_frame, h->d_kp_level.p, h->d_kp_count.p,
+                                                            h->d_blur.p, h->pyr_fstride, d_kp, d_desc, cap, d_counts, d_level_counts);
+    else
+        k_orient_describe<false><<<grid, 128, 0, h->stream>>>(h->view, h->d_levels.p, h->nlevels, h->kp_per_frame, h->d_kp_level.p, h->d_kp_count.p,
+                                                             nullptr, 0, d_kp, nullptr, cap, d_counts, d_level_counts);
+    LAUNCH_CHECK();
+    return ORBX_OK;
+}
+
+// level 0 := host frames (H2D straight into the resident pyramid block)
+static int upload_level0(orbx_extractor* h, const uint8_t* images, int B, int rows, int cols, size_t step, size_t frame_stride) {
+    const LevelGeom& g0 = h->levels[0];
+    for (int b = 0; b < B; ++b)
+        CU_TRY(cudaMemcpy2DAsync(h->d_pyr.p + (size_t)b * h->pyr_fstride + g0.off, g0.pitch, images + (size_t)b * frame_stride, step,
+                                 cols, rows, cudaMemcpyHostToDevice, h->stream));
+    h->view.l0 = h->d_pyr.p + g0.off; h->view.l0_fstride = h->pyr_fstride; h->view.l0_pitch = g0.pitch;
+    h->view.pyr = h->d_pyr.p; h->view.pyr_fstride = h->pyr_fstride;
+    return ORBX_OK;
+}
+
+static int check_args(orbx_extractor* h, const void* image, int rows, int cols, size_t step) {
+    if (!h) FAIL(ORBX_E_INVALID, "null handle");
+    if (!image || rows <= 0 || cols <= 0 || step < (size_t)cols) FAIL(ORBX_E_INVALID, "bad image arguments");
+    CU_TRY(cudaSetDevice(h->device));
+    return ORBX_OK;
+}
+
+static int upload_constants() {
+    // __constant__ tables are per-device module state; upload on every create (cheap, idempotent)
+    const int um[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+    char4 pt[8 * 32];
+    for (int i = 0; i < 32; ++i) for (int k = 0; k < 8; ++k) {
+        const signed char* p = k_brief_pattern_host + (size_t)(8 * i + k) * 4;
+        pt[k * 32 + i] = make_char4(p[0], p[1], p[2], p[3]);
+    }
+    CU_TRY(cudaMemcpyToSymbol(c_umax, um, sizeof(um)));
+    CU_TRY(cudaMemcpyToSymbol(c_pattern_t, pt, sizeof(pt)));
+    return ORBX_OK;
+}
+
+extern "C" {
+
+int orbx_create(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST, int device, orbx_extractor** out) {
+    if (!out) FAIL(ORBX_E_INVALID, "null out");
+    *out = nullptr;
+    if (nfeatures <= 0 || nlevels <= 0 || nlevels > ORBX_MAX_LEVELS || !(scaleFactor > 1.0f) || iniThFAST < 0 || minThFAST < 0 || minThFAST > 255)
+        FAIL(ORBX_E_INVALID, "bad extractor parameters");
+    int ndev = 0;
+    CU_TRY(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) FAIL(ORBX_E_CUDA, "no such CUDA device (this library has no CPU fallback)");
+    CU_TRY(cudaSetDevice(device));
+    orbx_extractor* h = new orbx_extractor();
+    h->nfeatures = nfeatures; h->scaleFactor = scaleFactor; h->nlevels = nlevels; h->iniThFAST = iniThFAST; h->minThFAST = minThFAST; h->device = device;
+    // scale tables: double product stored to float (ORBextractor.cc:506-524, include/ORBextractor.h:213)
+    h->mvScaleFactor.resize(nlevels); h->mvLevelSigma2.resize(nlevels); h->mvInvScaleFactor.resize(nlevels); h->mvInvLevelSigma2.resize(nlevels);
+    h->mvScaleFactor[0] = 1.0f; h->mvLevelSigma2[0] = 1.0f;
+    for (int i = 1; i < nlevels; i++) { h->mvScaleFactor[i] = (float)(h->mvScaleFactor[i - 1] * h->scaleFactor); h->mvLevelSigma2[i] = h->mvScaleFactor[i] * h->mvScaleFactor[i]; }
+    for (int i = 0; i < nlevels; i++) { h->mvInvScaleFactor[i] = 1.0f / h->mvScaleFactor[i]; h->mvInvLevelSigma2[i] = 1.0f / h->mvLevelSigma2[i]; }
+    // per-level quotas (:534-554)
+    h->mnFeaturesPerLevel.resize(nlevels);
+    float factor = (float)(1.0f / h->scaleFactor);
+    float nDesired = (float)(nfeatures * (1 - factor) / (1 - (float)std::pow((double)factor, (double)nlevels)));
+    int sum = 0;
+    for (int level = 0; level < nlevels - 1; level++) { h->mnFeaturesPerLevel[level] = cv_round_f(nDesired); sum += h->mnFeaturesPerLevel[level]; nDesired *= factor; }
+    h->mnFeaturesPerLevel[nlevels - 1] = std::max(nfeatures - sum, 0);
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete h; FAIL(ORBX_E_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e)); }
+    if (upload_constants() != ORBX_OK) { cudaStreamDestroy(h->stream); delete h; return ORBX_E_CUDA; }
+    cudaFuncSetAttribute(k_octree_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+    cudaFuncSetAttribute(k_octree_tree, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    *out = h;
+    return ORBX_OK;
+}
+
+void orbx_destroy(orbx_extractor* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    h->d_levels.release(); h->d_cells.release(); h->d_tiles.release(); h->d_tabs.release();
+    h->d_pyr.release(); h->d_blur.release(); h->d_slots.release(); h->d_ocand.release(); h->d_spk.release(); h->d_kp_level.release();
+    h->d_skey.release(); h->d_cell_counts.release(); h->d_ncand.release(); h->d_kp_count.release(); h->d_counts.release();
+    h->d_level_counts.release(); h->d_overflow.release(); h->d_kp_out.release(); h->d_desc_out.release();
+    h->d_kp_tmp.release(); h->d_desc_tmp.release(); h->d_mask.release(); h->d_mask2.release(); h->d_label.release(); h->d_ids.release();
+    cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int orbx_get_levels(const orbx_extractor* h) { return h ? h->nlevels : 0; }
+float orbx_get_scale_factor(const orbx_extractor* h) { return h ? (float)h->scaleFactor : 0.f; }
+#define GETTER(name, member, T) int name(const orbx_extractor* h, T* out) { if (!h || !out) return ORBX_E_INVALID; for (int i = 0; i < h->nlevels; ++i) out[i] = h->member[i]; return ORBX_OK; }
+GETTER(orbx_get_scale_factors, mvScaleFactor, float)
+GETTER(orbx_get_inverse_scale_factors, mvInvScaleFactor, float)
+GETTER(orbx_get_scale_sigma_squares, mvLevelSigma2, float)
+GETTER(orbx_get_inverse_scale_sigma_squares, mvInvLevelSigma2, float)
+GETTER(orbx_get_features_per_level, mnFeaturesPerLevel, int)
+void* orbx_stream(orbx_extractor* h) { return h ? (void*)h->stream : nullptr; }
+long long orbx_launch_count(const orbx_extractor* h) { return h ? h->launches : 0; }
+
+int orbx_max_keypoints(orbx_extractor* h, int rows, int cols) {
+    if (!h || rows <= 0 || cols <= 0) FAIL(ORBX_E_INVALID, "bad arguments");
+    if (cudaSetDevice(h->device) != cudaSuccess) return ORBX_E_CUDA;
+    int rc = build_plan(h, rows, cols);
+    return rc ? rc : h->max_kp;
+}
+
+int orbx_check_overflow(orbx_extractor* h) {
+    if (!h || !h->d_overflow.p) return 0;
+    int v = 0;
+    cudaSetDevice(h->device);
+    if (cudaMemcpyAsync(&v, h->d_overflow.p, 4, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) return ORBX_E_CUDA;
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) return ORBX_E_CUDA;
+    return v;
+}
+
+int orbx_extract_batch_device(orbx_extractor* h, const uint8_t* d_images, int B, int rows, int cols, size_t step, size_t frame_stride,
+                              orbx_keypoint* d_kp_out, uint8_t* d_desc_out, int cap, int* d_counts_out) {
+    int rc = check_args(h, d_images, rows, cols, step); if (rc) return rc;
+    if (B <= 0 || !d_kp_out || !d_desc_out || !d_counts_out || cap <= 0) FAIL(ORBX_E_INVALID, "bad batch arguments");
+    if ((rc = build_plan(h, rows, cols))) return rc;
+    if ((rc = ensure_capacity(h, B, 0))) return rc;
+    if (((uintptr_t)d_images & 3) == 0 && (step & 3) == 0 && (frame_stride & 3) == 0) {
+        h->view.l0 = d_images; h->view.l0_fstride = (long long)frame_stride; h->view.l0_pitch = (int)step;       // alias the caller's frames
+    } else {
+        const LevelGeom& g0 = h->levels[0];
+        for (int b = 0; b < B; ++b)
+            CU_TRY(cudaMemcpy2DAsync(h->d_pyr.p + (size_t)b * h->pyr_fstride + g0.off, g0.pitch, d_images + (size_t)b * frame_stride, step, cols, rows, cudaMemcpyDeviceToDevice, h->stream));
+        h->view.l0 = h->d_pyr.p + g0.off; h->view.l0_fstride = h->pyr_fstride; h->view.l0_pitch = g0.pitch;
+    }
+    h->view.pyr = h->d_pyr.p; h->view.pyr_fstride = h->pyr_fstride;
+    if ((rc = run_detect(h, B))) return rc;
+    if ((rc = run_blur(h, B))) return rc;
+    return run_orient(h, B, true, reinterpret_cast<KpOut*>(d_kp_out), d_desc_out, cap, d_counts_out, nullptr);
+}
+
+int orbx_extract_batch(orbx_extractor* h, const uint8_t* images, int B, int rows, int cols, size_t step, size_t frame_stride,
+                       orbx_keypoint* kp_out, uint8_t* desc_out, int cap, int* counts_out) {
+    int rc = check_args(h, images, rows, cols, step); if (rc) return rc;
+    if (B <= 0 || !kp_out || !desc_out || !counts_out || cap <= 0) FAIL(ORBX_E_INVALID, "bad batch arguments");
+    if ((rc = build_plan(h, rows, cols))) return rc;
+    if ((rc = ensure_capacity(h, B, cap))) return rc;
+    if ((rc = upload_level0(h, images, B, rows, cols, step, frame_stride))) return rc;
+    if ((rc = run_detect(h, B))) return rc;
+    if ((rc = run_blur(h, B))) return rc;
+    if ((rc = run_orient(h, B, true, h->d_kp_out.p, h->d_desc_out.p, cap, h->d_counts.p, nullptr))) return rc;
+    CU_TRY(cudaMemcpyAsync(kp_out, h->d_kp_out.p, (size_t)B * cap * sizeof(KpOut), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(cudaMemcpyAsync(desc_out, h->d_desc_out.p, (size_t)B * cap * 32, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(cudaMemcpyAsync(counts_out, h->d_counts.p, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    int ovf = 0;
+    CU_TRY(cudaMemcpyAsync(&ovf, h->d_overflow.p, 4, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    if (ovf) FAIL(ORBX_E_OVERFLOW, "internal bound exceeded in the quadtree stage");
+    return ORBX_OK;
+}
+
+int orbx_extract(orbx_extractor* h, const uint8_t* image, int rows, int cols, size_t step,
+                 orbx_keypoint* kp_out, uint8_t* desc_out, int cap, int* n_out) {
+    if (n_out) *n_out = 0;
+    if (!h) FAIL(ORBX_E_INVALID, "null handle");
+    if (!image || rows <= 0 || cols <= 0) return ORBX_OK;          // empty image: silent return, 0 keypoints (ORBextractor.cc:1553)
+    if (!kp_out || !desc_out || !n_out) FAIL(ORBX_E_INVALID, "null output");
+    int rc = check_args(h, image, rows, cols, step); if (rc) return rc;
+    if ((rc = build_plan(h, rows, cols))) return rc;
+    const int icap = h->max_kp;
+    if ((rc = ensure_capacity(h, 1, icap))) return rc;
+    if ((rc = upload_level0(h, image, 1, rows, cols, step, 0))) return rc;
+    if ((rc = run_detect(h, 1))) return rc;
+    if ((rc = run_blur(h, 1))) return rc;
+    if ((rc = run_orient(h, 1, true, h->d_kp_out.p, h->d_desc_out.p, icap, h->d_counts.p, nullptr))) return rc;
+    int n = 0, ovf = 0;
+    CU_TRY(cudaMemcpyAsync(&n, h->d_counts.p, 4, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(cudaMemcpyAsync(&ovf, h->d_overflow.p, 4, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    if (ovf) FAIL(ORBX_E_OVERFLOW, "internal bound exceeded in the quadtree stage");
+    *n_out = n;
+    if (n > cap) FAIL(ORBX_E_CAPACITY, "keypoint buffer too small");
+    if (n) {
+        CU_TRY(cudaMemcpyAsync(kp_out, h->d_kp_out.p, (size_t)n * sizeof(KpOut), cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(cudaMemcpyAsync(desc_out, h->d_desc_out.p, (size_t)n * 32, cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(cudaStreamSynchronize(h->stream));
+    }
+    return ORBX_OK;
+}
+
+int orbx_detect(orbx_extractor* h, const uint8_t* image, int rows, int cols, size_t step,
+                orbx_keypoint* kp_out, int* level_counts, int cap, int* n_out) {
+    if (n_out) *n_out = 0;
+    if (!h) FAIL(ORBX_E_INVALID, "null handle");
+    if (!image || rows <= 0 || cols <= 0) return ORBX_OK;
+    if (!kp_out || !level_counts || !n_out) FAIL(ORBX_E_INVALID, "null output");
+    int rc = check_args(h, image, rows, cols, step); if (rc) return rc;
+    if ((rc = build_plan(h, rows, cols))) return rc;
+    const int icap = h->max_kp;
+    if ((rc = ensure_capacity(h, 1, icap))) return rc;
+    if ((rc = upload_level0(h, image, 1, rows, cols, step, 0))) return rc;
+    if ((rc = run_detect(h, 1))) return rc;
+    if ((rc = run_orient(h, 1, false, h->d_kp_out.p, nullptr, icap, h->d_counts.p, h->d_level_counts.p))) return rc;
+    int n = 0, ovf = 0;
+    CU_TRY(cudaMemcpyAsync(&n, h->d_counts.p, 4, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(cudaMemcpyAsync(level_counts, h->d_level_counts.p, 4 * h->nlevels, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(cudaMemcpyAsync(&ovf, h->d_overflow.p, 4, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    if (ovf) FAIL(ORBX_E_OVERFLOW, "internal bound exceeded in the quadtree stage");
+    *n_out = n;
+    if (n > cap) FAIL(ORBX_E_CAPACITY, "keypoint buffer too small");
+    if (n) { CU_TRY(cudaMemcpyAsync(kp_out, h->d_kp_out.p, (size_t)n * sizeof(KpOut), cudaMemcpyDeviceToHost, h->stream)); CU_TRY(cudaStreamSynchronize(h->stream)); }
+    return ORBX_OK;
+}
+
+int orbx_describe(orbx_extractor* h, const orbx_keypoint* kp_in, const int* level_counts, orbx_keypoint* kp_out, uint8_t* desc_out, int cap, int* n_out) {
+    if (!h || !level_counts || !n_out) FAIL(ORBX_E_INVALID, "null argument");
+    if (!h->have_pyramid) FAIL(ORBX_E_STATE, "orbx_describe needs the pyramid of a previous orbx_detect / orbx_extract");
+    CU_TRY(cudaSetDevice(h->device));
+    int n = 0;
+    for (int l = 0; l < h->nlevels; ++l) { if (level_counts[l] < 0) FAIL(ORBX_E_INVALID, "negative level count"); n += level_counts[l]; }
+    *n_out = n;
+    if (n == 0) return ORBX_OK;
+    if (!kp_in || !kp_out || !desc_out) FAIL(ORBX_E_INVALID, "null buffer");
+    if (n > cap) FAIL(ORBX_E_CAPACITY, "keypoint buffer too small");
+    // the reference takes the level from the position in allKeypoints, not from kp.octave: stamp it
+    std::vector<KpOut> tmp(n);
+    std::memcpy(tmp.data(), kp_in, sizeof(KpOut) * n);
+    { int o = 0; for (int l = 0; l < h->nlevels; ++l) for (int i = 0; i < level_counts[l]; ++i, ++o) {
+        const LevelGeom& g = h->levels[l];
+        const int x = (int)lrintf(tmp[o].x), y = (int)lrintf(tmp[o].y);
+        if (x < ORBX_EDGE || y < ORBX_EDGE || x >= g.w - ORBX_EDGE || y >= g.h - ORBX_EDGE) FAIL(ORBX_E_INVALID, "keypoint closer than 19 px to the level border");
+        if (tmp[o].octave != l) FAIL(ORBX_E_INVALID, "keypoint octave does not match its level bucket");
+    } }
+    if (h->d_kp_tmp.ensure((size_t)n * 2) || h->d_desc_tmp.ensure((size_t)n * 32)) return ORBX_E_CUDA;
+    int rc;
+    if ((rc = run_blur(h, 1))) return rc;
+    CU_TRY(cudaMemcpyAsync(h->d_kp_tmp.p, tmp.data(), sizeof(KpOut) * n, cudaMemcpyHostToDevice, h->stream));
+    k_describe_given<<<(n + 3) / 4, 128, 0, h->stream>>>(h->d_levels.p, h->nlevels, h->d_kp_tmp.p, n, h->d_blur.p, h->d_kp_tmp.p + n, h->d_desc_tmp.p);
+    LAUNCH_CHECK();
+    CU_TRY(cudaMemcpyAsync(kp_out, h->d_kp_tmp.p + n, sizeof(KpOut) * n, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(cudaMemcpyAsync(desc_out, h->d_desc_tmp.p, (size_t)n * 32, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    return ORBX_OK;
+}
+
+static int copy_level(orbx_extractor* h, const uint8_t* base, int pitch, int level, int border, uint8_t* dst, size_t dst_step) {
+    const LevelGeom& g = h->levels[level];
+    if (border == 0) {
+        CU_TRY(cudaMemcpy2DAsync(dst, dst_step, base, pitch, g.w, g.h, cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(cudaStreamSynchronize(h->stream));
+        return ORBX_OK;
+    }
+    // padded export: BORDER_REFLECT_101 frame of `border` px, materialised by a small kernel
+    const int W = g.w + 2 * border, H = g.h + 2 * border;
+    if (h->d_mask.ensure((size_t)W * H)) return ORBX_E_CUDA;
+    k_border101<<<dim3((W + 31) / 32, (H + 7) / 8), dim3(32, 8), 0, h->stream>>>(base, pitch, g.w, g.h, border, h->d_mask.p, W, H);
+    LAUNCH_CHECK();
+    CU_TRY(cudaMemcpy2DAsync(dst, dst_step, h->d_mask.p, W, W, H, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    return ORBX_OK;
+}
+
+int orbx_pyramid_level(orbx_extractor* h, int level, int border, uint8_t* dst, size_t dst_step, int* rows_out, int* cols_out) {
+    if (!h) FAIL(ORBX_E_INVALID, "null handle");
+    if (!h->have_pyramid) FAIL(ORBX_E_STATE, "no resident pyramid");
+    if (level < 0 || level >= h->nlevels || border < 0 || border > 64) FAIL(ORBX_E_INVALID, "bad level / border");
+    CU_TRY(cudaSetDevice(h->device));
+    const LevelGeom& g = h->levels[level];
+    if (rows_out) *rows_out = g.h + 2 * border;
+    if (cols_out) *cols_out = g.w + 2 * border;
+    if (!dst) return ORBX_OK;
+    if (dst_step < (size_t)(g.w + 2 * border)) FAIL(ORBX_E_INVALID, "dst_step too small");
+    const uint8_t* base; int pitch;
+    if (level == 0) { base = h->view.l0; pitch = h->view.l0_pitch; } else { base = h->d_pyr.p + g.off; pitch = g.pitch; }
+    return copy_level(h, base, pitch, level, border, dst, dst_step);
+}
+
+int orbx_debug_pyramid_level(orbx_extractor* h, int b, int level, uint8_t* dst, size_t dst_step) {
+    if (!h || !h->have_pyramid || b < 0 || b >= h->lastB || level < 0 || level >= h->nlevels || !dst) FAIL(ORBX_E_INVALID, "bad arguments");
+    CU_TRY(cudaSetDevice(h->device));
+    const LevelGeom& g = h->levels[level];
+    const uint8_t* base; int pitch;
+    if (level == 0) { base = h->view.l0 + (long long)b * h->view.l0_fstride; pitch = h->view.l0_pitch; }
+    else { base = h->d_pyr.p + (size_t)b * h->pyr_fstride + g.off; pitch = g.pitch; }
+    return copy_level(h, base, pitch, level, 0, dst, dst_step);
+}
+
+int orbx_debug_blurred_level(orbx_extractor* h, int b, int level, uint8_t* dst, size_t dst_step) {
+    if (!h || !h->have_pyramid || b < 0 || b >= h->lastB || level < 0 || level >= h->nlevels || !dst) FAIL(ORBX_E_INVALID, "bad arguments");
+    CU_TRY(cudaSetDevice(h->device));
+    int rc; if ((rc = run_blur(h, h->lastB))) return rc;
+    const LevelGeom& g = h->levels[level];
+    return copy_level(h, h->d_blur.p + (size_t)b * h->pyr_fstride + g.off, g.pitch, level, 0, dst, dst_step);
+}
+
+int orbx_debug_level_candidates(orbx_extractor* h, int b, int level, orbx_keypoint* out, int cap, int* n_out) {
+    if (!h || !h->have_pyramid || b < 0 || b >= h->lastB || level < 0 || level >= h->nlevels || !n_out) FAIL(ORBX_E_INVALID, "bad arguments");
+    CU_TRY(cudaSetDevice(h->device));
+    const LevelGeom& g = h->levels[level];
+    int n = 0;
+    CU_TRY(cudaMemcpyAsync(&n, h->d_ncand.p + (size_t)b * h->nlevels + level, 4, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    *n_out = n;
+    if (n <= 0) return ORBX_OK;
+    if (n > cap || !out) FAIL(ORBX_E_CAPACITY, "candidate buffer too small");
+    std::vector<uint32_t> p(n);
+    CU_TRY(cudaMemcpyAsync(p.data(), h->d_ocand.p + (size_t)b * h->cand_per_frame + g.cand_off, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < n; ++i) {
+        out[i].x = (float)(p[i] & 0xFFF); out[i].y = (float)((p[i] >> 12) & 0xFFF); out[i].size = 7.f; out[i].angle = -1.f;
+        out[i].response = (float)(p[i] >> 24); out[i].octave = 0; out[i].class_id = -1;
+    }
+    return ORBX_OK;
+}
+
+}  // extern "C"
+
+#include "orbx_extractor_debug.inl"

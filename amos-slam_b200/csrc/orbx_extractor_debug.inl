@@ -1,0 +1,124 @@
+// orbx_extractor_debug.inl -- orbx_cull (MovingKeyPoints) and the quadtree stage tap; part of orbx_extractor.cu
+
+static int upload_ellipse() {
+    // cv::getStructuringElement(MORPH_ELLIPSE, 31x31): dx = cvRound(c * sqrt((r*r - dy*dy) * inv_r2))
+    int dxs[31];
+    const int r = 15, c = 15; const double inv_r2 = 1.0 / ((double)r * r);
+    for (int i = 0; i < 31; ++i) { const int dy = i - r; dxs[i] = (int)lrint(c * std::sqrt((r * r - dy * dy) * inv_r2)); }
+    CU_TRY(cudaMemcpyToSymbol(c_ell_dx, dxs, sizeof(dxs)));
+    return ORBX_OK;
+}
+
+extern "C" int orbx_cull(orbx_extractor* h, const uint8_t* mask, size_t mask_step, const double* label, size_t label_step,
+                         int rows, int cols, const int* centers_id, int ncenters, const int* rm_vector, int nrm,
+                         orbx_keypoint* kp_inout, int* level_counts, orbx_keypoint* culled_out, int* n_culled) {
+    if (n_culled) *n_culled = 0;
+    if (!h || !mask || !label || !level_counts || !n_culled || rows <= 0 || cols <= 0 || ncenters < 0 || nrm < 0) FAIL(ORBX_E_INVALID, "bad arguments");
+    if (mask_step < (size_t)cols || label_step < (size_t)cols * sizeof(double) || (label_step % sizeof(double))) FAIL(ORBX_E_INVALID, "bad steps");
+    if ((ncenters && !centers_id) || (nrm && !rm_vector)) FAIL(ORBX_E_INVALID, "null table");
+    CU_TRY(cudaSetDevice(h->device));
+    int n = 0;
+    for (int l = 0; l < h->nlevels; ++l) { if (level_counts[l] < 0) FAIL(ORBX_E_INVALID, "negative level count"); n += level_counts[l]; }
+    int rc;
+    if ((rc = upload_ellipse())) return rc;
+    const int pitch = align_up(cols, 128);
+    if (h->d_mask.ensure((size_t)pitch * rows) || h->d_mask2.ensure((size_t)pitch * rows) || h->d_label.ensure((size_t)rows * cols) ||
+        h->d_ids.ensure((size_t)ncenters + nrm + 4) || h->d_kp_tmp.ensure((size_t)std::max(n, 1) * 2) || h->d_desc_tmp.ensure((size_t)std::max(n, 1) * 32))
+        return ORBX_E_CUDA;
+    cudaStream_t s = h->stream;
+    CU_TRY(cudaMemcpy2DAsync(h->d_mask.p, pitch, mask, mask_step, cols, rows, cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpy2DAsync(h->d_label.p, (size_t)cols * 8, label, label_step, (size_t)cols * 8, rows, cudaMemcpyHostToDevice, s));
+    if (ncenters) CU_TRY(cudaMemcpyAsync(h->d_ids.p, centers_id, (size_t)ncenters * 4, cudaMemcpyHostToDevice, s));
+    if (nrm) CU_TRY(cudaMemcpyAsync(h->d_ids.p + ncenters, rm_vector, (size_t)nrm * 4, cudaMemcpyHostToDevice, s));
+    // closing = erode(dilate(mask))   (:1697-1704)
+    dim3 grid((cols + MORPH_TW - 1) / MORPH_TW, (rows + MORPH_TH - 1) / MORPH_TH), block(MORPH_TW, MORPH_TH);
+    k_morph_ellipse31<true><<<grid, block, 0, s>>>(h->d_mask.p, pitch, h->d_mask2.p, pitch, cols, rows);
+    LAUNCH_CHECK();
+    k_morph_ellipse31<false><<<grid, block, 0, s>>>(h->d_mask2.p, pitch, h->d_mask.p, pitch, cols, rows);
+    LAUNCH_CHECK();
+    if (n == 0) { CU_TRY(cudaStreamSynchronize(s)); return ORBX_OK; }
+    if (!kp_inout) FAIL(ORBX_E_INVALID, "null keypoints");
+    // per-keypoint scale: level 0 -> 1, else mvScaleFactor[level]  (:1712-1715); scales ride in the desc scratch
+    std::vector<float> scales(n);
+    { int o = 0; for (int l = 0; l < h->nlevels; ++l) for (int i = 0; i < level_counts[l]; ++i) scales[o++] = l ? h->mvScaleFactor[l] : 1.f; }
+    float* d_scales = reinterpret_cast<float*>(h->d_desc_tmp.p);
+    uint8_t* d_flags = h->d_desc_tmp.p + (size_t)n * 4;
+    CU_TRY(cudaMemcpyAsync(h->d_kp_tmp.p, kp_inout, sizeof(KpOut) * n, cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpyAsync(d_scales, scales.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    k_cull_flags<<<(n + 127) / 128, 128, 0, s>>>(reinterpret_cast<const KpIn*>(h->d_kp_tmp.p), d_scales, n, h->d_mask.p, pitch, h->d_label.p, cols,
+                                                  rows, cols, h->d_ids.p, ncenters, h->d_ids.p + ncenters, nrm, d_flags);
+    LAUNCH_CHECK();
+    std::vector<uint8_t> flags(n);
+    CU_TRY(cudaMemcpyAsync(flags.data(), d_flags, n, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    // stable erase per level, culled keypoints appended in visiting order (marshalling of the device flags)
+    int o = 0, w = 0, nc = 0;
+    for (int l = 0; l < h->nlevels; ++l) {
+        int kept = 0;
+        for (int i = 0; i < level_counts[l]; ++i, ++o) {
+            if (flags[o]) { if (culled_out) culled_out[nc] = kp_inout[o]; ++nc; }
+            else { kp_inout[w++] = kp_inout[o]; ++kept; }
+        }
+        level_counts[l] = kept;
+    }
+    *n_culled = nc;
+    return ORBX_OK;
+}
+
+// DistributeOctTree stage tap: the pipeline's own sort + tree kernels on caller-provided candidates
+extern "C" int orbx_debug_distribute(orbx_extractor* h, const orbx_keypoint* cand, int ncand, int minX, int maxX, int minY, int maxY, int N,
+                                     orbx_keypoint* out, int cap, int* n_out) {
+    if (!h || !n_out || ncand < 0 || (ncand && !cand) || maxX <= minX || maxY <= minY || N < 0) FAIL(ORBX_E_INVALID, "bad arguments");
+    *n_out = 0;
+    if (ncand == 0) return ORBX_OK;
+    if (maxX - minX > ORBX_MAX_DIM || maxY - minY > ORBX_MAX_DIM || ncand >= (1 << 20)) FAIL(ORBX_E_INVALID, "too large");
+    CU_TRY(cudaSetDevice(h->device));
+    LevelGeom g; std::memset(&g, 0, sizeof(g));
+    g.minBX = minX; g.maxBX = maxX; g.minBY = minY; g.maxBY = maxY; g.N = N;
+    g.nIni = (int)std::round(static_cast<float>(maxX - minX) / (maxY - minY));
+    if (g.nIni < 1 || g.nIni > 15) FAIL(ORBX_E_INVALID, "unsupported aspect ratio");
+    g.hX = static_cast<float>(maxX - minX) / g.nIni;
+    const int CH = 1024;
+    const int nc = (ncand + CH - 1) / CH;
+    g.cell_begin = 0; g.cell_count = nc; g.cand_off = 0; g.cand_cap = ncand; g.kp_off = 0; g.kp_cap = std::max(N + 2, 4 * g.nIni) + 2;
+    const int tcap = g.kp_cap + 8;
+    if (tcap > 32000) FAIL(ORBX_E_INVALID, "N too large");
+    std::vector<CellDesc> cells(nc); std::vector<uint16_t> counts(nc); std::vector<uint32_t> packed(ncand);
+    for (int c = 0; c < nc; ++c) { std::memset(&cells[c], 0, sizeof(CellDesc)); cells[c].slot = c * CH; counts[c] = (uint16_t)std::min(CH, ncand - c * CH); }
+    for (int i = 0; i < ncand; ++i) {
+        const int x = (int)cand[i].x, y = (int)cand[i].y, r = (int)cand[i].response;
+        if (x < 0 || y < 0 || x > ORBX_MAX_DIM || y > ORBX_MAX_DIM || r < 0 || r > 255 || (float)x != cand[i].x || (float)y != cand[i].y)
+            FAIL(ORBX_E_INVALID, "candidates must have integer coordinates in [0,4095] and response in [0,255]");
+        packed[i] = (uint32_t)x | ((uint32_t)y << 12) | ((uint32_t)r << 24);
+    }
+    DevBuf<LevelGeom> dl; DevBuf<CellDesc> dc; DevBuf<uint16_t> dcnt; DevBuf<uint32_t> dslots, doc, dspk, dkp; DevBuf<unsigned long long> dsk; DevBuf<int> dn, dkc;
+    struct Guard { DevBuf<LevelGeom>& a; DevBuf<CellDesc>& b; DevBuf<uint16_t>& c; DevBuf<uint32_t>&d, &e, &f, &g; DevBuf<unsigned long long>& hh; DevBuf<int>&i, &j;
+                   ~Guard() { a.release(); b.release(); c.release(); d.release(); e.release(); f.release(); g.release(); hh.release(); i.release(); j.release(); } } guard{dl, dc, dcnt, dslots, doc, dspk, dkp, dsk, dn, dkc};
+    if (dl.ensure(1) || dc.ensure(nc) || dcnt.ensure(nc) || dslots.ensure(ncand) || doc.ensure(ncand) || dspk.ensure(ncand) || dsk.ensure(ncand) ||
+        dkp.ensure(g.kp_cap) || dn.ensure(1) || dkc.ensure(1) || h->d_overflow.ensure(4)) return ORBX_E_CUDA;
+    cudaStream_t s = h->stream;
+    CU_TRY(cudaMemsetAsync(h->d_overflow.p, 0, 16, s));
+    CU_TRY(cudaMemcpyAsync(dl.p, &g, sizeof(g), cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpyAsync(dc.p, cells.data(), sizeof(CellDesc) * nc, cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpyAsync(dcnt.p, counts.data(), 2 * nc, cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpyAsync(dslots.p, packed.data(), 4 * (size_t)ncand, cudaMemcpyHostToDevice, s));
+    k_octree_sort<<<dim3(1, 1), SORT_THREADS, (size_t)h->sort_smem_keys * 8, s>>>(dl.p, dc.p, nc, ncand, ncand, 1, h->sort_smem_keys, dslots.p, dcnt.p, doc.p, dsk.p, dspk.p, dn.p);
+    LAUNCH_CHECK();
+    const size_t tsm = (size_t)tcap * (8 + 8 + 4 + 4 + 4 + 2 + 2 + 2 + 1) + 16;
+    k_octree_tree<<<dim3(1, 1), 32, tsm, s>>>(dl.p, 1, ncand, g.kp_cap, tcap, dsk.p, dspk.p, dn.p, dkp.p, dkc.p, h->d_overflow.p);
+    LAUNCH_CHECK();
+    int n = 0, ovf = 0;
+    std::vector<uint32_t> res(g.kp_cap);
+    CU_TRY(cudaMemcpyAsync(&n, dkc.p, 4, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(&ovf, h->d_overflow.p, 4, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(res.data(), dkp.p, 4 * (size_t)g.kp_cap, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    if (ovf) { CU_TRY(cudaMemsetAsync(h->d_overflow.p, 0, 16, s)); FAIL(ORBX_E_OVERFLOW, "internal bound exceeded in the quadtree stage"); }
+    *n_out = n;
+    if (n > cap || !out) FAIL(ORBX_E_CAPACITY, "output buffer too small");
+    for (int i = 0; i < n; ++i) {
+        out[i].x = (float)(res[i] & 0xFFF); out[i].y = (float)((res[i] >> 12) & 0xFFF); out[i].size = 7.f; out[i].angle = -1.f;
+        out[i].response = (float)(res[i] >> 24); out[i].octave = 0; out[i].class_id = -1;
+    }
+    return ORBX_OK;
+}

@@ -1,0 +1,240 @@
+/* orbx_b200.h -- C ABI of the B200-native ORB feature front-end (liborbx_b200.so).
+ *
+ * Drop-in boundary for the Amos-SLAM / ORB-SLAM2 hot path: ORBextractor (pyramid, per-cell FAST-9,
+ * quadtree distribution, IC orientation, 7x7 blur, rBRIEF, Amos dynamic-mask culling) and the
+ * ORBmatcher / Frame::ComputeStereoMatches 256-bit Hamming matching.  Plain pointers and sizes only;
+ * every entry point names the reference interface it replaces (paths relative to the reference root).
+ * The C++ classes in amos-slam_b200/host/ (ORB_SLAM2::ORBextractor / ORBmatcher with the reference's
+ * own signatures) marshal into these calls; INTEGRATION.md shows the binding a maintainer adds.
+ *
+ * Conventions
+ *   - every function returns an int status: ORBX_OK (0) or a negative ORBX_E_* code; no exceptions
+ *     or aborts cross this boundary.  orbx_last_error() returns a thread-local message.
+ *   - all output buffers are caller-allocated.  Host-pointer calls are synchronous (results are
+ *     valid on return); *_device calls are stream-ordered on the handle's stream (orbx_stream()).
+ *   - a handle is stateful and non-reentrant exactly like the reference's ORBextractor object
+ *     (it keeps mvImagePyramid between detect / cull / describe); distinct handles are independent
+ *     and may be driven from different threads (include/ORBextractor.h:93-168, src/Frame.cc:165-173).
+ *   - there is NO CPU fallback: if no CUDA device is usable, create fails with ORBX_E_CUDA.
+ */
+#ifndef ORBX_B200_H
+#define ORBX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORBX_OK 0
+#define ORBX_E_INVALID (-1)   /* bad argument (null pointer, non-positive size, unsupported geometry) */
+#define ORBX_E_CUDA (-2)      /* CUDA runtime error; see orbx_last_error() */
+#define ORBX_E_CAPACITY (-3)  /* caller buffer too small; *n_out holds the required count */
+#define ORBX_E_STATE (-4)     /* call sequence error (e.g. describe before detect) */
+#define ORBX_E_OVERFLOW (-5)  /* an internal worst-case bound was exceeded (reported, never silent) */
+
+/* Binary-identical to cv::KeyPoint (28 bytes): the C++ layer memcpy's straight into std::vector<cv::KeyPoint>. */
+typedef struct orbx_keypoint {
+    float x, y;       /* pt */
+    float size;       /* int(31 * scale[octave])            src/ORBextractor.cc:1175,1189 */
+    float angle;      /* degrees, IC_Angle / fastAtan2      src/ORBextractor.cc:108-161  */
+    float response;   /* FAST score S-1                      cv::FAST                     */
+    int32_t octave;
+    int32_t class_id; /* always -1 */
+} orbx_keypoint;
+
+typedef struct orbx_extractor orbx_extractor;
+
+const char* orbx_last_error(void);
+int orbx_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * ORBextractor::ORBextractor(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST)
+ *   include/ORBextractor.h:93, src/ORBextractor.cc:492-609.   `device` = CUDA ordinal.
+ * ---------------------------------------------------------------------------------------------- */
+int orbx_create(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST,
+                int device, orbx_extractor** out);
+void orbx_destroy(orbx_extractor* h);
+
+/* GetLevels / GetScaleFactor / GetScaleFactors / GetInverseScaleFactors / GetScaleSigmaSquares /
+ * GetInverseScaleSigmaSquares   include/ORBextractor.h:117-165.  Arrays hold nlevels floats/ints. */
+int orbx_get_levels(const orbx_extractor* h);
+float orbx_get_scale_factor(const orbx_extractor* h);
+int orbx_get_scale_factors(const orbx_extractor* h, float* out);
+int orbx_get_inverse_scale_factors(const orbx_extractor* h, float* out);
+int orbx_get_scale_sigma_squares(const orbx_extractor* h, float* out);
+int orbx_get_inverse_scale_sigma_squares(const orbx_extractor* h, float* out);
+int orbx_get_features_per_level(const orbx_extractor* h, int* out);   /* mnFeaturesPerLevel (protected member) */
+/* upper bound of keypoints one frame can return: sum over levels of max(N_l + 2, 4*nIni_l) for the
+ * geometry (rows, cols); use it to size kp/desc buffers. */
+int orbx_max_keypoints(orbx_extractor* h, int rows, int cols);
+/* the CUDA stream all work of this handle is ordered on (a cudaStream_t) */
+void* orbx_stream(orbx_extractor* h);
+
+/* ------------------------------------------------------------------------------------------------
+ * void ORBextractor::operator()(InputArray image, InputArray mask, vector<KeyPoint>& keypoints,
+ *                               OutputArray descriptors)          src/ORBextractor.cc:1544-1668
+ * image: CV_8UC1, rows x cols, `step` bytes per row (host memory).  The mask is ignored by the
+ * reference and therefore not part of this call.  Empty image (rows*cols == 0 or NULL) => 0 keypoints.
+ * kp_out[cap], desc_out[cap*32] (row-major N x 32, CV_8U); *n_out = N.
+ * ---------------------------------------------------------------------------------------------- */
+int orbx_extract(orbx_extractor* h, const uint8_t* image, int rows, int cols, size_t step,
+                 orbx_keypoint* kp_out, uint8_t* desc_out, int cap, int* n_out);
+
+/* ------------------------------------------------------------------------------------------------
+ * void ORBextractor::operator()(InputArray image, InputArray mask, vector<vector<KeyPoint>>& keypoints)
+ *   src/ORBextractor.cc:1672-1686  (Amos stage 1: pyramid + keypoints with orientation, no descriptors).
+ * Keypoints are returned level-major in LEVEL coordinates; level_counts[nlevels].
+ * The pyramid stays resident in the handle for orbx_cull / orbx_describe / orbx_pyramid_level.
+ * ---------------------------------------------------------------------------------------------- */
+int orbx_detect(orbx_extractor* h, const uint8_t* image, int rows, int cols, size_t step,
+                orbx_keypoint* kp_out, int* level_counts, int cap, int* n_out);
+
+/* ------------------------------------------------------------------------------------------------
+ * vector<KeyPoint> ORBextractor::MovingKeyPoints(imGray, imS, imLS, centers, rm_vector, DynaFlag, mvKeysT)
+ *   src/ORBextractor.cc:1688-1745.  mask = imS (CV_8U rows x cols), label = imLS (CV_64F rows x cols,
+ *   super-pixel ids, 1-based), centers_id[i] = centers[i].id, rm_vector[nrm].
+ * kp_inout / level_counts: per-level keypoints (level coordinates) filtered in place, order preserved;
+ * culled_out (may be NULL, capacity = number of input keypoints) receives the removed keypoints in
+ * removal order; *n_culled = return value of the reference call's size().
+ * ---------------------------------------------------------------------------------------------- */
+int orbx_cull(orbx_extractor* h, const uint8_t* mask, size_t mask_step, const double* label, size_t label_step,
+              int rows, int cols, const int* centers_id, int ncenters, const int* rm_vector, int nrm,
+              orbx_keypoint* kp_inout, int* level_counts, orbx_keypoint* culled_out, int* n_culled);
+
+/* ------------------------------------------------------------------------------------------------
+ * void ORBextractor::ProcessDesp(image, mask, allKeypoints, mKeypoints, descriptors)
+ *   src/ORBextractor.cc:1747-1820  (Amos stage 2: blur + rBRIEF on the surviving keypoints, then
+ *   pt *= scale).  Uses the pyramid kept by the last orbx_detect on this handle.
+ * ---------------------------------------------------------------------------------------------- */
+int orbx_describe(orbx_extractor* h, const orbx_keypoint* kp_in, const int* level_counts,
+                  orbx_keypoint* kp_out, uint8_t* desc_out, int cap, int* n_out);
+
+/* std::vector<cv::Mat> mvImagePyramid   include/ORBextractor.h:168.
+ * Copies level `level` of the resident pyramid to host memory.  border = 0 copies the ROI
+ * (rows_l x cols_l); border = 19 reproduces the reference's padded parent buffer
+ * ((rows_l+38) x (cols_l+38), BORDER_REFLECT_101, src/ORBextractor.cc:1859-1882).
+ * dst may be NULL to query the size only. */
+int orbx_pyramid_level(orbx_extractor* h, int level, int border, uint8_t* dst, size_t dst_step,
+                       int* rows_out, int* cols_out);
+
+/* ------------------------------------------------------------------------------------------------
+ * Batched extraction: B independent frames of identical geometry per call (frames / sequences are
+ * independent units).  Semantically B calls of operator()(image, mask, kps, desc).
+ *   images      : B frames, frame b at images + b*frame_stride, rows x cols, `step` bytes per row
+ *   kp_out      : B * cap keypoints   (frame b at kp_out + b*cap)
+ *   desc_out    : B * cap * 32 bytes
+ *   counts_out  : B ints
+ * orbx_extract_batch       : host pointers, synchronous (H2D + kernels + D2H inside the call)
+ * orbx_extract_batch_device: device pointers, asynchronous on orbx_stream(h); inputs must stay valid
+ *                            until the stream reaches the end of the call's work.
+ * ---------------------------------------------------------------------------------------------- */
+int orbx_extract_batch(orbx_extractor* h, const uint8_t* images, int B, int rows, int cols, size_t step,
+                       size_t frame_stride, orbx_keypoint* kp_out, uint8_t* desc_out, int cap, int* counts_out);
+int orbx_extract_batch_device(orbx_extractor* h, const uint8_t* d_images, int B, int rows, int cols, size_t step,
+                              size_t frame_stride, orbx_keypoint* d_kp_out, uint8_t* d_desc_out, int cap,
+                              int* d_counts_out);
+/* number of kernel launches issued by this handle so far (bench.py's gpu_launches) */
+long long orbx_launch_count(const orbx_extractor* h);
+/* last internal overflow flags of the handle (0 = none); synchronises the handle's stream */
+int orbx_check_overflow(orbx_extractor* h);
+
+/* Stage taps for parity tests (tests/ only; host pointers, synchronous, operate on frame `b` of the
+ * last call).  Candidates are vToDistributeKeys of src/ORBextractor.cc:1073-1157 in reference order. */
+int orbx_debug_level_candidates(orbx_extractor* h, int b, int level, orbx_keypoint* out, int cap, int* n_out);
+int orbx_debug_blurred_level(orbx_extractor* h, int b, int level, uint8_t* dst, size_t dst_step);
+int orbx_debug_pyramid_level(orbx_extractor* h, int b, int level, uint8_t* dst, size_t dst_step);
+/* DistributeOctTree (src/ORBextractor.cc:706-1049) on caller-provided candidates (x,y integer-valued
+ * floats relative to minX/minY, response) -- runs the same device kernels as the pipeline. */
+int orbx_debug_distribute(orbx_extractor* h, const orbx_keypoint* cand, int ncand, int minX, int maxX,
+                          int minY, int maxY, int N, orbx_keypoint* out, int cap, int* n_out);
+
+/* ================================================================================================
+ * ORBmatcher  (include/ORBmatcher.h:57-215, src/ORBmatcher.cc)
+ * ================================================================================================ */
+#define ORBX_TH_HIGH 100       /* ORBmatcher::TH_HIGH      src/ORBmatcher.cc:49 */
+#define ORBX_TH_LOW 50         /* ORBmatcher::TH_LOW       src/ORBmatcher.cc:50 */
+#define ORBX_HISTO_LENGTH 30   /* ORBmatcher::HISTO_LENGTH src/ORBmatcher.cc:51 */
+#define ORBX_FRAME_GRID_COLS 64   /* include/Frame.h:61 */
+#define ORBX_FRAME_GRID_ROWS 48   /* include/Frame.h:56 */
+
+typedef struct orbx_matcher orbx_matcher;
+
+/* ORBmatcher::ORBmatcher(float nnratio = 0.6, bool checkOri = true)   src/ORBmatcher.cc:54 */
+int orbx_matcher_create(float nnratio, int check_orientation, int device, orbx_matcher** out);
+void orbx_matcher_destroy(orbx_matcher* m);
+void* orbx_matcher_stream(orbx_matcher* m);
+long long orbx_matcher_launch_count(const orbx_matcher* m);
+
+/* static int ORBmatcher::DescriptorDistance(const Mat& a, const Mat& b)   src/ORBmatcher.cc:1913-1933
+ * n pairs: out[i] = popcount(a[i] xor b[i]) over 256 bits (device kernel; host pointers). */
+int orbx_descriptor_distance(orbx_matcher* m, const uint8_t* a, const uint8_t* b, int n, int* out);
+
+/* The part of a Frame the matchers read (src/Frame.cc:431-461 AssignFeaturesToGrid, :894-1003
+ * GetFeaturesInArea, :1007-1030 PosInGrid; include/Frame.h).  All pointers are host memory. */
+typedef struct orbx_frame_view {
+    int n;                          /* Frame::N */
+    const orbx_keypoint* keys_un;   /* mvKeysUn[n]  (undistorted keypoints; pt, octave, angle are read) */
+    const uint8_t* descriptors;     /* mDescriptors, n x 32 */
+    const float* u_right;           /* mvuRight[n] or NULL (treated as all -1) */
+    float min_x, min_y, max_x, max_y;                 /* mnMinX, mnMinY, mnMaxX, mnMaxY */
+    float grid_element_width_inv, grid_element_height_inv;   /* mfGridElementWidthInv / HeightInv */
+    int nlevels; const float* scale_factors;          /* mvScaleFactors[nlevels] */
+} orbx_frame_view;
+
+/* int ORBmatcher::SearchForInitialization(Frame& F1, Frame& F2, vector<Point2f>& vbPrevMatched,
+ *                                         vector<int>& vnMatches12, int windowSize = 10)
+ *   src/ORBmatcher.cc:515-643.  prev_matched: F1.n (x,y) float pairs, updated in place (:638-640);
+ *   matches12: F1.n ints (index into F2 or -1); *nmatches = return value. */
+int orbx_search_for_initialization(orbx_matcher* m, const orbx_frame_view* F1, const orbx_frame_view* F2,
+                                   float* prev_matched_xy, int* matches12, int window_size, int* nmatches);
+
+/* int ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, float th, bool bMono)
+ *   src/ORBmatcher.cc:1569-1728.  The pose algebra (Rcw, tcw, tlc) and the projection of LastFrame's
+ *   map points stay in the caller (they need MapPoint objects); the call receives, per LastFrame
+ *   feature i with a valid non-outlier map point that projects inside the image (:1597-1623):
+ *     proj_uv[2i], proj_uv[2i+1] = (u, v);  proj_invz[i];  last_octave[i] = LastFrame.mvKeys[i].octave;
+ *     last_angle[i] = LastFrame.mvKeysUn[i].angle;  mp_desc + 32 i = pMP->GetDescriptor();
+ *     valid[i] != 0.
+ *   cur_occupied[j] != 0 marks CurrentFrame features whose map point has Observations() > 0 (:1658-1660).
+ *   forward / backward = bForward / bBackward (:1591-1592); mbf = CurrentFrame.mbf.
+ *   Output: cur_match[j] = index i of the LastFrame feature whose map point is assigned to current
+ *   feature j (or -1), after the rotation-histogram filter (:1706-1725); *nmatches = return value. */
+int orbx_search_by_projection_frame(orbx_matcher* m, const orbx_frame_view* cur, int n_last,
+                                    const float* proj_uv, const float* proj_invz, const int* last_octave,
+                                    const float* last_angle, const uint8_t* mp_desc, const uint8_t* valid,
+                                    const uint8_t* cur_occupied, float th, int forward, int backward, float mbf,
+                                    int* cur_match, int* nmatches);
+
+/* int ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>& vpMapPoints, float th)
+ *   src/ORBmatcher.cc:70-175.  Per map point p (already filtered by mbTrackInView && !isBad(), :82-86):
+ *     track_uv (mTrackProjX, mTrackProjY), track_ur (mTrackProjXR), track_level (mnTrackScaleLevel),
+ *     track_view_cos (mTrackViewCos), mp_desc (GetDescriptor()).
+ *   f_occupied[j] != 0 marks F features that already hold a map point with Observations() > 0 (:124-126).
+ *   Output: f_match[j] = index p of the map point assigned to feature j (or -1); *nmatches. */
+int orbx_search_by_projection_points(orbx_matcher* m, const orbx_frame_view* F, int n_points,
+                                     const float* track_uv, const float* track_ur, const int* track_level,
+                                     const float* track_view_cos, const uint8_t* mp_desc,
+                                     const uint8_t* f_occupied, float th, int* f_match, int* nmatches);
+
+/* void Frame::ComputeStereoMatches()   src/Frame.cc:1179-1573.
+ *   left / right: the two extractor handles holding the pyramids of the current stereo pair
+ *   (mpORBextractorLeft / Right ->mvImagePyramid);  keys / descriptors as returned by orbx_extract
+ *   (mvKeys, mvKeysRight, mDescriptors, mDescriptorsRight).  mb and mbf are passed as the reference
+ *   has them AT THE TIME OF THE CALL (mb == 0 inside the stereo constructor: src/Frame.cc:131 vs :237).
+ *   Output: u_right[nl] (mvuRight), depth[nl] (mvDepth). */
+int orbx_compute_stereo_matches(orbx_matcher* m, orbx_extractor* left, orbx_extractor* right,
+                                const orbx_keypoint* keys_left, const uint8_t* desc_left, int nl,
+                                const orbx_keypoint* keys_right, const uint8_t* desc_right, int nr,
+                                float mb, float mbf, float* u_right, float* depth);
+
+/* Brute-force all-pairs Hamming with best / second-best (the inner kernel of all matchers, exposed for
+ * throughput measurement):  for every query q: best_idx, best_dist, second_dist over all n_train rows. */
+int orbx_match_bruteforce_device(orbx_matcher* m, const uint8_t* d_query, int n_query, const uint8_t* d_train,
+                                 int n_train, int* d_best_idx, int* d_best_dist, int* d_second_dist);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORBX_B200_H */
