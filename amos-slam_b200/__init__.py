@@ -74,6 +74,8 @@ def lib():
     L.orbx_stream.argtypes = [vp]; L.orbx_stream.restype = vp
     L.orbx_launch_count.argtypes = [vp]; L.orbx_launch_count.restype = C.c_longlong
     L.orbx_check_overflow.argtypes = [vp]
+    L.orbx_profile_enable.argtypes = [vp, ci]
+    L.orbx_profile_collect.argtypes = [vp, vp, C.POINTER(ci)]
     L.orbx_extract.argtypes = [vp, vp, ci, ci, sz, vp, vp, ci, C.POINTER(ci)]
     L.orbx_detect.argtypes = [vp, vp, ci, ci, sz, vp, vp, ci, C.POINTER(ci)]
     L.orbx_cull.argtypes = [vp, vp, sz, vp, sz, ci, ci, vp, ci, vp, ci, vp, vp, vp, C.POINTER(ci)]
@@ -179,6 +181,17 @@ class ORBextractor:
 
     def check_overflow(self):
         return self._lib.orbx_check_overflow(self._h)
+
+    STAGES = ("pyr_resize", "fast_cells", "octree_sort", "octree_tree", "gauss7", "orient_describe")
+
+    def profile_enable(self, on=True):
+        _check(self._lib.orbx_profile_enable(self._h, 1 if on else 0))
+
+    def profile_collect(self):
+        """-> (dict stage -> summed ms, number of profiled calls)"""
+        ms = np.zeros(6, np.float64); n = C.c_int()
+        _check(self._lib.orbx_profile_collect(self._h, _ptr(ms), C.byref(n)))
+        return dict(zip(self.STAGES, ms.tolist())), n.value
 
     # ---- operator()(image, mask, keypoints, descriptors) ----
     def __call__(self, image, mask=None):

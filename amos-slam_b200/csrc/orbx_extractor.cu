@@ -74,6 +74,9 @@ struct orbx_extractor {
     DevBuf<int> d_ncand, d_kp_count, d_counts, d_level_counts, d_overflow;
     DevBuf<KpOut> d_kp_out; DevBuf<uint8_t> d_desc_out; int out_cap = 0;
     PyrView view{}; bool have_pyramid = false, blur_valid = false;
+    // optional per-stage CUDA-event timing (bench.py's roofline): one event set per profiled call
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;     // ORBX_NSTAGES+1 events per call
     // small staging buffers for the single-frame calls
     DevBuf<KpOut> d_kp_tmp; DevBuf<uint8_t> d_desc_tmp; DevBuf<uint8_t> d_mask, d_mask2; DevBuf<double> d_label; DevBuf<int> d_ids;
 };
@@ -216,6 +219,13 @@ static int ensure_capacity(orbx_extractor* h, int B, int out_cap) {
     return ORBX_OK;
 }
 
+#define ORBX_NSTAGES 6   // resize, fast_cells, octree_sort, octree_tree, gauss7, orient_describe
+static inline void prof_mark(orbx_extractor* h) {
+    if (!h->profiling) return;
+    cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, h->stream); h->prof_events.push_back(e);
+}
+
 #define LAUNCH_CHECK() do { cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) { \
     orbx_set_error(std::string("kernel launch: ") + cudaGetErrorString(_e)); return ORBX_E_CUDA; } ++h->launches; } while (0)
 
@@ -223,6 +233,7 @@ static int ensure_capacity(orbx_extractor* h, int B, int out_cap) {
 static int run_detect(orbx_extractor* h, int B) {
     cudaStream_t s = h->stream;
     const int L = h->nlevels;
+    prof_mark(h);
     for (int l = 1; l < L; ++l) {
         const LevelGeom& g = h->levels[l]; const LevelGeom& gp = h->levels[l - 1];
         const uint8_t* src; long long sfs; int sp;
@@ -232,6 +243,7 @@ static int run_detect(orbx_extractor* h, int B) {
         k_pyr_resize<<<grid, block, 0, s>>>(src, sfs, sp, gp.w, gp.h, h->d_pyr.p + g.off, h->pyr_fstride, g.pitch, g.w, g.h, h->resize_tabs[l]);
         LAUNCH_CHECK();
     }
+    prof_mark(h);
     const int ncells = (int)h->cells.size();
     {
         dim3 grid((ncells + FAST_WARPS - 1) / FAST_WARPS, B);
@@ -240,16 +252,19 @@ static int run_detect(orbx_extractor* h, int B) {
                                                           h->fast_smem_per_warp, h->iniThFAST, h->minThFAST, h->d_slots.p, h->d_cell_counts.p);
         LAUNCH_CHECK();
     }
+    prof_mark(h);
     {
         dim3 grid(L, B);
         k_octree_sort<<<grid, SORT_THREADS, (size_t)h->sort_smem_keys * 8, s>>>(h->d_levels.p, h->d_cells.p, ncells, h->cand_per_frame, h->cand_per_frame, L,
                                                                                  h->sort_smem_keys, h->d_slots.p, h->d_cell_counts.p, h->d_ocand.p, h->d_skey.p, h->d_spk.p, h->d_ncand.p);
         LAUNCH_CHECK();
+        prof_mark(h);
         const size_t tsm = (size_t)h->tree_cap * (8 + 8 + 4 + 4 + 4 + 2 + 2 + 2 + 1) + 16;
         k_octree_tree<<<grid, 32, tsm, s>>>(h->d_levels.p, L, h->cand_per_frame, h->kp_per_frame, h->tree_cap, h->d_skey.p, h->d_spk.p, h->d_ncand.p,
                                             h->d_kp_level.p, h->d_kp_count.p, h->d_overflow.p);
         LAUNCH_CHECK();
     }
+    prof_mark(h);
     h->lastB = B; h->have_pyramid = true; h->blur_valid = false;
     return ORBX_OK;
 }
@@ -259,6 +274,7 @@ static int run_blur(orbx_extractor* h, int B) {
     dim3 grid((unsigned)h->tiles.size(), B);
     k_gauss7<<<grid, 256, 0, h->stream>>>(h->view, h->d_levels.p, h->d_tiles.p, h->d_blur.p, h->pyr_fstride);
     LAUNCH_CHECK();
+    prof_mark(h);
     h->blur_valid = true;
     return ORBX_OK;
 }
@@ -272,6 +288,7 @@ static int run_orient(orbx_extractor* h, int B, bool describe, KpOut* d_kp, uint
         k_orient_describe<false><<<grid, 128, 0, h->stream>>>(h->view, h->d_levels.p, h->nlevels, h->kp_per_frame, h->d_kp_level.p, h->d_kp_count.p,
                                                              nullptr, 0, d_kp, nullptr, cap, d_counts, d_level_counts);
     LAUNCH_CHECK();
+    if (describe) prof_mark(h);
     return ORBX_OK;
 }
 
@@ -364,6 +381,26 @@ GETTER(orbx_get_inverse_scale_sigma_squares, mvInvLevelSigma2, float)
 GETTER(orbx_get_features_per_level, mnFeaturesPerLevel, int)
 void* orbx_stream(orbx_extractor* h) { return h ? (void*)h->stream : nullptr; }
 long long orbx_launch_count(const orbx_extractor* h) { return h ? h->launches : 0; }
+
+// Per-stage device timing for bench.py: while enabled, every batched extract records CUDA events at the
+// stage boundaries on the handle's stream; orbx_profile_collect synchronises, sums the elapsed times per
+// stage over all profiled calls (ms), and clears the events.  Stage order: resize, fast_cells, octree_sort,
+// octree_tree, gauss7, orient_describe.
+int orbx_profile_enable(orbx_extractor* h, int on) { if (!h) return ORBX_E_INVALID; h->profiling = on != 0; return ORBX_OK; }
+int orbx_profile_collect(orbx_extractor* h, double* stage_ms, int* ncalls) {
+    if (!h || !stage_ms || !ncalls) return ORBX_E_INVALID;
+    if (cudaSetDevice(h->device) != cudaSuccess) return ORBX_E_CUDA;
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < ORBX_NSTAGES; ++i) stage_ms[i] = 0.0;
+    const size_t per = ORBX_NSTAGES + 1;
+    const size_t calls = h->prof_events.size() / per;
+    for (size_t c = 0; c < calls; ++c)
+        for (int i = 0; i < ORBX_NSTAGES; ++i) { float ms = 0.f; cudaEventElapsedTime(&ms, h->prof_events[c * per + i], h->prof_events[c * per + i + 1]); stage_ms[i] += ms; }
+    for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
+    h->prof_events.clear();
+    *ncalls = (int)calls;
+    return ORBX_OK;
+}
 
 int orbx_max_keypoints(orbx_extractor* h, int rows, int cols) {
     if (!h || rows <= 0 || cols <= 0) FAIL(ORBX_E_INVALID, "bad arguments");

@@ -1,0 +1,299 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the B200-native ORB front-end.
+
+Metric (BASELINE.json): ORB extraction frames/s at 640x480, 1000 features per frame (TUM RGB-D settings:
+scale 1.2, 8 levels, FAST 20/7), whole job over N GPUs.  One "step" = one pass of the extractor over one
+batch of B synthetic frames per GPU.  Frames shard independently across GPUs (no collective on the data
+path; torch.distributed is used only for the timing barrier and the max-over-ranks reduction).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B]          native arm (CUDA, C ABI)
+  python bench.py --impl reference ...                                      reference CPU arm (oracle/_ref)
+
+value   : device-resident throughput (inputs already in HBM), CUDA events on the extractor's stream
+e2e     : same metric through the host-pointer C-ABI call (pinned host frames in, keypoints/descriptors out,
+          H2D and D2H inside the timed region)
+roofline: dominant stage by live CUDA-event time; algorithmic bytes of that stage / its duration vs the
+          measured HBM peak (MEASURED_PEAKS.json)
+cpu_baseline: the reference's own ORBextractor.cc (oracle/_ref, all host cores) on a bounded sample
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+from tools.synth import synth_batch  # noqa: E402
+
+WIDTH, HEIGHT, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH = 640, 480, 1000, 1.2, 8, 20, 7
+WORKLOAD = "ORBextractor 640x480 grayscale, nFeatures=1000, scale 1.2, 8 levels, FAST 20/7 (TUM RGB-D settings)"
+
+
+def level_pixels():
+    s, tot, px = 1.0, 0, []
+    f = np.float32(1.0)
+    for l in range(NLEVELS):
+        inv = np.float32(1.0) / f
+        w, h = int(np.rint(np.float32(WIDTH) * inv)), int(np.rint(np.float32(HEIGHT) * inv))
+        px.append(w * h)
+        f = np.float32(np.float64(f) * np.float64(np.float32(SCALE)))
+    return px
+
+
+def stage_bytes(n_kp, n_cand):
+    """Algorithmic bytes per FRAME of each stage."""
+    P = level_pixels()
+    sp = sum(P)
+    return {
+        "pyr_resize": sum(P[l - 1] + P[l] for l in range(1, NLEVELS)),      # read P(l-1), write P(l)
+        "fast_cells": sp + 4 * n_cand,                                      # read every level once, write candidates
+        "octree_sort": n_cand * (4 + 4 + 8 + 4),                            # read slots, write ordered + sorted key + packed
+        "octree_tree": n_cand * 12 + 4 * n_kp,                              # read sorted keys + packed, write level keypoints
+        "gauss7": 2 * sp,                                                   # read + write every level
+        "orient_describe": n_kp * (749 + 512 + 60),                         # disc + samples + 28 B kp + 32 B descriptor
+    }
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples = index, False, []
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(s) > 2 + i and s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def cpu_reference_run(seconds_budget, frames, threads=None, steps=None, frames_per_thread_step=None):
+    """Times the reference's own CPU extractor (oracle/_ref; falls back to the port if _ref is absent) with one
+    independent extractor per host thread.  Either runs for ~seconds_budget (cpu_baseline leg) or for `steps`
+    steps of threads*frames_per_thread_step frames each (--impl reference)."""
+    import oracle
+    kind = "ref" if oracle.have_ref() else "port"
+    threads = threads or max(1, os.cpu_count() or 1)
+    exts = [oracle.Extractor(kind, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH) for _ in range(threads)]
+    nframes = len(frames)
+    done = [0] * threads
+    start_evt = threading.Event()
+
+    def worker(t, deadline_box, quota):
+        start_evt.wait()
+        i = t
+        while True:
+            if quota is not None and done[t] >= quota:
+                break
+            if quota is None and time.perf_counter() >= deadline_box[0]:
+                break
+            exts[t].extract(frames[i % nframes])
+            done[t] += 1
+            i += threads
+
+    def run(quota, budget):
+        for t in range(threads):
+            done[t] = 0
+        box = [0.0]
+        start_evt.clear()
+        ths = [threading.Thread(target=worker, args=(t, box, quota)) for t in range(threads)]
+        for th in ths:
+            th.start()
+        t0 = time.perf_counter(); box[0] = t0 + (budget or 1e9)
+        start_evt.set()
+        for th in ths:
+            th.join()
+        return sum(done), time.perf_counter() - t0
+
+    run(1, None)      # warm-up: one frame per thread
+    if steps is None:
+        n, dt = run(None, seconds_budget)
+        return {"frames": n, "seconds": dt, "fps": n / dt, "threads": threads, "kind": "reference" if kind == "ref" else "port", "step_times": None}
+    step_times, total = [], 0
+    for _ in range(steps):
+        n, dt = run(frames_per_thread_step, None)
+        step_times.append(dt); total += n
+    return {"frames": total, "seconds": sum(step_times), "fps": total / sum(step_times), "threads": threads,
+            "kind": "reference" if kind == "ref" else "port", "step_times": step_times}
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=512, help="frames per GPU per step")
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); local_rank = int(os.environ.get("LOCAL_RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    N, K, W, B = args.gpus, args.steps, max(args.warmup, 0), args.batch
+    config = {"workload": WORKLOAD, "frame": [WIDTH, HEIGHT], "nfeatures": NFEAT, "frames_per_gpu_per_step": B,
+              "parallelism": "frames sharded over %d GPU(s), no collective" % N,
+              "l2_policy": "working set per step (%.0f MB of frames, ~%.1f GB of pyramid+scratch) exceeds the 126 MB L2" % (B * WIDTH * HEIGHT / 1e6, B * 6.3e-3)}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        frames = synth_batch(64, WIDTH, HEIGHT, seed0=0, distinct=16)
+        threads = max(1, os.cpu_count() or 1)
+        res = cpu_reference_run(None, frames, threads=threads, steps=W + K, frames_per_thread_step=2)
+        st = res["step_times"][W:]
+        fps = threads * 2 * K / sum(st)
+        line = {"impl": "reference", "metric": "ORB extract frames/sec @640x480 1000 feat", "value": fps, "unit": "frames/s", "n_gpus": N, "steps": K, "warmup": W,
+                "ms_per_step": 1e3 * sum(st) / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": config,
+                "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": res["kind"],
+                                 "sample": "%d steps x %d threads x 2 frames, one independent extractor per thread, CPU: %s" % (K, threads, cpu_model())},
+                "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    orbx = importlib.import_module("amos-slam_b200")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (native arm) needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    frames = synth_batch(B, WIDTH, HEIGHT, seed0=1000 * rank, distinct=24)
+    ext = orbx.ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, device=local_rank)
+    cap = ext.max_keypoints(HEIGHT, WIDTH)
+    h_frames = torch.from_numpy(frames).pin_memory()
+    d_frames = h_frames.cuda(non_blocking=False)
+    d_kp = torch.empty((B, cap, 28), dtype=torch.uint8, device="cuda")
+    d_desc = torch.empty((B, cap, 32), dtype=torch.uint8, device="cuda")
+    d_counts = torch.zeros((B,), dtype=torch.int32, device="cuda")
+    h_kp = torch.empty((B, cap, 28), dtype=torch.uint8).pin_memory()
+    h_desc = torch.empty((B, cap, 32), dtype=torch.uint8).pin_memory()
+    h_counts = torch.zeros((B,), dtype=torch.int32).pin_memory()
+    stream = torch.cuda.ExternalStream(ext.stream)
+
+    def step_device():
+        ext.extract_batch_raw(d_frames.data_ptr(), B, HEIGHT, WIDTH, WIDTH, WIDTH * HEIGHT, d_kp.data_ptr(), d_desc.data_ptr(), cap, d_counts.data_ptr(), device=True)
+
+    def step_host():
+        ext.extract_batch_raw(h_frames.data_ptr(), B, HEIGHT, WIDTH, WIDTH, WIDTH * HEIGHT, h_kp.data_ptr(), h_desc.data_ptr(), cap, h_counts.data_ptr(), device=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(W, 3)):
+        step_device()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank); sampler.start()
+    ext.profile_enable(True)
+    l0 = ext.launch_count
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(K):
+        step_device()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ext.launch_count - l0
+    stage_ms, ncalls = ext.profile_collect()
+    ext.profile_enable(False)
+    n_kp = float(d_counts.float().mean().item())
+    if ext.check_overflow():
+        raise SystemExit("internal overflow flag set")
+
+    # ---- e2e through the host-pointer C-ABI call ----
+    for _ in range(2):
+        step_host()
+    barrier()
+    Ke = max(3, min(K, 10))
+    t0 = time.perf_counter()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record(stream)
+    for _ in range(Ke):
+        step_host()
+    g1.record(stream)
+    barrier()
+    ms_e2e = max(g0.elapsed_time(g1), 1e3 * (time.perf_counter() - t0))   # host call is synchronous: wall clock >= device clock
+    sampler.stop_flag = True; sampler.join(timeout=2)
+
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0].item()), float(t[1].item())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = N * B * K / (ms * 1e-3)
+    e2e = N * B * Ke / (ms_e2e * 1e-3)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0)); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    n_cand = float(sum(len(ext.debug_level_candidates(0, l)) for l in range(NLEVELS)))   # frame 0 of the last batch
+    sb = stage_bytes(n_kp, n_cand)
+    dom = max(stage_ms, key=lambda k: stage_ms[k])
+    launches_of = {"pyr_resize": NLEVELS - 1}
+    dom_ms_per_launch = stage_ms[dom] / max(ncalls, 1) / launches_of.get(dom, 1)
+    dom_bytes_per_launch = sb[dom] * B / launches_of.get(dom, 1)
+    achieved = dom_bytes_per_launch / (dom_ms_per_launch * 1e-3) / 1e9
+    total_stage = sum(stage_ms.values())
+    line = {"metric": "ORB extract frames/sec @640x480 1000 feat", "value": value, "unit": "frames/s", "n_gpus": N, "steps": K, "warmup": max(W, 3),
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": config,
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(B * WIDTH * HEIGHT), "d2h_bytes_per_step": int(B * cap * 60 + 4 * B + 4), "steps": Ke},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes_per_launch, "ms_per_launch": dom_ms_per_launch,
+                         "stage_ms_per_step": {k: v / max(ncalls, 1) for k, v in stage_ms.items()},
+                         "stage_share": {k: (v / total_stage if total_stage else 0.0) for k, v in stage_ms.items()},
+                         "whole_step_algorithmic_GBps": (2 * sum(level_pixels()) + 60 * n_kp) * B * K / (ms * 1e-3) / 1e9},
+            "keypoints_per_frame": n_kp}
+    if N == 1 and not args.no_cpu_baseline:
+        res = cpu_reference_run(args.cpu_seconds, frames[:64])
+        line["cpu_baseline"] = {"value": res["fps"], "unit": "frames/s", "cores": res["threads"], "kind": res["kind"],
+                                "sample": "%d frames in %.1f s, one independent extractor per thread on %d threads, CPU: %s" % (res["frames"], res["seconds"], res["threads"], cpu_model())}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -137,6 +137,11 @@ int orbx_extract_batch_device(orbx_extractor* h, const uint8_t* d_images, int B,
                               int* d_counts_out);
 /* number of kernel launches issued by this handle so far (bench.py's gpu_launches) */
 long long orbx_launch_count(const orbx_extractor* h);
+/* Per-stage device timing (bench.py): while enabled every batched extract records CUDA events at the stage
+ * boundaries on the handle's stream; collect synchronises, writes the summed elapsed ms of the 6 stages
+ * (resize, fast_cells, octree_sort, octree_tree, gauss7, orient_describe) and the number of profiled calls. */
+int orbx_profile_enable(orbx_extractor* h, int on);
+int orbx_profile_collect(orbx_extractor* h, double* stage_ms6, int* ncalls);
 /* last internal overflow flags of the handle (0 = none); synchronises the handle's stream */
 int orbx_check_overflow(orbx_extractor* h);
 
@@ -196,26 +201,28 @@ int orbx_search_for_initialization(orbx_matcher* m, const orbx_frame_view* F1, c
  *   feature i with a valid non-outlier map point that projects inside the image (:1597-1623):
  *     proj_uv[2i], proj_uv[2i+1] = (u, v);  proj_invz[i];  last_octave[i] = LastFrame.mvKeys[i].octave;
  *     last_angle[i] = LastFrame.mvKeysUn[i].angle;  mp_desc + 32 i = pMP->GetDescriptor();
- *     valid[i] != 0.
- *   cur_occupied[j] != 0 marks CurrentFrame features whose map point has Observations() > 0 (:1658-1660).
+ *     valid[i] != 0;  mp_observed[i] != 0 iff pMP->Observations() > 0.
+ *   cur_occupied[j] != 0 marks CurrentFrame features that already hold a map point with Observations() > 0
+ *   (:1658-1660).  A feature claimed earlier in the loop blocks later map points iff its claimer is observed;
+ *   otherwise it can be re-assigned, exactly as the reference's running mvpMapPoints state behaves.
  *   forward / backward = bForward / bBackward (:1591-1592); mbf = CurrentFrame.mbf.
  *   Output: cur_match[j] = index i of the LastFrame feature whose map point is assigned to current
  *   feature j (or -1), after the rotation-histogram filter (:1706-1725); *nmatches = return value. */
 int orbx_search_by_projection_frame(orbx_matcher* m, const orbx_frame_view* cur, int n_last,
                                     const float* proj_uv, const float* proj_invz, const int* last_octave,
                                     const float* last_angle, const uint8_t* mp_desc, const uint8_t* valid,
-                                    const uint8_t* cur_occupied, float th, int forward, int backward, float mbf,
+                                    const uint8_t* mp_observed, const uint8_t* cur_occupied, float th, int forward, int backward, float mbf,
                                     int* cur_match, int* nmatches);
 
 /* int ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>& vpMapPoints, float th)
  *   src/ORBmatcher.cc:70-175.  Per map point p (already filtered by mbTrackInView && !isBad(), :82-86):
  *     track_uv (mTrackProjX, mTrackProjY), track_ur (mTrackProjXR), track_level (mnTrackScaleLevel),
- *     track_view_cos (mTrackViewCos), mp_desc (GetDescriptor()).
+ *     track_view_cos (mTrackViewCos), mp_desc (GetDescriptor()), mp_observed (Observations() > 0).
  *   f_occupied[j] != 0 marks F features that already hold a map point with Observations() > 0 (:124-126).
  *   Output: f_match[j] = index p of the map point assigned to feature j (or -1); *nmatches. */
 int orbx_search_by_projection_points(orbx_matcher* m, const orbx_frame_view* F, int n_points,
                                      const float* track_uv, const float* track_ur, const int* track_level,
-                                     const float* track_view_cos, const uint8_t* mp_desc,
+                                     const float* track_view_cos, const uint8_t* mp_desc, const uint8_t* mp_observed,
                                      const uint8_t* f_occupied, float th, int* f_match, int* nmatches);
 
 /* void Frame::ComputeStereoMatches()   src/Frame.cc:1179-1573.

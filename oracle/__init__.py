@@ -189,33 +189,137 @@ def ref_lib():
     return _lib("ref")
 
 
+# Synthetic inputs live in tools/synth.py (neutral module shared by tests and bench.py); re-exported here.
+import sys as _sys
+_sys.path.insert(0, os.path.dirname(HERE))
+from tools.synth import synth_frame  # noqa: E402,F401
+
+
 # ------------------------------------------------------------------------------------------------
-# Synthetic inputs: seeded, exercises both FAST thresholds.  Pure numpy (no cv2) so
-# the same frames are generated on the GPU box and here.
+# Matcher oracles (ORBmatcher / Frame grid / ComputeStereoMatches)
 # ------------------------------------------------------------------------------------------------
-def synth_frame(seed, width=640, height=480):
-    rng = np.random.default_rng(1000 + int(seed))
-    img = np.full((height, width), 128.0, np.float32)
-    nshapes = (width * height) // 600
-    yy, xx = np.mgrid[0:height, 0:width]
-    kinds = rng.integers(0, 2, nshapes)
-    cx = rng.integers(0, width, nshapes); cy = rng.integers(0, height, nshapes)
-    sw = rng.integers(4, 61, nshapes); sh = rng.integers(4, 61, nshapes)
-    grey = rng.integers(0, 256, nshapes)
-    for k in range(nshapes):
-        x0, x1 = max(cx[k] - sw[k] // 2, 0), min(cx[k] + sw[k] // 2 + 1, width)
-        y0, y1 = max(cy[k] - sh[k] // 2, 0), min(cy[k] + sh[k] // 2 + 1, height)
-        if kinds[k] == 0:
-            img[y0:y1, x0:x1] = grey[k]
+class FrameViewC(C.Structure):
+    """Mirror of orbx_frame_view (include/orbx_b200.h)."""
+    _fields_ = [("n", C.c_int), ("keys_un", C.c_void_p), ("descriptors", C.c_void_p), ("u_right", C.c_void_p),
+                ("min_x", C.c_float), ("min_y", C.c_float), ("max_x", C.c_float), ("max_y", C.c_float),
+                ("gw_inv", C.c_float), ("gh_inv", C.c_float), ("nlevels", C.c_int), ("scale_factors", C.c_void_p)]
+
+
+class FrameData:
+    """What a Frame exposes to the matchers: undistorted keypoints, descriptors, image bounds, 64x48 grid constants
+    (mfGridElementWidthInv = 64/(mnMaxX-mnMinX) etc., /root/reference/src/Frame.cc:219-220)."""
+
+    def __init__(self, keys, desc, width, height, scale_factors, u_right=None):
+        self.keys = np.ascontiguousarray(keys, KP_DTYPE)
+        self.desc = np.ascontiguousarray(desc, np.uint8)
+        self.scale_factors = np.ascontiguousarray(scale_factors, np.float32)
+        self.u_right = None if u_right is None else np.ascontiguousarray(u_right, np.float32)
+        self.min_x, self.min_y, self.max_x, self.max_y = np.float32(0), np.float32(0), np.float32(width), np.float32(height)
+        self.gw_inv = np.float32(64.0) / (self.max_x - self.min_x)
+        self.gh_inv = np.float32(48.0) / (self.max_y - self.min_y)
+
+    def view(self):
+        v = FrameViewC()
+        v.n = len(self.keys); v.keys_un = self.keys.ctypes.data; v.descriptors = self.desc.ctypes.data
+        v.u_right = self.u_right.ctypes.data if self.u_right is not None else None
+        v.min_x, v.min_y, v.max_x, v.max_y = float(self.min_x), float(self.min_y), float(self.max_x), float(self.max_y)
+        v.gw_inv, v.gh_inv = float(self.gw_inv), float(self.gh_inv)
+        v.nlevels = len(self.scale_factors); v.scale_factors = self.scale_factors.ctypes.data
+        return v
+
+
+def _u8(a):
+    return None if a is None else np.ascontiguousarray(a, np.uint8)
+
+
+class Matcher:
+    """ORBmatcher(nnratio, checkOri) oracle, kind = 'ref' (reference bodies) | 'port' (restatement)."""
+
+    def __init__(self, kind, nnratio=0.6, check_ori=True):
+        self.kind, self.lib, self.p = kind, _lib(kind), kind + "_"
+        self.nnratio, self.check_ori = float(nnratio), int(bool(check_ori))
+        vp, ci, cf = C.c_void_p, C.c_int, C.c_float
+        fv = C.POINTER(FrameViewC)
+        f = getattr(self.lib, self.p + "descriptor_distance"); f.restype = None; f.argtypes = [vp, vp, ci, vp]
+        f = getattr(self.lib, self.p + "get_features_in_area"); f.restype = ci; f.argtypes = [fv, cf, cf, cf, ci, ci, vp, ci]
+        f = getattr(self.lib, self.p + "search_for_initialization"); f.restype = ci; f.argtypes = [cf, ci, fv, fv, vp, vp, ci]
+        f = getattr(self.lib, self.p + "search_by_projection_points"); f.restype = ci
+        f.argtypes = [cf, ci, fv, ci, vp, vp, vp, vp, vp, vp, vp, cf, vp]
+        if kind == "ref":
+            self.lib.ref_search_by_projection_frame.restype = ci
+            self.lib.ref_search_by_projection_frame.argtypes = [cf, ci, fv, ci, vp, vp, vp, vp, vp, vp, vp, cf, ci, cf, cf, cf, cf, cf, cf, vp, vp, vp]
+            self.lib.ref_compute_stereo_matches.restype = ci
+            self.lib.ref_compute_stereo_matches.argtypes = [vp, vp, vp, vp, ci, vp, vp, ci, cf, cf, vp, vp]
         else:
-            r = sw[k] / 2.0
-            sub = (xx[y0:y1, x0:x1] - cx[k]) ** 2 + (yy[y0:y1, x0:x1] - cy[k]) ** 2 <= r * r
-            img[y0:y1, x0:x1][sub] = grey[k]
-    # 3x3 Gaussian sigma 0.8 (separable, edge-replicated)
-    g = np.exp(-np.array([-1.0, 0.0, 1.0]) ** 2 / (2 * 0.8 * 0.8)); g /= g.sum()
-    p = np.pad(img, 1, mode="edge")
-    img = g[0] * p[1:-1, :-2] + g[1] * p[1:-1, 1:-1] + g[2] * p[1:-1, 2:]
-    p = np.pad(img, 1, mode="edge")
-    img = g[0] * p[:-2, 1:-1] + g[1] * p[1:-1, 1:-1] + g[2] * p[2:, 1:-1]
-    img = img + rng.normal(0.0, 3.0, img.shape)
-    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+            self.lib.port_search_by_projection_frame.restype = ci
+            self.lib.port_search_by_projection_frame.argtypes = [cf, ci, fv, ci, vp, vp, vp, vp, vp, vp, vp, vp, cf, ci, ci, cf, vp]
+            self.lib.port_compute_stereo_matches.restype = ci
+            self.lib.port_compute_stereo_matches.argtypes = [ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ci, vp, vp, ci, cf, cf, vp, vp]
+
+    def descriptor_distance(self, a, b):
+        a, b = _u8(a), _u8(b)
+        out = np.zeros(len(a), np.int32)
+        getattr(self.lib, self.p + "descriptor_distance")(a.ctypes.data, b.ctypes.data, len(a), out.ctypes.data)
+        return out
+
+    def features_in_area(self, F, x, y, r, min_level=-1, max_level=-1):
+        out = np.zeros(max(len(F.keys), 1), np.int32)
+        n = getattr(self.lib, self.p + "get_features_in_area")(C.byref(F.view()), x, y, r, min_level, max_level, out.ctypes.data, len(out))
+        return out[:n].copy()
+
+    def search_for_initialization(self, F1, F2, prev_matched, window_size=10):
+        prev = np.ascontiguousarray(prev_matched, np.float32).copy()
+        m12 = np.zeros(len(F1.keys), np.int32)
+        nm = getattr(self.lib, self.p + "search_for_initialization")(self.nnratio, self.check_ori, C.byref(F1.view()), C.byref(F2.view()), prev.ctypes.data, m12.ctypes.data, int(window_size))
+        return nm, m12, prev
+
+    def search_by_projection_points(self, F, track_uv, track_ur, track_level, track_view_cos, mp_desc, mp_observed, f_occupied, th):
+        uv = np.ascontiguousarray(track_uv, np.float32); ur = np.ascontiguousarray(track_ur, np.float32)
+        lv = np.ascontiguousarray(track_level, np.int32); vc = np.ascontiguousarray(track_view_cos, np.float32)
+        d, ob, oc = _u8(mp_desc), _u8(mp_observed), _u8(f_occupied)
+        fm = np.zeros(len(F.keys), np.int32)
+        nm = getattr(self.lib, self.p + "search_by_projection_points")(self.nnratio, self.check_ori, C.byref(F.view()), len(lv), uv.ctypes.data, ur.ctypes.data, lv.ctypes.data,
+                                                                       vc.ctypes.data, d.ctypes.data, ob.ctypes.data, oc.ctypes.data if oc is not None else None, float(th), fm.ctypes.data)
+        return nm, fm
+
+    def search_by_projection_frame_ref(self, cur, cam_xyz, last_octave, last_angle, mp_desc, valid, mp_observed, cur_occupied, th, b_mono, mb, mbf, fx, fy, cx, cy):
+        """Reference body with identity poses; returns (nmatches, cur_match, proj_uv, proj_invz)."""
+        assert self.kind == "ref"
+        xyz = np.ascontiguousarray(cam_xyz, np.float32); n = len(xyz)
+        lo = np.ascontiguousarray(last_octave, np.int32); la = np.ascontiguousarray(last_angle, np.float32)
+        d, va, ob, oc = _u8(mp_desc), _u8(valid), _u8(mp_observed), _u8(cur_occupied)
+        uv = np.zeros((n, 2), np.float32); iz = np.zeros(n, np.float32); cm = np.zeros(len(cur.keys), np.int32)
+        nm = self.lib.ref_search_by_projection_frame(self.nnratio, self.check_ori, C.byref(cur.view()), n, xyz.ctypes.data, lo.ctypes.data, la.ctypes.data, d.ctypes.data,
+                                                     va.ctypes.data, ob.ctypes.data, oc.ctypes.data if oc is not None else None, float(th), int(b_mono), float(mb), float(mbf),
+                                                     float(fx), float(fy), float(cx), float(cy), uv.ctypes.data, iz.ctypes.data, cm.ctypes.data)
+        return nm, cm, uv, iz
+
+    def search_by_projection_frame_port(self, cur, proj_uv, proj_invz, last_octave, last_angle, mp_desc, valid, mp_observed, cur_occupied, th, forward, backward, mbf):
+        assert self.kind == "port"
+        uv = np.ascontiguousarray(proj_uv, np.float32); iz = np.ascontiguousarray(proj_invz, np.float32)
+        lo = np.ascontiguousarray(last_octave, np.int32); la = np.ascontiguousarray(last_angle, np.float32)
+        d, va, ob, oc = _u8(mp_desc), _u8(valid), _u8(mp_observed), _u8(cur_occupied)
+        cm = np.zeros(len(cur.keys), np.int32)
+        nm = self.lib.port_search_by_projection_frame(self.nnratio, self.check_ori, C.byref(cur.view()), len(iz), uv.ctypes.data, iz.ctypes.data, lo.ctypes.data, la.ctypes.data,
+                                                      d.ctypes.data, va.ctypes.data, ob.ctypes.data, oc.ctypes.data if oc is not None else None, float(th), int(forward), int(backward),
+                                                      float(mbf), cm.ctypes.data)
+        return nm, cm
+
+    def compute_stereo_matches(self, ext_left, ext_right, keys_left, desc_left, keys_right, desc_right, mb, mbf):
+        """ext_left / ext_right: oracle.Extractor of the same kind whose last extract() saw the left / right image."""
+        kl = np.ascontiguousarray(keys_left, KP_DTYPE); kr = np.ascontiguousarray(keys_right, KP_DTYPE)
+        dl, dr = _u8(desc_left), _u8(desc_right)
+        ur = np.zeros(len(kl), np.float32); dep = np.zeros(len(kl), np.float32)
+        if self.kind == "ref":
+            self.lib.ref_compute_stereo_matches(ext_left.h, ext_right.h, kl.ctypes.data, dl.ctypes.data, len(kl), kr.ctypes.data, dr.ctypes.data, len(kr), float(mb), float(mbf),
+                                                ur.ctypes.data, dep.ctypes.data)
+        else:
+            nl = ext_left.nlevels
+            pl = [np.ascontiguousarray(ext_left.pyramid_level(l)) for l in range(nl)]; pr = [np.ascontiguousarray(ext_right.pyramid_level(l)) for l in range(nl)]
+            wl = np.array([p.shape[1] for p in pl], np.int32); hl = np.array([p.shape[0] for p in pl], np.int32)
+            wr = np.array([p.shape[1] for p in pr], np.int32); hr = np.array([p.shape[0] for p in pr], np.int32)
+            ptl = (C.c_void_p * nl)(*[p.ctypes.data for p in pl]); ptr_ = (C.c_void_p * nl)(*[p.ctypes.data for p in pr])
+            sc = np.ascontiguousarray(ext_left.scale_factors, np.float32); isc = (np.float32(1.0) / sc).astype(np.float32)
+            self.lib.port_compute_stereo_matches(nl, wl.ctypes.data, hl.ctypes.data, ptl, wr.ctypes.data, hr.ctypes.data, ptr_, sc.ctypes.data, isc.ctypes.data,
+                                                 kl.ctypes.data, dl.ctypes.data, len(kl), kr.ctypes.data, dr.ctypes.data, len(kr), float(mb), float(mbf), ur.ctypes.data, dep.ctypes.data)
+        return ur, dep

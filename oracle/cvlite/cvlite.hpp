@@ -563,7 +563,7 @@ static inline void FAST(InputArray _img, std::vector<KeyPoint>& keypoints, int t
                 for (int k = 0; k < 25; ++k) { if (ptr[pixel[k]] > vt) { if (++count > 8) { corner = true; break; } } else count = 0; }
             }
             if (corner) {
-                score[(size_t)y * W + x] = (uchar)(cvl_fast_S(ptr, (size_t)step) - 1);
+                if (nonmaxSuppression) score[(size_t)y * W + x] = (uchar)(cvl_fast_S(ptr, (size_t)step) - 1);   // OpenCV scores only under NMS
                 cpos.push_back(y * W + x);
             }
         }

@@ -1,0 +1,69 @@
+#!/usr/bin/env python3
+"""TEST INFRASTRUCTURE ONLY.  Build step of oracle/_ref: copies the bodies of the hot-path matcher functions out of
+the reference's own sources, verbatim, into a GENERATED include file under oracle/_ref/gen/ (git-ignored build
+output -- nothing is copied into the repository).  The functions are located by signature and brace matching:
+
+  src/ORBmatcher.cc : TH_HIGH/TH_LOW/HISTO_LENGTH + ctor, SearchByProjection(Frame&, vector<MapPoint*>&, th),
+                      RadiusByViewingCos, SearchForInitialization, SearchByProjection(Frame&, const Frame&, th, bMono),
+                      ComputeThreeMaxima, DescriptorDistance
+  src/Frame.cc      : AssignFeaturesToGrid, GetFeaturesInArea, PosInGrid, ComputeStereoMatches
+
+usage: gen_match_bodies.py <reference root> <out dir>
+"""
+import os, re, sys
+
+ref, out = sys.argv[1], sys.argv[2]
+
+
+def extract(path, starts):
+    src = open(os.path.join(ref, path), encoding="utf-8", errors="replace").read()
+    chunks = []
+    for sig in starts:
+        i = src.find(sig)
+        assert i >= 0, (path, sig)
+        assert src.find(sig, i + 1) < 0, ("ambiguous", sig)
+        j = src.index("{", i)
+        depth, k = 0, j
+        in_line_c = in_block_c = False
+        in_str = None
+        while True:
+            c = src[k]; n2 = src[k:k + 2]
+            if in_line_c:
+                if c == "\n": in_line_c = False
+            elif in_block_c:
+                if n2 == "*/": in_block_c = False; k += 1
+            elif in_str:
+                if c == "\\": k += 1
+                elif c == in_str: in_str = None
+            elif n2 == "//": in_line_c = True; k += 1
+            elif n2 == "/*": in_block_c = True; k += 1
+            elif c in "\"'": in_str = c
+            elif c == "{": depth += 1
+            elif c == "}":
+                depth -= 1
+                if depth == 0: break
+            k += 1
+        line0 = src.count("\n", 0, i) + 1
+        chunks.append("// ---- %s:%d ----\n#line %d \"%s\"\n%s\n" % (path, line0, line0, os.path.join(ref, path), src[i:k + 1]))
+    return "\n".join(chunks)
+
+
+m = extract("src/ORBmatcher.cc", [
+    "const int ORBmatcher::TH_HIGH = 100;\nconst int ORBmatcher::TH_LOW = 50;\nconst int ORBmatcher::HISTO_LENGTH = 30;",
+    "int ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, const float th)",
+    "float ORBmatcher::RadiusByViewingCos(const float &viewCos)",
+    "int ORBmatcher::SearchForInitialization(Frame &F1, Frame &F2, vector<cv::Point2f> &vbPrevMatched, vector<int> &vnMatches12, int windowSize)",
+    "int ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono)",
+    "void ORBmatcher::ComputeThreeMaxima(vector<int>* histo, const int L, int &ind1, int &ind2, int &ind3)",
+    "int ORBmatcher::DescriptorDistance(const cv::Mat &a, const cv::Mat &b)",
+])
+f = extract("src/Frame.cc", [
+    "void Frame::AssignFeaturesToGrid()",
+    "vector<size_t> Frame::GetFeaturesInArea(const float &x, const float  &y, const float  &r, const int minLevel, const int maxLevel) const",
+    "bool Frame::PosInGrid(",
+    "void Frame::ComputeStereoMatches()",
+])
+os.makedirs(out, exist_ok=True)
+# the first ORBmatcher chunk (constants) ends at the ctor's closing brace because the ctor follows immediately
+open(os.path.join(out, "ref_match_bodies.inc"), "w").write("// GENERATED from the reference sources by oracle/ref/gen_match_bodies.py -- do not commit\n" + m + "\n" + f)
+print("generated", os.path.join(out, "ref_match_bodies.inc"))

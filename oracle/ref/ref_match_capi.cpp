@@ -1,0 +1,228 @@
+// ref_match_capi.cpp -- TEST INFRASTRUCTURE ONLY (oracle/_ref build).
+//
+// Runs the reference's OWN matcher code: the bodies of ORBmatcher::{SearchByProjection x2, SearchForInitialization,
+// ComputeThreeMaxima, DescriptorDistance, RadiusByViewingCos} and Frame::{AssignFeaturesToGrid, GetFeaturesInArea,
+// PosInGrid, ComputeStereoMatches} are taken verbatim from /root/reference/src/{ORBmatcher,Frame}.cc at build time
+// (oracle/ref/gen_match_bodies.py -> oracle/_ref/gen/ref_match_bodies.inc) and compiled against the minimal
+// Frame / MapPoint / ORBmatcher declarations below, which carry exactly the members those bodies touch
+// (/root/reference/include/Frame.h, MapPoint.h, ORBmatcher.h).  The whole object graph of the reference
+// (KeyFrame, Map, DBoW2, g2o ...) is not needed by these functions and is not built.
+#include "ORBextractor.h"   // reference header (for mvImagePyramid in ComputeStereoMatches)
+#include <climits>
+#include <cstring>
+#include <set>
+#include <vector>
+#include <list>
+#include <cmath>
+#include <stdint.h>
+
+extern "C" void ref_arena_begin();
+extern "C" void ref_arena_end();
+
+#define FRAME_GRID_ROWS 48   // include/Frame.h:56
+#define FRAME_GRID_COLS 64   // include/Frame.h:61
+
+namespace ORB_SLAM2 {
+
+class Frame;
+class KeyFrame;
+
+class MapPoint {               // the members ORBmatcher.cc:70-175 and :1569-1728 read (include/MapPoint.h)
+public:
+    bool mbTrackInView; int mnTrackScaleLevel; float mTrackViewCos, mTrackProjX, mTrackProjY, mTrackProjXR;
+    bool bad; int nobs; cv::Mat desc, pos;
+    MapPoint() : mbTrackInView(true), mnTrackScaleLevel(0), mTrackViewCos(1.f), mTrackProjX(0), mTrackProjY(0), mTrackProjXR(0), bad(false), nobs(0) {}
+    bool isBad() { return bad; }
+    int Observations() { return nobs; }
+    cv::Mat GetDescriptor() { return desc.clone(); }
+    cv::Mat GetWorldPos() { return pos.clone(); }
+};
+
+class Frame {                  // include/Frame.h, only what the extracted bodies use
+public:
+    Frame() : mpORBextractorLeft(NULL), mpORBextractorRight(NULL), mbf(0), mb(0), N(0) {}
+    void AssignFeaturesToGrid();
+    std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const int minLevel = -1, const int maxLevel = -1) const;
+    bool PosInGrid(const cv::KeyPoint& kp, int& posX, int& posY);
+    void ComputeStereoMatches();
+    ORBextractor *mpORBextractorLeft, *mpORBextractorRight;
+    static float fx, fy, cx, cy;
+    float mbf, mb;
+    int N;
+    std::vector<cv::KeyPoint> mvKeys, mvKeysRight, mvKeysUn;
+    std::vector<float> mvuRight, mvDepth;
+    cv::Mat mDescriptors, mDescriptorsRight;
+    std::vector<MapPoint*> mvpMapPoints;
+    std::vector<bool> mvbOutlier;
+    static float mfGridElementWidthInv, mfGridElementHeightInv;
+    std::vector<std::size_t> mGrid[FRAME_GRID_COLS][FRAME_GRID_ROWS];
+    cv::Mat mTcw;
+    std::vector<float> mvScaleFactors, mvInvScaleFactors;
+    static float mnMinX, mnMaxX, mnMinY, mnMaxY;
+};
+float Frame::fx, Frame::fy, Frame::cx, Frame::cy, Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv;
+float Frame::mnMinX, Frame::mnMaxX, Frame::mnMinY, Frame::mnMaxY;
+
+class ORBmatcher {             // include/ORBmatcher.h:57-215, the subset on the hot path
+public:
+    ORBmatcher(float nnratio = 0.6, bool checkOri = true);
+    static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b);
+    int SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMapPoints, const float th = 3);
+    int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono);
+    int SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12, int windowSize = 10);
+    static const int TH_LOW, TH_HIGH, HISTO_LENGTH;
+protected:
+    float RadiusByViewingCos(const float& viewCos);
+    void ComputeThreeMaxima(std::vector<int>* histo, const int L, int& ind1, int& ind2, int& ind3);
+    float mfNNratio; bool mbCheckOrientation;
+};
+
+#include "ref_match_bodies.inc"   // GENERATED: verbatim reference function bodies
+
+}  // namespace ORB_SLAM2
+
+using namespace ORB_SLAM2;
+
+namespace {
+struct ArenaScope { ArenaScope() { ref_arena_begin(); } ~ArenaScope() { ref_arena_end(); } };
+
+// mirrors orbx_frame_view (include/orbx_b200.h)
+struct FrameView {
+    int n; const cv::KeyPoint* keys_un; const unsigned char* descriptors; const float* u_right;
+    float min_x, min_y, max_x, max_y, gw_inv, gh_inv; int nlevels; const float* scale_factors;
+};
+void fill_frame(Frame& F, const FrameView* v) {
+    F.N = v->n;
+    F.mvKeysUn.assign(v->keys_un, v->keys_un + v->n);
+    F.mvKeys = F.mvKeysUn;
+    F.mDescriptors = cv::Mat(v->n, 32, CV_8U, (void*)v->descriptors).clone();
+    if (v->u_right) F.mvuRight.assign(v->u_right, v->u_right + v->n); else F.mvuRight.assign(v->n, -1.f);
+    F.mvpMapPoints.assign(v->n, (MapPoint*)NULL);
+    F.mvbOutlier.assign(v->n, false);
+    F.mvScaleFactors.assign(v->scale_factors, v->scale_factors + v->nlevels);
+    Frame::mnMinX = v->min_x; Frame::mnMinY = v->min_y; Frame::mnMaxX = v->max_x; Frame::mnMaxY = v->max_y;
+    Frame::mfGridElementWidthInv = v->gw_inv; Frame::mfGridElementHeightInv = v->gh_inv;
+    F.AssignFeaturesToGrid();
+}
+}  // namespace
+
+extern "C" {
+
+// ORBmatcher::DescriptorDistance   ORBmatcher.cc:1913
+void ref_descriptor_distance(const unsigned char* a, const unsigned char* b, int n, int* out) {
+    for (int i = 0; i < n; ++i) {
+        cv::Mat ma(1, 32, CV_8U, (void*)(a + (size_t)i * 32)), mb(1, 32, CV_8U, (void*)(b + (size_t)i * 32));
+        out[i] = ORBmatcher::DescriptorDistance(ma, mb);
+    }
+}
+
+// Frame::GetFeaturesInArea   Frame.cc:894  (result order matters to the matchers' tie-breaks)
+int ref_get_features_in_area(const FrameView* v, float x, float y, float r, int minLevel, int maxLevel, int* out, int cap) {
+    ArenaScope scope;
+    int n;
+    { Frame F; fill_frame(F, v); std::vector<size_t> idx = F.GetFeaturesInArea(x, y, r, minLevel, maxLevel); n = (int)idx.size(); for (int i = 0; i < n && i < cap; ++i) out[i] = (int)idx[i]; }
+    return n;
+}
+
+// ORBmatcher::SearchForInitialization   ORBmatcher.cc:515
+int ref_search_for_initialization(float nnratio, int checkOri, const FrameView* v1, const FrameView* v2, float* prev_matched_xy, int* matches12, int windowSize) {
+    ArenaScope scope;
+    int nm;
+    {
+        Frame F1, F2; fill_frame(F1, v1); fill_frame(F2, v2);
+        std::vector<cv::Point2f> prev(v1->n);
+        for (int i = 0; i < v1->n; ++i) prev[i] = cv::Point2f(prev_matched_xy[2 * i], prev_matched_xy[2 * i + 1]);
+        std::vector<int> m12;
+        ORBmatcher matcher(nnratio, checkOri != 0);
+        nm = matcher.SearchForInitialization(F1, F2, prev, m12, windowSize);
+        for (int i = 0; i < v1->n; ++i) { matches12[i] = m12[i]; prev_matched_xy[2 * i] = prev[i].x; prev_matched_xy[2 * i + 1] = prev[i].y; }
+    }
+    return nm;
+}
+
+// ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono)   ORBmatcher.cc:1569
+// Poses are identity (Tcw = Tlw = I), so x3Dc == x3Dw == cam_xyz exactly; the projection the body computes
+// (:1608-1618) is returned in proj_uv / proj_invz so the caller can feed the same numbers to the C-ABI call.
+int ref_search_by_projection_frame(float nnratio, int checkOri, const FrameView* cur, int n_last, const float* cam_xyz,
+                                   const int* last_octave, const float* last_angle, const unsigned char* mp_desc, const unsigned char* valid,
+                                   const unsigned char* mp_observed, const unsigned char* cur_occupied, float th, int bMono, float mb, float mbf, float fx, float fy, float cx, float cy,
+                                   float* proj_uv, float* proj_invz, int* cur_match) {
+    ArenaScope scope;
+    int nm;
+    {
+        Frame C, L; fill_frame(C, cur);
+        Frame::fx = fx; Frame::fy = fy; Frame::cx = cx; Frame::cy = cy;
+        C.mb = mb; C.mbf = mbf;
+        C.mTcw = cv::Mat::eye(4, 4, CV_32F); L.mTcw = cv::Mat::eye(4, 4, CV_32F);
+        std::vector<MapPoint> pts(n_last), occ(cur->n);
+        L.N = n_last; L.mvKeys.resize(n_last); L.mvKeysUn.resize(n_last); L.mvpMapPoints.assign(n_last, (MapPoint*)NULL); L.mvbOutlier.assign(n_last, false);
+        for (int i = 0; i < n_last; ++i) {
+            L.mvKeys[i].octave = last_octave[i]; L.mvKeysUn[i].octave = last_octave[i]; L.mvKeysUn[i].angle = last_angle[i];
+            pts[i].pos = cv::Mat(3, 1, CV_32F); for (int k = 0; k < 3; ++k) pts[i].pos.at<float>(k) = cam_xyz[3 * i + k];
+            pts[i].desc = cv::Mat(1, 32, CV_8U, (void*)(mp_desc + (size_t)i * 32)).clone();
+            pts[i].nobs = (mp_observed && mp_observed[i]) ? 1 : 0;
+            if (valid[i]) L.mvpMapPoints[i] = &pts[i];
+            // the body's own projection, restated for the caller (:1608-1618)
+            const float xc = cam_xyz[3 * i], yc = cam_xyz[3 * i + 1];
+            const float invzc = 1.0 / cam_xyz[3 * i + 2];
+            proj_invz[i] = invzc; proj_uv[2 * i] = fx * xc * invzc + cx; proj_uv[2 * i + 1] = fy * yc * invzc + cy;
+        }
+        for (int j = 0; j < cur->n; ++j) if (cur_occupied && cur_occupied[j]) { occ[j].nobs = 1; C.mvpMapPoints[j] = &occ[j]; }
+        ORBmatcher matcher(nnratio, checkOri != 0);
+        nm = matcher.SearchByProjection(C, L, th, bMono != 0);
+        for (int j = 0; j < cur->n; ++j) {
+            MapPoint* p = C.mvpMapPoints[j];
+            cur_match[j] = (p && p >= &pts[0] && p < &pts[0] + n_last) ? (int)(p - &pts[0]) : -1;
+        }
+    }
+    return nm;
+}
+
+// ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th)   ORBmatcher.cc:70
+int ref_search_by_projection_points(float nnratio, int checkOri, const FrameView* Fv, int n_points, const float* track_uv, const float* track_ur,
+                                    const int* track_level, const float* track_view_cos, const unsigned char* mp_desc, const unsigned char* mp_observed,
+                                    const unsigned char* f_occupied, float th, int* f_match) {
+    ArenaScope scope;
+    int nm;
+    {
+        Frame F; fill_frame(F, Fv);
+        std::vector<MapPoint> pts(n_points), occ(Fv->n);
+        std::vector<MapPoint*> vp(n_points);
+        for (int i = 0; i < n_points; ++i) {
+            pts[i].mTrackProjX = track_uv[2 * i]; pts[i].mTrackProjY = track_uv[2 * i + 1]; pts[i].mTrackProjXR = track_ur[i];
+            pts[i].mnTrackScaleLevel = track_level[i]; pts[i].mTrackViewCos = track_view_cos[i];
+            pts[i].desc = cv::Mat(1, 32, CV_8U, (void*)(mp_desc + (size_t)i * 32)).clone();
+            pts[i].nobs = (mp_observed && mp_observed[i]) ? 1 : 0;
+            vp[i] = &pts[i];
+        }
+        for (int j = 0; j < Fv->n; ++j) if (f_occupied && f_occupied[j]) { occ[j].nobs = 1; F.mvpMapPoints[j] = &occ[j]; }
+        ORBmatcher matcher(nnratio, checkOri != 0);
+        nm = matcher.SearchByProjection(F, vp, th);
+        for (int j = 0; j < Fv->n; ++j) {
+            MapPoint* p = F.mvpMapPoints[j];
+            f_match[j] = (p && p >= &pts[0] && p < &pts[0] + n_points) ? (int)(p - &pts[0]) : -1;
+        }
+    }
+    return nm;
+}
+
+// Frame::ComputeStereoMatches   Frame.cc:1179.  left / right: handles from ref_extractor_create whose last
+// ref_extract call processed the left / right image (their mvImagePyramid is read).
+int ref_compute_stereo_matches(void* left, void* right, const cv::KeyPoint* keys_left, const unsigned char* desc_left, int nl,
+                               const cv::KeyPoint* keys_right, const unsigned char* desc_right, int nr, float mb, float mbf,
+                               float* u_right, float* depth) {
+    ArenaScope scope;
+    {
+        Frame F;
+        F.mpORBextractorLeft = (ORBextractor*)left; F.mpORBextractorRight = (ORBextractor*)right;
+        F.N = nl; F.mb = mb; F.mbf = mbf;
+        F.mvKeys.assign(keys_left, keys_left + nl); F.mvKeysRight.assign(keys_right, keys_right + nr);
+        F.mDescriptors = cv::Mat(nl, 32, CV_8U, (void*)desc_left).clone(); F.mDescriptorsRight = cv::Mat(nr, 32, CV_8U, (void*)desc_right).clone();
+        F.mvScaleFactors = F.mpORBextractorLeft->GetScaleFactors(); F.mvInvScaleFactors = F.mpORBextractorLeft->GetInverseScaleFactors();
+        F.ComputeStereoMatches();
+        for (int i = 0; i < nl; ++i) { u_right[i] = F.mvuRight[i]; depth[i] = F.mvDepth[i]; }
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,52 @@
+"""CPU: the C-ABI library loads and exports every symbol include/orbx_b200.h declares; host-side error behaviour
+that needs no GPU.  (No compute calls here: compute needs a B200 and lives in the -m gpu tests.)"""
+import ctypes
+import os
+import re
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "orbx_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(orbx_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol(orbx):
+    assert os.path.exists(orbx.LIB_PATH), "run __graft_entry__.build() first"
+    lib = ctypes.CDLL(orbx.LIB_PATH)
+    syms = declared_symbols()
+    assert len(syms) >= 30
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, missing
+
+
+def test_keypoint_layout_matches_cv_keypoint(orbx):
+    assert orbx.KP_DTYPE.itemsize == 28
+    assert [orbx.KP_DTYPE.fields[n][1] for n in ("x", "y", "size", "angle", "response", "octave", "class_id")] == [0, 4, 8, 12, 16, 20, 24]
+
+
+def test_no_cpu_fallback(orbx):
+    """Without a CUDA device the product must fail loudly, never compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(orbx.OrbxError) as e:
+        orbx.ORBextractor(1000, 1.2, 8, 20, 7)
+    assert e.value.code == orbx.E_CUDA
+    with pytest.raises(orbx.OrbxError):
+        orbx.ORBmatcher(0.9, True)
+
+
+def test_product_never_imports_oracle():
+    """The product path must not route through the oracle (or any CPU implementation)."""
+    pkg = os.path.join(ROOT, "amos-slam_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".inl", ".hpp", ".cpp")):
+                src = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "import oracle" not in src and "from oracle" not in src and "oracle/" not in src.replace("the oracle", ""), f
+                assert "cvlite" not in src or f.endswith(".hpp"), f

@@ -1,0 +1,212 @@
+"""GPU (B200) parity tests of the ORBextractor path, all through the C ABI (amos-slam_b200 -> liborbx_b200.so).
+Bit-exact against the port oracle on the same seeded inputs, against the committed golden outputs of the
+reference's own ORBextractor.cc, and -- where oracle/_ref travelled -- against the live reference build."""
+import os
+import threading
+import numpy as np
+import pytest
+from tools.synth import synth_frame, synth_batch, synth_mask
+
+pytestmark = pytest.mark.gpu
+R = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_extract.npz"))
+
+
+def kp_equal(a, b):
+    return len(a) == len(b) and all(np.array_equal(a[f], b[f]) for f in a.dtype.names)
+
+
+def assert_same(kg, dg, ko, do):
+    assert len(kg) == len(ko), (len(kg), len(ko))
+    for f in ko.dtype.names:                      # coordinates, octaves, responses, sizes exact; angles exact (<= 1e-3 rad is the contract)
+        assert np.array_equal(kg[f], ko[f]), f
+    assert np.array_equal(dg, do)
+
+
+@pytest.mark.parametrize("name", ["c1", "odd", "wide", "lv4"])
+def test_extract_matches_reference_golden(orbx, name):
+    w, h, nf, nl, it, mt, seed = [int(v) for v in R[name + "_params"]]
+    E = orbx.ORBextractor(nf, float(R[name + "_scale"]), nl, it, mt)
+    kp, desc = E(synth_frame(seed, w, h))
+    assert_same(kp, desc, R[name + "_kp"], R[name + "_desc"])
+    assert E.check_overflow() == 0
+
+
+@pytest.mark.parametrize("cfg", [(640, 480, 1000, 41), (752, 480, 2000, 42), (1241, 376, 2000, 43), (1920, 1080, 1000, 44), (160, 120, 100, 45)])
+def test_extract_matches_oracle_configs(orbx, oracle, cfg):
+    """C1 / C3 / C4 / C5 geometries (BASELINE.json configs) + a tiny frame."""
+    w, h, nf, seed = cfg
+    E = orbx.ORBextractor(nf, 1.2, 8, 20, 7); P = oracle.Extractor("port", nf, 1.2, 8, 20, 7)
+    img = synth_frame(seed, w, h)
+    kg, dg = E(img); ko, do = P.extract(img)
+    assert_same(kg, dg, ko, do)
+    for l in range(8):
+        po = P.pyramid_level(l)
+        assert np.array_equal(E.debug_pyramid_level(0, l, po.shape), po)
+        co, cg = P.level_candidates(l), E.debug_level_candidates(0, l)
+        assert len(co) == len(cg) and all(np.array_equal(co[f], cg[f]) for f in ("x", "y", "response"))
+    if oracle.have_ref() and w <= 1241:
+        kr, dr = oracle.Extractor("ref", nf, 1.2, 8, 20, 7).extract(img)
+        assert_same(kg, dg, kr, dr)
+
+
+def test_textured_and_flat_inputs(orbx, oracle):
+    rng = np.random.default_rng(3)
+    E = orbx.ORBextractor(500, 1.2, 8, 20, 7); P = oracle.Extractor("port", 500, 1.2, 8, 20, 7)
+    noise = rng.integers(0, 256, (240, 320), dtype=np.uint8)                 # corners everywhere: stresses cell capacity + quadtree
+    flat = np.full((240, 320), 77, np.uint8)                                  # no corner at all
+    grad = np.tile(np.arange(320, dtype=np.uint8), (240, 1))
+    checker = ((np.indices((240, 320)).sum(0) // 8) % 2 * 200 + 20).astype(np.uint8)   # many equal responses (tie-breaks)
+    for img in (noise, flat, grad, checker):
+        kg, dg = E(img); ko, do = P.extract(img)
+        assert_same(kg, dg, ko, do)
+    assert len(E(flat)[0]) == 0
+
+
+def test_empty_and_bad_inputs(orbx):
+    E = orbx.ORBextractor(1000, 1.2, 8, 20, 7)
+    kp, desc = E(np.zeros((0, 0), np.uint8))                                   # reference: silent return (ORBextractor.cc:1553)
+    assert len(kp) == 0 and desc.shape == (0, 32)
+    with pytest.raises(orbx.OrbxError):
+        E(np.zeros((480, 640, 3), np.uint8))                                   # assert(image.type()==CV_8UC1)
+    with pytest.raises(orbx.OrbxError) as e:
+        E(np.zeros((40, 40), np.uint8))                                        # too small for an 8-level pyramid
+    assert e.value.code == orbx.E_INVALID
+    with pytest.raises(orbx.OrbxError):
+        orbx.ORBextractor(0, 1.2, 8, 20, 7)
+
+
+def test_strided_input_and_geometry_change(orbx, oracle):
+    E = orbx.ORBextractor(600, 1.2, 8, 20, 7); P = oracle.Extractor("port", 600, 1.2, 8, 20, 7)
+    big = synth_frame(50, 700, 500)
+    view = big[10:490, 30:670]                                                 # non-contiguous rows (step 700)
+    kg, dg = E(view); ko, do = P.extract(np.ascontiguousarray(view))
+    assert_same(kg, dg, ko, do)
+    small = synth_frame(51, 400, 300)                                          # same handle, new geometry
+    kg, dg = E(small); ko, do = P.extract(small)
+    assert_same(kg, dg, ko, do)
+    kg, dg = E(view); ko, do = P.extract(np.ascontiguousarray(view))          # and back
+    assert_same(kg, dg, ko, do)
+
+
+def test_batch_equals_single(orbx, oracle):
+    imgs = synth_batch(12, 640, 480, seed0=60, distinct=12)
+    E = orbx.ORBextractor(1000, 1.2, 8, 20, 7); P = oracle.Extractor("port", 1000, 1.2, 8, 20, 7)
+    kp, desc, counts = E.extract_batch(imgs)
+    for b in (0, 5, 11):
+        ko, do = P.extract(imgs[b])
+        assert_same(kp[b][:counts[b]], desc[b][:counts[b]], ko, do)
+    for b in range(12):                                                        # batch == per-frame call (idempotence)
+        k1, d1 = E(imgs[b])
+        assert_same(kp[b][:counts[b]], desc[b][:counts[b]], k1, d1)
+    assert E.check_overflow() == 0
+
+
+def test_batch_full_size_properties(orbx):
+    """C5 shape (1920x1080): batch result is independent of batch position / batch size, and repeatable."""
+    E = orbx.ORBextractor(1000, 1.2, 8, 20, 7)
+    imgs = synth_batch(6, 1920, 1080, seed0=70, distinct=2)
+    kp, desc, counts = E.extract_batch(imgs)
+    kp2, desc2, counts2 = E.extract_batch(imgs[::-1].copy())
+    assert np.array_equal(counts, counts2[::-1])
+    for b in range(6):
+        assert np.array_equal(kp[b][:counts[b]], kp2[5 - b][:counts[b]]) and np.array_equal(desc[b][:counts[b]], desc2[5 - b][:counts[b]])
+    k1, d1 = E(imgs[3])
+    assert np.array_equal(k1, kp[3][:counts[3]]) and np.array_equal(d1, desc[3][:counts[3]])
+    assert (counts >= 1000).all() and (counts <= 1000 + 2 * 8).all()
+    assert E.check_overflow() == 0
+
+
+def test_quadtree_stage_adversarial(orbx, oracle):
+    """DistributeOctTree alone (device kernels) vs the reference's golden outputs and the port on adversarial sets."""
+    E = orbx.ORBextractor(1000, 1.2, 8, 20, 7); P = oracle.Extractor("port", 1000, 1.2, 8, 20, 7)
+    for k in [k for k in R.files if k.startswith("oct_") and k.endswith("_in")]:
+        N = int(k.split("_")[-2])
+        out = E.debug_distribute(R[k], 16, 16 + 608, 16, 16 + 448, N)
+        ref = R[k[:-3] + "_out"]
+        assert len(out) == len(ref) and all(np.array_equal(out[f], ref[f]) for f in ("x", "y", "response")), k
+    rng = np.random.default_rng(9)
+    for trial in range(12):
+        W, H = int(rng.integers(80, 1900)), int(rng.integers(60, 1060))
+        if not (0.5 <= W / H < 15.5):
+            continue
+        n = int(rng.integers(1, 6000))
+        xs = rng.integers(3, W - 3, n); ys = rng.integers(3, H - 3, n)
+        if trial % 3 == 0:                                                      # heavy clustering
+            xs = np.clip(rng.normal(W * 0.3, 6, n), 3, W - 4).astype(int); ys = np.clip(rng.normal(H * 0.6, 5, n), 3, H - 4).astype(int)
+        u = np.unique(np.stack([ys, xs], 1), axis=0); u = u[rng.permutation(len(u))]
+        c = np.zeros(len(u), oracle.KP_DTYPE); c["x"] = u[:, 1]; c["y"] = u[:, 0]
+        c["response"] = rng.integers(7, 40 if trial % 2 else 255, len(u)); c["size"] = 7; c["angle"] = -1; c["class_id"] = -1
+        N = int(rng.integers(1, 500))
+        out = E.debug_distribute(c, 16, 16 + W, 16, 16 + H, N); ref = P.distribute(c, 16, 16 + W, 16, 16 + H, N)
+        assert len(out) == len(ref) and all(np.array_equal(out[f], ref[f]) for f in ("x", "y", "response")), (trial, W, H, n, N)
+
+
+def test_amos_detect_cull_describe(orbx, oracle):
+    """operator()(img, mask, vector<vector<KeyPoint>>) -> MovingKeyPoints -> ProcessDesp vs the reference's golden run."""
+    E = orbx.ORBextractor(800, 1.2, 8, 20, 7)
+    kp, counts = E.detect(synth_frame(int(R["amos_frame_seed"]), 480, 360))
+    assert kp_equal(kp, R["amos_detect_kp"]) and np.array_equal(counts, R["amos_detect_counts"])
+    kp2, counts2, culled = E.MovingKeyPoints(R["amos_mask"], R["amos_label"], R["amos_centers_id"], R["amos_rm"], kp, counts)
+    assert kp_equal(kp2, R["amos_kept_kp"]) and np.array_equal(counts2, R["amos_kept_counts"]) and kp_equal(culled, R["amos_culled"])
+    kp3, desc3 = E.ProcessDesp(kp2, counts2)
+    assert kp_equal(kp3, R["amos_final_kp"]) and np.array_equal(desc3, R["amos_final_desc"])
+    # all-zero mask / no flagged super-pixel: nothing is culled, describe == 4-arg operator()
+    z = np.zeros((360, 480), np.uint8); lab = np.ones((360, 480), np.float64)
+    kp4, counts4, culled4 = E.MovingKeyPoints(z, lab, np.zeros(1, np.int32), np.zeros(1, np.int32), kp, counts)
+    assert len(culled4) == 0 and kp_equal(kp4, kp)
+    k5, d5 = E.ProcessDesp(kp4, counts4)
+    k6, d6 = E(synth_frame(int(R["amos_frame_seed"]), 480, 360))
+    assert kp_equal(k5, k6) and np.array_equal(d5, d6)
+
+
+def test_describe_requires_state(orbx):
+    E = orbx.ORBextractor(300, 1.2, 8, 20, 7)
+    with pytest.raises(orbx.OrbxError) as e:
+        E.ProcessDesp(np.zeros(1, orbx.KP_DTYPE), np.array([1, 0, 0, 0, 0, 0, 0, 0], np.int32))
+    assert e.value.code == orbx.E_STATE
+
+
+def test_pyramid_export_with_reflect101_border(orbx, oracle):
+    """mvImagePyramid export: ROI and the reference's padded parent buffer (copyMakeBorder REFLECT_101, 19 px)."""
+    E = orbx.ORBextractor(500, 1.2, 8, 20, 7); P = oracle.Extractor("port", 500, 1.2, 8, 20, 7)
+    img = synth_frame(80, 400, 300)
+    E(img); P.extract(img)
+    lib = oracle.port_lib()
+    for l in (0, 3, 7):
+        roi = P.pyramid_level(l)
+        assert np.array_equal(E.pyramid_level(l, 0), roi)
+        padded = np.zeros((roi.shape[0] + 38, roi.shape[1] + 38), np.uint8)
+        lib.cvl_c_border101(np.ascontiguousarray(roi), roi.shape[1], roi.shape[0], 19, padded)
+        assert np.array_equal(E.pyramid_level(l, 19), padded)
+    if oracle.have_ref():
+        Rf = oracle.Extractor("ref", 500, 1.2, 8, 20, 7); Rf.extract(img)
+        roi = Rf.pyramid_level(2)
+        padded = np.zeros((roi.shape[0] + 38, roi.shape[1] + 38), np.uint8)
+        oracle.ref_lib().ref_pyramid_level_padded(Rf.h, 2, padded)
+        assert np.array_equal(E.pyramid_level(2, 19), padded)
+
+
+def test_two_handles_two_threads(orbx, oracle):
+    """Left/right extractors run concurrently in two threads in the reference (Frame.cc:165-173)."""
+    imgs = [synth_frame(90, 640, 480), synth_frame(91, 640, 480)]
+    exts = [orbx.ORBextractor(1000, 1.2, 8, 20, 7) for _ in range(2)]
+    out = [None, None]
+
+    def run(i):
+        for _ in range(5):
+            out[i] = exts[i](imgs[i])
+    th = [threading.Thread(target=run, args=(i,)) for i in range(2)]
+    [t.start() for t in th]; [t.join() for t in th]
+    P = oracle.Extractor("port", 1000, 1.2, 8, 20, 7)
+    for i in range(2):
+        ko, do = P.extract(imgs[i])
+        assert_same(out[i][0], out[i][1], ko, do)
+
+
+def test_getters(orbx, oracle):
+    E = orbx.ORBextractor(1000, 1.2, 8, 20, 7); P = oracle.Extractor("port", 1000, 1.2, 8, 20, 7)
+    assert E.GetLevels() == 8 and abs(E.GetScaleFactor() - 1.2) < 1e-6
+    assert np.array_equal(E.GetScaleFactors(), P.scale_factors)
+    assert np.array_equal(E.GetInverseScaleFactors(), np.float32(1.0) / P.scale_factors)
+    assert np.array_equal(E.GetScaleSigmaSquares(), P.scale_factors * P.scale_factors)
+    assert np.array_equal(E.features_per_level(), P.features_per_level)

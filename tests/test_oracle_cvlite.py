@@ -1,0 +1,104 @@
+"""CPU: the OpenCV-free primitive restatements (oracle/cvlite) against (a) golden vectors produced by the real
+OpenCV 4.13 (tests/golden/cvlite_cv2.npz, made by tests/golden/make_golden.py) and (b) cv2 itself when importable.
+Bit-exact: these are integer / fixed-point / unfused-float algorithms."""
+import os
+import numpy as np
+import pytest
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "cvlite_cv2.npz"))
+
+
+def _fast(lib, oracle, img, th, nms):
+    kp = np.zeros(200000, oracle.KP_DTYPE)
+    n = lib.cvl_c_fast(np.ascontiguousarray(img), img.shape[1], img.shape[0], th, nms, kp, len(kp))
+    assert n >= 0
+    return np.stack([kp["x"][:n], kp["y"][:n], kp["response"][:n]], 1).astype(np.float32).reshape(-1, 3)
+
+
+def test_resize_blur_border_golden(oracle):
+    lib = oracle.port_lib()
+    for name in ("small", "synth"):
+        img = np.ascontiguousarray(G["img_" + name]); h, w = img.shape
+        ref = G["resize_" + name]
+        out = np.zeros_like(ref); lib.cvl_c_resize(img, w, h, out, ref.shape[1], ref.shape[0])
+        assert np.array_equal(out, ref)
+        b = np.zeros_like(img); lib.cvl_c_blur7(img, w, h, b)
+        assert np.array_equal(b, G["blur_" + name])
+    img = np.ascontiguousarray(G["img_small"]); h, w = img.shape
+    out = np.zeros((h + 38, w + 38), np.uint8); lib.cvl_c_border101(img, w, h, 19, out)
+    assert np.array_equal(out, G["border_small"])
+
+
+def test_fast_golden(oracle):
+    lib = oracle.port_lib()
+    img = G["img_synth"]
+    for th in (20, 7):
+        assert np.array_equal(_fast(lib, oracle, img, th, 1), G["fast%d" % th])          # content AND raster order
+        assert np.array_equal(_fast(lib, oracle, img, th, 0), G["fast%d_nonms" % th])
+
+
+def test_fast_score_map_equivalence(oracle):
+    """cv::FAST(t, NMS) == strict 3x3 local maxima of the S map with S > t, response S-1, raster order."""
+    lib = oracle.port_lib()
+    img = np.ascontiguousarray(G["img_synth"]); h, w = img.shape
+    S = np.zeros_like(img); lib.cvl_c_fast_smap(img, w, h, S)
+    Si = S.astype(np.int32)
+    for th in (20, 7):
+        P = np.pad(Si, 1)
+        c = P[1:-1, 1:-1]
+        ismax = np.ones_like(c, bool)
+        for dy in (-1, 0, 1):
+            for dx in (-1, 0, 1):
+                if dy or dx:
+                    ismax &= c > P[1 + dy:P.shape[0] - 1 + dy, 1 + dx:P.shape[1] - 1 + dx]
+        ys, xs = np.nonzero(ismax & (c > th))
+        mine = np.stack([xs, ys, c[ys, xs] - 1], 1).astype(np.float32)
+        assert np.array_equal(mine, G["fast%d" % th])
+
+
+def test_atan2_ellipse_close_golden(oracle):
+    lib = oracle.port_lib()
+    y, x = np.ascontiguousarray(G["atan_y"]), np.ascontiguousarray(G["atan_x"])
+    o = np.zeros_like(x); lib.cvl_c_atan2(y, x, o, len(x))
+    assert np.array_equal(o, G["atan_out"])                                              # exact float equality
+    e = np.zeros((31, 31), np.uint8); lib.cvl_c_ellipse31(e)
+    assert np.array_equal(e, G["ellipse31"])
+    m = np.ascontiguousarray(G["mask"]); c = np.zeros_like(m); lib.cvl_c_close31(m, m.shape[1], m.shape[0], c)
+    assert np.array_equal(c, G["mask_close"])
+
+
+def test_primitives_against_live_cv2(oracle):
+    cv2 = pytest.importorskip("cv2")
+    cv2.setNumThreads(1)
+    lib = oracle.port_lib()
+    rng = np.random.default_rng(7)
+    for (h, w) in [(480, 640), (376, 1241), (61, 75)]:
+        img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        dw, dh = int(round(w / 1.2)), int(round(h / 1.2))
+        out = np.zeros((dh, dw), np.uint8); lib.cvl_c_resize(img, w, h, out, dw, dh)
+        assert np.array_equal(out, cv2.resize(img, (dw, dh), interpolation=cv2.INTER_LINEAR))
+        b = np.zeros_like(img); lib.cvl_c_blur7(img, w, h, b)
+        assert np.array_equal(b, cv2.GaussianBlur(img, (7, 7), 2, 2, borderType=cv2.BORDER_REFLECT_101))
+    from tools.synth import synth_frame
+    img = synth_frame(4, 320, 240)
+    for th in (20, 7):
+        k = cv2.FastFeatureDetector_create(th, True).detect(img)
+        ref = np.array([(p.pt[0], p.pt[1], p.response) for p in k], np.float32).reshape(-1, 3)
+        assert np.array_equal(_fast(lib, oracle, img, th, 1), ref)
+
+
+def test_det_sincos_vs_libm(oracle):
+    """det_sincos (double polynomial, explicit fma, rounded to float) vs glibc sinf/cosf: the rBRIEF rotation uses
+    the former on both CPU oracle and GPU; differences against libm must be rare and exactly 1 ulp."""
+    lib = oracle.port_lib()
+    ang = (np.arange(0, 360000, dtype=np.float32) / np.float32(1000.0)) * np.float32(np.pi / 180.0)
+    s1, c1, s2, c2 = (np.zeros_like(ang) for _ in range(4))
+    lib.port_det_sincos(ang, s1, c1, len(ang)); lib.port_libm_sincosf(ang, s2, c2, len(ang))
+    exact = np.sin(ang.astype(np.float64)).astype(np.float32), np.cos(ang.astype(np.float64)).astype(np.float32)
+    assert np.array_equal(s1, exact[0]) and np.array_equal(c1, exact[1])      # correctly rounded on this grid
+    for a, b in ((s1, s2), (c1, c2)):
+        d = a != b
+        assert d.mean() < 0.05
+        if d.any():
+            ulp = np.abs(a[d].view(np.int32).astype(np.int64) - b[d].view(np.int32).astype(np.int64))
+            assert ulp.max() <= 1
