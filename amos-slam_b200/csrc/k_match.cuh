@@ -1,0 +1,535 @@
+// k_match.cuh -- 256-bit Hamming matching kernels (ORBmatcher / Frame grid / ComputeStereoMatches).
+//
+// Shape of every windowed matcher on the device:
+//   1. k_grid_build      Frame::AssignFeaturesToGrid + PosInGrid (/root/reference/src/Frame.cc:431-461,1007-1030):
+//                        bucket keypoints into the 64x48 grid; CSR layout sorted by (cell, index) so that a
+//                        column of cells is one contiguous, insertion-ordered range.
+//   2. k_window_search   Frame::GetFeaturesInArea (:894-1003) + ORBmatcher::DescriptorDistance
+//                        (/root/reference/src/ORBmatcher.cc:1913-1933): one warp per query; candidate indices in
+//                        the reference's exact order (cells column-major, insertion order inside), 8x __popc on
+//                        the xor of two uint4 halves per candidate; COUNT pass, scan, FILL pass (no caps).
+//   3. k_resolve_*       the order-dependent part of each matcher (running exclusions, steals, re-assignment,
+//                        30-bin rotation histogram + ComputeThreeMaxima) replayed by ONE warp in the reference's
+//                        loop order over the precomputed (index, distance) lists: lanes share a query's
+//                        candidates, warp-shuffle reductions give best / second best with first-wins tie-breaks.
+// No tensor cores: nothing here is a dense float contraction (popcount + integer compare only).
+#pragma once
+#include "orbx_common.cuh"
+
+#define GRID_COLS 64
+#define GRID_ROWS 48
+#define GRID_CELLS (GRID_COLS * GRID_ROWS)
+#define M_TH_HIGH 100
+#define M_TH_LOW 50
+#define M_HISTO 30
+
+struct KpM { float x, y, size, angle, response; int octave, class_id; };
+
+struct FrameDev {                 // device mirror of orbx_frame_view + its grid
+    int n; const KpM* keys; const uint8_t* desc; const float* u_right;
+    float min_x, min_y, max_x, max_y, gw_inv, gh_inv;
+    const float* scale; int nlevels;
+    const int* cell_start;        // GRID_CELLS + 1
+    const int* entries;           // keypoint indices sorted by (cell, index)
+};
+
+__device__ __forceinline__ int hamming256(const uint4 a0, const uint4 a1, const uint4* __restrict__ b) {
+    const uint4 b0 = __ldg(b), b1 = __ldg(b + 1);
+    return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+           __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+// ORBmatcher::DescriptorDistance on n independent pairs
+__global__ void k_descriptor_distance(const uint4* __restrict__ a, const uint4* __restrict__ b, int n, int* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = hamming256(__ldg(a + 2 * i), __ldg(a + 2 * i + 1), b + 2 * i);
+}
+
+// ---- grid build: keys = cell<<20 | index, bitonic sort (one CTA), then cell_start by binary search ----
+__global__ void __launch_bounds__(1024)
+k_grid_build(const KpM* __restrict__ keys, int n, float min_x, float min_y, float gw_inv, float gh_inv,
+             uint32_t* __restrict__ skeys, int* __restrict__ entries, int* __restrict__ cell_start) {
+    const int tid = threadIdx.x;
+    for (int i = tid; i < n; i += 1024) {
+        // posX = round((kp.pt.x - mnMinX) * mfGridElementWidthInv)   (roundf: half away from zero)
+        const int px = (int)roundf(__fmul_rn(__fsub_rn(keys[i].x, min_x), gw_inv));
+        const int py = (int)roundf(__fmul_rn(__fsub_rn(keys[i].y, min_y), gh_inv));
+        const uint32_t cell = (px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS) ? 0xFFFu : (uint32_t)(px * GRID_ROWS + py);
+        skeys[i] = (cell << 20) | (uint32_t)i;
+    }
+    __syncthreads();
+    for (int k = 2; (k >> 1) < n; k <<= 1) {
+        for (int i = tid; i < n; i += 1024) { const int j = i ^ (k - 1); if (j > i && j < n) { uint32_t a = skeys[i], c = skeys[j]; if (a > c) { skeys[i] = c; skeys[j] = a; } } }
+        __syncthreads();
+        for (int s = k >> 2; s > 0; s >>= 1) {
+            for (int i = tid; i < n; i += 1024) { const int j = i ^ s; if (j > i && j < n) { uint32_t a = skeys[i], c = skeys[j]; if (a > c) { skeys[i] = c; skeys[j] = a; } } }
+            __syncthreads();
+        }
+    }
+    for (int i = tid; i < n; i += 1024) entries[i] = (int)(skeys[i] & 0xFFFFFu);
+    for (int c = tid; c <= GRID_CELLS; c += 1024) {
+        const uint32_t T = (uint32_t)c << 20;
+        int lo = 0, hi = n;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (skeys[mid] < T) lo = mid + 1; else hi = mid; }
+        cell_start[c] = lo;
+    }
+}
+
+// ---- queries ----
+#define MODE_INIT 0
+#define MODE_PROJ_FRAME 1
+#define MODE_PROJ_POINTS 2
+struct QueryParams {
+    int mode, nq;
+    // INIT: F1 keys / desc, vbPrevMatched, windowSize
+    const KpM* q_keys; const uint8_t* q_desc; const float* q_xy; float window;
+    // PROJ_FRAME: proj_invz, last_octave, valid, th, forward/backward, mbf        (q_xy = proj_uv, q_desc = mp_desc)
+    const float* q_invz; const int* q_octave; const uint8_t* q_valid; float th; int forward, backward; float mbf;
+    // PROJ_POINTS: track_ur, track_level, track_view_cos, th                      (q_xy = track_uv, q_desc = mp_desc)
+    const float* q_ur; const float* q_viewcos;
+};
+
+// per-query window of GetFeaturesInArea and the static candidate filters; returns false if the query is skipped
+__device__ __forceinline__ bool query_window(const QueryParams& P, const FrameDev& F, int q, float& x, float& y, float& r,
+                                             int& minLevel, int& maxLevel, float& ur, bool& use_ur) {
+    use_ur = false; ur = 0.f;
+    if (P.mode == MODE_INIT) {
+        if (P.q_keys[q].octave > 0) return false;                                   // ORBmatcher.cc:537
+        x = P.q_xy[2 * q]; y = P.q_xy[2 * q + 1]; r = P.window; minLevel = 0; maxLevel = 0;
+        return true;
+    }
+    if (P.mode == MODE_PROJ_FRAME) {
+        if (!P.q_valid[q]) return false;
+        const float u = P.q_xy[2 * q], v = P.q_xy[2 * q + 1], invz = P.q_invz[q];
+        if (invz < 0.f) return false;                                               // :1612
+        if (u < F.min_x || u > F.max_x) return false;                               // :1620
+        if (v < F.min_y || v > F.max_y) return false;
+        const int oct = P.q_octave[q];
+        x = u; y = v; r = __fmul_rn(P.th, F.scale[oct]);                            // :1629
+        if (P.forward) { minLevel = oct; maxLevel = -1; }                           // :1637-1642
+        else if (P.backward) { minLevel = 0; maxLevel = oct; }
+        else { minLevel = oct - 1; maxLevel = oct + 1; }
+        ur = __fsub_rn(u, __fmul_rn(P.mbf, invz)); use_ur = true;                   // :1665
+        return true;
+    }
+    // MODE_PROJ_POINTS  (:89-103)
+    const int lvl = P.q_octave[q];
+    float rr = ((double)P.q_viewcos[q] > 0.998) ? 2.5f : 4.0f;                      // RadiusByViewingCos :178-185
+    if (P.th != 1.0f) rr = __fmul_rn(rr, P.th);
+    x = P.q_xy[2 * q]; y = P.q_xy[2 * q + 1]; r = __fmul_rn(rr, F.scale[lvl]);
+    minLevel = lvl - 1; maxLevel = lvl;
+    ur = P.q_ur[q]; use_ur = true;
+    return true;
+}
+
+// one warp per query.  FILL = false: counts[q] only.  FILL = true: cand[offsets[q] + k] = dist<<20 | index.
+template <bool FILL>
+__global__ void __launch_bounds__(128)
+k_window_search(QueryParams P, FrameDev F, int* __restrict__ counts, const int* __restrict__ offsets, uint32_t* __restrict__ cand) {
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (q >= P.nq) return;
+    float x, y, r, ur; int minLevel, maxLevel; bool use_ur;
+    if (!query_window(P, F, q, x, y, r, minLevel, maxLevel, ur, use_ur)) { if (!FILL && lane == 0) counts[q] = 0; return; }
+    // cell range (Frame.cc:913-939), float arithmetic in the reference's order
+    const int cx0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, F.min_x), r), F.gw_inv)));
+    const int cx1 = min(GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, F.min_x), r), F.gw_inv)));
+    const int cy0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, F.min_y), r), F.gh_inv)));
+    const int cy1 = min(GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, F.min_y), r), F.gh_inv)));
+    int n = 0;
+    if (!(cx0 >= GRID_COLS || cx1 < 0 || cy0 >= GRID_ROWS || cy1 < 0)) {
+        const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+        uint4 d0 = make_uint4(0, 0, 0, 0), d1 = d0;
+        uint32_t* out = nullptr;
+        if (FILL) {
+            const uint4* qd = reinterpret_cast<const uint4*>(P.q_desc) + 2 * q;
+            d0 = __ldg(qd); d1 = __ldg(qd + 1);
+            out = cand + offsets[q];
+        }
+        for (int ix = cx0; ix <= cx1; ++ix) {
+            const int e0 = F.cell_start[ix * GRID_ROWS + cy0], e1 = F.cell_start[ix * GRID_ROWS + cy1 + 1];
+            for (int e = e0; e < e1; e += 32) {
+                const int ee = e + lane;
+                bool keep = false; int j = -1;
+                if (ee < e1) {
+                    j = F.entries[ee];
+                    const KpM kp = F.keys[j];
+                    keep = true;
+                    if (bCheckLevels) {
+                        if (kp.octave < minLevel) keep = false;
+                        if (maxLevel >= 0 && kp.octave > maxLevel) keep = false;
+                    }
+                    if (keep && !(fabsf(__fsub_rn(kp.x, x)) < r && fabsf(__fsub_rn(kp.y, y)) < r)) keep = false;    // :986-991
+                    if (keep && use_ur && F.u_right) {
+                        const float urj = F.u_right[j];
+                        if (urj > 0.f && fabsf(__fsub_rn(ur, urj)) > r) keep = false;                                // :1662-1669 / :129-139
+                    }
+                }
+                const uint32_t m = __ballot_sync(0xffffffffu, keep);
+                if (FILL && keep) {
+                    const int d = hamming256(d0, d1, reinterpret_cast<const uint4*>(F.desc) + 2 * j);
+                    out[n + __popc(m & ((1u << lane) - 1u))] = ((uint32_t)d << 20) | (uint32_t)j;
+                }
+                n += __popc(m);
+            }
+        }
+    }
+    if (!FILL && lane == 0) counts[q] = n;
+}
+
+// exclusive scan of n counts by one CTA; total written to offsets[n]
+__global__ void __launch_bounds__(1024) k_scan_counts(const int* __restrict__ counts, int n, int* __restrict__ offsets) {
+    __shared__ int wsum[32];
+    __shared__ int carry_sm;
+    const int tid = threadIdx.x;
+    if (tid == 0) carry_sm = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + tid;
+        const int v = i < n ? counts[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += t; }
+        if ((tid & 31) == 31) wsum[tid >> 5] = incl;
+        __syncthreads();
+        if (tid < 32) { int w = wsum[tid], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, wi, o); if (tid >= o) wi += t; }
+            wsum[tid] = wi - w; if (tid == 31) wsum[31] = wi - w; }
+        __syncthreads();
+        const int carry = carry_sm;
+        if (i < n) offsets[i] = carry + wsum[tid >> 5] + incl - v;
+        __syncthreads();
+        if (tid == 1023) carry_sm = carry + wsum[31] + incl;
+        __syncthreads();
+    }
+    if (tid == 0) offsets[n] = carry_sm;
+}
+
+// two smallest candidate keys (dist<<20 | position-in-list) of a query under a per-candidate predicate
+struct Best2 { uint32_t k1, k2; };
+template <typename Pred>
+__device__ __forceinline__ Best2 warp_best2(const uint32_t* __restrict__ cand, int cnt, int lane, Pred ok) {
+    uint32_t k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
+    for (int p = lane; p < cnt; p += 32) {
+        const uint32_t c = cand[p];
+        if (!ok(c)) continue;
+        const uint32_t key = (c & 0xFFF00000u) | (uint32_t)p;       // distance, then order of appearance
+        if (key < k1) { k2 = k1; k1 = key; } else if (key < k2) k2 = key;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const uint32_t a1 = __shfl_xor_sync(0xffffffffu, k1, o), a2 = __shfl_xor_sync(0xffffffffu, k2, o);
+        // merge (k1,k2) with (a1,a2): two smallest of the four distinct keys
+        const uint32_t lo = min(k1, a1), hi = max(k1, a1);
+        k2 = min(hi, min(k2, a2)); k1 = lo;
+    }
+    Best2 b; b.k1 = k1; b.k2 = k2; return b;
+}
+
+__device__ __forceinline__ int rot_bin(float a1, float a2) {        // ORBmatcher.cc:597-602
+    const float factor = (float)M_HISTO / 360.0f;
+    float rot = __fsub_rn(a1, a2);
+    if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+    int bin = (int)roundf(__fmul_rn(rot, factor));
+    if (bin == M_HISTO) bin = 0;
+    return bin;
+}
+// ORBmatcher::ComputeThreeMaxima   ORBmatcher.cc:1866-1908
+__device__ __forceinline__ void three_maxima(const int* hist, int& ind1, int& ind2, int& ind3) {
+    int max1 = 0, max2 = 0, max3 = 0; ind1 = ind2 = ind3 = -1;
+    for (int i = 0; i < M_HISTO; i++) {
+        const int s = hist[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+    else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) ind3 = -1;
+}
+
+// ---- SearchForInitialization, sequential part (ORBmatcher.cc:532-640); one warp ----
+__global__ void __launch_bounds__(32)
+k_resolve_init(int n1, int n2, const KpM* __restrict__ k1s, const KpM* __restrict__ k2s, const int* __restrict__ counts, const int* __restrict__ offsets,
+               const uint32_t* __restrict__ cand, float nnratio, int checkOri,
+               int* __restrict__ matchedDist /*n2*/, int* __restrict__ m21 /*n2*/, int* __restrict__ m12 /*n1*/, int* __restrict__ bin_of /*n1*/,
+               float* __restrict__ prev_xy, int* __restrict__ nmatches_out) {
+    __shared__ int hist[M_HISTO];
+    const int lane = threadIdx.x;
+    for (int i = lane; i < n2; i += 32) { matchedDist[i] = INT_MAX; m21[i] = -1; }
+    for (int i = lane; i < n1; i += 32) { m12[i] = -1; bin_of[i] = -1; }
+    if (lane < M_HISTO) hist[lane] = 0;
+    __syncwarp();
+    int nmatches = 0;
+    for (int i1 = 0; i1 < n1; ++i1) {
+        const int cnt = counts[i1];
+        if (cnt == 0) continue;
+        const uint32_t* c = cand + offsets[i1];
+        const Best2 b = warp_best2(c, cnt, lane, [&](uint32_t v) { return !(matchedDist[v & 0xFFFFFu] <= (int)(v >> 20)); });   // :561
+        if (b.k1 == 0xFFFFFFFFu) continue;
+        const int bestDist = (int)(b.k1 >> 20);
+        const int bestDist2 = b.k2 == 0xFFFFFFFFu ? INT_MAX : (int)(b.k2 >> 20);
+        if (bestDist <= M_TH_LOW && (float)bestDist < __fmul_rn((float)bestDist2, nnratio)) {         // :577-579
+            const int bestIdx2 = (int)(c[b.k1 & 0xFFFFFu] & 0xFFFFFu);
+            const int old = m21[bestIdx2];
+            if (old >= 0) --nmatches;
+            ++nmatches;
+            if (lane == 0) {
+                if (old >= 0) m12[old] = -1;                                                       // :583-587
+                m12[i1] = bestIdx2; m21[bestIdx2] = i1; matchedDist[bestIdx2] = bestDist;
+                if (checkOri) { const int bin = rot_bin(k1s[i1].angle, k2s[bestIdx2].angle); bin_of[i1] = bin; hist[bin]++; }
+            }
+            __syncwarp();
+        }
+    }
+    if (checkOri) {
+        int ind1, ind2, ind3;
+        three_maxima(hist, ind1, ind2, ind3);
+        int removed = 0;
+        for (int i = lane; i < n1; i += 32) {
+            const int bin = bin_of[i];
+            if (bin >= 0 && bin != ind1 && bin != ind2 && bin != ind3 && m12[i] >= 0) { m12[i] = -1; ++removed; }   // :620-633
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, o);
+        nmatches -= removed;
+    }
+    __syncwarp();
+    for (int i = lane; i < n1; i += 32) { const int j = m12[i]; if (j >= 0) { prev_xy[2 * i] = k2s[j].x; prev_xy[2 * i + 1] = k2s[j].y; } }   // :638-640
+    if (lane == 0) *nmatches_out = nmatches;
+}
+
+// ---- SearchByProjection(Frame, Frame), sequential part (ORBmatcher.cc:1595-1725); one warp ----
+__global__ void __launch_bounds__(32)
+k_resolve_proj_frame(int n_last, int n_cur, const KpM* __restrict__ cur_keys, const float* __restrict__ last_angle, const uint8_t* __restrict__ mp_observed,
+                     const uint8_t* __restrict__ cur_occupied, const int* __restrict__ counts, const int* __restrict__ offsets, const uint32_t* __restrict__ cand,
+                     int checkOri, uint8_t* __restrict__ occupied /*n_cur*/, int* __restrict__ cur_match /*n_cur*/, int* __restrict__ pushes /*2*n_last*/,
+                     int* __restrict__ nmatches_out) {
+    __shared__ int hist[M_HISTO];
+    const int lane = threadIdx.x;
+    for (int j = lane; j < n_cur; j += 32) { cur_match[j] = -1; occupied[j] = cur_occupied ? (cur_occupied[j] != 0) : 0; }
+    if (lane < M_HISTO) hist[lane] = 0;
+    __syncwarp();
+    int nmatches = 0, npush = 0;
+    for (int i = 0; i < n_last; ++i) {
+        const int cnt = counts[i];
+        if (cnt == 0) continue;
+        const uint32_t* c = cand + offsets[i];
+        const Best2 b = warp_best2(c, cnt, lane, [&](uint32_t v) { return !occupied[v & 0xFFFFFu] && (v >> 20) < 256u; });   // :1658-1660, bestDist = 256
+        if (b.k1 == 0xFFFFFFFFu) continue;
+        const int bestDist = (int)(b.k1 >> 20);
+        if (bestDist <= M_TH_HIGH) {                                                               // :1683
+            const int j = (int)(c[b.k1 & 0xFFFFFu] & 0xFFFFFu);
+            if (lane == 0) {
+                cur_match[j] = i; occupied[j] = mp_observed ? (mp_observed[i] != 0) : 0;
+                if (checkOri) { const int bin = rot_bin(last_angle[i], cur_keys[j].angle); hist[bin]++; pushes[2 * npush] = bin; pushes[2 * npush + 1] = j; }
+            }
+            ++nmatches; ++npush;
+            __syncwarp();
+        }
+    }
+    if (checkOri) {
+        int ind1, ind2, ind3;
+        three_maxima(hist, ind1, ind2, ind3);
+        int removed = 0;
+        for (int e = lane; e < npush; e += 32) {
+            const int bin = pushes[2 * e];
+            if (bin != ind1 && bin != ind2 && bin != ind3) { cur_match[pushes[2 * e + 1]] = -1; ++removed; }   // :1714-1724 (every pushed entry counts)
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, o);
+        nmatches -= removed;
+    }
+    if (lane == 0) *nmatches_out = nmatches;
+}
+
+// ---- SearchByProjection(Frame, vpMapPoints), sequential part (ORBmatcher.cc:77-172); one warp ----
+__global__ void __launch_bounds__(32)
+k_resolve_proj_points(int n_points, int n_f, const KpM* __restrict__ f_keys, const uint8_t* __restrict__ mp_observed, const uint8_t* __restrict__ f_occupied,
+                      const int* __restrict__ counts, const int* __restrict__ offsets, const uint32_t* __restrict__ cand, float nnratio,
+                      uint8_t* __restrict__ occupied, int* __restrict__ f_match, int* __restrict__ nmatches_out) {
+    const int lane = threadIdx.x;
+    for (int j = lane; j < n_f; j += 32) { f_match[j] = -1; occupied[j] = f_occupied ? (f_occupied[j] != 0) : 0; }
+    __syncwarp();
+    int nmatches = 0;
+    for (int i = 0; i < n_points; ++i) {
+        const int cnt = counts[i];
+        if (cnt == 0) continue;
+        const uint32_t* c = cand + offsets[i];
+        const Best2 b = warp_best2(c, cnt, lane, [&](uint32_t v) { return !occupied[v & 0xFFFFFu] && (v >> 20) < 256u; });
+        if (b.k1 == 0xFFFFFFFFu) continue;
+        const int bestDist = (int)(b.k1 >> 20);
+        if (bestDist > M_TH_HIGH) continue;                                                        // :163
+        const int bestIdx = (int)(c[b.k1 & 0xFFFFFu] & 0xFFFFFu);
+        const int bestLevel = f_keys[bestIdx].octave;
+        int bestDist2 = 256, bestLevel2 = -1;
+        if (b.k2 != 0xFFFFFFFFu) { bestDist2 = (int)(b.k2 >> 20); bestLevel2 = f_keys[c[b.k2 & 0xFFFFFu] & 0xFFFFFu].octave; }
+        if (bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(nnratio, (float)bestDist2)) continue;   // :166
+        if (lane == 0) { f_match[bestIdx] = i; occupied[bestIdx] = mp_observed ? (mp_observed[i] != 0) : 0; }
+        ++nmatches;
+        __syncwarp();
+    }
+    if (lane == 0) *nmatches_out = nmatches;
+}
+
+// =================================================================================================
+// Frame::ComputeStereoMatches   /root/reference/src/Frame.cc:1179-1573
+// =================================================================================================
+struct PyrLevelDev { const uint8_t* ptr; int pitch, w, h; };
+struct StereoPyr { PyrLevelDev lv[ORBX_MAX_LEVELS]; };
+
+// one warp per left keypoint: row-band Hamming search over the right keypoints, then the 11-shift 11x11 SAD
+// refinement on the two pyramids, parabola sub-pixel fit, disparity -> depth.
+__global__ void __launch_bounds__(128)
+k_stereo_match(const KpM* __restrict__ kl, const uint8_t* __restrict__ dl, int nl, const KpM* __restrict__ kr, const uint8_t* __restrict__ dr, int nr,
+               StereoPyr PL, StereoPyr PR, const float* __restrict__ scale, const float* __restrict__ inv_scale, float mb, float mbf,
+               float* __restrict__ u_right, float* __restrict__ depth, int* __restrict__ sad_dist /* INT_MAX = not stored */) {
+    const int lane = threadIdx.x & 31;
+    const int iL = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (iL >= nl) return;
+    if (lane == 0) { u_right[iL] = -1.0f; depth[iL] = -1.0f; sad_dist[iL] = INT_MAX; }
+    const KpM kpL = kl[iL];
+    const int levelL = kpL.octave;
+    const float vL = kpL.y, uL = kpL.x;
+    const int row = (int)vL;                                                   // vRowIndices[vL]  :1298
+    const int nRows = PL.lv[0].h;
+    if (row < 0 || row >= nRows) return;
+    const float minZ = mb, minD = 0.f;
+    const float maxD = __fdiv_rn(mbf, minZ);                                   // :1272 (mb == 0 => +inf)
+    const float minU = __fsub_rn(uL, maxD), maxU = __fsub_rn(uL, minD);
+    if (maxU < 0.f) return;
+    const uint4* qd = reinterpret_cast<const uint4*>(dl) + 2 * iL;
+    const uint4 d0 = __ldg(qd), d1 = __ldg(qd + 1);
+    uint32_t best = 0xFFFFFFFFu;                                               // dist<<20 | iR ; first (smallest iR) wins ties
+    for (int iR = lane; iR < nr; iR += 32) {
+        const KpM kpR = kr[iR];
+        const float r = __fmul_rn(2.0f, scale[kpR.octave]);                    // :1239
+        const int maxr = (int)ceilf(__fadd_rn(kpR.y, r)), minr = (int)floorf(__fsub_rn(kpR.y, r));
+        if (row < minr || row > maxr) continue;
+        if (kpR.octave < levelL - 1 || kpR.octave > levelL + 1) continue;      // :1343
+        if (!(kpR.x >= minU && kpR.x <= maxU)) continue;                       // :1353
+        const int d = hamming256(d0, d1, reinterpret_cast<const uint4*>(dr) + 2 * iR);
+        if (d < M_TH_HIGH) best = min(best, ((uint32_t)d << 20) | (uint32_t)iR);     // bestDist starts at TH_HIGH  :1322
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (best == 0xFFFFFFFFu) return;
+    const int bestDist = (int)(best >> 20), bestIdxR = (int)(best & 0xFFFFFu);
+    if (!(bestDist < (M_TH_HIGH + M_TH_LOW) / 2)) return;                      // thOrbDist  :1194,1377
+    const float uR0 = kr[bestIdxR].x;
+    const float sf = inv_scale[levelL];
+    const float scaleduL = roundf(__fmul_rn(kpL.x, sf)), scaledvL = roundf(__fmul_rn(kpL.y, sf)), scaleduR0 = roundf(__fmul_rn(uR0, sf));
+    const int w = 5, L = 5;
+    const PyrLevelDev IL = PL.lv[levelL], IR = PR.lv[levelL];
+    const float iniu = __fsub_rn(__fadd_rn(scaleduR0, (float)L), (float)w), endu = __fadd_rn(__fadd_rn(__fadd_rn(scaleduR0, (float)L), (float)w), 1.f);
+    if (iniu < 0.f || endu >= (float)IR.w) return;                              // :1425
+    const int cy = (int)scaledvL, cxl = (int)scaleduL, cxr = (int)scaleduR0;
+    // the reference's rowRange/colRange would throw on windows leaving the level; cannot happen for keypoints that
+    // are >= 19 px inside their level, guarded here so foreign input can never read out of bounds
+    if (cy - w < 0 || cy + w >= IL.h || cy + w >= IR.h || cxl - w < 0 || cxl + w >= IL.w || cxr - L - w < 0 || cxr + L + w >= IR.w) return;
+    const int cl = IL.ptr[(size_t)cy * IL.pitch + cxl];
+    float vDists[11];
+    int bestS = INT_MAX, bestinc = 0;
+#pragma unroll 1
+    for (int inc = -L; inc <= L; ++inc) {
+        const int cr = IR.ptr[(size_t)cy * IR.pitch + cxr + inc];
+        int s = 0;
+        for (int p = lane; p < 121; p += 32) {
+            const int dy = p / 11 - w, dx = p % 11 - w;
+            const int a = (int)IL.ptr[(size_t)(cy + dy) * IL.pitch + cxl + dx] - cl;
+            const int b = (int)IR.ptr[(size_t)(cy + dy) * IR.pitch + cxr + inc + dx] - cr;
+            s += abs(a - b);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float dist = (float)s;                                           // cv::norm(IL, IR, NORM_L1): exact integers
+        if (dist < (float)bestS) { bestS = (int)dist; bestinc = inc; }         // :1449 (int bestDist compared as float)
+        vDists[L + inc] = dist;
+    }
+    if (bestinc == -L || bestinc == L) return;                                  // :1468
+    float dist1 = 0.f, dist2 = 0.f, dist3 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 11; ++k) { if (k == L + bestinc - 1) dist1 = vDists[k]; if (k == L + bestinc) dist2 = vDists[k]; if (k == L + bestinc + 1) dist3 = vDists[k]; }
+    // deltaR = (dist1-dist3)/(2.0f*(dist1+dist3-2.0f*dist2))   :1494
+    const float deltaR = __fdiv_rn(__fsub_rn(dist1, dist3), __fmul_rn(2.0f, __fsub_rn(__fadd_rn(dist1, dist3), __fmul_rn(2.0f, dist2))));
+    if (deltaR < -1.f || deltaR > 1.f) return;
+    float bestuR = __fmul_rn(scale[levelL], __fadd_rn(__fadd_rn(scaleduR0, (float)bestinc), deltaR));      // :1509
+    float disparity = __fsub_rn(uL, bestuR);
+    if (disparity >= minD && disparity < maxD) {
+        if (disparity <= 0.f) { disparity = 0.01f; bestuR = __fsub_rn(uL, 0.01f); }
+        if (lane == 0) { depth[iL] = __fdiv_rn(mbf, disparity); u_right[iL] = bestuR; sad_dist[iL] = bestS; }
+    }
+}
+
+// median cut (:1548-1569): thDist = 1.5f*1.4f*median(dist); entries with dist >= thDist are dropped.  One CTA.
+__global__ void __launch_bounds__(1024)
+k_stereo_median_cut(int nl, const int* __restrict__ sad_dist, float* __restrict__ u_right, float* __restrict__ depth) {
+    __shared__ int total_sm, median_sm;
+    const int tid = threadIdx.x;
+    if (tid == 0) { total_sm = 0; median_sm = -1; }
+    __syncthreads();
+    int cnt = 0;
+    for (int i = tid; i < nl; i += 1024) cnt += sad_dist[i] != INT_MAX;
+    atomicAdd(&total_sm, cnt);
+    __syncthreads();
+    const int total = total_sm;
+    if (total == 0) return;
+    const int k = total / 2;                                                   // vDistIdx[size/2].first of the sorted list
+    for (int i = tid; i < nl; i += 1024) {
+        const int d = sad_dist[i];
+        if (d == INT_MAX) continue;
+        int less = 0, leq = 0;
+        for (int j = 0; j < nl; ++j) { const int e = sad_dist[j]; if (e != INT_MAX) { less += e < d; leq += e <= d; } }
+        if (less <= k && k < leq) median_sm = d;                               // every qualifying thread writes the same value
+    }
+    __syncthreads();
+    const float median = (float)median_sm;
+    const float thDist = __fmul_rn(1.5f * 1.4f, median);
+    for (int i = tid; i < nl; i += 1024) {
+        const int d = sad_dist[i];
+        if (d != INT_MAX && !((float)d < thDist)) { u_right[i] = -1.f; depth[i] = -1.f; }
+    }
+}
+
+// =================================================================================================
+// Brute-force all-pairs best / second-best (throughput form of the inner kernel).  One warp per query;
+// train descriptors are staged tile by tile in shared memory as uint4 pairs and shared by the CTA's 8 queries.
+// =================================================================================================
+#define BF_TILE 256
+__global__ void __launch_bounds__(256)
+k_bruteforce_best2(const uint4* __restrict__ query, int nq, const uint4* __restrict__ train, int nt,
+                   int* __restrict__ best_idx, int* __restrict__ best_dist, int* __restrict__ second_dist) {
+    __shared__ uint4 tile[BF_TILE * 2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = blockIdx.x * 8 + warp;
+    uint4 d0 = make_uint4(0, 0, 0, 0), d1 = d0;
+    if (q < nq) { d0 = __ldg(query + 2 * q); d1 = __ldg(query + 2 * q + 1); }
+    uint32_t k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
+    for (int t0 = 0; t0 < nt; t0 += BF_TILE) {
+        const int tn = min(BF_TILE, nt - t0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < tn * 2; i += 256) tile[i] = __ldg(train + 2 * (size_t)t0 + i);
+        __syncthreads();
+        if (q < nq)
+            for (int j = lane; j < tn; j += 32) {
+                const uint4 b0 = tile[2 * j], b1 = tile[2 * j + 1];
+                const int d = __popc(d0.x ^ b0.x) + __popc(d0.y ^ b0.y) + __popc(d0.z ^ b0.z) + __popc(d0.w ^ b0.w) +
+                              __popc(d1.x ^ b1.x) + __popc(d1.y ^ b1.y) + __popc(d1.z ^ b1.z) + __popc(d1.w ^ b1.w);
+                const uint32_t key = ((uint32_t)d << 20) | (uint32_t)(t0 + j);
+                if (key < k1) { k2 = k1; k1 = key; } else if (key < k2) k2 = key;
+            }
+    }
+    if (q >= nq) return;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const uint32_t a1 = __shfl_xor_sync(0xffffffffu, k1, o), a2 = __shfl_xor_sync(0xffffffffu, k2, o);
+        const uint32_t lo = min(k1, a1), hi = max(k1, a1);
+        k2 = min(hi, min(k2, a2)); k1 = lo;
+    }
+    if (lane == 0) {
+        best_idx[q] = k1 == 0xFFFFFFFFu ? -1 : (int)(k1 & 0xFFFFFu);
+        best_dist[q] = k1 == 0xFFFFFFFFu ? INT_MAX : (int)(k1 >> 20);
+        second_dist[q] = k2 == 0xFFFFFFFFu ? INT_MAX : (int)(k2 >> 20);
+    }
+}

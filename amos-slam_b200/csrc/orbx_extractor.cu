@@ -7,6 +7,7 @@
 // per-geometry tables exactly as the reference's constructor / ComputePyramid / cell loop do.
 #include "../../include/orbx_b200.h"
 #include "orbx_common.cuh"
+#include "orbx_internal.h"
 #include "k_pyramid_fast.cuh"
 #include "k_octree.cuh"
 #include "k_describe.cuh"
@@ -616,3 +617,18 @@ int orbx_debug_level_candidates(orbx_extractor* h, int b, int level, orbx_keypoi
 }  // extern "C"
 
 #include "orbx_extractor_debug.inl"
+
+int orbx_internal_pyramid(orbx_extractor* h, OrbxPyramidInfo* out) {
+    if (!h || !out) FAIL(ORBX_E_INVALID, "null handle");
+    if (!h->have_pyramid) FAIL(ORBX_E_STATE, "extractor holds no pyramid (call extract / detect first)");
+    out->device = h->device; out->nlevels = h->nlevels; out->stream = h->stream;
+    for (int l = 0; l < h->nlevels; ++l) {
+        const LevelGeom& g = h->levels[l];
+        if (l == 0) { out->ptr[0] = h->view.l0; out->pitch[0] = h->view.l0_pitch; }
+        else { out->ptr[l] = h->d_pyr.p + g.off; out->pitch[l] = g.pitch; }
+        out->w[l] = g.w; out->h[l] = g.h;
+    }
+    out->scale = h->mvScaleFactor.data(); out->inv_scale = h->mvInvScaleFactor.data();
+    return ORBX_OK;
+}
+

@@ -1,0 +1,14 @@
+// orbx_internal.h -- private interface between the two translation units of liborbx_b200.so (not exported).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "orbx_common.cuh"
+
+struct orbx_extractor;
+// resident pyramid of frame 0 of an extractor handle (mvImagePyramid), device pointers
+struct OrbxPyramidInfo {
+    int device, nlevels; cudaStream_t stream;
+    const uint8_t* ptr[ORBX_MAX_LEVELS]; int pitch[ORBX_MAX_LEVELS], w[ORBX_MAX_LEVELS], h[ORBX_MAX_LEVELS];
+    const float* scale; const float* inv_scale;     // host arrays owned by the handle (mvScaleFactor / mvInvScaleFactor)
+};
+int orbx_internal_pyramid(orbx_extractor* h, OrbxPyramidInfo* out);

@@ -1,0 +1,303 @@
+// orbx_matcher.cu -- host side of the B200-native ORBmatcher / ComputeStereoMatches (C ABI of include/orbx_b200.h).
+//
+// Mirrors ORB_SLAM2::ORBmatcher (/root/reference/include/ORBmatcher.h:57-215, src/ORBmatcher.cc) and
+// Frame::ComputeStereoMatches (/root/reference/src/Frame.cc:1179-1573).  The host only marshals the caller's
+// arrays to the device and launches the kernels of k_match.cuh; there is no CPU matching path.
+#include "../../include/orbx_b200.h"
+#include "orbx_internal.h"
+#include "k_match.cuh"
+
+#include <climits>
+#include <cstring>
+#include <string>
+#include <vector>
+
+void orbx_set_error(const std::string& s);
+#define CU_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { \
+    orbx_set_error(std::string(#expr) + ": " + cudaGetErrorString(_e)); return ORBX_E_CUDA; } } while (0)
+#define FAIL(code, msg) do { orbx_set_error(msg); return (code); } while (0)
+#define LAUNCH_CHECK() do { cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) { \
+    orbx_set_error(std::string("kernel launch: ") + cudaGetErrorString(_e)); return ORBX_E_CUDA; } ++m->launches; } while (0)
+
+static_assert(sizeof(KpM) == 28, "KpM must match cv::KeyPoint");
+
+namespace {
+// bump allocator over one device arena, reset at the start of every call
+struct Arena {
+    uint8_t* base = nullptr; size_t cap = 0, off = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return ORBX_OK;
+        if (base) cudaFree(base);
+        base = nullptr; cap = 0;
+        size_t want = bytes + (bytes >> 2) + (1 << 20);
+        if (cudaMalloc((void**)&base, want) != cudaSuccess) { orbx_set_error("cudaMalloc (matcher arena)"); return ORBX_E_CUDA; }
+        cap = want; return ORBX_OK;
+    }
+    void reset() { off = 0; }
+    template <typename T> T* get(size_t count) {
+        size_t o = (off + 255) & ~(size_t)255;
+        off = o + count * sizeof(T);
+        return off <= cap ? reinterpret_cast<T*>(base + o) : nullptr;
+    }
+};
+inline size_t pad(size_t b) { return (b + 255) & ~(size_t)255; }
+}
+
+struct orbx_matcher {
+    float nnratio; int checkOri; int device; cudaStream_t stream = nullptr; long long launches = 0;
+    Arena arena; Arena cand_arena;
+};
+
+struct FrameUpload { FrameDev dev; };
+
+// bytes a frame needs in the arena
+static size_t frame_bytes(const orbx_frame_view* f) {
+    return pad((size_t)f->n * 28) + pad((size_t)f->n * 32) + pad((size_t)f->n * 4) + pad((size_t)f->nlevels * 4) +
+           pad((size_t)(GRID_CELLS + 1) * 4) + 2 * pad((size_t)f->n * 4) + 4096;
+}
+
+static int check_frame(const orbx_frame_view* f) {
+    if (!f || f->n < 0 || f->n >= (1 << 20) || (f->n && (!f->keys_un || !f->descriptors)) || f->nlevels <= 0 || f->nlevels > ORBX_MAX_LEVELS || !f->scale_factors)
+        FAIL(ORBX_E_INVALID, "bad frame view");
+    return ORBX_OK;
+}
+
+// upload a frame view and build its 64x48 grid on the device
+static int upload_frame(orbx_matcher* m, const orbx_frame_view* f, FrameDev& d) {
+    cudaStream_t s = m->stream;
+    const int n = f->n;
+    KpM* keys = m->arena.get<KpM>(n ? n : 1); uint8_t* desc = m->arena.get<uint8_t>((size_t)(n ? n : 1) * 32);
+    float* ur = f->u_right ? m->arena.get<float>(n ? n : 1) : nullptr; float* sc = m->arena.get<float>(f->nlevels);
+    int* cs = m->arena.get<int>(GRID_CELLS + 1); int* en = m->arena.get<int>(n ? n : 1); uint32_t* sk = m->arena.get<uint32_t>(n ? n : 1);
+    if (!keys || !desc || !sc || !cs || !en || !sk || (f->u_right && !ur)) FAIL(ORBX_E_CUDA, "matcher arena exhausted");
+    if (n) {
+        CU_TRY(cudaMemcpyAsync(keys, f->keys_un, (size_t)n * 28, cudaMemcpyHostToDevice, s));
+        CU_TRY(cudaMemcpyAsync(desc, f->descriptors, (size_t)n * 32, cudaMemcpyHostToDevice, s));
+        if (ur) CU_TRY(cudaMemcpyAsync(ur, f->u_right, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    }
+    CU_TRY(cudaMemcpyAsync(sc, f->scale_factors, (size_t)f->nlevels * 4, cudaMemcpyHostToDevice, s));
+    k_grid_build<<<1, 1024, 0, s>>>(keys, n, f->min_x, f->min_y, f->grid_element_width_inv, f->grid_element_height_inv, sk, en, cs);
+    LAUNCH_CHECK();
+    d.n = n; d.keys = keys; d.desc = desc; d.u_right = ur; d.min_x = f->min_x; d.min_y = f->min_y; d.max_x = f->max_x; d.max_y = f->max_y;
+    d.gw_inv = f->grid_element_width_inv; d.gh_inv = f->grid_element_height_inv; d.scale = sc; d.nlevels = f->nlevels; d.cell_start = cs; d.entries = en;
+    return ORBX_OK;
+}
+
+template <typename T> static int up(orbx_matcher* m, const T* host, size_t count, T*& dev) {
+    dev = m->arena.get<T>(count ? count : 1);
+    if (!dev) FAIL(ORBX_E_CUDA, "matcher arena exhausted");
+    if (count && host) CU_TRY(cudaMemcpyAsync(dev, host, count * sizeof(T), cudaMemcpyHostToDevice, m->stream));
+    return ORBX_OK;
+}
+
+// COUNT pass, scan, (host reads the total), FILL pass
+static int window_search(orbx_matcher* m, QueryParams& P, const FrameDev& F, int*& counts, int*& offsets, uint32_t*& cand) {
+    cudaStream_t s = m->stream;
+    const int nq = P.nq;
+    counts = m->arena.get<int>(nq + 1); offsets = m->arena.get<int>(nq + 2);
+    if (!counts || !offsets) FAIL(ORBX_E_CUDA, "matcher arena exhausted");
+    cand = nullptr;
+    if (nq == 0) return ORBX_OK;
+    k_window_search<false><<<(nq + 3) / 4, 128, 0, s>>>(P, F, counts, nullptr, nullptr);
+    LAUNCH_CHECK();
+    k_scan_counts<<<1, 1024, 0, s>>>(counts, nq, offsets);
+    LAUNCH_CHECK();
+    int total = 0;
+    CU_TRY(cudaMemcpyAsync(&total, offsets + nq, 4, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    int rc = m->cand_arena.reserve((size_t)(total + 1) * 4); if (rc) return rc;
+    cand = reinterpret_cast<uint32_t*>(m->cand_arena.base);
+    k_window_search<true><<<(nq + 3) / 4, 128, 0, s>>>(P, F, counts, offsets, cand);
+    LAUNCH_CHECK();
+    return ORBX_OK;
+}
+
+extern "C" {
+
+int orbx_matcher_create(float nnratio, int check_orientation, int device, orbx_matcher** out) {
+    if (!out) FAIL(ORBX_E_INVALID, "null out");
+    *out = nullptr;
+    int ndev = 0;
+    CU_TRY(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) FAIL(ORBX_E_CUDA, "no such CUDA device (this library has no CPU fallback)");
+    CU_TRY(cudaSetDevice(device));
+    orbx_matcher* m = new orbx_matcher();
+    m->nnratio = nnratio; m->checkOri = check_orientation != 0; m->device = device;
+    cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete m; FAIL(ORBX_E_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e)); }
+    *out = m;
+    return ORBX_OK;
+}
+void orbx_matcher_destroy(orbx_matcher* m) {
+    if (!m) return;
+    cudaSetDevice(m->device); cudaStreamSynchronize(m->stream);
+    if (m->arena.base) cudaFree(m->arena.base);
+    if (m->cand_arena.base) cudaFree(m->cand_arena.base);
+    cudaStreamDestroy(m->stream);
+    delete m;
+}
+void* orbx_matcher_stream(orbx_matcher* m) { return m ? (void*)m->stream : nullptr; }
+long long orbx_matcher_launch_count(const orbx_matcher* m) { return m ? m->launches : 0; }
+
+int orbx_descriptor_distance(orbx_matcher* m, const uint8_t* a, const uint8_t* b, int n, int* out) {
+    if (!m || n < 0 || (n && (!a || !b || !out))) FAIL(ORBX_E_INVALID, "bad arguments");
+    if (n == 0) return ORBX_OK;
+    CU_TRY(cudaSetDevice(m->device));
+    int rc = m->arena.reserve(2 * pad((size_t)n * 32) + pad((size_t)n * 4) + 4096); if (rc) return rc;
+    m->arena.reset();
+    uint8_t *da, *db; int* dout;
+    if ((rc = up(m, a, (size_t)n * 32, da)) || (rc = up(m, b, (size_t)n * 32, db)) || (rc = up<int>(m, nullptr, n, dout))) return rc;
+    k_descriptor_distance<<<(n + 127) / 128, 128, 0, m->stream>>>(reinterpret_cast<const uint4*>(da), reinterpret_cast<const uint4*>(db), n, dout);
+    LAUNCH_CHECK();
+    CU_TRY(cudaMemcpyAsync(out, dout, (size_t)n * 4, cudaMemcpyDeviceToHost, m->stream));
+    CU_TRY(cudaStreamSynchronize(m->stream));
+    return ORBX_OK;
+}
+
+int orbx_search_for_initialization(orbx_matcher* m, const orbx_frame_view* F1, const orbx_frame_view* F2, float* prev_matched_xy, int* matches12,
+                                   int window_size, int* nmatches) {
+    if (!m || !nmatches) FAIL(ORBX_E_INVALID, "null argument");
+    int rc;
+    if ((rc = check_frame(F1)) || (rc = check_frame(F2))) return rc;
+    if (F1->n && (!prev_matched_xy || !matches12)) FAIL(ORBX_E_INVALID, "null buffer");
+    *nmatches = 0;
+    if (F1->n == 0) return ORBX_OK;
+    CU_TRY(cudaSetDevice(m->device));
+    const int n1 = F1->n, n2 = F2->n;
+    if ((rc = m->arena.reserve(frame_bytes(F1) + frame_bytes(F2) + pad((size_t)n1 * 8) + 6 * pad((size_t)(n1 + n2 + 2) * 4) + 8192))) return rc;
+    m->arena.reset();
+    FrameDev d2;
+    if ((rc = upload_frame(m, F2, d2))) return rc;
+    KpM* k1; uint8_t* desc1; float* prev;
+    if ((rc = up(m, reinterpret_cast<const KpM*>(F1->keys_un), (size_t)n1, k1)) || (rc = up(m, F1->descriptors, (size_t)n1 * 32, desc1)) || (rc = up(m, prev_matched_xy, (size_t)n1 * 2, prev))) return rc;
+    QueryParams P; std::memset(&P, 0, sizeof(P));
+    P.mode = MODE_INIT; P.nq = n1; P.q_keys = k1; P.q_desc = desc1; P.q_xy = prev; P.window = (float)window_size;
+    int *counts, *offsets; uint32_t* cand;
+    if ((rc = window_search(m, P, d2, counts, offsets, cand))) return rc;
+    int* md = m->arena.get<int>(n2 + 1); int* m21 = m->arena.get<int>(n2 + 1); int* m12 = m->arena.get<int>(n1); int* binof = m->arena.get<int>(n1); int* dn = m->arena.get<int>(1);
+    if (!md || !m21 || !m12 || !binof || !dn) FAIL(ORBX_E_CUDA, "matcher arena exhausted");
+    k_resolve_init<<<1, 32, 0, m->stream>>>(n1, n2, k1, d2.keys, counts, offsets, cand, m->nnratio, m->checkOri, md, m21, m12, binof, prev, dn);
+    LAUNCH_CHECK();
+    CU_TRY(cudaMemcpyAsync(matches12, m12, (size_t)n1 * 4, cudaMemcpyDeviceToHost, m->stream));
+    CU_TRY(cudaMemcpyAsync(prev_matched_xy, prev, (size_t)n1 * 8, cudaMemcpyDeviceToHost, m->stream));
+    CU_TRY(cudaMemcpyAsync(nmatches, dn, 4, cudaMemcpyDeviceToHost, m->stream));
+    CU_TRY(cudaStreamSynchronize(m->stream));
+    return ORBX_OK;
+}
+
+int orbx_search_by_projection_frame(orbx_matcher* m, const orbx_frame_view* cur, int n_last, const float* proj_uv, const float* proj_invz,
+                                    const int* last_octave, const float* last_angle, const uint8_t* mp_desc, const uint8_t* valid, const uint8_t* mp_observed,
+                                    const uint8_t* cur_occupied, float th, int forward, int backward, float mbf, int* cur_match, int* nmatches) {
+    if (!m || !nmatches) FAIL(ORBX_E_INVALID, "null argument");
+    int rc;
+    if ((rc = check_frame(cur))) return rc;
+    if (n_last < 0 || n_last >= (1 << 20) || (n_last && (!proj_uv || !proj_invz || !last_octave || !last_angle || !mp_desc || !valid)) || (cur->n && !cur_match))
+        FAIL(ORBX_E_INVALID, "bad arguments");
+    *nmatches = 0;
+    for (int i = 0; i < n_last; ++i) if (valid[i] && (last_octave[i] < 0 || last_octave[i] >= cur->nlevels)) FAIL(ORBX_E_INVALID, "octave out of range");
+    CU_TRY(cudaSetDevice(m->device));
+    const int nc = cur->n;
+    if ((rc = m->arena.reserve(frame_bytes(cur) + pad((size_t)n_last * 32) + 8 * pad((size_t)(n_last + nc + 2) * 8) + 8192))) return rc;
+    m->arena.reset();
+    FrameDev dc;
+    if ((rc = upload_frame(m, cur, dc))) return rc;
+    float *uv, *iz, *la; int* lo; uint8_t *dd, *va, *ob = nullptr, *oc = nullptr;
+    if ((rc = up(m, proj_uv, (size_t)n_last * 2, uv)) || (rc = up(m, proj_invz, (size_t)n_last, iz)) || (rc = up(m, last_angle, (size_t)n_last, la)) ||
+        (rc = up(m, last_octave, (size_t)n_last, lo)) || (rc = up(m, mp_desc, (size_t)n_last * 32, dd)) || (rc = up(m, valid, (size_t)n_last, va))) return rc;
+    if (mp_observed && (rc = up(m, mp_observed, (size_t)n_last, ob))) return rc;
+    if (cur_occupied && (rc = up(m, cur_occupied, (size_t)nc, oc))) return rc;
+    QueryParams P; std::memset(&P, 0, sizeof(P));
+    P.mode = MODE_PROJ_FRAME; P.nq = n_last; P.q_desc = dd; P.q_xy = uv; P.q_invz = iz; P.q_octave = lo; P.q_valid = va; P.th = th; P.forward = forward; P.backward = backward; P.mbf = mbf;
+    int *counts, *offsets; uint32_t* cand;
+    if ((rc = window_search(m, P, dc, counts, offsets, cand))) return rc;
+    uint8_t* occ = m->arena.get<uint8_t>(nc + 1); int* cm = m->arena.get<int>(nc + 1); int* pushes = m->arena.get<int>(2 * (size_t)n_last + 2); int* dn = m->arena.get<int>(1);
+    if (!occ || !cm || !pushes || !dn) FAIL(ORBX_E_CUDA, "matcher arena exhausted");
+    k_resolve_proj_frame<<<1, 32, 0, m->stream>>>(n_last, nc, dc.keys, la, ob, oc, counts, offsets, cand, m->checkOri, occ, cm, pushes, dn);
+    LAUNCH_CHECK();
+    if (nc) CU_TRY(cudaMemcpyAsync(cur_match, cm, (size_t)nc * 4, cudaMemcpyDeviceToHost, m->stream));
+    CU_TRY(cudaMemcpyAsync(nmatches, dn, 4, cudaMemcpyDeviceToHost, m->stream));
+    CU_TRY(cudaStreamSynchronize(m->stream));
+    return ORBX_OK;
+}
+
+int orbx_search_by_projection_points(orbx_matcher* m, const orbx_frame_view* F, int n_points, const float* track_uv, const float* track_ur, const int* track_level,
+                                     const float* track_view_cos, const uint8_t* mp_desc, const uint8_t* mp_observed, const uint8_t* f_occupied, float th,
+                                     int* f_match, int* nmatches) {
+    if (!m || !nmatches) FAIL(ORBX_E_INVALID, "null argument");
+    int rc;
+    if ((rc = check_frame(F))) return rc;
+    if (n_points < 0 || n_points >= (1 << 20) || (n_points && (!track_uv || !track_ur || !track_level || !track_view_cos || !mp_desc)) || (F->n && !f_match))
+        FAIL(ORBX_E_INVALID, "bad arguments");
+    *nmatches = 0;
+    for (int i = 0; i < n_points; ++i) if (track_level[i] < 0 || track_level[i] >= F->nlevels) FAIL(ORBX_E_INVALID, "predicted level out of range");
+    CU_TRY(cudaSetDevice(m->device));
+    const int nf = F->n;
+    if ((rc = m->arena.reserve(frame_bytes(F) + pad((size_t)n_points * 32) + 8 * pad((size_t)(n_points + nf + 2) * 8) + 8192))) return rc;
+    m->arena.reset();
+    FrameDev df;
+    if ((rc = upload_frame(m, F, df))) return rc;
+    float *uv, *ur, *vc; int* lv; uint8_t *dd, *ob = nullptr, *oc = nullptr;
+    if ((rc = up(m, track_uv, (size_t)n_points * 2, uv)) || (rc = up(m, track_ur, (size_t)n_points, ur)) || (rc = up(m, track_view_cos, (size_t)n_points, vc)) ||
+        (rc = up(m, track_level, (size_t)n_points, lv)) || (rc = up(m, mp_desc, (size_t)n_points * 32, dd))) return rc;
+    if (mp_observed && (rc = up(m, mp_observed, (size_t)n_points, ob))) return rc;
+    if (f_occupied && (rc = up(m, f_occupied, (size_t)nf, oc))) return rc;
+    QueryParams P; std::memset(&P, 0, sizeof(P));
+    P.mode = MODE_PROJ_POINTS; P.nq = n_points; P.q_desc = dd; P.q_xy = uv; P.q_octave = lv; P.q_ur = ur; P.q_viewcos = vc; P.th = th;
+    int *counts, *offsets; uint32_t* cand;
+    if ((rc = window_search(m, P, df, counts, offsets, cand))) return rc;
+    uint8_t* occ = m->arena.get<uint8_t>(nf + 1); int* fm = m->arena.get<int>(nf + 1); int* dn = m->arena.get<int>(1);
+    if (!occ || !fm || !dn) FAIL(ORBX_E_CUDA, "matcher arena exhausted");
+    k_resolve_proj_points<<<1, 32, 0, m->stream>>>(n_points, nf, df.keys, ob, oc, counts, offsets, cand, m->nnratio, occ, fm, dn);
+    LAUNCH_CHECK();
+    if (nf) CU_TRY(cudaMemcpyAsync(f_match, fm, (size_t)nf * 4, cudaMemcpyDeviceToHost, m->stream));
+    CU_TRY(cudaMemcpyAsync(nmatches, dn, 4, cudaMemcpyDeviceToHost, m->stream));
+    CU_TRY(cudaStreamSynchronize(m->stream));
+    return ORBX_OK;
+}
+
+int orbx_compute_stereo_matches(orbx_matcher* m, orbx_extractor* left, orbx_extractor* right, const orbx_keypoint* keys_left, const uint8_t* desc_left, int nl,
+                                const orbx_keypoint* keys_right, const uint8_t* desc_right, int nr, float mb, float mbf, float* u_right, float* depth) {
+    if (!m || !left || !right || nl < 0 || nr < 0 || nr >= (1 << 20) || (nl && (!keys_left || !desc_left || !u_right || !depth)) || (nr && (!keys_right || !desc_right)))
+        FAIL(ORBX_E_INVALID, "bad arguments");
+    if (nl == 0) return ORBX_OK;
+    CU_TRY(cudaSetDevice(m->device));
+    OrbxPyramidInfo L, R;
+    int rc;
+    if ((rc = orbx_internal_pyramid(left, &L)) || (rc = orbx_internal_pyramid(right, &R))) return rc;
+    if (L.device != m->device || R.device != m->device) FAIL(ORBX_E_INVALID, "extractors and matcher must live on the same device");
+    if (L.nlevels != R.nlevels) FAIL(ORBX_E_INVALID, "left / right extractors differ in nlevels");
+    for (int i = 0; i < nl; ++i) if (keys_left[i].octave < 0 || keys_left[i].octave >= L.nlevels) FAIL(ORBX_E_INVALID, "octave out of range");
+    for (int i = 0; i < nr; ++i) if (keys_right[i].octave < 0 || keys_right[i].octave >= L.nlevels) FAIL(ORBX_E_INVALID, "octave out of range");
+    // both extractors' streams must have finished writing their pyramids
+    CU_TRY(cudaStreamSynchronize(L.stream)); CU_TRY(cudaStreamSynchronize(R.stream));
+    if ((rc = m->arena.reserve(pad((size_t)nl * 60) + pad((size_t)nr * 60) + 3 * pad((size_t)nl * 4) + 2 * pad((size_t)L.nlevels * 4) + 8192 + 64 * 256))) return rc;
+    m->arena.reset();
+    KpM *kl, *kr; uint8_t *dl, *dr; float *sc, *isc;
+    if ((rc = up(m, reinterpret_cast<const KpM*>(keys_left), (size_t)nl, kl)) || (rc = up(m, reinterpret_cast<const KpM*>(keys_right), (size_t)nr, kr)) ||
+        (rc = up(m, desc_left, (size_t)nl * 32, dl)) || (rc = up(m, desc_right, (size_t)nr * 32, dr)) ||
+        (rc = up(m, L.scale, (size_t)L.nlevels, sc)) || (rc = up(m, L.inv_scale, (size_t)L.nlevels, isc))) return rc;
+    float* dur = m->arena.get<float>(nl); float* ddep = m->arena.get<float>(nl); int* sad = m->arena.get<int>(nl);
+    if (!dur || !ddep || !sad) FAIL(ORBX_E_CUDA, "matcher arena exhausted");
+    StereoPyr PL, PR;
+    for (int l = 0; l < L.nlevels; ++l) { PL.lv[l] = {L.ptr[l], L.pitch[l], L.w[l], L.h[l]}; PR.lv[l] = {R.ptr[l], R.pitch[l], R.w[l], R.h[l]}; }
+    k_stereo_match<<<(nl + 3) / 4, 128, 0, m->stream>>>(kl, dl, nl, kr, dr, nr, PL, PR, sc, isc, mb, mbf, dur, ddep, sad);
+    LAUNCH_CHECK();
+    k_stereo_median_cut<<<1, 1024, 0, m->stream>>>(nl, sad, dur, ddep);
+    LAUNCH_CHECK();
+    CU_TRY(cudaMemcpyAsync(u_right, dur, (size_t)nl * 4, cudaMemcpyDeviceToHost, m->stream));
+    CU_TRY(cudaMemcpyAsync(depth, ddep, (size_t)nl * 4, cudaMemcpyDeviceToHost, m->stream));
+    CU_TRY(cudaStreamSynchronize(m->stream));
+    return ORBX_OK;
+}
+
+int orbx_match_bruteforce_device(orbx_matcher* m, const uint8_t* d_query, int n_query, const uint8_t* d_train, int n_train, int* d_best_idx, int* d_best_dist, int* d_second_dist) {
+    if (!m || n_query < 0 || n_train < 0 || n_train >= (1 << 20) || !d_query || !d_train || !d_best_idx || !d_best_dist || !d_second_dist) FAIL(ORBX_E_INVALID, "bad arguments");
+    if (((uintptr_t)d_query & 15) || ((uintptr_t)d_train & 15)) FAIL(ORBX_E_INVALID, "descriptor arrays must be 16-byte aligned");
+    if (n_query == 0) return ORBX_OK;
+    CU_TRY(cudaSetDevice(m->device));
+    k_bruteforce_best2<<<(n_query + 7) / 8, 256, 0, m->stream>>>(reinterpret_cast<const uint4*>(d_query), n_query, reinterpret_cast<const uint4*>(d_train), n_train, d_best_idx, d_best_dist, d_second_dist);
+    LAUNCH_CHECK();
+    return ORBX_OK;
+}
+
+}  // extern "C"
