@@ -17,8 +17,8 @@
 struct BlurTile { short level, tx, ty, pad; };
 
 __device__ __forceinline__ int reflect101(int p, int len) {
-    if (p < 0) p = -p;
-    if (p >= len) p = 2 * len - 2 - p;
+    if (len == 1) return 0;
+    while (p < 0 || p >= len) p = p < 0 ? -p : 2 * len - 2 - p;     // loops only on levels narrower than the 3-px halo
     return p;
 }
 

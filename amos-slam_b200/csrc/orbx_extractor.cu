@@ -122,9 +122,12 @@ static int build_plan(orbx_extractor* h, int rows, int cols) {
         g.minBX = ORBX_EDGE - 3; g.minBY = g.minBX; g.maxBX = g.w - ORBX_EDGE + 3; g.maxBY = g.h - ORBX_EDGE + 3;
         const float W = 30;
         const float width = (float)(g.maxBX - g.minBX), height = (float)(g.maxBY - g.minBY);
-        const int nCols = (int)(width / W), nRows = (int)(height / W);
-        if (nCols <= 0 || nRows <= 0) FAIL(ORBX_E_INVALID, "image too small for the pyramid (a level has no 30-px FAST cell)");
-        const int wCell = (int)std::ceil(width / nCols), hCell = (int)std::ceil(height / nRows);
+        if (g.w < 1 || g.h < 1) FAIL(ORBX_E_INVALID, "image too small: a pyramid level is empty");
+        int nCols = (int)(width / W), nRows = (int)(height / W);
+        // a level narrower than one 30-px cell has no detection cells: the reference's cell loops do not run and the
+        // level contributes no keypoints (ORBextractor.cc:1082-1089)
+        if (nCols <= 0 || nRows <= 0) nCols = nRows = 0;
+        const int wCell = nCols ? (int)std::ceil(width / nCols) : 0, hCell = nRows ? (int)std::ceil(height / nRows) : 0;
         g.cell_begin = (int)cells.size(); g.slot_off = cand_off; g.cand_off = cand_off;
         int slot = cand_off;
         for (int i = 0; i < nRows; i++) {
@@ -155,8 +158,13 @@ static int build_plan(orbx_extractor* h, int rows, int cols) {
         g.cand_cap = slot - cand_off; cand_off = slot;
         if (g.cand_cap >= (1 << 20)) FAIL(ORBX_E_INVALID, "level too large");
         // quadtree roots :719-722
-        if (g.maxBY - g.minBY <= 0) FAIL(ORBX_E_INVALID, "image too small");
+        if (g.maxBY - g.minBY == 0) FAIL(ORBX_E_INVALID, "a pyramid level is exactly 32 px high: the reference's nIni = width/0 is undefined");
         g.nIni = (int)std::round(static_cast<float>(g.maxBX - g.minBX) / (g.maxBY - g.minBY));
+        if (g.cell_count == 0) {
+            // no candidates can exist on this level; the reference still evaluates vpIniNodes.resize(nIni) and dies on nIni < 0
+            if (g.nIni < 0) FAIL(ORBX_E_INVALID, "degenerate level geometry (negative nIni in the reference)");
+            g.nIni = 1;
+        }
         if (g.nIni < 1 || g.nIni > 15) FAIL(ORBX_E_INVALID, "unsupported aspect ratio (nIni must be 1..15)");
         g.hX = static_cast<float>(g.maxBX - g.minBX) / g.nIni;
         g.kp_off = kp_off; g.kp_cap = std::max(g.N + 2, 4 * g.nIni) + 2; kp_off += g.kp_cap;
@@ -246,7 +254,7 @@ static int run_detect(orbx_extractor* h, int B) {
     }
     prof_mark(h);
     const int ncells = (int)h->cells.size();
-    {
+    if (ncells > 0) {
         dim3 grid((ncells + FAST_WARPS - 1) / FAST_WARPS, B);
         const int smem = h->fast_smem_per_warp * FAST_WARPS;
         k_fast_cells<<<grid, FAST_WARPS * 32, smem, s>>>(h->view, h->d_levels.p, h->d_cells.p, ncells, h->cand_per_frame,

@@ -1,0 +1,49 @@
+"""Seeded matcher inputs shared by the golden generator and the tests (CPU and GPU): the same arrays are rebuilt from
+seeds everywhere, so only the reference's OUTPUTS need to be committed as fixtures."""
+import numpy as np
+from tools.synth import synth_frame, warp_affine_nn, stereo_right_from_left
+
+FX, FY, CX, CY = 517.3, 516.5, 318.6, 255.3      # TUM1-like intrinsics (Examples/RGB-D/TUM1.yaml)
+BF_KITTI = 386.1448                               # Examples/Stereo/KITTI00-02.yaml:25
+
+
+def mono_pair(extract, seed=0, width=640, height=480):
+    """Frame A, frame B = A warped by a small affine; returns keypoints/descriptors of both (extract: img -> (kp, desc))."""
+    A = synth_frame(seed, width, height); B = warp_affine_nn(A, 7, -4, 2.0)
+    ka, da = extract(A); kb, db = extract(B)
+    return ka, da, kb, db
+
+
+def projection_inputs(ka, kb, seed=1):
+    rng = np.random.default_rng(seed)
+    n = len(ka)
+    z = rng.uniform(0.5, 8, n).astype(np.float32)
+    # camera-frame points that project close to A's keypoints shifted by the known motion (+7,-4)
+    xyz = np.stack([((ka['x'] + 7 + rng.normal(0, 1.5, n) - CX) / FX * z), ((ka['y'] - 4 + rng.normal(0, 1.5, n) - CY) / FY * z), z], 1).astype(np.float32)
+    xyz[::37, 2] *= -1                                      # some points behind the camera (invz < 0)
+    valid = (rng.random(n) < 0.8).astype(np.uint8); obs = (rng.random(n) < 0.6).astype(np.uint8)
+    occ = (rng.random(len(kb)) < 0.1).astype(np.uint8)
+    u_right = np.where(rng.random(len(kb)) < 0.5, kb['x'] - rng.uniform(1, 30, len(kb)).astype(np.float32), -1).astype(np.float32)
+    tuv = np.stack([ka['x'] + 7 + rng.normal(0, 2, n), ka['y'] - 4 + rng.normal(0, 2, n)], 1).astype(np.float32)
+    tur = (tuv[:, 0] - rng.uniform(1, 30, n)).astype(np.float32)
+    lvl = np.clip(ka['octave'] + rng.integers(-1, 2, n), 0, 7).astype(np.int32)
+    vc = rng.uniform(0.99, 1.0, n).astype(np.float32)
+    return dict(xyz=xyz, valid=valid, obs=obs, occ=occ, u_right=u_right, tuv=tuv, tur=tur, lvl=lvl, vc=vc)
+
+
+def project(xyz):
+    """ORBmatcher.cc:1608-1618 in float32, as the caller of the C ABI computes it (identity pose)."""
+    xc, yc = xyz[:, 0].astype(np.float32), xyz[:, 1].astype(np.float32)
+    invz = (1.0 / xyz[:, 2].astype(np.float64)).astype(np.float32)
+    u = (np.float32(FX) * xc) * invz + np.float32(CX)
+    v = (np.float32(FY) * yc) * invz + np.float32(CY)
+    return np.stack([u, v], 1).astype(np.float32), invz
+
+
+PROJ_FRAME_CASES = [(15.0, 1), (7.0, 0), (15.0, 0)]         # (th, bMono); TrackWithMotionModel uses 15 / 7 (Tracking.cc:1929-1944)
+PROJ_POINT_CASES = [1.0, 3.0, 5.0]                          # SearchLocalPoints th (Tracking.cc:2378-2389)
+
+
+def stereo_pair(seed=3, width=1241, height=376):
+    L = synth_frame(seed, width, height)
+    return L, stereo_right_from_left(L, seed + 1)

@@ -31,7 +31,7 @@ def test_extract_matches_reference_golden(orbx, name):
     assert E.check_overflow() == 0
 
 
-@pytest.mark.parametrize("cfg", [(640, 480, 1000, 41), (752, 480, 2000, 42), (1241, 376, 2000, 43), (1920, 1080, 1000, 44), (160, 120, 100, 45)])
+@pytest.mark.parametrize("cfg", [(640, 480, 1000, 41), (752, 480, 2000, 42), (1241, 376, 2000, 43), (1920, 1080, 1000, 44), (160, 120, 100, 45), (100, 100, 50, 46)])
 def test_extract_matches_oracle_configs(orbx, oracle, cfg):
     """C1 / C3 / C4 / C5 geometries (BASELINE.json configs) + a tiny frame."""
     w, h, nf, seed = cfg
@@ -68,8 +68,10 @@ def test_empty_and_bad_inputs(orbx):
     assert len(kp) == 0 and desc.shape == (0, 32)
     with pytest.raises(orbx.OrbxError):
         E(np.zeros((480, 640, 3), np.uint8))                                   # assert(image.type()==CV_8UC1)
+    kp, desc = E(np.full((60, 60), 9, np.uint8))                               # levels without a 30-px cell yield nothing (as the reference)
+    assert len(kp) == 0
     with pytest.raises(orbx.OrbxError) as e:
-        E(np.zeros((40, 40), np.uint8))                                        # too small for an 8-level pyramid
+        E(np.zeros((32, 64), np.uint8))                                        # level 0 is 32 px high: reference's nIni = w/0 is undefined
     assert e.value.code == orbx.E_INVALID
     with pytest.raises(orbx.OrbxError):
         orbx.ORBextractor(0, 1.2, 8, 20, 7)

@@ -1,0 +1,103 @@
+"""GPU (B200): ORBmatcher / ComputeStereoMatches through the C ABI against the reference's golden outputs and the port
+oracle on the same seeded inputs.  Match indices, counts, uRight and depth bit-exact."""
+import os
+import numpy as np
+import pytest
+import match_cases as mc
+
+pytestmark = pytest.mark.gpu
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_match.npz"))
+
+
+@pytest.fixture(scope="module")
+def case(orbx):
+    E = orbx.ORBextractor(1000, 1.2, 8, 20, 7)
+    ka, da, kb, db = mc.mono_pair(lambda img: E(img))
+    assert len(ka) == int(G["n_a"]) and len(kb) == int(G["n_b"])
+    pi = mc.projection_inputs(ka, kb)
+    sf = E.GetScaleFactors()
+    return dict(ka=ka, da=da, kb=kb, db=db, pi=pi, sf=sf, FA=orbx.FrameView(ka, da, 640, 480, sf), FB=orbx.FrameView(kb, db, 640, 480, sf),
+                FBu=orbx.FrameView(kb, db, 640, 480, sf, u_right=pi["u_right"]))
+
+
+def test_descriptor_distance(orbx, case):
+    m = orbx.ORBmatcher(0.9, True)
+    assert np.array_equal(m.DescriptorDistance(case["da"][:900], case["db"][:900]), G["dist"])
+    z = np.zeros((3, 32), np.uint8); o = np.full((3, 32), 255, np.uint8)
+    assert list(m.DescriptorDistance(z, o)) == [256, 256, 256] and list(m.DescriptorDistance(o, o)) == [0, 0, 0]
+
+
+def test_search_for_initialization(orbx, case):
+    prev = np.stack([case["ka"]["x"], case["ka"]["y"]], 1)
+    nm, m12, prev2 = orbx.ORBmatcher(0.9, True).SearchForInitialization(case["FA"], case["FB"], prev, 100)
+    assert nm == int(G["init_nm"]) and np.array_equal(m12, G["init_m12"]) and np.array_equal(prev2, G["init_prev"])
+    nm, m12, prev2 = orbx.ORBmatcher(0.9, False).SearchForInitialization(case["FA"], case["FB"], prev, 30)
+    assert nm == int(G["init2_nm"]) and np.array_equal(m12, G["init2_m12"]) and np.array_equal(prev2, G["init2_prev"])
+
+
+def test_search_by_projection_frame_and_points(orbx, case):
+    pi = case["pi"]; ka = case["ka"]
+    uv, iz = mc.project(pi["xyz"])
+    for i, (th, mono) in enumerate(mc.PROJ_FRAME_CASES):
+        nm, cm = orbx.ORBmatcher(0.9, True).SearchByProjectionFrame(case["FBu"], uv, iz, ka["octave"], ka["angle"], case["da"], pi["valid"], pi["obs"], pi["occ"], th, False, False, 40.0)
+        assert nm == int(G["pf%d_nm" % i]) and np.array_equal(cm, G["pf%d_cm" % i])
+    for i, th in enumerate(mc.PROJ_POINT_CASES):
+        nm, fm = orbx.ORBmatcher(0.8, True).SearchByProjectionPoints(case["FBu"], pi["tuv"], pi["tur"], pi["lvl"], pi["vc"], case["da"], pi["obs"], pi["occ"], th)
+        assert nm == int(G["pp%d_nm" % i]) and np.array_equal(fm, G["pp%d_fm" % i])
+
+
+def test_projection_variants_vs_port(orbx, oracle, case):
+    """forward / backward level ranges, no uRight, no observations, checkOri off."""
+    pi = case["pi"]; ka = case["ka"]
+    uv, iz = mc.project(pi["xyz"])
+    oFB = oracle.FrameData(case["kb"], case["db"], 640, 480, case["sf"]); oFBu = oracle.FrameData(case["kb"], case["db"], 640, 480, case["sf"], u_right=pi["u_right"])
+    for (th, fw, bw, ori, FBg, FBo, obs, occ) in [(15.0, 1, 0, True, case["FBu"], oFBu, pi["obs"], pi["occ"]), (7.0, 0, 1, True, case["FBu"], oFBu, pi["obs"], None),
+                                                  (15.0, 0, 0, False, case["FB"], oFB, np.zeros_like(pi["obs"]), pi["occ"]), (30.0, 0, 0, True, case["FB"], oFB, np.ones_like(pi["obs"]), None)]:
+        g = orbx.ORBmatcher(0.9, ori).SearchByProjectionFrame(FBg, uv, iz, ka["octave"], ka["angle"], case["da"], pi["valid"], obs, occ, th, fw, bw, 40.0)
+        o = oracle.Matcher("port", 0.9, ori).search_by_projection_frame_port(FBo, uv, iz, ka["octave"], ka["angle"], case["da"], pi["valid"], obs, occ, th, fw, bw, 40.0)
+        assert g[0] == o[0] and np.array_equal(g[1], o[1])
+        g = orbx.ORBmatcher(0.7, ori).SearchByProjectionPoints(FBg, pi["tuv"], pi["tur"], pi["lvl"], pi["vc"], case["da"], obs, occ, th / 5.0)
+        o = oracle.Matcher("port", 0.7, ori).search_by_projection_points(FBo, pi["tuv"], pi["tur"], pi["lvl"], pi["vc"], case["da"], obs, occ, th / 5.0)
+        assert g[0] == o[0] and np.array_equal(g[1], o[1])
+
+
+def test_compute_stereo_matches(orbx):
+    L, R = mc.stereo_pair()
+    EL, ER = orbx.ORBextractor(2000, 1.2, 8, 20, 7), orbx.ORBextractor(2000, 1.2, 8, 20, 7)
+    kl, dl = EL(L); kr, dr = ER(R)
+    assert len(kl) == int(G["stereo_nl"])
+    m = orbx.ORBmatcher()
+    ur, dep = m.ComputeStereoMatches(EL, ER, kl, dl, kr, dr, 0.0, mc.BF_KITTI)
+    assert np.array_equal(ur, G["stereo_ur"]) and np.array_equal(dep, G["stereo_depth"])
+    ur2, dep2 = m.ComputeStereoMatches(EL, ER, kl, dl, kr, dr, 0.5372, mc.BF_KITTI)
+    assert np.array_equal(ur2, G["stereo2_ur"]) and np.array_equal(dep2, G["stereo2_depth"])
+
+
+def test_empty_and_degenerate(orbx, case):
+    m = orbx.ORBmatcher(0.9, True)
+    E0 = orbx.FrameView(np.zeros(0, orbx.KP_DTYPE), np.zeros((0, 32), np.uint8), 640, 480, case["sf"])
+    nm, m12, _ = m.SearchForInitialization(E0, case["FB"], np.zeros((0, 2), np.float32), 100)
+    assert nm == 0 and len(m12) == 0
+    prev = np.stack([case["ka"]["x"], case["ka"]["y"]], 1)
+    nm, m12, _ = m.SearchForInitialization(case["FA"], E0, prev, 100)                      # nothing to match against
+    assert nm == 0 and (m12 == -1).all()
+    nm, cm = m.SearchByProjectionFrame(case["FB"], np.zeros((0, 2), np.float32), np.zeros(0, np.float32), np.zeros(0, np.int32), np.zeros(0, np.float32),
+                                       np.zeros((0, 32), np.uint8), np.zeros(0, np.uint8), None, None, 15.0)
+    assert nm == 0 and (cm == -1).all()
+    # identical frames: every level-0 keypoint matches itself with distance 0
+    nm, m12, _ = m.SearchForInitialization(case["FA"], case["FA"], prev, 10)
+    lv0 = case["ka"]["octave"] == 0
+    assert (m12[~lv0] == -1).all() and nm > 0.9 * lv0.sum() and (m12[m12 >= 0] == np.nonzero(m12 >= 0)[0]).all()
+
+
+def test_bruteforce_best2_properties(orbx, case):
+    """All-pairs best / second-best (device pointers): against numpy on the full 1000 x 1000 problem."""
+    import torch
+    m = orbx.ORBmatcher()
+    q = torch.from_numpy(case["da"]).cuda(); t = torch.from_numpy(case["db"]).cuda()
+    bi = torch.empty(len(q), dtype=torch.int32, device="cuda"); bd = torch.empty_like(bi); sd = torch.empty_like(bi)
+    m.match_bruteforce_device(q.data_ptr(), len(q), t.data_ptr(), len(t), bi.data_ptr(), bd.data_ptr(), sd.data_ptr())
+    torch.cuda.synchronize()
+    D = np.unpackbits(case["da"][:, None, :] ^ case["db"][None, :, :], axis=2).sum(2)
+    assert np.array_equal(bi.cpu().numpy(), D.argmin(1)) and np.array_equal(bd.cpu().numpy(), D.min(1))     # first index wins ties
+    assert np.array_equal(sd.cpu().numpy(), np.sort(D, axis=1)[:, 1])
