@@ -6,15 +6,18 @@
 // =================================================================================================
 // K6  gauss7: cv::GaussianBlur(7x7, sigma 2, BORDER_REFLECT_101) on every pyramid level
 // (/root/reference/src/ORBextractor.cc:1626-1634, 1791-1793), OpenCV's 8-bit fixed-point path
-// (SURVEY.md A.2):  q = [18,34,48,56,48,34,18]/256;  h = sum q*px (16-bit, no rounding);
+// (SURVEY.md A.2):  q = [18,34,48,56,48,34,18]/256;  h = sum q*px (16-bit range, no rounding);
 // v = sum q*h (32-bit);  out = (v + 32768) >> 16.  Reflection is at the LEVEL edge (the reference
-// blurs a clone of the ROI).  One CTA = one 64x16 output tile of one level of one frame; the tile list
-// covers all levels so a single launch blurs the whole pyramid of the whole batch.  Input tile +3 halo
-// staged in shared memory, horizontal pass to a u16 shared buffer, vertical pass, uchar4 stores.
+// blurs a clone of the ROI).
+// One warp = one tile of 128 columns x BLUR_STRIP rows of one level of one frame (the tile list covers all
+// levels, so a single launch blurs the whole pyramid of the whole batch).  Each lane owns 4 adjacent
+// columns = one aligned 32-bit word per row: it loads ONLY its own word, takes the two neighbouring words
+// from the adjacent lanes by shuffle, forms the 4 horizontal sums, keeps the last 7 rows of them in
+// registers and emits one output word per row.  No shared memory; HBM traffic = read level + write level.
+// Lanes whose 10-byte window crosses the image edge take a byte-wise reflect path (2 lanes per row).
 // =================================================================================================
-#define BLUR_TW 64
-#define BLUR_TH 16
-struct BlurTile { short level, tx, ty, pad; };
+#define BLUR_STRIP 64
+struct BlurTile { short level, xc, strip, pad; };
 
 __device__ __forceinline__ int reflect101(int p, int len) {
     if (len == 1) return 0;
@@ -22,41 +25,64 @@ __device__ __forceinline__ int reflect101(int p, int len) {
     return p;
 }
 
-__global__ void __launch_bounds__(256)
-k_gauss7(PyrView pv, const LevelGeom* __restrict__ levels, const BlurTile* __restrict__ tiles,
+__global__ void __launch_bounds__(128)
+k_gauss7(PyrView pv, const LevelGeom* __restrict__ levels, const BlurTile* __restrict__ tiles, int ntiles,
          uint8_t* __restrict__ blur, long long blur_fstride) {
-    __shared__ uint8_t in[BLUR_TH + 6][BLUR_TW + 8];
-    __shared__ uint16_t hb[BLUR_TH + 6][BLUR_TW];
-    const BlurTile t = tiles[blockIdx.x];
-    const int b = blockIdx.y, tid = threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int tile = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (tile >= ntiles) return;
+    const BlurTile t = tiles[tile];
+    const int b = blockIdx.y;
     const LevelGeom& g = levels[t.level];
     int pitch;
     const uint8_t* img = level_ptr(pv, g, t.level, b, pitch);
-    const int x0 = t.tx * BLUR_TW, y0 = t.ty * BLUR_TH;
-    for (int i = tid; i < (BLUR_TH + 6) * (BLUR_TW + 6); i += 256) {
-        const int r = i / (BLUR_TW + 6), c = i - r * (BLUR_TW + 6);
-        const int yy = reflect101(y0 + r - 3, g.h), xx = reflect101(x0 + c - 3, g.w);
-        in[r][c] = __ldg(img + (long long)yy * pitch + xx);
-    }
-    __syncthreads();
-    for (int i = tid; i < (BLUR_TH + 6) * BLUR_TW; i += 256) {
-        const int r = i / BLUR_TW, c = i - r * BLUR_TW;
-        const uint8_t* p = &in[r][c];
-        hb[r][c] = (uint16_t)(18u * (p[0] + p[6]) + 34u * (p[1] + p[5]) + 48u * (p[2] + p[4]) + 56u * p[3]);
-    }
-    __syncthreads();
-    const int ty = tid >> 4, tx = (tid & 15) * 4;
-    const int y = y0 + ty, x = x0 + tx;
-    if (y < g.h && x < g.w) {
-        uint32_t outw = 0;
+    const int x = t.xc * 128 + lane * 4;
+    const int y0 = t.strip * BLUR_STRIP, y1 = min(y0 + BLUR_STRIP, g.h);
+    const bool valid = x < g.w;
+    const bool inside_r = x + 6 <= g.w - 1;
+    const bool fast = valid && x >= 4 && inside_r;                   // window x-3 .. x+6 entirely inside the level
+    const bool left = valid && x == 0 && inside_r && g.w >= 4;       // left edge: pixels -3..-1 mirror bytes 3..1 of the own word
+    int xo[10];                                                      // slow lanes (right edge, tiny levels): reflected columns, row-invariant
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t v = 18u * ((uint32_t)hb[ty][tx + k] + hb[ty + 6][tx + k]) + 34u * ((uint32_t)hb[ty + 1][tx + k] + hb[ty + 5][tx + k]) +
-                               48u * ((uint32_t)hb[ty + 2][tx + k] + hb[ty + 4][tx + k]) + 56u * (uint32_t)hb[ty + 3][tx + k];
-            outw |= ((v + 32768u) >> 16) << (8 * k);
+    for (int j = 0; j < 10; ++j) xo[j] = (valid && !fast && !left) ? reflect101(x - 3 + j, g.w) : 0;
+    uint8_t* dst = blur + (long long)b * blur_fstride + g.off + x;
+    int hb[7][4];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) { hb[j][0] = hb[j][1] = hb[j][2] = hb[j][3] = 0; }
+#pragma unroll 7
+    for (int r = y0 - 3; r < y1 + 3; ++r) {
+        const uint8_t* row = img + (long long)reflect101(r, g.h) * pitch;
+        const uint32_t w1 = valid ? __ldg(reinterpret_cast<const uint32_t*>(row + x)) : 0u;
+        uint32_t w0 = __shfl_up_sync(0xffffffffu, w1, 1), w2 = __shfl_down_sync(0xffffffffu, w1, 1);
+        if (fast && lane == 0) w0 = __ldg(reinterpret_cast<const uint32_t*>(row + x - 4));
+        if ((fast || left) && lane == 31) w2 = __ldg(reinterpret_cast<const uint32_t*>(row + x + 4));
+        if (left) w0 = __byte_perm(w1, 0, 0x1230);                    // bytes (.,p3,p2,p1): reflect-101 of columns -3..-1
+        int B[10];                                                    // pixels x-3 .. x+6
+        if (fast || left) {
+            B[0] = (w0 >> 8) & 0xFF; B[1] = (w0 >> 16) & 0xFF; B[2] = w0 >> 24;
+            B[3] = w1 & 0xFF; B[4] = (w1 >> 8) & 0xFF; B[5] = (w1 >> 16) & 0xFF; B[6] = w1 >> 24;
+            B[7] = w2 & 0xFF; B[8] = (w2 >> 8) & 0xFF; B[9] = (w2 >> 16) & 0xFF;
+        } else if (valid) {
+#pragma unroll
+            for (int j = 0; j < 10; ++j) B[j] = row[xo[j]];
+        } else {
+#pragma unroll
+            for (int j = 0; j < 10; ++j) B[j] = 0;
         }
-        // blurred levels use the same per-frame layout as the pyramid block (level 0 at offset 0 here)
-        *reinterpret_cast<uint32_t*>(blur + (long long)b * blur_fstride + g.off + (long long)y * g.pitch + x) = outw;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) { hb[j][0] = hb[j + 1][0]; hb[j][1] = hb[j + 1][1]; hb[j][2] = hb[j + 1][2]; hb[j][3] = hb[j + 1][3]; }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) hb[6][k] = 18 * (B[k] + B[k + 6]) + 34 * (B[k + 1] + B[k + 5]) + 48 * (B[k + 2] + B[k + 4]) + 56 * B[k + 3];
+        const int o = r - 3;                                          // output row completed by this input row
+        if (o >= y0 && valid) {
+            uint32_t outw = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t v = 18u * (uint32_t)(hb[0][k] + hb[6][k]) + 34u * (uint32_t)(hb[1][k] + hb[5][k]) + 48u * (uint32_t)(hb[2][k] + hb[4][k]) + 56u * (uint32_t)hb[3][k];
+                outw |= ((v + 32768u) >> 16) << (8 * k);
+            }
+            *reinterpret_cast<uint32_t*>(dst + (long long)o * g.pitch) = outw;   // bytes past the level width land in row padding
+        }
     }
 }
 

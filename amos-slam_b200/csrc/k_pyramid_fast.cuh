@@ -83,21 +83,24 @@ __device__ __forceinline__ bool has_run9(uint32_t m16) {
     return (r9 & 0xFFFFu) != 0;
 }
 
+// compass pre-test at minTh: any 9-arc of the ring contains two ADJACENT compass points (k = 0,4,8,12), so a pixel
+// can only be a corner if two adjacent compass points are both brighter than v+t or both darker than v-t
+__device__ __forceinline__ bool fast_compass(const uint8_t* p, int ps, int minTh) {
+    const int v = p[0];
+    const int d0 = (int)p[3 * ps] - v, d4 = (int)p[3] - v, d8 = (int)p[-3 * ps] - v, d12 = (int)p[-3] - v;
+    const int hi = max(max(min(d0, d4), min(d4, d8)), max(min(d8, d12), min(d12, d0)));     // best adjacent "bright" pair
+    const int lo = min(min(max(d0, d4), max(d4, d8)), min(max(d8, d12), max(d12, d0)));     // best adjacent "dark" pair
+    return hi > minTh || lo < -minTh;
+}
+
 // FAST score of the pixel at p (shared-memory patch, row stride ps), 0 if S <= minTh
 __device__ __forceinline__ int fast_score(const uint8_t* p, int ps, int minTh) {
     const int v = p[0];
-    const int hi = v + minTh, lo = v - minTh;
-    // compass points k = 0 (0,+3), 4 (+3,0), 8 (0,-3), 12 (-3,0)
-    const int c0 = p[3 * ps], c4 = p[3], c8 = p[-3 * ps], c12 = p[-3];
-    const uint32_t bq = (c0 > hi) | ((c4 > hi) << 1) | ((c8 > hi) << 2) | ((c12 > hi) << 3);
-    const uint32_t dq = (c0 < lo) | ((c4 < lo) << 1) | ((c8 < lo) << 2) | ((c12 < lo) << 3);
-    const uint32_t adjb = bq & ((bq >> 1) | (bq << 3)), adjd = dq & ((dq >> 1) | (dq << 3));
-    if (((adjb | adjd) & 0xF) == 0) return 0;
     int d[16];   // v - p_k ; ring order (dx,dy): (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
-    d[0] = v - c0;               d[1] = v - p[3 * ps + 1];   d[2] = v - p[2 * ps + 2];   d[3] = v - p[ps + 3];
-    d[4] = v - c4;               d[5] = v - p[-ps + 3];      d[6] = v - p[-2 * ps + 2];  d[7] = v - p[-3 * ps + 1];
-    d[8] = v - c8;               d[9] = v - p[-3 * ps - 1];  d[10] = v - p[-2 * ps - 2]; d[11] = v - p[-ps - 3];
-    d[12] = v - c12;             d[13] = v - p[ps - 3];      d[14] = v - p[2 * ps - 2];  d[15] = v - p[3 * ps - 1];
+    d[0] = v - p[3 * ps];        d[1] = v - p[3 * ps + 1];   d[2] = v - p[2 * ps + 2];   d[3] = v - p[ps + 3];
+    d[4] = v - p[3];             d[5] = v - p[-ps + 3];      d[6] = v - p[-2 * ps + 2];  d[7] = v - p[-3 * ps + 1];
+    d[8] = v - p[-3 * ps];       d[9] = v - p[-3 * ps - 1];  d[10] = v - p[-2 * ps - 2]; d[11] = v - p[-ps - 3];
+    d[12] = v - p[-3];           d[13] = v - p[ps - 3];      d[14] = v - p[2 * ps - 2];  d[15] = v - p[3 * ps - 1];
     uint32_t mb = 0, md = 0;
 #pragma unroll
     for (int k = 0; k < 16; ++k) { mb |= (uint32_t)(d[k] < -minTh) << k; md |= (uint32_t)(d[k] > minTh) << k; }
@@ -130,46 +133,62 @@ k_fast_cells(PyrView pv, const LevelGeom* __restrict__ levels, const CellDesc* _
     uint8_t* sm = smem_raw + (size_t)warp * smem_per_warp;
     const int zw = c.cw - 6, zh = c.ch - 6;
     const int xs = c.x0 & ~3, shift = c.x0 & 3;
-    const int wpr = ((c.x0 + c.cw + 3) >> 2) - (xs >> 2);      // 32-bit words per patch row
+    const int wpr = ((c.x0 + c.cw + 3) >> 2) - (xs >> 2);      // 32-bit words per patch row (<= 18)
     const int ps = wpr * 4;                                    // patch row stride (bytes)
     uint32_t* patch32 = reinterpret_cast<uint32_t*>(sm);
     const int patch_bytes = ps * c.ch;
     const int sst = zw + 2;                                    // S row stride; 1-px zero ring
     const int s_bytes = (sst * (zh + 2) + 3) & ~3;
     uint8_t* S = sm + patch_bytes;
-    uint8_t* F = S + s_bytes;                                  // zw*zh: S where strict local max, else 0
+    uint16_t* queue = reinterpret_cast<uint16_t*>(S + s_bytes);   // zw*zh entries: candidate pixels in raster order
 
-    // stage the ROI (aligned words; level pitch and base are 4-byte aligned)
-    const int nwords = wpr * c.ch;
-    for (int w = lane; w < nwords; w += 32) {
-        const int r = w / wpr, col = w - r * wpr;
-        patch32[w] = __ldg(reinterpret_cast<const uint32_t*>(img + (long long)(c.y0 + r) * pitch + xs) + col);
+    // stage the ROI with aligned 32-bit loads: each iteration covers 32/wpr rows
+    {
+        const int rpi = 32 / wpr, lr = lane / wpr, lc = lane - lr * wpr;
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(img + (long long)c.y0 * pitch + xs) + lc;
+        if (lr < rpi)
+            for (int r = lr; r < c.ch; r += rpi) patch32[r * wpr + lc] = __ldg(src + (long long)r * (pitch >> 2));
     }
     for (int w = lane; w < (s_bytes >> 2); w += 32) reinterpret_cast<uint32_t*>(S)[w] = 0u;
     __syncwarp();
 
+    // pass A: compass pre-test on every zone pixel, passing pixels compacted (in raster order) into the queue
     const uint8_t* patch = sm + shift;
-    const int npx = zw * zh;
-    const uint32_t inv = ((1u << 20) + zw - 1) / zw;           // exact i / zw for i < 3600 (zw < 64)
-    for (int i = lane; i < npx; i += 32) {
-        const int y = (int)(((uint32_t)i * inv) >> 20), x = i - y * zw;
-        const int s = fast_score(patch + (y + 3) * ps + (x + 3), ps, minTh);
-        if (s) S[(y + 1) * sst + x + 1] = (uint8_t)s;
+    const uint32_t lt = (1u << lane) - 1u;
+    int qn = 0;
+    for (int y = 0; y < zh; ++y) {
+        const uint8_t* row = patch + (y + 3) * ps + 3;
+        for (int x0 = 0; x0 < zw; x0 += 32) {
+            const int x = x0 + lane;
+            const bool pass = x < zw && fast_compass(row + x, ps, minTh);
+            const uint32_t m = __ballot_sync(0xffffffffu, pass);
+            if (pass) queue[qn + __popc(m & lt)] = (uint16_t)((y << 6) | x);
+            qn += __popc(m);
+        }
     }
     __syncwarp();
-
-    // strict 3x3 local maxima; count those above iniTh
+    // pass B: full 16-pixel ring test + score, all lanes busy on compacted candidates
+    for (int k = lane; k < qn; k += 32) {
+        const int code = queue[k], y = code >> 6, x = code & 63;
+        const int s = fast_score(patch + (y + 3) * ps + (x + 3), ps, minTh);
+        if (s) S[(y + 1) * sst + x + 1] = (uint8_t)s; else queue[k] = 0xFFFFu;
+    }
+    __syncwarp();
+    // pass C: strict 3x3 local maxima among the corners; count those above iniTh
     int n_ini = 0;
-    for (int i0 = 0; i0 < npx; i0 += 32) {
-        const int i = i0 + lane;
+    for (int k0 = 0; k0 < qn; k0 += 32) {
+        const int k = k0 + lane;
         int f = 0;
-        if (i < npx) {
-            const int y = (int)(((uint32_t)i * inv) >> 20), x = i - y * zw;
-            const uint8_t* q = S + (y + 1) * sst + x + 1;
-            const int s = q[0];
-            if (s && s > q[-1] && s > q[1] && s > q[-sst - 1] && s > q[-sst] && s > q[-sst + 1] &&
-                s > q[sst - 1] && s > q[sst] && s > q[sst + 1]) f = s;
-            F[i] = (uint8_t)f;
+        if (k < qn) {
+            const int code = queue[k];
+            if (code != 0xFFFF) {
+                const int y = code >> 6, x = code & 63;
+                const uint8_t* q = S + (y + 1) * sst + x + 1;
+                const int s = q[0];
+                if (s > q[-1] && s > q[1] && s > q[-sst - 1] && s > q[-sst] && s > q[-sst + 1] &&
+                    s > q[sst - 1] && s > q[sst] && s > q[sst + 1]) f = s;
+                else queue[k] = 0xFFFFu;
+            }
         }
         n_ini += __popc(__ballot_sync(0xffffffffu, f > iniTh));
     }
@@ -177,16 +196,16 @@ k_fast_cells(PyrView pv, const LevelGeom* __restrict__ levels, const CellDesc* _
     const int th = n_ini > 0 ? iniTh : minTh;                  // retry at minTh iff the cell came back empty
     uint32_t* out = cand_slots + (long long)b * slots_per_frame + c.slot;
     int n = 0;
-    for (int i0 = 0; i0 < npx; i0 += 32) {
-        const int i = i0 + lane;
-        const int f = i < npx ? F[i] : 0;
+    for (int k0 = 0; k0 < qn; k0 += 32) {
+        const int k = k0 + lane;
+        int f = 0, x = 0, y = 0;
+        if (k < qn) {
+            const int code = queue[k];
+            if (code != 0xFFFF) { y = code >> 6; x = code & 63; f = S[(y + 1) * sst + x + 1]; }
+        }
         const bool keep = f > th;
         const uint32_t m = __ballot_sync(0xffffffffu, keep);
-        if (keep) {
-            const int y = (int)(((uint32_t)i * inv) >> 20), x = i - y * zw;
-            const int k = n + __popc(m & ((1u << lane) - 1u));
-            out[k] = (uint32_t)(x + 3 + c.sx) | ((uint32_t)(y + 3 + c.sy) << 12) | ((uint32_t)(f - 1) << 24);
-        }
+        if (keep) out[n + __popc(m & lt)] = (uint32_t)(x + 3 + c.sx) | ((uint32_t)(y + 3 + c.sy) << 12) | ((uint32_t)(f - 1) << 24);
         n += __popc(m);
     }
     if (lane == 0) cell_counts[(long long)b * ncells + cell] = (uint16_t)n;

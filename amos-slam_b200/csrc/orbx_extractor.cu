@@ -150,7 +150,7 @@ static int build_plan(orbx_extractor* h, int rows, int cols) {
                 c.slot = slot; slot += c.cap;
                 cells.push_back(c);
                 const int wpr = ((c.x0 + c.cw + 3) >> 2) - (c.x0 >> 2);
-                const int need = wpr * 4 * c.ch + (((zw + 2) * (zh + 2) + 3) & ~3) + ((zw * zh + 3) & ~3);
+                const int need = wpr * 4 * c.ch + (((zw + 2) * (zh + 2) + 3) & ~3) + ((2 * zw * zh + 3) & ~3);
                 smem_pw = std::max(smem_pw, need);
             }
         }
@@ -169,8 +169,8 @@ static int build_plan(orbx_extractor* h, int rows, int cols) {
         g.hX = static_cast<float>(g.maxBX - g.minBX) / g.nIni;
         g.kp_off = kp_off; g.kp_cap = std::max(g.N + 2, 4 * g.nIni) + 2; kp_off += g.kp_cap;
         tree_cap = std::max(tree_cap, g.kp_cap + 8);
-        for (int ty = 0; ty < (g.h + BLUR_TH - 1) / BLUR_TH; ++ty)
-            for (int tx = 0; tx < (g.w + BLUR_TW - 1) / BLUR_TW; ++tx) { BlurTile t; t.level = (short)l; t.tx = (short)tx; t.ty = (short)ty; t.pad = 0; tiles.push_back(t); }
+        for (int st = 0; st < (g.h + BLUR_STRIP - 1) / BLUR_STRIP; ++st)
+            for (int xc = 0; xc < (g.w + 127) / 128; ++xc) { BlurTile t; t.level = (short)l; t.xc = (short)xc; t.strip = (short)st; t.pad = 0; tiles.push_back(t); }
     }
     if (tree_cap > 32000) FAIL(ORBX_E_INVALID, "too many features per level");
     // resize tables for levels >= 1
@@ -280,8 +280,9 @@ static int run_detect(orbx_extractor* h, int B) {
 
 static int run_blur(orbx_extractor* h, int B) {
     if (h->blur_valid) return ORBX_OK;
-    dim3 grid((unsigned)h->tiles.size(), B);
-    k_gauss7<<<grid, 256, 0, h->stream>>>(h->view, h->d_levels.p, h->d_tiles.p, h->d_blur.p, h->pyr_fstride);
+    const int ntiles = (int)h->tiles.size();
+    dim3 grid((ntiles + 3) / 4, B);
+    k_gauss7<<<grid, 128, 0, h->stream>>>(h->view, h->d_levels.p, h->d_tiles.p, ntiles, h->d_blur.p, h->pyr_fstride);
     LAUNCH_CHECK();
     prof_mark(h);
     h->blur_valid = true;
