@@ -103,6 +103,8 @@ class ORBmatcher:
         cm = np.zeros(len(cur.keys), np.int32); nm = C.c_int(); v = cur.c()
         self._check(self._lib.orbx_search_by_projection_frame(self._h, C.byref(v), len(iz), _p(uv), _p(iz), _p(lo), _p(la), _p(d), _p(va), _p(ob), _p(oc),
                                                               float(th), int(forward), int(backward), float(mbf), _p(cm), C.byref(nm)))
+        self.last_raw_match = cm.copy()          # -2 marks entries assigned and then reset by the rotation check
+        cm[cm == -2] = -1
         return nm.value, cm
 
     # int SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, const float th=3)

@@ -335,7 +335,7 @@ k_resolve_proj_frame(int n_last, int n_cur, const KpM* __restrict__ cur_keys, co
         int removed = 0;
         for (int e = lane; e < npush; e += 32) {
             const int bin = pushes[2 * e];
-            if (bin != ind1 && bin != ind2 && bin != ind3) { cur_match[pushes[2 * e + 1]] = -1; ++removed; }   // :1714-1724 (every pushed entry counts)
+            if (bin != ind1 && bin != ind2 && bin != ind3) { cur_match[pushes[2 * e + 1]] = -2; ++removed; }   // :1714-1724 (every pushed entry counts); -2 = assigned, then reset to NULL
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, o);

@@ -1,0 +1,189 @@
+// ORBmatcher_b200.cc -- B200-native bodies of the ORBmatcher / Frame methods that lie on the hot path
+// (SURVEY.md 8a rows a14-a18).  They are member definitions of the reference's OWN classes, declared in
+// the reference's unchanged include/ORBmatcher.h and include/Frame.h, so Tracking / Initializer call
+// sites stay as they are; a maintainer compiles this file and removes (or #ifdef's out) the four
+// bodies it replaces in src/ORBmatcher.cc / src/Frame.cc:
+//
+//   ORBmatcher::SearchForInitialization(Frame&, Frame&, vector<Point2f>&, vector<int>&, int)   src/ORBmatcher.cc:515-643
+//   ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, float)                    src/ORBmatcher.cc:70-175
+//   ORBmatcher::SearchByProjection(Frame&, const Frame&, float, bool)                          src/ORBmatcher.cc:1569-1728
+//   Frame::ComputeStereoMatches()                                                               src/Frame.cc:1179-1573
+//
+// Each body only flattens the object graph (Frame / MapPoint) into the plain arrays of the C ABI
+// (include/orbx_b200.h), calls the CUDA implementation and writes the results back into the same
+// members the reference writes.  Descriptor distances, grid lookups, ratio tests, rotation histograms
+// and the SAD refinement all run on the GPU; nothing is matched on the CPU here.
+#include "ORBmatcher.h"
+#include "../../include/orbx_b200.h"
+
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+static_assert(sizeof(cv::KeyPoint) == sizeof(orbx_keypoint), "cv::KeyPoint must be the 28-byte POD the C ABI uses");
+
+namespace ORB_SLAM2
+{
+namespace
+{
+
+void check(int rc, const char* what) {
+    if (rc != ORBX_OK) throw std::runtime_error(std::string(what) + ": " + orbx_last_error());
+}
+
+// ORBmatcher objects are short-lived locals in the reference (Tracking.cc:1492, 1744, ...): keep one device
+// matcher per (thread, nnratio, checkOri) instead of creating a stream and scratch buffers per call.
+struct MatcherCache {
+    std::map<std::pair<float, bool>, orbx_matcher*> m;
+    ~MatcherCache() { for (auto& kv : m) orbx_matcher_destroy(kv.second); }
+    orbx_matcher* get(float nnratio, bool checkOri) {
+        auto key = std::make_pair(nnratio, checkOri);
+        auto it = m.find(key);
+        if (it != m.end()) return it->second;
+        const char* e = std::getenv("ORBX_DEVICE");
+        orbx_matcher* h = nullptr;
+        check(orbx_matcher_create(nnratio, checkOri ? 1 : 0, e ? std::atoi(e) : 0, &h), "orbx_matcher_create");
+        m[key] = h;
+        return h;
+    }
+};
+thread_local MatcherCache t_matchers;
+
+// what the matchers read from a Frame (Frame.h: mvKeysUn, mDescriptors, mvuRight, image bounds, grid constants)
+struct FrameFlat {
+    orbx_frame_view v;
+    std::vector<unsigned char> desc;     // only used when mDescriptors is not continuous
+    explicit FrameFlat(const Frame& F) {
+        v.n = F.N;
+        v.keys_un = reinterpret_cast<const orbx_keypoint*>(F.mvKeysUn.data());
+        if (F.mDescriptors.isContinuous()) v.descriptors = F.mDescriptors.ptr();
+        else {
+            desc.resize((size_t)F.N * 32);
+            for (int i = 0; i < F.N; ++i) std::memcpy(&desc[(size_t)i * 32], F.mDescriptors.ptr(i), 32);
+            v.descriptors = desc.data();
+        }
+        v.u_right = F.mvuRight.empty() ? nullptr : F.mvuRight.data();
+        v.min_x = Frame::mnMinX; v.min_y = Frame::mnMinY; v.max_x = Frame::mnMaxX; v.max_y = Frame::mnMaxY;
+        v.grid_element_width_inv = Frame::mfGridElementWidthInv; v.grid_element_height_inv = Frame::mfGridElementHeightInv;
+        v.nlevels = (int)F.mvScaleFactors.size(); v.scale_factors = F.mvScaleFactors.data();
+    }
+};
+
+// mvpMapPoints[j] already holds a map point with Observations() > 0   (ORBmatcher.cc:124-126, 1658-1660)
+std::vector<unsigned char> occupied_flags(const Frame& F) {
+    std::vector<unsigned char> occ(F.N, 0);
+    for (int j = 0; j < F.N; ++j) { MapPoint* p = F.mvpMapPoints[j]; if (p && p->Observations() > 0) occ[j] = 1; }
+    return occ;
+}
+
+}  // namespace
+
+int ORBmatcher::SearchForInitialization(Frame &F1, Frame &F2, std::vector<cv::Point2f> &vbPrevMatched, std::vector<int> &vnMatches12, int windowSize)
+{
+    vnMatches12.assign(F1.mvKeysUn.size(), -1);
+    FrameFlat a(F1), b(F2);
+    int nmatches = 0;
+    static_assert(sizeof(cv::Point2f) == 8, "cv::Point2f must be two floats");
+    check(orbx_search_for_initialization(t_matchers.get(mfNNratio, mbCheckOrientation), &a.v, &b.v,
+                                         vbPrevMatched.empty() ? nullptr : reinterpret_cast<float*>(vbPrevMatched.data()),
+                                         vnMatches12.data(), windowSize, &nmatches), "orbx_search_for_initialization");
+    return nmatches;
+}
+
+int ORBmatcher::SearchByProjection(Frame &F, const std::vector<MapPoint*> &vpMapPoints, const float th)
+{
+    // per map point that passes the reference's two filters (:82-86): projection, predicted level, viewing cosine, descriptor
+    std::vector<MapPoint*> pts; pts.reserve(vpMapPoints.size());
+    for (size_t i = 0; i < vpMapPoints.size(); ++i) { MapPoint* p = vpMapPoints[i]; if (p->mbTrackInView && !p->isBad()) pts.push_back(p); }
+    const int n = (int)pts.size();
+    std::vector<float> uv((size_t)n * 2), ur(n), vc(n);
+    std::vector<int> lvl(n);
+    std::vector<unsigned char> desc((size_t)n * 32), obs(n);
+    for (int i = 0; i < n; ++i) {
+        MapPoint* p = pts[i];
+        uv[2 * i] = p->mTrackProjX; uv[2 * i + 1] = p->mTrackProjY; ur[i] = p->mTrackProjXR;
+        lvl[i] = p->mnTrackScaleLevel; vc[i] = p->mTrackViewCos;
+        const cv::Mat d = p->GetDescriptor();
+        std::memcpy(&desc[(size_t)i * 32], d.ptr(), 32);
+        obs[i] = p->Observations() > 0;
+    }
+    std::vector<unsigned char> occ = occupied_flags(F);
+    std::vector<int> fmatch(F.N, -1);
+    FrameFlat f(F);
+    int nmatches = 0;
+    check(orbx_search_by_projection_points(t_matchers.get(mfNNratio, mbCheckOrientation), &f.v, n, uv.data(), ur.data(), lvl.data(), vc.data(),
+                                           desc.data(), obs.data(), occ.data(), th, fmatch.data(), &nmatches), "orbx_search_by_projection_points");
+    for (int j = 0; j < F.N; ++j) if (fmatch[j] >= 0) F.mvpMapPoints[j] = pts[fmatch[j]];       // :168
+    return nmatches;
+}
+
+int ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono)
+{
+    // pose algebra stays on the host: it needs the MapPoint objects and is O(N) (:1580-1623)
+    const cv::Mat Rcw = CurrentFrame.mTcw.rowRange(0, 3).colRange(0, 3);
+    const cv::Mat tcw = CurrentFrame.mTcw.rowRange(0, 3).col(3);
+    const cv::Mat twc = -Rcw.t() * tcw;
+    const cv::Mat Rlw = LastFrame.mTcw.rowRange(0, 3).colRange(0, 3);
+    const cv::Mat tlw = LastFrame.mTcw.rowRange(0, 3).col(3);
+    const cv::Mat tlc = Rlw * twc + tlw;
+    const bool bForward = tlc.at<float>(2) > CurrentFrame.mb && !bMono;
+    const bool bBackward = -tlc.at<float>(2) > CurrentFrame.mb && !bMono;
+
+    const int n = LastFrame.N;
+    std::vector<float> uv((size_t)n * 2, 0.f), invz(n, 0.f), angle(n, 0.f);
+    std::vector<int> octave(n, 0);
+    std::vector<unsigned char> desc((size_t)n * 32, 0), valid(n, 0), obs(n, 0);
+    for (int i = 0; i < n; ++i) {
+        MapPoint* pMP = LastFrame.mvpMapPoints[i];
+        if (!pMP || LastFrame.mvbOutlier[i]) continue;
+        const cv::Mat x3Dc = Rcw * pMP->GetWorldPos() + tcw;
+        const float xc = x3Dc.at<float>(0), yc = x3Dc.at<float>(1);
+        const float invzc = 1.0 / x3Dc.at<float>(2);
+        if (invzc < 0) continue;
+        const float u = CurrentFrame.fx * xc * invzc + CurrentFrame.cx;
+        const float v = CurrentFrame.fy * yc * invzc + CurrentFrame.cy;
+        if (u < CurrentFrame.mnMinX || u > CurrentFrame.mnMaxX || v < CurrentFrame.mnMinY || v > CurrentFrame.mnMaxY) continue;
+        uv[2 * i] = u; uv[2 * i + 1] = v; invz[i] = invzc;
+        octave[i] = LastFrame.mvKeys[i].octave; angle[i] = LastFrame.mvKeysUn[i].angle;
+        const cv::Mat d = pMP->GetDescriptor();
+        std::memcpy(&desc[(size_t)i * 32], d.ptr(), 32);
+        obs[i] = pMP->Observations() > 0;
+        valid[i] = 1;
+    }
+    std::vector<unsigned char> occ = occupied_flags(CurrentFrame);
+    std::vector<int> cmatch(CurrentFrame.N, -1);
+    FrameFlat c(CurrentFrame);
+    int nmatches = 0;
+    check(orbx_search_by_projection_frame(t_matchers.get(mfNNratio, mbCheckOrientation), &c.v, n, uv.data(), invz.data(), octave.data(), angle.data(),
+                                          desc.data(), valid.data(), obs.data(), occ.data(), th, bForward ? 1 : 0, bBackward ? 1 : 0, CurrentFrame.mbf,
+                                          cmatch.data(), &nmatches), "orbx_search_by_projection_frame");
+    for (int j = 0; j < CurrentFrame.N; ++j) {
+        if (cmatch[j] >= 0) CurrentFrame.mvpMapPoints[j] = LastFrame.mvpMapPoints[cmatch[j]];   // :1685
+        else if (cmatch[j] == -2) CurrentFrame.mvpMapPoints[j] = static_cast<MapPoint*>(NULL); // :1719
+    }
+    return nmatches;
+}
+
+void Frame::ComputeStereoMatches()
+{
+    mvuRight = std::vector<float>(N, -1.0f);                                                   // src/Frame.cc:1187-1188
+    mvDepth = std::vector<float>(N, -1.0f);
+    if (N == 0) return;
+    // both pyramids are still resident in the two extractor handles (ExtractORB ran just before, Frame.cc:165-176)
+    const unsigned char* dl = mDescriptors.ptr();
+    const unsigned char* dr = mDescriptorsRight.ptr();
+    std::vector<unsigned char> tl, tr;
+    if (!mDescriptors.isContinuous()) { tl.resize((size_t)N * 32); for (int i = 0; i < N; ++i) std::memcpy(&tl[(size_t)i * 32], mDescriptors.ptr(i), 32); dl = tl.data(); }
+    const int nr = (int)mvKeysRight.size();
+    if (!mDescriptorsRight.isContinuous()) { tr.resize((size_t)nr * 32); for (int i = 0; i < nr; ++i) std::memcpy(&tr[(size_t)i * 32], mDescriptorsRight.ptr(i), 32); dr = tr.data(); }
+    check(orbx_compute_stereo_matches(t_matchers.get(0.6f, true), mpORBextractorLeft->handle(), mpORBextractorRight->handle(),
+                                      reinterpret_cast<const orbx_keypoint*>(mvKeys.data()), dl, N,
+                                      reinterpret_cast<const orbx_keypoint*>(mvKeysRight.data()), dr, nr,
+                                      mb, mbf, mvuRight.data(), mvDepth.data()), "orbx_compute_stereo_matches");
+}
+
+} //namespace ORB_SLAM2

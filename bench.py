@@ -97,6 +97,7 @@ def cpu_reference_run(seconds_budget, frames, threads=None, steps=None, frames_p
     exts = [oracle.Extractor(kind, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH) for _ in range(threads)]
     nframes = len(frames)
     done = [0] * threads
+    errors = []
     start_evt = threading.Event()
 
     def worker(t, deadline_box, quota):
@@ -107,7 +108,11 @@ def cpu_reference_run(seconds_budget, frames, threads=None, steps=None, frames_p
                 break
             if quota is None and time.perf_counter() >= deadline_box[0]:
                 break
-            exts[t].extract(frames[i % nframes])
+            try:
+                exts[t].extract(frames[i % nframes])
+            except BaseException as e:      # a dead worker must not read as "0 frames/s"
+                errors.append(repr(e))
+                break
             done[t] += 1
             i += threads
 
@@ -123,6 +128,8 @@ def cpu_reference_run(seconds_budget, frames, threads=None, steps=None, frames_p
         start_evt.set()
         for th in ths:
             th.join()
+        if errors:
+            raise RuntimeError("CPU reference worker failed: " + errors[0])
         return sum(done), time.perf_counter() - t0
 
     run(1, None)      # warm-up: one frame per thread
@@ -156,6 +163,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-pointer leg (the line is then not a bench value)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); local_rank = int(os.environ.get("LOCAL_RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     N, K, W, B = args.gpus, args.steps, max(args.warmup, 0), args.batch
@@ -235,10 +243,10 @@ def main():
         raise SystemExit("internal overflow flag set")
 
     # ---- e2e through the host-pointer C-ABI call ----
-    for _ in range(2):
+    Ke = 0 if args.no_e2e else max(3, min(K, 10))
+    for _ in range(2 if Ke else 0):
         step_host()
     barrier()
-    Ke = max(3, min(K, 10))
     t0 = time.perf_counter()
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     g0.record(stream)
@@ -259,7 +267,7 @@ def main():
         return
 
     value = N * B * K / (ms * 1e-3)
-    e2e = N * B * Ke / (ms_e2e * 1e-3)
+    e2e = N * B * Ke / (ms_e2e * 1e-3) if Ke else None
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

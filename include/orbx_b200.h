@@ -207,7 +207,9 @@ int orbx_search_for_initialization(orbx_matcher* m, const orbx_frame_view* F1, c
  *   otherwise it can be re-assigned, exactly as the reference's running mvpMapPoints state behaves.
  *   forward / backward = bForward / bBackward (:1591-1592); mbf = CurrentFrame.mbf.
  *   Output: cur_match[j] = index i of the LastFrame feature whose map point is assigned to current
- *   feature j (or -1), after the rotation-histogram filter (:1706-1725); *nmatches = return value. */
+ *   feature j after the rotation-histogram filter (:1706-1725); -1 = mvpMapPoints[j] was never written by
+ *   the call; -2 = it was assigned and then reset to NULL by the histogram filter (:1719).
+ *   *nmatches = return value. */
 int orbx_search_by_projection_frame(orbx_matcher* m, const orbx_frame_view* cur, int n_last,
                                     const float* proj_uv, const float* proj_invz, const int* last_octave,
                                     const float* last_angle, const uint8_t* mp_desc, const uint8_t* valid,

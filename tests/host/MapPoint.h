@@ -1,0 +1,21 @@
+// tests/host/MapPoint.h -- TEST STAND-IN for the reference's include/MapPoint.h: just the members the on-path
+// matchers read (/root/reference/include/MapPoint.h:86,108,154,211,240-246), backed by plain fields.
+#ifndef MAPPOINT_H
+#define MAPPOINT_H
+#include <opencv2/core/core.hpp>
+namespace ORB_SLAM2 {
+class MapPoint {
+public:
+    cv::Mat GetWorldPos() { return mWorldPos; }
+    cv::Mat GetDescriptor() { return mDescriptor; }
+    int Observations() { return nObs; }
+    bool isBad() { return mbBad; }
+    float mTrackProjX = 0, mTrackProjY = 0, mTrackProjXR = 0;
+    bool mbTrackInView = false;
+    int mnTrackScaleLevel = 0;
+    float mTrackViewCos = 0;
+    // stand-in storage
+    cv::Mat mWorldPos, mDescriptor; int nObs = 0; bool mbBad = false;
+};
+}
+#endif

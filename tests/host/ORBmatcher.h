@@ -1,0 +1,25 @@
+// tests/host/ORBmatcher.h -- TEST STAND-IN for the reference's include/ORBmatcher.h:57-215 restricted to the
+// on-path methods (same signatures, same protected members), so that amos-slam_b200/host/ORBmatcher_b200.cc
+// compiles here exactly as it would inside the reference tree.
+#ifndef ORBMATCHER_H
+#define ORBMATCHER_H
+#include <vector>
+#include <opencv2/core/core.hpp>
+#include <opencv2/features2d/features2d.hpp>
+#include "MapPoint.h"
+#include "KeyFrame.h"
+#include "Frame.h"
+namespace ORB_SLAM2 {
+class ORBmatcher {
+public:
+    ORBmatcher(float nnratio = 0.6, bool checkOri = true) : mfNNratio(nnratio), mbCheckOrientation(checkOri) {}
+    int SearchByProjection(Frame &F, const std::vector<MapPoint*> &vpMapPoints, const float th = 3);
+    int SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono);
+    int SearchForInitialization(Frame &F1, Frame &F2, std::vector<cv::Point2f> &vbPrevMatched, std::vector<int> &vnMatches12, int windowSize = 10);
+    static const int TH_LOW, TH_HIGH, HISTO_LENGTH;
+protected:
+    float mfNNratio;
+    bool mbCheckOrientation;
+};
+}
+#endif

@@ -1,0 +1,114 @@
+// tests/host/host_dropin_main.cc -- drives the drop-in C++ classes (amos-slam_b200/host) the way the reference's
+// Frame / Tracking code drives its own ORBextractor / ORBmatcher, and dumps every result to a binary file that
+// tests/test_gpu_host_dropin.py compares with the C-ABI results (themselves bit-exact against the oracle).
+// cv:: types come from the OpenCV-free shim (oracle/shim) -- test infrastructure, not product.
+//
+// usage: host_dropin <in.bin> <out.bin>
+//   in.bin : int32 w,h ; u8 A[h*w] ; u8 B[h*w] ; int32 sw,sh ; u8 L[sh*sw] ; u8 R[sh*sw]
+#include "ORBextractor.h"
+#include "ORBmatcher.h"
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+using namespace ORB_SLAM2;
+
+float Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv, Frame::mnMinX, Frame::mnMaxX, Frame::mnMinY, Frame::mnMaxY;
+const int ORBmatcher::TH_HIGH = 100, ORBmatcher::TH_LOW = 50, ORBmatcher::HISTO_LENGTH = 30;
+
+static FILE* g_out;
+static void put(const void* p, size_t n) { fwrite(p, 1, n, g_out); }
+static void put_i(int v) { put(&v, 4); }
+static void put_kps(const std::vector<cv::KeyPoint>& k, const cv::Mat& d) {
+    put_i((int)k.size());
+    if (!k.empty()) put(k.data(), k.size() * sizeof(cv::KeyPoint));
+    for (int i = 0; i < (int)k.size(); ++i) put(d.ptr(i), 32);
+}
+static cv::Mat read_img(FILE* f, int w, int h) {
+    cv::Mat m(h, w, CV_8UC1);
+    if (fread(m.ptr(), 1, (size_t)w * h, f) != (size_t)w * h) { fprintf(stderr, "short read\n"); exit(2); }
+    return m;
+}
+static void fill_frame(Frame& F, ORBextractor& e, const std::vector<cv::KeyPoint>& k, const cv::Mat& d, int w, int h) {
+    F.N = (int)k.size(); F.mvKeys = k; F.mvKeysUn = k; F.mDescriptors = d;
+    F.mvpMapPoints.assign(F.N, (MapPoint*)NULL); F.mvbOutlier.assign(F.N, false);
+    F.mvuRight.assign(F.N, -1.f); F.mvDepth.assign(F.N, -1.f);
+    F.mvScaleFactors = e.GetScaleFactors(); F.mnScaleLevels = e.GetLevels();
+    Frame::mnMinX = 0.f; Frame::mnMaxX = (float)w; Frame::mnMinY = 0.f; Frame::mnMaxY = (float)h;       // Frame.cc:1148-1151 (no distortion)
+    Frame::mfGridElementWidthInv = 64.f / (Frame::mnMaxX - Frame::mnMinX);                              // Frame.cc:219-220
+    Frame::mfGridElementHeightInv = 48.f / (Frame::mnMaxY - Frame::mnMinY);
+}
+
+int main(int argc, char** argv) {
+    if (argc < 3) return 2;
+    FILE* f = fopen(argv[1], "rb"); g_out = fopen(argv[2], "wb");
+    if (!f || !g_out) return 2;
+    int w, h; if (fread(&w, 4, 1, f) != 1 || fread(&h, 4, 1, f) != 1) return 2;
+    cv::Mat A = read_img(f, w, h), B = read_img(f, w, h);
+    int sw, sh; if (fread(&sw, 4, 1, f) != 1 || fread(&sh, 4, 1, f) != 1) return 2;
+    cv::Mat L = read_img(f, sw, sh), R = read_img(f, sw, sh);
+
+    // ---- operator()(image, mask, keypoints, descriptors) as Frame::ExtractORB calls it (Frame.cc:464-472)
+    ORBextractor ext(1000, 1.2f, 8, 20, 7);
+    std::vector<cv::KeyPoint> ka, kb; cv::Mat da, db;
+    ext(A, cv::Mat(), ka, da);
+    put_kps(ka, da);
+    put_i(ext.GetLevels());
+    for (int l = 0; l < ext.GetLevels(); ++l) {                          // mvImagePyramid: ROI views inside 19-px padded buffers
+        const cv::Mat& m = ext.mvImagePyramid[l];
+        put_i(m.rows); put_i(m.cols);
+        for (int y = -19; y < m.rows + 19; ++y) put(m.data + (ptrdiff_t)y * (ptrdiff_t)m.step - 19, (size_t)m.cols + 38);
+    }
+    // ---- Amos two-stage path (Frame.cc:474-498, 633-636): detect -> MovingKeyPoints -> ProcessDesp
+    std::vector<std::vector<cv::KeyPoint> > per_level;
+    ext(A, cv::Mat(), per_level);
+    cv::Mat mask(h, w, CV_8UC1), label(h, w, CV_64F);
+    for (int y = 0; y < h; ++y) for (int x = 0; x < w; ++x) {
+        mask.at<uchar>(y, x) = (x > w / 3 && x < w / 2 && y > h / 4 && y < h / 2) ? 255 : 0;
+        label.at<double>(y, x) = 1 + (x / 80) + 8 * (y / 80);
+    }
+    std::vector<center> centers(64);
+    for (int i = 0; i < 64; ++i) { centers[i].id = i; }
+    std::vector<int> rm(64, 0); rm[5] = 1; rm[17] = 1;
+    std::vector<cv::KeyPoint> culled = ext.MovingKeyPoints(A, mask, label, centers, rm, std::vector<bool>(), per_level);
+    std::vector<cv::KeyPoint> kc; cv::Mat dc;
+    ext.ProcessDesp(A, cv::Mat(), per_level, kc, dc);
+    put_i((int)culled.size()); if (!culled.empty()) put(culled.data(), culled.size() * sizeof(cv::KeyPoint));
+    put_kps(kc, dc);
+    // ---- ORBmatcher::SearchForInitialization as Tracking::MonocularInitialization calls it (Tracking.cc:1492-1500)
+    ext.SetExportPyramid(false);
+    ext(B, cv::Mat(), kb, db);
+    Frame FA, FB; fill_frame(FA, ext, ka, da, w, h); fill_frame(FB, ext, kb, db, w, h);
+    std::vector<cv::Point2f> prev(ka.size());
+    for (size_t i = 0; i < ka.size(); ++i) prev[i] = ka[i].pt;
+    std::vector<int> m12;
+    ORBmatcher matcher(0.9, true);
+    int nm = matcher.SearchForInitialization(FA, FB, prev, m12, 100);
+    put_i(nm); put_i((int)m12.size()); if (!m12.empty()) put(m12.data(), m12.size() * 4);
+    // ---- ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th)  (Tracking.cc:2378-2389)
+    std::vector<MapPoint> store(ka.size());
+    std::vector<MapPoint*> pts;
+    for (size_t i = 0; i < ka.size(); ++i) {
+        MapPoint& p = store[i];
+        p.mTrackProjX = ka[i].pt.x + 7.f; p.mTrackProjY = ka[i].pt.y - 4.f; p.mTrackProjXR = -1.f;
+        p.mbTrackInView = (i % 3) != 0; p.mbBad = (i % 11) == 0;
+        p.mnTrackScaleLevel = ka[i].octave; p.mTrackViewCos = (i % 2) ? 0.9995f : 0.9f;
+        p.mDescriptor = da.row((int)i); p.nObs = (i % 5) ? 1 : 0;
+        pts.push_back(&p);
+    }
+    nm = ORBmatcher(0.8, true).SearchByProjection(FB, pts, 3.f);
+    put_i(nm);
+    for (int j = 0; j < FB.N; ++j) put_i(FB.mvpMapPoints[j] ? (int)(FB.mvpMapPoints[j] - store.data()) : -1);
+    // ---- Frame::ComputeStereoMatches (Frame.cc:165-176 then :1179)
+    ORBextractor eL(2000, 1.2f, 8, 20, 7), eR(2000, 1.2f, 8, 20, 7);
+    eL.SetExportPyramid(false); eR.SetExportPyramid(false);
+    Frame S; S.mpORBextractorLeft = &eL; S.mpORBextractorRight = &eR;
+    eL(L, cv::Mat(), S.mvKeys, S.mDescriptors);
+    eR(R, cv::Mat(), S.mvKeysRight, S.mDescriptorsRight);
+    S.N = (int)S.mvKeys.size(); S.mb = 0.f; S.mbf = 386.1448f;
+    S.ComputeStereoMatches();
+    put_i(S.N); put(S.mvuRight.data(), (size_t)S.N * 4); put(S.mvDepth.data(), (size_t)S.N * 4);
+    fclose(g_out); fclose(f);
+    printf("host drop-in ok: %zu / %zu keypoints, %d stereo keypoints\n", ka.size(), kb.size(), S.N);
+    return 0;
+}

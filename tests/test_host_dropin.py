@@ -1,0 +1,122 @@
+"""Drop-in C++ classes (amos-slam_b200/host): ORB_SLAM2::ORBextractor and the on-path ORBmatcher / Frame bodies.
+
+CPU: the sources compile and link against liborbx_b200.so exactly as they would inside the reference tree (the
+reference's headers are replaced by stand-ins in tests/host/, cv:: types by the OpenCV-free shim).
+GPU: a C++ driver calls them the way Frame / Tracking do and every result must equal the C-ABI result obtained
+through the Python binding (which the other GPU tests pin bit-exactly to the oracle / reference goldens)."""
+import importlib
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+import match_cases as mc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "amos-slam_b200", "host")
+BIN = os.path.join(ROOT, "tests", "host", "_build", "host_dropin")
+
+
+def build_driver():
+    orbx = importlib.import_module("amos-slam_b200")
+    orbx.build()
+    os.makedirs(os.path.dirname(BIN), exist_ok=True)
+    srcs = [os.path.join(ROOT, "tests", "host", "host_dropin_main.cc"), os.path.join(HOST, "ORBextractor.cc"), os.path.join(HOST, "ORBmatcher_b200.cc")]
+    deps = srcs + [os.path.join(HOST, "ORBextractor.h"), os.path.join(ROOT, "include", "orbx_b200.h"), orbx.LIB_PATH]
+    if os.path.exists(BIN) and all(os.path.getmtime(BIN) >= os.path.getmtime(d) for d in deps):
+        return BIN
+    cmd = ["g++", "-std=c++14", "-O2", "-I" + os.path.join(ROOT, "oracle", "shim"), "-I" + os.path.join(ROOT, "tests", "host"), "-I" + HOST] + srcs + \
+          ["-L" + os.path.dirname(orbx.LIB_PATH), "-lorbx_b200", "-Wl,-rpath," + os.path.dirname(orbx.LIB_PATH), "-o", BIN]
+    subprocess.check_call(cmd)
+    return BIN
+
+
+def test_host_classes_compile_and_link():
+    b = build_driver()
+    out = subprocess.run(["ldd", b], capture_output=True, text=True).stdout
+    assert "liborbx_b200.so" in out
+    syms = subprocess.run(["nm", "-C", b], capture_output=True, text=True).stdout
+    for s in ("ORB_SLAM2::ORBextractor::operator()", "ORB_SLAM2::ORBextractor::MovingKeyPoints", "ORB_SLAM2::ORBextractor::ProcessDesp",
+              "ORB_SLAM2::ORBmatcher::SearchForInitialization", "ORB_SLAM2::ORBmatcher::SearchByProjection", "ORB_SLAM2::Frame::ComputeStereoMatches"):
+        assert s in syms, s
+
+
+class Reader:
+    def __init__(self, buf):
+        self.b, self.o = buf, 0
+
+    def i(self):
+        v = struct.unpack_from("<i", self.b, self.o)[0]; self.o += 4
+        return v
+
+    def arr(self, dtype, n):
+        a = np.frombuffer(self.b, dtype, n, self.o).copy(); self.o += a.nbytes
+        return a
+
+    def kps(self, kp_dtype):
+        n = self.i()
+        return self.arr(kp_dtype, n), self.arr(np.uint8, n * 32).reshape(n, 32)
+
+
+@pytest.mark.gpu
+def test_host_classes_match_c_abi(orbx, tmp_path):
+    from tools.synth import synth_frame, warp_affine_nn
+    b = build_driver()
+    A = synth_frame(0, 640, 480); B = warp_affine_nn(A, 7, -4, 2.0)
+    L, R = mc.stereo_pair()
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    with open(fin, "wb") as f:
+        f.write(struct.pack("<ii", 640, 480)); f.write(A.tobytes()); f.write(B.tobytes())
+        f.write(struct.pack("<ii", L.shape[1], L.shape[0])); f.write(L.tobytes()); f.write(R.tobytes())
+    subprocess.check_call([b, fin, fout])
+    r = Reader(open(fout, "rb").read())
+
+    E = orbx.ORBextractor(1000, 1.2, 8, 20, 7)
+    ka, da = E(A)
+    hk, hd = r.kps(orbx.KP_DTYPE)
+    assert np.array_equal(hk, ka) and np.array_equal(hd, da)
+    assert r.i() == 8
+    for l in range(8):                                                   # mvImagePyramid incl. the 19-px REFLECT_101 frame
+        rows, cols = r.i(), r.i()
+        padded = r.arr(np.uint8, (rows + 38) * (cols + 38)).reshape(rows + 38, cols + 38)
+        assert np.array_equal(padded, E.pyramid_level(l, border=19))
+    # two-stage Amos path
+    kd, counts = E.detect(A)
+    yy, xx = np.mgrid[0:480, 0:640]
+    mask = (((xx > 640 // 3) & (xx < 320) & (yy > 120) & (yy < 240)) * 255).astype(np.uint8)
+    label = (1 + (xx // 80) + 8 * (yy // 80)).astype(np.float64)
+    rm = np.zeros(64, np.int32); rm[[5, 17]] = 1
+    kept, counts2, culled = E.MovingKeyPoints(mask, label, np.arange(64, dtype=np.int32), rm, kd, counts)
+    kc, dc = E.ProcessDesp(kept, counts2)
+    n = r.i(); hc = r.arr(orbx.KP_DTYPE, n)
+    assert n == len(culled) and n > 0 and np.array_equal(hc, culled)
+    hk2, hd2 = r.kps(orbx.KP_DTYPE)
+    assert np.array_equal(hk2, kc) and np.array_equal(hd2, dc)
+    # SearchForInitialization
+    kb, db = E(B)
+    sf = E.GetScaleFactors()
+    FA, FB = orbx.FrameView(ka, da, 640, 480, sf), orbx.FrameView(kb, db, 640, 480, sf)
+    nm, m12, _ = orbx.ORBmatcher(0.9, True).SearchForInitialization(FA, FB, np.stack([ka["x"], ka["y"]], 1), 100)
+    assert r.i() == nm and nm > 50
+    assert np.array_equal(r.arr(np.int32, r.i()), m12)
+    # SearchByProjection(Frame, MapPoints): rebuild the driver's synthetic tracks
+    idx = np.arange(len(ka))
+    sel = ((idx % 3) != 0) & ((idx % 11) != 0)
+    tuv = np.stack([ka["x"] + np.float32(7), ka["y"] - np.float32(4)], 1).astype(np.float32)[sel]
+    vc = np.where(idx % 2 == 1, np.float32(0.9995), np.float32(0.9)).astype(np.float32)[sel]
+    obs = (idx % 5 != 0).astype(np.uint8)[sel]
+    FBu = orbx.FrameView(kb, db, 640, 480, sf, u_right=np.full(len(kb), -1, np.float32))
+    nm2, fm = orbx.ORBmatcher(0.8, True).SearchByProjectionPoints(FBu, tuv, np.full(sel.sum(), -1, np.float32), ka["octave"][sel], vc, da[sel], obs, np.zeros(len(kb), np.uint8), 3.0)
+    assert r.i() == nm2 and nm2 > 50
+    host_fm = r.arr(np.int32, len(kb))
+    assert np.array_equal(host_fm, np.where(fm >= 0, idx[sel][np.maximum(fm, 0)], -1))
+    # ComputeStereoMatches
+    EL, ER = orbx.ORBextractor(2000, 1.2, 8, 20, 7), orbx.ORBextractor(2000, 1.2, 8, 20, 7)
+    kl, dl = EL(L); kr, dr = ER(R)
+    ur, dep = orbx.ORBmatcher().ComputeStereoMatches(EL, ER, kl, dl, kr, dr, 0.0, mc.BF_KITTI)
+    n = r.i()
+    assert n == len(kl)
+    assert np.array_equal(r.arr(np.float32, n), ur) and np.array_equal(r.arr(np.float32, n), dep)
+    assert (ur >= 0).sum() > 100
