@@ -51,28 +51,20 @@ k_pyr_resize(const uint8_t* __restrict__ src, long long src_fstride, int spitch,
 //   a cell's keypoints at threshold t = strict 3x3 local maxima of S inside the cell's zone with S > t
 //   (neighbours outside the zone count as 0), in raster order; if the cell yields none at iniTh, the
 //   same set at minTh is used.
-// One warp per cell, 4 cells per CTA.  The cell's ROI (zone + 3-px ring) is staged in shared memory
-// with aligned 32-bit loads; S is computed only where two adjacent compass points pass the minTh test
-// (any 9-arc contains two adjacent compass points) and a 9-run exists (bit tricks on 16-bit masks).
-// Candidates are written to the cell's fixed slot range (capacity = max possible local maxima), so
-// there are no atomics and the layout is deterministic; the octree stage gathers them in cell order,
-// which reproduces vToDistributeKeys' order exactly.
+// One warp per cell, 4 cells per CTA; the cell's ROI (zone + 3-px ring) is staged in shared memory with
+// aligned 32-bit loads.  The kernel is instruction-issue bound, so the work is arranged as a funnel of
+// warp-compacted queues in which every stage runs with all lanes busy on survivors of the previous one:
+//   A  4 pixels per lane per step (one 32-bit word): polarity-free compass pre-test with byte-SIMD
+//      (VABSDIFF4 + SWAR): any 9-arc contains ring point 0 or 8 and ring point 4 or 12, so a corner needs
+//      (|N-v| > t or |S-v| > t) and (|E-v| > t or |W-v| > t).  ~23 % of the pixels survive.
+//   B  exact 16-point test on the survivors: bright / dark ring masks built with one funnel shift per
+//      ring pixel, 9-run detection with shift-and.  ~7 % of the pixels are corners at minTh.
+//   C  score S of the corners only (3-input min/max network), written to a zero-initialised u8 map.
+//   D  strict 3x3 local maxima among the corners, count of those above iniTh, ordered emission.
+// Queues are filled by prefix sums over lanes (raster order is preserved end to end); candidates go to
+// the cell's fixed slot range (capacity = max possible local maxima): no atomics, deterministic layout;
+// the octree stage gathers them in cell order, which reproduces vToDistributeKeys' order exactly.
 // =================================================================================================
-__device__ __forceinline__ int fast_sliding_min9_max(const int (&a)[16]) {
-    // max over k of min(a[k..k+8]) on the circular ring (log-step sliding minimum)
-    int m2[16], m4[16], m8[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) m2[k] = min(a[k], a[(k + 1) & 15]);
-#pragma unroll
-    for (int k = 0; k < 16; ++k) m4[k] = min(m2[k], m2[(k + 2) & 15]);
-#pragma unroll
-    for (int k = 0; k < 16; ++k) m8[k] = min(m4[k], m4[(k + 4) & 15]);
-    int best = -256;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) best = max(best, min(m8[k], a[(k + 8) & 15]));
-    return best;
-}
-
 __device__ __forceinline__ bool has_run9(uint32_t m16) {
     // 9 contiguous set bits on a 16-bit circular mask
     uint32_t m = m16 | (m16 << 16);
@@ -83,35 +75,19 @@ __device__ __forceinline__ bool has_run9(uint32_t m16) {
     return (r9 & 0xFFFFu) != 0;
 }
 
-// compass pre-test at minTh: any 9-arc of the ring contains two ADJACENT compass points (k = 0,4,8,12), so a pixel
-// can only be a corner if two adjacent compass points are both brighter than v+t or both darker than v-t
-__device__ __forceinline__ bool fast_compass(const uint8_t* p, int ps, int minTh) {
-    const int v = p[0];
-    const int d0 = (int)p[3 * ps] - v, d4 = (int)p[3] - v, d8 = (int)p[-3 * ps] - v, d12 = (int)p[-3] - v;
-    const int hi = max(max(min(d0, d4), min(d4, d8)), max(min(d8, d12), min(d12, d0)));     // best adjacent "bright" pair
-    const int lo = min(min(max(d0, d4), max(d4, d8)), min(max(d8, d12), max(d12, d0)));     // best adjacent "dark" pair
-    return hi > minTh || lo < -minTh;
-}
+__device__ __forceinline__ int min3i(int a, int b, int c) { return min(min(a, b), c); }
+__device__ __forceinline__ int max3i(int a, int b, int c) { return max(max(a, b), c); }
 
-// FAST score of the pixel at p (shared-memory patch, row stride ps), 0 if S <= minTh
-__device__ __forceinline__ int fast_score(const uint8_t* p, int ps, int minTh) {
-    const int v = p[0];
-    int d[16];   // v - p_k ; ring order (dx,dy): (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
-    d[0] = v - p[3 * ps];        d[1] = v - p[3 * ps + 1];   d[2] = v - p[2 * ps + 2];   d[3] = v - p[ps + 3];
-    d[4] = v - p[3];             d[5] = v - p[-ps + 3];      d[6] = v - p[-2 * ps + 2];  d[7] = v - p[-3 * ps + 1];
-    d[8] = v - p[-3 * ps];       d[9] = v - p[-3 * ps - 1];  d[10] = v - p[-2 * ps - 2]; d[11] = v - p[-ps - 3];
-    d[12] = v - p[-3];           d[13] = v - p[ps - 3];      d[14] = v - p[2 * ps - 2];  d[15] = v - p[3 * ps - 1];
-    uint32_t mb = 0, md = 0;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) { mb |= (uint32_t)(d[k] < -minTh) << k; md |= (uint32_t)(d[k] > minTh) << k; }
-    if (has_run9(md)) return fast_sliding_min9_max(d);          // dark arc: min(v - p_k)
-    if (has_run9(mb)) {
-#pragma unroll
-        for (int k = 0; k < 16; ++k) d[k] = -d[k];
-        return fast_sliding_min9_max(d);                        // bright arc: min(p_k - v)
-    }
-    return 0;
-}
+// ring order (dx,dy): (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
+#define FAST_RING(p, ps, R) do { \
+    const int _s2 = 2 * (ps), _s3 = 3 * (ps); \
+    R[0] = (p)[_s3];        R[1] = (p)[_s3 + 1];   R[2] = (p)[_s2 + 2];    R[3] = (p)[(ps) + 3]; \
+    R[4] = (p)[3];          R[5] = (p)[3 - (ps)];  R[6] = (p)[2 - _s2];    R[7] = (p)[1 - _s3]; \
+    R[8] = (p)[-_s3];       R[9] = (p)[-_s3 - 1];  R[10] = (p)[-_s2 - 2];  R[11] = (p)[-(ps) - 3]; \
+    R[12] = (p)[-3];        R[13] = (p)[(ps) - 3]; R[14] = (p)[_s2 - 2];   R[15] = (p)[_s3 - 1]; } while (0)
+
+// byte-wise "non-zero" -> 0x80 flag per byte
+__device__ __forceinline__ uint32_t swar_nz(uint32_t x) { return (((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u; }
 
 #define FAST_WARPS 4
 
@@ -133,62 +109,136 @@ k_fast_cells(PyrView pv, const LevelGeom* __restrict__ levels, const CellDesc* _
     uint8_t* sm = smem_raw + (size_t)warp * smem_per_warp;
     const int zw = c.cw - 6, zh = c.ch - 6;
     const int xs = c.x0 & ~3, shift = c.x0 & 3;
-    const int wpr = ((c.x0 + c.cw + 3) >> 2) - (xs >> 2);      // 32-bit words per patch row (<= 18)
+    const int wpr = ((c.x0 + c.cw + 3) >> 2) - (xs >> 2);      // 32-bit words per patch row
     const int ps = wpr * 4;                                    // patch row stride (bytes)
     uint32_t* patch32 = reinterpret_cast<uint32_t*>(sm);
     const int patch_bytes = ps * c.ch;
     const int sst = zw + 2;                                    // S row stride; 1-px zero ring
     const int s_bytes = (sst * (zh + 2) + 3) & ~3;
     uint8_t* S = sm + patch_bytes;
-    uint16_t* queue = reinterpret_cast<uint16_t*>(S + s_bytes);   // zw*zh entries: candidate pixels in raster order
+    uint16_t* queue = reinterpret_cast<uint16_t*>(S + s_bytes);   // zw*zh entries: (dark<<15) | y<<6 | x, raster order
 
     // stage the ROI with aligned 32-bit loads: each iteration covers 32/wpr rows
     {
         const int rpi = 32 / wpr, lr = lane / wpr, lc = lane - lr * wpr;
         const uint32_t* src = reinterpret_cast<const uint32_t*>(img + (long long)c.y0 * pitch + xs) + lc;
+        const int p4 = pitch >> 2;
         if (lr < rpi)
-            for (int r = lr; r < c.ch; r += rpi) patch32[r * wpr + lc] = __ldg(src + (long long)r * (pitch >> 2));
+            for (int r = lr; r < c.ch; r += rpi) patch32[r * wpr + lc] = __ldg(src + r * p4);
     }
     for (int w = lane; w < (s_bytes >> 2); w += 32) reinterpret_cast<uint32_t*>(S)[w] = 0u;
     __syncwarp();
 
-    // pass A: compass pre-test on every zone pixel, passing pixels compacted (in raster order) into the queue
-    const uint8_t* patch = sm + shift;
     const uint32_t lt = (1u << lane) - 1u;
+    // ---- stage A: polarity-free compass pre-test, 4 pixels (one word) per lane per step ----
     int qn = 0;
-    for (int y = 0; y < zh; ++y) {
-        const uint8_t* row = patch + (y + 3) * ps + 3;
-        for (int x0 = 0; x0 < zw; x0 += 32) {
-            const int x = x0 + lane;
-            const bool pass = x < zw && fast_compass(row + x, ps, minTh);
-            const uint32_t m = __ballot_sync(0xffffffffu, pass);
-            if (pass) queue[qn + __popc(m & lt)] = (uint16_t)((y << 6) | x);
-            qn += __popc(m);
+    {
+        int tq = 0;                                            // largest 2^k - 1 <= minTh (exact for the default minTh = 7)
+        while (2 * tq + 1 <= minTh) tq = 2 * tq + 1;
+        const uint32_t keep = (uint32_t)(0xFF & ~tq) * 0x01010101u;
+        const int pc0 = shift + 3;                             // patch column of zone x = 0
+        const int wi0 = pc0 >> 2, wi1 = (pc0 + zw - 1) >> 2, nw = wi1 - wi0 + 1;
+        const uint32_t mfirst = 0xFFFFFFFFu << (8 * (pc0 & 3));
+        const uint32_t mlast = 0xFFFFFFFFu >> (8 * (3 - ((pc0 + zw - 1) & 3)));
+        const int ntask = zh * nw;
+        int y = lane / nw, w = lane - y * nw;                  // task = (row, word); each lane advances by 32 tasks per step
+        const int dy32 = 32 / nw, dw32 = 32 - dy32 * nw;
+        for (int t0 = 0; t0 < ntask; t0 += 32) {
+            uint32_t f = 0;
+            if (t0 + lane < ntask) {
+                const uint32_t* row = patch32 + (y + 3) * wpr + wi0 + w;
+                const uint32_t C = row[0], Cl = row[-1], Cr = row[1];
+                const uint32_t Nn = row[-3 * wpr], Ss = row[3 * wpr];
+                const uint32_t E = __byte_perm(C, Cr, 0x6543), Wn = __byte_perm(Cl, C, 0x4321);
+                const uint32_t u = (__vabsdiffu4(C, Nn) | __vabsdiffu4(C, Ss)) & keep;
+                const uint32_t v = (__vabsdiffu4(C, E) | __vabsdiffu4(C, Wn)) & keep;
+                f = swar_nz(u) & swar_nz(v);
+                if (w == 0) f &= mfirst;
+                if (w == nw - 1) f &= mlast;
+            }
+            const int cnt = __popc(f);
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += n; }
+            int pos = qn + incl - cnt;
+            const int xb = 4 * (wi0 + w) - pc0;
+            while (f) {
+                const int j = (__ffs(f) - 1) >> 3;
+                f &= f - 1;
+                queue[pos++] = (uint16_t)((y << 6) | (xb + j));
+            }
+            qn += __shfl_sync(0xffffffffu, incl, 31);
+            y += dy32; w += dw32;
+            if (w >= nw) { w -= nw; ++y; }
         }
     }
     __syncwarp();
-    // pass B: full 16-pixel ring test + score, all lanes busy on compacted candidates
-    for (int k = lane; k < qn; k += 32) {
-        const int code = queue[k], y = code >> 6, x = code & 63;
-        const int s = fast_score(patch + (y + 3) * ps + (x + 3), ps, minTh);
-        if (s) S[(y + 1) * sst + x + 1] = (uint8_t)s; else queue[k] = 0xFFFFu;
-    }
-    __syncwarp();
-    // pass C: strict 3x3 local maxima among the corners; count those above iniTh
-    int n_ini = 0;
+    const uint8_t* patch = sm + shift;
+    // ---- stage B: exact 16-point segment test on the survivors; corners compacted in place ----
+    int cn = 0;
     for (int k0 = 0; k0 < qn; k0 += 32) {
         const int k = k0 + lane;
-        int f = 0;
+        int code = 0, corner = 0;
         if (k < qn) {
-            const int code = queue[k];
-            if (code != 0xFFFF) {
-                const int y = code >> 6, x = code & 63;
-                const uint8_t* q = S + (y + 1) * sst + x + 1;
-                const int s = q[0];
-                if (s > q[-1] && s > q[1] && s > q[-sst - 1] && s > q[-sst] && s > q[-sst + 1] &&
-                    s > q[sst - 1] && s > q[sst] && s > q[sst + 1]) f = s;
-                else queue[k] = 0xFFFFu;
+            code = queue[k];
+            const int y = code >> 6, x = code & 63;
+            const uint8_t* p = patch + (y + 3) * ps + (x + 3);
+            const int hi = (int)p[0] + minTh, lo = (int)p[0] - minTh;
+            int R[16];
+            FAST_RING(p, ps, R);
+            uint32_t mb = 0, md = 0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                mb = __funnelshift_l((uint32_t)(hi - R[i]), mb, 1);          // sign bit <=> p_k > v + t
+                md = __funnelshift_l((uint32_t)(R[i] - lo), md, 1);          // sign bit <=> p_k < v - t
             }
+            const bool dark = has_run9(md & 0xFFFFu);
+            corner = dark || has_run9(mb & 0xFFFFu);
+            code |= dark ? 0x8000 : 0;
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, corner);
+        __syncwarp();
+        if (corner) queue[cn + __popc(m & lt)] = (uint16_t)code;
+        cn += __popc(m);
+    }
+    __syncwarp();
+    // ---- stage C: score of the corners ----
+    for (int k = lane; k < cn; k += 32) {
+        const int code = queue[k], y = (code >> 6) & 63, x = code & 63;
+        const uint8_t* p = patch + (y + 3) * ps + (x + 3);
+        const int v = p[0];
+        int R[16];
+        FAST_RING(p, ps, R);
+        int d[16];
+        if (code & 0x8000) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) d[i] = v - R[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) d[i] = R[i] - v;
+        }
+        int m3[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) m3[i] = min3i(d[i], d[(i + 1) & 15], d[(i + 2) & 15]);
+        int best = -256;
+#pragma unroll
+        for (int i = 0; i < 16; i += 2)
+            best = max3i(best, min3i(m3[i], m3[(i + 3) & 15], m3[(i + 6) & 15]), min3i(m3[(i + 1) & 15], m3[(i + 4) & 15], m3[(i + 7) & 15]));
+        S[(y + 1) * sst + x + 1] = (uint8_t)best;
+    }
+    __syncwarp();
+    // ---- stage D: strict 3x3 local maxima among the corners; count those above iniTh ----
+    int n_ini = 0;
+    for (int k0 = 0; k0 < cn; k0 += 32) {
+        const int k = k0 + lane;
+        int f = 0;
+        if (k < cn) {
+            const int code = queue[k], y = (code >> 6) & 63, x = code & 63;
+            const uint8_t* q = S + (y + 1) * sst + x + 1;
+            const int s = q[0];
+            if (s > q[-1] && s > q[1] && s > q[-sst - 1] && s > q[-sst] && s > q[-sst + 1] &&
+                s > q[sst - 1] && s > q[sst] && s > q[sst + 1]) f = s;
+            queue[k] = (uint16_t)((code & 0xFFF) | (f ? 0 : 0x8000));          // bit 15 now marks "suppressed"
         }
         n_ini += __popc(__ballot_sync(0xffffffffu, f > iniTh));
     }
@@ -196,16 +246,16 @@ k_fast_cells(PyrView pv, const LevelGeom* __restrict__ levels, const CellDesc* _
     const int th = n_ini > 0 ? iniTh : minTh;                  // retry at minTh iff the cell came back empty
     uint32_t* out = cand_slots + (long long)b * slots_per_frame + c.slot;
     int n = 0;
-    for (int k0 = 0; k0 < qn; k0 += 32) {
+    for (int k0 = 0; k0 < cn; k0 += 32) {
         const int k = k0 + lane;
         int f = 0, x = 0, y = 0;
-        if (k < qn) {
+        if (k < cn) {
             const int code = queue[k];
-            if (code != 0xFFFF) { y = code >> 6; x = code & 63; f = S[(y + 1) * sst + x + 1]; }
+            if (!(code & 0x8000)) { y = code >> 6; x = code & 63; f = S[(y + 1) * sst + x + 1]; }
         }
-        const bool keep = f > th;
-        const uint32_t m = __ballot_sync(0xffffffffu, keep);
-        if (keep) out[n + __popc(m & lt)] = (uint32_t)(x + 3 + c.sx) | ((uint32_t)(y + 3 + c.sy) << 12) | ((uint32_t)(f - 1) << 24);
+        const bool keepit = f > th;
+        const uint32_t m = __ballot_sync(0xffffffffu, keepit);
+        if (keepit) out[n + __popc(m & lt)] = (uint32_t)(x + 3 + c.sx) | ((uint32_t)(y + 3 + c.sy) << 12) | ((uint32_t)(f - 1) << 24);
         n += __popc(m);
     }
     if (lane == 0) cell_counts[(long long)b * ncells + cell] = (uint16_t)n;

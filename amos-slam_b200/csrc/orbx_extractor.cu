@@ -56,6 +56,8 @@ struct orbx_extractor {
     std::vector<float> mvScaleFactor, mvInvScaleFactor, mvLevelSigma2, mvInvLevelSigma2;
     std::vector<int> mnFeaturesPerLevel, umax;
     cudaStream_t stream = nullptr;
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;   // copy engines of the host-pointer batch call (overlap with compute)
+    std::vector<cudaEvent_t> ev_h2d, ev_done;        // one pair per chunk
     long long launches = 0;
 
     // ---- geometry plan for (rows, cols) ----
@@ -68,7 +70,7 @@ struct orbx_extractor {
 
     // ---- per-batch device state (the "stateful extractor": pyramid stays resident) ----
     int Bcap = 0, lastB = 0;
-    DevBuf<uint8_t> d_pyr, d_blur;
+    DevBuf<uint8_t> d_pyr, d_blur, d_l0;
     DevBuf<uint32_t> d_slots, d_ocand, d_spk, d_kp_level;
     DevBuf<unsigned long long> d_skey;
     DevBuf<uint16_t> d_cell_counts;
@@ -239,17 +241,23 @@ static inline void prof_mark(orbx_extractor* h) {
     orbx_set_error(std::string("kernel launch: ") + cudaGetErrorString(_e)); return ORBX_E_CUDA; } ++h->launches; } while (0)
 
 // pyramid (levels >= 1) + FAST cells + quadtree; leaves per-level keypoints in d_kp_level / d_kp_count
-static int run_detect(orbx_extractor* h, int B) {
+static int run_detect(orbx_extractor* h, int b0, int B) {
     cudaStream_t s = h->stream;
     const int L = h->nlevels;
+    PyrView view = h->view;
+    view.l0 += (long long)b0 * view.l0_fstride; view.pyr += (long long)b0 * view.pyr_fstride;
+    uint8_t* pyr = h->d_pyr.p + (size_t)b0 * h->pyr_fstride;
+    uint32_t* slots = h->d_slots.p + (size_t)b0 * h->cand_per_frame;
+    uint16_t* cell_counts = h->d_cell_counts.p + (size_t)b0 * h->cells.size();
+    const size_t co = (size_t)b0 * h->cand_per_frame;
     prof_mark(h);
     for (int l = 1; l < L; ++l) {
         const LevelGeom& g = h->levels[l]; const LevelGeom& gp = h->levels[l - 1];
         const uint8_t* src; long long sfs; int sp;
-        if (l == 1) { src = h->view.l0; sfs = h->view.l0_fstride; sp = h->view.l0_pitch; }
-        else { src = h->d_pyr.p + gp.off; sfs = h->pyr_fstride; sp = gp.pitch; }
+        if (l == 1) { src = view.l0; sfs = view.l0_fstride; sp = view.l0_pitch; }
+        else { src = pyr + gp.off; sfs = h->pyr_fstride; sp = gp.pitch; }
         dim3 grid((g.w + 127) / 128, (g.h + 7) / 8, B), block(32, 8);
-        k_pyr_resize<<<grid, block, 0, s>>>(src, sfs, sp, gp.w, gp.h, h->d_pyr.p + g.off, h->pyr_fstride, g.pitch, g.w, g.h, h->resize_tabs[l]);
+        k_pyr_resize<<<grid, block, 0, s>>>(src, sfs, sp, gp.w, gp.h, pyr + g.off, h->pyr_fstride, g.pitch, g.w, g.h, h->resize_tabs[l]);
         LAUNCH_CHECK();
     }
     prof_mark(h);
@@ -257,46 +265,61 @@ static int run_detect(orbx_extractor* h, int B) {
     if (ncells > 0) {
         dim3 grid((ncells + FAST_WARPS - 1) / FAST_WARPS, B);
         const int smem = h->fast_smem_per_warp * FAST_WARPS;
-        k_fast_cells<<<grid, FAST_WARPS * 32, smem, s>>>(h->view, h->d_levels.p, h->d_cells.p, ncells, h->cand_per_frame,
-                                                          h->fast_smem_per_warp, h->iniThFAST, h->minThFAST, h->d_slots.p, h->d_cell_counts.p);
+        k_fast_cells<<<grid, FAST_WARPS * 32, smem, s>>>(view, h->d_levels.p, h->d_cells.p, ncells, h->cand_per_frame,
+                                                          h->fast_smem_per_warp, h->iniThFAST, h->minThFAST, slots, cell_counts);
         LAUNCH_CHECK();
     }
     prof_mark(h);
     {
         dim3 grid(L, B);
         k_octree_sort<<<grid, SORT_THREADS, (size_t)h->sort_smem_keys * 8, s>>>(h->d_levels.p, h->d_cells.p, ncells, h->cand_per_frame, h->cand_per_frame, L,
-                                                                                 h->sort_smem_keys, h->d_slots.p, h->d_cell_counts.p, h->d_ocand.p, h->d_skey.p, h->d_spk.p, h->d_ncand.p);
+                                                                                 h->sort_smem_keys, slots, cell_counts, h->d_ocand.p + co, h->d_skey.p + co, h->d_spk.p + co, h->d_ncand.p + (size_t)b0 * L);
         LAUNCH_CHECK();
         prof_mark(h);
         const size_t tsm = (size_t)h->tree_cap * (8 + 8 + 4 + 4 + 4 + 2 + 2 + 2 + 1) + 16;
-        k_octree_tree<<<grid, 32, tsm, s>>>(h->d_levels.p, L, h->cand_per_frame, h->kp_per_frame, h->tree_cap, h->d_skey.p, h->d_spk.p, h->d_ncand.p,
-                                            h->d_kp_level.p, h->d_kp_count.p, h->d_overflow.p);
+        k_octree_tree<<<grid, 32, tsm, s>>>(h->d_levels.p, L, h->cand_per_frame, h->kp_per_frame, h->tree_cap, h->d_skey.p + co, h->d_spk.p + co, h->d_ncand.p + (size_t)b0 * L,
+                                            h->d_kp_level.p + (size_t)b0 * h->kp_per_frame, h->d_kp_count.p + (size_t)b0 * L, h->d_overflow.p);
         LAUNCH_CHECK();
     }
     prof_mark(h);
-    h->lastB = B; h->have_pyramid = true; h->blur_valid = false;
+    h->lastB = b0 + B; h->have_pyramid = true; h->blur_valid = false;
     return ORBX_OK;
 }
 
-static int run_blur(orbx_extractor* h, int B) {
-    if (h->blur_valid) return ORBX_OK;
+// blur of frames [b0, b0+B).  The single-frame entry points (describe, debug taps) use the cached form below.
+static int run_blur_range(orbx_extractor* h, int b0, int B) {
     const int ntiles = (int)h->tiles.size();
+    PyrView view = h->view;
+    view.l0 += (long long)b0 * view.l0_fstride; view.pyr += (long long)b0 * view.pyr_fstride;
     dim3 grid((ntiles + 3) / 4, B);
-    k_gauss7<<<grid, 128, 0, h->stream>>>(h->view, h->d_levels.p, h->d_tiles.p, ntiles, h->d_blur.p, h->pyr_fstride);
+    k_gauss7<<<grid, 128, 0, h->stream>>>(view, h->d_levels.p, h->d_tiles.p, ntiles, h->d_blur.p + (size_t)b0 * h->pyr_fstride, h->pyr_fstride);
     LAUNCH_CHECK();
     prof_mark(h);
+    return ORBX_OK;
+}
+static int run_blur(orbx_extractor* h, int B) {
+    if (h->blur_valid) return ORBX_OK;
+    int rc = run_blur_range(h, 0, B); if (rc) return rc;
     h->blur_valid = true;
     return ORBX_OK;
 }
 
-static int run_orient(orbx_extractor* h, int B, bool describe, KpOut* d_kp, uint8_t* d_desc, int cap, int* d_counts, int* d_level_counts) {
+// d_kp / d_desc / d_counts / d_level_counts are the buffers of the WHOLE batch; the range offset is applied here
+static int run_orient(orbx_extractor* h, int b0, int B, bool describe, KpOut* d_kp, uint8_t* d_desc, int cap, int* d_counts, int* d_level_counts) {
     dim3 grid((h->kp_per_frame + 3) / 4, B);
+    PyrView view = h->view;
+    view.l0 += (long long)b0 * view.l0_fstride; view.pyr += (long long)b0 * view.pyr_fstride;
+    const uint32_t* kp_level = h->d_kp_level.p + (size_t)b0 * h->kp_per_frame;
+    const int* kp_count = h->d_kp_count.p + (size_t)b0 * h->nlevels;
+    KpOut* kp = d_kp + (size_t)b0 * cap;
+    int* counts = d_counts ? d_counts + b0 : nullptr;
+    int* lcounts = d_level_counts ? d_level_counts + (size_t)b0 * h->nlevels : nullptr;
     if (describe)
-        k_orient_describe<true><<<grid, 128, 0, h->stream>>>(h->view, h->d_levels.p, h->nlevels, h->kp_per_frame, h->d_kp_level.p, h->d_kp_count.p,
-                                                            h->d_blur.p, h->pyr_fstride, d_kp, d_desc, cap, d_counts, d_level_counts);
+        k_orient_describe<true><<<grid, 128, 0, h->stream>>>(view, h->d_levels.p, h->nlevels, h->kp_per_frame, kp_level, kp_count,
+                                                            h->d_blur.p + (size_t)b0 * h->pyr_fstride, h->pyr_fstride, kp, d_desc + (size_t)b0 * cap * 32, cap, counts, lcounts);
     else
-        k_orient_describe<false><<<grid, 128, 0, h->stream>>>(h->view, h->d_levels.p, h->nlevels, h->kp_per_frame, h->d_kp_level.p, h->d_kp_count.p,
-                                                             nullptr, 0, d_kp, nullptr, cap, d_counts, d_level_counts);
+        k_orient_describe<false><<<grid, 128, 0, h->stream>>>(view, h->d_levels.p, h->nlevels, h->kp_per_frame, kp_level, kp_count,
+                                                             nullptr, 0, kp, nullptr, cap, counts, lcounts);
     LAUNCH_CHECK();
     if (describe) prof_mark(h);
     return ORBX_OK;
@@ -360,7 +383,10 @@ int orbx_create(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, in
     h->mnFeaturesPerLevel[nlevels - 1] = std::max(nfeatures - sum, 0);
     cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete h; FAIL(ORBX_E_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e)); }
-    if (upload_constants() != ORBX_OK) { cudaStreamDestroy(h->stream); delete h; return ORBX_E_CUDA; }
+    if (cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaStreamDestroy(h->stream); delete h; FAIL(ORBX_E_CUDA, "cudaStreamCreate (copy streams)");
+    }
+    if (upload_constants() != ORBX_OK) { cudaStreamDestroy(h->stream); cudaStreamDestroy(h->s_h2d); cudaStreamDestroy(h->s_d2h); delete h; return ORBX_E_CUDA; }
     cudaFuncSetAttribute(k_octree_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
     cudaFuncSetAttribute(k_octree_tree, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
@@ -372,6 +398,11 @@ void orbx_destroy(orbx_extractor* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    if (h->s_h2d) { cudaStreamSynchronize(h->s_h2d); cudaStreamDestroy(h->s_h2d); }
+    if (h->s_d2h) { cudaStreamSynchronize(h->s_d2h); cudaStreamDestroy(h->s_d2h); }
+    for (cudaEvent_t e : h->ev_h2d) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->ev_done) cudaEventDestroy(e);
+    h->d_l0.release();
     h->d_levels.release(); h->d_cells.release(); h->d_tiles.release(); h->d_tabs.release();
     h->d_pyr.release(); h->d_blur.release(); h->d_slots.release(); h->d_ocand.release(); h->d_spk.release(); h->d_kp_level.release();
     h->d_skey.release(); h->d_cell_counts.release(); h->d_ncand.release(); h->d_kp_count.release(); h->d_counts.release();
@@ -443,9 +474,20 @@ int orbx_extract_batch_device(orbx_extractor* h, const uint8_t* d_images, int B,
         h->view.l0 = h->d_pyr.p + g0.off; h->view.l0_fstride = h->pyr_fstride; h->view.l0_pitch = g0.pitch;
     }
     h->view.pyr = h->d_pyr.p; h->view.pyr_fstride = h->pyr_fstride;
-    if ((rc = run_detect(h, B))) return rc;
+    if ((rc = run_detect(h, 0, B))) return rc;
     if ((rc = run_blur(h, B))) return rc;
-    return run_orient(h, B, true, reinterpret_cast<KpOut*>(d_kp_out), d_desc_out, cap, d_counts_out, nullptr);
+    return run_orient(h, 0, B, true, reinterpret_cast<KpOut*>(d_kp_out), d_desc_out, cap, d_counts_out, nullptr);
+}
+
+// Host-pointer batch call = the reference-facing end-to-end path.  The batch is cut into chunks that flow through
+// three streams (H2D copy engine -> compute -> D2H copy engine), so the PCIe transfers of chunk i+1 / i-1 overlap the
+// kernels of chunk i.  Pinned host buffers give true overlap; pageable ones still work (the copies then serialise).
+static int chunk_frames(const orbx_extractor* h, int B) {
+    const long long px = (long long)h->rows * h->cols;
+    long long c = (64LL * 640 * 480 + px - 1) / px;          // ~64 VGA frames (20 MB) per chunk
+    if (c < 1) c = 1;
+    if (c > B) c = B;
+    return (int)c;
 }
 
 int orbx_extract_batch(orbx_extractor* h, const uint8_t* images, int B, int rows, int cols, size_t step, size_t frame_stride,
@@ -454,16 +496,56 @@ int orbx_extract_batch(orbx_extractor* h, const uint8_t* images, int B, int rows
     if (B <= 0 || !kp_out || !desc_out || !counts_out || cap <= 0) FAIL(ORBX_E_INVALID, "bad batch arguments");
     if ((rc = build_plan(h, rows, cols))) return rc;
     if ((rc = ensure_capacity(h, B, cap))) return rc;
-    if ((rc = upload_level0(h, images, B, rows, cols, step, frame_stride))) return rc;
-    if ((rc = run_detect(h, B))) return rc;
-    if ((rc = run_blur(h, B))) return rc;
-    if ((rc = run_orient(h, B, true, h->d_kp_out.p, h->d_desc_out.p, cap, h->d_counts.p, nullptr))) return rc;
-    CU_TRY(cudaMemcpyAsync(kp_out, h->d_kp_out.p, (size_t)B * cap * sizeof(KpOut), cudaMemcpyDeviceToHost, h->stream));
-    CU_TRY(cudaMemcpyAsync(desc_out, h->d_desc_out.p, (size_t)B * cap * 32, cudaMemcpyDeviceToHost, h->stream));
-    CU_TRY(cudaMemcpyAsync(counts_out, h->d_counts.p, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    // level 0: mirror the host layout on the device when it is word-aligned and dense enough (one copy per chunk);
+    // otherwise copy frame by frame into the pyramid block
+    const bool mirror = (step & 3) == 0 && (frame_stride & 3) == 0 && frame_stride >= step * (size_t)rows && frame_stride <= 2 * step * (size_t)rows;
+    if (mirror) {
+        if (h->d_l0.ensure((size_t)B * frame_stride)) return ORBX_E_CUDA;
+        h->view.l0 = h->d_l0.p; h->view.l0_fstride = (long long)frame_stride; h->view.l0_pitch = (int)step;
+    } else {
+        const LevelGeom& g0 = h->levels[0];
+        h->view.l0 = h->d_pyr.p + g0.off; h->view.l0_fstride = h->pyr_fstride; h->view.l0_pitch = g0.pitch;
+    }
+    h->view.pyr = h->d_pyr.p; h->view.pyr_fstride = h->pyr_fstride;
+    const int C = chunk_frames(h, B), nchunks = (B + C - 1) / C;
+    while ((int)h->ev_h2d.size() < nchunks) {
+        cudaEvent_t a, b;
+        CU_TRY(cudaEventCreateWithFlags(&a, cudaEventDisableTiming)); CU_TRY(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        h->ev_h2d.push_back(a); h->ev_done.push_back(b);
+    }
+    // the copy streams must not run ahead of work already queued on the compute stream (e.g. a previous call's kernels)
+    CU_TRY(cudaEventRecord(h->ev_done[0], h->stream));
+    CU_TRY(cudaStreamWaitEvent(h->s_h2d, h->ev_done[0], 0));
+    for (int c = 0; c < nchunks; ++c) {
+        const int b0 = c * C, nb = std::min(C, B - b0);
+        if (mirror) {
+            const size_t bytes = (size_t)(nb - 1) * frame_stride + (size_t)(rows - 1) * step + cols;     // never reads past the last row of the last frame
+            CU_TRY(cudaMemcpyAsync(h->d_l0.p + (size_t)b0 * frame_stride, images + (size_t)b0 * frame_stride, bytes, cudaMemcpyHostToDevice, h->s_h2d));
+        } else {
+            const LevelGeom& g0 = h->levels[0];
+            for (int b = b0; b < b0 + nb; ++b)
+                CU_TRY(cudaMemcpy2DAsync(h->d_pyr.p + (size_t)b * h->pyr_fstride + g0.off, g0.pitch, images + (size_t)b * frame_stride, step,
+                                         cols, rows, cudaMemcpyHostToDevice, h->s_h2d));
+        }
+        CU_TRY(cudaEventRecord(h->ev_h2d[c], h->s_h2d));
+    }
+    for (int c = 0; c < nchunks; ++c) {
+        const int b0 = c * C, nb = std::min(C, B - b0);
+        CU_TRY(cudaStreamWaitEvent(h->stream, h->ev_h2d[c], 0));
+        if ((rc = run_detect(h, b0, nb))) return rc;
+        if ((rc = run_blur_range(h, b0, nb))) return rc;
+        if ((rc = run_orient(h, b0, nb, true, h->d_kp_out.p, h->d_desc_out.p, cap, h->d_counts.p, nullptr))) return rc;
+        CU_TRY(cudaEventRecord(h->ev_done[c], h->stream));
+        CU_TRY(cudaStreamWaitEvent(h->s_d2h, h->ev_done[c], 0));
+        CU_TRY(cudaMemcpyAsync(kp_out + (size_t)b0 * cap, h->d_kp_out.p + (size_t)b0 * cap, (size_t)nb * cap * sizeof(KpOut), cudaMemcpyDeviceToHost, h->s_d2h));
+        CU_TRY(cudaMemcpyAsync(desc_out + (size_t)b0 * cap * 32, h->d_desc_out.p + (size_t)b0 * cap * 32, (size_t)nb * cap * 32, cudaMemcpyDeviceToHost, h->s_d2h));
+        CU_TRY(cudaMemcpyAsync(counts_out + b0, h->d_counts.p + b0, (size_t)nb * sizeof(int), cudaMemcpyDeviceToHost, h->s_d2h));
+    }
+    h->lastB = B; h->blur_valid = true;
     int ovf = 0;
     CU_TRY(cudaMemcpyAsync(&ovf, h->d_overflow.p, 4, cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(cudaStreamSynchronize(h->stream));
+    CU_TRY(cudaStreamSynchronize(h->s_d2h));
     if (ovf) FAIL(ORBX_E_OVERFLOW, "internal bound exceeded in the quadtree stage");
     return ORBX_OK;
 }
@@ -479,9 +561,9 @@ int orbx_extract(orbx_extractor* h, const uint8_t* image, int rows, int cols, si
     const int icap = h->max_kp;
     if ((rc = ensure_capacity(h, 1, icap))) return rc;
     if ((rc = upload_level0(h, image, 1, rows, cols, step, 0))) return rc;
-    if ((rc = run_detect(h, 1))) return rc;
+    if ((rc = run_detect(h, 0, 1))) return rc;
     if ((rc = run_blur(h, 1))) return rc;
-    if ((rc = run_orient(h, 1, true, h->d_kp_out.p, h->d_desc_out.p, icap, h->d_counts.p, nullptr))) return rc;
+    if ((rc = run_orient(h, 0, 1, true, h->d_kp_out.p, h->d_desc_out.p, icap, h->d_counts.p, nullptr))) return rc;
     int n = 0, ovf = 0;
     CU_TRY(cudaMemcpyAsync(&n, h->d_counts.p, 4, cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(cudaMemcpyAsync(&ovf, h->d_overflow.p, 4, cudaMemcpyDeviceToHost, h->stream));
@@ -508,8 +590,8 @@ int orbx_detect(orbx_extractor* h, const uint8_t* image, int rows, int cols, siz
     const int icap = h->max_kp;
     if ((rc = ensure_capacity(h, 1, icap))) return rc;
     if ((rc = upload_level0(h, image, 1, rows, cols, step, 0))) return rc;
-    if ((rc = run_detect(h, 1))) return rc;
-    if ((rc = run_orient(h, 1, false, h->d_kp_out.p, nullptr, icap, h->d_counts.p, h->d_level_counts.p))) return rc;
+    if ((rc = run_detect(h, 0, 1))) return rc;
+    if ((rc = run_orient(h, 0, 1, false, h->d_kp_out.p, nullptr, icap, h->d_counts.p, h->d_level_counts.p))) return rc;
     int n = 0, ovf = 0;
     CU_TRY(cudaMemcpyAsync(&n, h->d_counts.p, 4, cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(cudaMemcpyAsync(level_counts, h->d_level_counts.p, 4 * h->nlevels, cudaMemcpyDeviceToHost, h->stream));

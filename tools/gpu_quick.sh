@@ -1,0 +1,13 @@
+#!/bin/bash
+# quick GPU visit: parity tests + one bench line (no ncu).  usage: tools/gpu_quick.sh <tag> [pytest-args]
+TAG=${1:-q}; shift
+O=gpurun_out; mkdir -p $O
+python -m pytest tests -m gpu -x -q "$@" > $O/pytest_$TAG.log 2>&1; echo "pytest rc=$?"; tail -n 15 $O/pytest_$TAG.log
+python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $O/bench_$TAG.log 2> $O/bench_$TAG.err; echo "bench rc=$?"; tail -n 5 $O/bench_$TAG.err
+python - <<PY
+import json
+try:
+    d=json.loads(open('$O/bench_$TAG.log').read().strip().splitlines()[-1])
+    print('value %.0f e2e %.0f' % (d['value'], d['e2e']['value'])); print({k: round(v,3) for k,v in d['roofline']['stage_ms_per_step'].items()})
+except Exception as e: print('no bench line', e)
+PY
