@@ -9,17 +9,20 @@
 // (SURVEY.md A.2):  q = [18,34,48,56,48,34,18]/256;  h = sum q*px (16-bit range, no rounding);
 // v = sum q*h (32-bit);  out = (v + 32768) >> 16.  Reflection is at the LEVEL edge (the reference
 // blurs a clone of the ROI).
-// One warp = one tile of 128 columns x BLUR_STRIP rows of one level of one frame (the tile list covers all
-// levels, so a single launch blurs the whole pyramid of the whole batch).  Each lane owns 4 adjacent
-// columns = one aligned 32-bit word per row: it loads ONLY its own word, takes the two neighbouring words
-// from the adjacent lanes by shuffle, forms the 4 horizontal sums, keeps the last 7 rows of them in
-// registers and emits one output word per row.  No shared memory; HBM traffic = read level + write level.
-// Lanes whose 10-byte window crosses the image edge take a byte-wise reflect path (2 lanes per row).
+// One warp = one tile of 120 columns x BLUR_STRIP rows of one level of one frame (the tile list covers all
+// levels, so a single launch blurs the whole pyramid of the whole batch).  Each lane owns one aligned 32-bit
+// word (4 columns) per row; lanes 0 and 31 are halo lanes that only feed their neighbours.  Per input row a
+// lane takes the two neighbouring words by shuffle, forms its 4 horizontal sums with 8 integer dot products
+// (IDP.4A on PRMT-aligned byte windows), keeps the last 7 rows of them in registers and emits one output
+// word.  Words that touch the level edge are assembled from reflected byte loads (row-invariant columns).
+// The row loads run 7 rows ahead of the arithmetic (register ring), which is what keeps enough bytes in
+// flight per SM: the kernel has no shared memory and HBM traffic = read level + write level.
 // =================================================================================================
 #define BLUR_STRIP 64
+#define BLUR_TILE_W 120
 struct BlurTile { short level, xc, strip, pad; };
 
-__device__ __forceinline__ int reflect101(int p, int len) {
+__device__ __noinline__ int reflect101(int p, int len) {
     if (len == 1) return 0;
     while (p < 0 || p >= len) p = p < 0 ? -p : 2 * len - 2 - p;     // loops only on levels narrower than the 3-px halo
     return p;
@@ -34,54 +37,63 @@ k_gauss7(PyrView pv, const LevelGeom* __restrict__ levels, const BlurTile* __res
     const BlurTile t = tiles[tile];
     const int b = blockIdx.y;
     const LevelGeom& g = levels[t.level];
+    const int gw = g.w, gh = g.h, gpitch = g.pitch;                  // keep the geometry in registers (no reloads in the row loop)
     int pitch;
     const uint8_t* img = level_ptr(pv, g, t.level, b, pitch);
-    const int x = t.xc * 128 + lane * 4;
-    const int y0 = t.strip * BLUR_STRIP, y1 = min(y0 + BLUR_STRIP, g.h);
-    const bool valid = x < g.w;
-    const bool inside_r = x + 6 <= g.w - 1;
-    const bool fast = valid && x >= 4 && inside_r;                   // window x-3 .. x+6 entirely inside the level
-    const bool left = valid && x == 0 && inside_r && g.w >= 4;       // left edge: pixels -3..-1 mirror bytes 3..1 of the own word
-    int xo[10];                                                      // slow lanes (right edge, tiny levels): reflected columns, row-invariant
+    const int x = t.xc * BLUR_TILE_W + (lane - 1) * 4;
+    const int y0 = t.strip * BLUR_STRIP, y1 = min(y0 + BLUR_STRIP, gh);
+    const bool word_ok = x >= 0 && x + 3 < gw;                       // aligned word entirely inside the level
+    const bool needed = x + 3 >= -3 && x <= gw + 2;                  // some neighbour reads this word
+    const bool store = lane >= 1 && lane <= 30 && x < gw;
+    int rx[4];                                                       // edge words: reflected columns, row-invariant
 #pragma unroll
-    for (int j = 0; j < 10; ++j) xo[j] = (valid && !fast && !left) ? reflect101(x - 3 + j, g.w) : 0;
-    uint8_t* dst = blur + (long long)b * blur_fstride + g.off + x;
-    int hb[7][4];
-#pragma unroll
-    for (int j = 0; j < 7; ++j) { hb[j][0] = hb[j][1] = hb[j][2] = hb[j][3] = 0; }
-#pragma unroll 7
-    for (int r = y0 - 3; r < y1 + 3; ++r) {
-        const uint8_t* row = img + (long long)reflect101(r, g.h) * pitch;
-        const uint32_t w1 = valid ? __ldg(reinterpret_cast<const uint32_t*>(row + x)) : 0u;
-        uint32_t w0 = __shfl_up_sync(0xffffffffu, w1, 1), w2 = __shfl_down_sync(0xffffffffu, w1, 1);
-        if (fast && lane == 0) w0 = __ldg(reinterpret_cast<const uint32_t*>(row + x - 4));
-        if ((fast || left) && lane == 31) w2 = __ldg(reinterpret_cast<const uint32_t*>(row + x + 4));
-        if (left) w0 = __byte_perm(w1, 0, 0x1230);                    // bytes (.,p3,p2,p1): reflect-101 of columns -3..-1
-        int B[10];                                                    // pixels x-3 .. x+6
-        if (fast || left) {
-            B[0] = (w0 >> 8) & 0xFF; B[1] = (w0 >> 16) & 0xFF; B[2] = w0 >> 24;
-            B[3] = w1 & 0xFF; B[4] = (w1 >> 8) & 0xFF; B[5] = (w1 >> 16) & 0xFF; B[6] = w1 >> 24;
-            B[7] = w2 & 0xFF; B[8] = (w2 >> 8) & 0xFF; B[9] = (w2 >> 16) & 0xFF;
-        } else if (valid) {
-#pragma unroll
-            for (int j = 0; j < 10; ++j) B[j] = row[xo[j]];
-        } else {
-#pragma unroll
-            for (int j = 0; j < 10; ++j) B[j] = 0;
+    for (int j = 0; j < 4; ++j) rx[j] = (needed && !word_ok) ? reflect101(x + j, gw) : 0;
+    // warp-uniform: does any lane of this tile (halo lanes included) touch the left / right level edge?
+    const bool edge_tile = t.xc == 0 || t.xc * BLUR_TILE_W + 30 * 4 + 3 >= gw;
+    const int rlast = y1 + 2;
+    auto load_row = [&](int r) -> uint32_t {
+        int rr = min(r, rlast);                                          // the tail group re-reads the last row instead of running past it
+        if ((unsigned)rr >= (unsigned)gh) {                              // BORDER_REFLECT_101, closed form for |overshoot| <= 3 on any height >= 1
+            rr = rr < 0 ? -rr : rr; rr = rr >= gh ? 2 * gh - 2 - rr : rr;
+            rr = rr < 0 ? -rr : rr; rr = rr >= gh ? 2 * gh - 2 - rr : rr;
+            rr = max(rr, 0);
         }
+        const uint8_t* row = img + rr * pitch;                           // a frame's level is < 2^31 bytes
+        if (!edge_tile || word_ok) return __ldg(reinterpret_cast<const uint32_t*>(row + x));
+        if (!needed) return 0u;
+        return (uint32_t)__ldg(row + rx[0]) | ((uint32_t)__ldg(row + rx[1]) << 8) | ((uint32_t)__ldg(row + rx[2]) << 16) | ((uint32_t)__ldg(row + rx[3]) << 24);
+    };
+    uint8_t* dst = blur + (long long)b * blur_fstride + g.off + x;
+    const uint32_t Q0 = 18u | (34u << 8) | (48u << 16) | (56u << 24);     // taps -3..0
+    const uint32_t Q1 = 48u | (34u << 8) | (18u << 16);                   // taps +1..+3 (4th byte unused)
+    uint32_t hb[7][4];                                                    // ring of the horizontal sums of the last 7 input rows (<= 65280 each)
+    uint32_t pre[7];                                                      // ring of row words in flight
 #pragma unroll
-        for (int j = 0; j < 6; ++j) { hb[j][0] = hb[j + 1][0]; hb[j][1] = hb[j + 1][1]; hb[j][2] = hb[j + 1][2]; hb[j][3] = hb[j + 1][3]; }
+    for (int j = 0; j < 7; ++j) { hb[j][0] = hb[j][1] = hb[j][2] = hb[j][3] = 0; pre[j] = load_row(y0 - 3 + j); }
+    const int ngroups = (y1 - y0 + 6 + 6) / 7;                            // input rows y0-3 .. y1+2 in groups of 7 (the tail group over-reads reflected rows)
+    for (int gi = 0; gi < ngroups; ++gi) {
+        const int r0 = y0 - 3 + gi * 7;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) hb[6][k] = 18 * (B[k] + B[k + 6]) + 34 * (B[k + 1] + B[k + 5]) + 48 * (B[k + 2] + B[k + 4]) + 56 * B[k + 3];
-        const int o = r - 3;                                          // output row completed by this input row
-        if (o >= y0 && valid) {
-            uint32_t outw = 0;
+        for (int j = 0; j < 7; ++j) {                                     // ring slot j is static after unrolling: no register moves
+            const int r = r0 + j;
+            const uint32_t w1 = pre[j];
+            if (gi + 1 < ngroups) pre[j] = load_row(r + 7);
+            const uint32_t w0 = __shfl_up_sync(0xffffffffu, w1, 1), w2 = __shfl_down_sync(0xffffffffu, w1, 1);
+            // h(x+k) = sum_{i=0..6} q[i] * px(x+k-3+i): two 4-tap integer dot products on byte-aligned windows
+            hb[j][0] = __dp4a(__byte_perm(w0, w1, 0x4321), Q0, __dp4a(__byte_perm(w1, w2, 0x4321), Q1, 0u));
+            hb[j][1] = __dp4a(__byte_perm(w0, w1, 0x5432), Q0, __dp4a(__byte_perm(w1, w2, 0x5432), Q1, 0u));
+            hb[j][2] = __dp4a(__byte_perm(w0, w1, 0x6543), Q0, __dp4a(__byte_perm(w1, w2, 0x6543), Q1, 0u));
+            hb[j][3] = __dp4a(w1, Q0, __dp4a(w2, Q1, 0u));
+            const int o = r - 3;                                          // output row completed by this input row
+            uint32_t v[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint32_t v = 18u * (uint32_t)(hb[0][k] + hb[6][k]) + 34u * (uint32_t)(hb[1][k] + hb[5][k]) + 48u * (uint32_t)(hb[2][k] + hb[4][k]) + 56u * (uint32_t)hb[3][k];
-                outw |= ((v + 32768u) >> 16) << (8 * k);
-            }
-            *reinterpret_cast<uint32_t*>(dst + (long long)o * g.pitch) = outw;   // bytes past the level width land in row padding
+            for (int k = 0; k < 4; ++k)
+                v[k] = 18u * (hb[(j + 1) % 7][k] + hb[j][k]) + 34u * (hb[(j + 2) % 7][k] + hb[(j + 6) % 7][k]) +
+                       48u * (hb[(j + 3) % 7][k] + hb[(j + 5) % 7][k]) + (56u * hb[(j + 4) % 7][k] + 32768u);
+            // (v + 32768) >> 16 is byte 2 of each sum (v < 2^24)
+            const uint32_t outw = __byte_perm(__byte_perm(v[0], v[1], 0x0062), __byte_perm(v[2], v[3], 0x0062), 0x5410);
+            if (store && o >= y0 && o < y1)
+                *reinterpret_cast<uint32_t*>(dst + o * gpitch) = outw;   // bytes past the level width land in row padding
         }
     }
 }
@@ -94,17 +106,37 @@ k_gauss7(PyrView pv, const LevelGeom* __restrict__ levels, const BlurTile* __res
 __constant__ int c_umax[16];             // [15,15,15,15,14,14,14,13,13,12,11,10,9,8,6,3]
 __constant__ char4 c_pattern_t[8 * 32];  // rBRIEF pairs, transposed: [bit k][byte i] = (x0,y0,x1,y1) of pair 8*i+k
 
+// dot product of 4 unsigned bytes (pixels) with 4 signed bytes (weights)
+__device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// 27 lanes = 3 rows x 9 aligned 32-bit words cover one 31-pixel patch row each; 11 steps walk the 31 rows.
+// Per word: circle mask by SWAR compare of |u| against umax[|v|], then two integer dot products (sum of u*I and sum of I).
 __device__ __forceinline__ float ic_angle_warp(const uint8_t* center, int pitch, int lane) {
-    const int u = lane - ORBX_HALF_PATCH;
+    const unsigned long long UMAX_NIBBLES = 0x3689ABCDDEEEFFFFull;           // umax[|v|], 4 bits each (ORBextractor.cc:579-608)
+    const int rg = lane / 9, wi = lane - rg * 9;
+    const uint8_t* row0 = center - ORBX_HALF_PATCH;
+    const int a = (int)((uintptr_t)row0 & 3);                                 // same for every row: pitches are multiples of 4
+    const int u0 = 4 * wi - ORBX_HALF_PATCH - a;                              // u of byte 0 of this lane's word
+    const uint32_t wu = (uint32_t)((u0) & 0xFF) | ((uint32_t)((u0 + 1) & 0xFF) << 8) | ((uint32_t)((u0 + 2) & 0xFF) << 16) | ((uint32_t)((u0 + 3) & 0xFF) << 24);
+    const uint32_t absu = __vabsdiffu4(wu ^ 0x80808080u, 0x80808080u);       // |u| per byte (bias trick: u + 128 is unsigned)
+    const uint8_t* p = row0 - a + 4 * wi + (long long)(rg - ORBX_HALF_PATCH) * pitch;
     int m10 = 0, m01 = 0;
-    if (lane < 31) {
-        const int au = abs(u);
-#pragma unroll 1
-        for (int v = -ORBX_HALF_PATCH; v <= ORBX_HALF_PATCH; ++v) {
-            if (au <= c_umax[abs(v)]) {
-                const int val = __ldg(center + (long long)v * pitch + u);
-                m10 += u * val; m01 += v * val;
+    if (lane < 27) {
+#pragma unroll
+        for (int it = 0; it < 11; ++it) {
+            const int v = it * 3 + rg - ORBX_HALF_PATCH;
+            if (v <= ORBX_HALF_PATCH) {
+                const uint32_t um = (uint32_t)(UMAX_NIBBLES >> (4 * abs(v))) & 15u;
+                const uint32_t inside = ((um * 0x01010101u + 0x80808080u) - absu) & 0x80808080u;     // 0x80 where |u| <= umax
+                const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p)) & ((inside >> 7) * 255u);
+                m10 = dp4a_us(w, wu, m10);                                      // unsigned pixels x signed u
+                m01 += v * (int)__dp4a(w, 0x01010101u, 0u);
             }
+            p += 3 * (long long)pitch;
         }
     }
 #pragma unroll

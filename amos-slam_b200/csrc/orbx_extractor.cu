@@ -172,11 +172,11 @@ static int build_plan(orbx_extractor* h, int rows, int cols) {
         g.kp_off = kp_off; g.kp_cap = std::max(g.N + 2, 4 * g.nIni) + 2; kp_off += g.kp_cap;
         tree_cap = std::max(tree_cap, g.kp_cap + 8);
         for (int st = 0; st < (g.h + BLUR_STRIP - 1) / BLUR_STRIP; ++st)
-            for (int xc = 0; xc < (g.w + 127) / 128; ++xc) { BlurTile t; t.level = (short)l; t.xc = (short)xc; t.strip = (short)st; t.pad = 0; tiles.push_back(t); }
+            for (int xc = 0; xc < (g.w + BLUR_TILE_W - 1) / BLUR_TILE_W; ++xc) { BlurTile t; t.level = (short)l; t.xc = (short)xc; t.strip = (short)st; t.pad = 0; tiles.push_back(t); }
     }
     if (tree_cap > 32000) FAIL(ORBX_E_INVALID, "too many features per level");
     // resize tables for levels >= 1
-    std::vector<int> tabs; std::vector<size_t> tab_off((size_t)L * 4, 0);
+    std::vector<int> tabs; std::vector<size_t> tab_off((size_t)L * 4, 0), xg_off(L, 0); std::vector<int> wide_ok(L, 0);
     for (int l = 1; l < L; ++l) {
         std::vector<int> xo, yo; std::vector<short> xw, yw;
         linear_coefs(lv[l - 1].w, lv[l].w, lv[l].pitch, xo, xw);
@@ -184,6 +184,21 @@ static int build_plan(orbx_extractor* h, int rows, int cols) {
         auto push = [&](const void* p, size_t bytes) { size_t o = tabs.size(); tabs.resize(o + (bytes + 15) / 16 * 4); std::memcpy(&tabs[o], p, bytes); return o; };
         tab_off[l * 4 + 0] = push(xo.data(), xo.size() * 4); tab_off[l * 4 + 1] = push(xw.data(), xw.size() * 2);
         tab_off[l * 4 + 2] = push(yo.data(), yo.size() * 4); tab_off[l * 4 + 3] = push(yw.data(), yw.size() * 2);
+        // word-load form: per group of 4 destination columns, first source column + PRMT selectors of the (left,right) pairs
+        const int ngroups = lv[l].pitch / 4, sw = lv[l - 1].w;
+        std::vector<int> xg((size_t)ngroups * 2);
+        bool wide = true;
+        for (int gx = 0; gx < ngroups; ++gx) {
+            const int base = xo[4 * gx];
+            unsigned sel = 0;
+            for (int k = 0; k < 4; ++k) {
+                const int il = xo[4 * gx + k] - base, ir = std::min(xo[4 * gx + k] + 1, sw - 1) - base;
+                if (il < 0 || il > 7 || ir < 0 || ir > 7) wide = false;
+                sel |= ((unsigned)(il & 7) | ((unsigned)(ir & 7) << 4)) << (8 * k);
+            }
+            xg[2 * gx] = base; xg[2 * gx + 1] = (int)sel;
+        }
+        xg_off[l] = push(xg.data(), xg.size() * 4); wide_ok[l] = wide && (lv[l - 1].pitch % 4 == 0);
     }
     if (h->d_levels.ensure(L)) return ORBX_E_CUDA;
     if (h->d_cells.ensure(cells.size())) return ORBX_E_CUDA;
@@ -200,6 +215,8 @@ static int build_plan(orbx_extractor* h, int rows, int cols) {
         h->resize_tabs[l].xw = reinterpret_cast<const short2*>(h->d_tabs.p + tab_off[l * 4 + 1]);
         h->resize_tabs[l].yofs = h->d_tabs.p + tab_off[l * 4 + 2];
         h->resize_tabs[l].yw = reinterpret_cast<const short2*>(h->d_tabs.p + tab_off[l * 4 + 3]);
+        h->resize_tabs[l].xg = reinterpret_cast<const int2*>(h->d_tabs.p + xg_off[l]);
+        h->resize_tabs[l].wide = wide_ok[l];
     }
     h->levels.swap(lv); h->cells.swap(cells); h->tiles.swap(tiles);
     h->pyr_fstride = (off + 255) / 256 * 256;
@@ -257,7 +274,10 @@ static int run_detect(orbx_extractor* h, int b0, int B) {
         if (l == 1) { src = view.l0; sfs = view.l0_fstride; sp = view.l0_pitch; }
         else { src = pyr + gp.off; sfs = h->pyr_fstride; sp = gp.pitch; }
         dim3 grid((g.w + 127) / 128, (g.h + 7) / 8, B), block(32, 8);
-        k_pyr_resize<<<grid, block, 0, s>>>(src, sfs, sp, gp.w, gp.h, pyr + g.off, h->pyr_fstride, g.pitch, g.w, g.h, h->resize_tabs[l]);
+        if (h->resize_tabs[l].wide && (sp & 3) == 0)
+            k_pyr_resize_w<<<grid, block, 0, s>>>(src, sfs, sp, gp.w, gp.h, pyr + g.off, h->pyr_fstride, g.pitch, g.w, g.h, h->resize_tabs[l]);
+        else
+            k_pyr_resize<<<grid, block, 0, s>>>(src, sfs, sp, gp.w, gp.h, pyr + g.off, h->pyr_fstride, g.pitch, g.w, g.h, h->resize_tabs[l]);
         LAUNCH_CHECK();
     }
     prof_mark(h);

@@ -49,6 +49,19 @@ def test_extract_matches_oracle_configs(orbx, oracle, cfg):
         assert_same(kg, dg, kr, dr)
 
 
+@pytest.mark.parametrize("cfg", [(800, 600, 500, 2.5, 3, 47), (500, 375, 600, 1.07, 12, 48), (640, 480, 500, 2.0, 4, 49)])
+def test_unusual_scale_factors(orbx, oracle, cfg):
+    """scale > 2 takes the byte-gather resize kernel, scale <= 2 the word-load one; both must equal the oracle."""
+    w, h, nf, sf, nl, seed = cfg
+    E = orbx.ORBextractor(nf, sf, nl, 20, 7); P = oracle.Extractor("port", nf, sf, nl, 20, 7)
+    img = synth_frame(seed, w, h)
+    kg, dg = E(img); ko, do = P.extract(img)
+    assert_same(kg, dg, ko, do)
+    for l in range(nl):
+        po = P.pyramid_level(l)
+        assert np.array_equal(E.debug_pyramid_level(0, l, po.shape), po)
+
+
 def test_textured_and_flat_inputs(orbx, oracle):
     rng = np.random.default_rng(3)
     E = orbx.ORBextractor(500, 1.2, 8, 20, 7); P = oracle.Extractor("port", 500, 1.2, 8, 20, 7)
