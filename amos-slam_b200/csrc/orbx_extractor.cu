@@ -57,6 +57,10 @@ struct orbx_extractor {
     std::vector<int> mnFeaturesPerLevel, umax;
     cudaStream_t stream = nullptr;
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;   // copy engines of the host-pointer batch call (overlap with compute)
+    cudaStream_t s_alt = nullptr;                    // second compute stream: odd chunks of the host batch call run here, so the
+                                                     // latency-bound quadtree kernels of one chunk overlap the stencils of the next
+    cudaStream_t cur = nullptr;                      // stream the run_* helpers launch on (stream or s_alt)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::vector<cudaEvent_t> ev_h2d, ev_done;        // one pair per chunk
     long long launches = 0;
 
@@ -251,15 +255,20 @@ static int ensure_capacity(orbx_extractor* h, int B, int out_cap) {
 static inline void prof_mark(orbx_extractor* h) {
     if (!h->profiling) return;
     cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) return;
-    cudaEventRecord(e, h->stream); h->prof_events.push_back(e);
+    cudaEventRecord(e, h->cur); h->prof_events.push_back(e);
 }
 
 #define LAUNCH_CHECK() do { cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) { \
     orbx_set_error(std::string("kernel launch: ") + cudaGetErrorString(_e)); return ORBX_E_CUDA; } ++h->launches; } while (0)
 
-// pyramid (levels >= 1) + FAST cells + quadtree; leaves per-level keypoints in d_kp_level / d_kp_count
-static int run_detect(orbx_extractor* h, int b0, int B) {
-    cudaStream_t s = h->stream;
+static int run_blur_range(orbx_extractor* h, int b0, int B);
+
+// pyramid (levels >= 1) + FAST cells + quadtree; leaves per-level keypoints in d_kp_level / d_kp_count.
+// fork_blur: the blur only needs the pyramid, so it is launched on the second compute stream right after the resize
+// chain and runs next to the FAST / quadtree kernels (the quadtree is latency-bound and leaves most SMs idle);
+// the caller joins on ev_join before the descriptor stage.
+static int run_detect(orbx_extractor* h, int b0, int B, bool fork_blur = false) {
+    cudaStream_t s = h->cur;
     const int L = h->nlevels;
     PyrView view = h->view;
     view.l0 += (long long)b0 * view.l0_fstride; view.pyr += (long long)b0 * view.pyr_fstride;
@@ -281,6 +290,15 @@ static int run_detect(orbx_extractor* h, int b0, int B) {
         LAUNCH_CHECK();
     }
     prof_mark(h);
+    if (fork_blur) {
+        CU_TRY(cudaEventRecord(h->ev_fork, s));
+        CU_TRY(cudaStreamWaitEvent(h->s_alt, h->ev_fork, 0));
+        cudaStream_t keep = h->cur; h->cur = h->s_alt;
+        const int rc = run_blur_range(h, b0, B);
+        h->cur = keep;
+        if (rc) return rc;
+        CU_TRY(cudaEventRecord(h->ev_join, h->s_alt));
+    }
     const int ncells = (int)h->cells.size();
     if (ncells > 0) {
         dim3 grid((ncells + FAST_WARPS - 1) / FAST_WARPS, B);
@@ -312,7 +330,7 @@ static int run_blur_range(orbx_extractor* h, int b0, int B) {
     PyrView view = h->view;
     view.l0 += (long long)b0 * view.l0_fstride; view.pyr += (long long)b0 * view.pyr_fstride;
     dim3 grid((ntiles + 3) / 4, B);
-    k_gauss7<<<grid, 128, 0, h->stream>>>(view, h->d_levels.p, h->d_tiles.p, ntiles, h->d_blur.p + (size_t)b0 * h->pyr_fstride, h->pyr_fstride);
+    k_gauss7<<<grid, 128, 0, h->cur>>>(view, h->d_levels.p, h->d_tiles.p, ntiles, h->d_blur.p + (size_t)b0 * h->pyr_fstride, h->pyr_fstride);
     LAUNCH_CHECK();
     prof_mark(h);
     return ORBX_OK;
@@ -335,10 +353,10 @@ static int run_orient(orbx_extractor* h, int b0, int B, bool describe, KpOut* d_
     int* counts = d_counts ? d_counts + b0 : nullptr;
     int* lcounts = d_level_counts ? d_level_counts + (size_t)b0 * h->nlevels : nullptr;
     if (describe)
-        k_orient_describe<true><<<grid, 128, 0, h->stream>>>(view, h->d_levels.p, h->nlevels, h->kp_per_frame, kp_level, kp_count,
+        k_orient_describe<true><<<grid, 128, 0, h->cur>>>(view, h->d_levels.p, h->nlevels, h->kp_per_frame, kp_level, kp_count,
                                                             h->d_blur.p + (size_t)b0 * h->pyr_fstride, h->pyr_fstride, kp, d_desc + (size_t)b0 * cap * 32, cap, counts, lcounts);
     else
-        k_orient_describe<false><<<grid, 128, 0, h->stream>>>(view, h->d_levels.p, h->nlevels, h->kp_per_frame, kp_level, kp_count,
+        k_orient_describe<false><<<grid, 128, 0, h->cur>>>(view, h->d_levels.p, h->nlevels, h->kp_per_frame, kp_level, kp_count,
                                                              nullptr, 0, kp, nullptr, cap, counts, lcounts);
     LAUNCH_CHECK();
     if (describe) prof_mark(h);
@@ -403,7 +421,10 @@ int orbx_create(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, in
     h->mnFeaturesPerLevel[nlevels - 1] = std::max(nfeatures - sum, 0);
     cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete h; FAIL(ORBX_E_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e)); }
-    if (cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking) != cudaSuccess) {
+    h->cur = h->stream;
+    cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
+    if (cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->s_alt, cudaStreamNonBlocking) != cudaSuccess) {
         cudaStreamDestroy(h->stream); delete h; FAIL(ORBX_E_CUDA, "cudaStreamCreate (copy streams)");
     }
     if (upload_constants() != ORBX_OK) { cudaStreamDestroy(h->stream); cudaStreamDestroy(h->s_h2d); cudaStreamDestroy(h->s_d2h); delete h; return ORBX_E_CUDA; }
@@ -420,6 +441,9 @@ void orbx_destroy(orbx_extractor* h) {
     cudaStreamSynchronize(h->stream);
     if (h->s_h2d) { cudaStreamSynchronize(h->s_h2d); cudaStreamDestroy(h->s_h2d); }
     if (h->s_d2h) { cudaStreamSynchronize(h->s_d2h); cudaStreamDestroy(h->s_d2h); }
+    if (h->s_alt) { cudaStreamSynchronize(h->s_alt); cudaStreamDestroy(h->s_alt); }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     for (cudaEvent_t e : h->ev_h2d) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_done) cudaEventDestroy(e);
     h->d_l0.release();
@@ -494,8 +518,14 @@ int orbx_extract_batch_device(orbx_extractor* h, const uint8_t* d_images, int B,
         h->view.l0 = h->d_pyr.p + g0.off; h->view.l0_fstride = h->pyr_fstride; h->view.l0_pitch = g0.pitch;
     }
     h->view.pyr = h->d_pyr.p; h->view.pyr_fstride = h->pyr_fstride;
-    if ((rc = run_detect(h, 0, B))) return rc;
-    if ((rc = run_blur(h, B))) return rc;
+    if (h->profiling) {                                  // per-stage timing wants the stages back to back on one stream
+        if ((rc = run_detect(h, 0, B))) return rc;
+        if ((rc = run_blur(h, B))) return rc;
+    } else {
+        if ((rc = run_detect(h, 0, B, true))) return rc;
+        CU_TRY(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+        h->blur_valid = true;
+    }
     return run_orient(h, 0, B, true, reinterpret_cast<KpOut*>(d_kp_out), d_desc_out, cap, d_counts_out, nullptr);
 }
 
@@ -536,6 +566,7 @@ int orbx_extract_batch(orbx_extractor* h, const uint8_t* images, int B, int rows
     // the copy streams must not run ahead of work already queued on the compute stream (e.g. a previous call's kernels)
     CU_TRY(cudaEventRecord(h->ev_done[0], h->stream));
     CU_TRY(cudaStreamWaitEvent(h->s_h2d, h->ev_done[0], 0));
+    CU_TRY(cudaStreamWaitEvent(h->s_alt, h->ev_done[0], 0));
     for (int c = 0; c < nchunks; ++c) {
         const int b0 = c * C, nb = std::min(C, B - b0);
         if (mirror) {
@@ -551,11 +582,15 @@ int orbx_extract_batch(orbx_extractor* h, const uint8_t* images, int B, int rows
     }
     for (int c = 0; c < nchunks; ++c) {
         const int b0 = c * C, nb = std::min(C, B - b0);
-        CU_TRY(cudaStreamWaitEvent(h->stream, h->ev_h2d[c], 0));
-        if ((rc = run_detect(h, b0, nb))) return rc;
-        if ((rc = run_blur_range(h, b0, nb))) return rc;
-        if ((rc = run_orient(h, b0, nb, true, h->d_kp_out.p, h->d_desc_out.p, cap, h->d_counts.p, nullptr))) return rc;
-        CU_TRY(cudaEventRecord(h->ev_done[c], h->stream));
+        h->cur = (c & 1) ? h->s_alt : h->stream;
+        CU_TRY(cudaStreamWaitEvent(h->cur, h->ev_h2d[c], 0));
+        rc = run_detect(h, b0, nb);
+        if (!rc) rc = run_blur_range(h, b0, nb);
+        if (!rc) rc = run_orient(h, b0, nb, true, h->d_kp_out.p, h->d_desc_out.p, cap, h->d_counts.p, nullptr);
+        cudaStream_t used = h->cur;
+        h->cur = h->stream;
+        if (rc) return rc;
+        CU_TRY(cudaEventRecord(h->ev_done[c], used));
         CU_TRY(cudaStreamWaitEvent(h->s_d2h, h->ev_done[c], 0));
         CU_TRY(cudaMemcpyAsync(kp_out + (size_t)b0 * cap, h->d_kp_out.p + (size_t)b0 * cap, (size_t)nb * cap * sizeof(KpOut), cudaMemcpyDeviceToHost, h->s_d2h));
         CU_TRY(cudaMemcpyAsync(desc_out + (size_t)b0 * cap * 32, h->d_desc_out.p + (size_t)b0 * cap * 32, (size_t)nb * cap * 32, cudaMemcpyDeviceToHost, h->s_d2h));
@@ -563,9 +598,10 @@ int orbx_extract_batch(orbx_extractor* h, const uint8_t* images, int B, int rows
     }
     h->lastB = B; h->blur_valid = true;
     int ovf = 0;
+    CU_TRY(cudaStreamSynchronize(h->s_d2h));            // follows every chunk's kernels (ev_done) and copies
+    CU_TRY(cudaStreamSynchronize(h->s_alt));
     CU_TRY(cudaMemcpyAsync(&ovf, h->d_overflow.p, 4, cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(cudaStreamSynchronize(h->stream));
-    CU_TRY(cudaStreamSynchronize(h->s_d2h));
     if (ovf) FAIL(ORBX_E_OVERFLOW, "internal bound exceeded in the quadtree stage");
     return ORBX_OK;
 }
