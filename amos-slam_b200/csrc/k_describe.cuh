@@ -2,6 +2,7 @@
 #pragma once
 #include "orbx_common.cuh"
 #include "det_math.cuh"
+#include <cuda_pipeline.h>
 
 // =================================================================================================
 // K6  gauss7: cv::GaussianBlur(7x7, sigma 2, BORDER_REFLECT_101) on every pyramid level
@@ -144,8 +145,29 @@ __device__ __forceinline__ float ic_angle_warp(const uint8_t* center, int pitch,
     return fast_atan2_deg((float)m01, (float)m10);
 }
 
-// computeOrbDescriptor (ORBextractor.cc:173-227): lane i produces descriptor byte i
-__device__ __forceinline__ uint32_t brief_byte(const uint8_t* center, int pitch, float a, float b, int lane) {
+// computeOrbDescriptor (ORBextractor.cc:173-227): lane i produces descriptor byte i.
+// The rotated pattern stays within +-18 px of the keypoint, so the warp first stages the 37-row x 40-byte (10 aligned
+// words) blurred window into shared memory with coalesced loads and then gathers its 512 samples from there: the
+// random byte gathers cost shared-memory bank cycles instead of one L1 wavefront per lane.
+#define BRIEF_R 18
+#define BRIEF_ROWS (2 * BRIEF_R + 1)
+#define BRIEF_PS 40
+// asynchronous staging (LDGSTS): issued before the orientation is computed so that the copy overlaps IC_Angle
+__device__ __forceinline__ void brief_stage(const uint8_t* center, int pitch, int lane, uint8_t* sm) {
+    const uint8_t* row0 = center - BRIEF_R;
+    const int al = (int)((uintptr_t)row0 & 3);
+    const uint8_t* base = row0 - al - BRIEF_R * pitch;
+    for (int i = lane; i < BRIEF_ROWS * (BRIEF_PS / 4); i += 32) {
+        const int r = i / (BRIEF_PS / 4), w = i - r * (BRIEF_PS / 4);
+        __pipeline_memcpy_async(sm + 4 * i, base + r * pitch + 4 * w, 4);
+    }
+    __pipeline_commit();
+}
+__device__ __forceinline__ uint32_t brief_byte(const uint8_t* center, float a, float b, int lane, const uint8_t* sm) {
+    const int al = (int)((uintptr_t)(center - BRIEF_R) & 3);
+    __pipeline_wait_prior(0);
+    __syncwarp();
+    const uint8_t* c = sm + BRIEF_R * BRIEF_PS + BRIEF_R + al;
     uint32_t val = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -156,10 +178,11 @@ __device__ __forceinline__ uint32_t brief_byte(const uint8_t* center, int pitch,
         const int q0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
         const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
         const int q1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-        const int t0 = __ldg(center + (long long)r0 * pitch + q0);
-        const int t1 = __ldg(center + (long long)r1 * pitch + q1);
+        const int t0 = c[r0 * BRIEF_PS + q0];
+        const int t1 = c[r1 * BRIEF_PS + q1];
         val |= (uint32_t)(t0 < t1) << k;
     }
+    __syncwarp();
     return val;
 }
 
@@ -179,6 +202,7 @@ k_orient_describe(PyrView pv, const LevelGeom* __restrict__ levels, int nlevels,
                   const uint8_t* __restrict__ blur, long long blur_fstride,
                   KpOut* __restrict__ kp_out, uint8_t* __restrict__ desc_out, int cap, int* __restrict__ counts_out,
                   int* __restrict__ level_counts_out) {
+    __shared__ __align__(16) uint8_t brief_sm[DESCRIBE ? 4 : 1][DESCRIBE ? BRIEF_ROWS * BRIEF_PS : 4];
     const int lane = threadIdx.x & 31;
     const int slot = blockIdx.x * 4 + (threadIdx.x >> 5);
     const int b = blockIdx.y;
@@ -201,13 +225,14 @@ k_orient_describe(PyrView pv, const LevelGeom* __restrict__ levels, int nlevels,
     const int x = (int)(p & 0xFFF) + g.minBX, y = (int)((p >> 12) & 0xFFF) + g.minBY;   // :1184-1185
     int pitch;
     const uint8_t* img = level_ptr(pv, g, level, b, pitch);
+    const uint8_t* bl = DESCRIBE ? blur + (long long)b * blur_fstride + g.off + (long long)y * g.pitch + x : nullptr;
+    if (DESCRIBE) brief_stage(bl, g.pitch, lane, brief_sm[threadIdx.x >> 5]);
     const float angle = ic_angle_warp(img + (long long)y * pitch + x, pitch, lane);
     if (DESCRIBE) {
         const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);      // :164
         float sn, cs;
         det_sincos(__fmul_rn(angle, factorPI), &sn, &cs);
-        const uint8_t* bl = blur + (long long)b * blur_fstride + g.off + (long long)y * g.pitch + x;
-        const uint32_t byte = brief_byte(bl, g.pitch, cs, sn, lane);
+        const uint32_t byte = brief_byte(bl, cs, sn, lane, brief_sm[threadIdx.x >> 5]);
         desc_out[((long long)b * cap + oi) * 32 + lane] = (uint8_t)byte;
     }
     if (lane == 0) {
@@ -225,6 +250,7 @@ __global__ void __launch_bounds__(128)
 k_describe_given(const LevelGeom* __restrict__ levels, int nlevels, const KpOut* __restrict__ kp_in, int n,
                  const uint8_t* __restrict__ blur, KpOut* __restrict__ kp_out, uint8_t* __restrict__ desc_out) {
     const int lane = threadIdx.x & 31;
+    __shared__ __align__(16) uint8_t brief_sm[4][BRIEF_ROWS * BRIEF_PS];
     const int i = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (i >= n) return;
     KpOut kp = kp_in[i];
@@ -235,7 +261,8 @@ k_describe_given(const LevelGeom* __restrict__ levels, int nlevels, const KpOut*
     det_sincos(__fmul_rn(kp.angle, factorPI), &sn, &cs);
     const int x = __float2int_rn(kp.x), y = __float2int_rn(kp.y);
     const uint8_t* bl = blur + g.off + (long long)y * g.pitch + x;
-    const uint32_t byte = brief_byte(bl, g.pitch, cs, sn, lane);
+    brief_stage(bl, g.pitch, lane, brief_sm[threadIdx.x >> 5]);
+    const uint32_t byte = brief_byte(bl, cs, sn, lane, brief_sm[threadIdx.x >> 5]);
     desc_out[(long long)i * 32 + lane] = (uint8_t)byte;
     if (lane == 0) {
         if (level != 0) { kp.x = __fmul_rn(kp.x, g.scale); kp.y = __fmul_rn(kp.y, g.scale); }

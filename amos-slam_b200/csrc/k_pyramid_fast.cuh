@@ -186,35 +186,45 @@ k_fast_cells(PyrView pv, const LevelGeom* __restrict__ levels, const CellDesc* _
         const uint32_t mfirst = 0xFFFFFFFFu << (8 * (pc0 & 3));
         const uint32_t mlast = 0xFFFFFFFFu >> (8 * (3 - ((pc0 + zw - 1) & 3)));
         const int ntask = zh * nw;
-        int y = lane / nw, w = lane - y * nw;                  // task = (row, word); each lane advances by 32 tasks per step
+        // task = (row, word); a lane handles tasks t0+lane and t0+32+lane per step (8 pixels), so one packed prefix sum
+        // orders 256 pixels in raster order
+        int ya = lane / nw, wa = lane - ya * nw;
         const int dy32 = 32 / nw, dw32 = 32 - dy32 * nw;
-        for (int t0 = 0; t0 < ntask; t0 += 32) {
-            uint32_t f = 0;
-            if (t0 + lane < ntask) {
-                const uint32_t* row = patch32 + (y + 3) * wpr + wi0 + w;
-                const uint32_t C = row[0], Cl = row[-1], Cr = row[1];
-                const uint32_t Nn = row[-3 * wpr], Ss = row[3 * wpr];
-                const uint32_t E = __byte_perm(C, Cr, 0x6543), Wn = __byte_perm(Cl, C, 0x4321);
-                const uint32_t u = (__vabsdiffu4(C, Nn) | __vabsdiffu4(C, Ss)) & keep;
-                const uint32_t v = (__vabsdiffu4(C, E) | __vabsdiffu4(C, Wn)) & keep;
-                f = swar_nz(u) & swar_nz(v);
-                if (w == 0) f &= mfirst;
-                if (w == nw - 1) f &= mlast;
-            }
-            const int cnt = __popc(f);
-            int incl = cnt;
+        int yb = ya + dy32, wb = wa + dw32;
+        if (wb >= nw) { wb -= nw; ++yb; }
+        const int dy64 = 64 / nw, dw64 = 64 - dy64 * nw;
+        auto compass = [&](int y, int w) -> uint32_t {
+            const uint32_t* row = patch32 + (y + 3) * wpr + wi0 + w;
+            const uint32_t C = row[0], Cl = row[-1], Cr = row[1];
+            const uint32_t Nn = row[-3 * wpr], Ss = row[3 * wpr];
+            const uint32_t E = __byte_perm(C, Cr, 0x6543), Wn = __byte_perm(Cl, C, 0x4321);
+            const uint32_t u = (__vabsdiffu4(C, Nn) | __vabsdiffu4(C, Ss)) & keep;
+            const uint32_t v = (__vabsdiffu4(C, E) | __vabsdiffu4(C, Wn)) & keep;
+            uint32_t f = swar_nz(u) & swar_nz(v);
+            if (w == 0) f &= mfirst;
+            if (w == nw - 1) f &= mlast;
+            return f;
+        };
+        auto emit = [&](uint32_t f, int pos, int y, int w) {
+            const int code = (y << 6) + (4 * (wi0 + w) - pc0);              // + not |: the first word may start left of the zone (negative x of byte 0)
+            if (f & 0x00000080u) queue[pos++] = (uint16_t)code;
+            if (f & 0x00008000u) queue[pos++] = (uint16_t)(code + 1);
+            if (f & 0x00800000u) queue[pos++] = (uint16_t)(code + 2);
+            if (f & 0x80000000u) queue[pos] = (uint16_t)(code + 3);
+        };
+        for (int t0 = 0; t0 < ntask; t0 += 64) {
+            const uint32_t fa = (t0 + lane < ntask) ? compass(ya, wa) : 0u;
+            const uint32_t fb = (t0 + 32 + lane < ntask) ? compass(yb, wb) : 0u;
+            const int ca = __popc(fa), cb = __popc(fb);
+            int incl = ca | (cb << 16);
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += n; }
-            int pos = qn + incl - cnt;
-            const int xb = 4 * (wi0 + w) - pc0;
-            while (f) {
-                const int j = (__ffs(f) - 1) >> 3;
-                f &= f - 1;
-                queue[pos++] = (uint16_t)((y << 6) | (xb + j));
-            }
-            qn += __shfl_sync(0xffffffffu, incl, 31);
-            y += dy32; w += dw32;
-            if (w >= nw) { w -= nw; ++y; }
+            const int tot = __shfl_sync(0xffffffffu, incl, 31);
+            emit(fa, qn + (incl & 0xFFFF) - ca, ya, wa);
+            emit(fb, qn + (tot & 0xFFFF) + (incl >> 16) - cb, yb, wb);
+            qn += (tot & 0xFFFF) + (tot >> 16);
+            ya += dy64; wa += dw64; if (wa >= nw) { wa -= nw; ++ya; }
+            yb += dy64; wb += dw64; if (wb >= nw) { wb -= nw; ++yb; }
         }
     }
     __syncwarp();
