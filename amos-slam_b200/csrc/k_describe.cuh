@@ -104,8 +104,7 @@ k_gauss7(PyrView pv, const LevelGeom* __restrict__ levels, const BlurTile* __res
 // keypoint, lane = column u in [-15,15], loop over the 31 rows (coalesced 31-byte row reads), integer
 // moments reduced with shuffles, angle = fastAtan2((float)m01, (float)m10) in degrees.
 // =================================================================================================
-__constant__ int c_umax[16];             // [15,15,15,15,14,14,14,13,13,12,11,10,9,8,6,3]
-__constant__ char4 c_pattern_t[8 * 32];  // rBRIEF pairs, transposed: [bit k][byte i] = (x0,y0,x1,y1) of pair 8*i+k
+__device__ char4 g_pattern_t[8 * 32];    // rBRIEF pairs, transposed: [bit k][byte i] = (x0,y0,x1,y1) of pair 8*i+k
 
 // dot product of 4 unsigned bytes (pixels) with 4 signed bytes (weights)
 __device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {
@@ -151,27 +150,29 @@ __device__ __forceinline__ float ic_angle_warp(const uint8_t* center, int pitch,
 // random byte gathers cost shared-memory bank cycles instead of one L1 wavefront per lane.
 #define BRIEF_R 18
 #define BRIEF_ROWS (2 * BRIEF_R + 1)
-#define BRIEF_PS 40
-// asynchronous staging (LDGSTS): issued before the orientation is computed so that the copy overlaps IC_Angle
+#define BRIEF_PS 80                  // bytes per staged row: 64 (4 x 16-byte chunks cover 37 px at any alignment) + 16 padding to spread banks
+// asynchronous staging (LDGSTS.128): issued before the orientation is computed so that the copy overlaps IC_Angle
 __device__ __forceinline__ void brief_stage(const uint8_t* center, int pitch, int lane, uint8_t* sm) {
     const uint8_t* row0 = center - BRIEF_R;
-    const int al = (int)((uintptr_t)row0 & 3);
-    const uint8_t* base = row0 - al - BRIEF_R * pitch;
-    for (int i = lane; i < BRIEF_ROWS * (BRIEF_PS / 4); i += 32) {
-        const int r = i / (BRIEF_PS / 4), w = i - r * (BRIEF_PS / 4);
-        __pipeline_memcpy_async(sm + 4 * i, base + r * pitch + 4 * w, 4);
+    const int al = (int)((uintptr_t)row0 & 15);
+    const uint8_t* base = row0 - al - BRIEF_R * pitch + 16 * (lane & 3);
+    uint8_t* dst = sm + 16 * (lane & 3);
+#pragma unroll
+    for (int it = 0; it < (BRIEF_ROWS * 4 + 31) / 32; ++it) {
+        const int r = it * 8 + (lane >> 2);
+        if (r < BRIEF_ROWS) __pipeline_memcpy_async(dst + r * BRIEF_PS, base + r * pitch, 16);
     }
     __pipeline_commit();
 }
 __device__ __forceinline__ uint32_t brief_byte(const uint8_t* center, float a, float b, int lane, const uint8_t* sm) {
-    const int al = (int)((uintptr_t)(center - BRIEF_R) & 3);
+    const int al = (int)((uintptr_t)(center - BRIEF_R) & 15);
     __pipeline_wait_prior(0);
     __syncwarp();
     const uint8_t* c = sm + BRIEF_R * BRIEF_PS + BRIEF_R + al;
     uint32_t val = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const char4 pt = c_pattern_t[k * 32 + lane];
+        const char4 pt = g_pattern_t[k * 32 + lane];                      // coalesced (a lane-indexed __constant__ read would serialise 32-way)
         const float x0 = (float)pt.x, y0 = (float)pt.y, x1 = (float)pt.z, y1 = (float)pt.w;
         // center[cvRound(x*b + y*a)*step + cvRound(x*a - y*b)], unfused, round-half-even
         const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));

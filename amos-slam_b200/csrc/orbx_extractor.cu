@@ -383,14 +383,12 @@ static int check_args(orbx_extractor* h, const void* image, int rows, int cols, 
 
 static int upload_constants() {
     // __constant__ tables are per-device module state; upload on every create (cheap, idempotent)
-    const int um[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
     char4 pt[8 * 32];
     for (int i = 0; i < 32; ++i) for (int k = 0; k < 8; ++k) {
         const signed char* p = k_brief_pattern_host + (size_t)(8 * i + k) * 4;
         pt[k * 32 + i] = make_char4(p[0], p[1], p[2], p[3]);
     }
-    CU_TRY(cudaMemcpyToSymbol(c_umax, um, sizeof(um)));
-    CU_TRY(cudaMemcpyToSymbol(c_pattern_t, pt, sizeof(pt)));
+    CU_TRY(cudaMemcpyToSymbol(g_pattern_t, pt, sizeof(pt)));
     return ORBX_OK;
 }
 
