@@ -98,6 +98,7 @@ def lib():
         L.orbx_search_by_projection_points.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp, vp, vp, cf, vp, C.POINTER(ci)]
         L.orbx_compute_stereo_matches.argtypes = [vp, vp, vp, vp, vp, ci, vp, vp, ci, cf, cf, vp, vp]
         L.orbx_match_bruteforce_device.argtypes = [vp, vp, ci, vp, ci, vp, vp, vp]
+        L.orbx_match_bruteforce_batch_device.argtypes = [vp, ci, vp, ci, vp, ci, vp, vp, vp]
     _lib = L
     return L
 

@@ -129,3 +129,8 @@ class ORBmatcher:
     def match_bruteforce_device(self, d_query_ptr, n_query, d_train_ptr, n_train, d_best_idx_ptr, d_best_dist_ptr, d_second_dist_ptr):
         self._check(self._lib.orbx_match_bruteforce_device(self._h, C.c_void_p(d_query_ptr), n_query, C.c_void_p(d_train_ptr), n_train,
                                                            C.c_void_p(d_best_idx_ptr), C.c_void_p(d_best_dist_ptr), C.c_void_p(d_second_dist_ptr)))
+
+    def match_bruteforce_batch_device(self, n_pairs, d_query_ptr, n_query, d_train_ptr, n_train, d_best_idx_ptr, d_best_dist_ptr, d_second_dist_ptr):
+        """n_pairs independent frame pairs in one launch (device pointers, asynchronous on .stream)."""
+        self._check(self._lib.orbx_match_bruteforce_batch_device(self._h, int(n_pairs), C.c_void_p(d_query_ptr), n_query, C.c_void_p(d_train_ptr), n_train,
+                                                                 C.c_void_p(d_best_idx_ptr), C.c_void_p(d_best_dist_ptr), C.c_void_p(d_second_dist_ptr)))

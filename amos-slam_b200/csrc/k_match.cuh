@@ -500,6 +500,9 @@ k_stereo_median_cut(int nl, const int* __restrict__ sad_dist, float* __restrict_
 __global__ void __launch_bounds__(256)
 k_bruteforce_best2(const uint4* __restrict__ query, int nq, const uint4* __restrict__ train, int nt,
                    int* __restrict__ best_idx, int* __restrict__ best_dist, int* __restrict__ second_dist) {
+    // blockIdx.y = frame pair of a batch: pair p matches query[p*nq ..] against train[p*nt ..]
+    query += 2 * (size_t)blockIdx.y * nq; train += 2 * (size_t)blockIdx.y * nt;
+    best_idx += (size_t)blockIdx.y * nq; best_dist += (size_t)blockIdx.y * nq; second_dist += (size_t)blockIdx.y * nq;
     __shared__ uint4 tile[BF_TILE * 2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int q = blockIdx.x * 8 + warp;

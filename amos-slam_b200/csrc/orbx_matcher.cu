@@ -291,11 +291,15 @@ int orbx_compute_stereo_matches(orbx_matcher* m, orbx_extractor* left, orbx_extr
 }
 
 int orbx_match_bruteforce_device(orbx_matcher* m, const uint8_t* d_query, int n_query, const uint8_t* d_train, int n_train, int* d_best_idx, int* d_best_dist, int* d_second_dist) {
-    if (!m || n_query < 0 || n_train < 0 || n_train >= (1 << 20) || !d_query || !d_train || !d_best_idx || !d_best_dist || !d_second_dist) FAIL(ORBX_E_INVALID, "bad arguments");
+    return orbx_match_bruteforce_batch_device(m, 1, d_query, n_query, d_train, n_train, d_best_idx, d_best_dist, d_second_dist);
+}
+
+int orbx_match_bruteforce_batch_device(orbx_matcher* m, int n_pairs, const uint8_t* d_query, int n_query, const uint8_t* d_train, int n_train, int* d_best_idx, int* d_best_dist, int* d_second_dist) {
+    if (!m || n_pairs < 0 || n_pairs > 65535 || n_query < 0 || n_train < 0 || n_train >= (1 << 20) || !d_query || !d_train || !d_best_idx || !d_best_dist || !d_second_dist) FAIL(ORBX_E_INVALID, "bad arguments");
     if (((uintptr_t)d_query & 15) || ((uintptr_t)d_train & 15)) FAIL(ORBX_E_INVALID, "descriptor arrays must be 16-byte aligned");
-    if (n_query == 0) return ORBX_OK;
+    if (n_query == 0 || n_pairs == 0) return ORBX_OK;
     CU_TRY(cudaSetDevice(m->device));
-    k_bruteforce_best2<<<(n_query + 7) / 8, 256, 0, m->stream>>>(reinterpret_cast<const uint4*>(d_query), n_query, reinterpret_cast<const uint4*>(d_train), n_train, d_best_idx, d_best_dist, d_second_dist);
+    k_bruteforce_best2<<<dim3((n_query + 7) / 8, n_pairs), 256, 0, m->stream>>>(reinterpret_cast<const uint4*>(d_query), n_query, reinterpret_cast<const uint4*>(d_train), n_train, d_best_idx, d_best_dist, d_second_dist);
     LAUNCH_CHECK();
     return ORBX_OK;
 }

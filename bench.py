@@ -144,6 +144,44 @@ def cpu_reference_run(seconds_budget, frames, threads=None, steps=None, frames_p
             "kind": "reference" if kind == "ref" else "port", "step_times": step_times}
 
 
+def matcher_bench(orbx, torch, ext, frames, device):
+    """Second half of BASELINE's metric: Hamming matches/s.  (a) batched brute-force best/second-best over P frame pairs of
+    1000 x 1000 descriptors resident in HBM (distance evaluations/s, pairs/s); (b) ORBmatcher::SearchForInitialization through
+    the host-pointer C-ABI call on two extracted frames (pairs/s, H2D/D2H of keypoints + descriptors included)."""
+    P, NQ = 256, 1000
+    g = torch.Generator(device="cuda"); g.manual_seed(7)
+    q = torch.randint(0, 256, (P, NQ, 32), dtype=torch.uint8, device="cuda", generator=g)
+    t = torch.randint(0, 256, (P, NQ, 32), dtype=torch.uint8, device="cuda", generator=g)
+    bi = torch.empty((P, NQ), dtype=torch.int32, device="cuda"); bd = torch.empty_like(bi); sd = torch.empty_like(bi)
+    m = orbx.ORBmatcher(0.9, True, device=device)
+    st = torch.cuda.ExternalStream(m.stream)
+    call = lambda: m.match_bruteforce_batch_device(P, q.data_ptr(), NQ, t.data_ptr(), NQ, bi.data_ptr(), bd.data_ptr(), sd.data_ptr())
+    for _ in range(3):
+        call()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    e0.record(st)
+    for _ in range(reps):
+        call()
+    e1.record(st)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    kp_a, d_a = ext(frames[0]); kp_b, d_b = ext(frames[1])
+    sf = ext.GetScaleFactors()
+    FA, FB = orbx.FrameView(kp_a, d_a, WIDTH, HEIGHT, sf), orbx.FrameView(kp_b, d_b, WIDTH, HEIGHT, sf)
+    prev = np.stack([kp_a["x"], kp_a["y"]], 1)
+    for _ in range(3):
+        m.SearchForInitialization(FA, FB, prev, 100)
+    t0 = time.perf_counter(); reps2 = 50
+    for _ in range(reps2):
+        m.SearchForInitialization(FA, FB, prev, 100)
+    dt = (time.perf_counter() - t0) / reps2
+    return {"bruteforce_pairs_per_s": P / (ms * 1e-3), "hamming_distances_per_s": P * NQ * NQ / (ms * 1e-3),
+            "bruteforce_config": "%d pairs x %d x %d descriptors per launch, device-resident" % (P, NQ, NQ),
+            "search_for_initialization_pairs_per_s": 1.0 / dt, "search_for_initialization_config": "host-pointer call, window 100, one pair per call (latency-bound)"}
+
+
 def cpu_model():
     try:
         for line in open("/proc/cpuinfo"):
@@ -260,6 +298,8 @@ def main():
     ms_e2e = max(g0.elapsed_time(g1), 1e3 * (time.perf_counter() - t0))   # host call is synchronous: wall clock >= device clock
     sampler.stop_flag = True; sampler.join(timeout=2)
 
+    matcher_line = matcher_bench(orbx, torch, ext, frames, local_rank) if rank == 0 else None
+
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -285,18 +325,28 @@ def main():
     dom_bytes_per_launch = sb[dom] * B / launches_of.get(dom, 1)
     achieved = dom_bytes_per_launch / (dom_ms_per_launch * 1e-3) / 1e9
     total_stage = sum(stage_ms.values())
+    # DRAM traffic of the dominant kernel: dram__bytes_read.sum + dram__bytes_write.sum per frame from the committed ncu --set full
+    # capture (profiles/traffic.json, written by tools/profile_digest.py), scaled to this launch's frame count
+    kernel_of = {"pyr_resize": "k_pyr_resize_w", "fast_cells": "k_fast_cells", "octree_sort": "k_octree_sort", "octree_tree": "k_octree_tree",
+                 "gauss7": "k_gauss7", "orient_describe": "k_orient_describe"}
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj["dram_bytes_per_frame"][kernel_of[dom]] * B / launches_of.get(dom, 1)
+    except Exception:
+        pass
     line = {"metric": "ORB extract frames/sec @640x480 1000 feat", "value": value, "unit": "frames/s", "n_gpus": N, "steps": K, "warmup": max(W, 3),
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": config,
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(B * WIDTH * HEIGHT), "d2h_bytes_per_step": int(B * cap * 60 + 4 * B + 4), "steps": Ke},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes_per_launch, "ms_per_launch": dom_ms_per_launch,
                          "stage_ms_per_step": {k: v / max(ncalls, 1) for k, v in stage_ms.items()},
                          "stage_share": {k: (v / total_stage if total_stage else 0.0) for k, v in stage_ms.items()},
                          "whole_step_algorithmic_GBps": (2 * sum(level_pixels()) + 60 * n_kp) * B * K / (ms * 1e-3) / 1e9},
-            "keypoints_per_frame": n_kp}
+            "keypoints_per_frame": n_kp, "matcher": matcher_line}
     if N == 1 and not args.no_cpu_baseline:
         res = cpu_reference_run(args.cpu_seconds, frames[:64])
         line["cpu_baseline"] = {"value": res["fps"], "unit": "frames/s", "cores": res["threads"], "kind": res["kind"],

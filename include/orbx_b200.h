@@ -242,6 +242,10 @@ int orbx_compute_stereo_matches(orbx_matcher* m, orbx_extractor* left, orbx_extr
  * throughput measurement):  for every query q: best_idx, best_dist, second_dist over all n_train rows. */
 int orbx_match_bruteforce_device(orbx_matcher* m, const uint8_t* d_query, int n_query, const uint8_t* d_train,
                                  int n_train, int* d_best_idx, int* d_best_dist, int* d_second_dist);
+/* The same for n_pairs independent frame pairs in one launch: pair p matches d_query[p][n_query][32] against
+ * d_train[p][n_train][32]; outputs are [n_pairs][n_query].  Asynchronous on orbx_matcher_stream(m). */
+int orbx_match_bruteforce_batch_device(orbx_matcher* m, int n_pairs, const uint8_t* d_query, int n_query, const uint8_t* d_train,
+                                       int n_train, int* d_best_idx, int* d_best_dist, int* d_second_dist);
 
 #ifdef __cplusplus
 }

@@ -101,3 +101,22 @@ def test_bruteforce_best2_properties(orbx, case):
     D = np.unpackbits(case["da"][:, None, :] ^ case["db"][None, :, :], axis=2).sum(2)
     assert np.array_equal(bi.cpu().numpy(), D.argmin(1)) and np.array_equal(bd.cpu().numpy(), D.min(1))     # first index wins ties
     assert np.array_equal(sd.cpu().numpy(), np.sort(D, axis=1)[:, 1])
+
+
+def test_bruteforce_batch_pairs(orbx, case):
+    """n_pairs frame pairs in one launch == the single-pair call per pair."""
+    import torch
+    m = orbx.ORBmatcher()
+    rng = np.random.default_rng(5)
+    P, nq, nt = 3, 257, 300
+    Q = rng.integers(0, 256, (P, nq, 32), dtype=np.uint8); T = rng.integers(0, 256, (P, nt, 32), dtype=np.uint8)
+    T[1, 7] = Q[1, 100]; T[1, 9] = Q[1, 100]                                     # exact duplicates: first index wins, second distance 0
+    q = torch.from_numpy(Q).cuda(); t = torch.from_numpy(T).cuda()
+    bi = torch.empty((P, nq), dtype=torch.int32, device="cuda"); bd = torch.empty_like(bi); sd = torch.empty_like(bi)
+    m.match_bruteforce_batch_device(P, q.data_ptr(), nq, t.data_ptr(), nt, bi.data_ptr(), bd.data_ptr(), sd.data_ptr())
+    torch.cuda.synchronize()
+    for p in range(P):
+        D = np.unpackbits(Q[p][:, None, :] ^ T[p][None, :, :], axis=2).sum(2)
+        assert np.array_equal(bi[p].cpu().numpy(), D.argmin(1)) and np.array_equal(bd[p].cpu().numpy(), D.min(1))
+        assert np.array_equal(sd[p].cpu().numpy(), np.sort(D, axis=1)[:, 1])
+    assert bi[1, 100].item() == 7 and bd[1, 100].item() == 0 and sd[1, 100].item() == 0
