@@ -519,11 +519,13 @@ int orbx_extract_batch_device(orbx_extractor* h, const uint8_t* d_images, int B,
     if (h->profiling) {                                  // per-stage timing wants the stages back to back on one stream
         if ((rc = run_detect(h, 0, B))) return rc;
         if ((rc = run_blur(h, B))) return rc;
-    } else {
-        if ((rc = run_detect(h, 0, B, true))) return rc;
-        CU_TRY(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
-        h->blur_valid = true;
+        return run_orient(h, 0, B, true, reinterpret_cast<KpOut*>(d_kp_out), d_desc_out, cap, d_counts_out, nullptr);
     }
+    // one pass; the blur is forked next to FAST / quadtree.  (Chunking the batch over the two compute streams, as the host
+    // path does, was measured and gains nothing here: every kernel already fills the GPU.)
+    if ((rc = run_detect(h, 0, B, true))) return rc;
+    CU_TRY(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+    h->blur_valid = true;
     return run_orient(h, 0, B, true, reinterpret_cast<KpOut*>(d_kp_out), d_desc_out, cap, d_counts_out, nullptr);
 }
 
