@@ -40,6 +40,11 @@ __device__ __forceinline__ uint32_t octree_code(int x, int y, const LevelGeom& g
 }
 
 #define SORT_THREADS 256
+#define SORT_WARPS (SORT_THREADS / 32)
+
+// Shared-memory layout of the radix path for `cap` keys: key ping/pong (u32), index ping/pong (u16), per-warp digit
+// histograms (u16 [SORT_WARPS][256]).
+__host__ __device__ inline size_t octree_sort_smem_bytes(int cap) { return (size_t)cap * 12 + SORT_WARPS * 256 * 2 + 64; }
 
 __global__ void __launch_bounds__(SORT_THREADS)
 k_octree_sort(const LevelGeom* __restrict__ levels, const CellDesc* __restrict__ cells, int ncells,
@@ -49,10 +54,10 @@ k_octree_sort(const LevelGeom* __restrict__ levels, const CellDesc* __restrict__
               unsigned long long* __restrict__ skey, // [B][cand_per_frame] sorted (code<<32 | index)
               uint32_t* __restrict__ spk,            // [B][cand_per_frame] packed candidate per sorted position
               int* __restrict__ ncand) {             // [B][nlevels]
-    extern __shared__ __align__(16) unsigned long long skeys_sm[];
-    __shared__ int warp_sums[SORT_THREADS / 32];
+    extern __shared__ __align__(16) uint8_t sort_sm[];
+    __shared__ int warp_sums[SORT_WARPS];
     __shared__ int total_sm;
-    const int level = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const int level = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const LevelGeom& g = levels[level];
     const uint16_t* counts = cell_counts + (long long)b * ncells + g.cell_begin;
     const uint32_t* slots = cand_slots + (long long)b * slots_per_frame;
@@ -67,36 +72,112 @@ k_octree_sort(const LevelGeom* __restrict__ levels, const CellDesc* __restrict__
     for (int c = c0; c < c1; ++c) mine += counts[c];
     int incl = mine;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += v; }
-    if ((tid & 31) == 31) warp_sums[tid >> 5] = incl;
+    for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) warp_sums[warp] = incl;
     __syncthreads();
     if (tid < 32) {
-        int w = tid < SORT_THREADS / 32 ? warp_sums[tid] : 0;
+        int w = tid < SORT_WARPS ? warp_sums[tid] : 0;
         int wi = w;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, wi, o); if (tid >= o) wi += v; }
-        if (tid < SORT_THREADS / 32) warp_sums[tid] = wi - w;
-        if (tid == SORT_THREADS / 32 - 1) total_sm = wi;
+        if (tid < SORT_WARPS) warp_sums[tid] = wi - w;
+        if (tid == SORT_WARPS - 1) total_sm = wi;
     }
     __syncthreads();
     const int n = total_sm;
-    const bool in_smem = n <= smem_keys;
-    unsigned long long* sk = in_smem ? skeys_sm : sk_g;
     if (n > g.cand_cap) { if (tid == 0) ncand[b * nlevels + level] = -1; return; }   // cannot happen (cap is the worst case)
-    int pos = warp_sums[tid >> 5] + incl - mine;
-    for (int c = c0; c < c1; ++c) {
+    const bool radix = n <= smem_keys;
+    uint32_t* keyA = reinterpret_cast<uint32_t*>(sort_sm);
+    uint32_t* keyB = keyA + smem_keys;
+    uint16_t* idxA = reinterpret_cast<uint16_t*>(keyB + smem_keys);
+    uint16_t* idxB = idxA + smem_keys;
+    uint16_t* hist = idxB + smem_keys;                                   // [SORT_WARPS][256]
+    int pos = warp_sums[warp] + incl - mine;
+    for (int c = c0; c < c1; ++c) {                                      // ordered copy only (few threads own cells) ...
         const int cnt = counts[c];
         const uint32_t* src = slots + cells[g.cell_begin + c].slot;
-        for (int k = 0; k < cnt; ++k, ++pos) {
-            const uint32_t p = src[k];
-            oc[pos] = p;
-            const uint32_t code = octree_code((int)(p & 0xFFF), (int)((p >> 12) & 0xFFF), g);
-            sk[pos] = ((unsigned long long)code << 32) | (unsigned)pos;
-        }
+        for (int k = 0; k < cnt; ++k, ++pos) oc[pos] = src[k];
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += SORT_THREADS) {                        // ... the path codes are computed by all threads
+        const uint32_t p = oc[i];
+        const uint32_t code = octree_code((int)(p & 0xFFF), (int)((p >> 12) & 0xFFF), g);
+        if (radix) { keyA[i] = code; idxA[i] = (uint16_t)i; }
+        else sk_g[i] = ((unsigned long long)code << 32) | (unsigned)i;
     }
     __syncthreads();
 
-    // ---- bitonic sort, all-ascending formulation (works for any n, no padding) ----
+    if (radix) {
+        // ---- stable LSD radix sort on the path code, 8 bits per pass.  Digits below the depth at which a node is one
+        // pixel wide are constant (both halves of a 1-px interval send every key left), so they are skipped. ----
+        const int span = max(g.maxBX - g.minBX, g.maxBY - g.minBY);
+        int nd = 1; while ((1 << nd) < span && nd < ORBX_MAXD) ++nd;     // an interval is one pixel wide after ceil(log2(span)) splits
+        nd = min(nd + 2, ORBX_MAXD);                                     // + 2: keys the float root assignment put just outside their root interval settle one level later
+        const int low = 2 * (ORBX_MAXD - nd);                            // constant low bits
+        int rootbits = 0; while ((1 << rootbits) < g.nIni) ++rootbits;
+        const int nbits = 2 * nd + rootbits;
+        const int seg = (n + SORT_WARPS - 1) / SORT_WARPS;               // contiguous segment per warp keeps the sort stable
+        const int s0 = min(warp * seg, n), s1 = min(s0 + seg, n);
+        const uint32_t lt = (1u << lane) - 1u;
+        uint16_t* myhist = hist + warp * 256;
+        for (int shift = low; shift < low + nbits; shift += 8) {
+            for (int i = lane; i < 256; i += 32) myhist[i] = 0;
+            __syncwarp();
+            for (int i0 = s0; i0 < s1; i0 += 32) {
+                const int i = i0 + lane;
+                const bool act = i < s1;
+                const uint32_t d = act ? ((keyA[i] >> shift) & 255u) : 256u;
+                const uint32_t peers = __match_any_sync(0xffffffffu, d);
+                if (act && (peers & lt) == 0) myhist[d] += (uint16_t)__popc(peers);      // one leader per digit value
+                __syncwarp();
+            }
+            __syncthreads();
+            {   // offsets: digit-major, warp-minor exclusive scan; thread d owns digit d
+                int tot = 0;
+                int part[SORT_WARPS];
+#pragma unroll
+                for (int w = 0; w < SORT_WARPS; ++w) { part[w] = tot; tot += hist[w * 256 + tid]; }
+                int inc = tot;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+                if (lane == 31) warp_sums[warp] = inc;
+                __syncthreads();
+                int basew = 0;
+#pragma unroll
+                for (int w = 0; w < SORT_WARPS; ++w) if (w < warp) basew += warp_sums[w];
+                const int excl = basew + inc - tot;
+#pragma unroll
+                for (int w = 0; w < SORT_WARPS; ++w) hist[w * 256 + tid] = (uint16_t)(excl + part[w]);
+            }
+            __syncthreads();
+            for (int i0 = s0; i0 < s1; i0 += 32) {
+                const int i = i0 + lane;
+                const bool act = i < s1;
+                const uint32_t k = act ? keyA[i] : 0u;
+                const uint32_t d = act ? ((k >> shift) & 255u) : 256u;
+                const uint32_t peers = __match_any_sync(0xffffffffu, d);
+                int dst = 0;
+                if (act) dst = myhist[d] + __popc(peers & lt);
+                __syncwarp();
+                if (act && (peers & lt) == 0) myhist[d] += (uint16_t)__popc(peers);
+                if (act) { keyB[dst] = k; idxB[dst] = idxA[i]; }
+                __syncwarp();
+            }
+            __syncthreads();
+            uint32_t* tk = keyA; keyA = keyB; keyB = tk;
+            uint16_t* ti = idxA; idxA = idxB; idxB = ti;
+        }
+        for (int i = tid; i < n; i += SORT_THREADS) {
+            const unsigned oi = idxA[i];
+            sk_g[i] = ((unsigned long long)keyA[i] << 32) | oi;
+            sp[i] = oc[oi];
+        }
+        if (tid == 0) ncand[b * nlevels + level] = n;
+        return;
+    }
+
+    // ---- oversized level: bitonic sort in global memory, all-ascending formulation (works for any n, no padding) ----
+    unsigned long long* sk = sk_g;
     for (int k = 2; (k >> 1) < n; k <<= 1) {
         for (int i = tid; i < n; i += SORT_THREADS) {          // first substage: mirror partner
             const int j = i ^ (k - 1);
@@ -111,11 +192,7 @@ k_octree_sort(const LevelGeom* __restrict__ levels, const CellDesc* __restrict__
             __syncthreads();
         }
     }
-    for (int i = tid; i < n; i += SORT_THREADS) {
-        const unsigned long long v = sk[i];
-        if (in_smem) sk_g[i] = v;
-        sp[i] = oc[(unsigned)(v & 0xFFFFFFFFull)];
-    }
+    for (int i = tid; i < n; i += SORT_THREADS) sp[i] = oc[(unsigned)(sk[i] & 0xFFFFFFFFull)];
     if (tid == 0) ncand[b * nlevels + level] = n;
 }
 

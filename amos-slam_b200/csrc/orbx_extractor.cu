@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -59,6 +60,7 @@ struct orbx_extractor {
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;   // copy engines of the host-pointer batch call (overlap with compute)
     cudaStream_t s_alt = nullptr;                    // second compute stream: odd chunks of the host batch call run here, so the
                                                      // latency-bound quadtree kernels of one chunk overlap the stencils of the next
+    cudaStream_t s_more[2] = {nullptr, nullptr};     // third / fourth compute stream of the host batch call
     cudaStream_t cur = nullptr;                      // stream the run_* helpers launch on (stream or s_alt)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::vector<cudaEvent_t> ev_h2d, ev_done;        // one pair per chunk
@@ -228,6 +230,9 @@ static int build_plan(orbx_extractor* h, int rows, int cols) {
     h->max_kp = 0; for (int l = 0; l < L; ++l) h->max_kp += h->levels[l].kp_cap;
     h->fast_smem_per_warp = align_up(smem_pw, 16);
     h->tree_cap = tree_cap;
+    // radix-sort capacity per (level, frame): ~1 candidate per 100 px of level 0 is generous for real images; larger levels fall back
+    // to the global-memory bitonic path inside the kernel
+    { int k = 4096; while (k < (rows * cols) / 100 && k < 16384) k *= 2; h->sort_smem_keys = k; }
     h->rows = rows; h->cols = cols; h->Bcap = 0; h->have_pyramid = false;
     return ORBX_OK;
 }
@@ -310,7 +315,7 @@ static int run_detect(orbx_extractor* h, int b0, int B, bool fork_blur = false) 
     prof_mark(h);
     {
         dim3 grid(L, B);
-        k_octree_sort<<<grid, SORT_THREADS, (size_t)h->sort_smem_keys * 8, s>>>(h->d_levels.p, h->d_cells.p, ncells, h->cand_per_frame, h->cand_per_frame, L,
+        k_octree_sort<<<grid, SORT_THREADS, octree_sort_smem_bytes(h->sort_smem_keys), s>>>(h->d_levels.p, h->d_cells.p, ncells, h->cand_per_frame, h->cand_per_frame, L,
                                                                                  h->sort_smem_keys, slots, cell_counts, h->d_ocand.p + co, h->d_skey.p + co, h->d_spk.p + co, h->d_ncand.p + (size_t)b0 * L);
         LAUNCH_CHECK();
         prof_mark(h);
@@ -422,11 +427,12 @@ int orbx_create(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, in
     h->cur = h->stream;
     cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
     if (cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&h->s_alt, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaStreamCreateWithFlags(&h->s_alt, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->s_more[0], cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&h->s_more[1], cudaStreamNonBlocking) != cudaSuccess) {
         cudaStreamDestroy(h->stream); delete h; FAIL(ORBX_E_CUDA, "cudaStreamCreate (copy streams)");
     }
     if (upload_constants() != ORBX_OK) { cudaStreamDestroy(h->stream); cudaStreamDestroy(h->s_h2d); cudaStreamDestroy(h->s_d2h); delete h; return ORBX_E_CUDA; }
-    cudaFuncSetAttribute(k_octree_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+    cudaFuncSetAttribute(k_octree_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)octree_sort_smem_bytes(16384));
     cudaFuncSetAttribute(k_octree_tree, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     *out = h;
@@ -440,6 +446,7 @@ void orbx_destroy(orbx_extractor* h) {
     if (h->s_h2d) { cudaStreamSynchronize(h->s_h2d); cudaStreamDestroy(h->s_h2d); }
     if (h->s_d2h) { cudaStreamSynchronize(h->s_d2h); cudaStreamDestroy(h->s_d2h); }
     if (h->s_alt) { cudaStreamSynchronize(h->s_alt); cudaStreamDestroy(h->s_alt); }
+    for (cudaStream_t x : h->s_more) if (x) { cudaStreamSynchronize(x); cudaStreamDestroy(x); }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     for (cudaEvent_t e : h->ev_h2d) cudaEventDestroy(e);
@@ -534,7 +541,8 @@ int orbx_extract_batch_device(orbx_extractor* h, const uint8_t* d_images, int B,
 // kernels of chunk i.  Pinned host buffers give true overlap; pageable ones still work (the copies then serialise).
 static int chunk_frames(const orbx_extractor* h, int B) {
     const long long px = (long long)h->rows * h->cols;
-    long long c = (64LL * 640 * 480 + px - 1) / px;          // ~64 VGA frames (20 MB) per chunk
+    static const int tune = [] { const char* e = std::getenv("ORBX_CHUNK_FRAMES"); return e ? std::atoi(e) : 0; }();   // tuning knob (VGA-equivalent frames per chunk)
+    long long c = ((tune > 0 ? tune : 64) * 640LL * 480 + px - 1) / px;          // default ~64 VGA frames (20 MB) per chunk
     if (c < 1) c = 1;
     if (c > B) c = B;
     return (int)c;
@@ -566,7 +574,9 @@ int orbx_extract_batch(orbx_extractor* h, const uint8_t* images, int B, int rows
     // the copy streams must not run ahead of work already queued on the compute stream (e.g. a previous call's kernels)
     CU_TRY(cudaEventRecord(h->ev_done[0], h->stream));
     CU_TRY(cudaStreamWaitEvent(h->s_h2d, h->ev_done[0], 0));
-    CU_TRY(cudaStreamWaitEvent(h->s_alt, h->ev_done[0], 0));
+    static const int nstreams = [] { const char* e = std::getenv("ORBX_HOST_STREAMS"); int v = e ? std::atoi(e) : 3; return v < 1 ? 1 : (v > 4 ? 4 : v); }();
+    cudaStream_t cs[4] = {h->stream, h->s_alt, h->s_more[0], h->s_more[1]};
+    for (int i = 1; i < nstreams; ++i) CU_TRY(cudaStreamWaitEvent(cs[i], h->ev_done[0], 0));
     for (int c = 0; c < nchunks; ++c) {
         const int b0 = c * C, nb = std::min(C, B - b0);
         if (mirror) {
@@ -582,7 +592,7 @@ int orbx_extract_batch(orbx_extractor* h, const uint8_t* images, int B, int rows
     }
     for (int c = 0; c < nchunks; ++c) {
         const int b0 = c * C, nb = std::min(C, B - b0);
-        h->cur = (c & 1) ? h->s_alt : h->stream;
+        h->cur = cs[c % nstreams];
         CU_TRY(cudaStreamWaitEvent(h->cur, h->ev_h2d[c], 0));
         rc = run_detect(h, b0, nb);
         if (!rc) rc = run_blur_range(h, b0, nb);
@@ -599,7 +609,7 @@ int orbx_extract_batch(orbx_extractor* h, const uint8_t* images, int B, int rows
     h->lastB = B; h->blur_valid = true;
     int ovf = 0;
     CU_TRY(cudaStreamSynchronize(h->s_d2h));            // follows every chunk's kernels (ev_done) and copies
-    CU_TRY(cudaStreamSynchronize(h->s_alt));
+    for (int i = 1; i < nstreams; ++i) CU_TRY(cudaStreamSynchronize(cs[i]));
     CU_TRY(cudaMemcpyAsync(&ovf, h->d_overflow.p, 4, cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(cudaStreamSynchronize(h->stream));
     if (ovf) FAIL(ORBX_E_OVERFLOW, "internal bound exceeded in the quadtree stage");
