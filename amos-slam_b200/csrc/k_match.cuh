@@ -249,40 +249,85 @@ __device__ __forceinline__ void three_maxima(const int* hist, int& ind1, int& in
     else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) ind3 = -1;
 }
 
-// ---- SearchForInitialization, sequential part (ORBmatcher.cc:532-640); one warp ----
-__global__ void __launch_bounds__(32)
+// ---- SearchForInitialization, sequential part (ORBmatcher.cc:532-640) ----
+// The loop over F1's keypoints is order-dependent (running vMatchedDistance exclusion :561, steals :583-591), so one warp
+// replays it; what makes it fast is that nothing on the serial chain touches global memory: the whole block first stages
+// the candidate lists, a compacted list of the queries that have candidates, the angles and the running match state in
+// shared memory (falling back to the global arrays only if the lists exceed the shared-memory budget).
+#define RESOLVE_THREADS 256
+__global__ void __launch_bounds__(RESOLVE_THREADS)
 k_resolve_init(int n1, int n2, const KpM* __restrict__ k1s, const KpM* __restrict__ k2s, const int* __restrict__ counts, const int* __restrict__ offsets,
-               const uint32_t* __restrict__ cand, float nnratio, int checkOri,
+               const uint32_t* __restrict__ cand, float nnratio, int checkOri, int smem_words,
                int* __restrict__ matchedDist /*n2*/, int* __restrict__ m21 /*n2*/, int* __restrict__ m12 /*n1*/, int* __restrict__ bin_of /*n1*/,
                float* __restrict__ prev_xy, int* __restrict__ nmatches_out) {
+    extern __shared__ __align__(16) uint32_t rs_sm[];
     __shared__ int hist[M_HISTO];
-    const int lane = threadIdx.x;
-    for (int i = lane; i < n2; i += 32) { matchedDist[i] = INT_MAX; m21[i] = -1; }
-    for (int i = lane; i < n1; i += 32) { m12[i] = -1; bin_of[i] = -1; }
-    if (lane < M_HISTO) hist[lane] = 0;
-    __syncwarp();
+    __shared__ int wsum[RESOLVE_THREADS / 32];
+    __shared__ int nact_sm;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int total = offsets[n1];
+    // shared-memory plan (32-bit words): active[n1] | aoff[n1+1] | md[n2] | s21[n2] | ang1[n1] | ang2[n2] | lists[total]
+    const bool staged = 3 * n1 + 1 + 3 * n2 + total <= smem_words;
+    uint32_t* act = rs_sm;                       // query index of the k-th query that has candidates
+    uint32_t* aoff = act + n1;                   // start of its list inside `lists`
+    int* md = staged ? reinterpret_cast<int*>(aoff + n1 + 1) : matchedDist;
+    int* s21 = staged ? md + n2 : m21;
+    float* ang1 = reinterpret_cast<float*>(rs_sm + 2 * n1 + 1 + 2 * n2);
+    float* ang2 = ang1 + n1;
+    uint32_t* lists = reinterpret_cast<uint32_t*>(ang2 + n2);
+    for (int i = tid; i < n2; i += RESOLVE_THREADS) { md[i] = INT_MAX; s21[i] = -1; if (staged) ang2[i] = k2s[i].angle; }
+    for (int i = tid; i < n1; i += RESOLVE_THREADS) { m12[i] = -1; bin_of[i] = -1; if (staged) ang1[i] = k1s[i].angle; }
+    if (tid < M_HISTO) hist[tid] = 0;
+    int nact = 0;
+    if (staged) {
+        for (int i = tid; i < total; i += RESOLVE_THREADS) lists[i] = cand[i];
+        // ordered compaction of the queries with a non-empty list (block scan, chunk by chunk)
+        for (int base = 0; base < n1; base += RESOLVE_THREADS) {
+            const int i = base + tid;
+            const int has = (i < n1 && counts[i] > 0) ? 1 : 0;
+            const uint32_t m = __ballot_sync(0xffffffffu, has);
+            if (lane == 0) wsum[warp] = __popc(m);
+            __syncthreads();
+            int before = 0, chunk = 0;
+#pragma unroll
+            for (int w = 0; w < RESOLVE_THREADS / 32; ++w) { const int c = wsum[w]; if (w < warp) before += c; chunk += c; }
+            if (has) { const int k = nact + before + __popc(m & ((1u << lane) - 1u)); act[k] = (uint32_t)i; aoff[k] = (uint32_t)offsets[i]; }
+            nact += chunk;
+            __syncthreads();
+        }
+        if (tid == 0) { aoff[nact] = (uint32_t)total; nact_sm = nact; }
+    }
+    __syncthreads();
+    if (warp != 0) return;
+    const uint32_t* L = staged ? lists : cand;
+    const int niter = staged ? nact_sm : n1;
     int nmatches = 0;
-    for (int i1 = 0; i1 < n1; ++i1) {
-        const int cnt = counts[i1];
-        if (cnt == 0) continue;
-        const uint32_t* c = cand + offsets[i1];
-        const Best2 b = warp_best2(c, cnt, lane, [&](uint32_t v) { return !(matchedDist[v & 0xFFFFFu] <= (int)(v >> 20)); });   // :561
+    for (int it = 0; it < niter; ++it) {
+        int i1, lo, cnt;
+        if (staged) { i1 = (int)act[it]; lo = (int)aoff[it]; cnt = (int)aoff[it + 1] - lo; }
+        else { i1 = it; cnt = counts[i1]; if (cnt == 0) continue; lo = offsets[i1]; }
+        const uint32_t* c = L + lo;
+        const Best2 b = warp_best2(c, cnt, lane, [&](uint32_t v) { return !(md[v & 0xFFFFFu] <= (int)(v >> 20)); });   // :561
         if (b.k1 == 0xFFFFFFFFu) continue;
         const int bestDist = (int)(b.k1 >> 20);
         const int bestDist2 = b.k2 == 0xFFFFFFFFu ? INT_MAX : (int)(b.k2 >> 20);
         if (bestDist <= M_TH_LOW && (float)bestDist < __fmul_rn((float)bestDist2, nnratio)) {         // :577-579
             const int bestIdx2 = (int)(c[b.k1 & 0xFFFFFu] & 0xFFFFFu);
-            const int old = m21[bestIdx2];
+            const int old = s21[bestIdx2];
             if (old >= 0) --nmatches;
             ++nmatches;
             if (lane == 0) {
                 if (old >= 0) m12[old] = -1;                                                       // :583-587
-                m12[i1] = bestIdx2; m21[bestIdx2] = i1; matchedDist[bestIdx2] = bestDist;
-                if (checkOri) { const int bin = rot_bin(k1s[i1].angle, k2s[bestIdx2].angle); bin_of[i1] = bin; hist[bin]++; }
+                m12[i1] = bestIdx2; s21[bestIdx2] = i1; md[bestIdx2] = bestDist;
+                if (checkOri) {
+                    const int bin = staged ? rot_bin(ang1[i1], ang2[bestIdx2]) : rot_bin(k1s[i1].angle, k2s[bestIdx2].angle);
+                    bin_of[i1] = bin; hist[bin]++;
+                }
             }
             __syncwarp();
         }
     }
+    __syncwarp();
     if (checkOri) {
         int ind1, ind2, ind3;
         three_maxima(hist, ind1, ind2, ind3);

@@ -112,6 +112,8 @@ static int window_search(orbx_matcher* m, QueryParams& P, const FrameDev& F, int
     return ORBX_OK;
 }
 
+#define RESOLVE_SMEM_BYTES (160 * 1024)
+
 extern "C" {
 
 int orbx_matcher_create(float nnratio, int check_orientation, int device, orbx_matcher** out) {
@@ -125,6 +127,7 @@ int orbx_matcher_create(float nnratio, int check_orientation, int device, orbx_m
     m->nnratio = nnratio; m->checkOri = check_orientation != 0; m->device = device;
     cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete m; FAIL(ORBX_E_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e)); }
+    cudaFuncSetAttribute(k_resolve_init, cudaFuncAttributeMaxDynamicSharedMemorySize, RESOLVE_SMEM_BYTES);   // per device
     *out = m;
     return ORBX_OK;
 }
@@ -176,7 +179,9 @@ int orbx_search_for_initialization(orbx_matcher* m, const orbx_frame_view* F1, c
     if ((rc = window_search(m, P, d2, counts, offsets, cand))) return rc;
     int* md = m->arena.get<int>(n2 + 1); int* m21 = m->arena.get<int>(n2 + 1); int* m12 = m->arena.get<int>(n1); int* binof = m->arena.get<int>(n1); int* dn = m->arena.get<int>(1);
     if (!md || !m21 || !m12 || !binof || !dn) FAIL(ORBX_E_CUDA, "matcher arena exhausted");
-    k_resolve_init<<<1, 32, 0, m->stream>>>(n1, n2, k1, d2.keys, counts, offsets, cand, m->nnratio, m->checkOri, md, m21, m12, binof, prev, dn);
+    const int resolve_smem = RESOLVE_SMEM_BYTES;
+    k_resolve_init<<<1, RESOLVE_THREADS, resolve_smem, m->stream>>>(n1, n2, k1, d2.keys, counts, offsets, cand, m->nnratio, m->checkOri, resolve_smem / 4,
+                                                                     md, m21, m12, binof, prev, dn);
     LAUNCH_CHECK();
     CU_TRY(cudaMemcpyAsync(matches12, m12, (size_t)n1 * 4, cudaMemcpyDeviceToHost, m->stream));
     CU_TRY(cudaMemcpyAsync(prev_matched_xy, prev, (size_t)n1 * 8, cudaMemcpyDeviceToHost, m->stream));
