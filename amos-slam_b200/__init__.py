@@ -83,6 +83,8 @@ def lib():
     L.orbx_pyramid_level.argtypes = [vp, ci, ci, vp, sz, C.POINTER(ci), C.POINTER(ci)]
     L.orbx_extract_batch.argtypes = [vp, vp, ci, ci, ci, sz, sz, vp, vp, ci, vp]
     L.orbx_extract_batch_device.argtypes = [vp, vp, ci, ci, ci, sz, sz, vp, vp, ci, vp]
+    L.orbx_extract_masked_batch.argtypes = [vp, vp, vp, ci, ci, ci, sz, sz, sz, sz, vp, vp, ci, vp, vp]
+    L.orbx_extract_masked_batch_device.argtypes = [vp, vp, vp, ci, ci, ci, sz, sz, sz, sz, vp, vp, ci, vp, vp]
     L.orbx_debug_level_candidates.argtypes = [vp, ci, ci, vp, ci, C.POINTER(ci)]
     L.orbx_debug_blurred_level.argtypes = [vp, ci, ci, vp, sz]
     L.orbx_debug_pyramid_level.argtypes = [vp, ci, ci, vp, sz]
@@ -257,6 +259,22 @@ class ORBextractor:
         kp = np.zeros((B, cap), KP_DTYPE); desc = np.zeros((B, cap, 32), np.uint8); counts = np.zeros(B, np.int32)
         _check(self._lib.orbx_extract_batch(self._h, _ptr(images), B, rows, cols, images.strides[1], images.strides[0], _ptr(kp), _ptr(desc), cap, _ptr(counts)))
         return kp, desc, counts
+
+    def extract_masked_batch(self, images, masks, cap=None):
+        """Batched Amos path: images, masks (B, rows, cols) uint8 host arrays -> (kp[B,cap], desc[B,cap,32], counts[B], culled[B])."""
+        if images.dtype != np.uint8 or images.ndim != 3 or masks.dtype != np.uint8 or masks.shape != images.shape:
+            raise OrbxError(E_INVALID, "images and masks must be (B, rows, cols) uint8 of the same shape")
+        images = np.ascontiguousarray(images); masks = np.ascontiguousarray(masks)
+        B, rows, cols = images.shape
+        cap = cap or self.max_keypoints(rows, cols)
+        kp = np.zeros((B, cap), KP_DTYPE); desc = np.zeros((B, cap, 32), np.uint8); counts = np.zeros(B, np.int32); culled = np.zeros(B, np.int32)
+        _check(self._lib.orbx_extract_masked_batch(self._h, _ptr(images), _ptr(masks), B, rows, cols, images.strides[1], images.strides[0],
+                                                   masks.strides[1], masks.strides[0], _ptr(kp), _ptr(desc), cap, _ptr(counts), _ptr(culled)))
+        return kp, desc, counts, culled
+
+    def extract_masked_batch_raw_device(self, images_ptr, masks_ptr, B, rows, cols, step, frame_stride, mask_step, mask_frame_stride, kp_ptr, desc_ptr, cap, counts_ptr, culled_ptr=0):
+        _check(self._lib.orbx_extract_masked_batch_device(self._h, C.c_void_p(images_ptr), C.c_void_p(masks_ptr), B, rows, cols, step, frame_stride, mask_step,
+                                                          mask_frame_stride, C.c_void_p(kp_ptr), C.c_void_p(desc_ptr), cap, C.c_void_p(counts_ptr), C.c_void_p(culled_ptr) if culled_ptr else None))
 
     def extract_batch_raw(self, images_ptr, B, rows, cols, step, frame_stride, kp_ptr, desc_ptr, cap, counts_ptr, device=False):
         """Raw-pointer form (ints): host pointers (synchronous) or device pointers (asynchronous on .stream)."""

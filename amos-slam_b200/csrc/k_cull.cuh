@@ -17,33 +17,102 @@ __global__ void k_border101(const uint8_t* __restrict__ src, int pitch, int w, i
 // half-widths of the 31x31 MORPH_ELLIPSE rows (cv::getStructuringElement), filled by the host
 __constant__ int c_ell_dx[31];
 
-// grey-scale dilate / erode with the 31x31 ellipse; pixels outside the image are ignored
-// (cv::morphologyDefaultBorderValue).  CTA = 32x16 outputs, input tile + 15-px halo in shared memory.
-#define MORPH_TW 32
-#define MORPH_TH 16
-template <bool DILATE>
-__global__ void __launch_bounds__(MORPH_TW * MORPH_TH)
-k_morph_ellipse31(const uint8_t* __restrict__ src, int spitch, uint8_t* __restrict__ dst, int dpitch, int w, int h) {
-    __shared__ uint8_t tile[MORPH_TH + 30][MORPH_TW + 32];
-    const int x0 = blockIdx.x * MORPH_TW, y0 = blockIdx.y * MORPH_TH;
-    const int tid = threadIdx.y * MORPH_TW + threadIdx.x;
-    const uint8_t neutral = DILATE ? 0 : 255;
-    for (int i = tid; i < (MORPH_TH + 30) * (MORPH_TW + 30); i += MORPH_TW * MORPH_TH) {
-        const int r = i / (MORPH_TW + 30), c = i - r * (MORPH_TW + 30);
-        const int yy = y0 + r - 15, xx = x0 + c - 15;
-        tile[r][c] = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? src[(size_t)yy * spitch + xx] : neutral;
+// -------------------------------------------------------------------------------------------------
+// closing = erode(dilate(mask, ellipse31), ellipse31)  (:1697-1704) is only ever tested for "!= 0" (:1734-1735).
+// With cv's default border (outside pixels ignored by both passes) that predicate depends only on the binary
+// image (mask != 0):  closing(p) != 0  <=>  every q in p+E has some r in q+E with mask(r) != 0.  So the masks
+// are bit-packed (1 bit per pixel, 32 pixels per word, LSB = leftmost) and both passes are binary dilations:
+//   D = dilate(M);   closing != 0  ==  ~dilate(~D)   (bits outside the image are 0 in M, ~D and ignored).
+// One thread per output word; per ellipse row it ORs the window of half-width dx over the (left, mid, right)
+// words with a doubling OR (two overlapping power-of-two windows).  The bit-planes are tiny (260 KB at 1080p)
+// and stay in L2; this replaces a 729-tap grey-scale max/min per pixel.
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t swar_nz_byte(uint32_t x) { return (((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u; }
+__device__ __forceinline__ uint32_t nz_nibble(uint32_t w) { return (((swar_nz_byte(w) >> 7) * 0x00204081u) >> 21) & 0xFu; }   // 4 bytes -> 4 bits
+
+// mask: [B] frames of rows x pitch bytes (pitch multiple of 32, rows of padding past `cols` may hold garbage)
+__global__ void k_mask_pack(const uint8_t* __restrict__ mask, long long fstride, int pitch, int rows, int cols,
+                            uint32_t* __restrict__ bits, int wpr) {
+    const int wx = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
+    if (wx >= wpr) return;
+    const uint4* src = reinterpret_cast<const uint4*>(mask + (long long)b * fstride + (long long)y * pitch + 32 * wx);
+    const uint4 a = __ldg(src), c = __ldg(src + 1);
+    uint32_t w = nz_nibble(a.x) | (nz_nibble(a.y) << 4) | (nz_nibble(a.z) << 8) | (nz_nibble(a.w) << 12) |
+                 (nz_nibble(c.x) << 16) | (nz_nibble(c.y) << 20) | (nz_nibble(c.z) << 24) | (nz_nibble(c.w) << 28);
+    const int valid = cols - 32 * wx;
+    if (valid < 32) w &= (1u << valid) - 1u;
+    bits[((long long)b * rows + y) * wpr + wx] = w;
+}
+
+__device__ __forceinline__ unsigned long long or_window(unsigned long long x, int n) {   // OR of x >> k, k = 0..n-1, 1 <= n <= 16
+    unsigned long long t = x; int p = 1;
+    if (n >= 2) { t |= t >> 1; p = 2; }
+    if (n >= 4) { t |= t >> 2; p = 4; }
+    if (n >= 8) { t |= t >> 4; p = 8; }
+    if (n >= 16) { t |= t >> 8; p = 16; }
+    return t | (t >> (n - p));
+}
+
+// out = dilate(COMPLEMENT ? ~in : in) with the 31x31 ellipse, complemented again if COMPLEMENT (i.e. an erosion)
+template <bool COMPLEMENT>
+__global__ void k_bin_dilate31(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int wpr, int rows, int cols) {
+    const int wx = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
+    if (wx >= wpr) return;
+    const uint32_t* plane = in + (long long)b * rows * wpr;
+    const int lastw = wpr - 1;
+    const uint32_t lastmask = (cols & 31) ? ((1u << (cols & 31)) - 1u) : 0xFFFFFFFFu;
+    uint32_t acc = 0;
+    for (int dy = -15; dy <= 15; ++dy) {
+        const int yy = y + dy;
+        if (yy < 0 || yy >= rows) continue;
+        const int d = c_ell_dx[dy + 15];
+        const uint32_t* row = plane + (long long)yy * wpr;
+        uint32_t M = __ldg(row + wx), L = wx > 0 ? __ldg(row + wx - 1) : 0u, R = wx < lastw ? __ldg(row + wx + 1) : 0u;
+        if (COMPLEMENT) {
+            M = ~M; if (wx == lastw) M &= lastmask;
+            L = wx > 0 ? ~L : 0u;
+            R = wx < lastw ? ~R : 0u; if (wx + 1 == lastw) R &= lastmask;
+        }
+        const unsigned long long A = ((unsigned long long)M << 32) | L, Bw = ((unsigned long long)R << 32) | M;
+        acc |= (uint32_t)(or_window(A >> (32 - d), d + 1) | or_window(Bw, d + 1));
     }
-    __syncthreads();
-    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-    if (x >= w || y >= h) return;
-    int acc = neutral;
-#pragma unroll 1
-    for (int dy = 0; dy < 31; ++dy) {
-        const int dx = c_ell_dx[dy];
-        const uint8_t* row = &tile[threadIdx.y + dy][threadIdx.x + 15 - dx];
-        for (int k = 0; k <= 2 * dx; ++k) acc = DILATE ? max(acc, (int)row[k]) : min(acc, (int)row[k]);
+    if (COMPLEMENT) { acc = ~acc; }
+    if (wx == lastw) acc &= lastmask;
+    out[((long long)b * rows + y) * wpr + wx] = acc;
+}
+
+// Batched MovingKeyPoints on the per-level keypoint slots of the quadtree stage (mask term only, :1734-1741): one warp per
+// (level, frame) drops the keypoints whose position p = (int)(pt * scale) lies on a set bit of the closed mask, keeps the
+// order of the survivors (stable erase) and rewrites the level's count.
+__global__ void __launch_bounds__(32)
+k_cull_levelkp(const LevelGeom* __restrict__ levels, int nlevels, int kp_per_frame, uint32_t* __restrict__ kp_level, int* __restrict__ kp_count,
+               const uint32_t* __restrict__ closed, int wpr, int rows, int cols, int* __restrict__ culled_count) {
+    const int level = blockIdx.x, b = blockIdx.y, lane = threadIdx.x;
+    const LevelGeom& g = levels[level];
+    uint32_t* kp = kp_level + (long long)b * kp_per_frame + g.kp_off;
+    const int n = kp_count[b * nlevels + level];
+    const uint32_t* plane = closed + (long long)b * rows * wpr;
+    const float scale = level ? g.scale : 1.0f;                          // :1712-1715
+    int kept = 0;
+    for (int k0 = 0; k0 < n; k0 += 32) {
+        const int k = k0 + lane;
+        uint32_t p = 0; bool keep = false;
+        if (k < n) {
+            p = kp[k];
+            const float x = (float)((int)(p & 0xFFF) + g.minBX), y = (float)((int)((p >> 12) & 0xFFF) + g.minBY);
+            const int px = (int)__fmul_rn(x, scale), py = (int)__fmul_rn(y, scale);
+            keep = true;
+            if (px >= 0 && py >= 0 && px < cols && py < rows) keep = ((plane[(long long)py * wpr + (px >> 5)] >> (px & 31)) & 1u) == 0u;
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, keep);
+        __syncwarp();
+        if (keep) kp[kept + __popc(m & ((1u << lane) - 1u))] = p;        // kept + rank <= k: in-place compaction is safe after the sync
+        kept += __popc(m);
     }
-    dst[(size_t)y * dpitch + x] = (uint8_t)acc;
+    if (lane == 0) {
+        kp_count[b * nlevels + level] = kept;
+        if (culled_count && n > kept) atomicAdd(culled_count + b, n - kept);
+    }
 }
 
 struct KpIn { float x, y, size, angle, response; int octave, class_id; };
@@ -52,7 +121,7 @@ struct KpIn { float x, y, size, angle, response; int octave, class_id; };
 // p = (int)(pt * scale).  flags[i] = 1 => culled.  Out-of-range label / id indices (undefined behaviour
 // in the reference) are treated as "not flagged".
 __global__ void k_cull_flags(const KpIn* __restrict__ kp, const float* __restrict__ kp_scale, int n,
-                             const uint8_t* __restrict__ closed, int cpitch, const double* __restrict__ label, int lpitch_elems,
+                             const uint32_t* __restrict__ closed, int wpr, const double* __restrict__ label, int lpitch_elems,
                              int rows, int cols, const int* __restrict__ centers_id, int ncenters,
                              const int* __restrict__ rm_vector, int nrm, uint8_t* __restrict__ flags) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -67,7 +136,7 @@ __global__ void k_cull_flags(const KpIn* __restrict__ kp, const float* __restric
             const int id = centers_id[(size_t)idxd];
             if (id >= 0 && id < nrm && rm_vector[id] == 1) flag = 1;
         }
-        if (closed[(size_t)py * cpitch + px] != 0) flag = 1;
+        if ((closed[(size_t)py * wpr + (px >> 5)] >> (px & 31)) & 1u) flag = 1;
     }
     flags[i] = (uint8_t)flag;
 }

@@ -87,7 +87,7 @@ struct orbx_extractor {
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;     // ORBX_NSTAGES+1 events per call
     // small staging buffers for the single-frame calls
-    DevBuf<KpOut> d_kp_tmp; DevBuf<uint8_t> d_desc_tmp; DevBuf<uint8_t> d_mask, d_mask2; DevBuf<double> d_label; DevBuf<int> d_ids;
+    DevBuf<KpOut> d_kp_tmp; DevBuf<uint8_t> d_desc_tmp; DevBuf<uint8_t> d_mask; DevBuf<uint32_t> d_bits0, d_bits1; DevBuf<double> d_label; DevBuf<int> d_ids, d_culled;
 };
 
 // -------------------------------------------------------------------------------------------------
@@ -456,7 +456,7 @@ void orbx_destroy(orbx_extractor* h) {
     h->d_pyr.release(); h->d_blur.release(); h->d_slots.release(); h->d_ocand.release(); h->d_spk.release(); h->d_kp_level.release();
     h->d_skey.release(); h->d_cell_counts.release(); h->d_ncand.release(); h->d_kp_count.release(); h->d_counts.release();
     h->d_level_counts.release(); h->d_overflow.release(); h->d_kp_out.release(); h->d_desc_out.release();
-    h->d_kp_tmp.release(); h->d_desc_tmp.release(); h->d_mask.release(); h->d_mask2.release(); h->d_label.release(); h->d_ids.release();
+    h->d_kp_tmp.release(); h->d_desc_tmp.release(); h->d_mask.release(); h->d_bits0.release(); h->d_bits1.release(); h->d_culled.release(); h->d_label.release(); h->d_ids.release();
     cudaStreamDestroy(h->stream);
     delete h;
 }

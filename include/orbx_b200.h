@@ -135,6 +135,22 @@ int orbx_extract_batch(orbx_extractor* h, const uint8_t* images, int B, int rows
 int orbx_extract_batch_device(orbx_extractor* h, const uint8_t* d_images, int B, int rows, int cols, size_t step,
                               size_t frame_stride, orbx_keypoint* d_kp_out, uint8_t* d_desc_out, int cap,
                               int* d_counts_out);
+/* ------------------------------------------------------------------------------------------------
+ * Batched Amos path (BASELINE config 5: multi-sequence extraction with dynamic-mask keypoint culling).  Per frame b:
+ *   operator()(image_b, mask, vector<vector<KeyPoint>>&)                         src/ORBextractor.cc:1672-1686
+ *   MovingKeyPoints(.., imS = mask_b, ..) with no flagged super-pixel (rm_vector all 0)       :1688-1745
+ *   ProcessDesp(..)                                                                            :1747-1820
+ * i.e. the keypoints of operator()(image, mask, kps, desc) minus those whose position lies where
+ * erode(dilate(mask_b, ellipse31), ellipse31) != 0, with descriptors of the survivors only.
+ * masks: CV_8UC1, rows x cols, frame b at masks + b*mask_frame_stride, `mask_step` bytes per row.
+ * culled_out (may be NULL): number of keypoints removed per frame.
+ * ---------------------------------------------------------------------------------------------- */
+int orbx_extract_masked_batch(orbx_extractor* h, const uint8_t* images, const uint8_t* masks, int B, int rows, int cols,
+                              size_t step, size_t frame_stride, size_t mask_step, size_t mask_frame_stride,
+                              orbx_keypoint* kp_out, uint8_t* desc_out, int cap, int* counts_out, int* culled_out);
+int orbx_extract_masked_batch_device(orbx_extractor* h, const uint8_t* d_images, const uint8_t* d_masks, int B, int rows, int cols,
+                                     size_t step, size_t frame_stride, size_t mask_step, size_t mask_frame_stride,
+                                     orbx_keypoint* d_kp_out, uint8_t* d_desc_out, int cap, int* d_counts_out, int* d_culled_out);
 /* number of kernel launches issued by this handle so far (bench.py's gpu_launches) */
 long long orbx_launch_count(const orbx_extractor* h);
 /* Per-stage device timing (bench.py): while enabled every batched extract records CUDA events at the stage

@@ -174,6 +174,53 @@ def test_amos_detect_cull_describe(orbx, oracle):
     assert kp_equal(k5, k6) and np.array_equal(d5, d6)
 
 
+def test_grayscale_and_ragged_masks_vs_oracle(orbx, oracle):
+    """The closing is evaluated as binary morphology on (mask != 0) -- exact because the reference only tests closing != 0.
+    Grey-scale masks, speckle, masks touching every border and an odd width exercise that equivalence against the port's
+    grey-scale erode(dilate()) (cv semantics)."""
+    rng = np.random.default_rng(11)
+    w, h = 403, 301
+    E = orbx.ORBextractor(700, 1.2, 8, 20, 7); P = oracle.Extractor("port", 700, 1.2, 8, 20, 7)
+    img = synth_frame(95, w, h)
+    kp, counts = E.detect(img); ko, co = P.detect(img)
+    assert kp_equal(kp, ko) and np.array_equal(counts, co)
+    lab = np.ones((h, w), np.float64); ids = np.zeros(1, np.int32); rm = np.zeros(1, np.int32)
+    masks = [synth_mask(3, w, h),
+             (synth_mask(4, w, h) // 255 * rng.integers(1, 256, (h, w))).astype(np.uint8),          # grey levels 1..255
+             (rng.random((h, w)) < 0.004).astype(np.uint8) * 7,                                      # speckle: closing fills between dots
+             np.pad(np.zeros((h - 40, w - 40), np.uint8), 20, constant_values=200),                  # frame touching all four borders
+             np.full((h, w), 1, np.uint8), np.zeros((h, w), np.uint8)]
+    for m in masks:
+        kg, cg, ug = E.MovingKeyPoints(m, lab, ids, rm, kp, counts)
+        kr, cr, ur = P.moving_keypoints(m, lab, ids, rm, kp, counts)
+        assert kp_equal(kg, kr) and np.array_equal(cg, cr) and kp_equal(ug, ur)
+    assert len(E.MovingKeyPoints(masks[4], lab, ids, rm, kp, counts)[0]) == 0
+
+
+@pytest.mark.parametrize("cfg", [(640, 480, 1000, 5, 300), (1920, 1080, 1000, 3, 310)])
+def test_masked_batch_equals_two_stage_path(orbx, cfg):
+    """Config C5 (batched extraction with dynamic-mask culling): the batched call must equal, frame by frame,
+    detect -> MovingKeyPoints(mask, no flagged super-pixel) -> ProcessDesp, which the tests above pin to the reference."""
+    w, h, nf, B, seed = cfg
+    E = orbx.ORBextractor(nf, 1.2, 8, 20, 7)
+    imgs = synth_batch(B, w, h, seed0=seed, distinct=B)
+    masks = np.stack([synth_mask(seed + b, w, h) for b in range(B)])
+    masks[B - 1] = 0                                                               # one frame without dynamic objects
+    kp, desc, counts, culled = E.extract_masked_batch(imgs, masks)
+    lab = np.ones((h, w), np.float64); ids = np.zeros(1, np.int32); rm = np.zeros(1, np.int32)
+    E2 = orbx.ORBextractor(nf, 1.2, 8, 20, 7)
+    for b in range(B):
+        kd, cd = E2.detect(imgs[b])
+        kk, ck, cu = E2.MovingKeyPoints(masks[b], lab, ids, rm, kd, cd)
+        kf, df = E2.ProcessDesp(kk, ck)
+        assert counts[b] == len(kf) and culled[b] == len(cu)
+        assert kp_equal(kp[b][:counts[b]], kf) and np.array_equal(desc[b][:counts[b]], df)
+    assert culled[:B - 1].sum() > 0 and culled[B - 1] == 0
+    k0, d0 = E2(imgs[B - 1])                                                       # empty mask == plain operator()
+    assert kp_equal(kp[B - 1][:counts[B - 1]], k0) and np.array_equal(desc[B - 1][:counts[B - 1]], d0)
+    assert E.check_overflow() == 0
+
+
 def test_describe_requires_state(orbx):
     E = orbx.ORBextractor(300, 1.2, 8, 20, 7)
     with pytest.raises(orbx.OrbxError) as e:
