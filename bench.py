@@ -33,6 +33,17 @@ from tools.synth import synth_batch  # noqa: E402
 
 WIDTH, HEIGHT, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH = 640, 480, 1000, 1.2, 8, 20, 7
 WORKLOAD = "ORBextractor 640x480 grayscale, nFeatures=1000, scale 1.2, 8 levels, FAST 20/7 (TUM RGB-D settings)"
+METRIC = "ORB extract frames/sec @640x480 1000 feat"
+MASKED = False
+# BASELINE.json configs that are a single-GPU extraction workload: c1 is the one the headline metric is quoted on (default);
+# c3 / c5 are selectable for the record (python bench.py --workload c5), they are not the driver's bench line.
+WORKLOADS = {
+    "c1": (640, 480, 1000, 512, False, WORKLOAD, METRIC),
+    "c3": (752, 480, 2000, 512, False, "ORBextractor 752x480 grayscale (EuRoC-shape monocular initialiser frames), nFeatures=2000, scale 1.2, 8 levels, FAST 20/7",
+           "ORB extract frames/sec @752x480 2000 feat"),
+    "c5": (1920, 1080, 1000, 64, True, "batched 1920x1080 multi-sequence ORB extraction with dynamic-mask keypoint culling (detect -> MovingKeyPoints -> ProcessDesp), "
+           "nFeatures=1000, scale 1.2, 8 levels, FAST 20/7", "masked ORB extract frames/sec @1920x1080 1000 feat"),
+}
 
 
 def level_pixels():
@@ -96,6 +107,18 @@ def cpu_reference_run(seconds_budget, frames, threads=None, steps=None, frames_p
     threads = threads or max(1, os.cpu_count() or 1)
     exts = [oracle.Extractor(kind, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH) for _ in range(threads)]
     nframes = len(frames)
+    if MASKED:      # config c5: the reference's two-stage Amos path per frame
+        from tools.synth import synth_mask
+        masks = [synth_mask(i, WIDTH, HEIGHT) for i in range(min(nframes, 8))]
+        lab = np.ones((HEIGHT, WIDTH), np.float64); ids = np.zeros(1, np.int32); rm = np.zeros(1, np.int32)
+
+        def one(ext, i):
+            kp, counts = ext.detect(frames[i % nframes])
+            kp, counts, _ = ext.moving_keypoints(masks[i % len(masks)], lab, ids, rm, kp, counts)
+            ext.process_desp(kp, counts)
+    else:
+        def one(ext, i):
+            ext.extract(frames[i % nframes])
     done = [0] * threads
     errors = []
     start_evt = threading.Event()
@@ -109,7 +132,7 @@ def cpu_reference_run(seconds_budget, frames, threads=None, steps=None, frames_p
             if quota is None and time.perf_counter() >= deadline_box[0]:
                 break
             try:
-                exts[t].extract(frames[i % nframes])
+                one(exts[t], i)
             except BaseException as e:      # a dead worker must not read as "0 frames/s"
                 errors.append(repr(e))
                 break
@@ -197,28 +220,31 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=512, help="frames per GPU per step")
+    ap.add_argument("--batch", type=int, default=0, help="frames per GPU per step (default: 512; 64 for c5)")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c1", choices=sorted(WORKLOADS), help="BASELINE.json config (c1 = headline metric)")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-pointer leg (the line is then not a bench value)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); local_rank = int(os.environ.get("LOCAL_RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
-    N, K, W, B = args.gpus, args.steps, max(args.warmup, 0), args.batch
+    global WIDTH, HEIGHT, NFEAT, WORKLOAD, METRIC, MASKED
+    WIDTH, HEIGHT, NFEAT, defB, MASKED, WORKLOAD, METRIC = WORKLOADS[args.workload]
+    N, K, W, B = args.gpus, args.steps, max(args.warmup, 0), (args.batch or defB)
     config = {"workload": WORKLOAD, "frame": [WIDTH, HEIGHT], "nfeatures": NFEAT, "frames_per_gpu_per_step": B,
               "parallelism": "frames sharded over %d GPU(s), no collective" % N,
-              "l2_policy": "working set per step (%.0f MB of frames, ~%.1f GB of pyramid+scratch) exceeds the 126 MB L2" % (B * WIDTH * HEIGHT / 1e6, B * 6.3e-3)}
+              "l2_policy": "working set per step (%.0f MB of frames, ~%.1f GB of pyramid+scratch) exceeds the 126 MB L2" % (B * WIDTH * HEIGHT / 1e6, B * 6.3e-3 * WIDTH * HEIGHT / 307200.0)}
 
     if args.impl == "reference":
         if rank != 0:
             return
-        frames = synth_batch(64, WIDTH, HEIGHT, seed0=0, distinct=16)
+        frames = synth_batch(64, WIDTH, HEIGHT, seed0=0, distinct=16 if WIDTH * HEIGHT < 1000000 else 4)
         threads = max(1, os.cpu_count() or 1)
         FPT = 8            # frames per thread per step: long enough that thread start/join is noise, short enough for K steps in seconds
         res = cpu_reference_run(None, frames, threads=threads, steps=W + K, frames_per_thread_step=FPT)
         st = res["step_times"][W:]
         fps = threads * FPT * K / sum(st)
-        line = {"impl": "reference", "metric": "ORB extract frames/sec @640x480 1000 feat", "value": fps, "unit": "frames/s", "n_gpus": N, "steps": K, "warmup": W,
+        line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": N, "steps": K, "warmup": W,
                 "ms_per_step": 1e3 * sum(st) / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                 "config": config,
                 "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": res["kind"],
@@ -236,7 +262,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    frames = synth_batch(B, WIDTH, HEIGHT, seed0=1000 * rank, distinct=24)
+    frames = synth_batch(B, WIDTH, HEIGHT, seed0=1000 * rank, distinct=24 if WIDTH * HEIGHT < 1000000 else 8)
     ext = orbx.ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, device=local_rank)
     cap = ext.max_keypoints(HEIGHT, WIDTH)
     h_frames = torch.from_numpy(frames).pin_memory()
@@ -249,11 +275,27 @@ def main():
     h_counts = torch.zeros((B,), dtype=torch.int32).pin_memory()
     stream = torch.cuda.ExternalStream(ext.stream)
 
-    def step_device():
-        ext.extract_batch_raw(d_frames.data_ptr(), B, HEIGHT, WIDTH, WIDTH, WIDTH * HEIGHT, d_kp.data_ptr(), d_desc.data_ptr(), cap, d_counts.data_ptr(), device=True)
+    if MASKED:
+        from tools.synth import synth_mask
+        h_masks = torch.from_numpy(np.stack([synth_mask(1000 * rank + b, WIDTH, HEIGHT) for b in range(B)])).pin_memory()
+        d_masks = h_masks.cuda()
+        d_culled = torch.zeros((B,), dtype=torch.int32, device="cuda"); h_culled = torch.zeros((B,), dtype=torch.int32).pin_memory()
 
-    def step_host():
-        ext.extract_batch_raw(h_frames.data_ptr(), B, HEIGHT, WIDTH, WIDTH, WIDTH * HEIGHT, h_kp.data_ptr(), h_desc.data_ptr(), cap, h_counts.data_ptr(), device=False)
+        def step_device():
+            ext.extract_masked_batch_raw_device(d_frames.data_ptr(), d_masks.data_ptr(), B, HEIGHT, WIDTH, WIDTH, WIDTH * HEIGHT, WIDTH, WIDTH * HEIGHT,
+                                                d_kp.data_ptr(), d_desc.data_ptr(), cap, d_counts.data_ptr(), d_culled.data_ptr())
+
+        def step_host():
+            import ctypes as C
+            orbx._check(ext._lib.orbx_extract_masked_batch(ext._h, C.c_void_p(h_frames.data_ptr()), C.c_void_p(h_masks.data_ptr()), B, HEIGHT, WIDTH, WIDTH, WIDTH * HEIGHT,
+                                                           WIDTH, WIDTH * HEIGHT, C.c_void_p(h_kp.data_ptr()), C.c_void_p(h_desc.data_ptr()), cap,
+                                                           C.c_void_p(h_counts.data_ptr()), C.c_void_p(h_culled.data_ptr())))
+    else:
+        def step_device():
+            ext.extract_batch_raw(d_frames.data_ptr(), B, HEIGHT, WIDTH, WIDTH, WIDTH * HEIGHT, d_kp.data_ptr(), d_desc.data_ptr(), cap, d_counts.data_ptr(), device=True)
+
+        def step_host():
+            ext.extract_batch_raw(h_frames.data_ptr(), B, HEIGHT, WIDTH, WIDTH, WIDTH * HEIGHT, h_kp.data_ptr(), h_desc.data_ptr(), cap, h_counts.data_ptr(), device=False)
 
     def barrier():
         if world > 1:
@@ -299,7 +341,7 @@ def main():
     ms_e2e = max(g0.elapsed_time(g1), 1e3 * (time.perf_counter() - t0))   # host call is synchronous: wall clock >= device clock
     sampler.stop_flag = True; sampler.join(timeout=2)
 
-    matcher_line = matcher_bench(orbx, torch, ext, frames, local_rank) if rank == 0 else None
+    matcher_line = matcher_bench(orbx, torch, ext, frames, local_rank) if (rank == 0 and args.workload == "c1") else None
 
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -336,10 +378,10 @@ def main():
         traffic = tj["dram_bytes_per_frame"][kernel_of[dom]] * B / launches_of.get(dom, 1)
     except Exception:
         pass
-    line = {"metric": "ORB extract frames/sec @640x480 1000 feat", "value": value, "unit": "frames/s", "n_gpus": N, "steps": K, "warmup": max(W, 3),
+    line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": N, "steps": K, "warmup": max(W, 3),
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": config,
-            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(B * WIDTH * HEIGHT), "d2h_bytes_per_step": int(B * cap * 60 + 4 * B + 4), "steps": Ke},
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(B * WIDTH * HEIGHT * (2 if MASKED else 1)), "d2h_bytes_per_step": int(B * cap * 60 + 4 * B + 4), "steps": Ke},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
@@ -351,7 +393,9 @@ def main():
     if N == 1 and not args.no_cpu_baseline:
         res = cpu_reference_run(args.cpu_seconds, frames[:64])
         line["cpu_baseline"] = {"value": res["fps"], "unit": "frames/s", "cores": res["threads"], "kind": res["kind"],
-                                "sample": "%d frames in %.1f s, one independent extractor per thread on %d threads, CPU: %s" % (res["frames"], res["seconds"], res["threads"], cpu_model())}
+                                "sample": "%d frames in %.1f s, one independent extractor per thread on %d threads, CPU: %s%s" % (
+                                    res["frames"], res["seconds"], res["threads"], cpu_model(),
+                                    "; NOTE: the shim's erode/dilate is an unoptimised 729-tap loop, so this c5 CPU figure is not representative of OpenCV's morphology" if MASKED else "")}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
