@@ -218,13 +218,11 @@ __device__ __forceinline__ Best2 warp_best2(const uint32_t* __restrict__ cand, i
         const uint32_t key = (c & 0xFFF00000u) | (uint32_t)p;       // distance, then order of appearance
         if (key < k1) { k2 = k1; k1 = key; } else if (key < k2) k2 = key;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const uint32_t a1 = __shfl_xor_sync(0xffffffffu, k1, o), a2 = __shfl_xor_sync(0xffffffffu, k2, o);
-        // merge (k1,k2) with (a1,a2): two smallest of the four distinct keys
-        const uint32_t lo = min(k1, a1), hi = max(k1, a1);
-        k2 = min(hi, min(k2, a2)); k1 = lo;
-    }
+    // two hardware warp reductions (REDUX.MIN): keys are distinct per lane except for the 0xFFFFFFFF sentinel, so the
+    // runner-up is the minimum over lanes of (the winner lane's second key, every other lane's first key)
+    const uint32_t g1 = __reduce_min_sync(0xffffffffu, k1);
+    const uint32_t g2 = __reduce_min_sync(0xffffffffu, (k1 == g1 && g1 != 0xFFFFFFFFu) ? k2 : k1);
+    k1 = g1; k2 = g2;
     Best2 b; b.k1 = k1; b.k2 = k2; return b;
 }
 
@@ -249,12 +247,61 @@ __device__ __forceinline__ void three_maxima(const int* hist, int& ind1, int& in
     else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) ind3 = -1;
 }
 
-// ---- SearchForInitialization, sequential part (ORBmatcher.cc:532-640) ----
-// The loop over F1's keypoints is order-dependent (running vMatchedDistance exclusion :561, steals :583-591), so one warp
-// replays it; what makes it fast is that nothing on the serial chain touches global memory: the whole block first stages
-// the candidate lists, a compacted list of the queries that have candidates, the angles and the running match state in
-// shared memory (falling back to the global arrays only if the lists exceed the shared-memory budget).
+// -------------------------------------------------------------------------------------------------
+// Sequential "resolve" passes.  SearchForInitialization and both SearchByProjection variants are order-dependent
+// (running exclusions, steals, occupied flags), so one warp replays the reference's loop; what makes that fast is
+// that nothing on the serial chain touches global memory: the whole block (RESOLVE_THREADS) first stages the
+// candidate lists, a compacted list of the queries that have candidates, and the per-kernel state / lookup arrays
+// in shared memory.  If the lists do not fit the shared-memory budget the kernels fall back to the global arrays.
+// -------------------------------------------------------------------------------------------------
 #define RESOLVE_THREADS 256
+struct StagedLists {
+    bool staged;            // lists / act / aoff are valid shared-memory copies
+    const uint32_t* lists;  // concatenated candidate lists
+    const uint32_t* act;    // query index of the k-th query with a non-empty list
+    const uint32_t* aoff;   // start of its list; aoff[niter] = total
+    int niter;              // staged: number of active queries; else: n
+    uint32_t* free_words;   // first shared word after the staged lists
+};
+// words needed besides the lists themselves: act[n] + aoff[n+1]
+__device__ __forceinline__ StagedLists stage_lists(uint32_t* sm, int sm_words, int extra_words, int n, const int* __restrict__ counts,
+                                                   const int* __restrict__ offsets, const uint32_t* __restrict__ cand) {
+    __shared__ int sl_wsum[RESOLVE_THREADS / 32];
+    __shared__ int sl_nact;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int total = offsets[n];
+    StagedLists r;
+    r.staged = 2 * n + 1 + total + extra_words <= sm_words;
+    uint32_t* act = sm; uint32_t* aoff = act + n; uint32_t* lists = aoff + n + 1;
+    r.lists = r.staged ? lists : cand; r.act = act; r.aoff = aoff; r.niter = n; r.free_words = r.staged ? lists + total : sm;
+    if (!r.staged) return r;
+    for (int i = tid; i < total; i += RESOLVE_THREADS) lists[i] = cand[i];
+    int nact = 0;
+    for (int base = 0; base < n; base += RESOLVE_THREADS) {               // ordered compaction of the queries with candidates
+        const int i = base + tid;
+        const int has = (i < n && counts[i] > 0) ? 1 : 0;
+        const uint32_t m = __ballot_sync(0xffffffffu, has);
+        if (lane == 0) sl_wsum[warp] = __popc(m);
+        __syncthreads();
+        int before = 0, chunk = 0;
+#pragma unroll
+        for (int w = 0; w < RESOLVE_THREADS / 32; ++w) { const int c = sl_wsum[w]; if (w < warp) before += c; chunk += c; }
+        if (has) { const int k = nact + before + __popc(m & ((1u << lane) - 1u)); act[k] = (uint32_t)i; aoff[k] = (uint32_t)offsets[i]; }
+        nact += chunk;
+        __syncthreads();
+    }
+    if (tid == 0) { aoff[nact] = (uint32_t)total; sl_nact = nact; }
+    __syncthreads();
+    r.niter = sl_nact;
+    return r;
+}
+// iteration `it` of the replay loop -> (query index, list pointer, list length); cnt == 0 means "skip"
+#define RESOLVE_QUERY(SL, it, qi, c, cnt) \
+    int qi, cnt; const uint32_t* c; \
+    if ((SL).staged) { qi = (int)(SL).act[it]; const int _lo = (int)(SL).aoff[it]; cnt = (int)(SL).aoff[(it) + 1] - _lo; c = (SL).lists + _lo; } \
+    else { qi = (it); cnt = counts[qi]; c = (SL).lists + (cnt ? offsets[qi] : 0); }
+
+// ---- SearchForInitialization, sequential part (ORBmatcher.cc:532-640) ----
 __global__ void __launch_bounds__(RESOLVE_THREADS)
 k_resolve_init(int n1, int n2, const KpM* __restrict__ k1s, const KpM* __restrict__ k2s, const int* __restrict__ counts, const int* __restrict__ offsets,
                const uint32_t* __restrict__ cand, float nnratio, int checkOri, int smem_words,
@@ -262,51 +309,23 @@ k_resolve_init(int n1, int n2, const KpM* __restrict__ k1s, const KpM* __restric
                float* __restrict__ prev_xy, int* __restrict__ nmatches_out) {
     extern __shared__ __align__(16) uint32_t rs_sm[];
     __shared__ int hist[M_HISTO];
-    __shared__ int wsum[RESOLVE_THREADS / 32];
-    __shared__ int nact_sm;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int total = offsets[n1];
-    // shared-memory plan (32-bit words): active[n1] | aoff[n1+1] | md[n2] | s21[n2] | ang1[n1] | ang2[n2] | lists[total]
-    const bool staged = 3 * n1 + 1 + 3 * n2 + total <= smem_words;
-    uint32_t* act = rs_sm;                       // query index of the k-th query that has candidates
-    uint32_t* aoff = act + n1;                   // start of its list inside `lists`
-    int* md = staged ? reinterpret_cast<int*>(aoff + n1 + 1) : matchedDist;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const StagedLists SL = stage_lists(rs_sm, smem_words, 3 * n2 + n1, n1, counts, offsets, cand);
+    const bool staged = SL.staged;
+    // extra shared arrays: md[n2] | s21[n2] | ang2[n2] | ang1[n1]
+    int* md = staged ? reinterpret_cast<int*>(SL.free_words) : matchedDist;
     int* s21 = staged ? md + n2 : m21;
-    float* ang1 = reinterpret_cast<float*>(rs_sm + 2 * n1 + 1 + 2 * n2);
-    float* ang2 = ang1 + n1;
-    uint32_t* lists = reinterpret_cast<uint32_t*>(ang2 + n2);
+    float* ang2 = reinterpret_cast<float*>(SL.free_words) + 2 * n2;
+    float* ang1 = ang2 + n2;
     for (int i = tid; i < n2; i += RESOLVE_THREADS) { md[i] = INT_MAX; s21[i] = -1; if (staged) ang2[i] = k2s[i].angle; }
     for (int i = tid; i < n1; i += RESOLVE_THREADS) { m12[i] = -1; bin_of[i] = -1; if (staged) ang1[i] = k1s[i].angle; }
     if (tid < M_HISTO) hist[tid] = 0;
-    int nact = 0;
-    if (staged) {
-        for (int i = tid; i < total; i += RESOLVE_THREADS) lists[i] = cand[i];
-        // ordered compaction of the queries with a non-empty list (block scan, chunk by chunk)
-        for (int base = 0; base < n1; base += RESOLVE_THREADS) {
-            const int i = base + tid;
-            const int has = (i < n1 && counts[i] > 0) ? 1 : 0;
-            const uint32_t m = __ballot_sync(0xffffffffu, has);
-            if (lane == 0) wsum[warp] = __popc(m);
-            __syncthreads();
-            int before = 0, chunk = 0;
-#pragma unroll
-            for (int w = 0; w < RESOLVE_THREADS / 32; ++w) { const int c = wsum[w]; if (w < warp) before += c; chunk += c; }
-            if (has) { const int k = nact + before + __popc(m & ((1u << lane) - 1u)); act[k] = (uint32_t)i; aoff[k] = (uint32_t)offsets[i]; }
-            nact += chunk;
-            __syncthreads();
-        }
-        if (tid == 0) { aoff[nact] = (uint32_t)total; nact_sm = nact; }
-    }
     __syncthreads();
-    if (warp != 0) return;
-    const uint32_t* L = staged ? lists : cand;
-    const int niter = staged ? nact_sm : n1;
+    if (tid >= 32) return;
     int nmatches = 0;
-    for (int it = 0; it < niter; ++it) {
-        int i1, lo, cnt;
-        if (staged) { i1 = (int)act[it]; lo = (int)aoff[it]; cnt = (int)aoff[it + 1] - lo; }
-        else { i1 = it; cnt = counts[i1]; if (cnt == 0) continue; lo = offsets[i1]; }
-        const uint32_t* c = L + lo;
+    for (int it = 0; it < SL.niter; ++it) {
+        RESOLVE_QUERY(SL, it, i1, c, cnt);
+        if (cnt == 0) continue;
         const Best2 b = warp_best2(c, cnt, lane, [&](uint32_t v) { return !(md[v & 0xFFFFFu] <= (int)(v >> 20)); });   // :561
         if (b.k1 == 0xFFFFFFFFu) continue;
         const int bestDist = (int)(b.k1 >> 20);
@@ -345,35 +364,55 @@ k_resolve_init(int n1, int n2, const KpM* __restrict__ k1s, const KpM* __restric
     if (lane == 0) *nmatches_out = nmatches;
 }
 
-// ---- SearchByProjection(Frame, Frame), sequential part (ORBmatcher.cc:1595-1725); one warp ----
-__global__ void __launch_bounds__(32)
+// ---- SearchByProjection(Frame, Frame), sequential part (ORBmatcher.cc:1595-1725) ----
+__global__ void __launch_bounds__(RESOLVE_THREADS)
 k_resolve_proj_frame(int n_last, int n_cur, const KpM* __restrict__ cur_keys, const float* __restrict__ last_angle, const uint8_t* __restrict__ mp_observed,
                      const uint8_t* __restrict__ cur_occupied, const int* __restrict__ counts, const int* __restrict__ offsets, const uint32_t* __restrict__ cand,
-                     int checkOri, uint8_t* __restrict__ occupied /*n_cur*/, int* __restrict__ cur_match /*n_cur*/, int* __restrict__ pushes /*2*n_last*/,
+                     int checkOri, int smem_words, uint8_t* __restrict__ occupied_g /*n_cur*/, int* __restrict__ cur_match /*n_cur*/, int* __restrict__ pushes /*2*n_last*/,
                      int* __restrict__ nmatches_out) {
+    extern __shared__ __align__(16) uint32_t rs_sm[];
     __shared__ int hist[M_HISTO];
-    const int lane = threadIdx.x;
-    for (int j = lane; j < n_cur; j += 32) { cur_match[j] = -1; occupied[j] = cur_occupied ? (cur_occupied[j] != 0) : 0; }
-    if (lane < M_HISTO) hist[lane] = 0;
-    __syncwarp();
+    const int tid = threadIdx.x, lane = tid & 31;
+    // extra shared arrays: occ[n_cur] (ints) | angc[n_cur] | angl[n_last] | obs[n_last] (ints)
+    const StagedLists SL = stage_lists(rs_sm, smem_words, 2 * n_cur + 2 * n_last, n_last, counts, offsets, cand);
+    const bool staged = SL.staged;
+    int* occ = reinterpret_cast<int*>(SL.free_words);
+    float* angc = reinterpret_cast<float*>(occ + n_cur);
+    float* angl = angc + n_cur;
+    int* obs = reinterpret_cast<int*>(angl + n_last);
+    for (int j = tid; j < n_cur; j += RESOLVE_THREADS) {
+        cur_match[j] = -1;
+        const int o = cur_occupied ? (cur_occupied[j] != 0) : 0;
+        if (staged) { occ[j] = o; angc[j] = cur_keys[j].angle; } else occupied_g[j] = (uint8_t)o;
+    }
+    if (staged) for (int i = tid; i < n_last; i += RESOLVE_THREADS) { angl[i] = last_angle[i]; obs[i] = mp_observed ? (mp_observed[i] != 0) : 0; }
+    if (tid < M_HISTO) hist[tid] = 0;
+    __syncthreads();
+    if (tid >= 32) return;
     int nmatches = 0, npush = 0;
-    for (int i = 0; i < n_last; ++i) {
-        const int cnt = counts[i];
+    for (int it = 0; it < SL.niter; ++it) {
+        RESOLVE_QUERY(SL, it, i, c, cnt);
         if (cnt == 0) continue;
-        const uint32_t* c = cand + offsets[i];
-        const Best2 b = warp_best2(c, cnt, lane, [&](uint32_t v) { return !occupied[v & 0xFFFFFu] && (v >> 20) < 256u; });   // :1658-1660, bestDist = 256
+        const Best2 b = staged ? warp_best2(c, cnt, lane, [&](uint32_t v) { return !occ[v & 0xFFFFFu] && (v >> 20) < 256u; })            // :1658-1660, bestDist = 256
+                               : warp_best2(c, cnt, lane, [&](uint32_t v) { return !occupied_g[v & 0xFFFFFu] && (v >> 20) < 256u; });
         if (b.k1 == 0xFFFFFFFFu) continue;
         const int bestDist = (int)(b.k1 >> 20);
         if (bestDist <= M_TH_HIGH) {                                                               // :1683
             const int j = (int)(c[b.k1 & 0xFFFFFu] & 0xFFFFFu);
             if (lane == 0) {
-                cur_match[j] = i; occupied[j] = mp_observed ? (mp_observed[i] != 0) : 0;
-                if (checkOri) { const int bin = rot_bin(last_angle[i], cur_keys[j].angle); hist[bin]++; pushes[2 * npush] = bin; pushes[2 * npush + 1] = j; }
+                cur_match[j] = i;
+                const int o = staged ? obs[i] : (mp_observed ? (mp_observed[i] != 0) : 0);
+                if (staged) occ[j] = o; else occupied_g[j] = (uint8_t)o;
+                if (checkOri) {
+                    const int bin = staged ? rot_bin(angl[i], angc[j]) : rot_bin(last_angle[i], cur_keys[j].angle);
+                    hist[bin]++; pushes[2 * npush] = bin; pushes[2 * npush + 1] = j;
+                }
             }
             ++nmatches; ++npush;
             __syncwarp();
         }
     }
+    __syncwarp();
     if (checkOri) {
         int ind1, ind2, ind3;
         three_maxima(hist, ind1, ind2, ind3);
@@ -389,29 +428,46 @@ k_resolve_proj_frame(int n_last, int n_cur, const KpM* __restrict__ cur_keys, co
     if (lane == 0) *nmatches_out = nmatches;
 }
 
-// ---- SearchByProjection(Frame, vpMapPoints), sequential part (ORBmatcher.cc:77-172); one warp ----
-__global__ void __launch_bounds__(32)
+// ---- SearchByProjection(Frame, vpMapPoints), sequential part (ORBmatcher.cc:77-172) ----
+__global__ void __launch_bounds__(RESOLVE_THREADS)
 k_resolve_proj_points(int n_points, int n_f, const KpM* __restrict__ f_keys, const uint8_t* __restrict__ mp_observed, const uint8_t* __restrict__ f_occupied,
-                      const int* __restrict__ counts, const int* __restrict__ offsets, const uint32_t* __restrict__ cand, float nnratio,
-                      uint8_t* __restrict__ occupied, int* __restrict__ f_match, int* __restrict__ nmatches_out) {
-    const int lane = threadIdx.x;
-    for (int j = lane; j < n_f; j += 32) { f_match[j] = -1; occupied[j] = f_occupied ? (f_occupied[j] != 0) : 0; }
-    __syncwarp();
+                      const int* __restrict__ counts, const int* __restrict__ offsets, const uint32_t* __restrict__ cand, float nnratio, int smem_words,
+                      uint8_t* __restrict__ occupied_g, int* __restrict__ f_match, int* __restrict__ nmatches_out) {
+    extern __shared__ __align__(16) uint32_t rs_sm[];
+    const int tid = threadIdx.x, lane = tid & 31;
+    // extra shared arrays: occ[n_f] | oct[n_f] | obs[n_points]
+    const StagedLists SL = stage_lists(rs_sm, smem_words, 2 * n_f + n_points, n_points, counts, offsets, cand);
+    const bool staged = SL.staged;
+    int* occ = reinterpret_cast<int*>(SL.free_words);
+    int* oct = occ + n_f;
+    int* obs = oct + n_f;
+    for (int j = tid; j < n_f; j += RESOLVE_THREADS) {
+        f_match[j] = -1;
+        const int o = f_occupied ? (f_occupied[j] != 0) : 0;
+        if (staged) { occ[j] = o; oct[j] = f_keys[j].octave; } else occupied_g[j] = (uint8_t)o;
+    }
+    if (staged) for (int i = tid; i < n_points; i += RESOLVE_THREADS) obs[i] = mp_observed ? (mp_observed[i] != 0) : 0;
+    __syncthreads();
+    if (tid >= 32) return;
     int nmatches = 0;
-    for (int i = 0; i < n_points; ++i) {
-        const int cnt = counts[i];
+    for (int it = 0; it < SL.niter; ++it) {
+        RESOLVE_QUERY(SL, it, i, c, cnt);
         if (cnt == 0) continue;
-        const uint32_t* c = cand + offsets[i];
-        const Best2 b = warp_best2(c, cnt, lane, [&](uint32_t v) { return !occupied[v & 0xFFFFFu] && (v >> 20) < 256u; });
+        const Best2 b = staged ? warp_best2(c, cnt, lane, [&](uint32_t v) { return !occ[v & 0xFFFFFu] && (v >> 20) < 256u; })
+                               : warp_best2(c, cnt, lane, [&](uint32_t v) { return !occupied_g[v & 0xFFFFFu] && (v >> 20) < 256u; });
         if (b.k1 == 0xFFFFFFFFu) continue;
         const int bestDist = (int)(b.k1 >> 20);
         if (bestDist > M_TH_HIGH) continue;                                                        // :163
         const int bestIdx = (int)(c[b.k1 & 0xFFFFFu] & 0xFFFFFu);
-        const int bestLevel = f_keys[bestIdx].octave;
+        const int bestLevel = staged ? oct[bestIdx] : f_keys[bestIdx].octave;
         int bestDist2 = 256, bestLevel2 = -1;
-        if (b.k2 != 0xFFFFFFFFu) { bestDist2 = (int)(b.k2 >> 20); bestLevel2 = f_keys[c[b.k2 & 0xFFFFFu] & 0xFFFFFu].octave; }
+        if (b.k2 != 0xFFFFFFFFu) { bestDist2 = (int)(b.k2 >> 20); const int j2 = (int)(c[b.k2 & 0xFFFFFu] & 0xFFFFFu); bestLevel2 = staged ? oct[j2] : f_keys[j2].octave; }
         if (bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(nnratio, (float)bestDist2)) continue;   // :166
-        if (lane == 0) { f_match[bestIdx] = i; occupied[bestIdx] = mp_observed ? (mp_observed[i] != 0) : 0; }
+        if (lane == 0) {
+            f_match[bestIdx] = i;
+            const int o = staged ? obs[i] : (mp_observed ? (mp_observed[i] != 0) : 0);
+            if (staged) occ[bestIdx] = o; else occupied_g[bestIdx] = (uint8_t)o;
+        }
         ++nmatches;
         __syncwarp();
     }

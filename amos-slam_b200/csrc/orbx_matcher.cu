@@ -128,6 +128,8 @@ int orbx_matcher_create(float nnratio, int check_orientation, int device, orbx_m
     cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete m; FAIL(ORBX_E_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e)); }
     cudaFuncSetAttribute(k_resolve_init, cudaFuncAttributeMaxDynamicSharedMemorySize, RESOLVE_SMEM_BYTES);   // per device
+    cudaFuncSetAttribute(k_resolve_proj_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, RESOLVE_SMEM_BYTES);
+    cudaFuncSetAttribute(k_resolve_proj_points, cudaFuncAttributeMaxDynamicSharedMemorySize, RESOLVE_SMEM_BYTES);
     *out = m;
     return ORBX_OK;
 }
@@ -217,7 +219,7 @@ int orbx_search_by_projection_frame(orbx_matcher* m, const orbx_frame_view* cur,
     if ((rc = window_search(m, P, dc, counts, offsets, cand))) return rc;
     uint8_t* occ = m->arena.get<uint8_t>(nc + 1); int* cm = m->arena.get<int>(nc + 1); int* pushes = m->arena.get<int>(2 * (size_t)n_last + 2); int* dn = m->arena.get<int>(1);
     if (!occ || !cm || !pushes || !dn) FAIL(ORBX_E_CUDA, "matcher arena exhausted");
-    k_resolve_proj_frame<<<1, 32, 0, m->stream>>>(n_last, nc, dc.keys, la, ob, oc, counts, offsets, cand, m->checkOri, occ, cm, pushes, dn);
+    k_resolve_proj_frame<<<1, RESOLVE_THREADS, RESOLVE_SMEM_BYTES, m->stream>>>(n_last, nc, dc.keys, la, ob, oc, counts, offsets, cand, m->checkOri, RESOLVE_SMEM_BYTES / 4, occ, cm, pushes, dn);
     LAUNCH_CHECK();
     if (nc) CU_TRY(cudaMemcpyAsync(cur_match, cm, (size_t)nc * 4, cudaMemcpyDeviceToHost, m->stream));
     CU_TRY(cudaMemcpyAsync(nmatches, dn, 4, cudaMemcpyDeviceToHost, m->stream));
@@ -252,7 +254,7 @@ int orbx_search_by_projection_points(orbx_matcher* m, const orbx_frame_view* F, 
     if ((rc = window_search(m, P, df, counts, offsets, cand))) return rc;
     uint8_t* occ = m->arena.get<uint8_t>(nf + 1); int* fm = m->arena.get<int>(nf + 1); int* dn = m->arena.get<int>(1);
     if (!occ || !fm || !dn) FAIL(ORBX_E_CUDA, "matcher arena exhausted");
-    k_resolve_proj_points<<<1, 32, 0, m->stream>>>(n_points, nf, df.keys, ob, oc, counts, offsets, cand, m->nnratio, occ, fm, dn);
+    k_resolve_proj_points<<<1, RESOLVE_THREADS, RESOLVE_SMEM_BYTES, m->stream>>>(n_points, nf, df.keys, ob, oc, counts, offsets, cand, m->nnratio, RESOLVE_SMEM_BYTES / 4, occ, fm, dn);
     LAUNCH_CHECK();
     if (nf) CU_TRY(cudaMemcpyAsync(f_match, fm, (size_t)nf * 4, cudaMemcpyDeviceToHost, m->stream));
     CU_TRY(cudaMemcpyAsync(nmatches, dn, 4, cudaMemcpyDeviceToHost, m->stream));
