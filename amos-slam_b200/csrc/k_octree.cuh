@@ -196,13 +196,13 @@ k_octree_sort(const LevelGeom* __restrict__ levels, const CellDesc* __restrict__
     if (tid == 0) ncand[b * nlevels + level] = n;
 }
 
-// ---- warp-cooperative lower bound on the sorted keys: first index in [lo,hi) with key >= T ----
-__device__ __forceinline__ int warp_lower_bound(const unsigned long long* __restrict__ key, int lo, int hi,
-                                                unsigned long long T, int lane) {
+// ---- warp-cooperative lower bound on the sorted path codes: first index in [lo,hi) with code >= T ----
+// codes are read as ck[pos * cs]: cs = 1 for the shared-memory copy, 2 for the high words of the 64-bit global keys
+__device__ __forceinline__ int warp_lower_bound(const uint32_t* __restrict__ ck, int cs, int lo, int hi, uint32_t T, int lane) {
     while (hi - lo > 32) {
         const int step = (hi - lo + 31) >> 5;
         const int pos = lo + lane * step;
-        const bool pred = pos < hi && key[pos] < T;
+        const bool pred = pos < hi && ck[pos * cs] < T;
         const int c = __popc(__ballot_sync(0xffffffffu, pred));
         if (c == 0) return lo;
         const int nlo = lo + (c - 1) * step + 1;
@@ -210,7 +210,7 @@ __device__ __forceinline__ int warp_lower_bound(const unsigned long long* __rest
         lo = nlo;
     }
     const int pos = lo + lane;
-    const bool pred = pos < hi && key[pos] < T;
+    const bool pred = pos < hi && ck[pos * cs] < T;
     return lo + __popc(__ballot_sync(0xffffffffu, pred));
 }
 
@@ -220,7 +220,7 @@ struct TreeSmem {
 };
 
 __global__ void __launch_bounds__(32)
-k_octree_tree(const LevelGeom* __restrict__ levels, int nlevels, int cand_per_frame, int kp_per_frame, int cap_max,
+k_octree_tree(const LevelGeom* __restrict__ levels, int nlevels, int cand_per_frame, int kp_per_frame, int cap_max, int code_cap,
               const unsigned long long* __restrict__ skey, const uint32_t* __restrict__ spk, const int* __restrict__ ncand,
               uint32_t* __restrict__ kp_level,      // [B][kp_per_frame] packed x:12|y:12|resp:8 (relative to minBorder)
               int* __restrict__ kp_count,           // [B][nlevels]
@@ -235,6 +235,15 @@ k_octree_tree(const LevelGeom* __restrict__ levels, int nlevels, int cand_per_fr
     if (n <= 0) { if (lane == 0) { kp_count[b * nlevels + level] = 0; if (n < 0) atomicOr(overflow, ORBX_OVF_SORT); } return; }
 
     const int cap = cap_max;     // node slots available (>= kp_cap + 8 for every level)
+    // the serial replay probes the sorted codes thousands of times: keep them in shared memory (after the node records)
+    // whenever the level's candidates fit; otherwise read the high words of the global 64-bit keys
+    uint32_t* codes_sm = reinterpret_cast<uint32_t*>(tree_sm + (((size_t)cap * (8 + 8 + 4 + 4 + 4 + 2 + 2 + 2 + 1) + 15) & ~(size_t)15));
+    const uint32_t* ck; int cs;
+    if (n <= code_cap) {
+        for (int i = lane; i < n; i += 32) codes_sm[i] = (uint32_t)(key[i] >> 32);
+        ck = codes_sm; cs = 1;
+    } else { ck = reinterpret_cast<const uint32_t*>(key) + 1; cs = 2; }
+    __syncwarp();
     unsigned long long* vcur = reinterpret_cast<unsigned long long*>(tree_sm);
     unsigned long long* vprev = vcur + cap;
     int* nlo = reinterpret_cast<int*>(vprev + cap);
@@ -258,8 +267,8 @@ k_octree_tree(const LevelGeom* __restrict__ levels, int nlevels, int cand_per_fr
 
     // ---- initial nodes (:733-788): nIni roots in order (push_back), empty ones erased ----
     for (int i = 0; i < g.nIni; ++i) {
-        const int rlo = warp_lower_bound(key, 0, n, (unsigned long long)i << (32 + ORBX_ROOT_SHIFT), lane);
-        const int rhi = warp_lower_bound(key, rlo, n, (unsigned long long)(i + 1) << (32 + ORBX_ROOT_SHIFT), lane);
+        const int rlo = warp_lower_bound(ck, cs, 0, n, (uint32_t)i << ORBX_ROOT_SHIFT, lane);
+        const int rhi = warp_lower_bound(ck, cs, rlo, n, (uint32_t)(i + 1) << ORBX_ROOT_SHIFT, lane);
         ++nextCid;
         if (rhi > rlo) {
             int s; NODE_ALLOC(s);
@@ -281,15 +290,15 @@ k_octree_tree(const LevelGeom* __restrict__ levels, int nlevels, int cand_per_fr
         bnd[0] = lo; bnd[4] = hi;
         if (hi - lo <= 32) {
             const int pos = lo + lane;
-            const unsigned digit = pos < hi ? (unsigned)((key[pos] >> (32 + shift)) & 3ull) : 4u;
+            const unsigned digit = pos < hi ? ((ck[pos * cs] >> shift) & 3u) : 4u;
             bnd[1] = lo + __popc(__ballot_sync(0xffffffffu, digit < 1u));
             bnd[2] = lo + __popc(__ballot_sync(0xffffffffu, digit < 2u));
             bnd[3] = lo + __popc(__ballot_sync(0xffffffffu, digit < 3u));
         } else {
-            const unsigned long long prefix = key[lo] >> (32 + shift + 2);
-            bnd[1] = warp_lower_bound(key, lo, hi, ((prefix << 2) | 1ull) << (32 + shift), lane);
-            bnd[2] = warp_lower_bound(key, bnd[1], hi, ((prefix << 2) | 2ull) << (32 + shift), lane);
-            bnd[3] = warp_lower_bound(key, bnd[2], hi, ((prefix << 2) | 3ull) << (32 + shift), lane);
+            const uint32_t prefix = ck[lo * cs] >> (shift + 2);
+            bnd[1] = warp_lower_bound(ck, cs, lo, hi, ((prefix << 2) | 1u) << shift, lane);
+            bnd[2] = warp_lower_bound(ck, cs, bnd[1], hi, ((prefix << 2) | 2u) << shift, lane);
+            bnd[3] = warp_lower_bound(ck, cs, bnd[2], hi, ((prefix << 2) | 3u) << shift, lane);
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {

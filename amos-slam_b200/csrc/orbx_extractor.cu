@@ -319,8 +319,11 @@ static int run_detect(orbx_extractor* h, int b0, int B, bool fork_blur = false) 
                                                                                  h->sort_smem_keys, slots, cell_counts, h->d_ocand.p + co, h->d_skey.p + co, h->d_spk.p + co, h->d_ncand.p + (size_t)b0 * L);
         LAUNCH_CHECK();
         prof_mark(h);
-        const size_t tsm = (size_t)h->tree_cap * (8 + 8 + 4 + 4 + 4 + 2 + 2 + 2 + 1) + 16;
-        k_octree_tree<<<grid, 32, tsm, s>>>(h->d_levels.p, L, h->cand_per_frame, h->kp_per_frame, h->tree_cap, h->d_skey.p + co, h->d_spk.p + co, h->d_ncand.p + (size_t)b0 * L,
+        // sorted path codes staged in shared memory per (level, frame) instance: shortens the serial replay ~2x, but the extra 16 KB
+        // cuts the resident instances per SM from 25 to 9, so it only pays while all instances fit in one wave (small batches, latency)
+        const int code_cap = (L * B <= 148 * 9) ? 4096 : 0;
+        const size_t tsm = (((size_t)h->tree_cap * (8 + 8 + 4 + 4 + 4 + 2 + 2 + 2 + 1) + 15) & ~(size_t)15) + (size_t)code_cap * 4 + 16;
+        k_octree_tree<<<grid, 32, tsm, s>>>(h->d_levels.p, L, h->cand_per_frame, h->kp_per_frame, h->tree_cap, code_cap, h->d_skey.p + co, h->d_spk.p + co, h->d_ncand.p + (size_t)b0 * L,
                                             h->d_kp_level.p + (size_t)b0 * h->kp_per_frame, h->d_kp_count.p + (size_t)b0 * L, h->d_overflow.p);
         LAUNCH_CHECK();
     }
@@ -627,17 +630,24 @@ int orbx_extract(orbx_extractor* h, const uint8_t* image, int rows, int cols, si
     const int icap = h->max_kp;
     if ((rc = ensure_capacity(h, 1, icap))) return rc;
     if ((rc = upload_level0(h, image, 1, rows, cols, step, 0))) return rc;
-    if ((rc = run_detect(h, 0, 1))) return rc;
-    if ((rc = run_blur(h, 1))) return rc;
+    if ((rc = run_detect(h, 0, 1, true))) return rc;                 // blur forked next to FAST / quadtree
+    CU_TRY(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+    h->blur_valid = true;
     if ((rc = run_orient(h, 0, 1, true, h->d_kp_out.p, h->d_desc_out.p, icap, h->d_counts.p, nullptr))) return rc;
     int n = 0, ovf = 0;
     CU_TRY(cudaMemcpyAsync(&n, h->d_counts.p, 4, cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(cudaMemcpyAsync(&ovf, h->d_overflow.p, 4, cudaMemcpyDeviceToHost, h->stream));
+    // a caller buffer sized with orbx_max_keypoints() takes every possible result: copy speculatively and save a round trip
+    const bool spec = cap >= icap;
+    if (spec) {
+        CU_TRY(cudaMemcpyAsync(kp_out, h->d_kp_out.p, (size_t)icap * sizeof(KpOut), cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(cudaMemcpyAsync(desc_out, h->d_desc_out.p, (size_t)icap * 32, cudaMemcpyDeviceToHost, h->stream));
+    }
     CU_TRY(cudaStreamSynchronize(h->stream));
     if (ovf) FAIL(ORBX_E_OVERFLOW, "internal bound exceeded in the quadtree stage");
     *n_out = n;
     if (n > cap) FAIL(ORBX_E_CAPACITY, "keypoint buffer too small");
-    if (n) {
+    if (n && !spec) {
         CU_TRY(cudaMemcpyAsync(kp_out, h->d_kp_out.p, (size_t)n * sizeof(KpOut), cudaMemcpyDeviceToHost, h->stream));
         CU_TRY(cudaMemcpyAsync(desc_out, h->d_desc_out.p, (size_t)n * 32, cudaMemcpyDeviceToHost, h->stream));
         CU_TRY(cudaStreamSynchronize(h->stream));
