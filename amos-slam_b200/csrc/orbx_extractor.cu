@@ -551,8 +551,13 @@ static int chunk_frames(const orbx_extractor* h, int B) {
     return (int)c;
 }
 
-int orbx_extract_batch(orbx_extractor* h, const uint8_t* images, int B, int rows, int cols, size_t step, size_t frame_stride,
-                       orbx_keypoint* kp_out, uint8_t* desc_out, int cap, int* counts_out) {
+static int run_masked_range(orbx_extractor* h, int b0, int nb, const uint8_t* d_masks, long long mfs, int mpitch, int rows, int cols,
+                            KpOut* d_kp, uint8_t* d_desc, int cap, int* d_counts, int* d_culled);
+static int ensure_closing(orbx_extractor* h, int nframes, int rows, int cols);
+
+// masks == nullptr: operator()(image, mask, keypoints, descriptors) per frame; otherwise the two-stage Amos path with culling
+static int host_batch_pipeline(orbx_extractor* h, const uint8_t* images, const uint8_t* masks, int B, int rows, int cols, size_t step, size_t frame_stride,
+                               size_t mask_step, size_t mask_frame_stride, orbx_keypoint* kp_out, uint8_t* desc_out, int cap, int* counts_out, int* culled_out) {
     int rc = check_args(h, images, rows, cols, step); if (rc) return rc;
     if (B <= 0 || !kp_out || !desc_out || !counts_out || cap <= 0) FAIL(ORBX_E_INVALID, "bad batch arguments");
     if ((rc = build_plan(h, rows, cols))) return rc;
@@ -568,6 +573,12 @@ int orbx_extract_batch(orbx_extractor* h, const uint8_t* images, int B, int rows
         h->view.l0 = h->d_pyr.p + g0.off; h->view.l0_fstride = h->pyr_fstride; h->view.l0_pitch = g0.pitch;
     }
     h->view.pyr = h->d_pyr.p; h->view.pyr_fstride = h->pyr_fstride;
+    const int mpitch = align_up(cols, 128);
+    const size_t mfs = (size_t)mpitch * rows;
+    if (masks) {
+        if ((rc = ensure_closing(h, B, rows, cols))) return rc;
+        if (h->d_mask.ensure(mfs * B + 64) || h->d_culled.ensure(B)) return ORBX_E_CUDA;
+    }
     const int C = chunk_frames(h, B), nchunks = (B + C - 1) / C;
     while ((int)h->ev_h2d.size() < nchunks) {
         cudaEvent_t a, b;
@@ -591,15 +602,25 @@ int orbx_extract_batch(orbx_extractor* h, const uint8_t* images, int B, int rows
                 CU_TRY(cudaMemcpy2DAsync(h->d_pyr.p + (size_t)b * h->pyr_fstride + g0.off, g0.pitch, images + (size_t)b * frame_stride, step,
                                          cols, rows, cudaMemcpyHostToDevice, h->s_h2d));
         }
+        if (masks) {
+            if (mask_step == (size_t)mpitch && mask_frame_stride == mfs)                                  // dense and already pitched: one copy per chunk
+                CU_TRY(cudaMemcpyAsync(h->d_mask.p + (size_t)b0 * mfs, masks + (size_t)b0 * mask_frame_stride, (size_t)nb * mfs, cudaMemcpyHostToDevice, h->s_h2d));
+            else
+                for (int b = b0; b < b0 + nb; ++b)
+                    CU_TRY(cudaMemcpy2DAsync(h->d_mask.p + (size_t)b * mfs, mpitch, masks + (size_t)b * mask_frame_stride, mask_step, cols, rows, cudaMemcpyHostToDevice, h->s_h2d));
+        }
         CU_TRY(cudaEventRecord(h->ev_h2d[c], h->s_h2d));
     }
     for (int c = 0; c < nchunks; ++c) {
         const int b0 = c * C, nb = std::min(C, B - b0);
         h->cur = cs[c % nstreams];
         CU_TRY(cudaStreamWaitEvent(h->cur, h->ev_h2d[c], 0));
-        rc = run_detect(h, b0, nb);
-        if (!rc) rc = run_blur_range(h, b0, nb);
-        if (!rc) rc = run_orient(h, b0, nb, true, h->d_kp_out.p, h->d_desc_out.p, cap, h->d_counts.p, nullptr);
+        if (masks) rc = run_masked_range(h, b0, nb, h->d_mask.p + (size_t)b0 * mfs, (long long)mfs, mpitch, rows, cols, h->d_kp_out.p, h->d_desc_out.p, cap, h->d_counts.p, h->d_culled.p);
+        else {
+            rc = run_detect(h, b0, nb);
+            if (!rc) rc = run_blur_range(h, b0, nb);
+            if (!rc) rc = run_orient(h, b0, nb, true, h->d_kp_out.p, h->d_desc_out.p, cap, h->d_counts.p, nullptr);
+        }
         cudaStream_t used = h->cur;
         h->cur = h->stream;
         if (rc) return rc;
@@ -608,6 +629,7 @@ int orbx_extract_batch(orbx_extractor* h, const uint8_t* images, int B, int rows
         CU_TRY(cudaMemcpyAsync(kp_out + (size_t)b0 * cap, h->d_kp_out.p + (size_t)b0 * cap, (size_t)nb * cap * sizeof(KpOut), cudaMemcpyDeviceToHost, h->s_d2h));
         CU_TRY(cudaMemcpyAsync(desc_out + (size_t)b0 * cap * 32, h->d_desc_out.p + (size_t)b0 * cap * 32, (size_t)nb * cap * 32, cudaMemcpyDeviceToHost, h->s_d2h));
         CU_TRY(cudaMemcpyAsync(counts_out + b0, h->d_counts.p + b0, (size_t)nb * sizeof(int), cudaMemcpyDeviceToHost, h->s_d2h));
+        if (masks && culled_out) CU_TRY(cudaMemcpyAsync(culled_out + b0, h->d_culled.p + b0, (size_t)nb * sizeof(int), cudaMemcpyDeviceToHost, h->s_d2h));
     }
     h->lastB = B; h->blur_valid = true;
     int ovf = 0;
@@ -617,6 +639,11 @@ int orbx_extract_batch(orbx_extractor* h, const uint8_t* images, int B, int rows
     CU_TRY(cudaStreamSynchronize(h->stream));
     if (ovf) FAIL(ORBX_E_OVERFLOW, "internal bound exceeded in the quadtree stage");
     return ORBX_OK;
+}
+
+int orbx_extract_batch(orbx_extractor* h, const uint8_t* images, int B, int rows, int cols, size_t step, size_t frame_stride,
+                       orbx_keypoint* kp_out, uint8_t* desc_out, int cap, int* counts_out) {
+    return host_batch_pipeline(h, images, nullptr, B, rows, cols, step, frame_stride, 0, 0, kp_out, desc_out, cap, counts_out, nullptr);
 }
 
 int orbx_extract(orbx_extractor* h, const uint8_t* image, int rows, int cols, size_t step,

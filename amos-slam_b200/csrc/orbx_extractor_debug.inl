@@ -10,20 +10,26 @@ static int upload_ellipse() {
     return ORBX_OK;
 }
 
-// bit-pack nframes masks (u8, pitch multiple of 32) and close them; result: h->d_bits1 = (closing != 0), [nframes][rows][wpr]
-static int run_closing(orbx_extractor* h, const uint8_t* d_mask, long long fstride, int pitch, int nframes, int rows, int cols, cudaStream_t s) {
+// bit-pack the masks of frames [b0, b0+nframes) (u8, pitch multiple of 32; d_mask points at frame b0) and close them on h->cur;
+// result: h->d_bits0 = (closing != 0), [B][rows][wpr].  The caller has sized d_bits0 / d_bits1 for the whole batch.
+static int run_closing(orbx_extractor* h, const uint8_t* d_mask, long long fstride, int pitch, int b0, int nframes, int rows, int cols) {
+    const int wpr = (cols + 31) / 32;
+    cudaStream_t s = h->cur;
+    uint32_t* a = h->d_bits0.p + (size_t)b0 * rows * wpr; uint32_t* b = h->d_bits1.p + (size_t)b0 * rows * wpr;
+    dim3 grid((wpr + 63) / 64, rows, nframes);
+    k_mask_pack<<<grid, 64, 0, s>>>(d_mask, fstride, pitch, rows, cols, a, wpr);
+    LAUNCH_CHECK();
+    k_bin_dilate31<false><<<grid, 64, 0, s>>>(a, b, wpr, rows, cols);
+    LAUNCH_CHECK();
+    k_bin_dilate31<true><<<grid, 64, 0, s>>>(b, a, wpr, rows, cols);
+    LAUNCH_CHECK();
+    return ORBX_OK;
+}
+static int ensure_closing(orbx_extractor* h, int nframes, int rows, int cols) {
     int rc;
     if ((rc = upload_ellipse())) return rc;
-    const int wpr = (cols + 31) / 32;
-    if (h->d_bits0.ensure((size_t)nframes * rows * wpr) || h->d_bits1.ensure((size_t)nframes * rows * wpr)) return ORBX_E_CUDA;
-    dim3 grid((wpr + 63) / 64, rows, nframes);
-    k_mask_pack<<<grid, 64, 0, s>>>(d_mask, fstride, pitch, rows, cols, h->d_bits0.p, wpr);
-    LAUNCH_CHECK();
-    k_bin_dilate31<false><<<grid, 64, 0, s>>>(h->d_bits0.p, h->d_bits1.p, wpr, rows, cols);
-    LAUNCH_CHECK();
-    k_bin_dilate31<true><<<grid, 64, 0, s>>>(h->d_bits1.p, h->d_bits0.p, wpr, rows, cols);
-    LAUNCH_CHECK();
-    std::swap(h->d_bits0, h->d_bits1);
+    const size_t words = (size_t)nframes * rows * ((cols + 31) / 32);
+    if (h->d_bits0.ensure(words) || h->d_bits1.ensure(words)) return ORBX_E_CUDA;
     return ORBX_OK;
 }
 
@@ -38,7 +44,6 @@ extern "C" int orbx_cull(orbx_extractor* h, const uint8_t* mask, size_t mask_ste
     int n = 0;
     for (int l = 0; l < h->nlevels; ++l) { if (level_counts[l] < 0) FAIL(ORBX_E_INVALID, "negative level count"); n += level_counts[l]; }
     int rc;
-    if ((rc = upload_ellipse())) return rc;
     const int pitch = align_up(cols, 128);
     if (h->d_mask.ensure((size_t)pitch * rows + 64) || h->d_label.ensure((size_t)rows * cols) ||
         h->d_ids.ensure((size_t)ncenters + nrm + 4) || h->d_kp_tmp.ensure((size_t)std::max(n, 1) * 2) || h->d_desc_tmp.ensure((size_t)std::max(n, 1) * 32))
@@ -49,7 +54,8 @@ extern "C" int orbx_cull(orbx_extractor* h, const uint8_t* mask, size_t mask_ste
     if (ncenters) CU_TRY(cudaMemcpyAsync(h->d_ids.p, centers_id, (size_t)ncenters * 4, cudaMemcpyHostToDevice, s));
     if (nrm) CU_TRY(cudaMemcpyAsync(h->d_ids.p + ncenters, rm_vector, (size_t)nrm * 4, cudaMemcpyHostToDevice, s));
     // closing = erode(dilate(mask))   (:1697-1704), as two binary dilations on the bit-packed mask (k_cull.cuh)
-    if ((rc = run_closing(h, h->d_mask.p, (long long)pitch * rows, pitch, 1, rows, cols, s))) return rc;
+    if ((rc = ensure_closing(h, 1, rows, cols))) return rc;
+    if ((rc = run_closing(h, h->d_mask.p, (long long)pitch * rows, pitch, 0, 1, rows, cols))) return rc;
     const int wpr = (cols + 31) / 32;
     if (n == 0) { CU_TRY(cudaStreamSynchronize(s)); return ORBX_OK; }
     if (!kp_inout) FAIL(ORBX_E_INVALID, "null keypoints");
@@ -60,7 +66,7 @@ extern "C" int orbx_cull(orbx_extractor* h, const uint8_t* mask, size_t mask_ste
     uint8_t* d_flags = h->d_desc_tmp.p + (size_t)n * 4;
     CU_TRY(cudaMemcpyAsync(h->d_kp_tmp.p, kp_inout, sizeof(KpOut) * n, cudaMemcpyHostToDevice, s));
     CU_TRY(cudaMemcpyAsync(d_scales, scales.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
-    k_cull_flags<<<(n + 127) / 128, 128, 0, s>>>(reinterpret_cast<const KpIn*>(h->d_kp_tmp.p), d_scales, n, h->d_bits1.p, wpr, h->d_label.p, cols,
+    k_cull_flags<<<(n + 127) / 128, 128, 0, s>>>(reinterpret_cast<const KpIn*>(h->d_kp_tmp.p), d_scales, n, h->d_bits0.p, wpr, h->d_label.p, cols,
                                                   rows, cols, h->d_ids.p, ncenters, h->d_ids.p + ncenters, nrm, d_flags);
     LAUNCH_CHECK();
     std::vector<uint8_t> flags(n);
@@ -81,7 +87,22 @@ extern "C" int orbx_cull(orbx_extractor* h, const uint8_t* mask, size_t mask_ste
 }
 
 // Batched Amos path (BASELINE config 5): per frame  operator()(img, mask, vector<vector<KeyPoint>>&)  ->  MovingKeyPoints with the
-// dynamic mask (no super-pixel labels)  ->  ProcessDesp.  Device pointers, asynchronous on orbx_stream(h).
+// dynamic mask (no super-pixel labels)  ->  ProcessDesp.  Frames [b0, b0+nb) on h->cur; d_masks points at frame b0's mask.
+static int run_masked_range(orbx_extractor* h, int b0, int nb, const uint8_t* d_masks, long long mfs, int mpitch, int rows, int cols,
+                            KpOut* d_kp, uint8_t* d_desc, int cap, int* d_counts, int* d_culled) {
+    int rc;
+    if ((rc = run_detect(h, b0, nb))) return rc;
+    if ((rc = run_closing(h, d_masks, mfs, mpitch, b0, nb, rows, cols))) return rc;
+    if (d_culled) CU_TRY(cudaMemsetAsync(d_culled + b0, 0, (size_t)nb * sizeof(int), h->cur));
+    const int wpr = (cols + 31) / 32;
+    k_cull_levelkp<<<dim3(h->nlevels, nb), 32, 0, h->cur>>>(h->d_levels.p, h->nlevels, h->kp_per_frame, h->d_kp_level.p + (size_t)b0 * h->kp_per_frame,
+                                                              h->d_kp_count.p + (size_t)b0 * h->nlevels, h->d_bits0.p + (size_t)b0 * rows * wpr, wpr, rows, cols,
+                                                              d_culled ? d_culled + b0 : nullptr);
+    LAUNCH_CHECK();
+    if ((rc = run_blur_range(h, b0, nb))) return rc;
+    return run_orient(h, b0, nb, true, d_kp, d_desc, cap, d_counts, nullptr);
+}
+
 extern "C" int orbx_extract_masked_batch_device(orbx_extractor* h, const uint8_t* d_images, const uint8_t* d_masks, int B, int rows, int cols,
                                                 size_t step, size_t frame_stride, size_t mask_step, size_t mask_frame_stride,
                                                 orbx_keypoint* d_kp_out, uint8_t* d_desc_out, int cap, int* d_counts_out, int* d_culled_out) {
@@ -89,57 +110,31 @@ extern "C" int orbx_extract_masked_batch_device(orbx_extractor* h, const uint8_t
     if (B <= 0 || !d_masks || !d_kp_out || !d_desc_out || !d_counts_out || cap <= 0 || mask_step < (size_t)cols) FAIL(ORBX_E_INVALID, "bad batch arguments");
     if ((rc = build_plan(h, rows, cols))) return rc;
     if ((rc = ensure_capacity(h, B, 0))) return rc;
+    if ((rc = ensure_closing(h, B, rows, cols))) return rc;
     if (((uintptr_t)d_images & 3) || (step & 3) || (frame_stride & 3)) FAIL(ORBX_E_INVALID, "device frames must be 4-byte aligned (pointer, step, frame stride)");
     h->view.l0 = d_images; h->view.l0_fstride = (long long)frame_stride; h->view.l0_pitch = (int)step;
     h->view.pyr = h->d_pyr.p; h->view.pyr_fstride = h->pyr_fstride;
-    cudaStream_t s = h->stream;
     // masks: pack needs 32-byte row alignment; repack into our own pitched buffer unless the caller's layout already qualifies
     const uint8_t* mk = d_masks; long long mfs = (long long)mask_frame_stride; int mpitch = (int)mask_step;
     if (((uintptr_t)d_masks & 15) || (mask_step & 31) || (mask_frame_stride & 15) || mask_step < (size_t)align_up(cols, 32)) {
         mpitch = align_up(cols, 128); mfs = (long long)mpitch * rows;
         if (h->d_mask.ensure((size_t)mfs * B + 64)) return ORBX_E_CUDA;
         for (int b = 0; b < B; ++b)
-            CU_TRY(cudaMemcpy2DAsync(h->d_mask.p + (size_t)b * mfs, mpitch, d_masks + (size_t)b * mask_frame_stride, mask_step, cols, rows, cudaMemcpyDeviceToDevice, s));
+            CU_TRY(cudaMemcpy2DAsync(h->d_mask.p + (size_t)b * mfs, mpitch, d_masks + (size_t)b * mask_frame_stride, mask_step, cols, rows, cudaMemcpyDeviceToDevice, h->stream));
         mk = h->d_mask.p;
     }
-    if ((rc = run_detect(h, 0, B, !h->profiling))) return rc;              // blur forked next to FAST / quadtree / mask closing
-    if ((rc = run_closing(h, mk, mfs, mpitch, B, rows, cols, s))) return rc;
-    if (d_culled_out) CU_TRY(cudaMemsetAsync(d_culled_out, 0, (size_t)B * sizeof(int), s));
-    k_cull_levelkp<<<dim3(h->nlevels, B), 32, 0, s>>>(h->d_levels.p, h->nlevels, h->kp_per_frame, h->d_kp_level.p, h->d_kp_count.p,
-                                                       h->d_bits1.p, (cols + 31) / 32, rows, cols, d_culled_out);
-    LAUNCH_CHECK();
-    if (h->profiling) { if ((rc = run_blur(h, B))) return rc; }
-    else { CU_TRY(cudaStreamWaitEvent(h->stream, h->ev_join, 0)); h->blur_valid = true; }
-    return run_orient(h, 0, B, true, reinterpret_cast<KpOut*>(d_kp_out), d_desc_out, cap, d_counts_out, nullptr);
+    h->cur = h->stream;
+    rc = run_masked_range(h, 0, B, mk, mfs, mpitch, rows, cols, reinterpret_cast<KpOut*>(d_kp_out), d_desc_out, cap, d_counts_out, d_culled_out);
+    if (!rc) { h->lastB = B; h->blur_valid = true; }
+    return rc;
 }
 
-// host-pointer form: synchronous; frames and masks are uploaded, results downloaded
+// host-pointer form: same chunked H2D -> compute -> D2H pipeline as orbx_extract_batch, with the masks riding along
 extern "C" int orbx_extract_masked_batch(orbx_extractor* h, const uint8_t* images, const uint8_t* masks, int B, int rows, int cols,
                                          size_t step, size_t frame_stride, size_t mask_step, size_t mask_frame_stride,
                                          orbx_keypoint* kp_out, uint8_t* desc_out, int cap, int* counts_out, int* culled_out) {
-    int rc = check_args(h, images, rows, cols, step); if (rc) return rc;
-    if (B <= 0 || !masks || !kp_out || !desc_out || !counts_out || cap <= 0 || mask_step < (size_t)cols) FAIL(ORBX_E_INVALID, "bad batch arguments");
-    if ((rc = build_plan(h, rows, cols))) return rc;
-    if ((rc = ensure_capacity(h, B, cap))) return rc;
-    const int p0 = align_up(cols, 128);
-    const size_t fs = (size_t)p0 * rows;
-    if (h->d_l0.ensure(fs * B + 64) || h->d_mask.ensure(fs * B + 64) || h->d_culled.ensure(B)) return ORBX_E_CUDA;
-    cudaStream_t s = h->stream;
-    for (int b = 0; b < B; ++b) {
-        CU_TRY(cudaMemcpy2DAsync(h->d_l0.p + b * fs, p0, images + (size_t)b * frame_stride, step, cols, rows, cudaMemcpyHostToDevice, s));
-        CU_TRY(cudaMemcpy2DAsync(h->d_mask.p + b * fs, p0, masks + (size_t)b * mask_frame_stride, mask_step, cols, rows, cudaMemcpyHostToDevice, s));
-    }
-    if ((rc = orbx_extract_masked_batch_device(h, h->d_l0.p, h->d_mask.p, B, rows, cols, p0, fs, p0, fs, reinterpret_cast<orbx_keypoint*>(h->d_kp_out.p),
-                                               h->d_desc_out.p, cap, h->d_counts.p, h->d_culled.p))) return rc;
-    CU_TRY(cudaMemcpyAsync(kp_out, h->d_kp_out.p, (size_t)B * cap * sizeof(KpOut), cudaMemcpyDeviceToHost, s));
-    CU_TRY(cudaMemcpyAsync(desc_out, h->d_desc_out.p, (size_t)B * cap * 32, cudaMemcpyDeviceToHost, s));
-    CU_TRY(cudaMemcpyAsync(counts_out, h->d_counts.p, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, s));
-    if (culled_out) CU_TRY(cudaMemcpyAsync(culled_out, h->d_culled.p, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, s));
-    int ovf = 0;
-    CU_TRY(cudaMemcpyAsync(&ovf, h->d_overflow.p, 4, cudaMemcpyDeviceToHost, s));
-    CU_TRY(cudaStreamSynchronize(s));
-    if (ovf) FAIL(ORBX_E_OVERFLOW, "internal bound exceeded in the quadtree stage");
-    return ORBX_OK;
+    if (!masks || mask_step < (size_t)cols) FAIL(ORBX_E_INVALID, "bad mask arguments");
+    return host_batch_pipeline(h, images, masks, B, rows, cols, step, frame_stride, mask_step, mask_frame_stride, kp_out, desc_out, cap, counts_out, culled_out);
 }
 
 // DistributeOctTree stage tap: the pipeline's own sort + tree kernels on caller-provided candidates
