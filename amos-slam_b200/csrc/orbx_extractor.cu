@@ -579,7 +579,12 @@ static int host_batch_pipeline(orbx_extractor* h, const uint8_t* images, const u
         if ((rc = ensure_closing(h, B, rows, cols))) return rc;
         if (h->d_mask.ensure(mfs * B + 64) || h->d_culled.ensure(B)) return ORBX_E_CUDA;
     }
-    const int C = chunk_frames(h, B), nchunks = (B + C - 1) / C;
+    // chunk boundaries: short first chunks (C/4, C/2, then C) let compute start while most of the batch is still on the bus
+    const int C = chunk_frames(h, B);
+    static const int ramp = [] { const char* e = std::getenv("ORBX_CHUNK_RAMP"); return e ? std::atoi(e) : 1; }();
+    std::vector<int> cb(1, 0);
+    for (int sz = ramp ? std::max(1, C / 4) : C; cb.back() < B; sz = std::min(C, sz * 2)) cb.push_back(std::min(B, cb.back() + sz));
+    const int nchunks = (int)cb.size() - 1;
     while ((int)h->ev_h2d.size() < nchunks) {
         cudaEvent_t a, b;
         CU_TRY(cudaEventCreateWithFlags(&a, cudaEventDisableTiming)); CU_TRY(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
@@ -588,11 +593,11 @@ static int host_batch_pipeline(orbx_extractor* h, const uint8_t* images, const u
     // the copy streams must not run ahead of work already queued on the compute stream (e.g. a previous call's kernels)
     CU_TRY(cudaEventRecord(h->ev_done[0], h->stream));
     CU_TRY(cudaStreamWaitEvent(h->s_h2d, h->ev_done[0], 0));
-    static const int nstreams = [] { const char* e = std::getenv("ORBX_HOST_STREAMS"); int v = e ? std::atoi(e) : 3; return v < 1 ? 1 : (v > 4 ? 4 : v); }();
+    static const int nstreams = [] { const char* e = std::getenv("ORBX_HOST_STREAMS"); int v = e ? std::atoi(e) : 4; return v < 1 ? 1 : (v > 4 ? 4 : v); }();
     cudaStream_t cs[4] = {h->stream, h->s_alt, h->s_more[0], h->s_more[1]};
     for (int i = 1; i < nstreams; ++i) CU_TRY(cudaStreamWaitEvent(cs[i], h->ev_done[0], 0));
     for (int c = 0; c < nchunks; ++c) {
-        const int b0 = c * C, nb = std::min(C, B - b0);
+        const int b0 = cb[c], nb = cb[c + 1] - b0;
         if (mirror) {
             const size_t bytes = (size_t)(nb - 1) * frame_stride + (size_t)(rows - 1) * step + cols;     // never reads past the last row of the last frame
             CU_TRY(cudaMemcpyAsync(h->d_l0.p + (size_t)b0 * frame_stride, images + (size_t)b0 * frame_stride, bytes, cudaMemcpyHostToDevice, h->s_h2d));
@@ -612,7 +617,7 @@ static int host_batch_pipeline(orbx_extractor* h, const uint8_t* images, const u
         CU_TRY(cudaEventRecord(h->ev_h2d[c], h->s_h2d));
     }
     for (int c = 0; c < nchunks; ++c) {
-        const int b0 = c * C, nb = std::min(C, B - b0);
+        const int b0 = cb[c], nb = cb[c + 1] - b0;
         h->cur = cs[c % nstreams];
         CU_TRY(cudaStreamWaitEvent(h->cur, h->ev_h2d[c], 0));
         if (masks) rc = run_masked_range(h, b0, nb, h->d_mask.p + (size_t)b0 * mfs, (long long)mfs, mpitch, rows, cols, h->d_kp_out.p, h->d_desc_out.p, cap, h->d_counts.p, h->d_culled.p);
