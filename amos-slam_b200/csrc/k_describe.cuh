@@ -44,13 +44,47 @@ k_gauss7(PyrView pv, const LevelGeom* __restrict__ levels, const BlurTile* __res
     const int x = t.xc * BLUR_TILE_W + (lane - 1) * 4;
     const int y0 = t.strip * BLUR_STRIP, y1 = min(y0 + BLUR_STRIP, gh);
     const bool word_ok = x >= 0 && x + 3 < gw;                       // aligned word entirely inside the level
+    const bool word_in = x >= 0 && x < gw;                           // word starts inside the level (row pitches are multiples of 4: a partial word stays in its row)
     const bool needed = x + 3 >= -3 && x <= gw + 2;                  // some neighbour reads this word
     const bool store = lane >= 1 && lane <= 30 && x < gw;
-    int rx[4];                                                       // edge words: reflected columns, row-invariant
-#pragma unroll
-    for (int j = 0; j < 4; ++j) rx[j] = (needed && !word_ok) ? reflect101(x + j, gw) : 0;
     // warp-uniform: does any lane of this tile (halo lanes included) touch the left / right level edge?
     const bool edge_tile = t.xc == 0 || t.xc * BLUR_TILE_W + 30 * 4 + 3 >= gw;
+    // Edge words (BORDER_REFLECT_101 columns): the reflected source columns of a word are 4 consecutive columns in descending order,
+    // i.e. bytes of at most two aligned words that other lanes of this warp load anyway.  Row-invariant per lane: the two source
+    // lanes and two PRMT selectors (gather the reflected bytes; merge with the lane's own in-range bytes).  Lanes whose sources fall
+    // outside the warp (last tile with < 4 valid columns, levels narrower than the halo) fall back to reflected byte loads.
+    int srcA = lane, srcB = lane; uint32_t selG = 0x3210u, selM = 0x3210u; bool fix = false, slow = false;
+    int rx[4] = {0, 0, 0, 0};
+    if (edge_tile && needed && !word_ok) {
+        int ln[4], by[4]; bool own[4];
+        int lo = 64, hi = -1;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = x + j;
+            own[j] = c >= 0 && c < gw;
+            rx[j] = reflect101(c, gw);
+            const int rel = rx[j] - (t.xc * BLUR_TILE_W - 4);                // column offset from lane 0's word
+            ln[j] = rel >= 0 ? (rel >> 2) : -1; by[j] = rx[j] & 3;
+            if (!own[j]) { lo = min(lo, ln[j]); hi = max(hi, ln[j]); }
+        }
+        fix = true;
+        if (lo < 0 || hi > 31 || hi - lo > 1) slow = true;                   // sources not available as two neighbouring words of this warp
+        // the source words must themselves be plain loads (start inside the level)
+        if (!slow) {
+            srcA = lo; srcB = hi; selG = 0; selM = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t gsel = own[j] ? 0u : (uint32_t)((ln[j] == lo ? 0 : 4) + by[j]);
+                selG |= gsel << (4 * j);
+                selM |= (uint32_t)(own[j] ? j : 4 + j) << (4 * j);
+            }
+        }
+    }
+    // a source lane must hold a genuinely loaded word: its x must start inside the level
+    {
+        const int xa = t.xc * BLUR_TILE_W + (srcA - 1) * 4, xb = t.xc * BLUR_TILE_W + (srcB - 1) * 4;
+        if (fix && !slow && !(xa >= 0 && xa < gw && xb >= 0 && xb < gw)) slow = true;
+    }
     const int rlast = y1 + 2;
     auto load_row = [&](int r) -> uint32_t {
         int rr = min(r, rlast);                                          // the tail group re-reads the last row instead of running past it
@@ -60,8 +94,10 @@ k_gauss7(PyrView pv, const LevelGeom* __restrict__ levels, const BlurTile* __res
             rr = max(rr, 0);
         }
         const uint8_t* row = img + rr * pitch;                           // a frame's level is < 2^31 bytes
-        if (!edge_tile || word_ok) return __ldg(reinterpret_cast<const uint32_t*>(row + x));
-        if (!needed) return 0u;
+        if (!edge_tile || word_in) {
+            if (!(edge_tile && slow)) return __ldg(reinterpret_cast<const uint32_t*>(row + x));
+        }
+        if (!needed || !slow) return 0u;
         return (uint32_t)__ldg(row + rx[0]) | ((uint32_t)__ldg(row + rx[1]) << 8) | ((uint32_t)__ldg(row + rx[2]) << 16) | ((uint32_t)__ldg(row + rx[3]) << 24);
     };
     uint8_t* dst = blur + (long long)b * blur_fstride + g.off + x;
@@ -77,8 +113,12 @@ k_gauss7(PyrView pv, const LevelGeom* __restrict__ levels, const BlurTile* __res
 #pragma unroll
         for (int j = 0; j < 7; ++j) {                                     // ring slot j is static after unrolling: no register moves
             const int r = r0 + j;
-            const uint32_t w1 = pre[j];
+            uint32_t w1 = pre[j];
             if (gi + 1 < ngroups) pre[j] = load_row(r + 7);
+            if (edge_tile) {                                              // warp-uniform: rebuild the edge words from their neighbours' loads
+                const uint32_t wa = __shfl_sync(0xffffffffu, w1, srcA), wb = __shfl_sync(0xffffffffu, w1, srcB);
+                if (fix && !slow) w1 = __byte_perm(w1, __byte_perm(wa, wb, selG), selM);
+            }
             const uint32_t w0 = __shfl_up_sync(0xffffffffu, w1, 1), w2 = __shfl_down_sync(0xffffffffu, w1, 1);
             // h(x+k) = sum_{i=0..6} q[i] * px(x+k-3+i): two 4-tap integer dot products on byte-aligned windows
             hb[j][0] = __dp4a(__byte_perm(w0, w1, 0x4321), Q0, __dp4a(__byte_perm(w1, w2, 0x4321), Q1, 0u));
