@@ -248,18 +248,20 @@ k_orient_describe(PyrView pv, const LevelGeom* __restrict__ levels, int nlevels,
     const int slot = blockIdx.x * 4 + (threadIdx.x >> 5);
     const int b = blockIdx.y;
     if (slot >= kp_per_frame) return;
-    int level = 0;
-    while (level + 1 < nlevels && slot >= levels[level + 1].kp_off) ++level;
+    // level of this slot and output position of its first keypoint: lane l looks at level l, one ballot + two warp reductions
+    const int* cnt = kp_count + b * nlevels;
+    const int off_l = lane < nlevels ? levels[lane].kp_off : 0x7FFFFFFF;
+    const int cnt_l = lane < nlevels ? cnt[lane] : 0;
+    const int level = __popc(__ballot_sync(0xffffffffu, slot >= off_l)) - 1;
+    const int base = __reduce_add_sync(0xffffffffu, lane < level ? cnt_l : 0);
+    const int total = __reduce_add_sync(0xffffffffu, cnt_l);
     const LevelGeom& g = levels[level];
     const int k = slot - g.kp_off;
-    const int* cnt = kp_count + b * nlevels;
-    int base = 0, total = 0;
-    for (int l = 0; l < nlevels; ++l) { const int c = cnt[l]; if (l < level) base += c; total += c; }
     if (slot == 0 && lane == 0) {
         if (counts_out) counts_out[b] = min(total, cap);
         if (level_counts_out) for (int l = 0; l < nlevels; ++l) level_counts_out[b * nlevels + l] = cnt[l];
     }
-    if (k >= cnt[level]) return;
+    if (k >= __shfl_sync(0xffffffffu, cnt_l, level)) return;
     const int oi = base + k;
     if (oi >= cap) return;                                      // caller capacity (status reported by the host)
     const uint32_t p = kp_level[(long long)b * kp_per_frame + slot];

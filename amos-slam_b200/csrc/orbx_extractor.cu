@@ -269,8 +269,8 @@ static inline void prof_mark(orbx_extractor* h) {
 static int run_blur_range(orbx_extractor* h, int b0, int B);
 
 // pyramid (levels >= 1) + FAST cells + quadtree; leaves per-level keypoints in d_kp_level / d_kp_count.
-// fork_blur: the blur only needs the pyramid, so it is launched on the second compute stream right after the resize
-// chain and runs next to the FAST / quadtree kernels (the quadtree is latency-bound and leaves most SMs idle);
+// fork_blur: the blur only needs the pyramid, so it is launched on the second compute stream -- after FAST, which fills the GPU
+// by itself -- and runs next to the quadtree kernels (latency-bound: one serial warp per level, most SMs idle);
 // the caller joins on ev_join before the descriptor stage.
 static int run_detect(orbx_extractor* h, int b0, int B, bool fork_blur = false) {
     cudaStream_t s = h->cur;
@@ -295,15 +295,6 @@ static int run_detect(orbx_extractor* h, int b0, int B, bool fork_blur = false) 
         LAUNCH_CHECK();
     }
     prof_mark(h);
-    if (fork_blur) {
-        CU_TRY(cudaEventRecord(h->ev_fork, s));
-        CU_TRY(cudaStreamWaitEvent(h->s_alt, h->ev_fork, 0));
-        cudaStream_t keep = h->cur; h->cur = h->s_alt;
-        const int rc = run_blur_range(h, b0, B);
-        h->cur = keep;
-        if (rc) return rc;
-        CU_TRY(cudaEventRecord(h->ev_join, h->s_alt));
-    }
     const int ncells = (int)h->cells.size();
     if (ncells > 0) {
         dim3 grid((ncells + FAST_WARPS - 1) / FAST_WARPS, B);
@@ -313,6 +304,7 @@ static int run_detect(orbx_extractor* h, int b0, int B, bool fork_blur = false) 
         LAUNCH_CHECK();
     }
     prof_mark(h);
+    if (fork_blur) CU_TRY(cudaEventRecord(h->ev_fork, s));        // the blur may start once FAST is done ...
     {
         dim3 grid(L, B);
         k_octree_sort<<<grid, SORT_THREADS, octree_sort_smem_bytes(h->sort_smem_keys), s>>>(h->d_levels.p, h->d_cells.p, ncells, h->cand_per_frame, h->cand_per_frame, L,
@@ -328,6 +320,14 @@ static int run_detect(orbx_extractor* h, int b0, int B, bool fork_blur = false) 
         LAUNCH_CHECK();
     }
     prof_mark(h);
+    if (fork_blur) {                                                     // ... but is submitted after the quadtree kernels, so it fills the SMs they leave idle
+        CU_TRY(cudaStreamWaitEvent(h->s_alt, h->ev_fork, 0));
+        cudaStream_t keep = h->cur; h->cur = h->s_alt;
+        const int rc = run_blur_range(h, b0, B);
+        h->cur = keep;
+        if (rc) return rc;
+        CU_TRY(cudaEventRecord(h->ev_join, h->s_alt));
+    }
     h->lastB = b0 + B; h->have_pyramid = true; h->blur_valid = false;
     return ORBX_OK;
 }
