@@ -395,3 +395,238 @@ k_octree_tree(const LevelGeom* __restrict__ levels, int nlevels, int cand_per_fr
 #undef NODE_ALLOC
 #undef NODE_FREE
 }
+
+// =================================================================================================
+// K4'  k_octree_tree_par: the same replay as k_octree_tree, reorganised as a handful of block-wide rounds.
+// The reference's list surgery is deterministic given the round structure:
+//   * a "full pass" (:824-899) divides EVERY multi-key node of the list snapshot.  Children are push_front'ed in order
+//     n1..n4, so afterwards the list is: for the divided nodes in REVERSE visiting order, their non-empty children in
+//     REVERSE child order; then the undivided nodes in their old order.  Creation ids follow visiting order.
+//   * a "largest first" round (:929-1011) visits the candidates of the previous round by (size, creation id) descending
+//     and stops right after the divide that brings the node count to >= N.  With the per-candidate child counts known,
+//     the stopping point is a prefix sum away, and the list afterwards has the same closed form as above.
+// So each round is: one thread per node computes the child boundaries (binary searches on the sorted path codes),
+// block-wide prefix sums give list positions / creation ids / candidate slots, and a scatter writes the next list.
+// A level of the C1 workload takes ~6 rounds instead of ~100 dependent divides by a single warp.
+// =================================================================================================
+#define PTREE_THREADS 128
+#define PTREE_MAXCAP 1024      // node capacity handled by this kernel (levels asking for more use the serial kernel)
+
+__host__ __device__ inline size_t ptree_smem_bytes(int cap, int code_cap) {
+    // codes | 2 x (lo, hi, cid: int) + 2 x dep (short) | b1 b2 b3 sM sE sU (int) | vcur vprev (u64) | order (int)
+    return (size_t)code_cap * 4 + (size_t)cap * (2 * 12 + 2 * 2 + 6 * 4 + 2 * 8 + 4) + 64;
+}
+
+__device__ __forceinline__ int ptree_lower_bound(const uint32_t* __restrict__ ck, int cs, int lo, int hi, uint32_t T) {
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (ck[mid * cs] < T) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+// inclusive prefix sum of a[0..n) in shared memory, n <= 1024; every thread of the block calls it
+__device__ __forceinline__ void ptree_scan(int* a, int n, int* seg) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nseg = (n + 31) >> 5;
+    for (int s = warp; s < nseg; s += PTREE_THREADS / 32) {
+        const int i = s * 32 + lane;
+        int v = i < n ? a[i] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+        if (i < n) a[i] = v;
+        if (lane == 31) seg[s] = v;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        int v = lane < nseg ? seg[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+        seg[lane] = v;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += PTREE_THREADS) { const int s = i >> 5; if (s > 0) a[i] += seg[s - 1]; }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(PTREE_THREADS)
+k_octree_tree_par(const LevelGeom* __restrict__ levels, int nlevels, int cand_per_frame, int kp_per_frame, int cap, int code_cap,
+                  const unsigned long long* __restrict__ skey, const uint32_t* __restrict__ spk, const int* __restrict__ ncand,
+                  uint32_t* __restrict__ kp_level, int* __restrict__ kp_count, int* __restrict__ overflow) {
+    extern __shared__ __align__(16) uint8_t pt_sm[];
+    __shared__ int seg[32];
+    __shared__ int s_ovf, s_rstar;
+    const int level = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const LevelGeom& g = levels[level];
+    const int n = ncand[b * nlevels + level];
+    const unsigned long long* key = skey + (long long)b * cand_per_frame + g.cand_off;
+    const uint32_t* pk = spk + (long long)b * cand_per_frame + g.cand_off;
+    uint32_t* out = kp_level + (long long)b * kp_per_frame + g.kp_off;
+    if (n <= 0) { if (tid == 0) { kp_count[b * nlevels + level] = 0; if (n < 0) atomicOr(overflow, ORBX_OVF_SORT); } return; }
+
+    uint32_t* codes_sm = reinterpret_cast<uint32_t*>(pt_sm);
+    int* base = reinterpret_cast<int*>(codes_sm + code_cap);
+    int* nlo[2] = {base, base + cap}; int* nhi[2] = {base + 2 * cap, base + 3 * cap}; int* ncid[2] = {base + 4 * cap, base + 5 * cap};
+    int* b1 = base + 6 * cap; int* b2 = b1 + cap; int* b3 = b2 + cap; int* sM = b3 + cap; int* sE = sM + cap; int* sU = sE + cap; int* order = sU + cap;
+    unsigned long long* vA = reinterpret_cast<unsigned long long*>(order + cap + (cap & 1));
+    unsigned long long* vB = vA + cap;
+    short* ndep[2] = {reinterpret_cast<short*>(vB + cap), reinterpret_cast<short*>(vB + cap) + cap};
+
+    const uint32_t* ck; int cs;
+    if (n <= code_cap) {
+        for (int i = tid; i < n; i += PTREE_THREADS) codes_sm[i] = (uint32_t)(key[i] >> 32);
+        ck = codes_sm; cs = 1;
+    } else { ck = reinterpret_cast<const uint32_t*>(key) + 1; cs = 2; }
+    if (tid == 0) s_ovf = 0;
+    __syncthreads();
+
+    const int N = g.N;
+    int cur = 0;                               // node buffer holding the current list, in list order
+    unsigned long long* vcur = vA; unsigned long long* vprev = vB;
+    // child boundaries of node (lo, hi, dep): c[0..4]; returns the number of non-empty children, *multi = those with > 1 key
+    auto children = [&](int lo, int hi, int dep, int& c1, int& c2, int& c3, int& multi) -> int {
+        const int shift = 2 * (ORBX_MAXD - dep - 1);
+        const uint32_t prefix = ck[lo * cs] >> (shift + 2);
+        c1 = ptree_lower_bound(ck, cs, lo, hi, ((prefix << 2) | 1u) << shift);
+        c2 = ptree_lower_bound(ck, cs, c1, hi, ((prefix << 2) | 2u) << shift);
+        c3 = ptree_lower_bound(ck, cs, c2, hi, ((prefix << 2) | 3u) << shift);
+        const int s0 = c1 - lo, s1 = c2 - c1, s2 = c3 - c2, s3 = hi - c3;
+        multi = (s0 > 1) + (s1 > 1) + (s2 > 1) + (s3 > 1);
+        return (s0 > 0) + (s1 > 0) + (s2 > 0) + (s3 > 0);
+    };
+    // scatter the children of one divided node into list `nx`: non-empty children in order n1..n4 get creation ids cid0, cid0+1, ...
+    // and list positions blockstart + m-1, blockstart + m-2, ...; children with > 1 key are appended to vcur from slot e0
+    auto emit_children = [&](int nx, int lo, int c1, int c2, int c3, int hi, int dep, int m, int blockstart, int cid0, int e0) {
+        const int bnd[5] = {lo, c1, c2, c3, hi};
+        int q = 0, t = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int sz = bnd[k + 1] - bnd[k];
+            if (sz > 0) {
+                const int pos = blockstart + (m - 1 - q);
+                nlo[nx][pos] = bnd[k]; nhi[nx][pos] = bnd[k + 1]; ncid[nx][pos] = cid0 + q; ndep[nx][pos] = (short)(dep + 1);
+                if (sz > 1) { vcur[e0 + t] = ((unsigned long long)sz << 40) | ((unsigned long long)((unsigned)(cid0 + q) & 0xFFFFFFu) << 16) | (unsigned)pos; ++t; }
+                ++q;
+            }
+        }
+    };
+
+    // ---- initial nodes (:733-788): nIni roots in order, empty ones dropped; creation ids 0..nIni-1 ----
+    for (int i = tid; i < g.nIni; i += PTREE_THREADS) {
+        const int rlo = ptree_lower_bound(ck, cs, 0, n, (uint32_t)i << ORBX_ROOT_SHIFT);
+        const int rhi = ptree_lower_bound(ck, cs, rlo, n, (uint32_t)(i + 1) << ORBX_ROOT_SHIFT);
+        b1[i] = rlo; b2[i] = rhi; sM[i] = rhi > rlo ? 1 : 0;
+    }
+    __syncthreads();
+    ptree_scan(sM, g.nIni, seg);
+    int count = sM[g.nIni - 1], nextCid = g.nIni, nv = 0;
+    for (int i = tid; i < g.nIni; i += PTREE_THREADS)
+        if (b2[i] > b1[i]) { const int pos = sM[i] - 1; nlo[0][pos] = b1[i]; nhi[0][pos] = b2[i]; ncid[0][pos] = i; ndep[0][pos] = 0; }
+    __syncthreads();
+
+    bool finish = false;
+    while (!finish) {
+        // ================= full pass =================
+        const int prevSize = count;
+        for (int i = tid; i < count; i += PTREE_THREADS) {
+            const int lo = nlo[cur][i], hi = nhi[cur][i], dep = ndep[cur][i];
+            int m = 0, e = 0, c1 = lo, c2 = lo, c3 = lo;
+            if (hi - lo > 1) {
+                if (dep >= ORBX_MAXD) s_ovf = 1;
+                else m = children(lo, hi, dep, c1, c2, c3, e);
+            }
+            b1[i] = c1; b2[i] = c2; b3[i] = c3; sM[i] = m; sE[i] = e; sU[i] = m == 0 ? 1 : 0;
+        }
+        __syncthreads();
+        if (s_ovf) break;
+        ptree_scan(sM, count, seg); ptree_scan(sE, count, seg); ptree_scan(sU, count, seg);
+        const int F = sM[count - 1], Etot = sE[count - 1], newcount = F + sU[count - 1];
+        if (newcount > cap) { if (tid == 0) s_ovf = 1; __syncthreads(); break; }
+        const int nx = cur ^ 1;
+        for (int i = tid; i < count; i += PTREE_THREADS) {
+            const int lo = nlo[cur][i], hi = nhi[cur][i], dep = ndep[cur][i];
+            const int m = sM[i] - (i ? sM[i - 1] : 0);
+            if (m > 0) {
+                const int e = sE[i] - (i ? sE[i - 1] : 0);
+                emit_children(nx, lo, b1[i], b2[i], b3[i], hi, dep, m, F - sM[i], nextCid + sM[i] - m, sE[i] - e);
+            } else {
+                const int pos = F + sU[i] - 1;
+                nlo[nx][pos] = lo; nhi[nx][pos] = hi; ncid[nx][pos] = ncid[cur][i]; ndep[nx][pos] = (short)dep;
+            }
+        }
+        __syncthreads();
+        cur = nx; count = newcount; nextCid += F; nv = Etot;
+        const int nToExpand = Etot;
+        if (count >= N || count == prevSize) { finish = true; break; }          // :907
+        if (count + nToExpand * 3 > N) {                                          // :929
+            // ================= "largest first" rounds =================
+            while (!finish) {
+                const int prevSize2 = count;
+                { unsigned long long* t = vprev; vprev = vcur; vcur = t; }
+                const int np = nv; nv = 0;
+                if (np == 0) { finish = true; break; }                             // nothing left to divide: size unchanged (:1009)
+                // rank of every candidate by (size, creation id) descending (:948-950, canonical tie-break)
+                for (int e = tid; e < np; e += PTREE_THREADS) {
+                    const unsigned long long v = vprev[e];
+                    int r = 0;
+                    for (int f = 0; f < np; ++f) r += vprev[f] > v;
+                    order[r] = e;
+                }
+                if (tid == 0) s_rstar = np - 1;
+                __syncthreads();
+                for (int r = tid; r < np; r += PTREE_THREADS) {
+                    const int pos = (int)(vprev[order[r]] & 0xFFFFull);
+                    const int lo = nlo[cur][pos], hi = nhi[cur][pos], dep = ndep[cur][pos];
+                    int m = 1, e = 0, c1 = lo, c2 = lo, c3 = lo;
+                    if (dep >= ORBX_MAXD) s_ovf = 1;
+                    else m = children(lo, hi, dep, c1, c2, c3, e);
+                    b1[r] = c1; b2[r] = c2; b3[r] = c3; sM[r] = m; sE[r] = e;
+                }
+                for (int i = tid; i < count; i += PTREE_THREADS) sU[i] = 1;
+                __syncthreads();
+                if (s_ovf) break;
+                ptree_scan(sM, np, seg); ptree_scan(sE, np, seg);
+                // first candidate (in visiting order) after whose divide the list holds >= N nodes (:1003)
+                for (int r = tid; r < np; r += PTREE_THREADS)
+                    if (count + sM[r] - (r + 1) >= N) atomicMin(&s_rstar, r);
+                __syncthreads();
+                const int rstar = s_rstar, P = rstar + 1, F = sM[rstar], Etot = sE[rstar], newcount = count + F - P;
+                if (newcount > cap) { if (tid == 0) s_ovf = 1; __syncthreads(); break; }
+                for (int r = tid; r < P; r += PTREE_THREADS) sU[(int)(vprev[order[r]] & 0xFFFFull)] = 0;      // visited nodes leave the list
+                __syncthreads();
+                ptree_scan(sU, count, seg);
+                const int nx = cur ^ 1;
+                for (int r = tid; r < P; r += PTREE_THREADS) {
+                    const int pos = (int)(vprev[order[r]] & 0xFFFFull);
+                    const int m = sM[r] - (r ? sM[r - 1] : 0), e = sE[r] - (r ? sE[r - 1] : 0);
+                    emit_children(nx, nlo[cur][pos], b1[r], b2[r], b3[r], nhi[cur][pos], ndep[cur][pos], m, F - sM[r], nextCid + sM[r] - m, sE[r] - e);
+                }
+                for (int i = tid; i < count; i += PTREE_THREADS) {
+                    const bool stays = (sU[i] - (i ? sU[i - 1] : 0)) != 0;
+                    if (stays) { const int pos = F + sU[i] - 1; nlo[nx][pos] = nlo[cur][i]; nhi[nx][pos] = nhi[cur][i]; ncid[nx][pos] = ncid[cur][i]; ndep[nx][pos] = ndep[cur][i]; }
+                }
+                __syncthreads();
+                cur = nx; count = newcount; nextCid += F; nv = Etot;
+                if (count >= N || count == prevSize2) finish = true;               // :1009
+            }
+            break;
+        }
+    }
+    __syncthreads();
+    const bool ovf = s_ovf != 0;
+
+    // ---- result: one keypoint per node in list order (:1018-1048): max response, first in the original order ----
+    const int nout = min(count, g.kp_cap);
+    for (int k = tid; k < nout; k += PTREE_THREADS) {
+        const int lo = nlo[cur][k], hi = nhi[cur][k];
+        uint32_t bestp = 0; int bestr = -1; unsigned besti = 0xFFFFFFFFu;
+        for (int i = lo; i < hi; ++i) {
+            const uint32_t p = pk[i];
+            const int r = (int)(p >> 24);
+            const unsigned oi = (unsigned)(key[i] & 0xFFFFFFFFull);
+            if (r > bestr || (r == bestr && oi < besti)) { bestr = r; besti = oi; bestp = p; }
+        }
+        out[k] = bestp;
+    }
+    if (tid == 0) {
+        kp_count[b * nlevels + level] = nout;
+        if (ovf || count > g.kp_cap) atomicOr(overflow, ORBX_OVF_TREE);
+    }
+}

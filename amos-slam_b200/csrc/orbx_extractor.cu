@@ -311,12 +311,19 @@ static int run_detect(orbx_extractor* h, int b0, int B, bool fork_blur = false) 
                                                                                  h->sort_smem_keys, slots, cell_counts, h->d_ocand.p + co, h->d_skey.p + co, h->d_spk.p + co, h->d_ncand.p + (size_t)b0 * L);
         LAUNCH_CHECK();
         prof_mark(h);
-        // sorted path codes staged in shared memory per (level, frame) instance: shortens the serial replay ~2x, but the extra 16 KB
-        // cuts the resident instances per SM from 25 to 9, so it only pays while all instances fit in one wave (small batches, latency)
-        const int code_cap = (L * B <= 148 * 9) ? 4096 : 0;
-        const size_t tsm = (((size_t)h->tree_cap * (8 + 8 + 4 + 4 + 4 + 2 + 2 + 2 + 1) + 15) & ~(size_t)15) + (size_t)code_cap * 4 + 16;
-        k_octree_tree<<<grid, 32, tsm, s>>>(h->d_levels.p, L, h->cand_per_frame, h->kp_per_frame, h->tree_cap, code_cap, h->d_skey.p + co, h->d_spk.p + co, h->d_ncand.p + (size_t)b0 * L,
-                                            h->d_kp_level.p + (size_t)b0 * h->kp_per_frame, h->d_kp_count.p + (size_t)b0 * L, h->d_overflow.p);
+        // sorted path codes staged in shared memory per (level, frame) instance: the extra 16 KB lowers the number of resident
+        // instances per SM, so it only pays while all instances fit in one wave (small batches, latency)
+        static const int tree_mode = [] { const char* e = std::getenv("ORBX_TREE"); return e ? std::atoi(e) : 0; }();   // 1 = force the serial kernel (A/B testing)
+        static const int cc_env = [] { const char* e = std::getenv("ORBX_TREE_CODECAP"); return e ? std::atoi(e) : -1; }();
+        const int code_cap = cc_env >= 0 ? cc_env : 3072;          // 12 KB: covers ~2.4 k candidates of a VGA level 0; larger instances search the global keys
+        if (h->tree_cap <= PTREE_MAXCAP && tree_mode != 1) {
+            k_octree_tree_par<<<grid, PTREE_THREADS, ptree_smem_bytes(h->tree_cap, code_cap), s>>>(h->d_levels.p, L, h->cand_per_frame, h->kp_per_frame, h->tree_cap, code_cap,
+                h->d_skey.p + co, h->d_spk.p + co, h->d_ncand.p + (size_t)b0 * L, h->d_kp_level.p + (size_t)b0 * h->kp_per_frame, h->d_kp_count.p + (size_t)b0 * L, h->d_overflow.p);
+        } else {
+            const size_t tsm = (((size_t)h->tree_cap * (8 + 8 + 4 + 4 + 4 + 2 + 2 + 2 + 1) + 15) & ~(size_t)15) + (size_t)code_cap * 4 + 16;
+            k_octree_tree<<<grid, 32, tsm, s>>>(h->d_levels.p, L, h->cand_per_frame, h->kp_per_frame, h->tree_cap, code_cap, h->d_skey.p + co, h->d_spk.p + co, h->d_ncand.p + (size_t)b0 * L,
+                                                h->d_kp_level.p + (size_t)b0 * h->kp_per_frame, h->d_kp_count.p + (size_t)b0 * L, h->d_overflow.p);
+        }
         LAUNCH_CHECK();
     }
     prof_mark(h);
@@ -437,6 +444,7 @@ int orbx_create(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, in
     if (upload_constants() != ORBX_OK) { cudaStreamDestroy(h->stream); cudaStreamDestroy(h->s_h2d); cudaStreamDestroy(h->s_d2h); delete h; return ORBX_E_CUDA; }
     cudaFuncSetAttribute(k_octree_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)octree_sort_smem_bytes(16384));
     cudaFuncSetAttribute(k_octree_tree, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_octree_tree_par, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ptree_smem_bytes(PTREE_MAXCAP, 4096));
     cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     *out = h;
     return ORBX_OK;

@@ -178,7 +178,10 @@ extern "C" int orbx_debug_distribute(orbx_extractor* h, const orbx_keypoint* can
     LAUNCH_CHECK();
     const int code_cap = 4096;
     const size_t tsm = (((size_t)tcap * (8 + 8 + 4 + 4 + 4 + 2 + 2 + 2 + 1) + 15) & ~(size_t)15) + (size_t)code_cap * 4 + 16;
-    k_octree_tree<<<dim3(1, 1), 32, tsm, s>>>(dl.p, 1, ncand, g.kp_cap, tcap, code_cap, dsk.p, dspk.p, dn.p, dkp.p, dkc.p, h->d_overflow.p);
+    if (tcap <= PTREE_MAXCAP)
+        k_octree_tree_par<<<dim3(1, 1), PTREE_THREADS, ptree_smem_bytes(tcap, code_cap), s>>>(dl.p, 1, ncand, g.kp_cap, tcap, code_cap, dsk.p, dspk.p, dn.p, dkp.p, dkc.p, h->d_overflow.p);
+    else
+        k_octree_tree<<<dim3(1, 1), 32, tsm, s>>>(dl.p, 1, ncand, g.kp_cap, tcap, code_cap, dsk.p, dspk.p, dn.p, dkp.p, dkc.p, h->d_overflow.p);
     LAUNCH_CHECK();
     int n = 0, ovf = 0;
     std::vector<uint32_t> res(g.kp_cap);
