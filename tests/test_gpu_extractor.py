@@ -62,6 +62,22 @@ def test_unusual_scale_factors(orbx, oracle, cfg):
         assert np.array_equal(E.debug_pyramid_level(0, l, po.shape), po)
 
 
+def test_large_frame_many_features_fallback_paths(orbx, oracle):
+    """A big, corner-dense frame with a large quota: more candidates per level than the radix sort / code staging hold in shared
+    memory (global-memory bitonic sort, global key searches) and more nodes per level than the round-based quadtree kernel
+    handles (serial replay kernel).  Same bit-exact contract."""
+    rng = np.random.default_rng(21)
+    img = synth_frame(61, 1600, 1200)
+    img[200:1000, 300:1300] = rng.integers(0, 256, (800, 1000), dtype=np.uint8)          # dense corners: > 16 k candidates on level 0
+    for nf in (6000, 1500):
+        E = orbx.ORBextractor(nf, 1.2, 8, 20, 7); P = oracle.Extractor("port", nf, 1.2, 8, 20, 7)
+        kg, dg = E(img); ko, do = P.extract(img)
+        assert_same(kg, dg, ko, do)
+        assert E.check_overflow() == 0
+        n0 = len(E.debug_level_candidates(0, 0))
+        assert n0 > 16384, n0
+
+
 def test_textured_and_flat_inputs(orbx, oracle):
     rng = np.random.default_rng(3)
     E = orbx.ORBextractor(500, 1.2, 8, 20, 7); P = oracle.Extractor("port", 500, 1.2, 8, 20, 7)
