@@ -205,6 +205,29 @@ def matcher_bench(orbx, torch, ext, frames, device):
             "search_for_initialization_pairs_per_s": 1.0 / dt, "search_for_initialization_config": "host-pointer call, window 100, one pair per call (latency-bound)"}
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPUs that are local to GPU `index` (its PCIe root's NUMA node) BEFORE the pinned host buffers are
+    allocated, so first-touch places them on the right socket: with 8 ranks feeding 8 GPUs, frames crossing the inter-socket link
+    are what limits the end-to-end figure.  Best effort: any failure leaves the affinity untouched."""
+    try:
+        out = subprocess.run(["nvidia-smi", "-i", str(index), "--query-gpu=pci.bus_id", "--format=csv,noheader"], capture_output=True, text=True, timeout=10).stdout.strip()
+        bdf = out.lower()
+        if bdf.startswith("00000000:"):
+            bdf = bdf[4:]
+        cpus = open("/sys/bus/pci/devices/%s/local_cpulist" % bdf).read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            ids.update(range(int(a), int(b or a) + 1))
+        ids &= os.sched_getaffinity(0)
+        if ids:
+            os.sched_setaffinity(0, ids)
+            return "%s -> cpus %s" % (bdf, cpus)
+    except Exception as e:
+        return "unbound (%s)" % type(e).__name__
+    return "unbound"
+
+
 def cpu_model():
     try:
         for line in open("/proc/cpuinfo"):
@@ -259,6 +282,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (native arm) needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else "single rank: not bound"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -389,7 +413,7 @@ def main():
                          "stage_ms_per_step": {k: v / max(ncalls, 1) for k, v in stage_ms.items()},
                          "stage_share": {k: (v / total_stage if total_stage else 0.0) for k, v in stage_ms.items()},
                          "whole_step_algorithmic_GBps": (2 * sum(level_pixels()) + 60 * n_kp) * B * K / (ms * 1e-3) / 1e9},
-            "keypoints_per_frame": n_kp, "matcher": matcher_line}
+            "keypoints_per_frame": n_kp, "matcher": matcher_line, "host_affinity_rank0": numa}
     if N == 1 and not args.no_cpu_baseline:
         res = cpu_reference_run(args.cpu_seconds, frames[:64])
         line["cpu_baseline"] = {"value": res["fps"], "unit": "frames/s", "cores": res["threads"], "kind": res["kind"],
