@@ -126,10 +126,11 @@ __device__ __forceinline__ bool query_window(const QueryParams& P, const FrameDe
 // one warp per query.  FILL = false: counts[q] only.  FILL = true: cand[offsets[q] + k] = dist<<20 | index.
 template <bool FILL>
 __global__ void __launch_bounds__(128)
-k_window_search(QueryParams P, FrameDev F, int* __restrict__ counts, const int* __restrict__ offsets, uint32_t* __restrict__ cand) {
+k_window_search(QueryParams P, FrameDev F, int* __restrict__ counts, const int* __restrict__ offsets, uint32_t* __restrict__ cand, int cand_cap) {
     const int lane = threadIdx.x & 31;
     const int q = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (q >= P.nq) return;
+    if (FILL && offsets[P.nq] > cand_cap) return;                   // lists do not fit: the host grows the arena and repeats the call
     float x, y, r, ur; int minLevel, maxLevel; bool use_ur;
     if (!query_window(P, F, q, x, y, r, minLevel, maxLevel, ur, use_ur)) { if (!FILL && lane == 0) counts[q] = 0; return; }
     // cell range (Frame.cc:913-939), float arithmetic in the reference's order
@@ -304,12 +305,13 @@ __device__ __forceinline__ StagedLists stage_lists(uint32_t* sm, int sm_words, i
 // ---- SearchForInitialization, sequential part (ORBmatcher.cc:532-640) ----
 __global__ void __launch_bounds__(RESOLVE_THREADS)
 k_resolve_init(int n1, int n2, const KpM* __restrict__ k1s, const KpM* __restrict__ k2s, const int* __restrict__ counts, const int* __restrict__ offsets,
-               const uint32_t* __restrict__ cand, float nnratio, int checkOri, int smem_words,
+               const uint32_t* __restrict__ cand, int cand_cap, float nnratio, int checkOri, int smem_words,
                int* __restrict__ matchedDist /*n2*/, int* __restrict__ m21 /*n2*/, int* __restrict__ m12 /*n1*/, int* __restrict__ bin_of /*n1*/,
                float* __restrict__ prev_xy, int* __restrict__ nmatches_out) {
     extern __shared__ __align__(16) uint32_t rs_sm[];
     __shared__ int hist[M_HISTO];
     const int tid = threadIdx.x, lane = tid & 31;
+    if (offsets[n1] > cand_cap) return;                            // candidate lists were not written (see k_window_search)
     const StagedLists SL = stage_lists(rs_sm, smem_words, 3 * n2 + n1, n1, counts, offsets, cand);
     const bool staged = SL.staged;
     // extra shared arrays: md[n2] | s21[n2] | ang2[n2] | ang1[n1]
@@ -368,11 +370,12 @@ k_resolve_init(int n1, int n2, const KpM* __restrict__ k1s, const KpM* __restric
 __global__ void __launch_bounds__(RESOLVE_THREADS)
 k_resolve_proj_frame(int n_last, int n_cur, const KpM* __restrict__ cur_keys, const float* __restrict__ last_angle, const uint8_t* __restrict__ mp_observed,
                      const uint8_t* __restrict__ cur_occupied, const int* __restrict__ counts, const int* __restrict__ offsets, const uint32_t* __restrict__ cand,
-                     int checkOri, int smem_words, uint8_t* __restrict__ occupied_g /*n_cur*/, int* __restrict__ cur_match /*n_cur*/, int* __restrict__ pushes /*2*n_last*/,
+                     int cand_cap, int checkOri, int smem_words, uint8_t* __restrict__ occupied_g /*n_cur*/, int* __restrict__ cur_match /*n_cur*/, int* __restrict__ pushes /*2*n_last*/,
                      int* __restrict__ nmatches_out) {
     extern __shared__ __align__(16) uint32_t rs_sm[];
     __shared__ int hist[M_HISTO];
     const int tid = threadIdx.x, lane = tid & 31;
+    if (offsets[n_last] > cand_cap) return;
     // extra shared arrays: occ[n_cur] (ints) | angc[n_cur] | angl[n_last] | obs[n_last] (ints)
     const StagedLists SL = stage_lists(rs_sm, smem_words, 2 * n_cur + 2 * n_last, n_last, counts, offsets, cand);
     const bool staged = SL.staged;
@@ -431,10 +434,11 @@ k_resolve_proj_frame(int n_last, int n_cur, const KpM* __restrict__ cur_keys, co
 // ---- SearchByProjection(Frame, vpMapPoints), sequential part (ORBmatcher.cc:77-172) ----
 __global__ void __launch_bounds__(RESOLVE_THREADS)
 k_resolve_proj_points(int n_points, int n_f, const KpM* __restrict__ f_keys, const uint8_t* __restrict__ mp_observed, const uint8_t* __restrict__ f_occupied,
-                      const int* __restrict__ counts, const int* __restrict__ offsets, const uint32_t* __restrict__ cand, float nnratio, int smem_words,
+                      const int* __restrict__ counts, const int* __restrict__ offsets, const uint32_t* __restrict__ cand, int cand_cap, float nnratio, int smem_words,
                       uint8_t* __restrict__ occupied_g, int* __restrict__ f_match, int* __restrict__ nmatches_out) {
     extern __shared__ __align__(16) uint32_t rs_sm[];
     const int tid = threadIdx.x, lane = tid & 31;
+    if (offsets[n_points] > cand_cap) return;
     // extra shared arrays: occ[n_f] | oct[n_f] | obs[n_points]
     const StagedLists SL = stage_lists(rs_sm, smem_words, 2 * n_f + n_points, n_points, counts, offsets, cand);
     const bool staged = SL.staged;

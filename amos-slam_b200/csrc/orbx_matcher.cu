@@ -8,6 +8,7 @@
 #include "k_match.cuh"
 
 #include <climits>
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -43,10 +44,42 @@ struct Arena {
 inline size_t pad(size_t b) { return (b + 255) & ~(size_t)255; }
 }
 
+// host -> device uploads of one call are packed into a pinned mirror of a device arena and sent with ONE cudaMemcpyAsync
+struct UploadArena {
+    uint8_t* dbase = nullptr; uint8_t* hbase = nullptr; size_t cap = 0, off = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return ORBX_OK;
+        if (dbase) cudaFree(dbase);
+        if (hbase) cudaFreeHost(hbase);
+        dbase = hbase = nullptr; cap = 0;
+        size_t want = bytes + (bytes >> 2) + (1 << 20);
+        if (cudaMalloc((void**)&dbase, want) != cudaSuccess || cudaHostAlloc((void**)&hbase, want, cudaHostAllocDefault) != cudaSuccess) {
+            orbx_set_error("cudaMalloc / cudaHostAlloc (matcher upload arena)"); return ORBX_E_CUDA;
+        }
+        cap = want; return ORBX_OK;
+    }
+    void reset() { off = 0; }
+    // returns the device address; the bytes are copied into the pinned mirror now and travel at flush()
+    void* put(const void* host, size_t bytes) {
+        size_t o = (off + 255) & ~(size_t)255;
+        if (o + bytes > cap) return nullptr;
+        off = o + bytes;
+        if (host && bytes) std::memcpy(hbase + o, host, bytes);
+        return dbase + o;
+    }
+    void release() { if (dbase) cudaFree(dbase); if (hbase) cudaFreeHost(hbase); dbase = hbase = nullptr; cap = 0; }
+};
+
 struct orbx_matcher {
     float nnratio; int checkOri; int device; cudaStream_t stream = nullptr; long long launches = 0;
-    Arena arena; Arena cand_arena;
+    Arena arena; Arena cand_arena; UploadArena uparena;
+    size_t cand_cap = 0;           // candidate entries the cand arena holds
 };
+
+static int flush_uploads(orbx_matcher* m) {
+    if (m->uparena.off) CU_TRY(cudaMemcpyAsync(m->uparena.dbase, m->uparena.hbase, m->uparena.off, cudaMemcpyHostToDevice, m->stream));
+    return ORBX_OK;
+}
 
 struct FrameUpload { FrameDev dev; };
 
@@ -62,54 +95,61 @@ static int check_frame(const orbx_frame_view* f) {
     return ORBX_OK;
 }
 
-// upload a frame view and build its 64x48 grid on the device
-static int upload_frame(orbx_matcher* m, const orbx_frame_view* f, FrameDev& d) {
-    cudaStream_t s = m->stream;
+// stage a frame view for upload (uparena) and reserve its grid arrays; build_grid() launches the 64x48 grid build after the flush
+static int upload_frame(orbx_matcher* m, const orbx_frame_view* f, FrameDev& d, uint32_t*& sort_keys) {
     const int n = f->n;
-    KpM* keys = m->arena.get<KpM>(n ? n : 1); uint8_t* desc = m->arena.get<uint8_t>((size_t)(n ? n : 1) * 32);
-    float* ur = f->u_right ? m->arena.get<float>(n ? n : 1) : nullptr; float* sc = m->arena.get<float>(f->nlevels);
+    KpM* keys = reinterpret_cast<KpM*>(m->uparena.put(n ? f->keys_un : nullptr, n ? (size_t)n * 28 : 28));
+    uint8_t* desc = reinterpret_cast<uint8_t*>(m->uparena.put(n ? f->descriptors : nullptr, n ? (size_t)n * 32 : 32));
+    float* ur = f->u_right ? reinterpret_cast<float*>(m->uparena.put(n ? f->u_right : nullptr, n ? (size_t)n * 4 : 4)) : nullptr;
+    float* sc = reinterpret_cast<float*>(m->uparena.put(f->scale_factors, (size_t)f->nlevels * 4));
     int* cs = m->arena.get<int>(GRID_CELLS + 1); int* en = m->arena.get<int>(n ? n : 1); uint32_t* sk = m->arena.get<uint32_t>(n ? n : 1);
     if (!keys || !desc || !sc || !cs || !en || !sk || (f->u_right && !ur)) FAIL(ORBX_E_CUDA, "matcher arena exhausted");
-    if (n) {
-        CU_TRY(cudaMemcpyAsync(keys, f->keys_un, (size_t)n * 28, cudaMemcpyHostToDevice, s));
-        CU_TRY(cudaMemcpyAsync(desc, f->descriptors, (size_t)n * 32, cudaMemcpyHostToDevice, s));
-        if (ur) CU_TRY(cudaMemcpyAsync(ur, f->u_right, (size_t)n * 4, cudaMemcpyHostToDevice, s));
-    }
-    CU_TRY(cudaMemcpyAsync(sc, f->scale_factors, (size_t)f->nlevels * 4, cudaMemcpyHostToDevice, s));
-    k_grid_build<<<1, 1024, 0, s>>>(keys, n, f->min_x, f->min_y, f->grid_element_width_inv, f->grid_element_height_inv, sk, en, cs);
-    LAUNCH_CHECK();
     d.n = n; d.keys = keys; d.desc = desc; d.u_right = ur; d.min_x = f->min_x; d.min_y = f->min_y; d.max_x = f->max_x; d.max_y = f->max_y;
     d.gw_inv = f->grid_element_width_inv; d.gh_inv = f->grid_element_height_inv; d.scale = sc; d.nlevels = f->nlevels; d.cell_start = cs; d.entries = en;
+    sort_keys = sk;
+    return ORBX_OK;
+}
+static int build_grid(orbx_matcher* m, const FrameDev& d, uint32_t* sort_keys) {
+    k_grid_build<<<1, 1024, 0, m->stream>>>(d.keys, d.n, d.min_x, d.min_y, d.gw_inv, d.gh_inv, sort_keys, const_cast<int*>(d.entries), const_cast<int*>(d.cell_start));
+    LAUNCH_CHECK();
     return ORBX_OK;
 }
 
+// host array -> staged upload (host != nullptr) or plain device scratch (host == nullptr)
 template <typename T> static int up(orbx_matcher* m, const T* host, size_t count, T*& dev) {
-    dev = m->arena.get<T>(count ? count : 1);
+    dev = host ? reinterpret_cast<T*>(m->uparena.put(count ? host : nullptr, (count ? count : 1) * sizeof(T))) : m->arena.get<T>(count ? count : 1);
     if (!dev) FAIL(ORBX_E_CUDA, "matcher arena exhausted");
-    if (count && host) CU_TRY(cudaMemcpyAsync(dev, host, count * sizeof(T), cudaMemcpyHostToDevice, m->stream));
     return ORBX_OK;
 }
 
-// COUNT pass, scan, (host reads the total), FILL pass
+// COUNT pass, scan, FILL pass -- no host round trip in between: the candidate arena keeps the capacity of earlier calls (at least
+// 64 per query); the FILL pass and the resolve kernels refuse to touch it when the total exceeds that capacity, and the caller, which
+// reads the total back together with its results, grows the arena and repeats the call (rare).
 static int window_search(orbx_matcher* m, QueryParams& P, const FrameDev& F, int*& counts, int*& offsets, uint32_t*& cand) {
     cudaStream_t s = m->stream;
     const int nq = P.nq;
     counts = m->arena.get<int>(nq + 1); offsets = m->arena.get<int>(nq + 2);
     if (!counts || !offsets) FAIL(ORBX_E_CUDA, "matcher arena exhausted");
-    cand = nullptr;
-    if (nq == 0) return ORBX_OK;
-    k_window_search<false><<<(nq + 3) / 4, 128, 0, s>>>(P, F, counts, nullptr, nullptr);
+    const size_t want = std::max<size_t>((size_t)nq * 64, 1 << 16);
+    if (m->cand_cap < want) {
+        int rc = m->cand_arena.reserve(want * 4); if (rc) return rc;
+        m->cand_cap = m->cand_arena.cap / 4;
+    }
+    cand = reinterpret_cast<uint32_t*>(m->cand_arena.base);
+    if (nq == 0) { CU_TRY(cudaMemsetAsync(offsets, 0, 8, s)); return ORBX_OK; }
+    k_window_search<false><<<(nq + 3) / 4, 128, 0, s>>>(P, F, counts, nullptr, nullptr, 0);
     LAUNCH_CHECK();
     k_scan_counts<<<1, 1024, 0, s>>>(counts, nq, offsets);
     LAUNCH_CHECK();
-    int total = 0;
-    CU_TRY(cudaMemcpyAsync(&total, offsets + nq, 4, cudaMemcpyDeviceToHost, s));
-    CU_TRY(cudaStreamSynchronize(s));
-    int rc = m->cand_arena.reserve((size_t)(total + 1) * 4); if (rc) return rc;
-    cand = reinterpret_cast<uint32_t*>(m->cand_arena.base);
-    k_window_search<true><<<(nq + 3) / 4, 128, 0, s>>>(P, F, counts, offsets, cand);
+    k_window_search<true><<<(nq + 3) / 4, 128, 0, s>>>(P, F, counts, offsets, cand, (int)std::min<size_t>(m->cand_cap, 0x7FFFFFFF));
     LAUNCH_CHECK();
     return ORBX_OK;
+}
+// after the call's final synchronisation: did the candidate lists fit?  If not, grow and tell the caller to run again.
+static bool cand_overflow(orbx_matcher* m, int total) {
+    if ((size_t)total <= m->cand_cap) return false;
+    if (m->cand_arena.reserve(((size_t)total + total / 2 + 1024) * 4) == ORBX_OK) m->cand_cap = m->cand_arena.cap / 4;
+    return true;
 }
 
 #define RESOLVE_SMEM_BYTES (160 * 1024)
@@ -138,6 +178,7 @@ void orbx_matcher_destroy(orbx_matcher* m) {
     cudaSetDevice(m->device); cudaStreamSynchronize(m->stream);
     if (m->arena.base) cudaFree(m->arena.base);
     if (m->cand_arena.base) cudaFree(m->cand_arena.base);
+    m->uparena.release();
     cudaStreamDestroy(m->stream);
     delete m;
 }
@@ -148,10 +189,12 @@ int orbx_descriptor_distance(orbx_matcher* m, const uint8_t* a, const uint8_t* b
     if (!m || n < 0 || (n && (!a || !b || !out))) FAIL(ORBX_E_INVALID, "bad arguments");
     if (n == 0) return ORBX_OK;
     CU_TRY(cudaSetDevice(m->device));
-    int rc = m->arena.reserve(2 * pad((size_t)n * 32) + pad((size_t)n * 4) + 4096); if (rc) return rc;
-    m->arena.reset();
+    int rc = m->arena.reserve(pad((size_t)n * 4) + 4096); if (rc) return rc;
+    if ((rc = m->uparena.reserve(2 * pad((size_t)n * 32) + 4096))) return rc;
+    m->arena.reset(); m->uparena.reset();
     uint8_t *da, *db; int* dout;
     if ((rc = up(m, a, (size_t)n * 32, da)) || (rc = up(m, b, (size_t)n * 32, db)) || (rc = up<int>(m, nullptr, n, dout))) return rc;
+    if ((rc = flush_uploads(m))) return rc;
     k_descriptor_distance<<<(n + 127) / 128, 128, 0, m->stream>>>(reinterpret_cast<const uint4*>(da), reinterpret_cast<const uint4*>(db), n, dout);
     LAUNCH_CHECK();
     CU_TRY(cudaMemcpyAsync(out, dout, (size_t)n * 4, cudaMemcpyDeviceToHost, m->stream));
@@ -169,12 +212,15 @@ int orbx_search_for_initialization(orbx_matcher* m, const orbx_frame_view* F1, c
     if (F1->n == 0) return ORBX_OK;
     CU_TRY(cudaSetDevice(m->device));
     const int n1 = F1->n, n2 = F2->n;
-    if ((rc = m->arena.reserve(frame_bytes(F1) + frame_bytes(F2) + pad((size_t)n1 * 8) + 6 * pad((size_t)(n1 + n2 + 2) * 4) + 8192))) return rc;
-    m->arena.reset();
-    FrameDev d2;
-    if ((rc = upload_frame(m, F2, d2))) return rc;
+    const size_t need = frame_bytes(F1) + frame_bytes(F2) + pad((size_t)n1 * 8) + 6 * pad((size_t)(n1 + n2 + 2) * 4) + 8192;
+    if ((rc = m->arena.reserve(need)) || (rc = m->uparena.reserve(need))) return rc;
+retry:
+    m->arena.reset(); m->uparena.reset();
+    FrameDev d2; uint32_t* sk2;
+    if ((rc = upload_frame(m, F2, d2, sk2))) return rc;
     KpM* k1; uint8_t* desc1; float* prev;
     if ((rc = up(m, reinterpret_cast<const KpM*>(F1->keys_un), (size_t)n1, k1)) || (rc = up(m, F1->descriptors, (size_t)n1 * 32, desc1)) || (rc = up(m, prev_matched_xy, (size_t)n1 * 2, prev))) return rc;
+    if ((rc = flush_uploads(m)) || (rc = build_grid(m, d2, sk2))) return rc;
     QueryParams P; std::memset(&P, 0, sizeof(P));
     P.mode = MODE_INIT; P.nq = n1; P.q_keys = k1; P.q_desc = desc1; P.q_xy = prev; P.window = (float)window_size;
     int *counts, *offsets; uint32_t* cand;
@@ -182,12 +228,16 @@ int orbx_search_for_initialization(orbx_matcher* m, const orbx_frame_view* F1, c
     int* md = m->arena.get<int>(n2 + 1); int* m21 = m->arena.get<int>(n2 + 1); int* m12 = m->arena.get<int>(n1); int* binof = m->arena.get<int>(n1); int* dn = m->arena.get<int>(1);
     if (!md || !m21 || !m12 || !binof || !dn) FAIL(ORBX_E_CUDA, "matcher arena exhausted");
     const int resolve_smem = RESOLVE_SMEM_BYTES;
-    k_resolve_init<<<1, RESOLVE_THREADS, resolve_smem, m->stream>>>(n1, n2, k1, d2.keys, counts, offsets, cand, m->nnratio, m->checkOri, resolve_smem / 4,
+    k_resolve_init<<<1, RESOLVE_THREADS, resolve_smem, m->stream>>>(n1, n2, k1, d2.keys, counts, offsets, cand, (int)std::min<size_t>(m->cand_cap, 0x7FFFFFFF), m->nnratio, m->checkOri, resolve_smem / 4,
                                                                      md, m21, m12, binof, prev, dn);
     LAUNCH_CHECK();
+    int total = 0;
+    CU_TRY(cudaMemcpyAsync(&total, offsets + n1, 4, cudaMemcpyDeviceToHost, m->stream));
+    CU_TRY(cudaMemcpyAsync(nmatches, dn, 4, cudaMemcpyDeviceToHost, m->stream));
+    CU_TRY(cudaStreamSynchronize(m->stream));
+    if (cand_overflow(m, total)) goto retry;                       // prev_matched_xy is only written below, so the inputs are still intact
     CU_TRY(cudaMemcpyAsync(matches12, m12, (size_t)n1 * 4, cudaMemcpyDeviceToHost, m->stream));
     CU_TRY(cudaMemcpyAsync(prev_matched_xy, prev, (size_t)n1 * 8, cudaMemcpyDeviceToHost, m->stream));
-    CU_TRY(cudaMemcpyAsync(nmatches, dn, 4, cudaMemcpyDeviceToHost, m->stream));
     CU_TRY(cudaStreamSynchronize(m->stream));
     return ORBX_OK;
 }
@@ -204,26 +254,32 @@ int orbx_search_by_projection_frame(orbx_matcher* m, const orbx_frame_view* cur,
     for (int i = 0; i < n_last; ++i) if (valid[i] && (last_octave[i] < 0 || last_octave[i] >= cur->nlevels)) FAIL(ORBX_E_INVALID, "octave out of range");
     CU_TRY(cudaSetDevice(m->device));
     const int nc = cur->n;
-    if ((rc = m->arena.reserve(frame_bytes(cur) + pad((size_t)n_last * 32) + 8 * pad((size_t)(n_last + nc + 2) * 8) + 8192))) return rc;
-    m->arena.reset();
-    FrameDev dc;
-    if ((rc = upload_frame(m, cur, dc))) return rc;
+    const size_t need = frame_bytes(cur) + pad((size_t)n_last * 32) + 8 * pad((size_t)(n_last + nc + 2) * 8) + 8192;
+    if ((rc = m->arena.reserve(need)) || (rc = m->uparena.reserve(need))) return rc;
+retry:
+    m->arena.reset(); m->uparena.reset();
+    FrameDev dc; uint32_t* skc;
+    if ((rc = upload_frame(m, cur, dc, skc))) return rc;
     float *uv, *iz, *la; int* lo; uint8_t *dd, *va, *ob = nullptr, *oc = nullptr;
     if ((rc = up(m, proj_uv, (size_t)n_last * 2, uv)) || (rc = up(m, proj_invz, (size_t)n_last, iz)) || (rc = up(m, last_angle, (size_t)n_last, la)) ||
         (rc = up(m, last_octave, (size_t)n_last, lo)) || (rc = up(m, mp_desc, (size_t)n_last * 32, dd)) || (rc = up(m, valid, (size_t)n_last, va))) return rc;
     if (mp_observed && (rc = up(m, mp_observed, (size_t)n_last, ob))) return rc;
     if (cur_occupied && (rc = up(m, cur_occupied, (size_t)nc, oc))) return rc;
+    if ((rc = flush_uploads(m)) || (rc = build_grid(m, dc, skc))) return rc;
     QueryParams P; std::memset(&P, 0, sizeof(P));
     P.mode = MODE_PROJ_FRAME; P.nq = n_last; P.q_desc = dd; P.q_xy = uv; P.q_invz = iz; P.q_octave = lo; P.q_valid = va; P.th = th; P.forward = forward; P.backward = backward; P.mbf = mbf;
     int *counts, *offsets; uint32_t* cand;
     if ((rc = window_search(m, P, dc, counts, offsets, cand))) return rc;
     uint8_t* occ = m->arena.get<uint8_t>(nc + 1); int* cm = m->arena.get<int>(nc + 1); int* pushes = m->arena.get<int>(2 * (size_t)n_last + 2); int* dn = m->arena.get<int>(1);
     if (!occ || !cm || !pushes || !dn) FAIL(ORBX_E_CUDA, "matcher arena exhausted");
-    k_resolve_proj_frame<<<1, RESOLVE_THREADS, RESOLVE_SMEM_BYTES, m->stream>>>(n_last, nc, dc.keys, la, ob, oc, counts, offsets, cand, m->checkOri, RESOLVE_SMEM_BYTES / 4, occ, cm, pushes, dn);
+    k_resolve_proj_frame<<<1, RESOLVE_THREADS, RESOLVE_SMEM_BYTES, m->stream>>>(n_last, nc, dc.keys, la, ob, oc, counts, offsets, cand, (int)std::min<size_t>(m->cand_cap, 0x7FFFFFFF), m->checkOri, RESOLVE_SMEM_BYTES / 4, occ, cm, pushes, dn);
     LAUNCH_CHECK();
+    int total = 0;
+    CU_TRY(cudaMemcpyAsync(&total, offsets + n_last, 4, cudaMemcpyDeviceToHost, m->stream));
     if (nc) CU_TRY(cudaMemcpyAsync(cur_match, cm, (size_t)nc * 4, cudaMemcpyDeviceToHost, m->stream));
     CU_TRY(cudaMemcpyAsync(nmatches, dn, 4, cudaMemcpyDeviceToHost, m->stream));
     CU_TRY(cudaStreamSynchronize(m->stream));
+    if (cand_overflow(m, total)) goto retry;
     return ORBX_OK;
 }
 
@@ -239,26 +295,32 @@ int orbx_search_by_projection_points(orbx_matcher* m, const orbx_frame_view* F, 
     for (int i = 0; i < n_points; ++i) if (track_level[i] < 0 || track_level[i] >= F->nlevels) FAIL(ORBX_E_INVALID, "predicted level out of range");
     CU_TRY(cudaSetDevice(m->device));
     const int nf = F->n;
-    if ((rc = m->arena.reserve(frame_bytes(F) + pad((size_t)n_points * 32) + 8 * pad((size_t)(n_points + nf + 2) * 8) + 8192))) return rc;
-    m->arena.reset();
-    FrameDev df;
-    if ((rc = upload_frame(m, F, df))) return rc;
+    const size_t need = frame_bytes(F) + pad((size_t)n_points * 32) + 8 * pad((size_t)(n_points + nf + 2) * 8) + 8192;
+    if ((rc = m->arena.reserve(need)) || (rc = m->uparena.reserve(need))) return rc;
+retry:
+    m->arena.reset(); m->uparena.reset();
+    FrameDev df; uint32_t* skf;
+    if ((rc = upload_frame(m, F, df, skf))) return rc;
     float *uv, *ur, *vc; int* lv; uint8_t *dd, *ob = nullptr, *oc = nullptr;
     if ((rc = up(m, track_uv, (size_t)n_points * 2, uv)) || (rc = up(m, track_ur, (size_t)n_points, ur)) || (rc = up(m, track_view_cos, (size_t)n_points, vc)) ||
         (rc = up(m, track_level, (size_t)n_points, lv)) || (rc = up(m, mp_desc, (size_t)n_points * 32, dd))) return rc;
     if (mp_observed && (rc = up(m, mp_observed, (size_t)n_points, ob))) return rc;
     if (f_occupied && (rc = up(m, f_occupied, (size_t)nf, oc))) return rc;
+    if ((rc = flush_uploads(m)) || (rc = build_grid(m, df, skf))) return rc;
     QueryParams P; std::memset(&P, 0, sizeof(P));
     P.mode = MODE_PROJ_POINTS; P.nq = n_points; P.q_desc = dd; P.q_xy = uv; P.q_octave = lv; P.q_ur = ur; P.q_viewcos = vc; P.th = th;
     int *counts, *offsets; uint32_t* cand;
     if ((rc = window_search(m, P, df, counts, offsets, cand))) return rc;
     uint8_t* occ = m->arena.get<uint8_t>(nf + 1); int* fm = m->arena.get<int>(nf + 1); int* dn = m->arena.get<int>(1);
     if (!occ || !fm || !dn) FAIL(ORBX_E_CUDA, "matcher arena exhausted");
-    k_resolve_proj_points<<<1, RESOLVE_THREADS, RESOLVE_SMEM_BYTES, m->stream>>>(n_points, nf, df.keys, ob, oc, counts, offsets, cand, m->nnratio, RESOLVE_SMEM_BYTES / 4, occ, fm, dn);
+    k_resolve_proj_points<<<1, RESOLVE_THREADS, RESOLVE_SMEM_BYTES, m->stream>>>(n_points, nf, df.keys, ob, oc, counts, offsets, cand, (int)std::min<size_t>(m->cand_cap, 0x7FFFFFFF), m->nnratio, RESOLVE_SMEM_BYTES / 4, occ, fm, dn);
     LAUNCH_CHECK();
+    int total = 0;
+    CU_TRY(cudaMemcpyAsync(&total, offsets + n_points, 4, cudaMemcpyDeviceToHost, m->stream));
     if (nf) CU_TRY(cudaMemcpyAsync(f_match, fm, (size_t)nf * 4, cudaMemcpyDeviceToHost, m->stream));
     CU_TRY(cudaMemcpyAsync(nmatches, dn, 4, cudaMemcpyDeviceToHost, m->stream));
     CU_TRY(cudaStreamSynchronize(m->stream));
+    if (cand_overflow(m, total)) goto retry;
     return ORBX_OK;
 }
 
@@ -277,14 +339,16 @@ int orbx_compute_stereo_matches(orbx_matcher* m, orbx_extractor* left, orbx_extr
     for (int i = 0; i < nr; ++i) if (keys_right[i].octave < 0 || keys_right[i].octave >= L.nlevels) FAIL(ORBX_E_INVALID, "octave out of range");
     // both extractors' streams must have finished writing their pyramids
     CU_TRY(cudaStreamSynchronize(L.stream)); CU_TRY(cudaStreamSynchronize(R.stream));
-    if ((rc = m->arena.reserve(pad((size_t)nl * 60) + pad((size_t)nr * 60) + 3 * pad((size_t)nl * 4) + 2 * pad((size_t)L.nlevels * 4) + 8192 + 64 * 256))) return rc;
-    m->arena.reset();
+    const size_t need = pad((size_t)nl * 60) + pad((size_t)nr * 60) + 3 * pad((size_t)nl * 4) + 2 * pad((size_t)L.nlevels * 4) + 8192 + 64 * 256;
+    if ((rc = m->arena.reserve(need)) || (rc = m->uparena.reserve(need))) return rc;
+    m->arena.reset(); m->uparena.reset();
     KpM *kl, *kr; uint8_t *dl, *dr; float *sc, *isc;
     if ((rc = up(m, reinterpret_cast<const KpM*>(keys_left), (size_t)nl, kl)) || (rc = up(m, reinterpret_cast<const KpM*>(keys_right), (size_t)nr, kr)) ||
         (rc = up(m, desc_left, (size_t)nl * 32, dl)) || (rc = up(m, desc_right, (size_t)nr * 32, dr)) ||
         (rc = up(m, L.scale, (size_t)L.nlevels, sc)) || (rc = up(m, L.inv_scale, (size_t)L.nlevels, isc))) return rc;
     float* dur = m->arena.get<float>(nl); float* ddep = m->arena.get<float>(nl); int* sad = m->arena.get<int>(nl);
     if (!dur || !ddep || !sad) FAIL(ORBX_E_CUDA, "matcher arena exhausted");
+    if ((rc = flush_uploads(m))) return rc;
     StereoPyr PL, PR;
     for (int l = 0; l < L.nlevels; ++l) { PL.lv[l] = {L.ptr[l], L.pitch[l], L.w[l], L.h[l]}; PR.lv[l] = {R.ptr[l], R.pitch[l], R.w[l], R.h[l]}; }
     k_stereo_match<<<(nl + 3) / 4, 128, 0, m->stream>>>(kl, dl, nl, kr, dr, nr, PL, PR, sc, isc, mb, mbf, dur, ddep, sad);
