@@ -1,6 +1,7 @@
 // k_pyramid_fast.cuh -- image pyramid (bilinear, fixed point) and per-cell FAST-9 detection kernels.
 #pragma once
 #include "orbx_common.cuh"
+#include <cuda_pipeline.h>
 
 // =================================================================================================
 // K1  pyr_resize: level l from level l-1 (chained, /root/reference/src/ORBextractor.cc:1826-1886),
@@ -136,51 +137,64 @@ __device__ __forceinline__ uint32_t swar_nz(uint32_t x) { return (((x & 0x7F7F7F
 
 #define FAST_WARPS 4
 
+// Each warp walks cells cell0, cell0 + W, cell0 + 2W, ... of its frame (W = warps per frame) and double-buffers the ROI:
+// the LDGSTS copies of the next cell are in flight while the current cell is processed, so the warp never waits for
+// its patch except on the first cell.
+__device__ __forceinline__ void fast_issue_patch(const PyrView& pv, const LevelGeom* __restrict__ levels, const CellDesc& c, int b, int lane, uint8_t* dst) {
+    const LevelGeom& g = levels[c.level];
+    int pitch;
+    const uint8_t* img = level_ptr(pv, g, c.level, b, pitch);
+    const int xs = c.x0 & ~3;
+    const int wpr = ((c.x0 + c.cw + 3) >> 2) - (xs >> 2);      // 32-bit words per patch row
+    const int rpi = 32 / wpr, lr = lane / wpr, lc = lane - lr * wpr;
+    const uint8_t* src = img + (long long)c.y0 * pitch + xs + 4 * lc;
+    if (lr < rpi)
+        for (int r = lr; r < c.ch; r += rpi) __pipeline_memcpy_async(dst + 4 * (r * wpr + lc), src + r * pitch, 4);
+}
+
 __global__ void __launch_bounds__(FAST_WARPS * 32)
 k_fast_cells(PyrView pv, const LevelGeom* __restrict__ levels, const CellDesc* __restrict__ cells, int ncells,
-             int slots_per_frame, int smem_per_warp, int iniTh, int minTh,
+             int slots_per_frame, int smem_per_warp, int patch_cap, int s_cap, int iniTh, int minTh,
              uint32_t* __restrict__ cand_slots,      // [B][slots_per_frame]  packed x:12|y:12|resp:8 (x,y relative to minBorder)
              uint16_t* __restrict__ cell_counts) {   // [B][ncells]
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int cell = blockIdx.x * FAST_WARPS + warp;
     const int b = blockIdx.y;
+    const int W = gridDim.x * FAST_WARPS;
+    int cell = blockIdx.x * FAST_WARPS + warp;
     if (cell >= ncells) return;
-    const CellDesc c = cells[cell];
-    const LevelGeom& g = levels[c.level];
-    int pitch;
-    const uint8_t* img = level_ptr(pv, g, c.level, b, pitch);
+    uint8_t* smw = smem_raw + (size_t)warp * smem_per_warp;    // [patch 0 | patch 1 | S | queue]
+    uint8_t* S = smw + 2 * patch_cap;
+    uint16_t* queue = reinterpret_cast<uint16_t*>(S + s_cap);  // zw*zh entries: (dark<<15) | y<<6 | x, raster order
+    const uint32_t lt = (1u << lane) - 1u;
+    int tq = 0;                                                // largest 2^k - 1 <= minTh (exact for the default minTh = 7)
+    while (2 * tq + 1 <= minTh) tq = 2 * tq + 1;
+    const uint32_t keep = (uint32_t)(0xFF & ~tq) * 0x01010101u;
 
-    uint8_t* sm = smem_raw + (size_t)warp * smem_per_warp;
+    CellDesc c = cells[cell];
+    fast_issue_patch(pv, levels, c, b, lane, smw);
+    __pipeline_commit();
+    for (int buf = 0; cell < ncells; cell += W, buf ^= 1) {
+    const int next = cell + W;
+    CellDesc cnext = c;
+    if (next < ncells) { cnext = cells[next]; fast_issue_patch(pv, levels, cnext, b, lane, smw + (buf ^ 1) * patch_cap); }
+    __pipeline_commit();
+
+    uint8_t* sm = smw + buf * patch_cap;
     const int zw = c.cw - 6, zh = c.ch - 6;
     const int xs = c.x0 & ~3, shift = c.x0 & 3;
     const int wpr = ((c.x0 + c.cw + 3) >> 2) - (xs >> 2);      // 32-bit words per patch row
     const int ps = wpr * 4;                                    // patch row stride (bytes)
     uint32_t* patch32 = reinterpret_cast<uint32_t*>(sm);
-    const int patch_bytes = ps * c.ch;
     const int sst = zw + 2;                                    // S row stride; 1-px zero ring
     const int s_bytes = (sst * (zh + 2) + 3) & ~3;
-    uint8_t* S = sm + patch_bytes;
-    uint16_t* queue = reinterpret_cast<uint16_t*>(S + s_bytes);   // zw*zh entries: (dark<<15) | y<<6 | x, raster order
-
-    // stage the ROI with aligned 32-bit loads: each iteration covers 32/wpr rows
-    {
-        const int rpi = 32 / wpr, lr = lane / wpr, lc = lane - lr * wpr;
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(img + (long long)c.y0 * pitch + xs) + lc;
-        const int p4 = pitch >> 2;
-        if (lr < rpi)
-            for (int r = lr; r < c.ch; r += rpi) patch32[r * wpr + lc] = __ldg(src + r * p4);
-    }
     for (int w = lane; w < (s_bytes >> 2); w += 32) reinterpret_cast<uint32_t*>(S)[w] = 0u;
+    __pipeline_wait_prior(1);                                  // this cell's patch has landed (the next one may still be in flight)
     __syncwarp();
 
-    const uint32_t lt = (1u << lane) - 1u;
     // ---- stage A: polarity-free compass pre-test, 4 pixels (one word) per lane per step ----
     int qn = 0;
     {
-        int tq = 0;                                            // largest 2^k - 1 <= minTh (exact for the default minTh = 7)
-        while (2 * tq + 1 <= minTh) tq = 2 * tq + 1;
-        const uint32_t keep = (uint32_t)(0xFF & ~tq) * 0x01010101u;
         const int pc0 = shift + 3;                             // patch column of zone x = 0
         const int wi0 = pc0 >> 2, wi1 = (pc0 + zw - 1) >> 2, nw = wi1 - wi0 + 1;
         const uint32_t mfirst = 0xFFFFFFFFu << (8 * (pc0 & 3));
@@ -314,4 +328,7 @@ k_fast_cells(PyrView pv, const LevelGeom* __restrict__ levels, const CellDesc* _
         n += __popc(m);
     }
     if (lane == 0) cell_counts[(long long)b * ncells + cell] = (uint16_t)n;
+    c = cnext;
+    __syncwarp();                                              // S / queue are reused by the next cell
+    }
 }

@@ -70,7 +70,7 @@ struct orbx_extractor {
     int rows = 0, cols = 0;
     std::vector<LevelGeom> levels; std::vector<CellDesc> cells; std::vector<BlurTile> tiles;
     long long pyr_fstride = 0; int cand_per_frame = 0, kp_per_frame = 0, max_kp = 0;
-    int fast_smem_per_warp = 0, tree_cap = 0, sort_smem_keys = 4096;
+    int fast_smem_per_warp = 0, fast_patch_cap = 0, fast_s_cap = 0, tree_cap = 0, sort_smem_keys = 4096;
     DevBuf<LevelGeom> d_levels; DevBuf<CellDesc> d_cells; DevBuf<BlurTile> d_tiles; DevBuf<int> d_tabs;
     std::vector<ResizeTabs> resize_tabs;
 
@@ -114,7 +114,7 @@ static int build_plan(orbx_extractor* h, int rows, int cols) {
     const int L = h->nlevels;
     std::vector<LevelGeom> lv(L);
     std::vector<CellDesc> cells; std::vector<BlurTile> tiles;
-    long long off = 0; int cand_off = 0, kp_off = 0, smem_pw = 0, tree_cap = 0;
+    long long off = 0; int cand_off = 0, kp_off = 0, patch_cap = 0, s_cap = 0, q_cap = 0, tree_cap = 0;
     for (int l = 0; l < L; ++l) {
         LevelGeom& g = lv[l];
         std::memset(&g, 0, sizeof(g));
@@ -158,8 +158,7 @@ static int build_plan(orbx_extractor* h, int rows, int cols) {
                 c.slot = slot; slot += c.cap;
                 cells.push_back(c);
                 const int wpr = ((c.x0 + c.cw + 3) >> 2) - (c.x0 >> 2);
-                const int need = wpr * 4 * c.ch + (((zw + 2) * (zh + 2) + 3) & ~3) + ((2 * zw * zh + 3) & ~3);
-                smem_pw = std::max(smem_pw, need);
+                patch_cap = std::max(patch_cap, wpr * 4 * c.ch); s_cap = std::max(s_cap, ((zw + 2) * (zh + 2) + 3) & ~3); q_cap = std::max(q_cap, (2 * zw * zh + 3) & ~3);
             }
         }
         g.cell_count = (int)cells.size() - g.cell_begin;
@@ -228,7 +227,8 @@ static int build_plan(orbx_extractor* h, int rows, int cols) {
     h->pyr_fstride = (off + 255) / 256 * 256;
     h->cand_per_frame = cand_off; h->kp_per_frame = kp_off;
     h->max_kp = 0; for (int l = 0; l < L; ++l) h->max_kp += h->levels[l].kp_cap;
-    h->fast_smem_per_warp = align_up(smem_pw, 16);
+    h->fast_patch_cap = align_up(patch_cap, 16); h->fast_s_cap = align_up(s_cap, 16);
+    h->fast_smem_per_warp = 2 * h->fast_patch_cap + h->fast_s_cap + align_up(q_cap, 16);     // [patch 0 | patch 1 | S | queue]
     h->tree_cap = tree_cap;
     // radix-sort capacity per (level, frame): ~1 candidate per 100 px of level 0 is generous for real images; larger levels fall back
     // to the global-memory bitonic path inside the kernel
@@ -297,10 +297,12 @@ static int run_detect(orbx_extractor* h, int b0, int B, bool fork_blur = false) 
     prof_mark(h);
     const int ncells = (int)h->cells.size();
     if (ncells > 0) {
-        dim3 grid((ncells + FAST_WARPS - 1) / FAST_WARPS, B);
+        // each warp walks FAST_CELLS_PER_WARP cells of its frame with the next ROI prefetched while the current one is processed
+        static const int cpw = [] { const char* e = std::getenv("ORBX_FAST_CPW"); int v = e ? std::atoi(e) : 4; return v < 1 ? 1 : v; }();
+        dim3 grid((ncells + FAST_WARPS * cpw - 1) / (FAST_WARPS * cpw), B);
         const int smem = h->fast_smem_per_warp * FAST_WARPS;
         k_fast_cells<<<grid, FAST_WARPS * 32, smem, s>>>(view, h->d_levels.p, h->d_cells.p, ncells, h->cand_per_frame,
-                                                          h->fast_smem_per_warp, h->iniThFAST, h->minThFAST, slots, cell_counts);
+                                                          h->fast_smem_per_warp, h->fast_patch_cap, h->fast_s_cap, h->iniThFAST, h->minThFAST, slots, cell_counts);
         LAUNCH_CHECK();
     }
     prof_mark(h);
