@@ -132,6 +132,56 @@ def test_batch_equals_single(orbx, oracle):
     assert E.check_overflow() == 0
 
 
+def test_host_batch_pipeline_many_chunks(orbx):
+    """The host-pointer batch call cuts large batches into chunks over several streams (H2D / compute / D2H overlapped):
+    a 150-frame batch (ramped chunks 16, 32, 64, 38) must equal the per-frame call frame by frame, also from a strided,
+    non-dense host layout (per-frame copy path) and when called twice in a row (buffer reuse across calls)."""
+    B = 150
+    imgs = synth_batch(B, 640, 480, seed0=400, distinct=10)
+    E = orbx.ORBextractor(1000, 1.2, 8, 20, 7); E1 = orbx.ORBextractor(1000, 1.2, 8, 20, 7)
+    probe = sorted(set(list(range(0, B, 7)) + [15, 16, 17, 47, 48, 111, 112, B - 1]))          # incl. both sides of every chunk boundary
+    singles = {b: E1(imgs[b]) for b in probe}
+    first = None
+    for rep in range(2):
+        kp, desc, counts = E.extract_batch(imgs)
+        for b in probe:
+            k1, d1 = singles[b]
+            assert counts[b] == len(k1), (rep, b)
+            assert kp_equal(kp[b][:counts[b]], k1) and np.array_equal(desc[b][:counts[b]], d1), (rep, b)
+        if first is None:
+            first = (kp.copy(), desc.copy(), counts.copy())
+        else:
+            assert np.array_equal(counts, first[2])
+            for b in range(B):
+                assert np.array_equal(kp[b][:counts[b]], first[0][b][:counts[b]]) and np.array_equal(desc[b][:counts[b]], first[1][b][:counts[b]])
+    # odd geometry + row padding: the mirror path does not apply (step % 4 != 0), frames are copied one by one
+    big = np.zeros((70, 300, 403), np.uint8)
+    src = synth_batch(70, 401, 300, seed0=410, distinct=5)
+    big[:, :, :401] = src
+    view = big[:, :, :401]                                                       # step 403, width 401
+    cap = E.max_keypoints(300, 401)
+    kp = np.zeros((70, cap), orbx.KP_DTYPE); desc = np.zeros((70, cap, 32), np.uint8); counts = np.zeros(70, np.int32)
+    E.extract_batch_raw(view.ctypes.data, 70, 300, 401, view.strides[1], view.strides[0], kp.ctypes.data, desc.ctypes.data, cap, counts.ctypes.data, device=False)
+    for b in range(0, 70, 3):
+        k1, d1 = E1(np.ascontiguousarray(src[b]))
+        assert counts[b] == len(k1) and kp_equal(kp[b][:counts[b]], k1) and np.array_equal(desc[b][:counts[b]], d1), b
+    assert E.check_overflow() == 0
+
+
+def test_masked_batch_many_chunks(orbx):
+    """Same for the masked (C5) host call: 1080p chunks are 10 frames, so 24 frames run as several chunks on several streams."""
+    B, w, h = 24, 1920, 1080
+    E = orbx.ORBextractor(1000, 1.2, 8, 20, 7); E2 = orbx.ORBextractor(1000, 1.2, 8, 20, 7)
+    imgs = synth_batch(B, w, h, seed0=420, distinct=3)
+    masks = np.stack([synth_mask(420 + (b % 4), w, h) for b in range(B)])
+    kp, desc, counts, culled = E.extract_masked_batch(imgs, masks)
+    lab = np.ones((h, w), np.float64); ids = np.zeros(1, np.int32); rm = np.zeros(1, np.int32)
+    for b in (0, 2, 9, 10, 11, 19, 20, B - 1):                                      # both sides of the 1080p chunk boundaries
+        kd, cd = E2.detect(imgs[b]); kk, ck, cu = E2.MovingKeyPoints(masks[b], lab, ids, rm, kd, cd); kf, df = E2.ProcessDesp(kk, ck)
+        assert counts[b] == len(kf) and culled[b] == len(cu), b
+        assert kp_equal(kp[b][:counts[b]], kf) and np.array_equal(desc[b][:counts[b]], df), b
+
+
 def test_batch_full_size_properties(orbx):
     """C5 shape (1920x1080): batch result is independent of batch position / batch size, and repeatable."""
     E = orbx.ORBextractor(1000, 1.2, 8, 20, 7)
