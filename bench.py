@@ -396,10 +396,12 @@ def main():
     # capture (profiles/traffic.json, written by tools/profile_digest.py), scaled to this launch's frame count
     kernel_of = {"pyr_resize": "k_pyr_resize_w", "fast_cells": "k_fast_cells", "octree_sort": "k_octree_sort", "octree_tree": "k_octree_tree",
                  "gauss7": "k_gauss7", "orient_describe": "k_orient_describe"}
-    traffic = None
+    traffic = None; ncu_note = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         traffic = tj["dram_bytes_per_frame"][kernel_of[dom]] * B / launches_of.get(dom, 1)
+        ncu_note = {"source": "profiles/" + tj["source"], "issue_active_pct": tj["issue_active_pct"][kernel_of[dom]], "dram_throughput_pct": tj["dram_throughput_pct"][kernel_of[dom]],
+                    "reading": "the kernel is bound by instruction issue (integer byte work), not by HBM: traffic ~= algorithmic bytes, DRAM a few % busy"}
     except Exception:
         pass
     line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": N, "steps": K, "warmup": max(W, 3),
@@ -408,7 +410,7 @@ def main():
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(B * WIDTH * HEIGHT * (2 if MASKED else 1)), "d2h_bytes_per_step": int(B * cap * 60 + 4 * B + 4), "steps": Ke},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "ncu": ncu_note,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes_per_launch, "ms_per_launch": dom_ms_per_launch,
                          "stage_ms_per_step": {k: v / max(ncalls, 1) for k, v in stage_ms.items()},
                          "stage_share": {k: (v / total_stage if total_stage else 0.0) for k, v in stage_ms.items()},

@@ -43,7 +43,7 @@ if os.path.exists(rep):
             "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
             "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__thread_inst_executed_per_inst_executed.ratio"]
     want = [w for w in want if w in idx]
-    traffic = {}
+    traffic = {}; issue = {}; dram_pct = {}
     def to_bytes(v, u):
         v = float(v.replace(",", "")); m = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         return v * m.get(u, 1)
@@ -55,10 +55,17 @@ if os.path.exists(rep):
             k = short(r[idx["Kernel Name"]])
             b = to_bytes(r[idx["dram__bytes_read.sum"]], units[idx["dram__bytes_read.sum"]]) + to_bytes(r[idx["dram__bytes_write.sum"]], units[idx["dram__bytes_write.sum"]])
             traffic.setdefault(k, []).append(b / frames)
+            try:
+                issue.setdefault(k, []).append(float(r[idx["smsp__issue_active.avg.pct_of_peak_sustained_active"]]))
+                dram_pct.setdefault(k, []).append(float(r[idx["gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"]]))
+            except Exception:
+                pass
     tj = {k: sum(v) / len(v) for k, v in traffic.items()}
     # k_pyr_resize launches once per level: report the per-frame SUM over the 7 levels
     for k in list(tj):
         if "resize" in k:
             tj[k] = sum(traffic[k]) / max(1, len(traffic[k]) // 7)
-    json.dump({"source": "%s_full_raw.csv" % tag, "frames_per_launch": frames, "dram_bytes_per_frame": tj}, open(os.path.join(P, "traffic.json"), "w"), indent=1)
+    json.dump({"source": "%s_full_raw.csv" % tag, "frames_per_launch": frames, "dram_bytes_per_frame": tj,
+               "issue_active_pct": {k: sum(v) / len(v) for k, v in issue.items()}, "dram_throughput_pct": {k: sum(v) / len(v) for k, v in dram_pct.items()}},
+              open(os.path.join(P, "traffic.json"), "w"), indent=1)
     print(json.dumps(tj, indent=1))
