@@ -126,7 +126,8 @@ __device__ __forceinline__ bool query_window(const QueryParams& P, const FrameDe
 // one warp per query.  FILL = false: counts[q] only.  FILL = true: cand[offsets[q] + k] = dist<<20 | index.
 template <bool FILL>
 __global__ void __launch_bounds__(128)
-k_window_search(QueryParams P, FrameDev F, int* __restrict__ counts, const int* __restrict__ offsets, uint32_t* __restrict__ cand, int cand_cap) {
+k_window_search(QueryParams P, FrameDev F, int* __restrict__ counts, const int* __restrict__ offsets, uint32_t* __restrict__ cand, int cand_cap,
+                uint2* __restrict__ pre_best /* FILL: per query (best, second) key = dist<<20 | position in list, ignoring running exclusions */) {
     const int lane = threadIdx.x & 31;
     const int q = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (q >= P.nq) return;
@@ -139,6 +140,8 @@ k_window_search(QueryParams P, FrameDev F, int* __restrict__ counts, const int* 
     const int cy0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, F.min_y), r), F.gh_inv)));
     const int cy1 = min(GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, F.min_y), r), F.gh_inv)));
     int n = 0;
+    uint32_t pk1 = 0xFFFFFFFFu, pk2 = 0xFFFFFFFFu;
+    const uint32_t dlimit = P.mode == MODE_INIT ? 0xFFFu : 256u;    // the projection matchers start from bestDist = 256 (strict <)
     if (!(cx0 >= GRID_COLS || cx1 < 0 || cy0 >= GRID_ROWS || cy1 < 0)) {
         const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
         uint4 d0 = make_uint4(0, 0, 0, 0), d1 = d0;
@@ -170,13 +173,23 @@ k_window_search(QueryParams P, FrameDev F, int* __restrict__ counts, const int* 
                 const uint32_t m = __ballot_sync(0xffffffffu, keep);
                 if (FILL && keep) {
                     const int d = hamming256(d0, d1, reinterpret_cast<const uint4*>(F.desc) + 2 * j);
-                    out[n + __popc(m & ((1u << lane) - 1u))] = ((uint32_t)d << 20) | (uint32_t)j;
+                    const int pos = n + __popc(m & ((1u << lane) - 1u));
+                    out[pos] = ((uint32_t)d << 20) | (uint32_t)j;
+                    if ((uint32_t)d < dlimit) {
+                        const uint32_t key = ((uint32_t)d << 20) | (uint32_t)pos;
+                        if (key < pk1) { pk2 = pk1; pk1 = key; } else if (key < pk2) pk2 = key;
+                    }
                 }
                 n += __popc(m);
             }
         }
     }
     if (!FILL && lane == 0) counts[q] = n;
+    if (FILL) {
+        const uint32_t g1 = __reduce_min_sync(0xffffffffu, pk1);
+        const uint32_t g2 = __reduce_min_sync(0xffffffffu, (pk1 == g1 && g1 != 0xFFFFFFFFu) ? pk2 : pk1);
+        if (lane == 0) pre_best[q] = make_uint2(g1, g2);
+    }
 }
 
 // exclusive scan of n counts by one CTA; total written to offsets[n]
@@ -261,20 +274,21 @@ struct StagedLists {
     const uint32_t* lists;  // concatenated candidate lists
     const uint32_t* act;    // query index of the k-th query with a non-empty list
     const uint32_t* aoff;   // start of its list; aoff[niter] = total
+    const uint2* pre;       // staged: (best, second) of the k-th active query; else: indexed by query
     int niter;              // staged: number of active queries; else: n
     uint32_t* free_words;   // first shared word after the staged lists
 };
-// words needed besides the lists themselves: act[n] + aoff[n+1]
+// words needed besides the lists themselves: act[n] + aoff[n+1] + pre[2n]
 __device__ __forceinline__ StagedLists stage_lists(uint32_t* sm, int sm_words, int extra_words, int n, const int* __restrict__ counts,
-                                                   const int* __restrict__ offsets, const uint32_t* __restrict__ cand) {
+                                                   const int* __restrict__ offsets, const uint32_t* __restrict__ cand, const uint2* __restrict__ pre_best) {
     __shared__ int sl_wsum[RESOLVE_THREADS / 32];
     __shared__ int sl_nact;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int total = offsets[n];
     StagedLists r;
-    r.staged = 2 * n + 1 + total + extra_words <= sm_words;
-    uint32_t* act = sm; uint32_t* aoff = act + n; uint32_t* lists = aoff + n + 1;
-    r.lists = r.staged ? lists : cand; r.act = act; r.aoff = aoff; r.niter = n; r.free_words = r.staged ? lists + total : sm;
+    r.staged = 4 * n + 2 + total + extra_words <= sm_words;
+    uint32_t* act = sm; uint32_t* aoff = act + n; uint2* pre = reinterpret_cast<uint2*>(aoff + n + 2);     /* act[n] + aoff[n+1] is an odd number of words: one pad word keeps uint2 aligned */ uint32_t* lists = reinterpret_cast<uint32_t*>(pre + n);
+    r.lists = r.staged ? lists : cand; r.act = act; r.aoff = aoff; r.pre = r.staged ? pre : pre_best; r.niter = n; r.free_words = r.staged ? lists + total : sm;
     if (!r.staged) return r;
     for (int i = tid; i < total; i += RESOLVE_THREADS) lists[i] = cand[i];
     int nact = 0;
@@ -287,7 +301,7 @@ __device__ __forceinline__ StagedLists stage_lists(uint32_t* sm, int sm_words, i
         int before = 0, chunk = 0;
 #pragma unroll
         for (int w = 0; w < RESOLVE_THREADS / 32; ++w) { const int c = sl_wsum[w]; if (w < warp) before += c; chunk += c; }
-        if (has) { const int k = nact + before + __popc(m & ((1u << lane) - 1u)); act[k] = (uint32_t)i; aoff[k] = (uint32_t)offsets[i]; }
+        if (has) { const int k = nact + before + __popc(m & ((1u << lane) - 1u)); act[k] = (uint32_t)i; aoff[k] = (uint32_t)offsets[i]; pre[k] = pre_best[i]; }
         nact += chunk;
         __syncthreads();
     }
@@ -297,22 +311,22 @@ __device__ __forceinline__ StagedLists stage_lists(uint32_t* sm, int sm_words, i
     return r;
 }
 // iteration `it` of the replay loop -> (query index, list pointer, list length); cnt == 0 means "skip"
-#define RESOLVE_QUERY(SL, it, qi, c, cnt) \
-    int qi, cnt; const uint32_t* c; \
-    if ((SL).staged) { qi = (int)(SL).act[it]; const int _lo = (int)(SL).aoff[it]; cnt = (int)(SL).aoff[(it) + 1] - _lo; c = (SL).lists + _lo; } \
-    else { qi = (it); cnt = counts[qi]; c = (SL).lists + (cnt ? offsets[qi] : 0); }
+#define RESOLVE_QUERY(SL, it, qi, c, cnt, pb) \
+    int qi, cnt; const uint32_t* c; uint2 pb; \
+    if ((SL).staged) { qi = (int)(SL).act[it]; const int _lo = (int)(SL).aoff[it]; cnt = (int)(SL).aoff[(it) + 1] - _lo; c = (SL).lists + _lo; pb = (SL).pre[it]; } \
+    else { qi = (it); cnt = counts[qi]; c = (SL).lists + (cnt ? offsets[qi] : 0); pb = cnt ? (SL).pre[qi] : make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu); }
 
 // ---- SearchForInitialization, sequential part (ORBmatcher.cc:532-640) ----
 __global__ void __launch_bounds__(RESOLVE_THREADS)
 k_resolve_init(int n1, int n2, const KpM* __restrict__ k1s, const KpM* __restrict__ k2s, const int* __restrict__ counts, const int* __restrict__ offsets,
-               const uint32_t* __restrict__ cand, int cand_cap, float nnratio, int checkOri, int smem_words,
+               const uint32_t* __restrict__ cand, const uint2* __restrict__ pre_best, int cand_cap, float nnratio, int checkOri, int smem_words,
                int* __restrict__ matchedDist /*n2*/, int* __restrict__ m21 /*n2*/, int* __restrict__ m12 /*n1*/, int* __restrict__ bin_of /*n1*/,
                float* __restrict__ prev_xy, int* __restrict__ nmatches_out) {
     extern __shared__ __align__(16) uint32_t rs_sm[];
     __shared__ int hist[M_HISTO];
     const int tid = threadIdx.x, lane = tid & 31;
     if (offsets[n1] > cand_cap) return;                            // candidate lists were not written (see k_window_search)
-    const StagedLists SL = stage_lists(rs_sm, smem_words, 3 * n2 + n1, n1, counts, offsets, cand);
+    const StagedLists SL = stage_lists(rs_sm, smem_words, 3 * n2 + n1, n1, counts, offsets, cand, pre_best);
     const bool staged = SL.staged;
     // extra shared arrays: md[n2] | s21[n2] | ang2[n2] | ang1[n1]
     int* md = staged ? reinterpret_cast<int*>(SL.free_words) : matchedDist;
@@ -326,9 +340,15 @@ k_resolve_init(int n1, int n2, const KpM* __restrict__ k1s, const KpM* __restric
     if (tid >= 32) return;
     int nmatches = 0;
     for (int it = 0; it < SL.niter; ++it) {
-        RESOLVE_QUERY(SL, it, i1, c, cnt);
+        RESOLVE_QUERY(SL, it, i1, c, cnt, pb);
         if (cnt == 0) continue;
-        const Best2 b = warp_best2(c, cnt, lane, [&](uint32_t v) { return !(md[v & 0xFFFFFu] <= (int)(v >> 20)); });   // :561
+        // the two best of the whole list were found when the list was written; they still are the two best under the running
+        // exclusion (:561) unless one of them has been claimed at an equal or smaller distance in the meantime -- only then rescan
+        Best2 b; b.k1 = pb.x; b.k2 = pb.y;
+        bool clean = true;
+        if (pb.x != 0xFFFFFFFFu) { const uint32_t v = c[pb.x & 0xFFFFFu]; clean = !(md[v & 0xFFFFFu] <= (int)(v >> 20)); }
+        if (clean && pb.y != 0xFFFFFFFFu) { const uint32_t v = c[pb.y & 0xFFFFFu]; clean = !(md[v & 0xFFFFFu] <= (int)(v >> 20)); }
+        if (!clean) b = warp_best2(c, cnt, lane, [&](uint32_t v) { return !(md[v & 0xFFFFFu] <= (int)(v >> 20)); });   // :561
         if (b.k1 == 0xFFFFFFFFu) continue;
         const int bestDist = (int)(b.k1 >> 20);
         const int bestDist2 = b.k2 == 0xFFFFFFFFu ? INT_MAX : (int)(b.k2 >> 20);
@@ -370,14 +390,14 @@ k_resolve_init(int n1, int n2, const KpM* __restrict__ k1s, const KpM* __restric
 __global__ void __launch_bounds__(RESOLVE_THREADS)
 k_resolve_proj_frame(int n_last, int n_cur, const KpM* __restrict__ cur_keys, const float* __restrict__ last_angle, const uint8_t* __restrict__ mp_observed,
                      const uint8_t* __restrict__ cur_occupied, const int* __restrict__ counts, const int* __restrict__ offsets, const uint32_t* __restrict__ cand,
-                     int cand_cap, int checkOri, int smem_words, uint8_t* __restrict__ occupied_g /*n_cur*/, int* __restrict__ cur_match /*n_cur*/, int* __restrict__ pushes /*2*n_last*/,
+                     const uint2* __restrict__ pre_best, int cand_cap, int checkOri, int smem_words, uint8_t* __restrict__ occupied_g /*n_cur*/, int* __restrict__ cur_match /*n_cur*/, int* __restrict__ pushes /*2*n_last*/,
                      int* __restrict__ nmatches_out) {
     extern __shared__ __align__(16) uint32_t rs_sm[];
     __shared__ int hist[M_HISTO];
     const int tid = threadIdx.x, lane = tid & 31;
     if (offsets[n_last] > cand_cap) return;
     // extra shared arrays: occ[n_cur] (ints) | angc[n_cur] | angl[n_last] | obs[n_last] (ints)
-    const StagedLists SL = stage_lists(rs_sm, smem_words, 2 * n_cur + 2 * n_last, n_last, counts, offsets, cand);
+    const StagedLists SL = stage_lists(rs_sm, smem_words, 2 * n_cur + 2 * n_last, n_last, counts, offsets, cand, pre_best);
     const bool staged = SL.staged;
     int* occ = reinterpret_cast<int*>(SL.free_words);
     float* angc = reinterpret_cast<float*>(occ + n_cur);
@@ -394,9 +414,13 @@ k_resolve_proj_frame(int n_last, int n_cur, const KpM* __restrict__ cur_keys, co
     if (tid >= 32) return;
     int nmatches = 0, npush = 0;
     for (int it = 0; it < SL.niter; ++it) {
-        RESOLVE_QUERY(SL, it, i, c, cnt);
+        RESOLVE_QUERY(SL, it, i, c, cnt, pb);
         if (cnt == 0) continue;
-        const Best2 b = staged ? warp_best2(c, cnt, lane, [&](uint32_t v) { return !occ[v & 0xFFFFFu] && (v >> 20) < 256u; })            // :1658-1660, bestDist = 256
+        // only the best candidate matters here: the precomputed one stands unless its feature has been occupied since (:1658-1660)
+        Best2 b; b.k1 = pb.x; b.k2 = pb.y;
+        bool clean = true;
+        if (pb.x != 0xFFFFFFFFu) { const uint32_t j = c[pb.x & 0xFFFFFu] & 0xFFFFFu; clean = staged ? !occ[j] : !occupied_g[j]; }
+        if (!clean) b = staged ? warp_best2(c, cnt, lane, [&](uint32_t v) { return !occ[v & 0xFFFFFu] && (v >> 20) < 256u; })            // bestDist = 256
                                : warp_best2(c, cnt, lane, [&](uint32_t v) { return !occupied_g[v & 0xFFFFFu] && (v >> 20) < 256u; });
         if (b.k1 == 0xFFFFFFFFu) continue;
         const int bestDist = (int)(b.k1 >> 20);
@@ -434,13 +458,14 @@ k_resolve_proj_frame(int n_last, int n_cur, const KpM* __restrict__ cur_keys, co
 // ---- SearchByProjection(Frame, vpMapPoints), sequential part (ORBmatcher.cc:77-172) ----
 __global__ void __launch_bounds__(RESOLVE_THREADS)
 k_resolve_proj_points(int n_points, int n_f, const KpM* __restrict__ f_keys, const uint8_t* __restrict__ mp_observed, const uint8_t* __restrict__ f_occupied,
-                      const int* __restrict__ counts, const int* __restrict__ offsets, const uint32_t* __restrict__ cand, int cand_cap, float nnratio, int smem_words,
+                      const int* __restrict__ counts, const int* __restrict__ offsets, const uint32_t* __restrict__ cand, const uint2* __restrict__ pre_best,
+                      int cand_cap, float nnratio, int smem_words,
                       uint8_t* __restrict__ occupied_g, int* __restrict__ f_match, int* __restrict__ nmatches_out) {
     extern __shared__ __align__(16) uint32_t rs_sm[];
     const int tid = threadIdx.x, lane = tid & 31;
     if (offsets[n_points] > cand_cap) return;
     // extra shared arrays: occ[n_f] | oct[n_f] | obs[n_points]
-    const StagedLists SL = stage_lists(rs_sm, smem_words, 2 * n_f + n_points, n_points, counts, offsets, cand);
+    const StagedLists SL = stage_lists(rs_sm, smem_words, 2 * n_f + n_points, n_points, counts, offsets, cand, pre_best);
     const bool staged = SL.staged;
     int* occ = reinterpret_cast<int*>(SL.free_words);
     int* oct = occ + n_f;
@@ -455,9 +480,14 @@ k_resolve_proj_points(int n_points, int n_f, const KpM* __restrict__ f_keys, con
     if (tid >= 32) return;
     int nmatches = 0;
     for (int it = 0; it < SL.niter; ++it) {
-        RESOLVE_QUERY(SL, it, i, c, cnt);
+        RESOLVE_QUERY(SL, it, i, c, cnt, pb);
         if (cnt == 0) continue;
-        const Best2 b = staged ? warp_best2(c, cnt, lane, [&](uint32_t v) { return !occ[v & 0xFFFFFu] && (v >> 20) < 256u; })
+        // best and second best both matter (level-aware ratio test): keep the precomputed pair unless either feature is occupied now
+        Best2 b; b.k1 = pb.x; b.k2 = pb.y;
+        bool clean = true;
+        if (pb.x != 0xFFFFFFFFu) { const uint32_t j = c[pb.x & 0xFFFFFu] & 0xFFFFFu; clean = staged ? !occ[j] : !occupied_g[j]; }
+        if (clean && pb.y != 0xFFFFFFFFu) { const uint32_t j = c[pb.y & 0xFFFFFu] & 0xFFFFFu; clean = staged ? !occ[j] : !occupied_g[j]; }
+        if (!clean) b = staged ? warp_best2(c, cnt, lane, [&](uint32_t v) { return !occ[v & 0xFFFFFu] && (v >> 20) < 256u; })
                                : warp_best2(c, cnt, lane, [&](uint32_t v) { return !occupied_g[v & 0xFFFFFu] && (v >> 20) < 256u; });
         if (b.k1 == 0xFFFFFFFFu) continue;
         const int bestDist = (int)(b.k1 >> 20);

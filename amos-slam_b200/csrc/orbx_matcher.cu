@@ -125,11 +125,11 @@ template <typename T> static int up(orbx_matcher* m, const T* host, size_t count
 // COUNT pass, scan, FILL pass -- no host round trip in between: the candidate arena keeps the capacity of earlier calls (at least
 // 64 per query); the FILL pass and the resolve kernels refuse to touch it when the total exceeds that capacity, and the caller, which
 // reads the total back together with its results, grows the arena and repeats the call (rare).
-static int window_search(orbx_matcher* m, QueryParams& P, const FrameDev& F, int*& counts, int*& offsets, uint32_t*& cand) {
+static int window_search(orbx_matcher* m, QueryParams& P, const FrameDev& F, int*& counts, int*& offsets, uint32_t*& cand, uint2*& pre_best) {
     cudaStream_t s = m->stream;
     const int nq = P.nq;
-    counts = m->arena.get<int>(nq + 1); offsets = m->arena.get<int>(nq + 2);
-    if (!counts || !offsets) FAIL(ORBX_E_CUDA, "matcher arena exhausted");
+    counts = m->arena.get<int>(nq + 1); offsets = m->arena.get<int>(nq + 2); pre_best = m->arena.get<uint2>(nq + 1);
+    if (!counts || !offsets || !pre_best) FAIL(ORBX_E_CUDA, "matcher arena exhausted");
     const size_t want = std::max<size_t>((size_t)nq * 64, 1 << 16);
     if (m->cand_cap < want) {
         int rc = m->cand_arena.reserve(want * 4); if (rc) return rc;
@@ -137,11 +137,11 @@ static int window_search(orbx_matcher* m, QueryParams& P, const FrameDev& F, int
     }
     cand = reinterpret_cast<uint32_t*>(m->cand_arena.base);
     if (nq == 0) { CU_TRY(cudaMemsetAsync(offsets, 0, 8, s)); return ORBX_OK; }
-    k_window_search<false><<<(nq + 3) / 4, 128, 0, s>>>(P, F, counts, nullptr, nullptr, 0);
+    k_window_search<false><<<(nq + 3) / 4, 128, 0, s>>>(P, F, counts, nullptr, nullptr, 0, nullptr);
     LAUNCH_CHECK();
     k_scan_counts<<<1, 1024, 0, s>>>(counts, nq, offsets);
     LAUNCH_CHECK();
-    k_window_search<true><<<(nq + 3) / 4, 128, 0, s>>>(P, F, counts, offsets, cand, (int)std::min<size_t>(m->cand_cap, 0x7FFFFFFF));
+    k_window_search<true><<<(nq + 3) / 4, 128, 0, s>>>(P, F, counts, offsets, cand, (int)std::min<size_t>(m->cand_cap, 0x7FFFFFFF), pre_best);
     LAUNCH_CHECK();
     return ORBX_OK;
 }
@@ -223,12 +223,12 @@ retry:
     if ((rc = flush_uploads(m)) || (rc = build_grid(m, d2, sk2))) return rc;
     QueryParams P; std::memset(&P, 0, sizeof(P));
     P.mode = MODE_INIT; P.nq = n1; P.q_keys = k1; P.q_desc = desc1; P.q_xy = prev; P.window = (float)window_size;
-    int *counts, *offsets; uint32_t* cand;
-    if ((rc = window_search(m, P, d2, counts, offsets, cand))) return rc;
+    int *counts, *offsets; uint32_t* cand; uint2* pre;
+    if ((rc = window_search(m, P, d2, counts, offsets, cand, pre))) return rc;
     int* md = m->arena.get<int>(n2 + 1); int* m21 = m->arena.get<int>(n2 + 1); int* m12 = m->arena.get<int>(n1); int* binof = m->arena.get<int>(n1); int* dn = m->arena.get<int>(1);
     if (!md || !m21 || !m12 || !binof || !dn) FAIL(ORBX_E_CUDA, "matcher arena exhausted");
     const int resolve_smem = RESOLVE_SMEM_BYTES;
-    k_resolve_init<<<1, RESOLVE_THREADS, resolve_smem, m->stream>>>(n1, n2, k1, d2.keys, counts, offsets, cand, (int)std::min<size_t>(m->cand_cap, 0x7FFFFFFF), m->nnratio, m->checkOri, resolve_smem / 4,
+    k_resolve_init<<<1, RESOLVE_THREADS, resolve_smem, m->stream>>>(n1, n2, k1, d2.keys, counts, offsets, cand, pre, (int)std::min<size_t>(m->cand_cap, 0x7FFFFFFF), m->nnratio, m->checkOri, resolve_smem / 4,
                                                                      md, m21, m12, binof, prev, dn);
     LAUNCH_CHECK();
     int total = 0;
@@ -268,11 +268,11 @@ retry:
     if ((rc = flush_uploads(m)) || (rc = build_grid(m, dc, skc))) return rc;
     QueryParams P; std::memset(&P, 0, sizeof(P));
     P.mode = MODE_PROJ_FRAME; P.nq = n_last; P.q_desc = dd; P.q_xy = uv; P.q_invz = iz; P.q_octave = lo; P.q_valid = va; P.th = th; P.forward = forward; P.backward = backward; P.mbf = mbf;
-    int *counts, *offsets; uint32_t* cand;
-    if ((rc = window_search(m, P, dc, counts, offsets, cand))) return rc;
+    int *counts, *offsets; uint32_t* cand; uint2* pre;
+    if ((rc = window_search(m, P, dc, counts, offsets, cand, pre))) return rc;
     uint8_t* occ = m->arena.get<uint8_t>(nc + 1); int* cm = m->arena.get<int>(nc + 1); int* pushes = m->arena.get<int>(2 * (size_t)n_last + 2); int* dn = m->arena.get<int>(1);
     if (!occ || !cm || !pushes || !dn) FAIL(ORBX_E_CUDA, "matcher arena exhausted");
-    k_resolve_proj_frame<<<1, RESOLVE_THREADS, RESOLVE_SMEM_BYTES, m->stream>>>(n_last, nc, dc.keys, la, ob, oc, counts, offsets, cand, (int)std::min<size_t>(m->cand_cap, 0x7FFFFFFF), m->checkOri, RESOLVE_SMEM_BYTES / 4, occ, cm, pushes, dn);
+    k_resolve_proj_frame<<<1, RESOLVE_THREADS, RESOLVE_SMEM_BYTES, m->stream>>>(n_last, nc, dc.keys, la, ob, oc, counts, offsets, cand, pre, (int)std::min<size_t>(m->cand_cap, 0x7FFFFFFF), m->checkOri, RESOLVE_SMEM_BYTES / 4, occ, cm, pushes, dn);
     LAUNCH_CHECK();
     int total = 0;
     CU_TRY(cudaMemcpyAsync(&total, offsets + n_last, 4, cudaMemcpyDeviceToHost, m->stream));
@@ -309,11 +309,11 @@ retry:
     if ((rc = flush_uploads(m)) || (rc = build_grid(m, df, skf))) return rc;
     QueryParams P; std::memset(&P, 0, sizeof(P));
     P.mode = MODE_PROJ_POINTS; P.nq = n_points; P.q_desc = dd; P.q_xy = uv; P.q_octave = lv; P.q_ur = ur; P.q_viewcos = vc; P.th = th;
-    int *counts, *offsets; uint32_t* cand;
-    if ((rc = window_search(m, P, df, counts, offsets, cand))) return rc;
+    int *counts, *offsets; uint32_t* cand; uint2* pre;
+    if ((rc = window_search(m, P, df, counts, offsets, cand, pre))) return rc;
     uint8_t* occ = m->arena.get<uint8_t>(nf + 1); int* fm = m->arena.get<int>(nf + 1); int* dn = m->arena.get<int>(1);
     if (!occ || !fm || !dn) FAIL(ORBX_E_CUDA, "matcher arena exhausted");
-    k_resolve_proj_points<<<1, RESOLVE_THREADS, RESOLVE_SMEM_BYTES, m->stream>>>(n_points, nf, df.keys, ob, oc, counts, offsets, cand, (int)std::min<size_t>(m->cand_cap, 0x7FFFFFFF), m->nnratio, RESOLVE_SMEM_BYTES / 4, occ, fm, dn);
+    k_resolve_proj_points<<<1, RESOLVE_THREADS, RESOLVE_SMEM_BYTES, m->stream>>>(n_points, nf, df.keys, ob, oc, counts, offsets, cand, pre, (int)std::min<size_t>(m->cand_cap, 0x7FFFFFFF), m->nnratio, RESOLVE_SMEM_BYTES / 4, occ, fm, dn);
     LAUNCH_CHECK();
     int total = 0;
     CU_TRY(cudaMemcpyAsync(&total, offsets + n_points, 4, cudaMemcpyDeviceToHost, m->stream));
