@@ -316,7 +316,104 @@ __device__ __forceinline__ StagedLists stage_lists(uint32_t* sm, int sm_words, i
     if ((SL).staged) { qi = (int)(SL).act[it]; const int _lo = (int)(SL).aoff[it]; cnt = (int)(SL).aoff[(it) + 1] - _lo; c = (SL).lists + _lo; pb = (SL).pre[it]; } \
     else { qi = (it); cnt = counts[qi]; c = (SL).lists + (cnt ? offsets[qi] : 0); pb = cnt ? (SL).pre[qi] : make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu); }
 
+// -------------------------------------------------------------------------------------------------
+// Order-preserving replay, 32 queries per step.  Every lane takes one query (in loop order) and evaluates it against the state as
+// it stands: if its precomputed best pair is still selectable ("clean") the acceptance test is O(1).  A lane may be committed
+// together with its predecessors of the step unless one of them claims a feature that the lane's decision READ (its best /
+// second-best feature) -- then the state it saw is stale.  So: commit the longest conflict-free prefix in lane order, re-evaluate
+// from the first stale lane, and run the (rare) lanes whose pair is no longer clean through the warp-cooperative rescan on their
+// own.  The result equals the reference's one-by-one loop; the serial chain shrinks from one query to one 32-query step.
+//   Ops:  bool clean(uint32_t cand_entry)                      candidate still selectable under the running state
+//         Best2 rescan(const uint32_t* c, int cnt, int lane)   warp-cooperative best-2 under the running state
+//         bool decide(int qi, const uint32_t* c, Best2 b, int& j)   acceptance test (reads only static data besides b)
+//         bool commit(int qi, int j, Best2 b, int rank)        state update by one lane; returns true if it displaced a match
+//         void post(int naccept, int ndisplaced)               uniform counters
+// -------------------------------------------------------------------------------------------------
+#define NOJ 0xFFFFFFFFu
+template <bool USE_SECOND, class Ops>
+__device__ __forceinline__ void replay_queries(const StagedLists& SL, const int* __restrict__ counts, const int* __restrict__ offsets, int lane, Ops& ops,
+                                               volatile uint32_t* /* unused */) {
+    const uint32_t lt = (1u << lane) - 1u;
+    for (int base = 0; base < SL.niter; base += 32) {
+        const int it = base + lane;
+        const bool act = it < SL.niter;
+        int qi = 0, cnt = 0, lo = 0; uint2 pb = make_uint2(NOJ, NOJ);
+        if (act) {
+            if (SL.staged) { qi = (int)SL.act[it]; lo = (int)SL.aoff[it]; cnt = (int)SL.aoff[it + 1] - lo; pb = SL.pre[it]; }
+            else { qi = it; cnt = counts[qi]; if (cnt) { lo = offsets[qi]; pb = SL.pre[qi]; } }
+        }
+        const uint32_t* c = SL.lists + lo;
+        const int nb = min(32, SL.niter - base);
+        int start = 0;
+        while (start < nb) {
+            Best2 b; b.k1 = pb.x; b.k2 = pb.y;
+            bool slow = false, accept = false; int j = -1; uint32_t r1 = NOJ, r2 = NOJ;
+            if (act && lane >= start && cnt > 0) {
+                if (pb.x != NOJ) { const uint32_t v = c[pb.x & 0xFFFFFu]; r1 = v & 0xFFFFFu; slow = !ops.clean(v); }
+                if (USE_SECOND && !slow && pb.y != NOJ) { const uint32_t v = c[pb.y & 0xFFFFFu]; r2 = v & 0xFFFFFu; slow = !ops.clean(v); }
+                if (!slow) accept = ops.decide(qi, c, b, j);
+            }
+            // does a predecessor of this step (lanes start .. lane-1) claim a feature this lane's decision read?  32 independent shuffles
+            const uint32_t myclaim = accept ? (uint32_t)j : NOJ;
+            bool stale = false;
+#pragma unroll
+            for (int K = 0; K < 31; ++K) {
+                const uint32_t v = __shfl_sync(0xffffffffu, myclaim, K);
+                stale |= (K >= start) & (K < lane) & (v != NOJ) & ((v == r1) | (v == r2));
+            }
+            const uint32_t stop = __ballot_sync(0xffffffffu, lane >= start && lane < nb && (slow || stale));
+            const int L = stop ? __ffs(stop) - 1 : nb;             // first lane that cannot be committed with its predecessors
+            const bool mine = accept && lane >= start && lane < L;
+            const uint32_t am = __ballot_sync(0xffffffffu, mine);
+            bool displaced = false;
+            if (mine) displaced = ops.commit(qi, j, b, __popc(am & lt));
+            const uint32_t dm = __ballot_sync(0xffffffffu, displaced);
+            ops.post(__popc(am), __popc(dm));
+            __syncwarp();
+            start = L;
+            if (L < nb && __shfl_sync(0xffffffffu, (int)slow, L)) {   // lane L's pair is no longer selectable: rescan its list with the whole warp
+                const int qL = __shfl_sync(0xffffffffu, qi, L), cntL = __shfl_sync(0xffffffffu, cnt, L), loL = __shfl_sync(0xffffffffu, lo, L);
+                const uint32_t* cL = SL.lists + loL;
+                const Best2 bb = ops.rescan(cL, cntL, lane);
+                int jj = -1;
+                const bool acc = ops.decide(qL, cL, bb, jj);          // uniform across the warp
+                bool disp = false;
+                if (acc && lane == 0) disp = ops.commit(qL, jj, bb, 0);
+                disp = __shfl_sync(0xffffffffu, (int)disp, 0) != 0;
+                ops.post(acc ? 1 : 0, disp ? 1 : 0);
+                __syncwarp();
+                start = L + 1;
+            }
+        }
+    }
+}
+
 // ---- SearchForInitialization, sequential part (ORBmatcher.cc:532-640) ----
+struct InitOps {
+    int* md; int* s21; int* m12; int* bin_of; int* hist; const float* ang1; const float* ang2; const KpM* k1s; const KpM* k2s;
+    float nnratio; int checkOri; bool staged; int nmatches;
+    __device__ __forceinline__ bool clean(uint32_t v) const { return !(md[v & 0xFFFFFu] <= (int)(v >> 20)); }                   // :561
+    __device__ __forceinline__ Best2 rescan(const uint32_t* c, int cnt, int lane) const {
+        int* mdp = md; return warp_best2(c, cnt, lane, [&](uint32_t v) { return !(mdp[v & 0xFFFFFu] <= (int)(v >> 20)); });
+    }
+    __device__ __forceinline__ bool decide(int, const uint32_t* c, Best2 b, int& j) const {
+        if (b.k1 == NOJ) return false;
+        const int bestDist = (int)(b.k1 >> 20);
+        const int bestDist2 = b.k2 == NOJ ? INT_MAX : (int)(b.k2 >> 20);
+        if (!(bestDist <= M_TH_LOW && (float)bestDist < __fmul_rn((float)bestDist2, nnratio))) return false;                  // :577-579
+        j = (int)(c[b.k1 & 0xFFFFFu] & 0xFFFFFu);
+        return true;
+    }
+    __device__ __forceinline__ bool commit(int i1, int j, Best2 b, int) {
+        const int old = s21[j];
+        if (old >= 0) m12[old] = -1;                                                                                           // :583-587
+        m12[i1] = j; s21[j] = i1; md[j] = (int)(b.k1 >> 20);
+        if (checkOri) { const int bin = staged ? rot_bin(ang1[i1], ang2[j]) : rot_bin(k1s[i1].angle, k2s[j].angle); bin_of[i1] = bin; atomicAdd(&hist[bin], 1); }
+        return old >= 0;
+    }
+    __device__ __forceinline__ void post(int na, int nd) { nmatches += na - nd; }
+};
+
 __global__ void __launch_bounds__(RESOLVE_THREADS)
 k_resolve_init(int n1, int n2, const KpM* __restrict__ k1s, const KpM* __restrict__ k2s, const int* __restrict__ counts, const int* __restrict__ offsets,
                const uint32_t* __restrict__ cand, const uint2* __restrict__ pre_best, int cand_cap, float nnratio, int checkOri, int smem_words,
@@ -324,6 +421,7 @@ k_resolve_init(int n1, int n2, const KpM* __restrict__ k1s, const KpM* __restric
                float* __restrict__ prev_xy, int* __restrict__ nmatches_out) {
     extern __shared__ __align__(16) uint32_t rs_sm[];
     __shared__ int hist[M_HISTO];
+    __shared__ uint32_t claim[32];
     const int tid = threadIdx.x, lane = tid & 31;
     if (offsets[n1] > cand_cap) return;                            // candidate lists were not written (see k_window_search)
     const StagedLists SL = stage_lists(rs_sm, smem_words, 3 * n2 + n1, n1, counts, offsets, cand, pre_best);
@@ -338,36 +436,9 @@ k_resolve_init(int n1, int n2, const KpM* __restrict__ k1s, const KpM* __restric
     if (tid < M_HISTO) hist[tid] = 0;
     __syncthreads();
     if (tid >= 32) return;
-    int nmatches = 0;
-    for (int it = 0; it < SL.niter; ++it) {
-        RESOLVE_QUERY(SL, it, i1, c, cnt, pb);
-        if (cnt == 0) continue;
-        // the two best of the whole list were found when the list was written; they still are the two best under the running
-        // exclusion (:561) unless one of them has been claimed at an equal or smaller distance in the meantime -- only then rescan
-        Best2 b; b.k1 = pb.x; b.k2 = pb.y;
-        bool clean = true;
-        if (pb.x != 0xFFFFFFFFu) { const uint32_t v = c[pb.x & 0xFFFFFu]; clean = !(md[v & 0xFFFFFu] <= (int)(v >> 20)); }
-        if (clean && pb.y != 0xFFFFFFFFu) { const uint32_t v = c[pb.y & 0xFFFFFu]; clean = !(md[v & 0xFFFFFu] <= (int)(v >> 20)); }
-        if (!clean) b = warp_best2(c, cnt, lane, [&](uint32_t v) { return !(md[v & 0xFFFFFu] <= (int)(v >> 20)); });   // :561
-        if (b.k1 == 0xFFFFFFFFu) continue;
-        const int bestDist = (int)(b.k1 >> 20);
-        const int bestDist2 = b.k2 == 0xFFFFFFFFu ? INT_MAX : (int)(b.k2 >> 20);
-        if (bestDist <= M_TH_LOW && (float)bestDist < __fmul_rn((float)bestDist2, nnratio)) {         // :577-579
-            const int bestIdx2 = (int)(c[b.k1 & 0xFFFFFu] & 0xFFFFFu);
-            const int old = s21[bestIdx2];
-            if (old >= 0) --nmatches;
-            ++nmatches;
-            if (lane == 0) {
-                if (old >= 0) m12[old] = -1;                                                       // :583-587
-                m12[i1] = bestIdx2; s21[bestIdx2] = i1; md[bestIdx2] = bestDist;
-                if (checkOri) {
-                    const int bin = staged ? rot_bin(ang1[i1], ang2[bestIdx2]) : rot_bin(k1s[i1].angle, k2s[bestIdx2].angle);
-                    bin_of[i1] = bin; hist[bin]++;
-                }
-            }
-            __syncwarp();
-        }
-    }
+    InitOps ops{md, s21, m12, bin_of, hist, ang1, ang2, k1s, k2s, nnratio, checkOri, staged, 0};
+    replay_queries<true>(SL, counts, offsets, lane, ops, claim);
+    int nmatches = ops.nmatches;
     __syncwarp();
     if (checkOri) {
         int ind1, ind2, ind3;
@@ -387,58 +458,60 @@ k_resolve_init(int n1, int n2, const KpM* __restrict__ k1s, const KpM* __restric
 }
 
 // ---- SearchByProjection(Frame, Frame), sequential part (ORBmatcher.cc:1595-1725) ----
+struct ProjFrameOps {
+    int* occ; int* cur_match; int* pushes; int* hist; const int* obs; const uint8_t* mp_observed; const float* angl; const float* angc;
+    const float* last_angle; const KpM* cur_keys; int checkOri; bool staged; int nmatches, npush;
+    __device__ __forceinline__ bool clean(uint32_t v) const { return !occ[v & 0xFFFFFu]; }                                        // :1658-1660
+    __device__ __forceinline__ Best2 rescan(const uint32_t* c, int cnt, int lane) const {
+        int* o = occ; return warp_best2(c, cnt, lane, [&](uint32_t v) { return !o[v & 0xFFFFFu] && (v >> 20) < 256u; });          // bestDist = 256
+    }
+    __device__ __forceinline__ bool decide(int, const uint32_t* c, Best2 b, int& j) const {
+        if (b.k1 == NOJ || (int)(b.k1 >> 20) > M_TH_HIGH) return false;                                                          // :1683
+        j = (int)(c[b.k1 & 0xFFFFFu] & 0xFFFFFu);
+        return true;
+    }
+    __device__ __forceinline__ bool commit(int i, int j, Best2, int rank) {
+        cur_match[j] = i;
+        occ[j] = staged ? obs[i] : (mp_observed ? (mp_observed[i] != 0) : 0);
+        if (checkOri) {
+            const int bin = staged ? rot_bin(angl[i], angc[j]) : rot_bin(last_angle[i], cur_keys[j].angle);
+            atomicAdd(&hist[bin], 1); pushes[2 * (npush + rank)] = bin; pushes[2 * (npush + rank) + 1] = j;
+        }
+        return false;
+    }
+    __device__ __forceinline__ void post(int na, int) { nmatches += na; npush += na; }
+};
+
 __global__ void __launch_bounds__(RESOLVE_THREADS)
 k_resolve_proj_frame(int n_last, int n_cur, const KpM* __restrict__ cur_keys, const float* __restrict__ last_angle, const uint8_t* __restrict__ mp_observed,
                      const uint8_t* __restrict__ cur_occupied, const int* __restrict__ counts, const int* __restrict__ offsets, const uint32_t* __restrict__ cand,
-                     const uint2* __restrict__ pre_best, int cand_cap, int checkOri, int smem_words, uint8_t* __restrict__ occupied_g /*n_cur*/, int* __restrict__ cur_match /*n_cur*/, int* __restrict__ pushes /*2*n_last*/,
-                     int* __restrict__ nmatches_out) {
+                     const uint2* __restrict__ pre_best, int cand_cap, int checkOri, int smem_words, int* __restrict__ occupied_g /*n_cur*/, int* __restrict__ cur_match /*n_cur*/,
+                     int* __restrict__ pushes /*2*n_last*/, int* __restrict__ nmatches_out) {
     extern __shared__ __align__(16) uint32_t rs_sm[];
     __shared__ int hist[M_HISTO];
+    __shared__ uint32_t claim[32];
     const int tid = threadIdx.x, lane = tid & 31;
     if (offsets[n_last] > cand_cap) return;
     // extra shared arrays: occ[n_cur] (ints) | angc[n_cur] | angl[n_last] | obs[n_last] (ints)
     const StagedLists SL = stage_lists(rs_sm, smem_words, 2 * n_cur + 2 * n_last, n_last, counts, offsets, cand, pre_best);
     const bool staged = SL.staged;
-    int* occ = reinterpret_cast<int*>(SL.free_words);
-    float* angc = reinterpret_cast<float*>(occ + n_cur);
+    int* occ = staged ? reinterpret_cast<int*>(SL.free_words) : occupied_g;
+    float* angc = reinterpret_cast<float*>(SL.free_words) + n_cur;
     float* angl = angc + n_cur;
     int* obs = reinterpret_cast<int*>(angl + n_last);
     for (int j = tid; j < n_cur; j += RESOLVE_THREADS) {
         cur_match[j] = -1;
-        const int o = cur_occupied ? (cur_occupied[j] != 0) : 0;
-        if (staged) { occ[j] = o; angc[j] = cur_keys[j].angle; } else occupied_g[j] = (uint8_t)o;
+        occ[j] = cur_occupied ? (cur_occupied[j] != 0) : 0;
+        if (staged) angc[j] = cur_keys[j].angle;
     }
     if (staged) for (int i = tid; i < n_last; i += RESOLVE_THREADS) { angl[i] = last_angle[i]; obs[i] = mp_observed ? (mp_observed[i] != 0) : 0; }
     if (tid < M_HISTO) hist[tid] = 0;
     __syncthreads();
     if (tid >= 32) return;
-    int nmatches = 0, npush = 0;
-    for (int it = 0; it < SL.niter; ++it) {
-        RESOLVE_QUERY(SL, it, i, c, cnt, pb);
-        if (cnt == 0) continue;
-        // only the best candidate matters here: the precomputed one stands unless its feature has been occupied since (:1658-1660)
-        Best2 b; b.k1 = pb.x; b.k2 = pb.y;
-        bool clean = true;
-        if (pb.x != 0xFFFFFFFFu) { const uint32_t j = c[pb.x & 0xFFFFFu] & 0xFFFFFu; clean = staged ? !occ[j] : !occupied_g[j]; }
-        if (!clean) b = staged ? warp_best2(c, cnt, lane, [&](uint32_t v) { return !occ[v & 0xFFFFFu] && (v >> 20) < 256u; })            // bestDist = 256
-                               : warp_best2(c, cnt, lane, [&](uint32_t v) { return !occupied_g[v & 0xFFFFFu] && (v >> 20) < 256u; });
-        if (b.k1 == 0xFFFFFFFFu) continue;
-        const int bestDist = (int)(b.k1 >> 20);
-        if (bestDist <= M_TH_HIGH) {                                                               // :1683
-            const int j = (int)(c[b.k1 & 0xFFFFFu] & 0xFFFFFu);
-            if (lane == 0) {
-                cur_match[j] = i;
-                const int o = staged ? obs[i] : (mp_observed ? (mp_observed[i] != 0) : 0);
-                if (staged) occ[j] = o; else occupied_g[j] = (uint8_t)o;
-                if (checkOri) {
-                    const int bin = staged ? rot_bin(angl[i], angc[j]) : rot_bin(last_angle[i], cur_keys[j].angle);
-                    hist[bin]++; pushes[2 * npush] = bin; pushes[2 * npush + 1] = j;
-                }
-            }
-            ++nmatches; ++npush;
-            __syncwarp();
-        }
-    }
+    ProjFrameOps ops{occ, cur_match, pushes, hist, obs, mp_observed, angl, angc, last_angle, cur_keys, checkOri, staged, 0, 0};
+    replay_queries<false>(SL, counts, offsets, lane, ops, claim);
+    int nmatches = ops.nmatches;
+    const int npush = ops.npush;
     __syncwarp();
     if (checkOri) {
         int ind1, ind2, ind3;
@@ -456,56 +529,57 @@ k_resolve_proj_frame(int n_last, int n_cur, const KpM* __restrict__ cur_keys, co
 }
 
 // ---- SearchByProjection(Frame, vpMapPoints), sequential part (ORBmatcher.cc:77-172) ----
+struct ProjPointsOps {
+    int* occ; int* f_match; const int* oct; const KpM* f_keys; const int* obs; const uint8_t* mp_observed; float nnratio; bool staged; int nmatches;
+    __device__ __forceinline__ bool clean(uint32_t v) const { return !occ[v & 0xFFFFFu]; }                                        // :124-126
+    __device__ __forceinline__ Best2 rescan(const uint32_t* c, int cnt, int lane) const {
+        int* o = occ; return warp_best2(c, cnt, lane, [&](uint32_t v) { return !o[v & 0xFFFFFu] && (v >> 20) < 256u; });
+    }
+    __device__ __forceinline__ bool decide(int, const uint32_t* c, Best2 b, int& j) const {
+        if (b.k1 == NOJ) return false;
+        const int bestDist = (int)(b.k1 >> 20);
+        if (bestDist > M_TH_HIGH) return false;                                                                                  // :163
+        const int bestIdx = (int)(c[b.k1 & 0xFFFFFu] & 0xFFFFFu);
+        const int bestLevel = staged ? oct[bestIdx] : f_keys[bestIdx].octave;
+        int bestDist2 = 256, bestLevel2 = -1;
+        if (b.k2 != NOJ) { bestDist2 = (int)(b.k2 >> 20); const int j2 = (int)(c[b.k2 & 0xFFFFFu] & 0xFFFFFu); bestLevel2 = staged ? oct[j2] : f_keys[j2].octave; }
+        if (bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(nnratio, (float)bestDist2)) return false;                     // :166
+        j = bestIdx;
+        return true;
+    }
+    __device__ __forceinline__ bool commit(int i, int j, Best2, int) {
+        f_match[j] = i;
+        occ[j] = staged ? obs[i] : (mp_observed ? (mp_observed[i] != 0) : 0);
+        return false;
+    }
+    __device__ __forceinline__ void post(int na, int) { nmatches += na; }
+};
+
 __global__ void __launch_bounds__(RESOLVE_THREADS)
 k_resolve_proj_points(int n_points, int n_f, const KpM* __restrict__ f_keys, const uint8_t* __restrict__ mp_observed, const uint8_t* __restrict__ f_occupied,
                       const int* __restrict__ counts, const int* __restrict__ offsets, const uint32_t* __restrict__ cand, const uint2* __restrict__ pre_best,
-                      int cand_cap, float nnratio, int smem_words,
-                      uint8_t* __restrict__ occupied_g, int* __restrict__ f_match, int* __restrict__ nmatches_out) {
+                      int cand_cap, float nnratio, int smem_words, int* __restrict__ occupied_g, int* __restrict__ f_match, int* __restrict__ nmatches_out) {
     extern __shared__ __align__(16) uint32_t rs_sm[];
+    __shared__ uint32_t claim[32];
     const int tid = threadIdx.x, lane = tid & 31;
     if (offsets[n_points] > cand_cap) return;
     // extra shared arrays: occ[n_f] | oct[n_f] | obs[n_points]
     const StagedLists SL = stage_lists(rs_sm, smem_words, 2 * n_f + n_points, n_points, counts, offsets, cand, pre_best);
     const bool staged = SL.staged;
-    int* occ = reinterpret_cast<int*>(SL.free_words);
-    int* oct = occ + n_f;
+    int* occ = staged ? reinterpret_cast<int*>(SL.free_words) : occupied_g;
+    int* oct = reinterpret_cast<int*>(SL.free_words) + n_f;
     int* obs = oct + n_f;
     for (int j = tid; j < n_f; j += RESOLVE_THREADS) {
         f_match[j] = -1;
-        const int o = f_occupied ? (f_occupied[j] != 0) : 0;
-        if (staged) { occ[j] = o; oct[j] = f_keys[j].octave; } else occupied_g[j] = (uint8_t)o;
+        occ[j] = f_occupied ? (f_occupied[j] != 0) : 0;
+        if (staged) oct[j] = f_keys[j].octave;
     }
     if (staged) for (int i = tid; i < n_points; i += RESOLVE_THREADS) obs[i] = mp_observed ? (mp_observed[i] != 0) : 0;
     __syncthreads();
     if (tid >= 32) return;
-    int nmatches = 0;
-    for (int it = 0; it < SL.niter; ++it) {
-        RESOLVE_QUERY(SL, it, i, c, cnt, pb);
-        if (cnt == 0) continue;
-        // best and second best both matter (level-aware ratio test): keep the precomputed pair unless either feature is occupied now
-        Best2 b; b.k1 = pb.x; b.k2 = pb.y;
-        bool clean = true;
-        if (pb.x != 0xFFFFFFFFu) { const uint32_t j = c[pb.x & 0xFFFFFu] & 0xFFFFFu; clean = staged ? !occ[j] : !occupied_g[j]; }
-        if (clean && pb.y != 0xFFFFFFFFu) { const uint32_t j = c[pb.y & 0xFFFFFu] & 0xFFFFFu; clean = staged ? !occ[j] : !occupied_g[j]; }
-        if (!clean) b = staged ? warp_best2(c, cnt, lane, [&](uint32_t v) { return !occ[v & 0xFFFFFu] && (v >> 20) < 256u; })
-                               : warp_best2(c, cnt, lane, [&](uint32_t v) { return !occupied_g[v & 0xFFFFFu] && (v >> 20) < 256u; });
-        if (b.k1 == 0xFFFFFFFFu) continue;
-        const int bestDist = (int)(b.k1 >> 20);
-        if (bestDist > M_TH_HIGH) continue;                                                        // :163
-        const int bestIdx = (int)(c[b.k1 & 0xFFFFFu] & 0xFFFFFu);
-        const int bestLevel = staged ? oct[bestIdx] : f_keys[bestIdx].octave;
-        int bestDist2 = 256, bestLevel2 = -1;
-        if (b.k2 != 0xFFFFFFFFu) { bestDist2 = (int)(b.k2 >> 20); const int j2 = (int)(c[b.k2 & 0xFFFFFu] & 0xFFFFFu); bestLevel2 = staged ? oct[j2] : f_keys[j2].octave; }
-        if (bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(nnratio, (float)bestDist2)) continue;   // :166
-        if (lane == 0) {
-            f_match[bestIdx] = i;
-            const int o = staged ? obs[i] : (mp_observed ? (mp_observed[i] != 0) : 0);
-            if (staged) occ[bestIdx] = o; else occupied_g[bestIdx] = (uint8_t)o;
-        }
-        ++nmatches;
-        __syncwarp();
-    }
-    if (lane == 0) *nmatches_out = nmatches;
+    ProjPointsOps ops{occ, f_match, oct, f_keys, obs, mp_observed, nnratio, staged, 0};
+    replay_queries<true>(SL, counts, offsets, lane, ops, claim);
+    if (lane == 0) *nmatches_out = ops.nmatches;
 }
 
 // =================================================================================================

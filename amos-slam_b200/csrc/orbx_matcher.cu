@@ -270,7 +270,7 @@ retry:
     P.mode = MODE_PROJ_FRAME; P.nq = n_last; P.q_desc = dd; P.q_xy = uv; P.q_invz = iz; P.q_octave = lo; P.q_valid = va; P.th = th; P.forward = forward; P.backward = backward; P.mbf = mbf;
     int *counts, *offsets; uint32_t* cand; uint2* pre;
     if ((rc = window_search(m, P, dc, counts, offsets, cand, pre))) return rc;
-    uint8_t* occ = m->arena.get<uint8_t>(nc + 1); int* cm = m->arena.get<int>(nc + 1); int* pushes = m->arena.get<int>(2 * (size_t)n_last + 2); int* dn = m->arena.get<int>(1);
+    int* occ = m->arena.get<int>(nc + 1); int* cm = m->arena.get<int>(nc + 1); int* pushes = m->arena.get<int>(2 * (size_t)n_last + 2); int* dn = m->arena.get<int>(1);
     if (!occ || !cm || !pushes || !dn) FAIL(ORBX_E_CUDA, "matcher arena exhausted");
     k_resolve_proj_frame<<<1, RESOLVE_THREADS, RESOLVE_SMEM_BYTES, m->stream>>>(n_last, nc, dc.keys, la, ob, oc, counts, offsets, cand, pre, (int)std::min<size_t>(m->cand_cap, 0x7FFFFFFF), m->checkOri, RESOLVE_SMEM_BYTES / 4, occ, cm, pushes, dn);
     LAUNCH_CHECK();
@@ -311,7 +311,7 @@ retry:
     P.mode = MODE_PROJ_POINTS; P.nq = n_points; P.q_desc = dd; P.q_xy = uv; P.q_octave = lv; P.q_ur = ur; P.q_viewcos = vc; P.th = th;
     int *counts, *offsets; uint32_t* cand; uint2* pre;
     if ((rc = window_search(m, P, df, counts, offsets, cand, pre))) return rc;
-    uint8_t* occ = m->arena.get<uint8_t>(nf + 1); int* fm = m->arena.get<int>(nf + 1); int* dn = m->arena.get<int>(1);
+    int* occ = m->arena.get<int>(nf + 1); int* fm = m->arena.get<int>(nf + 1); int* dn = m->arena.get<int>(1);
     if (!occ || !fm || !dn) FAIL(ORBX_E_CUDA, "matcher arena exhausted");
     k_resolve_proj_points<<<1, RESOLVE_THREADS, RESOLVE_SMEM_BYTES, m->stream>>>(n_points, nf, df.keys, ob, oc, counts, offsets, cand, pre, (int)std::min<size_t>(m->cand_cap, 0x7FFFFFFF), m->nnratio, RESOLVE_SMEM_BYTES / 4, occ, fm, dn);
     LAUNCH_CHECK();
