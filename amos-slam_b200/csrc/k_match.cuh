@@ -318,21 +318,20 @@ __device__ __forceinline__ StagedLists stage_lists(uint32_t* sm, int sm_words, i
 
 // -------------------------------------------------------------------------------------------------
 // Order-preserving replay, 32 queries per step.  Every lane takes one query (in loop order) and evaluates it against the state as
-// it stands: if its precomputed best pair is still selectable ("clean") the acceptance test is O(1).  A lane may be committed
-// together with its predecessors of the step unless one of them claims a feature that the lane's decision READ (its best /
-// second-best feature) -- then the state it saw is stale.  So: commit the longest conflict-free prefix in lane order, re-evaluate
-// from the first stale lane, and run the (rare) lanes whose pair is no longer clean through the warp-cooperative rescan on their
-// own.  The result equals the reference's one-by-one loop; the serial chain shrinks from one query to one 32-query step.
+// it stands: if its precomputed best pair is still selectable the acceptance test is O(1); otherwise the lane rescans its own
+// (short) list under the running exclusions.  A lane may be committed together with its predecessors of the step unless one of
+// them claims a feature that the lane's decision rests on (its best / second-best feature) -- the running state only ever
+// removes candidates, so nothing else can change the outcome.  So: commit the longest conflict-free prefix in lane order and
+// re-evaluate from the first stale lane.  The result equals the reference's one-by-one loop.
 //   Ops:  bool clean(uint32_t cand_entry)                      candidate still selectable under the running state
-//         Best2 rescan(const uint32_t* c, int cnt, int lane)   warp-cooperative best-2 under the running state
+//         uint32_t dlimit                                      candidates at this distance or above never win (256 / none)
 //         bool decide(int qi, const uint32_t* c, Best2 b, int& j)   acceptance test (reads only static data besides b)
 //         bool commit(int qi, int j, Best2 b, int rank)        state update by one lane; returns true if it displaced a match
 //         void post(int naccept, int ndisplaced)               uniform counters
 // -------------------------------------------------------------------------------------------------
 #define NOJ 0xFFFFFFFFu
 template <bool USE_SECOND, class Ops>
-__device__ __forceinline__ void replay_queries(const StagedLists& SL, const int* __restrict__ counts, const int* __restrict__ offsets, int lane, Ops& ops,
-                                               volatile uint32_t* /* unused */) {
+__device__ __forceinline__ void replay_queries(const StagedLists& SL, const int* __restrict__ counts, const int* __restrict__ offsets, int lane, Ops& ops) {
     const uint32_t lt = (1u << lane) - 1u;
     for (int base = 0; base < SL.niter; base += 32) {
         const int it = base + lane;
@@ -344,16 +343,29 @@ __device__ __forceinline__ void replay_queries(const StagedLists& SL, const int*
         }
         const uint32_t* c = SL.lists + lo;
         const int nb = min(32, SL.niter - base);
+        Best2 b; b.k1 = pb.x; b.k2 = pb.y;                     // best pair under the running state (starts as the unconstrained pair)
         int start = 0;
         while (start < nb) {
-            Best2 b; b.k1 = pb.x; b.k2 = pb.y;
-            bool slow = false, accept = false; int j = -1; uint32_t r1 = NOJ, r2 = NOJ;
+            bool accept = false; int j = -1; uint32_t r1 = NOJ, r2 = NOJ;
             if (act && lane >= start && cnt > 0) {
-                if (pb.x != NOJ) { const uint32_t v = c[pb.x & 0xFFFFFu]; r1 = v & 0xFFFFFu; slow = !ops.clean(v); }
-                if (USE_SECOND && !slow && pb.y != NOJ) { const uint32_t v = c[pb.y & 0xFFFFFu]; r2 = v & 0xFFFFFu; slow = !ops.clean(v); }
-                if (!slow) accept = ops.decide(qi, c, b, j);
+                bool ok = true;
+                if (b.k1 != NOJ) ok = ops.clean(c[b.k1 & 0xFFFFFu]);
+                if (ok && USE_SECOND && b.k2 != NOJ) ok = ops.clean(c[b.k2 & 0xFFFFFu]);
+                if (!ok) {                                         // one of the pair has been taken: this lane rescans its own list
+                    uint32_t k1 = NOJ, k2 = NOJ;
+                    for (int p = 0; p < cnt; ++p) {
+                        const uint32_t v = c[p];
+                        if ((v >> 20) >= ops.dlimit || !ops.clean(v)) continue;
+                        const uint32_t key = (v & 0xFFF00000u) | (uint32_t)p;
+                        if (key < k1) { k2 = k1; k1 = key; } else if (key < k2) k2 = key;
+                    }
+                    b.k1 = k1; b.k2 = k2;
+                }
+                if (b.k1 != NOJ) r1 = c[b.k1 & 0xFFFFFu] & 0xFFFFFu;
+                if (USE_SECOND && b.k2 != NOJ) r2 = c[b.k2 & 0xFFFFFu] & 0xFFFFFu;
+                accept = ops.decide(qi, c, b, j);
             }
-            // does a predecessor of this step (lanes start .. lane-1) claim a feature this lane's decision read?  32 independent shuffles
+            // does a predecessor of this step (lanes start .. lane-1) claim a feature this lane's decision rests on?
             const uint32_t myclaim = accept ? (uint32_t)j : NOJ;
             bool stale = false;
 #pragma unroll
@@ -361,8 +373,8 @@ __device__ __forceinline__ void replay_queries(const StagedLists& SL, const int*
                 const uint32_t v = __shfl_sync(0xffffffffu, myclaim, K);
                 stale |= (K >= start) & (K < lane) & (v != NOJ) & ((v == r1) | (v == r2));
             }
-            const uint32_t stop = __ballot_sync(0xffffffffu, lane >= start && lane < nb && (slow || stale));
-            const int L = stop ? __ffs(stop) - 1 : nb;             // first lane that cannot be committed with its predecessors
+            const uint32_t stop = __ballot_sync(0xffffffffu, lane >= start && lane < nb && stale);
+            const int L = stop ? __ffs(stop) - 1 : nb;             // first lane that cannot be committed with its predecessors (never `start` itself)
             const bool mine = accept && lane >= start && lane < L;
             const uint32_t am = __ballot_sync(0xffffffffu, mine);
             bool displaced = false;
@@ -371,19 +383,6 @@ __device__ __forceinline__ void replay_queries(const StagedLists& SL, const int*
             ops.post(__popc(am), __popc(dm));
             __syncwarp();
             start = L;
-            if (L < nb && __shfl_sync(0xffffffffu, (int)slow, L)) {   // lane L's pair is no longer selectable: rescan its list with the whole warp
-                const int qL = __shfl_sync(0xffffffffu, qi, L), cntL = __shfl_sync(0xffffffffu, cnt, L), loL = __shfl_sync(0xffffffffu, lo, L);
-                const uint32_t* cL = SL.lists + loL;
-                const Best2 bb = ops.rescan(cL, cntL, lane);
-                int jj = -1;
-                const bool acc = ops.decide(qL, cL, bb, jj);          // uniform across the warp
-                bool disp = false;
-                if (acc && lane == 0) disp = ops.commit(qL, jj, bb, 0);
-                disp = __shfl_sync(0xffffffffu, (int)disp, 0) != 0;
-                ops.post(acc ? 1 : 0, disp ? 1 : 0);
-                __syncwarp();
-                start = L + 1;
-            }
         }
     }
 }
@@ -393,9 +392,7 @@ struct InitOps {
     int* md; int* s21; int* m12; int* bin_of; int* hist; const float* ang1; const float* ang2; const KpM* k1s; const KpM* k2s;
     float nnratio; int checkOri; bool staged; int nmatches;
     __device__ __forceinline__ bool clean(uint32_t v) const { return !(md[v & 0xFFFFFu] <= (int)(v >> 20)); }                   // :561
-    __device__ __forceinline__ Best2 rescan(const uint32_t* c, int cnt, int lane) const {
-        int* mdp = md; return warp_best2(c, cnt, lane, [&](uint32_t v) { return !(mdp[v & 0xFFFFFu] <= (int)(v >> 20)); });
-    }
+    static constexpr uint32_t dlimit = 0xFFFu;                                                                                   // no distance cut in the list scan
     __device__ __forceinline__ bool decide(int, const uint32_t* c, Best2 b, int& j) const {
         if (b.k1 == NOJ) return false;
         const int bestDist = (int)(b.k1 >> 20);
@@ -421,7 +418,6 @@ k_resolve_init(int n1, int n2, const KpM* __restrict__ k1s, const KpM* __restric
                float* __restrict__ prev_xy, int* __restrict__ nmatches_out) {
     extern __shared__ __align__(16) uint32_t rs_sm[];
     __shared__ int hist[M_HISTO];
-    __shared__ uint32_t claim[32];
     const int tid = threadIdx.x, lane = tid & 31;
     if (offsets[n1] > cand_cap) return;                            // candidate lists were not written (see k_window_search)
     const StagedLists SL = stage_lists(rs_sm, smem_words, 3 * n2 + n1, n1, counts, offsets, cand, pre_best);
@@ -437,7 +433,7 @@ k_resolve_init(int n1, int n2, const KpM* __restrict__ k1s, const KpM* __restric
     __syncthreads();
     if (tid >= 32) return;
     InitOps ops{md, s21, m12, bin_of, hist, ang1, ang2, k1s, k2s, nnratio, checkOri, staged, 0};
-    replay_queries<true>(SL, counts, offsets, lane, ops, claim);
+    replay_queries<true>(SL, counts, offsets, lane, ops);
     int nmatches = ops.nmatches;
     __syncwarp();
     if (checkOri) {
@@ -462,9 +458,7 @@ struct ProjFrameOps {
     int* occ; int* cur_match; int* pushes; int* hist; const int* obs; const uint8_t* mp_observed; const float* angl; const float* angc;
     const float* last_angle; const KpM* cur_keys; int checkOri; bool staged; int nmatches, npush;
     __device__ __forceinline__ bool clean(uint32_t v) const { return !occ[v & 0xFFFFFu]; }                                        // :1658-1660
-    __device__ __forceinline__ Best2 rescan(const uint32_t* c, int cnt, int lane) const {
-        int* o = occ; return warp_best2(c, cnt, lane, [&](uint32_t v) { return !o[v & 0xFFFFFu] && (v >> 20) < 256u; });          // bestDist = 256
-    }
+    static constexpr uint32_t dlimit = 256u;                                                                                     // bestDist starts at 256, strict <
     __device__ __forceinline__ bool decide(int, const uint32_t* c, Best2 b, int& j) const {
         if (b.k1 == NOJ || (int)(b.k1 >> 20) > M_TH_HIGH) return false;                                                          // :1683
         j = (int)(c[b.k1 & 0xFFFFFu] & 0xFFFFFu);
@@ -489,7 +483,6 @@ k_resolve_proj_frame(int n_last, int n_cur, const KpM* __restrict__ cur_keys, co
                      int* __restrict__ pushes /*2*n_last*/, int* __restrict__ nmatches_out) {
     extern __shared__ __align__(16) uint32_t rs_sm[];
     __shared__ int hist[M_HISTO];
-    __shared__ uint32_t claim[32];
     const int tid = threadIdx.x, lane = tid & 31;
     if (offsets[n_last] > cand_cap) return;
     // extra shared arrays: occ[n_cur] (ints) | angc[n_cur] | angl[n_last] | obs[n_last] (ints)
@@ -509,7 +502,7 @@ k_resolve_proj_frame(int n_last, int n_cur, const KpM* __restrict__ cur_keys, co
     __syncthreads();
     if (tid >= 32) return;
     ProjFrameOps ops{occ, cur_match, pushes, hist, obs, mp_observed, angl, angc, last_angle, cur_keys, checkOri, staged, 0, 0};
-    replay_queries<false>(SL, counts, offsets, lane, ops, claim);
+    replay_queries<false>(SL, counts, offsets, lane, ops);
     int nmatches = ops.nmatches;
     const int npush = ops.npush;
     __syncwarp();
@@ -532,9 +525,7 @@ k_resolve_proj_frame(int n_last, int n_cur, const KpM* __restrict__ cur_keys, co
 struct ProjPointsOps {
     int* occ; int* f_match; const int* oct; const KpM* f_keys; const int* obs; const uint8_t* mp_observed; float nnratio; bool staged; int nmatches;
     __device__ __forceinline__ bool clean(uint32_t v) const { return !occ[v & 0xFFFFFu]; }                                        // :124-126
-    __device__ __forceinline__ Best2 rescan(const uint32_t* c, int cnt, int lane) const {
-        int* o = occ; return warp_best2(c, cnt, lane, [&](uint32_t v) { return !o[v & 0xFFFFFu] && (v >> 20) < 256u; });
-    }
+    static constexpr uint32_t dlimit = 256u;
     __device__ __forceinline__ bool decide(int, const uint32_t* c, Best2 b, int& j) const {
         if (b.k1 == NOJ) return false;
         const int bestDist = (int)(b.k1 >> 20);
@@ -560,7 +551,6 @@ k_resolve_proj_points(int n_points, int n_f, const KpM* __restrict__ f_keys, con
                       const int* __restrict__ counts, const int* __restrict__ offsets, const uint32_t* __restrict__ cand, const uint2* __restrict__ pre_best,
                       int cand_cap, float nnratio, int smem_words, int* __restrict__ occupied_g, int* __restrict__ f_match, int* __restrict__ nmatches_out) {
     extern __shared__ __align__(16) uint32_t rs_sm[];
-    __shared__ uint32_t claim[32];
     const int tid = threadIdx.x, lane = tid & 31;
     if (offsets[n_points] > cand_cap) return;
     // extra shared arrays: occ[n_f] | oct[n_f] | obs[n_points]
@@ -578,7 +568,7 @@ k_resolve_proj_points(int n_points, int n_f, const KpM* __restrict__ f_keys, con
     __syncthreads();
     if (tid >= 32) return;
     ProjPointsOps ops{occ, f_match, oct, f_keys, obs, mp_observed, nnratio, staged, 0};
-    replay_queries<true>(SL, counts, offsets, lane, ops, claim);
+    replay_queries<true>(SL, counts, offsets, lane, ops);
     if (lane == 0) *nmatches_out = ops.nmatches;
 }
 
