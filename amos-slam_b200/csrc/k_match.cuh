@@ -46,10 +46,13 @@ __global__ void k_descriptor_distance(const uint4* __restrict__ a, const uint4* 
     out[i] = hamming256(__ldg(a + 2 * i), __ldg(a + 2 * i + 1), b + 2 * i);
 }
 
-// ---- grid build: keys = cell<<20 | index, bitonic sort (one CTA), then cell_start by binary search ----
+// ---- grid build: keys = cell<<20 | index, bitonic sort (one CTA; in shared memory when the frame fits), then cell_start by binary search ----
+#define GRID_SMEM_KEYS 8192
 __global__ void __launch_bounds__(1024)
 k_grid_build(const KpM* __restrict__ keys, int n, float min_x, float min_y, float gw_inv, float gh_inv,
-             uint32_t* __restrict__ skeys, int* __restrict__ entries, int* __restrict__ cell_start) {
+             uint32_t* __restrict__ skeys_g, int* __restrict__ entries, int* __restrict__ cell_start) {
+    __shared__ uint32_t skeys_s[GRID_SMEM_KEYS];
+    uint32_t* skeys = n <= GRID_SMEM_KEYS ? skeys_s : skeys_g;
     const int tid = threadIdx.x;
     for (int i = tid; i < n; i += 1024) {
         // posX = round((kp.pt.x - mnMinX) * mfGridElementWidthInv)   (roundf: half away from zero)
