@@ -665,25 +665,39 @@ k_stereo_match(const KpM* __restrict__ kl, const uint8_t* __restrict__ dl, int n
 }
 
 // median cut (:1548-1569): thDist = 1.5f*1.4f*median(dist); entries with dist >= thDist are dropped.  One CTA.
+#define STEREO_SMEM_VALS 8192
 __global__ void __launch_bounds__(1024)
 k_stereo_median_cut(int nl, const int* __restrict__ sad_dist, float* __restrict__ u_right, float* __restrict__ depth) {
+    // the SAD values of the surviving matches are compacted into shared memory (order is irrelevant for a rank), so the rank
+    // counting below reads broadcast shared words instead of re-walking the global array once per match
+    __shared__ int vals[STEREO_SMEM_VALS];
     __shared__ int total_sm, median_sm;
     const int tid = threadIdx.x;
     if (tid == 0) { total_sm = 0; median_sm = -1; }
     __syncthreads();
-    int cnt = 0;
-    for (int i = tid; i < nl; i += 1024) cnt += sad_dist[i] != INT_MAX;
-    atomicAdd(&total_sm, cnt);
+    for (int i = tid; i < nl; i += 1024) {
+        const int d = sad_dist[i];
+        if (d != INT_MAX) { const int p = atomicAdd(&total_sm, 1); if (p < STEREO_SMEM_VALS) vals[p] = d; }
+    }
     __syncthreads();
     const int total = total_sm;
     if (total == 0) return;
     const int k = total / 2;                                                   // vDistIdx[size/2].first of the sorted list
-    for (int i = tid; i < nl; i += 1024) {
-        const int d = sad_dist[i];
-        if (d == INT_MAX) continue;
-        int less = 0, leq = 0;
-        for (int j = 0; j < nl; ++j) { const int e = sad_dist[j]; if (e != INT_MAX) { less += e < d; leq += e <= d; } }
-        if (less <= k && k < leq) median_sm = d;                               // every qualifying thread writes the same value
+    if (total <= STEREO_SMEM_VALS) {
+        for (int i = tid; i < total; i += 1024) {
+            const int d = vals[i];
+            int less = 0, leq = 0;
+            for (int j = 0; j < total; ++j) { const int e = vals[j]; less += e < d; leq += e <= d; }
+            if (less <= k && k < leq) median_sm = d;                           // every qualifying thread writes the same value
+        }
+    } else {
+        for (int i = tid; i < nl; i += 1024) {
+            const int d = sad_dist[i];
+            if (d == INT_MAX) continue;
+            int less = 0, leq = 0;
+            for (int j = 0; j < nl; ++j) { const int e = sad_dist[j]; if (e != INT_MAX) { less += e < d; leq += e <= d; } }
+            if (less <= k && k < leq) median_sm = d;
+        }
     }
     __syncthreads();
     const float median = (float)median_sm;
