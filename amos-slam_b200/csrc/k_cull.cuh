@@ -61,11 +61,18 @@ __global__ void k_bin_dilate31(const uint32_t* __restrict__ in, uint32_t* __rest
     const uint32_t* plane = in + (long long)b * rows * wpr;
     const int lastw = wpr - 1;
     const uint32_t lastmask = (cols & 31) ? ((1u << (cols & 31)) - 1u) : 0xFFFFFFFFu;
-    uint32_t acc = 0;
-    for (int dy = -15; dy <= 15; ++dy) {
-        const int yy = y + dy;
-        if (yy < 0 || yy >= rows) continue;
-        const int d = c_ell_dx[dy + 15];
+    // rows y-k and y+k share the half-width dx[15-k], and consecutive k often do too (15: k=0..3, 14: k=4..6, 13: k=7,8, ...):
+    // dilation distributes over OR, so the rows of one half-width are OR-ed first and dilated horizontally once (10 window
+    // passes per output word instead of 31)
+    uint32_t acc = 0, gL = 0, gM = 0, gR = 0;
+    int gd = c_ell_dx[0];                                            // half-width of the group being collected (k = 15 first)
+    auto flush = [&]() {
+        const unsigned long long A = ((unsigned long long)gM << 32) | gL, Bw = ((unsigned long long)gR << 32) | gM;
+        acc |= (uint32_t)(or_window(A >> (32 - gd), gd + 1) | or_window(Bw, gd + 1));
+        gL = gM = gR = 0;
+    };
+    auto add_row = [&](int yy) {
+        if (yy < 0 || yy >= rows) return;
         const uint32_t* row = plane + (long long)yy * wpr;
         uint32_t M = __ldg(row + wx), L = wx > 0 ? __ldg(row + wx - 1) : 0u, R = wx < lastw ? __ldg(row + wx + 1) : 0u;
         if (COMPLEMENT) {
@@ -73,9 +80,15 @@ __global__ void k_bin_dilate31(const uint32_t* __restrict__ in, uint32_t* __rest
             L = wx > 0 ? ~L : 0u;
             R = wx < lastw ? ~R : 0u; if (wx + 1 == lastw) R &= lastmask;
         }
-        const unsigned long long A = ((unsigned long long)M << 32) | L, Bw = ((unsigned long long)R << 32) | M;
-        acc |= (uint32_t)(or_window(A >> (32 - d), d + 1) | or_window(Bw, d + 1));
+        gL |= L; gM |= M; gR |= R;
+    };
+    for (int k = 15; k >= 0; --k) {
+        const int d = c_ell_dx[15 - k];
+        if (d != gd) { flush(); gd = d; }
+        add_row(y - k);
+        if (k) add_row(y + k);
     }
+    flush();
     if (COMPLEMENT) { acc = ~acc; }
     if (wx == lastw) acc &= lastmask;
     out[((long long)b * rows + y) * wpr + wx] = acc;
