@@ -232,7 +232,7 @@ static int build_plan(orbx_extractor* h, int rows, int cols) {
     h->tree_cap = tree_cap;
     // radix-sort capacity per (level, frame): ~1 candidate per 100 px of level 0 is generous for real images; larger levels fall back
     // to the global-memory bitonic path inside the kernel
-    { int k = 4096; while (k < (rows * cols) / 100 && k < 16384) k *= 2; h->sort_smem_keys = k; }
+    { const long long want = (long long)rows * cols / 100; int k = 4096; if (want > 4096) k = (int)std::min<long long>(18432, (want + want / 4 + 2047) / 2048 * 2048); h->sort_smem_keys = k; }
     h->rows = rows; h->cols = cols; h->Bcap = 0; h->have_pyramid = false;
     return ORBX_OK;
 }
@@ -444,7 +444,7 @@ int orbx_create(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, in
         cudaStreamDestroy(h->stream); delete h; FAIL(ORBX_E_CUDA, "cudaStreamCreate (copy streams)");
     }
     if (upload_constants() != ORBX_OK) { cudaStreamDestroy(h->stream); cudaStreamDestroy(h->s_h2d); cudaStreamDestroy(h->s_d2h); delete h; return ORBX_E_CUDA; }
-    cudaFuncSetAttribute(k_octree_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)octree_sort_smem_bytes(16384));
+    cudaFuncSetAttribute(k_octree_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)octree_sort_smem_bytes(18432));
     cudaFuncSetAttribute(k_octree_tree, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_octree_tree_par, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ptree_smem_bytes(PTREE_MAXCAP, 4096));
     cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
