@@ -6,7 +6,7 @@ O=gpurun_out; mkdir -p $O
 python -m pytest tests -m gpu -x -q > $O/pytest_$TAG.log 2>&1; echo "pytest rc=$?" | tee -a $O/pytest_$TAG.log
 python bench.py --steps 10 --warmup 3 > $O/bench_$TAG.log 2> $O/bench_$TAG.err; echo "bench rc=$?"
 python bench.py --impl reference --steps 3 --warmup 1 > $O/benchref_$TAG.log 2> $O/benchref_$TAG.err; echo "benchref rc=$?"
-CMD="python bench.py --steps 1 --warmup 1 --batch 256 --no-cpu-baseline --no-e2e"
+CMD="python bench.py --steps 1 --warmup 1 --batch 256 --streams 1 --no-cpu-baseline --no-e2e"
 $CMD > $O/plain_$TAG.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $O/launches_$TAG.csv $CMD > $O/ncu_l_$TAG.log 2>&1
 $CMD > $O/plain2_$TAG.log 2>&1 && \
