@@ -167,9 +167,16 @@ k_fast_cells(PyrView pv, const LevelGeom* __restrict__ levels, const CellDesc* _
     uint8_t* S = smw + 2 * patch_cap;
     uint16_t* queue = reinterpret_cast<uint16_t*>(S + s_cap);  // zw*zh entries: (dark<<15) | y<<6 | x, raster order
     const uint32_t lt = (1u << lane) - 1u;
-    int tq = 0;                                                // largest 2^k - 1 <= minTh (exact for the default minTh = 7)
-    while (2 * tq + 1 <= minTh) tq = 2 * tq + 1;
-    const uint32_t keep = (uint32_t)(0xFF & ~tq) * 0x01010101u;
+    // stage-A masks for both thresholds: |d| > 2^k - 1 with the largest 2^k - 1 <= T (exact for minTh = 7, 15 for iniTh = 20)
+    uint32_t keep_ini, keep_min;
+    {
+        int tq = 0;
+        while (2 * tq + 1 <= iniTh) tq = 2 * tq + 1;
+        keep_ini = (uint32_t)(0xFF & ~tq) * 0x01010101u;
+        tq = 0;
+        while (2 * tq + 1 <= minTh) tq = 2 * tq + 1;
+        keep_min = (uint32_t)(0xFF & ~tq) * 0x01010101u;
+    }
 
     CellDesc c = cells[cell];
     fast_issue_patch(pv, levels, c, b, lane, smw);
@@ -192,6 +199,15 @@ k_fast_cells(PyrView pv, const LevelGeom* __restrict__ levels, const CellDesc* _
     __pipeline_wait_prior(1);                                  // this cell's patch has landed (the next one may still be in flight)
     __syncwarp();
 
+    // The reference runs FAST at iniThFAST and only re-runs a cell at minThFAST when that came back empty
+    // (src/ORBextractor.cc:1126-1139).  Same here: the whole funnel runs at T = iniTh, and again at minTh only for cells
+    // without a surviving corner (the scores already in S are a subset of the second pass's and identical, so S is kept).
+    const uint8_t* patch = sm + shift;
+    uint32_t* out = cand_slots + (long long)b * slots_per_frame + c.slot;
+    int n = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+    const int T = pass ? minTh : iniTh;
+    const uint32_t keep = pass ? keep_min : keep_ini;
     // ---- stage A: polarity-free compass pre-test, 4 pixels (one word) per lane per step ----
     int qn = 0;
     {
@@ -242,7 +258,6 @@ k_fast_cells(PyrView pv, const LevelGeom* __restrict__ levels, const CellDesc* _
         }
     }
     __syncwarp();
-    const uint8_t* patch = sm + shift;
     // ---- stage B: exact 16-point segment test on the survivors; corners compacted in place ----
     int cn = 0;
     for (int k0 = 0; k0 < qn; k0 += 32) {
@@ -252,7 +267,7 @@ k_fast_cells(PyrView pv, const LevelGeom* __restrict__ levels, const CellDesc* _
             code = queue[k];
             const int y = code >> 6, x = code & 63;
             const uint8_t* p = patch + (y + 3) * ps + (x + 3);
-            const int hi = (int)p[0] + minTh, lo = (int)p[0] - minTh;
+            const int hi = (int)p[0] + T, lo = (int)p[0] - T;
             int R[16];
             FAST_RING(p, ps, R);
             uint32_t mb = 0, md = 0;
@@ -296,36 +311,24 @@ k_fast_cells(PyrView pv, const LevelGeom* __restrict__ levels, const CellDesc* _
         S[(y + 1) * sst + x + 1] = (uint8_t)best;
     }
     __syncwarp();
-    // ---- stage D: strict 3x3 local maxima among the corners; count those above iniTh ----
-    int n_ini = 0;
-    for (int k0 = 0; k0 < cn; k0 += 32) {
-        const int k = k0 + lane;
-        int f = 0;
-        if (k < cn) {
-            const int code = queue[k], y = (code >> 6) & 63, x = code & 63;
-            const uint8_t* q = S + (y + 1) * sst + x + 1;
-            const int s = q[0];
-            if (s > q[-1] && s > q[1] && s > q[-sst - 1] && s > q[-sst] && s > q[-sst + 1] &&
-                s > q[sst - 1] && s > q[sst] && s > q[sst + 1]) f = s;
-            queue[k] = (uint16_t)((code & 0xFFF) | (f ? 0 : 0x8000));          // bit 15 now marks "suppressed"
-        }
-        n_ini += __popc(__ballot_sync(0xffffffffu, f > iniTh));
-    }
-    __syncwarp();
-    const int th = n_ini > 0 ? iniTh : minTh;                  // retry at minTh iff the cell came back empty
-    uint32_t* out = cand_slots + (long long)b * slots_per_frame + c.slot;
-    int n = 0;
+    // ---- stage D: strict 3x3 local maxima among the corners (all score > T), emitted in raster order ----
     for (int k0 = 0; k0 < cn; k0 += 32) {
         const int k = k0 + lane;
         int f = 0, x = 0, y = 0;
         if (k < cn) {
             const int code = queue[k];
-            if (!(code & 0x8000)) { y = code >> 6; x = code & 63; f = S[(y + 1) * sst + x + 1]; }
+            y = (code >> 6) & 63; x = code & 63;
+            const uint8_t* q = S + (y + 1) * sst + x + 1;
+            const int s = q[0];
+            if (s > q[-1] && s > q[1] && s > q[-sst - 1] && s > q[-sst] && s > q[-sst + 1] &&
+                s > q[sst - 1] && s > q[sst] && s > q[sst + 1]) f = s;
         }
-        const bool keepit = f > th;
-        const uint32_t m = __ballot_sync(0xffffffffu, keepit);
-        if (keepit) out[n + __popc(m & lt)] = (uint32_t)(x + 3 + c.sx) | ((uint32_t)(y + 3 + c.sy) << 12) | ((uint32_t)(f - 1) << 24);
+        const uint32_t m = __ballot_sync(0xffffffffu, f != 0);
+        if (f) out[n + __popc(m & lt)] = (uint32_t)(x + 3 + c.sx) | ((uint32_t)(y + 3 + c.sy) << 12) | ((uint32_t)(f - 1) << 24);
         n += __popc(m);
+    }
+    if (n > 0 || minTh == iniTh) break;
+    __syncwarp();                                              // queue is rebuilt by the second pass
     }
     if (lane == 0) cell_counts[(long long)b * ncells + cell] = (uint16_t)n;
     c = cnext;
