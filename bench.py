@@ -426,6 +426,29 @@ def main():
             dist.barrier()
     sampler.stop_flag = True; sampler.join(timeout=2)
 
+    # the link the e2e leg rides on: pinned host -> device copy rate of this GPU's PCIe link, measured alone (rank 0, after the timed regions)
+    pcie_h2d = None
+    if rank == 0 and Ke:
+        hp = torch.empty(256 << 20, dtype=torch.uint8).pin_memory(); dp = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        half = hp.numel() // 2
+        s2 = [torch.cuda.Stream(), torch.cuda.Stream()]
+        pcie_h2d = 0.0
+        for rep in range(4):                                      # two copy streams, like the e2e leg's two handles; best of 3 after one warm-up
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i, st in enumerate(s2):
+                st.wait_event(e0)
+                with torch.cuda.stream(st):
+                    for _ in range(2):
+                        dp[i * half:(i + 1) * half].copy_(hp[i * half:(i + 1) * half], non_blocking=True)
+            for st in s2:
+                torch.cuda.current_stream().wait_stream(st)
+            e1.record(); torch.cuda.synchronize()
+            if rep:
+                pcie_h2d = max(pcie_h2d, 2 * hp.numel() / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+        del hp, dp
+
     matcher_line = matcher_bench(orbx, torch, ext, frames, local_rank) if (rank == 0 and args.workload == "c1") else None
 
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
@@ -469,7 +492,10 @@ def main():
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": config,
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(B * WIDTH * HEIGHT * (2 if MASKED else 1)), "d2h_bytes_per_step": int(B * cap * 60 + 4 * B + 4), "steps": Ke,
-                    "streams_per_gpu": NS, "note": "one host thread per extractor handle, each calling the synchronous host-pointer batch API on its share of the step's frames"},
+                    "streams_per_gpu": NS,
+                    "h2d_GBps_per_gpu": (e2e / N * WIDTH * HEIGHT * (2 if MASKED else 1) / 1e9) if e2e else None, "pcie_h2d_peak_GBps": pcie_h2d,
+                    "pcie_frac": (e2e / N * WIDTH * HEIGHT * (2 if MASKED else 1) / 1e9 / pcie_h2d) if (e2e and pcie_h2d) else None,
+                    "note": "one host thread per extractor handle, each calling the synchronous host-pointer batch API on its share of the step's frames"},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "ncu": ncu_note,
