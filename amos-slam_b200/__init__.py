@@ -101,6 +101,18 @@ def lib():
         L.orbx_compute_stereo_matches.argtypes = [vp, vp, vp, vp, vp, ci, vp, vp, ci, cf, cf, vp, vp]
         L.orbx_match_bruteforce_device.argtypes = [vp, vp, ci, vp, ci, vp, vp, vp]
         L.orbx_match_bruteforce_batch_device.argtypes = [vp, ci, vp, ci, vp, ci, vp, vp, vp]
+        L.orbx_frame_create.argtypes = [ci, C.POINTER(vp)]
+        L.orbx_frame_destroy.argtypes = [vp]; L.orbx_frame_destroy.restype = None
+        L.orbx_frame_assign.argtypes = [vp, vp, vp, ci, ci, vp, sz]
+        L.orbx_frame_assign_host.argtypes = [vp, vp, vp, ci, ci, vp, vp, ci, ci, vp, sz]
+        L.orbx_frame_set_stereo.argtypes = [vp, vp, vp]
+        L.orbx_frame_size.argtypes = [vp]
+        L.orbx_frame_read.argtypes = [vp, vp, vp, vp, vp]
+        L.orbx_frame_grid.argtypes = [vp, vp, vp]
+        L.orbx_frame_features_in_area.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp, vp, ci, C.POINTER(ci)]
+        L.orbx_search_for_initialization_frames.argtypes = [vp, vp, vp, vp, vp, ci, C.POINTER(ci)]
+        L.orbx_search_by_projection_frame_dev.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp, vp, vp, vp, cf, ci, ci, cf, vp, C.POINTER(ci)]
+        L.orbx_search_by_projection_points_dev.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp, vp, vp, cf, vp, C.POINTER(ci)]
     _lib = L
     return L
 
@@ -307,4 +319,4 @@ class ORBextractor:
         return out[:n.value].copy()
 
 
-from ._matcher import ORBmatcher, FrameView  # noqa: E402,F401
+from ._matcher import ORBmatcher, FrameView, Frame, Camera  # noqa: E402,F401

@@ -45,6 +45,90 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+class Camera(C.Structure):
+    """orbx_camera: mK (fx, fy, cx, cy), mDistCoef (k1, k2, p1, p2, k3) and mbf, all float like the reference's CV_32F matrices."""
+    _fields_ = [(n, C.c_float) for n in ("fx", "fy", "cx", "cy", "k1", "k2", "p1", "p2", "k3", "bf")]
+
+    @classmethod
+    def make(cls, fx, fy, cx, cy, k1=0.0, k2=0.0, p1=0.0, p2=0.0, k3=0.0, bf=0.0):
+        return cls(fx, fy, cx, cy, k1, k2, p1, p2, k3, bf)
+
+
+class Frame:
+    """Device-resident Frame: mvKeysUn, mDescriptors, mvuRight, mvDepth, image bounds and mGrid stay on the GPU between the extractor
+    and the matchers (UndistortKeyPoints, ComputeStereoFromRGBD, AssignFeaturesToGrid: /root/reference/src/Frame.cc:1052-1117,
+    1576-1614, 431-461, in the order Frame::CalDyna runs them, :636-645)."""
+
+    def __init__(self, device=0):
+        from . import lib, _check
+        self._lib, self._check = lib(), _check
+        h = C.c_void_p()
+        _check(self._lib.orbx_frame_create(int(device), C.byref(h)))
+        self._h = h
+        self.keys = []                     # len(F.keys) == N for the matcher wrappers
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.orbx_frame_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _depth_args(self, depth, rows, cols):
+        if depth is None:
+            return None, None, 0
+        d = np.asarray(depth)
+        if d.ndim == 2:                    # the whole CV_32F image; a row-strided view (cv::Mat ROI) is passed as it is
+            if d.dtype != np.float32 or d.strides[1] != 4 or d.strides[0] < 4 * cols:
+                d = np.ascontiguousarray(d, np.float32)
+            assert d.shape == (rows, cols)
+            return d, _p(d), d.strides[0]
+        d = np.ascontiguousarray(d, np.float32)
+        return d, _p(d), 0                 # per-keypoint values gathered by the caller
+
+    def assign(self, extractor, cam, rows, cols, depth=None):
+        """From the result the extractor handle still holds on the device (its last __call__ / ProcessDesp)."""
+        d, dp, stride = self._depth_args(depth, rows, cols)
+        self._check(self._lib.orbx_frame_assign(self._h, extractor._h, C.byref(cam), int(rows), int(cols), dp, stride))
+        self.keys = range(self.N)
+        return self
+
+    def assign_host(self, keys, descriptors, scale_factors, cam, rows, cols, depth=None):
+        from . import KP_DTYPE
+        k = np.ascontiguousarray(keys, KP_DTYPE); ds = _u8(descriptors).reshape(-1, 32); sf = np.ascontiguousarray(scale_factors, np.float32)
+        d, dp, stride = self._depth_args(depth, rows, cols)
+        self._check(self._lib.orbx_frame_assign_host(self._h, _p(k), _p(ds), len(k), len(sf), _p(sf), C.byref(cam), int(rows), int(cols), dp, stride))
+        self.keys = range(self.N)
+        return self
+
+    def set_stereo(self, u_right, depth):
+        ur = np.ascontiguousarray(u_right, np.float32); dp = np.ascontiguousarray(depth, np.float32)
+        assert len(ur) == self.N and len(dp) == self.N
+        self._check(self._lib.orbx_frame_set_stereo(self._h, _p(ur), _p(dp)))
+
+    @property
+    def N(self):
+        return self._lib.orbx_frame_size(self._h)
+
+    def read(self):
+        """(mvKeysUn, mvuRight, mvDepth, bounds[6] = mnMinX, mnMaxX, mnMinY, mnMaxY, mfGridElementWidthInv, mfGridElementHeightInv)."""
+        from . import KP_DTYPE
+        n = self.N
+        ku = np.zeros(max(n, 1), KP_DTYPE); ur = np.zeros(max(n, 1), np.float32); dp = np.zeros(max(n, 1), np.float32); b = np.zeros(6, np.float32)
+        self._check(self._lib.orbx_frame_read(self._h, _p(ku), _p(ur), _p(dp), _p(b)))
+        return ku[:n], ur[:n], dp[:n], b
+
+    def grid(self):
+        """mGrid flattened: cell (x, y) = entries[cell_start[x * 48 + y] : cell_start[x * 48 + y + 1]]."""
+        cs = np.zeros(64 * 48 + 1, np.int32); en = np.zeros(max(self.N, 1), np.int32)
+        self._check(self._lib.orbx_frame_grid(self._h, _p(cs), _p(en)))
+        return cs, en[:cs[-1]]
+
+
 def _u8(a):
     return None if a is None else np.ascontiguousarray(a, np.uint8)
 
@@ -91,6 +175,9 @@ class ORBmatcher:
     def SearchForInitialization(self, F1, F2, vbPrevMatched, windowSize=10):
         prev = np.ascontiguousarray(vbPrevMatched, np.float32).copy()
         m12 = np.zeros(len(F1.keys), np.int32); nm = C.c_int()
+        if isinstance(F1, Frame):          # device-resident frames: no upload, no grid build
+            self._check(self._lib.orbx_search_for_initialization_frames(self._h, F1._h, F2._h, _p(prev), _p(m12), int(windowSize), C.byref(nm)))
+            return nm.value, m12, prev
         v1, v2 = F1.c(), F2.c()
         self._check(self._lib.orbx_search_for_initialization(self._h, C.byref(v1), C.byref(v2), _p(prev), _p(m12), int(windowSize), C.byref(nm)))
         return nm.value, m12, prev
@@ -100,8 +187,12 @@ class ORBmatcher:
         uv = np.ascontiguousarray(proj_uv, np.float32); iz = np.ascontiguousarray(proj_invz, np.float32)
         lo = np.ascontiguousarray(last_octave, np.int32); la = np.ascontiguousarray(last_angle, np.float32)
         d, va, ob, oc = _u8(mp_desc), _u8(valid), _u8(mp_observed), _u8(cur_occupied)
-        cm = np.zeros(len(cur.keys), np.int32); nm = C.c_int(); v = cur.c()
-        self._check(self._lib.orbx_search_by_projection_frame(self._h, C.byref(v), len(iz), _p(uv), _p(iz), _p(lo), _p(la), _p(d), _p(va), _p(ob), _p(oc),
+        cm = np.zeros(len(cur.keys), np.int32); nm = C.c_int()
+        if isinstance(cur, Frame):
+            fn, fa = self._lib.orbx_search_by_projection_frame_dev, cur._h
+        else:
+            v = cur.c(); fn, fa = self._lib.orbx_search_by_projection_frame, C.byref(v)
+        self._check(fn(self._h, fa, len(iz), _p(uv), _p(iz), _p(lo), _p(la), _p(d), _p(va), _p(ob), _p(oc),
                                                               float(th), int(forward), int(backward), float(mbf), _p(cm), C.byref(nm)))
         self.last_raw_match = cm.copy()          # -2 marks entries assigned and then reset by the rotation check
         cm[cm == -2] = -1
@@ -112,8 +203,12 @@ class ORBmatcher:
         uv = np.ascontiguousarray(track_uv, np.float32); ur = np.ascontiguousarray(track_ur, np.float32)
         lv = np.ascontiguousarray(track_level, np.int32); vc = np.ascontiguousarray(track_view_cos, np.float32)
         d, ob, oc = _u8(mp_desc), _u8(mp_observed), _u8(f_occupied)
-        fm = np.zeros(len(F.keys), np.int32); nm = C.c_int(); v = F.c()
-        self._check(self._lib.orbx_search_by_projection_points(self._h, C.byref(v), len(lv), _p(uv), _p(ur), _p(lv), _p(vc), _p(d), _p(ob), _p(oc), float(th), _p(fm), C.byref(nm)))
+        fm = np.zeros(len(F.keys), np.int32); nm = C.c_int()
+        if isinstance(F, Frame):
+            fn, fa = self._lib.orbx_search_by_projection_points_dev, F._h
+        else:
+            v = F.c(); fn, fa = self._lib.orbx_search_by_projection_points, C.byref(v)
+        self._check(fn(self._h, fa, len(lv), _p(uv), _p(ur), _p(lv), _p(vc), _p(d), _p(ob), _p(oc), float(th), _p(fm), C.byref(nm)))
         return nm.value, fm
 
     # void Frame::ComputeStereoMatches()
@@ -125,6 +220,22 @@ class ORBmatcher:
         self._check(self._lib.orbx_compute_stereo_matches(self._h, extractor_left._h, extractor_right._h, _p(kl), _p(dl), len(kl), _p(kr), _p(dr), len(kr),
                                                           float(mb), float(mbf), _p(ur), _p(dep)))
         return ur, dep
+
+    # vector<size_t> Frame::GetFeaturesInArea(x, y, r, minLevel, maxLevel) for many windows at once, on a device-resident Frame
+    def GetFeaturesInArea(self, F, xy, r, min_level=None, max_level=None):
+        xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2); nq = len(xy)
+        r = np.ascontiguousarray(np.broadcast_to(np.asarray(r, np.float32), (nq,)), np.float32)
+        mn = np.ascontiguousarray(np.broadcast_to(np.asarray(-1 if min_level is None else min_level, np.int32), (nq,)), np.int32)
+        mx = np.ascontiguousarray(np.broadcast_to(np.asarray(-1 if max_level is None else max_level, np.int32), (nq,)), np.int32)
+        off = np.zeros(nq + 1, np.int32); tot = C.c_int()
+        cap = max(64 * nq, 1024)
+        while True:
+            idx = np.zeros(cap, np.int32)
+            rc = self._lib.orbx_frame_features_in_area(self._h, F._h, nq, _p(xy), _p(r), _p(mn), _p(mx), _p(off), _p(idx), cap, C.byref(tot))
+            if rc == -3 and tot.value > cap:           # ORBX_E_CAPACITY: grow and repeat
+                cap = tot.value; continue
+            self._check(rc)
+            return [idx[off[q]:off[q + 1]].copy() for q in range(nq)]
 
     def match_bruteforce_device(self, d_query_ptr, n_query, d_train_ptr, n_train, d_best_idx_ptr, d_best_dist_ptr, d_second_dist_ptr):
         self._check(self._lib.orbx_match_bruteforce_device(self._h, C.c_void_p(d_query_ptr), n_query, C.c_void_p(d_train_ptr), n_train,

@@ -83,6 +83,7 @@ k_grid_build(const KpM* __restrict__ keys, int n, float min_x, float min_y, floa
 #define MODE_INIT 0
 #define MODE_PROJ_FRAME 1
 #define MODE_PROJ_POINTS 2
+#define MODE_AREA 3               // plain Frame::GetFeaturesInArea(x, y, r, minLevel, maxLevel) windows
 struct QueryParams {
     int mode, nq;
     // INIT: F1 keys / desc, vbPrevMatched, windowSize
@@ -91,6 +92,8 @@ struct QueryParams {
     const float* q_invz; const int* q_octave; const uint8_t* q_valid; float th; int forward, backward; float mbf;
     // PROJ_POINTS: track_ur, track_level, track_view_cos, th                      (q_xy = track_uv, q_desc = mp_desc)
     const float* q_ur; const float* q_viewcos;
+    // AREA: q_xy = (x, y), q_r, q_minlevel, q_maxlevel
+    const float* q_r; const int* q_minlevel; const int* q_maxlevel;
 };
 
 // per-query window of GetFeaturesInArea and the static candidate filters; returns false if the query is skipped
@@ -114,6 +117,10 @@ __device__ __forceinline__ bool query_window(const QueryParams& P, const FrameDe
         else if (P.backward) { minLevel = 0; maxLevel = oct; }
         else { minLevel = oct - 1; maxLevel = oct + 1; }
         ur = __fsub_rn(u, __fmul_rn(P.mbf, invz)); use_ur = true;                   // :1665
+        return true;
+    }
+    if (P.mode == MODE_AREA) {
+        x = P.q_xy[2 * q]; y = P.q_xy[2 * q + 1]; r = P.q_r[q]; minLevel = P.q_minlevel[q]; maxLevel = P.q_maxlevel[q];
         return true;
     }
     // MODE_PROJ_POINTS  (:89-103)
@@ -150,8 +157,10 @@ k_window_search(QueryParams P, FrameDev F, int* __restrict__ counts, const int* 
         uint4 d0 = make_uint4(0, 0, 0, 0), d1 = d0;
         uint32_t* out = nullptr;
         if (FILL) {
-            const uint4* qd = reinterpret_cast<const uint4*>(P.q_desc) + 2 * q;
-            d0 = __ldg(qd); d1 = __ldg(qd + 1);
+            if (P.mode != MODE_AREA) {
+                const uint4* qd = reinterpret_cast<const uint4*>(P.q_desc) + 2 * q;
+                d0 = __ldg(qd); d1 = __ldg(qd + 1);
+            }
             out = cand + offsets[q];
         }
         for (int ix = cx0; ix <= cx1; ++ix) {
@@ -175,7 +184,7 @@ k_window_search(QueryParams P, FrameDev F, int* __restrict__ counts, const int* 
                 }
                 const uint32_t m = __ballot_sync(0xffffffffu, keep);
                 if (FILL && keep) {
-                    const int d = hamming256(d0, d1, reinterpret_cast<const uint4*>(F.desc) + 2 * j);
+                    const int d = P.mode == MODE_AREA ? 0 : hamming256(d0, d1, reinterpret_cast<const uint4*>(F.desc) + 2 * j);
                     const int pos = n + __popc(m & ((1u << lane) - 1u));
                     out[pos] = ((uint32_t)d << 20) | (uint32_t)j;
                     if ((uint32_t)d < dlimit) {

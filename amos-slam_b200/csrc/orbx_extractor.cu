@@ -82,6 +82,7 @@ struct orbx_extractor {
     DevBuf<uint16_t> d_cell_counts;
     DevBuf<int> d_ncand, d_kp_count, d_counts, d_level_counts, d_overflow;
     DevBuf<KpOut> d_kp_out; DevBuf<uint8_t> d_desc_out; int out_cap = 0;
+    const KpOut* last_kp = nullptr; const uint8_t* last_desc = nullptr; int last_n = -1;   // frame 0 of the last extract / describe (orbx_frame_assign)
     PyrView view{}; bool have_pyramid = false, blur_valid = false;
     // optional per-stage CUDA-event timing (bench.py's roofline): one event set per profiled call
     bool profiling = false;
@@ -238,6 +239,7 @@ static int build_plan(orbx_extractor* h, int rows, int cols) {
 }
 
 static int ensure_capacity(orbx_extractor* h, int B, int out_cap) {
+    h->last_n = -1;                                              // every detect / extract path passes here: the previous result is about to be overwritten
     if (B > h->Bcap) {
         const size_t b = (size_t)B;
         if (h->d_pyr.ensure(b * h->pyr_fstride) || h->d_blur.ensure(b * h->pyr_fstride) ||
@@ -688,6 +690,7 @@ int orbx_extract(orbx_extractor* h, const uint8_t* image, int rows, int cols, si
     CU_TRY(cudaStreamSynchronize(h->stream));
     if (ovf) FAIL(ORBX_E_OVERFLOW, "internal bound exceeded in the quadtree stage");
     *n_out = n;
+    h->last_kp = h->d_kp_out.p; h->last_desc = h->d_desc_out.p; h->last_n = n;
     if (n > cap) FAIL(ORBX_E_CAPACITY, "keypoint buffer too small");
     if (n && !spec) {
         CU_TRY(cudaMemcpyAsync(kp_out, h->d_kp_out.p, (size_t)n * sizeof(KpOut), cudaMemcpyDeviceToHost, h->stream));
@@ -729,7 +732,7 @@ int orbx_describe(orbx_extractor* h, const orbx_keypoint* kp_in, const int* leve
     int n = 0;
     for (int l = 0; l < h->nlevels; ++l) { if (level_counts[l] < 0) FAIL(ORBX_E_INVALID, "negative level count"); n += level_counts[l]; }
     *n_out = n;
-    if (n == 0) return ORBX_OK;
+    if (n == 0) { h->last_kp = nullptr; h->last_desc = nullptr; h->last_n = 0; return ORBX_OK; }
     if (!kp_in || !kp_out || !desc_out) FAIL(ORBX_E_INVALID, "null buffer");
     if (n > cap) FAIL(ORBX_E_CAPACITY, "keypoint buffer too small");
     // the reference takes the level from the position in allKeypoints, not from kp.octave: stamp it
@@ -750,6 +753,7 @@ int orbx_describe(orbx_extractor* h, const orbx_keypoint* kp_in, const int* leve
     CU_TRY(cudaMemcpyAsync(kp_out, h->d_kp_tmp.p + n, sizeof(KpOut) * n, cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(cudaMemcpyAsync(desc_out, h->d_desc_tmp.p, (size_t)n * 32, cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(cudaStreamSynchronize(h->stream));
+    h->last_kp = h->d_kp_tmp.p + n; h->last_desc = h->d_desc_tmp.p; h->last_n = n;
     return ORBX_OK;
 }
 
@@ -841,3 +845,11 @@ int orbx_internal_pyramid(orbx_extractor* h, OrbxPyramidInfo* out) {
     return ORBX_OK;
 }
 
+
+int orbx_internal_last_result(orbx_extractor* h, OrbxLastResult* out) {
+    if (!h || !out) FAIL(ORBX_E_INVALID, "null handle");
+    if (h->last_n < 0) FAIL(ORBX_E_STATE, "extractor holds no result (call orbx_extract or orbx_describe first)");
+    out->device = h->device; out->n = h->last_n; out->nlevels = h->nlevels; out->stream = h->stream;
+    out->keys = h->last_kp; out->desc = h->last_desc; out->scale = h->mvScaleFactor.data();
+    return ORBX_OK;
+}

@@ -12,3 +12,12 @@ struct OrbxPyramidInfo {
     const float* scale; const float* inv_scale;     // host arrays owned by the handle (mvScaleFactor / mvInvScaleFactor)
 };
 int orbx_internal_pyramid(orbx_extractor* h, OrbxPyramidInfo* out);
+
+// keypoints / descriptors of frame 0 of the handle's last orbx_extract or orbx_describe call, still on the device
+struct OrbxLastResult {
+    int device, n, nlevels; cudaStream_t stream;
+    const void* keys;            // n x 28-byte cv::KeyPoint records
+    const uint8_t* desc;         // n x 32
+    const float* scale;          // host: mvScaleFactor[nlevels]
+};
+int orbx_internal_last_result(orbx_extractor* h, OrbxLastResult* out);

@@ -6,6 +6,7 @@
 #include "../../include/orbx_b200.h"
 #include "orbx_internal.h"
 #include "k_match.cuh"
+#include "k_frame.cuh"
 
 #include <climits>
 #include <algorithm>
@@ -115,6 +116,52 @@ static int build_grid(orbx_matcher* m, const FrameDev& d, uint32_t* sort_keys) {
     return ORBX_OK;
 }
 
+// ---- device-resident Frame (include/orbx_b200.h, "Device-resident Frame") ----
+template <typename T> struct FBuf {
+    T* p = nullptr; size_t n = 0;
+    int ensure(size_t count) {
+        if (count <= n) return ORBX_OK;
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+        count += count >> 2;
+        if (cudaMalloc((void**)&p, count * sizeof(T)) != cudaSuccess) { orbx_set_error("cudaMalloc (frame)"); return ORBX_E_CUDA; }
+        n = count; return ORBX_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+struct orbx_frame {
+    int device; cudaStream_t stream = nullptr; long long launches = 0;
+    int n = -1, nlevels = 0;
+    FBuf<KpM> keys_in, keys_un; FBuf<uint8_t> desc; FBuf<float> u_right, depth, scale, depth_img, bounds4;
+    FBuf<int> cell_start, entries; FBuf<uint32_t> sort_keys;
+    FrameDev dev;
+    // ComputeImageBounds cache (the reference computes them once, Frame::mbInitialComputations)
+    bool bounds_valid = false; orbx_camera bcam; int brows = 0, bcols = 0;
+    float min_x = 0, max_x = 0, min_y = 0, max_y = 0, gw_inv = 0, gh_inv = 0;
+};
+
+// a matcher argument that is either a host frame view (uploaded + gridded per call) or a device-resident frame
+struct FrameArg {
+    const orbx_frame_view* v; const orbx_frame* f;
+    int n() const { return v ? v->n : f->n; }
+    int nlevels() const { return v ? v->nlevels : f->nlevels; }
+};
+static int check_frame_arg(const orbx_matcher* m, const FrameArg& a) {
+    if (a.v) return check_frame(a.v);
+    if (!a.f || a.f->n < 0) FAIL(ORBX_E_STATE, "device frame is empty (call orbx_frame_assign first)");
+    if (m && a.f->device != m->device) FAIL(ORBX_E_INVALID, "frame and matcher must live on the same device");
+    return ORBX_OK;
+}
+static size_t frame_arg_bytes(const FrameArg& a) { return a.v ? frame_bytes(a.v) : 4096; }
+static int stage_frame(orbx_matcher* m, const FrameArg& a, FrameDev& d, uint32_t*& sort_keys) {
+    if (a.v) return upload_frame(m, a.v, d, sort_keys);
+    d = a.f->dev; sort_keys = nullptr;
+    return ORBX_OK;
+}
+static int grid_frame(orbx_matcher* m, const FrameArg& a, const FrameDev& d, uint32_t* sort_keys) {
+    return a.v ? build_grid(m, d, sort_keys) : ORBX_OK;        // a device frame built its grid in orbx_frame_assign
+}
+
 // host array -> staged upload (host != nullptr) or plain device scratch (host == nullptr)
 template <typename T> static int up(orbx_matcher* m, const T* host, size_t count, T*& dev) {
     dev = host ? reinterpret_cast<T*>(m->uparena.put(count ? host : nullptr, (count ? count : 1) * sizeof(T))) : m->arena.get<T>(count ? count : 1);
@@ -202,25 +249,29 @@ int orbx_descriptor_distance(orbx_matcher* m, const uint8_t* a, const uint8_t* b
     return ORBX_OK;
 }
 
-int orbx_search_for_initialization(orbx_matcher* m, const orbx_frame_view* F1, const orbx_frame_view* F2, float* prev_matched_xy, int* matches12,
-                                   int window_size, int* nmatches) {
+static int search_init_impl(orbx_matcher* m, const FrameArg A1, const FrameArg A2, float* prev_matched_xy, int* matches12, int window_size, int* nmatches) {
     if (!m || !nmatches) FAIL(ORBX_E_INVALID, "null argument");
     int rc;
-    if ((rc = check_frame(F1)) || (rc = check_frame(F2))) return rc;
-    if (F1->n && (!prev_matched_xy || !matches12)) FAIL(ORBX_E_INVALID, "null buffer");
+    if ((rc = check_frame_arg(m, A1)) || (rc = check_frame_arg(m, A2))) return rc;
+    const int n1 = A1.n(), n2 = A2.n();
+    if (n1 && (!prev_matched_xy || !matches12)) FAIL(ORBX_E_INVALID, "null buffer");
     *nmatches = 0;
-    if (F1->n == 0) return ORBX_OK;
+    if (n1 == 0) return ORBX_OK;
     CU_TRY(cudaSetDevice(m->device));
-    const int n1 = F1->n, n2 = F2->n;
-    const size_t need = frame_bytes(F1) + frame_bytes(F2) + pad((size_t)n1 * 8) + 6 * pad((size_t)(n1 + n2 + 2) * 4) + 8192;
+    const size_t need = frame_arg_bytes(A1) + frame_arg_bytes(A2) + pad((size_t)n1 * 8) + 6 * pad((size_t)(n1 + n2 + 2) * 4) + 8192;
     if ((rc = m->arena.reserve(need)) || (rc = m->uparena.reserve(need))) return rc;
 retry:
     m->arena.reset(); m->uparena.reset();
     FrameDev d2; uint32_t* sk2;
-    if ((rc = upload_frame(m, F2, d2, sk2))) return rc;
-    KpM* k1; uint8_t* desc1; float* prev;
-    if ((rc = up(m, reinterpret_cast<const KpM*>(F1->keys_un), (size_t)n1, k1)) || (rc = up(m, F1->descriptors, (size_t)n1 * 32, desc1)) || (rc = up(m, prev_matched_xy, (size_t)n1 * 2, prev))) return rc;
-    if ((rc = flush_uploads(m)) || (rc = build_grid(m, d2, sk2))) return rc;
+    if ((rc = stage_frame(m, A2, d2, sk2))) return rc;
+    const KpM* k1; const uint8_t* desc1; float* prev;
+    if (A1.v) {
+        KpM* k1u; uint8_t* d1u;
+        if ((rc = up(m, reinterpret_cast<const KpM*>(A1.v->keys_un), (size_t)n1, k1u)) || (rc = up(m, A1.v->descriptors, (size_t)n1 * 32, d1u))) return rc;
+        k1 = k1u; desc1 = d1u;
+    } else { k1 = A1.f->dev.keys; desc1 = A1.f->dev.desc; }
+    if ((rc = up(m, prev_matched_xy, (size_t)n1 * 2, prev))) return rc;
+    if ((rc = flush_uploads(m)) || (rc = grid_frame(m, A2, d2, sk2))) return rc;
     QueryParams P; std::memset(&P, 0, sizeof(P));
     P.mode = MODE_INIT; P.nq = n1; P.q_keys = k1; P.q_desc = desc1; P.q_xy = prev; P.window = (float)window_size;
     int *counts, *offsets; uint32_t* cand; uint2* pre;
@@ -242,30 +293,30 @@ retry:
     return ORBX_OK;
 }
 
-int orbx_search_by_projection_frame(orbx_matcher* m, const orbx_frame_view* cur, int n_last, const float* proj_uv, const float* proj_invz,
+static int search_proj_frame_impl(orbx_matcher* m, const FrameArg cur, int n_last, const float* proj_uv, const float* proj_invz,
                                     const int* last_octave, const float* last_angle, const uint8_t* mp_desc, const uint8_t* valid, const uint8_t* mp_observed,
                                     const uint8_t* cur_occupied, float th, int forward, int backward, float mbf, int* cur_match, int* nmatches) {
     if (!m || !nmatches) FAIL(ORBX_E_INVALID, "null argument");
     int rc;
-    if ((rc = check_frame(cur))) return rc;
-    if (n_last < 0 || n_last >= (1 << 20) || (n_last && (!proj_uv || !proj_invz || !last_octave || !last_angle || !mp_desc || !valid)) || (cur->n && !cur_match))
+    if ((rc = check_frame_arg(m, cur))) return rc;
+    if (n_last < 0 || n_last >= (1 << 20) || (n_last && (!proj_uv || !proj_invz || !last_octave || !last_angle || !mp_desc || !valid)) || (cur.n() && !cur_match))
         FAIL(ORBX_E_INVALID, "bad arguments");
     *nmatches = 0;
-    for (int i = 0; i < n_last; ++i) if (valid[i] && (last_octave[i] < 0 || last_octave[i] >= cur->nlevels)) FAIL(ORBX_E_INVALID, "octave out of range");
+    for (int i = 0; i < n_last; ++i) if (valid[i] && (last_octave[i] < 0 || last_octave[i] >= cur.nlevels())) FAIL(ORBX_E_INVALID, "octave out of range");
     CU_TRY(cudaSetDevice(m->device));
-    const int nc = cur->n;
-    const size_t need = frame_bytes(cur) + pad((size_t)n_last * 32) + 8 * pad((size_t)(n_last + nc + 2) * 8) + 8192;
+    const int nc = cur.n();
+    const size_t need = frame_arg_bytes(cur) + pad((size_t)n_last * 32) + 8 * pad((size_t)(n_last + nc + 2) * 8) + 8192;
     if ((rc = m->arena.reserve(need)) || (rc = m->uparena.reserve(need))) return rc;
 retry:
     m->arena.reset(); m->uparena.reset();
     FrameDev dc; uint32_t* skc;
-    if ((rc = upload_frame(m, cur, dc, skc))) return rc;
+    if ((rc = stage_frame(m, cur, dc, skc))) return rc;
     float *uv, *iz, *la; int* lo; uint8_t *dd, *va, *ob = nullptr, *oc = nullptr;
     if ((rc = up(m, proj_uv, (size_t)n_last * 2, uv)) || (rc = up(m, proj_invz, (size_t)n_last, iz)) || (rc = up(m, last_angle, (size_t)n_last, la)) ||
         (rc = up(m, last_octave, (size_t)n_last, lo)) || (rc = up(m, mp_desc, (size_t)n_last * 32, dd)) || (rc = up(m, valid, (size_t)n_last, va))) return rc;
     if (mp_observed && (rc = up(m, mp_observed, (size_t)n_last, ob))) return rc;
     if (cur_occupied && (rc = up(m, cur_occupied, (size_t)nc, oc))) return rc;
-    if ((rc = flush_uploads(m)) || (rc = build_grid(m, dc, skc))) return rc;
+    if ((rc = flush_uploads(m)) || (rc = grid_frame(m, cur, dc, skc))) return rc;
     QueryParams P; std::memset(&P, 0, sizeof(P));
     P.mode = MODE_PROJ_FRAME; P.nq = n_last; P.q_desc = dd; P.q_xy = uv; P.q_invz = iz; P.q_octave = lo; P.q_valid = va; P.th = th; P.forward = forward; P.backward = backward; P.mbf = mbf;
     int *counts, *offsets; uint32_t* cand; uint2* pre;
@@ -283,30 +334,30 @@ retry:
     return ORBX_OK;
 }
 
-int orbx_search_by_projection_points(orbx_matcher* m, const orbx_frame_view* F, int n_points, const float* track_uv, const float* track_ur, const int* track_level,
+static int search_proj_points_impl(orbx_matcher* m, const FrameArg F, int n_points, const float* track_uv, const float* track_ur, const int* track_level,
                                      const float* track_view_cos, const uint8_t* mp_desc, const uint8_t* mp_observed, const uint8_t* f_occupied, float th,
                                      int* f_match, int* nmatches) {
     if (!m || !nmatches) FAIL(ORBX_E_INVALID, "null argument");
     int rc;
-    if ((rc = check_frame(F))) return rc;
-    if (n_points < 0 || n_points >= (1 << 20) || (n_points && (!track_uv || !track_ur || !track_level || !track_view_cos || !mp_desc)) || (F->n && !f_match))
+    if ((rc = check_frame_arg(m, F))) return rc;
+    if (n_points < 0 || n_points >= (1 << 20) || (n_points && (!track_uv || !track_ur || !track_level || !track_view_cos || !mp_desc)) || (F.n() && !f_match))
         FAIL(ORBX_E_INVALID, "bad arguments");
     *nmatches = 0;
-    for (int i = 0; i < n_points; ++i) if (track_level[i] < 0 || track_level[i] >= F->nlevels) FAIL(ORBX_E_INVALID, "predicted level out of range");
+    for (int i = 0; i < n_points; ++i) if (track_level[i] < 0 || track_level[i] >= F.nlevels()) FAIL(ORBX_E_INVALID, "predicted level out of range");
     CU_TRY(cudaSetDevice(m->device));
-    const int nf = F->n;
-    const size_t need = frame_bytes(F) + pad((size_t)n_points * 32) + 8 * pad((size_t)(n_points + nf + 2) * 8) + 8192;
+    const int nf = F.n();
+    const size_t need = frame_arg_bytes(F) + pad((size_t)n_points * 32) + 8 * pad((size_t)(n_points + nf + 2) * 8) + 8192;
     if ((rc = m->arena.reserve(need)) || (rc = m->uparena.reserve(need))) return rc;
 retry:
     m->arena.reset(); m->uparena.reset();
     FrameDev df; uint32_t* skf;
-    if ((rc = upload_frame(m, F, df, skf))) return rc;
+    if ((rc = stage_frame(m, F, df, skf))) return rc;
     float *uv, *ur, *vc; int* lv; uint8_t *dd, *ob = nullptr, *oc = nullptr;
     if ((rc = up(m, track_uv, (size_t)n_points * 2, uv)) || (rc = up(m, track_ur, (size_t)n_points, ur)) || (rc = up(m, track_view_cos, (size_t)n_points, vc)) ||
         (rc = up(m, track_level, (size_t)n_points, lv)) || (rc = up(m, mp_desc, (size_t)n_points * 32, dd))) return rc;
     if (mp_observed && (rc = up(m, mp_observed, (size_t)n_points, ob))) return rc;
     if (f_occupied && (rc = up(m, f_occupied, (size_t)nf, oc))) return rc;
-    if ((rc = flush_uploads(m)) || (rc = build_grid(m, df, skf))) return rc;
+    if ((rc = flush_uploads(m)) || (rc = grid_frame(m, F, df, skf))) return rc;
     QueryParams P; std::memset(&P, 0, sizeof(P));
     P.mode = MODE_PROJ_POINTS; P.nq = n_points; P.q_desc = dd; P.q_xy = uv; P.q_octave = lv; P.q_ur = ur; P.q_viewcos = vc; P.th = th;
     int *counts, *offsets; uint32_t* cand; uint2* pre;
@@ -358,6 +409,231 @@ int orbx_compute_stereo_matches(orbx_matcher* m, orbx_extractor* left, orbx_extr
     CU_TRY(cudaMemcpyAsync(u_right, dur, (size_t)nl * 4, cudaMemcpyDeviceToHost, m->stream));
     CU_TRY(cudaMemcpyAsync(depth, ddep, (size_t)nl * 4, cudaMemcpyDeviceToHost, m->stream));
     CU_TRY(cudaStreamSynchronize(m->stream));
+    return ORBX_OK;
+}
+
+// ---- public windowed matchers: host frame views and device-resident frames share one implementation ----
+int orbx_search_for_initialization(orbx_matcher* m, const orbx_frame_view* F1, const orbx_frame_view* F2, float* prev_matched_xy, int* matches12,
+                                   int window_size, int* nmatches) {
+    if (!F1 || !F2) FAIL(ORBX_E_INVALID, "bad frame view");
+    return search_init_impl(m, FrameArg{F1, nullptr}, FrameArg{F2, nullptr}, prev_matched_xy, matches12, window_size, nmatches);
+}
+int orbx_search_for_initialization_frames(orbx_matcher* m, const orbx_frame* F1, const orbx_frame* F2, float* prev_matched_xy, int* matches12,
+                                          int window_size, int* nmatches) {
+    if (!F1 || !F2) FAIL(ORBX_E_INVALID, "null frame");
+    return search_init_impl(m, FrameArg{nullptr, F1}, FrameArg{nullptr, F2}, prev_matched_xy, matches12, window_size, nmatches);
+}
+int orbx_search_by_projection_frame(orbx_matcher* m, const orbx_frame_view* cur, int n_last, const float* proj_uv, const float* proj_invz,
+                                    const int* last_octave, const float* last_angle, const uint8_t* mp_desc, const uint8_t* valid, const uint8_t* mp_observed,
+                                    const uint8_t* cur_occupied, float th, int forward, int backward, float mbf, int* cur_match, int* nmatches) {
+    if (!cur) FAIL(ORBX_E_INVALID, "bad frame view");
+    return search_proj_frame_impl(m, FrameArg{cur, nullptr}, n_last, proj_uv, proj_invz, last_octave, last_angle, mp_desc, valid, mp_observed, cur_occupied, th, forward, backward, mbf, cur_match, nmatches);
+}
+int orbx_search_by_projection_frame_dev(orbx_matcher* m, const orbx_frame* cur, int n_last, const float* proj_uv, const float* proj_invz,
+                                        const int* last_octave, const float* last_angle, const uint8_t* mp_desc, const uint8_t* valid, const uint8_t* mp_observed,
+                                        const uint8_t* cur_occupied, float th, int forward, int backward, float mbf, int* cur_match, int* nmatches) {
+    if (!cur) FAIL(ORBX_E_INVALID, "null frame");
+    return search_proj_frame_impl(m, FrameArg{nullptr, cur}, n_last, proj_uv, proj_invz, last_octave, last_angle, mp_desc, valid, mp_observed, cur_occupied, th, forward, backward, mbf, cur_match, nmatches);
+}
+int orbx_search_by_projection_points(orbx_matcher* m, const orbx_frame_view* F, int n_points, const float* track_uv, const float* track_ur, const int* track_level,
+                                     const float* track_view_cos, const uint8_t* mp_desc, const uint8_t* mp_observed, const uint8_t* f_occupied, float th,
+                                     int* f_match, int* nmatches) {
+    if (!F) FAIL(ORBX_E_INVALID, "bad frame view");
+    return search_proj_points_impl(m, FrameArg{F, nullptr}, n_points, track_uv, track_ur, track_level, track_view_cos, mp_desc, mp_observed, f_occupied, th, f_match, nmatches);
+}
+int orbx_search_by_projection_points_dev(orbx_matcher* m, const orbx_frame* F, int n_points, const float* track_uv, const float* track_ur, const int* track_level,
+                                         const float* track_view_cos, const uint8_t* mp_desc, const uint8_t* mp_observed, const uint8_t* f_occupied, float th,
+                                         int* f_match, int* nmatches) {
+    if (!F) FAIL(ORBX_E_INVALID, "null frame");
+    return search_proj_points_impl(m, FrameArg{nullptr, F}, n_points, track_uv, track_ur, track_level, track_view_cos, mp_desc, mp_observed, f_occupied, th, f_match, nmatches);
+}
+
+// ---- device-resident Frame ----
+#define FLAUNCH_CHECK() do { cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) { \
+    orbx_set_error(std::string("kernel launch: ") + cudaGetErrorString(_e)); return ORBX_E_CUDA; } ++f->launches; } while (0)
+
+int orbx_frame_create(int device, orbx_frame** out) {
+    if (!out) FAIL(ORBX_E_INVALID, "null out");
+    *out = nullptr;
+    int ndev = 0;
+    CU_TRY(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) FAIL(ORBX_E_CUDA, "no such CUDA device (this library has no CPU fallback)");
+    CU_TRY(cudaSetDevice(device));
+    orbx_frame* f = new orbx_frame();
+    f->device = device;
+    cudaError_t e = cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete f; FAIL(ORBX_E_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e)); }
+    std::memset(&f->dev, 0, sizeof(f->dev));
+    *out = f;
+    return ORBX_OK;
+}
+void orbx_frame_destroy(orbx_frame* f) {
+    if (!f) return;
+    cudaSetDevice(f->device); cudaStreamSynchronize(f->stream);
+    f->keys_in.release(); f->keys_un.release(); f->desc.release(); f->u_right.release(); f->depth.release(); f->scale.release();
+    f->depth_img.release(); f->bounds4.release(); f->cell_start.release(); f->entries.release(); f->sort_keys.release();
+    cudaStreamDestroy(f->stream);
+    delete f;
+}
+
+static CamDev make_cam(const orbx_camera& c) {
+    CamDev d;
+    d.fx = (double)c.fx; d.fy = (double)c.fy; d.cx = (double)c.cx; d.cy = (double)c.cy;
+    d.ifx = 1.0 / d.fx; d.ify = 1.0 / d.fy;
+    d.k1 = (double)c.k1; d.k2 = (double)c.k2; d.p1 = (double)c.p1; d.p2 = (double)c.p2; d.k3 = (double)c.k3;
+    d.distorted = (c.k1 != 0.0f); d.bf = c.bf;
+    return d;
+}
+
+// the part common to both assign calls: keys (device, n records) -> mvKeysUn, mvuRight / mvDepth, grid
+static int frame_build(orbx_frame* f, const KpM* d_keys, int n, int nlevels, const float* scale_host, const orbx_camera* cam,
+                       int rows, int cols, const float* depth, size_t depth_stride) {
+    if (!cam || rows <= 0 || cols <= 0 || nlevels <= 0 || nlevels > ORBX_MAX_LEVELS || !scale_host) FAIL(ORBX_E_INVALID, "bad frame arguments");
+    if (!(cam->fx != 0.f) || !(cam->fy != 0.f)) FAIL(ORBX_E_INVALID, "camera focal length is zero");
+    if (depth && depth_stride && (depth_stride % 4 || depth_stride < (size_t)cols * 4)) FAIL(ORBX_E_INVALID, "bad depth stride");
+    cudaStream_t s = f->stream;
+    const CamDev cd = make_cam(*cam);
+    int rc;
+    // ComputeImageBounds (Frame.cc:1120-1176), cached like Frame::mbInitialComputations
+    if (!f->bounds_valid || std::memcmp(&f->bcam, cam, sizeof(orbx_camera)) || f->brows != rows || f->bcols != cols) {
+        if (cd.distorted) {
+            if ((rc = f->bounds4.ensure(4))) return rc;
+            k_frame_bounds<<<1, 32, 0, s>>>(cd, rows, cols, f->bounds4.p);
+            FLAUNCH_CHECK();
+            float b[4];
+            CU_TRY(cudaMemcpyAsync(b, f->bounds4.p, 16, cudaMemcpyDeviceToHost, s));
+            CU_TRY(cudaStreamSynchronize(s));
+            f->min_x = b[0]; f->max_x = b[1]; f->min_y = b[2]; f->max_y = b[3];
+        } else { f->min_x = 0.f; f->max_x = (float)cols; f->min_y = 0.f; f->max_y = (float)rows; }
+        f->gw_inv = (float)GRID_COLS / (f->max_x - f->min_x);             // Frame.cc:219-220 / :301-302
+        f->gh_inv = (float)GRID_ROWS / (f->max_y - f->min_y);
+        f->bcam = *cam; f->brows = rows; f->bcols = cols; f->bounds_valid = true;
+    }
+    const size_t nn = n ? n : 1;
+    if ((rc = f->keys_un.ensure(nn)) || (rc = f->u_right.ensure(nn)) || (rc = f->depth.ensure(nn)) || (rc = f->scale.ensure(ORBX_MAX_LEVELS)) ||
+        (rc = f->cell_start.ensure(GRID_CELLS + 1)) || (rc = f->entries.ensure(nn)) || (rc = f->sort_keys.ensure(nn))) return rc;
+    CU_TRY(cudaMemcpyAsync(f->scale.p, scale_host, (size_t)nlevels * 4, cudaMemcpyHostToDevice, s));
+    int mode = 0, pitch = 0; const float* d_depth = nullptr;
+    if (depth && n) {
+        if (depth_stride) {
+            if ((rc = f->depth_img.ensure((size_t)rows * cols))) return rc;
+            CU_TRY(cudaMemcpy2DAsync(f->depth_img.p, (size_t)cols * 4, depth, depth_stride, (size_t)cols * 4, rows, cudaMemcpyHostToDevice, s));
+            mode = 1; pitch = cols;
+        } else {
+            if ((rc = f->depth_img.ensure(nn))) return rc;
+            CU_TRY(cudaMemcpyAsync(f->depth_img.p, depth, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+            mode = 2;
+        }
+        d_depth = f->depth_img.p;
+    }
+    if (n) {
+        k_frame_undistort_stereo<<<(n + 127) / 128, 128, 0, s>>>(d_keys, n, cd, d_depth, mode, pitch, rows, cols, f->keys_un.p, f->u_right.p, f->depth.p);
+        FLAUNCH_CHECK();
+    }
+    k_grid_build<<<1, 1024, 0, s>>>(f->keys_un.p, n, f->min_x, f->min_y, f->gw_inv, f->gh_inv, f->sort_keys.p, f->entries.p, f->cell_start.p);
+    FLAUNCH_CHECK();
+    CU_TRY(cudaStreamSynchronize(s));
+    f->n = n; f->nlevels = nlevels;
+    FrameDev& d = f->dev;
+    d.n = n; d.keys = f->keys_un.p; d.desc = f->desc.p; d.u_right = f->u_right.p; d.min_x = f->min_x; d.min_y = f->min_y; d.max_x = f->max_x; d.max_y = f->max_y;
+    d.gw_inv = f->gw_inv; d.gh_inv = f->gh_inv; d.scale = f->scale.p; d.nlevels = nlevels; d.cell_start = f->cell_start.p; d.entries = f->entries.p;
+    return ORBX_OK;
+}
+
+int orbx_frame_assign(orbx_frame* f, orbx_extractor* h, const orbx_camera* cam, int img_rows, int img_cols, const float* depth, size_t depth_stride_bytes) {
+    if (!f || !h) FAIL(ORBX_E_INVALID, "null handle");
+    f->n = -1;
+    CU_TRY(cudaSetDevice(f->device));
+    OrbxLastResult r; int rc;
+    if ((rc = orbx_internal_last_result(h, &r))) return rc;
+    if (r.device != f->device) FAIL(ORBX_E_INVALID, "extractor and frame must live on the same device");
+    if (r.n >= (1 << 20)) FAIL(ORBX_E_INVALID, "too many keypoints");
+    CU_TRY(cudaStreamSynchronize(r.stream));                    // the extractor call has returned, so this is a no-op guard
+    if ((rc = f->desc.ensure((size_t)(r.n ? r.n : 1) * 32))) return rc;
+    if (r.n) CU_TRY(cudaMemcpyAsync(f->desc.p, r.desc, (size_t)r.n * 32, cudaMemcpyDeviceToDevice, f->stream));
+    return frame_build(f, reinterpret_cast<const KpM*>(r.keys), r.n, r.nlevels, r.scale, cam, img_rows, img_cols, depth, depth_stride_bytes);
+}
+
+int orbx_frame_assign_host(orbx_frame* f, const orbx_keypoint* keys, const uint8_t* descriptors, int n, int nlevels, const float* scale_factors,
+                           const orbx_camera* cam, int img_rows, int img_cols, const float* depth, size_t depth_stride_bytes) {
+    if (!f || n < 0 || n >= (1 << 20) || (n && (!keys || !descriptors))) FAIL(ORBX_E_INVALID, "bad arguments");
+    f->n = -1;
+    CU_TRY(cudaSetDevice(f->device));
+    int rc;
+    if ((rc = f->keys_in.ensure(n ? n : 1)) || (rc = f->desc.ensure((size_t)(n ? n : 1) * 32))) return rc;
+    if (n) {
+        CU_TRY(cudaMemcpyAsync(f->keys_in.p, keys, (size_t)n * 28, cudaMemcpyHostToDevice, f->stream));
+        CU_TRY(cudaMemcpyAsync(f->desc.p, descriptors, (size_t)n * 32, cudaMemcpyHostToDevice, f->stream));
+    }
+    return frame_build(f, f->keys_in.p, n, nlevels, scale_factors, cam, img_rows, img_cols, depth, depth_stride_bytes);
+}
+
+int orbx_frame_set_stereo(orbx_frame* f, const float* u_right, const float* depth) {
+    if (!f || f->n < 0) FAIL(ORBX_E_STATE, "device frame is empty (call orbx_frame_assign first)");
+    if (f->n && (!u_right || !depth)) FAIL(ORBX_E_INVALID, "null buffer");
+    if (f->n == 0) return ORBX_OK;
+    CU_TRY(cudaSetDevice(f->device));
+    CU_TRY(cudaMemcpyAsync(f->u_right.p, u_right, (size_t)f->n * 4, cudaMemcpyHostToDevice, f->stream));
+    CU_TRY(cudaMemcpyAsync(f->depth.p, depth, (size_t)f->n * 4, cudaMemcpyHostToDevice, f->stream));
+    CU_TRY(cudaStreamSynchronize(f->stream));
+    return ORBX_OK;
+}
+
+int orbx_frame_size(const orbx_frame* f) { return f ? f->n : -1; }
+
+int orbx_frame_read(orbx_frame* f, orbx_keypoint* keys_un, float* u_right, float* depth, float* bounds) {
+    if (!f || f->n < 0) FAIL(ORBX_E_STATE, "device frame is empty (call orbx_frame_assign first)");
+    CU_TRY(cudaSetDevice(f->device));
+    const size_t n = (size_t)f->n;
+    if (keys_un && n) CU_TRY(cudaMemcpyAsync(keys_un, f->keys_un.p, n * 28, cudaMemcpyDeviceToHost, f->stream));
+    if (u_right && n) CU_TRY(cudaMemcpyAsync(u_right, f->u_right.p, n * 4, cudaMemcpyDeviceToHost, f->stream));
+    if (depth && n) CU_TRY(cudaMemcpyAsync(depth, f->depth.p, n * 4, cudaMemcpyDeviceToHost, f->stream));
+    CU_TRY(cudaStreamSynchronize(f->stream));
+    if (bounds) { bounds[0] = f->min_x; bounds[1] = f->max_x; bounds[2] = f->min_y; bounds[3] = f->max_y; bounds[4] = f->gw_inv; bounds[5] = f->gh_inv; }
+    return ORBX_OK;
+}
+
+int orbx_frame_grid(orbx_frame* f, int* cell_start, int* entries) {
+    if (!f || f->n < 0) FAIL(ORBX_E_STATE, "device frame is empty (call orbx_frame_assign first)");
+    if (!cell_start || (f->n && !entries)) FAIL(ORBX_E_INVALID, "null buffer");
+    CU_TRY(cudaSetDevice(f->device));
+    CU_TRY(cudaMemcpyAsync(cell_start, f->cell_start.p, (size_t)(GRID_CELLS + 1) * 4, cudaMemcpyDeviceToHost, f->stream));
+    if (f->n) CU_TRY(cudaMemcpyAsync(entries, f->entries.p, (size_t)f->n * 4, cudaMemcpyDeviceToHost, f->stream));
+    CU_TRY(cudaStreamSynchronize(f->stream));
+    return ORBX_OK;
+}
+
+int orbx_frame_features_in_area(orbx_matcher* m, const orbx_frame* f, int nq, const float* xy, const float* r, const int* min_level, const int* max_level,
+                                int* offsets_out, int* indices, int cap, int* total_out) {
+    if (!m || !total_out || nq < 0 || nq >= (1 << 20) || (nq && (!xy || !r || !min_level || !max_level)) || !offsets_out || cap < 0 || (cap && !indices))
+        FAIL(ORBX_E_INVALID, "bad arguments");
+    int rc;
+    if ((rc = check_frame_arg(m, FrameArg{nullptr, f}))) return rc;
+    *total_out = 0; offsets_out[0] = 0;
+    if (nq == 0) return ORBX_OK;
+    CU_TRY(cudaSetDevice(m->device));
+    const size_t need = 8 * pad((size_t)(nq + 2) * 8) + 8192;
+    if ((rc = m->arena.reserve(need)) || (rc = m->uparena.reserve(need))) return rc;
+retry:
+    m->arena.reset(); m->uparena.reset();
+    float *dxy, *dr; int *dmin, *dmax;
+    if ((rc = up(m, xy, (size_t)nq * 2, dxy)) || (rc = up(m, r, (size_t)nq, dr)) || (rc = up(m, min_level, (size_t)nq, dmin)) || (rc = up(m, max_level, (size_t)nq, dmax))) return rc;
+    if ((rc = flush_uploads(m))) return rc;
+    QueryParams P; std::memset(&P, 0, sizeof(P));
+    P.mode = MODE_AREA; P.nq = nq; P.q_xy = dxy; P.q_r = dr; P.q_minlevel = dmin; P.q_maxlevel = dmax;
+    int *counts, *offsets; uint32_t* cand; uint2* pre;
+    if ((rc = window_search(m, P, f->dev, counts, offsets, cand, pre))) return rc;
+    CU_TRY(cudaMemcpyAsync(offsets_out, offsets, (size_t)(nq + 1) * 4, cudaMemcpyDeviceToHost, m->stream));
+    CU_TRY(cudaStreamSynchronize(m->stream));
+    const int total = offsets_out[nq];
+    if (cand_overflow(m, total)) goto retry;
+    *total_out = total;
+    if (total > cap) FAIL(ORBX_E_CAPACITY, "index buffer too small");
+    if (total) {
+        CU_TRY(cudaMemcpyAsync(indices, cand, (size_t)total * 4, cudaMemcpyDeviceToHost, m->stream));
+        CU_TRY(cudaStreamSynchronize(m->stream));
+        for (int i = 0; i < total; ++i) indices[i] &= 0xFFFFF;        // entries are dist << 20 | index with dist == 0
+    }
     return ORBX_OK;
 }
 

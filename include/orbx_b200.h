@@ -264,6 +264,74 @@ int orbx_match_bruteforce_device(orbx_matcher* m, const uint8_t* d_query, int n_
 int orbx_match_bruteforce_batch_device(orbx_matcher* m, int n_pairs, const uint8_t* d_query, int n_query, const uint8_t* d_train,
                                        int n_train, int* d_best_idx, int* d_best_dist, int* d_second_dist);
 
+/* ------------------------------------------------------------------------------------------------
+ * Device-resident Frame: the per-frame steps the reference runs between the
+ * extractor and the matchers, kept on the GPU so that keypoints / descriptors are not uploaded again
+ * by every matcher call and the 64x48 grid is built once per frame:
+ *   Frame::UndistortKeyPoints()          src/Frame.cc:1052-1117   (cv::undistortPoints, 5 iterations, double)
+ *   Frame::ComputeImageBounds()          src/Frame.cc:1120-1176   (cached per camera and image size)
+ *   Frame::ComputeStereoFromRGBD()       src/Frame.cc:1576-1614
+ *   Frame::AssignFeaturesToGrid()        src/Frame.cc:431-461, PosInGrid :1007-1030
+ *   Frame::GetFeaturesInArea()           src/Frame.cc:894-1003
+ * in the order Frame::CalDyna runs them (src/Frame.cc:636-645) and the stereo / mono constructors do.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct orbx_frame orbx_frame;
+
+/* mK (fx, fy, cx, cy), mDistCoef (k1, k2, p1, p2, k3; k1 == 0 means "already rectified", :1058) and mbf,
+ * as float like the reference's CV_32F matrices (src/Tracking.cc camera block). */
+typedef struct orbx_camera {
+    float fx, fy, cx, cy;
+    float k1, k2, p1, p2, k3;
+    float bf;
+} orbx_camera;
+
+int  orbx_frame_create(int device, orbx_frame** out);
+void orbx_frame_destroy(orbx_frame* f);
+
+/* Builds the frame from the result the extractor handle still holds on the device (its last orbx_extract or
+ * orbx_describe call: mvKeys / mDescriptors), without a host round trip:
+ *   N = mvKeys.size(); UndistortKeyPoints(); ComputeStereoFromRGBD(imDepth); AssignFeaturesToGrid().
+ * depth: host pointer, CV_32F.  depth_stride_bytes > 0: the whole image (img_rows x img_cols, row stride in
+ * bytes), read as imDepth.at<float>(v, u) with the keypoint's float coordinates truncated (:1595);
+ * depth_stride_bytes == 0: depth[i] is that value already gathered by the caller for keypoint i;
+ * depth == NULL: monocular / stereo frame, mvuRight = mvDepth = -1 until orbx_frame_set_stereo().
+ * Image bounds follow ComputeImageBounds for (cam, img_rows, img_cols) and are cached in the handle. */
+int orbx_frame_assign(orbx_frame* f, orbx_extractor* h, const orbx_camera* cam, int img_rows, int img_cols,
+                      const float* depth, size_t depth_stride_bytes);
+/* The same from host arrays (frames whose keypoints did not come from an extractor handle of this process). */
+int orbx_frame_assign_host(orbx_frame* f, const orbx_keypoint* keys, const uint8_t* descriptors, int n,
+                           int nlevels, const float* scale_factors, const orbx_camera* cam, int img_rows, int img_cols,
+                           const float* depth, size_t depth_stride_bytes);
+/* mvuRight / mvDepth computed elsewhere (orbx_compute_stereo_matches): host arrays of N floats. */
+int orbx_frame_set_stereo(orbx_frame* f, const float* u_right, const float* depth);
+
+int orbx_frame_size(const orbx_frame* f);           /* Frame::N */
+/* Host copies; any pointer may be NULL.  keys_un[N] (mvKeysUn), u_right[N], depth[N],
+ * bounds[6] = mnMinX, mnMaxX, mnMinY, mnMaxY, mfGridElementWidthInv, mfGridElementHeightInv. */
+int orbx_frame_read(orbx_frame* f, orbx_keypoint* keys_un, float* u_right, float* depth, float* bounds);
+/* mGrid: cell (x, y) holds entries[cell_start[x * 48 + y] .. cell_start[x * 48 + y + 1]) in push_back order;
+ * cell_start has 64 * 48 + 1 ints, entries N ints (keypoints outside the grid are in no cell, :1020-1024). */
+int orbx_frame_grid(orbx_frame* f, int* cell_start, int* entries);
+/* vector<size_t> Frame::GetFeaturesInArea(x, y, r, minLevel, maxLevel) for nq windows at once (src/Frame.cc:894-1003):
+ * window q returns counts[q] indices, in the reference's order, at indices[offsets[q]..); offsets has nq + 1 ints.
+ * *total = offsets[nq]; if it exceeds cap nothing is written to indices and ORBX_E_CAPACITY is returned. */
+int orbx_frame_features_in_area(orbx_matcher* m, const orbx_frame* f, int nq, const float* xy, const float* r,
+                                const int* min_level, const int* max_level, int* offsets, int* indices, int cap, int* total);
+
+/* The three windowed matchers on device-resident frames: same semantics as the orbx_frame_view calls above,
+ * minus the per-call upload of keypoints / descriptors / mvuRight and the per-call grid build. */
+int orbx_search_for_initialization_frames(orbx_matcher* m, const orbx_frame* F1, const orbx_frame* F2,
+                                          float* prev_matched_xy, int* matches12, int window_size, int* nmatches);
+int orbx_search_by_projection_frame_dev(orbx_matcher* m, const orbx_frame* cur, int n_last,
+                                        const float* proj_uv, const float* proj_invz, const int* last_octave,
+                                        const float* last_angle, const uint8_t* mp_desc, const uint8_t* valid,
+                                        const uint8_t* mp_observed, const uint8_t* cur_occupied, float th, int forward, int backward, float mbf,
+                                        int* cur_match, int* nmatches);
+int orbx_search_by_projection_points_dev(orbx_matcher* m, const orbx_frame* F, int n_points,
+                                         const float* track_uv, const float* track_ur, const int* track_level,
+                                         const float* track_view_cos, const uint8_t* mp_desc, const uint8_t* mp_observed,
+                                         const uint8_t* f_occupied, float th, int* f_match, int* nmatches);
+
 #ifdef __cplusplus
 }
 #endif

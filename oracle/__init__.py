@@ -323,3 +323,40 @@ class Matcher:
             self.lib.port_compute_stereo_matches(nl, wl.ctypes.data, hl.ctypes.data, ptl, wr.ctypes.data, hr.ctypes.data, ptr_, sc.ctypes.data, isc.ctypes.data,
                                                  kl.ctypes.data, dl.ctypes.data, len(kl), kr.ctypes.data, dr.ctypes.data, len(kr), float(mb), float(mbf), ur.ctypes.data, dep.ctypes.data)
         return ur, dep
+
+
+# ------------------------------------------------------------------------------------------------
+# Frame steps between extractor and matchers (UndistortKeyPoints / ComputeImageBounds / ComputeStereoFromRGBD /
+# AssignFeaturesToGrid; /root/reference/src/Frame.cc:1052-1176, 1576-1614, 431-461)
+# ------------------------------------------------------------------------------------------------
+def _cam9(cam):
+    """cam = (fx, fy, cx, cy, k1, k2, p1, p2[, k3]) -> (float32[9], ndist)."""
+    c = np.zeros(9, np.float32); c[:len(cam)] = np.asarray(cam, np.float32)
+    return c, len(cam) - 4
+
+
+def undistort_points(kind, pts, cam):
+    """cv::undistortPoints(pts, pts, K, D, Mat(), K) of the oracle (kind = 'ref': the shim's, 'port': the restatement)."""
+    lib = _lib(kind)
+    pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 2); out = np.zeros_like(pts)
+    c, nd = _cam9(cam)
+    f = getattr(lib, kind + "_undistort_points"); f.restype = None; f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    f(pts.ctypes.data, len(pts), c.ctypes.data, nd, out.ctypes.data)
+    return out
+
+
+def frame_build(kind, keys, cam, bf, rows, cols, depth_img=None):
+    """Returns dict(keys_un, u_right, depth, bounds[6], cell_start[3073], entries[n]) as the reference's Frame holds them
+    after UndistortKeyPoints -> ComputeStereoFromRGBD -> AssignFeaturesToGrid."""
+    lib = _lib(kind)
+    keys = np.ascontiguousarray(keys, KP_DTYPE); n = len(keys)
+    c, nd = _cam9(cam)
+    dimg = None if depth_img is None else np.ascontiguousarray(depth_img, np.float32)
+    assert dimg is None or dimg.shape == (rows, cols)
+    ku = np.zeros(max(n, 1), KP_DTYPE); ur = np.zeros(max(n, 1), np.float32); dep = np.zeros(max(n, 1), np.float32)
+    b = np.zeros(6, np.float32); cs = np.zeros(64 * 48 + 1, np.int32); en = np.zeros(max(n, 1), np.int32)
+    f = getattr(lib, kind + "_frame_build"); f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_void_p] + [C.c_void_p] * 6
+    f(keys.ctypes.data, n, c.ctypes.data, nd, float(bf), rows, cols, None if dimg is None else dimg.ctypes.data,
+      ku.ctypes.data, ur.ctypes.data, dep.ctypes.data, b.ctypes.data, cs.ctypes.data, en.ctypes.data)
+    return dict(keys_un=ku[:n], u_right=ur[:n], depth=dep[:n], bounds=b, cell_start=cs, entries=en[:cs[-1]])

@@ -16,6 +16,7 @@
 //   cv::getStructuringElement / dilate / erode   /root/reference/src/ORBextractor.cc:1699-1704
 //   cv::norm(NORM_L1), Mat::convertTo, small float Mat algebra   /root/reference/src/Frame.cc:1401-1445,
 //                                                                 /root/reference/src/ORBmatcher.cc:1579-1606
+//   cv::undistortPoints, Mat::reshape   /root/reference/src/Frame.cc:1087-1093, 1151-1153
 //
 // Two users: (1) oracle/shim/* exposes this as <opencv2/...> so the reference's own
 // ORBextractor.cc compiles UNMODIFIED into oracle/_ref/; (2) oracle/port/* (our plain restatement).
@@ -244,6 +245,8 @@ public:
         for (int y = 0; y < rows; ++y) for (int x = 0; x < cols; ++x) out.setd(y, x, getd(y, x));
         dst = out;
     }
+    // reshape(cn): the shim has no channels; an N x 2 CV_32F matrix doubles as N two-channel points (undistortPoints below)
+    Mat reshape(int /*cn*/, int /*rows*/ = 0) const { return *this; }
     // transpose (float/double)
     Mat t() const {
         Mat m(cols, rows, mtype);
@@ -608,6 +611,64 @@ static inline CVL_NOFMA float fastAtan2(float y, float x) {
     if (x < 0) a = 180.f - a;
     if (y < 0) a = 360.f - a;
     return a;
+}
+
+// =============================================================================================
+// Primitive 7: undistortPoints(src, dst, K, distCoeffs, R = noArray(), P = noArray())
+// OpenCV's iterative inverse of the Brown-Conrady model (calib3d undistort, cvUndistortPointsInternal), restated from its
+// published algorithm and pinned against cv2 4.13 (tests/golden/frame_cv2.npz):  everything in double; x = (u - cx) * (1/fx);
+// default termination criteria = 5 iterations, no epsilon test;  icdist = (1 + ((k6 r2 + k5) r2 + k4) r2) / (1 + ((k3 r2 + k2) r2 + k1) r2);
+// a negative icdist restarts from the normalised point and stops;  dX = 2 p1 x y + p2 (r2 + 2 x x) + s1 r2 + s2 r2 r2;  x = (x0 - dX) icdist;
+// re-projection by RR = P * R (R empty = identity):  xx = RR00 x + RR01 y + RR02, ww = 1 / (RR20 x + RR21 y + RR22);  result cast to float.
+// src / dst: N x 2 CV_32F (one point per row, see Mat::reshape); distCoeffs: 4 or 5 (k1 k2 p1 p2 [k3]) CV_32F or CV_64F, any orientation.
+// =============================================================================================
+static inline CVL_NOFMA void undistortPoints(InputArray _src, OutputArray _dst, InputArray _K, InputArray _D,
+                                             InputArray _R = noArray(), InputArray _P = noArray()) {
+    Mat src = _src.getMat(), Km = _K.getMat();
+    assert(src.depth() == CV_32F && src.cols == 2 && Km.rows == 3 && Km.cols == 3);
+    double k[14] = {0};
+    if (!_D.empty()) {
+        Mat D = _D.getMat();
+        const int nd = D.rows * D.cols;
+        assert(nd <= 14);
+        for (int i = 0; i < nd; ++i) k[i] = D.rows == 1 ? D.getd(0, i) : D.getd(i, 0);
+    }
+    const double fx = Km.getd(0, 0), fy = Km.getd(1, 1), cx = Km.getd(0, 2), cy = Km.getd(1, 2);
+    const double ifx = 1. / fx, ify = 1. / fy;
+    double RR[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    if (!_R.empty()) { Mat R = _R.getMat(); for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) RR[i][j] = R.getd(i, j); }
+    if (!_P.empty()) {
+        Mat P = _P.getMat();
+        double PP[3][3], T[3][3];
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) PP[i][j] = P.getd(i, j);
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { volatile double acc = 0; for (int q = 0; q < 3; ++q) acc = acc + PP[i][q] * RR[q][j]; T[i][j] = acc; }
+        std::memcpy(RR, T, sizeof(RR));
+    }
+    const int n = src.rows;
+    Mat out(n, 2, CV_32F);
+    for (int i = 0; i < n; ++i) {
+        volatile double x, y, x0, y0;
+        const double u = src.at<float>(i, 0), v = src.at<float>(i, 1);
+        x = (u - cx) * ifx; y = (v - cy) * ify;
+        if (!_D.empty()) {
+            x0 = x; y0 = y;
+            for (int j = 0; j < 5; ++j) {
+                volatile double r2 = x * x + y * y;
+                volatile double icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+                if (icdist < 0) { x = (u - cx) * ifx; y = (v - cy) * ify; break; }
+                volatile double deltaX = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r2 * r2;
+                volatile double deltaY = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2;
+                x = (x0 - deltaX) * icdist;
+                y = (y0 - deltaY) * icdist;
+            }
+        }
+        volatile double xx = RR[0][0] * x + RR[0][1] * y + RR[0][2];
+        volatile double yy = RR[1][0] * x + RR[1][1] * y + RR[1][2];
+        volatile double ww = 1. / (RR[2][0] * x + RR[2][1] * y + RR[2][2]);
+        out.at<float>(i, 0) = (float)(xx * ww);
+        out.at<float>(i, 1) = (float)(yy * ww);
+    }
+    if (_dst.m) *_dst.m = out;
 }
 
 // =============================================================================================

@@ -3,6 +3,7 @@
 //     (/root/reference/src/ORBmatcher.cc:1913-1933, 515-643, 1569-1728, 70-175, 1866-1908)
 //   Frame::AssignFeaturesToGrid / PosInGrid / GetFeaturesInArea / ComputeStereoMatches
 //     (/root/reference/src/Frame.cc:431-461, 1007-1030, 894-1003, 1179-1573)
+//   Frame::UndistortKeyPoints / ComputeImageBounds / ComputeStereoFromRGBD   (/root/reference/src/Frame.cc:1052-1176, 1576-1614)
 // Pinned against oracle/_ref (the reference's own bodies) by tests/test_oracle_matcher.py and by the golden
 // vectors in tests/golden/ref_match.npz.  Same argument layout as the product's C ABI (include/orbx_b200.h).
 #include "../cvlite/cvlite.hpp"
@@ -327,9 +328,77 @@ static void ComputeStereoMatches(const Pyr& PL, const Pyr& PR, const float* scal
     }
 }
 
+// ---- the frame steps between extractor and matchers ----
+struct Camera { float fx, fy, cx, cy, k1, k2, p1, p2, k3, bf; };
+
+// cv::undistortPoints(pts, pts, mK, mDistCoef, Mat(), mK) for one point, written out for the 5-coefficient model
+// (cvlite.hpp "Primitive 7" is the general restatement; both are pinned against cv2 goldens)
+static CVL_NOFMA void undistort_one(const Camera& c, float uf, float vf, float& ox, float& oy) {
+    const double fx = c.fx, fy = c.fy, cx = c.cx, cy = c.cy, k1 = c.k1, k2 = c.k2, p1 = c.p1, p2 = c.p2, k3 = c.k3;
+    const double u = uf, v = vf;
+    volatile double x = (u - cx) * (1. / fx), y = (v - cy) * (1. / fy);
+    const double x0 = x, y0 = y;
+    for (int it = 0; it < 5; ++it) {
+        volatile double r2 = x * x + y * y;
+        volatile double icdist = 1. / (1 + ((k3 * r2 + k2) * r2 + k1) * r2);      // numerator 1 + ((0 r2 + 0) r2 + 0) r2 == 1 exactly
+        if (icdist < 0) { x = x0; y = y0; break; }
+        volatile double dX = 2 * p1 * x * y + p2 * (r2 + 2 * x * x);              // the zero thin-prism terms add +0.0
+        volatile double dY = p1 * (r2 + 2 * y * y) + 2 * p2 * x * y;
+        x = (x0 - dX) * icdist; y = (y0 - dY) * icdist;
+    }
+    volatile double xx = fx * x + cx, yy = fy * y + cy;                            // + 0 * y, * (1 / 1): exact no-ops
+    ox = (float)xx; oy = (float)yy;
+}
+
+// Frame.cc:1120-1176 + :301-302
+static void ImageBounds(const Camera& c, int rows, int cols, float b[6]) {
+    if (c.k1 != 0.0f) {
+        float x[4], y[4];
+        undistort_one(c, 0.f, 0.f, x[0], y[0]); undistort_one(c, (float)cols, 0.f, x[1], y[1]);
+        undistort_one(c, 0.f, (float)rows, x[2], y[2]); undistort_one(c, (float)cols, (float)rows, x[3], y[3]);
+        b[0] = std::min(x[0], x[2]); b[1] = std::max(x[1], x[3]); b[2] = std::min(y[0], y[1]); b[3] = std::max(y[2], y[3]);
+    } else { b[0] = 0.f; b[1] = (float)cols; b[2] = 0.f; b[3] = (float)rows; }
+    b[4] = (float)GRID_COLS / (b[1] - b[0]); b[5] = (float)GRID_ROWS / (b[3] - b[2]);
+}
+
+// UndistortKeyPoints (:1052-1117), ComputeStereoFromRGBD (:1576-1614), AssignFeaturesToGrid (:431-461)
+static void FrameBuild(const KeyPoint* keys, int n, const Camera& c, int rows, int cols, const float* depth_img,
+                       KeyPoint* keys_un, float* u_right, float* depth_out, float* bounds, int* cell_start, int* entries) {
+    ImageBounds(c, rows, cols, bounds);
+    for (int i = 0; i < n; ++i) {
+        keys_un[i] = keys[i];
+        if (c.k1 != 0.0f) undistort_one(c, keys[i].pt.x, keys[i].pt.y, keys_un[i].pt.x, keys_un[i].pt.y);
+        u_right[i] = -1.f; depth_out[i] = -1.f;
+        if (depth_img) {
+            const float d = depth_img[(size_t)(int)keys[i].pt.y * cols + (int)keys[i].pt.x];      // at<float>(v, u): truncation
+            if (d > 0) { depth_out[i] = d; volatile float q = c.bf / d; u_right[i] = keys_un[i].pt.x - q; }
+        }
+    }
+    FrameView v; v.n = n; v.keys_un = keys_un; v.descriptors = nullptr; v.u_right = u_right;
+    v.min_x = bounds[0]; v.max_x = bounds[1]; v.min_y = bounds[2]; v.max_y = bounds[3]; v.gw_inv = bounds[4]; v.gh_inv = bounds[5];
+    v.nlevels = 0; v.scale_factors = nullptr;
+    Grid g(&v);
+    int o = 0;
+    for (int x = 0; x < GRID_COLS; ++x) for (int y = 0; y < GRID_ROWS; ++y) {
+        cell_start[x * GRID_ROWS + y] = o;
+        for (size_t q = 0; q < g.cell[x][y].size(); ++q) entries[o++] = g.cell[x][y][q];
+    }
+    cell_start[GRID_COLS * GRID_ROWS] = o;
+}
+
 }  // namespace port
 
 extern "C" {
+int port_frame_build(const cv::KeyPoint* keys, int n, const float* cam9, int ndist, float bf, int rows, int cols, const float* depth_img,
+                     cv::KeyPoint* keys_un, float* u_right, float* depth_out, float* bounds, int* cell_start, int* entries) {
+    port::Camera c = {cam9[0], cam9[1], cam9[2], cam9[3], cam9[4], cam9[5], cam9[6], cam9[7], ndist > 4 ? cam9[8] : 0.f, bf};
+    port::FrameBuild(keys, n, c, rows, cols, depth_img, keys_un, u_right, depth_out, bounds, cell_start, entries);
+    return 0;
+}
+void port_undistort_points(const float* pts, int n, const float* cam9, int ndist, float* out) {
+    port::Camera c = {cam9[0], cam9[1], cam9[2], cam9[3], cam9[4], cam9[5], cam9[6], cam9[7], ndist > 4 ? cam9[8] : 0.f, 0.f};
+    for (int i = 0; i < n; ++i) port::undistort_one(c, pts[2 * i], pts[2 * i + 1], out[2 * i], out[2 * i + 1]);
+}
 using port::FrameView; using port::KeyPoint;
 
 void port_descriptor_distance(const unsigned char* a, const unsigned char* b, int n, int* out) { for (int i = 0; i < n; ++i) out[i] = port::DescriptorDistance(a + (size_t)i * 32, b + (size_t)i * 32); }

@@ -6,7 +6,8 @@ output -- nothing is copied into the repository).  The functions are located by 
   src/ORBmatcher.cc : TH_HIGH/TH_LOW/HISTO_LENGTH + ctor, SearchByProjection(Frame&, vector<MapPoint*>&, th),
                       RadiusByViewingCos, SearchForInitialization, SearchByProjection(Frame&, const Frame&, th, bMono),
                       ComputeThreeMaxima, DescriptorDistance
-  src/Frame.cc      : AssignFeaturesToGrid, GetFeaturesInArea, PosInGrid, ComputeStereoMatches
+  src/Frame.cc      : AssignFeaturesToGrid, GetFeaturesInArea, PosInGrid, ComputeStereoMatches,
+                      UndistortKeyPoints, ComputeImageBounds, ComputeStereoFromRGBD
 
 usage: gen_match_bodies.py <reference root> <out dir>
 """
@@ -62,6 +63,9 @@ f = extract("src/Frame.cc", [
     "vector<size_t> Frame::GetFeaturesInArea(const float &x, const float  &y, const float  &r, const int minLevel, const int maxLevel) const",
     "bool Frame::PosInGrid(",
     "void Frame::ComputeStereoMatches()",
+    "void Frame::UndistortKeyPoints()",
+    "void Frame::ComputeImageBounds(const cv::Mat &imLeft)",
+    "void Frame::ComputeStereoFromRGBD(const cv::Mat &imDepth)",
 ])
 os.makedirs(out, exist_ok=True)
 # the first ORBmatcher chunk (constants) ends at the ctor's closing brace because the ctor follows immediately

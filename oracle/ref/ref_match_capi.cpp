@@ -2,7 +2,7 @@
 //
 // Runs the reference's OWN matcher code: the bodies of ORBmatcher::{SearchByProjection x2, SearchForInitialization,
 // ComputeThreeMaxima, DescriptorDistance, RadiusByViewingCos} and Frame::{AssignFeaturesToGrid, GetFeaturesInArea,
-// PosInGrid, ComputeStereoMatches} are taken verbatim from /root/reference/src/{ORBmatcher,Frame}.cc at build time
+// PosInGrid, ComputeStereoMatches, UndistortKeyPoints, ComputeImageBounds, ComputeStereoFromRGBD} are taken verbatim from /root/reference/src/{ORBmatcher,Frame}.cc at build time
 // (oracle/ref/gen_match_bodies.py -> oracle/_ref/gen/ref_match_bodies.inc) and compiled against the minimal
 // Frame / MapPoint / ORBmatcher declarations below, which carry exactly the members those bodies touch
 // (/root/reference/include/Frame.h, MapPoint.h, ORBmatcher.h).  The whole object graph of the reference
@@ -45,6 +45,10 @@ public:
     std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const int minLevel = -1, const int maxLevel = -1) const;
     bool PosInGrid(const cv::KeyPoint& kp, int& posX, int& posY);
     void ComputeStereoMatches();
+    void UndistortKeyPoints();
+    void ComputeImageBounds(const cv::Mat& imLeft);
+    void ComputeStereoFromRGBD(const cv::Mat& imDepth);
+    cv::Mat mK, mDistCoef;
     ORBextractor *mpORBextractorLeft, *mpORBextractorRight;
     static float fx, fy, cx, cy;
     float mbf, mb;
@@ -204,6 +208,57 @@ int ref_search_by_projection_points(float nnratio, int checkOri, const FrameView
         }
     }
     return nm;
+}
+
+// The frame steps between extractor and matchers, in the order Frame::CalDyna runs them (Frame.cc:636-645), preceded by the
+// constructor's one-time ComputeImageBounds + grid constants (:296-303):
+//   UndistortKeyPoints (:1052) -> ComputeStereoFromRGBD (:1576, when depth != NULL) -> AssignFeaturesToGrid (:431).
+// cam9 = fx fy cx cy k1 k2 p1 p2 k3 (mK / mDistCoef are CV_32F as in Tracking.cc); ndist = 4 or 5 coefficients.
+// Outputs: keys_un[n], u_right[n], depth_out[n], bounds[6] = minX maxX minY maxY gridWInv gridHInv,
+// cell_start[64*48+1] / entries[n] = mGrid flattened cell-major (x * 48 + y), push_back order inside a cell.
+int ref_frame_build(const cv::KeyPoint* keys, int n, const float* cam9, int ndist, float bf, int rows, int cols, const float* depth_img,
+                    cv::KeyPoint* keys_un, float* u_right, float* depth_out, float* bounds, int* cell_start, int* entries) {
+    ArenaScope scope;
+    {
+        Frame F;
+        F.N = n; F.mvKeys.assign(keys, keys + n); F.mbf = bf;
+        F.mK = cv::Mat::eye(3, 3, CV_32F);
+        F.mK.at<float>(0, 0) = cam9[0]; F.mK.at<float>(1, 1) = cam9[1]; F.mK.at<float>(0, 2) = cam9[2]; F.mK.at<float>(1, 2) = cam9[3];
+        F.mDistCoef = cv::Mat(ndist, 1, CV_32F);
+        for (int i = 0; i < ndist; ++i) F.mDistCoef.at<float>(i) = cam9[4 + i];
+        cv::Mat gray(rows, cols, CV_8UC1);                                  // ComputeImageBounds only reads its size
+        F.ComputeImageBounds(gray);
+        Frame::mfGridElementWidthInv = static_cast<float>(FRAME_GRID_COLS) / static_cast<float>(Frame::mnMaxX - Frame::mnMinX);     // Frame.cc:301-302
+        Frame::mfGridElementHeightInv = static_cast<float>(FRAME_GRID_ROWS) / static_cast<float>(Frame::mnMaxY - Frame::mnMinY);
+        F.UndistortKeyPoints();
+        if (depth_img) {
+            cv::Mat imD(rows, cols, CV_32F, (void*)depth_img);
+            F.ComputeStereoFromRGBD(imD);
+        } else { F.mvuRight.assign(n, -1.f); F.mvDepth.assign(n, -1.f); }
+        F.AssignFeaturesToGrid();
+        for (int i = 0; i < n; ++i) { keys_un[i] = F.mvKeysUn[i]; u_right[i] = F.mvuRight[i]; depth_out[i] = F.mvDepth[i]; }
+        bounds[0] = Frame::mnMinX; bounds[1] = Frame::mnMaxX; bounds[2] = Frame::mnMinY; bounds[3] = Frame::mnMaxY;
+        bounds[4] = Frame::mfGridElementWidthInv; bounds[5] = Frame::mfGridElementHeightInv;
+        int o = 0;
+        for (int x = 0; x < FRAME_GRID_COLS; ++x) for (int y = 0; y < FRAME_GRID_ROWS; ++y) {
+            cell_start[x * FRAME_GRID_ROWS + y] = o;
+            for (size_t q = 0; q < F.mGrid[x][y].size(); ++q) entries[o++] = (int)F.mGrid[x][y][q];
+        }
+        cell_start[FRAME_GRID_COLS * FRAME_GRID_ROWS] = o;
+    }
+    return 0;
+}
+
+// cv::undistortPoints(pts, pts, K, D, Mat(), K) of the shim alone (pinned against cv2 goldens)
+void ref_undistort_points(const float* pts, int n, const float* cam9, int ndist, float* out) {
+    cv::Mat K = cv::Mat::eye(3, 3, CV_32F);
+    K.at<float>(0, 0) = cam9[0]; K.at<float>(1, 1) = cam9[1]; K.at<float>(0, 2) = cam9[2]; K.at<float>(1, 2) = cam9[3];
+    cv::Mat D(ndist, 1, CV_32F);
+    for (int i = 0; i < ndist; ++i) D.at<float>(i) = cam9[4 + i];
+    cv::Mat m(n, 2, CV_32F);
+    std::memcpy(m.data, pts, (size_t)n * 8);
+    cv::undistortPoints(m, m, K, D, cv::Mat(), K);
+    std::memcpy(out, m.data, (size_t)n * 8);
 }
 
 // Frame::ComputeStereoMatches   Frame.cc:1179.  left / right: handles from ref_extractor_create whose last
