@@ -106,7 +106,13 @@ def lib():
         L.orbx_frame_assign.argtypes = [vp, vp, vp, ci, ci, vp, sz]
         L.orbx_frame_assign_host.argtypes = [vp, vp, vp, ci, ci, vp, vp, ci, ci, vp, sz]
         L.orbx_frame_set_stereo.argtypes = [vp, vp, vp]
+        L.orbx_frame_take.argtypes = [vp, vp]
+        L.orbx_frame_take_host.argtypes = [vp, vp, vp, ci, ci, vp]
+        L.orbx_frame_undistort_keypoints.argtypes = [vp, vp, vp]
+        L.orbx_frame_compute_stereo_from_rgbd.argtypes = [vp, cf, vp, sz, ci, ci, vp, vp]
+        L.orbx_frame_assign_features_to_grid.argtypes = [vp, vp, vp, vp]
         L.orbx_frame_size.argtypes = [vp]
+        L.orbx_frame_taken.argtypes = [vp]
         L.orbx_frame_read.argtypes = [vp, vp, vp, vp, vp]
         L.orbx_frame_grid.argtypes = [vp, vp, vp]
         L.orbx_frame_features_in_area.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp, vp, ci, C.POINTER(ci)]

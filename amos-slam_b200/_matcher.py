@@ -105,9 +105,40 @@ class Frame:
         self.keys = range(self.N)
         return self
 
+    # ---- the same steps one by one, as the reference's Frame constructors call them ----
+    def take(self, extractor):
+        self._check(self._lib.orbx_frame_take(self._h, extractor._h)); self.keys = []
+        return self
+
+    def take_host(self, keys, descriptors, scale_factors):
+        from . import KP_DTYPE
+        k = np.ascontiguousarray(keys, KP_DTYPE); ds = _u8(descriptors).reshape(-1, 32); sf = np.ascontiguousarray(scale_factors, np.float32)
+        self._check(self._lib.orbx_frame_take_host(self._h, _p(k), _p(ds), len(k), len(sf), _p(sf))); self.keys = []
+        self._n_taken = len(k)
+        return self
+
+    def UndistortKeyPoints(self, cam, n):
+        from . import KP_DTYPE
+        ku = np.zeros(max(n, 1), KP_DTYPE)
+        self._check(self._lib.orbx_frame_undistort_keypoints(self._h, C.byref(cam), _p(ku)))
+        return ku[:n]
+
+    def ComputeStereoFromRGBD(self, bf, depth, rows, cols, n):
+        d, dp, stride = self._depth_args(depth, rows, cols)
+        ur = np.zeros(max(n, 1), np.float32); de = np.zeros(max(n, 1), np.float32)
+        self._check(self._lib.orbx_frame_compute_stereo_from_rgbd(self._h, float(bf), dp, stride, int(rows), int(cols), _p(ur), _p(de)))
+        return ur[:n], de[:n]
+
+    def AssignFeaturesToGrid(self, bounds6, n):
+        b = np.ascontiguousarray(bounds6, np.float32); cs = np.zeros(64 * 48 + 1, np.int32); en = np.zeros(max(n, 1), np.int32)
+        self._check(self._lib.orbx_frame_assign_features_to_grid(self._h, _p(b), _p(cs), _p(en)))
+        self.keys = range(self.N)
+        return cs, en[:cs[-1]]
+
     def set_stereo(self, u_right, depth):
         ur = np.ascontiguousarray(u_right, np.float32); dp = np.ascontiguousarray(depth, np.float32)
-        assert len(ur) == self.N and len(dp) == self.N
+        n = self._lib.orbx_frame_taken(self._h)            # allowed between UndistortKeyPoints and AssignFeaturesToGrid (stereo constructor order)
+        assert len(ur) == n and len(dp) == n
         self._check(self._lib.orbx_frame_set_stereo(self._h, _p(ur), _p(dp)))
 
     @property

@@ -68,6 +68,22 @@ k_frame_undistort_stereo(const KpM* __restrict__ keys, int n, CamDev cam, const 
     u_right[i] = ur; depth_out[i] = dd;
 }
 
+// ComputeStereoFromRGBD alone (mvKeysUn already computed): depth looked up at the RAW keypoint, uRight from the undistorted x
+__global__ void __launch_bounds__(128)
+k_frame_rgbd(const KpM* __restrict__ keys, const KpM* __restrict__ keys_un, int n, float bf, const float* __restrict__ depth, int depth_mode, int depth_pitch,
+             int rows, int cols, float* __restrict__ u_right, float* __restrict__ depth_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float d;
+    if (depth_mode == 1) {
+        const int r = (int)keys[i].y, c = (int)keys[i].x;
+        d = (r >= 0 && r < rows && c >= 0 && c < cols) ? depth[(size_t)r * depth_pitch + c] : 0.f;
+    } else d = depth[i];
+    float ur = -1.f, dd = -1.f;
+    if (d > 0.f) { dd = d; ur = __fsub_rn(keys_un[i].x, __fdiv_rn(bf, d)); }
+    u_right[i] = ur; depth_out[i] = dd;
+}
+
 // ComputeImageBounds with distortion: the four image corners through undistortPoints (:1136-1163)
 __global__ void k_frame_bounds(CamDev cam, int rows, int cols, float* __restrict__ out /* minX, maxX, minY, maxY */) {
     if (threadIdx.x != 0) return;

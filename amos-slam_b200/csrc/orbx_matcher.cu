@@ -131,14 +131,19 @@ template <typename T> struct FBuf {
 };
 struct orbx_frame {
     int device; cudaStream_t stream = nullptr; long long launches = 0;
-    int n = -1, nlevels = 0;
+    int n = -1, nlevels = 0;       // n >= 0 once the grid is built (the frame is then usable by the matchers)
+    int n_pending = 0, state = 0;  // keypoints taken / undistorted / gridded (FRAME_HAS_*)
     FBuf<KpM> keys_in, keys_un; FBuf<uint8_t> desc; FBuf<float> u_right, depth, scale, depth_img, bounds4;
     FBuf<int> cell_start, entries; FBuf<uint32_t> sort_keys;
     FrameDev dev;
     // ComputeImageBounds cache (the reference computes them once, Frame::mbInitialComputations)
     bool bounds_valid = false; orbx_camera bcam; int brows = 0, bcols = 0;
-    float min_x = 0, max_x = 0, min_y = 0, max_y = 0, gw_inv = 0, gh_inv = 0;
+    float cmin_x = 0, cmax_x = 0, cmin_y = 0, cmax_y = 0;
+    float min_x = 0, max_x = 0, min_y = 0, max_y = 0, gw_inv = 0, gh_inv = 0;          // bounds the current grid was built with
 };
+#define FRAME_HAS_KEYS 1
+#define FRAME_HAS_UN 2
+#define FRAME_HAS_GRID 4
 
 // a matcher argument that is either a host frame view (uploaded + gridded per call) or a device-resident frame
 struct FrameArg {
@@ -484,102 +489,200 @@ static CamDev make_cam(const orbx_camera& c) {
     d.distorted = (c.k1 != 0.0f); d.bf = c.bf;
     return d;
 }
-
-// the part common to both assign calls: keys (device, n records) -> mvKeysUn, mvuRight / mvDepth, grid
-static int frame_build(orbx_frame* f, const KpM* d_keys, int n, int nlevels, const float* scale_host, const orbx_camera* cam,
-                       int rows, int cols, const float* depth, size_t depth_stride) {
-    if (!cam || rows <= 0 || cols <= 0 || nlevels <= 0 || nlevels > ORBX_MAX_LEVELS || !scale_host) FAIL(ORBX_E_INVALID, "bad frame arguments");
+static int check_cam(const orbx_camera* cam) {
+    if (!cam) FAIL(ORBX_E_INVALID, "null camera");
     if (!(cam->fx != 0.f) || !(cam->fy != 0.f)) FAIL(ORBX_E_INVALID, "camera focal length is zero");
-    if (depth && depth_stride && (depth_stride % 4 || depth_stride < (size_t)cols * 4)) FAIL(ORBX_E_INVALID, "bad depth stride");
-    cudaStream_t s = f->stream;
-    const CamDev cd = make_cam(*cam);
-    int rc;
-    // ComputeImageBounds (Frame.cc:1120-1176), cached like Frame::mbInitialComputations
-    if (!f->bounds_valid || std::memcmp(&f->bcam, cam, sizeof(orbx_camera)) || f->brows != rows || f->bcols != cols) {
-        if (cd.distorted) {
-            if ((rc = f->bounds4.ensure(4))) return rc;
-            k_frame_bounds<<<1, 32, 0, s>>>(cd, rows, cols, f->bounds4.p);
-            FLAUNCH_CHECK();
-            float b[4];
-            CU_TRY(cudaMemcpyAsync(b, f->bounds4.p, 16, cudaMemcpyDeviceToHost, s));
-            CU_TRY(cudaStreamSynchronize(s));
-            f->min_x = b[0]; f->max_x = b[1]; f->min_y = b[2]; f->max_y = b[3];
-        } else { f->min_x = 0.f; f->max_x = (float)cols; f->min_y = 0.f; f->max_y = (float)rows; }
-        f->gw_inv = (float)GRID_COLS / (f->max_x - f->min_x);             // Frame.cc:219-220 / :301-302
-        f->gh_inv = (float)GRID_ROWS / (f->max_y - f->min_y);
-        f->bcam = *cam; f->brows = rows; f->bcols = cols; f->bounds_valid = true;
-    }
-    const size_t nn = n ? n : 1;
-    if ((rc = f->keys_un.ensure(nn)) || (rc = f->u_right.ensure(nn)) || (rc = f->depth.ensure(nn)) || (rc = f->scale.ensure(ORBX_MAX_LEVELS)) ||
-        (rc = f->cell_start.ensure(GRID_CELLS + 1)) || (rc = f->entries.ensure(nn)) || (rc = f->sort_keys.ensure(nn))) return rc;
-    CU_TRY(cudaMemcpyAsync(f->scale.p, scale_host, (size_t)nlevels * 4, cudaMemcpyHostToDevice, s));
-    int mode = 0, pitch = 0; const float* d_depth = nullptr;
-    if (depth && n) {
-        if (depth_stride) {
-            if ((rc = f->depth_img.ensure((size_t)rows * cols))) return rc;
-            CU_TRY(cudaMemcpy2DAsync(f->depth_img.p, (size_t)cols * 4, depth, depth_stride, (size_t)cols * 4, rows, cudaMemcpyHostToDevice, s));
-            mode = 1; pitch = cols;
-        } else {
-            if ((rc = f->depth_img.ensure(nn))) return rc;
-            CU_TRY(cudaMemcpyAsync(f->depth_img.p, depth, (size_t)n * 4, cudaMemcpyHostToDevice, s));
-            mode = 2;
-        }
-        d_depth = f->depth_img.p;
-    }
-    if (n) {
-        k_frame_undistort_stereo<<<(n + 127) / 128, 128, 0, s>>>(d_keys, n, cd, d_depth, mode, pitch, rows, cols, f->keys_un.p, f->u_right.p, f->depth.p);
-        FLAUNCH_CHECK();
-    }
-    k_grid_build<<<1, 1024, 0, s>>>(f->keys_un.p, n, f->min_x, f->min_y, f->gw_inv, f->gh_inv, f->sort_keys.p, f->entries.p, f->cell_start.p);
-    FLAUNCH_CHECK();
-    CU_TRY(cudaStreamSynchronize(s));
-    f->n = n; f->nlevels = nlevels;
-    FrameDev& d = f->dev;
-    d.n = n; d.keys = f->keys_un.p; d.desc = f->desc.p; d.u_right = f->u_right.p; d.min_x = f->min_x; d.min_y = f->min_y; d.max_x = f->max_x; d.max_y = f->max_y;
-    d.gw_inv = f->gw_inv; d.gh_inv = f->gh_inv; d.scale = f->scale.p; d.nlevels = nlevels; d.cell_start = f->cell_start.p; d.entries = f->entries.p;
     return ORBX_OK;
 }
 
-int orbx_frame_assign(orbx_frame* f, orbx_extractor* h, const orbx_camera* cam, int img_rows, int img_cols, const float* depth, size_t depth_stride_bytes) {
+// Every step below is asynchronous on the frame's stream; the public calls that hand results to the host (or make the frame
+// visible to the matchers) synchronise.
+
+// mvKeys / mDescriptors: device source (an extractor's result) or host arrays
+static int frame_take(orbx_frame* f, const KpM* d_keys, const uint8_t* d_desc, const orbx_keypoint* h_keys, const uint8_t* h_desc, int n, int nlevels, const float* scale_host) {
+    if (nlevels <= 0 || nlevels > ORBX_MAX_LEVELS || !scale_host) FAIL(ORBX_E_INVALID, "bad pyramid description");
+    cudaStream_t s = f->stream;
+    f->state = 0; f->n = -1;
+    const size_t nn = n ? n : 1;
+    int rc;
+    if ((rc = f->keys_in.ensure(nn)) || (rc = f->keys_un.ensure(nn)) || (rc = f->desc.ensure(nn * 32)) || (rc = f->u_right.ensure(nn)) || (rc = f->depth.ensure(nn)) ||
+        (rc = f->scale.ensure(ORBX_MAX_LEVELS)) || (rc = f->cell_start.ensure(GRID_CELLS + 1)) || (rc = f->entries.ensure(nn)) || (rc = f->sort_keys.ensure(nn))) return rc;
+    if (n) {
+        const cudaMemcpyKind kind = d_keys ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        CU_TRY(cudaMemcpyAsync(f->keys_in.p, d_keys ? (const void*)d_keys : (const void*)h_keys, (size_t)n * 28, kind, s));
+        CU_TRY(cudaMemcpyAsync(f->desc.p, d_keys ? (const void*)d_desc : (const void*)h_desc, (size_t)n * 32, kind, s));
+    }
+    CU_TRY(cudaMemcpyAsync(f->scale.p, scale_host, (size_t)nlevels * 4, cudaMemcpyHostToDevice, s));
+    f->n_pending = n; f->nlevels = nlevels; f->state = FRAME_HAS_KEYS;
+    return ORBX_OK;
+}
+
+// depth argument of the RGB-D step -> device pointer, mode, pitch
+static int frame_stage_depth(orbx_frame* f, const float* depth, size_t depth_stride, int rows, int cols, const float*& d_depth, int& mode, int& pitch) {
+    d_depth = nullptr; mode = 0; pitch = 0;
+    const int n = f->n_pending;
+    if (!depth || !n) return ORBX_OK;
+    int rc;
+    if (depth_stride) {
+        if (rows <= 0 || cols <= 0 || depth_stride % 4 || depth_stride < (size_t)cols * 4) FAIL(ORBX_E_INVALID, "bad depth image geometry");
+        if ((rc = f->depth_img.ensure((size_t)rows * cols))) return rc;
+        CU_TRY(cudaMemcpy2DAsync(f->depth_img.p, (size_t)cols * 4, depth, depth_stride, (size_t)cols * 4, rows, cudaMemcpyHostToDevice, f->stream));
+        mode = 1; pitch = cols;
+    } else {
+        if ((rc = f->depth_img.ensure(n))) return rc;
+        CU_TRY(cudaMemcpyAsync(f->depth_img.p, depth, (size_t)n * 4, cudaMemcpyHostToDevice, f->stream));
+        mode = 2;
+    }
+    d_depth = f->depth_img.p;
+    return ORBX_OK;
+}
+
+// UndistortKeyPoints (+ ComputeStereoFromRGBD when with_stereo): one kernel
+static int frame_undistort(orbx_frame* f, const CamDev& cd, bool with_stereo, const float* d_depth, int mode, int pitch, int rows, int cols) {
+    if (!(f->state & FRAME_HAS_KEYS)) FAIL(ORBX_E_STATE, "device frame holds no keypoints (orbx_frame_take first)");
+    const int n = f->n_pending;
+    if (n) {
+        k_frame_undistort_stereo<<<(n + 127) / 128, 128, 0, f->stream>>>(f->keys_in.p, n, cd, d_depth, with_stereo ? mode : 0, pitch, rows, cols, f->keys_un.p, f->u_right.p, f->depth.p);
+        FLAUNCH_CHECK();
+    }
+    f->state |= FRAME_HAS_UN;
+    return ORBX_OK;
+}
+
+// ComputeStereoFromRGBD on its own (mvKeysUn already on the device)
+static int frame_rgbd(orbx_frame* f, float bf, const float* d_depth, int mode, int pitch, int rows, int cols) {
+    if (!(f->state & FRAME_HAS_UN)) FAIL(ORBX_E_STATE, "ComputeStereoFromRGBD needs the undistorted keypoints (orbx_frame_undistort_keypoints first)");
+    const int n = f->n_pending;
+    if (n) {
+        k_frame_rgbd<<<(n + 127) / 128, 128, 0, f->stream>>>(f->keys_in.p, f->keys_un.p, n, bf, d_depth, mode, pitch, rows, cols, f->u_right.p, f->depth.p);
+        FLAUNCH_CHECK();
+    }
+    return ORBX_OK;
+}
+
+// AssignFeaturesToGrid with the given image bounds; publishes the frame to the matchers
+static int frame_grid(orbx_frame* f, float min_x, float max_x, float min_y, float max_y, float gw_inv, float gh_inv) {
+    if (!(f->state & FRAME_HAS_UN)) FAIL(ORBX_E_STATE, "AssignFeaturesToGrid needs the undistorted keypoints (orbx_frame_undistort_keypoints first)");
+    const int n = f->n_pending;
+    f->min_x = min_x; f->max_x = max_x; f->min_y = min_y; f->max_y = max_y; f->gw_inv = gw_inv; f->gh_inv = gh_inv;
+    k_grid_build<<<1, 1024, 0, f->stream>>>(f->keys_un.p, n, min_x, min_y, gw_inv, gh_inv, f->sort_keys.p, f->entries.p, f->cell_start.p);
+    FLAUNCH_CHECK();
+    CU_TRY(cudaStreamSynchronize(f->stream));
+    f->n = n; f->state |= FRAME_HAS_GRID;
+    FrameDev& d = f->dev;
+    d.n = n; d.keys = f->keys_un.p; d.desc = f->desc.p; d.u_right = f->u_right.p; d.min_x = min_x; d.min_y = min_y; d.max_x = max_x; d.max_y = max_y;
+    d.gw_inv = gw_inv; d.gh_inv = gh_inv; d.scale = f->scale.p; d.nlevels = f->nlevels; d.cell_start = f->cell_start.p; d.entries = f->entries.p;
+    return ORBX_OK;
+}
+
+// ComputeImageBounds (Frame.cc:1120-1176) + grid constants (:301-302), cached like Frame::mbInitialComputations
+static int frame_bounds(orbx_frame* f, const orbx_camera* cam, const CamDev& cd, int rows, int cols) {
+    if (rows <= 0 || cols <= 0) FAIL(ORBX_E_INVALID, "bad image size");
+    if (f->bounds_valid && !std::memcmp(&f->bcam, cam, sizeof(orbx_camera)) && f->brows == rows && f->bcols == cols) return ORBX_OK;
+    if (cd.distorted) {
+        int rc;
+        if ((rc = f->bounds4.ensure(4))) return rc;
+        k_frame_bounds<<<1, 32, 0, f->stream>>>(cd, rows, cols, f->bounds4.p);
+        FLAUNCH_CHECK();
+        float b[4];
+        CU_TRY(cudaMemcpyAsync(b, f->bounds4.p, 16, cudaMemcpyDeviceToHost, f->stream));
+        CU_TRY(cudaStreamSynchronize(f->stream));
+        f->cmin_x = b[0]; f->cmax_x = b[1]; f->cmin_y = b[2]; f->cmax_y = b[3];
+    } else { f->cmin_x = 0.f; f->cmax_x = (float)cols; f->cmin_y = 0.f; f->cmax_y = (float)rows; }
+    f->bcam = *cam; f->brows = rows; f->bcols = cols; f->bounds_valid = true;
+    return ORBX_OK;
+}
+
+static int frame_build(orbx_frame* f, const orbx_camera* cam, int rows, int cols, const float* depth, size_t depth_stride) {
+    int rc;
+    if ((rc = check_cam(cam))) return rc;
+    const CamDev cd = make_cam(*cam);
+    if ((rc = frame_bounds(f, cam, cd, rows, cols))) return rc;
+    const float* d_depth; int mode, pitch;
+    if ((rc = frame_stage_depth(f, depth, depth_stride, rows, cols, d_depth, mode, pitch))) return rc;
+    if ((rc = frame_undistort(f, cd, true, d_depth, mode, pitch, rows, cols))) return rc;
+    return frame_grid(f, f->cmin_x, f->cmax_x, f->cmin_y, f->cmax_y, (float)GRID_COLS / (f->cmax_x - f->cmin_x), (float)GRID_ROWS / (f->cmax_y - f->cmin_y));
+}
+
+static int take_from_extractor(orbx_frame* f, orbx_extractor* h) {
     if (!f || !h) FAIL(ORBX_E_INVALID, "null handle");
-    f->n = -1;
+    f->n = -1; f->state = 0;
     CU_TRY(cudaSetDevice(f->device));
     OrbxLastResult r; int rc;
     if ((rc = orbx_internal_last_result(h, &r))) return rc;
     if (r.device != f->device) FAIL(ORBX_E_INVALID, "extractor and frame must live on the same device");
     if (r.n >= (1 << 20)) FAIL(ORBX_E_INVALID, "too many keypoints");
     CU_TRY(cudaStreamSynchronize(r.stream));                    // the extractor call has returned, so this is a no-op guard
-    if ((rc = f->desc.ensure((size_t)(r.n ? r.n : 1) * 32))) return rc;
-    if (r.n) CU_TRY(cudaMemcpyAsync(f->desc.p, r.desc, (size_t)r.n * 32, cudaMemcpyDeviceToDevice, f->stream));
-    return frame_build(f, reinterpret_cast<const KpM*>(r.keys), r.n, r.nlevels, r.scale, cam, img_rows, img_cols, depth, depth_stride_bytes);
+    return frame_take(f, reinterpret_cast<const KpM*>(r.keys), r.desc, nullptr, nullptr, r.n, r.nlevels, r.scale);
+}
+static int take_from_host(orbx_frame* f, const orbx_keypoint* keys, const uint8_t* descriptors, int n, int nlevels, const float* scale_factors) {
+    if (!f || n < 0 || n >= (1 << 20) || (n && (!keys || !descriptors))) FAIL(ORBX_E_INVALID, "bad arguments");
+    f->n = -1; f->state = 0;
+    CU_TRY(cudaSetDevice(f->device));
+    return frame_take(f, nullptr, nullptr, keys, descriptors, n, nlevels, scale_factors);
 }
 
+int orbx_frame_assign(orbx_frame* f, orbx_extractor* h, const orbx_camera* cam, int img_rows, int img_cols, const float* depth, size_t depth_stride_bytes) {
+    int rc = take_from_extractor(f, h);
+    return rc ? rc : frame_build(f, cam, img_rows, img_cols, depth, depth_stride_bytes);
+}
 int orbx_frame_assign_host(orbx_frame* f, const orbx_keypoint* keys, const uint8_t* descriptors, int n, int nlevels, const float* scale_factors,
                            const orbx_camera* cam, int img_rows, int img_cols, const float* depth, size_t depth_stride_bytes) {
-    if (!f || n < 0 || n >= (1 << 20) || (n && (!keys || !descriptors))) FAIL(ORBX_E_INVALID, "bad arguments");
-    f->n = -1;
+    int rc = take_from_host(f, keys, descriptors, n, nlevels, scale_factors);
+    return rc ? rc : frame_build(f, cam, img_rows, img_cols, depth, depth_stride_bytes);
+}
+
+// ---- the same steps one by one, as the reference's Frame constructors call them ----
+int orbx_frame_take(orbx_frame* f, orbx_extractor* h) { return take_from_extractor(f, h); }
+int orbx_frame_take_host(orbx_frame* f, const orbx_keypoint* keys, const uint8_t* descriptors, int n, int nlevels, const float* scale_factors) {
+    return take_from_host(f, keys, descriptors, n, nlevels, scale_factors);
+}
+int orbx_frame_undistort_keypoints(orbx_frame* f, const orbx_camera* cam, orbx_keypoint* keys_un_out) {
+    if (!f) FAIL(ORBX_E_INVALID, "null handle");
+    int rc;
+    if ((rc = check_cam(cam))) return rc;
+    CU_TRY(cudaSetDevice(f->device));
+    if ((rc = frame_undistort(f, make_cam(*cam), false, nullptr, 0, 0, 0, 0))) return rc;
+    if (keys_un_out && f->n_pending) CU_TRY(cudaMemcpyAsync(keys_un_out, f->keys_un.p, (size_t)f->n_pending * 28, cudaMemcpyDeviceToHost, f->stream));
+    CU_TRY(cudaStreamSynchronize(f->stream));
+    return ORBX_OK;
+}
+int orbx_frame_compute_stereo_from_rgbd(orbx_frame* f, float bf, const float* depth, size_t depth_stride_bytes, int img_rows, int img_cols, float* u_right_out, float* depth_out) {
+    if (!f || !depth) FAIL(ORBX_E_INVALID, "null argument");
+    if (!(f->state & FRAME_HAS_UN)) FAIL(ORBX_E_STATE, "ComputeStereoFromRGBD needs the undistorted keypoints (orbx_frame_undistort_keypoints first)");
+    CU_TRY(cudaSetDevice(f->device));
+    int rc; const float* d_depth; int mode, pitch;
+    if ((rc = frame_stage_depth(f, depth, depth_stride_bytes, img_rows, img_cols, d_depth, mode, pitch))) return rc;
+    if ((rc = frame_rgbd(f, bf, d_depth, mode, pitch, img_rows, img_cols))) return rc;
+    const size_t n = (size_t)f->n_pending;
+    if (u_right_out && n) CU_TRY(cudaMemcpyAsync(u_right_out, f->u_right.p, n * 4, cudaMemcpyDeviceToHost, f->stream));
+    if (depth_out && n) CU_TRY(cudaMemcpyAsync(depth_out, f->depth.p, n * 4, cudaMemcpyDeviceToHost, f->stream));
+    CU_TRY(cudaStreamSynchronize(f->stream));
+    return ORBX_OK;
+}
+int orbx_frame_assign_features_to_grid(orbx_frame* f, const float* bounds6, int* cell_start_out, int* entries_out) {
+    if (!f || !bounds6) FAIL(ORBX_E_INVALID, "null argument");
     CU_TRY(cudaSetDevice(f->device));
     int rc;
-    if ((rc = f->keys_in.ensure(n ? n : 1)) || (rc = f->desc.ensure((size_t)(n ? n : 1) * 32))) return rc;
-    if (n) {
-        CU_TRY(cudaMemcpyAsync(f->keys_in.p, keys, (size_t)n * 28, cudaMemcpyHostToDevice, f->stream));
-        CU_TRY(cudaMemcpyAsync(f->desc.p, descriptors, (size_t)n * 32, cudaMemcpyHostToDevice, f->stream));
-    }
-    return frame_build(f, f->keys_in.p, n, nlevels, scale_factors, cam, img_rows, img_cols, depth, depth_stride_bytes);
+    if ((rc = frame_grid(f, bounds6[0], bounds6[1], bounds6[2], bounds6[3], bounds6[4], bounds6[5]))) return rc;
+    if (cell_start_out) return orbx_frame_grid(f, cell_start_out, entries_out);
+    return ORBX_OK;
 }
 
 int orbx_frame_set_stereo(orbx_frame* f, const float* u_right, const float* depth) {
-    if (!f || f->n < 0) FAIL(ORBX_E_STATE, "device frame is empty (call orbx_frame_assign first)");
-    if (f->n && (!u_right || !depth)) FAIL(ORBX_E_INVALID, "null buffer");
-    if (f->n == 0) return ORBX_OK;
+    if (!f || !(f->state & FRAME_HAS_UN)) FAIL(ORBX_E_STATE, "device frame is empty (call orbx_frame_assign first)");
+    const int n = f->n_pending;
+    if (n && (!u_right || !depth)) FAIL(ORBX_E_INVALID, "null buffer");
+    if (n == 0) return ORBX_OK;
     CU_TRY(cudaSetDevice(f->device));
-    CU_TRY(cudaMemcpyAsync(f->u_right.p, u_right, (size_t)f->n * 4, cudaMemcpyHostToDevice, f->stream));
-    CU_TRY(cudaMemcpyAsync(f->depth.p, depth, (size_t)f->n * 4, cudaMemcpyHostToDevice, f->stream));
+    CU_TRY(cudaMemcpyAsync(f->u_right.p, u_right, (size_t)n * 4, cudaMemcpyHostToDevice, f->stream));
+    CU_TRY(cudaMemcpyAsync(f->depth.p, depth, (size_t)n * 4, cudaMemcpyHostToDevice, f->stream));
     CU_TRY(cudaStreamSynchronize(f->stream));
     return ORBX_OK;
 }
 
 int orbx_frame_size(const orbx_frame* f) { return f ? f->n : -1; }
+int orbx_frame_taken(const orbx_frame* f) { return (f && (f->state & FRAME_HAS_KEYS)) ? f->n_pending : -1; }
 
 int orbx_frame_read(orbx_frame* f, orbx_keypoint* keys_un, float* u_right, float* depth, float* bounds) {
     if (!f || f->n < 0) FAIL(ORBX_E_STATE, "device frame is empty (call orbx_frame_assign first)");

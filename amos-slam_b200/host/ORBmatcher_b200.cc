@@ -73,6 +73,16 @@ struct FrameFlat {
     }
 };
 
+// the device-resident frame built by Frame_b200.cc, when the Frame carries one that matches its current keypoints
+#ifdef ORBX_FRAME_HAS_DEVICE
+const orbx_frame* device_of(const Frame& F) {
+    const orbx_frame* f = F.mpDeviceFrame.get();
+    return (f && orbx_frame_size(f) == F.N) ? f : nullptr;
+}
+#else
+const orbx_frame* device_of(const Frame&) { return nullptr; }
+#endif
+
 // mvpMapPoints[j] already holds a map point with Observations() > 0   (ORBmatcher.cc:124-126, 1658-1660)
 std::vector<unsigned char> occupied_flags(const Frame& F) {
     std::vector<unsigned char> occ(F.N, 0);
@@ -85,9 +95,16 @@ std::vector<unsigned char> occupied_flags(const Frame& F) {
 int ORBmatcher::SearchForInitialization(Frame &F1, Frame &F2, std::vector<cv::Point2f> &vbPrevMatched, std::vector<int> &vnMatches12, int windowSize)
 {
     vnMatches12.assign(F1.mvKeysUn.size(), -1);
-    FrameFlat a(F1), b(F2);
     int nmatches = 0;
     static_assert(sizeof(cv::Point2f) == 8, "cv::Point2f must be two floats");
+    const orbx_frame *d1 = device_of(F1), *d2 = device_of(F2);
+    if (d1 && d2) {
+        check(orbx_search_for_initialization_frames(t_matchers.get(mfNNratio, mbCheckOrientation), d1, d2,
+                                                    vbPrevMatched.empty() ? nullptr : reinterpret_cast<float*>(vbPrevMatched.data()),
+                                                    vnMatches12.data(), windowSize, &nmatches), "orbx_search_for_initialization_frames");
+        return nmatches;
+    }
+    FrameFlat a(F1), b(F2);
     check(orbx_search_for_initialization(t_matchers.get(mfNNratio, mbCheckOrientation), &a.v, &b.v,
                                          vbPrevMatched.empty() ? nullptr : reinterpret_cast<float*>(vbPrevMatched.data()),
                                          vnMatches12.data(), windowSize, &nmatches), "orbx_search_for_initialization");
@@ -113,10 +130,15 @@ int ORBmatcher::SearchByProjection(Frame &F, const std::vector<MapPoint*> &vpMap
     }
     std::vector<unsigned char> occ = occupied_flags(F);
     std::vector<int> fmatch(F.N, -1);
-    FrameFlat f(F);
     int nmatches = 0;
-    check(orbx_search_by_projection_points(t_matchers.get(mfNNratio, mbCheckOrientation), &f.v, n, uv.data(), ur.data(), lvl.data(), vc.data(),
-                                           desc.data(), obs.data(), occ.data(), th, fmatch.data(), &nmatches), "orbx_search_by_projection_points");
+    if (const orbx_frame* df = device_of(F))
+        check(orbx_search_by_projection_points_dev(t_matchers.get(mfNNratio, mbCheckOrientation), df, n, uv.data(), ur.data(), lvl.data(), vc.data(),
+                                                   desc.data(), obs.data(), occ.data(), th, fmatch.data(), &nmatches), "orbx_search_by_projection_points_dev");
+    else {
+        FrameFlat f(F);
+        check(orbx_search_by_projection_points(t_matchers.get(mfNNratio, mbCheckOrientation), &f.v, n, uv.data(), ur.data(), lvl.data(), vc.data(),
+                                               desc.data(), obs.data(), occ.data(), th, fmatch.data(), &nmatches), "orbx_search_by_projection_points");
+    }
     for (int j = 0; j < F.N; ++j) if (fmatch[j] >= 0) F.mvpMapPoints[j] = pts[fmatch[j]];       // :168
     return nmatches;
 }
@@ -156,11 +178,17 @@ int ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, 
     }
     std::vector<unsigned char> occ = occupied_flags(CurrentFrame);
     std::vector<int> cmatch(CurrentFrame.N, -1);
-    FrameFlat c(CurrentFrame);
     int nmatches = 0;
-    check(orbx_search_by_projection_frame(t_matchers.get(mfNNratio, mbCheckOrientation), &c.v, n, uv.data(), invz.data(), octave.data(), angle.data(),
-                                          desc.data(), valid.data(), obs.data(), occ.data(), th, bForward ? 1 : 0, bBackward ? 1 : 0, CurrentFrame.mbf,
-                                          cmatch.data(), &nmatches), "orbx_search_by_projection_frame");
+    if (const orbx_frame* dc = device_of(CurrentFrame))
+        check(orbx_search_by_projection_frame_dev(t_matchers.get(mfNNratio, mbCheckOrientation), dc, n, uv.data(), invz.data(), octave.data(), angle.data(),
+                                                  desc.data(), valid.data(), obs.data(), occ.data(), th, bForward ? 1 : 0, bBackward ? 1 : 0, CurrentFrame.mbf,
+                                                  cmatch.data(), &nmatches), "orbx_search_by_projection_frame_dev");
+    else {
+        FrameFlat c(CurrentFrame);
+        check(orbx_search_by_projection_frame(t_matchers.get(mfNNratio, mbCheckOrientation), &c.v, n, uv.data(), invz.data(), octave.data(), angle.data(),
+                                              desc.data(), valid.data(), obs.data(), occ.data(), th, bForward ? 1 : 0, bBackward ? 1 : 0, CurrentFrame.mbf,
+                                              cmatch.data(), &nmatches), "orbx_search_by_projection_frame");
+    }
     for (int j = 0; j < CurrentFrame.N; ++j) {
         if (cmatch[j] >= 0) CurrentFrame.mvpMapPoints[j] = LastFrame.mvpMapPoints[cmatch[j]];   // :1685
         else if (cmatch[j] == -2) CurrentFrame.mvpMapPoints[j] = static_cast<MapPoint*>(NULL); // :1719

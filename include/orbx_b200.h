@@ -302,10 +302,26 @@ int orbx_frame_assign(orbx_frame* f, orbx_extractor* h, const orbx_camera* cam, 
 int orbx_frame_assign_host(orbx_frame* f, const orbx_keypoint* keys, const uint8_t* descriptors, int n,
                            int nlevels, const float* scale_factors, const orbx_camera* cam, int img_rows, int img_cols,
                            const float* depth, size_t depth_stride_bytes);
+/* The same steps one by one, in whatever order the reference's constructors run them (stereo: :187-240, mono: :378-428,
+ * Amos RGB-D: :636-645), for a drop-in that keeps Frame's call sites untouched.  Each call returns after its result is
+ * complete; optional *_out pointers receive the host copy the reference's members need.
+ *   take                      N = mvKeys.size(): mvKeys / mDescriptors from the extractor's device result or from host arrays
+ *   undistort_keypoints       Frame::UndistortKeyPoints()                 -> keys_un_out[N]  (mvKeysUn)
+ *   compute_stereo_from_rgbd  Frame::ComputeStereoFromRGBD(imDepth)       -> u_right_out[N], depth_out[N]; depth as in orbx_frame_assign
+ *   assign_features_to_grid   Frame::AssignFeaturesToGrid() with bounds6 = Frame::mnMinX, mnMaxX, mnMinY, mnMaxY,
+ *                             mfGridElementWidthInv, mfGridElementHeightInv -> cell_start_out / entries_out as orbx_frame_grid;
+ *                             only after this call do the matchers accept the frame. */
+int orbx_frame_take(orbx_frame* f, orbx_extractor* h);
+int orbx_frame_take_host(orbx_frame* f, const orbx_keypoint* keys, const uint8_t* descriptors, int n, int nlevels, const float* scale_factors);
+int orbx_frame_undistort_keypoints(orbx_frame* f, const orbx_camera* cam, orbx_keypoint* keys_un_out);
+int orbx_frame_compute_stereo_from_rgbd(orbx_frame* f, float bf, const float* depth, size_t depth_stride_bytes, int img_rows, int img_cols,
+                                        float* u_right_out, float* depth_out);
+int orbx_frame_assign_features_to_grid(orbx_frame* f, const float* bounds6, int* cell_start_out, int* entries_out);
 /* mvuRight / mvDepth computed elsewhere (orbx_compute_stereo_matches): host arrays of N floats. */
 int orbx_frame_set_stereo(orbx_frame* f, const float* u_right, const float* depth);
 
-int orbx_frame_size(const orbx_frame* f);           /* Frame::N */
+int orbx_frame_size(const orbx_frame* f);           /* Frame::N once the grid is built (the matchers accept the frame), else -1 */
+int orbx_frame_taken(const orbx_frame* f);          /* keypoints held after orbx_frame_take*, whatever the later steps; -1 = none */
 /* Host copies; any pointer may be NULL.  keys_un[N] (mvKeysUn), u_right[N], depth[N],
  * bounds[6] = mnMinX, mnMaxX, mnMinY, mnMaxY, mfGridElementWidthInv, mfGridElementHeightInv. */
 int orbx_frame_read(orbx_frame* f, orbx_keypoint* keys_un, float* u_right, float* depth, float* bounds);

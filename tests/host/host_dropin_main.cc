@@ -4,7 +4,7 @@
 // cv:: types come from the OpenCV-free shim (oracle/shim) -- test infrastructure, not product.
 //
 // usage: host_dropin <in.bin> <out.bin>
-//   in.bin : int32 w,h ; u8 A[h*w] ; u8 B[h*w] ; int32 sw,sh ; u8 L[sh*sw] ; u8 R[sh*sw]
+//   in.bin : int32 w,h ; u8 A[h*w] ; u8 B[h*w] ; int32 sw,sh ; u8 L[sh*sw] ; u8 R[sh*sw] ; f32 cam[10] (fx fy cx cy k1 k2 p1 p2 k3 bf) ; f32 bounds[6]
 #include "ORBextractor.h"
 #include "ORBmatcher.h"
 #include <cstdio>
@@ -108,6 +108,60 @@ int main(int argc, char** argv) {
     S.N = (int)S.mvKeys.size(); S.mb = 0.f; S.mbf = 386.1448f;
     S.ComputeStereoMatches();
     put_i(S.N); put(S.mvuRight.data(), (size_t)S.N * 4); put(S.mvDepth.data(), (size_t)S.N * 4);
+    // ---- device-resident Frame: UndistortKeyPoints / ComputeStereoFromRGBD / AssignFeaturesToGrid as Frame::CalDyna calls them
+    //      (Frame.cc:636-645), then the matchers on frames that carry a device frame
+    float cam[10], bounds[6];
+    if (fread(cam, 4, 10, f) != 10 || fread(bounds, 4, 6, f) != 6) return 2;
+    {
+        Frame D; D.mpORBextractorLeft = &ext;
+        ext(A, cv::Mat(), D.mvKeys, D.mDescriptors);                      // ExtractORBDesp: the result stays on the device
+        D.N = (int)D.mvKeys.size(); D.mbf = cam[9]; D.mvScaleFactors = ext.GetScaleFactors();
+        D.mK = cv::Mat::eye(3, 3, CV_32F);
+        D.mK.at<float>(0, 0) = cam[0]; D.mK.at<float>(1, 1) = cam[1]; D.mK.at<float>(0, 2) = cam[2]; D.mK.at<float>(1, 2) = cam[3];
+        D.mDistCoef = cv::Mat(5, 1, CV_32F);
+        for (int i = 0; i < 5; ++i) D.mDistCoef.at<float>(i) = cam[4 + i];
+        Frame::mnMinX = bounds[0]; Frame::mnMaxX = bounds[1]; Frame::mnMinY = bounds[2]; Frame::mnMaxY = bounds[3];   // ComputeImageBounds stays the reference's
+        Frame::mfGridElementWidthInv = bounds[4]; Frame::mfGridElementHeightInv = bounds[5];
+        cv::Mat imD(h, w, CV_32F);
+        for (int y = 0; y < h; ++y) for (int x = 0; x < w; ++x) imD.at<float>(y, x) = (float)((x * 7 + y * 13) % 97) / 16.0f - 0.5f;
+        D.UndistortKeyPoints();
+        D.ComputeStereoFromRGBD(imD);
+        D.AssignFeaturesToGrid();
+        put_i(D.N);
+        put(D.mvKeysUn.data(), (size_t)D.N * sizeof(cv::KeyPoint)); put(D.mvuRight.data(), (size_t)D.N * 4); put(D.mvDepth.data(), (size_t)D.N * 4);
+        for (int x = 0; x < 64; ++x) for (int y = 0; y < 48; ++y) {
+            put_i((int)D.mGrid[x][y].size());
+            for (size_t q = 0; q < D.mGrid[x][y].size(); ++q) put_i((int)D.mGrid[x][y][q]);
+        }
+        // a frame whose keypoints did NOT just come from the extractor (N differs from its device result): host upload path
+        Frame H = D; H.mpDeviceFrame.reset(); H.mpORBextractorLeft = &ext;
+        H.N = D.N - 7; H.mvKeys.resize(H.N); H.mDescriptors = D.mDescriptors.rowRange(0, H.N);
+        H.UndistortKeyPoints();
+        put_i(H.N); put(H.mvKeysUn.data(), (size_t)H.N * sizeof(cv::KeyPoint));
+    }
+    {   // rectified camera (k1 == 0), mono constructor order (Frame.cc:367-428): the matchers must give what they gave on host frames
+        Frame D1, D2;
+        Frame* Fs[2] = {&D1, &D2}; cv::Mat* imgs[2] = {&A, &B};
+        for (int q = 0; q < 2; ++q) {
+            Frame& D = *Fs[q];
+            D.mpORBextractorLeft = &ext;
+            ext(*imgs[q], cv::Mat(), D.mvKeys, D.mDescriptors);
+            fill_frame(D, ext, D.mvKeys, D.mDescriptors, w, h);
+            D.mK = cv::Mat::eye(3, 3, CV_32F); D.mK.at<float>(0, 0) = cam[0]; D.mK.at<float>(1, 1) = cam[1]; D.mK.at<float>(0, 2) = cam[2]; D.mK.at<float>(1, 2) = cam[3];
+            D.mDistCoef = cv::Mat::zeros(4, 1, CV_32F);
+            D.UndistortKeyPoints();
+            D.mvuRight = std::vector<float>(D.N, -1); D.mvDepth = std::vector<float>(D.N, -1);         // :381-382
+            D.AssignFeaturesToGrid();
+        }
+        std::vector<cv::Point2f> prev2(D1.mvKeysUn.size());
+        for (size_t i = 0; i < prev2.size(); ++i) prev2[i] = D1.mvKeysUn[i].pt;
+        std::vector<int> m12b;
+        int nm2 = ORBmatcher(0.9, true).SearchForInitialization(D1, D2, prev2, m12b, 100);
+        put_i(nm2); put_i((int)m12b.size()); if (!m12b.empty()) put(m12b.data(), m12b.size() * 4);
+        nm2 = ORBmatcher(0.8, true).SearchByProjection(D2, pts, 3.f);
+        put_i(nm2);
+        for (int j = 0; j < D2.N; ++j) put_i(D2.mvpMapPoints[j] ? (int)(D2.mvpMapPoints[j] - store.data()) : -1);
+    }
     fclose(g_out); fclose(f);
     printf("host drop-in ok: %zu / %zu keypoints, %d stereo keypoints\n", ka.size(), kb.size(), S.N);
     return 0;

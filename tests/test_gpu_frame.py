@@ -38,6 +38,36 @@ def test_frame_from_host_arrays_matches_reference(orbx, name):
     assert np.array_equal(ur2, ur) and np.array_equal(dp2, dep)
 
 
+@pytest.mark.parametrize("name", ["tum1", "tum3"])
+def test_stepwise_calls_match_reference(orbx, name):
+    """UndistortKeyPoints / ComputeStereoFromRGBD / AssignFeaturesToGrid as separate calls, in the constructors' orders."""
+    k = fc.keys(orbx.KP_DTYPE); n = len(k); desc = np.zeros((n, 32), np.uint8); dimg = fc.depth_image(); cam = fc.cam_struct(orbx, name)
+    g = lambda key, tag="rgbd": G["%s_%s_%s" % (name, tag, key)]
+    F = orbx.Frame().take_host(k, desc, SF)
+    with pytest.raises(orbx.OrbxError):
+        F.AssignFeaturesToGrid(g("bounds"), n)                                          # grid before undistortion: call-sequence error
+    with pytest.raises(orbx.OrbxError):
+        orbx.ORBmatcher(0.9, True).SearchForInitialization(F, F, np.zeros((n, 2), np.float32), 10)   # not gridded yet
+    assert np.array_equal(F.UndistortKeyPoints(cam, n).view(np.uint8), g("keys_un"))
+    ur, de = F.ComputeStereoFromRGBD(fc.BF, dimg, fc.ROWS, fc.COLS, n)                  # RGB-D order (Frame.cc:640-645)
+    assert np.array_equal(ur, g("u_right")) and np.array_equal(de, g("depth"))
+    cs, en = F.AssignFeaturesToGrid(g("bounds"), n)
+    assert np.array_equal(cs, g("cell_start")) and np.array_equal(en, g("entries")) and F.N == n
+    ku, ur2, de2, b = F.read()
+    assert np.array_equal(ku.view(np.uint8), g("keys_un")) and np.array_equal(ur2, ur) and np.array_equal(b, g("bounds"))
+    # stereo order (Frame.cc:187-240): undistort, stereo results from ComputeStereoMatches, then the grid
+    F.take_host(k, desc, SF)
+    F.UndistortKeyPoints(cam, n)
+    F.set_stereo(g("u_right"), g("depth"))
+    cs, en = F.AssignFeaturesToGrid(g("bounds"), n)
+    _, ur3, de3, _ = F.read()
+    assert np.array_equal(cs, g("cell_start")) and np.array_equal(ur3, g("u_right")) and np.array_equal(de3, g("depth"))
+    # gathered depth, mono order
+    F.take_host(k, desc, SF); F.UndistortKeyPoints(cam, n)
+    ur, de = F.ComputeStereoFromRGBD(fc.BF, dimg[k["y"].astype(np.int32), k["x"].astype(np.int32)], 0, 0, n)
+    assert np.array_equal(ur, g("u_right")) and np.array_equal(de, g("depth"))
+
+
 def test_frame_from_extractor_result_and_amos_sequence(orbx, oracle):
     from tools.synth import synth_frame
     img = synth_frame(4, 640, 480); dimg = fc.depth_image()

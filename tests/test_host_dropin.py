@@ -23,8 +23,10 @@ def build_driver():
     orbx = importlib.import_module("amos-slam_b200")
     orbx.build()
     os.makedirs(os.path.dirname(BIN), exist_ok=True)
-    srcs = [os.path.join(ROOT, "tests", "host", "host_dropin_main.cc"), os.path.join(HOST, "ORBextractor.cc"), os.path.join(HOST, "ORBmatcher_b200.cc")]
-    deps = srcs + [os.path.join(HOST, "ORBextractor.h"), os.path.join(ROOT, "include", "orbx_b200.h"), orbx.LIB_PATH]
+    srcs = [os.path.join(ROOT, "tests", "host", "host_dropin_main.cc"), os.path.join(HOST, "ORBextractor.cc"), os.path.join(HOST, "ORBmatcher_b200.cc"),
+            os.path.join(HOST, "Frame_b200.cc")]
+    deps = srcs + [os.path.join(HOST, "ORBextractor.h"), os.path.join(ROOT, "include", "orbx_b200.h"), orbx.LIB_PATH] + \
+           [os.path.join(ROOT, "tests", "host", h) for h in ("Frame.h", "MapPoint.h", "ORBmatcher.h")]
     if os.path.exists(BIN) and all(os.path.getmtime(BIN) >= os.path.getmtime(d) for d in deps):
         return BIN
     cmd = ["g++", "-std=c++14", "-O2", "-I" + os.path.join(ROOT, "oracle", "shim"), "-I" + os.path.join(ROOT, "tests", "host"), "-I" + HOST] + srcs + \
@@ -39,7 +41,8 @@ def test_host_classes_compile_and_link():
     assert "liborbx_b200.so" in out
     syms = subprocess.run(["nm", "-C", b], capture_output=True, text=True).stdout
     for s in ("ORB_SLAM2::ORBextractor::operator()", "ORB_SLAM2::ORBextractor::MovingKeyPoints", "ORB_SLAM2::ORBextractor::ProcessDesp",
-              "ORB_SLAM2::ORBmatcher::SearchForInitialization", "ORB_SLAM2::ORBmatcher::SearchByProjection", "ORB_SLAM2::Frame::ComputeStereoMatches"):
+              "ORB_SLAM2::ORBmatcher::SearchForInitialization", "ORB_SLAM2::ORBmatcher::SearchByProjection", "ORB_SLAM2::Frame::ComputeStereoMatches",
+              "ORB_SLAM2::Frame::UndistortKeyPoints", "ORB_SLAM2::Frame::ComputeStereoFromRGBD", "ORB_SLAM2::Frame::AssignFeaturesToGrid"):
         assert s in syms, s
 
 
@@ -70,11 +73,16 @@ def test_host_classes_match_c_abi(orbx, tmp_path):
     with open(fin, "wb") as f:
         f.write(struct.pack("<ii", 640, 480)); f.write(A.tobytes()); f.write(B.tobytes())
         f.write(struct.pack("<ii", L.shape[1], L.shape[0])); f.write(L.tobytes()); f.write(R.tobytes())
-    subprocess.check_call([b, fin, fout])
-    r = Reader(open(fout, "rb").read())
-
+    # the device-Frame part needs the camera and the image bounds (ComputeImageBounds stays the reference's host code)
+    import frame_cases as fc
     E = orbx.ORBextractor(1000, 1.2, 8, 20, 7)
     ka, da = E(A)
+    cam = fc.cam_struct(orbx, "tum1")
+    FD = orbx.Frame().assign(E, cam, 480, 640, fc.depth_image())
+    with open(fin, "ab") as f:
+        f.write(struct.pack("<10f", *[getattr(cam, n) for n, _ in cam._fields_])); f.write(FD.read()[3].tobytes())
+    subprocess.check_call([b, fin, fout])
+    r = Reader(open(fout, "rb").read())
     hk, hd = r.kps(orbx.KP_DTYPE)
     assert np.array_equal(hk, ka) and np.array_equal(hd, da)
     assert r.i() == 8
@@ -120,3 +128,20 @@ def test_host_classes_match_c_abi(orbx, tmp_path):
     assert n == len(kl)
     assert np.array_equal(r.arr(np.float32, n), ur) and np.array_equal(r.arr(np.float32, n), dep)
     assert (ur >= 0).sum() > 100
+    # device-resident Frame through the reference's own method names == the C-ABI frame (pinned to the reference bodies in test_gpu_frame.py)
+    ku, urd, dpd, _ = FD.read(); cs, en = FD.grid()
+    n = r.i()
+    assert n == len(ka)
+    assert np.array_equal(r.arr(orbx.KP_DTYPE, n), ku) and np.array_equal(r.arr(np.float32, n), urd) and np.array_equal(r.arr(np.float32, n), dpd)
+    assert (np.abs(ku["x"] - ka["x"]) > 0.5).any() and (urd > 0).sum() > 100
+    for c in range(64 * 48):
+        m = r.i()
+        assert m == cs[c + 1] - cs[c] and np.array_equal(r.arr(np.int32, m), en[cs[c]:cs[c + 1]])
+    n2 = r.i()
+    assert n2 == n - 7 and np.array_equal(r.arr(orbx.KP_DTYPE, n2), ku[:n2])               # host-upload path of UndistortKeyPoints
+    # matchers on frames that carry a device frame (rectified camera): same answers as on host frames above
+    assert r.i() == nm
+    assert np.array_equal(r.arr(np.int32, r.i()), m12)
+    assert r.i() == nm2
+    assert np.array_equal(r.arr(np.int32, len(kb)), host_fm)
+    assert r.o == len(r.b)
