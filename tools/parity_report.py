@@ -1,0 +1,130 @@
+#!/usr/bin/env python3
+"""Parity counters of SURVEY.md 8(d) "Reporting": the CUDA path through the C ABI against the reference's own code
+(oracle/_ref: the reference sources compiled against the OpenCV-free shim; the port restatement if _ref is absent) on many
+seeded frames per configuration.  Run on a B200:  python tools/parity_report.py [--frames N] > gpurun_out/parity.md
+Test infrastructure: uses oracle/ as the checker only."""
+import argparse, importlib, os, sys, time
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import oracle                                   # noqa: E402
+import match_cases as mc                        # noqa: E402
+import frame_cases as fc                        # noqa: E402
+from tools.synth import synth_frame, warp_affine_nn   # noqa: E402
+
+orbx = importlib.import_module("amos-slam_b200")
+FIELDS = ("x", "y", "size", "angle", "response", "octave", "class_id")
+
+
+def extractor_rows(name, w, h, nfeat, frames, kind):
+    E = orbx.ORBextractor(nfeat, 1.2, 8, 20, 7); O = oracle.Extractor(kind, nfeat, 1.2, 8, 20, 7)
+    tot = dict(frames=0, kp_ref=0, kp_gpu=0, count_mismatch=0, desc_bytes_diff=0, angle_max_abs=0.0, **{f: 0 for f in FIELDS})
+    t_ref = 0.0
+    for s in range(frames):
+        img = synth_frame(1000 + s, w, h)
+        kg, dg = E(img)
+        t0 = time.perf_counter(); kr, dr = O.extract(img); t_ref += time.perf_counter() - t0
+        tot["frames"] += 1; tot["kp_ref"] += len(kr); tot["kp_gpu"] += len(kg)
+        if len(kg) != len(kr):
+            tot["count_mismatch"] += 1; continue
+        for f in FIELDS:
+            tot[f] += int((kg[f] != kr[f]).sum())
+        tot["desc_bytes_diff"] += int((dg != dr).sum())
+        if len(kg):
+            tot["angle_max_abs"] = max(tot["angle_max_abs"], float(np.abs(kg["angle"] - kr["angle"]).max()))
+    tot["ref_ms_per_frame_1core"] = 1e3 * t_ref / max(frames, 1)
+    return name, tot
+
+
+def matcher_rows(pairs, kind):
+    E = orbx.ORBextractor(1000, 1.2, 8, 20, 7)
+    sf = E.GetScaleFactors()
+    out = dict(pairs=0, init_queries=0, init_idx_diff=0, init_count_diff=0, projf_idx_diff=0, projf_count_diff=0, projp_idx_diff=0, projp_count_diff=0, matches=0)
+    for s in range(pairs):
+        A = synth_frame(2000 + s, 640, 480); B = warp_affine_nn(A, 7, -4, 2.0)
+        ka, da = E(A); kb, db = E(B)
+        pi = mc.projection_inputs(ka, kb, seed=s + 1)
+        FA, FB = orbx.FrameView(ka, da, 640, 480, sf), orbx.FrameView(kb, db, 640, 480, sf, u_right=pi["u_right"])
+        oFA, oFB = oracle.FrameData(ka, da, 640, 480, sf), oracle.FrameData(kb, db, 640, 480, sf, u_right=pi["u_right"])
+        prev = np.stack([ka["x"], ka["y"]], 1)
+        g = orbx.ORBmatcher(0.9, True).SearchForInitialization(FA, FB, prev, 100)
+        o = oracle.Matcher(kind, 0.9, True).search_for_initialization(oFA, oFB, prev, 100)
+        out["pairs"] += 1; out["init_queries"] += len(ka); out["matches"] += int(o[0])
+        out["init_idx_diff"] += int((g[1] != o[1]).sum()) + int((g[2] != o[2]).any(1).sum()); out["init_count_diff"] += int(g[0] != o[0])
+        uv, iz = mc.project(pi["xyz"])
+        for th, mono in mc.PROJ_FRAME_CASES:
+            g = orbx.ORBmatcher(0.9, True).SearchByProjectionFrame(FB, uv, iz, ka["octave"], ka["angle"], da, pi["valid"], pi["obs"], pi["occ"], th, False, False, 40.0)
+            o = oracle.Matcher("port", 0.9, True).search_by_projection_frame_port(oFB, uv, iz, ka["octave"], ka["angle"], da, pi["valid"], pi["obs"], pi["occ"], th, False, False, 40.0)
+            out["projf_idx_diff"] += int((g[1] != o[1]).sum()); out["projf_count_diff"] += int(g[0] != o[0]); out["matches"] += int(o[0])
+        for th in mc.PROJ_POINT_CASES:
+            g = orbx.ORBmatcher(0.8, True).SearchByProjectionPoints(FB, pi["tuv"], pi["tur"], pi["lvl"], pi["vc"], da, pi["obs"], pi["occ"], th)
+            o = oracle.Matcher(kind, 0.8, True).search_by_projection_points(oFB, pi["tuv"], pi["tur"], pi["lvl"], pi["vc"], da, pi["obs"], pi["occ"], th)
+            out["projp_idx_diff"] += int((g[1] != o[1]).sum()); out["projp_count_diff"] += int(g[0] != o[0]); out["matches"] += int(o[0])
+    return out
+
+
+def stereo_rows(pairs, kind):
+    out = dict(pairs=0, left_keypoints=0, matched=0, u_right_diff=0, depth_diff=0)
+    EL, ER = orbx.ORBextractor(2000, 1.2, 8, 20, 7), orbx.ORBextractor(2000, 1.2, 8, 20, 7)
+    OL, OR = oracle.Extractor(kind, 2000, 1.2, 8, 20, 7), oracle.Extractor(kind, 2000, 1.2, 8, 20, 7)
+    for s in range(pairs):
+        L, R = mc.stereo_pair(seed=3 + 2 * s)
+        kl, dl = EL(L); kr, dr = ER(R)
+        okl, odl = OL.extract(L); okr, odr = OR.extract(R)
+        ur, dep = orbx.ORBmatcher().ComputeStereoMatches(EL, ER, kl, dl, kr, dr, 0.0, mc.BF_KITTI)
+        our, odep = oracle.Matcher(kind).compute_stereo_matches(OL, OR, okl, odl, okr, odr, 0.0, mc.BF_KITTI)
+        out["pairs"] += 1; out["left_keypoints"] += len(okl); out["matched"] += int((our >= 0).sum())
+        if len(ur) != len(our):
+            out["u_right_diff"] += max(len(ur), len(our)); continue
+        out["u_right_diff"] += int((ur != our).sum()); out["depth_diff"] += int((dep != odep).sum())
+    return out
+
+
+def frame_rows(frames, kind):
+    out = dict(frames=0, keypoints=0, keys_un_diff=0, u_right_diff=0, depth_diff=0, grid_diff=0, bounds_diff=0)
+    E = orbx.ORBextractor(1000, 1.2, 8, 20, 7); F = orbx.Frame(); dimg = fc.depth_image()
+    for s in range(frames):
+        name = ("tum1", "tum2", "four", "tum3")[s % 4]
+        k, d = E(synth_frame(3000 + s, 640, 480))
+        F.assign(E, fc.cam_struct(orbx, name), 480, 640, dimg)
+        o = oracle.frame_build(kind, k, fc.CAMS[name], fc.BF, 480, 640, dimg)
+        ku, ur, dp, b = F.read(); cs, en = F.grid()
+        out["frames"] += 1; out["keypoints"] += len(k)
+        out["keys_un_diff"] += int((ku != o["keys_un"]).sum()); out["u_right_diff"] += int((ur != o["u_right"]).sum()); out["depth_diff"] += int((dp != o["depth"]).sum())
+        out["grid_diff"] += int(not (np.array_equal(cs, o["cell_start"]) and np.array_equal(en, o["entries"]))); out["bounds_diff"] += int((b != o["bounds"]).sum())
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser(); ap.add_argument("--frames", type=int, default=100); a = ap.parse_args()
+    kind = "ref" if oracle.have_ref() else "port"
+    oracle.build_port()
+    print("# Parity report (GPU through the C ABI vs `oracle/%s`)\n" % ("_ref: the reference's own sources" if kind == "ref" else "port"))
+    print("Seeded synthetic frames (`tools/synth.py`, seeds 1000+i); every number below is a count of DIFFERENCES unless named otherwise.\n")
+    print("## Extractor `operator()` (a1-a10)\n")
+    print("| config | frames | keypoints (ref) | keypoints (gpu) | frames with different count | x | y | size | angle | response | octave | descriptor bytes | max abs angle diff | ref ms/frame (1 core) |")
+    print("|---|---|---|---|---|---|---|---|---|---|---|---|---|---|")
+    for name, w, h, nf, n in (("C1 640x480/1000", 640, 480, 1000, a.frames), ("C3 752x480/2000", 752, 480, 2000, max(a.frames // 2, 1)),
+                              ("C4 1241x376/2000", 1241, 376, 2000, max(a.frames // 4, 1)), ("C5 1920x1080/1000", 1920, 1080, 1000, max(a.frames // 10, 1))):
+        _, t = extractor_rows(name, w, h, nf, n, kind)
+        print("| %s | %d | %d | %d | %d | %d | %d | %d | %d | %d | %d | %d | %g | %.1f |" % (name, t["frames"], t["kp_ref"], t["kp_gpu"], t["count_mismatch"], t["x"], t["y"], t["size"], t["angle"],
+                                                                                            t["response"], t["octave"], t["desc_bytes_diff"], t["angle_max_abs"], t["ref_ms_per_frame_1core"]))
+    m = matcher_rows(max(a.frames // 5, 1), kind)
+    print("\n## Matchers (a13-a17), C2-style pairs (frame B = frame A warped by (+7, -4) px, 2 deg)\n")
+    print("| pairs | F1 queries | accepted matches (all calls) | SearchForInitialization: index/prev diffs, count diffs | SearchByProjection(Frame,Frame) x3 th: index, count | SearchByProjection(Frame,MapPoints) x3 th: index, count |")
+    print("|---|---|---|---|---|---|")
+    print("| %d | %d | %d | %d, %d | %d, %d | %d, %d |" % (m["pairs"], m["init_queries"], m["matches"], m["init_idx_diff"], m["init_count_diff"], m["projf_idx_diff"], m["projf_count_diff"],
+                                                         m["projp_idx_diff"], m["projp_count_diff"]))
+    s = stereo_rows(max(a.frames // 20, 1), kind)
+    print("\n## ComputeStereoMatches (a18), C4 pairs\n")
+    print("| pairs | left keypoints | matched (ref) | mvuRight diffs | mvDepth diffs |\n|---|---|---|---|---|")
+    print("| %d | %d | %d | %d | %d |" % (s["pairs"], s["left_keypoints"], s["matched"], s["u_right_diff"], s["depth_diff"]))
+    f = frame_rows(max(a.frames // 2, 4), kind)
+    print("\n## Device-resident Frame (8f rank 1): UndistortKeyPoints / ComputeStereoFromRGBD / AssignFeaturesToGrid, cameras TUM1, TUM2, 4-coefficient, rectified\n")
+    print("| frames | keypoints | mvKeysUn diffs | mvuRight diffs | mvDepth diffs | frames with a different mGrid | bounds diffs |\n|---|---|---|---|---|---|---|")
+    print("| %d | %d | %d | %d | %d | %d | %d |" % (f["frames"], f["keypoints"], f["keys_un_diff"], f["u_right_diff"], f["depth_diff"], f["grid_diff"], f["bounds_diff"]))
+
+
+if __name__ == "__main__":
+    main()
