@@ -447,15 +447,19 @@ def main():
             dist.barrier()
     sampler.stop_flag = True; sampler.join(timeout=2)
 
-    # the link the e2e leg rides on: pinned host -> device copy rate of this GPU's PCIe link, measured alone (rank 0, after the timed regions)
+    # the links the e2e leg rides on: pinned host -> device copy rate of every rank's GPU, all ranks copying AT THE SAME TIME (barrier
+    # before each repetition), so that at N > 1 the figure includes the contention on the host side (memory, root complexes) that the
+    # e2e leg also sees; reported as the mean per GPU of the slowest repetition-best across ranks
     pcie_h2d = None
-    if rank == 0 and Ke:
+    if Ke:
         hp = torch.empty(256 << 20, dtype=torch.uint8).pin_memory(); dp = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
         half = hp.numel() // 2
         s2 = [torch.cuda.Stream(), torch.cuda.Stream()]
-        pcie_h2d = 0.0
+        best = 0.0
         for rep in range(4):                                      # two copy streams, like the e2e leg's two handles; best of 3 after one warm-up
             torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for i, st in enumerate(s2):
@@ -467,8 +471,12 @@ def main():
                 torch.cuda.current_stream().wait_stream(st)
             e1.record(); torch.cuda.synchronize()
             if rep:
-                pcie_h2d = max(pcie_h2d, 2 * hp.numel() / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+                best = max(best, 2 * hp.numel() / (e0.elapsed_time(e1) * 1e-3) / 1e9)
         del hp, dp
+        tb = torch.tensor([best], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tb, op=dist.ReduceOp.SUM)
+        pcie_h2d = float(tb[0].item()) / world
 
     matcher_line = matcher_bench(orbx, torch, ext, frames, local_rank) if (rank == 0 and args.workload == "c1") else None
 
@@ -514,7 +522,7 @@ def main():
             "config": config,
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(B * WIDTH * HEIGHT * (2 if MASKED else 1)), "d2h_bytes_per_step": int(B * cap * 60 + 4 * B + 4), "steps": Ke,
                     "streams_per_gpu": NS,
-                    "h2d_GBps_per_gpu": (e2e / N * WIDTH * HEIGHT * (2 if MASKED else 1) / 1e9) if e2e else None, "pcie_h2d_peak_GBps": pcie_h2d,
+                    "h2d_GBps_per_gpu": (e2e / N * WIDTH * HEIGHT * (2 if MASKED else 1) / 1e9) if e2e else None, "pcie_h2d_peak_GBps": pcie_h2d, "pcie_probe": "pinned 256 MiB H2D on two streams per GPU, all %d ranks concurrently, mean per GPU" % world,
                     "pcie_frac": (e2e / N * WIDTH * HEIGHT * (2 if MASKED else 1) / 1e9 / pcie_h2d) if (e2e and pcie_h2d) else None,
                     "note": "one host thread per extractor handle, each calling the synchronous host-pointer batch API on its share of the step's frames"},
             "gpu_launches": int(launches),
