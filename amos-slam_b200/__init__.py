@@ -101,6 +101,11 @@ def lib():
         L.orbx_compute_stereo_matches.argtypes = [vp, vp, vp, vp, vp, ci, vp, vp, ci, cf, cf, vp, vp]
         L.orbx_match_bruteforce_device.argtypes = [vp, vp, ci, vp, ci, vp, vp, vp]
         L.orbx_match_bruteforce_batch_device.argtypes = [vp, ci, vp, ci, vp, ci, vp, vp, vp]
+        L.orbx_vocabulary_create.argtypes = [ci, ci, ci, ci, ci, ci, vp, vp, vp, vp, C.POINTER(vp)]
+        L.orbx_vocabulary_destroy.argtypes = [vp]; L.orbx_vocabulary_destroy.restype = None
+        L.orbx_vocabulary_words.argtypes = [vp]
+        L.orbx_vocabulary_transform.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp, C.POINTER(ci), vp, vp, vp, C.POINTER(ci)]
+        L.orbx_search_by_bow.argtypes = [vp, ci, vp, vp, vp, vp, C.POINTER(ci)]
         L.orbx_frame_create.argtypes = [ci, C.POINTER(vp)]
         L.orbx_frame_destroy.argtypes = [vp]; L.orbx_frame_destroy.restype = None
         L.orbx_frame_assign.argtypes = [vp, vp, vp, ci, ci, vp, sz]
@@ -325,4 +330,4 @@ class ORBextractor:
         return out[:n.value].copy()
 
 
-from ._matcher import ORBmatcher, FrameView, Frame, Camera  # noqa: E402,F401
+from ._matcher import ORBmatcher, FrameView, Frame, Camera, ORBVocabulary  # noqa: E402,F401

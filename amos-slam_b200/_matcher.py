@@ -164,6 +164,51 @@ def _u8(a):
     return None if a is None else np.ascontiguousarray(a, np.uint8)
 
 
+class _BowSideC(C.Structure):
+    _fields_ = [("n", C.c_int), ("keys", C.c_void_p), ("descriptors", C.c_void_p), ("valid", C.c_void_p),
+                ("n_fv", C.c_int), ("fv_nodes", C.c_void_p), ("fv_offsets", C.c_void_p), ("fv_indices", C.c_void_p)]
+
+
+class ORBVocabulary:
+    """ORB_SLAM2::ORBVocabulary (DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB>, /root/reference/include/ORBVocabulary.h:40-41) on the
+    device, from the node table of ORBvoc.txt: parent[i], is_leaf[i], descriptor[i], weight[i] describe node i + 1."""
+    TF_IDF, TF, IDF, BINARY = 0, 1, 2, 3
+    L1_NORM, L2_NORM, CHI_SQUARE, KL, BHATTACHARYYA, DOT_PRODUCT = 0, 1, 2, 3, 4, 5
+
+    def __init__(self, k, L, parent, is_leaf, descriptors, weights, weighting=0, scoring=0, device=0):
+        from . import lib, _check
+        self._lib, self._check = lib(), _check
+        pa = np.ascontiguousarray(parent, np.int32); lf = np.ascontiguousarray(is_leaf, np.uint8)
+        ds = np.ascontiguousarray(descriptors, np.uint8).reshape(-1, 32); w = np.ascontiguousarray(weights, np.float64)
+        assert len(pa) == len(lf) == len(ds) == len(w)
+        h = C.c_void_p()
+        _check(self._lib.orbx_vocabulary_create(int(device), int(k), int(L), int(weighting), int(scoring), len(pa), _p(pa), _p(lf), _p(ds), _p(w), C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.orbx_vocabulary_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def size(self):
+        return self._lib.orbx_vocabulary_words(self._h)
+
+    # void transform(const vector<TDescriptor>& features, BowVector &v, FeatureVector &fv, int levelsup) const
+    def transform(self, descriptors, levelsup=4):
+        """-> dict(word, node: per feature; bow_ids, bow_vals: mBowVec in map order; fv_nodes, fv_offsets, fv_idx: mFeatVec)."""
+        d = _u8(descriptors).reshape(-1, 32); n = len(d); m = max(n, 1)
+        word = np.zeros(m, np.int32); node = np.zeros(m, np.int32); bi = np.zeros(m, np.int32); bv = np.zeros(m, np.float64)
+        fn = np.zeros(m, np.int32); fo = np.zeros(m + 1, np.int32); fi = np.zeros(m, np.int32); nb, nf = C.c_int(), C.c_int()
+        self._check(self._lib.orbx_vocabulary_transform(self._h, _p(d), n, int(levelsup), _p(word), _p(node), _p(bi), _p(bv), C.byref(nb), _p(fn), _p(fo), _p(fi), C.byref(nf)))
+        return dict(word=word[:n], node=node[:n], bow_ids=bi[:nb.value], bow_vals=bv[:nb.value], fv_nodes=fn[:nf.value], fv_offsets=fo[:nf.value + 1], fv_idx=fi[:fo[nf.value]])
+
+
 class ORBmatcher:
     TH_HIGH, TH_LOW, HISTO_LENGTH = 100, 50, 30
 
@@ -251,6 +296,25 @@ class ORBmatcher:
         self._check(self._lib.orbx_compute_stereo_matches(self._h, extractor_left._h, extractor_right._h, _p(kl), _p(dl), len(kl), _p(kr), _p(dr), len(kr),
                                                           float(mb), float(mbf), _p(ur), _p(dep)))
         return ur, dep
+
+    # int SearchByBoW(KeyFrame* pKF, Frame &F, vector<MapPoint*> &vpMapPointMatches)            (kf_kf = False)
+    # int SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, vector<MapPoint*> &vpMatches12)           (kf_kf = True)
+    def SearchByBoW(self, kf_kf, keys1, desc1, valid1, fv1, keys2, desc2, valid2, fv2):
+        """fv = dict with fv_nodes / fv_offsets / fv_idx as ORBVocabulary.transform returns.  -> (nmatches, match12, match21)."""
+        from . import KP_DTYPE
+        hold = []
+
+        def side(keys, desc, valid, fv):
+            k = np.ascontiguousarray(keys, KP_DTYPE); d = _u8(desc).reshape(-1, 32); v = _u8(valid)
+            a = [np.ascontiguousarray(fv[x], np.int32) for x in ("fv_nodes", "fv_offsets", "fv_idx")]
+            hold.extend([k, d, v] + a)
+            s = _BowSideC(); s.n = len(k); s.keys = k.ctypes.data; s.descriptors = d.ctypes.data; s.valid = v.ctypes.data if v is not None else None
+            s.n_fv = len(a[0]); s.fv_nodes = a[0].ctypes.data; s.fv_offsets = a[1].ctypes.data; s.fv_indices = a[2].ctypes.data
+            return s
+        s1, s2 = side(keys1, desc1, valid1, fv1), side(keys2, desc2, valid2, fv2)
+        m12 = np.zeros(max(s1.n, 1), np.int32); m21 = np.zeros(max(s2.n, 1), np.int32); nm = C.c_int()
+        self._check(self._lib.orbx_search_by_bow(self._h, int(bool(kf_kf)), C.byref(s1), C.byref(s2), _p(m12), _p(m21), C.byref(nm)))
+        return nm.value, m12[:s1.n], m21[:s2.n]
 
     # vector<size_t> Frame::GetFeaturesInArea(x, y, r, minLevel, maxLevel) for many windows at once, on a device-resident Frame
     def GetFeaturesInArea(self, F, xy, r, min_level=None, max_level=None):

@@ -7,6 +7,7 @@
 #include "orbx_internal.h"
 #include "k_match.cuh"
 #include "k_frame.cuh"
+#include "k_bow.cuh"
 
 #include <climits>
 #include <algorithm>
@@ -737,6 +738,159 @@ retry:
         CU_TRY(cudaStreamSynchronize(m->stream));
         for (int i = 0; i < total; ++i) indices[i] &= 0xFFFFF;        // entries are dist << 20 | index with dist == 0
     }
+    return ORBX_OK;
+}
+
+// ---- bag of words ----
+struct orbx_vocabulary {
+    int device; cudaStream_t stream = nullptr; long long launches = 0;
+    int k, L, weighting, scoring, n = 0, nwords = 0;
+    FBuf<int> child_off, child_id, word; FBuf<uint8_t> child_desc; FBuf<double> weight;
+    // transform scratch
+    FBuf<uint8_t> desc; FBuf<int> word_of, node_of, flags, bow_ids, fv_nodes, fv_offsets, fv_idx, counts; FBuf<double> weight_of, stage, bow_vals; FBuf<unsigned long long> keys;
+};
+#define VLAUNCH_CHECK() do { cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) { \
+    orbx_set_error(std::string("kernel launch: ") + cudaGetErrorString(_e)); return ORBX_E_CUDA; } ++v->launches; } while (0)
+
+int orbx_vocabulary_create(int device, int k, int L, int weighting, int scoring, int n_nodes, const int* parent, const uint8_t* is_leaf,
+                           const uint8_t* descriptors, const double* weights, orbx_vocabulary** out) {
+    if (!out) FAIL(ORBX_E_INVALID, "null out");
+    *out = nullptr;
+    if (k < 2 || L < 1 || n_nodes < 1 || n_nodes >= (1 << 28) || weighting < 0 || weighting > 3 || scoring < 0 || scoring > 5 || !parent || !is_leaf || !descriptors || !weights)
+        FAIL(ORBX_E_INVALID, "bad vocabulary arguments");
+    const int n = n_nodes + 1;
+    // children in push_back (= file) order, counted then filled
+    std::vector<int> off(n + 1, 0), cid(n_nodes), word(n, -1);
+    for (int i = 0; i < n_nodes; ++i) { if (parent[i] < 0 || parent[i] > i) FAIL(ORBX_E_INVALID, "vocabulary node listed before its parent"); ++off[parent[i] + 1]; }
+    for (int i = 0; i < n; ++i) off[i + 1] += off[i];
+    { std::vector<int> fill(off.begin(), off.end() - 1); for (int i = 0; i < n_nodes; ++i) cid[fill[parent[i]]++] = i + 1; }
+    int nw = 0;
+    for (int i = 0; i < n_nodes; ++i) {
+        const bool childless = off[i + 2] == off[i + 1];
+        if ((is_leaf[i] != 0) != childless) FAIL(ORBX_E_INVALID, "vocabulary leaf flag does not agree with the tree");
+        if (is_leaf[i]) word[i + 1] = nw++;
+    }
+    if (off[1] == off[0]) FAIL(ORBX_E_INVALID, "vocabulary root has no children");
+    std::vector<uint8_t> cdesc((size_t)n_nodes * 32); std::vector<double> w(n, 0.0);
+    for (int c = 0; c < n_nodes; ++c) std::memcpy(&cdesc[(size_t)c * 32], descriptors + (size_t)(cid[c] - 1) * 32, 32);
+    for (int i = 0; i < n_nodes; ++i) w[i + 1] = weights[i];
+    int ndev = 0;
+    CU_TRY(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) FAIL(ORBX_E_CUDA, "no such CUDA device (this library has no CPU fallback)");
+    CU_TRY(cudaSetDevice(device));
+    orbx_vocabulary* v = new orbx_vocabulary();
+    v->device = device; v->k = k; v->L = L; v->weighting = weighting; v->scoring = scoring; v->n = n; v->nwords = nw;
+    if (cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking) != cudaSuccess) { delete v; FAIL(ORBX_E_CUDA, "cudaStreamCreate"); }
+    if (v->child_off.ensure(n + 1) || v->child_id.ensure(n_nodes) || v->word.ensure(n) || v->child_desc.ensure((size_t)n_nodes * 32) || v->weight.ensure(n)) { orbx_vocabulary_destroy(v); return ORBX_E_CUDA; }
+    cudaMemcpyAsync(v->child_off.p, off.data(), (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, v->stream);
+    cudaMemcpyAsync(v->child_id.p, cid.data(), (size_t)n_nodes * 4, cudaMemcpyHostToDevice, v->stream);
+    cudaMemcpyAsync(v->word.p, word.data(), (size_t)n * 4, cudaMemcpyHostToDevice, v->stream);
+    cudaMemcpyAsync(v->child_desc.p, cdesc.data(), cdesc.size(), cudaMemcpyHostToDevice, v->stream);
+    cudaMemcpyAsync(v->weight.p, w.data(), (size_t)n * 8, cudaMemcpyHostToDevice, v->stream);
+    if (cudaStreamSynchronize(v->stream) != cudaSuccess) { orbx_vocabulary_destroy(v); FAIL(ORBX_E_CUDA, "vocabulary upload"); }
+    *out = v;
+    return ORBX_OK;
+}
+void orbx_vocabulary_destroy(orbx_vocabulary* v) {
+    if (!v) return;
+    cudaSetDevice(v->device); if (v->stream) cudaStreamSynchronize(v->stream);
+    v->child_off.release(); v->child_id.release(); v->word.release(); v->child_desc.release(); v->weight.release();
+    v->desc.release(); v->word_of.release(); v->node_of.release(); v->flags.release(); v->bow_ids.release(); v->fv_nodes.release(); v->fv_offsets.release(); v->fv_idx.release();
+    v->counts.release(); v->weight_of.release(); v->stage.release(); v->bow_vals.release(); v->keys.release();
+    if (v->stream) cudaStreamDestroy(v->stream);
+    delete v;
+}
+int orbx_vocabulary_words(const orbx_vocabulary* v) { return v ? v->nwords : -1; }
+
+int orbx_vocabulary_transform(orbx_vocabulary* v, const uint8_t* descriptors, int n, int levelsup, int* word_of, int* node_of,
+                              int* bow_ids, double* bow_values, int* n_bow, int* fv_nodes, int* fv_offsets, int* fv_indices, int* n_fv) {
+    if (!v || n < 0 || n >= (1 << 20) || !n_bow || !n_fv || !fv_offsets || (n && (!descriptors || !bow_ids || !bow_values || !fv_nodes || !fv_indices)))
+        FAIL(ORBX_E_INVALID, "bad arguments");
+    *n_bow = 0; *n_fv = 0; fv_offsets[0] = 0;
+    if (n == 0) return ORBX_OK;
+    CU_TRY(cudaSetDevice(v->device));
+    const size_t nn = n;
+    int rc;
+    if ((rc = v->desc.ensure(nn * 32)) || (rc = v->word_of.ensure(nn)) || (rc = v->node_of.ensure(nn)) || (rc = v->weight_of.ensure(nn)) || (rc = v->keys.ensure(nn + 1)) ||
+        (rc = v->flags.ensure(nn + 1)) || (rc = v->stage.ensure(nn)) || (rc = v->bow_ids.ensure(nn)) || (rc = v->bow_vals.ensure(nn)) || (rc = v->fv_nodes.ensure(nn)) ||
+        (rc = v->fv_offsets.ensure(nn + 1)) || (rc = v->fv_idx.ensure(nn)) || (rc = v->counts.ensure(2))) return rc;
+    cudaStream_t s = v->stream;
+    CU_TRY(cudaMemcpyAsync(v->desc.p, descriptors, nn * 32, cudaMemcpyHostToDevice, s));
+    VocDev d; d.k = v->k; d.L = v->L; d.weighting = v->weighting; d.scoring = v->scoring; d.n = v->n;
+    d.child_off = v->child_off.p; d.child_id = v->child_id.p; d.child_desc = reinterpret_cast<const uint4*>(v->child_desc.p); d.weight = v->weight.p; d.word = v->word.p;
+    k_bow_descend<<<(n + 3) / 4, 128, 0, s>>>(d, reinterpret_cast<const uint4*>(v->desc.p), n, levelsup, v->word_of.p, v->node_of.p, v->weight_of.p);
+    VLAUNCH_CHECK();
+    k_bow_assemble<<<1, 1024, 0, s>>>(n, v->weighting, v->scoring, v->word_of.p, v->node_of.p, v->weight_of.p, v->keys.p, v->flags.p, v->stage.p,
+                                      v->bow_ids.p, v->bow_vals.p, v->fv_nodes.p, v->fv_offsets.p, v->fv_idx.p, v->counts.p);
+    VLAUNCH_CHECK();
+    int counts[2] = {0, 0};
+    CU_TRY(cudaMemcpyAsync(counts, v->counts.p, 8, cudaMemcpyDeviceToHost, s));
+    if (word_of) CU_TRY(cudaMemcpyAsync(word_of, v->word_of.p, nn * 4, cudaMemcpyDeviceToHost, s));
+    if (node_of) CU_TRY(cudaMemcpyAsync(node_of, v->node_of.p, nn * 4, cudaMemcpyDeviceToHost, s));
+    // the vectors are at most n long: copy them whole in the same round trip, the counts say how much is meaningful
+    CU_TRY(cudaMemcpyAsync(bow_ids, v->bow_ids.p, nn * 4, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(bow_values, v->bow_vals.p, nn * 8, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(fv_nodes, v->fv_nodes.p, nn * 4, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(fv_offsets, v->fv_offsets.p, (nn + 1) * 4, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(fv_indices, v->fv_idx.p, nn * 4, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    *n_bow = counts[0]; *n_fv = counts[1];
+    return ORBX_OK;
+}
+
+static int check_bow_side(const orbx_bow_side* s, bool need_valid) {
+    if (!s || s->n < 0 || s->n >= (1 << 20) || s->n_fv < 0 || s->n_fv > s->n || (s->n && (!s->keys || !s->descriptors)) || (need_valid && s->n && !s->valid) ||
+        (s->n_fv && (!s->fv_nodes || !s->fv_offsets || !s->fv_indices))) FAIL(ORBX_E_INVALID, "bad bag-of-words side");
+    if (s->n_fv) {
+        if (s->fv_offsets[0] != 0 || s->fv_offsets[s->n_fv] > s->n) FAIL(ORBX_E_INVALID, "bad feature-vector offsets");
+        for (int q = 0; q < s->n_fv; ++q) {
+            if (s->fv_offsets[q + 1] < s->fv_offsets[q] || (q && s->fv_nodes[q] <= s->fv_nodes[q - 1])) FAIL(ORBX_E_INVALID, "feature vector is not in map order");
+        }
+        for (int e = 0; e < s->fv_offsets[s->n_fv]; ++e) if (s->fv_indices[e] < 0 || s->fv_indices[e] >= s->n) FAIL(ORBX_E_INVALID, "feature index out of range");
+    }
+    return ORBX_OK;
+}
+
+int orbx_search_by_bow(orbx_matcher* m, int kf_kf, const orbx_bow_side* s1, const orbx_bow_side* s2, int* match12, int* match21, int* nmatches) {
+    if (!m || !nmatches) FAIL(ORBX_E_INVALID, "null argument");
+    int rc;
+    if ((rc = check_bow_side(s1, true)) || (rc = check_bow_side(s2, false))) return rc;
+    if ((s1->n && !match12) || (s2->n && !match21)) FAIL(ORBX_E_INVALID, "null output");
+    *nmatches = 0;
+    for (int i = 0; i < s1->n; ++i) match12[i] = -1;
+    for (int j = 0; j < s2->n; ++j) match21[j] = -1;
+    // the merge of the two node lists (:250-360): positions of the nodes both feature vectors hold
+    std::vector<int2> pairs;
+    for (int a = 0, b = 0; a < s1->n_fv && b < s2->n_fv;) {
+        if (s1->fv_nodes[a] < s2->fv_nodes[b]) ++a; else if (s2->fv_nodes[b] < s1->fv_nodes[a]) ++b; else { pairs.push_back(make_int2(a, b)); ++a; ++b; }
+    }
+    if (pairs.empty()) return ORBX_OK;
+    CU_TRY(cudaSetDevice(m->device));
+    const int n1 = s1->n, n2 = s2->n, np = (int)pairs.size();
+    const size_t need = pad((size_t)n1 * 60) + pad((size_t)n2 * 60) + 8 * pad((size_t)(n1 + n2 + 2) * 4) + pad((size_t)np * 8) + 16384;
+    if ((rc = m->arena.reserve(need)) || (rc = m->uparena.reserve(need))) return rc;
+    m->arena.reset(); m->uparena.reset();
+    KpM *k1, *k2; uint8_t *d1, *d2, *v1, *v2 = nullptr; int *o1, *i1, *o2, *i2; int2* dp;
+    if ((rc = up(m, reinterpret_cast<const KpM*>(s1->keys), (size_t)n1, k1)) || (rc = up(m, reinterpret_cast<const KpM*>(s2->keys), (size_t)n2, k2)) ||
+        (rc = up(m, s1->descriptors, (size_t)n1 * 32, d1)) || (rc = up(m, s2->descriptors, (size_t)n2 * 32, d2)) || (rc = up(m, s1->valid, (size_t)n1, v1)) ||
+        (rc = up(m, s1->fv_offsets, (size_t)s1->n_fv + 1, o1)) || (rc = up(m, s1->fv_indices, (size_t)s1->fv_offsets[s1->n_fv], i1)) ||
+        (rc = up(m, s2->fv_offsets, (size_t)s2->n_fv + 1, o2)) || (rc = up(m, s2->fv_indices, (size_t)s2->fv_offsets[s2->n_fv], i2)) ||
+        (rc = up(m, pairs.data(), (size_t)np, dp))) return rc;
+    if (kf_kf && s2->valid && (rc = up(m, s2->valid, (size_t)n2, v2))) return rc;
+    int* m12 = m->arena.get<int>(n1 + 1); int* m21 = m->arena.get<int>(n2 + 1); int* binof = m->arena.get<int>(n1 + 1); int* hist = m->arena.get<int>(32); int* dn = m->arena.get<int>(1);
+    if (!m12 || !m21 || !binof || !hist || !dn) FAIL(ORBX_E_CUDA, "matcher arena exhausted");
+    if ((rc = flush_uploads(m))) return rc;
+    cudaStream_t s = m->stream;
+    CU_TRY(cudaMemsetAsync(m12, 0xFF, (size_t)(n1 + 1) * 4, s)); CU_TRY(cudaMemsetAsync(m21, 0xFF, (size_t)(n2 + 1) * 4, s)); CU_TRY(cudaMemsetAsync(hist, 0, 32 * 4, s));
+    BowSideDev a = {n1, k1, reinterpret_cast<const uint4*>(d1), v1, o1, i1}, b = {n2, k2, reinterpret_cast<const uint4*>(d2), v2, o2, i2};
+    k_bow_match<<<(np + 3) / 4, 128, 0, s>>>(np, dp, a, b, kf_kf ? 1 : 0, m->nnratio, m->checkOri, m12, m21, binof, hist);
+    LAUNCH_CHECK();
+    k_bow_finish<<<1, 1024, 0, s>>>(n1, m->checkOri, hist, binof, m12, m21, dn);
+    LAUNCH_CHECK();
+    if (n1) CU_TRY(cudaMemcpyAsync(match12, m12, (size_t)n1 * 4, cudaMemcpyDeviceToHost, s));
+    if (n2) CU_TRY(cudaMemcpyAsync(match21, m21, (size_t)n2 * 4, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(nmatches, dn, 4, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
     return ORBX_OK;
 }
 

@@ -348,6 +348,47 @@ int orbx_search_by_projection_points_dev(orbx_matcher* m, const orbx_frame* F, i
                                          const float* track_view_cos, const uint8_t* mp_desc, const uint8_t* mp_observed,
                                          const uint8_t* f_occupied, float th, int* f_match, int* nmatches);
 
+/* ------------------------------------------------------------------------------------------------
+ * Bag of words: DBoW2's vocabulary tree and the two BoW-guided matchers.
+ *   ORBVocabulary = DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB>   include/ORBVocabulary.h:40-41
+ *   transform(features, BowVector&, FeatureVector&, levelsup)   Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1124-1197
+ *   transform(feature, word_id, weight, nid, levelsup)          Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1217-1259
+ *   Frame::ComputeBoW / KeyFrame::ComputeBoW                    src/Frame.cc:1033-1049
+ *   ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&)            src/ORBmatcher.cc:230-382
+ *   ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&)         src/ORBmatcher.cc:656-799
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct orbx_vocabulary orbx_vocabulary;
+
+/* The node table of the vocabulary as ORBVocabulary::loadFromTextFile reads it (TemplatedVocabulary.h:1336-1424): row i describes
+ * node i + 1 (node 0 is the root): parent id, leaf flag, 32-byte descriptor, weight.  Children keep file order; word ids are given to
+ * the leaves in file order.  weighting: 0 TF_IDF, 1 TF, 2 IDF, 3 BINARY; scoring: 0 L1_NORM, 1 L2_NORM, 2 CHI_SQUARE, 3 KL,
+ * 4 BHATTACHARYYA, 5 DOT_PRODUCT (BowVector.h:25-49).  The tree is copied to the device (35 MB for ORBvoc: it stays in L2). */
+int  orbx_vocabulary_create(int device, int k, int L, int weighting, int scoring, int n_nodes, const int* parent,
+                            const uint8_t* is_leaf, const uint8_t* descriptors, const double* weights, orbx_vocabulary** out);
+void orbx_vocabulary_destroy(orbx_vocabulary* v);
+int  orbx_vocabulary_words(const orbx_vocabulary* v);      /* size() */
+
+/* mpORBvocabulary->transform(vCurrentDesc, mBowVec, mFeatVec, levelsup) for n descriptors (host pointers).
+ * word_of / node_of [n] (may be NULL): the per-feature word id and the id of its ancestor on level L - levelsup.
+ * mBowVec: bow_ids / bow_values [capacity n] in std::map order (ascending word id), *n_bow entries, weights normalised as the
+ * scoring type asks.  mFeatVec: fv_nodes [n] ascending, fv_offsets [n + 1], fv_indices [n]: node q holds the feature indices
+ * fv_indices[fv_offsets[q] .. fv_offsets[q + 1]) in ascending order; *n_fv nodes.  Stopped words (weight <= 0) are in neither. */
+int orbx_vocabulary_transform(orbx_vocabulary* v, const uint8_t* descriptors, int n, int levelsup, int* word_of, int* node_of,
+                              int* bow_ids, double* bow_values, int* n_bow, int* fv_nodes, int* fv_offsets, int* fv_indices, int* n_fv);
+
+/* One side of SearchByBoW: keypoints (mvKeysUn of a KeyFrame, mvKeys of a Frame: only .angle is read), descriptors, valid[i] != 0 iff
+ * the feature holds a map point that is not bad (side 1 always; side 2 only in the KeyFrame x KeyFrame form, NULL = all valid), and
+ * the feature vector as orbx_vocabulary_transform returns it. */
+typedef struct orbx_bow_side {
+    int n; const orbx_keypoint* keys; const uint8_t* descriptors; const uint8_t* valid;
+    int n_fv; const int* fv_nodes; const int* fv_offsets; const int* fv_indices;
+} orbx_bow_side;
+
+/* kf_kf == 0: SearchByBoW(pKF = s1, F = s2): match21[j] = index of the KeyFrame feature whose map point goes to vpMapPointMatches[j].
+ * kf_kf != 0: SearchByBoW(pKF1 = s1, pKF2 = s2): match12[i] = index of the pKF2 feature whose map point goes to vpMatches12[i].
+ * Both arrays are always filled (-1 = no match); *nmatches = return value. */
+int orbx_search_by_bow(orbx_matcher* m, int kf_kf, const orbx_bow_side* s1, const orbx_bow_side* s2, int* match12, int* match21, int* nmatches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,7 +24,7 @@ KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4
                      ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
 assert KP_DTYPE.itemsize == 28
 
-PORT_SOURCES = ["port/orb_port.cpp", "port/match_port.cpp"]
+PORT_SOURCES = ["port/orb_port.cpp", "port/match_port.cpp", "port/bow_port.cpp"]
 
 
 def build_port(force=False):
@@ -360,3 +360,52 @@ def frame_build(kind, keys, cam, bf, rows, cols, depth_img=None):
     f(keys.ctypes.data, n, c.ctypes.data, nd, float(bf), rows, cols, None if dimg is None else dimg.ctypes.data,
       ku.ctypes.data, ur.ctypes.data, dep.ctypes.data, b.ctypes.data, cs.ctypes.data, en.ctypes.data)
     return dict(keys_un=ku[:n], u_right=ur[:n], depth=dep[:n], bounds=b, cell_start=cs, entries=en[:cs[-1]])
+
+
+# ------------------------------------------------------------------------------------------------
+# Bag of words: DBoW2 transform (Frame::ComputeBoW) and ORBmatcher::SearchByBoW x2
+# (/root/reference/Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1124-1259, /root/reference/src/ORBmatcher.cc:230-382, 656-799)
+# ------------------------------------------------------------------------------------------------
+class Vocabulary:
+    """ORBVocabulary from a flat node table (the rows of ORBvoc.txt): parent[i], is_leaf[i], descriptor[i], weight[i] describe node i + 1.
+    weighting: 0 TF_IDF, 1 TF, 2 IDF, 3 BINARY; scoring: 0 L1_NORM, 1 L2_NORM, 2 CHI_SQUARE, 3 KL, 4 BHATTACHARYYA, 5 DOT_PRODUCT."""
+
+    def __init__(self, kind, k, L, parent, is_leaf, desc, weight, weighting=0, scoring=0):
+        self.kind, self.lib = kind, _lib(kind)
+        self.parent = np.ascontiguousarray(parent, np.int32); self.is_leaf = np.ascontiguousarray(is_leaf, np.uint8)
+        self.desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32); self.weight = np.ascontiguousarray(weight, np.float64)
+        f = getattr(self.lib, kind + "_voc_create"); f.restype = C.c_void_p
+        f.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        self.h = f(k, L, weighting, scoring, len(self.parent), self.parent.ctypes.data, self.is_leaf.ctypes.data, self.desc.ctypes.data, self.weight.ctypes.data)
+        g = getattr(self.lib, kind + "_voc_destroy"); g.restype = None; g.argtypes = [C.c_void_p]
+
+    def __del__(self):
+        try:
+            getattr(self.lib, self.kind + "_voc_destroy")(self.h)
+        except Exception:
+            pass
+
+    def transform(self, desc, levelsup=4):
+        """-> dict(word, node: per feature; bow_ids, bow_vals: BowVector in map order; fv_nodes, fv_offsets, fv_idx: FeatureVector)."""
+        d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32); n = len(d); m = max(n, 1)
+        word = np.zeros(m, np.int32); node = np.zeros(m, np.int32); bi = np.zeros(m, np.int32); bv = np.zeros(m, np.float64)
+        fn = np.zeros(m, np.int32); fo = np.zeros(m + 1, np.int32); fi = np.zeros(m, np.int32); nb, nf = C.c_int(), C.c_int()
+        f = getattr(self.lib, self.kind + "_voc_transform"); f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.POINTER(C.c_int)] + [C.c_void_p] * 3 + [C.POINTER(C.c_int)]
+        f(self.h, d.ctypes.data, n, levelsup, word.ctypes.data, node.ctypes.data, bi.ctypes.data, bv.ctypes.data, C.byref(nb), fn.ctypes.data, fo.ctypes.data, fi.ctypes.data, C.byref(nf))
+        return dict(word=word[:n], node=node[:n], bow_ids=bi[:nb.value], bow_vals=bv[:nb.value], fv_nodes=fn[:nf.value], fv_offsets=fo[:nf.value + 1], fv_idx=fi[:fo[nf.value]])
+
+
+def search_by_bow(kind, nnratio, check_ori, kf_kf, keys1, desc1, valid1, fv1, keys2, desc2, valid2, fv2):
+    """fv = dict with fv_nodes / fv_offsets / fv_idx (Vocabulary.transform).  -> (nmatches, match12[n1], match21[n2])."""
+    lib = _lib(kind)
+    k1 = np.ascontiguousarray(keys1, KP_DTYPE); k2 = np.ascontiguousarray(keys2, KP_DTYPE)
+    d1 = np.ascontiguousarray(desc1, np.uint8).reshape(-1, 32); d2 = np.ascontiguousarray(desc2, np.uint8).reshape(-1, 32)
+    v1 = np.ascontiguousarray(valid1, np.uint8); v2 = np.ascontiguousarray(np.ones(len(k2), np.uint8) if valid2 is None else valid2, np.uint8)
+    a = [np.ascontiguousarray(fv1[x], np.int32) for x in ("fv_nodes", "fv_offsets", "fv_idx")]; b = [np.ascontiguousarray(fv2[x], np.int32) for x in ("fv_nodes", "fv_offsets", "fv_idx")]
+    m12 = np.zeros(max(len(k1), 1), np.int32); m21 = np.zeros(max(len(k2), 1), np.int32)
+    f = getattr(lib, kind + "_search_by_bow"); f.restype = C.c_int
+    f.argtypes = [C.c_float, C.c_int, C.c_int] + [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p] * 2 + [C.c_void_p, C.c_void_p]
+    nm = f(float(nnratio), int(bool(check_ori)), int(bool(kf_kf)), len(k1), k1.ctypes.data, d1.ctypes.data, v1.ctypes.data, len(a[0]), a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data,
+           len(k2), k2.ctypes.data, d2.ctypes.data, v2.ctypes.data, len(b[0]), b[0].ctypes.data, b[1].ctypes.data, b[2].ctypes.data, m12.ctypes.data, m21.ctypes.data)
+    return nm, m12[:len(k1)], m21[:len(k2)]

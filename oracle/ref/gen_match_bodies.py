@@ -6,6 +6,8 @@ output -- nothing is copied into the repository).  The functions are located by 
   src/ORBmatcher.cc : TH_HIGH/TH_LOW/HISTO_LENGTH + ctor, SearchByProjection(Frame&, vector<MapPoint*>&, th),
                       RadiusByViewingCos, SearchForInitialization, SearchByProjection(Frame&, const Frame&, th, bMono),
                       ComputeThreeMaxima, DescriptorDistance
+                      SearchByBoW(KeyFrame*, Frame&, ...), SearchByBoW(KeyFrame*, KeyFrame*, ...)
+  Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h : transform(features, BowVector, FeatureVector, levelsup), transform(feature, ...)
   src/Frame.cc      : AssignFeaturesToGrid, GetFeaturesInArea, PosInGrid, ComputeStereoMatches,
                       UndistortKeyPoints, ComputeImageBounds, ComputeStereoFromRGBD
 
@@ -57,6 +59,8 @@ m = extract("src/ORBmatcher.cc", [
     "int ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono)",
     "void ORBmatcher::ComputeThreeMaxima(vector<int>* histo, const int L, int &ind1, int &ind2, int &ind3)",
     "int ORBmatcher::DescriptorDistance(const cv::Mat &a, const cv::Mat &b)",
+    "int ORBmatcher::SearchByBoW(KeyFrame* pKF,Frame &F, vector<MapPoint*> &vpMapPointMatches)",
+    "int ORBmatcher::SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, vector<MapPoint *> &vpMatches12)",
 ])
 f = extract("src/Frame.cc", [
     "void Frame::AssignFeaturesToGrid()",
@@ -67,7 +71,14 @@ f = extract("src/Frame.cc", [
     "void Frame::ComputeImageBounds(const cv::Mat &imLeft)",
     "void Frame::ComputeStereoFromRGBD(const cv::Mat &imDepth)",
 ])
+# DBoW2 (vendored in the reference tree): the two transform() members of the vocabulary template, for oracle/ref/ref_bow_capi.cpp
+b = extract("Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h", [
+    "void TemplatedVocabulary<TDescriptor,F>::transform(\n  const std::vector<TDescriptor>& features,\n  BowVector &v, FeatureVector &fv, int levelsup) const",
+    "void TemplatedVocabulary<TDescriptor,F>::transform(const TDescriptor &feature, \n  WordId &word_id, WordValue &weight, NodeId *nid, int levelsup) const",
+])
+b = b.replace("void TemplatedVocabulary<TDescriptor,F>::transform(", "template<class TDescriptor, class F>\nvoid TemplatedVocabulary<TDescriptor,F>::transform(")
 os.makedirs(out, exist_ok=True)
+open(os.path.join(out, "ref_bow_bodies.inc"), "w").write("// GENERATED from the reference sources by oracle/ref/gen_match_bodies.py -- do not commit\n" + b)
 # the first ORBmatcher chunk (constants) ends at the ctor's closing brace because the ctor follows immediately
 open(os.path.join(out, "ref_match_bodies.inc"), "w").write("// GENERATED from the reference sources by oracle/ref/gen_match_bodies.py -- do not commit\n" + m + "\n" + f)
 print("generated", os.path.join(out, "ref_match_bodies.inc"))

@@ -1,6 +1,6 @@
 // ref_match_capi.cpp -- TEST INFRASTRUCTURE ONLY (oracle/_ref build).
 //
-// Runs the reference's OWN matcher code: the bodies of ORBmatcher::{SearchByProjection x2, SearchForInitialization,
+// Runs the reference's OWN matcher code: the bodies of ORBmatcher::{SearchByProjection x2, SearchByBoW x2, SearchForInitialization,
 // ComputeThreeMaxima, DescriptorDistance, RadiusByViewingCos} and Frame::{AssignFeaturesToGrid, GetFeaturesInArea,
 // PosInGrid, ComputeStereoMatches, UndistortKeyPoints, ComputeImageBounds, ComputeStereoFromRGBD} are taken verbatim from /root/reference/src/{ORBmatcher,Frame}.cc at build time
 // (oracle/ref/gen_match_bodies.py -> oracle/_ref/gen/ref_match_bodies.inc) and compiled against the minimal
@@ -8,6 +8,7 @@
 // (/root/reference/include/Frame.h, MapPoint.h, ORBmatcher.h).  The whole object graph of the reference
 // (KeyFrame, Map, DBoW2, g2o ...) is not needed by these functions and is not built.
 #include "ORBextractor.h"   // reference header (for mvImagePyramid in ComputeStereoMatches)
+#include "Thirdparty/DBoW2/DBoW2/FeatureVector.h"   // reference header (mFeatVec in SearchByBoW); FeatureVector.cpp is built in ref_bow_capi.cpp
 #include <climits>
 #include <cstring>
 #include <set>
@@ -63,6 +64,16 @@ public:
     cv::Mat mTcw;
     std::vector<float> mvScaleFactors, mvInvScaleFactors;
     static float mnMinX, mnMaxX, mnMinY, mnMaxY;
+    DBoW2::FeatureVector mFeatVec;
+};
+
+class KeyFrame {               // include/KeyFrame.h, the members SearchByBoW reads (ORBmatcher.cc:230-382, 656-799)
+public:
+    std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
+    std::vector<MapPoint*> mvpMapPoints;
+    std::vector<cv::KeyPoint> mvKeysUn;
+    cv::Mat mDescriptors;
+    DBoW2::FeatureVector mFeatVec;
 };
 float Frame::fx, Frame::fy, Frame::cx, Frame::cy, Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv;
 float Frame::mnMinX, Frame::mnMaxX, Frame::mnMinY, Frame::mnMaxY;
@@ -74,6 +85,8 @@ public:
     int SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMapPoints, const float th = 3);
     int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono);
     int SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12, int windowSize = 10);
+    int SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches);
+    int SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12);
     static const int TH_LOW, TH_HIGH, HISTO_LENGTH;
 protected:
     float RadiusByViewingCos(const float& viewCos);
@@ -259,6 +272,47 @@ void ref_undistort_points(const float* pts, int n, const float* cam9, int ndist,
     std::memcpy(m.data, pts, (size_t)n * 8);
     cv::undistortPoints(m, m, K, D, cv::Mat(), K);
     std::memcpy(out, m.data, (size_t)n * 8);
+}
+
+// ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&)  ORBmatcher.cc:230  and  (KeyFrame*, KeyFrame*, ...)  :656.
+// Feature vectors arrive flattened (nodes ascending, offsets, feature indices) as ref_voc_transform returns them.
+// valid1 / valid2: the feature holds a map point that is not bad.  Outputs: match21[j] = side-1 index assigned to side-2
+// feature j (KF x Frame: vpMapPointMatches[j] = KF's map point), match12[i] = side-2 index (KF x KF: vpMatches12[i]).
+static void fill_fv(DBoW2::FeatureVector& fv, int n_fv, const int* nodes, const int* offsets, const int* idx) {
+    for (int q = 0; q < n_fv; ++q) for (int e = offsets[q]; e < offsets[q + 1]; ++e) fv.addFeature(nodes[q], idx[e]);
+}
+int ref_search_by_bow(float nnratio, int checkOri, int kf_kf, int n1, const cv::KeyPoint* keys1, const unsigned char* desc1, const unsigned char* valid1,
+                      int n_fv1, const int* fv1_nodes, const int* fv1_offsets, const int* fv1_idx,
+                      int n2, const cv::KeyPoint* keys2, const unsigned char* desc2, const unsigned char* valid2,
+                      int n_fv2, const int* fv2_nodes, const int* fv2_offsets, const int* fv2_idx, int* match12, int* match21) {
+    ArenaScope scope;
+    int nm;
+    {
+        std::vector<MapPoint> p1(n1), p2(n2);
+        KeyFrame K1; K1.mvKeysUn.assign(keys1, keys1 + n1); K1.mDescriptors = cv::Mat(n1, 32, CV_8U, (void*)desc1).clone();
+        K1.mvpMapPoints.assign(n1, (MapPoint*)NULL);
+        for (int i = 0; i < n1; ++i) if (valid1[i]) K1.mvpMapPoints[i] = &p1[i];
+        fill_fv(K1.mFeatVec, n_fv1, fv1_nodes, fv1_offsets, fv1_idx);
+        for (int i = 0; i < n1; ++i) match12[i] = -1;
+        for (int j = 0; j < n2; ++j) match21[j] = -1;
+        ORBmatcher matcher(nnratio, checkOri != 0);
+        if (kf_kf) {
+            KeyFrame K2; K2.mvKeysUn.assign(keys2, keys2 + n2); K2.mDescriptors = cv::Mat(n2, 32, CV_8U, (void*)desc2).clone();
+            K2.mvpMapPoints.assign(n2, (MapPoint*)NULL);
+            for (int j = 0; j < n2; ++j) if (valid2[j]) K2.mvpMapPoints[j] = &p2[j];
+            fill_fv(K2.mFeatVec, n_fv2, fv2_nodes, fv2_offsets, fv2_idx);
+            std::vector<MapPoint*> m12;
+            nm = matcher.SearchByBoW(&K1, &K2, m12);
+            for (int i = 0; i < n1; ++i) if (m12[i]) { match12[i] = (int)(m12[i] - &p2[0]); match21[match12[i]] = i; }
+        } else {
+            Frame F; F.N = n2; F.mvKeys.assign(keys2, keys2 + n2); F.mDescriptors = cv::Mat(n2, 32, CV_8U, (void*)desc2).clone();
+            fill_fv(F.mFeatVec, n_fv2, fv2_nodes, fv2_offsets, fv2_idx);
+            std::vector<MapPoint*> mf;
+            nm = matcher.SearchByBoW(&K1, F, mf);
+            for (int j = 0; j < n2; ++j) if (mf[j]) { match21[j] = (int)(mf[j] - &p1[0]); match12[match21[j]] = j; }
+        }
+    }
+    return nm;
 }
 
 // Frame::ComputeStereoMatches   Frame.cc:1179.  left / right: handles from ref_extractor_create whose last

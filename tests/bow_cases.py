@@ -1,0 +1,55 @@
+"""Seeded bag-of-words inputs shared by the golden generator and the tests: a synthetic ORB vocabulary (the real ORBvoc.txt is a
+145 MB download the reference does not vendor) built by hierarchical k-medoid-style clustering of real ORB descriptors, with
+idf-like weights and a few stopped (weight 0) words."""
+import numpy as np
+
+
+def hamming(a, b):
+    return np.unpackbits(a[:, None, :] ^ b[None, :, :], axis=2).sum(2)
+
+
+def build_vocabulary(pool, k=10, L=3, seed=11):
+    """pool: M x 32 uint8 descriptors.  Returns (parent, is_leaf, desc, weight) for nodes 1..n in the file order of ORBvoc.txt
+    (a node's children are listed after it; ids grow in that order)."""
+    rng = np.random.default_rng(seed)
+    parent, leaf, desc, weight = [], [], [], []
+
+    def grow(pid, members, level):
+        # k centres drawn from the members (random descriptors when the cluster ran dry), members assigned to the nearest
+        if len(members) >= k:
+            centres = pool[rng.choice(members, k, replace=False)]
+        else:
+            centres = rng.integers(0, 256, (k, 32), dtype=np.uint8)
+        assign = hamming(pool[members], centres).argmin(1) if len(members) else np.zeros(0, np.int64)
+        ids = []
+        for c in range(k):
+            parent.append(pid); desc.append(centres[c]); leaf.append(1 if level == L else 0)
+            w = 0.0 if (level == L and rng.random() < 0.03) else float(np.log(1.0 + rng.uniform(1.0, 400.0)))
+            weight.append(w if level == L else 0.0)
+            ids.append(len(parent))
+        if level < L:
+            for c in range(k):
+                grow(ids[c], members[assign == c] if len(members) else members, level + 1)
+
+    # breadth is not required by the loader: depth-first file order keeps every parent before its children
+    grow(0, np.arange(len(pool)), 1)
+    return np.array(parent, np.int32), np.array(leaf, np.uint8), np.array(desc, np.uint8), np.array(weight, np.float64)
+
+
+def pool_and_frames(extract, n_pool_frames=6):
+    """extract: img -> (keypoints, descriptors).  Returns the descriptor pool and two related frames (A, B = A warped)."""
+    from tools.synth import synth_frame, warp_affine_nn
+    pool = np.concatenate([extract(synth_frame(500 + s, 640, 480))[1] for s in range(n_pool_frames)])
+    A = synth_frame(0, 640, 480); B = warp_affine_nn(A, 7, -4, 2.0)
+    ka, da = extract(A); kb, db = extract(B)
+    return pool, (ka, da), (kb, db)
+
+
+def validity(n, seed):
+    rng = np.random.default_rng(seed)
+    return (rng.random(n) < 0.8).astype(np.uint8)
+
+
+VOC_VARIANTS = [(0, 0), (1, 1), (2, 5), (3, 0), (0, 5)]      # (weighting, scoring): TF_IDF/L1 (ORBvoc), TF/L2, IDF/DOT, BINARY/L1, TF_IDF/DOT
+LEVELSUP = [4, 2, 1, 0]                                      # L = 3: root, level 1, level 2 (what levelsup = 4 gives with L = 6), words
+MATCH_VARIANTS = [(0.7, True), (0.75, False), (0.9, True)]   # TrackReferenceKeyFrame 0.7 / relocalisation 0.75 / loop closing 0.75 (Tracking.cc, LoopClosing.cc)

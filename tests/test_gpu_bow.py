@@ -1,0 +1,69 @@
+"""GPU (B200): bag of words through the C ABI: DBoW2 transform (word / node per feature, BowVector with its
+double-precision weights, FeatureVector) and both ORBmatcher::SearchByBoW forms, bit-exact against the outputs of the reference's own
+sources (tests/golden/ref_bow.npz) and the port oracle."""
+import os
+import numpy as np
+import pytest
+import bow_cases as bc
+
+pytestmark = pytest.mark.gpu
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_bow.npz"))
+TKEYS = ("word", "node", "bow_ids", "bow_vals", "fv_nodes", "fv_offsets", "fv_idx")
+VOC = (G["voc_parent"], G["voc_leaf"], G["voc_desc"], G["voc_weight"])
+
+
+@pytest.mark.parametrize("wt,sc", bc.VOC_VARIANTS)
+def test_transform_matches_reference_dbow2(orbx, wt, sc):
+    V = orbx.ORBVocabulary(10, 3, *VOC, weighting=wt, scoring=sc)
+    assert V.size() == int(G["voc_leaf"].sum())
+    for lu in bc.LEVELSUP:
+        r = V.transform(G["da"], lu)
+        for key in TKEYS:
+            assert np.array_equal(r[key], G["t_%d_%d_%d_%s" % (wt, sc, lu, key)]), (wt, sc, lu, key)
+
+
+def test_extracted_frame_gives_the_golden_descriptors(orbx):
+    """The goldens were produced from the reference extractor's descriptors: the GPU extractor must give the same ones."""
+    from tools.synth import synth_frame
+    k, d = orbx.ORBextractor(1000, 1.2, 8, 20, 7)(synth_frame(0, 640, 480))
+    assert np.array_equal(d, G["da"]) and np.array_equal(k.view(np.uint8), G["ka"])
+
+
+def test_search_by_bow_matches_reference_bodies(orbx):
+    ka, da, kb, db = G["ka"].view(orbx.KP_DTYPE), G["da"], G["kb"].view(orbx.KP_DTYPE), G["db"]
+    V = orbx.ORBVocabulary(10, 3, *VOC)
+    fa, fb = V.transform(da, 1), V.transform(db, 1)
+    va, vb = bc.validity(len(ka), 1), bc.validity(len(kb), 2)
+    for kfkf in (0, 1):
+        for i, (nn, ori) in enumerate(bc.MATCH_VARIANTS):
+            nm, m12, m21 = orbx.ORBmatcher(nn, ori).SearchByBoW(kfkf, ka, da, va, fa, kb, db, vb if kfkf else None, fb)
+            assert nm == int(G["m_%d_%d_nm" % (kfkf, i)])
+            assert np.array_equal(m12, G["m_%d_%d_m12" % (kfkf, i)]) and np.array_equal(m21, G["m_%d_%d_m21" % (kfkf, i)])
+
+
+def test_bow_variants_vs_port(orbx, oracle):
+    """Other shapes: every feature in one node (levelsup >= L: a single warp replays 1000 x 1000), deep tree, few / no valid features, empty sides."""
+    ka, da, kb, db = G["ka"].view(orbx.KP_DTYPE), G["da"], G["kb"].view(orbx.KP_DTYPE), G["db"]
+    V = orbx.ORBVocabulary(10, 3, *VOC); P = oracle.Vocabulary("port", 10, 3, *VOC)
+    rng = np.random.default_rng(5)
+    for lu, pv in ((4, 0.8), (2, 0.3), (0, 1.0), (1, 0.0)):
+        fa, fb = V.transform(da, lu), V.transform(db, lu)
+        va = (rng.random(len(ka)) < pv).astype(np.uint8); vb = (rng.random(len(kb)) < 0.9).astype(np.uint8)
+        for kfkf in (0, 1):
+            g = orbx.ORBmatcher(0.75, True).SearchByBoW(kfkf, ka, da, va, fa, kb, db, vb if kfkf else None, fb)
+            o = oracle.search_by_bow("port", 0.75, True, kfkf, ka, da, va, fa, kb, db, vb, fb)
+            assert g[0] == o[0] and np.array_equal(g[1], o[1]) and np.array_equal(g[2], o[2]), (lu, pv, kfkf)
+    # deeper, narrower tree and a different descriptor set
+    pool = np.concatenate([da, db])
+    voc2 = bc.build_vocabulary(pool, k=4, L=5, seed=3)
+    V2 = orbx.ORBVocabulary(4, 5, *voc2); P2 = oracle.Vocabulary("port", 4, 5, *voc2)
+    for lu in (4, 3, 1):
+        g, o = V2.transform(db, lu), P2.transform(db, lu)
+        for key in TKEYS:
+            assert np.array_equal(g[key], o[key]), (lu, key)
+    # empty inputs
+    e = V.transform(np.zeros((0, 32), np.uint8), 4)
+    assert len(e["bow_ids"]) == 0 and len(e["fv_nodes"]) == 0
+    fa = V.transform(da, 1)
+    nm, m12, m21 = orbx.ORBmatcher(0.7, True).SearchByBoW(0, ka, da, np.ones(len(ka), np.uint8), fa, kb[:0], db[:0], None, e)
+    assert nm == 0 and np.all(m12 == -1) and len(m21) == 0
