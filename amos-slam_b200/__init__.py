@@ -104,6 +104,7 @@ def lib():
         L.orbx_vocabulary_create.argtypes = [ci, ci, ci, ci, ci, ci, vp, vp, vp, vp, C.POINTER(vp)]
         L.orbx_vocabulary_destroy.argtypes = [vp]; L.orbx_vocabulary_destroy.restype = None
         L.orbx_vocabulary_words.argtypes = [vp]
+        L.orbx_vocabulary_load_text.argtypes = [ci, C.c_char_p, C.POINTER(vp)]
         L.orbx_vocabulary_transform.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp, C.POINTER(ci), vp, vp, vp, C.POINTER(ci)]
         L.orbx_search_by_bow.argtypes = [vp, ci, vp, vp, vp, vp, C.POINTER(ci)]
         L.orbx_frame_create.argtypes = [ci, C.POINTER(vp)]

@@ -185,6 +185,17 @@ class ORBVocabulary:
         _check(self._lib.orbx_vocabulary_create(int(device), int(k), int(L), int(weighting), int(scoring), len(pa), _p(pa), _p(lf), _p(ds), _p(w), C.byref(h)))
         self._h = h
 
+    @classmethod
+    def load_text(cls, path, device=0):
+        """bool loadFromTextFile(const std::string &filename) (src/System.cc:84)."""
+        from . import lib, _check
+        self = cls.__new__(cls)
+        self._lib, self._check = lib(), _check
+        h = C.c_void_p()
+        _check(self._lib.orbx_vocabulary_load_text(int(device), str(path).encode(), C.byref(h)))
+        self._h = h
+        return self
+
     def close(self):
         if getattr(self, "_h", None):
             self._lib.orbx_vocabulary_destroy(self._h)

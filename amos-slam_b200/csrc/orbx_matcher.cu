@@ -10,6 +10,7 @@
 #include "k_bow.cuh"
 
 #include <climits>
+#include <cstdio>
 #include <algorithm>
 #include <cstring>
 #include <string>
@@ -790,6 +791,29 @@ int orbx_vocabulary_create(int device, int k, int L, int weighting, int scoring,
     if (cudaStreamSynchronize(v->stream) != cudaSuccess) { orbx_vocabulary_destroy(v); FAIL(ORBX_E_CUDA, "vocabulary upload"); }
     *out = v;
     return ORBX_OK;
+}
+int orbx_vocabulary_load_text(int device, const char* path, orbx_vocabulary** out) {
+    if (!out || !path) FAIL(ORBX_E_INVALID, "null argument");
+    *out = nullptr;
+    FILE* f = std::fopen(path, "r");
+    if (!f) FAIL(ORBX_E_INVALID, std::string("cannot open vocabulary file ") + path);
+    int k = 0, L = 0, n1 = -1, n2 = -1;
+    if (std::fscanf(f, "%d %d %d %d", &k, &L, &n1, &n2) != 4 || k < 0 || k > 20 || L < 1 || L > 10 || n1 < 0 || n1 > 5 || n2 < 0 || n2 > 3) {
+        std::fclose(f); FAIL(ORBX_E_INVALID, "not a vocabulary text file");                 // the reference's own header check (TemplatedVocabulary.h:1358)
+    }
+    std::vector<int> parent; std::vector<uint8_t> leaf, desc; std::vector<double> weight;
+    while (true) {
+        int pid, isleaf;
+        if (std::fscanf(f, "%d %d", &pid, &isleaf) != 2) break;
+        uint8_t d[32]; bool ok = true;
+        for (int i = 0; i < 32 && ok; ++i) { int b; ok = std::fscanf(f, "%d", &b) == 1; d[i] = (uint8_t)b; }
+        double w;
+        if (!ok || std::fscanf(f, "%lf", &w) != 1) { std::fclose(f); FAIL(ORBX_E_INVALID, "truncated vocabulary node line"); }
+        parent.push_back(pid); leaf.push_back(isleaf > 0 ? 1 : 0); desc.insert(desc.end(), d, d + 32); weight.push_back(w);
+    }
+    std::fclose(f);
+    if (parent.empty()) FAIL(ORBX_E_INVALID, "vocabulary file holds no nodes");
+    return orbx_vocabulary_create(device, k, L, n2, n1, (int)parent.size(), parent.data(), leaf.data(), desc.data(), weight.data(), out);
 }
 void orbx_vocabulary_destroy(orbx_vocabulary* v) {
     if (!v) return;

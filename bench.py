@@ -219,7 +219,31 @@ def matcher_bench(orbx, torch, ext, frames, device):
     for _ in range(reps2):
         m.SearchForInitialization(DA, DB, prev, 100)
     dt_dev = (time.perf_counter() - t0) / reps2
-    return {"frame_build_us": dt_build * 1e6, "frame_build_config": "orbx_frame_assign on the extractor's device result: %d keypoints, 5-coefficient undistortion, RGB-D stereo, grid" % len(kp_b),
+    # bag of words at the size of ORBvoc.txt (k = 10, L = 6: 1 111 110 nodes, 10^6 words; random node descriptors -- the timing does not
+    # depend on their values): Frame::ComputeBoW = transform(descriptors, mBowVec, mFeatVec, 4), then SearchByBoW(KeyFrame, Frame)
+    rngv = np.random.default_rng(5)
+    nn = (10 ** 7 - 10) // 9
+    ids = np.arange(1, nn + 1, dtype=np.int64)
+    vparent = ((ids - 1) // 10).astype(np.int32); vleaf = (ids > (10 ** 6 - 10) // 9).astype(np.uint8)
+    V = orbx.ORBVocabulary(10, 6, vparent, vleaf, rngv.integers(0, 256, (nn, 32), dtype=np.uint8), np.where(vleaf > 0, rngv.uniform(0.5, 9.0, nn), 0.0), device=device)
+    for _ in range(3):
+        fa = V.transform(d_a, 4); fb = V.transform(d_b, 4)
+    t0 = time.perf_counter()
+    for _ in range(reps2):
+        fb = V.transform(d_b, 4)
+    dt_bow = (time.perf_counter() - t0) / reps2
+    va = np.ones(len(kp_a), np.uint8)
+    mb = orbx.ORBmatcher(0.7, True, device=device)
+    for _ in range(3):
+        mb.SearchByBoW(0, kp_a, d_a, va, fa, kp_b, d_b, None, fb)
+    t0 = time.perf_counter()
+    for _ in range(reps2):
+        nbow = mb.SearchByBoW(0, kp_a, d_a, va, fa, kp_b, d_b, None, fb)[0]
+    dt_sbow = (time.perf_counter() - t0) / reps2
+    bow = {"compute_bow_us": dt_bow * 1e6, "compute_bow_config": "orbx_vocabulary_transform, %d descriptors, k=10 L=6 tree (%d nodes) resident in HBM/L2, levelsup 4, host pointers in/out" % (len(d_b), nn),
+           "search_by_bow_us": dt_sbow * 1e6, "search_by_bow_config": "KeyFrame x Frame form, %d x %d features in %d / %d nodes, host pointers in/out" % (len(kp_a), len(kp_b), len(fa["fv_nodes"]), len(fb["fv_nodes"])),
+           "search_by_bow_matches": int(nbow)}
+    return {"bow": bow, "frame_build_us": dt_build * 1e6, "frame_build_config": "orbx_frame_assign on the extractor's device result: %d keypoints, 5-coefficient undistortion, RGB-D stereo, grid" % len(kp_b),
             "search_for_initialization_device_frames_pairs_per_s": 1.0 / dt_dev,
             "bruteforce_pairs_per_s": P / (ms * 1e-3), "hamming_distances_per_s": P * NQ * NQ / (ms * 1e-3),
             "bruteforce_config": "%d pairs x %d x %d descriptors per launch, device-resident" % (P, NQ, NQ),

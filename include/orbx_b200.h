@@ -365,6 +365,10 @@ typedef struct orbx_vocabulary orbx_vocabulary;
  * 4 BHATTACHARYYA, 5 DOT_PRODUCT (BowVector.h:25-49).  The tree is copied to the device (35 MB for ORBvoc: it stays in L2). */
 int  orbx_vocabulary_create(int device, int k, int L, int weighting, int scoring, int n_nodes, const int* parent,
                             const uint8_t* is_leaf, const uint8_t* descriptors, const double* weights, orbx_vocabulary** out);
+/* The same from the text file ORBVocabulary::loadFromTextFile reads (src/System.cc:84; first line "k L scoring weighting", then one
+ * line per node "parent is_leaf d0 ... d31 weight").  A trailing empty line is ignored (the reference's reader turns it into a
+ * childless, weightless extra child of the root with an all-zero descriptor, which no ORB descriptor descends into). */
+int  orbx_vocabulary_load_text(int device, const char* path, orbx_vocabulary** out);
 void orbx_vocabulary_destroy(orbx_vocabulary* v);
 int  orbx_vocabulary_words(const orbx_vocabulary* v);      /* size() */
 

@@ -53,3 +53,12 @@ def validity(n, seed):
 VOC_VARIANTS = [(0, 0), (1, 1), (2, 5), (3, 0), (0, 5)]      # (weighting, scoring): TF_IDF/L1 (ORBvoc), TF/L2, IDF/DOT, BINARY/L1, TF_IDF/DOT
 LEVELSUP = [4, 2, 1, 0]                                      # L = 3: root, level 1, level 2 (what levelsup = 4 gives with L = 6), words
 MATCH_VARIANTS = [(0.7, True), (0.75, False), (0.9, True)]   # TrackReferenceKeyFrame 0.7 / relocalisation 0.75 / loop closing 0.75 (Tracking.cc, LoopClosing.cc)
+
+
+def write_text(path, k, L, scoring, weighting, voc):
+    """ORBvoc.txt format (TemplatedVocabulary.h:1336-1424)."""
+    parent, leaf, desc, weight = voc
+    with open(path, "w") as f:
+        f.write("%d %d %d %d\n" % (k, L, scoring, weighting))
+        for i in range(len(parent)):
+            f.write("%d %d %s %r\n" % (parent[i], leaf[i], " ".join(str(int(b)) for b in desc[i]), float(weight[i])))

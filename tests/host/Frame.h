@@ -7,6 +7,7 @@
 #include <vector>
 #include <opencv2/core/core.hpp>
 #include "MapPoint.h"
+#include "DBoW2_standin.h"
 #include "ORBextractor.h"
 struct orbx_frame;                                          // include/orbx_b200.h (global namespace)
 namespace ORB_SLAM2 {
@@ -16,6 +17,10 @@ public:
     void UndistortKeyPoints();
     void ComputeStereoFromRGBD(const cv::Mat& imDepth);
     void AssignFeaturesToGrid();
+    void ComputeBoW();
+    ORBVocabulary* mpORBvocabulary = nullptr;
+    DBoW2::BowVector mBowVec;
+    DBoW2::FeatureVector mFeatVec;
     cv::Mat mK, mDistCoef;
     std::vector<std::size_t> mGrid[64][48];                 // FRAME_GRID_COLS x FRAME_GRID_ROWS (include/Frame.h:56-61, 459)
     std::shared_ptr<orbx_frame> mpDeviceFrame;             // the ONE member a maintainer adds to include/Frame.h

@@ -3,15 +3,17 @@
 // tests/test_gpu_host_dropin.py compares with the C-ABI results (themselves bit-exact against the oracle).
 // cv:: types come from the OpenCV-free shim (oracle/shim) -- test infrastructure, not product.
 //
-// usage: host_dropin <in.bin> <out.bin>
+// usage: host_dropin <in.bin> <out.bin> [vocabulary.txt]
 //   in.bin : int32 w,h ; u8 A[h*w] ; u8 B[h*w] ; int32 sw,sh ; u8 L[sh*sw] ; u8 R[sh*sw] ; f32 cam[10] (fx fy cx cy k1 k2 p1 p2 k3 bf) ; f32 bounds[6]
 #include "ORBextractor.h"
 #include "ORBmatcher.h"
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 using namespace ORB_SLAM2;
+namespace ORB_SLAM2 { void RegisterDeviceVocabulary(const ORBVocabulary* voc, const std::string& file); }   // amos-slam_b200/host/BoW_b200.cc
 
 float Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv, Frame::mnMinX, Frame::mnMaxX, Frame::mnMinY, Frame::mnMaxY;
 const int ORBmatcher::TH_HIGH = 100, ORBmatcher::TH_LOW = 50, ORBmatcher::HISTO_LENGTH = 30;
@@ -161,6 +163,34 @@ int main(int argc, char** argv) {
         nm2 = ORBmatcher(0.8, true).SearchByProjection(D2, pts, 3.f);
         put_i(nm2);
         for (int j = 0; j < D2.N; ++j) put_i(D2.mvpMapPoints[j] ? (int)(D2.mvpMapPoints[j] - store.data()) : -1);
+    }
+    // ---- bag of words: Frame::ComputeBoW / KeyFrame::ComputeBoW and both SearchByBoW forms (Tracking.cc:1740-1752, LoopClosing)
+    if (argc > 3) {
+        ORBVocabulary voc;
+        RegisterDeviceVocabulary(&voc, argv[3]);                                                   // System.cc:84, once
+        Frame F2; fill_frame(F2, ext, kb, db, w, h); F2.mpORBvocabulary = &voc;
+        F2.ComputeBoW();
+        put_i((int)F2.mBowVec.size());
+        for (DBoW2::BowVector::const_iterator it = F2.mBowVec.begin(); it != F2.mBowVec.end(); ++it) { put_i((int)it->first); put(&it->second, 8); }
+        put_i((int)F2.mFeatVec.size());
+        for (DBoW2::FeatureVector::const_iterator it = F2.mFeatVec.begin(); it != F2.mFeatVec.end(); ++it) {
+            put_i((int)it->first); put_i((int)it->second.size());
+            for (size_t q = 0; q < it->second.size(); ++q) put_i((int)it->second[q]);
+        }
+        std::vector<MapPoint> mp1(ka.size()), mp2(kb.size());
+        KeyFrame K1; K1.mvKeysUn = ka; K1.mDescriptors = da; K1.mpORBvocabulary = &voc; K1.mvpMapPoints.assign(ka.size(), (MapPoint*)NULL);
+        for (size_t i = 0; i < ka.size(); ++i) { if (i % 5) K1.mvpMapPoints[i] = &mp1[i]; mp1[i].mbBad = (i % 11) == 0; }
+        K1.ComputeBoW();
+        KeyFrame K2; K2.mvKeysUn = kb; K2.mDescriptors = db; K2.mpORBvocabulary = &voc; K2.mvpMapPoints.assign(kb.size(), (MapPoint*)NULL);
+        for (size_t j = 0; j < kb.size(); ++j) { if (j % 7) K2.mvpMapPoints[j] = &mp2[j]; mp2[j].mbBad = (j % 13) == 0; }
+        K2.ComputeBoW();
+        std::vector<MapPoint*> mf, m12;
+        int nb1 = ORBmatcher(0.7, true).SearchByBoW(&K1, F2, mf);
+        put_i(nb1); put_i((int)mf.size());
+        for (size_t j = 0; j < mf.size(); ++j) put_i(mf[j] ? (int)(mf[j] - mp1.data()) : -1);
+        int nb2 = ORBmatcher(0.75, true).SearchByBoW(&K1, &K2, m12);
+        put_i(nb2); put_i((int)m12.size());
+        for (size_t i = 0; i < m12.size(); ++i) put_i(m12[i] ? (int)(m12[i] - mp2.data()) : -1);
     }
     fclose(g_out); fclose(f);
     printf("host drop-in ok: %zu / %zu keypoints, %d stereo keypoints\n", ka.size(), kb.size(), S.N);

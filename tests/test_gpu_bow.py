@@ -67,3 +67,16 @@ def test_bow_variants_vs_port(orbx, oracle):
     fa = V.transform(da, 1)
     nm, m12, m21 = orbx.ORBmatcher(0.7, True).SearchByBoW(0, ka, da, np.ones(len(ka), np.uint8), fa, kb[:0], db[:0], None, e)
     assert nm == 0 and np.all(m12 == -1) and len(m21) == 0
+
+
+def test_vocabulary_text_file_loader(orbx, tmp_path):
+    path = str(tmp_path / "voc.txt")
+    bc.write_text(path, 10, 3, 1, 1, VOC)                                # scoring L2_NORM, weighting TF
+    V = orbx.ORBVocabulary.load_text(path)
+    r = V.transform(G["da"], 2)
+    for key in TKEYS:
+        assert np.array_equal(r[key], G["t_1_1_2_%s" % key]), key
+    with pytest.raises(orbx.OrbxError):
+        orbx.ORBVocabulary.load_text(str(tmp_path / "missing.txt"))
+    with pytest.raises(orbx.OrbxError):
+        orbx.ORBVocabulary(10, 3, VOC[0], 1 - VOC[1], VOC[2], VOC[3])    # leaf flags contradict the tree

@@ -24,9 +24,9 @@ def build_driver():
     orbx.build()
     os.makedirs(os.path.dirname(BIN), exist_ok=True)
     srcs = [os.path.join(ROOT, "tests", "host", "host_dropin_main.cc"), os.path.join(HOST, "ORBextractor.cc"), os.path.join(HOST, "ORBmatcher_b200.cc"),
-            os.path.join(HOST, "Frame_b200.cc")]
+            os.path.join(HOST, "Frame_b200.cc"), os.path.join(HOST, "BoW_b200.cc")]
     deps = srcs + [os.path.join(HOST, "ORBextractor.h"), os.path.join(ROOT, "include", "orbx_b200.h"), orbx.LIB_PATH] + \
-           [os.path.join(ROOT, "tests", "host", h) for h in ("Frame.h", "MapPoint.h", "ORBmatcher.h")]
+           [os.path.join(ROOT, "tests", "host", h) for h in ("Frame.h", "MapPoint.h", "ORBmatcher.h", "KeyFrame.h", "DBoW2_standin.h")]
     if os.path.exists(BIN) and all(os.path.getmtime(BIN) >= os.path.getmtime(d) for d in deps):
         return BIN
     cmd = ["g++", "-std=c++14", "-O2", "-I" + os.path.join(ROOT, "oracle", "shim"), "-I" + os.path.join(ROOT, "tests", "host"), "-I" + HOST] + srcs + \
@@ -42,7 +42,8 @@ def test_host_classes_compile_and_link():
     syms = subprocess.run(["nm", "-C", b], capture_output=True, text=True).stdout
     for s in ("ORB_SLAM2::ORBextractor::operator()", "ORB_SLAM2::ORBextractor::MovingKeyPoints", "ORB_SLAM2::ORBextractor::ProcessDesp",
               "ORB_SLAM2::ORBmatcher::SearchForInitialization", "ORB_SLAM2::ORBmatcher::SearchByProjection", "ORB_SLAM2::Frame::ComputeStereoMatches",
-              "ORB_SLAM2::Frame::UndistortKeyPoints", "ORB_SLAM2::Frame::ComputeStereoFromRGBD", "ORB_SLAM2::Frame::AssignFeaturesToGrid"):
+              "ORB_SLAM2::Frame::UndistortKeyPoints", "ORB_SLAM2::Frame::ComputeStereoFromRGBD", "ORB_SLAM2::Frame::AssignFeaturesToGrid",
+              "ORB_SLAM2::Frame::ComputeBoW", "ORB_SLAM2::KeyFrame::ComputeBoW", "ORB_SLAM2::ORBmatcher::SearchByBoW", "ORB_SLAM2::RegisterDeviceVocabulary"):
         assert s in syms, s
 
 
@@ -81,7 +82,14 @@ def test_host_classes_match_c_abi(orbx, tmp_path):
     FD = orbx.Frame().assign(E, cam, 480, 640, fc.depth_image())
     with open(fin, "ab") as f:
         f.write(struct.pack("<10f", *[getattr(cam, n) for n, _ in cam._fields_])); f.write(FD.read()[3].tobytes())
-    subprocess.check_call([b, fin, fout])
+    # bag of words: a k = 4, L = 5 vocabulary grown from the two frames' descriptors, as the text file the reference loads
+    import bow_cases as bc
+    kb0, db0 = E(B)
+    E(A)                                                                 # leave A's result on the device, as the driver's first call does
+    voc = bc.build_vocabulary(np.concatenate([da, db0]), k=4, L=5, seed=3)
+    fvoc = str(tmp_path / "voc.txt")
+    bc.write_text(fvoc, 4, 5, 0, 0, voc)
+    subprocess.check_call([b, fin, fout, fvoc])
     r = Reader(open(fout, "rb").read())
     hk, hd = r.kps(orbx.KP_DTYPE)
     assert np.array_equal(hk, ka) and np.array_equal(hd, da)
@@ -144,4 +152,25 @@ def test_host_classes_match_c_abi(orbx, tmp_path):
     assert np.array_equal(r.arr(np.int32, r.i()), m12)
     assert r.i() == nm2
     assert np.array_equal(r.arr(np.int32, len(kb)), host_fm)
+    # bag of words through Frame::ComputeBoW / KeyFrame::ComputeBoW / ORBmatcher::SearchByBoW == the C-ABI results (pinned to DBoW2 in test_gpu_bow.py)
+    V = orbx.ORBVocabulary(4, 5, *voc)
+    ta, tb = V.transform(da, 4), V.transform(db, 4)
+    nb_ = r.i()
+    assert nb_ == len(tb["bow_ids"]) and nb_ > 50
+    rec = np.frombuffer(r.b, np.dtype([("id", "<i4"), ("v", "<f8")]), nb_, r.o); r.o += 12 * nb_
+    assert np.array_equal(rec["id"], tb["bow_ids"]) and np.array_equal(rec["v"], tb["bow_vals"])
+    nf_ = r.i()
+    assert nf_ == len(tb["fv_nodes"])
+    for q in range(nf_):
+        assert r.i() == tb["fv_nodes"][q]
+        m = r.i()
+        assert np.array_equal(r.arr(np.int32, m), tb["fv_idx"][tb["fv_offsets"][q]:tb["fv_offsets"][q + 1]])
+    i1 = np.arange(len(ka)); j2 = np.arange(len(kb))
+    v1 = ((i1 % 5 != 0) & (i1 % 11 != 0)).astype(np.uint8); v2 = ((j2 % 7 != 0) & (j2 % 13 != 0)).astype(np.uint8)
+    g = orbx.ORBmatcher(0.7, True).SearchByBoW(0, ka, da, v1, ta, kb, db, None, tb)
+    assert r.i() == g[0] and g[0] > 20 and r.i() == len(kb)
+    assert np.array_equal(r.arr(np.int32, len(kb)), g[2])
+    g = orbx.ORBmatcher(0.75, True).SearchByBoW(1, ka, da, v1, ta, kb, db, v2, tb)
+    assert r.i() == g[0] and g[0] > 20 and r.i() == len(ka)
+    assert np.array_equal(r.arr(np.int32, len(ka)), g[1])
     assert r.o == len(r.b)
