@@ -80,12 +80,15 @@ __device__ int block_scan_excl(int* sc, int n, int tid, int nt, int* carry_sm) {
     return *carry_sm;
 }
 
+#define BOW_SMEM_KEYS 4096
 // keys: scratch [n + 1] u64; flags: scratch [n + 1] int; stage: scratch [n] double.  Outputs as the C ABI describes them; counts[0] = n_bow, counts[1] = n_fv.
 __global__ void __launch_bounds__(1024)
 k_bow_assemble(int n, int weighting, int scoring, const int* __restrict__ word_of, const int* __restrict__ node_of, const double* __restrict__ weight_of,
                unsigned long long* __restrict__ keys, int* __restrict__ flags, double* __restrict__ stage,
                int* __restrict__ bow_ids, double* __restrict__ bow_vals, int* __restrict__ fv_nodes, int* __restrict__ fv_offsets, int* __restrict__ fv_idx, int* __restrict__ counts) {
     __shared__ int carry, n_live_sm;
+    __shared__ unsigned long long skeys[BOW_SMEM_KEYS + 1];             // a frame's worth of keys sorts in shared memory
+    if (n <= BOW_SMEM_KEYS) keys = skeys;
     const int tid = threadIdx.x, nt = blockDim.x;
     // ---- BowVector: sort (word, feature) of the non-stopped features ----
     for (int i = tid; i < n; i += nt) keys[i] = (weight_of[i] > 0.0) ? (((unsigned long long)(uint32_t)word_of[i] << 32) | (uint32_t)i) : ~0ull;
@@ -112,17 +115,21 @@ k_bow_assemble(int n, int weighting, int scoring, const int* __restrict__ word_o
     __syncthreads();
     // normalisation (BowVector::normalize, or the "/ size" of un-normalised TF weights): sums in map (word id) order by ONE thread
     const bool must = scoring != 5;                                     // DOT_PRODUCT is the only scoring that does not normalise
+    double* sv = reinterpret_cast<double*>(keys);                       // the sorted keys are spent: reuse the buffer for the serial sum
+    for (int i = tid; i < n_bow; i += nt) sv[i] = (scoring == 1) ? __dmul_rn(bow_vals[i], bow_vals[i]) : fabs(bow_vals[i]);
+    __syncthreads();
     if (tid == 0) {
         double norm = 0.0;
         if (must) {
-            if (scoring == 1) { for (int i = 0; i < n_bow; ++i) norm = __dadd_rn(norm, __dmul_rn(bow_vals[i], bow_vals[i])); norm = __dsqrt_rn(norm); }
-            else for (int i = 0; i < n_bow; ++i) norm = __dadd_rn(norm, fabs(bow_vals[i]));
+            for (int i = 0; i < n_bow; ++i) norm = __dadd_rn(norm, sv[i]);
+            if (scoring == 1) norm = __dsqrt_rn(norm);
         } else if (weighting == 0 || weighting == 1) norm = (double)n_bow;
-        reinterpret_cast<double*>(keys)[n] = norm;                     // keys has n + 1 slots
+        sv[n] = norm;                                                  // keys has n + 1 slots
         counts[0] = n_bow;
     }
     __syncthreads();
-    const double norm = reinterpret_cast<double*>(keys)[n];
+    const double norm = sv[n];
+    __syncthreads();
     if (norm > 0.0) for (int i = tid; i < n_bow; i += nt) bow_vals[i] = __ddiv_rn(bow_vals[i], norm);
     __syncthreads();
     // ---- FeatureVector: sort (node, feature) of the same features ----

@@ -77,6 +77,15 @@ struct orbx_matcher {
     float nnratio; int checkOri; int device; cudaStream_t stream = nullptr; long long launches = 0;
     Arena arena; Arena cand_arena; UploadArena uparena;
     size_t cand_cap = 0;           // candidate entries the cand arena holds
+    uint8_t* dl_host = nullptr; size_t dl_cap = 0;     // pinned landing buffer for results that come back in one copy
+    int ensure_download(size_t bytes) {
+        if (bytes <= dl_cap) return ORBX_OK;
+        if (dl_host) cudaFreeHost(dl_host);
+        dl_host = nullptr; dl_cap = 0;
+        const size_t want = bytes + (bytes >> 2) + 4096;
+        if (cudaHostAlloc((void**)&dl_host, want, cudaHostAllocDefault) != cudaSuccess) { orbx_set_error("cudaHostAlloc (matcher download buffer)"); return ORBX_E_CUDA; }
+        dl_cap = want; return ORBX_OK;
+    }
 };
 
 static int flush_uploads(orbx_matcher* m) {
@@ -233,6 +242,7 @@ void orbx_matcher_destroy(orbx_matcher* m) {
     if (m->arena.base) cudaFree(m->arena.base);
     if (m->cand_arena.base) cudaFree(m->cand_arena.base);
     m->uparena.release();
+    if (m->dl_host) cudaFreeHost(m->dl_host);
     cudaStreamDestroy(m->stream);
     delete m;
 }
@@ -748,7 +758,8 @@ struct orbx_vocabulary {
     int k, L, weighting, scoring, n = 0, nwords = 0;
     FBuf<int> child_off, child_id, word; FBuf<uint8_t> child_desc; FBuf<double> weight;
     // transform scratch
-    FBuf<uint8_t> desc; FBuf<int> word_of, node_of, flags, bow_ids, fv_nodes, fv_offsets, fv_idx, counts; FBuf<double> weight_of, stage, bow_vals; FBuf<unsigned long long> keys;
+    FBuf<uint8_t> desc, pack; FBuf<int> flags; FBuf<double> weight_of, stage; FBuf<unsigned long long> keys;
+    uint8_t* hpack = nullptr; size_t hpack_cap = 0;               // pinned mirror of `pack` (all outputs of one transform)
 };
 #define VLAUNCH_CHECK() do { cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) { \
     orbx_set_error(std::string("kernel launch: ") + cudaGetErrorString(_e)); return ORBX_E_CUDA; } ++v->launches; } while (0)
@@ -819,8 +830,8 @@ void orbx_vocabulary_destroy(orbx_vocabulary* v) {
     if (!v) return;
     cudaSetDevice(v->device); if (v->stream) cudaStreamSynchronize(v->stream);
     v->child_off.release(); v->child_id.release(); v->word.release(); v->child_desc.release(); v->weight.release();
-    v->desc.release(); v->word_of.release(); v->node_of.release(); v->flags.release(); v->bow_ids.release(); v->fv_nodes.release(); v->fv_offsets.release(); v->fv_idx.release();
-    v->counts.release(); v->weight_of.release(); v->stage.release(); v->bow_vals.release(); v->keys.release();
+    v->desc.release(); v->pack.release(); v->flags.release(); v->weight_of.release(); v->stage.release(); v->keys.release();
+    if (v->hpack) cudaFreeHost(v->hpack);
     if (v->stream) cudaStreamDestroy(v->stream);
     delete v;
 }
@@ -835,30 +846,40 @@ int orbx_vocabulary_transform(orbx_vocabulary* v, const uint8_t* descriptors, in
     CU_TRY(cudaSetDevice(v->device));
     const size_t nn = n;
     int rc;
-    if ((rc = v->desc.ensure(nn * 32)) || (rc = v->word_of.ensure(nn)) || (rc = v->node_of.ensure(nn)) || (rc = v->weight_of.ensure(nn)) || (rc = v->keys.ensure(nn + 1)) ||
-        (rc = v->flags.ensure(nn + 1)) || (rc = v->stage.ensure(nn)) || (rc = v->bow_ids.ensure(nn)) || (rc = v->bow_vals.ensure(nn)) || (rc = v->fv_nodes.ensure(nn)) ||
-        (rc = v->fv_offsets.ensure(nn + 1)) || (rc = v->fv_idx.ensure(nn)) || (rc = v->counts.ensure(2))) return rc;
+    // every output lives in ONE device block mirrored by a pinned host block, so the results come back in a single copy:
+    // [counts 2 | word_of n | node_of n | bow_ids n | fv_nodes n | fv_offsets n + 1 | fv_idx n] ints, then bow_vals n doubles (8-aligned)
+    const size_t n_int = 2 + 6 * nn + 1, off_d = (n_int * 4 + 7) & ~(size_t)7, pack_bytes = off_d + nn * 8;
+    if ((rc = v->desc.ensure(nn * 32)) || (rc = v->weight_of.ensure(nn)) || (rc = v->keys.ensure(nn + 1)) || (rc = v->flags.ensure(nn + 1)) || (rc = v->stage.ensure(nn)) ||
+        (rc = v->pack.ensure(pack_bytes))) return rc;
+    if (v->hpack_cap < pack_bytes) {
+        if (v->hpack) cudaFreeHost(v->hpack);
+        v->hpack = nullptr; v->hpack_cap = 0;
+        CU_TRY(cudaHostAlloc((void**)&v->hpack, pack_bytes + (pack_bytes >> 2), cudaHostAllocDefault));
+        v->hpack_cap = pack_bytes + (pack_bytes >> 2);
+    }
+    int* pi = reinterpret_cast<int*>(v->pack.p);
+    int *d_counts = pi, *d_word = pi + 2, *d_node = d_word + nn, *d_bid = d_node + nn, *d_fn = d_bid + nn, *d_fo = d_fn + nn, *d_fi = d_fo + nn + 1;
+    double* d_bv = reinterpret_cast<double*>(v->pack.p + off_d);
     cudaStream_t s = v->stream;
     CU_TRY(cudaMemcpyAsync(v->desc.p, descriptors, nn * 32, cudaMemcpyHostToDevice, s));
     VocDev d; d.k = v->k; d.L = v->L; d.weighting = v->weighting; d.scoring = v->scoring; d.n = v->n;
     d.child_off = v->child_off.p; d.child_id = v->child_id.p; d.child_desc = reinterpret_cast<const uint4*>(v->child_desc.p); d.weight = v->weight.p; d.word = v->word.p;
-    k_bow_descend<<<(n + 3) / 4, 128, 0, s>>>(d, reinterpret_cast<const uint4*>(v->desc.p), n, levelsup, v->word_of.p, v->node_of.p, v->weight_of.p);
+    k_bow_descend<<<(n + 3) / 4, 128, 0, s>>>(d, reinterpret_cast<const uint4*>(v->desc.p), n, levelsup, d_word, d_node, v->weight_of.p);
     VLAUNCH_CHECK();
-    k_bow_assemble<<<1, 1024, 0, s>>>(n, v->weighting, v->scoring, v->word_of.p, v->node_of.p, v->weight_of.p, v->keys.p, v->flags.p, v->stage.p,
-                                      v->bow_ids.p, v->bow_vals.p, v->fv_nodes.p, v->fv_offsets.p, v->fv_idx.p, v->counts.p);
+    k_bow_assemble<<<1, 1024, 0, s>>>(n, v->weighting, v->scoring, d_word, d_node, v->weight_of.p, v->keys.p, v->flags.p, v->stage.p, d_bid, d_bv, d_fn, d_fo, d_fi, d_counts);
     VLAUNCH_CHECK();
-    int counts[2] = {0, 0};
-    CU_TRY(cudaMemcpyAsync(counts, v->counts.p, 8, cudaMemcpyDeviceToHost, s));
-    if (word_of) CU_TRY(cudaMemcpyAsync(word_of, v->word_of.p, nn * 4, cudaMemcpyDeviceToHost, s));
-    if (node_of) CU_TRY(cudaMemcpyAsync(node_of, v->node_of.p, nn * 4, cudaMemcpyDeviceToHost, s));
-    // the vectors are at most n long: copy them whole in the same round trip, the counts say how much is meaningful
-    CU_TRY(cudaMemcpyAsync(bow_ids, v->bow_ids.p, nn * 4, cudaMemcpyDeviceToHost, s));
-    CU_TRY(cudaMemcpyAsync(bow_values, v->bow_vals.p, nn * 8, cudaMemcpyDeviceToHost, s));
-    CU_TRY(cudaMemcpyAsync(fv_nodes, v->fv_nodes.p, nn * 4, cudaMemcpyDeviceToHost, s));
-    CU_TRY(cudaMemcpyAsync(fv_offsets, v->fv_offsets.p, (nn + 1) * 4, cudaMemcpyDeviceToHost, s));
-    CU_TRY(cudaMemcpyAsync(fv_indices, v->fv_idx.p, nn * 4, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(v->hpack, v->pack.p, pack_bytes, cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaStreamSynchronize(s));
-    *n_bow = counts[0]; *n_fv = counts[1];
+    const int* hi = reinterpret_cast<const int*>(v->hpack);
+    const int nb = hi[0], nf = hi[1];
+    if (word_of) std::memcpy(word_of, hi + 2, nn * 4);
+    if (node_of) std::memcpy(node_of, hi + 2 + nn, nn * 4);
+    std::memcpy(bow_ids, hi + 2 + 2 * nn, (size_t)nb * 4);
+    std::memcpy(bow_values, v->hpack + off_d, (size_t)nb * 8);
+    std::memcpy(fv_nodes, hi + 2 + 3 * nn, (size_t)nf * 4);
+    std::memcpy(fv_offsets, hi + 2 + 4 * nn, (size_t)(nf + 1) * 4);
+    std::memcpy(fv_indices, hi + 2 + 5 * nn + 1, (size_t)fv_offsets[nf] * 4);
+    *n_bow = nb; *n_fv = nf;
     return ORBX_OK;
 }
 
@@ -901,20 +922,26 @@ int orbx_search_by_bow(orbx_matcher* m, int kf_kf, const orbx_bow_side* s1, cons
         (rc = up(m, s2->fv_offsets, (size_t)s2->n_fv + 1, o2)) || (rc = up(m, s2->fv_indices, (size_t)s2->fv_offsets[s2->n_fv], i2)) ||
         (rc = up(m, pairs.data(), (size_t)np, dp))) return rc;
     if (kf_kf && s2->valid && (rc = up(m, s2->valid, (size_t)n2, v2))) return rc;
-    int* m12 = m->arena.get<int>(n1 + 1); int* m21 = m->arena.get<int>(n2 + 1); int* binof = m->arena.get<int>(n1 + 1); int* hist = m->arena.get<int>(32); int* dn = m->arena.get<int>(1);
-    if (!m12 || !m21 || !binof || !hist || !dn) FAIL(ORBX_E_CUDA, "matcher arena exhausted");
+    int* res = m->arena.get<int>((size_t)n1 + n2 + 3);             // [nmatches | match12 n1 + 1 | match21 n2 + 1]: one copy back
+    int* binof = m->arena.get<int>(n1 + 1); int* hist = m->arena.get<int>(32);
+    if (!res || !binof || !hist) FAIL(ORBX_E_CUDA, "matcher arena exhausted");
+    int *dn = res, *m12 = res + 1, *m21 = res + 2 + n1;
+    const size_t res_bytes = ((size_t)n1 + n2 + 3) * 4;
+    if ((rc = m->ensure_download(res_bytes))) return rc;
     if ((rc = flush_uploads(m))) return rc;
     cudaStream_t s = m->stream;
-    CU_TRY(cudaMemsetAsync(m12, 0xFF, (size_t)(n1 + 1) * 4, s)); CU_TRY(cudaMemsetAsync(m21, 0xFF, (size_t)(n2 + 1) * 4, s)); CU_TRY(cudaMemsetAsync(hist, 0, 32 * 4, s));
+    CU_TRY(cudaMemsetAsync(res, 0xFF, res_bytes, s)); CU_TRY(cudaMemsetAsync(hist, 0, 32 * 4, s));
     BowSideDev a = {n1, k1, reinterpret_cast<const uint4*>(d1), v1, o1, i1}, b = {n2, k2, reinterpret_cast<const uint4*>(d2), v2, o2, i2};
     k_bow_match<<<(np + 3) / 4, 128, 0, s>>>(np, dp, a, b, kf_kf ? 1 : 0, m->nnratio, m->checkOri, m12, m21, binof, hist);
     LAUNCH_CHECK();
     k_bow_finish<<<1, 1024, 0, s>>>(n1, m->checkOri, hist, binof, m12, m21, dn);
     LAUNCH_CHECK();
-    if (n1) CU_TRY(cudaMemcpyAsync(match12, m12, (size_t)n1 * 4, cudaMemcpyDeviceToHost, s));
-    if (n2) CU_TRY(cudaMemcpyAsync(match21, m21, (size_t)n2 * 4, cudaMemcpyDeviceToHost, s));
-    CU_TRY(cudaMemcpyAsync(nmatches, dn, 4, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(m->dl_host, res, res_bytes, cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaStreamSynchronize(s));
+    const int* hr = reinterpret_cast<const int*>(m->dl_host);
+    *nmatches = hr[0];
+    if (n1) std::memcpy(match12, hr + 1, (size_t)n1 * 4);
+    if (n2) std::memcpy(match21, hr + 2 + n1, (size_t)n2 * 4);
     return ORBX_OK;
 }
 

@@ -11,6 +11,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import oracle                                   # noqa: E402
 import match_cases as mc                        # noqa: E402
 import frame_cases as fc                        # noqa: E402
+import bow_cases as bc                          # noqa: E402
 from tools.synth import synth_frame, warp_affine_nn   # noqa: E402
 
 orbx = importlib.import_module("amos-slam_b200")
@@ -96,6 +97,45 @@ def frame_rows(frames, kind):
     return out
 
 
+def bow_rows(pairs, kind):
+    out = dict(frames=0, features=0, word_diff=0, node_diff=0, bow_id_diff=0, bow_val_diff=0, fv_diff=0, bow_entries=0, sb_calls=0, sb_matches=0, sb_idx_diff=0, sb_count_diff=0)
+    E = orbx.ORBextractor(1000, 1.2, 8, 20, 7)
+    pool = np.concatenate([E(synth_frame(500 + s, 640, 480))[1] for s in range(6)])
+    voc = bc.build_vocabulary(pool, 10, 3)
+    V = orbx.ORBVocabulary(10, 3, *voc); O = oracle.Vocabulary(kind, 10, 3, *voc)
+    keys = ("word", "node", "bow_ids", "bow_vals", "fv_nodes", "fv_offsets", "fv_idx")
+    for s in range(pairs):
+        A = synth_frame(4000 + s, 640, 480); B = warp_affine_nn(A, 7, -4, 2.0)
+        ka, da = E(A); kb, db = E(B)
+        res = []
+        for d in (da, db):
+            g, o = V.transform(d, 1), O.transform(d, 1)
+            out["frames"] += 1; out["features"] += len(d); out["bow_entries"] += len(o["bow_ids"])
+            out["word_diff"] += int((g["word"] != o["word"]).sum()); out["node_diff"] += int((g["node"] != o["node"]).sum())
+            same_len = len(g["bow_ids"]) == len(o["bow_ids"])
+            out["bow_id_diff"] += int((g["bow_ids"] != o["bow_ids"]).sum()) if same_len else max(len(g["bow_ids"]), len(o["bow_ids"]))
+            out["bow_val_diff"] += int((g["bow_vals"] != o["bow_vals"]).sum()) if same_len else max(len(g["bow_ids"]), len(o["bow_ids"]))
+            out["fv_diff"] += int(not all(np.array_equal(g[k], o[k]) for k in ("fv_nodes", "fv_offsets", "fv_idx")))
+            res.append(o)
+        va, vb = bc.validity(len(ka), s + 1), bc.validity(len(kb), s + 100)
+        for kfkf in (0, 1):
+            for nn, ori in bc.MATCH_VARIANTS:
+                g = orbx.ORBmatcher(nn, ori).SearchByBoW(kfkf, ka, da, va, res[0], kb, db, vb if kfkf else None, res[1])
+                o = oracle.search_by_bow(kind, nn, ori, kfkf, ka, da, va, res[0], kb, db, vb, res[1])
+                out["sb_calls"] += 1; out["sb_matches"] += int(o[0]); out["sb_count_diff"] += int(g[0] != o[0])
+                out["sb_idx_diff"] += int((g[1] != o[1]).sum()) + int((g[2] != o[2]).sum())
+    # CPU time of the reference's transform at the size of ORBvoc.txt (k = 10, L = 6, random node descriptors)
+    rng = np.random.default_rng(5); nn_ = (10 ** 7 - 10) // 9; ids = np.arange(1, nn_ + 1, dtype=np.int64)
+    leaf = (ids > (10 ** 6 - 10) // 9).astype(np.uint8)
+    big = oracle.Vocabulary(kind, 10, 6, ((ids - 1) // 10).astype(np.int32), leaf, rng.integers(0, 256, (nn_, 32), dtype=np.uint8), np.where(leaf > 0, rng.uniform(0.5, 9.0, nn_), 0.0))
+    big.transform(da, 4)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        big.transform(da, 4)
+    out["ref_transform_ms"] = 1e3 * (time.perf_counter() - t0) / 5
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser(); ap.add_argument("--frames", type=int, default=100); a = ap.parse_args()
     kind = "ref" if oracle.have_ref() else "port"
@@ -120,6 +160,12 @@ def main():
     print("\n## ComputeStereoMatches (a18), C4 pairs\n")
     print("| pairs | left keypoints | matched (ref) | mvuRight diffs | mvDepth diffs |\n|---|---|---|---|---|")
     print("| %d | %d | %d | %d | %d |" % (s["pairs"], s["left_keypoints"], s["matched"], s["u_right_diff"], s["depth_diff"]))
+    w = bow_rows(max(a.frames // 5, 1), kind)
+    print("\n## Bag of words (8f rank 2): DBoW2 transform (levelsup 1 on a k = 10, L = 3 tree grown from real descriptors) and SearchByBoW, both forms x 3 (ratio, orientation) settings\n")
+    print("| frames | features | word id diffs | node id diffs | BowVector entries | BowVector id diffs | BowVector weight diffs (double, exact) | frames with a different FeatureVector | SearchByBoW calls | matches (ref) | match index diffs | count diffs | ref transform ms / 1000 features at ORBvoc size (1 core) |")
+    print("|---|---|---|---|---|---|---|---|---|---|---|---|---|")
+    print("| %d | %d | %d | %d | %d | %d | %d | %d | %d | %d | %d | %d | %.2f |" % (w["frames"], w["features"], w["word_diff"], w["node_diff"], w["bow_entries"], w["bow_id_diff"], w["bow_val_diff"], w["fv_diff"],
+                                                                                 w["sb_calls"], w["sb_matches"], w["sb_idx_diff"], w["sb_count_diff"], w["ref_transform_ms"]))
     f = frame_rows(max(a.frames // 2, 4), kind)
     print("\n## Device-resident Frame (8f rank 1): UndistortKeyPoints / ComputeStereoFromRGBD / AssignFeaturesToGrid, cameras TUM1, TUM2, 4-coefficient, rectified\n")
     print("| frames | keypoints | mvKeysUn diffs | mvuRight diffs | mvDepth diffs | frames with a different mGrid | bounds diffs |\n|---|---|---|---|---|---|---|")
