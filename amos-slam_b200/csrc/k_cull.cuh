@@ -134,22 +134,13 @@ struct KpIn { float x, y, size, angle, response; int octave, class_id; };
 // p = (int)(pt * scale).  flags[i] = 1 => culled.  Out-of-range label / id indices (undefined behaviour
 // in the reference) are treated as "not flagged".
 __global__ void k_cull_flags(const KpIn* __restrict__ kp, const float* __restrict__ kp_scale, int n,
-                             const uint32_t* __restrict__ closed, int wpr, const double* __restrict__ label, int lpitch_elems,
-                             int rows, int cols, const int* __restrict__ centers_id, int ncenters,
-                             const int* __restrict__ rm_vector, int nrm, uint8_t* __restrict__ flags) {
+                             const uint32_t* __restrict__ closed, int wpr, const uint8_t* __restrict__ rm_flag,
+                             int rows, int cols, uint8_t* __restrict__ flags) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float s = kp_scale[i];
     const int px = (int)__fmul_rn(kp[i].x, s), py = (int)__fmul_rn(kp[i].y, s);
-    int flag = 0;
-    if (px >= 0 && py >= 0 && px < cols && py < rows) {
-        const double sp = label[(size_t)py * lpitch_elems + px];
-        const double idxd = sp - 1.0;
-        if (idxd >= 0.0 && idxd < (double)ncenters) {
-            const int id = centers_id[(size_t)idxd];
-            if (id >= 0 && id < nrm && rm_vector[id] == 1) flag = 1;
-        }
-        if ((closed[(size_t)py * wpr + (px >> 5)] >> (px & 31)) & 1u) flag = 1;
-    }
+    int flag = rm_flag[i];                                   // rm_vector[centers[label(p) - 1].id] == 1, looked up by the caller-side marshalling
+    if (px >= 0 && py >= 0 && px < cols && py < rows && ((closed[(size_t)py * wpr + (px >> 5)] >> (px & 31)) & 1u)) flag = 1;
     flags[i] = (uint8_t)flag;
 }

@@ -82,6 +82,7 @@ struct orbx_extractor {
     DevBuf<uint16_t> d_cell_counts;
     DevBuf<int> d_ncand, d_kp_count, d_counts, d_level_counts, d_overflow;
     DevBuf<KpOut> d_kp_out; DevBuf<uint8_t> d_desc_out; int out_cap = 0;
+    DevBuf<uint8_t> d_gather; uint8_t* h_gather = nullptr; size_t h_gather_cap = 0;   // single-frame result block and its pinned landing buffer
     const KpOut* last_kp = nullptr; const uint8_t* last_desc = nullptr; int last_n = -1;   // frame 0 of the last extract / describe (orbx_frame_assign)
     PyrView view{}; bool have_pyramid = false, blur_valid = false;
     // optional per-stage CUDA-event timing (bench.py's roofline): one event set per profiled call
@@ -465,6 +466,7 @@ void orbx_destroy(orbx_extractor* h) {
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->ev_block) cudaEventDestroy(h->ev_block);
+    h->d_gather.release(); if (h->h_gather) cudaFreeHost(h->h_gather);
     for (cudaEvent_t e : h->ev_h2d) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_done) cudaEventDestroy(e);
     h->d_l0.release();
@@ -688,25 +690,31 @@ int orbx_extract(orbx_extractor* h, const uint8_t* image, int rows, int cols, si
     CU_TRY(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     h->blur_valid = true;
     if ((rc = run_orient(h, 0, 1, true, h->d_kp_out.p, h->d_desc_out.p, icap, h->d_counts.p, nullptr))) return rc;
-    int n = 0, ovf = 0;
-    CU_TRY(cudaMemcpyAsync(&n, h->d_counts.p, 4, cudaMemcpyDeviceToHost, h->stream));
-    CU_TRY(cudaMemcpyAsync(&ovf, h->d_overflow.p, 4, cudaMemcpyDeviceToHost, h->stream));
-    // a caller buffer sized with orbx_max_keypoints() takes every possible result: copy speculatively and save a round trip
-    const bool spec = cap >= icap;
-    if (spec) {
-        CU_TRY(cudaMemcpyAsync(kp_out, h->d_kp_out.p, (size_t)icap * sizeof(KpOut), cudaMemcpyDeviceToHost, h->stream));
-        CU_TRY(cudaMemcpyAsync(desc_out, h->d_desc_out.p, (size_t)icap * 32, cudaMemcpyDeviceToHost, h->stream));
+    // Everything the call returns (count, overflow flag, all icap keypoint / descriptor slots) is gathered into one device block and
+    // comes back in ONE copy into a pinned landing buffer: copies straight into the caller's pageable arrays would each be a blocking,
+    // staged transfer of its own.  The count is not known before the copy, so all slots travel (61 KB at C1) and n of them are handed out.
+    const size_t kb = (size_t)icap * sizeof(KpOut), db = (size_t)icap * 32, blk = 16 + kb + db;
+    if (h->d_gather.ensure(blk)) return ORBX_E_CUDA;
+    if (h->h_gather_cap < blk) {
+        if (h->h_gather) cudaFreeHost(h->h_gather);
+        h->h_gather = nullptr; h->h_gather_cap = 0;
+        CU_TRY(cudaHostAlloc((void**)&h->h_gather, blk, cudaHostAllocDefault));
+        h->h_gather_cap = blk;
     }
+    CU_TRY(cudaMemcpyAsync(h->d_gather.p, h->d_counts.p, 4, cudaMemcpyDeviceToDevice, h->stream));
+    CU_TRY(cudaMemcpyAsync(h->d_gather.p + 4, h->d_overflow.p, 4, cudaMemcpyDeviceToDevice, h->stream));
+    CU_TRY(cudaMemcpyAsync(h->d_gather.p + 16, h->d_kp_out.p, kb, cudaMemcpyDeviceToDevice, h->stream));
+    CU_TRY(cudaMemcpyAsync(h->d_gather.p + 16 + kb, h->d_desc_out.p, db, cudaMemcpyDeviceToDevice, h->stream));
+    CU_TRY(cudaMemcpyAsync(h->h_gather, h->d_gather.p, blk, cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(cudaStreamSynchronize(h->stream));
+    int n, ovf;
+    std::memcpy(&n, h->h_gather, 4); std::memcpy(&ovf, h->h_gather + 4, 4);
     if (ovf) FAIL(ORBX_E_OVERFLOW, "internal bound exceeded in the quadtree stage");
     *n_out = n;
     h->last_kp = h->d_kp_out.p; h->last_desc = h->d_desc_out.p; h->last_n = n;
     if (n > cap) FAIL(ORBX_E_CAPACITY, "keypoint buffer too small");
-    if (n && !spec) {
-        CU_TRY(cudaMemcpyAsync(kp_out, h->d_kp_out.p, (size_t)n * sizeof(KpOut), cudaMemcpyDeviceToHost, h->stream));
-        CU_TRY(cudaMemcpyAsync(desc_out, h->d_desc_out.p, (size_t)n * 32, cudaMemcpyDeviceToHost, h->stream));
-        CU_TRY(cudaStreamSynchronize(h->stream));
-    }
+    std::memcpy(kp_out, h->h_gather + 16, (size_t)n * sizeof(KpOut));
+    std::memcpy(desc_out, h->h_gather + 16 + kb, (size_t)n * 32);
     return ORBX_OK;
 }
 
@@ -723,15 +731,28 @@ int orbx_detect(orbx_extractor* h, const uint8_t* image, int rows, int cols, siz
     if ((rc = upload_level0(h, image, 1, rows, cols, step, 0))) return rc;
     if ((rc = run_detect(h, 0, 1))) return rc;
     if ((rc = run_orient(h, 0, 1, false, h->d_kp_out.p, nullptr, icap, h->d_counts.p, h->d_level_counts.p))) return rc;
-    int n = 0, ovf = 0;
-    CU_TRY(cudaMemcpyAsync(&n, h->d_counts.p, 4, cudaMemcpyDeviceToHost, h->stream));
-    CU_TRY(cudaMemcpyAsync(level_counts, h->d_level_counts.p, 4 * h->nlevels, cudaMemcpyDeviceToHost, h->stream));
-    CU_TRY(cudaMemcpyAsync(&ovf, h->d_overflow.p, 4, cudaMemcpyDeviceToHost, h->stream));
+    // one gathered block, one copy into the pinned landing buffer (see orbx_extract): [n | overflow | level counts | all icap keypoint slots]
+    const size_t lc = (size_t)4 * h->nlevels, o_kp = (8 + lc + 15) & ~(size_t)15, kb = (size_t)icap * sizeof(KpOut), blk = o_kp + kb;
+    if (h->d_gather.ensure(blk)) return ORBX_E_CUDA;
+    if (h->h_gather_cap < blk) {
+        if (h->h_gather) cudaFreeHost(h->h_gather);
+        h->h_gather = nullptr; h->h_gather_cap = 0;
+        CU_TRY(cudaHostAlloc((void**)&h->h_gather, blk, cudaHostAllocDefault));
+        h->h_gather_cap = blk;
+    }
+    CU_TRY(cudaMemcpyAsync(h->d_gather.p, h->d_counts.p, 4, cudaMemcpyDeviceToDevice, h->stream));
+    CU_TRY(cudaMemcpyAsync(h->d_gather.p + 4, h->d_overflow.p, 4, cudaMemcpyDeviceToDevice, h->stream));
+    CU_TRY(cudaMemcpyAsync(h->d_gather.p + 8, h->d_level_counts.p, lc, cudaMemcpyDeviceToDevice, h->stream));
+    CU_TRY(cudaMemcpyAsync(h->d_gather.p + o_kp, h->d_kp_out.p, kb, cudaMemcpyDeviceToDevice, h->stream));
+    CU_TRY(cudaMemcpyAsync(h->h_gather, h->d_gather.p, blk, cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(cudaStreamSynchronize(h->stream));
+    int n, ovf;
+    std::memcpy(&n, h->h_gather, 4); std::memcpy(&ovf, h->h_gather + 4, 4);
     if (ovf) FAIL(ORBX_E_OVERFLOW, "internal bound exceeded in the quadtree stage");
+    std::memcpy(level_counts, h->h_gather + 8, lc);
     *n_out = n;
     if (n > cap) FAIL(ORBX_E_CAPACITY, "keypoint buffer too small");
-    if (n) { CU_TRY(cudaMemcpyAsync(kp_out, h->d_kp_out.p, (size_t)n * sizeof(KpOut), cudaMemcpyDeviceToHost, h->stream)); CU_TRY(cudaStreamSynchronize(h->stream)); }
+    std::memcpy(kp_out, h->h_gather + o_kp, (size_t)n * sizeof(KpOut));
     return ORBX_OK;
 }
 

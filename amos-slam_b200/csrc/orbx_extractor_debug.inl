@@ -45,33 +45,52 @@ extern "C" int orbx_cull(orbx_extractor* h, const uint8_t* mask, size_t mask_ste
     for (int l = 0; l < h->nlevels; ++l) { if (level_counts[l] < 0) FAIL(ORBX_E_INVALID, "negative level count"); n += level_counts[l]; }
     int rc;
     const int pitch = align_up(cols, 128);
-    if (h->d_mask.ensure((size_t)pitch * rows + 64) || h->d_label.ensure((size_t)rows * cols) ||
-        h->d_ids.ensure((size_t)ncenters + nrm + 4) || h->d_kp_tmp.ensure((size_t)std::max(n, 1) * 2) || h->d_desc_tmp.ensure((size_t)std::max(n, 1) * 32))
+    if (n && !kp_inout) FAIL(ORBX_E_INVALID, "null keypoints");
+    if (h->d_mask.ensure((size_t)pitch * rows + 64) || h->d_kp_tmp.ensure((size_t)std::max(n, 1) * 2) || h->d_desc_tmp.ensure((size_t)std::max(n, 1) * 32))
         return ORBX_E_CUDA;
     cudaStream_t s = h->stream;
     CU_TRY(cudaMemcpy2DAsync(h->d_mask.p, pitch, mask, mask_step, cols, rows, cudaMemcpyHostToDevice, s));
-    CU_TRY(cudaMemcpy2DAsync(h->d_label.p, (size_t)cols * 8, label, label_step, (size_t)cols * 8, rows, cudaMemcpyHostToDevice, s));
-    if (ncenters) CU_TRY(cudaMemcpyAsync(h->d_ids.p, centers_id, (size_t)ncenters * 4, cudaMemcpyHostToDevice, s));
-    if (nrm) CU_TRY(cudaMemcpyAsync(h->d_ids.p + ncenters, rm_vector, (size_t)nrm * 4, cudaMemcpyHostToDevice, s));
     // closing = erode(dilate(mask))   (:1697-1704), as two binary dilations on the bit-packed mask (k_cull.cuh)
     if ((rc = ensure_closing(h, 1, rows, cols))) return rc;
     if ((rc = run_closing(h, h->d_mask.p, (long long)pitch * rows, pitch, 0, 1, rows, cols))) return rc;
     const int wpr = (cols + 31) / 32;
     if (n == 0) { CU_TRY(cudaStreamSynchronize(s)); return ORBX_OK; }
-    if (!kp_inout) FAIL(ORBX_E_INVALID, "null keypoints");
-    // per-keypoint scale: level 0 -> 1, else mvScaleFactor[level]  (:1712-1715); scales ride in the desc scratch
-    std::vector<float> scales(n);
-    { int o = 0; for (int l = 0; l < h->nlevels; ++l) for (int i = 0; i < level_counts[l]; ++i) scales[o++] = l ? h->mvScaleFactor[l] : 1.f; }
-    float* d_scales = reinterpret_cast<float*>(h->d_desc_tmp.p);
-    uint8_t* d_flags = h->d_desc_tmp.p + (size_t)n * 4;
-    CU_TRY(cudaMemcpyAsync(h->d_kp_tmp.p, kp_inout, sizeof(KpOut) * n, cudaMemcpyHostToDevice, s));
-    CU_TRY(cudaMemcpyAsync(d_scales, scales.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
-    k_cull_flags<<<(n + 127) / 128, 128, 0, s>>>(reinterpret_cast<const KpIn*>(h->d_kp_tmp.p), d_scales, n, h->d_bits0.p, wpr, h->d_label.p, cols,
-                                                  rows, cols, h->d_ids.p, ncenters, h->d_ids.p + ncenters, nrm, d_flags);
+    // One pinned block up: keypoints, their scale (level 0 -> 1, else mvScaleFactor[level], :1712-1715) and the super-pixel term of the
+    // test, rm_vector[centers[label(p) - 1].id] == 1 (:1722-1736).  That term reads three caller-side tables at N positions, so it is
+    // evaluated while marshalling (N look-ups) instead of uploading the 8 B/pixel label map; p = (int)(pt * scale) is the same float
+    // product the kernel forms for the mask term.  Out-of-range label / id indices (undefined behaviour in the reference) = not flagged.
+    const size_t o_sc = (size_t)n * sizeof(KpOut), o_rm = o_sc + (size_t)n * 4, up_bytes = (o_rm + n + 15) & ~(size_t)15;
+    if (h->h_gather_cap < up_bytes) {
+        if (h->h_gather) cudaFreeHost(h->h_gather);
+        h->h_gather = nullptr; h->h_gather_cap = 0;
+        CU_TRY(cudaHostAlloc((void**)&h->h_gather, up_bytes + (up_bytes >> 1), cudaHostAllocDefault));
+        h->h_gather_cap = up_bytes + (up_bytes >> 1);
+    }
+    if (h->d_gather.ensure(up_bytes)) return ORBX_E_CUDA;
+    std::memcpy(h->h_gather, kp_inout, o_sc);
+    float* hs = reinterpret_cast<float*>(h->h_gather + o_sc); uint8_t* hr = h->h_gather + o_rm;
+    const size_t lpitch = label_step / sizeof(double);
+    { int o = 0; for (int l = 0; l < h->nlevels; ++l) for (int i = 0; i < level_counts[l]; ++i, ++o) {
+        const float sc = l ? h->mvScaleFactor[l] : 1.f;
+        hs[o] = sc;
+        volatile float fx = kp_inout[o].x * sc, fy = kp_inout[o].y * sc;          // one rounded float product each, as cv::Point2f * float
+        const int px = (int)fx, py = (int)fy;
+        uint8_t flag = 0;
+        if (px >= 0 && py >= 0 && px < cols && py < rows) {
+            const double idxd = label[(size_t)py * lpitch + px] - 1.0;
+            if (idxd >= 0.0 && idxd < (double)ncenters) { const int id = centers_id[(size_t)idxd]; if (id >= 0 && id < nrm && rm_vector[id] == 1) flag = 1; }
+        }
+        hr[o] = flag;
+    } }
+    CU_TRY(cudaMemcpyAsync(h->d_gather.p, h->h_gather, up_bytes, cudaMemcpyHostToDevice, s));
+    uint8_t* d_flags = h->d_desc_tmp.p;
+    k_cull_flags<<<(n + 127) / 128, 128, 0, s>>>(reinterpret_cast<const KpIn*>(h->d_gather.p), reinterpret_cast<const float*>(h->d_gather.p + o_sc), n, h->d_bits0.p, wpr,
+                                                  h->d_gather.p + o_rm, rows, cols, d_flags);
     LAUNCH_CHECK();
-    std::vector<uint8_t> flags(n);
-    CU_TRY(cudaMemcpyAsync(flags.data(), d_flags, n, cudaMemcpyDeviceToHost, s));
+    // the flags land in the pinned block (the upload has been consumed by then: same stream)
+    CU_TRY(cudaMemcpyAsync(h->h_gather, d_flags, n, cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaStreamSynchronize(s));
+    const uint8_t* flags = h->h_gather;
     // stable erase per level, culled keypoints appended in visiting order (marshalling of the device flags)
     int o = 0, w = 0, nc = 0;
     for (int l = 0; l < h->nlevels; ++l) {

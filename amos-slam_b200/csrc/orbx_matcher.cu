@@ -215,6 +215,31 @@ static bool cand_overflow(orbx_matcher* m, int total) {
     return true;
 }
 
+// Results come back in ONE copy into a pinned landing buffer (pageable destinations make every cudaMemcpyAsync a blocking, staged
+// transfer of its own): the pieces are gathered into a contiguous device block first (device-to-device copies are cheap to enqueue).
+struct Gather {
+    orbx_matcher* m; uint8_t* dblock = nullptr; size_t bytes = 0, off = 0;
+    int begin(size_t total) {
+        bytes = (total + 15) & ~(size_t)15; off = 0;
+        dblock = m->arena.get<uint8_t>(bytes);
+        if (!dblock) { orbx_set_error("matcher arena exhausted"); return ORBX_E_CUDA; }
+        return m->ensure_download(bytes);
+    }
+    // returns the offset of the piece inside the block
+    size_t add(const void* dsrc, size_t n) {
+        const size_t o = off; off += (n + 3) & ~(size_t)3;
+        if (n) cudaMemcpyAsync(dblock + o, dsrc, n, cudaMemcpyDeviceToDevice, m->stream);
+        return o;
+    }
+    int finish() {
+        if (cudaMemcpyAsync(m->dl_host, dblock, off, cudaMemcpyDeviceToHost, m->stream) != cudaSuccess || cudaStreamSynchronize(m->stream) != cudaSuccess) {
+            orbx_set_error(std::string("result download: ") + cudaGetErrorString(cudaGetLastError())); return ORBX_E_CUDA;
+        }
+        return ORBX_OK;
+    }
+    const uint8_t* host(size_t o) const { return m->dl_host + o; }
+};
+
 #define RESOLVE_SMEM_BYTES (160 * 1024)
 
 extern "C" {
@@ -275,7 +300,7 @@ static int search_init_impl(orbx_matcher* m, const FrameArg A1, const FrameArg A
     *nmatches = 0;
     if (n1 == 0) return ORBX_OK;
     CU_TRY(cudaSetDevice(m->device));
-    const size_t need = frame_arg_bytes(A1) + frame_arg_bytes(A2) + pad((size_t)n1 * 8) + 6 * pad((size_t)(n1 + n2 + 2) * 4) + 8192;
+    const size_t need = frame_arg_bytes(A1) + frame_arg_bytes(A2) + pad((size_t)n1 * 8) + 6 * pad((size_t)(n1 + n2 + 2) * 4) + pad((size_t)n1 * 12 + 256) + 8192;
     if ((rc = m->arena.reserve(need)) || (rc = m->uparena.reserve(need))) return rc;
 retry:
     m->arena.reset(); m->uparena.reset();
@@ -299,14 +324,15 @@ retry:
     k_resolve_init<<<1, RESOLVE_THREADS, resolve_smem, m->stream>>>(n1, n2, k1, d2.keys, counts, offsets, cand, pre, (int)std::min<size_t>(m->cand_cap, 0x7FFFFFFF), m->nnratio, m->checkOri, resolve_smem / 4,
                                                                      md, m21, m12, binof, prev, dn);
     LAUNCH_CHECK();
-    int total = 0;
-    CU_TRY(cudaMemcpyAsync(&total, offsets + n1, 4, cudaMemcpyDeviceToHost, m->stream));
-    CU_TRY(cudaMemcpyAsync(nmatches, dn, 4, cudaMemcpyDeviceToHost, m->stream));
-    CU_TRY(cudaStreamSynchronize(m->stream));
-    if (cand_overflow(m, total)) goto retry;                       // prev_matched_xy is only written below, so the inputs are still intact
-    CU_TRY(cudaMemcpyAsync(matches12, m12, (size_t)n1 * 4, cudaMemcpyDeviceToHost, m->stream));
-    CU_TRY(cudaMemcpyAsync(prev_matched_xy, prev, (size_t)n1 * 8, cudaMemcpyDeviceToHost, m->stream));
-    CU_TRY(cudaStreamSynchronize(m->stream));
+    Gather g{m};
+    if ((rc = g.begin(8 + (size_t)n1 * 12 + 64))) return rc;
+    const size_t o_total = g.add(offsets + n1, 4), o_n = g.add(dn, 4), o_m12 = g.add(m12, (size_t)n1 * 4), o_prev = g.add(prev, (size_t)n1 * 8);
+    if ((rc = g.finish())) return rc;
+    int total; std::memcpy(&total, g.host(o_total), 4);
+    if (cand_overflow(m, total)) goto retry;                       // the caller's arrays are only written below, so the inputs are still intact
+    std::memcpy(nmatches, g.host(o_n), 4);
+    std::memcpy(matches12, g.host(o_m12), (size_t)n1 * 4);
+    std::memcpy(prev_matched_xy, g.host(o_prev), (size_t)n1 * 8);
     return ORBX_OK;
 }
 
@@ -322,7 +348,7 @@ static int search_proj_frame_impl(orbx_matcher* m, const FrameArg cur, int n_las
     for (int i = 0; i < n_last; ++i) if (valid[i] && (last_octave[i] < 0 || last_octave[i] >= cur.nlevels())) FAIL(ORBX_E_INVALID, "octave out of range");
     CU_TRY(cudaSetDevice(m->device));
     const int nc = cur.n();
-    const size_t need = frame_arg_bytes(cur) + pad((size_t)n_last * 32) + 8 * pad((size_t)(n_last + nc + 2) * 8) + 8192;
+    const size_t need = frame_arg_bytes(cur) + pad((size_t)n_last * 32) + 8 * pad((size_t)(n_last + nc + 2) * 8) + pad((size_t)nc * 4 + 256) + 8192;
     if ((rc = m->arena.reserve(need)) || (rc = m->uparena.reserve(need))) return rc;
 retry:
     m->arena.reset(); m->uparena.reset();
@@ -342,12 +368,14 @@ retry:
     if (!occ || !cm || !pushes || !dn) FAIL(ORBX_E_CUDA, "matcher arena exhausted");
     k_resolve_proj_frame<<<1, RESOLVE_THREADS, RESOLVE_SMEM_BYTES, m->stream>>>(n_last, nc, dc.keys, la, ob, oc, counts, offsets, cand, pre, (int)std::min<size_t>(m->cand_cap, 0x7FFFFFFF), m->checkOri, RESOLVE_SMEM_BYTES / 4, occ, cm, pushes, dn);
     LAUNCH_CHECK();
-    int total = 0;
-    CU_TRY(cudaMemcpyAsync(&total, offsets + n_last, 4, cudaMemcpyDeviceToHost, m->stream));
-    if (nc) CU_TRY(cudaMemcpyAsync(cur_match, cm, (size_t)nc * 4, cudaMemcpyDeviceToHost, m->stream));
-    CU_TRY(cudaMemcpyAsync(nmatches, dn, 4, cudaMemcpyDeviceToHost, m->stream));
-    CU_TRY(cudaStreamSynchronize(m->stream));
+    Gather g{m};
+    if ((rc = g.begin(8 + (size_t)nc * 4 + 64))) return rc;
+    const size_t o_total = g.add(offsets + n_last, 4), o_n = g.add(dn, 4), o_cm = g.add(cm, (size_t)nc * 4);
+    if ((rc = g.finish())) return rc;
+    int total; std::memcpy(&total, g.host(o_total), 4);
     if (cand_overflow(m, total)) goto retry;
+    std::memcpy(nmatches, g.host(o_n), 4);
+    if (nc) std::memcpy(cur_match, g.host(o_cm), (size_t)nc * 4);
     return ORBX_OK;
 }
 
@@ -363,7 +391,7 @@ static int search_proj_points_impl(orbx_matcher* m, const FrameArg F, int n_poin
     for (int i = 0; i < n_points; ++i) if (track_level[i] < 0 || track_level[i] >= F.nlevels()) FAIL(ORBX_E_INVALID, "predicted level out of range");
     CU_TRY(cudaSetDevice(m->device));
     const int nf = F.n();
-    const size_t need = frame_arg_bytes(F) + pad((size_t)n_points * 32) + 8 * pad((size_t)(n_points + nf + 2) * 8) + 8192;
+    const size_t need = frame_arg_bytes(F) + pad((size_t)n_points * 32) + 8 * pad((size_t)(n_points + nf + 2) * 8) + pad((size_t)nf * 4 + 256) + 8192;
     if ((rc = m->arena.reserve(need)) || (rc = m->uparena.reserve(need))) return rc;
 retry:
     m->arena.reset(); m->uparena.reset();
@@ -383,12 +411,14 @@ retry:
     if (!occ || !fm || !dn) FAIL(ORBX_E_CUDA, "matcher arena exhausted");
     k_resolve_proj_points<<<1, RESOLVE_THREADS, RESOLVE_SMEM_BYTES, m->stream>>>(n_points, nf, df.keys, ob, oc, counts, offsets, cand, pre, (int)std::min<size_t>(m->cand_cap, 0x7FFFFFFF), m->nnratio, RESOLVE_SMEM_BYTES / 4, occ, fm, dn);
     LAUNCH_CHECK();
-    int total = 0;
-    CU_TRY(cudaMemcpyAsync(&total, offsets + n_points, 4, cudaMemcpyDeviceToHost, m->stream));
-    if (nf) CU_TRY(cudaMemcpyAsync(f_match, fm, (size_t)nf * 4, cudaMemcpyDeviceToHost, m->stream));
-    CU_TRY(cudaMemcpyAsync(nmatches, dn, 4, cudaMemcpyDeviceToHost, m->stream));
-    CU_TRY(cudaStreamSynchronize(m->stream));
+    Gather g{m};
+    if ((rc = g.begin(8 + (size_t)nf * 4 + 64))) return rc;
+    const size_t o_total = g.add(offsets + n_points, 4), o_n = g.add(dn, 4), o_fm = g.add(fm, (size_t)nf * 4);
+    if ((rc = g.finish())) return rc;
+    int total; std::memcpy(&total, g.host(o_total), 4);
     if (cand_overflow(m, total)) goto retry;
+    std::memcpy(nmatches, g.host(o_n), 4);
+    if (nf) std::memcpy(f_match, g.host(o_fm), (size_t)nf * 4);
     return ORBX_OK;
 }
 
@@ -407,7 +437,7 @@ int orbx_compute_stereo_matches(orbx_matcher* m, orbx_extractor* left, orbx_extr
     for (int i = 0; i < nr; ++i) if (keys_right[i].octave < 0 || keys_right[i].octave >= L.nlevels) FAIL(ORBX_E_INVALID, "octave out of range");
     // both extractors' streams must have finished writing their pyramids
     CU_TRY(cudaStreamSynchronize(L.stream)); CU_TRY(cudaStreamSynchronize(R.stream));
-    const size_t need = pad((size_t)nl * 60) + pad((size_t)nr * 60) + 3 * pad((size_t)nl * 4) + 2 * pad((size_t)L.nlevels * 4) + 8192 + 64 * 256;
+    const size_t need = pad((size_t)nl * 60) + pad((size_t)nr * 60) + 3 * pad((size_t)nl * 4) + 2 * pad((size_t)L.nlevels * 4) + pad((size_t)nl * 8 + 256) + 8192 + 64 * 256;
     if ((rc = m->arena.reserve(need)) || (rc = m->uparena.reserve(need))) return rc;
     m->arena.reset(); m->uparena.reset();
     KpM *kl, *kr; uint8_t *dl, *dr; float *sc, *isc;
@@ -423,9 +453,12 @@ int orbx_compute_stereo_matches(orbx_matcher* m, orbx_extractor* left, orbx_extr
     LAUNCH_CHECK();
     k_stereo_median_cut<<<1, 1024, 0, m->stream>>>(nl, sad, dur, ddep);
     LAUNCH_CHECK();
-    CU_TRY(cudaMemcpyAsync(u_right, dur, (size_t)nl * 4, cudaMemcpyDeviceToHost, m->stream));
-    CU_TRY(cudaMemcpyAsync(depth, ddep, (size_t)nl * 4, cudaMemcpyDeviceToHost, m->stream));
-    CU_TRY(cudaStreamSynchronize(m->stream));
+    Gather g{m};
+    if ((rc = g.begin((size_t)nl * 8 + 64))) return rc;
+    const size_t o_ur = g.add(dur, (size_t)nl * 4), o_dep = g.add(ddep, (size_t)nl * 4);
+    if ((rc = g.finish())) return rc;
+    std::memcpy(u_right, g.host(o_ur), (size_t)nl * 4);
+    std::memcpy(depth, g.host(o_dep), (size_t)nl * 4);
     return ORBX_OK;
 }
 

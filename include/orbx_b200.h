@@ -77,8 +77,8 @@ void* orbx_stream(orbx_extractor* h);
  *                               OutputArray descriptors)          src/ORBextractor.cc:1544-1668
  * image: CV_8UC1, rows x cols, `step` bytes per row (host memory).  The mask is ignored by the
  * reference and therefore not part of this call.  Empty image (rows*cols == 0 or NULL) => 0 keypoints.
- * kp_out[cap], desc_out[cap*32] (row-major N x 32, CV_8U); *n_out = N.  Entries past N are unspecified (with
- * cap >= orbx_max_keypoints() the whole device buffer is copied in one transfer instead of a count round trip).
+ * kp_out[cap], desc_out[cap*32] (row-major N x 32, CV_8U); *n_out = N.  Entries past N are left untouched.  If N > cap
+ * nothing is written and ORBX_E_CAPACITY is returned (*n_out = N); orbx_max_keypoints() is always enough.
  * ---------------------------------------------------------------------------------------------- */
 int orbx_extract(orbx_extractor* h, const uint8_t* image, int rows, int cols, size_t step,
                  orbx_keypoint* kp_out, uint8_t* desc_out, int cap, int* n_out);
