@@ -285,6 +285,21 @@ class ORBmatcher:
         cm[cm == -2] = -1
         return nm.value, cm
 
+    # int SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const set<MapPoint*> &sAlreadyFound, const float th, const int ORBdist)
+    def SearchByProjectionKeyFrame(self, cur, proj_uv, predicted_level, kf_angle, mp_desc, valid, cur_occupied, th, ORBdist):
+        uv = np.ascontiguousarray(proj_uv, np.float32); lv = np.ascontiguousarray(predicted_level, np.int32); an = np.ascontiguousarray(kf_angle, np.float32)
+        d, va, oc = _u8(mp_desc), _u8(valid), _u8(cur_occupied)
+        cm = np.zeros(max(len(cur.keys), 1), np.int32); nm = C.c_int()
+        if isinstance(cur, Frame):
+            fn, fa = self._lib.orbx_search_by_projection_keyframe_dev, cur._h
+        else:
+            v = cur.c(); fn, fa = self._lib.orbx_search_by_projection_keyframe, C.byref(v)
+        self._check(fn(self._h, fa, len(lv), _p(uv), _p(lv), _p(an), _p(d), _p(va), _p(oc), float(th), int(ORBdist), _p(cm), C.byref(nm)))
+        cm = cm[:len(cur.keys)]
+        self.last_raw_match = cm.copy()
+        cm[cm == -2] = -1
+        return nm.value, cm
+
     # int SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, const float th=3)
     def SearchByProjectionPoints(self, F, track_uv, track_ur, track_level, track_view_cos, mp_desc, mp_observed, f_occupied, th=3.0):
         uv = np.ascontiguousarray(track_uv, np.float32); ur = np.ascontiguousarray(track_ur, np.float32)

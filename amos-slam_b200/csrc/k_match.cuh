@@ -89,7 +89,7 @@ struct QueryParams {
     // INIT: F1 keys / desc, vbPrevMatched, windowSize
     const KpM* q_keys; const uint8_t* q_desc; const float* q_xy; float window;
     // PROJ_FRAME: proj_invz, last_octave, valid, th, forward/backward, mbf        (q_xy = proj_uv, q_desc = mp_desc)
-    const float* q_invz; const int* q_octave; const uint8_t* q_valid; float th; int forward, backward; float mbf;
+    const float* q_invz; const int* q_octave; const uint8_t* q_valid; float th; int forward, backward; float mbf; int no_ur;   // no_ur: the KeyFrame form has no uRight test
     // PROJ_POINTS: track_ur, track_level, track_view_cos, th                      (q_xy = track_uv, q_desc = mp_desc)
     const float* q_ur; const float* q_viewcos;
     // AREA: q_xy = (x, y), q_r, q_minlevel, q_maxlevel
@@ -116,7 +116,7 @@ __device__ __forceinline__ bool query_window(const QueryParams& P, const FrameDe
         if (P.forward) { minLevel = oct; maxLevel = -1; }                           // :1637-1642
         else if (P.backward) { minLevel = 0; maxLevel = oct; }
         else { minLevel = oct - 1; maxLevel = oct + 1; }
-        ur = __fsub_rn(u, __fmul_rn(P.mbf, invz)); use_ur = true;                   // :1665
+        ur = __fsub_rn(u, __fmul_rn(P.mbf, invz)); use_ur = !P.no_ur;               // :1665
         return true;
     }
     if (P.mode == MODE_AREA) {
@@ -468,11 +468,11 @@ k_resolve_init(int n1, int n2, const KpM* __restrict__ k1s, const KpM* __restric
 // ---- SearchByProjection(Frame, Frame), sequential part (ORBmatcher.cc:1595-1725) ----
 struct ProjFrameOps {
     int* occ; int* cur_match; int* pushes; int* hist; const int* obs; const uint8_t* mp_observed; const float* angl; const float* angc;
-    const float* last_angle; const KpM* cur_keys; int checkOri; bool staged; int nmatches, npush;
+    const float* last_angle; const KpM* cur_keys; int checkOri; bool staged; int nmatches, npush; int max_dist;
     __device__ __forceinline__ bool clean(uint32_t v) const { return !occ[v & 0xFFFFFu]; }                                        // :1658-1660
     static constexpr uint32_t dlimit = 256u;                                                                                     // bestDist starts at 256, strict <
     __device__ __forceinline__ bool decide(int, const uint32_t* c, Best2 b, int& j) const {
-        if (b.k1 == NOJ || (int)(b.k1 >> 20) > M_TH_HIGH) return false;                                                          // :1683
+        if (b.k1 == NOJ || (int)(b.k1 >> 20) > max_dist) return false;                                                           // :1683 (TH_HIGH) / :1820 (ORBdist)
         j = (int)(c[b.k1 & 0xFFFFFu] & 0xFFFFFu);
         return true;
     }
@@ -491,7 +491,7 @@ struct ProjFrameOps {
 __global__ void __launch_bounds__(RESOLVE_THREADS)
 k_resolve_proj_frame(int n_last, int n_cur, const KpM* __restrict__ cur_keys, const float* __restrict__ last_angle, const uint8_t* __restrict__ mp_observed,
                      const uint8_t* __restrict__ cur_occupied, const int* __restrict__ counts, const int* __restrict__ offsets, const uint32_t* __restrict__ cand,
-                     const uint2* __restrict__ pre_best, int cand_cap, int checkOri, int smem_words, int* __restrict__ occupied_g /*n_cur*/, int* __restrict__ cur_match /*n_cur*/,
+                     const uint2* __restrict__ pre_best, int cand_cap, int checkOri, int max_dist, int smem_words, int* __restrict__ occupied_g /*n_cur*/, int* __restrict__ cur_match /*n_cur*/,
                      int* __restrict__ pushes /*2*n_last*/, int* __restrict__ nmatches_out) {
     extern __shared__ __align__(16) uint32_t rs_sm[];
     __shared__ int hist[M_HISTO];
@@ -513,7 +513,7 @@ k_resolve_proj_frame(int n_last, int n_cur, const KpM* __restrict__ cur_keys, co
     if (tid < M_HISTO) hist[tid] = 0;
     __syncthreads();
     if (tid >= 32) return;
-    ProjFrameOps ops{occ, cur_match, pushes, hist, obs, mp_observed, angl, angc, last_angle, cur_keys, checkOri, staged, 0, 0};
+    ProjFrameOps ops{occ, cur_match, pushes, hist, obs, mp_observed, angl, angc, last_angle, cur_keys, checkOri, staged, 0, 0, max_dist};
     replay_queries<false>(SL, counts, offsets, lane, ops);
     int nmatches = ops.nmatches;
     const int npush = ops.npush;

@@ -338,7 +338,8 @@ retry:
 
 static int search_proj_frame_impl(orbx_matcher* m, const FrameArg cur, int n_last, const float* proj_uv, const float* proj_invz,
                                     const int* last_octave, const float* last_angle, const uint8_t* mp_desc, const uint8_t* valid, const uint8_t* mp_observed,
-                                    const uint8_t* cur_occupied, float th, int forward, int backward, float mbf, int* cur_match, int* nmatches) {
+                                    const uint8_t* cur_occupied, float th, int forward, int backward, float mbf, int* cur_match, int* nmatches,
+                                  int max_dist = M_TH_HIGH, int no_ur = 0) {
     if (!m || !nmatches) FAIL(ORBX_E_INVALID, "null argument");
     int rc;
     if ((rc = check_frame_arg(m, cur))) return rc;
@@ -361,12 +362,12 @@ retry:
     if (cur_occupied && (rc = up(m, cur_occupied, (size_t)nc, oc))) return rc;
     if ((rc = flush_uploads(m)) || (rc = grid_frame(m, cur, dc, skc))) return rc;
     QueryParams P; std::memset(&P, 0, sizeof(P));
-    P.mode = MODE_PROJ_FRAME; P.nq = n_last; P.q_desc = dd; P.q_xy = uv; P.q_invz = iz; P.q_octave = lo; P.q_valid = va; P.th = th; P.forward = forward; P.backward = backward; P.mbf = mbf;
+    P.mode = MODE_PROJ_FRAME; P.nq = n_last; P.q_desc = dd; P.q_xy = uv; P.q_invz = iz; P.q_octave = lo; P.q_valid = va; P.th = th; P.forward = forward; P.backward = backward; P.mbf = mbf; P.no_ur = no_ur;
     int *counts, *offsets; uint32_t* cand; uint2* pre;
     if ((rc = window_search(m, P, dc, counts, offsets, cand, pre))) return rc;
     int* occ = m->arena.get<int>(nc + 1); int* cm = m->arena.get<int>(nc + 1); int* pushes = m->arena.get<int>(2 * (size_t)n_last + 2); int* dn = m->arena.get<int>(1);
     if (!occ || !cm || !pushes || !dn) FAIL(ORBX_E_CUDA, "matcher arena exhausted");
-    k_resolve_proj_frame<<<1, RESOLVE_THREADS, RESOLVE_SMEM_BYTES, m->stream>>>(n_last, nc, dc.keys, la, ob, oc, counts, offsets, cand, pre, (int)std::min<size_t>(m->cand_cap, 0x7FFFFFFF), m->checkOri, RESOLVE_SMEM_BYTES / 4, occ, cm, pushes, dn);
+    k_resolve_proj_frame<<<1, RESOLVE_THREADS, RESOLVE_SMEM_BYTES, m->stream>>>(n_last, nc, dc.keys, la, ob, oc, counts, offsets, cand, pre, (int)std::min<size_t>(m->cand_cap, 0x7FFFFFFF), m->checkOri, max_dist, RESOLVE_SMEM_BYTES / 4, occ, cm, pushes, dn);
     LAUNCH_CHECK();
     Gather g{m};
     if ((rc = g.begin(8 + (size_t)nc * 4 + 64))) return rc;
@@ -484,6 +485,25 @@ int orbx_search_by_projection_frame_dev(orbx_matcher* m, const orbx_frame* cur, 
                                         const uint8_t* cur_occupied, float th, int forward, int backward, float mbf, int* cur_match, int* nmatches) {
     if (!cur) FAIL(ORBX_E_INVALID, "null frame");
     return search_proj_frame_impl(m, FrameArg{nullptr, cur}, n_last, proj_uv, proj_invz, last_octave, last_angle, mp_desc, valid, mp_observed, cur_occupied, th, forward, backward, mbf, cur_match, nmatches);
+}
+// SearchByProjection(Frame&, KeyFrame*, const set<MapPoint*>&, th, ORBdist)  (ORBmatcher.cc:1731-1863) is the Frame x Frame search with the
+// level predicted from the distance, every claim blocking (mvpMapPoints[i2] != NULL), no uRight test, and ORBdist as the acceptance bound
+static int search_proj_keyframe(orbx_matcher* m, const FrameArg cur, int n_kf, const float* proj_uv, const int* predicted_level, const float* kf_angle, const uint8_t* mp_desc,
+                                const uint8_t* valid, const uint8_t* cur_occupied, float th, int orb_dist, int* cur_match, int* nmatches) {
+    if (n_kf < 0 || n_kf >= (1 << 20)) FAIL(ORBX_E_INVALID, "bad arguments");
+    std::vector<float> invz((size_t)std::max(n_kf, 1), 0.f);                     // only the sign test of the Frame x Frame form reads it
+    std::vector<uint8_t> blocks((size_t)std::max(n_kf, 1), 1);                  // a feature claimed in this call is never re-assigned (:1808)
+    return search_proj_frame_impl(m, cur, n_kf, proj_uv, invz.data(), predicted_level, kf_angle, mp_desc, valid, blocks.data(), cur_occupied, th, 0, 0, 0.f, cur_match, nmatches, orb_dist, 1);
+}
+int orbx_search_by_projection_keyframe(orbx_matcher* m, const orbx_frame_view* cur, int n_kf, const float* proj_uv, const int* predicted_level, const float* kf_angle,
+                                       const uint8_t* mp_desc, const uint8_t* valid, const uint8_t* cur_occupied, float th, int orb_dist, int* cur_match, int* nmatches) {
+    if (!cur) FAIL(ORBX_E_INVALID, "bad frame view");
+    return search_proj_keyframe(m, FrameArg{cur, nullptr}, n_kf, proj_uv, predicted_level, kf_angle, mp_desc, valid, cur_occupied, th, orb_dist, cur_match, nmatches);
+}
+int orbx_search_by_projection_keyframe_dev(orbx_matcher* m, const orbx_frame* cur, int n_kf, const float* proj_uv, const int* predicted_level, const float* kf_angle,
+                                           const uint8_t* mp_desc, const uint8_t* valid, const uint8_t* cur_occupied, float th, int orb_dist, int* cur_match, int* nmatches) {
+    if (!cur) FAIL(ORBX_E_INVALID, "null frame");
+    return search_proj_keyframe(m, FrameArg{nullptr, cur}, n_kf, proj_uv, predicted_level, kf_angle, mp_desc, valid, cur_occupied, th, orb_dist, cur_match, nmatches);
 }
 int orbx_search_by_projection_points(orbx_matcher* m, const orbx_frame_view* F, int n_points, const float* track_uv, const float* track_ur, const int* track_level,
                                      const float* track_view_cos, const uint8_t* mp_desc, const uint8_t* mp_observed, const uint8_t* f_occupied, float th,

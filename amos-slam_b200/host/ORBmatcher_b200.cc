@@ -8,6 +8,7 @@
 //   ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, float)                    src/ORBmatcher.cc:70-175
 //   ORBmatcher::SearchByProjection(Frame&, const Frame&, float, bool)                          src/ORBmatcher.cc:1569-1728
 //   Frame::ComputeStereoMatches()                                                               src/Frame.cc:1179-1573
+//   ORBmatcher::SearchByProjection(Frame&, KeyFrame*, const set<MapPoint*>&, float, int)       src/ORBmatcher.cc:1731-1863  (8f rank 3, first function)
 //
 // Each body only flattens the object graph (Frame / MapPoint) into the plain arrays of the C ABI
 // (include/orbx_b200.h), calls the CUDA implementation and writes the results back into the same
@@ -19,6 +20,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <set>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -192,6 +194,56 @@ int ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, 
     for (int j = 0; j < CurrentFrame.N; ++j) {
         if (cmatch[j] >= 0) CurrentFrame.mvpMapPoints[j] = LastFrame.mvpMapPoints[cmatch[j]];   // :1685
         else if (cmatch[j] == -2) CurrentFrame.mvpMapPoints[j] = static_cast<MapPoint*>(NULL); // :1719
+    }
+    return nmatches;
+}
+
+int ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const std::set<MapPoint*> &sAlreadyFound, const float th, const int ORBdist)
+{
+    // pose algebra, scale prediction and the set lookup stay on the host: they need the MapPoint objects and are O(N) (:1737-1789)
+    const cv::Mat Rcw = CurrentFrame.mTcw.rowRange(0, 3).colRange(0, 3);
+    const cv::Mat tcw = CurrentFrame.mTcw.rowRange(0, 3).col(3);
+    const cv::Mat Ow = -Rcw.t() * tcw;
+    const std::vector<MapPoint*> vpMPs = pKF->GetMapPointMatches();
+    const int n = (int)vpMPs.size();
+    std::vector<float> uv((size_t)n * 2, 0.f), angle(n, 0.f);
+    std::vector<int> level(n, 0);
+    std::vector<unsigned char> desc((size_t)n * 32, 0), valid(n, 0);
+    for (int i = 0; i < n; ++i) {
+        MapPoint* pMP = vpMPs[i];
+        if (!pMP || pMP->isBad() || sAlreadyFound.count(pMP)) continue;
+        cv::Mat x3Dw = pMP->GetWorldPos();
+        cv::Mat x3Dc = Rcw * x3Dw + tcw;
+        const float xc = x3Dc.at<float>(0), yc = x3Dc.at<float>(1);
+        const float invzc = 1.0 / x3Dc.at<float>(2);
+        const float u = CurrentFrame.fx * xc * invzc + CurrentFrame.cx;
+        const float v = CurrentFrame.fy * yc * invzc + CurrentFrame.cy;
+        if (u < CurrentFrame.mnMinX || u > CurrentFrame.mnMaxX || v < CurrentFrame.mnMinY || v > CurrentFrame.mnMaxY) continue;
+        cv::Mat PO = x3Dw - Ow;
+        float dist3D = cv::norm(PO);
+        if (dist3D < pMP->GetMinDistanceInvariance() || dist3D > pMP->GetMaxDistanceInvariance()) continue;
+        uv[2 * i] = u; uv[2 * i + 1] = v;
+        level[i] = pMP->PredictScale(dist3D, &CurrentFrame);
+        angle[i] = pKF->mvKeysUn[i].angle;
+        const cv::Mat d = pMP->GetDescriptor();
+        std::memcpy(&desc[(size_t)i * 32], d.ptr(), 32);
+        valid[i] = 1;
+    }
+    std::vector<unsigned char> occ(CurrentFrame.N, 0);
+    for (int j = 0; j < CurrentFrame.N; ++j) if (CurrentFrame.mvpMapPoints[j]) occ[j] = 1;                                    // :1808: any map point blocks
+    std::vector<int> cmatch(CurrentFrame.N ? CurrentFrame.N : 1, -1);
+    int nmatches = 0;
+    if (const orbx_frame* dc = device_of(CurrentFrame))
+        check(orbx_search_by_projection_keyframe_dev(t_matchers.get(mfNNratio, mbCheckOrientation), dc, n, uv.data(), level.data(), angle.data(), desc.data(), valid.data(),
+                                                     occ.data(), th, ORBdist, cmatch.data(), &nmatches), "orbx_search_by_projection_keyframe_dev");
+    else {
+        FrameFlat c(CurrentFrame);
+        check(orbx_search_by_projection_keyframe(t_matchers.get(mfNNratio, mbCheckOrientation), &c.v, n, uv.data(), level.data(), angle.data(), desc.data(), valid.data(),
+                                                 occ.data(), th, ORBdist, cmatch.data(), &nmatches), "orbx_search_by_projection_keyframe");
+    }
+    for (int j = 0; j < CurrentFrame.N; ++j) {
+        if (cmatch[j] >= 0) CurrentFrame.mvpMapPoints[j] = vpMPs[cmatch[j]];                                                 // :1822
+        else if (cmatch[j] == -2) CurrentFrame.mvpMapPoints[j] = static_cast<MapPoint*>(NULL);                               // :1853
     }
     return nmatches;
 }

@@ -348,6 +348,20 @@ int orbx_search_by_projection_points_dev(orbx_matcher* m, const orbx_frame* F, i
                                          const float* track_view_cos, const uint8_t* mp_desc, const uint8_t* mp_observed,
                                          const uint8_t* f_occupied, float th, int* f_match, int* nmatches);
 
+/* int ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const set<MapPoint*> &sAlreadyFound, float th, int ORBdist)
+ *   src/ORBmatcher.cc:1731-1863 (relocalisation, src/Tracking.cc:2663; first function of SURVEY.md 8f rank 3).  As in the Frame x Frame
+ *   form the pose algebra stays in the caller; per KeyFrame map point i that is neither NULL, bad nor in sAlreadyFound, projects
+ *   inside the image bounds and lies within its scale-invariance distances (:1753-1785):  proj_uv (u, v); predicted_level[i] =
+ *   pMP->PredictScale(dist3D, &CurrentFrame); kf_angle[i] = pKF->mvKeysUn[i].angle; mp_desc = GetDescriptor(); valid[i] != 0.
+ *   cur_occupied[j] != 0 iff CurrentFrame.mvpMapPoints[j] is not NULL (:1808; any map point blocks, so does every claim made earlier in
+ *   the call).  A match needs bestDist <= orb_dist (:1820).  cur_match as for orbx_search_by_projection_frame (-2 = reset by :1853). */
+int orbx_search_by_projection_keyframe(orbx_matcher* m, const orbx_frame_view* cur, int n_kf, const float* proj_uv,
+                                       const int* predicted_level, const float* kf_angle, const uint8_t* mp_desc, const uint8_t* valid,
+                                       const uint8_t* cur_occupied, float th, int orb_dist, int* cur_match, int* nmatches);
+int orbx_search_by_projection_keyframe_dev(orbx_matcher* m, const orbx_frame* cur, int n_kf, const float* proj_uv,
+                                           const int* predicted_level, const float* kf_angle, const uint8_t* mp_desc, const uint8_t* valid,
+                                           const uint8_t* cur_occupied, float th, int orb_dist, int* cur_match, int* nmatches);
+
 /* ------------------------------------------------------------------------------------------------
  * Bag of words: DBoW2's vocabulary tree and the two BoW-guided matchers.
  *   ORBVocabulary = DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB>   include/ORBVocabulary.h:40-41

@@ -305,6 +305,31 @@ class Matcher:
                                                       float(mbf), cm.ctypes.data)
         return nm, cm
 
+    def search_by_projection_keyframe_ref(self, cur, cam_xyz, predicted_level, kf_angle, mp_desc, state, min_dist, max_dist, cur_occupied, th, orb_dist, fx, fy, cx, cy):
+        """Reference body (ORBmatcher.cc:1731) with identity pose; state: 0 none, 1 good, 2 bad, 3 already found.  -> (nmatches, cur_match, proj_uv)."""
+        assert self.kind == "ref"
+        xyz = np.ascontiguousarray(cam_xyz, np.float32); n = len(xyz)
+        lv = np.ascontiguousarray(predicted_level, np.int32); an = np.ascontiguousarray(kf_angle, np.float32)
+        d, st, oc = _u8(mp_desc), _u8(state), _u8(cur_occupied)
+        mn = np.ascontiguousarray(min_dist, np.float32); mx = np.ascontiguousarray(max_dist, np.float32)
+        uv = np.zeros((n, 2), np.float32); cm = np.zeros(max(len(cur.keys), 1), np.int32)
+        f = self.lib.ref_search_by_projection_keyframe; f.restype = C.c_int
+        f.argtypes = [C.c_float, C.c_int, C.POINTER(FrameViewC), C.c_int] + [C.c_void_p] * 8 + [C.c_float, C.c_int] + [C.c_float] * 4 + [C.c_void_p, C.c_void_p]
+        nm = f(self.nnratio, self.check_ori, C.byref(cur.view()), n, xyz.ctypes.data, lv.ctypes.data, an.ctypes.data, d.ctypes.data, st.ctypes.data, mn.ctypes.data, mx.ctypes.data,
+               oc.ctypes.data if oc is not None else None, float(th), int(orb_dist), float(fx), float(fy), float(cx), float(cy), uv.ctypes.data, cm.ctypes.data)
+        return nm, cm[:len(cur.keys)], uv
+
+    def search_by_projection_keyframe_port(self, cur, proj_uv, predicted_level, kf_angle, mp_desc, valid, cur_occupied, th, orb_dist):
+        assert self.kind == "port"
+        uv = np.ascontiguousarray(proj_uv, np.float32); lv = np.ascontiguousarray(predicted_level, np.int32); an = np.ascontiguousarray(kf_angle, np.float32)
+        d, va, oc = _u8(mp_desc), _u8(valid), _u8(cur_occupied)
+        cm = np.zeros(max(len(cur.keys), 1), np.int32)
+        f = self.lib.port_search_by_projection_keyframe; f.restype = C.c_int
+        f.argtypes = [C.c_float, C.c_int, C.POINTER(FrameViewC), C.c_int] + [C.c_void_p] * 6 + [C.c_float, C.c_int, C.c_void_p]
+        nm = f(self.nnratio, self.check_ori, C.byref(cur.view()), len(lv), uv.ctypes.data, lv.ctypes.data, an.ctypes.data, d.ctypes.data, va.ctypes.data,
+               oc.ctypes.data if oc is not None else None, float(th), int(orb_dist), cm.ctypes.data)
+        return nm, cm[:len(cur.keys)]
+
     def compute_stereo_matches(self, ext_left, ext_right, keys_left, desc_left, keys_right, desc_right, mb, mbf):
         """ext_left / ext_right: oracle.Extractor of the same kind whose last extract() saw the left / right image."""
         kl = np.ascontiguousarray(keys_left, KP_DTYPE); kr = np.ascontiguousarray(keys_right, KP_DTYPE)

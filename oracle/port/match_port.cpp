@@ -198,6 +198,44 @@ static int SearchByProjectionFrame(bool checkOri, const FrameView* cur, int n_la
     return nmatches;
 }
 
+// ORBmatcher::SearchByProjection(Frame& Cur, KeyFrame*, const set<MapPoint*>&, th, ORBdist)   ORBmatcher.cc:1731-1863
+// (per KeyFrame map point the caller supplies the projection, the predicted level and valid = not NULL / bad / already found,
+//  inside the image, within its distance range)
+static int SearchByProjectionKeyFrame(bool checkOri, const FrameView* cur, int n_kf, const float* proj_uv, const int* predicted_level, const float* kf_angle,
+                                      const unsigned char* mp_desc, const unsigned char* valid, const unsigned char* cur_occupied, float th, int ORBdist, int* cur_match) {
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    std::vector<unsigned char> taken(cur->n, 0);                       // CurrentFrame.mvpMapPoints[i2] != NULL, before or during the call (:1808)
+    for (int j = 0; j < cur->n; ++j) { cur_match[j] = -1; taken[j] = cur_occupied ? (cur_occupied[j] != 0) : 0; }
+    Grid g(cur);
+    std::vector<int> cands;
+    for (int i = 0; i < n_kf; i++) {
+        if (!valid[i]) continue;
+        const float u = proj_uv[2 * i], v = proj_uv[2 * i + 1];
+        if (u < cur->min_x || u > cur->max_x || v < cur->min_y || v > cur->max_y) continue;
+        const int lvl = predicted_level[i];
+        g.area(u, v, th * cur->scale_factors[lvl], lvl - 1, lvl + 1, cands);
+        int bestDist = 256, bestIdx2 = -1;
+        for (size_t k = 0; k < cands.size(); ++k) {
+            if (taken[cands[k]]) continue;
+            const int dist = DescriptorDistance(mp_desc + (size_t)i * 32, cur->descriptors + (size_t)cands[k] * 32);
+            if (dist < bestDist) { bestDist = dist; bestIdx2 = cands[k]; }
+        }
+        if (bestDist <= ORBdist) {
+            cur_match[bestIdx2] = i; taken[bestIdx2] = 1; nmatches++;
+            if (checkOri) rotHist[rot_bin(kf_angle[i], cur->keys_un[bestIdx2].angle)].push_back(bestIdx2);
+        }
+    }
+    if (checkOri) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        ComputeThreeMaxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++)
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (size_t j = 0; j < rotHist[i].size(); j++) { cur_match[rotHist[i][j]] = -1; nmatches--; }
+    }
+    return nmatches;
+}
+
 // ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>&, th)   ORBmatcher.cc:70-175
 static int SearchByProjectionPoints(float nnratio, const FrameView* F, int n_points, const float* track_uv, const float* track_ur, const int* track_level,
                                     const float* track_view_cos, const unsigned char* mp_desc, const unsigned char* mp_observed, const unsigned char* f_occupied,
@@ -415,6 +453,11 @@ int port_search_by_projection_frame(float nnratio, int checkOri, const FrameView
                                     const unsigned char* cur_occupied, float th, int forward, int backward, float mbf, int* cur_match) {
     (void)nnratio;
     return port::SearchByProjectionFrame(checkOri != 0, cur, n_last, proj_uv, proj_invz, last_octave, last_angle, mp_desc, valid, mp_observed, cur_occupied, th, forward != 0, backward != 0, mbf, cur_match);
+}
+int port_search_by_projection_keyframe(float nnratio, int checkOri, const FrameView* cur, int n_kf, const float* proj_uv, const int* predicted_level, const float* kf_angle,
+                                       const unsigned char* mp_desc, const unsigned char* valid, const unsigned char* cur_occupied, float th, int orb_dist, int* cur_match) {
+    (void)nnratio;
+    return port::SearchByProjectionKeyFrame(checkOri != 0, cur, n_kf, proj_uv, predicted_level, kf_angle, mp_desc, valid, cur_occupied, th, orb_dist, cur_match);
 }
 int port_search_by_projection_points(float nnratio, int checkOri, const FrameView* F, int n_points, const float* track_uv, const float* track_ur, const int* track_level,
                                      const float* track_view_cos, const unsigned char* mp_desc, const unsigned char* mp_observed, const unsigned char* f_occupied,

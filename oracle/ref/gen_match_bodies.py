@@ -6,7 +6,8 @@ output -- nothing is copied into the repository).  The functions are located by 
   src/ORBmatcher.cc : TH_HIGH/TH_LOW/HISTO_LENGTH + ctor, SearchByProjection(Frame&, vector<MapPoint*>&, th),
                       RadiusByViewingCos, SearchForInitialization, SearchByProjection(Frame&, const Frame&, th, bMono),
                       ComputeThreeMaxima, DescriptorDistance
-                      SearchByBoW(KeyFrame*, Frame&, ...), SearchByBoW(KeyFrame*, KeyFrame*, ...)
+                      SearchByBoW(KeyFrame*, Frame&, ...), SearchByBoW(KeyFrame*, KeyFrame*, ...),
+                      SearchByProjection(Frame&, KeyFrame*, const set<MapPoint*>&, th, ORBdist)
   Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h : transform(features, BowVector, FeatureVector, levelsup), transform(feature, ...)
   src/Frame.cc      : AssignFeaturesToGrid, GetFeaturesInArea, PosInGrid, ComputeStereoMatches,
                       UndistortKeyPoints, ComputeImageBounds, ComputeStereoFromRGBD
@@ -59,6 +60,7 @@ m = extract("src/ORBmatcher.cc", [
     "int ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono)",
     "void ORBmatcher::ComputeThreeMaxima(vector<int>* histo, const int L, int &ind1, int &ind2, int &ind3)",
     "int ORBmatcher::DescriptorDistance(const cv::Mat &a, const cv::Mat &b)",
+    "int ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const set<MapPoint*> &sAlreadyFound, const float th , const int ORBdist)",
     "int ORBmatcher::SearchByBoW(KeyFrame* pKF,Frame &F, vector<MapPoint*> &vpMapPointMatches)",
     "int ORBmatcher::SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, vector<MapPoint *> &vpMatches12)",
 ])

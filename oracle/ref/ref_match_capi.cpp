@@ -31,8 +31,11 @@ class KeyFrame;
 class MapPoint {               // the members ORBmatcher.cc:70-175 and :1569-1728 read (include/MapPoint.h)
 public:
     bool mbTrackInView; int mnTrackScaleLevel; float mTrackViewCos, mTrackProjX, mTrackProjY, mTrackProjXR;
-    bool bad; int nobs; cv::Mat desc, pos;
-    MapPoint() : mbTrackInView(true), mnTrackScaleLevel(0), mTrackViewCos(1.f), mTrackProjX(0), mTrackProjY(0), mTrackProjXR(0), bad(false), nobs(0) {}
+    bool bad; int nobs; cv::Mat desc, pos; float maxd, mind; int plevel;
+    MapPoint() : mbTrackInView(true), mnTrackScaleLevel(0), mTrackViewCos(1.f), mTrackProjX(0), mTrackProjY(0), mTrackProjXR(0), bad(false), nobs(0), maxd(1e30f), mind(0.f), plevel(0) {}
+    float GetMaxDistanceInvariance() { return maxd; }
+    float GetMinDistanceInvariance() { return mind; }
+    int PredictScale(const float&, Frame*) { return plevel; }          // the level is an input of the C-ABI call: the harness supplies it
     bool isBad() { return bad; }
     int Observations() { return nobs; }
     cv::Mat GetDescriptor() { return desc.clone(); }
@@ -86,6 +89,7 @@ public:
     int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono);
     int SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12, int windowSize = 10);
     int SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches);
+    int SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const std::set<MapPoint*>& sAlreadyFound, const float th, const int ORBdist);
     int SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12);
     static const int TH_LOW, TH_HIGH, HISTO_LENGTH;
 protected:
@@ -272,6 +276,43 @@ void ref_undistort_points(const float* pts, int n, const float* cam9, int ndist,
     std::memcpy(m.data, pts, (size_t)n * 8);
     cv::undistortPoints(m, m, K, D, cv::Mat(), K);
     std::memcpy(out, m.data, (size_t)n * 8);
+}
+
+// ORBmatcher::SearchByProjection(Frame&, KeyFrame*, const set<MapPoint*>&, th, ORBdist)   ORBmatcher.cc:1731.  Identity pose as above:
+// x3Dc == x3Dw == cam_xyz; the body's projection is returned in proj_uv.  state[i]: 0 = no map point, 1 = good, 2 = bad, 3 = already found.
+int ref_search_by_projection_keyframe(float nnratio, int checkOri, const FrameView* cur, int n_kf, const float* cam_xyz, const int* predicted_level, const float* kf_angle,
+                                      const unsigned char* mp_desc, const unsigned char* state, const float* min_dist, const float* max_dist,
+                                      const unsigned char* cur_occupied, float th, int orb_dist, float fx, float fy, float cx, float cy, float* proj_uv, int* cur_match) {
+    ArenaScope scope;
+    int nm;
+    {
+        Frame C; fill_frame(C, cur);
+        Frame::fx = fx; Frame::fy = fy; Frame::cx = cx; Frame::cy = cy;
+        C.mTcw = cv::Mat::eye(4, 4, CV_32F);
+        std::vector<MapPoint> pts(n_kf), occ(cur->n);
+        KeyFrame K; K.mvKeysUn.resize(n_kf); K.mvpMapPoints.assign(n_kf, (MapPoint*)NULL);
+        std::set<MapPoint*> found;
+        for (int i = 0; i < n_kf; ++i) {
+            K.mvKeysUn[i].angle = kf_angle[i];
+            pts[i].pos = cv::Mat(3, 1, CV_32F); for (int k = 0; k < 3; ++k) pts[i].pos.at<float>(k) = cam_xyz[3 * i + k];
+            pts[i].desc = cv::Mat(1, 32, CV_8U, (void*)(mp_desc + (size_t)i * 32)).clone();
+            pts[i].plevel = predicted_level[i]; pts[i].mind = min_dist[i]; pts[i].maxd = max_dist[i];
+            if (state[i]) K.mvpMapPoints[i] = &pts[i];
+            if (state[i] == 2) pts[i].bad = true;
+            if (state[i] == 3) found.insert(&pts[i]);
+            const float xc = cam_xyz[3 * i], yc = cam_xyz[3 * i + 1];
+            const float invzc = 1.0 / cam_xyz[3 * i + 2];
+            proj_uv[2 * i] = fx * xc * invzc + cx; proj_uv[2 * i + 1] = fy * yc * invzc + cy;
+        }
+        for (int j = 0; j < cur->n; ++j) if (cur_occupied && cur_occupied[j]) C.mvpMapPoints[j] = &occ[j];
+        ORBmatcher matcher(nnratio, checkOri != 0);
+        nm = matcher.SearchByProjection(C, &K, found, th, orb_dist);
+        for (int j = 0; j < cur->n; ++j) {
+            MapPoint* p = C.mvpMapPoints[j];
+            cur_match[j] = (p && p >= &pts[0] && p < &pts[0] + n_kf) ? (int)(p - &pts[0]) : -1;
+        }
+    }
+    return nm;
 }
 
 // ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&)  ORBmatcher.cc:230  and  (KeyFrame*, KeyFrame*, ...)  :656.

@@ -1,0 +1,24 @@
+#!/usr/bin/env python3
+"""Generates tests/golden/ref_match_kf.npz: outputs of the reference's own ORBmatcher::SearchByProjection(Frame&, KeyFrame*,
+const set<MapPoint*>&, th, ORBdist) body (src/ORBmatcher.cc:1731-1863, compiled into oracle/_ref) on the seeded inputs of
+tests/match_cases.py.  usage: python tests/golden/make_golden_match_kf.py"""
+import os, sys
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import oracle                      # noqa: E402
+import match_cases as mc           # noqa: E402
+
+assert oracle.build_ref(), "needs /root/reference"
+E = oracle.Extractor("ref", 1000, 1.2, 8, 20, 7)
+ka, da, kb, db = mc.mono_pair(lambda img: E.extract(img))
+pi = mc.projection_inputs(ka, kb); kf = mc.keyframe_inputs(ka, kb, pi)
+F = oracle.FrameData(kb, db, 640, 480, E.scale_factors)
+out = {"n_a": np.array(len(ka)), "n_b": np.array(len(kb))}
+for i, (th, od, ori) in enumerate(mc.KF_CASES):
+    nm, cm, uv = oracle.Matcher("ref", 0.9, ori).search_by_projection_keyframe_ref(F, pi["xyz"], kf["lvl"], ka["angle"], da, kf["state"], kf["mind"], kf["maxd"], kf["occ"],
+                                                                                 th, od, mc.FX, mc.FY, mc.CX, mc.CY)
+    out["kf%d_nm" % i] = np.array(nm); out["kf%d_cm" % i] = cm; out["uv"] = uv
+np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_match_kf.npz"), **out)
+print("wrote ref_match_kf.npz", [int(out["kf%d_nm" % i]) for i in range(len(mc.KF_CASES))])

@@ -10,6 +10,10 @@ public:
     cv::Mat GetDescriptor() { return mDescriptor; }
     int Observations() { return nObs; }
     bool isBad() { return mbBad; }
+    float GetMinDistanceInvariance() { return mfMinDistance; }
+    float GetMaxDistanceInvariance() { return mfMaxDistance; }
+    template <class FrameT> int PredictScale(const float&, FrameT*) { return nPredictedLevel; }
+    float mfMinDistance = 0.f, mfMaxDistance = 1e30f; int nPredictedLevel = 0;
     float mTrackProjX = 0, mTrackProjY = 0, mTrackProjXR = 0;
     bool mbTrackInView = false;
     int mnTrackScaleLevel = 0;

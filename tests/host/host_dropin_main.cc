@@ -164,6 +164,30 @@ int main(int argc, char** argv) {
         put_i(nm2);
         for (int j = 0; j < D2.N; ++j) put_i(D2.mvpMapPoints[j] ? (int)(D2.mvpMapPoints[j] - store.data()) : -1);
     }
+    // ---- ORBmatcher::SearchByProjection(Frame&, KeyFrame*, set&, th, ORBdist)  (relocalisation, Tracking.cc:2663): identity pose,
+    //      map points placed so that they project onto A's keypoints shifted by the known motion
+    {
+        Frame C; fill_frame(C, ext, kb, db, w, h);
+        C.fx = 517.3f; C.fy = 516.5f; C.cx = 318.6f; C.cy = 255.3f;
+        C.mTcw = cv::Mat::eye(4, 4, CV_32F);
+        std::vector<MapPoint> mps(ka.size());
+        KeyFrame K; K.mvKeysUn = ka; K.mvpMapPoints.assign(ka.size(), (MapPoint*)NULL);
+        std::set<MapPoint*> found;
+        for (size_t i = 0; i < ka.size(); ++i) {
+            MapPoint& p = mps[i];
+            const float z = 1.f + (float)(i % 7);
+            p.mWorldPos = cv::Mat(3, 1, CV_32F);
+            p.mWorldPos.at<float>(0) = (ka[i].pt.x + 7.f - C.cx) / C.fx * z; p.mWorldPos.at<float>(1) = (ka[i].pt.y - 4.f - C.cy) / C.fy * z; p.mWorldPos.at<float>(2) = z;
+            p.mDescriptor = da.row((int)i); p.nPredictedLevel = ka[i].octave; p.mbBad = (i % 11) == 0;
+            if (i % 13 == 0) p.mfMaxDistance = 0.5f;                                   // out of its scale-invariance range
+            if (i % 4) K.mvpMapPoints[i] = &p;
+            if (i % 9 == 0) found.insert(&p);
+        }
+        for (int j = 0; j < C.N; ++j) if (j % 10 == 0) C.mvpMapPoints[j] = &mps[0];      // pre-existing assignments block
+        int nk = ORBmatcher(0.9, true).SearchByProjection(C, &K, found, 10.f, 100);
+        put_i(nk);
+        for (int j = 0; j < C.N; ++j) put_i((C.mvpMapPoints[j] && j % 10) ? (int)(C.mvpMapPoints[j] - mps.data()) : -1);
+    }
     // ---- bag of words: Frame::ComputeBoW / KeyFrame::ComputeBoW and both SearchByBoW forms (Tracking.cc:1740-1752, LoopClosing)
     if (argc > 3) {
         ORBVocabulary voc;

@@ -47,3 +47,20 @@ PROJ_POINT_CASES = [1.0, 3.0, 5.0]                          # SearchLocalPoints 
 def stereo_pair(seed=3, width=1241, height=376):
     L = synth_frame(seed, width, height)
     return L, stereo_right_from_left(L, seed + 1)
+
+
+KF_CASES = [(10.0, 100, True), (3.0, 64, True), (10.0, 100, False)]     # (th, ORBdist, checkOri); relocalisation uses (10, 100) and (3, 64) (Tracking.cc:2663-2720)
+
+
+def keyframe_inputs(ka, kb, pi, seed=9):
+    """Inputs of SearchByProjection(Frame&, KeyFrame*, set&, th, ORBdist): map-point state (0 none, 1 good, 2 bad, 3 already found),
+    predicted level, scale-invariance distance range, occupancy of the current frame; `valid` is what the C-ABI caller derives."""
+    rng = np.random.default_rng(seed); n = len(ka)
+    state = rng.choice([0, 1, 1, 1, 1, 2, 3], n).astype(np.uint8)
+    lvl = np.clip(ka["octave"] + rng.integers(-1, 2, n), 0, 7).astype(np.int32)
+    xyz = pi["xyz"].astype(np.float32)
+    d3 = np.sqrt((xyz.astype(np.float64) ** 2).sum(1)).astype(np.float32)                # float dist3D = cv::norm(PO)  (double accumulate, :1773-1774)
+    mind = (d3 * rng.choice([0.5, 0.5, 1.2], n)).astype(np.float32); maxd = (d3 * rng.choice([2.0, 2.0, 0.8], n)).astype(np.float32)
+    occ = (rng.random(len(kb)) < 0.15).astype(np.uint8)
+    valid = ((state == 1) & ~((d3 < mind) | (d3 > maxd))).astype(np.uint8)
+    return dict(state=state, lvl=lvl, mind=mind, maxd=maxd, occ=occ, valid=valid)

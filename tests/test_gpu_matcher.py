@@ -120,3 +120,17 @@ def test_bruteforce_batch_pairs(orbx, case):
         assert np.array_equal(bi[p].cpu().numpy(), D.argmin(1)) and np.array_equal(bd[p].cpu().numpy(), D.min(1))
         assert np.array_equal(sd[p].cpu().numpy(), np.sort(D, axis=1)[:, 1])
     assert bi[1, 100].item() == 7 and bd[1, 100].item() == 0 and sd[1, 100].item() == 0
+
+
+def test_search_by_projection_keyframe(orbx, case):
+    """SearchByProjection(Frame&, KeyFrame*, set&, th, ORBdist) (relocalisation) against the reference body's golden, on a host view and on a device frame."""
+    GK = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_match_kf.npz"))
+    ka, kb, pi = case["ka"], case["kb"], case["pi"]
+    kf = mc.keyframe_inputs(ka, kb, pi)
+    uv, _ = mc.project(pi["xyz"])
+    D = orbx.Frame().assign_host(kb, case["db"], case["sf"], orbx.Camera.make(mc.FX, mc.FY, mc.CX, mc.CY), 480, 640)
+    D.set_stereo(pi["u_right"], np.where(pi["u_right"] > 0, 1.0, -1.0).astype(np.float32))          # must be ignored by this matcher
+    for i, (th, od, ori) in enumerate(mc.KF_CASES):
+        for F in (case["FB"], case["FBu"], D):
+            nm, cm = orbx.ORBmatcher(0.9, ori).SearchByProjectionKeyFrame(F, uv, kf["lvl"], ka["angle"], case["da"], kf["valid"], kf["occ"], th, od)
+            assert nm == int(GK["kf%d_nm" % i]) and np.array_equal(cm, GK["kf%d_cm" % i])

@@ -152,6 +152,19 @@ def test_host_classes_match_c_abi(orbx, tmp_path):
     assert np.array_equal(r.arr(np.int32, r.i()), m12)
     assert r.i() == nm2
     assert np.array_equal(r.arr(np.int32, len(kb)), host_fm)
+    # relocalisation matcher: rebuild the driver's map points and compare with the C-ABI call
+    fx, fy, cx, cy = np.float32(517.3), np.float32(516.5), np.float32(318.6), np.float32(255.3)
+    z = (np.float32(1.0) + (idx % 7).astype(np.float32))
+    X = ((ka["x"] + np.float32(7) - cx) / fx * z).astype(np.float32); Y = ((ka["y"] - np.float32(4) - cy) / fy * z).astype(np.float32)
+    invz = (1.0 / z.astype(np.float64)).astype(np.float32)
+    uvk = np.stack([fx * X * invz + cx, fy * Y * invz + cy], 1).astype(np.float32)
+    d3 = np.sqrt(X.astype(np.float64) ** 2 + Y.astype(np.float64) ** 2 + z.astype(np.float64) ** 2).astype(np.float32)
+    okk = (idx % 4 != 0) & (idx % 11 != 0) & (idx % 9 != 0) & ~((idx % 13 == 0) & (d3 > 0.5))
+    okk &= (uvk[:, 0] >= 0) & (uvk[:, 0] <= 640) & (uvk[:, 1] >= 0) & (uvk[:, 1] <= 480)
+    occk = (np.arange(len(kb)) % 10 == 0).astype(np.uint8)
+    nk, cmk = orbx.ORBmatcher(0.9, True).SearchByProjectionKeyFrame(orbx.FrameView(kb, db, 640, 480, sf), uvk, ka["octave"], ka["angle"], da, okk.astype(np.uint8), occk, 10.0, 100)
+    assert r.i() == nk and nk > 50
+    assert np.array_equal(r.arr(np.int32, len(kb)), cmk)
     # bag of words through Frame::ComputeBoW / KeyFrame::ComputeBoW / ORBmatcher::SearchByBoW == the C-ABI results (pinned to DBoW2 in test_gpu_bow.py)
     V = orbx.ORBVocabulary(4, 5, *voc)
     ta, tb = V.transform(da, 4), V.transform(db, 4)

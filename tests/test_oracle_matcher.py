@@ -86,3 +86,19 @@ def test_grid_queries_and_live_reference(oracle, case):
         mr = oracle.Matcher("ref")
         for q, r in zip(qs, res):
             assert np.array_equal(mr.features_in_area(case["FA"], *q), r)          # same candidates in the same ORDER
+
+
+def test_port_keyframe_projection_matches_reference_golden(oracle):
+    """SearchByProjection(Frame&, KeyFrame*, set&, th, ORBdist) (ORBmatcher.cc:1731-1863): port vs the reference body's committed outputs."""
+    import os
+    GK = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_match_kf.npz"))
+    E = oracle.Extractor("port", 1000, 1.2, 8, 20, 7)
+    ka, da, kb, db = mc.mono_pair(lambda img: E.extract(img))
+    assert len(ka) == int(GK["n_a"]) and len(kb) == int(GK["n_b"])
+    pi = mc.projection_inputs(ka, kb); kf = mc.keyframe_inputs(ka, kb, pi)
+    F = oracle.FrameData(kb, db, 640, 480, E.scale_factors)
+    uv, _ = mc.project(pi["xyz"])
+    assert np.array_equal(uv, GK["uv"])                                   # the caller-side projection equals the body's own
+    for i, (th, od, ori) in enumerate(mc.KF_CASES):
+        nm, cm = oracle.Matcher("port", 0.9, ori).search_by_projection_keyframe_port(F, uv, kf["lvl"], ka["angle"], da, kf["valid"], kf["occ"], th, od)
+        assert nm == int(GK["kf%d_nm" % i]) and nm > 30 and np.array_equal(cm, GK["kf%d_cm" % i])
