@@ -300,6 +300,18 @@ class ORBmatcher:
         cm[cm == -2] = -1
         return nm.value, cm
 
+    # int SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*> &vpPoints, vector<MapPoint*> &vpMatched, int th)
+    def SearchByProjectionKeyFramePoints(self, kf, proj_uv, predicted_level, mp_desc, valid, kf_matched, th):
+        uv = np.ascontiguousarray(proj_uv, np.float32); lv = np.ascontiguousarray(predicted_level, np.int32)
+        d, va, km = _u8(mp_desc), _u8(valid), _u8(kf_matched)
+        out = np.zeros(max(len(kf.keys), 1), np.int32); nm = C.c_int()
+        if isinstance(kf, Frame):
+            fn, fa = self._lib.orbx_search_by_projection_keyframe_points_dev, kf._h
+        else:
+            v = kf.c(); fn, fa = self._lib.orbx_search_by_projection_keyframe_points, C.byref(v)
+        self._check(fn(self._h, fa, len(lv), _p(uv), _p(lv), _p(d), _p(va), _p(km), float(th), _p(out), C.byref(nm)))
+        return nm.value, out[:len(kf.keys)]
+
     # int SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, const float th=3)
     def SearchByProjectionPoints(self, F, track_uv, track_ur, track_level, track_view_cos, mp_desc, mp_observed, f_occupied, th=3.0):
         uv = np.ascontiguousarray(track_uv, np.float32); ur = np.ascontiguousarray(track_ur, np.float32)

@@ -113,7 +113,8 @@ __device__ __forceinline__ bool query_window(const QueryParams& P, const FrameDe
         if (v < F.min_y || v > F.max_y) return false;
         const int oct = P.q_octave[q];
         x = u; y = v; r = __fmul_rn(P.th, F.scale[oct]);                            // :1629
-        if (P.forward) { minLevel = oct; maxLevel = -1; }                           // :1637-1642
+        if (P.forward == 2) { minLevel = oct - 1; maxLevel = oct; }                 // KeyFrame x map points: kpLevel in [nPredictedLevel - 1, nPredictedLevel] (:462-463)
+        else if (P.forward) { minLevel = oct; maxLevel = -1; }                      // :1637-1642
         else if (P.backward) { minLevel = 0; maxLevel = oct; }
         else { minLevel = oct - 1; maxLevel = oct + 1; }
         ur = __fsub_rn(u, __fmul_rn(P.mbf, invz)); use_ur = !P.no_ur;               // :1665

@@ -339,7 +339,7 @@ retry:
 static int search_proj_frame_impl(orbx_matcher* m, const FrameArg cur, int n_last, const float* proj_uv, const float* proj_invz,
                                     const int* last_octave, const float* last_angle, const uint8_t* mp_desc, const uint8_t* valid, const uint8_t* mp_observed,
                                     const uint8_t* cur_occupied, float th, int forward, int backward, float mbf, int* cur_match, int* nmatches,
-                                  int max_dist = M_TH_HIGH, int no_ur = 0) {
+                                  int max_dist = M_TH_HIGH, int no_ur = 0, int check_ori = -1 /* -1: the matcher's own setting */) {
     if (!m || !nmatches) FAIL(ORBX_E_INVALID, "null argument");
     int rc;
     if ((rc = check_frame_arg(m, cur))) return rc;
@@ -367,7 +367,7 @@ retry:
     if ((rc = window_search(m, P, dc, counts, offsets, cand, pre))) return rc;
     int* occ = m->arena.get<int>(nc + 1); int* cm = m->arena.get<int>(nc + 1); int* pushes = m->arena.get<int>(2 * (size_t)n_last + 2); int* dn = m->arena.get<int>(1);
     if (!occ || !cm || !pushes || !dn) FAIL(ORBX_E_CUDA, "matcher arena exhausted");
-    k_resolve_proj_frame<<<1, RESOLVE_THREADS, RESOLVE_SMEM_BYTES, m->stream>>>(n_last, nc, dc.keys, la, ob, oc, counts, offsets, cand, pre, (int)std::min<size_t>(m->cand_cap, 0x7FFFFFFF), m->checkOri, max_dist, RESOLVE_SMEM_BYTES / 4, occ, cm, pushes, dn);
+    k_resolve_proj_frame<<<1, RESOLVE_THREADS, RESOLVE_SMEM_BYTES, m->stream>>>(n_last, nc, dc.keys, la, ob, oc, counts, offsets, cand, pre, (int)std::min<size_t>(m->cand_cap, 0x7FFFFFFF), check_ori < 0 ? m->checkOri : check_ori, max_dist, RESOLVE_SMEM_BYTES / 4, occ, cm, pushes, dn);
     LAUNCH_CHECK();
     Gather g{m};
     if ((rc = g.begin(8 + (size_t)nc * 4 + 64))) return rc;
@@ -494,6 +494,27 @@ static int search_proj_keyframe(orbx_matcher* m, const FrameArg cur, int n_kf, c
     std::vector<float> invz((size_t)std::max(n_kf, 1), 0.f);                     // only the sign test of the Frame x Frame form reads it
     std::vector<uint8_t> blocks((size_t)std::max(n_kf, 1), 1);                  // a feature claimed in this call is never re-assigned (:1808)
     return search_proj_frame_impl(m, cur, n_kf, proj_uv, invz.data(), predicted_level, kf_angle, mp_desc, valid, blocks.data(), cur_occupied, th, 0, 0, 0.f, cur_match, nmatches, orb_dist, 1);
+}
+// SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th)  (ORBmatcher.cc:388-512, loop closing): the same search on a KeyFrame's
+// features (KeyFrame::GetFeaturesInArea walks the same grid in the same order, src/KeyFrame.cc:752-797) with levels
+// [predicted - 1, predicted], TH_LOW as acceptance bound, no rotation histogram
+static int search_proj_kf_points(orbx_matcher* m, const FrameArg kf, int n_points, const float* proj_uv, const int* predicted_level, const uint8_t* mp_desc, const uint8_t* valid,
+                                 const uint8_t* kf_matched, float th, int* kf_match, int* nmatches) {
+    if (n_points < 0 || n_points >= (1 << 20)) FAIL(ORBX_E_INVALID, "bad arguments");
+    const size_t nn = (size_t)std::max(n_points, 1);
+    std::vector<float> zeros(nn, 0.f); std::vector<uint8_t> blocks(nn, 1);
+    return search_proj_frame_impl(m, kf, n_points, proj_uv, zeros.data(), predicted_level, zeros.data(), mp_desc, valid, blocks.data(), kf_matched, th, 2, 0, 0.f, kf_match, nmatches,
+                                  M_TH_LOW, 1, 0);
+}
+int orbx_search_by_projection_keyframe_points(orbx_matcher* m, const orbx_frame_view* kf, int n_points, const float* proj_uv, const int* predicted_level, const uint8_t* mp_desc,
+                                              const uint8_t* valid, const uint8_t* kf_matched, float th, int* kf_match, int* nmatches) {
+    if (!kf) FAIL(ORBX_E_INVALID, "bad frame view");
+    return search_proj_kf_points(m, FrameArg{kf, nullptr}, n_points, proj_uv, predicted_level, mp_desc, valid, kf_matched, th, kf_match, nmatches);
+}
+int orbx_search_by_projection_keyframe_points_dev(orbx_matcher* m, const orbx_frame* kf, int n_points, const float* proj_uv, const int* predicted_level, const uint8_t* mp_desc,
+                                                  const uint8_t* valid, const uint8_t* kf_matched, float th, int* kf_match, int* nmatches) {
+    if (!kf) FAIL(ORBX_E_INVALID, "null frame");
+    return search_proj_kf_points(m, FrameArg{nullptr, kf}, n_points, proj_uv, predicted_level, mp_desc, valid, kf_matched, th, kf_match, nmatches);
 }
 int orbx_search_by_projection_keyframe(orbx_matcher* m, const orbx_frame_view* cur, int n_kf, const float* proj_uv, const int* predicted_level, const float* kf_angle,
                                        const uint8_t* mp_desc, const uint8_t* valid, const uint8_t* cur_occupied, float th, int orb_dist, int* cur_match, int* nmatches) {

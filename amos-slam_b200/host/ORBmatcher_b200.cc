@@ -8,7 +8,8 @@
 //   ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, float)                    src/ORBmatcher.cc:70-175
 //   ORBmatcher::SearchByProjection(Frame&, const Frame&, float, bool)                          src/ORBmatcher.cc:1569-1728
 //   Frame::ComputeStereoMatches()                                                               src/Frame.cc:1179-1573
-//   ORBmatcher::SearchByProjection(Frame&, KeyFrame*, const set<MapPoint*>&, float, int)       src/ORBmatcher.cc:1731-1863  (8f rank 3, first function)
+//   ORBmatcher::SearchByProjection(Frame&, KeyFrame*, const set<MapPoint*>&, float, int)       src/ORBmatcher.cc:1731-1863  (8f rank 3)
+//   ORBmatcher::SearchByProjection(KeyFrame*, cv::Mat Scw, const vector<MapPoint*>&, vector<MapPoint*>&, int)   src/ORBmatcher.cc:388-512  (8f rank 3)
 //
 // Each body only flattens the object graph (Frame / MapPoint) into the plain arrays of the C ABI
 // (include/orbx_b200.h), calls the CUDA implementation and writes the results back into the same
@@ -17,6 +18,7 @@
 #include "ORBmatcher.h"
 #include "../../include/orbx_b200.h"
 
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -245,6 +247,63 @@ int ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const std
         if (cmatch[j] >= 0) CurrentFrame.mvpMapPoints[j] = vpMPs[cmatch[j]];                                                 // :1822
         else if (cmatch[j] == -2) CurrentFrame.mvpMapPoints[j] = static_cast<MapPoint*>(NULL);                               // :1853
     }
+    return nmatches;
+}
+
+int ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const std::vector<MapPoint*> &vpPoints, std::vector<MapPoint*> &vpMatched, int th)
+{
+    // Sim3 decomposition, projection, distance / viewing-angle gates and scale prediction stay on the host (:391-446)
+    const float &fx = pKF->fx, &fy = pKF->fy, &cx = pKF->cx, &cy = pKF->cy;
+    cv::Mat sRcw = Scw.rowRange(0, 3).colRange(0, 3);
+    const float scw = sqrt(sRcw.row(0).dot(sRcw.row(0)));
+    cv::Mat Rcw = sRcw / scw;
+    cv::Mat tcw = Scw.rowRange(0, 3).col(3) / scw;
+    cv::Mat Ow = -Rcw.t() * tcw;
+    std::set<MapPoint*> spAlreadyFound(vpMatched.begin(), vpMatched.end());
+    spAlreadyFound.erase(static_cast<MapPoint*>(NULL));
+    const int n = (int)vpPoints.size();
+    std::vector<float> uv((size_t)n * 2, 0.f);
+    std::vector<int> level(n, 0);
+    std::vector<unsigned char> desc((size_t)n * 32, 0), valid(n, 0);
+    for (int i = 0; i < n; ++i) {
+        MapPoint* pMP = vpPoints[i];
+        if (pMP->isBad() || spAlreadyFound.count(pMP)) continue;
+        cv::Mat p3Dw = pMP->GetWorldPos();
+        cv::Mat p3Dc = Rcw * p3Dw + tcw;
+        if (p3Dc.at<float>(2) < 0.0) continue;
+        const float invz = 1 / p3Dc.at<float>(2);
+        const float x = p3Dc.at<float>(0) * invz, y = p3Dc.at<float>(1) * invz;
+        const float u = fx * x + cx, v = fy * y + cy;
+        if (!pKF->IsInImage(u, v)) continue;
+        cv::Mat PO = p3Dw - Ow;
+        const float dist = cv::norm(PO);
+        if (dist < pMP->GetMinDistanceInvariance() || dist > pMP->GetMaxDistanceInvariance()) continue;
+        cv::Mat Pn = pMP->GetNormal();
+        if (PO.dot(Pn) < 0.5 * dist) continue;
+        uv[2 * i] = u; uv[2 * i + 1] = v;
+        level[i] = pMP->PredictScale(dist, pKF);
+        const cv::Mat d = pMP->GetDescriptor();
+        std::memcpy(&desc[(size_t)i * 32], d.ptr(), 32);
+        valid[i] = 1;
+    }
+    const int nk = (int)pKF->mvKeysUn.size();
+    std::vector<unsigned char> taken(nk, 0);
+    for (int j = 0; j < nk; ++j) if (vpMatched[j]) taken[j] = 1;                                                            // :459
+    // the KeyFrame as a frame view: its grid is the Frame's (src/KeyFrame.cc:58-66), its bounds are the integer members (include/KeyFrame.h:408-411)
+    orbx_frame_view kv;
+    std::vector<unsigned char> dtmp;
+    kv.n = nk; kv.keys_un = reinterpret_cast<const orbx_keypoint*>(pKF->mvKeysUn.data());
+    if (pKF->mDescriptors.isContinuous()) kv.descriptors = pKF->mDescriptors.ptr();
+    else { dtmp.resize((size_t)nk * 32); for (int j = 0; j < nk; ++j) std::memcpy(&dtmp[(size_t)j * 32], pKF->mDescriptors.ptr(j), 32); kv.descriptors = dtmp.data(); }
+    kv.u_right = NULL;
+    kv.min_x = (float)pKF->mnMinX; kv.min_y = (float)pKF->mnMinY; kv.max_x = (float)pKF->mnMaxX; kv.max_y = (float)pKF->mnMaxY;
+    kv.grid_element_width_inv = pKF->mfGridElementWidthInv; kv.grid_element_height_inv = pKF->mfGridElementHeightInv;
+    kv.nlevels = (int)pKF->mvScaleFactors.size(); kv.scale_factors = pKF->mvScaleFactors.data();
+    std::vector<int> kmatch(nk ? nk : 1, -1);
+    int nmatches = 0;
+    check(orbx_search_by_projection_keyframe_points(t_matchers.get(mfNNratio, mbCheckOrientation), &kv, n, uv.data(), level.data(), desc.data(), valid.data(), taken.data(),
+                                                    (float)th, kmatch.data(), &nmatches), "orbx_search_by_projection_keyframe_points");
+    for (int j = 0; j < nk; ++j) if (kmatch[j] >= 0) vpMatched[j] = vpPoints[kmatch[j]];                                    // :483
     return nmatches;
 }
 

@@ -362,6 +362,20 @@ int orbx_search_by_projection_keyframe_dev(orbx_matcher* m, const orbx_frame* cu
                                            const int* predicted_level, const float* kf_angle, const uint8_t* mp_desc, const uint8_t* valid,
                                            const uint8_t* cur_occupied, float th, int orb_dist, int* cur_match, int* nmatches);
 
+/* int ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*> &vpPoints, vector<MapPoint*> &vpMatched, int th)
+ *   src/ORBmatcher.cc:388-512 (loop closing, src/LoopClosing.cc).  kf = the KeyFrame's mvKeysUn / mDescriptors / grid (KeyFrame copies them
+ *   from its Frame; KeyFrame::GetFeaturesInArea, src/KeyFrame.cc:752-797, walks the grid as Frame's does).  Per map point p that is not
+ *   bad, not already in vpMatched, in front of the camera, inside the image, within its distance range and seen from less than 60 deg
+ *   (:411-446): proj_uv (u, v); predicted_level[p] = PredictScale(dist, pKF); mp_desc; valid[p] != 0.  kf_matched[j] != 0 iff
+ *   vpMatched[j] is not NULL.  Candidates must lie on level predicted - 1 or predicted (:462-463); a match needs bestDist <= TH_LOW.
+ *   Output: kf_match[j] = index p newly written to vpMatched[j] (or -1); *nmatches = return value. */
+int orbx_search_by_projection_keyframe_points(orbx_matcher* m, const orbx_frame_view* kf, int n_points, const float* proj_uv,
+                                              const int* predicted_level, const uint8_t* mp_desc, const uint8_t* valid,
+                                              const uint8_t* kf_matched, float th, int* kf_match, int* nmatches);
+int orbx_search_by_projection_keyframe_points_dev(orbx_matcher* m, const orbx_frame* kf, int n_points, const float* proj_uv,
+                                                  const int* predicted_level, const uint8_t* mp_desc, const uint8_t* valid,
+                                                  const uint8_t* kf_matched, float th, int* kf_match, int* nmatches);
+
 /* ------------------------------------------------------------------------------------------------
  * Bag of words: DBoW2's vocabulary tree and the two BoW-guided matchers.
  *   ORBVocabulary = DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB>   include/ORBVocabulary.h:40-41

@@ -330,6 +330,30 @@ class Matcher:
                oc.ctypes.data if oc is not None else None, float(th), int(orb_dist), cm.ctypes.data)
         return nm, cm[:len(cur.keys)]
 
+    def search_by_projection_keyframe_points_ref(self, kf, cam_xyz, predicted_level, mp_desc, state, found_at, facing, min_dist, max_dist, kf_matched, th, fx, fy, cx, cy):
+        """Reference body (ORBmatcher.cc:388) with Scw = identity.  -> (nmatches, kf_match, proj_uv)."""
+        assert self.kind == "ref"
+        xyz = np.ascontiguousarray(cam_xyz, np.float32); n = len(xyz)
+        lv = np.ascontiguousarray(predicted_level, np.int32); fa = np.ascontiguousarray(found_at, np.int32)
+        d, st, fc_, km = _u8(mp_desc), _u8(state), _u8(facing), _u8(kf_matched)
+        mn = np.ascontiguousarray(min_dist, np.float32); mx = np.ascontiguousarray(max_dist, np.float32)
+        uv = np.zeros((n, 2), np.float32); out = np.zeros(max(len(kf.keys), 1), np.int32)
+        f = self.lib.ref_search_by_projection_keyframe_points; f.restype = C.c_int
+        f.argtypes = [C.c_float, C.c_int, C.POINTER(FrameViewC), C.c_int] + [C.c_void_p] * 9 + [C.c_int] + [C.c_float] * 4 + [C.c_void_p, C.c_void_p]
+        nm = f(self.nnratio, self.check_ori, C.byref(kf.view()), n, xyz.ctypes.data, lv.ctypes.data, d.ctypes.data, st.ctypes.data, fa.ctypes.data, fc_.ctypes.data,
+               mn.ctypes.data, mx.ctypes.data, km.ctypes.data if km is not None else None, int(th), float(fx), float(fy), float(cx), float(cy), uv.ctypes.data, out.ctypes.data)
+        return nm, out[:len(kf.keys)], uv
+
+    def search_by_projection_keyframe_points_port(self, kf, proj_uv, predicted_level, mp_desc, valid, kf_matched, th):
+        assert self.kind == "port"
+        uv = np.ascontiguousarray(proj_uv, np.float32); lv = np.ascontiguousarray(predicted_level, np.int32)
+        d, va, km = _u8(mp_desc), _u8(valid), _u8(kf_matched)
+        out = np.zeros(max(len(kf.keys), 1), np.int32)
+        f = self.lib.port_search_by_projection_keyframe_points; f.restype = C.c_int
+        f.argtypes = [C.POINTER(FrameViewC), C.c_int] + [C.c_void_p] * 5 + [C.c_float, C.c_void_p]
+        nm = f(C.byref(kf.view()), len(lv), uv.ctypes.data, lv.ctypes.data, d.ctypes.data, va.ctypes.data, km.ctypes.data if km is not None else None, float(th), out.ctypes.data)
+        return nm, out[:len(kf.keys)]
+
     def compute_stereo_matches(self, ext_left, ext_right, keys_left, desc_left, keys_right, desc_right, mb, mbf):
         """ext_left / ext_right: oracle.Extractor of the same kind whose last extract() saw the left / right image."""
         kl = np.ascontiguousarray(keys_left, KP_DTYPE); kr = np.ascontiguousarray(keys_right, KP_DTYPE)

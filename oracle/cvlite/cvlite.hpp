@@ -247,6 +247,14 @@ public:
     }
     // reshape(cn): the shim has no channels; an N x 2 CV_32F matrix doubles as N two-channel points (undistortPoints below)
     Mat reshape(int /*cn*/, int /*rows*/ = 0) const { return *this; }
+    // dot product of two equally sized CV_32F matrices, accumulated in double (cv::Mat::dot, dotProd_32f); the reference's uses on the
+    // matcher path are a scale factor of a similarity (exactly 1 for the rigid poses the harness feeds) and the 60-degree viewing gate,
+    // which the harness keeps away from its boundary
+    double dot(const Mat& o) const {
+        double s = 0;
+        for (int y = 0; y < rows; ++y) for (int x = 0; x < cols; ++x) s += (double)at<float>(y, x) * (double)o.at<float>(y, x);
+        return s;
+    }
     // transpose (float/double)
     Mat t() const {
         Mat m(cols, rows, mtype);
@@ -276,6 +284,12 @@ static inline Mat operator*(double s, const Mat& a) {
     return m;
 }
 static inline Mat operator*(const Mat& a, double s) { return s * a; }
+static inline Mat operator/(const Mat& a, double s) {
+    assert(a.type() == CV_32F);
+    Mat m(a.rows, a.cols, CV_32F);
+    for (int y = 0; y < a.rows; ++y) for (int x = 0; x < a.cols; ++x) m.at<float>(y, x) = (float)(a.at<float>(y, x) / s);
+    return m;
+}
 static inline Mat operator-(const Mat& a) { return -1.0 * a; }
 // matrix product, float, accumulation in double then rounded (OpenCV gemm for tiny 32F matrices
 // accumulates in double: cv::gemm GEMMSingleMul<float,double>)

@@ -236,6 +236,33 @@ static int SearchByProjectionKeyFrame(bool checkOri, const FrameView* cur, int n
     return nmatches;
 }
 
+// ORBmatcher::SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th)   ORBmatcher.cc:388-512  (KeyFrame::GetFeaturesInArea,
+// src/KeyFrame.cc:752-797, walks the same grid in the same order as Frame's, without a level filter; the level test is at :462-463)
+static int SearchByProjectionKeyFramePoints(const FrameView* kf, int n_points, const float* proj_uv, const int* predicted_level, const unsigned char* mp_desc,
+                                            const unsigned char* valid, const unsigned char* kf_matched, float th, int* kf_match) {
+    int nmatches = 0;
+    std::vector<unsigned char> taken(kf->n, 0);
+    for (int j = 0; j < kf->n; ++j) { kf_match[j] = -1; taken[j] = kf_matched ? (kf_matched[j] != 0) : 0; }
+    Grid g(kf);
+    std::vector<int> cands;
+    for (int p = 0; p < n_points; ++p) {
+        if (!valid[p]) continue;
+        const int lvl = predicted_level[p];
+        g.area(proj_uv[2 * p], proj_uv[2 * p + 1], th * kf->scale_factors[lvl], -1, -1, cands);
+        int bestDist = 256, bestIdx = -1;
+        for (size_t k = 0; k < cands.size(); ++k) {
+            const int idx = cands[k];
+            if (taken[idx]) continue;
+            const int kpLevel = kf->keys_un[idx].octave;
+            if (kpLevel < lvl - 1 || kpLevel > lvl) continue;
+            const int dist = DescriptorDistance(mp_desc + (size_t)p * 32, kf->descriptors + (size_t)idx * 32);
+            if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+        }
+        if (bestDist <= TH_LOW) { kf_match[bestIdx] = p; taken[bestIdx] = 1; nmatches++; }
+    }
+    return nmatches;
+}
+
 // ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>&, th)   ORBmatcher.cc:70-175
 static int SearchByProjectionPoints(float nnratio, const FrameView* F, int n_points, const float* track_uv, const float* track_ur, const int* track_level,
                                     const float* track_view_cos, const unsigned char* mp_desc, const unsigned char* mp_observed, const unsigned char* f_occupied,
@@ -458,6 +485,10 @@ int port_search_by_projection_keyframe(float nnratio, int checkOri, const FrameV
                                        const unsigned char* mp_desc, const unsigned char* valid, const unsigned char* cur_occupied, float th, int orb_dist, int* cur_match) {
     (void)nnratio;
     return port::SearchByProjectionKeyFrame(checkOri != 0, cur, n_kf, proj_uv, predicted_level, kf_angle, mp_desc, valid, cur_occupied, th, orb_dist, cur_match);
+}
+int port_search_by_projection_keyframe_points(const FrameView* kf, int n_points, const float* proj_uv, const int* predicted_level, const unsigned char* mp_desc,
+                                              const unsigned char* valid, const unsigned char* kf_matched, float th, int* kf_match) {
+    return port::SearchByProjectionKeyFramePoints(kf, n_points, proj_uv, predicted_level, mp_desc, valid, kf_matched, th, kf_match);
 }
 int port_search_by_projection_points(float nnratio, int checkOri, const FrameView* F, int n_points, const float* track_uv, const float* track_ur, const int* track_level,
                                      const float* track_view_cos, const unsigned char* mp_desc, const unsigned char* mp_observed, const unsigned char* f_occupied,

@@ -8,6 +8,7 @@ output -- nothing is copied into the repository).  The functions are located by 
                       ComputeThreeMaxima, DescriptorDistance
                       SearchByBoW(KeyFrame*, Frame&, ...), SearchByBoW(KeyFrame*, KeyFrame*, ...),
                       SearchByProjection(Frame&, KeyFrame*, const set<MapPoint*>&, th, ORBdist)
+  src/KeyFrame.cc   : GetFeaturesInArea, IsInImage
   Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h : transform(features, BowVector, FeatureVector, levelsup), transform(feature, ...)
   src/Frame.cc      : AssignFeaturesToGrid, GetFeaturesInArea, PosInGrid, ComputeStereoMatches,
                       UndistortKeyPoints, ComputeImageBounds, ComputeStereoFromRGBD
@@ -61,6 +62,7 @@ m = extract("src/ORBmatcher.cc", [
     "void ORBmatcher::ComputeThreeMaxima(vector<int>* histo, const int L, int &ind1, int &ind2, int &ind3)",
     "int ORBmatcher::DescriptorDistance(const cv::Mat &a, const cv::Mat &b)",
     "int ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const set<MapPoint*> &sAlreadyFound, const float th , const int ORBdist)",
+    "int ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*> &vpPoints, vector<MapPoint*> &vpMatched, int th)",
     "int ORBmatcher::SearchByBoW(KeyFrame* pKF,Frame &F, vector<MapPoint*> &vpMapPointMatches)",
     "int ORBmatcher::SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, vector<MapPoint *> &vpMatches12)",
 ])
@@ -73,6 +75,10 @@ f = extract("src/Frame.cc", [
     "void Frame::ComputeImageBounds(const cv::Mat &imLeft)",
     "void Frame::ComputeStereoFromRGBD(const cv::Mat &imDepth)",
 ])
+kf = extract("src/KeyFrame.cc", [
+    "vector<size_t> KeyFrame::GetFeaturesInArea(const float &x, const float &y, const float &r) const",
+    "bool KeyFrame::IsInImage(const float &x, const float &y) const",
+])
 # DBoW2 (vendored in the reference tree): the two transform() members of the vocabulary template, for oracle/ref/ref_bow_capi.cpp
 b = extract("Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h", [
     "void TemplatedVocabulary<TDescriptor,F>::transform(\n  const std::vector<TDescriptor>& features,\n  BowVector &v, FeatureVector &fv, int levelsup) const",
@@ -82,5 +88,5 @@ b = b.replace("void TemplatedVocabulary<TDescriptor,F>::transform(", "template<c
 os.makedirs(out, exist_ok=True)
 open(os.path.join(out, "ref_bow_bodies.inc"), "w").write("// GENERATED from the reference sources by oracle/ref/gen_match_bodies.py -- do not commit\n" + b)
 # the first ORBmatcher chunk (constants) ends at the ctor's closing brace because the ctor follows immediately
-open(os.path.join(out, "ref_match_bodies.inc"), "w").write("// GENERATED from the reference sources by oracle/ref/gen_match_bodies.py -- do not commit\n" + m + "\n" + f)
+open(os.path.join(out, "ref_match_bodies.inc"), "w").write("// GENERATED from the reference sources by oracle/ref/gen_match_bodies.py -- do not commit\n" + m + "\n" + f + "\n" + kf)
 print("generated", os.path.join(out, "ref_match_bodies.inc"))

@@ -36,6 +36,9 @@ public:
     float GetMaxDistanceInvariance() { return maxd; }
     float GetMinDistanceInvariance() { return mind; }
     int PredictScale(const float&, Frame*) { return plevel; }          // the level is an input of the C-ABI call: the harness supplies it
+    int PredictScale(const float&, KeyFrame*) { return plevel; }
+    cv::Mat normal;
+    cv::Mat GetNormal() { return normal.clone(); }
     bool isBad() { return bad; }
     int Observations() { return nobs; }
     cv::Mat GetDescriptor() { return desc.clone(); }
@@ -70,13 +73,22 @@ public:
     DBoW2::FeatureVector mFeatVec;
 };
 
-class KeyFrame {               // include/KeyFrame.h, the members SearchByBoW reads (ORBmatcher.cc:230-382, 656-799)
+class KeyFrame {               // include/KeyFrame.h, the members SearchByBoW / SearchByProjection(KeyFrame*, Scw, ...) read
 public:
+    KeyFrame() : N(0), fx(0), fy(0), cx(0), cy(0), mnGridCols(FRAME_GRID_COLS), mnGridRows(FRAME_GRID_ROWS), mfGridElementWidthInv(0), mfGridElementHeightInv(0),
+                 mnMinX(0), mnMinY(0), mnMaxX(0), mnMaxY(0) {}
     std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
+    std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r) const;
+    bool IsInImage(const float& x, const float& y) const;
     std::vector<MapPoint*> mvpMapPoints;
     std::vector<cv::KeyPoint> mvKeysUn;
     cv::Mat mDescriptors;
     DBoW2::FeatureVector mFeatVec;
+    int N; float fx, fy, cx, cy;
+    const int mnGridCols, mnGridRows; float mfGridElementWidthInv, mfGridElementHeightInv;
+    int mnMinX, mnMinY, mnMaxX, mnMaxY;                      // include/KeyFrame.h:408-411 (ints there)
+    std::vector<float> mvScaleFactors;
+    std::vector<std::vector<std::vector<size_t> > > mGrid;   // include/KeyFrame.h:383
 };
 float Frame::fx, Frame::fy, Frame::cx, Frame::cy, Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv;
 float Frame::mnMinX, Frame::mnMaxX, Frame::mnMinY, Frame::mnMaxY;
@@ -90,6 +102,7 @@ public:
     int SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12, int windowSize = 10);
     int SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches);
     int SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const std::set<MapPoint*>& sAlreadyFound, const float th, const int ORBdist);
+    int SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const std::vector<MapPoint*>& vpPoints, std::vector<MapPoint*>& vpMatched, int th);
     int SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12);
     static const int TH_LOW, TH_HIGH, HISTO_LENGTH;
 protected:
@@ -311,6 +324,48 @@ int ref_search_by_projection_keyframe(float nnratio, int checkOri, const FrameVi
             MapPoint* p = C.mvpMapPoints[j];
             cur_match[j] = (p && p >= &pts[0] && p < &pts[0] + n_kf) ? (int)(p - &pts[0]) : -1;
         }
+    }
+    return nm;
+}
+
+// ORBmatcher::SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th)   ORBmatcher.cc:388 (KeyFrame::GetFeaturesInArea / IsInImage from
+// src/KeyFrame.cc:752-804).  Scw = identity, so p3Dc == p3Dw == cam_xyz.  state[p]: 1 good, 2 bad, 3 already in vpMatched (placed at
+// KeyFrame feature found_at[p]); facing[p] != 0: the point's normal looks at the camera (passes the 60-degree gate), else away from it.
+int ref_search_by_projection_keyframe_points(float nnratio, int checkOri, const FrameView* kfv, int n_points, const float* cam_xyz, const int* predicted_level,
+                                             const unsigned char* mp_desc, const unsigned char* state, const int* found_at, const unsigned char* facing,
+                                             const float* min_dist, const float* max_dist, const unsigned char* kf_matched, int th,
+                                             float fx, float fy, float cx, float cy, float* proj_uv, int* kf_match) {
+    ArenaScope scope;
+    int nm;
+    {
+        Frame G; fill_frame(G, kfv);                                   // builds the 64 x 48 grid the KeyFrame constructor copies (src/KeyFrame.cc:58-66)
+        KeyFrame K; K.N = kfv->n; K.fx = fx; K.fy = fy; K.cx = cx; K.cy = cy;
+        K.mvKeysUn = G.mvKeysUn; K.mDescriptors = G.mDescriptors; K.mvScaleFactors = G.mvScaleFactors;
+        K.mnMinX = (int)Frame::mnMinX; K.mnMinY = (int)Frame::mnMinY; K.mnMaxX = (int)Frame::mnMaxX; K.mnMaxY = (int)Frame::mnMaxY;
+        K.mfGridElementWidthInv = Frame::mfGridElementWidthInv; K.mfGridElementHeightInv = Frame::mfGridElementHeightInv;
+        K.mGrid.resize(FRAME_GRID_COLS);
+        for (int i = 0; i < FRAME_GRID_COLS; ++i) { K.mGrid[i].resize(FRAME_GRID_ROWS); for (int j = 0; j < FRAME_GRID_ROWS; ++j) K.mGrid[i][j] = G.mGrid[i][j]; }
+        std::vector<MapPoint> pts(n_points), old(kfv->n);
+        std::vector<MapPoint*> vp(n_points), matched(kfv->n, (MapPoint*)NULL);
+        for (int j = 0; j < kfv->n; ++j) if (kf_matched && kf_matched[j]) matched[j] = &old[j];
+        for (int p = 0; p < n_points; ++p) {
+            pts[p].pos = cv::Mat(3, 1, CV_32F); pts[p].normal = cv::Mat(3, 1, CV_32F);
+            const float x = cam_xyz[3 * p], y = cam_xyz[3 * p + 1], z = cam_xyz[3 * p + 2];
+            const float len = std::sqrt(x * x + y * y + z * z), sgn = facing[p] ? 1.f : -1.f;
+            pts[p].pos.at<float>(0) = x; pts[p].pos.at<float>(1) = y; pts[p].pos.at<float>(2) = z;
+            pts[p].normal.at<float>(0) = sgn * x / len; pts[p].normal.at<float>(1) = sgn * y / len; pts[p].normal.at<float>(2) = sgn * z / len;
+            pts[p].desc = cv::Mat(1, 32, CV_8U, (void*)(mp_desc + (size_t)p * 32)).clone();
+            pts[p].plevel = predicted_level[p]; pts[p].mind = min_dist[p]; pts[p].maxd = max_dist[p];
+            pts[p].bad = state[p] == 2;
+            if (state[p] == 3) matched[found_at[p]] = &pts[p];
+            vp[p] = &pts[p];
+            const float invz = 1 / z;
+            proj_uv[2 * p] = fx * (x * invz) + cx; proj_uv[2 * p + 1] = fy * (y * invz) + cy;          // :417-421
+        }
+        const std::vector<MapPoint*> before = matched;
+        ORBmatcher matcher(nnratio, checkOri != 0);
+        nm = matcher.SearchByProjection(&K, cv::Mat::eye(4, 4, CV_32F), vp, matched, th);
+        for (int j = 0; j < kfv->n; ++j) kf_match[j] = (matched[j] != before[j] && matched[j]) ? (int)(matched[j] - &pts[0]) : -1;
     }
     return nm;
 }

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Generates tests/golden/ref_match_kf.npz: outputs of the reference's own ORBmatcher::SearchByProjection(Frame&, KeyFrame*,
-const set<MapPoint*>&, th, ORBdist) body (src/ORBmatcher.cc:1731-1863, compiled into oracle/_ref) on the seeded inputs of
-tests/match_cases.py.  usage: python tests/golden/make_golden_match_kf.py"""
+const set<MapPoint*>&, th, ORBdist) (src/ORBmatcher.cc:1731-1863) and SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th)
+(:388-512) bodies, compiled into oracle/_ref, on the seeded inputs of tests/match_cases.py.  usage: python tests/golden/make_golden_match_kf.py"""
 import os, sys
 import numpy as np
 
@@ -20,5 +20,11 @@ for i, (th, od, ori) in enumerate(mc.KF_CASES):
     nm, cm, uv = oracle.Matcher("ref", 0.9, ori).search_by_projection_keyframe_ref(F, pi["xyz"], kf["lvl"], ka["angle"], da, kf["state"], kf["mind"], kf["maxd"], kf["occ"],
                                                                                  th, od, mc.FX, mc.FY, mc.CX, mc.CY)
     out["kf%d_nm" % i] = np.array(nm); out["kf%d_cm" % i] = cm; out["uv"] = uv
+# SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th)  (src/ORBmatcher.cc:388-512)
+kp = mc.keyframe_points_inputs(ka, kb, pi)
+for i, th in enumerate(mc.KFP_CASES):
+    nm, km, uv2 = oracle.Matcher("ref", 0.9, True).search_by_projection_keyframe_points_ref(F, pi["xyz"], kp["lvl"], da, kp["state"], kp["found_at"], kp["facing"], kp["mind"], kp["maxd"],
+                                                                                          kp["kf_matched"], th, mc.FX, mc.FY, mc.CX, mc.CY)
+    out["kfp%d_nm" % i] = np.array(nm); out["kfp%d_km" % i] = km; out["uv2"] = uv2
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_match_kf.npz"), **out)
 print("wrote ref_match_kf.npz", [int(out["kf%d_nm" % i]) for i in range(len(mc.KF_CASES))])

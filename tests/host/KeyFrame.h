@@ -17,6 +17,11 @@ public:
     DBoW2::BowVector mBowVec;
     DBoW2::FeatureVector mFeatVec;
     ORBVocabulary* mpORBvocabulary = nullptr;
+    bool IsInImage(const float &x, const float &y) const { return (x >= mnMinX && x < mnMaxX && y >= mnMinY && y < mnMaxY); }   // src/KeyFrame.cc:799-802
+    float fx = 0, fy = 0, cx = 0, cy = 0;
+    int mnMinX = 0, mnMinY = 0, mnMaxX = 0, mnMaxY = 0;
+    float mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;
+    std::vector<float> mvScaleFactors;
 };
 }
 #endif

@@ -8,6 +8,8 @@ class MapPoint {
 public:
     cv::Mat GetWorldPos() { return mWorldPos; }
     cv::Mat GetDescriptor() { return mDescriptor; }
+    cv::Mat GetNormal() { return mNormalVector; }
+    cv::Mat mNormalVector;
     int Observations() { return nObs; }
     bool isBad() { return mbBad; }
     float GetMinDistanceInvariance() { return mfMinDistance; }

@@ -7,6 +7,7 @@
 //   in.bin : int32 w,h ; u8 A[h*w] ; u8 B[h*w] ; int32 sw,sh ; u8 L[sh*sw] ; u8 R[sh*sw] ; f32 cam[10] (fx fy cx cy k1 k2 p1 p2 k3 bf) ; f32 bounds[6]
 #include "ORBextractor.h"
 #include "ORBmatcher.h"
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -187,6 +188,30 @@ int main(int argc, char** argv) {
         int nk = ORBmatcher(0.9, true).SearchByProjection(C, &K, found, 10.f, 100);
         put_i(nk);
         for (int j = 0; j < C.N; ++j) put_i((C.mvpMapPoints[j] && j % 10) ? (int)(C.mvpMapPoints[j] - mps.data()) : -1);
+    }
+    // ---- ORBmatcher::SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th)  (LoopClosing): Scw = identity
+    {
+        const float fx = 517.3f, fy = 516.5f, cx = 318.6f, cy = 255.3f;
+        KeyFrame K; K.mvKeysUn = kb; K.mDescriptors = db; K.fx = fx; K.fy = fy; K.cx = cx; K.cy = cy;
+        K.mnMinX = 0; K.mnMinY = 0; K.mnMaxX = w; K.mnMaxY = h; K.mfGridElementWidthInv = 64.f / (float)w; K.mfGridElementHeightInv = 48.f / (float)h;
+        K.mvScaleFactors = ext.GetScaleFactors();
+        std::vector<MapPoint> mps(ka.size()); MapPoint dummy;
+        std::vector<MapPoint*> pts(ka.size()), matched(kb.size(), (MapPoint*)NULL);
+        for (size_t i = 0; i < ka.size(); ++i) {
+            MapPoint& p = mps[i];
+            const float z = 1.f + (float)(i % 7);
+            const float X = (ka[i].pt.x + 7.f - cx) / fx * z, Y = (ka[i].pt.y - 4.f - cy) / fy * z;
+            p.mWorldPos = cv::Mat(3, 1, CV_32F); p.mWorldPos.at<float>(0) = X; p.mWorldPos.at<float>(1) = Y; p.mWorldPos.at<float>(2) = z;
+            const float len = std::sqrt(X * X + Y * Y + z * z), sgn = (i % 6) ? 1.f : -1.f;
+            p.mNormalVector = cv::Mat(3, 1, CV_32F); p.mNormalVector.at<float>(0) = sgn * X / len; p.mNormalVector.at<float>(1) = sgn * Y / len; p.mNormalVector.at<float>(2) = sgn * z / len;
+            p.mDescriptor = da.row((int)i); p.nPredictedLevel = ka[i].octave; p.mbBad = (i % 11) == 0;
+            if (i % 13 == 0) p.mfMaxDistance = 0.5f;
+            pts[i] = &p;
+        }
+        for (size_t j = 0; j < kb.size(); ++j) if (j % 10 == 0) matched[j] = &dummy;
+        int nk = ORBmatcher(0.75, true).SearchByProjection(&K, cv::Mat::eye(4, 4, CV_32F), pts, matched, 10);
+        put_i(nk);
+        for (size_t j = 0; j < kb.size(); ++j) put_i((matched[j] && matched[j] != &dummy) ? (int)(matched[j] - mps.data()) : -1);
     }
     // ---- bag of words: Frame::ComputeBoW / KeyFrame::ComputeBoW and both SearchByBoW forms (Tracking.cc:1740-1752, LoopClosing)
     if (argc > 3) {

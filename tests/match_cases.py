@@ -64,3 +64,27 @@ def keyframe_inputs(ka, kb, pi, seed=9):
     occ = (rng.random(len(kb)) < 0.15).astype(np.uint8)
     valid = ((state == 1) & ~((d3 < mind) | (d3 > maxd))).astype(np.uint8)
     return dict(state=state, lvl=lvl, mind=mind, maxd=maxd, occ=occ, valid=valid)
+
+
+KFP_CASES = [10, 3]                                                     # th of LoopClosing (SearchByProjection(pKF, Scw, vpPoints, vpMatched, 10))
+
+
+def keyframe_points_inputs(ka, kb, pi, seed=13):
+    """Inputs of SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th): per map point its state (1 good, 2 bad, 3 already in vpMatched at
+    KeyFrame feature found_at), whether its normal faces the camera, predicted level, distance range; kf_matched = vpMatched[j] != NULL."""
+    rng = np.random.default_rng(seed); n = len(ka)
+    state = rng.choice([1, 1, 1, 1, 2, 3], n).astype(np.uint8)
+    found_at = rng.permutation(len(kb))[:n].astype(np.int32) if len(kb) >= n else rng.integers(0, len(kb), n).astype(np.int32)
+    facing = (rng.random(n) < 0.85).astype(np.uint8)
+    lvl = np.clip(ka["octave"] + rng.integers(0, 2, n), 0, 7).astype(np.int32)
+    xyz = pi["xyz"].astype(np.float32)
+    d3 = np.sqrt((xyz.astype(np.float64) ** 2).sum(1)).astype(np.float32)
+    mind = (d3 * rng.choice([0.5, 0.5, 1.2], n)).astype(np.float32); maxd = (d3 * rng.choice([2.0, 2.0, 0.8], n)).astype(np.float32)
+    kf_matched = (rng.random(len(kb)) < 0.1).astype(np.uint8)
+    kf_matched[found_at[state == 3]] = 1
+    # projection exactly as the body forms it (:417-421): x = X * invz, u = fx * x + cx
+    invz = (np.float32(1.0) / xyz[:, 2]).astype(np.float32)
+    u = (np.float32(FX) * (xyz[:, 0] * invz) + np.float32(CX)).astype(np.float32); v = (np.float32(FY) * (xyz[:, 1] * invz) + np.float32(CY)).astype(np.float32)
+    inimg = (u >= 0) & (u < 640) & (v >= 0) & (v < 480)                  # KeyFrame::IsInImage
+    valid = ((state == 1) & (xyz[:, 2] >= 0) & inimg & ~((d3 < mind) | (d3 > maxd)) & (facing > 0)).astype(np.uint8)
+    return dict(state=state, found_at=found_at, facing=facing, lvl=lvl, mind=mind, maxd=maxd, kf_matched=kf_matched, valid=valid, uv=np.stack([u, v], 1).astype(np.float32))

@@ -134,3 +134,17 @@ def test_search_by_projection_keyframe(orbx, case):
         for F in (case["FB"], case["FBu"], D):
             nm, cm = orbx.ORBmatcher(0.9, ori).SearchByProjectionKeyFrame(F, uv, kf["lvl"], ka["angle"], case["da"], kf["valid"], kf["occ"], th, od)
             assert nm == int(GK["kf%d_nm" % i]) and np.array_equal(cm, GK["kf%d_cm" % i])
+
+
+def test_search_by_projection_keyframe_points(orbx, case):
+    """SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th) (loop closing) against the reference body's golden; the rotation check and
+    uRight of the frame must play no role."""
+    GK = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_match_kf.npz"))
+    ka, kb, pi = case["ka"], case["kb"], case["pi"]
+    kp = mc.keyframe_points_inputs(ka, kb, pi)
+    D = orbx.Frame().assign_host(kb, case["db"], case["sf"], orbx.Camera.make(mc.FX, mc.FY, mc.CX, mc.CY), 480, 640)
+    for i, th in enumerate(mc.KFP_CASES):
+        for F in (case["FB"], case["FBu"], D):
+            for ori in (True, False):
+                nm, km = orbx.ORBmatcher(0.9, ori).SearchByProjectionKeyFramePoints(F, kp["uv"], kp["lvl"], case["da"], kp["valid"], kp["kf_matched"], th)
+                assert nm == int(GK["kfp%d_nm" % i]) and np.array_equal(km, GK["kfp%d_km" % i])

@@ -165,6 +165,14 @@ def test_host_classes_match_c_abi(orbx, tmp_path):
     nk, cmk = orbx.ORBmatcher(0.9, True).SearchByProjectionKeyFrame(orbx.FrameView(kb, db, 640, 480, sf), uvk, ka["octave"], ka["angle"], da, okk.astype(np.uint8), occk, 10.0, 100)
     assert r.i() == nk and nk > 50
     assert np.array_equal(r.arr(np.int32, len(kb)), cmk)
+    # loop-closing matcher SearchByProjection(pKF, Scw, vpPoints, vpMatched, th): same map points, normals facing the camera except every 6th
+    xk = (X * invz).astype(np.float32); yk = (Y * invz).astype(np.float32)
+    uvp = np.stack([fx * xk + cx, fy * yk + cy], 1).astype(np.float32)
+    okp = (idx % 11 != 0) & ~((idx % 13 == 0) & (d3 > 0.5)) & (idx % 6 != 0)
+    okp &= (uvp[:, 0] >= 0) & (uvp[:, 0] < 640) & (uvp[:, 1] >= 0) & (uvp[:, 1] < 480)
+    np_, kmp = orbx.ORBmatcher(0.75, True).SearchByProjectionKeyFramePoints(orbx.FrameView(kb, db, 640, 480, sf), uvp, ka["octave"], da, okp.astype(np.uint8), occk, 10)
+    assert r.i() == np_ and np_ > 50
+    assert np.array_equal(r.arr(np.int32, len(kb)), kmp)
     # bag of words through Frame::ComputeBoW / KeyFrame::ComputeBoW / ORBmatcher::SearchByBoW == the C-ABI results (pinned to DBoW2 in test_gpu_bow.py)
     V = orbx.ORBVocabulary(4, 5, *voc)
     ta, tb = V.transform(da, 4), V.transform(db, 4)

@@ -102,3 +102,17 @@ def test_port_keyframe_projection_matches_reference_golden(oracle):
     for i, (th, od, ori) in enumerate(mc.KF_CASES):
         nm, cm = oracle.Matcher("port", 0.9, ori).search_by_projection_keyframe_port(F, uv, kf["lvl"], ka["angle"], da, kf["valid"], kf["occ"], th, od)
         assert nm == int(GK["kf%d_nm" % i]) and nm > 30 and np.array_equal(cm, GK["kf%d_cm" % i])
+
+
+def test_port_keyframe_points_projection_matches_reference_golden(oracle):
+    """SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th) (ORBmatcher.cc:388-512): port vs the reference body's committed outputs."""
+    import os
+    GK = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_match_kf.npz"))
+    E = oracle.Extractor("port", 1000, 1.2, 8, 20, 7)
+    ka, da, kb, db = mc.mono_pair(lambda img: E.extract(img))
+    pi = mc.projection_inputs(ka, kb); kp = mc.keyframe_points_inputs(ka, kb, pi)
+    assert np.array_equal(kp["uv"], GK["uv2"])
+    F = oracle.FrameData(kb, db, 640, 480, E.scale_factors)
+    for i, th in enumerate(mc.KFP_CASES):
+        nm, km = oracle.Matcher("port").search_by_projection_keyframe_points_port(F, kp["uv"], kp["lvl"], da, kp["valid"], kp["kf_matched"], th)
+        assert nm == int(GK["kfp%d_nm" % i]) and nm > 30 and np.array_equal(km, GK["kfp%d_km" % i])
