@@ -312,6 +312,15 @@ class ORBmatcher:
         self._check(fn(self._h, fa, len(lv), _p(uv), _p(lv), _p(d), _p(va), _p(km), float(th), _p(out), C.byref(nm)))
         return nm.value, out[:len(kf.keys)]
 
+    # int SearchBySim3(KeyFrame *pKF1, KeyFrame *pKF2, vector<MapPoint*> &vpMatches12, const float &s12, const cv::Mat &R12, const cv::Mat &t12, const float th)
+    def SearchBySim3(self, kf1, kf2, uv1, lvl1, desc1, valid1, uv2, lvl2, desc2, valid2, th):
+        a = [np.ascontiguousarray(uv1, np.float32), np.ascontiguousarray(lvl1, np.int32), _u8(desc1), _u8(valid1),
+             np.ascontiguousarray(uv2, np.float32), np.ascontiguousarray(lvl2, np.int32), _u8(desc2), _u8(valid2)]
+        m12 = np.zeros(max(len(kf1.keys), 1), np.int32); nf = C.c_int()
+        v1, v2 = kf1.c(), kf2.c()
+        self._check(self._lib.orbx_search_by_sim3(self._h, C.byref(v1), C.byref(v2), *[_p(x) for x in a], float(th), _p(m12), C.byref(nf)))
+        return nf.value, m12[:len(kf1.keys)]
+
     # int SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, const float th=3)
     def SearchByProjectionPoints(self, F, track_uv, track_ur, track_level, track_view_cos, mp_desc, mp_observed, f_occupied, th=3.0):
         uv = np.ascontiguousarray(track_uv, np.float32); ur = np.ascontiguousarray(track_ur, np.float32)

@@ -234,6 +234,27 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const int* __restrict__ co
     if (tid == 0) offsets[n] = carry_sm;
 }
 
+// independent best match of every query (no running state): the FILL pass already reduced each list to its best key
+__global__ void k_best_extract(int nq, const int* __restrict__ offsets, const uint32_t* __restrict__ cand, const uint2* __restrict__ pre_best, int cand_cap, int max_dist,
+                               int* __restrict__ best_idx) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    int out = -1;
+    if (offsets[nq] <= cand_cap && offsets[q + 1] > offsets[q]) {                // skipped queries have an empty list and no pre_best entry
+        const uint32_t k = pre_best[q].x;
+        if (k != 0xFFFFFFFFu && (int)(k >> 20) <= max_dist) out = (int)(cand[offsets[q] + (int)(k & 0xFFFFFu)] & 0xFFFFFu);
+    }
+    best_idx[q] = out;
+}
+// SearchBySim3's mutual-consistency check (ORBmatcher.cc:1535-1550)
+__global__ void k_mutual_check(int n1, const int* __restrict__ match1, const int* __restrict__ match2, int* __restrict__ match12, int* __restrict__ nfound) {
+    const int i1 = blockIdx.x * blockDim.x + threadIdx.x;
+    int ok = 0, idx2 = -1;
+    if (i1 < n1) { idx2 = match1[i1]; ok = idx2 >= 0 && match2[idx2] == i1; match12[i1] = ok ? idx2 : -1; }
+    const unsigned m = __ballot_sync(0xffffffffu, ok);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(nfound, __popc(m));
+}
+
 // two smallest candidate keys (dist<<20 | position-in-list) of a query under a per-candidate predicate
 struct Best2 { uint32_t k1, k2; };
 template <typename Pred>

@@ -516,6 +516,68 @@ int orbx_search_by_projection_keyframe_points_dev(orbx_matcher* m, const orbx_fr
     if (!kf) FAIL(ORBX_E_INVALID, "null frame");
     return search_proj_kf_points(m, FrameArg{nullptr, kf}, n_points, proj_uv, predicted_level, mp_desc, valid, kf_matched, th, kf_match, nmatches);
 }
+// SearchBySim3 (ORBmatcher.cc:1290-1555): two order-independent passes (map points of one KeyFrame against the features of the other, levels
+// [predicted - 1, predicted], best distance <= TH_HIGH, no exclusions) and the mutual-consistency check, all on the device
+struct Sim3Side { int n; const float* proj_uv; const int* predicted_level; const uint8_t* mp_desc; const uint8_t* valid; };
+static int sim3_pass(orbx_matcher* m, const FrameDev& target, const Sim3Side& q, float th, int* d_best, int*& d_total) {
+    int rc;
+    float *uv, *iz; int* lv; uint8_t *dd, *va;
+    std::vector<float> zeros((size_t)std::max(q.n, 1), 0.f);
+    if ((rc = up(m, q.proj_uv, (size_t)q.n * 2, uv)) || (rc = up(m, zeros.data(), (size_t)q.n, iz)) || (rc = up(m, q.predicted_level, (size_t)q.n, lv)) ||
+        (rc = up(m, q.mp_desc, (size_t)q.n * 32, dd)) || (rc = up(m, q.valid, (size_t)q.n, va))) return rc;
+    if ((rc = flush_uploads(m))) return rc;
+    QueryParams P; std::memset(&P, 0, sizeof(P));
+    P.mode = MODE_PROJ_FRAME; P.nq = q.n; P.q_desc = dd; P.q_xy = uv; P.q_invz = iz; P.q_octave = lv; P.q_valid = va; P.th = th; P.forward = 2; P.no_ur = 1;
+    int *counts, *offsets; uint32_t* cand; uint2* pre;
+    if ((rc = window_search(m, P, target, counts, offsets, cand, pre))) return rc;
+    if (q.n) { k_best_extract<<<(q.n + 127) / 128, 128, 0, m->stream>>>(q.n, offsets, cand, pre, (int)std::min<size_t>(m->cand_cap, 0x7FFFFFFF), M_TH_HIGH, d_best); LAUNCH_CHECK(); }
+    d_total = offsets + q.n;
+    return ORBX_OK;
+}
+int orbx_search_by_sim3(orbx_matcher* m, const orbx_frame_view* kf1, const orbx_frame_view* kf2, const float* proj_uv1, const int* predicted_level1, const uint8_t* mp_desc1,
+                        const uint8_t* valid1, const float* proj_uv2, const int* predicted_level2, const uint8_t* mp_desc2, const uint8_t* valid2, float th,
+                        int* match12, int* nfound) {
+    if (!m || !nfound) FAIL(ORBX_E_INVALID, "null argument");
+    int rc;
+    if ((rc = check_frame(kf1)) || (rc = check_frame(kf2))) return rc;
+    const int n1 = kf1->n, n2 = kf2->n;
+    if ((n1 && (!proj_uv1 || !predicted_level1 || !mp_desc1 || !valid1 || !match12)) || (n2 && (!proj_uv2 || !predicted_level2 || !mp_desc2 || !valid2))) FAIL(ORBX_E_INVALID, "null buffer");
+    for (int i = 0; i < n1; ++i) if (valid1[i] && (predicted_level1[i] < 0 || predicted_level1[i] >= kf2->nlevels)) FAIL(ORBX_E_INVALID, "predicted level out of range");
+    for (int i = 0; i < n2; ++i) if (valid2[i] && (predicted_level2[i] < 0 || predicted_level2[i] >= kf1->nlevels)) FAIL(ORBX_E_INVALID, "predicted level out of range");
+    *nfound = 0;
+    for (int i = 0; i < n1; ++i) match12[i] = -1;
+    if (n1 == 0 || n2 == 0) return ORBX_OK;
+    CU_TRY(cudaSetDevice(m->device));
+    const size_t need = frame_bytes(kf1) + frame_bytes(kf2) + 2 * (pad((size_t)(n1 + n2) * 44) + 8 * pad((size_t)(n1 + n2 + 2) * 8)) + 16384;
+    if ((rc = m->arena.reserve(need)) || (rc = m->uparena.reserve(need))) return rc;
+retry:
+    m->arena.reset(); m->uparena.reset();
+    FrameDev d1, d2; uint32_t *sk1, *sk2;
+    if ((rc = upload_frame(m, kf1, d1, sk1)) || (rc = upload_frame(m, kf2, d2, sk2))) return rc;
+    if ((rc = flush_uploads(m)) || (rc = build_grid(m, d1, sk1)) || (rc = build_grid(m, d2, sk2))) return rc;
+    // the upload arena keeps growing inside one call: later flushes resend the earlier bytes unchanged, which is harmless
+    int* best1 = m->arena.get<int>(n1 + 1); int* best2 = m->arena.get<int>(n2 + 1); int* res = m->arena.get<int>((size_t)n1 + 4);
+    if (!best1 || !best2 || !res) FAIL(ORBX_E_CUDA, "matcher arena exhausted");
+    int *tot1, *tot2;
+    Sim3Side q1{n1, proj_uv1, predicted_level1, mp_desc1, valid1}, q2{n2, proj_uv2, predicted_level2, mp_desc2, valid2};
+    if ((rc = sim3_pass(m, d2, q1, th, best1, tot1))) return rc;                 // map points of KF1 into KF2 (:1367-1440)
+    CU_TRY(cudaMemcpyAsync(res + 1, tot1, 4, cudaMemcpyDeviceToDevice, m->stream));
+    if ((rc = sim3_pass(m, d1, q2, th, best2, tot2))) return rc;                 // map points of KF2 into KF1 (:1443-1530)
+    CU_TRY(cudaMemcpyAsync(res + 2, tot2, 4, cudaMemcpyDeviceToDevice, m->stream));
+    CU_TRY(cudaMemsetAsync(res, 0, 4, m->stream));
+    k_mutual_check<<<(n1 + 127) / 128, 128, 0, m->stream>>>(n1, best1, best2, res + 3, res);
+    LAUNCH_CHECK();
+    const size_t res_bytes = ((size_t)n1 + 3) * 4;
+    if ((rc = m->ensure_download(res_bytes))) return rc;
+    CU_TRY(cudaMemcpyAsync(m->dl_host, res, res_bytes, cudaMemcpyDeviceToHost, m->stream));
+    CU_TRY(cudaStreamSynchronize(m->stream));
+    const int* hr = reinterpret_cast<const int*>(m->dl_host);
+    if (cand_overflow(m, std::max(hr[1], hr[2]))) goto retry;
+    *nfound = hr[0];
+    std::memcpy(match12, hr + 3, (size_t)n1 * 4);
+    return ORBX_OK;
+}
+
 int orbx_search_by_projection_keyframe(orbx_matcher* m, const orbx_frame_view* cur, int n_kf, const float* proj_uv, const int* predicted_level, const float* kf_angle,
                                        const uint8_t* mp_desc, const uint8_t* valid, const uint8_t* cur_occupied, float th, int orb_dist, int* cur_match, int* nmatches) {
     if (!cur) FAIL(ORBX_E_INVALID, "bad frame view");

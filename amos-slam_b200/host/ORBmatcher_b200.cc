@@ -10,6 +10,7 @@
 //   Frame::ComputeStereoMatches()                                                               src/Frame.cc:1179-1573
 //   ORBmatcher::SearchByProjection(Frame&, KeyFrame*, const set<MapPoint*>&, float, int)       src/ORBmatcher.cc:1731-1863  (8f rank 3)
 //   ORBmatcher::SearchByProjection(KeyFrame*, cv::Mat Scw, const vector<MapPoint*>&, vector<MapPoint*>&, int)   src/ORBmatcher.cc:388-512  (8f rank 3)
+//   ORBmatcher::SearchBySim3(KeyFrame*, KeyFrame*, vector<MapPoint*>&, const float&, const cv::Mat&, const cv::Mat&, float)   src/ORBmatcher.cc:1314-1555  (8f rank 3)
 //
 // Each body only flattens the object graph (Frame / MapPoint) into the plain arrays of the C ABI
 // (include/orbx_b200.h), calls the CUDA implementation and writes the results back into the same
@@ -305,6 +306,74 @@ int ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const std::vector
                                                     (float)th, kmatch.data(), &nmatches), "orbx_search_by_projection_keyframe_points");
     for (int j = 0; j < nk; ++j) if (kmatch[j] >= 0) vpMatched[j] = vpPoints[kmatch[j]];                                    // :483
     return nmatches;
+}
+
+namespace
+{
+// a KeyFrame as the frame view the C ABI takes: its grid is the Frame's (src/KeyFrame.cc:58-66), its bounds are the integer members (include/KeyFrame.h:408-411)
+struct KeyFrameFlat {
+    orbx_frame_view v; std::vector<unsigned char> desc;
+    explicit KeyFrameFlat(KeyFrame* pKF) {
+        v.n = (int)pKF->mvKeysUn.size(); v.keys_un = reinterpret_cast<const orbx_keypoint*>(pKF->mvKeysUn.data());
+        if (pKF->mDescriptors.isContinuous()) v.descriptors = pKF->mDescriptors.ptr();
+        else { desc.resize((size_t)v.n * 32); for (int j = 0; j < v.n; ++j) std::memcpy(&desc[(size_t)j * 32], pKF->mDescriptors.ptr(j), 32); v.descriptors = desc.data(); }
+        v.u_right = NULL;
+        v.min_x = (float)pKF->mnMinX; v.min_y = (float)pKF->mnMinY; v.max_x = (float)pKF->mnMaxX; v.max_y = (float)pKF->mnMaxY;
+        v.grid_element_width_inv = pKF->mfGridElementWidthInv; v.grid_element_height_inv = pKF->mfGridElementHeightInv;
+        v.nlevels = (int)pKF->mvScaleFactors.size(); v.scale_factors = pKF->mvScaleFactors.data();
+    }
+};
+// one direction of SearchBySim3 (:1367-1398 / :1443-1480): which map points of `from` are searched in `to`, and where
+struct Sim3Queries {
+    std::vector<float> uv; std::vector<int> level; std::vector<unsigned char> desc, valid;
+    Sim3Queries(const std::vector<MapPoint*>& mps, const std::vector<bool>& already, const cv::Mat& Rfw, const cv::Mat& tfw, const cv::Mat& sR, const cv::Mat& t,
+                KeyFrame* to, float fx, float fy, float cx, float cy) {
+        const int n = (int)mps.size();
+        uv.assign((size_t)n * 2, 0.f); level.assign(n, 0); desc.assign((size_t)n * 32, 0); valid.assign(n, 0);
+        for (int i = 0; i < n; ++i) {
+            MapPoint* pMP = mps[i];
+            if (!pMP || already[i] || pMP->isBad()) continue;
+            cv::Mat p3Dw = pMP->GetWorldPos();
+            cv::Mat p3Dcf = Rfw * p3Dw + tfw;
+            cv::Mat p3Dct = sR * p3Dcf + t;
+            if (p3Dct.at<float>(2) < 0.0) continue;
+            const float invz = 1.0 / p3Dct.at<float>(2);
+            const float x = p3Dct.at<float>(0) * invz, y = p3Dct.at<float>(1) * invz;
+            const float u = fx * x + cx, v = fy * y + cy;
+            if (!to->IsInImage(u, v)) continue;
+            const float dist3D = cv::norm(p3Dct);
+            if (dist3D < pMP->GetMinDistanceInvariance() || dist3D > pMP->GetMaxDistanceInvariance()) continue;
+            uv[2 * i] = u; uv[2 * i + 1] = v; level[i] = pMP->PredictScale(dist3D, to);
+            const cv::Mat d = pMP->GetDescriptor();
+            std::memcpy(&desc[(size_t)i * 32], d.ptr(), 32);
+            valid[i] = 1;
+        }
+    }
+};
+}  // namespace
+
+int ORBmatcher::SearchBySim3(KeyFrame *pKF1, KeyFrame *pKF2, std::vector<MapPoint*> &vpMatches12, const float &s12, const cv::Mat &R12, const cv::Mat &t12, const float th)
+{
+    const float &fx = pKF1->fx, &fy = pKF1->fy, &cx = pKF1->cx, &cy = pKF1->cy;
+    cv::Mat R1w = pKF1->GetRotation(), t1w = pKF1->GetTranslation(), R2w = pKF2->GetRotation(), t2w = pKF2->GetTranslation();
+    cv::Mat sR12 = s12 * R12;
+    cv::Mat sR21 = (1.0 / s12) * R12.t();
+    cv::Mat t21 = -sR21 * t12;
+    const std::vector<MapPoint*> vpMapPoints1 = pKF1->GetMapPointMatches(), vpMapPoints2 = pKF2->GetMapPointMatches();
+    const int N1 = (int)vpMapPoints1.size(), N2 = (int)vpMapPoints2.size();
+    std::vector<bool> vbAlreadyMatched1(N1, false), vbAlreadyMatched2(N2, false);
+    for (int i = 0; i < N1; i++) {                                                                                          // :1344-1355
+        MapPoint* pMP = vpMatches12[i];
+        if (pMP) { vbAlreadyMatched1[i] = true; const int idx2 = pMP->GetIndexInKeyFrame(pKF2); if (idx2 >= 0 && idx2 < N2) vbAlreadyMatched2[idx2] = true; }
+    }
+    Sim3Queries q1(vpMapPoints1, vbAlreadyMatched1, R1w, t1w, sR21, t21, pKF2, fx, fy, cx, cy), q2(vpMapPoints2, vbAlreadyMatched2, R2w, t2w, sR12, t12, pKF1, fx, fy, cx, cy);
+    KeyFrameFlat k1(pKF1), k2(pKF2);
+    std::vector<int> m12(N1 ? N1 : 1, -1);
+    int nFound = 0;
+    check(orbx_search_by_sim3(t_matchers.get(mfNNratio, mbCheckOrientation), &k1.v, &k2.v, q1.uv.data(), q1.level.data(), q1.desc.data(), q1.valid.data(),
+                              q2.uv.data(), q2.level.data(), q2.desc.data(), q2.valid.data(), th, m12.data(), &nFound), "orbx_search_by_sim3");
+    for (int i1 = 0; i1 < N1; ++i1) if (m12[i1] >= 0) vpMatches12[i1] = vpMapPoints2[m12[i1]];                               // :1544
+    return nFound;
 }
 
 void Frame::ComputeStereoMatches()

@@ -376,6 +376,18 @@ int orbx_search_by_projection_keyframe_points_dev(orbx_matcher* m, const orbx_fr
                                                   const int* predicted_level, const uint8_t* mp_desc, const uint8_t* valid,
                                                   const uint8_t* kf_matched, float th, int* kf_match, int* nmatches);
 
+/* int ORBmatcher::SearchBySim3(KeyFrame *pKF1, KeyFrame *pKF2, vector<MapPoint*> &vpMatches12, const float &s12, const cv::Mat &R12,
+ *                              const cv::Mat &t12, const float th)        src/ORBmatcher.cc:1290-1555 (loop closing)
+ *   kf1 / kf2: the two KeyFrames as frame views.  Side 1, per feature i of pKF1 whose map point exists, is not bad, is not already
+ *   matched (vbAlreadyMatched1), lands in front of camera 2, inside its image and within its distance range (:1369-1398):
+ *   proj_uv1 = its projection into pKF2, predicted_level1 = PredictScale(dist3D, pKF2), mp_desc1, valid1 != 0.  Side 2 likewise into pKF1.
+ *   Both passes take the best feature on level predicted - 1 or predicted with distance <= TH_HIGH, independently of each other;
+ *   match12[i] = index in pKF2 for the pairs that agree both ways (-1 otherwise); *nfound = return value. */
+int orbx_search_by_sim3(orbx_matcher* m, const orbx_frame_view* kf1, const orbx_frame_view* kf2,
+                        const float* proj_uv1, const int* predicted_level1, const uint8_t* mp_desc1, const uint8_t* valid1,
+                        const float* proj_uv2, const int* predicted_level2, const uint8_t* mp_desc2, const uint8_t* valid2,
+                        float th, int* match12, int* nfound);
+
 /* ------------------------------------------------------------------------------------------------
  * Bag of words: DBoW2's vocabulary tree and the two BoW-guided matchers.
  *   ORBVocabulary = DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB>   include/ORBVocabulary.h:40-41

@@ -354,6 +354,29 @@ class Matcher:
         nm = f(C.byref(kf.view()), len(lv), uv.ctypes.data, lv.ctypes.data, d.ctypes.data, va.ctypes.data, km.ctypes.data if km is not None else None, float(th), out.ctypes.data)
         return nm, out[:len(kf.keys)]
 
+    def search_by_sim3_ref(self, kf1, kf2, side1, side2, already12, th, fx, fy, cx, cy):
+        """Reference body (ORBmatcher.cc:1290), identity Sim3.  side = dict(xyz, lvl, desc, state, mind, maxd).  -> (nfound, match12)."""
+        assert self.kind == "ref"
+        def arrs(s):
+            return [np.ascontiguousarray(s["xyz"], np.float32), np.ascontiguousarray(s["lvl"], np.int32), _u8(s["desc"]), _u8(s["state"]),
+                    np.ascontiguousarray(s["mind"], np.float32), np.ascontiguousarray(s["maxd"], np.float32)]
+        a, b = arrs(side1), arrs(side2); al = np.ascontiguousarray(already12, np.int32)
+        m12 = np.zeros(max(len(kf1.keys), 1), np.int32)
+        f = self.lib.ref_search_by_sim3; f.restype = C.c_int
+        f.argtypes = [C.POINTER(FrameViewC)] * 2 + [C.c_void_p] * 13 + [C.c_float] * 5 + [C.c_void_p]
+        nf = f(C.byref(kf1.view()), C.byref(kf2.view()), *[x.ctypes.data for x in a], *[x.ctypes.data for x in b], al.ctypes.data, float(th), float(fx), float(fy), float(cx), float(cy), m12.ctypes.data)
+        return nf, m12[:len(kf1.keys)]
+
+    def search_by_sim3_port(self, kf1, kf2, uv1, lvl1, desc1, valid1, uv2, lvl2, desc2, valid2, th):
+        assert self.kind == "port"
+        a = [np.ascontiguousarray(uv1, np.float32), np.ascontiguousarray(lvl1, np.int32), _u8(desc1), _u8(valid1),
+             np.ascontiguousarray(uv2, np.float32), np.ascontiguousarray(lvl2, np.int32), _u8(desc2), _u8(valid2)]
+        m12 = np.zeros(max(len(kf1.keys), 1), np.int32)
+        f = self.lib.port_search_by_sim3; f.restype = C.c_int
+        f.argtypes = [C.POINTER(FrameViewC)] * 2 + [C.c_void_p] * 8 + [C.c_float, C.c_void_p]
+        nf = f(C.byref(kf1.view()), C.byref(kf2.view()), *[x.ctypes.data for x in a], float(th), m12.ctypes.data)
+        return nf, m12[:len(kf1.keys)]
+
     def compute_stereo_matches(self, ext_left, ext_right, keys_left, desc_left, keys_right, desc_right, mb, mbf):
         """ext_left / ext_right: oracle.Extractor of the same kind whose last extract() saw the left / right image."""
         kl = np.ascontiguousarray(keys_left, KP_DTYPE); kr = np.ascontiguousarray(keys_right, KP_DTYPE)

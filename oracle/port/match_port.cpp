@@ -263,6 +263,27 @@ static int SearchByProjectionKeyFramePoints(const FrameView* kf, int n_points, c
     return nmatches;
 }
 
+// ORBmatcher::SearchBySim3   ORBmatcher.cc:1290-1555: one pass per direction (independent best feature on level predicted - 1 or predicted,
+// distance <= TH_HIGH), then the pairs that agree both ways
+static void Sim3Pass(const FrameView* target, int nq, const float* proj_uv, const int* predicted_level, const unsigned char* mp_desc, const unsigned char* valid, float th, std::vector<int>& best) {
+    best.assign(nq, -1);
+    Grid g(target);
+    std::vector<int> cands;
+    for (int q = 0; q < nq; ++q) {
+        if (!valid[q]) continue;
+        const int lvl = predicted_level[q];
+        g.area(proj_uv[2 * q], proj_uv[2 * q + 1], th * target->scale_factors[lvl], -1, -1, cands);
+        int bestDist = INT_MAX, bestIdx = -1;
+        for (size_t k = 0; k < cands.size(); ++k) {
+            const int oct = target->keys_un[cands[k]].octave;
+            if (oct < lvl - 1 || oct > lvl) continue;
+            const int dist = DescriptorDistance(mp_desc + (size_t)q * 32, target->descriptors + (size_t)cands[k] * 32);
+            if (dist < bestDist) { bestDist = dist; bestIdx = cands[k]; }
+        }
+        if (bestDist <= TH_HIGH) best[q] = bestIdx;
+    }
+}
+
 // ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>&, th)   ORBmatcher.cc:70-175
 static int SearchByProjectionPoints(float nnratio, const FrameView* F, int n_points, const float* track_uv, const float* track_ur, const int* track_level,
                                     const float* track_view_cos, const unsigned char* mp_desc, const unsigned char* mp_observed, const unsigned char* f_occupied,
@@ -489,6 +510,18 @@ int port_search_by_projection_keyframe(float nnratio, int checkOri, const FrameV
 int port_search_by_projection_keyframe_points(const FrameView* kf, int n_points, const float* proj_uv, const int* predicted_level, const unsigned char* mp_desc,
                                               const unsigned char* valid, const unsigned char* kf_matched, float th, int* kf_match) {
     return port::SearchByProjectionKeyFramePoints(kf, n_points, proj_uv, predicted_level, mp_desc, valid, kf_matched, th, kf_match);
+}
+int port_search_by_sim3(const FrameView* kf1, const FrameView* kf2, const float* proj_uv1, const int* level1, const unsigned char* desc1, const unsigned char* valid1,
+                        const float* proj_uv2, const int* level2, const unsigned char* desc2, const unsigned char* valid2, float th, int* match12) {
+    std::vector<int> m1, m2;
+    port::Sim3Pass(kf2, kf1->n, proj_uv1, level1, desc1, valid1, th, m1);
+    port::Sim3Pass(kf1, kf2->n, proj_uv2, level2, desc2, valid2, th, m2);
+    int nFound = 0;
+    for (int i1 = 0; i1 < kf1->n; ++i1) {
+        match12[i1] = -1;
+        if (m1[i1] >= 0 && m2[m1[i1]] == i1) { match12[i1] = m1[i1]; ++nFound; }
+    }
+    return nFound;
 }
 int port_search_by_projection_points(float nnratio, int checkOri, const FrameView* F, int n_points, const float* track_uv, const float* track_ur, const int* track_level,
                                      const float* track_view_cos, const unsigned char* mp_desc, const unsigned char* mp_observed, const unsigned char* f_occupied,

@@ -63,6 +63,7 @@ m = extract("src/ORBmatcher.cc", [
     "int ORBmatcher::DescriptorDistance(const cv::Mat &a, const cv::Mat &b)",
     "int ORBmatcher::SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const set<MapPoint*> &sAlreadyFound, const float th , const int ORBdist)",
     "int ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*> &vpPoints, vector<MapPoint*> &vpMatched, int th)",
+    "int ORBmatcher::SearchBySim3(KeyFrame *pKF1, KeyFrame *pKF2, vector<MapPoint*> &vpMatches12,\n                             const float &s12, const cv::Mat &R12, const cv::Mat &t12, const float th)",
     "int ORBmatcher::SearchByBoW(KeyFrame* pKF,Frame &F, vector<MapPoint*> &vpMapPointMatches)",
     "int ORBmatcher::SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, vector<MapPoint *> &vpMatches12)",
 ])

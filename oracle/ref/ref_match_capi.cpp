@@ -32,13 +32,15 @@ class MapPoint {               // the members ORBmatcher.cc:70-175 and :1569-172
 public:
     bool mbTrackInView; int mnTrackScaleLevel; float mTrackViewCos, mTrackProjX, mTrackProjY, mTrackProjXR;
     bool bad; int nobs; cv::Mat desc, pos; float maxd, mind; int plevel;
-    MapPoint() : mbTrackInView(true), mnTrackScaleLevel(0), mTrackViewCos(1.f), mTrackProjX(0), mTrackProjY(0), mTrackProjXR(0), bad(false), nobs(0), maxd(1e30f), mind(0.f), plevel(0) {}
+    MapPoint() : mbTrackInView(true), mnTrackScaleLevel(0), mTrackViewCos(1.f), mTrackProjX(0), mTrackProjY(0), mTrackProjXR(0), bad(false), nobs(0), maxd(1e30f), mind(0.f), plevel(0), in_kf(NULL), in_idx(-1) {}
     float GetMaxDistanceInvariance() { return maxd; }
     float GetMinDistanceInvariance() { return mind; }
     int PredictScale(const float&, Frame*) { return plevel; }          // the level is an input of the C-ABI call: the harness supplies it
     int PredictScale(const float&, KeyFrame*) { return plevel; }
     cv::Mat normal;
     cv::Mat GetNormal() { return normal.clone(); }
+    KeyFrame* in_kf; int in_idx;                                       // one observation is enough for SearchBySim3's vbAlreadyMatched2 (:1350)
+    int GetIndexInKeyFrame(KeyFrame* kf) { return kf == in_kf ? in_idx : -1; }
     bool isBad() { return bad; }
     int Observations() { return nobs; }
     cv::Mat GetDescriptor() { return desc.clone(); }
@@ -78,6 +80,8 @@ public:
     KeyFrame() : N(0), fx(0), fy(0), cx(0), cy(0), mnGridCols(FRAME_GRID_COLS), mnGridRows(FRAME_GRID_ROWS), mfGridElementWidthInv(0), mfGridElementHeightInv(0),
                  mnMinX(0), mnMinY(0), mnMaxX(0), mnMaxY(0) {}
     std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
+    cv::Mat GetRotation() { return cv::Mat::eye(3, 3, CV_32F); }      // the harness keeps both KeyFrames at the world origin
+    cv::Mat GetTranslation() { return cv::Mat::zeros(3, 1, CV_32F); }
     std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r) const;
     bool IsInImage(const float& x, const float& y) const;
     std::vector<MapPoint*> mvpMapPoints;
@@ -103,6 +107,7 @@ public:
     int SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches);
     int SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const std::set<MapPoint*>& sAlreadyFound, const float th, const int ORBdist);
     int SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const std::vector<MapPoint*>& vpPoints, std::vector<MapPoint*>& vpMatched, int th);
+    int SearchBySim3(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12, const float& s12, const cv::Mat& R12, const cv::Mat& t12, const float th);
     int SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12);
     static const int TH_LOW, TH_HIGH, HISTO_LENGTH;
 protected:
@@ -368,6 +373,51 @@ int ref_search_by_projection_keyframe_points(float nnratio, int checkOri, const 
         for (int j = 0; j < kfv->n; ++j) kf_match[j] = (matched[j] != before[j] && matched[j]) ? (int)(matched[j] - &pts[0]) : -1;
     }
     return nm;
+}
+
+// ORBmatcher::SearchBySim3   ORBmatcher.cc:1290.  Both KeyFrames at the world origin, s12 = 1, R12 = I, t12 = 0, so every map point's camera
+// coordinates in either KeyFrame are its world coordinates (xyz1 / xyz2).  state: 0 no map point, 1 good, 2 bad; already12[i] >= 0: vpMatches12[i]
+// holds, on entry, the map point of pKF2's feature already12[i] (=> vbAlreadyMatched1[i] and vbAlreadyMatched2[already12[i]]).
+namespace {
+void fill_keyframe(KeyFrame& K, Frame& G, const FrameView* v, float fx, float fy, float cx, float cy) {
+    fill_frame(G, v);
+    K.N = v->n; K.fx = fx; K.fy = fy; K.cx = cx; K.cy = cy;
+    K.mvKeysUn = G.mvKeysUn; K.mDescriptors = G.mDescriptors; K.mvScaleFactors = G.mvScaleFactors;
+    K.mnMinX = (int)Frame::mnMinX; K.mnMinY = (int)Frame::mnMinY; K.mnMaxX = (int)Frame::mnMaxX; K.mnMaxY = (int)Frame::mnMaxY;
+    K.mfGridElementWidthInv = Frame::mfGridElementWidthInv; K.mfGridElementHeightInv = Frame::mfGridElementHeightInv;
+    K.mGrid.resize(FRAME_GRID_COLS);
+    for (int i = 0; i < FRAME_GRID_COLS; ++i) { K.mGrid[i].resize(FRAME_GRID_ROWS); for (int j = 0; j < FRAME_GRID_ROWS; ++j) K.mGrid[i][j] = G.mGrid[i][j]; }
+}
+void fill_points(std::vector<MapPoint>& pts, KeyFrame& K, int n, const float* xyz, const int* level, const unsigned char* desc, const unsigned char* state, const float* mind, const float* maxd) {
+    K.mvpMapPoints.assign(n, (MapPoint*)NULL);
+    for (int i = 0; i < n; ++i) {
+        pts[i].pos = cv::Mat(3, 1, CV_32F); for (int k = 0; k < 3; ++k) pts[i].pos.at<float>(k) = xyz[3 * i + k];
+        pts[i].desc = cv::Mat(1, 32, CV_8U, (void*)(desc + (size_t)i * 32)).clone();
+        pts[i].plevel = level[i]; pts[i].mind = mind[i]; pts[i].maxd = maxd[i]; pts[i].bad = state[i] == 2;
+        pts[i].in_kf = &K; pts[i].in_idx = i;
+        if (state[i]) K.mvpMapPoints[i] = &pts[i];
+    }
+}
+}
+int ref_search_by_sim3(const FrameView* v1, const FrameView* v2, const float* xyz1, const int* level1, const unsigned char* desc1, const unsigned char* state1,
+                       const float* mind1, const float* maxd1, const float* xyz2, const int* level2, const unsigned char* desc2, const unsigned char* state2,
+                       const float* mind2, const float* maxd2, const int* already12, float th, float fx, float fy, float cx, float cy, int* match12) {
+    ArenaScope scope;
+    int nf;
+    {
+        Frame G1, G2; KeyFrame K1, K2;
+        fill_keyframe(K1, G1, v1, fx, fy, cx, cy); fill_keyframe(K2, G2, v2, fx, fy, cx, cy);
+        std::vector<MapPoint> p1(v1->n), p2(v2->n);
+        fill_points(p1, K1, v1->n, xyz1, level1, desc1, state1, mind1, maxd1);
+        fill_points(p2, K2, v2->n, xyz2, level2, desc2, state2, mind2, maxd2);
+        std::vector<MapPoint*> m12(v1->n, (MapPoint*)NULL);
+        for (int i = 0; i < v1->n; ++i) if (already12[i] >= 0) m12[i] = &p2[already12[i]];
+        const std::vector<MapPoint*> before = m12;
+        ORBmatcher matcher(0.6f, true);
+        nf = matcher.SearchBySim3(&K1, &K2, m12, 1.0f, cv::Mat::eye(3, 3, CV_32F), cv::Mat::zeros(3, 1, CV_32F), th);
+        for (int i = 0; i < v1->n; ++i) match12[i] = (m12[i] && m12[i] != before[i]) ? (int)(m12[i] - &p2[0]) : -1;
+    }
+    return nf;
 }
 
 // ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&)  ORBmatcher.cc:230  and  (KeyFrame*, KeyFrame*, ...)  :656.

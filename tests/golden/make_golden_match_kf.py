@@ -26,5 +26,11 @@ for i, th in enumerate(mc.KFP_CASES):
     nm, km, uv2 = oracle.Matcher("ref", 0.9, True).search_by_projection_keyframe_points_ref(F, pi["xyz"], kp["lvl"], da, kp["state"], kp["found_at"], kp["facing"], kp["mind"], kp["maxd"],
                                                                                           kp["kf_matched"], th, mc.FX, mc.FY, mc.CX, mc.CY)
     out["kfp%d_nm" % i] = np.array(nm); out["kfp%d_km" % i] = km; out["uv2"] = uv2
+# SearchBySim3  (src/ORBmatcher.cc:1290-1555), identity similarity
+F1 = oracle.FrameData(ka, da, 640, 480, E.scale_factors)
+s1, s2, already12 = mc.sim3_inputs(ka, kb)
+for i, th in enumerate(mc.SIM3_TH):
+    nf, m12 = oracle.Matcher("ref").search_by_sim3_ref(F1, F, dict(s1, desc=da), dict(s2, desc=db), already12, th, mc.FX, mc.FY, mc.CX, mc.CY)
+    out["sim3_%d_nf" % i] = np.array(nf); out["sim3_%d_m12" % i] = m12
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_match_kf.npz"), **out)
 print("wrote ref_match_kf.npz", [int(out["kf%d_nm" % i]) for i in range(len(mc.KF_CASES))])

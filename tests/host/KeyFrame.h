@@ -18,6 +18,9 @@ public:
     DBoW2::FeatureVector mFeatVec;
     ORBVocabulary* mpORBvocabulary = nullptr;
     bool IsInImage(const float &x, const float &y) const { return (x >= mnMinX && x < mnMaxX && y >= mnMinY && y < mnMaxY); }   // src/KeyFrame.cc:799-802
+    cv::Mat GetRotation() { return mRcw; }
+    cv::Mat GetTranslation() { return mtcw; }
+    cv::Mat mRcw, mtcw;
     float fx = 0, fy = 0, cx = 0, cy = 0;
     int mnMinX = 0, mnMinY = 0, mnMaxX = 0, mnMaxY = 0;
     float mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;

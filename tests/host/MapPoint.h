@@ -15,6 +15,8 @@ public:
     float GetMinDistanceInvariance() { return mfMinDistance; }
     float GetMaxDistanceInvariance() { return mfMaxDistance; }
     template <class FrameT> int PredictScale(const float&, FrameT*) { return nPredictedLevel; }
+    template <class KF> int GetIndexInKeyFrame(KF* kf) { return (const void*)kf == pInKF ? nIdxInKF : -1; }
+    const void* pInKF = nullptr; int nIdxInKF = -1;
     float mfMinDistance = 0.f, mfMaxDistance = 1e30f; int nPredictedLevel = 0;
     float mTrackProjX = 0, mTrackProjY = 0, mTrackProjXR = 0;
     bool mbTrackInView = false;

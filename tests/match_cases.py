@@ -88,3 +88,34 @@ def keyframe_points_inputs(ka, kb, pi, seed=13):
     inimg = (u >= 0) & (u < 640) & (v >= 0) & (v < 480)                  # KeyFrame::IsInImage
     valid = ((state == 1) & (xyz[:, 2] >= 0) & inimg & ~((d3 < mind) | (d3 > maxd)) & (facing > 0)).astype(np.uint8)
     return dict(state=state, found_at=found_at, facing=facing, lvl=lvl, mind=mind, maxd=maxd, kf_matched=kf_matched, valid=valid, uv=np.stack([u, v], 1).astype(np.float32))
+
+
+SIM3_TH = [7.5, 3.0]                                                    # LoopClosing::ComputeSim3 uses 7.5
+
+
+def sim3_inputs(ka, kb, seed=21):
+    """Inputs of SearchBySim3 with an identity similarity and both KeyFrames at the origin: a map point of KeyFrame 1 sits where its feature
+    back-projects, shifted by the known image motion, so that it lands near the matching feature of KeyFrame 2 (and vice versa)."""
+    rng = np.random.default_rng(seed)
+
+    def side(k, dx, dy, other_n):
+        n = len(k)
+        z = rng.uniform(0.5, 8, n).astype(np.float32)
+        xyz = np.stack([(k["x"] + dx + rng.normal(0, 1.0, n) - CX) / FX * z, (k["y"] + dy + rng.normal(0, 1.0, n) - CY) / FY * z, z], 1).astype(np.float32)
+        xyz[::41, 2] *= -1
+        state = rng.choice([0, 1, 1, 1, 1, 2], n).astype(np.uint8)
+        lvl = np.clip(k["octave"] + rng.integers(0, 2, n), 0, 7).astype(np.int32)
+        d3 = np.sqrt((xyz.astype(np.float64) ** 2).sum(1)).astype(np.float32)            # cv::norm(p3Dc), double accumulate
+        mind = (d3 * rng.choice([0.5, 0.5, 1.2], n)).astype(np.float32); maxd = (d3 * rng.choice([2.0, 2.0, 0.8], n)).astype(np.float32)
+        invz = (1.0 / xyz[:, 2].astype(np.float64)).astype(np.float32)                   # const float invz = 1.0/z  (:1379)
+        u = (np.float32(FX) * (xyz[:, 0] * invz) + np.float32(CX)).astype(np.float32); v = (np.float32(FY) * (xyz[:, 1] * invz) + np.float32(CY)).astype(np.float32)
+        ok = (state == 1) & (xyz[:, 2] >= 0) & (u >= 0) & (u < 640) & (v >= 0) & (v < 480) & ~((d3 < mind) | (d3 > maxd))
+        return dict(xyz=xyz, state=state, lvl=lvl, mind=mind, maxd=maxd, uv=np.stack([u, v], 1).astype(np.float32), ok=ok)
+
+    s1, s2 = side(ka, 7, -4, len(kb)), side(kb, -7, 4, len(ka))
+    already12 = np.full(len(ka), -1, np.int32)
+    pick = rng.choice(len(ka), 40, replace=False); already12[pick] = rng.choice(len(kb), 40, replace=False)
+    s1["valid"] = (s1["ok"] & (already12 < 0)).astype(np.uint8)
+    am2 = np.zeros(len(kb), bool); am2[already12[already12 >= 0]] = True
+    s2["valid"] = (s2["ok"] & ~am2).astype(np.uint8)
+    return s1, s2, already12

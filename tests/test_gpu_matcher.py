@@ -148,3 +148,16 @@ def test_search_by_projection_keyframe_points(orbx, case):
             for ori in (True, False):
                 nm, km = orbx.ORBmatcher(0.9, ori).SearchByProjectionKeyFramePoints(F, kp["uv"], kp["lvl"], case["da"], kp["valid"], kp["kf_matched"], th)
                 assert nm == int(GK["kfp%d_nm" % i]) and np.array_equal(km, GK["kfp%d_km" % i])
+
+
+def test_search_by_sim3(orbx, case):
+    """SearchBySim3 (loop closing): both passes and the mutual check on the device, against the reference body's golden."""
+    GK = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_match_kf.npz"))
+    ka, kb = case["ka"], case["kb"]
+    s1, s2, _ = mc.sim3_inputs(ka, kb)
+    for i, th in enumerate(mc.SIM3_TH):
+        nf, m12 = orbx.ORBmatcher(0.6, True).SearchBySim3(case["FA"], case["FB"], s1["uv"], s1["lvl"], case["da"], s1["valid"], s2["uv"], s2["lvl"], case["db"], s2["valid"], th)
+        assert nf == int(GK["sim3_%d_nf" % i]) and np.array_equal(m12, GK["sim3_%d_m12" % i])
+    e = orbx.FrameView(kb[:0], case["db"][:0], 640, 480, case["sf"])
+    nf, m12 = orbx.ORBmatcher().SearchBySim3(case["FA"], e, s1["uv"], s1["lvl"], case["da"], s1["valid"], s2["uv"][:0], s2["lvl"][:0], case["db"][:0], s2["valid"][:0], 7.5)
+    assert nf == 0 and np.all(m12 == -1)

@@ -116,3 +116,16 @@ def test_port_keyframe_points_projection_matches_reference_golden(oracle):
     for i, th in enumerate(mc.KFP_CASES):
         nm, km = oracle.Matcher("port").search_by_projection_keyframe_points_port(F, kp["uv"], kp["lvl"], da, kp["valid"], kp["kf_matched"], th)
         assert nm == int(GK["kfp%d_nm" % i]) and nm > 30 and np.array_equal(km, GK["kfp%d_km" % i])
+
+
+def test_port_search_by_sim3_matches_reference_golden(oracle):
+    """SearchBySim3 (ORBmatcher.cc:1290-1555): port vs the reference body's committed outputs."""
+    import os
+    GK = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_match_kf.npz"))
+    E = oracle.Extractor("port", 1000, 1.2, 8, 20, 7)
+    ka, da, kb, db = mc.mono_pair(lambda img: E.extract(img))
+    s1, s2, _ = mc.sim3_inputs(ka, kb)
+    F1 = oracle.FrameData(ka, da, 640, 480, E.scale_factors); F2 = oracle.FrameData(kb, db, 640, 480, E.scale_factors)
+    for i, th in enumerate(mc.SIM3_TH):
+        nf, m12 = oracle.Matcher("port").search_by_sim3_port(F1, F2, s1["uv"], s1["lvl"], da, s1["valid"], s2["uv"], s2["lvl"], db, s2["valid"], th)
+        assert nf == int(GK["sim3_%d_nf" % i]) and nf > 5 and np.array_equal(m12, GK["sim3_%d_m12" % i])
