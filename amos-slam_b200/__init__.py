@@ -112,6 +112,7 @@ def lib():
         L.orbx_vocabulary_load_text.argtypes = [ci, C.c_char_p, C.POINTER(vp)]
         L.orbx_vocabulary_transform.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp, C.POINTER(ci), vp, vp, vp, C.POINTER(ci)]
         L.orbx_search_by_bow.argtypes = [vp, ci, vp, vp, vp, vp, C.POINTER(ci)]
+        L.orbx_search_for_triangulation.argtypes = [vp, vp, vp, vp, vp, vp, cf, cf, ci, vp, vp, ci, vp, C.POINTER(ci)]
         L.orbx_frame_create.argtypes = [ci, C.POINTER(vp)]
         L.orbx_frame_destroy.argtypes = [vp]; L.orbx_frame_destroy.restype = None
         L.orbx_frame_assign.argtypes = [vp, vp, vp, ci, ci, vp, sz]

@@ -363,6 +363,27 @@ class ORBmatcher:
         self._check(self._lib.orbx_search_by_bow(self._h, int(bool(kf_kf)), C.byref(s1), C.byref(s2), _p(m12), _p(m21), C.byref(nm)))
         return nm.value, m12[:s1.n], m21[:s2.n]
 
+    # int SearchForTriangulation(KeyFrame *pKF1, KeyFrame *pKF2, cv::Mat F12, vector<pair<size_t,size_t>> &vMatchedPairs, const bool bOnlyStereo)
+    def SearchForTriangulation(self, keys1, desc1, free1, ur1, fv1, keys2, desc2, free2, ur2, fv2, F12, epipole, scale_factors2, level_sigma2_2, bOnlyStereo=False):
+        """free = the feature holds no map point; epipole = (ex, ey) as the caller computes it (:818-825).  -> (nmatches, match12)."""
+        from . import KP_DTYPE
+        hold = []
+
+        def side(keys, desc, valid, fv):
+            k = np.ascontiguousarray(keys, KP_DTYPE); d = _u8(desc).reshape(-1, 32); v = _u8(valid)
+            a = [np.ascontiguousarray(fv[x], np.int32) for x in ("fv_nodes", "fv_offsets", "fv_idx")]
+            hold.extend([k, d, v] + a)
+            s = _BowSideC(); s.n = len(k); s.keys = k.ctypes.data; s.descriptors = d.ctypes.data; s.valid = v.ctypes.data
+            s.n_fv = len(a[0]); s.fv_nodes = a[0].ctypes.data; s.fv_offsets = a[1].ctypes.data; s.fv_indices = a[2].ctypes.data
+            return s
+        s1, s2 = side(keys1, desc1, free1, fv1), side(keys2, desc2, free2, fv2)
+        u1 = np.ascontiguousarray(ur1, np.float32); u2 = np.ascontiguousarray(ur2, np.float32)
+        F = np.ascontiguousarray(F12, np.float32).reshape(9); sc = np.ascontiguousarray(scale_factors2, np.float32); sg = np.ascontiguousarray(level_sigma2_2, np.float32)
+        m12 = np.zeros(max(s1.n, 1), np.int32); nm = C.c_int()
+        self._check(self._lib.orbx_search_for_triangulation(self._h, C.byref(s1), C.byref(s2), _p(u1), _p(u2), _p(F), float(epipole[0]), float(epipole[1]), len(sc), _p(sc), _p(sg),
+                                                            int(bool(bOnlyStereo)), _p(m12), C.byref(nm)))
+        return nm.value, m12[:s1.n]
+
     # vector<size_t> Frame::GetFeaturesInArea(x, y, r, minLevel, maxLevel) for many windows at once, on a device-resident Frame
     def GetFeaturesInArea(self, F, xy, r, min_level=None, max_level=None):
         xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2); nq = len(xy)

@@ -186,6 +186,71 @@ k_bow_match(int n_pairs, const int2* __restrict__ pairs /* (position in fv1, pos
     }
 }
 
+// ---- SearchForTriangulation (ORBmatcher.cc:810-1010): same node-by-node replay, other candidate rules ----
+struct TriParams {
+    float F[9];                       // F12, row-major (CV_32F)
+    float ex, ey;                     // epipole of camera 1 in image 2 (:822-825)
+    const float* ur1; const float* ur2;            // mvuRight of both KeyFrames (stereo iff >= 0)
+    const float* scale2; const float* sigma2_2;    // pKF2->mvScaleFactors, mvLevelSigma2
+    int only_stereo;
+};
+// CheckDistEpipolarLine (:188-215): every operation a rounded float product / sum in the reference's order; the last comparison in double
+__device__ __forceinline__ bool epipolar_ok(const TriParams& T, float x1, float y1, float x2, float y2, int oct2) {
+    const float a = __fadd_rn(__fadd_rn(__fmul_rn(x1, T.F[0]), __fmul_rn(y1, T.F[3])), T.F[6]);
+    const float b = __fadd_rn(__fadd_rn(__fmul_rn(x1, T.F[1]), __fmul_rn(y1, T.F[4])), T.F[7]);
+    const float c = __fadd_rn(__fadd_rn(__fmul_rn(x1, T.F[2]), __fmul_rn(y1, T.F[5])), T.F[8]);
+    const float num = __fadd_rn(__fadd_rn(__fmul_rn(a, x2), __fmul_rn(b, y2)), c);
+    const float den = __fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b));
+    if (den == 0.f) return false;
+    const float dsqr = __fdiv_rn(__fmul_rn(num, num), den);
+    return (double)dsqr < __dmul_rn(3.84, (double)T.sigma2_2[oct2]);
+}
+
+__global__ void __launch_bounds__(128)
+k_tri_match(int n_pairs, const int2* __restrict__ pairs, BowSideDev s1, BowSideDev s2, TriParams T, int checkOri,
+            int* __restrict__ match12, int* __restrict__ matched2, int* __restrict__ bin_of, int* __restrict__ hist) {
+    const int lane = threadIdx.x & 31;
+    const int p = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (p >= n_pairs) return;
+    const int2 pr = pairs[p];
+    const int a0 = s1.fv_offsets[pr.x], a1 = s1.fv_offsets[pr.x + 1], b0 = s2.fv_offsets[pr.y], b1 = s2.fv_offsets[pr.y + 1];
+    volatile int* m2 = matched2;
+    for (int e1 = a0; e1 < a1; ++e1) {
+        const int i1 = s1.fv_idx[e1];
+        if (!s1.valid[i1]) continue;                                            // holds a map point already (:843-845)
+        const bool stereo1 = T.ur1[i1] >= 0.f;
+        if (T.only_stereo && !stereo1) continue;
+        const KpM kp1 = s1.keys[i1];
+        const uint4 d0 = __ldg(s1.desc + 2 * i1), d1 = __ldg(s1.desc + 2 * i1 + 1);
+        // the reference keeps the LAST candidate among those with the smallest distance that pass the geometric gates
+        // (dist > bestDist is skipped, dist == bestDist replaces): key = dist << 20 | (0xFFFFF - position), smallest wins
+        uint32_t best = 0xFFFFFFFFu;
+        for (int e2 = b0 + lane; e2 < b1; e2 += 32) {
+            const int i2 = s2.fv_idx[e2];
+            if (m2[i2] >= 0 || !s2.valid[i2]) continue;                         // vbMatched2[idx2] || pMP2  (:862)
+            const bool stereo2 = T.ur2[i2] >= 0.f;
+            if (T.only_stereo && !stereo2) continue;
+            const int dist = hamming256(d0, d1, s2.desc + 2 * i2);
+            if (dist > 50) continue;                                            // TH_LOW (:873)
+            const KpM kp2 = s2.keys[i2];
+            if (!stereo1 && !stereo2) {
+                const float dx = __fsub_rn(T.ex, kp2.x), dy = __fsub_rn(T.ey, kp2.y);
+                if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < __fmul_rn(100.f, T.scale2[kp2.octave])) continue;   // too close to the epipole (:880-885)
+            }
+            if (!epipolar_ok(T, kp1.x, kp1.y, kp2.x, kp2.y, kp2.octave)) continue;
+            best = min(best, ((uint32_t)dist << 20) | (0xFFFFFu - (uint32_t)(e2 - b0)));
+        }
+        best = __reduce_min_sync(0xffffffffu, best);
+        if (best == 0xFFFFFFFFu) continue;
+        const int bidx = s2.fv_idx[b0 + (int)(0xFFFFFu - (best & 0xFFFFFu))];
+        if (lane == 0) {
+            match12[i1] = bidx; m2[bidx] = i1;
+            if (checkOri) { const int bin = rot_bin(kp1.angle, s2.keys[bidx].angle); bin_of[i1] = bin; atomicAdd(&hist[bin], 1); }
+        }
+        __syncwarp();
+    }
+}
+
 // ComputeThreeMaxima (:1866-1908) + removal of the matches outside the three strongest rotation bins; counts the survivors
 __global__ void __launch_bounds__(1024)
 k_bow_finish(int n1, int checkOri, const int* __restrict__ hist, const int* __restrict__ bin_of, int* __restrict__ match12, int* __restrict__ match21, int* __restrict__ nmatches) {

@@ -1081,6 +1081,57 @@ int orbx_search_by_bow(orbx_matcher* m, int kf_kf, const orbx_bow_side* s1, cons
     return ORBX_OK;
 }
 
+int orbx_search_for_triangulation(orbx_matcher* m, const orbx_bow_side* s1, const orbx_bow_side* s2, const float* u_right1, const float* u_right2,
+                                  const float* F12, float ex, float ey, int nlevels2, const float* scale_factors2, const float* level_sigma2_2, int only_stereo,
+                                  int* match12, int* nmatches) {
+    if (!m || !nmatches || !F12 || nlevels2 <= 0 || nlevels2 > ORBX_MAX_LEVELS || !scale_factors2 || !level_sigma2_2) FAIL(ORBX_E_INVALID, "null argument");
+    int rc;
+    if ((rc = check_bow_side(s1, true)) || (rc = check_bow_side(s2, true))) return rc;
+    if ((s1->n && (!match12 || !u_right1)) || (s2->n && !u_right2)) FAIL(ORBX_E_INVALID, "null buffer");
+    for (int j = 0; j < s2->n; ++j) if (s2->keys[j].octave < 0 || s2->keys[j].octave >= nlevels2) FAIL(ORBX_E_INVALID, "octave out of range");
+    *nmatches = 0;
+    for (int i = 0; i < s1->n; ++i) match12[i] = -1;
+    std::vector<int2> pairs;
+    for (int a = 0, b = 0; a < s1->n_fv && b < s2->n_fv;) {
+        if (s1->fv_nodes[a] < s2->fv_nodes[b]) ++a; else if (s2->fv_nodes[b] < s1->fv_nodes[a]) ++b; else { pairs.push_back(make_int2(a, b)); ++a; ++b; }
+    }
+    if (pairs.empty()) return ORBX_OK;
+    CU_TRY(cudaSetDevice(m->device));
+    const int n1 = s1->n, n2 = s2->n, np = (int)pairs.size();
+    const size_t need = pad((size_t)n1 * 68) + pad((size_t)n2 * 68) + 8 * pad((size_t)(n1 + n2 + 2) * 4) + pad((size_t)np * 8) + 16384;
+    if ((rc = m->arena.reserve(need)) || (rc = m->uparena.reserve(need))) return rc;
+    m->arena.reset(); m->uparena.reset();
+    KpM *k1, *k2; uint8_t *d1, *d2, *v1, *v2; int *o1, *i1, *o2, *i2; int2* dp; float *ur1, *ur2, *sc2, *sg2;
+    if ((rc = up(m, reinterpret_cast<const KpM*>(s1->keys), (size_t)n1, k1)) || (rc = up(m, reinterpret_cast<const KpM*>(s2->keys), (size_t)n2, k2)) ||
+        (rc = up(m, s1->descriptors, (size_t)n1 * 32, d1)) || (rc = up(m, s2->descriptors, (size_t)n2 * 32, d2)) || (rc = up(m, s1->valid, (size_t)n1, v1)) ||
+        (rc = up(m, s2->valid, (size_t)n2, v2)) || (rc = up(m, u_right1, (size_t)n1, ur1)) || (rc = up(m, u_right2, (size_t)n2, ur2)) ||
+        (rc = up(m, scale_factors2, (size_t)nlevels2, sc2)) || (rc = up(m, level_sigma2_2, (size_t)nlevels2, sg2)) ||
+        (rc = up(m, s1->fv_offsets, (size_t)s1->n_fv + 1, o1)) || (rc = up(m, s1->fv_indices, (size_t)s1->fv_offsets[s1->n_fv], i1)) ||
+        (rc = up(m, s2->fv_offsets, (size_t)s2->n_fv + 1, o2)) || (rc = up(m, s2->fv_indices, (size_t)s2->fv_offsets[s2->n_fv], i2)) ||
+        (rc = up(m, pairs.data(), (size_t)np, dp))) return rc;
+    int* res = m->arena.get<int>((size_t)n1 + n2 + 3);             // [nmatches | match12 n1 + 1 | matched2 n2 + 1]
+    int* binof = m->arena.get<int>(n1 + 1); int* hist = m->arena.get<int>(32);
+    if (!res || !binof || !hist) FAIL(ORBX_E_CUDA, "matcher arena exhausted");
+    int *dn = res, *m12 = res + 1, *m21 = res + 2 + n1;
+    const size_t res_bytes = ((size_t)n1 + 2) * 4;
+    if ((rc = m->ensure_download(res_bytes))) return rc;
+    if ((rc = flush_uploads(m))) return rc;
+    cudaStream_t s = m->stream;
+    CU_TRY(cudaMemsetAsync(res, 0xFF, ((size_t)n1 + n2 + 3) * 4, s)); CU_TRY(cudaMemsetAsync(hist, 0, 32 * 4, s));
+    BowSideDev a = {n1, k1, reinterpret_cast<const uint4*>(d1), v1, o1, i1}, b = {n2, k2, reinterpret_cast<const uint4*>(d2), v2, o2, i2};
+    TriParams T; std::memcpy(T.F, F12, 36); T.ex = ex; T.ey = ey; T.ur1 = ur1; T.ur2 = ur2; T.scale2 = sc2; T.sigma2_2 = sg2; T.only_stereo = only_stereo ? 1 : 0;
+    k_tri_match<<<(np + 3) / 4, 128, 0, s>>>(np, dp, a, b, T, m->checkOri, m12, m21, binof, hist);
+    LAUNCH_CHECK();
+    k_bow_finish<<<1, 1024, 0, s>>>(n1, m->checkOri, hist, binof, m12, m21, dn);
+    LAUNCH_CHECK();
+    CU_TRY(cudaMemcpyAsync(m->dl_host, res, res_bytes, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    const int* hr = reinterpret_cast<const int*>(m->dl_host);
+    *nmatches = hr[0];
+    if (n1) std::memcpy(match12, hr + 1, (size_t)n1 * 4);
+    return ORBX_OK;
+}
+
 int orbx_match_bruteforce_device(orbx_matcher* m, const uint8_t* d_query, int n_query, const uint8_t* d_train, int n_train, int* d_best_idx, int* d_best_dist, int* d_second_dist) {
     return orbx_match_bruteforce_batch_device(m, 1, d_query, n_query, d_train, n_train, d_best_idx, d_best_dist, d_second_dist);
 }

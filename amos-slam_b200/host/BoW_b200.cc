@@ -8,6 +8,7 @@
 //   KeyFrame::ComputeBoW()                                                        src/KeyFrame.cc:79-89
 //   ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&)                src/ORBmatcher.cc:230-382
 //   ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&)             src/ORBmatcher.cc:656-799
+//   ORBmatcher::SearchForTriangulation(KeyFrame*, KeyFrame*, cv::Mat F12, vector<pair<size_t,size_t>>&, bool)   src/ORBmatcher.cc:810-1010  (8f rank 3)
 //
 // The tree descent (60 Hamming distances per descriptor for ORBvoc), the BowVector / FeatureVector assembly with DBoW2's exact
 // double arithmetic, the per-node best / second-best search, the ratio test and the rotation histogram run on the GPU; the bodies
@@ -149,6 +150,34 @@ int ORBmatcher::SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, std::vector<MapPoint
     int nmatches = 0;
     check(orbx_search_by_bow(t_bow_matchers.get(mfNNratio, mbCheckOrientation), 1, &a.s, &b.s, m12.data(), m21.data(), &nmatches), "orbx_search_by_bow");
     for (int i = 0; i < a.s.n; ++i) if (m12[i] >= 0) vpMatches12[i] = vpMapPoints2[m12[i]];                               // :746
+    return nmatches;
+}
+
+int ORBmatcher::SearchForTriangulation(KeyFrame *pKF1, KeyFrame *pKF2, cv::Mat F12, std::vector<std::pair<size_t, size_t> > &vMatchedPairs, const bool bOnlyStereo)
+{
+    // epipole of camera 1 in image 2 (:816-825)
+    cv::Mat Cw = pKF1->GetCameraCenter();
+    cv::Mat R2w = pKF2->GetRotation();
+    cv::Mat t2w = pKF2->GetTranslation();
+    cv::Mat C2 = R2w * Cw + t2w;
+    const float invz = 1.0f / C2.at<float>(2);
+    const float ex = pKF2->fx * C2.at<float>(0) * invz + pKF2->cx;
+    const float ey = pKF2->fy * C2.at<float>(1) * invz + pKF2->cy;
+    Side a(pKF1->mvKeysUn, pKF1->mDescriptors, pKF1->mFeatVec, NULL), b(pKF2->mvKeysUn, pKF2->mDescriptors, pKF2->mFeatVec, NULL);
+    a.valid.assign(a.s.n, 0); b.valid.assign(b.s.n, 0);                                  // only features WITHOUT a map point take part (:843-845, :862)
+    for (int i = 0; i < a.s.n; ++i) a.valid[i] = pKF1->GetMapPoint(i) ? 0 : 1;
+    for (int j = 0; j < b.s.n; ++j) b.valid[j] = pKF2->GetMapPoint(j) ? 0 : 1;
+    a.s.valid = a.valid.data(); b.s.valid = b.valid.data();
+    float F[9];
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) F[3 * r + c] = F12.at<float>(r, c);
+    std::vector<int> m12(a.s.n ? a.s.n : 1, -1);
+    int nmatches = 0;
+    check(orbx_search_for_triangulation(t_bow_matchers.get(mfNNratio, mbCheckOrientation), &a.s, &b.s, pKF1->mvuRight.data(), pKF2->mvuRight.data(), F, ex, ey,
+                                        (int)pKF2->mvScaleFactors.size(), pKF2->mvScaleFactors.data(), pKF2->mvLevelSigma2.data(), bOnlyStereo ? 1 : 0, m12.data(), &nmatches),
+          "orbx_search_for_triangulation");
+    vMatchedPairs.clear();
+    vMatchedPairs.reserve(nmatches);
+    for (int i = 0; i < a.s.n; ++i) if (m12[i] >= 0) vMatchedPairs.push_back(std::make_pair((size_t)i, (size_t)m12[i]));    // :1000-1006
     return nmatches;
 }
 

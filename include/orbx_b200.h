@@ -433,6 +433,19 @@ typedef struct orbx_bow_side {
  * Both arrays are always filled (-1 = no match); *nmatches = return value. */
 int orbx_search_by_bow(orbx_matcher* m, int kf_kf, const orbx_bow_side* s1, const orbx_bow_side* s2, int* match12, int* match21, int* nmatches);
 
+/* int ORBmatcher::SearchForTriangulation(KeyFrame *pKF1, KeyFrame *pKF2, cv::Mat F12, vector<pair<size_t,size_t>> &vMatchedPairs, bool bOnlyStereo)
+ *   src/ORBmatcher.cc:810-1010 (LocalMapping::CreateNewMapPoints), with CheckDistEpipolarLine :188-215.
+ *   s1 / s2: both KeyFrames as bag-of-words sides (mvKeysUn, mDescriptors, mFeatVec); valid[i] != 0 iff the feature holds NO map point
+ *   (:843-845, :862).  u_right1 / u_right2: mvuRight (stereo iff >= 0).  F12: the 3 x 3 fundamental matrix, row-major float.
+ *   (ex, ey): the epipole of camera 1 in image 2 as the caller computes it (:818-825).  scale_factors2 / level_sigma2_2: pKF2->mvScaleFactors
+ *   and mvLevelSigma2.  Inside a common vocabulary node every side-1 feature takes, among the still unmatched side-2 features with distance
+ *   <= TH_LOW that are not too close to the epipole (both monocular) and lie on the epipolar line (3.84 sigma^2), the one with the smallest
+ *   distance -- the last such one in list order on ties, as the reference's running comparison does; then the rotation histogram.
+ *   match12[i] = index in pKF2 (-1 = none): vMatchedPairs is its list of (i, match12[i]) in ascending i.  *nmatches = return value. */
+int orbx_search_for_triangulation(orbx_matcher* m, const orbx_bow_side* s1, const orbx_bow_side* s2, const float* u_right1, const float* u_right2,
+                                  const float* F12, float ex, float ey, int nlevels2, const float* scale_factors2, const float* level_sigma2_2,
+                                  int only_stereo, int* match12, int* nmatches);
+
 #ifdef __cplusplus
 }
 #endif

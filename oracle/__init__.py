@@ -481,3 +481,32 @@ def search_by_bow(kind, nnratio, check_ori, kf_kf, keys1, desc1, valid1, fv1, ke
     nm = f(float(nnratio), int(bool(check_ori)), int(bool(kf_kf)), len(k1), k1.ctypes.data, d1.ctypes.data, v1.ctypes.data, len(a[0]), a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data,
            len(k2), k2.ctypes.data, d2.ctypes.data, v2.ctypes.data, len(b[0]), b[0].ctypes.data, b[1].ctypes.data, b[2].ctypes.data, m12.ctypes.data, m21.ctypes.data)
     return nm, m12[:len(k1)], m21[:len(k2)]
+
+
+def search_for_triangulation(kind, check_ori, keys1, desc1, free1, ur1, fv1, keys2, desc2, free2, ur2, fv2, F12, c2_or_epipole, cam, scale_factors, level_sigma2, only_stereo):
+    """ORBmatcher::SearchForTriangulation (ORBmatcher.cc:810).  free = the feature holds no map point.  kind 'ref': c2_or_epipole = camera 1's
+    centre in camera 2 (the body derives the epipole, returned as third value); 'port': the epipole itself.  -> (nmatches, match12[, epipole])."""
+    lib = _lib(kind)
+    k1 = np.ascontiguousarray(keys1, KP_DTYPE); k2 = np.ascontiguousarray(keys2, KP_DTYPE)
+    d1 = np.ascontiguousarray(desc1, np.uint8).reshape(-1, 32); d2 = np.ascontiguousarray(desc2, np.uint8).reshape(-1, 32)
+    f1 = np.ascontiguousarray(free1, np.uint8); f2 = np.ascontiguousarray(free2, np.uint8)
+    u1 = np.ascontiguousarray(ur1, np.float32); u2 = np.ascontiguousarray(ur2, np.float32)
+    a = [np.ascontiguousarray(fv1[x], np.int32) for x in ("fv_nodes", "fv_offsets", "fv_idx")]; b = [np.ascontiguousarray(fv2[x], np.int32) for x in ("fv_nodes", "fv_offsets", "fv_idx")]
+    F = np.ascontiguousarray(F12, np.float32).reshape(9); sc = np.ascontiguousarray(scale_factors, np.float32); sg = np.ascontiguousarray(level_sigma2, np.float32)
+    m12 = np.zeros(max(len(k1), 1), np.int32)
+    vp, ci, cf = C.c_void_p, C.c_int, C.c_float
+    if kind == "ref":
+        c2 = np.ascontiguousarray(c2_or_epipole, np.float32); has1 = (1 - f1).astype(np.uint8); has2 = (1 - f2).astype(np.uint8); epi = np.zeros(2, np.float32)
+        f = lib.ref_search_for_triangulation; f.restype = ci
+        f.argtypes = [cf, ci] + [ci, vp, vp, vp, vp, ci, vp, vp, vp] * 2 + [vp, vp, cf, cf, cf, cf, ci, vp, vp, ci, vp, vp]
+        nm = f(0.6, int(bool(check_ori)), len(k1), k1.ctypes.data, d1.ctypes.data, has1.ctypes.data, u1.ctypes.data, len(a[0]), a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data,
+               len(k2), k2.ctypes.data, d2.ctypes.data, has2.ctypes.data, u2.ctypes.data, len(b[0]), b[0].ctypes.data, b[1].ctypes.data, b[2].ctypes.data,
+               F.ctypes.data, c2.ctypes.data, *[float(x) for x in cam], len(sc), sc.ctypes.data, sg.ctypes.data, int(bool(only_stereo)), m12.ctypes.data, epi.ctypes.data)
+        return nm, m12[:len(k1)], epi
+    ex, ey = float(c2_or_epipole[0]), float(c2_or_epipole[1])
+    f = lib.port_search_for_triangulation; f.restype = ci
+    f.argtypes = [ci] + [ci, vp, vp, vp, vp, ci, vp, vp, vp] * 2 + [vp, cf, cf, vp, vp, ci, vp]
+    nm = f(int(bool(check_ori)), len(k1), k1.ctypes.data, d1.ctypes.data, f1.ctypes.data, u1.ctypes.data, len(a[0]), a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data,
+           len(k2), k2.ctypes.data, d2.ctypes.data, f2.ctypes.data, u2.ctypes.data, len(b[0]), b[0].ctypes.data, b[1].ctypes.data, b[2].ctypes.data,
+           F.ctypes.data, ex, ey, sc.ctypes.data, sg.ctypes.data, int(bool(only_stereo)), m12.ctypes.data)
+    return nm, m12[:len(k1)]

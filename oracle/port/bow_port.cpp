@@ -163,4 +163,76 @@ int port_search_by_bow(float nnratio, int checkOri, int kf_kf, int n1, const uns
     return nmatches;
 }
 
+
+// ORBmatcher::SearchForTriangulation (ORBmatcher.cc:810-1010) with CheckDistEpipolarLine (:188-215).  free1 / free2: the feature holds no map point.
+int port_search_for_triangulation(int checkOri, int n1, const unsigned char* keys1, const unsigned char* desc1, const unsigned char* free1, const float* ur1,
+                                  int n_fv1, const int* fv1_nodes, const int* fv1_offsets, const int* fv1_idx,
+                                  int n2, const unsigned char* keys2, const unsigned char* desc2, const unsigned char* free2, const float* ur2,
+                                  int n_fv2, const int* fv2_nodes, const int* fv2_offsets, const int* fv2_idx,
+                                  const float* F, float ex, float ey, const float* scale2, const float* sigma2_2, int only_stereo, int* match12) {
+    const int TH_LOW = 50, HISTO_LENGTH = 30;
+    struct KP { float x, y, size, angle, response; int octave, class_id; };
+    const KP* k1 = (const KP*)keys1; const KP* k2 = (const KP*)keys2;
+    for (int i = 0; i < n1; ++i) match12[i] = -1;
+    std::vector<unsigned char> matched2(n2, 0);
+    std::vector<int> hist[30];
+    int nmatches = 0, a = 0, b = 0;
+    while (a < n_fv1 && b < n_fv2) {
+        if (fv1_nodes[a] < fv2_nodes[b]) { ++a; continue; }
+        if (fv2_nodes[b] < fv1_nodes[a]) { ++b; continue; }
+        for (int e1 = fv1_offsets[a]; e1 < fv1_offsets[a + 1]; ++e1) {
+            const int i1 = fv1_idx[e1];
+            if (!free1[i1]) continue;
+            const bool stereo1 = ur1[i1] >= 0;
+            if (only_stereo && !stereo1) continue;
+            // epipolar line of kp1 in image 2
+            volatile float la = k1[i1].x * F[0] + k1[i1].y * F[3] + F[6], lb = k1[i1].x * F[1] + k1[i1].y * F[4] + F[7], lc = k1[i1].x * F[2] + k1[i1].y * F[5] + F[8];
+            int bestDist = TH_LOW, bestIdx2 = -1;
+            for (int e2 = fv2_offsets[b]; e2 < fv2_offsets[b + 1]; ++e2) {
+                const int i2 = fv2_idx[e2];
+                if (matched2[i2] || !free2[i2]) continue;
+                const bool stereo2 = ur2[i2] >= 0;
+                if (only_stereo && !stereo2) continue;
+                const int dist = hamming(desc1 + (size_t)i1 * 32, desc2 + (size_t)i2 * 32);
+                if (dist > TH_LOW || dist > bestDist) continue;
+                if (!stereo1 && !stereo2) {
+                    volatile float dx = ex - k2[i2].x, dy = ey - k2[i2].y;
+                    volatile float d2 = dx * dx + dy * dy, lim = 100 * scale2[k2[i2].octave];
+                    if (d2 < lim) continue;
+                }
+                volatile float num = la * k2[i2].x + lb * k2[i2].y + lc, den = la * la + lb * lb;
+                if (den == 0) continue;
+                volatile float dsqr = num * num / den;
+                if (!((double)dsqr < 3.84 * (double)sigma2_2[k2[i2].octave])) continue;
+                bestIdx2 = i2; bestDist = dist;
+            }
+            if (bestIdx2 < 0) continue;
+            match12[i1] = bestIdx2; matched2[bestIdx2] = 1; ++nmatches;
+            if (checkOri) {
+                float rot = k1[i1].angle - k2[bestIdx2].angle;
+                if (rot < 0.0) rot += 360.0f;
+                int bin = (int)std::round(rot * ((float)HISTO_LENGTH / 360.0f));
+                if (bin == HISTO_LENGTH) bin = 0;
+                hist[bin].push_back(i1);
+            }
+        }
+        ++a; ++b;
+    }
+    if (checkOri) {
+        int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            const int s = (int)hist[i].size();
+            if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+            else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+            else if (s > max3) { max3 = s; ind3 = i; }
+        }
+        if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; } else if (max3 < 0.1f * (float)max1) ind3 = -1;
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (size_t j = 0; j < hist[i].size(); ++j) { match12[hist[i][j]] = -1; --nmatches; }
+        }
+    }
+    return nmatches;
+}
+
 }  // extern "C"

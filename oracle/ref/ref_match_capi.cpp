@@ -80,8 +80,12 @@ public:
     KeyFrame() : N(0), fx(0), fy(0), cx(0), cy(0), mnGridCols(FRAME_GRID_COLS), mnGridRows(FRAME_GRID_ROWS), mfGridElementWidthInv(0), mfGridElementHeightInv(0),
                  mnMinX(0), mnMinY(0), mnMaxX(0), mnMaxY(0) {}
     std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
-    cv::Mat GetRotation() { return cv::Mat::eye(3, 3, CV_32F); }      // the harness keeps both KeyFrames at the world origin
-    cv::Mat GetTranslation() { return cv::Mat::zeros(3, 1, CV_32F); }
+    cv::Mat Rcw, tcw, Ow;                                              // empty = KeyFrame at the world origin
+    cv::Mat GetRotation() { return Rcw.empty() ? cv::Mat(cv::Mat::eye(3, 3, CV_32F)) : Rcw.clone(); }
+    cv::Mat GetTranslation() { return tcw.empty() ? cv::Mat(cv::Mat::zeros(3, 1, CV_32F)) : tcw.clone(); }
+    cv::Mat GetCameraCenter() { return Ow.empty() ? cv::Mat(cv::Mat::zeros(3, 1, CV_32F)) : Ow.clone(); }
+    MapPoint* GetMapPoint(const size_t& idx) { return mvpMapPoints[idx]; }
+    std::vector<float> mvuRight, mvLevelSigma2;
     std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r) const;
     bool IsInImage(const float& x, const float& y) const;
     std::vector<MapPoint*> mvpMapPoints;
@@ -108,6 +112,8 @@ public:
     int SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const std::set<MapPoint*>& sAlreadyFound, const float th, const int ORBdist);
     int SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const std::vector<MapPoint*>& vpPoints, std::vector<MapPoint*>& vpMatched, int th);
     int SearchBySim3(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12, const float& s12, const cv::Mat& R12, const cv::Mat& t12, const float th);
+    int SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F12, std::vector<std::pair<size_t, size_t> >& vMatchedPairs, const bool bOnlyStereo);
+    bool CheckDistEpipolarLine(const cv::KeyPoint& kp1, const cv::KeyPoint& kp2, const cv::Mat& F12, const KeyFrame* pKF);
     int SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12);
     static const int TH_LOW, TH_HIGH, HISTO_LENGTH;
 protected:
@@ -144,6 +150,10 @@ void fill_frame(Frame& F, const FrameView* v) {
     F.AssignFeaturesToGrid();
 }
 }  // namespace
+
+static void fill_fv(DBoW2::FeatureVector& fv, int n_fv, const int* nodes, const int* offsets, const int* idx) {
+    for (int q = 0; q < n_fv; ++q) for (int e = offsets[q]; e < offsets[q + 1]; ++e) fv.addFeature(nodes[q], idx[e]);
+}
 
 extern "C" {
 
@@ -420,13 +430,45 @@ int ref_search_by_sim3(const FrameView* v1, const FrameView* v2, const float* xy
     return nf;
 }
 
+// ORBmatcher::SearchForTriangulation   ORBmatcher.cc:810 (+ CheckDistEpipolarLine :188).  KeyFrame 1 at the world origin, KeyFrame 2 with
+// rotation I and translation c2 (= camera 1's centre in camera 2, from which the body derives the epipole).  has_mp: the feature holds a
+// map point.  Output match12[i] = second of the pair (i, .) in vMatchedPairs, -1 if absent; epi[2] = the epipole the body computed.
+int ref_search_for_triangulation(float nnratio, int checkOri, int n1, const cv::KeyPoint* keys1, const unsigned char* desc1, const unsigned char* has_mp1, const float* ur1,
+                                 int n_fv1, const int* fv1_nodes, const int* fv1_offsets, const int* fv1_idx,
+                                 int n2, const cv::KeyPoint* keys2, const unsigned char* desc2, const unsigned char* has_mp2, const float* ur2,
+                                 int n_fv2, const int* fv2_nodes, const int* fv2_offsets, const int* fv2_idx,
+                                 const float* F12, const float* c2, float fx, float fy, float cx, float cy, int nlevels, const float* scale_factors, const float* level_sigma2,
+                                 int only_stereo, int* match12, float* epi) {
+    ArenaScope scope;
+    int nm;
+    {
+        std::vector<MapPoint> p1(n1), p2(n2);
+        KeyFrame K1, K2;
+        K1.N = n1; K1.mvKeysUn.assign(keys1, keys1 + n1); K1.mDescriptors = cv::Mat(n1, 32, CV_8U, (void*)desc1).clone(); K1.mvuRight.assign(ur1, ur1 + n1);
+        K2.N = n2; K2.mvKeysUn.assign(keys2, keys2 + n2); K2.mDescriptors = cv::Mat(n2, 32, CV_8U, (void*)desc2).clone(); K2.mvuRight.assign(ur2, ur2 + n2);
+        K1.mvpMapPoints.assign(n1, (MapPoint*)NULL); K2.mvpMapPoints.assign(n2, (MapPoint*)NULL);
+        for (int i = 0; i < n1; ++i) if (has_mp1[i]) K1.mvpMapPoints[i] = &p1[i];
+        for (int j = 0; j < n2; ++j) if (has_mp2[j]) K2.mvpMapPoints[j] = &p2[j];
+        fill_fv(K1.mFeatVec, n_fv1, fv1_nodes, fv1_offsets, fv1_idx); fill_fv(K2.mFeatVec, n_fv2, fv2_nodes, fv2_offsets, fv2_idx);
+        K2.fx = fx; K2.fy = fy; K2.cx = cx; K2.cy = cy;
+        K2.mvScaleFactors.assign(scale_factors, scale_factors + nlevels); K2.mvLevelSigma2.assign(level_sigma2, level_sigma2 + nlevels);
+        K2.tcw = cv::Mat(3, 1, CV_32F); for (int k = 0; k < 3; ++k) K2.tcw.at<float>(k) = c2[k];
+        cv::Mat F(3, 3, CV_32F); for (int k = 0; k < 9; ++k) F.at<float>(k / 3, k % 3) = F12[k];
+        const float invz = 1.0f / c2[2];                                 // the body's own epipole (:822-825), restated for the caller
+        epi[0] = fx * c2[0] * invz + cx; epi[1] = fy * c2[1] * invz + cy;
+        for (int i = 0; i < n1; ++i) match12[i] = -1;
+        std::vector<std::pair<size_t, size_t> > pairs;
+        ORBmatcher matcher(nnratio, checkOri != 0);
+        nm = matcher.SearchForTriangulation(&K1, &K2, F, pairs, only_stereo != 0);
+        for (size_t q = 0; q < pairs.size(); ++q) match12[pairs[q].first] = (int)pairs[q].second;
+    }
+    return nm;
+}
+
 // ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&)  ORBmatcher.cc:230  and  (KeyFrame*, KeyFrame*, ...)  :656.
 // Feature vectors arrive flattened (nodes ascending, offsets, feature indices) as ref_voc_transform returns them.
 // valid1 / valid2: the feature holds a map point that is not bad.  Outputs: match21[j] = side-1 index assigned to side-2
 // feature j (KF x Frame: vpMapPointMatches[j] = KF's map point), match12[i] = side-2 index (KF x KF: vpMatches12[i]).
-static void fill_fv(DBoW2::FeatureVector& fv, int n_fv, const int* nodes, const int* offsets, const int* idx) {
-    for (int q = 0; q < n_fv; ++q) for (int e = offsets[q]; e < offsets[q + 1]; ++e) fv.addFeature(nodes[q], idx[e]);
-}
 int ref_search_by_bow(float nnratio, int checkOri, int kf_kf, int n1, const cv::KeyPoint* keys1, const unsigned char* desc1, const unsigned char* valid1,
                       int n_fv1, const int* fv1_nodes, const int* fv1_offsets, const int* fv1_idx,
                       int n2, const cv::KeyPoint* keys2, const unsigned char* desc2, const unsigned char* valid2,

@@ -62,3 +62,20 @@ def write_text(path, k, L, scoring, weighting, voc):
         f.write("%d %d %d %d\n" % (k, L, scoring, weighting))
         for i in range(len(parent)):
             f.write("%d %d %s %r\n" % (parent[i], leaf[i], " ".join(str(int(b)) for b in desc[i]), float(weight[i])))
+
+
+# SearchForTriangulation inputs: frame B = frame A moved by (+7, -4) px and rotated by 2 degrees, so a fundamental matrix of a pure image
+# translation along (7, -4) puts the true matches within a few pixels of their epipolar lines near the image centre and further away
+# towards the borders; the epipole used for the "too close to the epipole" test is an independent input.
+TRI_F12 = [[0.0, 0.0, -0.004], [0.0, 0.0, -0.007], [0.004, 0.007, 0.0]]
+TRI_C2 = (0.02, 0.01, 0.5)                                   # camera 1's centre in camera 2 -> epipole (339.3, 265.6) with the TUM1-like intrinsics below
+TRI_CAM = (517.3, 516.5, 318.6, 255.3)
+TRI_VARIANTS = [(True, False), (False, False), (True, True)] # (checkOri, bOnlyStereo)
+
+
+def tri_inputs(n1, n2, seed=31):
+    rng = np.random.default_rng(seed)
+    free1 = (rng.random(n1) < 0.7).astype(np.uint8); free2 = (rng.random(n2) < 0.7).astype(np.uint8)
+    ur1 = np.where(rng.random(n1) < 0.4, rng.uniform(0, 600, n1), -1).astype(np.float32); ur2 = np.where(rng.random(n2) < 0.4, rng.uniform(0, 600, n2), -1).astype(np.float32)
+    sf = (np.float32(1.2) ** np.arange(8, dtype=np.float32)).astype(np.float32)
+    return dict(free1=free1, free2=free2, ur1=ur1, ur2=ur2, sf=sf, sigma2=(sf * sf).astype(np.float32))

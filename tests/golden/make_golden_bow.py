@@ -32,5 +32,10 @@ for kfkf in (0, 1):
     for i, (nn, ori) in enumerate(bc.MATCH_VARIANTS):
         nm, m12, m21 = oracle.search_by_bow("ref", nn, ori, kfkf, ka, da, va, fa, kb, db, vb, fb)
         out["m_%d_%d_nm" % (kfkf, i)] = np.array(nm); out["m_%d_%d_m12" % (kfkf, i)] = m12; out["m_%d_%d_m21" % (kfkf, i)] = m21
+# ORBmatcher::SearchForTriangulation (src/ORBmatcher.cc:810-1010)
+t = bc.tri_inputs(len(ka), len(kb))
+for i, (ori, st) in enumerate(bc.TRI_VARIANTS):
+    nm, m12, epi = oracle.search_for_triangulation("ref", ori, ka, da, t["free1"], t["ur1"], fa, kb, db, t["free2"], t["ur2"], fb, bc.TRI_F12, bc.TRI_C2, bc.TRI_CAM, t["sf"], t["sigma2"], st)
+    out["tri_%d_nm" % i] = np.array(nm); out["tri_%d_m12" % i] = m12; out["tri_epi"] = epi
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_bow.npz"), **out)
 print("wrote ref_bow.npz:", len(out), "arrays")

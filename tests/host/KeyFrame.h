@@ -18,6 +18,10 @@ public:
     DBoW2::FeatureVector mFeatVec;
     ORBVocabulary* mpORBvocabulary = nullptr;
     bool IsInImage(const float &x, const float &y) const { return (x >= mnMinX && x < mnMaxX && y >= mnMinY && y < mnMaxY); }   // src/KeyFrame.cc:799-802
+    MapPoint* GetMapPoint(const size_t &idx) { return mvpMapPoints[idx]; }
+    cv::Mat GetCameraCenter() { return mOw; }
+    cv::Mat mOw;
+    std::vector<float> mvuRight, mvLevelSigma2;
     cv::Mat GetRotation() { return mRcw; }
     cv::Mat GetTranslation() { return mtcw; }
     cv::Mat mRcw, mtcw;

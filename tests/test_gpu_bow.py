@@ -80,3 +80,22 @@ def test_vocabulary_text_file_loader(orbx, tmp_path):
         orbx.ORBVocabulary.load_text(str(tmp_path / "missing.txt"))
     with pytest.raises(orbx.OrbxError):
         orbx.ORBVocabulary(10, 3, VOC[0], 1 - VOC[1], VOC[2], VOC[3])    # leaf flags contradict the tree
+
+
+def test_search_for_triangulation_matches_reference_body(orbx, oracle):
+    """SearchForTriangulation (LocalMapping::CreateNewMapPoints): node-by-node replay with the epipole and epipolar-line gates, against the reference's golden."""
+    ka, da, kb, db = G["ka"].view(orbx.KP_DTYPE), G["da"], G["kb"].view(orbx.KP_DTYPE), G["db"]
+    V = orbx.ORBVocabulary(10, 3, *VOC)
+    fa, fb = V.transform(da, 1), V.transform(db, 1)
+    t = bc.tri_inputs(len(ka), len(kb))
+    for i, (ori, st) in enumerate(bc.TRI_VARIANTS):
+        nm, m12 = orbx.ORBmatcher(0.6, ori).SearchForTriangulation(ka, da, t["free1"], t["ur1"], fa, kb, db, t["free2"], t["ur2"], fb, bc.TRI_F12, G["tri_epi"], t["sf"], t["sigma2"], st)
+        assert nm == int(G["tri_%d_nm" % i]) and np.array_equal(m12, G["tri_%d_m12" % i])
+    # other node granularities (one node holding everything; one node per word) and a different geometry, against the port
+    rng = np.random.default_rng(8)
+    F2 = rng.normal(0, 0.01, (3, 3)).astype(np.float32)
+    for lu in (4, 0):
+        fa, fb = V.transform(da, lu), V.transform(db, lu)
+        g = orbx.ORBmatcher(0.6, True).SearchForTriangulation(ka, da, t["free1"], t["ur1"], fa, kb, db, t["free2"], t["ur2"], fb, F2, (100.0, 400.0), t["sf"], t["sigma2"], False)
+        o = oracle.search_for_triangulation("port", True, ka, da, t["free1"], t["ur1"], fa, kb, db, t["free2"], t["ur2"], fb, F2, (100.0, 400.0), bc.TRI_CAM, t["sf"], t["sigma2"], False)
+        assert g[0] == o[0] and np.array_equal(g[1], o[1]), lu

@@ -59,3 +59,14 @@ def test_golden_properties():
         m12, m21 = G["m_%d_0_m12" % kfkf], G["m_%d_0_m21" % kfkf]
         i = np.nonzero(m12 >= 0)[0]
         assert np.array_equal(m21[m12[i]], i) and int(G["m_%d_0_nm" % kfkf]) == len(i)
+
+
+def test_port_search_for_triangulation_matches_reference_body(oracle):
+    """ORBmatcher::SearchForTriangulation + CheckDistEpipolarLine (ORBmatcher.cc:810-1010, 188-215): port vs the reference bodies' committed outputs."""
+    ka, da, kb, db = frames(oracle)
+    P = oracle.Vocabulary("port", 10, 3, *VOC)
+    fa, fb = P.transform(da, 1), P.transform(db, 1)
+    t = bc.tri_inputs(len(ka), len(kb))
+    for i, (ori, st) in enumerate(bc.TRI_VARIANTS):
+        nm, m12 = oracle.search_for_triangulation("port", ori, ka, da, t["free1"], t["ur1"], fa, kb, db, t["free2"], t["ur2"], fb, bc.TRI_F12, G["tri_epi"], bc.TRI_CAM, t["sf"], t["sigma2"], st)
+        assert nm == int(G["tri_%d_nm" % i]) and nm > 10 and np.array_equal(m12, G["tri_%d_m12" % i])
