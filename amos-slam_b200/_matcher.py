@@ -312,6 +312,14 @@ class ORBmatcher:
         self._check(fn(self._h, fa, len(lv), _p(uv), _p(lv), _p(d), _p(va), _p(km), float(th), _p(out), C.byref(nm)))
         return nm.value, out[:len(kf.keys)]
 
+    # the search of int Fuse(KeyFrame *pKF, const vector<MapPoint*> &vpMapPoints, th) / Fuse(KeyFrame *pKF, cv::Mat Scw, vpPoints, th, vpReplacePoint)
+    def FuseSearch(self, kf, proj_uv, proj_ur, predicted_level, mp_desc, valid, inv_level_sigma2, th):
+        uv = np.ascontiguousarray(proj_uv, np.float32); lv = np.ascontiguousarray(predicted_level, np.int32); d, va = _u8(mp_desc), _u8(valid)
+        ur = None if proj_ur is None else np.ascontiguousarray(proj_ur, np.float32); isg = np.ascontiguousarray(inv_level_sigma2, np.float32)
+        best = np.zeros(max(len(lv), 1), np.int32); v = kf.c()
+        self._check(self._lib.orbx_fuse_search(self._h, C.byref(v), len(lv), _p(uv), _p(ur), _p(lv), _p(d), _p(va), _p(isg), float(th), _p(best)))
+        return best[:len(lv)]
+
     # int SearchBySim3(KeyFrame *pKF1, KeyFrame *pKF2, vector<MapPoint*> &vpMatches12, const float &s12, const cv::Mat &R12, const cv::Mat &t12, const float th)
     def SearchBySim3(self, kf1, kf2, uv1, lvl1, desc1, valid1, uv2, lvl2, desc2, valid2, th):
         a = [np.ascontiguousarray(uv1, np.float32), np.ascontiguousarray(lvl1, np.int32), _u8(desc1), _u8(valid1),

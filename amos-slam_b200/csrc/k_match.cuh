@@ -92,6 +92,9 @@ struct QueryParams {
     const float* q_invz; const int* q_octave; const uint8_t* q_valid; float th; int forward, backward; float mbf; int no_ur;   // no_ur: the KeyFrame form has no uRight test
     // PROJ_POINTS: track_ur, track_level, track_view_cos, th                      (q_xy = track_uv, q_desc = mp_desc)
     const float* q_ur; const float* q_viewcos;
+    // Fuse: chi2 != 0 adds the reprojection gate of ORBmatcher::Fuse (:1097-1137) to PROJ_FRAME: q_ur = the point's right-image coordinate,
+    // q_invsigma2 = mvInvLevelSigma2 by level
+    int chi2; const float* q_invsigma2;
     // AREA: q_xy = (x, y), q_r, q_minlevel, q_maxlevel
     const float* q_r; const int* q_minlevel; const int* q_maxlevel;
 };
@@ -118,6 +121,7 @@ __device__ __forceinline__ bool query_window(const QueryParams& P, const FrameDe
         else if (P.backward) { minLevel = 0; maxLevel = oct; }
         else { minLevel = oct - 1; maxLevel = oct + 1; }
         ur = __fsub_rn(u, __fmul_rn(P.mbf, invz)); use_ur = !P.no_ur;               // :1665
+        if (P.chi2) ur = P.q_ur[q];
         return true;
     }
     if (P.mode == MODE_AREA) {
@@ -178,6 +182,19 @@ k_window_search(QueryParams P, FrameDev F, int* __restrict__ counts, const int* 
                         if (maxLevel >= 0 && kp.octave > maxLevel) keep = false;
                     }
                     if (keep && !(fabsf(__fsub_rn(kp.x, x)) < r && fabsf(__fsub_rn(kp.y, y)) < r)) keep = false;    // :986-991
+                    if (keep && P.chi2) {                                                                              // Fuse: chi-square gate on the reprojection error
+                        const float ex = __fsub_rn(x, kp.x), ey = __fsub_rn(y, kp.y);
+                        const float urj = F.u_right ? F.u_right[j] : -1.f;
+                        const float inv = P.q_invsigma2[kp.octave];
+                        if (urj >= 0.f) {
+                            const float er = __fsub_rn(ur, urj);
+                            const float e2 = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(er, er));
+                            if ((double)__fmul_rn(e2, inv) > 7.8) keep = false;                                          // :1111-1113
+                        } else {
+                            const float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+                            if ((double)__fmul_rn(e2, inv) > 5.99) keep = false;                                         // :1123-1125
+                        }
+                    }
                     if (keep && use_ur && F.u_right) {
                         const float urj = F.u_right[j];
                         if (urj > 0.f && fabsf(__fsub_rn(ur, urj)) > r) keep = false;                                // :1662-1669 / :129-139

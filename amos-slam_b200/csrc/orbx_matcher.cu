@@ -519,19 +519,59 @@ int orbx_search_by_projection_keyframe_points_dev(orbx_matcher* m, const orbx_fr
 // SearchBySim3 (ORBmatcher.cc:1290-1555): two order-independent passes (map points of one KeyFrame against the features of the other, levels
 // [predicted - 1, predicted], best distance <= TH_HIGH, no exclusions) and the mutual-consistency check, all on the device
 struct Sim3Side { int n; const float* proj_uv; const int* predicted_level; const uint8_t* mp_desc; const uint8_t* valid; };
-static int sim3_pass(orbx_matcher* m, const FrameDev& target, const Sim3Side& q, float th, int* d_best, int*& d_total) {
+// independent best match of every query on level predicted - 1 or predicted within max_dist; proj_ur / inv_sigma2 != NULL adds Fuse's chi-square gate
+static int sim3_pass(orbx_matcher* m, const FrameDev& target, const Sim3Side& q, float th, int* d_best, int*& d_total, int max_dist = M_TH_HIGH,
+                     const float* proj_ur = nullptr, const float* inv_sigma2 = nullptr, int nlevels = 0) {
     int rc;
-    float *uv, *iz; int* lv; uint8_t *dd, *va;
+    float *uv, *iz, *dur = nullptr, *dis = nullptr; int* lv; uint8_t *dd, *va;
     std::vector<float> zeros((size_t)std::max(q.n, 1), 0.f);
     if ((rc = up(m, q.proj_uv, (size_t)q.n * 2, uv)) || (rc = up(m, zeros.data(), (size_t)q.n, iz)) || (rc = up(m, q.predicted_level, (size_t)q.n, lv)) ||
         (rc = up(m, q.mp_desc, (size_t)q.n * 32, dd)) || (rc = up(m, q.valid, (size_t)q.n, va))) return rc;
+    if (proj_ur && ((rc = up(m, proj_ur, (size_t)q.n, dur)) || (rc = up(m, inv_sigma2, (size_t)nlevels, dis)))) return rc;
     if ((rc = flush_uploads(m))) return rc;
     QueryParams P; std::memset(&P, 0, sizeof(P));
     P.mode = MODE_PROJ_FRAME; P.nq = q.n; P.q_desc = dd; P.q_xy = uv; P.q_invz = iz; P.q_octave = lv; P.q_valid = va; P.th = th; P.forward = 2; P.no_ur = 1;
+    if (proj_ur) { P.chi2 = 1; P.q_ur = dur; P.q_invsigma2 = dis; }
     int *counts, *offsets; uint32_t* cand; uint2* pre;
     if ((rc = window_search(m, P, target, counts, offsets, cand, pre))) return rc;
-    if (q.n) { k_best_extract<<<(q.n + 127) / 128, 128, 0, m->stream>>>(q.n, offsets, cand, pre, (int)std::min<size_t>(m->cand_cap, 0x7FFFFFFF), M_TH_HIGH, d_best); LAUNCH_CHECK(); }
+    if (q.n) { k_best_extract<<<(q.n + 127) / 128, 128, 0, m->stream>>>(q.n, offsets, cand, pre, (int)std::min<size_t>(m->cand_cap, 0x7FFFFFFF), max_dist, d_best); LAUNCH_CHECK(); }
     d_total = offsets + q.n;
+    return ORBX_OK;
+}
+
+// The search of both ORBmatcher::Fuse forms (ORBmatcher.cc:1020-1175, 1179-1310): per map point, the best KeyFrame feature on level
+// predicted - 1 or predicted within TH_LOW; proj_ur != NULL: the pose form with its chi-square reprojection gate (stereo 7.8, mono 5.99)
+int orbx_fuse_search(orbx_matcher* m, const orbx_frame_view* kf, int n_points, const float* proj_uv, const float* proj_ur, const int* predicted_level,
+                     const uint8_t* mp_desc, const uint8_t* valid, const float* inv_level_sigma2, float th, int* best_idx) {
+    if (!m) FAIL(ORBX_E_INVALID, "null argument");
+    int rc;
+    if ((rc = check_frame(kf))) return rc;
+    if (n_points < 0 || n_points >= (1 << 20) || (n_points && (!proj_uv || !predicted_level || !mp_desc || !valid || !best_idx)) || (proj_ur && !inv_level_sigma2))
+        FAIL(ORBX_E_INVALID, "bad arguments");
+    for (int i = 0; i < n_points; ++i) { best_idx[i] = -1; if (valid[i] && (predicted_level[i] < 0 || predicted_level[i] >= kf->nlevels)) FAIL(ORBX_E_INVALID, "predicted level out of range"); }
+    for (int j = 0; j < kf->n; ++j) if (kf->keys_un[j].octave < 0 || kf->keys_un[j].octave >= kf->nlevels) FAIL(ORBX_E_INVALID, "octave out of range");
+    if (n_points == 0 || kf->n == 0) return ORBX_OK;
+    CU_TRY(cudaSetDevice(m->device));
+    const size_t need = frame_bytes(kf) + pad((size_t)n_points * 52) + 8 * pad((size_t)(n_points + kf->n + 2) * 8) + 16384;
+    if ((rc = m->arena.reserve(need)) || (rc = m->uparena.reserve(need))) return rc;
+retry:
+    m->arena.reset(); m->uparena.reset();
+    FrameDev d; uint32_t* sk;
+    if ((rc = upload_frame(m, kf, d, sk))) return rc;
+    if ((rc = flush_uploads(m)) || (rc = build_grid(m, d, sk))) return rc;
+    int* res = m->arena.get<int>((size_t)n_points + 2);
+    if (!res) FAIL(ORBX_E_CUDA, "matcher arena exhausted");
+    int* tot;
+    Sim3Side q{n_points, proj_uv, predicted_level, mp_desc, valid};
+    if ((rc = sim3_pass(m, d, q, th, res + 1, tot, M_TH_LOW, proj_ur, inv_level_sigma2, kf->nlevels))) return rc;
+    CU_TRY(cudaMemcpyAsync(res, tot, 4, cudaMemcpyDeviceToDevice, m->stream));
+    const size_t res_bytes = ((size_t)n_points + 1) * 4;
+    if ((rc = m->ensure_download(res_bytes))) return rc;
+    CU_TRY(cudaMemcpyAsync(m->dl_host, res, res_bytes, cudaMemcpyDeviceToHost, m->stream));
+    CU_TRY(cudaStreamSynchronize(m->stream));
+    const int* hr = reinterpret_cast<const int*>(m->dl_host);
+    if (cand_overflow(m, hr[0])) goto retry;
+    std::memcpy(best_idx, hr + 1, (size_t)n_points * 4);
     return ORBX_OK;
 }
 int orbx_search_by_sim3(orbx_matcher* m, const orbx_frame_view* kf1, const orbx_frame_view* kf2, const float* proj_uv1, const int* predicted_level1, const uint8_t* mp_desc1,

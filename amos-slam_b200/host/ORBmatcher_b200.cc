@@ -11,6 +11,7 @@
 //   ORBmatcher::SearchByProjection(Frame&, KeyFrame*, const set<MapPoint*>&, float, int)       src/ORBmatcher.cc:1731-1863  (8f rank 3)
 //   ORBmatcher::SearchByProjection(KeyFrame*, cv::Mat Scw, const vector<MapPoint*>&, vector<MapPoint*>&, int)   src/ORBmatcher.cc:388-512  (8f rank 3)
 //   ORBmatcher::SearchBySim3(KeyFrame*, KeyFrame*, vector<MapPoint*>&, const float&, const cv::Mat&, const cv::Mat&, float)   src/ORBmatcher.cc:1314-1555  (8f rank 3)
+//   ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, float)  and  Fuse(KeyFrame*, cv::Mat Scw, const vector<MapPoint*>&, float, vector<MapPoint*>&)   src/ORBmatcher.cc:1020-1310  (8f rank 3)
 //
 // Each body only flattens the object graph (Frame / MapPoint) into the plain arrays of the C ABI
 // (include/orbx_b200.h), calls the CUDA implementation and writes the results back into the same
@@ -374,6 +375,98 @@ int ORBmatcher::SearchBySim3(KeyFrame *pKF1, KeyFrame *pKF2, std::vector<MapPoin
                               q2.uv.data(), q2.level.data(), q2.desc.data(), q2.valid.data(), th, m12.data(), &nFound), "orbx_search_by_sim3");
     for (int i1 = 0; i1 < N1; ++i1) if (m12[i1] >= 0) vpMatches12[i1] = vpMapPoints2[m12[i1]];                               // :1544
     return nFound;
+}
+
+namespace
+{
+// caller-side part of both Fuse forms (:1036-1085 / :1200-1243): projection, gates, predicted level; returns the queries of orbx_fuse_search
+struct FuseQueries {
+    std::vector<float> uv, ur; std::vector<int> level; std::vector<unsigned char> desc, valid;
+    FuseQueries(KeyFrame* pKF, const std::vector<MapPoint*>& pts, const cv::Mat& Rcw, const cv::Mat& tcw, const cv::Mat& Ow, const std::set<MapPoint*>* found, bool pose_form) {
+        const float &fx = pKF->fx, &fy = pKF->fy, &cx = pKF->cx, &cy = pKF->cy;
+        const int n = (int)pts.size();
+        uv.assign((size_t)n * 2, 0.f); ur.assign(n, 0.f); level.assign(n, 0); desc.assign((size_t)n * 32, 0); valid.assign(n, 0);
+        for (int i = 0; i < n; ++i) {
+            MapPoint* pMP = pts[i];
+            if (!pMP || pMP->isBad()) continue;
+            if (pose_form ? pMP->IsInKeyFrame(pKF) : (found->count(pMP) != 0)) continue;
+            cv::Mat p3Dw = pMP->GetWorldPos();
+            cv::Mat p3Dc = Rcw * p3Dw + tcw;
+            if (p3Dc.at<float>(2) < 0.0f) continue;
+            const float invz = pose_form ? 1 / p3Dc.at<float>(2) : (float)(1.0 / p3Dc.at<float>(2));
+            const float x = p3Dc.at<float>(0) * invz, y = p3Dc.at<float>(1) * invz;
+            const float u = fx * x + cx, v = fy * y + cy;
+            if (!pKF->IsInImage(u, v)) continue;
+            cv::Mat PO = p3Dw - Ow;
+            const float dist3D = cv::norm(PO);
+            if (dist3D < pMP->GetMinDistanceInvariance() || dist3D > pMP->GetMaxDistanceInvariance()) continue;
+            cv::Mat Pn = pMP->GetNormal();
+            if (PO.dot(Pn) < 0.5 * dist3D) continue;
+            uv[2 * i] = u; uv[2 * i + 1] = v; if (pose_form) ur[i] = u - pKF->mbf * invz;
+            level[i] = pMP->PredictScale(dist3D, pKF);
+            const cv::Mat d = pMP->GetDescriptor();
+            std::memcpy(&desc[(size_t)i * 32], d.ptr(), 32);
+            valid[i] = 1;
+        }
+    }
+};
+}  // namespace
+
+int ORBmatcher::Fuse(KeyFrame *pKF, const std::vector<MapPoint *> &vpMapPoints, const float th)
+{
+    cv::Mat Rcw = pKF->GetRotation(), tcw = pKF->GetTranslation(), Ow = pKF->GetCameraCenter();
+    const int nMPs = (int)vpMapPoints.size();
+    FuseQueries q(pKF, vpMapPoints, Rcw, tcw, Ow, NULL, true);
+    KeyFrameFlat k(pKF);
+    k.v.u_right = pKF->mvuRight.empty() ? NULL : pKF->mvuRight.data();
+    std::vector<int> best(nMPs ? nMPs : 1, -1);
+    check(orbx_fuse_search(t_matchers.get(mfNNratio, mbCheckOrientation), &k.v, nMPs, q.uv.data(), q.ur.data(), q.level.data(), q.desc.data(), q.valid.data(),
+                           pKF->mvInvLevelSigma2.data(), th, best.data()), "orbx_fuse_search");
+    // the map surgery of :1143-1172, point by point in the reference's order; a point touched by an earlier Replace is re-checked as the reference would see it
+    int nFused = 0;
+    for (int i = 0; i < nMPs; ++i) {
+        if (best[i] < 0) continue;
+        MapPoint* pMP = vpMapPoints[i];
+        if (pMP->isBad() || pMP->IsInKeyFrame(pKF)) continue;
+        MapPoint* pMPinKF = pKF->GetMapPoint(best[i]);
+        if (pMPinKF) {
+            if (!pMPinKF->isBad()) {
+                if (pMPinKF->Observations() > pMP->Observations()) pMP->Replace(pMPinKF);
+                else pMPinKF->Replace(pMP);
+            }
+        } else {
+            pMP->AddObservation(pKF, best[i]);
+            pKF->AddMapPoint(pMP, best[i]);
+        }
+        nFused++;
+    }
+    return nFused;
+}
+
+int ORBmatcher::Fuse(KeyFrame *pKF, cv::Mat Scw, const std::vector<MapPoint *> &vpPoints, float th, std::vector<MapPoint *> &vpReplacePoint)
+{
+    cv::Mat sRcw = Scw.rowRange(0, 3).colRange(0, 3);
+    const float scw = sqrt(sRcw.row(0).dot(sRcw.row(0)));
+    cv::Mat Rcw = sRcw / scw;
+    cv::Mat tcw = Scw.rowRange(0, 3).col(3) / scw;
+    cv::Mat Ow = -Rcw.t() * tcw;
+    const std::set<MapPoint*> spAlreadyFound = pKF->GetMapPoints();
+    const int nPoints = (int)vpPoints.size();
+    FuseQueries q(pKF, vpPoints, Rcw, tcw, Ow, &spAlreadyFound, false);
+    KeyFrameFlat k(pKF);
+    std::vector<int> best(nPoints ? nPoints : 1, -1);
+    check(orbx_fuse_search(t_matchers.get(mfNNratio, mbCheckOrientation), &k.v, nPoints, q.uv.data(), NULL, q.level.data(), q.desc.data(), q.valid.data(), NULL, th, best.data()),
+          "orbx_fuse_search");
+    int nFused = 0;
+    for (int iMP = 0; iMP < nPoints; ++iMP) {                                                                              // :1287-1305
+        if (best[iMP] < 0) continue;
+        MapPoint* pMP = vpPoints[iMP];
+        MapPoint* pMPinKF = pKF->GetMapPoint(best[iMP]);
+        if (pMPinKF) { if (!pMPinKF->isBad()) vpReplacePoint[iMP] = pMPinKF; }
+        else { pMP->AddObservation(pKF, best[iMP]); pKF->AddMapPoint(pMP, best[iMP]); }
+        nFused++;
+    }
+    return nFused;
 }
 
 void Frame::ComputeStereoMatches()

@@ -388,6 +388,20 @@ int orbx_search_by_sim3(orbx_matcher* m, const orbx_frame_view* kf1, const orbx_
                         const float* proj_uv2, const int* predicted_level2, const uint8_t* mp_desc2, const uint8_t* valid2,
                         float th, int* match12, int* nfound);
 
+/* The search inside both ORBmatcher::Fuse forms:
+ *   int Fuse(KeyFrame *pKF, const vector<MapPoint*> &vpMapPoints, const float th)                                   src/ORBmatcher.cc:1020-1175
+ *   int Fuse(KeyFrame *pKF, cv::Mat Scw, const vector<MapPoint*> &vpPoints, float th, vector<MapPoint*> &vpReplacePoint)   :1179-1310
+ * Per map point that passes the caller-side tests (not NULL / bad / already in the KeyFrame, in front of the camera, inside the image, within its
+ * distance range, seen from less than 60 deg): proj_uv (u, v), predicted_level = PredictScale(dist3D, pKF), mp_desc, valid != 0.
+ * Pose form: proj_ur[p] = u - bf * invz and inv_level_sigma2 = pKF->mvInvLevelSigma2 (kf->u_right = pKF->mvuRight): a candidate must pass the
+ * chi-square gate e2 * invSigma2 <= 7.8 (stereo feature) / 5.99 (monocular) (:1097-1137).  Sim3 form: proj_ur = NULL, no gate.
+ * best_idx[p] = the KeyFrame feature with the smallest distance on level predicted - 1 or predicted if that distance is <= TH_LOW, else -1.
+ * The map surgery that follows a hit (Replace / AddObservation / AddMapPoint / vpReplacePoint, :1146-1170, :1289-1303) needs the MapPoint
+ * objects and stays in the caller; it does not feed back into the search of later points. */
+int orbx_fuse_search(orbx_matcher* m, const orbx_frame_view* kf, int n_points, const float* proj_uv, const float* proj_ur,
+                     const int* predicted_level, const uint8_t* mp_desc, const uint8_t* valid, const float* inv_level_sigma2,
+                     float th, int* best_idx);
+
 /* ------------------------------------------------------------------------------------------------
  * Bag of words: DBoW2's vocabulary tree and the two BoW-guided matchers.
  *   ORBVocabulary = DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB>   include/ORBVocabulary.h:40-41

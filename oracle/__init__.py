@@ -377,6 +377,30 @@ class Matcher:
         nf = f(C.byref(kf1.view()), C.byref(kf2.view()), *[x.ctypes.data for x in a], float(th), m12.ctypes.data)
         return nf, m12[:len(kf1.keys)]
 
+    def fuse_ref(self, sim3_form, kf, kf_has_mp, cam_xyz, predicted_level, mp_desc, state, facing, min_dist, max_dist, inv_sigma2, th, bf, fx, fy, cx, cy):
+        """Both ORBmatcher::Fuse bodies (ORBmatcher.cc:1020, 1179) at an identity pose.  -> (nFused, best_idx, proj_uv, proj_ur)."""
+        assert self.kind == "ref"
+        xyz = np.ascontiguousarray(cam_xyz, np.float32); n = len(xyz)
+        lv = np.ascontiguousarray(predicted_level, np.int32); d, st, fc_, hm = _u8(mp_desc), _u8(state), _u8(facing), _u8(kf_has_mp)
+        mn = np.ascontiguousarray(min_dist, np.float32); mx = np.ascontiguousarray(max_dist, np.float32); isg = np.ascontiguousarray(inv_sigma2, np.float32)
+        ur_kf = np.ascontiguousarray(kf.u_right if kf.u_right is not None else np.full(len(kf.keys), -1, np.float32), np.float32)
+        uv = np.zeros((n, 2), np.float32); ur = np.zeros(n, np.float32); best = np.zeros(max(n, 1), np.int32)
+        f = self.lib.ref_fuse; f.restype = C.c_int
+        f.argtypes = [C.c_int, C.POINTER(FrameViewC), C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 8 + [C.c_float] * 6 + [C.c_void_p] * 3
+        nf = f(int(bool(sim3_form)), C.byref(kf.view()), ur_kf.ctypes.data, hm.ctypes.data, n, xyz.ctypes.data, lv.ctypes.data, d.ctypes.data, st.ctypes.data, fc_.ctypes.data,
+               mn.ctypes.data, mx.ctypes.data, isg.ctypes.data, float(th), float(bf), float(fx), float(fy), float(cx), float(cy), uv.ctypes.data, ur.ctypes.data, best.ctypes.data)
+        return nf, best[:n], uv, ur
+
+    def fuse_search_port(self, kf, proj_uv, proj_ur, predicted_level, mp_desc, valid, inv_sigma2, th):
+        assert self.kind == "port"
+        uv = np.ascontiguousarray(proj_uv, np.float32); lv = np.ascontiguousarray(predicted_level, np.int32); d, va = _u8(mp_desc), _u8(valid)
+        ur = None if proj_ur is None else np.ascontiguousarray(proj_ur, np.float32); isg = np.ascontiguousarray(inv_sigma2, np.float32)
+        best = np.zeros(max(len(lv), 1), np.int32)
+        f = self.lib.port_fuse_search; f.restype = None
+        f.argtypes = [C.POINTER(FrameViewC), C.c_int] + [C.c_void_p] * 6 + [C.c_float, C.c_void_p]
+        f(C.byref(kf.view()), len(lv), uv.ctypes.data, None if ur is None else ur.ctypes.data, lv.ctypes.data, d.ctypes.data, va.ctypes.data, isg.ctypes.data, float(th), best.ctypes.data)
+        return best[:len(lv)]
+
     def compute_stereo_matches(self, ext_left, ext_right, keys_left, desc_left, keys_right, desc_right, mb, mbf):
         """ext_left / ext_right: oracle.Extractor of the same kind whose last extract() saw the left / right image."""
         kl = np.ascontiguousarray(keys_left, KP_DTYPE); kr = np.ascontiguousarray(keys_right, KP_DTYPE)

@@ -284,6 +284,40 @@ static void Sim3Pass(const FrameView* target, int nq, const float* proj_uv, cons
     }
 }
 
+// The search inside ORBmatcher::Fuse (pose form :1020-1175 with its chi-square gate when proj_ur is given, Sim3 form :1179-1310 without)
+static void FuseSearch(const FrameView* kf, int n_points, const float* proj_uv, const float* proj_ur, const int* predicted_level, const unsigned char* mp_desc,
+                       const unsigned char* valid, const float* inv_sigma2, float th, int* best_idx) {
+    Grid g(kf);
+    std::vector<int> cands;
+    for (int p = 0; p < n_points; ++p) {
+        best_idx[p] = -1;
+        if (!valid[p]) continue;
+        const float u = proj_uv[2 * p], v = proj_uv[2 * p + 1];
+        const int lvl = predicted_level[p];
+        g.area(u, v, th * kf->scale_factors[lvl], -1, -1, cands);
+        int bestDist = 256, bestIdx = -1;
+        for (size_t k = 0; k < cands.size(); ++k) {
+            const int idx = cands[k];
+            const KeyPoint& kp = kf->keys_un[idx];
+            if (kp.octave < lvl - 1 || kp.octave > lvl) continue;
+            if (proj_ur) {
+                volatile float ex = u - kp.pt.x, ey = v - kp.pt.y;
+                if (kf->u_right && kf->u_right[idx] >= 0) {
+                    volatile float er = proj_ur[p] - kf->u_right[idx];
+                    volatile float e2 = ex * ex + ey * ey + er * er, s = e2 * inv_sigma2[kp.octave];
+                    if ((double)s > 7.8) continue;
+                } else {
+                    volatile float e2 = ex * ex + ey * ey, s = e2 * inv_sigma2[kp.octave];
+                    if ((double)s > 5.99) continue;
+                }
+            }
+            const int dist = DescriptorDistance(mp_desc + (size_t)p * 32, kf->descriptors + (size_t)idx * 32);
+            if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+        }
+        if (bestDist <= TH_LOW) best_idx[p] = bestIdx;
+    }
+}
+
 // ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>&, th)   ORBmatcher.cc:70-175
 static int SearchByProjectionPoints(float nnratio, const FrameView* F, int n_points, const float* track_uv, const float* track_ur, const int* track_level,
                                     const float* track_view_cos, const unsigned char* mp_desc, const unsigned char* mp_observed, const unsigned char* f_occupied,
@@ -522,6 +556,10 @@ int port_search_by_sim3(const FrameView* kf1, const FrameView* kf2, const float*
         if (m1[i1] >= 0 && m2[m1[i1]] == i1) { match12[i1] = m1[i1]; ++nFound; }
     }
     return nFound;
+}
+void port_fuse_search(const FrameView* kf, int n_points, const float* proj_uv, const float* proj_ur, const int* predicted_level, const unsigned char* mp_desc,
+                      const unsigned char* valid, const float* inv_sigma2, float th, int* best_idx) {
+    port::FuseSearch(kf, n_points, proj_uv, proj_ur, predicted_level, mp_desc, valid, inv_sigma2, th, best_idx);
 }
 int port_search_by_projection_points(float nnratio, int checkOri, const FrameView* F, int n_points, const float* track_uv, const float* track_ur, const int* track_level,
                                      const float* track_view_cos, const unsigned char* mp_desc, const unsigned char* mp_observed, const unsigned char* f_occupied,

@@ -32,7 +32,7 @@ class MapPoint {               // the members ORBmatcher.cc:70-175 and :1569-172
 public:
     bool mbTrackInView; int mnTrackScaleLevel; float mTrackViewCos, mTrackProjX, mTrackProjY, mTrackProjXR;
     bool bad; int nobs; cv::Mat desc, pos; float maxd, mind; int plevel;
-    MapPoint() : mbTrackInView(true), mnTrackScaleLevel(0), mTrackViewCos(1.f), mTrackProjX(0), mTrackProjY(0), mTrackProjXR(0), bad(false), nobs(0), maxd(1e30f), mind(0.f), plevel(0), in_kf(NULL), in_idx(-1) {}
+    MapPoint() : mbTrackInView(true), mnTrackScaleLevel(0), mTrackViewCos(1.f), mTrackProjX(0), mTrackProjY(0), mTrackProjXR(0), bad(false), nobs(0), maxd(1e30f), mind(0.f), plevel(0), in_kf(NULL), in_idx(-1), fused_idx(-1), replaced_with(NULL) {}
     float GetMaxDistanceInvariance() { return maxd; }
     float GetMinDistanceInvariance() { return mind; }
     int PredictScale(const float&, Frame*) { return plevel; }          // the level is an input of the C-ABI call: the harness supplies it
@@ -41,11 +41,19 @@ public:
     cv::Mat GetNormal() { return normal.clone(); }
     KeyFrame* in_kf; int in_idx;                                       // one observation is enough for SearchBySim3's vbAlreadyMatched2 (:1350)
     int GetIndexInKeyFrame(KeyFrame* kf) { return kf == in_kf ? in_idx : -1; }
+    bool IsInKeyFrame(KeyFrame* kf) { return kf == in_kf; }
+    // Fuse's map surgery is recorded, not performed: the harness reads which KeyFrame feature each point was fused with
+    int fused_idx; MapPoint* replaced_with;
+    void Replace(MapPoint* p);                                         // logged (below)
+    void AddObservation(KeyFrame*, size_t idx) { fused_idx = (int)idx; }
     bool isBad() { return bad; }
     int Observations() { return nobs; }
     cv::Mat GetDescriptor() { return desc.clone(); }
     cv::Mat GetWorldPos() { return pos.clone(); }
 };
+
+static std::vector<std::pair<MapPoint*, MapPoint*> > g_replace_log;  // (this, argument) of every MapPoint::Replace call, in order
+inline void MapPoint::Replace(MapPoint* p) { replaced_with = p; g_replace_log.push_back(std::make_pair(this, p)); }
 
 class Frame {                  // include/Frame.h, only what the extracted bodies use
 public:
@@ -85,7 +93,10 @@ public:
     cv::Mat GetTranslation() { return tcw.empty() ? cv::Mat(cv::Mat::zeros(3, 1, CV_32F)) : tcw.clone(); }
     cv::Mat GetCameraCenter() { return Ow.empty() ? cv::Mat(cv::Mat::zeros(3, 1, CV_32F)) : Ow.clone(); }
     MapPoint* GetMapPoint(const size_t& idx) { return mvpMapPoints[idx]; }
-    std::vector<float> mvuRight, mvLevelSigma2;
+    void AddMapPoint(MapPoint* p, const size_t& idx) { mvpMapPoints[idx] = p; }
+    std::set<MapPoint*> GetMapPoints() { std::set<MapPoint*> s; for (size_t i = 0; i < mvpMapPoints.size(); ++i) if (mvpMapPoints[i]) s.insert(mvpMapPoints[i]); return s; }
+    float mbf;
+    std::vector<float> mvuRight, mvLevelSigma2, mvInvLevelSigma2;
     std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r) const;
     bool IsInImage(const float& x, const float& y) const;
     std::vector<MapPoint*> mvpMapPoints;
@@ -112,6 +123,8 @@ public:
     int SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const std::set<MapPoint*>& sAlreadyFound, const float th, const int ORBdist);
     int SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const std::vector<MapPoint*>& vpPoints, std::vector<MapPoint*>& vpMatched, int th);
     int SearchBySim3(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12, const float& s12, const cv::Mat& R12, const cv::Mat& t12, const float th);
+    int Fuse(KeyFrame* pKF, const std::vector<MapPoint*>& vpMapPoints, const float th = 3.0);
+    int Fuse(KeyFrame* pKF, cv::Mat Scw, const std::vector<MapPoint*>& vpPoints, float th, std::vector<MapPoint*>& vpReplacePoint);
     int SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F12, std::vector<std::pair<size_t, size_t> >& vMatchedPairs, const bool bOnlyStereo);
     bool CheckDistEpipolarLine(const cv::KeyPoint& kp1, const cv::KeyPoint& kp2, const cv::Mat& F12, const KeyFrame* pKF);
     int SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12);
@@ -463,6 +476,66 @@ int ref_search_for_triangulation(float nnratio, int checkOri, int n1, const cv::
         for (size_t q = 0; q < pairs.size(); ++q) match12[pairs[q].first] = (int)pairs[q].second;
     }
     return nm;
+}
+
+// ORBmatcher::Fuse, both forms (ORBmatcher.cc:1020, 1179), KeyFrame at the world origin / Scw = identity.  The KeyFrame's own map points
+// (kf_has_mp) are good and never in vpMapPoints; state[p]: 1 good, 2 bad, 3 already observed in the KeyFrame; facing as above.
+// Output best_idx[p] = the KeyFrame feature the body fused point p with (from the recorded Replace / AddObservation / vpReplacePoint), -1 = none.
+int ref_fuse(int sim3_form, const FrameView* kfv, const float* kf_uright, const unsigned char* kf_has_mp, int n_points, const float* cam_xyz, const int* predicted_level,
+             const unsigned char* mp_desc, const unsigned char* state, const unsigned char* facing, const float* min_dist, const float* max_dist,
+             const float* inv_level_sigma2, float th, float bf, float fx, float fy, float cx, float cy, float* proj_uv, float* proj_ur, int* best_idx) {
+    ArenaScope scope;
+    int nf;
+    {
+        Frame G; KeyFrame K;
+        fill_keyframe(K, G, kfv, fx, fy, cx, cy);
+        K.mbf = bf; K.mvuRight.assign(kf_uright, kf_uright + kfv->n); K.mvInvLevelSigma2.assign(inv_level_sigma2, inv_level_sigma2 + kfv->nlevels);
+        std::vector<MapPoint> own(kfv->n), pts(n_points);
+        K.mvpMapPoints.assign(kfv->n, (MapPoint*)NULL);
+        for (int j = 0; j < kfv->n; ++j) if (kf_has_mp[j]) { K.mvpMapPoints[j] = &own[j]; own[j].in_kf = &K; own[j].in_idx = j; own[j].nobs = 1 + j % 3; }   // with the points' 1 + p % 4 both Replace directions occur
+        std::vector<MapPoint*> vp(n_points);
+        for (int p = 0; p < n_points; ++p) {
+            const float x = cam_xyz[3 * p], y = cam_xyz[3 * p + 1], z = cam_xyz[3 * p + 2];
+            pts[p].pos = cv::Mat(3, 1, CV_32F); pts[p].normal = cv::Mat(3, 1, CV_32F);
+            const float len = std::sqrt(x * x + y * y + z * z), sgn = facing[p] ? 1.f : -1.f;
+            pts[p].pos.at<float>(0) = x; pts[p].pos.at<float>(1) = y; pts[p].pos.at<float>(2) = z;
+            pts[p].normal.at<float>(0) = sgn * x / len; pts[p].normal.at<float>(1) = sgn * y / len; pts[p].normal.at<float>(2) = sgn * z / len;
+            pts[p].desc = cv::Mat(1, 32, CV_8U, (void*)(mp_desc + (size_t)p * 32)).clone();
+            pts[p].plevel = predicted_level[p]; pts[p].mind = min_dist[p]; pts[p].maxd = max_dist[p]; pts[p].nobs = 1 + p % 4;
+            pts[p].bad = state[p] == 2 || (sim3_form && state[p] == 3);    // "already in the KeyFrame" is a caller-side skip in both forms
+            if (state[p] == 3) pts[p].in_kf = &K;
+            vp[p] = &pts[p];
+            const float invz = 1 / z;
+            proj_uv[2 * p] = fx * (x * invz) + cx; proj_uv[2 * p + 1] = fy * (y * invz) + cy; proj_ur[p] = proj_uv[2 * p] - bf * invz;     // :1054-1065
+            best_idx[p] = -1;
+        }
+        ORBmatcher matcher(0.6f, true);
+        g_replace_log.clear();
+        if (!sim3_form) {
+            nf = matcher.Fuse(&K, vp, th);
+            // which KeyFrame feature did each point meet?  AddObservation names it directly; a Replace pairs the point with the map point that
+            // held the feature (a KeyFrame-owned one, or an earlier point that was added there)
+            for (size_t q = 0; q < g_replace_log.size(); ++q) {
+                MapPoint *a = g_replace_log[q].first, *b = g_replace_log[q].second;
+                for (int pass = 0; pass < 2; ++pass, std::swap(a, b)) {
+                    const bool a_is_point = a >= &pts[0] && a < &pts[0] + n_points;
+                    if (!a_is_point || a->fused_idx >= 0 || best_idx[a - &pts[0]] >= 0) continue;
+                    const bool b_is_own = kfv->n && b >= &own[0] && b < &own[0] + kfv->n;
+                    const int j = b_is_own ? (int)(b - &own[0]) : ((b >= &pts[0] && b < &pts[0] + n_points) ? b->fused_idx : -1);
+                    if (j >= 0) { best_idx[a - &pts[0]] = j; break; }
+                }
+            }
+            for (int p = 0; p < n_points; ++p) if (pts[p].fused_idx >= 0) best_idx[p] = pts[p].fused_idx;
+        } else {
+            std::vector<MapPoint*> repl(n_points, (MapPoint*)NULL);
+            nf = matcher.Fuse(&K, cv::Mat::eye(4, 4, CV_32F), vp, th, repl);
+            for (int p = 0; p < n_points; ++p) {
+                if (pts[p].fused_idx >= 0) best_idx[p] = pts[p].fused_idx;                       // AddObservation(pKF, bestIdx)  (:1299)
+                else if (repl[p]) best_idx[p] = (repl[p] >= &pts[0] && repl[p] < &pts[0] + n_points) ? repl[p]->fused_idx : repl[p]->in_idx;   // vpReplacePoint (:1294)
+            }
+        }
+    }
+    return nf;
 }
 
 // ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&)  ORBmatcher.cc:230  and  (KeyFrame*, KeyFrame*, ...)  :656.

@@ -32,5 +32,13 @@ s1, s2, already12 = mc.sim3_inputs(ka, kb)
 for i, th in enumerate(mc.SIM3_TH):
     nf, m12 = oracle.Matcher("ref").search_by_sim3_ref(F1, F, dict(s1, desc=da), dict(s2, desc=db), already12, th, mc.FX, mc.FY, mc.CX, mc.CY)
     out["sim3_%d_nf" % i] = np.array(nf); out["sim3_%d_m12" % i] = m12
+# both ORBmatcher::Fuse forms  (src/ORBmatcher.cc:1020-1175, 1179-1310): which KeyFrame feature every point was fused with
+fu = mc.fuse_inputs(ka, kb, pi)
+Fu = oracle.FrameData(kb, db, 640, 480, E.scale_factors, u_right=pi["u_right"])
+for i, th in enumerate(mc.FUSE_TH):
+    for sim3 in (0, 1):
+        nf, best, uvf, urf = oracle.Matcher("ref").fuse_ref(sim3, Fu, fu["kf_has_mp"], fu["xyz"], fu["lvl"], da, fu["state"], fu["facing"], fu["mind"], fu["maxd"], fu["inv_sigma2"],
+                                                          th, 40.0, mc.FX, mc.FY, mc.CX, mc.CY)
+        out["fuse_%d_%d_nf" % (i, sim3)] = np.array(nf); out["fuse_%d_%d_best" % (i, sim3)] = best; out["fuse_uv"] = uvf; out["fuse_ur"] = urf
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_match_kf.npz"), **out)
 print("wrote ref_match_kf.npz", [int(out["kf%d_nm" % i]) for i in range(len(mc.KF_CASES))])

@@ -2,6 +2,7 @@
 // forms touch (/root/reference/include/KeyFrame.h:84-92, 214, 337-364, 401), no behaviour.
 #ifndef KEYFRAME_H
 #define KEYFRAME_H
+#include <set>
 #include <vector>
 #include <opencv2/core/core.hpp>
 #include "MapPoint.h"
@@ -19,6 +20,10 @@ public:
     ORBVocabulary* mpORBvocabulary = nullptr;
     bool IsInImage(const float &x, const float &y) const { return (x >= mnMinX && x < mnMaxX && y >= mnMinY && y < mnMaxY); }   // src/KeyFrame.cc:799-802
     MapPoint* GetMapPoint(const size_t &idx) { return mvpMapPoints[idx]; }
+    void AddMapPoint(MapPoint* pMP, const size_t &idx) { mvpMapPoints[idx] = pMP; }
+    std::set<MapPoint*> GetMapPoints() { std::set<MapPoint*> s; for (size_t i = 0; i < mvpMapPoints.size(); ++i) if (mvpMapPoints[i]) s.insert(mvpMapPoints[i]); return s; }
+    float mbf = 0;
+    std::vector<float> mvInvLevelSigma2;
     cv::Mat GetCameraCenter() { return mOw; }
     cv::Mat mOw;
     std::vector<float> mvuRight, mvLevelSigma2;

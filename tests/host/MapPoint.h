@@ -15,6 +15,10 @@ public:
     float GetMinDistanceInvariance() { return mfMinDistance; }
     float GetMaxDistanceInvariance() { return mfMaxDistance; }
     template <class FrameT> int PredictScale(const float&, FrameT*) { return nPredictedLevel; }
+    template <class KF> bool IsInKeyFrame(KF* kf) { return (const void*)kf == pInKF; }
+    template <class KF> void AddObservation(KF* kf, size_t idx) { pInKF = kf; nIdxInKF = (int)idx; ++nObs; }
+    void Replace(MapPoint* p) { pReplaced = p; mbBad = true; }
+    MapPoint* pReplaced = nullptr;
     template <class KF> int GetIndexInKeyFrame(KF* kf) { return (const void*)kf == pInKF ? nIdxInKF : -1; }
     const void* pInKF = nullptr; int nIdxInKF = -1;
     float mfMinDistance = 0.f, mfMaxDistance = 1e30f; int nPredictedLevel = 0;

@@ -119,3 +119,30 @@ def sim3_inputs(ka, kb, seed=21):
     am2 = np.zeros(len(kb), bool); am2[already12[already12 >= 0]] = True
     s2["valid"] = (s2["ok"] & ~am2).astype(np.uint8)
     return s1, s2, already12
+
+
+FUSE_TH = [3.0, 4.0]                                                     # LocalMapping::SearchInNeighbors: Fuse(pKFi, vpMapPointMatches) with th = 3; LoopClosing: 4
+
+
+def fuse_inputs(ka, kb, pi, seed=29):
+    """Inputs of both ORBmatcher::Fuse forms (identity pose): map points near the features of KeyFrame B, state 1 good / 2 bad / 3 already in
+    the KeyFrame, normals facing or not, and which KeyFrame features hold a map point."""
+    rng = np.random.default_rng(seed); n = len(ka)
+    state = rng.choice([1, 1, 1, 1, 2, 3], n).astype(np.uint8)
+    facing = (rng.random(n) < 0.85).astype(np.uint8)
+    lvl = np.clip(ka["octave"] + rng.integers(0, 2, n), 0, 7).astype(np.int32)
+    z = rng.uniform(0.5, 8, n).astype(np.float32)
+    xyz = np.stack([(ka["x"] + 7 + rng.normal(0, 0.7, n) - CX) / FX * z, (ka["y"] - 4 + rng.normal(0, 0.7, n) - CY) / FY * z, z], 1).astype(np.float32)
+    xyz[::43, 2] *= -1
+    d3 = np.sqrt((xyz.astype(np.float64) ** 2).sum(1)).astype(np.float32)
+    mind = (d3 * rng.choice([0.5, 0.5, 1.2], n)).astype(np.float32); maxd = (d3 * rng.choice([2.0, 2.0, 0.8], n)).astype(np.float32)
+    kf_has_mp = (rng.random(len(kb)) < 0.5).astype(np.uint8)
+    invz = (np.float32(1.0) / xyz[:, 2]).astype(np.float32)
+    u = (np.float32(FX) * (xyz[:, 0] * invz) + np.float32(CX)).astype(np.float32); v = (np.float32(FY) * (xyz[:, 1] * invz) + np.float32(CY)).astype(np.float32)
+    ur = (u - np.float32(40.0) * invz).astype(np.float32)
+    inimg = (u >= 0) & (u < 640) & (v >= 0) & (v < 480)
+    valid = ((state == 1) & (xyz[:, 2] >= 0) & inimg & ~((d3 < mind) | (d3 > maxd)) & (facing > 0)).astype(np.uint8)
+    sf = (np.float32(1.2) ** np.arange(8, dtype=np.float32)).astype(np.float32)
+    inv_sigma2 = (np.float32(1.0) / (sf * sf)).astype(np.float32)                          # mvInvLevelSigma2 (ORBextractor.cc:519-523)
+    return dict(state=state, facing=facing, lvl=lvl, xyz=xyz, mind=mind, maxd=maxd, kf_has_mp=kf_has_mp, uv=np.stack([u, v], 1).astype(np.float32), ur=ur, valid=valid,
+                inv_sigma2=inv_sigma2)

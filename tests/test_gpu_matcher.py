@@ -161,3 +161,14 @@ def test_search_by_sim3(orbx, case):
     e = orbx.FrameView(kb[:0], case["db"][:0], 640, 480, case["sf"])
     nf, m12 = orbx.ORBmatcher().SearchBySim3(case["FA"], e, s1["uv"], s1["lvl"], case["da"], s1["valid"], s2["uv"][:0], s2["lvl"][:0], case["db"][:0], s2["valid"][:0], 7.5)
     assert nf == 0 and np.all(m12 == -1)
+
+
+def test_fuse_search(orbx, case):
+    """The search of both ORBmatcher::Fuse forms (chi-square gated / plain) against what the reference bodies fused each point with."""
+    GK = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_match_kf.npz"))
+    ka, kb, pi = case["ka"], case["kb"], case["pi"]
+    fu = mc.fuse_inputs(ka, kb, pi)
+    for i, th in enumerate(mc.FUSE_TH):
+        for sim3 in (0, 1):
+            best = orbx.ORBmatcher().FuseSearch(case["FBu"], fu["uv"], None if sim3 else fu["ur"], fu["lvl"], case["da"], fu["valid"], fu["inv_sigma2"], th)
+            assert np.array_equal(best, GK["fuse_%d_%d_best" % (i, sim3)])

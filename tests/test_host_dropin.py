@@ -44,7 +44,7 @@ def test_host_classes_compile_and_link():
               "ORB_SLAM2::ORBmatcher::SearchForInitialization", "ORB_SLAM2::ORBmatcher::SearchByProjection", "ORB_SLAM2::Frame::ComputeStereoMatches",
               "ORB_SLAM2::Frame::UndistortKeyPoints", "ORB_SLAM2::Frame::ComputeStereoFromRGBD", "ORB_SLAM2::Frame::AssignFeaturesToGrid",
               "ORB_SLAM2::Frame::ComputeBoW", "ORB_SLAM2::KeyFrame::ComputeBoW", "ORB_SLAM2::ORBmatcher::SearchByBoW", "ORB_SLAM2::RegisterDeviceVocabulary",
-              "ORB_SLAM2::ORBmatcher::SearchBySim3", "ORB_SLAM2::ORBmatcher::SearchForTriangulation"):
+              "ORB_SLAM2::ORBmatcher::SearchBySim3", "ORB_SLAM2::ORBmatcher::SearchForTriangulation", "ORB_SLAM2::ORBmatcher::Fuse"):
         assert s in syms, s
 
 

@@ -129,3 +129,18 @@ def test_port_search_by_sim3_matches_reference_golden(oracle):
     for i, th in enumerate(mc.SIM3_TH):
         nf, m12 = oracle.Matcher("port").search_by_sim3_port(F1, F2, s1["uv"], s1["lvl"], da, s1["valid"], s2["uv"], s2["lvl"], db, s2["valid"], th)
         assert nf == int(GK["sim3_%d_nf" % i]) and nf > 5 and np.array_equal(m12, GK["sim3_%d_m12" % i])
+
+
+def test_port_fuse_search_matches_reference_golden(oracle):
+    """Both ORBmatcher::Fuse forms (ORBmatcher.cc:1020-1310): the feature each point is fused with, port vs the reference bodies' committed outputs."""
+    import os
+    GK = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_match_kf.npz"))
+    E = oracle.Extractor("port", 1000, 1.2, 8, 20, 7)
+    ka, da, kb, db = mc.mono_pair(lambda img: E.extract(img))
+    pi = mc.projection_inputs(ka, kb); fu = mc.fuse_inputs(ka, kb, pi)
+    assert np.array_equal(fu["uv"], GK["fuse_uv"]) and np.array_equal(fu["ur"], GK["fuse_ur"])
+    F = oracle.FrameData(kb, db, 640, 480, E.scale_factors, u_right=pi["u_right"])
+    for i, th in enumerate(mc.FUSE_TH):
+        for sim3 in (0, 1):
+            best = oracle.Matcher("port").fuse_search_port(F, fu["uv"], None if sim3 else fu["ur"], fu["lvl"], da, fu["valid"], fu["inv_sigma2"], th)
+            assert np.array_equal(best, GK["fuse_%d_%d_best" % (i, sim3)]) and int((best >= 0).sum()) == int(GK["fuse_%d_%d_nf" % (i, sim3)]) > 10
