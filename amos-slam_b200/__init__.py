@@ -102,6 +102,7 @@ def lib():
         L.orbx_search_by_projection_keyframe_points.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp, cf, vp, C.POINTER(ci)]
         L.orbx_search_by_projection_keyframe_points_dev.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp, cf, vp, C.POINTER(ci)]
         L.orbx_fuse_search.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp, vp, cf, vp]
+        L.orbx_distinctive_descriptors.argtypes = [vp, ci, vp, vp, vp]
         L.orbx_search_by_sim3.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, cf, vp, C.POINTER(ci)]
         L.orbx_search_by_projection_keyframe_dev.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp, vp, cf, ci, vp, C.POINTER(ci)]
         L.orbx_compute_stereo_matches.argtypes = [vp, vp, vp, vp, vp, ci, vp, vp, ci, cf, cf, vp, vp]

@@ -320,6 +320,13 @@ class ORBmatcher:
         self._check(self._lib.orbx_fuse_search(self._h, C.byref(v), len(lv), _p(uv), _p(ur), _p(lv), _p(d), _p(va), _p(isg), float(th), _p(best)))
         return best[:len(lv)]
 
+    # void MapPoint::ComputeDistinctiveDescriptors(), batched over map points
+    def ComputeDistinctiveDescriptors(self, offsets, descriptors):
+        off = np.ascontiguousarray(offsets, np.int32); d = _u8(descriptors).reshape(-1, 32)
+        best = np.zeros(max(len(off) - 1, 1), np.int32)
+        self._check(self._lib.orbx_distinctive_descriptors(self._h, len(off) - 1, _p(off), _p(d), _p(best)))
+        return best[:len(off) - 1]
+
     # int SearchBySim3(KeyFrame *pKF1, KeyFrame *pKF2, vector<MapPoint*> &vpMatches12, const float &s12, const cv::Mat &R12, const cv::Mat &t12, const float th)
     def SearchBySim3(self, kf1, kf2, uv1, lvl1, desc1, valid1, uv2, lvl2, desc2, valid2, th):
         a = [np.ascontiguousarray(uv1, np.float32), np.ascontiguousarray(lvl1, np.int32), _u8(desc1), _u8(valid1),

@@ -251,6 +251,43 @@ k_tri_match(int n_pairs, const int2* __restrict__ pairs, BowSideDev s1, BowSideD
     }
 }
 
+// ---- MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:359-439), batched: one warp per map point ----
+// Row i of the N x N distance matrix (diagonal 0) is histogrammed over its 257 possible values in shared memory; the reference's
+// vDists[0.5 * (N - 1)] of the sorted row is the first value whose cumulative count exceeds that rank.  The first row with the smallest median wins.
+__global__ void __launch_bounds__(128)
+k_distinctive(int n_points, const int* __restrict__ offsets, const uint4* __restrict__ desc, int* __restrict__ best_idx) {
+    __shared__ int hist_s[4][264];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int p = blockIdx.x * 4 + w;
+    if (p >= n_points) return;
+    int* hist = hist_s[w];
+    const int o = offsets[p], N = offsets[p + 1] - o;
+    if (N <= 0) { if (lane == 0) best_idx[p] = -1; return; }
+    const int rank = (int)(0.5 * (double)(N - 1));
+    int bestMedian = 0x7FFFFFFF, bestIdx = 0;
+    for (int i = 0; i < N; ++i) {
+        for (int b = lane; b < 264; b += 32) hist[b] = 0;
+        __syncwarp();
+        const uint4 d0 = __ldg(desc + 2 * (o + i)), d1 = __ldg(desc + 2 * (o + i) + 1);
+        for (int j = lane; j < N; j += 32) atomicAdd(&hist[j == i ? 0 : hamming256(d0, d1, desc + 2 * (o + j))], 1);
+        __syncwarp();
+        // 257 bins, 9 per lane (lane 31 has fewer): exclusive prefix over the lanes, then the bin where the cumulative count passes the rank
+        int loc[9], sum = 0;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { const int b = lane * 9 + k; loc[k] = b < 257 ? hist[b] : 0; sum += loc[k]; }
+        int incl = sum;
+#pragma unroll
+        for (int s2 = 1; s2 < 32; s2 <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, s2); if (lane >= s2) incl += t; }
+        int cum = incl - sum, med = 0x7FFFFFFF;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { cum += loc[k]; if (med == 0x7FFFFFFF && cum > rank) med = lane * 9 + k; }
+        med = __reduce_min_sync(0xffffffffu, (unsigned)med);
+        if (med < bestMedian) { bestMedian = med; bestIdx = i; }
+        __syncwarp();
+    }
+    if (lane == 0) best_idx[p] = bestIdx;
+}
+
 // ComputeThreeMaxima (:1866-1908) + removal of the matches outside the three strongest rotation bins; counts the survivors
 __global__ void __launch_bounds__(1024)
 k_bow_finish(int n1, int checkOri, const int* __restrict__ hist, const int* __restrict__ bin_of, int* __restrict__ match12, int* __restrict__ match21, int* __restrict__ nmatches) {

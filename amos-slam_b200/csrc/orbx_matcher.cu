@@ -1172,6 +1172,31 @@ int orbx_search_for_triangulation(orbx_matcher* m, const orbx_bow_side* s1, cons
     return ORBX_OK;
 }
 
+int orbx_distinctive_descriptors(orbx_matcher* m, int n_points, const int* offsets, const uint8_t* descriptors, int* best_idx) {
+    if (!m || n_points < 0 || (n_points && (!offsets || !best_idx))) FAIL(ORBX_E_INVALID, "bad arguments");
+    if (n_points == 0) return ORBX_OK;
+    if (offsets[0] != 0) FAIL(ORBX_E_INVALID, "offsets must start at 0");
+    for (int p = 0; p < n_points; ++p) if (offsets[p + 1] < offsets[p]) FAIL(ORBX_E_INVALID, "offsets must not decrease");
+    const int total = offsets[n_points];
+    if (total && !descriptors) FAIL(ORBX_E_INVALID, "null descriptors");
+    CU_TRY(cudaSetDevice(m->device));
+    int rc;
+    const size_t need = pad((size_t)total * 32) + 2 * pad((size_t)(n_points + 1) * 4) + 8192;
+    if ((rc = m->arena.reserve(need)) || (rc = m->uparena.reserve(need))) return rc;
+    m->arena.reset(); m->uparena.reset();
+    uint8_t* dd; int* doff;
+    if ((rc = up(m, descriptors, (size_t)total * 32, dd)) || (rc = up(m, offsets, (size_t)n_points + 1, doff))) return rc;
+    int* dbest = m->arena.get<int>(n_points);
+    if (!dbest) FAIL(ORBX_E_CUDA, "matcher arena exhausted");
+    if ((rc = flush_uploads(m)) || (rc = m->ensure_download((size_t)n_points * 4))) return rc;
+    k_distinctive<<<(n_points + 3) / 4, 128, 0, m->stream>>>(n_points, doff, reinterpret_cast<const uint4*>(dd), dbest);
+    LAUNCH_CHECK();
+    CU_TRY(cudaMemcpyAsync(m->dl_host, dbest, (size_t)n_points * 4, cudaMemcpyDeviceToHost, m->stream));
+    CU_TRY(cudaStreamSynchronize(m->stream));
+    std::memcpy(best_idx, m->dl_host, (size_t)n_points * 4);
+    return ORBX_OK;
+}
+
 int orbx_match_bruteforce_device(orbx_matcher* m, const uint8_t* d_query, int n_query, const uint8_t* d_train, int n_train, int* d_best_idx, int* d_best_dist, int* d_second_dist) {
     return orbx_match_bruteforce_batch_device(m, 1, d_query, n_query, d_train, n_train, d_best_idx, d_best_dist, d_second_dist);
 }

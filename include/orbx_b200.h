@@ -460,6 +460,13 @@ int orbx_search_for_triangulation(orbx_matcher* m, const orbx_bow_side* s1, cons
                                   const float* F12, float ex, float ey, int nlevels2, const float* scale_factors2, const float* level_sigma2_2,
                                   int only_stereo, int* match12, int* nmatches);
 
+/* void MapPoint::ComputeDistinctiveDescriptors()   src/MapPoint.cc:359-439, for n_points map points at once.
+ *   Point p owns the descriptors [offsets[p], offsets[p + 1]) of `descriptors` (32 bytes each): those of its observations in non-bad
+ *   KeyFrames, in the iteration order of its mObservations map.  best_idx[p] = the index, inside that range, of the descriptor whose sorted
+ *   distance row has the smallest vDists[0.5 * (N - 1)] (first one on ties); -1 for a point without descriptors.  The caller then sets
+ *   mDescriptor = vDescriptors[best_idx].clone(). */
+int orbx_distinctive_descriptors(orbx_matcher* m, int n_points, const int* offsets, const uint8_t* descriptors, int* best_idx);
+
 #ifdef __cplusplus
 }
 #endif

@@ -534,3 +534,19 @@ def search_for_triangulation(kind, check_ori, keys1, desc1, free1, ur1, fv1, key
            len(k2), k2.ctypes.data, d2.ctypes.data, f2.ctypes.data, u2.ctypes.data, len(b[0]), b[0].ctypes.data, b[1].ctypes.data, b[2].ctypes.data,
            F.ctypes.data, ex, ey, sc.ctypes.data, sg.ctypes.data, int(bool(only_stereo)), m12.ctypes.data)
     return nm, m12[:len(k1)]
+
+
+def distinctive_descriptors(kind, offsets, obs_desc, kf_of=None, kf_bad=None):
+    """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:359).  'ref': the reference body on observation slots (kf_of[s] = KeyFrame of slot s,
+    kf_bad per KeyFrame) -> chosen descriptors [n_points, 32]; 'port': best index per point over the given (already filtered) descriptors."""
+    lib = _lib(kind)
+    off = np.ascontiguousarray(offsets, np.int32); d = np.ascontiguousarray(obs_desc, np.uint8).reshape(-1, 32); n = len(off) - 1
+    if kind == "ref":
+        ko = np.ascontiguousarray(kf_of, np.int32); kb = np.ascontiguousarray(kf_bad, np.uint8); out = np.zeros((max(n, 1), 32), np.uint8)
+        f = lib.ref_distinctive_descriptors; f.restype = C.c_int; f.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        f(n, off.ctypes.data, d.ctypes.data, len(kb), ko.ctypes.data, kb.ctypes.data, out.ctypes.data)
+        return out[:n]
+    best = np.zeros(max(n, 1), np.int32)
+    f = lib.port_distinctive_descriptors; f.restype = None; f.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    f(n, off.ctypes.data, d.ctypes.data, best.ctypes.data)
+    return best[:n]

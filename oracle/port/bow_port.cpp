@@ -7,6 +7,8 @@
 //   ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, ...)   /root/reference/src/ORBmatcher.cc:656-799
 // Pinned against oracle/_ref (the reference's own DBoW2 sources and matcher bodies) by tests/test_oracle_bow.py and the golden
 // vectors in tests/golden/ref_bow.npz.  Same argument layout as the product's C ABI (include/orbx_b200.h).
+#include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstring>
 #include <map>
@@ -233,6 +235,25 @@ int port_search_for_triangulation(int checkOri, int n1, const unsigned char* key
         }
     }
     return nmatches;
+}
+
+
+// MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:359-439) for many points: per point the descriptor with the least median distance to the others
+void port_distinctive_descriptors(int n_points, const int* offsets, const unsigned char* desc, int* best_idx) {
+    for (int p = 0; p < n_points; ++p) {
+        const int o = offsets[p], N = offsets[p + 1] - o;
+        best_idx[p] = -1;
+        if (N <= 0) continue;
+        int bestMedian = INT_MAX, best = 0;
+        std::vector<int> row(N);
+        for (int i = 0; i < N; ++i) {
+            for (int j = 0; j < N; ++j) row[j] = i == j ? 0 : hamming(desc + (size_t)(o + i) * 32, desc + (size_t)(o + j) * 32);
+            std::sort(row.begin(), row.end());
+            const int median = row[(size_t)(0.5 * (N - 1))];
+            if (median < bestMedian) { bestMedian = median; best = i; }
+        }
+        best_idx[p] = best;
+    }
 }
 
 }  // extern "C"

@@ -9,6 +9,7 @@ output -- nothing is copied into the repository).  The functions are located by 
                       SearchByBoW(KeyFrame*, Frame&, ...), SearchByBoW(KeyFrame*, KeyFrame*, ...),
                       SearchByProjection(Frame&, KeyFrame*, const set<MapPoint*>&, th, ORBdist)
   src/KeyFrame.cc   : GetFeaturesInArea, IsInImage
+  src/MapPoint.cc   : ComputeDistinctiveDescriptors
   Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h : transform(features, BowVector, FeatureVector, levelsup), transform(feature, ...)
   src/Frame.cc      : AssignFeaturesToGrid, GetFeaturesInArea, PosInGrid, ComputeStereoMatches,
                       UndistortKeyPoints, ComputeImageBounds, ComputeStereoFromRGBD
@@ -84,6 +85,7 @@ kf = extract("src/KeyFrame.cc", [
     "vector<size_t> KeyFrame::GetFeaturesInArea(const float &x, const float &y, const float &r) const",
     "bool KeyFrame::IsInImage(const float &x, const float &y) const",
 ])
+mp = extract("src/MapPoint.cc", ["void MapPoint::ComputeDistinctiveDescriptors()"])
 # DBoW2 (vendored in the reference tree): the two transform() members of the vocabulary template, for oracle/ref/ref_bow_capi.cpp
 b = extract("Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h", [
     "void TemplatedVocabulary<TDescriptor,F>::transform(\n  const std::vector<TDescriptor>& features,\n  BowVector &v, FeatureVector &fv, int levelsup) const",
@@ -93,5 +95,5 @@ b = b.replace("void TemplatedVocabulary<TDescriptor,F>::transform(", "template<c
 os.makedirs(out, exist_ok=True)
 open(os.path.join(out, "ref_bow_bodies.inc"), "w").write("// GENERATED from the reference sources by oracle/ref/gen_match_bodies.py -- do not commit\n" + b)
 # the first ORBmatcher chunk (constants) ends at the ctor's closing brace because the ctor follows immediately
-open(os.path.join(out, "ref_match_bodies.inc"), "w").write("// GENERATED from the reference sources by oracle/ref/gen_match_bodies.py -- do not commit\n" + m + "\n" + f + "\n" + kf)
+open(os.path.join(out, "ref_match_bodies.inc"), "w").write("// GENERATED from the reference sources by oracle/ref/gen_match_bodies.py -- do not commit\n" + m + "\n" + f + "\n" + kf + "\n" + mp)
 print("generated", os.path.join(out, "ref_match_bodies.inc"))

@@ -11,6 +11,8 @@
 #include "Thirdparty/DBoW2/DBoW2/FeatureVector.h"   // reference header (mFeatVec in SearchByBoW); FeatureVector.cpp is built in ref_bow_capi.cpp
 #include <climits>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <set>
 #include <vector>
 #include <list>
@@ -32,7 +34,7 @@ class MapPoint {               // the members ORBmatcher.cc:70-175 and :1569-172
 public:
     bool mbTrackInView; int mnTrackScaleLevel; float mTrackViewCos, mTrackProjX, mTrackProjY, mTrackProjXR;
     bool bad; int nobs; cv::Mat desc, pos; float maxd, mind; int plevel;
-    MapPoint() : mbTrackInView(true), mnTrackScaleLevel(0), mTrackViewCos(1.f), mTrackProjX(0), mTrackProjY(0), mTrackProjXR(0), bad(false), nobs(0), maxd(1e30f), mind(0.f), plevel(0), in_kf(NULL), in_idx(-1), fused_idx(-1), replaced_with(NULL) {}
+    MapPoint() : mbTrackInView(true), mnTrackScaleLevel(0), mTrackViewCos(1.f), mTrackProjX(0), mTrackProjY(0), mTrackProjXR(0), bad(false), nobs(0), maxd(1e30f), mind(0.f), plevel(0), in_kf(NULL), in_idx(-1), mbBad(false), fused_idx(-1), replaced_with(NULL) {}
     float GetMaxDistanceInvariance() { return maxd; }
     float GetMinDistanceInvariance() { return mind; }
     int PredictScale(const float&, Frame*) { return plevel; }          // the level is an input of the C-ABI call: the harness supplies it
@@ -43,6 +45,9 @@ public:
     int GetIndexInKeyFrame(KeyFrame* kf) { return kf == in_kf ? in_idx : -1; }
     bool IsInKeyFrame(KeyFrame* kf) { return kf == in_kf; }
     // Fuse's map surgery is recorded, not performed: the harness reads which KeyFrame feature each point was fused with
+    // MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:359-439) reads these (include/MapPoint.h:228-262)
+    void ComputeDistinctiveDescriptors();
+    std::mutex mMutexFeatures; bool mbBad; std::map<KeyFrame*, size_t> mObservations; cv::Mat mDescriptor;
     int fused_idx; MapPoint* replaced_with;
     void Replace(MapPoint* p);                                         // logged (below)
     void AddObservation(KeyFrame*, size_t idx) { fused_idx = (int)idx; }
@@ -85,9 +90,10 @@ public:
 
 class KeyFrame {               // include/KeyFrame.h, the members SearchByBoW / SearchByProjection(KeyFrame*, Scw, ...) read
 public:
-    KeyFrame() : N(0), fx(0), fy(0), cx(0), cy(0), mnGridCols(FRAME_GRID_COLS), mnGridRows(FRAME_GRID_ROWS), mfGridElementWidthInv(0), mfGridElementHeightInv(0),
+    KeyFrame() : kf_bad(false), N(0), fx(0), fy(0), cx(0), cy(0), mnGridCols(FRAME_GRID_COLS), mnGridRows(FRAME_GRID_ROWS), mfGridElementWidthInv(0), mfGridElementHeightInv(0),
                  mnMinX(0), mnMinY(0), mnMaxX(0), mnMaxY(0) {}
     std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
+    bool kf_bad; bool isBad() { return kf_bad; }
     cv::Mat Rcw, tcw, Ow;                                              // empty = KeyFrame at the world origin
     cv::Mat GetRotation() { return Rcw.empty() ? cv::Mat(cv::Mat::eye(3, 3, CV_32F)) : Rcw.clone(); }
     cv::Mat GetTranslation() { return tcw.empty() ? cv::Mat(cv::Mat::zeros(3, 1, CV_32F)) : tcw.clone(); }
@@ -536,6 +542,26 @@ int ref_fuse(int sim3_form, const FrameView* kfv, const float* kf_uright, const 
         }
     }
     return nf;
+}
+
+// MapPoint::ComputeDistinctiveDescriptors   MapPoint.cc:359.  Point p is observed in KeyFrames kf_of[offsets[p] .. offsets[p + 1]) (ascending, which
+// is also the address order of the harness's KeyFrame array and therefore the iteration order of mObservations) at feature 0 of a one-row
+// descriptor matrix each; kf_bad marks bad KeyFrames.  Output: chosen[p][32] = mDescriptor after the call (zeros if it was never set).
+int ref_distinctive_descriptors(int n_points, const int* offsets, const unsigned char* obs_desc, int n_kf, const int* kf_of, const unsigned char* kf_bad, unsigned char* chosen) {
+    ArenaScope scope;
+    {
+        const int total = offsets[n_points];
+        // one KeyFrame object per observation slot keeps "descriptor row of this observation" simple: slot s lives in KeyFrame s
+        std::vector<KeyFrame> kfs(total);
+        for (int s = 0; s < total; ++s) { kfs[s].mDescriptors = cv::Mat(1, 32, CV_8U, (void*)(obs_desc + (size_t)s * 32)).clone(); kfs[s].kf_bad = kf_bad[kf_of[s]] != 0; }
+        std::vector<MapPoint> pts(n_points);
+        for (int p = 0; p < n_points; ++p) {
+            for (int s = offsets[p]; s < offsets[p + 1]; ++s) pts[p].mObservations[&kfs[s]] = 0;
+            pts[p].ComputeDistinctiveDescriptors();
+            if (!pts[p].mDescriptor.empty()) std::memcpy(chosen + (size_t)p * 32, pts[p].mDescriptor.ptr(), 32); else std::memset(chosen + (size_t)p * 32, 0, 32);
+        }
+    }
+    return 0;
 }
 
 // ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&)  ORBmatcher.cc:230  and  (KeyFrame*, KeyFrame*, ...)  :656.

@@ -79,3 +79,26 @@ def tri_inputs(n1, n2, seed=31):
     ur1 = np.where(rng.random(n1) < 0.4, rng.uniform(0, 600, n1), -1).astype(np.float32); ur2 = np.where(rng.random(n2) < 0.4, rng.uniform(0, 600, n2), -1).astype(np.float32)
     sf = (np.float32(1.2) ** np.arange(8, dtype=np.float32)).astype(np.float32)
     return dict(free1=free1, free2=free2, ur1=ur1, ur2=ur2, sf=sf, sigma2=(sf * sf).astype(np.float32))
+
+
+def distinctive_inputs(pool, n_points=300, n_kf=60, seed=41):
+    """Map points with 0..40 observations: noisy copies of one pool descriptor each (plus a few outliers), spread over n_kf KeyFrames of which some
+    are bad.  Returns the observation slots (offsets, descriptors, KeyFrame of every slot, bad flags) and the filtered lists a C-ABI caller passes."""
+    rng = np.random.default_rng(seed)
+    counts = rng.integers(0, 41, n_points); counts[:6] = [0, 1, 2, 3, 40, 33]
+    offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    desc = np.zeros((offsets[-1], 32), np.uint8); kf_of = np.zeros(offsets[-1], np.int32)
+    for p in range(n_points):
+        base = pool[rng.integers(0, len(pool))]
+        for s in range(offsets[p], offsets[p + 1]):
+            d = base.copy() if rng.random() > 0.1 else pool[rng.integers(0, len(pool))].copy()
+            flips = rng.integers(0, 256, rng.integers(0, 30))
+            for b in flips:
+                d[b >> 3] ^= np.uint8(1 << (b & 7))
+            desc[s] = d
+        kf_of[offsets[p]:offsets[p + 1]] = np.sort(rng.choice(n_kf, counts[p], replace=False))
+    kf_bad = (rng.random(n_kf) < 0.1).astype(np.uint8)
+    keep = kf_bad[kf_of] == 0
+    f_counts = np.array([keep[offsets[p]:offsets[p + 1]].sum() for p in range(n_points)])
+    f_offsets = np.concatenate([[0], np.cumsum(f_counts)]).astype(np.int32)
+    return dict(offsets=offsets, desc=desc, kf_of=kf_of, kf_bad=kf_bad, f_offsets=f_offsets, f_desc=desc[keep])

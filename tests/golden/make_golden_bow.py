@@ -37,5 +37,8 @@ t = bc.tri_inputs(len(ka), len(kb))
 for i, (ori, st) in enumerate(bc.TRI_VARIANTS):
     nm, m12, epi = oracle.search_for_triangulation("ref", ori, ka, da, t["free1"], t["ur1"], fa, kb, db, t["free2"], t["ur2"], fb, bc.TRI_F12, bc.TRI_C2, bc.TRI_CAM, t["sf"], t["sigma2"], st)
     out["tri_%d_nm" % i] = np.array(nm); out["tri_%d_m12" % i] = m12; out["tri_epi"] = epi
+# MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:359-439): the descriptor the reference body selects for every seeded map point
+di = bc.distinctive_inputs(np.concatenate([da, db]))
+out["distinctive_chosen"] = oracle.distinctive_descriptors("ref", di["offsets"], di["desc"], di["kf_of"], di["kf_bad"])
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ref_bow.npz"), **out)
 print("wrote ref_bow.npz:", len(out), "arrays")

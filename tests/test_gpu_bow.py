@@ -99,3 +99,17 @@ def test_search_for_triangulation_matches_reference_body(orbx, oracle):
         g = orbx.ORBmatcher(0.6, True).SearchForTriangulation(ka, da, t["free1"], t["ur1"], fa, kb, db, t["free2"], t["ur2"], fb, F2, (100.0, 400.0), t["sf"], t["sigma2"], False)
         o = oracle.search_for_triangulation("port", True, ka, da, t["free1"], t["ur1"], fa, kb, db, t["free2"], t["ur2"], fb, F2, (100.0, 400.0), bc.TRI_CAM, t["sf"], t["sigma2"], False)
         assert g[0] == o[0] and np.array_equal(g[1], o[1]), lu
+
+
+def test_distinctive_descriptors_match_reference_body(orbx, oracle):
+    """MapPoint::ComputeDistinctiveDescriptors batched over 300 map points (0..40 observations each) against the reference body's selection."""
+    from test_oracle_bow import check_distinctive
+    di = bc.distinctive_inputs(np.concatenate([G["da"], G["db"]]))
+    best = orbx.ORBmatcher().ComputeDistinctiveDescriptors(di["f_offsets"], di["f_desc"])
+    check_distinctive(best, di)
+    assert np.array_equal(best, oracle.distinctive_descriptors("port", di["f_offsets"], di["f_desc"]))
+    # one point with many observations (more than one histogram pass per lane) and an empty call
+    big = np.concatenate([G["da"][:700], G["db"][:300]])
+    off = np.array([0, 1000], np.int32)
+    assert np.array_equal(orbx.ORBmatcher().ComputeDistinctiveDescriptors(off, big), oracle.distinctive_descriptors("port", off, big))
+    assert len(orbx.ORBmatcher().ComputeDistinctiveDescriptors(np.array([0], np.int32), np.zeros((0, 32), np.uint8))) == 0

@@ -70,3 +70,19 @@ def test_port_search_for_triangulation_matches_reference_body(oracle):
     for i, (ori, st) in enumerate(bc.TRI_VARIANTS):
         nm, m12 = oracle.search_for_triangulation("port", ori, ka, da, t["free1"], t["ur1"], fa, kb, db, t["free2"], t["ur2"], fb, bc.TRI_F12, G["tri_epi"], bc.TRI_CAM, t["sf"], t["sigma2"], st)
         assert nm == int(G["tri_%d_nm" % i]) and nm > 10 and np.array_equal(m12, G["tri_%d_m12" % i])
+
+
+def check_distinctive(best, di):
+    ch = G["distinctive_chosen"]
+    assert len(best) == len(ch) and (best < 0).sum() >= 1
+    for p in range(len(best)):
+        if best[p] < 0:
+            assert not ch[p].any() and di["f_offsets"][p + 1] == di["f_offsets"][p]
+        else:
+            assert np.array_equal(ch[p], di["f_desc"][di["f_offsets"][p] + best[p]]), p
+
+
+def test_port_distinctive_descriptors_match_reference_body(oracle):
+    """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:359-439): port vs the descriptors the reference body selected."""
+    di = bc.distinctive_inputs(np.concatenate([G["da"], G["db"]]))
+    check_distinctive(oracle.distinctive_descriptors("port", di["f_offsets"], di["f_desc"]), di)
