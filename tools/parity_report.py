@@ -136,6 +136,54 @@ def bow_rows(pairs, kind):
     return out
 
 
+def rank3_rows(pairs):
+    """The rank-3 matchers and the batched descriptor selection against the port oracle (itself pinned to the reference bodies by the golden tests)."""
+    out = dict(pairs=0, kf=[0, 0], kfp=[0, 0], sim3=[0, 0], fuse=[0, 0], tri=[0, 0], dist=[0, 0])
+    E = orbx.ORBextractor(1000, 1.2, 8, 20, 7); sf = E.GetScaleFactors()
+    pool = np.concatenate([E(synth_frame(500 + s, 640, 480))[1] for s in range(6)])
+    voc = bc.build_vocabulary(pool, 10, 3); V = orbx.ORBVocabulary(10, 3, *voc)
+    P = oracle.Matcher("port", 0.9, True)
+    for s in range(pairs):
+        A = synth_frame(5000 + s, 640, 480); B = warp_affine_nn(A, 7, -4, 2.0)
+        ka, da = E(A); kb, db = E(B)
+        pi = mc.projection_inputs(ka, kb, seed=s + 1)
+        FA, FB = orbx.FrameView(ka, da, 640, 480, sf), orbx.FrameView(kb, db, 640, 480, sf, u_right=pi["u_right"])
+        oFA, oFB = oracle.FrameData(ka, da, 640, 480, sf), oracle.FrameData(kb, db, 640, 480, sf, u_right=pi["u_right"])
+        uv, _ = mc.project(pi["xyz"])
+        kf = mc.keyframe_inputs(ka, kb, pi, seed=s + 9)
+        for th, od, ori in mc.KF_CASES:
+            g = orbx.ORBmatcher(0.9, ori).SearchByProjectionKeyFrame(FB, uv, kf["lvl"], ka["angle"], da, kf["valid"], kf["occ"], th, od)
+            o = oracle.Matcher("port", 0.9, ori).search_by_projection_keyframe_port(oFB, uv, kf["lvl"], ka["angle"], da, kf["valid"], kf["occ"], th, od)
+            out["kf"][0] += int(o[0]); out["kf"][1] += int(g[0] != o[0]) + int((g[1] != o[1]).sum())
+        kp = mc.keyframe_points_inputs(ka, kb, pi, seed=s + 13)
+        for th in mc.KFP_CASES:
+            g = orbx.ORBmatcher().SearchByProjectionKeyFramePoints(FB, kp["uv"], kp["lvl"], da, kp["valid"], kp["kf_matched"], th)
+            o = P.search_by_projection_keyframe_points_port(oFB, kp["uv"], kp["lvl"], da, kp["valid"], kp["kf_matched"], th)
+            out["kfp"][0] += int(o[0]); out["kfp"][1] += int(g[0] != o[0]) + int((g[1] != o[1]).sum())
+        s1, s2, _ = mc.sim3_inputs(ka, kb, seed=s + 21)
+        for th in mc.SIM3_TH:
+            g = orbx.ORBmatcher().SearchBySim3(FA, FB, s1["uv"], s1["lvl"], da, s1["valid"], s2["uv"], s2["lvl"], db, s2["valid"], th)
+            o = P.search_by_sim3_port(oFA, oFB, s1["uv"], s1["lvl"], da, s1["valid"], s2["uv"], s2["lvl"], db, s2["valid"], th)
+            out["sim3"][0] += int(o[0]); out["sim3"][1] += int(g[0] != o[0]) + int((g[1] != o[1]).sum())
+        fu = mc.fuse_inputs(ka, kb, pi, seed=s + 29)
+        for th in mc.FUSE_TH:
+            for sim3 in (0, 1):
+                g = orbx.ORBmatcher().FuseSearch(FB, fu["uv"], None if sim3 else fu["ur"], fu["lvl"], da, fu["valid"], fu["inv_sigma2"], th)
+                o = P.fuse_search_port(oFB, fu["uv"], None if sim3 else fu["ur"], fu["lvl"], da, fu["valid"], fu["inv_sigma2"], th)
+                out["fuse"][0] += int((o >= 0).sum()); out["fuse"][1] += int((g != o).sum())
+        fa, fb = V.transform(da, 1), V.transform(db, 1)
+        t = bc.tri_inputs(len(ka), len(kb), seed=s + 31)
+        for ori, st in bc.TRI_VARIANTS:
+            g = orbx.ORBmatcher(0.6, ori).SearchForTriangulation(ka, da, t["free1"], t["ur1"], fa, kb, db, t["free2"], t["ur2"], fb, bc.TRI_F12, (339.292, 265.63), t["sf"], t["sigma2"], st)
+            o = oracle.search_for_triangulation("port", ori, ka, da, t["free1"], t["ur1"], fa, kb, db, t["free2"], t["ur2"], fb, bc.TRI_F12, (339.292, 265.63), bc.TRI_CAM, t["sf"], t["sigma2"], st)
+            out["tri"][0] += int(o[0]); out["tri"][1] += int(g[0] != o[0]) + int((g[1] != o[1]).sum())
+        di = bc.distinctive_inputs(np.concatenate([da, db]), seed=s + 41)
+        g = orbx.ORBmatcher().ComputeDistinctiveDescriptors(di["f_offsets"], di["f_desc"]); o = oracle.distinctive_descriptors("port", di["f_offsets"], di["f_desc"])
+        out["dist"][0] += len(o); out["dist"][1] += int((g != o).sum())
+        out["pairs"] += 1
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser(); ap.add_argument("--frames", type=int, default=100); a = ap.parse_args()
     kind = "ref" if oracle.have_ref() else "port"
@@ -166,6 +214,12 @@ def main():
     print("|---|---|---|---|---|---|---|---|---|---|---|---|---|")
     print("| %d | %d | %d | %d | %d | %d | %d | %d | %d | %d | %d | %d | %.2f |" % (w["frames"], w["features"], w["word_diff"], w["node_diff"], w["bow_entries"], w["bow_id_diff"], w["bow_val_diff"], w["fv_diff"],
                                                                                  w["sb_calls"], w["sb_matches"], w["sb_idx_diff"], w["sb_count_diff"], w["ref_transform_ms"]))
+    r3 = rank3_rows(max(a.frames // 10, 1))
+    print("\n## Remaining windowed matchers (8f rank 3) and batched descriptor selection (rank 4), vs the port oracle (pinned to the reference bodies by `tests/golden/ref_match_kf.npz`, `ref_bow.npz`)\n")
+    print("| frame pairs | function | accepted matches / selections (oracle) | differences (count + index) |\n|---|---|---|---|")
+    for key, name in (("kf", "SearchByProjection(Frame&, KeyFrame*, set&, th, ORBdist) x3 settings"), ("kfp", "SearchByProjection(KeyFrame*, Scw, points, matched, th) x2 th"),
+                      ("sim3", "SearchBySim3 x2 th"), ("fuse", "Fuse search, pose + Sim3 forms x2 th"), ("tri", "SearchForTriangulation x3 settings"), ("dist", "ComputeDistinctiveDescriptors, 300 map points per pair")):
+        print("| %d | %s | %d | %d |" % (r3["pairs"], name, r3[key][0], r3[key][1]))
     f = frame_rows(max(a.frames // 2, 4), kind)
     print("\n## Device-resident Frame (8f rank 1): UndistortKeyPoints / ComputeStereoFromRGBD / AssignFeaturesToGrid, cameras TUM1, TUM2, 4-coefficient, rectified\n")
     print("| frames | keypoints | mvKeysUn diffs | mvuRight diffs | mvDepth diffs | frames with a different mGrid | bounds diffs |\n|---|---|---|---|---|---|---|")
