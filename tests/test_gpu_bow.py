@@ -113,3 +113,28 @@ def test_distinctive_descriptors_match_reference_body(orbx, oracle):
     off = np.array([0, 1000], np.int32)
     assert np.array_equal(orbx.ORBmatcher().ComputeDistinctiveDescriptors(off, big), oracle.distinctive_descriptors("port", off, big))
     assert len(orbx.ORBmatcher().ComputeDistinctiveDescriptors(np.array([0], np.int32), np.zeros((0, 32), np.uint8))) == 0
+
+
+def test_large_descriptor_sets_take_the_global_memory_paths(orbx, oracle):
+    """More than 4096 descriptors: the BowVector / FeatureVector keys no longer sort in shared memory; 2000-feature frames as in C3 / C4."""
+    rng = np.random.default_rng(12)
+    base = np.concatenate([G["da"], G["db"]])
+    big = base[rng.integers(0, len(base), 6000)].copy()
+    flip = rng.integers(0, 256, (6000, 3))
+    for c in range(3):
+        big[np.arange(6000), flip[:, c] >> 3] ^= (1 << (flip[:, c] & 7)).astype(np.uint8)
+    V = orbx.ORBVocabulary(10, 3, *VOC); P = oracle.Vocabulary("port", 10, 3, *VOC)
+    for n in (4096, 4097, 6000):
+        g, o = V.transform(big[:n], 2), P.transform(big[:n], 2)
+        for key in TKEYS:
+            assert np.array_equal(g[key], o[key]), (n, key)
+    # SearchByBoW on 2000 x 2000 features
+    k1 = np.zeros(2000, orbx.KP_DTYPE); k2 = np.zeros(2000, orbx.KP_DTYPE)
+    k1["angle"] = rng.uniform(0, 360, 2000); k2["angle"] = (k1["angle"] + rng.normal(0, 3, 2000)) % 360
+    d1, d2 = big[:2000], big[2000:4000].copy(); d2[:1500] = d1[:1500]; d2[np.arange(1500), 5] ^= 1
+    f1, f2 = V.transform(d1, 1), V.transform(d2, 1)
+    v1 = (rng.random(2000) < 0.9).astype(np.uint8); v2 = (rng.random(2000) < 0.9).astype(np.uint8)
+    for kfkf in (0, 1):
+        g = orbx.ORBmatcher(0.7, True).SearchByBoW(kfkf, k1, d1, v1, f1, k2, d2, v2 if kfkf else None, f2)
+        o = oracle.search_by_bow("port", 0.7, True, kfkf, k1, d1, v1, f1, k2, d2, v2, f2)
+        assert g[0] == o[0] and g[0] > 500 and np.array_equal(g[1], o[1]) and np.array_equal(g[2], o[2])
