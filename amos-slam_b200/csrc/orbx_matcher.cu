@@ -228,11 +228,12 @@ struct Gather {
     // returns the offset of the piece inside the block
     size_t add(const void* dsrc, size_t n) {
         const size_t o = off; off += (n + 3) & ~(size_t)3;
-        if (n) cudaMemcpyAsync(dblock + o, dsrc, n, cudaMemcpyDeviceToDevice, m->stream);
+        if (n && cudaMemcpyAsync(dblock + o, dsrc, n, cudaMemcpyDeviceToDevice, m->stream) != cudaSuccess) failed = true;
         return o;
     }
+    bool failed = false;
     int finish() {
-        if (cudaMemcpyAsync(m->dl_host, dblock, off, cudaMemcpyDeviceToHost, m->stream) != cudaSuccess || cudaStreamSynchronize(m->stream) != cudaSuccess) {
+        if (failed || cudaMemcpyAsync(m->dl_host, dblock, off, cudaMemcpyDeviceToHost, m->stream) != cudaSuccess || cudaStreamSynchronize(m->stream) != cudaSuccess) {
             orbx_set_error(std::string("result download: ") + cudaGetErrorString(cudaGetLastError())); return ORBX_E_CUDA;
         }
         return ORBX_OK;
