@@ -474,7 +474,7 @@ def main():
     # the links the e2e leg rides on: pinned host -> device copy rate of every rank's GPU, all ranks copying AT THE SAME TIME (barrier
     # before each repetition), so that at N > 1 the figure includes the contention on the host side (memory, root complexes) that the
     # e2e leg also sees; reported as the mean per GPU of the slowest repetition-best across ranks
-    pcie_h2d = None
+    pcie_h2d = None; pcie_h2d_bi = None
     if Ke:
         hp = torch.empty(256 << 20, dtype=torch.uint8).pin_memory(); dp = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
         half = hp.numel() // 2
@@ -496,11 +496,34 @@ def main():
             e1.record(); torch.cuda.synchronize()
             if rep:
                 best = max(best, 2 * hp.numel() / (e0.elapsed_time(e1) * 1e-3) / 1e9)
-        del hp, dp
-        tb = torch.tensor([best], dtype=torch.float64, device="cuda")
+        # the same with the result traffic running against it: a third stream copies device -> host in the e2e leg's proportion (1 : 5)
+        hq = torch.empty(52 << 20, dtype=torch.uint8).pin_memory(); dq = torch.empty(52 << 20, dtype=torch.uint8, device="cuda")
+        s3 = torch.cuda.Stream(); best_bi = 0.0
+        for rep in range(3):
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            s3.wait_event(e0)
+            with torch.cuda.stream(s3):
+                for _ in range(2):
+                    hq.copy_(dq, non_blocking=True)
+            for i, st in enumerate(s2):
+                st.wait_event(e0)
+                with torch.cuda.stream(st):
+                    for _ in range(2):
+                        dp[i * half:(i + 1) * half].copy_(hp[i * half:(i + 1) * half], non_blocking=True)
+            for st in s2:
+                torch.cuda.current_stream().wait_stream(st)
+            e1.record(); torch.cuda.synchronize()
+            if rep:
+                best_bi = max(best_bi, 2 * hp.numel() / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+        del hp, dp, hq, dq
+        tb = torch.tensor([best, best_bi], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(tb, op=dist.ReduceOp.SUM)
-        pcie_h2d = float(tb[0].item()) / world
+        pcie_h2d = float(tb[0].item()) / world; pcie_h2d_bi = float(tb[1].item()) / world
 
     matcher_line = matcher_bench(orbx, torch, ext, frames, local_rank) if (rank == 0 and args.workload == "c1") else None
 
@@ -546,8 +569,8 @@ def main():
             "config": config,
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(B * WIDTH * HEIGHT * (2 if MASKED else 1)), "d2h_bytes_per_step": int(B * cap * 60 + 4 * B + 4), "steps": Ke,
                     "streams_per_gpu": NS,
-                    "h2d_GBps_per_gpu": (e2e / N * WIDTH * HEIGHT * (2 if MASKED else 1) / 1e9) if e2e else None, "pcie_h2d_peak_GBps": pcie_h2d, "pcie_probe": "pinned 256 MiB H2D on two streams per GPU, all %d ranks concurrently, mean per GPU" % world,
-                    "pcie_frac": (e2e / N * WIDTH * HEIGHT * (2 if MASKED else 1) / 1e9 / pcie_h2d) if (e2e and pcie_h2d) else None,
+                    "h2d_GBps_per_gpu": (e2e / N * WIDTH * HEIGHT * (2 if MASKED else 1) / 1e9) if e2e else None, "pcie_h2d_peak_GBps": pcie_h2d, "pcie_h2d_with_d2h_GBps": pcie_h2d_bi, "pcie_probe": "pinned 256 MiB H2D on two streams per GPU, all %d ranks concurrently, mean per GPU; _with_d2h: a third stream copies results device -> host at the e2e leg's 1:5 ratio" % world,
+                    "pcie_frac": (e2e / N * WIDTH * HEIGHT * (2 if MASKED else 1) / 1e9 / pcie_h2d_bi) if (e2e and pcie_h2d_bi) else None,   # against the probe WITH result traffic
                     "note": "one host thread per extractor handle, each calling the synchronous host-pointer batch API on its share of the step's frames"},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
