@@ -301,7 +301,10 @@ static int run_detect(orbx_extractor* h, int b0, int B, bool fork_blur = false) 
     const int ncells = (int)h->cells.size();
     if (ncells > 0) {
         // each warp walks FAST_CELLS_PER_WARP cells of its frame with the next ROI prefetched while the current one is processed
-        static const int cpw = [] { const char* e = std::getenv("ORBX_FAST_CPW"); int v = e ? std::atoi(e) : 4; return v < 1 ? 1 : v; }();
+        // (4 cells per warp for throughput; a small batch would leave most SMs idle that way, so it gets one CTA per 4 cells: 148 SMs x 7 CTAs per wave)
+        static const int cpw_env = [] { const char* e = std::getenv("ORBX_FAST_CPW"); int v = e ? std::atoi(e) : 0; return v < 0 ? 0 : v; }();
+        const long long cells_total = (long long)ncells * B;
+        const int cpw = cpw_env ? cpw_env : (cells_total >= 16LL * 2072 ? 4 : (cells_total >= 8LL * 2072 ? 2 : 1));
         dim3 grid((ncells + FAST_WARPS * cpw - 1) / (FAST_WARPS * cpw), B);
         const int smem = h->fast_smem_per_warp * FAST_WARPS;
         k_fast_cells<<<grid, FAST_WARPS * 32, smem, s>>>(view, h->d_levels.p, h->d_cells.p, ncells, h->cand_per_frame,
