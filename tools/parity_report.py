@@ -38,6 +38,45 @@ def extractor_rows(name, w, h, nfeat, frames, kind):
     return name, tot
 
 
+def random_config_rows(n_cfg, kind, seed=77):
+    """Randomised extractor configurations (image size, feature count, scale factor, levels, FAST thresholds, row padding): every field of every keypoint
+    and every descriptor byte against the reference build; configurations the reference itself cannot run (a level too small for its cell grid) are skipped."""
+    rng = np.random.default_rng(seed)
+    out = dict(configs=0, skipped=0, frames=0, keypoints=0, diff_fields=0, diff_desc=0, count_mismatch=0, worst="")
+    tries = 0
+    while out["configs"] < n_cfg and tries < 4 * n_cfg:
+        tries += 1
+        w = int(rng.integers(96, 1400)); h = int(rng.integers(96, 900)); nf = int(rng.choice([150, 500, 1000, 2000, 3000]))
+        sf = float(rng.choice([1.1, 1.2, 1.25, 1.3, 1.5, 2.0])); nl = int(rng.integers(1, 9)); ini = int(rng.choice([10, 20, 30, 45])); mn = int(rng.choice([3, 5, 7, 12]))
+        wl, hl = w / sf ** (nl - 1), h / sf ** (nl - 1)                    # smallest level: needs a cell grid and round(width / height) >= 1 quadtree roots (:719)
+        if mn > ini or min(wl, hl) < 64 or (wl - 32) / (hl - 32) < 0.6:
+            out["skipped"] += 1; continue
+        try:
+            E = orbx.ORBextractor(nf, sf, nl, ini, mn); O = oracle.Extractor(kind, nf, sf, nl, ini, mn)
+        except Exception:
+            out["skipped"] += 1; continue
+        out["configs"] += 1
+        for s in range(2):
+            img = synth_frame(7000 + 10 * out["configs"] + s, w, h)
+            if s == 1:                                                     # a padded row stride (cv::Mat ROI)
+                buf = np.zeros((h, w + 13), np.uint8); buf[:, :w] = img; img_g = buf[:, :w]
+            else:
+                img_g = img
+            try:
+                kg, dg = E(img_g)
+            except orbx.OrbxError:
+                out["skipped"] += 1; break
+            kr, dr = O.extract(img)
+            out["frames"] += 1; out["keypoints"] += len(kr)
+            if len(kg) != len(kr):
+                out["count_mismatch"] += 1; out["worst"] = "%dx%d nf=%d sf=%g nl=%d th=%d/%d" % (w, h, nf, sf, nl, ini, mn); continue
+            d = sum(int((kg[f] != kr[f]).sum()) for f in FIELDS)
+            out["diff_fields"] += d; out["diff_desc"] += int((dg != dr).sum())
+            if d:
+                out["worst"] = "%dx%d nf=%d sf=%g nl=%d th=%d/%d" % (w, h, nf, sf, nl, ini, mn)
+    return out
+
+
 def matcher_rows(pairs, kind):
     E = orbx.ORBextractor(1000, 1.2, 8, 20, 7)
     sf = E.GetScaleFactors()
@@ -198,6 +237,11 @@ def main():
         _, t = extractor_rows(name, w, h, nf, n, kind)
         print("| %s | %d | %d | %d | %d | %d | %d | %d | %d | %d | %d | %d | %g | %.1f |" % (name, t["frames"], t["kp_ref"], t["kp_gpu"], t["count_mismatch"], t["x"], t["y"], t["size"], t["angle"],
                                                                                             t["response"], t["octave"], t["desc_bytes_diff"], t["angle_max_abs"], t["ref_ms_per_frame_1core"]))
+    rc = random_config_rows(max(a.frames // 3, 5), kind)
+    print("\n### Randomised configurations (size 96-1400 x 96-900, 150-3000 features, scale factor 1.1-2.0, 1-8 levels, FAST thresholds 10-45 / 3-12, one frame with a padded row stride)\n")
+    print("| configurations | frames | keypoints (ref) | frames with different count | keypoint field diffs | descriptor byte diffs | skipped (geometry the reference cannot run) |\n|---|---|---|---|---|---|---|")
+    print("| %d | %d | %d | %d | %d | %d | %d |%s" % (rc["configs"], rc["frames"], rc["keypoints"], rc["count_mismatch"], rc["diff_fields"], rc["diff_desc"], rc["skipped"],
+                                                     (" first differing configuration: " + rc["worst"]) if rc["worst"] else ""))
     m = matcher_rows(max(a.frames // 5, 1), kind)
     print("\n## Matchers (a13-a17), C2-style pairs (frame B = frame A warped by (+7, -4) px, 2 deg)\n")
     print("| pairs | F1 queries | accepted matches (all calls) | SearchForInitialization: index/prev diffs, count diffs | SearchByProjection(Frame,Frame) x3 th: index, count | SearchByProjection(Frame,MapPoints) x3 th: index, count |")
