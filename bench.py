@@ -38,7 +38,7 @@ MASKED = False
 # BASELINE.json configs that are a single-GPU extraction workload: c1 is the one the headline metric is quoted on (default);
 # c3 / c5 are selectable for the record (python bench.py --workload c5), they are not the driver's bench line.
 WORKLOADS = {
-    "c1": (640, 480, 1000, 512, False, WORKLOAD, METRIC),
+    "c1": (640, 480, 1000, 1024, False, WORKLOAD, METRIC),
     "c3": (752, 480, 2000, 512, False, "ORBextractor 752x480 grayscale (EuRoC-shape monocular initialiser frames), nFeatures=2000, scale 1.2, 8 levels, FAST 20/7",
            "ORB extract frames/sec @752x480 2000 feat"),
     "c5": (1920, 1080, 1000, 64, True, "batched 1920x1080 multi-sequence ORB extraction with dynamic-mask keypoint culling (detect -> MovingKeyPoints -> ProcessDesp), "
@@ -288,7 +288,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=0, help="frames per GPU per step (default: 512; 64 for c5)")
+    ap.add_argument("--batch", type=int, default=0, help="frames per GPU per step (default: 1024 for c1 = the batch SURVEY.md 8d names, 512 for c3, 64 for c5)")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
