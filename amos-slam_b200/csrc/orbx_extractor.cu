@@ -82,7 +82,6 @@ struct orbx_extractor {
     DevBuf<uint16_t> d_cell_counts;
     DevBuf<int> d_ncand, d_kp_count, d_counts, d_level_counts, d_overflow;
     DevBuf<KpOut> d_kp_out; DevBuf<uint8_t> d_desc_out; int out_cap = 0;
-    uint8_t* h_stage = nullptr; size_t h_stage_cap = 0;                               // pinned staging of one pageable input frame
     DevBuf<uint8_t> d_gather; uint8_t* h_gather = nullptr; size_t h_gather_cap = 0;   // single-frame result block and its pinned landing buffer
     const KpOut* last_kp = nullptr; const uint8_t* last_desc = nullptr; int last_n = -1;   // frame 0 of the last extract / describe (orbx_frame_assign)
     PyrView view{}; bool have_pyramid = false, blur_valid = false;
@@ -390,30 +389,6 @@ static int run_orient(orbx_extractor* h, int b0, int B, bool describe, KpOut* d_
 // level 0 := host frames (H2D straight into the resident pyramid block)
 static int upload_level0(orbx_extractor* h, const uint8_t* images, int B, int rows, int cols, size_t step, size_t frame_stride) {
     const LevelGeom& g0 = h->levels[0];
-    // One frame from pageable memory (the per-frame calls Tracking makes): stage it band by band through a pinned buffer, so that the DMA
-    // of one band runs while the next one is being copied, instead of leaving the whole pageable transfer to the driver (opt-in: ORBX_STAGE_BANDS=<bands>)
-    static const int bands = [] { const char* e = std::getenv("ORBX_STAGE_BANDS"); int v = e ? std::atoi(e) : 0; return v < 0 ? 0 : v; }();
-    if (B == 1 && bands > 0 && (size_t)rows * cols >= (64u << 10)) {
-        const size_t need = (size_t)rows * cols;
-        if (h->h_stage_cap < need) {
-            if (h->h_stage) cudaFreeHost(h->h_stage);
-            h->h_stage = nullptr; h->h_stage_cap = 0;
-            CU_TRY(cudaHostAlloc((void**)&h->h_stage, need, cudaHostAllocDefault));
-            h->h_stage_cap = need;
-        }
-        CU_TRY(cudaStreamSynchronize(h->stream));                 // the previous call's DMA out of the staging buffer is over (calls are synchronous anyway)
-        const int nb = std::min(bands, rows);
-        for (int k = 0; k < nb; ++k) {
-            const int r0 = (int)((long long)rows * k / nb), r1 = (int)((long long)rows * (k + 1) / nb);
-            uint8_t* dstp = h->h_stage + (size_t)r0 * cols;
-            if (step == (size_t)cols) std::memcpy(dstp, images + (size_t)r0 * step, (size_t)(r1 - r0) * cols);
-            else for (int r = r0; r < r1; ++r) std::memcpy(dstp + (size_t)(r - r0) * cols, images + (size_t)r * step, cols);
-            CU_TRY(cudaMemcpy2DAsync(h->d_pyr.p + g0.off + (size_t)r0 * g0.pitch, g0.pitch, dstp, cols, cols, r1 - r0, cudaMemcpyHostToDevice, h->stream));
-        }
-        h->view.l0 = h->d_pyr.p + g0.off; h->view.l0_fstride = h->pyr_fstride; h->view.l0_pitch = g0.pitch;
-        h->view.pyr = h->d_pyr.p; h->view.pyr_fstride = h->pyr_fstride;
-        return ORBX_OK;
-    }
     for (int b = 0; b < B; ++b)
         CU_TRY(cudaMemcpy2DAsync(h->d_pyr.p + (size_t)b * h->pyr_fstride + g0.off, g0.pitch, images + (size_t)b * frame_stride, step,
                                  cols, rows, cudaMemcpyHostToDevice, h->stream));
@@ -495,7 +470,6 @@ void orbx_destroy(orbx_extractor* h) {
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->ev_block) cudaEventDestroy(h->ev_block);
     h->d_gather.release(); if (h->h_gather) cudaFreeHost(h->h_gather);
-    if (h->h_stage) cudaFreeHost(h->h_stage);
     for (cudaEvent_t e : h->ev_h2d) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_done) cudaEventDestroy(e);
     h->d_l0.release();
