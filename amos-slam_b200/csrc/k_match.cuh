@@ -757,46 +757,78 @@ k_stereo_median_cut(int nl, const int* __restrict__ sad_dist, float* __restrict_
 }
 
 // =================================================================================================
-// Brute-force all-pairs best / second-best (throughput form of the inner kernel).  One warp per query;
-// train descriptors are staged tile by tile in shared memory as uint4 pairs and shared by the CTA's 8 queries.
+// Brute-force all-pairs best / second-best (throughput form of the inner kernel).
+// The first version (one query per warp, 8 POPC per distance, one 32-byte shared-memory read per distance) ran into two walls at once
+// (profiles/r01h_bruteforce_raw.csv): the XU pipe, which executes POPC, at 118 % of its sustained rate and the LSU wavefronts at 93 %
+// (2-way bank conflicts on the 32-byte descriptor stride), with the ALU pipe at 16 %.  This version moves work to where there is room:
+//   * every warp holds BF_QPW queries in registers, so a train descriptor read from shared memory serves BF_QPW distances;
+//   * the tile is stored as two 16-byte planes, so a warp's reads are conflict-free;
+//   * the 8 XOR words of a distance go through a carry-save adder tree (14 LOP3 on the ALU pipe) and need 4 POPC instead of 8:
+//     d = popc(ones) + 2 popc(twos) + 4 popc(fours) + 8 popc(eights)  (Harley-Seal), the weighted sum on the FMA pipe (IMAD).
+// Results are identical: key = distance << 20 | train index, smallest two keys per query.
 // =================================================================================================
 #define BF_TILE 256
+#define BF_QPW 4
+__device__ __forceinline__ void csa(uint32_t a, uint32_t b, uint32_t c, uint32_t& sum, uint32_t& carry) {
+    sum = a ^ b ^ c; carry = (a & b) | (a & c) | (b & c);                       // one LOP3 each
+}
+__device__ __forceinline__ int hamming256_hs(const uint32_t* __restrict__ q, const uint4 b0, const uint4 b1) {
+    const uint32_t x0 = q[0] ^ b0.x, x1 = q[1] ^ b0.y, x2 = q[2] ^ b0.z, x3 = q[3] ^ b0.w, x4 = q[4] ^ b1.x, x5 = q[5] ^ b1.y, x6 = q[6] ^ b1.z, x7 = q[7] ^ b1.w;
+    uint32_t s0, c0, s1, c1, s2, c2, t0, e0;
+    csa(x0, x1, x2, s0, c0); csa(x3, x4, x5, s1, c1); csa(s0, s1, x6, s2, c2);
+    const uint32_t ones = s2 ^ x7, c3 = s2 & x7;
+    csa(c0, c1, c2, t0, e0);
+    const uint32_t twos = t0 ^ c3, e1 = t0 & c3;
+    const uint32_t fours = e0 ^ e1, eights = e0 & e1;
+    return __popc(ones) + 2 * __popc(twos) + 4 * __popc(fours) + 8 * __popc(eights);
+}
 __global__ void __launch_bounds__(256)
 k_bruteforce_best2(const uint4* __restrict__ query, int nq, const uint4* __restrict__ train, int nt,
                    int* __restrict__ best_idx, int* __restrict__ best_dist, int* __restrict__ second_dist) {
     // blockIdx.y = frame pair of a batch: pair p matches query[p*nq ..] against train[p*nt ..]
     query += 2 * (size_t)blockIdx.y * nq; train += 2 * (size_t)blockIdx.y * nt;
     best_idx += (size_t)blockIdx.y * nq; best_dist += (size_t)blockIdx.y * nq; second_dist += (size_t)blockIdx.y * nq;
-    __shared__ uint4 tile[BF_TILE * 2];
+    __shared__ uint4 tile_lo[BF_TILE], tile_hi[BF_TILE];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int q = blockIdx.x * 8 + warp;
-    uint4 d0 = make_uint4(0, 0, 0, 0), d1 = d0;
-    if (q < nq) { d0 = __ldg(query + 2 * q); d1 = __ldg(query + 2 * q + 1); }
-    uint32_t k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
+    const int q0 = (blockIdx.x * 8 + warp) * BF_QPW;
+    uint32_t qd[BF_QPW][8], k1[BF_QPW], k2[BF_QPW];
+#pragma unroll
+    for (int u = 0; u < BF_QPW; ++u) {
+        uint4 a = make_uint4(0, 0, 0, 0), b = a;
+        if (q0 + u < nq) { a = __ldg(query + 2 * (q0 + u)); b = __ldg(query + 2 * (q0 + u) + 1); }
+        qd[u][0] = a.x; qd[u][1] = a.y; qd[u][2] = a.z; qd[u][3] = a.w; qd[u][4] = b.x; qd[u][5] = b.y; qd[u][6] = b.z; qd[u][7] = b.w;
+        k1[u] = 0xFFFFFFFFu; k2[u] = 0xFFFFFFFFu;
+    }
     for (int t0 = 0; t0 < nt; t0 += BF_TILE) {
         const int tn = min(BF_TILE, nt - t0);
         __syncthreads();
-        for (int i = threadIdx.x; i < tn * 2; i += 256) tile[i] = __ldg(train + 2 * (size_t)t0 + i);
+        for (int i = threadIdx.x; i < tn * 2; i += 256) { const uint4 v = __ldg(train + 2 * (size_t)t0 + i); if (i & 1) tile_hi[i >> 1] = v; else tile_lo[i >> 1] = v; }
         __syncthreads();
-        if (q < nq)
+        if (q0 < nq)
             for (int j = lane; j < tn; j += 32) {
-                const uint4 b0 = tile[2 * j], b1 = tile[2 * j + 1];
-                const int d = __popc(d0.x ^ b0.x) + __popc(d0.y ^ b0.y) + __popc(d0.z ^ b0.z) + __popc(d0.w ^ b0.w) +
-                              __popc(d1.x ^ b1.x) + __popc(d1.y ^ b1.y) + __popc(d1.z ^ b1.z) + __popc(d1.w ^ b1.w);
-                const uint32_t key = ((uint32_t)d << 20) | (uint32_t)(t0 + j);
-                if (key < k1) { k2 = k1; k1 = key; } else if (key < k2) k2 = key;
+                const uint4 b0 = tile_lo[j], b1 = tile_hi[j];
+#pragma unroll
+                for (int u = 0; u < BF_QPW; ++u) {
+                    const uint32_t key = ((uint32_t)hamming256_hs(qd[u], b0, b1) << 20) | (uint32_t)(t0 + j);
+                    if (key < k1[u]) { k2[u] = k1[u]; k1[u] = key; } else if (key < k2[u]) k2[u] = key;
+                }
             }
     }
-    if (q >= nq) return;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const uint32_t a1 = __shfl_xor_sync(0xffffffffu, k1, o), a2 = __shfl_xor_sync(0xffffffffu, k2, o);
-        const uint32_t lo = min(k1, a1), hi = max(k1, a1);
-        k2 = min(hi, min(k2, a2)); k1 = lo;
-    }
-    if (lane == 0) {
-        best_idx[q] = k1 == 0xFFFFFFFFu ? -1 : (int)(k1 & 0xFFFFFu);
-        best_dist[q] = k1 == 0xFFFFFFFFu ? INT_MAX : (int)(k1 >> 20);
-        second_dist[q] = k2 == 0xFFFFFFFFu ? INT_MAX : (int)(k2 >> 20);
+    for (int u = 0; u < BF_QPW; ++u) {
+        const int q = q0 + u;
+        if (q >= nq) break;                                                     // uniform across the warp
+        uint32_t a = k1[u], b = k2[u];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const uint32_t a1 = __shfl_xor_sync(0xffffffffu, a, o), a2 = __shfl_xor_sync(0xffffffffu, b, o);
+            const uint32_t lo = min(a, a1), hi = max(a, a1);
+            b = min(hi, min(b, a2)); a = lo;
+        }
+        if (lane == 0) {
+            best_idx[q] = a == 0xFFFFFFFFu ? -1 : (int)(a & 0xFFFFFu);
+            best_dist[q] = a == 0xFFFFFFFFu ? INT_MAX : (int)(a >> 20);
+            second_dist[q] = b == 0xFFFFFFFFu ? INT_MAX : (int)(b >> 20);
+        }
     }
 }

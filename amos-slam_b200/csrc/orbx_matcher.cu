@@ -1207,7 +1207,7 @@ int orbx_match_bruteforce_batch_device(orbx_matcher* m, int n_pairs, const uint8
     if (((uintptr_t)d_query & 15) || ((uintptr_t)d_train & 15)) FAIL(ORBX_E_INVALID, "descriptor arrays must be 16-byte aligned");
     if (n_query == 0 || n_pairs == 0) return ORBX_OK;
     CU_TRY(cudaSetDevice(m->device));
-    k_bruteforce_best2<<<dim3((n_query + 7) / 8, n_pairs), 256, 0, m->stream>>>(reinterpret_cast<const uint4*>(d_query), n_query, reinterpret_cast<const uint4*>(d_train), n_train, d_best_idx, d_best_dist, d_second_dist);
+    k_bruteforce_best2<<<dim3((n_query + 8 * BF_QPW - 1) / (8 * BF_QPW), n_pairs), 256, 0, m->stream>>>(reinterpret_cast<const uint4*>(d_query), n_query, reinterpret_cast<const uint4*>(d_train), n_train, d_best_idx, d_best_dist, d_second_dist);
     LAUNCH_CHECK();
     return ORBX_OK;
 }
