@@ -763,8 +763,9 @@ k_stereo_median_cut(int nl, const int* __restrict__ sad_dist, float* __restrict_
 // (2-way bank conflicts on the 32-byte descriptor stride), with the ALU pipe at 16 %.  This version moves work to where there is room:
 //   * every warp holds BF_QPW queries in registers, so a train descriptor read from shared memory serves BF_QPW distances;
 //   * the tile is stored as two 16-byte planes, so a warp's reads are conflict-free;
-//   * the 8 XOR words of a distance go through a carry-save adder tree (14 LOP3 on the ALU pipe) and need 4 POPC instead of 8:
-//     d = popc(ones) + 2 popc(twos) + 4 popc(fours) + 8 popc(eights)  (Harley-Seal), the weighted sum on the FMA pipe (IMAD).
+//   * the 8 XOR words of a distance go through four carry-save adders (8 LOP3 on the ALU pipe) and need 4 POPC instead of 8:
+//     d = popc(s2) + popc(x7) + 2 popc(twos) + 4 popc(fours)  (a truncated Harley-Seal tree, chosen so that ALU and XU pipes are
+//     loaded about equally), the weighted sum on the FMA pipe (IMAD).
 // Results are identical: key = distance << 20 | train index, smallest two keys per query.
 // =================================================================================================
 #define BF_TILE 256
@@ -775,12 +776,9 @@ __device__ __forceinline__ void csa(uint32_t a, uint32_t b, uint32_t c, uint32_t
 __device__ __forceinline__ int hamming256_hs(const uint32_t* __restrict__ q, const uint4 b0, const uint4 b1) {
     const uint32_t x0 = q[0] ^ b0.x, x1 = q[1] ^ b0.y, x2 = q[2] ^ b0.z, x3 = q[3] ^ b0.w, x4 = q[4] ^ b1.x, x5 = q[5] ^ b1.y, x6 = q[6] ^ b1.z, x7 = q[7] ^ b1.w;
     uint32_t s0, c0, s1, c1, s2, c2, t0, e0;
-    csa(x0, x1, x2, s0, c0); csa(x3, x4, x5, s1, c1); csa(s0, s1, x6, s2, c2);
-    const uint32_t ones = s2 ^ x7, c3 = s2 & x7;
-    csa(c0, c1, c2, t0, e0);
-    const uint32_t twos = t0 ^ c3, e1 = t0 & c3;
-    const uint32_t fours = e0 ^ e1, eights = e0 & e1;
-    return __popc(ones) + 2 * __popc(twos) + 4 * __popc(fours) + 8 * __popc(eights);
+    csa(x0, x1, x2, s0, c0); csa(x3, x4, x5, s1, c1); csa(s0, s1, x6, s2, c2);    // ones: s2 and x7 remain
+    csa(c0, c1, c2, t0, e0);                                                       // twos: t0 remains; fours: e0
+    return __popc(s2) + __popc(x7) + 2 * __popc(t0) + 4 * __popc(e0);
 }
 __global__ void __launch_bounds__(256)
 k_bruteforce_best2(const uint4* __restrict__ query, int nq, const uint4* __restrict__ train, int nt,
@@ -810,7 +808,7 @@ k_bruteforce_best2(const uint4* __restrict__ query, int nq, const uint4* __restr
 #pragma unroll
                 for (int u = 0; u < BF_QPW; ++u) {
                     const uint32_t key = ((uint32_t)hamming256_hs(qd[u], b0, b1) << 20) | (uint32_t)(t0 + j);
-                    if (key < k1[u]) { k2[u] = k1[u]; k1[u] = key; } else if (key < k2[u]) k2[u] = key;
+                    k2[u] = min(k2[u], max(k1[u], key)); k1[u] = min(k1[u], key);    // smallest two keys, branch-free (keys are distinct)
                 }
             }
     }
