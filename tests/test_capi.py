@@ -50,3 +50,18 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "import oracle" not in src and "from oracle" not in src and "oracle/" not in src.replace("the oracle", ""), f
                 assert "cvlite" not in src or f.endswith(".hpp"), f
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: the header must compile as C99 (no C++-isms, no torch / CUDA types) and a C program must link against the library."""
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "orbx_b200.h")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr])
+    src = tmp_path / "link.c"
+    src.write_text('#include "orbx_b200.h"\n#include <stdio.h>\nint main(void) { orbx_extractor* h = 0; int rc = orbx_create(1000, 1.2f, 8, 20, 7, 0, &h);\n'
+                   '  printf("%d %s\\n", rc, rc ? orbx_last_error() : "ok"); if (!rc) orbx_destroy(h); return 0; }\n')
+    lib_dir = os.path.join(ROOT, "amos-slam_b200")
+    exe = str(tmp_path / "link")
+    subprocess.check_call(["gcc", "-std=c99", "-I" + os.path.join(ROOT, "include"), str(src), "-L" + lib_dir, "-lorbx_b200", "-Wl,-rpath," + lib_dir, "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip()           # without a GPU: a negative status and a message, never a crash or a CPU result
