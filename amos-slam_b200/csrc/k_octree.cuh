@@ -44,18 +44,21 @@ __device__ __forceinline__ uint32_t octree_code(int x, int y, const LevelGeom& g
 
 // Shared-memory layout of the radix path for `cap` keys: key ping/pong (u32), index ping/pong (u16), per-warp digit
 // histograms (u16 [SORT_WARPS][256]).
-__host__ __device__ inline size_t octree_sort_smem_bytes(int cap) { return (size_t)cap * 12 + SORT_WARPS * 256 * 2 + 64; }
+__host__ __device__ inline size_t octree_sort_smem_bytes(int cap, int threads = SORT_THREADS) { return (size_t)cap * 12 + (size_t)(threads / 32) * 256 * 2 + 64; }
+#define SORT_THREADS_WIDE 1024     // per-frame calls: one CTA per level, so a wide CTA shortens every pass of the level-0 sort
 
-__global__ void __launch_bounds__(SORT_THREADS)
-k_octree_sort(const LevelGeom* __restrict__ levels, const CellDesc* __restrict__ cells, int ncells,
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_octree_sort_t(const LevelGeom* __restrict__ levels, const CellDesc* __restrict__ cells, int ncells,
               int slots_per_frame, int cand_per_frame, int nlevels, int smem_keys,
               const uint32_t* __restrict__ cand_slots, const uint16_t* __restrict__ cell_counts,
               uint32_t* __restrict__ ocand,          // [B][cand_per_frame] candidates in reference order
               unsigned long long* __restrict__ skey, // [B][cand_per_frame] sorted (code<<32 | index)
               uint32_t* __restrict__ spk,            // [B][cand_per_frame] packed candidate per sorted position
               int* __restrict__ ncand) {             // [B][nlevels]
+    constexpr int WARPS = THREADS / 32;
     extern __shared__ __align__(16) uint8_t sort_sm[];
-    __shared__ int warp_sums[SORT_WARPS];
+    __shared__ int warp_sums[32];
     __shared__ int total_sm;
     const int level = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const LevelGeom& g = levels[level];
@@ -66,7 +69,7 @@ k_octree_sort(const LevelGeom* __restrict__ levels, const CellDesc* __restrict__
     uint32_t* sp = spk + (long long)b * cand_per_frame + g.cand_off;
 
     // ---- ordered gather: exclusive scan of the per-cell counts, each thread owns a run of cells ----
-    const int per = (g.cell_count + SORT_THREADS - 1) / SORT_THREADS;
+    const int per = (g.cell_count + THREADS - 1) / THREADS;
     const int c0 = min(tid * per, g.cell_count), c1 = min(c0 + per, g.cell_count);
     int mine = 0;
     for (int c = c0; c < c1; ++c) mine += counts[c];
@@ -76,12 +79,12 @@ k_octree_sort(const LevelGeom* __restrict__ levels, const CellDesc* __restrict__
     if (lane == 31) warp_sums[warp] = incl;
     __syncthreads();
     if (tid < 32) {
-        int w = tid < SORT_WARPS ? warp_sums[tid] : 0;
+        int w = tid < WARPS ? warp_sums[tid] : 0;
         int wi = w;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, wi, o); if (tid >= o) wi += v; }
-        if (tid < SORT_WARPS) warp_sums[tid] = wi - w;
-        if (tid == SORT_WARPS - 1) total_sm = wi;
+        if (tid < WARPS) warp_sums[tid] = wi - w;
+        if (tid == WARPS - 1) total_sm = wi;
     }
     __syncthreads();
     const int n = total_sm;
@@ -91,7 +94,7 @@ k_octree_sort(const LevelGeom* __restrict__ levels, const CellDesc* __restrict__
     uint32_t* keyB = keyA + smem_keys;
     uint16_t* idxA = reinterpret_cast<uint16_t*>(keyB + smem_keys);
     uint16_t* idxB = idxA + smem_keys;
-    uint16_t* hist = idxB + smem_keys;                                   // [SORT_WARPS][256]
+    uint16_t* hist = idxB + smem_keys;                                   // [WARPS][256]
     int pos = warp_sums[warp] + incl - mine;
     for (int c = c0; c < c1; ++c) {                                      // ordered copy only (few threads own cells) ...
         const int cnt = counts[c];
@@ -99,7 +102,7 @@ k_octree_sort(const LevelGeom* __restrict__ levels, const CellDesc* __restrict__
         for (int k = 0; k < cnt; ++k, ++pos) oc[pos] = src[k];
     }
     __syncthreads();
-    for (int i = tid; i < n; i += SORT_THREADS) {                        // ... the path codes are computed by all threads
+    for (int i = tid; i < n; i += THREADS) {                        // ... the path codes are computed by all threads
         const uint32_t p = oc[i];
         const uint32_t code = octree_code((int)(p & 0xFFF), (int)((p >> 12) & 0xFFF), g);
         if (radix) { keyA[i] = code; idxA[i] = (uint16_t)i; }
@@ -116,7 +119,7 @@ k_octree_sort(const LevelGeom* __restrict__ levels, const CellDesc* __restrict__
         const int low = 2 * (ORBX_MAXD - nd);                            // constant low bits
         int rootbits = 0; while ((1 << rootbits) < g.nIni) ++rootbits;
         const int nbits = 2 * nd + rootbits;
-        const int seg = (n + SORT_WARPS - 1) / SORT_WARPS;               // contiguous segment per warp keeps the sort stable
+        const int seg = (n + WARPS - 1) / WARPS;               // contiguous segment per warp keeps the sort stable
         const int s0 = min(warp * seg, n), s1 = min(s0 + seg, n);
         const uint32_t lt = (1u << lane) - 1u;
         uint16_t* myhist = hist + warp * 256;
@@ -132,22 +135,26 @@ k_octree_sort(const LevelGeom* __restrict__ levels, const CellDesc* __restrict__
                 __syncwarp();
             }
             __syncthreads();
-            {   // offsets: digit-major, warp-minor exclusive scan; thread d owns digit d
-                int tot = 0;
-                int part[SORT_WARPS];
+            {   // offsets: digit-major, warp-minor exclusive scan; thread d < 256 owns digit d (the first 8 warps)
+                int tot = 0, inc = 0;
+                int part[WARPS];
+                if (tid < 256) {
 #pragma unroll
-                for (int w = 0; w < SORT_WARPS; ++w) { part[w] = tot; tot += hist[w * 256 + tid]; }
-                int inc = tot;
+                    for (int w = 0; w < WARPS; ++w) { part[w] = tot; tot += hist[w * 256 + tid]; }
+                    inc = tot;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
-                if (lane == 31) warp_sums[warp] = inc;
+                    for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+                    if (lane == 31) warp_sums[warp] = inc;
+                }
                 __syncthreads();
-                int basew = 0;
+                if (tid < 256) {
+                    int basew = 0;
 #pragma unroll
-                for (int w = 0; w < SORT_WARPS; ++w) if (w < warp) basew += warp_sums[w];
-                const int excl = basew + inc - tot;
+                    for (int w = 0; w < 8; ++w) if (w < warp) basew += warp_sums[w];
+                    const int excl = basew + inc - tot;
 #pragma unroll
-                for (int w = 0; w < SORT_WARPS; ++w) hist[w * 256 + tid] = (uint16_t)(excl + part[w]);
+                    for (int w = 0; w < WARPS; ++w) hist[w * 256 + tid] = (uint16_t)(excl + part[w]);
+                }
             }
             __syncthreads();
             for (int i0 = s0; i0 < s1; i0 += 32) {
@@ -167,7 +174,7 @@ k_octree_sort(const LevelGeom* __restrict__ levels, const CellDesc* __restrict__
             uint32_t* tk = keyA; keyA = keyB; keyB = tk;
             uint16_t* ti = idxA; idxA = idxB; idxB = ti;
         }
-        for (int i = tid; i < n; i += SORT_THREADS) {
+        for (int i = tid; i < n; i += THREADS) {
             const unsigned oi = idxA[i];
             sk_g[i] = ((unsigned long long)keyA[i] << 32) | oi;
             sp[i] = oc[oi];
@@ -179,20 +186,20 @@ k_octree_sort(const LevelGeom* __restrict__ levels, const CellDesc* __restrict__
     // ---- oversized level: bitonic sort in global memory, all-ascending formulation (works for any n, no padding) ----
     unsigned long long* sk = sk_g;
     for (int k = 2; (k >> 1) < n; k <<= 1) {
-        for (int i = tid; i < n; i += SORT_THREADS) {          // first substage: mirror partner
+        for (int i = tid; i < n; i += THREADS) {          // first substage: mirror partner
             const int j = i ^ (k - 1);
             if (j > i && j < n) { unsigned long long a = sk[i], c = sk[j]; if (a > c) { sk[i] = c; sk[j] = a; } }
         }
         __syncthreads();
         for (int s = k >> 2; s > 0; s >>= 1) {
-            for (int i = tid; i < n; i += SORT_THREADS) {
+            for (int i = tid; i < n; i += THREADS) {
                 const int j = i ^ s;
                 if (j > i && j < n) { unsigned long long a = sk[i], c = sk[j]; if (a > c) { sk[i] = c; sk[j] = a; } }
             }
             __syncthreads();
         }
     }
-    for (int i = tid; i < n; i += SORT_THREADS) sp[i] = oc[(unsigned)(sk[i] & 0xFFFFFFFFull)];
+    for (int i = tid; i < n; i += THREADS) sp[i] = oc[(unsigned)(sk[i] & 0xFFFFFFFFull)];
     if (tid == 0) ncand[b * nlevels + level] = n;
 }
 

@@ -315,8 +315,17 @@ static int run_detect(orbx_extractor* h, int b0, int B, bool fork_blur = false) 
     if (fork_blur) CU_TRY(cudaEventRecord(h->ev_fork, s));        // the blur may start once FAST is done ...
     {
         dim3 grid(L, B);
-        k_octree_sort<<<grid, SORT_THREADS, octree_sort_smem_bytes(h->sort_smem_keys), s>>>(h->d_levels.p, h->d_cells.p, ncells, h->cand_per_frame, h->cand_per_frame, L,
-                                                                                 h->sort_smem_keys, slots, cell_counts, h->d_ocand.p + co, h->d_skey.p + co, h->d_spk.p + co, h->d_ncand.p + (size_t)b0 * L);
+        // a handful of frames: one CTA per level cannot fill the GPU anyway, so each CTA is made wide and the level-0 sort gets 4x the threads per pass
+        static const int wide_env = [] { const char* e = std::getenv("ORBX_SORT_WIDE"); return e ? std::atoi(e) : -1; }();
+        const bool wide = (wide_env < 0 ? B <= 4 : wide_env != 0) && h->sort_smem_keys <= 8192;
+        if (wide)
+            k_octree_sort_t<SORT_THREADS_WIDE><<<grid, SORT_THREADS_WIDE, octree_sort_smem_bytes(h->sort_smem_keys, SORT_THREADS_WIDE), s>>>(
+                h->d_levels.p, h->d_cells.p, ncells, h->cand_per_frame, h->cand_per_frame, L, h->sort_smem_keys, slots, cell_counts, h->d_ocand.p + co, h->d_skey.p + co,
+                h->d_spk.p + co, h->d_ncand.p + (size_t)b0 * L);
+        else
+            k_octree_sort_t<SORT_THREADS><<<grid, SORT_THREADS, octree_sort_smem_bytes(h->sort_smem_keys), s>>>(
+                h->d_levels.p, h->d_cells.p, ncells, h->cand_per_frame, h->cand_per_frame, L, h->sort_smem_keys, slots, cell_counts, h->d_ocand.p + co, h->d_skey.p + co,
+                h->d_spk.p + co, h->d_ncand.p + (size_t)b0 * L);
         LAUNCH_CHECK();
         prof_mark(h);
         // sorted path codes staged in shared memory per (level, frame) instance: the extra 16 KB lowers the number of resident
@@ -450,7 +459,8 @@ int orbx_create(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, in
         cudaStreamDestroy(h->stream); delete h; FAIL(ORBX_E_CUDA, "cudaStreamCreate (copy streams)");
     }
     if (upload_constants() != ORBX_OK) { cudaStreamDestroy(h->stream); cudaStreamDestroy(h->s_h2d); cudaStreamDestroy(h->s_d2h); delete h; return ORBX_E_CUDA; }
-    cudaFuncSetAttribute(k_octree_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)octree_sort_smem_bytes(18432));
+    cudaFuncSetAttribute(k_octree_sort_t<SORT_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)octree_sort_smem_bytes(18432));
+    cudaFuncSetAttribute(k_octree_sort_t<SORT_THREADS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)octree_sort_smem_bytes(8192, SORT_THREADS_WIDE));
     cudaFuncSetAttribute(k_octree_tree, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_octree_tree_par, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ptree_smem_bytes(PTREE_MAXCAP, 4096));
     cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);

@@ -193,7 +193,7 @@ extern "C" int orbx_debug_distribute(orbx_extractor* h, const orbx_keypoint* can
     CU_TRY(cudaMemcpyAsync(dc.p, cells.data(), sizeof(CellDesc) * nc, cudaMemcpyHostToDevice, s));
     CU_TRY(cudaMemcpyAsync(dcnt.p, counts.data(), 2 * nc, cudaMemcpyHostToDevice, s));
     CU_TRY(cudaMemcpyAsync(dslots.p, packed.data(), 4 * (size_t)ncand, cudaMemcpyHostToDevice, s));
-    k_octree_sort<<<dim3(1, 1), SORT_THREADS, octree_sort_smem_bytes(h->sort_smem_keys), s>>>(dl.p, dc.p, nc, ncand, ncand, 1, h->sort_smem_keys, dslots.p, dcnt.p, doc.p, dsk.p, dspk.p, dn.p);
+    k_octree_sort_t<SORT_THREADS><<<dim3(1, 1), SORT_THREADS, octree_sort_smem_bytes(h->sort_smem_keys), s>>>(dl.p, dc.p, nc, ncand, ncand, 1, h->sort_smem_keys, dslots.p, dcnt.p, doc.p, dsk.p, dspk.p, dn.p);
     LAUNCH_CHECK();
     const int code_cap = 4096;
     const size_t tsm = (((size_t)tcap * (8 + 8 + 4 + 4 + 4 + 2 + 2 + 2 + 1) + 15) & ~(size_t)15) + (size_t)code_cap * 4 + 16;
