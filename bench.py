@@ -559,8 +559,9 @@ def main():
     traffic = None; ncu_note = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = tj["dram_bytes_per_frame"][kernel_of[dom]] * B / launches_of.get(dom, 1)
-        ncu_note = {"source": "profiles/" + tj["source"], "issue_active_pct": tj["issue_active_pct"][kernel_of[dom]], "dram_throughput_pct": tj["dram_throughput_pct"][kernel_of[dom]],
+        kname = kernel_of[dom] if kernel_of[dom] in tj["dram_bytes_per_frame"] else kernel_of[dom] + "_t"      # templated kernels appear with a _t suffix in newer captures
+        traffic = tj["dram_bytes_per_frame"][kname] * B / launches_of.get(dom, 1)
+        ncu_note = {"source": "profiles/" + tj["source"], "issue_active_pct": tj["issue_active_pct"][kname], "dram_throughput_pct": tj["dram_throughput_pct"][kname],
                     "reading": "the kernel is bound by instruction issue (integer byte work), not by HBM: traffic ~= algorithmic bytes, DRAM a few % busy"}
     except Exception:
         pass
