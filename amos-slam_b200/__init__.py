@@ -89,6 +89,7 @@ def lib():
     L.orbx_debug_blurred_level.argtypes = [vp, ci, ci, vp, sz]
     L.orbx_debug_pyramid_level.argtypes = [vp, ci, ci, vp, sz]
     L.orbx_debug_distribute.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, vp, ci, C.POINTER(ci)]
+    L.orbx_debug_sincos.argtypes = [vp, C.c_uint, ci, vp, vp]
     if hasattr(L, "orbx_matcher_create"):
         L.orbx_matcher_create.argtypes = [cf, ci, ci, C.POINTER(vp)]
         L.orbx_matcher_destroy.argtypes = [vp]; L.orbx_matcher_destroy.restype = None
@@ -330,6 +331,12 @@ class ORBextractor:
         out = np.zeros(shape, np.uint8)
         _check(self._lib.orbx_debug_blurred_level(self._h, b, level, _ptr(out), out.strides[0]))
         return out
+
+    def debug_sincos(self, lo_bits, n):
+        """sin / cos of the rBRIEF rotation as the device evaluates them, for the n floats with bit patterns lo_bits, lo_bits + 1, ..."""
+        s = np.zeros(n, np.float32); c = np.zeros(n, np.float32)
+        _check(self._lib.orbx_debug_sincos(self._h, int(lo_bits), int(n), _ptr(s), _ptr(c)))
+        return s, c
 
     def debug_distribute(self, cand, minX, maxX, minY, maxY, N):
         cand = np.ascontiguousarray(cand, KP_DTYPE)

@@ -258,12 +258,12 @@ k_orient_describe(PyrView pv, const LevelGeom* __restrict__ levels, int nlevels,
     const LevelGeom& g = levels[level];
     const int k = slot - g.kp_off;
     if (slot == 0 && lane == 0) {
-        if (counts_out) counts_out[b] = min(total, cap);
+        if (counts_out) counts_out[b] = total;                  // the true count: a value above cap tells the caller that keypoints were dropped
         if (level_counts_out) for (int l = 0; l < nlevels; ++l) level_counts_out[b * nlevels + l] = cnt[l];
     }
     if (k >= __shfl_sync(0xffffffffu, cnt_l, level)) return;
     const int oi = base + k;
-    if (oi >= cap) return;                                      // caller capacity (status reported by the host)
+    if (oi >= cap) return;                                      // caller capacity: counts_out[b] > cap reports it (ORBX_E_CAPACITY from the host calls)
     const uint32_t p = kp_level[(long long)b * kp_per_frame + slot];
     const int x = (int)(p & 0xFFF) + g.minBX, y = (int)((p >> 12) & 0xFFF) + g.minBY;   // :1184-1185
     int pitch;

@@ -6,6 +6,7 @@
 // (k_pyramid_fast.cuh, k_octree.cuh, k_describe.cuh, k_cull.cuh); the host only computes the small
 // per-geometry tables exactly as the reference's constructor / ComputePyramid / cell loop do.
 #include "../../include/orbx_b200.h"
+#include "../../include/orbx_b200_testtaps.h"
 #include "orbx_common.cuh"
 #include "orbx_internal.h"
 #include "k_pyramid_fast.cuh"
@@ -536,6 +537,7 @@ int orbx_check_overflow(orbx_extractor* h) {
     cudaSetDevice(h->device);
     if (cudaMemcpyAsync(&v, h->d_overflow.p, 4, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) return ORBX_E_CUDA;
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) return ORBX_E_CUDA;
+    if (v && cudaMemsetAsync(h->d_overflow.p, 0, 16, h->stream) != cudaSuccess) return ORBX_E_CUDA;   // reported once, then cleared
     return v;
 }
 
@@ -679,7 +681,8 @@ static int host_batch_pipeline(orbx_extractor* h, const uint8_t* images, const u
     for (int i = 1; i < nstreams; ++i) CU_TRY(cudaStreamSynchronize(cs[i]));
     CU_TRY(cudaMemcpyAsync(&ovf, h->d_overflow.p, 4, cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(cudaStreamSynchronize(h->stream));
-    if (ovf) FAIL(ORBX_E_OVERFLOW, "internal bound exceeded in the quadtree stage");
+    if (ovf) { CU_TRY(cudaMemsetAsync(h->d_overflow.p, 0, 16, h->stream)); FAIL(ORBX_E_OVERFLOW, "internal bound exceeded in the quadtree stage"); }
+    for (int b = 0; b < B; ++b) if (counts_out[b] > cap) FAIL(ORBX_E_CAPACITY, "keypoint buffer too small: a frame holds more than `cap` keypoints (counts_out has the true counts)");
     return ORBX_OK;
 }
 
@@ -722,7 +725,7 @@ int orbx_extract(orbx_extractor* h, const uint8_t* image, int rows, int cols, si
     CU_TRY(cudaStreamSynchronize(h->stream));
     int n, ovf;
     std::memcpy(&n, h->h_gather, 4); std::memcpy(&ovf, h->h_gather + 4, 4);
-    if (ovf) FAIL(ORBX_E_OVERFLOW, "internal bound exceeded in the quadtree stage");
+    if (ovf) { CU_TRY(cudaMemsetAsync(h->d_overflow.p, 0, 16, h->stream)); FAIL(ORBX_E_OVERFLOW, "internal bound exceeded in the quadtree stage"); }
     *n_out = n;
     h->last_kp = h->d_kp_out.p; h->last_desc = h->d_desc_out.p; h->last_n = n;
     if (n > cap) FAIL(ORBX_E_CAPACITY, "keypoint buffer too small");
@@ -761,7 +764,7 @@ int orbx_detect(orbx_extractor* h, const uint8_t* image, int rows, int cols, siz
     CU_TRY(cudaStreamSynchronize(h->stream));
     int n, ovf;
     std::memcpy(&n, h->h_gather, 4); std::memcpy(&ovf, h->h_gather + 4, 4);
-    if (ovf) FAIL(ORBX_E_OVERFLOW, "internal bound exceeded in the quadtree stage");
+    if (ovf) { CU_TRY(cudaMemsetAsync(h->d_overflow.p, 0, 16, h->stream)); FAIL(ORBX_E_OVERFLOW, "internal bound exceeded in the quadtree stage"); }
     std::memcpy(level_counts, h->h_gather + 8, lc);
     *n_out = n;
     if (n > cap) FAIL(ORBX_E_CAPACITY, "keypoint buffer too small");
@@ -833,47 +836,10 @@ int orbx_pyramid_level(orbx_extractor* h, int level, int border, uint8_t* dst, s
     return copy_level(h, base, pitch, level, border, dst, dst_step);
 }
 
-int orbx_debug_pyramid_level(orbx_extractor* h, int b, int level, uint8_t* dst, size_t dst_step) {
-    if (!h || !h->have_pyramid || b < 0 || b >= h->lastB || level < 0 || level >= h->nlevels || !dst) FAIL(ORBX_E_INVALID, "bad arguments");
-    CU_TRY(cudaSetDevice(h->device));
-    const LevelGeom& g = h->levels[level];
-    const uint8_t* base; int pitch;
-    if (level == 0) { base = h->view.l0 + (long long)b * h->view.l0_fstride; pitch = h->view.l0_pitch; }
-    else { base = h->d_pyr.p + (size_t)b * h->pyr_fstride + g.off; pitch = g.pitch; }
-    return copy_level(h, base, pitch, level, 0, dst, dst_step);
-}
-
-int orbx_debug_blurred_level(orbx_extractor* h, int b, int level, uint8_t* dst, size_t dst_step) {
-    if (!h || !h->have_pyramid || b < 0 || b >= h->lastB || level < 0 || level >= h->nlevels || !dst) FAIL(ORBX_E_INVALID, "bad arguments");
-    CU_TRY(cudaSetDevice(h->device));
-    int rc; if ((rc = run_blur(h, h->lastB))) return rc;
-    const LevelGeom& g = h->levels[level];
-    return copy_level(h, h->d_blur.p + (size_t)b * h->pyr_fstride + g.off, g.pitch, level, 0, dst, dst_step);
-}
-
-int orbx_debug_level_candidates(orbx_extractor* h, int b, int level, orbx_keypoint* out, int cap, int* n_out) {
-    if (!h || !h->have_pyramid || b < 0 || b >= h->lastB || level < 0 || level >= h->nlevels || !n_out) FAIL(ORBX_E_INVALID, "bad arguments");
-    CU_TRY(cudaSetDevice(h->device));
-    const LevelGeom& g = h->levels[level];
-    int n = 0;
-    CU_TRY(cudaMemcpyAsync(&n, h->d_ncand.p + (size_t)b * h->nlevels + level, 4, cudaMemcpyDeviceToHost, h->stream));
-    CU_TRY(cudaStreamSynchronize(h->stream));
-    *n_out = n;
-    if (n <= 0) return ORBX_OK;
-    if (n > cap || !out) FAIL(ORBX_E_CAPACITY, "candidate buffer too small");
-    std::vector<uint32_t> p(n);
-    CU_TRY(cudaMemcpyAsync(p.data(), h->d_ocand.p + (size_t)b * h->cand_per_frame + g.cand_off, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
-    CU_TRY(cudaStreamSynchronize(h->stream));
-    for (int i = 0; i < n; ++i) {
-        out[i].x = (float)(p[i] & 0xFFF); out[i].y = (float)((p[i] >> 12) & 0xFFF); out[i].size = 7.f; out[i].angle = -1.f;
-        out[i].response = (float)(p[i] >> 24); out[i].octave = 0; out[i].class_id = -1;
-    }
-    return ORBX_OK;
-}
-
 }  // extern "C"
 
-#include "orbx_extractor_debug.inl"
+#include "orbx_extractor_amos.inl"
+#include "orbx_extractor_taps.inl"
 
 int orbx_internal_pyramid(orbx_extractor* h, OrbxPyramidInfo* out) {
     if (!h || !out) FAIL(ORBX_E_INVALID, "null handle");

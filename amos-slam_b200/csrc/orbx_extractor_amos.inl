@@ -1,5 +1,5 @@
-// orbx_extractor_debug.inl -- orbx_cull (MovingKeyPoints), the batched masked extraction (config C5) and the quadtree stage tap;
-// part of orbx_extractor.cu
+// orbx_extractor_amos.inl -- the Amos-SLAM stage of the extractor: orbx_cull (MovingKeyPoints) and the batched masked extraction
+// (config C5); part of orbx_extractor.cu
 
 static int upload_ellipse() {
     // cv::getStructuringElement(MORPH_ELLIPSE, 31x31): dx = cvRound(c * sqrt((r*r - dy*dy) * inv_r2))
@@ -156,64 +156,3 @@ extern "C" int orbx_extract_masked_batch(orbx_extractor* h, const uint8_t* image
     return host_batch_pipeline(h, images, masks, B, rows, cols, step, frame_stride, mask_step, mask_frame_stride, kp_out, desc_out, cap, counts_out, culled_out);
 }
 
-// DistributeOctTree stage tap: the pipeline's own sort + tree kernels on caller-provided candidates
-extern "C" int orbx_debug_distribute(orbx_extractor* h, const orbx_keypoint* cand, int ncand, int minX, int maxX, int minY, int maxY, int N,
-                                     orbx_keypoint* out, int cap, int* n_out) {
-    if (!h || !n_out || ncand < 0 || (ncand && !cand) || maxX <= minX || maxY <= minY || N < 0) FAIL(ORBX_E_INVALID, "bad arguments");
-    *n_out = 0;
-    if (ncand == 0) return ORBX_OK;
-    if (maxX - minX > ORBX_MAX_DIM || maxY - minY > ORBX_MAX_DIM || ncand >= (1 << 20)) FAIL(ORBX_E_INVALID, "too large");
-    CU_TRY(cudaSetDevice(h->device));
-    LevelGeom g; std::memset(&g, 0, sizeof(g));
-    g.minBX = minX; g.maxBX = maxX; g.minBY = minY; g.maxBY = maxY; g.N = N;
-    g.nIni = (int)std::round(static_cast<float>(maxX - minX) / (maxY - minY));
-    if (g.nIni < 1 || g.nIni > 15) FAIL(ORBX_E_INVALID, "unsupported aspect ratio");
-    g.hX = static_cast<float>(maxX - minX) / g.nIni;
-    const int CH = 1024;
-    const int nc = (ncand + CH - 1) / CH;
-    g.cell_begin = 0; g.cell_count = nc; g.cand_off = 0; g.cand_cap = ncand; g.kp_off = 0; g.kp_cap = std::max(N + 2, 4 * g.nIni) + 2;
-    const int tcap = g.kp_cap + 8;
-    if (tcap > 32000) FAIL(ORBX_E_INVALID, "N too large");
-    std::vector<CellDesc> cells(nc); std::vector<uint16_t> counts(nc); std::vector<uint32_t> packed(ncand);
-    for (int c = 0; c < nc; ++c) { std::memset(&cells[c], 0, sizeof(CellDesc)); cells[c].slot = c * CH; counts[c] = (uint16_t)std::min(CH, ncand - c * CH); }
-    for (int i = 0; i < ncand; ++i) {
-        const int x = (int)cand[i].x, y = (int)cand[i].y, r = (int)cand[i].response;
-        if (x < 0 || y < 0 || x > ORBX_MAX_DIM || y > ORBX_MAX_DIM || r < 0 || r > 255 || (float)x != cand[i].x || (float)y != cand[i].y)
-            FAIL(ORBX_E_INVALID, "candidates must have integer coordinates in [0,4095] and response in [0,255]");
-        packed[i] = (uint32_t)x | ((uint32_t)y << 12) | ((uint32_t)r << 24);
-    }
-    DevBuf<LevelGeom> dl; DevBuf<CellDesc> dc; DevBuf<uint16_t> dcnt; DevBuf<uint32_t> dslots, doc, dspk, dkp; DevBuf<unsigned long long> dsk; DevBuf<int> dn, dkc;
-    struct Guard { DevBuf<LevelGeom>& a; DevBuf<CellDesc>& b; DevBuf<uint16_t>& c; DevBuf<uint32_t>&d, &e, &f, &g; DevBuf<unsigned long long>& hh; DevBuf<int>&i, &j;
-                   ~Guard() { a.release(); b.release(); c.release(); d.release(); e.release(); f.release(); g.release(); hh.release(); i.release(); j.release(); } } guard{dl, dc, dcnt, dslots, doc, dspk, dkp, dsk, dn, dkc};
-    if (dl.ensure(1) || dc.ensure(nc) || dcnt.ensure(nc) || dslots.ensure(ncand) || doc.ensure(ncand) || dspk.ensure(ncand) || dsk.ensure(ncand) ||
-        dkp.ensure(g.kp_cap) || dn.ensure(1) || dkc.ensure(1) || h->d_overflow.ensure(4)) return ORBX_E_CUDA;
-    cudaStream_t s = h->stream;
-    CU_TRY(cudaMemsetAsync(h->d_overflow.p, 0, 16, s));
-    CU_TRY(cudaMemcpyAsync(dl.p, &g, sizeof(g), cudaMemcpyHostToDevice, s));
-    CU_TRY(cudaMemcpyAsync(dc.p, cells.data(), sizeof(CellDesc) * nc, cudaMemcpyHostToDevice, s));
-    CU_TRY(cudaMemcpyAsync(dcnt.p, counts.data(), 2 * nc, cudaMemcpyHostToDevice, s));
-    CU_TRY(cudaMemcpyAsync(dslots.p, packed.data(), 4 * (size_t)ncand, cudaMemcpyHostToDevice, s));
-    k_octree_sort_t<SORT_THREADS><<<dim3(1, 1), SORT_THREADS, octree_sort_smem_bytes(h->sort_smem_keys), s>>>(dl.p, dc.p, nc, ncand, ncand, 1, h->sort_smem_keys, dslots.p, dcnt.p, doc.p, dsk.p, dspk.p, dn.p);
-    LAUNCH_CHECK();
-    const int code_cap = 4096;
-    const size_t tsm = (((size_t)tcap * (8 + 8 + 4 + 4 + 4 + 2 + 2 + 2 + 1) + 15) & ~(size_t)15) + (size_t)code_cap * 4 + 16;
-    if (tcap <= PTREE_MAXCAP)
-        k_octree_tree_par<<<dim3(1, 1), PTREE_THREADS, ptree_smem_bytes(tcap, code_cap), s>>>(dl.p, 1, ncand, g.kp_cap, tcap, code_cap, dsk.p, dspk.p, dn.p, dkp.p, dkc.p, h->d_overflow.p);
-    else
-        k_octree_tree<<<dim3(1, 1), 32, tsm, s>>>(dl.p, 1, ncand, g.kp_cap, tcap, code_cap, dsk.p, dspk.p, dn.p, dkp.p, dkc.p, h->d_overflow.p);
-    LAUNCH_CHECK();
-    int n = 0, ovf = 0;
-    std::vector<uint32_t> res(g.kp_cap);
-    CU_TRY(cudaMemcpyAsync(&n, dkc.p, 4, cudaMemcpyDeviceToHost, s));
-    CU_TRY(cudaMemcpyAsync(&ovf, h->d_overflow.p, 4, cudaMemcpyDeviceToHost, s));
-    CU_TRY(cudaMemcpyAsync(res.data(), dkp.p, 4 * (size_t)g.kp_cap, cudaMemcpyDeviceToHost, s));
-    CU_TRY(cudaStreamSynchronize(s));
-    if (ovf) { CU_TRY(cudaMemsetAsync(h->d_overflow.p, 0, 16, s)); FAIL(ORBX_E_OVERFLOW, "internal bound exceeded in the quadtree stage"); }
-    *n_out = n;
-    if (n > cap || !out) FAIL(ORBX_E_CAPACITY, "output buffer too small");
-    for (int i = 0; i < n; ++i) {
-        out[i].x = (float)(res[i] & 0xFFF); out[i].y = (float)((res[i] >> 12) & 0xFFF); out[i].size = 7.f; out[i].angle = -1.f;
-        out[i].response = (float)(res[i] >> 24); out[i].octave = 0; out[i].class_id = -1;
-    }
-    return ORBX_OK;
-}

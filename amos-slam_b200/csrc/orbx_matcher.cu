@@ -77,6 +77,7 @@ struct orbx_matcher {
     float nnratio; int checkOri; int device; cudaStream_t stream = nullptr; long long launches = 0;
     Arena arena; Arena cand_arena; UploadArena uparena;
     size_t cand_cap = 0;           // candidate entries the cand arena holds
+    int cand_tries = 0;            // consecutive grow-and-repeat rounds of the current call (bounded)
     uint8_t* dl_host = nullptr; size_t dl_cap = 0;     // pinned landing buffer for results that come back in one copy
     int ensure_download(size_t bytes) {
         if (bytes <= dl_cap) return ORBX_OK;
@@ -195,8 +196,9 @@ static int window_search(orbx_matcher* m, QueryParams& P, const FrameDev& F, int
     if (!counts || !offsets || !pre_best) FAIL(ORBX_E_CUDA, "matcher arena exhausted");
     const size_t want = std::max<size_t>((size_t)nq * 64, 1 << 16);
     if (m->cand_cap < want) {
-        int rc = m->cand_arena.reserve(want * 4); if (rc) return rc;
-        m->cand_cap = m->cand_arena.cap / 4;
+        const int rc = m->cand_arena.reserve(want * 4);
+        m->cand_cap = m->cand_arena.cap / 4;                     // 0 after a failed grow: nothing stale survives
+        if (rc) return rc;
     }
     cand = reinterpret_cast<uint32_t*>(m->cand_arena.base);
     if (nq == 0) { CU_TRY(cudaMemsetAsync(offsets, 0, 8, s)); return ORBX_OK; }
@@ -209,11 +211,17 @@ static int window_search(orbx_matcher* m, QueryParams& P, const FrameDev& F, int
     return ORBX_OK;
 }
 // after the call's final synchronisation: did the candidate lists fit?  If not, grow and tell the caller to run again.
-static bool cand_overflow(orbx_matcher* m, int total) {
-    if ((size_t)total <= m->cand_cap) return false;
-    if (m->cand_arena.reserve(((size_t)total + total / 2 + 1024) * 4) == ORBX_OK) m->cand_cap = m->cand_arena.cap / 4;
-    return true;
+// Returns 0 = they fit, 1 = the arena has been grown (run the call again), < 0 = error.  A failed grow leaves the arena empty
+// (Arena::reserve frees first), so the capacity is re-read from it either way and the error is returned instead of a retry.
+static int cand_overflow(orbx_matcher* m, long long total) {
+    if (total >= 0 && (size_t)total <= m->cand_cap) { m->cand_tries = 0; return 0; }
+    if (total < 0 || ++m->cand_tries > 2) { m->cand_tries = 0; FAIL(ORBX_E_OVERFLOW, "candidate lists do not fit after growing the arena"); }
+    const int rc = m->cand_arena.reserve(((size_t)total + (size_t)total / 2 + 1024) * 4);
+    m->cand_cap = m->cand_arena.cap / 4;
+    if (rc) { m->cand_tries = 0; return rc; }
+    return 1;
 }
+#define CAND_RETRY(total) do { const int _ov = cand_overflow(m, (total)); if (_ov < 0) return _ov; if (_ov) goto retry; } while (0)
 
 // Results come back in ONE copy into a pinned landing buffer (pageable destinations make every cudaMemcpyAsync a blocking, staged
 // transfer of its own): the pieces are gathered into a contiguous device block first (device-to-device copies are cheap to enqueue).
@@ -330,7 +338,7 @@ retry:
     const size_t o_total = g.add(offsets + n1, 4), o_n = g.add(dn, 4), o_m12 = g.add(m12, (size_t)n1 * 4), o_prev = g.add(prev, (size_t)n1 * 8);
     if ((rc = g.finish())) return rc;
     int total; std::memcpy(&total, g.host(o_total), 4);
-    if (cand_overflow(m, total)) goto retry;                       // the caller's arrays are only written below, so the inputs are still intact
+    CAND_RETRY(total);                       // the caller's arrays are only written below, so the inputs are still intact
     std::memcpy(nmatches, g.host(o_n), 4);
     std::memcpy(matches12, g.host(o_m12), (size_t)n1 * 4);
     std::memcpy(prev_matched_xy, g.host(o_prev), (size_t)n1 * 8);
@@ -375,7 +383,7 @@ retry:
     const size_t o_total = g.add(offsets + n_last, 4), o_n = g.add(dn, 4), o_cm = g.add(cm, (size_t)nc * 4);
     if ((rc = g.finish())) return rc;
     int total; std::memcpy(&total, g.host(o_total), 4);
-    if (cand_overflow(m, total)) goto retry;
+    CAND_RETRY(total);
     std::memcpy(nmatches, g.host(o_n), 4);
     if (nc) std::memcpy(cur_match, g.host(o_cm), (size_t)nc * 4);
     return ORBX_OK;
@@ -418,7 +426,7 @@ retry:
     const size_t o_total = g.add(offsets + n_points, 4), o_n = g.add(dn, 4), o_fm = g.add(fm, (size_t)nf * 4);
     if ((rc = g.finish())) return rc;
     int total; std::memcpy(&total, g.host(o_total), 4);
-    if (cand_overflow(m, total)) goto retry;
+    CAND_RETRY(total);
     std::memcpy(nmatches, g.host(o_n), 4);
     if (nf) std::memcpy(f_match, g.host(o_fm), (size_t)nf * 4);
     return ORBX_OK;
@@ -571,7 +579,7 @@ retry:
     CU_TRY(cudaMemcpyAsync(m->dl_host, res, res_bytes, cudaMemcpyDeviceToHost, m->stream));
     CU_TRY(cudaStreamSynchronize(m->stream));
     const int* hr = reinterpret_cast<const int*>(m->dl_host);
-    if (cand_overflow(m, hr[0])) goto retry;
+    CAND_RETRY(hr[0]);
     std::memcpy(best_idx, hr + 1, (size_t)n_points * 4);
     return ORBX_OK;
 }
@@ -613,7 +621,7 @@ retry:
     CU_TRY(cudaMemcpyAsync(m->dl_host, res, res_bytes, cudaMemcpyDeviceToHost, m->stream));
     CU_TRY(cudaStreamSynchronize(m->stream));
     const int* hr = reinterpret_cast<const int*>(m->dl_host);
-    if (cand_overflow(m, std::max(hr[1], hr[2]))) goto retry;
+    CAND_RETRY(std::max(hr[1], hr[2]));
     *nfound = hr[0];
     std::memcpy(match12, hr + 3, (size_t)n1 * 4);
     return ORBX_OK;
@@ -918,7 +926,7 @@ retry:
     CU_TRY(cudaMemcpyAsync(offsets_out, offsets, (size_t)(nq + 1) * 4, cudaMemcpyDeviceToHost, m->stream));
     CU_TRY(cudaStreamSynchronize(m->stream));
     const int total = offsets_out[nq];
-    if (cand_overflow(m, total)) goto retry;
+    CAND_RETRY(total);
     *total_out = total;
     if (total > cap) FAIL(ORBX_E_CAPACITY, "index buffer too small");
     if (total) {

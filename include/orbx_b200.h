@@ -130,6 +130,11 @@ int orbx_pyramid_level(orbx_extractor* h, int level, int border, uint8_t* dst, s
  * orbx_extract_batch       : host pointers, synchronous (H2D + kernels + D2H inside the call)
  * orbx_extract_batch_device: device pointers, asynchronous on orbx_stream(h); inputs must stay valid
  *                            until the stream reaches the end of the call's work.
+ * Capacity: counts_out[b] is always the TRUE number of keypoints of frame b.  If it exceeds cap only the first cap of
+ * them (level-major order) were written: the host-pointer calls then return ORBX_E_CAPACITY, callers of the *_device
+ * forms compare counts_out with cap themselves.  cap >= orbx_max_keypoints() never truncates.
+ * Overflow: the host-pointer calls return ORBX_E_OVERFLOW (and clear the flag) when an internal worst-case bound of the
+ * quadtree stage was exceeded; the *_device forms cannot (they do not synchronise): poll orbx_check_overflow().
  * ---------------------------------------------------------------------------------------------- */
 int orbx_extract_batch(orbx_extractor* h, const uint8_t* images, int B, int rows, int cols, size_t step,
                        size_t frame_stride, orbx_keypoint* kp_out, uint8_t* desc_out, int cap, int* counts_out);
@@ -159,18 +164,9 @@ long long orbx_launch_count(const orbx_extractor* h);
  * (resize, fast_cells, octree_sort, octree_tree, gauss7, orient_describe) and the number of profiled calls. */
 int orbx_profile_enable(orbx_extractor* h, int on);
 int orbx_profile_collect(orbx_extractor* h, double* stage_ms6, int* ncalls);
-/* last internal overflow flags of the handle (0 = none); synchronises the handle's stream */
+/* internal overflow flags raised since the last report (0 = none, else ORBX_OVF bits of the quadtree stage); synchronises the
+ * handle's stream and clears the flags, so one bad frame is reported once and later calls on the handle are unaffected */
 int orbx_check_overflow(orbx_extractor* h);
-
-/* Stage taps for parity tests (tests/ only; host pointers, synchronous, operate on frame `b` of the
- * last call).  Candidates are vToDistributeKeys of src/ORBextractor.cc:1073-1157 in reference order. */
-int orbx_debug_level_candidates(orbx_extractor* h, int b, int level, orbx_keypoint* out, int cap, int* n_out);
-int orbx_debug_blurred_level(orbx_extractor* h, int b, int level, uint8_t* dst, size_t dst_step);
-int orbx_debug_pyramid_level(orbx_extractor* h, int b, int level, uint8_t* dst, size_t dst_step);
-/* DistributeOctTree (src/ORBextractor.cc:706-1049) on caller-provided candidates (x,y integer-valued
- * floats relative to minX/minY, response) -- runs the same device kernels as the pipeline. */
-int orbx_debug_distribute(orbx_extractor* h, const orbx_keypoint* cand, int ncand, int minX, int maxX,
-                          int minY, int maxY, int N, orbx_keypoint* out, int cap, int* n_out);
 
 /* ================================================================================================
  * ORBmatcher  (include/ORBmatcher.h:57-215, src/ORBmatcher.cc)

@@ -34,7 +34,7 @@ def build_port(force=False):
     if not force and os.path.exists(PORT_SO) and all(os.path.getmtime(PORT_SO) >= os.path.getmtime(d) for d in deps):
         return PORT_SO
     os.makedirs(os.path.dirname(PORT_SO), exist_ok=True)
-    cmd = ["g++", "-O3", "-march=x86-64-v3", "-ffp-contract=off", "-std=c++14", "-fPIC", "-shared", "-w",
+    cmd = ["g++", "-O3", "-march=x86-64-v3", "-ffp-contract=off", "-std=gnu++17", "-fPIC", "-shared", "-w",
            "-o", PORT_SO] + srcs + ["-lpthread"]
     subprocess.check_call(cmd)
     return PORT_SO
@@ -98,6 +98,7 @@ def _lib(kind):
         lib.cvl_c_border101.restype = None; lib.cvl_c_border101.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, _u8p]
         lib.port_det_sincos.restype = None; lib.port_det_sincos.argtypes = [_f32p, _f32p, _f32p, C.c_int]
         lib.port_libm_sincosf.restype = None; lib.port_libm_sincosf.argtypes = [_f32p, _f32p, _f32p, C.c_int]
+        lib.port_sincos_sweep.restype = C.c_longlong; lib.port_sincos_sweep.argtypes = [C.c_uint, C.c_uint, np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS"), C.c_int]
     else:
         lib.ref_pyramid_level_padded.restype = C.c_int; lib.ref_pyramid_level_padded.argtypes = [C.c_void_p, C.c_int, _u8p]
     _libs[kind] = lib

@@ -9,9 +9,8 @@
 // Differences from the reference, all deliberate and all stated in DESIGN.md:
 //   1. DistributeOctTree tie-break is the canonical rule "equal size => newest node first" made
 //      explicit with creation ids (the reference sorts by heap address, ORBextractor.cc:948).
-//   2. cos/sin for the BRIEF rotation use det_sincos() (double polynomial with explicit fma,
-//      rounded to float) instead of glibc cosf/sinf, so that CPU and GPU agree bit for bit.
-//      Keypoints where glibc's value differs are counted separately by the tests.
+//   2. cos/sin for the BRIEF rotation: det_sincos() restates glibc's sincosf (FMA variant), the function the
+//      reference build calls, operation by operation; tests pin it against the live libm (0 differences).
 //   3. Per-cell FAST is stated in its "score map" form: S(p) once per pixel, candidates are the
 //      strict 3x3 local maxima of S inside the cell zone, threshold applied afterwards
 //      (equivalent to two cv::FAST calls).
@@ -34,40 +33,61 @@ static const int EDGE_THRESHOLD = 19;    // ORBextractor.cc:93
 struct Image { int w = 0, h = 0; std::vector<unsigned char> px; const unsigned char* row(int y) const { return px.data() + (size_t)y * w; } unsigned char* row(int y) { return px.data() + (size_t)y * w; } };
 
 // ---------------------------------------------------------------------------------------------
-// det_sincos: deterministic sin/cos of a float angle in radians, evaluated in double with explicit
-// fma() so that the CUDA kernel (amos-slam_b200/csrc/det_math.cuh) reproduces it bit for bit.
-// Cody-Waite reduction by pi/2 (3 parts), fdlibm __kernel_sin/__kernel_cos minimax polynomials.
+// det_sincos: sin/cos of a float angle in radians exactly as the reference computes them.  The reference writes
+// `cos(angle)`, `sin(angle)` on a float under `using namespace std` (ORBextractor.cc:178-181); GCC merges the pair into
+// one sincosf call (oracle/_ref imports `sincosf` and nothing else from libm), which glibc >= 2.28 evaluates as a
+// double-precision polynomial after a pi/2 reduction (sysdeps/ieee754/flt-32/s_sincosf.c, sincosf_poly.h; constants
+// from __sincosf_table).  The contract is glibc's FMA ifunc variant (__sincosf_fma, selected on every FMA + AVX2
+// CPU): in the disassembly of glibc 2.39's libm every `a + b * c` of sincosf_poly and the `x - n * hpi` of
+// reduce_fast is one fused multiply-add and every bare product is rounded -- restated here with explicit
+// std::fma (this file is compiled with -ffp-contract=off) and mirrored operation by operation by the CUDA
+// kernel (amos-slam_b200/csrc/det_math.cuh).  Pinned against the live libm by tests/test_oracle_cvlite.py.
 // ---------------------------------------------------------------------------------------------
-static inline void det_sincos(float xf, float* s_out, float* c_out) {
-    const double x = (double)xf;
-    const double TWO_OVER_PI = 6.36619772367581382433e-01;
-    const double PIO2_1 = 1.57079632673412561417e+00;   // first 33 bits of pi/2
-    const double PIO2_2 = 6.07710050650619224932e-11;   // next 33 bits
-    const double PIO2_3 = 2.02226624879595063154e-21;   // rest
-    double kd = std::nearbyint(x * TWO_OVER_PI);
-    int k = (int)kd;
-    double r = std::fma(-kd, PIO2_1, x);
-    r = std::fma(-kd, PIO2_2, r);
-    r = std::fma(-kd, PIO2_3, r);
-    const double z = r * r;
-    // sin(r) = r + r*z*(S1 + z*(S2 + ... ))
-    const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03, S3 = -1.98412698298579493134e-04,
-                 S4 = 2.75573137070700676789e-06, S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
-    double ps = std::fma(z, S6, S5); ps = std::fma(z, ps, S4); ps = std::fma(z, ps, S3); ps = std::fma(z, ps, S2); ps = std::fma(z, ps, S1);
-    double sn = std::fma(r * z, ps, r);
-    // cos(r) = 1 - z/2 + z*z*(C1 + z*(C2 + ...))
-    const double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03, C3 = 2.48015872894767294178e-05,
-                 C4 = -2.75573143513906633035e-07, C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
-    double pc = std::fma(z, C6, C5); pc = std::fma(z, pc, C4); pc = std::fma(z, pc, C3); pc = std::fma(z, pc, C2); pc = std::fma(z, pc, C1);
-    double cs = std::fma(z * z, pc, std::fma(-0.5, z, 1.0));
-    double s, c;
-    switch (k & 3) {
-        case 0: s = sn; c = cs; break;
-        case 1: s = cs; c = -sn; break;
-        case 2: s = -sn; c = -cs; break;
-        default: s = -cs; c = sn; break;
-    }
-    *s_out = (float)s; *c_out = (float)c;
+static inline void det_sincos(float y, float* sinp, float* cosp) {
+    // __sincosf_table[0] / [1] (the second one negates the cosine polynomial for quadrants 2, 3)
+    static const double SIGN[4] = {1.0, -1.0, -1.0, 1.0};
+    const double HPI_INV = 0x1.45F306DC9C883p+23;     // 2/pi * 2^24
+    const double HPI = 0x1.921FB54442D18p0;
+    const double C0 = 0x1p0, C1 = -0x1.ffffffd0c621cp-2, C2 = 0x1.55553e1068f19p-5, C3 = -0x1.6c087e89a359dp-10, C4 = 0x1.99343027bf8c3p-16;
+    const double S1 = -0x1.555545995a603p-3, S2 = 0x1.1107605230bc4p-7, S3 = -0x1.994eb3774cf24p-13;
+    static const uint32_t INV_PIO4[24] = {0xa2, 0xa2f9, 0xa2f983, 0xa2f9836e, 0xf9836e4e, 0x836e4e44, 0x6e4e4415, 0x4e441529, 0x441529fc, 0x1529fc27, 0x29fc2757, 0xfc2757d1,
+                                          0x2757d1f5, 0x57d1f534, 0xd1f534dd, 0xf534ddc0, 0x34ddc0db, 0xddc0db62, 0xc0db6295, 0xdb629599, 0x6295993c, 0x95993c43, 0x993c4390, 0x3c439041};
+    uint32_t xi; std::memcpy(&xi, &y, 4);
+    const uint32_t top = (xi >> 20) & 0x7ff;          // abstop12
+    double x = (double)y, s = 1.0, cneg = 1.0;        // cneg = -1 selects __sincosf_table[1]
+    int n = 0;
+    if (top < 0x3f4) {                                // |y| < pi/4
+        if (top < 0x398) { *sinp = y; *cosp = 1.0f; return; }   // |y| < 2^-12
+    } else if (top < 0x42f) {                         // |y| < 120: reduce_fast
+        const double r = x * HPI_INV;
+        n = ((int32_t)r + 0x800000) >> 24;
+        x = std::fma(-(double)n, HPI, x);
+        s = SIGN[n & 3];
+        if (n & 2) cneg = -1.0;
+    } else if (top < 0x7f8) {                         // reduce_large
+        const uint32_t* arr = &INV_PIO4[(xi >> 26) & 15];
+        const int shift = (xi >> 23) & 7, sign = xi >> 31;
+        uint32_t m = ((xi & 0xffffff) | 0x800000) << shift;
+        uint64_t res0 = (uint32_t)(m * arr[0]), res1 = (uint64_t)m * arr[4], res2 = (uint64_t)m * arr[8];
+        res0 = (res2 >> 32) | (res0 << 32);
+        res0 += res1;
+        const uint64_t nn = (res0 + (1ULL << 61)) >> 62;
+        res0 -= nn << 62;
+        x = (double)(int64_t)res0 * 0x1.921FB54442D18p-62;
+        n = (int)nn;
+        s = SIGN[(n + sign) & 3];
+        if ((n + sign) & 2) cneg = -1.0;
+    } else { *sinp = *cosp = y - y; return; }         // inf / nan
+    // sincosf_poly(x * s, x * x, p, n, sinp, cosp)
+    const double xs = x * s, x2 = x * x;
+    const double c0 = cneg * C0, c1 = cneg * C1, c2 = cneg * C2, c3 = cneg * C3, c4 = cneg * C4;     // exact sign flips
+    const double s1v = std::fma(x2, S3, S2), c2v = std::fma(x2, c4, c3);
+    const double x3 = x2 * xs, x4 = x2 * x2;
+    const double x5 = x2 * x3, x6 = x2 * x4;
+    const double c1v = std::fma(x2, c1, c0);
+    const double sv = std::fma(x3, S1, xs), cv = std::fma(x4, c2, c1v);
+    const float fs = (float)std::fma(s1v, x5, sv), fc = (float)std::fma(c2v, x6, cv);
+    if (n & 1) { *sinp = fc; *cosp = fs; } else { *sinp = fs; *cosp = fc; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -498,6 +518,18 @@ void cvl_c_border101(const unsigned char* src, int w, int h, int b, unsigned cha
     for (int y = 0; y < d.rows; ++y) std::memcpy(dst + (size_t)y * d.cols, d.ptr(y), (size_t)d.cols);
 }
 void port_det_sincos(const float* x, float* s, float* c, int n) { for (int i = 0; i < n; ++i) port::det_sincos(x[i], &s[i], &c[i]); }
-void port_libm_sincosf(const float* x, float* s, float* c, int n) { for (int i = 0; i < n; ++i) { s[i] = sinf(x[i]); c[i] = cosf(x[i]); } }
+void port_libm_sincosf(const float* x, float* s, float* c, int n) { for (int i = 0; i < n; ++i) sincosf(x[i], &s[i], &c[i]); }   // the libm entry point the reference build imports
+// exhaustive pin: every float whose bit pattern lies in [lo, hi) through det_sincos and the live libm sincosf; returns the number of
+// inputs where either output differs in any bit (the first `cap` such bit patterns go to `bad`)
+long long port_sincos_sweep(unsigned lo, unsigned hi, unsigned* bad, int cap) {
+    long long nbad = 0;
+    for (unsigned long long b = lo; b < hi; ++b) {
+        const unsigned u = (unsigned)b; float x, s1, c1, s2, c2;
+        std::memcpy(&x, &u, 4);
+        port::det_sincos(x, &s1, &c1); sincosf(x, &s2, &c2);
+        if (std::memcmp(&s1, &s2, 4) || std::memcmp(&c1, &c2, 4)) { if (nbad < cap) bad[nbad] = u; ++nbad; }
+    }
+    return nbad;
+}
 
 }  // extern "C"

@@ -24,7 +24,12 @@ thread_local Arena g_arena;
 const size_t kArenaBytes = (size_t)1 << 30;   // virtual reservation; pages are touched lazily
 }
 
+// ORB_REF_GLIBC_HEAP=1: leave every allocation to glibc malloc -- the reference exactly as shipped, whose quadtree order then depends
+// on the heap's history.  Used only by tools/heap_order_report.py to measure how far that behaviour is from the canonical contract.
+static bool glibc_heap() { static const bool v = [] { const char* e = std::getenv("ORB_REF_GLIBC_HEAP"); return e && std::atoi(e) != 0; }(); return v; }
+
 extern "C" void ref_arena_begin() {
+    if (glibc_heap()) return;
     Arena& a = g_arena;
     if (!a.base) {
         a.base = (char*)std::malloc(kArenaBytes);

@@ -338,3 +338,53 @@ def test_getters(orbx, oracle):
     assert np.array_equal(E.GetInverseScaleFactors(), np.float32(1.0) / P.scale_factors)
     assert np.array_equal(E.GetScaleSigmaSquares(), P.scale_factors * P.scale_factors)
     assert np.array_equal(E.features_per_level(), P.features_per_level)
+
+
+def test_device_sincos_is_glibc_sincosf(orbx, oracle):
+    """det_sincos on the device == the oracle's restatement of glibc's sincosf (itself pinned against the live libm for every float,
+    tests/test_oracle_cvlite.py): 40 blocks of 2^22 consecutive bit patterns spread over [0, 7.0) -- every octave of the angle range,
+    both reduction branches, all four quadrants -- plus blocks of negative, large (reduce_large) and non-finite arguments."""
+    E = orbx.ORBextractor(500, 1.2, 8, 20, 7)
+    lib = oracle.port_lib()
+    hi = int(np.float32(7.0).view(np.uint32)); n = 1 << 22
+    starts = [int(x) for x in np.linspace(0, hi - n, 32)] + [int(np.float32(v).view(np.uint32)) - n // 2 for v in (np.pi / 4, np.pi / 2, np.pi, 3 * np.pi / 2, 2 * np.pi)]
+    starts += [0x80000000 + starts[20], int(np.float32(119.0).view(np.uint32)), int(np.float32(1e6).view(np.uint32)), 0x7F800000 - n // 2]
+    for lo in starts:
+        sg, cg = E.debug_sincos(lo, n)
+        x = (np.arange(n, dtype=np.uint64) + lo).astype(np.uint32).view(np.float32)
+        so, co = np.zeros(n, np.float32), np.zeros(n, np.float32)
+        lib.port_det_sincos(x, so, co, n)
+        for g, o in ((sg, so), (cg, co)):                          # bit for bit; NaN results (inf / nan arguments) only have to be NaN on both sides
+            nan = np.isnan(o)
+            assert np.array_equal(np.isnan(g), nan) and np.array_equal(g.view(np.uint32)[~nan], o.view(np.uint32)[~nan]), hex(lo)
+
+
+def test_descriptors_at_sincos_sensitive_angles(orbx, oracle):
+    """>= 10^5 ADVERSARIAL orientations -- angles where glibc's sincosf (what the reference calls, src/ORBextractor.cc:181) differs from
+    the correctly rounded sin / cos, i.e. exactly the keypoints a 'mathematically right' sin/cos would get wrong -- pushed through
+    ProcessDesp on a textured frame: descriptors must equal the reference build's (oracle/_ref where it travelled, else the port)."""
+    lib = oracle.port_lib()
+    rng = np.random.default_rng(5)
+    deg = (rng.random(6_000_000) * 360.0).astype(np.float32)
+    rad = deg * np.float32(np.pi / 180.0)                      # angle * factorPI in float, as :178 does
+    s, c = np.zeros_like(rad), np.zeros_like(rad)
+    lib.port_libm_sincosf(rad, s, c, len(rad))
+    adv = (s != np.sin(rad.astype(np.float64)).astype(np.float32)) | (c != np.cos(rad.astype(np.float64)).astype(np.float32))
+    deg = deg[adv]
+    assert len(deg) >= 100_000, len(deg)
+    deg = deg[:120_000]
+    img = synth_frame(77, 320, 240)
+    E = orbx.ORBextractor(500, 1.2, 8, 20, 7)
+    kind = "ref" if oracle.have_ref() else "port"
+    P = oracle.Extractor(kind, 500, 1.2, 8, 20, 7)
+    kp, counts = E.detect(img); ko, co = P.detect(img)
+    assert kp_equal(kp, ko)
+    # level-0 keypoints re-used round-robin, each with one adversarial angle
+    base = kp[:counts[0]]
+    big = np.repeat(base[:1], len(deg)); big[:] = base[np.arange(len(deg)) % len(base)]; big["angle"] = deg
+    cnt = np.zeros(8, np.int32); cnt[0] = len(big)
+    kg, dg = E.ProcessDesp(big, cnt)
+    kr, dr = P.process_desp(big, cnt)
+    assert kp_equal(kg, kr)
+    nbad = int((dg != dr).any(axis=1).sum())
+    assert nbad == 0, "%d of %d sincos-sensitive keypoints differ" % (nbad, len(deg))

@@ -87,18 +87,35 @@ def test_primitives_against_live_cv2(oracle):
         assert np.array_equal(_fast(lib, oracle, img, th, 1), ref)
 
 
-def test_det_sincos_vs_libm(oracle):
-    """det_sincos (double polynomial, explicit fma, rounded to float) vs glibc sinf/cosf: the rBRIEF rotation uses
-    the former on both CPU oracle and GPU; differences against libm must be rare and exactly 1 ulp."""
+def test_det_sincos_is_glibc_sincosf(oracle):
+    """The rBRIEF rotation (src/ORBextractor.cc:178-181) is glibc's sincosf in the reference build.  The oracle's restatement of
+    that function (FMA variant; mirrored by the CUDA kernel) must equal the live libm bit for bit: EVERY float in [0, 7.0) --
+    a superset of every angle the path can produce (degrees in [0, 360] times pi/180) -- and 2^27 strided patterns of the rest."""
+    import threading
     lib = oracle.port_lib()
+    hi = int(np.float32(7.0).view(np.uint32))
+    nthr = 4; res = [None] * nthr
+    def run(i):
+        bad = np.zeros(8, np.uint32)
+        lo_i, hi_i = hi * i // nthr, hi * (i + 1) // nthr
+        res[i] = (lib.port_sincos_sweep(lo_i, hi_i, bad, 8), bad.copy())
+    th = [threading.Thread(target=run, args=(i,)) for i in range(nthr)]
+    [t.start() for t in th]; [t.join() for t in th]
+    assert sum(r[0] for r in res) == 0, [hex(int(x)) for r in res for x in r[1][:int(min(r[0], 8))]]
+    # the rest of the float range (negative, large-argument reduction, inf / nan): blocks of 2^12 patterns every 2^17
+    bad = np.zeros(8, np.uint32)
+    tot = 0
+    for blk in range(0, 1 << 32, 1 << 17):
+        if blk + 4096 <= hi: continue
+        tot += lib.port_sincos_sweep(blk, min(blk + 4096, (1 << 32) - 1), bad, 8)
+    assert tot == 0, [hex(int(x)) for x in bad]
+    # and it is NOT the correctly rounded value everywhere (why a structural port is needed): count the angles where they differ
     ang = (np.arange(0, 360000, dtype=np.float32) / np.float32(1000.0)) * np.float32(np.pi / 180.0)
-    s1, c1, s2, c2 = (np.zeros_like(ang) for _ in range(4))
-    lib.port_det_sincos(ang, s1, c1, len(ang)); lib.port_libm_sincosf(ang, s2, c2, len(ang))
-    exact = np.sin(ang.astype(np.float64)).astype(np.float32), np.cos(ang.astype(np.float64)).astype(np.float32)
-    assert np.array_equal(s1, exact[0]) and np.array_equal(c1, exact[1])      # correctly rounded on this grid
-    for a, b in ((s1, s2), (c1, c2)):
-        d = a != b
-        assert d.mean() < 0.05
-        if d.any():
-            ulp = np.abs(a[d].view(np.int32).astype(np.int64) - b[d].view(np.int32).astype(np.int64))
-            assert ulp.max() <= 1
+    s1, c1 = np.zeros_like(ang), np.zeros_like(ang)
+    lib.port_det_sincos(ang, s1, c1, len(ang))
+    exact_s, exact_c = np.sin(ang.astype(np.float64)).astype(np.float32), np.cos(ang.astype(np.float64)).astype(np.float32)
+    d = (s1 != exact_s) | (c1 != exact_c)
+    assert 0.001 < d.mean() < 0.06
+    for a, b in ((s1, exact_s), (c1, exact_c)):
+        ulp = np.abs(a.view(np.int32).astype(np.int64) - b.view(np.int32).astype(np.int64))
+        assert ulp.max() <= 1

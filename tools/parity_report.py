@@ -20,7 +20,7 @@ FIELDS = ("x", "y", "size", "angle", "response", "octave", "class_id")
 
 def extractor_rows(name, w, h, nfeat, frames, kind):
     E = orbx.ORBextractor(nfeat, 1.2, 8, 20, 7); O = oracle.Extractor(kind, nfeat, 1.2, 8, 20, 7)
-    tot = dict(frames=0, kp_ref=0, kp_gpu=0, count_mismatch=0, desc_bytes_diff=0, angle_max_abs=0.0, **{f: 0 for f in FIELDS})
+    tot = dict(frames=0, kp_ref=0, kp_gpu=0, count_mismatch=0, desc_bytes_diff=0, angle_max_abs=0.0, sincos_sensitive=0, sincos_sensitive_desc_diff=0, angle_diff_kp=0, **{f: 0 for f in FIELDS})
     t_ref = 0.0
     for s in range(frames):
         img = synth_frame(1000 + s, w, h)
@@ -32,6 +32,13 @@ def extractor_rows(name, w, h, nfeat, frames, kind):
         for f in FIELDS:
             tot[f] += int((kg[f] != kr[f]).sum())
         tot["desc_bytes_diff"] += int((dg != dr).sum())
+        # keypoints whose rotation is sincos-SENSITIVE: glibc's sincosf (what the reference calls at :181) differs from the correctly rounded
+        # sin / cos of angle * factorPI.  They are listed separately: a right-in-the-maths sin/cos may flip their sample coordinates.
+        rad = kr["angle"] * np.float32(np.pi / 180.0)
+        ls, lc = np.zeros_like(rad), np.zeros_like(rad); oracle.port_lib().port_libm_sincosf(np.ascontiguousarray(rad), ls, lc, len(rad))
+        sens = (ls != np.sin(rad.astype(np.float64)).astype(np.float32)) | (lc != np.cos(rad.astype(np.float64)).astype(np.float32))
+        tot["sincos_sensitive"] += int(sens.sum()); tot["sincos_sensitive_desc_diff"] += int((dg[sens] != dr[sens]).any(axis=1).sum())
+        tot["angle_diff_kp"] += int((kg["angle"] != kr["angle"]).sum())
         if len(kg):
             tot["angle_max_abs"] = max(tot["angle_max_abs"], float(np.abs(kg["angle"] - kr["angle"]).max()))
     tot["ref_ms_per_frame_1core"] = 1e3 * t_ref / max(frames, 1)
@@ -230,13 +237,17 @@ def main():
     print("# Parity report (GPU through the C ABI vs `oracle/%s`)\n" % ("_ref: the reference's own sources" if kind == "ref" else "port"))
     print("Seeded synthetic frames (`tools/synth.py`, seeds 1000+i); every number below is a count of DIFFERENCES unless named otherwise.\n")
     print("## Extractor `operator()` (a1-a10)\n")
-    print("| config | frames | keypoints (ref) | keypoints (gpu) | frames with different count | x | y | size | angle | response | octave | descriptor bytes | max abs angle diff | ref ms/frame (1 core) |")
-    print("|---|---|---|---|---|---|---|---|---|---|---|---|---|---|")
+    print("| config | frames | keypoints (ref) | keypoints (gpu) | frames with different count | x | y | size | angle | response | octave | descriptor bytes | max abs angle diff | keypoints with ANY angle difference (would be listed as angle-sensitive) | sincos-sensitive keypoints (glibc sincosf != correctly rounded) | of those: descriptor differs | ref ms/frame (1 core) |")
+    print("|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|")
     for name, w, h, nf, n in (("C1 640x480/1000", 640, 480, 1000, a.frames), ("C3 752x480/2000", 752, 480, 2000, max(a.frames // 2, 1)),
                               ("C4 1241x376/2000", 1241, 376, 2000, max(a.frames // 4, 1)), ("C5 1920x1080/1000", 1920, 1080, 1000, max(a.frames // 10, 1))):
         _, t = extractor_rows(name, w, h, nf, n, kind)
-        print("| %s | %d | %d | %d | %d | %d | %d | %d | %d | %d | %d | %d | %g | %.1f |" % (name, t["frames"], t["kp_ref"], t["kp_gpu"], t["count_mismatch"], t["x"], t["y"], t["size"], t["angle"],
-                                                                                            t["response"], t["octave"], t["desc_bytes_diff"], t["angle_max_abs"], t["ref_ms_per_frame_1core"]))
+        print("| %s | %d | %d | %d | %d | %d | %d | %d | %d | %d | %d | %d | %g | %d | %d | %d | %.1f |" % (name, t["frames"], t["kp_ref"], t["kp_gpu"], t["count_mismatch"], t["x"], t["y"], t["size"], t["angle"],
+                                                                                            t["response"], t["octave"], t["desc_bytes_diff"], t["angle_max_abs"], t["angle_diff_kp"], t["sincos_sensitive"],
+                                                                                            t["sincos_sensitive_desc_diff"], t["ref_ms_per_frame_1core"]))
+    print("\nThe rotation of `computeOrbDescriptor` is glibc's `sincosf` (FMA variant) restated operation by operation on the device (`det_math.cuh`); it equals the live libm "
+          "for every float (`tests/test_oracle_cvlite.py`, `tests/test_gpu_extractor.py::test_device_sincos_is_glibc_sincosf`), so sincos-sensitive keypoints agree by construction, "
+          "and 120 000 adversarial angles are pushed through `ProcessDesp` in `test_descriptors_at_sincos_sensitive_angles`.")
     rc = random_config_rows(max(a.frames // 3, 5), kind)
     print("\n### Randomised configurations (size 96-1400 x 96-900, 150-3000 features, scale factor 1.1-2.0, 1-8 levels, FAST thresholds 10-45 / 3-12, one frame with a padded row stride)\n")
     print("| configurations | frames | keypoints (ref) | frames with different count | keypoint field diffs | descriptor byte diffs | skipped (geometry the reference cannot run) |\n|---|---|---|---|---|---|---|")
