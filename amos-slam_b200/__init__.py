@@ -32,6 +32,20 @@ TH_HIGH, TH_LOW, HISTO_LENGTH = 100, 50, 30
 FRAME_GRID_COLS, FRAME_GRID_ROWS = 64, 48
 
 
+class LabelsC(C.Structure):
+    """orbx_labels (include/orbx_b200.h): super-pixel ids + per-frame flag tables of the batched MovingKeyPoints."""
+    _fields_ = [("labels", C.c_void_p), ("label_step", C.c_size_t), ("label_frame_stride", C.c_size_t), ("flagged", C.c_void_p), ("n_labels", C.c_int)]
+
+
+def label_flags(centers_id, rm_vector):
+    """flagged[id - 1] = (rm_vector[centers[id - 1].id] == 1)  (src/ORBextractor.cc:1727); out-of-range ids count as not flagged."""
+    cid = np.asarray(centers_id, np.int64); rm = np.asarray(rm_vector, np.int64)
+    ok = (cid >= 0) & (cid < len(rm))
+    out = np.zeros(len(cid), np.uint8)
+    out[ok] = (rm[cid[ok]] == 1)
+    return out
+
+
 class OrbxError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("orbx error %d: %s" % (code, msg))
@@ -85,6 +99,8 @@ def lib():
     L.orbx_extract_batch_device.argtypes = [vp, vp, ci, ci, ci, sz, sz, vp, vp, ci, vp]
     L.orbx_extract_masked_batch.argtypes = [vp, vp, vp, ci, ci, ci, sz, sz, sz, sz, vp, vp, ci, vp, vp]
     L.orbx_extract_masked_batch_device.argtypes = [vp, vp, vp, ci, ci, ci, sz, sz, sz, sz, vp, vp, ci, vp, vp]
+    L.orbx_extract_masked_batch_labels.argtypes = [vp, vp, vp, vp, ci, ci, ci, sz, sz, sz, sz, vp, vp, ci, vp, vp]
+    L.orbx_extract_masked_batch_labels_device.argtypes = [vp, vp, vp, vp, ci, ci, ci, sz, sz, sz, sz, vp, vp, ci, vp, vp]
     L.orbx_debug_level_candidates.argtypes = [vp, ci, ci, vp, ci, C.POINTER(ci)]
     L.orbx_debug_blurred_level.argtypes = [vp, ci, ci, vp, sz]
     L.orbx_debug_pyramid_level.argtypes = [vp, ci, ci, vp, sz]
@@ -293,16 +309,25 @@ class ORBextractor:
         _check(self._lib.orbx_extract_batch(self._h, _ptr(images), B, rows, cols, images.strides[1], images.strides[0], _ptr(kp), _ptr(desc), cap, _ptr(counts)))
         return kp, desc, counts
 
-    def extract_masked_batch(self, images, masks, cap=None):
-        """Batched Amos path: images, masks (B, rows, cols) uint8 host arrays -> (kp[B,cap], desc[B,cap,32], counts[B], culled[B])."""
+    def extract_masked_batch(self, images, masks, labels=None, flagged=None, cap=None):
+        """Batched Amos path: images, masks (B, rows, cols) uint8 host arrays -> (kp[B,cap], desc[B,cap,32], counts[B], culled[B]).
+        labels (B, rows, cols) super-pixel ids (1-based; any integer-valued dtype, sent as uint16) and flagged (B, n_labels) uint8 =
+        label_flags(centers_id, rm_vector) per frame add the super-pixel term of MovingKeyPoints."""
         if images.dtype != np.uint8 or images.ndim != 3 or masks.dtype != np.uint8 or masks.shape != images.shape:
             raise OrbxError(E_INVALID, "images and masks must be (B, rows, cols) uint8 of the same shape")
         images = np.ascontiguousarray(images); masks = np.ascontiguousarray(masks)
         B, rows, cols = images.shape
         cap = cap or self.max_keypoints(rows, cols)
         kp = np.zeros((B, cap), KP_DTYPE); desc = np.zeros((B, cap, 32), np.uint8); counts = np.zeros(B, np.int32); culled = np.zeros(B, np.int32)
-        _check(self._lib.orbx_extract_masked_batch(self._h, _ptr(images), _ptr(masks), B, rows, cols, images.strides[1], images.strides[0],
-                                                   masks.strides[1], masks.strides[0], _ptr(kp), _ptr(desc), cap, _ptr(counts), _ptr(culled)))
+        lab = None
+        if labels is not None:
+            l16 = np.ascontiguousarray(labels, np.uint16); fl = np.ascontiguousarray(flagged, np.uint8)
+            if l16.shape != images.shape or fl.ndim != 2 or fl.shape[0] != B:
+                raise OrbxError(E_INVALID, "labels must be (B, rows, cols) and flagged (B, n_labels)")
+            lab = LabelsC(_ptr(l16), cols, rows * cols, _ptr(fl), fl.shape[1])
+        _check(self._lib.orbx_extract_masked_batch_labels(self._h, _ptr(images), _ptr(masks), C.byref(lab) if lab is not None else None, B, rows, cols,
+                                                          images.strides[1], images.strides[0], masks.strides[1], masks.strides[0],
+                                                          _ptr(kp), _ptr(desc), cap, _ptr(counts), _ptr(culled)))
         return kp, desc, counts, culled
 
     def extract_masked_batch_raw_device(self, images_ptr, masks_ptr, B, rows, cols, step, frame_stride, mask_step, mask_frame_stride, kp_ptr, desc_ptr, cap, counts_ptr, culled_ptr=0):

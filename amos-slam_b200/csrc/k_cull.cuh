@@ -94,12 +94,17 @@ __global__ void k_bin_dilate31(const uint32_t* __restrict__ in, uint32_t* __rest
     out[((long long)b * rows + y) * wpr + wx] = acc;
 }
 
-// Batched MovingKeyPoints on the per-level keypoint slots of the quadtree stage (mask term only, :1734-1741): one warp per
+// Batched MovingKeyPoints on the per-level keypoint slots of the quadtree stage (:1718-1741): one warp per
 // (level, frame) drops the keypoints whose position p = (int)(pt * scale) lies on a set bit of the closed mask, keeps the
 // order of the survivors (stable erase) and rewrites the level's count.
+// Optional super-pixel term (:1722-1736): labels = imLS as 16-bit super-pixel ids (1-based; the reference stores them as CV_64F), flagged[id - 1] =
+// (rm_vector[centers[id - 1].id] == 1) per frame, prepared by the caller from the two small tables.  An id outside [1, n_labels] (undefined
+// behaviour in the reference) counts as "not flagged".
+struct LabelView { const uint16_t* labels; long long fstride; int pitch; const uint8_t* flagged; int n_labels; };
+
 __global__ void __launch_bounds__(32)
 k_cull_levelkp(const LevelGeom* __restrict__ levels, int nlevels, int kp_per_frame, uint32_t* __restrict__ kp_level, int* __restrict__ kp_count,
-               const uint32_t* __restrict__ closed, int wpr, int rows, int cols, int* __restrict__ culled_count) {
+               const uint32_t* __restrict__ closed, int wpr, int rows, int cols, LabelView lv, int* __restrict__ culled_count) {
     const int level = blockIdx.x, b = blockIdx.y, lane = threadIdx.x;
     const LevelGeom& g = levels[level];
     uint32_t* kp = kp_level + (long long)b * kp_per_frame + g.kp_off;
@@ -115,7 +120,13 @@ k_cull_levelkp(const LevelGeom* __restrict__ levels, int nlevels, int kp_per_fra
             const float x = (float)((int)(p & 0xFFF) + g.minBX), y = (float)((int)((p >> 12) & 0xFFF) + g.minBY);
             const int px = (int)__fmul_rn(x, scale), py = (int)__fmul_rn(y, scale);
             keep = true;
-            if (px >= 0 && py >= 0 && px < cols && py < rows) keep = ((plane[(long long)py * wpr + (px >> 5)] >> (px & 31)) & 1u) == 0u;
+            if (px >= 0 && py >= 0 && px < cols && py < rows) {
+                keep = ((plane[(long long)py * wpr + (px >> 5)] >> (px & 31)) & 1u) == 0u;
+                if (keep && lv.labels) {
+                    const int id = lv.labels[(long long)b * lv.fstride + (long long)py * lv.pitch + px];
+                    if (id >= 1 && id <= lv.n_labels && lv.flagged[(long long)b * lv.n_labels + id - 1]) keep = false;
+                }
+            }
         }
         const uint32_t m = __ballot_sync(0xffffffffu, keep);
         __syncwarp();

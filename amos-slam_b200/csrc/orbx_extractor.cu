@@ -90,7 +90,7 @@ struct orbx_extractor {
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;     // ORBX_NSTAGES+1 events per call
     // small staging buffers for the single-frame calls
-    DevBuf<KpOut> d_kp_tmp; DevBuf<uint8_t> d_desc_tmp; DevBuf<uint8_t> d_mask; DevBuf<uint32_t> d_bits0, d_bits1; DevBuf<double> d_label; DevBuf<int> d_ids, d_culled;
+    DevBuf<KpOut> d_kp_tmp; DevBuf<uint8_t> d_desc_tmp; DevBuf<uint8_t> d_mask; DevBuf<uint32_t> d_bits0, d_bits1; DevBuf<double> d_label; DevBuf<int> d_ids, d_culled; DevBuf<uint16_t> d_label16; DevBuf<uint8_t> d_lflags;
 };
 
 // -------------------------------------------------------------------------------------------------
@@ -488,7 +488,7 @@ void orbx_destroy(orbx_extractor* h) {
     h->d_pyr.release(); h->d_blur.release(); h->d_slots.release(); h->d_ocand.release(); h->d_spk.release(); h->d_kp_level.release();
     h->d_skey.release(); h->d_cell_counts.release(); h->d_ncand.release(); h->d_kp_count.release(); h->d_counts.release();
     h->d_level_counts.release(); h->d_overflow.release(); h->d_kp_out.release(); h->d_desc_out.release();
-    h->d_kp_tmp.release(); h->d_desc_tmp.release(); h->d_mask.release(); h->d_bits0.release(); h->d_bits1.release(); h->d_culled.release(); h->d_label.release(); h->d_ids.release();
+    h->d_kp_tmp.release(); h->d_desc_tmp.release(); h->d_mask.release(); h->d_bits0.release(); h->d_bits1.release(); h->d_culled.release(); h->d_label.release(); h->d_ids.release(); h->d_label16.release(); h->d_lflags.release();
     cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -581,12 +581,12 @@ static int chunk_frames(const orbx_extractor* h, int B) {
     return (int)c;
 }
 
-static int run_masked_range(orbx_extractor* h, int b0, int nb, const uint8_t* d_masks, long long mfs, int mpitch, int rows, int cols,
+static int run_masked_range(orbx_extractor* h, int b0, int nb, const uint8_t* d_masks, long long mfs, int mpitch, int rows, int cols, LabelView lv,
                             KpOut* d_kp, uint8_t* d_desc, int cap, int* d_counts, int* d_culled);
 static int ensure_closing(orbx_extractor* h, int nframes, int rows, int cols);
 
 // masks == nullptr: operator()(image, mask, keypoints, descriptors) per frame; otherwise the two-stage Amos path with culling
-static int host_batch_pipeline(orbx_extractor* h, const uint8_t* images, const uint8_t* masks, int B, int rows, int cols, size_t step, size_t frame_stride,
+static int host_batch_pipeline(orbx_extractor* h, const uint8_t* images, const uint8_t* masks, const orbx_labels* labels, int B, int rows, int cols, size_t step, size_t frame_stride,
                                size_t mask_step, size_t mask_frame_stride, orbx_keypoint* kp_out, uint8_t* desc_out, int cap, int* counts_out, int* culled_out) {
     int rc = check_args(h, images, rows, cols, step); if (rc) return rc;
     if (B <= 0 || !kp_out || !desc_out || !counts_out || cap <= 0) FAIL(ORBX_E_INVALID, "bad batch arguments");
@@ -609,6 +609,9 @@ static int host_batch_pipeline(orbx_extractor* h, const uint8_t* images, const u
         if ((rc = ensure_closing(h, B, rows, cols))) return rc;
         if (h->d_mask.ensure(mfs * B + 64) || h->d_culled.ensure(B)) return ORBX_E_CUDA;
     }
+    // super-pixel labels ride along with the masks: 16-bit ids in a dense device mirror (cols elements per row) + the per-frame flag tables
+    const size_t lfs = (size_t)rows * cols;
+    if (labels && (h->d_label16.ensure(lfs * B) || h->d_lflags.ensure((size_t)labels->n_labels * B))) return ORBX_E_CUDA;
     // chunk boundaries: short first chunks (C/4, C/2, then C) let compute start while most of the batch is still on the bus
     const int C = chunk_frames(h, B);
     static const int ramp = [] { const char* e = std::getenv("ORBX_CHUNK_RAMP"); return e ? std::atoi(e) : 1; }();
@@ -644,13 +647,26 @@ static int host_batch_pipeline(orbx_extractor* h, const uint8_t* images, const u
                 for (int b = b0; b < b0 + nb; ++b)
                     CU_TRY(cudaMemcpy2DAsync(h->d_mask.p + (size_t)b * mfs, mpitch, masks + (size_t)b * mask_frame_stride, mask_step, cols, rows, cudaMemcpyHostToDevice, h->s_h2d));
         }
+        if (labels) {
+            if (labels->label_step == (size_t)cols && labels->label_frame_stride == lfs)
+                CU_TRY(cudaMemcpyAsync(h->d_label16.p + (size_t)b0 * lfs, labels->labels + (size_t)b0 * lfs, (size_t)nb * lfs * 2, cudaMemcpyHostToDevice, h->s_h2d));
+            else
+                for (int b = b0; b < b0 + nb; ++b)
+                    CU_TRY(cudaMemcpy2DAsync(h->d_label16.p + (size_t)b * lfs, (size_t)cols * 2, labels->labels + (size_t)b * labels->label_frame_stride, labels->label_step * 2,
+                                             (size_t)cols * 2, rows, cudaMemcpyHostToDevice, h->s_h2d));
+            CU_TRY(cudaMemcpyAsync(h->d_lflags.p + (size_t)b0 * labels->n_labels, labels->flagged + (size_t)b0 * labels->n_labels, (size_t)nb * labels->n_labels, cudaMemcpyHostToDevice, h->s_h2d));
+        }
         CU_TRY(cudaEventRecord(h->ev_h2d[c], h->s_h2d));
     }
     for (int c = 0; c < nchunks; ++c) {
         const int b0 = cb[c], nb = cb[c + 1] - b0;
         h->cur = cs[c % nstreams];
         CU_TRY(cudaStreamWaitEvent(h->cur, h->ev_h2d[c], 0));
-        if (masks) rc = run_masked_range(h, b0, nb, h->d_mask.p + (size_t)b0 * mfs, (long long)mfs, mpitch, rows, cols, h->d_kp_out.p, h->d_desc_out.p, cap, h->d_counts.p, h->d_culled.p);
+        if (masks) {
+            LabelView lv{nullptr, 0, 0, nullptr, 0};
+            if (labels) lv = LabelView{h->d_label16.p + (size_t)b0 * lfs, (long long)lfs, cols, h->d_lflags.p + (size_t)b0 * labels->n_labels, labels->n_labels};
+            rc = run_masked_range(h, b0, nb, h->d_mask.p + (size_t)b0 * mfs, (long long)mfs, mpitch, rows, cols, lv, h->d_kp_out.p, h->d_desc_out.p, cap, h->d_counts.p, h->d_culled.p);
+        }
         else {
             rc = run_detect(h, b0, nb);
             if (!rc) rc = run_blur_range(h, b0, nb);
@@ -688,7 +704,7 @@ static int host_batch_pipeline(orbx_extractor* h, const uint8_t* images, const u
 
 int orbx_extract_batch(orbx_extractor* h, const uint8_t* images, int B, int rows, int cols, size_t step, size_t frame_stride,
                        orbx_keypoint* kp_out, uint8_t* desc_out, int cap, int* counts_out) {
-    return host_batch_pipeline(h, images, nullptr, B, rows, cols, step, frame_stride, 0, 0, kp_out, desc_out, cap, counts_out, nullptr);
+    return host_batch_pipeline(h, images, nullptr, nullptr, B, rows, cols, step, frame_stride, 0, 0, kp_out, desc_out, cap, counts_out, nullptr);
 }
 
 int orbx_extract(orbx_extractor* h, const uint8_t* image, int rows, int cols, size_t step,

@@ -106,8 +106,8 @@ extern "C" int orbx_cull(orbx_extractor* h, const uint8_t* mask, size_t mask_ste
 }
 
 // Batched Amos path (BASELINE config 5): per frame  operator()(img, mask, vector<vector<KeyPoint>>&)  ->  MovingKeyPoints with the
-// dynamic mask (no super-pixel labels)  ->  ProcessDesp.  Frames [b0, b0+nb) on h->cur; d_masks points at frame b0's mask.
-static int run_masked_range(orbx_extractor* h, int b0, int nb, const uint8_t* d_masks, long long mfs, int mpitch, int rows, int cols,
+// dynamic mask and, when lv.labels is set, the super-pixel term  ->  ProcessDesp.  Frames [b0, b0+nb) on h->cur; d_masks points at frame b0's mask.
+static int run_masked_range(orbx_extractor* h, int b0, int nb, const uint8_t* d_masks, long long mfs, int mpitch, int rows, int cols, LabelView lv,
                             KpOut* d_kp, uint8_t* d_desc, int cap, int* d_counts, int* d_culled) {
     int rc;
     if ((rc = run_detect(h, b0, nb))) return rc;
@@ -116,16 +116,24 @@ static int run_masked_range(orbx_extractor* h, int b0, int nb, const uint8_t* d_
     const int wpr = (cols + 31) / 32;
     k_cull_levelkp<<<dim3(h->nlevels, nb), 32, 0, h->cur>>>(h->d_levels.p, h->nlevels, h->kp_per_frame, h->d_kp_level.p + (size_t)b0 * h->kp_per_frame,
                                                               h->d_kp_count.p + (size_t)b0 * h->nlevels, h->d_bits0.p + (size_t)b0 * rows * wpr, wpr, rows, cols,
-                                                              d_culled ? d_culled + b0 : nullptr);
+                                                              lv, d_culled ? d_culled + b0 : nullptr);      // lv points at frame b0's labels / flags
     LAUNCH_CHECK();
     if ((rc = run_blur_range(h, b0, nb))) return rc;
     return run_orient(h, b0, nb, true, d_kp, d_desc, cap, d_counts, nullptr);
 }
 
-extern "C" int orbx_extract_masked_batch_device(orbx_extractor* h, const uint8_t* d_images, const uint8_t* d_masks, int B, int rows, int cols,
-                                                size_t step, size_t frame_stride, size_t mask_step, size_t mask_frame_stride,
-                                                orbx_keypoint* d_kp_out, uint8_t* d_desc_out, int cap, int* d_counts_out, int* d_culled_out) {
+static int check_labels(const orbx_labels* L, int rows, int cols) {
+    if (!L) return ORBX_OK;
+    if (!L->labels || !L->flagged || L->n_labels <= 0 || L->n_labels > 65535 || L->label_step < (size_t)cols || L->label_frame_stride < L->label_step * (size_t)(rows - 1) + (size_t)cols)
+        FAIL(ORBX_E_INVALID, "bad label arguments");
+    return ORBX_OK;
+}
+
+extern "C" int orbx_extract_masked_batch_labels_device(orbx_extractor* h, const uint8_t* d_images, const uint8_t* d_masks, const orbx_labels* d_labels, int B, int rows, int cols,
+                                                       size_t step, size_t frame_stride, size_t mask_step, size_t mask_frame_stride,
+                                                       orbx_keypoint* d_kp_out, uint8_t* d_desc_out, int cap, int* d_counts_out, int* d_culled_out) {
     int rc = check_args(h, d_images, rows, cols, step); if (rc) return rc;
+    if ((rc = check_labels(d_labels, rows, cols))) return rc;
     if (B <= 0 || !d_masks || !d_kp_out || !d_desc_out || !d_counts_out || cap <= 0 || mask_step < (size_t)cols) FAIL(ORBX_E_INVALID, "bad batch arguments");
     if ((rc = build_plan(h, rows, cols))) return rc;
     if ((rc = ensure_capacity(h, B, 0))) return rc;
@@ -143,9 +151,16 @@ extern "C" int orbx_extract_masked_batch_device(orbx_extractor* h, const uint8_t
         mk = h->d_mask.p;
     }
     h->cur = h->stream;
-    rc = run_masked_range(h, 0, B, mk, mfs, mpitch, rows, cols, reinterpret_cast<KpOut*>(d_kp_out), d_desc_out, cap, d_counts_out, d_culled_out);
+    LabelView lv{nullptr, 0, 0, nullptr, 0};
+    if (d_labels) lv = LabelView{d_labels->labels, (long long)d_labels->label_frame_stride, (int)d_labels->label_step, d_labels->flagged, d_labels->n_labels};
+    rc = run_masked_range(h, 0, B, mk, mfs, mpitch, rows, cols, lv, reinterpret_cast<KpOut*>(d_kp_out), d_desc_out, cap, d_counts_out, d_culled_out);
     if (!rc) { h->lastB = B; h->blur_valid = true; }
     return rc;
+}
+extern "C" int orbx_extract_masked_batch_device(orbx_extractor* h, const uint8_t* d_images, const uint8_t* d_masks, int B, int rows, int cols,
+                                                size_t step, size_t frame_stride, size_t mask_step, size_t mask_frame_stride,
+                                                orbx_keypoint* d_kp_out, uint8_t* d_desc_out, int cap, int* d_counts_out, int* d_culled_out) {
+    return orbx_extract_masked_batch_labels_device(h, d_images, d_masks, nullptr, B, rows, cols, step, frame_stride, mask_step, mask_frame_stride, d_kp_out, d_desc_out, cap, d_counts_out, d_culled_out);
 }
 
 // host-pointer form: same chunked H2D -> compute -> D2H pipeline as orbx_extract_batch, with the masks riding along
@@ -153,6 +168,13 @@ extern "C" int orbx_extract_masked_batch(orbx_extractor* h, const uint8_t* image
                                          size_t step, size_t frame_stride, size_t mask_step, size_t mask_frame_stride,
                                          orbx_keypoint* kp_out, uint8_t* desc_out, int cap, int* counts_out, int* culled_out) {
     if (!masks || mask_step < (size_t)cols) FAIL(ORBX_E_INVALID, "bad mask arguments");
-    return host_batch_pipeline(h, images, masks, B, rows, cols, step, frame_stride, mask_step, mask_frame_stride, kp_out, desc_out, cap, counts_out, culled_out);
+    return host_batch_pipeline(h, images, masks, nullptr, B, rows, cols, step, frame_stride, mask_step, mask_frame_stride, kp_out, desc_out, cap, counts_out, culled_out);
+}
+extern "C" int orbx_extract_masked_batch_labels(orbx_extractor* h, const uint8_t* images, const uint8_t* masks, const orbx_labels* labels, int B, int rows, int cols,
+                                                size_t step, size_t frame_stride, size_t mask_step, size_t mask_frame_stride,
+                                                orbx_keypoint* kp_out, uint8_t* desc_out, int cap, int* counts_out, int* culled_out) {
+    if (!masks || mask_step < (size_t)cols) FAIL(ORBX_E_INVALID, "bad mask arguments");
+    int rc = check_labels(labels, rows, cols); if (rc) return rc;
+    return host_batch_pipeline(h, images, masks, labels, B, rows, cols, step, frame_stride, mask_step, mask_frame_stride, kp_out, desc_out, cap, counts_out, culled_out);
 }
 

@@ -157,6 +157,23 @@ int orbx_extract_masked_batch(orbx_extractor* h, const uint8_t* images, const ui
 int orbx_extract_masked_batch_device(orbx_extractor* h, const uint8_t* d_images, const uint8_t* d_masks, int B, int rows, int cols,
                                      size_t step, size_t frame_stride, size_t mask_step, size_t mask_frame_stride,
                                      orbx_keypoint* d_kp_out, uint8_t* d_desc_out, int cap, int* d_counts_out, int* d_culled_out);
+/* The same with the super-pixel term of MovingKeyPoints (src/ORBextractor.cc:1722-1736): a keypoint is also removed when
+ *   rm_vector[centers[imLS(p) - 1].id] == 1,  p = (int)(pt * scale).
+ * imLS travels as 16-bit super-pixel ids (the reference keeps them in a CV_64F image; ids are 1-based integers), frame b at
+ * labels + b * label_frame_stride, label_step ELEMENTS per row; flagged[b * n_labels + id - 1] = (rm_vector[centers[id - 1].id] == 1),
+ * which the caller folds from its two small tables (centers, rm_vector) per frame.  Ids outside [1, n_labels] (undefined behaviour
+ * in the reference) count as not flagged.  labels == NULL behaves like the calls above.  Host pointers for the host call,
+ * device pointers (the struct itself on the host) for the *_device call. */
+typedef struct orbx_labels {
+    const uint16_t* labels; size_t label_step, label_frame_stride;   /* in elements */
+    const uint8_t* flagged; int n_labels;
+} orbx_labels;
+int orbx_extract_masked_batch_labels(orbx_extractor* h, const uint8_t* images, const uint8_t* masks, const orbx_labels* labels, int B, int rows, int cols,
+                                     size_t step, size_t frame_stride, size_t mask_step, size_t mask_frame_stride,
+                                     orbx_keypoint* kp_out, uint8_t* desc_out, int cap, int* counts_out, int* culled_out);
+int orbx_extract_masked_batch_labels_device(orbx_extractor* h, const uint8_t* d_images, const uint8_t* d_masks, const orbx_labels* d_labels, int B, int rows, int cols,
+                                            size_t step, size_t frame_stride, size_t mask_step, size_t mask_frame_stride,
+                                            orbx_keypoint* d_kp_out, uint8_t* d_desc_out, int cap, int* d_counts_out, int* d_culled_out);
 /* number of kernel launches issued by this handle so far (bench.py's gpu_launches) */
 long long orbx_launch_count(const orbx_extractor* h);
 /* Per-stage device timing (bench.py): while enabled every batched extract records CUDA events at the stage

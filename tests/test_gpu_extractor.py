@@ -388,3 +388,36 @@ def test_descriptors_at_sincos_sensitive_angles(orbx, oracle):
     assert kp_equal(kg, kr)
     nbad = int((dg != dr).any(axis=1).sum())
     assert nbad == 0, "%d of %d sincos-sensitive keypoints differ" % (nbad, len(deg))
+
+
+def test_masked_batch_with_label_map_vs_reference(orbx, oracle):
+    """Batched C5 path WITH the super-pixel term of MovingKeyPoints (src/ORBextractor.cc:1722-1736): frame 0 is the reference build's
+    golden run (24-px block label map, tests/golden/ref_extract.npz); the other frames carry the 5x5-block label map of SURVEY.md 8d and
+    are checked against the oracle's detect -> MovingKeyPoints -> ProcessDesp (oracle/_ref where it travelled, else the port)."""
+    from tools.synth import synth_labels
+    w, h, B = 480, 360, 5
+    E = orbx.ORBextractor(800, 1.2, 8, 20, 7)
+    imgs = np.stack([synth_frame(int(R["amos_frame_seed"]) + b, w, h) for b in range(B)])
+    masks = np.stack([R["amos_mask"]] + [synth_mask(600 + b, w, h) for b in range(1, B)])
+    labs = [(R["amos_label"], R["amos_centers_id"], R["amos_rm"])] + [synth_labels(b, w, h) for b in range(1, B)]
+    masks[B - 1] = 0                                                               # last frame: only the super-pixel term culls
+    nl = max(len(l[1]) for l in labs)
+    flagged = np.zeros((B, nl), np.uint8)
+    for b, (_, cid, rm) in enumerate(labs):
+        flagged[b, :len(cid)] = orbx.label_flags(cid, rm)
+    labels = np.stack([l[0] for l in labs])
+    kp, desc, counts, culled = E.extract_masked_batch(imgs, masks, labels=labels, flagged=flagged)
+    assert counts[0] == len(R["amos_final_kp"]) and kp_equal(kp[0][:counts[0]], R["amos_final_kp"]) and np.array_equal(desc[0][:counts[0]], R["amos_final_desc"])
+    assert culled[0] == len(R["amos_culled"])
+    P = oracle.Extractor("ref" if oracle.have_ref() else "port", 800, 1.2, 8, 20, 7)
+    for b in range(1, B):
+        kd, cd = P.detect(imgs[b])
+        kk, ck, cu = P.moving_keypoints(masks[b], labs[b][0], labs[b][1], labs[b][2], kd, cd)
+        kf, df = P.process_desp(kk, ck)
+        assert counts[b] == len(kf) and culled[b] == len(cu), b
+        assert kp_equal(kp[b][:counts[b]], kf) and np.array_equal(desc[b][:counts[b]], df), b
+    assert culled[B - 1] > 0
+    # without labels the same call drops fewer keypoints (mask term only)
+    _, _, counts_m, culled_m = E.extract_masked_batch(imgs, masks)
+    assert (culled_m <= culled).all() and culled_m[B - 1] == 0 and culled_m.sum() < culled.sum()
+    assert E.check_overflow() == 0

@@ -87,3 +87,15 @@ def stereo_right_from_left(left, seed=0):
         right[y:y + bh] = np.concatenate([band[:, d:], np.repeat(band[:, -1:], d, axis=1)], axis=1)   # xR = xL - d
         y += bh
     return right
+
+
+def synth_labels(seed, width, height, blocks=5):
+    """Super-pixel stand-in of SURVEY.md 8d: a blocks x blocks label map (ids 1..blocks^2, CV_64F like imLS), the cluster id of every
+    super-pixel (centers[i].id) and rm_vector with 2-4 flagged clusters."""
+    rng = np.random.default_rng(9000 + int(seed))
+    by = np.minimum(np.arange(height) * blocks // height, blocks - 1); bx = np.minimum(np.arange(width) * blocks // width, blocks - 1)
+    label = (by[:, None] * blocks + bx[None, :] + 1).astype(np.float64)
+    nclusters = 8
+    centers_id = rng.integers(0, nclusters, blocks * blocks).astype(np.int32)
+    rm = np.zeros(nclusters, np.int32); rm[rng.choice(nclusters, int(rng.integers(2, 5)), replace=False)] = 1
+    return label, centers_id, rm
