@@ -148,6 +148,8 @@ def lib():
         L.orbx_frame_grid.argtypes = [vp, vp, vp]
         L.orbx_frame_features_in_area.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp, vp, ci, C.POINTER(ci)]
         L.orbx_search_for_initialization_frames.argtypes = [vp, vp, vp, vp, vp, ci, C.POINTER(ci)]
+        L.orbx_search_for_initialization_batch.argtypes = [vp, ci, vp, vp, vp, vp, ci, vp]
+        L.orbx_search_for_initialization_frames_batch.argtypes = [vp, ci, vp, vp, vp, vp, ci, vp]
         L.orbx_search_by_projection_frame_dev.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp, vp, vp, vp, cf, ci, ci, cf, vp, C.POINTER(ci)]
         L.orbx_search_by_projection_points_dev.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp, vp, vp, cf, vp, C.POINTER(ci)]
     _lib = L

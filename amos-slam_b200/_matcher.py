@@ -269,6 +269,22 @@ class ORBmatcher:
         self._check(self._lib.orbx_search_for_initialization(self._h, C.byref(v1), C.byref(v2), _p(prev), _p(m12), int(windowSize), C.byref(nm)))
         return nm.value, m12, prev
 
+    def SearchForInitializationBatch(self, F1s, F2s, prevs, windowSize=10):
+        """P independent frame pairs in one call (config C2's shard unit).  F1s / F2s: lists of FrameView (host) or Frame (device);
+        prevs: list of (n1, 2) float arrays.  Returns (nmatches[P], [matches12], [prev])."""
+        P = len(F1s)
+        prev = [np.ascontiguousarray(v, np.float32).copy() for v in prevs]
+        m12 = [np.zeros(len(f.keys), np.int32) for f in F1s]
+        nm = np.zeros(max(P, 1), np.int32)
+        pp = (C.c_void_p * max(P, 1))(*[v.ctypes.data for v in prev]); mp = (C.c_void_p * max(P, 1))(*[v.ctypes.data for v in m12])
+        if P and isinstance(F1s[0], Frame):
+            a1 = (C.c_void_p * P)(*[f._h.value if hasattr(f._h, "value") else f._h for f in F1s]); a2 = (C.c_void_p * P)(*[f._h.value if hasattr(f._h, "value") else f._h for f in F2s])
+            self._check(self._lib.orbx_search_for_initialization_frames_batch(self._h, P, a1, a2, pp, mp, int(windowSize), _p(nm)))
+        else:
+            v1 = (_FrameViewC * max(P, 1))(*[f.c() for f in F1s]); v2 = (_FrameViewC * max(P, 1))(*[f.c() for f in F2s])
+            self._check(self._lib.orbx_search_for_initialization_batch(self._h, P, v1, v2, pp, mp, int(windowSize), _p(nm)))
+        return nm[:P], m12, prev
+
     # int SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono)
     def SearchByProjectionFrame(self, cur, proj_uv, proj_invz, last_octave, last_angle, mp_desc, valid, mp_observed, cur_occupied, th, forward=False, backward=False, mbf=0.0):
         uv = np.ascontiguousarray(proj_uv, np.float32); iz = np.ascontiguousarray(proj_invz, np.float32)

@@ -48,8 +48,7 @@ __global__ void k_descriptor_distance(const uint4* __restrict__ a, const uint4* 
 
 // ---- grid build: keys = cell<<20 | index, bitonic sort (one CTA; in shared memory when the frame fits), then cell_start by binary search ----
 #define GRID_SMEM_KEYS 8192
-__global__ void __launch_bounds__(1024)
-k_grid_build(const KpM* __restrict__ keys, int n, float min_x, float min_y, float gw_inv, float gh_inv,
+__device__ __forceinline__ void grid_build_body(const KpM* __restrict__ keys, int n, float min_x, float min_y, float gw_inv, float gh_inv,
              uint32_t* __restrict__ skeys_g, int* __restrict__ entries, int* __restrict__ cell_start) {
     __shared__ uint32_t skeys_s[GRID_SMEM_KEYS];
     uint32_t* skeys = n <= GRID_SMEM_KEYS ? skeys_s : skeys_g;
@@ -77,6 +76,11 @@ k_grid_build(const KpM* __restrict__ keys, int n, float min_x, float min_y, floa
         while (lo < hi) { const int mid = (lo + hi) >> 1; if (skeys[mid] < T) lo = mid + 1; else hi = mid; }
         cell_start[c] = lo;
     }
+}
+__global__ void __launch_bounds__(1024)
+k_grid_build(const KpM* __restrict__ keys, int n, float min_x, float min_y, float gw_inv, float gh_inv,
+             uint32_t* __restrict__ skeys_g, int* __restrict__ entries, int* __restrict__ cell_start) {
+    grid_build_body(keys, n, min_x, min_y, gw_inv, gh_inv, skeys_g, entries, cell_start);
 }
 
 // ---- queries ----
@@ -140,11 +144,8 @@ __device__ __forceinline__ bool query_window(const QueryParams& P, const FrameDe
 
 // one warp per query.  FILL = false: counts[q] only.  FILL = true: cand[offsets[q] + k] = dist<<20 | index.
 template <bool FILL>
-__global__ void __launch_bounds__(128)
-k_window_search(QueryParams P, FrameDev F, int* __restrict__ counts, const int* __restrict__ offsets, uint32_t* __restrict__ cand, int cand_cap,
-                uint2* __restrict__ pre_best /* FILL: per query (best, second) key = dist<<20 | position in list, ignoring running exclusions */) {
-    const int lane = threadIdx.x & 31;
-    const int q = blockIdx.x * 4 + (threadIdx.x >> 5);
+__device__ __forceinline__ void window_search_body(const QueryParams& P, const FrameDev& F, int* __restrict__ counts, const int* __restrict__ offsets, uint32_t* __restrict__ cand, int cand_cap,
+                uint2* __restrict__ pre_best /* FILL: per query (best, second) key = dist<<20 | position in list, ignoring running exclusions */, int q, int lane) {
     if (q >= P.nq) return;
     if (FILL && offsets[P.nq] > cand_cap) return;                   // lists do not fit: the host grows the arena and repeats the call
     float x, y, r, ur; int minLevel, maxLevel; bool use_ur;
@@ -221,9 +222,14 @@ k_window_search(QueryParams P, FrameDev F, int* __restrict__ counts, const int* 
         if (lane == 0) pre_best[q] = make_uint2(g1, g2);
     }
 }
+template <bool FILL>
+__global__ void __launch_bounds__(128)
+k_window_search(QueryParams P, FrameDev F, int* __restrict__ counts, const int* __restrict__ offsets, uint32_t* __restrict__ cand, int cand_cap, uint2* __restrict__ pre_best) {
+    window_search_body<FILL>(P, F, counts, offsets, cand, cand_cap, pre_best, blockIdx.x * 4 + (threadIdx.x >> 5), threadIdx.x & 31);
+}
 
 // exclusive scan of n counts by one CTA; total written to offsets[n]
-__global__ void __launch_bounds__(1024) k_scan_counts(const int* __restrict__ counts, int n, int* __restrict__ offsets) {
+__device__ __forceinline__ void scan_counts_body(const int* __restrict__ counts, int n, int* __restrict__ offsets) {
     __shared__ int wsum[32];
     __shared__ int carry_sm;
     const int tid = threadIdx.x;
@@ -250,6 +256,7 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const int* __restrict__ co
     }
     if (tid == 0) offsets[n] = carry_sm;
 }
+__global__ void __launch_bounds__(1024) k_scan_counts(const int* __restrict__ counts, int n, int* __restrict__ offsets) { scan_counts_body(counts, n, offsets); }
 
 // independent best match of every query (no running state): the FILL pass already reduced each list to its best key
 __global__ void k_best_extract(int nq, const int* __restrict__ offsets, const uint32_t* __restrict__ cand, const uint2* __restrict__ pre_best, int cand_cap, int max_dist,
@@ -462,8 +469,7 @@ struct InitOps {
     __device__ __forceinline__ void post(int na, int nd) { nmatches += na - nd; }
 };
 
-__global__ void __launch_bounds__(RESOLVE_THREADS)
-k_resolve_init(int n1, int n2, const KpM* __restrict__ k1s, const KpM* __restrict__ k2s, const int* __restrict__ counts, const int* __restrict__ offsets,
+__device__ __forceinline__ void resolve_init_body(int n1, int n2, const KpM* __restrict__ k1s, const KpM* __restrict__ k2s, const int* __restrict__ counts, const int* __restrict__ offsets,
                const uint32_t* __restrict__ cand, const uint2* __restrict__ pre_best, int cand_cap, float nnratio, int checkOri, int smem_words,
                int* __restrict__ matchedDist /*n2*/, int* __restrict__ m21 /*n2*/, int* __restrict__ m12 /*n1*/, int* __restrict__ bin_of /*n1*/,
                float* __restrict__ prev_xy, int* __restrict__ nmatches_out) {
@@ -502,6 +508,47 @@ k_resolve_init(int n1, int n2, const KpM* __restrict__ k1s, const KpM* __restric
     __syncwarp();
     for (int i = lane; i < n1; i += 32) { const int j = m12[i]; if (j >= 0) { prev_xy[2 * i] = k2s[j].x; prev_xy[2 * i + 1] = k2s[j].y; } }   // :638-640
     if (lane == 0) *nmatches_out = nmatches;
+}
+__global__ void __launch_bounds__(RESOLVE_THREADS)
+k_resolve_init(int n1, int n2, const KpM* __restrict__ k1s, const KpM* __restrict__ k2s, const int* __restrict__ counts, const int* __restrict__ offsets,
+               const uint32_t* __restrict__ cand, const uint2* __restrict__ pre_best, int cand_cap, float nnratio, int checkOri, int smem_words,
+               int* __restrict__ matchedDist, int* __restrict__ m21, int* __restrict__ m12, int* __restrict__ bin_of, float* __restrict__ prev_xy, int* __restrict__ nmatches_out) {
+    resolve_init_body(n1, n2, k1s, k2s, counts, offsets, cand, pre_best, cand_cap, nnratio, checkOri, smem_words, matchedDist, m21, m12, bin_of, prev_xy, nmatches_out);
+}
+
+// ---- SearchForInitialization for P independent frame pairs per launch (the shard unit of config C2): the same four steps,
+// one grid-build CTA / scan CTA / resolve CTA per pair and one warp per (pair, query) in between.  Every pair owns a fixed slice of the
+// candidate arena; a pair whose lists do not fit reports its total and the host repeats the call with a larger slice. ----
+struct InitPair {
+    FrameDev F2; uint32_t* sort_keys;            // sort_keys == nullptr: F2's grid is already built (device-resident frame)
+    const KpM* k1; const uint8_t* d1; float* prev; int n1;
+    int* counts; int* offsets; uint2* pre; uint32_t* cand;
+    int* md; int* m21; int* m12; int* binof; int* nmatches; int* total;
+};
+__global__ void __launch_bounds__(1024) k_grid_build_pairs(const InitPair* __restrict__ pairs) {
+    const InitPair& p = pairs[blockIdx.x];
+    if (!p.sort_keys) return;
+    grid_build_body(p.F2.keys, p.F2.n, p.F2.min_x, p.F2.min_y, p.F2.gw_inv, p.F2.gh_inv, p.sort_keys, const_cast<int*>(p.F2.entries), const_cast<int*>(p.F2.cell_start));
+}
+template <bool FILL>
+__global__ void __launch_bounds__(128) k_window_search_pairs(const InitPair* __restrict__ pairs, float window, int cand_cap) {
+    const InitPair& p = pairs[blockIdx.y];
+    const int q = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (q >= p.n1) return;
+    QueryParams P;
+    P.mode = MODE_INIT; P.nq = p.n1; P.q_keys = p.k1; P.q_desc = p.d1; P.q_xy = p.prev; P.window = window;
+    P.q_invz = nullptr; P.q_octave = nullptr; P.q_valid = nullptr; P.th = 0.f; P.forward = P.backward = 0; P.mbf = 0.f; P.no_ur = 0; P.q_ur = nullptr; P.q_viewcos = nullptr;
+    P.chi2 = 0; P.q_invsigma2 = nullptr; P.q_r = nullptr; P.q_minlevel = nullptr; P.q_maxlevel = nullptr;
+    window_search_body<FILL>(P, p.F2, p.counts, p.offsets, p.cand, cand_cap, p.pre, q, threadIdx.x & 31);
+}
+__global__ void __launch_bounds__(1024) k_scan_counts_pairs(const InitPair* __restrict__ pairs) {
+    const InitPair& p = pairs[blockIdx.x];
+    scan_counts_body(p.counts, p.n1, p.offsets);
+    if (threadIdx.x == 0) *p.total = p.offsets[p.n1];          // written by this thread inside scan_counts_body
+}
+__global__ void __launch_bounds__(RESOLVE_THREADS) k_resolve_init_pairs(const InitPair* __restrict__ pairs, int cand_cap, float nnratio, int checkOri, int smem_words) {
+    const InitPair& p = pairs[blockIdx.x];
+    resolve_init_body(p.n1, p.F2.n, p.k1, p.F2.keys, p.counts, p.offsets, p.cand, p.pre, cand_cap, nnratio, checkOri, smem_words, p.md, p.m21, p.m12, p.binof, p.prev, p.nmatches);
 }
 
 // ---- SearchByProjection(Frame, Frame), sequential part (ORBmatcher.cc:1595-1725) ----

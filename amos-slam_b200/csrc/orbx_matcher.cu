@@ -265,6 +265,7 @@ int orbx_matcher_create(float nnratio, int check_orientation, int device, orbx_m
     cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete m; FAIL(ORBX_E_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e)); }
     cudaFuncSetAttribute(k_resolve_init, cudaFuncAttributeMaxDynamicSharedMemorySize, RESOLVE_SMEM_BYTES);   // per device
+    cudaFuncSetAttribute(k_resolve_init_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, RESOLVE_SMEM_BYTES);
     cudaFuncSetAttribute(k_resolve_proj_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, RESOLVE_SMEM_BYTES);
     cudaFuncSetAttribute(k_resolve_proj_points, cudaFuncAttributeMaxDynamicSharedMemorySize, RESOLVE_SMEM_BYTES);
     *out = m;
@@ -342,6 +343,120 @@ retry:
     std::memcpy(nmatches, g.host(o_n), 4);
     std::memcpy(matches12, g.host(o_m12), (size_t)n1 * 4);
     std::memcpy(prev_matched_xy, g.host(o_prev), (size_t)n1 * 8);
+    return ORBX_OK;
+}
+
+// SearchForInitialization for n_pairs independent frame pairs: one upload, five launches, one download (see k_match.cuh, InitPair)
+static int search_init_batch_impl(orbx_matcher* m, int n_pairs, const FrameArg* A1, const FrameArg* A2, float* const* prev_matched_xy, int* const* matches12,
+                                  int window_size, int* nmatches) {
+    if (!m || !nmatches || n_pairs < 0 || (n_pairs && (!A1 || !A2 || !prev_matched_xy || !matches12))) FAIL(ORBX_E_INVALID, "null argument");
+    if (n_pairs == 0) return ORBX_OK;
+    int rc;
+    size_t need_up = 8192 + pad(sizeof(InitPair) * (size_t)n_pairs), need_dev = 8192, n1sum = 0;
+    int n1max = 0, n2max = 0;
+    for (int p = 0; p < n_pairs; ++p) {
+        if ((rc = check_frame_arg(m, A1[p])) || (rc = check_frame_arg(m, A2[p]))) return rc;
+        const int n1 = A1[p].n(), n2 = A2[p].n();
+        if (n1 && (!prev_matched_xy[p] || !matches12[p])) FAIL(ORBX_E_INVALID, "null buffer");
+        need_up += frame_arg_bytes(A1[p]) + frame_arg_bytes(A2[p]) + pad((size_t)n1 * 8) + 1024;
+        need_dev += 4 * pad((size_t)(n1 + 2) * 4) + pad((size_t)(n1 + 1) * 8) + 2 * pad((size_t)(n2 + 1) * 4) + frame_arg_bytes(A2[p]) + 2048;
+        n1max = std::max(n1max, n1); n2max = std::max(n2max, n2); n1sum += (size_t)n1;
+    }
+    need_dev += pad((size_t)n_pairs * 8) + pad(n1sum * 4);
+    CU_TRY(cudaSetDevice(m->device));
+    if ((rc = m->arena.reserve(need_dev)) || (rc = m->uparena.reserve(need_up))) return rc;
+    // every pair owns a fixed slice of the candidate arena (the lists of SearchForInitialization hold the level-0 features inside the window only)
+    size_t slice = std::max<size_t>((size_t)16 * (size_t)std::max(n1max, 1), 4096);
+    cudaStream_t s = m->stream;
+    std::vector<InitPair> hp((size_t)n_pairs);
+retry:
+    if (m->cand_cap < slice * (size_t)n_pairs) {
+        rc = m->cand_arena.reserve(slice * (size_t)n_pairs * 4);
+        m->cand_cap = m->cand_arena.cap / 4;
+        if (rc) return rc;
+    }
+    m->arena.reset(); m->uparena.reset();
+    int* d_nm = m->arena.get<int>(n_pairs); int* d_tot = m->arena.get<int>(n_pairs); int* d_m12 = m->arena.get<int>(n1sum ? n1sum : 1);
+    if (!d_nm || !d_tot || !d_m12) FAIL(ORBX_E_CUDA, "matcher arena exhausted");
+    std::vector<size_t> o1((size_t)n_pairs + 1, 0);
+    std::vector<float*> dprev((size_t)n_pairs);
+    for (int p = 0; p < n_pairs; ++p) {
+        InitPair& ip = hp[p]; std::memset(&ip, 0, sizeof(ip));
+        const int n1 = A1[p].n(), n2 = A2[p].n();
+        uint32_t* sk2 = nullptr;
+        if ((rc = stage_frame(m, A2[p], ip.F2, sk2))) return rc;
+        ip.sort_keys = sk2;
+        if (A1[p].v) {
+            KpM* k1u; uint8_t* d1u;
+            if ((rc = up(m, reinterpret_cast<const KpM*>(A1[p].v->keys_un), (size_t)n1, k1u)) || (rc = up(m, A1[p].v->descriptors, (size_t)n1 * 32, d1u))) return rc;
+            ip.k1 = k1u; ip.d1 = d1u;
+        } else { ip.k1 = A1[p].f->dev.keys; ip.d1 = A1[p].f->dev.desc; }
+        ip.n1 = n1;
+        ip.counts = m->arena.get<int>(n1 + 1); ip.offsets = m->arena.get<int>(n1 + 2); ip.pre = m->arena.get<uint2>(n1 + 1);
+        ip.md = m->arena.get<int>(n2 + 1); ip.m21 = m->arena.get<int>(n2 + 1); ip.binof = m->arena.get<int>(n1 + 1);
+        if (!ip.counts || !ip.offsets || !ip.pre || !ip.md || !ip.m21 || !ip.binof) FAIL(ORBX_E_CUDA, "matcher arena exhausted");
+        ip.m12 = d_m12 + o1[p]; o1[p + 1] = o1[p] + (size_t)n1;
+        ip.cand = reinterpret_cast<uint32_t*>(m->cand_arena.base) + (size_t)p * slice;
+        ip.nmatches = d_nm + p; ip.total = d_tot + p;
+    }
+    for (int p = 0; p < n_pairs; ++p) {                                // vbPrevMatched of all pairs back to back: they come back in one copy
+        if ((rc = up(m, prev_matched_xy[p], (size_t)A1[p].n() * 2, hp[p].prev))) return rc;
+        dprev[p] = hp[p].prev;
+    }
+    InitPair* d_pairs;
+    if ((rc = up(m, hp.data(), (size_t)n_pairs, d_pairs))) return rc;
+    if ((rc = flush_uploads(m))) return rc;
+    CU_TRY(cudaMemsetAsync(d_nm, 0, (size_t)n_pairs * 4, s));
+    const int icap = (int)std::min<size_t>(slice, 0x7FFFFFFF);
+    k_grid_build_pairs<<<n_pairs, 1024, 0, s>>>(d_pairs);
+    LAUNCH_CHECK();
+    if (n1max > 0) {
+        const dim3 grid((n1max + 3) / 4, n_pairs);
+        k_window_search_pairs<false><<<grid, 128, 0, s>>>(d_pairs, (float)window_size, icap);
+        LAUNCH_CHECK();
+        k_scan_counts_pairs<<<n_pairs, 1024, 0, s>>>(d_pairs);
+        LAUNCH_CHECK();
+        k_window_search_pairs<true><<<grid, 128, 0, s>>>(d_pairs, (float)window_size, icap);
+        LAUNCH_CHECK();
+        // shared memory of one resolve CTA: the lists of a typical pair (window 100 on a VGA frame: ~7 candidates per feature of F1) staged
+        // with the state arrays; larger pairs read their lists from global memory (same result)
+        const size_t want_words = (size_t)5 * n1max + (size_t)3 * n2max + (size_t)10 * n1max + 64;
+        const int resolve_smem = (int)std::min<size_t>(RESOLVE_SMEM_BYTES, (want_words * 4 + 1023) & ~(size_t)1023);
+        k_resolve_init_pairs<<<n_pairs, RESOLVE_THREADS, resolve_smem, s>>>(d_pairs, icap, m->nnratio, m->checkOri, resolve_smem / 4);
+        LAUNCH_CHECK();
+    }
+    // results: [nmatches | totals | all m12] are contiguous in the arena; the prev arrays live in the upload arena (contiguous per pair)
+    if ((rc = m->ensure_download(2 * pad((size_t)n_pairs * 4) + pad(n1sum * 4) + n1sum * 8 + (size_t)n_pairs * 256 + 4096))) return rc;
+    uint8_t* hd = m->dl_host;
+    const size_t o_tot = pad((size_t)n_pairs * 4), o_m12 = 2 * o_tot, o_prev = o_m12 + pad(n1sum * 4);
+    CU_TRY(cudaMemcpyAsync(hd, d_nm, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(hd + o_tot, d_tot, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, s));
+    if (n1sum) CU_TRY(cudaMemcpyAsync(hd + o_m12, d_m12, n1sum * 4, cudaMemcpyDeviceToHost, s));
+    // the prev arrays were staged one after the other (256-byte aligned): fetch the span that covers them in one copy
+    const uint8_t* pv_lo = reinterpret_cast<const uint8_t*>(dprev[0]);
+    const uint8_t* pv_hi = reinterpret_cast<const uint8_t*>(dprev[n_pairs - 1]) + (size_t)A1[n_pairs - 1].n() * 8;
+    if (n1sum) {
+        CU_TRY(cudaMemcpyAsync(hd + o_prev, pv_lo, (size_t)(pv_hi - pv_lo), cudaMemcpyDeviceToHost, s));
+    }
+    CU_TRY(cudaStreamSynchronize(s));
+    if (n1max > 0) {
+        const int* tot = reinterpret_cast<const int*>(hd + o_tot);
+        long long worst = 0;
+        for (int p = 0; p < n_pairs; ++p) worst = std::max<long long>(worst, tot[p]);
+        if ((size_t)worst > slice) {                                   // some pair's lists did not fit its slice: grow every slice and run again
+            if (++m->cand_tries > 2) { m->cand_tries = 0; FAIL(ORBX_E_OVERFLOW, "candidate lists do not fit after growing the arena"); }
+            slice = (size_t)worst + (size_t)worst / 2 + 1024;
+            goto retry;
+        }
+        m->cand_tries = 0;
+    }
+    std::memcpy(nmatches, hd, (size_t)n_pairs * 4);
+    for (int p = 0; p < n_pairs; ++p) {
+        const int n1 = A1[p].n();
+        if (!n1) continue;
+        std::memcpy(matches12[p], hd + o_m12 + o1[p] * 4, (size_t)n1 * 4);
+        std::memcpy(prev_matched_xy[p], hd + o_prev + (reinterpret_cast<const uint8_t*>(dprev[p]) - pv_lo), (size_t)n1 * 8);
+    }
     return ORBX_OK;
 }
 
@@ -482,6 +597,20 @@ int orbx_search_for_initialization_frames(orbx_matcher* m, const orbx_frame* F1,
                                           int window_size, int* nmatches) {
     if (!F1 || !F2) FAIL(ORBX_E_INVALID, "null frame");
     return search_init_impl(m, FrameArg{nullptr, F1}, FrameArg{nullptr, F2}, prev_matched_xy, matches12, window_size, nmatches);
+}
+int orbx_search_for_initialization_batch(orbx_matcher* m, int n_pairs, const orbx_frame_view* F1, const orbx_frame_view* F2, float* const* prev_matched_xy,
+                                         int* const* matches12, int window_size, int* nmatches) {
+    if (n_pairs < 0 || (n_pairs && (!F1 || !F2))) FAIL(ORBX_E_INVALID, "bad frame views");
+    std::vector<FrameArg> a1((size_t)n_pairs), a2((size_t)n_pairs);
+    for (int p = 0; p < n_pairs; ++p) { a1[p] = FrameArg{F1 + p, nullptr}; a2[p] = FrameArg{F2 + p, nullptr}; }
+    return search_init_batch_impl(m, n_pairs, a1.data(), a2.data(), prev_matched_xy, matches12, window_size, nmatches);
+}
+int orbx_search_for_initialization_frames_batch(orbx_matcher* m, int n_pairs, const orbx_frame* const* F1, const orbx_frame* const* F2, float* const* prev_matched_xy,
+                                                int* const* matches12, int window_size, int* nmatches) {
+    if (n_pairs < 0 || (n_pairs && (!F1 || !F2))) FAIL(ORBX_E_INVALID, "null frames");
+    std::vector<FrameArg> a1((size_t)n_pairs), a2((size_t)n_pairs);
+    for (int p = 0; p < n_pairs; ++p) { if (!F1[p] || !F2[p]) FAIL(ORBX_E_INVALID, "null frame"); a1[p] = FrameArg{nullptr, F1[p]}; a2[p] = FrameArg{nullptr, F2[p]}; }
+    return search_init_batch_impl(m, n_pairs, a1.data(), a2.data(), prev_matched_xy, matches12, window_size, nmatches);
 }
 int orbx_search_by_projection_frame(orbx_matcher* m, const orbx_frame_view* cur, int n_last, const float* proj_uv, const float* proj_invz,
                                     const int* last_octave, const float* last_angle, const uint8_t* mp_desc, const uint8_t* valid, const uint8_t* mp_observed,

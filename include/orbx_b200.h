@@ -225,6 +225,14 @@ typedef struct orbx_frame_view {
 int orbx_search_for_initialization(orbx_matcher* m, const orbx_frame_view* F1, const orbx_frame_view* F2,
                                    float* prev_matched_xy, int* matches12, int window_size, int* nmatches);
 
+/* The same for n_pairs independent frame pairs in one call (the frame pair is the shard unit of BASELINE config 2):
+ * semantically n_pairs calls of ORBmatcher::SearchForInitialization(F1[p], F2[p], prev_matched_xy[p], matches12[p], window_size) on
+ * fresh matcher objects with this handle's (nnratio, checkOri) -- one upload, five kernel launches, one download for the whole batch
+ * (grid build, windowed Hamming search and ordered resolve run one CTA / one warp per pair, query).  F1 / F2: arrays of n_pairs views;
+ * prev_matched_xy[p]: F1[p].n (x, y) pairs, updated in place; matches12[p]: F1[p].n ints; nmatches[p] = return value of pair p. */
+int orbx_search_for_initialization_batch(orbx_matcher* m, int n_pairs, const orbx_frame_view* F1, const orbx_frame_view* F2,
+                                         float* const* prev_matched_xy, int* const* matches12, int window_size, int* nmatches);
+
 /* int ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, float th, bool bMono)
  *   src/ORBmatcher.cc:1569-1728.  The pose algebra (Rcw, tcw, tlc) and the projection of LastFrame's
  *   map points stay in the caller (they need MapPoint objects); the call receives, per LastFrame
@@ -351,6 +359,8 @@ int orbx_frame_features_in_area(orbx_matcher* m, const orbx_frame* f, int nq, co
  * minus the per-call upload of keypoints / descriptors / mvuRight and the per-call grid build. */
 int orbx_search_for_initialization_frames(orbx_matcher* m, const orbx_frame* F1, const orbx_frame* F2,
                                           float* prev_matched_xy, int* matches12, int window_size, int* nmatches);
+int orbx_search_for_initialization_frames_batch(orbx_matcher* m, int n_pairs, const orbx_frame* const* F1, const orbx_frame* const* F2,
+                                                float* const* prev_matched_xy, int* const* matches12, int window_size, int* nmatches);
 int orbx_search_by_projection_frame_dev(orbx_matcher* m, const orbx_frame* cur, int n_last,
                                         const float* proj_uv, const float* proj_invz, const int* last_octave,
                                         const float* last_angle, const uint8_t* mp_desc, const uint8_t* valid,

@@ -172,3 +172,40 @@ def test_fuse_search(orbx, case):
         for sim3 in (0, 1):
             best = orbx.ORBmatcher().FuseSearch(case["FBu"], fu["uv"], None if sim3 else fu["ur"], fu["lvl"], case["da"], fu["valid"], fu["inv_sigma2"], th)
             assert np.array_equal(best, GK["fuse_%d_%d_best" % (i, sim3)])
+
+
+def test_search_for_initialization_batch(orbx, oracle, case):
+    """P pairs per call == P single calls: pair 0 is the reference golden (ref_match.npz), the others are ragged pairs (different
+    feature counts, an empty F1, an empty F2, windows that overflow the default candidate slice) checked against the single-pair
+    call and the oracle.  Host views and device-resident frames."""
+    from tools.synth import synth_frame, warp_affine_nn
+    E = orbx.ORBextractor(1000, 1.2, 8, 20, 7); E2 = orbx.ORBextractor(300, 1.2, 8, 20, 7)
+    sf = case["sf"]
+    pairs = [(case["ka"], case["da"], case["kb"], case["db"])]
+    for s in range(5):
+        ext = E if s % 2 == 0 else E2
+        A = synth_frame(800 + s, 640, 480); B = warp_affine_nn(A, 3 + s, -2 - s, 1.0 + 0.5 * s)
+        ka, da = ext(A); kb, db = ext(B)
+        pairs.append((ka, da, kb, db))
+    empty_k, empty_d = case["ka"][:0], case["da"][:0]
+    pairs.append((empty_k, empty_d, case["kb"], case["db"]))
+    pairs.append((case["ka"], case["da"], empty_k, empty_d))
+    F1 = [orbx.FrameView(p[0], p[1], 640, 480, sf) for p in pairs]; F2 = [orbx.FrameView(p[2], p[3], 640, 480, sf) for p in pairs]
+    prevs = [np.stack([p[0]["x"], p[0]["y"]], 1).astype(np.float32).reshape(-1, 2) for p in pairs]
+    for (nn, ori, win) in ((0.9, True, 100), (0.9, False, 30), (0.7, True, 400)):       # window 400: lists far beyond the default slice -> grow + retry
+        M = orbx.ORBmatcher(nn, ori)
+        nm, m12, prev2 = M.SearchForInitializationBatch(F1, F2, prevs, win)
+        for p in range(len(pairs)):
+            n1, a, b = orbx.ORBmatcher(nn, ori).SearchForInitialization(F1[p], F2[p], prevs[p], win)
+            assert nm[p] == n1 and np.array_equal(m12[p], a) and np.array_equal(prev2[p], b), (p, win)
+            o = oracle.Matcher("port", nn, ori).search_for_initialization(oracle.FrameData(pairs[p][0], pairs[p][1], 640, 480, sf), oracle.FrameData(pairs[p][2], pairs[p][3], 640, 480, sf), prevs[p], win)
+            assert nm[p] == o[0] and np.array_equal(m12[p], o[1]) and np.array_equal(prev2[p], o[2]), (p, win)
+    nm, m12, prev2 = orbx.ORBmatcher(0.9, True).SearchForInitializationBatch(F1, F2, prevs, 100)
+    assert nm[0] == int(G["init_nm"]) and np.array_equal(m12[0], G["init_m12"]) and np.array_equal(prev2[0], G["init_prev"])
+    # device-resident frames (grid already built: the batch skips the grid launch work)
+    cam = orbx.Camera.make(500.0, 500.0, 320.0, 240.0, 0, 0, 0, 0, 0, 40.0)
+    D1 = [orbx.Frame().assign_host(p[0], p[1], sf, cam, 480, 640) for p in pairs[:6]]; D2 = [orbx.Frame().assign_host(p[2], p[3], sf, cam, 480, 640) for p in pairs[:6]]
+    nm_d, m12_d, prev_d = orbx.ORBmatcher(0.9, True).SearchForInitializationBatch(D1, D2, prevs[:6], 100)
+    for p in range(6):
+        assert nm_d[p] == nm[p] and np.array_equal(m12_d[p], m12[p]) and np.array_equal(prev_d[p], prev2[p]), p
+    assert orbx.ORBmatcher(0.9, True).SearchForInitializationBatch([], [], [], 100)[0].size == 0
