@@ -123,6 +123,8 @@ def lib():
         L.orbx_search_by_sim3.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, cf, vp, C.POINTER(ci)]
         L.orbx_search_by_projection_keyframe_dev.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp, vp, cf, ci, vp, C.POINTER(ci)]
         L.orbx_compute_stereo_matches.argtypes = [vp, vp, vp, vp, vp, ci, vp, vp, ci, cf, cf, vp, vp]
+        L.orbx_compute_stereo_matches_batch.argtypes = [vp, vp, vp, ci, ci, cf, cf, vp, vp]
+        L.orbx_compute_stereo_matches_batch_device.argtypes = [vp, vp, vp, ci, ci, cf, cf, vp, vp]
         L.orbx_match_bruteforce_device.argtypes = [vp, vp, ci, vp, ci, vp, vp, vp]
         L.orbx_match_bruteforce_batch_device.argtypes = [vp, ci, vp, ci, vp, ci, vp, vp, vp]
         L.orbx_vocabulary_create.argtypes = [ci, ci, ci, ci, ci, ci, vp, vp, vp, vp, C.POINTER(vp)]

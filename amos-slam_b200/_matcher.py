@@ -269,6 +269,12 @@ class ORBmatcher:
         self._check(self._lib.orbx_search_for_initialization(self._h, C.byref(v1), C.byref(v2), _p(prev), _p(m12), int(windowSize), C.byref(nm)))
         return nm.value, m12, prev
 
+    def ComputeStereoMatchesBatch(self, ext_left, ext_right, B, cap, mb, mbf):
+        """Frame::ComputeStereoMatches for the B stereo pairs of the two extractors' last batched extract call -> (mvuRight[B, cap], mvDepth[B, cap])."""
+        ur = np.zeros((B, cap), np.float32); dep = np.zeros((B, cap), np.float32)
+        self._check(self._lib.orbx_compute_stereo_matches_batch(self._h, ext_left._h, ext_right._h, int(B), int(cap), float(mb), float(mbf), _p(ur), _p(dep)))
+        return ur, dep
+
     def SearchForInitializationBatch(self, F1s, F2s, prevs, windowSize=10):
         """P independent frame pairs in one call (config C2's shard unit).  F1s / F2s: lists of FrameView (host) or Frame (device);
         prevs: list of (n1, 2) float arrays.  Returns (nmatches[P], [matches12], [prev])."""

@@ -673,7 +673,9 @@ k_resolve_proj_points(int n_points, int n_f, const KpM* __restrict__ f_keys, con
 // =================================================================================================
 // Frame::ComputeStereoMatches   /root/reference/src/Frame.cc:1179-1573
 // =================================================================================================
-struct PyrLevelDev { const uint8_t* ptr; int pitch, w, h; };
+struct PyrLevelDev { const uint8_t* ptr; int pitch, w, h; long long fstride; };    // fstride: distance between the frames of a batch (0 for a single frame)
+// batched form: stereo pair b = blockIdx.y reads its keypoints at k + b * stride, descriptors at d + b * stride * 32, counts from nl_arr / nr_arr
+struct StereoBatch { const int* nl_arr; const int* nr_arr; int stride; };
 struct StereoPyr { PyrLevelDev lv[ORBX_MAX_LEVELS]; };
 
 // one warp per left keypoint: row-band Hamming search over the right keypoints, then the 11-shift 11x11 SAD
@@ -681,10 +683,16 @@ struct StereoPyr { PyrLevelDev lv[ORBX_MAX_LEVELS]; };
 __global__ void __launch_bounds__(128)
 k_stereo_match(const KpM* __restrict__ kl, const uint8_t* __restrict__ dl, int nl, const KpM* __restrict__ kr, const uint8_t* __restrict__ dr, int nr,
                StereoPyr PL, StereoPyr PR, const float* __restrict__ scale, const float* __restrict__ inv_scale, float mb, float mbf,
-               float* __restrict__ u_right, float* __restrict__ depth, int* __restrict__ sad_dist /* INT_MAX = not stored */) {
+               float* __restrict__ u_right, float* __restrict__ depth, int* __restrict__ sad_dist /* INT_MAX = not stored */, StereoBatch SB) {
     const int lane = threadIdx.x & 31;
     const int iL = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (iL >= nl) return;
+    const int fb = blockIdx.y;
+    if (SB.nl_arr) {
+        nl = min(SB.nl_arr[fb], SB.stride); nr = min(SB.nr_arr[fb], SB.stride);
+        const size_t o = (size_t)fb * SB.stride;
+        kl += o; kr += o; dl += o * 32; dr += o * 32; u_right += o; depth += o; sad_dist += o;
+    }
+    if (iL >= nl) { if (SB.nl_arr && iL < SB.stride && lane == 0) { u_right[iL] = -1.0f; depth[iL] = -1.0f; sad_dist[iL] = INT_MAX; } return; }
     if (lane == 0) { u_right[iL] = -1.0f; depth[iL] = -1.0f; sad_dist[iL] = INT_MAX; }
     const KpM kpL = kl[iL];
     const int levelL = kpL.octave;
@@ -718,7 +726,8 @@ k_stereo_match(const KpM* __restrict__ kl, const uint8_t* __restrict__ dl, int n
     const float sf = inv_scale[levelL];
     const float scaleduL = roundf(__fmul_rn(kpL.x, sf)), scaledvL = roundf(__fmul_rn(kpL.y, sf)), scaleduR0 = roundf(__fmul_rn(uR0, sf));
     const int w = 5, L = 5;
-    const PyrLevelDev IL = PL.lv[levelL], IR = PR.lv[levelL];
+    PyrLevelDev IL = PL.lv[levelL], IR = PR.lv[levelL];
+    IL.ptr += fb * IL.fstride; IR.ptr += fb * IR.fstride;
     const float iniu = __fsub_rn(__fadd_rn(scaleduR0, (float)L), (float)w), endu = __fadd_rn(__fadd_rn(__fadd_rn(scaleduR0, (float)L), (float)w), 1.f);
     if (iniu < 0.f || endu >= (float)IR.w) return;                              // :1425
     const int cy = (int)scaledvL, cxl = (int)scaleduL, cxr = (int)scaleduR0;
@@ -762,7 +771,8 @@ k_stereo_match(const KpM* __restrict__ kl, const uint8_t* __restrict__ dl, int n
 // median cut (:1548-1569): thDist = 1.5f*1.4f*median(dist); entries with dist >= thDist are dropped.  One CTA.
 #define STEREO_SMEM_VALS 8192
 __global__ void __launch_bounds__(1024)
-k_stereo_median_cut(int nl, const int* __restrict__ sad_dist, float* __restrict__ u_right, float* __restrict__ depth) {
+k_stereo_median_cut(int nl, const int* __restrict__ sad_dist, float* __restrict__ u_right, float* __restrict__ depth, StereoBatch SB) {
+    if (SB.nl_arr) { nl = min(SB.nl_arr[blockIdx.x], SB.stride); const size_t o = (size_t)blockIdx.x * SB.stride; sad_dist += o; u_right += o; depth += o; }
     // the SAD values of the surviving matches are compacted into shared memory (order is irrelevant for a rank), so the rank
     // counting below reads broadcast shared words instead of re-walking the global array once per match
     __shared__ int vals[STEREO_SMEM_VALS];

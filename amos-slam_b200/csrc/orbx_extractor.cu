@@ -84,6 +84,7 @@ struct orbx_extractor {
     DevBuf<int> d_ncand, d_kp_count, d_counts, d_level_counts, d_overflow;
     DevBuf<KpOut> d_kp_out; DevBuf<uint8_t> d_desc_out; int out_cap = 0;
     DevBuf<uint8_t> d_gather; uint8_t* h_gather = nullptr; size_t h_gather_cap = 0;   // single-frame result block and its pinned landing buffer
+    const KpOut* lb_kp = nullptr; const uint8_t* lb_desc = nullptr; const int* lb_counts = nullptr; int lb_cap = 0, lb_B = 0;   // outputs of the last batched call (orbx_compute_stereo_matches_batch)
     const KpOut* last_kp = nullptr; const uint8_t* last_desc = nullptr; int last_n = -1;   // frame 0 of the last extract / describe (orbx_frame_assign)
     PyrView view{}; bool have_pyramid = false, blur_valid = false;
     // optional per-stage CUDA-event timing (bench.py's roofline): one event set per profiled call
@@ -241,7 +242,7 @@ static int build_plan(orbx_extractor* h, int rows, int cols) {
 }
 
 static int ensure_capacity(orbx_extractor* h, int B, int out_cap) {
-    h->last_n = -1;                                              // every detect / extract path passes here: the previous result is about to be overwritten
+    h->last_n = -1; h->lb_B = 0;                                 // every detect / extract path passes here: the previous result is about to be overwritten
     if (B > h->Bcap) {
         const size_t b = (size_t)B;
         if (h->d_pyr.ensure(b * h->pyr_fstride) || h->d_blur.ensure(b * h->pyr_fstride) ||
@@ -559,6 +560,7 @@ int orbx_extract_batch_device(orbx_extractor* h, const uint8_t* d_images, int B,
     if (h->profiling) {                                  // per-stage timing wants the stages back to back on one stream
         if ((rc = run_detect(h, 0, B))) return rc;
         if ((rc = run_blur(h, B))) return rc;
+        h->lb_kp = reinterpret_cast<KpOut*>(d_kp_out); h->lb_desc = d_desc_out; h->lb_counts = d_counts_out; h->lb_cap = cap; h->lb_B = B;
         return run_orient(h, 0, B, true, reinterpret_cast<KpOut*>(d_kp_out), d_desc_out, cap, d_counts_out, nullptr);
     }
     // one pass; the blur is forked next to FAST / quadtree.  (Chunking the batch over the two compute streams, as the host
@@ -566,6 +568,7 @@ int orbx_extract_batch_device(orbx_extractor* h, const uint8_t* d_images, int B,
     if ((rc = run_detect(h, 0, B, true))) return rc;
     CU_TRY(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     h->blur_valid = true;
+    h->lb_kp = reinterpret_cast<KpOut*>(d_kp_out); h->lb_desc = d_desc_out; h->lb_counts = d_counts_out; h->lb_cap = cap; h->lb_B = B;
     return run_orient(h, 0, B, true, reinterpret_cast<KpOut*>(d_kp_out), d_desc_out, cap, d_counts_out, nullptr);
 }
 
@@ -698,6 +701,7 @@ static int host_batch_pipeline(orbx_extractor* h, const uint8_t* images, const u
     CU_TRY(cudaMemcpyAsync(&ovf, h->d_overflow.p, 4, cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(cudaStreamSynchronize(h->stream));
     if (ovf) { CU_TRY(cudaMemsetAsync(h->d_overflow.p, 0, 16, h->stream)); FAIL(ORBX_E_OVERFLOW, "internal bound exceeded in the quadtree stage"); }
+    h->lb_kp = h->d_kp_out.p; h->lb_desc = h->d_desc_out.p; h->lb_counts = h->d_counts.p; h->lb_cap = cap; h->lb_B = B;
     for (int b = 0; b < B; ++b) if (counts_out[b] > cap) FAIL(ORBX_E_CAPACITY, "keypoint buffer too small: a frame holds more than `cap` keypoints (counts_out has the true counts)");
     return ORBX_OK;
 }
@@ -877,5 +881,20 @@ int orbx_internal_last_result(orbx_extractor* h, OrbxLastResult* out) {
     if (h->last_n < 0) FAIL(ORBX_E_STATE, "extractor holds no result (call orbx_extract or orbx_describe first)");
     out->device = h->device; out->n = h->last_n; out->nlevels = h->nlevels; out->stream = h->stream;
     out->keys = h->last_kp; out->desc = h->last_desc; out->scale = h->mvScaleFactor.data();
+    return ORBX_OK;
+}
+
+int orbx_internal_last_batch(orbx_extractor* h, OrbxBatchInfo* out) {
+    if (!h || !out) FAIL(ORBX_E_INVALID, "null handle");
+    if (!h->have_pyramid || h->lb_B <= 0) FAIL(ORBX_E_STATE, "extractor holds no batched result (call orbx_extract_batch[_device] first)");
+    out->device = h->device; out->nlevels = h->nlevels; out->B = h->lb_B; out->cap = h->lb_cap; out->stream = h->stream;
+    for (int l = 0; l < h->nlevels; ++l) {
+        const LevelGeom& g = h->levels[l];
+        if (l == 0) { out->ptr[0] = h->view.l0; out->pitch[0] = h->view.l0_pitch; out->fstride[0] = h->view.l0_fstride; }
+        else { out->ptr[l] = h->d_pyr.p + g.off; out->pitch[l] = g.pitch; out->fstride[l] = h->pyr_fstride; }
+        out->w[l] = g.w; out->h[l] = g.h;
+    }
+    out->keys = h->lb_kp; out->desc = h->lb_desc; out->counts = h->lb_counts;
+    out->scale = h->mvScaleFactor.data(); out->inv_scale = h->mvInvScaleFactor.data();
     return ORBX_OK;
 }

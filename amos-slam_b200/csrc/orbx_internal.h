@@ -21,3 +21,13 @@ struct OrbxLastResult {
     const float* scale;          // host: mvScaleFactor[nlevels]
 };
 int orbx_internal_last_result(orbx_extractor* h, OrbxLastResult* out);
+
+// result and pyramids of the handle's last BATCHED extract call (frames 0 .. B-1), still on the device: frame b's level l starts at
+// ptr[l] + b * fstride[l]; its keypoints at keys + b * cap (28-byte records), descriptors at desc + b * cap * 32, count at counts[b]
+struct OrbxBatchInfo {
+    int device, nlevels, B, cap; cudaStream_t stream;
+    const uint8_t* ptr[ORBX_MAX_LEVELS]; long long fstride[ORBX_MAX_LEVELS]; int pitch[ORBX_MAX_LEVELS], w[ORBX_MAX_LEVELS], h[ORBX_MAX_LEVELS];
+    const void* keys; const uint8_t* desc; const int* counts;
+    const float* scale; const float* inv_scale;
+};
+int orbx_internal_last_batch(orbx_extractor* h, OrbxBatchInfo* out);

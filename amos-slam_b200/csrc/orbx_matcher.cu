@@ -78,6 +78,9 @@ struct orbx_matcher {
     Arena arena; Arena cand_arena; UploadArena uparena;
     size_t cand_cap = 0;           // candidate entries the cand arena holds
     int cand_tries = 0;            // consecutive grow-and-repeat rounds of the current call (bounded)
+    cudaEvent_t ev_left = nullptr, ev_right = nullptr;     // stereo batch: the matcher stream waits for both extractors' streams
+    float* stereo_out = nullptr; size_t stereo_out_n = 0;  // device results of the host-pointer stereo batch call
+    float* stereo_scale = nullptr; std::vector<float> stereo_scale_host;   // mvScaleFactor | mvInvScaleFactor of the extractors, persistent
     uint8_t* dl_host = nullptr; size_t dl_cap = 0;     // pinned landing buffer for results that come back in one copy
     int ensure_download(size_t bytes) {
         if (bytes <= dl_cap) return ORBX_OK;
@@ -278,6 +281,10 @@ void orbx_matcher_destroy(orbx_matcher* m) {
     if (m->cand_arena.base) cudaFree(m->cand_arena.base);
     m->uparena.release();
     if (m->dl_host) cudaFreeHost(m->dl_host);
+    if (m->stereo_out) cudaFree(m->stereo_out);
+    if (m->stereo_scale) cudaFree(m->stereo_scale);
+    if (m->ev_left) cudaEventDestroy(m->ev_left);
+    if (m->ev_right) cudaEventDestroy(m->ev_right);
     cudaStreamDestroy(m->stream);
     delete m;
 }
@@ -573,10 +580,11 @@ int orbx_compute_stereo_matches(orbx_matcher* m, orbx_extractor* left, orbx_extr
     if (!dur || !ddep || !sad) FAIL(ORBX_E_CUDA, "matcher arena exhausted");
     if ((rc = flush_uploads(m))) return rc;
     StereoPyr PL, PR;
-    for (int l = 0; l < L.nlevels; ++l) { PL.lv[l] = {L.ptr[l], L.pitch[l], L.w[l], L.h[l]}; PR.lv[l] = {R.ptr[l], R.pitch[l], R.w[l], R.h[l]}; }
-    k_stereo_match<<<(nl + 3) / 4, 128, 0, m->stream>>>(kl, dl, nl, kr, dr, nr, PL, PR, sc, isc, mb, mbf, dur, ddep, sad);
+    for (int l = 0; l < L.nlevels; ++l) { PL.lv[l] = {L.ptr[l], L.pitch[l], L.w[l], L.h[l], 0}; PR.lv[l] = {R.ptr[l], R.pitch[l], R.w[l], R.h[l], 0}; }
+    const StereoBatch single{nullptr, nullptr, 0};
+    k_stereo_match<<<(nl + 3) / 4, 128, 0, m->stream>>>(kl, dl, nl, kr, dr, nr, PL, PR, sc, isc, mb, mbf, dur, ddep, sad, single);
     LAUNCH_CHECK();
-    k_stereo_median_cut<<<1, 1024, 0, m->stream>>>(nl, sad, dur, ddep);
+    k_stereo_median_cut<<<1, 1024, 0, m->stream>>>(nl, sad, dur, ddep, single);
     LAUNCH_CHECK();
     Gather g{m};
     if ((rc = g.begin((size_t)nl * 8 + 64))) return rc;
@@ -584,6 +592,60 @@ int orbx_compute_stereo_matches(orbx_matcher* m, orbx_extractor* left, orbx_extr
     if ((rc = g.finish())) return rc;
     std::memcpy(u_right, g.host(o_ur), (size_t)nl * 4);
     std::memcpy(depth, g.host(o_dep), (size_t)nl * 4);
+    return ORBX_OK;
+}
+
+// Frame::ComputeStereoMatches for the B stereo pairs of the two handles' last batched extract call: everything it reads (both pyramids,
+// keypoints, descriptors, counts) is still on the device, so the call is two launches on the matcher's stream behind the extractors' work.
+static int stereo_batch_launch(orbx_matcher* m, orbx_extractor* left, orbx_extractor* right, int B, int cap, float mb, float mbf, float* d_ur, float* d_dep) {
+    if (!m || !left || !right || B <= 0 || cap <= 0 || !d_ur || !d_dep) FAIL(ORBX_E_INVALID, "bad arguments");
+    CU_TRY(cudaSetDevice(m->device));
+    OrbxBatchInfo L, R; int rc;
+    if ((rc = orbx_internal_last_batch(left, &L)) || (rc = orbx_internal_last_batch(right, &R))) return rc;
+    if (L.device != m->device || R.device != m->device) FAIL(ORBX_E_INVALID, "extractors and matcher must live on the same device");
+    if (L.nlevels != R.nlevels || L.B != B || R.B != B || L.cap != cap || R.cap != cap) FAIL(ORBX_E_INVALID, "left / right batches differ (levels, frames or keypoint capacity)");
+    if (!m->ev_left) { CU_TRY(cudaEventCreateWithFlags(&m->ev_left, cudaEventDisableTiming)); CU_TRY(cudaEventCreateWithFlags(&m->ev_right, cudaEventDisableTiming)); }
+    CU_TRY(cudaEventRecord(m->ev_left, L.stream)); CU_TRY(cudaEventRecord(m->ev_right, R.stream));
+    CU_TRY(cudaStreamWaitEvent(m->stream, m->ev_left, 0)); CU_TRY(cudaStreamWaitEvent(m->stream, m->ev_right, 0));
+    const size_t need = pad((size_t)B * cap * 4) + 8192;
+    if ((rc = m->arena.reserve(need))) return rc;
+    m->arena.reset();
+    // scale tables: a persistent device copy (the call is asynchronous, so nothing may travel through the per-call pinned mirror)
+    if (!m->stereo_scale) CU_TRY(cudaMalloc((void**)&m->stereo_scale, 2 * ORBX_MAX_LEVELS * sizeof(float)));
+    if (m->stereo_scale_host.size() != (size_t)2 * L.nlevels || std::memcmp(m->stereo_scale_host.data(), L.scale, (size_t)L.nlevels * 4) != 0) {
+        m->stereo_scale_host.assign(L.scale, L.scale + L.nlevels); m->stereo_scale_host.insert(m->stereo_scale_host.end(), L.inv_scale, L.inv_scale + L.nlevels);
+        CU_TRY(cudaMemcpyAsync(m->stereo_scale, m->stereo_scale_host.data(), (size_t)2 * L.nlevels * 4, cudaMemcpyHostToDevice, m->stream));
+        CU_TRY(cudaStreamSynchronize(m->stream));
+    }
+    const float* sc = m->stereo_scale; const float* isc = m->stereo_scale + L.nlevels;
+    int* sad = m->arena.get<int>((size_t)B * cap);
+    if (!sad) FAIL(ORBX_E_CUDA, "matcher arena exhausted");
+    StereoPyr PL, PR;
+    for (int l = 0; l < L.nlevels; ++l) { PL.lv[l] = {L.ptr[l], L.pitch[l], L.w[l], L.h[l], L.fstride[l]}; PR.lv[l] = {R.ptr[l], R.pitch[l], R.w[l], R.h[l], R.fstride[l]}; }
+    const StereoBatch SB{L.counts, R.counts, cap};
+    k_stereo_match<<<dim3((cap + 3) / 4, B), 128, 0, m->stream>>>(reinterpret_cast<const KpM*>(L.keys), L.desc, 0, reinterpret_cast<const KpM*>(R.keys), R.desc, 0, PL, PR, sc, isc, mb, mbf, d_ur, d_dep, sad, SB);
+    LAUNCH_CHECK();
+    k_stereo_median_cut<<<B, 1024, 0, m->stream>>>(0, sad, d_ur, d_dep, SB);
+    LAUNCH_CHECK();
+    return ORBX_OK;
+}
+int orbx_compute_stereo_matches_batch_device(orbx_matcher* m, orbx_extractor* left, orbx_extractor* right, int B, int cap, float mb, float mbf, float* d_u_right, float* d_depth) {
+    return stereo_batch_launch(m, left, right, B, cap, mb, mbf, d_u_right, d_depth);
+}
+int orbx_compute_stereo_matches_batch(orbx_matcher* m, orbx_extractor* left, orbx_extractor* right, int B, int cap, float mb, float mbf, float* u_right, float* depth) {
+    if (!m || !u_right || !depth || B <= 0 || cap <= 0) FAIL(ORBX_E_INVALID, "bad arguments");
+    CU_TRY(cudaSetDevice(m->device));
+    const size_t n = (size_t)B * cap;
+    if (m->stereo_out_n < 2 * n) {
+        if (m->stereo_out) cudaFree(m->stereo_out);
+        m->stereo_out = nullptr; m->stereo_out_n = 0;
+        CU_TRY(cudaMalloc((void**)&m->stereo_out, 2 * n * sizeof(float)));
+        m->stereo_out_n = 2 * n;
+    }
+    int rc = stereo_batch_launch(m, left, right, B, cap, mb, mbf, m->stereo_out, m->stereo_out + n); if (rc) return rc;
+    CU_TRY(cudaMemcpyAsync(u_right, m->stereo_out, n * 4, cudaMemcpyDeviceToHost, m->stream));
+    CU_TRY(cudaMemcpyAsync(depth, m->stereo_out + n, n * 4, cudaMemcpyDeviceToHost, m->stream));
+    CU_TRY(cudaStreamSynchronize(m->stream));
     return ORBX_OK;
 }
 

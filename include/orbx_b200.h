@@ -276,6 +276,16 @@ int orbx_compute_stereo_matches(orbx_matcher* m, orbx_extractor* left, orbx_extr
                                 const orbx_keypoint* keys_right, const uint8_t* desc_right, int nr,
                                 float mb, float mbf, float* u_right, float* depth);
 
+/* The same for the B stereo pairs that went through the LAST BATCHED extract call of the two handles (orbx_extract_batch[_device] on
+ * `left` with the B left images, on `right` with the B right images, same cap): both pyramids, keypoints, descriptors and counts are
+ * still on the device, so nothing is uploaded.  Outputs are [B][cap] floats (pair b at + b * cap; entries past the pair's left keypoint
+ * count are -1).  The host form is synchronous; the device form is asynchronous on orbx_matcher_stream(m), which first waits for the
+ * work queued on both extractors' streams.  The stereo pair is the shard unit of BASELINE config 4. */
+int orbx_compute_stereo_matches_batch(orbx_matcher* m, orbx_extractor* left, orbx_extractor* right, int B, int cap, float mb, float mbf,
+                                      float* u_right, float* depth);
+int orbx_compute_stereo_matches_batch_device(orbx_matcher* m, orbx_extractor* left, orbx_extractor* right, int B, int cap, float mb, float mbf,
+                                             float* d_u_right, float* d_depth);
+
 /* Brute-force all-pairs Hamming with best / second-best (the inner kernel of all matchers, exposed for
  * throughput measurement):  for every query q: best_idx, best_dist, second_dist over all n_train rows. */
 int orbx_match_bruteforce_device(orbx_matcher* m, const uint8_t* d_query, int n_query, const uint8_t* d_train,

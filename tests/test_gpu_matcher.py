@@ -209,3 +209,40 @@ def test_search_for_initialization_batch(orbx, oracle, case):
     for p in range(6):
         assert nm_d[p] == nm[p] and np.array_equal(m12_d[p], m12[p]) and np.array_equal(prev_d[p], prev2[p]), p
     assert orbx.ORBmatcher(0.9, True).SearchForInitializationBatch([], [], [], 100)[0].size == 0
+
+
+def test_compute_stereo_matches_batch(orbx):
+    """B stereo pairs per call (config C4's shard unit) == B single calls; pair 0 is the reference golden.  Host-pointer batch extraction
+    on both handles, then ComputeStereoMatches on what they still hold on the device; also through the device-batch extraction."""
+    import torch
+    B = 4
+    pairs = [mc.stereo_pair()] + [mc.stereo_pair(seed=11 + 2 * s) for s in range(B - 1)]
+    Ls = np.stack([p[0] for p in pairs]); Rs = np.stack([p[1] for p in pairs])
+    EL, ER = orbx.ORBextractor(2000, 1.2, 8, 20, 7), orbx.ORBextractor(2000, 1.2, 8, 20, 7)
+    kl, dl, cl = EL.extract_batch(Ls); kr, dr, cr = ER.extract_batch(Rs)
+    cap = kl.shape[1]
+    m = orbx.ORBmatcher()
+    for mb, tag in ((0.0, "stereo"), (0.5372, "stereo2")):
+        ur, dep = m.ComputeStereoMatchesBatch(EL, ER, B, cap, mb, mc.BF_KITTI)
+        assert np.array_equal(ur[0][:cl[0]], G[tag + "_ur"]) and np.array_equal(dep[0][:cl[0]], G[tag + "_depth"])
+        E1, E2 = orbx.ORBextractor(2000, 1.2, 8, 20, 7), orbx.ORBextractor(2000, 1.2, 8, 20, 7)
+        for b in range(B):
+            k1, d1 = E1(pairs[b][0]); k2, d2 = E2(pairs[b][1])
+            u1, p1 = orbx.ORBmatcher().ComputeStereoMatches(E1, E2, k1, d1, k2, d2, mb, mc.BF_KITTI)
+            assert cl[b] == len(k1) and np.array_equal(ur[b][:cl[b]], u1) and np.array_equal(dep[b][:cl[b]], p1), b
+            assert (ur[b][cl[b]:] == -1).all() and (dep[b][cl[b]:] == -1).all()
+        assert ((ur >= 0).sum(1) > 200).all()
+    # device-resident form: frames in HBM, extraction and matching queued without a host round trip
+    dL = torch.from_numpy(Ls).cuda(); dR = torch.from_numpy(Rs).cuda()
+    outs = []
+    for E, d in ((EL, dL), (ER, dR)):
+        k = torch.empty((B, cap, 28), dtype=torch.uint8, device="cuda"); ds = torch.empty((B, cap, 32), dtype=torch.uint8, device="cuda"); c = torch.empty(B, dtype=torch.int32, device="cuda")
+        E.extract_batch_raw(d.data_ptr(), B, 376, 1241, 1241, 1241 * 376, k.data_ptr(), ds.data_ptr(), cap, c.data_ptr(), device=True)
+        outs.append((k, ds, c))
+    dur = torch.empty((B, cap), dtype=torch.float32, device="cuda"); ddep = torch.empty((B, cap), dtype=torch.float32, device="cuda")
+    orbx._check(m._lib.orbx_compute_stereo_matches_batch_device(m._h, EL._h, ER._h, B, cap, 0.0, mc.BF_KITTI, dur.data_ptr(), ddep.data_ptr()))
+    m.synchronize() if hasattr(m, "synchronize") else torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    ur0, dep0 = m.ComputeStereoMatchesBatch(EL, ER, B, cap, 0.0, mc.BF_KITTI)
+    assert np.array_equal(dur.cpu().numpy(), ur0) and np.array_equal(ddep.cpu().numpy(), dep0)
+    assert np.array_equal(ur0[0][:cl[0]], G["stereo_ur"])
