@@ -111,6 +111,8 @@ def lib():
         L.orbx_matcher_destroy.argtypes = [vp]; L.orbx_matcher_destroy.restype = None
         L.orbx_matcher_stream.argtypes = [vp]; L.orbx_matcher_stream.restype = vp
         L.orbx_matcher_launch_count.argtypes = [vp]; L.orbx_matcher_launch_count.restype = C.c_longlong
+        L.orbx_matcher_profile_enable.argtypes = [vp, ci]
+        L.orbx_matcher_profile_collect.argtypes = [vp, ci, vp, C.POINTER(ci)]
         L.orbx_descriptor_distance.argtypes = [vp, vp, vp, ci, vp]
         L.orbx_search_for_initialization.argtypes = [vp, vp, vp, vp, vp, ci, C.POINTER(ci)]
         L.orbx_search_by_projection_frame.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp, vp, vp, vp, cf, ci, ci, cf, vp, C.POINTER(ci)]

@@ -597,9 +597,15 @@ static int host_batch_pipeline(orbx_extractor* h, const uint8_t* images, const u
     if ((rc = ensure_capacity(h, B, cap))) return rc;
     // level 0: mirror the host layout on the device when it is word-aligned and dense enough (one copy per chunk);
     // otherwise copy frame by frame into the pyramid block
-    const bool mirror = (step & 3) == 0 && (frame_stride & 3) == 0 && frame_stride >= step * (size_t)rows && frame_stride <= 2 * step * (size_t)rows;
-    if (mirror) {
+    const bool dense = frame_stride >= step * (size_t)rows && frame_stride <= 2 * step * (size_t)rows;
+    const bool mirror = dense && (step & 3) == 0 && (frame_stride & 3) == 0;
+    // rows that are not word-aligned (KITTI: 1241 px): still ONE dense copy per chunk over the bus -- a strided 2-D copy of 1241-byte rows
+    // runs at a fraction of the link rate -- followed by a device-side re-pitch into the pyramid block
+    const bool repitch = dense && !mirror;
+    if (mirror || repitch) {
         if (h->d_l0.ensure((size_t)B * frame_stride)) return ORBX_E_CUDA;
+    }
+    if (mirror) {
         h->view.l0 = h->d_l0.p; h->view.l0_fstride = (long long)frame_stride; h->view.l0_pitch = (int)step;
     } else {
         const LevelGeom& g0 = h->levels[0];
@@ -634,9 +640,15 @@ static int host_batch_pipeline(orbx_extractor* h, const uint8_t* images, const u
     for (int i = 1; i < nstreams; ++i) CU_TRY(cudaStreamWaitEvent(cs[i], h->ev_done[0], 0));
     for (int c = 0; c < nchunks; ++c) {
         const int b0 = cb[c], nb = cb[c + 1] - b0;
-        if (mirror) {
+        if (mirror || repitch) {
             const size_t bytes = (size_t)(nb - 1) * frame_stride + (size_t)(rows - 1) * step + cols;     // never reads past the last row of the last frame
             CU_TRY(cudaMemcpyAsync(h->d_l0.p + (size_t)b0 * frame_stride, images + (size_t)b0 * frame_stride, bytes, cudaMemcpyHostToDevice, h->s_h2d));
+            if (repitch) {
+                const LevelGeom& g0 = h->levels[0];
+                for (int b = b0; b < b0 + nb; ++b)
+                    CU_TRY(cudaMemcpy2DAsync(h->d_pyr.p + (size_t)b * h->pyr_fstride + g0.off, g0.pitch, h->d_l0.p + (size_t)b * frame_stride, step,
+                                             cols, rows, cudaMemcpyDeviceToDevice, h->s_h2d));
+            }
         } else {
             const LevelGeom& g0 = h->levels[0];
             for (int b = b0; b < b0 + nb; ++b)

@@ -81,6 +81,8 @@ struct orbx_matcher {
     cudaEvent_t ev_left = nullptr, ev_right = nullptr;     // stereo batch: the matcher stream waits for both extractors' streams
     float* stereo_out = nullptr; size_t stereo_out_n = 0;  // device results of the host-pointer stereo batch call
     float* stereo_scale = nullptr; std::vector<float> stereo_scale_host;   // mvScaleFactor | mvInvScaleFactor of the extractors, persistent
+    bool profiling = false; std::vector<cudaEvent_t> prof_events;          // per-stage events of the batched calls (bench.py's roofline)
+    void mark() { if (!profiling) return; cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) return; cudaEventRecord(e, stream); prof_events.push_back(e); }
     uint8_t* dl_host = nullptr; size_t dl_cap = 0;     // pinned landing buffer for results that come back in one copy
     int ensure_download(size_t bytes) {
         if (bytes <= dl_cap) return ORBX_OK;
@@ -289,6 +291,24 @@ void orbx_matcher_destroy(orbx_matcher* m) {
     delete m;
 }
 void* orbx_matcher_stream(orbx_matcher* m) { return m ? (void*)m->stream : nullptr; }
+// Per-stage device timing of the batched calls (bench.py): while enabled, orbx_search_for_initialization[_frames]_batch records an event
+// before each of its 5 launches and after the last (6 marks: grid build, window count, scan, window fill, resolve) and
+// orbx_compute_stereo_matches_batch[_device] 3 marks (row-band Hamming + SAD, median cut).  collect synchronises, sums the elapsed ms of
+// the `nstages` consecutive intervals of every profiled call, and clears the events.
+int orbx_matcher_profile_enable(orbx_matcher* m, int on) { if (!m) return ORBX_E_INVALID; m->profiling = on != 0; return ORBX_OK; }
+int orbx_matcher_profile_collect(orbx_matcher* m, int nstages, double* stage_ms, int* ncalls) {
+    if (!m || nstages <= 0 || !stage_ms || !ncalls) return ORBX_E_INVALID;
+    if (cudaSetDevice(m->device) != cudaSuccess) return ORBX_E_CUDA;
+    CU_TRY(cudaStreamSynchronize(m->stream));
+    for (int i = 0; i < nstages; ++i) stage_ms[i] = 0.0;
+    const size_t per = (size_t)nstages + 1, calls = m->prof_events.size() / per;
+    for (size_t c = 0; c < calls; ++c)
+        for (int i = 0; i < nstages; ++i) { float ms = 0.f; cudaEventElapsedTime(&ms, m->prof_events[c * per + i], m->prof_events[c * per + i + 1]); stage_ms[i] += ms; }
+    for (cudaEvent_t e : m->prof_events) cudaEventDestroy(e);
+    m->prof_events.clear();
+    *ncalls = (int)calls;
+    return ORBX_OK;
+}
 long long orbx_matcher_launch_count(const orbx_matcher* m) { return m ? m->launches : 0; }
 
 int orbx_descriptor_distance(orbx_matcher* m, const uint8_t* a, const uint8_t* b, int n, int* out) {
@@ -415,22 +435,28 @@ retry:
     if ((rc = flush_uploads(m))) return rc;
     CU_TRY(cudaMemsetAsync(d_nm, 0, (size_t)n_pairs * 4, s));
     const int icap = (int)std::min<size_t>(slice, 0x7FFFFFFF);
+    m->mark();
     k_grid_build_pairs<<<n_pairs, 1024, 0, s>>>(d_pairs);
     LAUNCH_CHECK();
+    m->mark();
     if (n1max > 0) {
         const dim3 grid((n1max + 3) / 4, n_pairs);
         k_window_search_pairs<false><<<grid, 128, 0, s>>>(d_pairs, (float)window_size, icap);
         LAUNCH_CHECK();
+        m->mark();
         k_scan_counts_pairs<<<n_pairs, 1024, 0, s>>>(d_pairs);
         LAUNCH_CHECK();
+        m->mark();
         k_window_search_pairs<true><<<grid, 128, 0, s>>>(d_pairs, (float)window_size, icap);
         LAUNCH_CHECK();
+        m->mark();
         // shared memory of one resolve CTA: the lists of a typical pair (window 100 on a VGA frame: ~7 candidates per feature of F1) staged
         // with the state arrays; larger pairs read their lists from global memory (same result)
         const size_t want_words = (size_t)5 * n1max + (size_t)3 * n2max + (size_t)10 * n1max + 64;
         const int resolve_smem = (int)std::min<size_t>(RESOLVE_SMEM_BYTES, (want_words * 4 + 1023) & ~(size_t)1023);
         k_resolve_init_pairs<<<n_pairs, RESOLVE_THREADS, resolve_smem, s>>>(d_pairs, icap, m->nnratio, m->checkOri, resolve_smem / 4);
         LAUNCH_CHECK();
+        m->mark();
     }
     // results: [nmatches | totals | all m12] are contiguous in the arena; the prev arrays live in the upload arena (contiguous per pair)
     if ((rc = m->ensure_download(2 * pad((size_t)n_pairs * 4) + pad(n1sum * 4) + n1sum * 8 + (size_t)n_pairs * 256 + 4096))) return rc;
@@ -623,10 +649,13 @@ static int stereo_batch_launch(orbx_matcher* m, orbx_extractor* left, orbx_extra
     StereoPyr PL, PR;
     for (int l = 0; l < L.nlevels; ++l) { PL.lv[l] = {L.ptr[l], L.pitch[l], L.w[l], L.h[l], L.fstride[l]}; PR.lv[l] = {R.ptr[l], R.pitch[l], R.w[l], R.h[l], R.fstride[l]}; }
     const StereoBatch SB{L.counts, R.counts, cap};
+    m->mark();
     k_stereo_match<<<dim3((cap + 3) / 4, B), 128, 0, m->stream>>>(reinterpret_cast<const KpM*>(L.keys), L.desc, 0, reinterpret_cast<const KpM*>(R.keys), R.desc, 0, PL, PR, sc, isc, mb, mbf, d_ur, d_dep, sad, SB);
     LAUNCH_CHECK();
+    m->mark();
     k_stereo_median_cut<<<B, 1024, 0, m->stream>>>(0, sad, d_ur, d_dep, SB);
     LAUNCH_CHECK();
+    m->mark();
     return ORBX_OK;
 }
 int orbx_compute_stereo_matches_batch_device(orbx_matcher* m, orbx_extractor* left, orbx_extractor* right, int B, int cap, float mb, float mbf, float* d_u_right, float* d_depth) {

@@ -46,6 +46,16 @@ WORKLOADS = {
 }
 
 
+PAIR_WORKLOADS = {
+    # name: (width, height, nfeatures, pairs per GPU per step, workload text, metric)
+    "c2": (640, 480, 1000, 256, "ORBmatcher::SearchForInitialization between two synthetic 1000-keypoint 640x480 frames (frame B = frame A warped by (+7, -4) px, 2 deg), "
+           "ORBmatcher(0.9, true), window 100: 64x48 grid build + windowed 256-bit Hamming search + ratio test + ordered resolve + rotation histogram, per frame pair",
+           "SearchForInitialization frame pairs/sec @1000x1000 keypoints, window 100"),
+    "c4": (1241, 376, 2000, 64, "KITTI stereo 1241x376: ORB extraction of the left and the right image (nFeatures=2000, scale 1.2, 8 levels, FAST 20/7) + Frame::ComputeStereoMatches "
+           "(row-band Hamming + 11-shift SAD + parabola + median cut), per stereo pair", "stereo pairs/sec @1241x376 2000 feat (2 extractions + ComputeStereoMatches)"),
+}
+
+
 def level_pixels():
     s, tot, px = 1.0, 0, []
     f = np.float32(1.0)
@@ -96,6 +106,53 @@ class ClockSampler(threading.Thread):
         reasons = [n for i, n in enumerate(names) if any(len(s) > 2 + i and s[2 + i].lower().startswith("active") for s in self.samples)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
                 "reasons": reasons, "samples": len(self.samples)}
+
+
+def cpu_threads_run(make_worker, seconds_budget=None, threads=None, steps=None, units_per_thread_step=None):
+    """Runs one independent worker per host thread (make_worker(t) -> callable(i) doing one unit of work; ctypes calls release the GIL).
+    Either for ~seconds_budget (cpu_baseline leg) or for `steps` steps of threads * units_per_thread_step units (--impl reference)."""
+    threads = threads or max(1, os.cpu_count() or 1)
+    workers = [make_worker(t) for t in range(threads)]
+    done = [0] * threads; errors = []; start_evt = threading.Event()
+
+    def body(t, deadline_box, quota):
+        start_evt.wait()
+        i = t
+        while True:
+            if quota is not None and done[t] >= quota:
+                break
+            if quota is None and time.perf_counter() >= deadline_box[0]:
+                break
+            try:
+                workers[t](i)
+            except BaseException as e:
+                errors.append(repr(e)); break
+            done[t] += 1; i += threads
+
+    def run(quota, budget):
+        for t in range(threads):
+            done[t] = 0
+        box = [0.0]; start_evt.clear()
+        ths = [threading.Thread(target=body, args=(t, box, quota)) for t in range(threads)]
+        for th in ths:
+            th.start()
+        t0 = time.perf_counter(); box[0] = t0 + (budget or 1e9)
+        start_evt.set()
+        for th in ths:
+            th.join()
+        if errors:
+            raise RuntimeError("CPU reference worker failed: " + errors[0])
+        return sum(done), time.perf_counter() - t0
+
+    run(1, None)
+    if steps is None:
+        n, dt = run(None, seconds_budget)
+        return {"units": n, "seconds": dt, "rate": n / dt, "threads": threads, "step_times": None}
+    st, total = [], 0
+    for _ in range(steps):
+        n, dt = run(units_per_thread_step, None)
+        st.append(dt); total += n
+    return {"units": total, "seconds": sum(st), "rate": total / sum(st), "threads": threads, "step_times": st}
 
 
 def cpu_reference_run(seconds_budget, frames, threads=None, steps=None, frames_per_thread_step=None):
@@ -250,6 +307,349 @@ def matcher_bench(orbx, torch, ext, frames, device):
             "search_for_initialization_pairs_per_s": 1.0 / dt, "search_for_initialization_config": "host-pointer call, window 100, one pair per call (latency-bound)"}
 
 
+def _peaks():
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        peaks = {}
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    return peak, ("measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)")
+
+
+def _timed_device_steps(torch, dist, world, stream, K, W, fn):
+    """W warm-up calls, then K calls bracketed by CUDA events on `stream` with a barrier + synchronize on both sides; max over ranks (ms)."""
+    for _ in range(max(W, 3)):
+        fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(K):
+        fn()
+    e1.record(stream)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1)
+
+
+def _c2_frames(P, rank, world=1):
+    """P frame pairs: frame A synthetic (distinct seed per pair), frame B = A warped by (+7, -4) px, 2 deg."""
+    from tools.synth import synth_batch_distinct, warp_affine_nn
+    A = synth_batch_distinct(P, WIDTH, HEIGHT, seed0=2000 + rank * P, workers=max(1, min(32, (os.cpu_count() or 1) // max(world, 1))))
+    return A, np.stack([warp_affine_nn(a, 7, -4, 2.0) for a in A])
+
+
+def _c2_pairs(orbx, device, A, Bf):
+    """both frames of every pair extracted on the GPU (setup, outside the timed region)"""
+    P = len(A)
+    E = orbx.ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, device=device)
+    ka, da, ca = E.extract_batch(A); kb, db, cb = E.extract_batch(Bf)
+    sf = E.GetScaleFactors()
+    pairs = [(ka[p][:ca[p]].copy(), da[p][:ca[p]].copy(), kb[p][:cb[p]].copy(), db[p][:cb[p]].copy()) for p in range(P)]
+    return pairs, sf
+
+
+def bench_c2(args, rank, local_rank, world):
+    """BASELINE config 2: SearchForInitialization frame pairs/s (the "Hamming matches/sec" half of the metric), P pairs per call."""
+    import ctypes as C
+    N, K, W, P = args.gpus, args.steps, max(args.warmup, 0), (args.batch or PAIR_WORKLOADS["c2"][3])
+    A, Bf = _c2_frames(P, rank, world)                   # before CUDA is initialised (the generator forks)
+    import torch
+    import torch.distributed as dist
+    orbx = importlib.import_module("amos-slam_b200")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    pairs, sf = _c2_pairs(orbx, local_rank, A, Bf)
+    from importlib import import_module
+    mm = import_module("amos-slam_b200._matcher")
+    M = orbx.ORBmatcher(0.9, True, device=local_rank)
+    L = M._lib
+    views1 = [orbx.FrameView(p[0], p[1], WIDTH, HEIGHT, sf) for p in pairs]; views2 = [orbx.FrameView(p[2], p[3], WIDTH, HEIGHT, sf) for p in pairs]
+    v1 = (mm._FrameViewC * P)(*[v.c() for v in views1]); v2 = (mm._FrameViewC * P)(*[v.c() for v in views2])
+    n1 = np.array([len(p[0]) for p in pairs]); o1 = np.concatenate([[0], np.cumsum(n1)])
+    prev0 = np.concatenate([np.stack([p[0]["x"], p[0]["y"]], 1) for p in pairs]).astype(np.float32)
+    prev = prev0.copy(); m12 = np.zeros(int(o1[-1]), np.int32); nm = np.zeros(P, np.int32)
+    pp = (C.c_void_p * P)(*[prev.ctypes.data + 8 * int(o1[p]) for p in range(P)]); mp = (C.c_void_p * P)(*[m12.ctypes.data + 4 * int(o1[p]) for p in range(P)])
+    cam0 = orbx.Camera.make(517.306408, 516.469215, 318.643040, 255.313989, bf=40.0)
+    D1 = [orbx.Frame(local_rank).assign_host(p[0], p[1], sf, cam0, HEIGHT, WIDTH) for p in pairs]; D2 = [orbx.Frame(local_rank).assign_host(p[2], p[3], sf, cam0, HEIGHT, WIDTH) for p in pairs]
+    a1 = (C.c_void_p * P)(*[f._h.value for f in D1]); a2 = (C.c_void_p * P)(*[f._h.value for f in D2])
+    nmv = nm.ctypes.data_as(C.c_void_p)
+
+    def step_device():       # frames resident in HBM (keypoints, descriptors, grids); vbPrevMatched in, matches out
+        prev[:] = prev0
+        orbx._check(L.orbx_search_for_initialization_frames_batch(M._h, P, a1, a2, pp, mp, 100, nmv))
+
+    def step_host():         # host frame views in (keypoints + descriptors uploaded every call), matches out
+        prev[:] = prev0
+        orbx._check(L.orbx_search_for_initialization_batch(M._h, P, v1, v2, pp, mp, 100, nmv))
+
+    stream = torch.cuda.ExternalStream(M.stream)
+    sampler = ClockSampler(local_rank); sampler.start()
+    l0 = M.launch_count
+    ms = _timed_device_steps(torch, dist, world, stream, K, W, step_device)
+    launches = M.launch_count - l0
+    nm_dev = nm.copy(); m12_dev = m12.copy()
+    # stage breakdown (a separate pass with events between the five launches)
+    orbx._check(L.orbx_matcher_profile_enable(M._h, 1))
+    for _ in range(5):
+        step_device()
+    st = (C.c_double * 5)(); nc = C.c_int()
+    orbx._check(L.orbx_matcher_profile_collect(M._h, 5, st, C.byref(nc)))
+    orbx._check(L.orbx_matcher_profile_enable(M._h, 0))
+    stage_names = ["grid_build", "window_count", "scan", "window_fill", "resolve"]
+    stage_ms = {k: st[i] / max(nc.value, 1) for i, k in enumerate(stage_names)}
+    # e2e: wall clock around K synchronous host-view calls
+    Ke = max(3, min(K, 20))
+    for _ in range(3):
+        step_host()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        step_host()
+    ms_e2e = 1e3 * (time.perf_counter() - t0)
+    if world > 1:
+        dist.barrier()
+    sampler.stop_flag = True; sampler.join(timeout=2)
+    assert np.array_equal(nm, nm_dev) and np.array_equal(m12, m12_dev), "host-view and device-frame calls disagree"
+    # work per pair: candidate distances actually evaluated = sum of the list lengths (one call of the windows API gives them)
+    tq = np.concatenate([[len(p[0])] for p in pairs])
+    lv0 = sum(int((p[0]["octave"] == 0).sum()) for p in pairs)
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0].item()), float(t[1].item())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # distances per pair, measured once with the single-pair windows API (counts = GetFeaturesInArea result sizes of the level-0 features)
+    ndist = 0
+    for p in range(min(P, 16)):
+        q = pairs[p][0]["octave"] == 0
+        xy = np.stack([pairs[p][0]["x"][q], pairs[p][0]["y"][q]], 1).astype(np.float32)
+        ndist += sum(len(c) for c in M.GetFeaturesInArea(D2[p], xy, 100.0, 0, 0))
+    ndist_pair = ndist / float(min(P, 16))
+    value = N * P * K / (ms * 1e-3); e2e = N * P * Ke / (ms_e2e * 1e-3)
+    peak, peak_src = _peaks()
+    dom = max(stage_ms, key=lambda k: stage_ms[k])
+    nkeys = float(np.mean([len(p[0]) + len(p[2]) for p in pairs]))
+    bytes_of = {"grid_build": 28 * nkeys / 2 + 4 * (nkeys / 2 + 3073), "window_count": 28 * ndist_pair + 8 * lv0 / P, "scan": 8 * nkeys / 2,
+                "window_fill": (28 + 32 + 4) * ndist_pair + 32 * lv0 / P, "resolve": 4 * ndist_pair + 24 * nkeys / 2}
+    achieved = bytes_of[dom] * P / (stage_ms[dom] * 1e-3) / 1e9
+    h2d = int(sum((len(p[0]) + len(p[2])) * 60 + len(p[0]) * 8 for p in pairs) + P * 200); d2h = int(sum(len(p[0]) * 12 for p in pairs) + 8 * P)
+    line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": N, "steps": K, "warmup": max(W, 3), "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "pairs_per_gpu_per_step": P, "keypoints_per_frame": nkeys / 2, "level0_queries_per_pair": lv0 / P, "hamming_distances_per_pair": ndist_pair,
+                       "parallelism": "frame pairs sharded over %d GPU(s), no collective; one batched call per step" % N,
+                       "l2_policy": "per-step working set is %.1f MB of keypoints + descriptors (< L2): the path is latency / issue bound, not HBM bound; every step re-reads the same resident frames" % (P * nkeys * 60 / 1e6)},
+            "hamming_distances_per_s": value * ndist_pair,
+            "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
+                    "note": "orbx_search_for_initialization_batch on host frame views: keypoints, descriptors and vbPrevMatched uploaded, matches / vbPrevMatched / counts downloaded, every step"},
+            "gpu_launches": int(launches), "clocks": sampler.summary(),
+            "roofline": {"bound": "hbm", "kernel": {"grid_build": "k_grid_build_pairs", "window_count": "k_window_search_pairs<false>", "scan": "k_scan_counts_pairs", "window_fill": "k_window_search_pairs<true>",
+                                                   "resolve": "k_resolve_init_pairs"}[dom],
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": bytes_of[dom] * P, "ms_per_launch": stage_ms[dom], "stage_ms_per_step": stage_ms,
+                         "reading": "matching is integer-pipe / latency work on a few MB: the HBM fraction is reported because the contract asks for it; the pipe utilisation of the Hamming kernels is in profiles/ (ncu smsp__inst_executed_pipe_*)"},
+            "matches_per_pair": float(nm.mean())}
+    if N == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = _c2_cpu(pairs, sf, args.cpu_seconds, None, None)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _c2_cpu(pairs, sf, seconds, steps, per_thread):
+    """The reference's own SearchForInitialization body (oracle/_ref, else the port) on all host cores, one matcher per thread."""
+    import oracle
+    kind = "ref" if oracle.have_ref() else "port"
+    fd = [(oracle.FrameData(p[0], p[1], WIDTH, HEIGHT, sf), oracle.FrameData(p[2], p[3], WIDTH, HEIGHT, sf), np.stack([p[0]["x"], p[0]["y"]], 1).astype(np.float32)) for p in pairs[:64]]
+
+    def make(t):
+        m = oracle.Matcher(kind, 0.9, True)
+        return lambda i: m.search_for_initialization(fd[i % len(fd)][0], fd[i % len(fd)][1], fd[i % len(fd)][2], 100)
+    res = cpu_threads_run(make, seconds_budget=seconds, steps=steps, units_per_thread_step=per_thread)
+    res["kind"] = "reference" if kind == "ref" else "port"
+    if steps is not None:
+        return res
+    return {"value": res["rate"], "unit": "pairs/s", "cores": res["threads"], "kind": res["kind"],
+            "sample": "%d pairs in %.1f s, one independent ORBmatcher per thread on %d threads (frames already extracted), CPU: %s" % (res["units"], res["seconds"], res["threads"], cpu_model())}
+
+
+def _c4_pairs(P, rank):
+    from tools.synth import synth_batch_distinct, stereo_right_from_left
+    Ls = synth_batch_distinct(P, WIDTH, HEIGHT, seed0=3000 + rank * P)
+    Rs = np.stack([stereo_right_from_left(Ls[b], 3000 + rank * P + b + 1) for b in range(P)])
+    return Ls, Rs
+
+
+BF_KITTI = 386.1448          # Examples/Stereo/KITTI00-02.yaml:25
+
+
+def bench_c4(args, rank, local_rank, world):
+    """BASELINE config 4: KITTI stereo pairs/s = left + right extraction (two handles, two streams) + Frame::ComputeStereoMatches, B pairs per step."""
+    import ctypes as C
+    Ls, Rs = _c4_pairs(args.batch or PAIR_WORKLOADS["c4"][3], rank)       # before CUDA is initialised (the generator forks)
+    import torch
+    import torch.distributed as dist
+    orbx = importlib.import_module("amos-slam_b200")
+    N, K, W, B = args.gpus, args.steps, max(args.warmup, 0), len(Ls)
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    EL = orbx.ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, device=local_rank); ER = orbx.ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, device=local_rank)
+    M = orbx.ORBmatcher(device=local_rank); Lb = M._lib
+    cap = EL.max_keypoints(HEIGHT, WIDTH); ER.max_keypoints(HEIGHT, WIDTH)
+    hL = torch.from_numpy(Ls).pin_memory(); hR = torch.from_numpy(Rs).pin_memory(); dL = hL.cuda(); dR = hR.cuda()
+    dev = [(torch.empty((B, cap, 28), dtype=torch.uint8, device="cuda"), torch.empty((B, cap, 32), dtype=torch.uint8, device="cuda"), torch.zeros(B, dtype=torch.int32, device="cuda")) for _ in range(2)]
+    hst = [(torch.empty((B, cap, 28), dtype=torch.uint8).pin_memory(), torch.empty((B, cap, 32), dtype=torch.uint8).pin_memory(), torch.zeros(B, dtype=torch.int32).pin_memory()) for _ in range(2)]
+    d_ur = torch.empty((B, cap), dtype=torch.float32, device="cuda"); d_dep = torch.empty_like(d_ur)
+    h_ur = torch.empty((B, cap), dtype=torch.float32).pin_memory(); h_dep = torch.empty_like(h_ur).pin_memory()
+
+    def step_device():
+        for E, d, o in ((EL, dL, dev[0]), (ER, dR, dev[1])):
+            E.extract_batch_raw(d.data_ptr(), B, HEIGHT, WIDTH, WIDTH, WIDTH * HEIGHT, o[0].data_ptr(), o[1].data_ptr(), cap, o[2].data_ptr(), device=True)
+        orbx._check(Lb.orbx_compute_stereo_matches_batch_device(M._h, EL._h, ER._h, B, cap, 0.0, BF_KITTI, C.c_void_p(d_ur.data_ptr()), C.c_void_p(d_dep.data_ptr())))
+
+    errs = []
+
+    def host_extract(E, h, o):
+        try:
+            torch.cuda.set_device(local_rank)
+            E.extract_batch_raw(h.data_ptr(), B, HEIGHT, WIDTH, WIDTH, WIDTH * HEIGHT, o[0].data_ptr(), o[1].data_ptr(), cap, o[2].data_ptr(), device=False)
+        except BaseException as ex:
+            errs.append(repr(ex))
+
+    def step_host():         # the reference runs the two extractions in two threads (src/Frame.cc:165-173), then ComputeStereoMatches
+        ths = [threading.Thread(target=host_extract, args=(EL, hL, hst[0])), threading.Thread(target=host_extract, args=(ER, hR, hst[1]))]
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+        if errs:
+            raise SystemExit("e2e worker failed: " + errs[0])
+        orbx._check(Lb.orbx_compute_stereo_matches_batch(M._h, EL._h, ER._h, B, cap, 0.0, BF_KITTI, C.c_void_p(h_ur.data_ptr()), C.c_void_p(h_dep.data_ptr())))
+
+    stream = torch.cuda.ExternalStream(M.stream)          # the matcher's stream waits for both extractors' streams: its events cover the whole step
+    sampler = ClockSampler(local_rank); sampler.start()
+    l0 = EL.launch_count + ER.launch_count + M.launch_count
+    ms = _timed_device_steps(torch, dist, world, stream, K, W, step_device)
+    launches = EL.launch_count + ER.launch_count + M.launch_count - l0
+    ur_dev = d_ur.cpu().numpy().copy()
+    # stage breakdown: extractor stages of the left handle (serialised pass) and the two matcher launches
+    EL.profile_enable(True); orbx._check(Lb.orbx_matcher_profile_enable(M._h, 1))
+    for _ in range(3):
+        step_device()
+    ext_ms, ncalls = EL.profile_collect(); EL.profile_enable(False)
+    st = (C.c_double * 2)(); nc = C.c_int()
+    orbx._check(Lb.orbx_matcher_profile_collect(M._h, 2, st, C.byref(nc))); orbx._check(Lb.orbx_matcher_profile_enable(M._h, 0))
+    stage_ms = {("extract_" + k): 2 * v / max(ncalls, 1) for k, v in ext_ms.items()}                     # x2: left and right image
+    stage_ms["stereo_match"] = st[0] / max(nc.value, 1); stage_ms["stereo_median_cut"] = st[1] / max(nc.value, 1)
+    Ke = max(3, min(K, 10))
+    for _ in range(2):
+        step_host()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        step_host()
+    ms_e2e = 1e3 * (time.perf_counter() - t0)
+    if world > 1:
+        dist.barrier()
+    sampler.stop_flag = True; sampler.join(timeout=2)
+    assert np.array_equal(h_ur.numpy(), ur_dev), "host and device stereo paths disagree"
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0].item()), float(t[1].item())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    n_kp = float(hst[0][2].float().mean().item()); matched = float((h_ur.numpy() >= 0).sum(1).mean())
+    value = N * B * K / (ms * 1e-3); e2e = N * B * Ke / (ms_e2e * 1e-3)
+    peak, peak_src = _peaks()
+    n_cand = float(sum(len(EL.debug_level_candidates(0, l)) for l in range(NLEVELS)))
+    sb = {("extract_" + k): 2 * v for k, v in stage_bytes(n_kp, n_cand).items()}
+    sb["stereo_match"] = 2 * n_kp * 60 + n_kp * n_kp * 28 / 32.0 + matched * 11 * 121 * 2; sb["stereo_median_cut"] = n_kp * 12
+    dom = max(stage_ms, key=lambda k: stage_ms[k])
+    nl = (NLEVELS - 1) if dom == "extract_pyr_resize" else 1
+    achieved = sb[dom] * B / (stage_ms[dom] * 1e-3) / 1e9
+    line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": N, "steps": K, "warmup": max(W, 3), "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frame": [WIDTH, HEIGHT], "nfeatures": NFEAT, "stereo_pairs_per_gpu_per_step": B, "keypoints_per_image": n_kp, "stereo_matches_per_pair": matched,
+                       "parallelism": "stereo pairs sharded over %d GPU(s), no collective; left / right extractor handles on two streams, matcher stream behind both" % N,
+                       "l2_policy": "working set per step (%.0f MB of images, ~%.1f GB of pyramids + scratch) exceeds the 126 MB L2" % (2 * B * WIDTH * HEIGHT / 1e6, 2 * B * 6.3e-3 * WIDTH * HEIGHT / 307200.0)},
+            "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": int(2 * B * WIDTH * HEIGHT), "d2h_bytes_per_step": int(2 * (B * cap * 60 + 4 * B) + 8 * B * cap), "steps": Ke,
+                    "note": "two host threads call orbx_extract_batch (left / right images, pinned host in, keypoints + descriptors out), then orbx_compute_stereo_matches_batch (mvuRight / mvDepth out)"},
+            "gpu_launches": int(launches), "clocks": sampler.summary(),
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": sb[dom] * B / nl, "ms_per_launch": stage_ms[dom] / nl, "stage_ms_per_step": stage_ms}}
+    if N == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = _c4_cpu(Ls, Rs, args.cpu_seconds, None, None)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _c4_cpu(Ls, Rs, seconds, steps, per_thread):
+    """The reference's own code per stereo pair: ORBextractor on the left and on the right image + Frame::ComputeStereoMatches (oracle/_ref, else the
+    port).  One pair per thread (the reference itself uses two threads per pair, src/Frame.cc:165-173; with every core busy the throughput is the same)."""
+    import oracle
+    kind = "ref" if oracle.have_ref() else "port"
+    n = min(len(Ls), 16)
+
+    def make(t):
+        el = oracle.Extractor(kind, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH); er = oracle.Extractor(kind, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH); m = oracle.Matcher(kind)
+
+        def one(i):
+            kl, dl = el.extract(Ls[i % n]); kr, dr = er.extract(Rs[i % n])
+            m.compute_stereo_matches(el, er, kl, dl, kr, dr, 0.0, BF_KITTI)
+        return one
+    res = cpu_threads_run(make, seconds_budget=seconds, steps=steps, units_per_thread_step=per_thread)
+    res["kind"] = "reference" if kind == "ref" else "port"
+    if steps is not None:
+        return res
+    return {"value": res["rate"], "unit": "pairs/s", "cores": res["threads"], "kind": res["kind"],
+            "sample": "%d stereo pairs in %.1f s, one pair at a time per thread on %d threads, CPU: %s" % (res["units"], res["seconds"], res["threads"], cpu_model())}
+
+
+def reference_pairs(args, defP):
+    """--impl reference for the pair workloads: the reference's own CPU code on all host cores, same metric / config keys."""
+    K, W = args.steps, max(args.warmup, 0)
+    threads = max(1, os.cpu_count() or 1)
+    if args.workload == "c2":
+        # the frames are extracted with the CPU reference as well (no GPU on this arm)
+        import oracle
+        from tools.synth import synth_batch_distinct, warp_affine_nn
+        kind = "ref" if oracle.have_ref() else "port"
+        A = synth_batch_distinct(32, WIDTH, HEIGHT, seed0=2000)
+        E = oracle.Extractor(kind, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH)
+        pairs = []
+        for a in A:
+            ka, da = E.extract(a); kb, db = E.extract(warp_affine_nn(a, 7, -4, 2.0))
+            pairs.append((ka, da, kb, db))
+        sf = np.cumprod(np.concatenate([[1.0], np.full(NLEVELS - 1, SCALE)])).astype(np.float32)
+        per = 512
+        res = _c2_cpu(pairs, sf, None, W + K, per)
+    else:
+        Ls, Rs = _c4_pairs(16, 0)
+        per = 16
+        res = _c4_cpu(Ls, Rs, None, W + K, per)
+    st = res["step_times"][W:]
+    rate = threads * per * K / sum(st)
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": "pairs/s", "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": 1e3 * sum(st) / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": {"workload": WORKLOAD},
+            "cpu_baseline": {"value": rate, "unit": "pairs/s", "cores": threads, "kind": res["kind"],
+                             "sample": "%d steps x %d threads x %d pairs, one independent worker per thread, CPU: %s" % (K, threads, per, cpu_model())},
+            "e2e": {"value": rate, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
 def bind_to_gpu_numa_node(index):
     """Pin this process to the CPUs that are local to GPU `index` (its PCIe root's NUMA node) BEFORE the pinned host buffers are
     allocated, so first-touch places them on the right socket: with 8 ranks feeding 8 GPUs, frames crossing the inter-socket link
@@ -292,12 +692,20 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="c1", choices=sorted(WORKLOADS), help="BASELINE.json config (c1 = headline metric)")
+    ap.add_argument("--workload", default="c1", choices=sorted(list(WORKLOADS) + list(PAIR_WORKLOADS)), help="BASELINE.json config (c1 = headline metric)")
     ap.add_argument("--streams", type=int, default=2, help="extractor handles (camera streams) per GPU; the step's frames are split evenly between them")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-pointer leg (the line is then not a bench value)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); local_rank = int(os.environ.get("LOCAL_RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     global WIDTH, HEIGHT, NFEAT, WORKLOAD, METRIC, MASKED
+    if args.workload in PAIR_WORKLOADS:
+        WIDTH, HEIGHT, NFEAT, defP, WORKLOAD, METRIC = PAIR_WORKLOADS[args.workload]
+        if args.impl == "reference":
+            if rank == 0:
+                reference_pairs(args, defP)
+            return
+        (bench_c2 if args.workload == "c2" else bench_c4)(args, rank, local_rank, world)
+        return
     WIDTH, HEIGHT, NFEAT, defB, MASKED, WORKLOAD, METRIC = WORKLOADS[args.workload]
     N, K, W, B = args.gpus, args.steps, max(args.warmup, 0), (args.batch or defB)
     config = {"workload": WORKLOAD, "frame": [WIDTH, HEIGHT], "nfeatures": NFEAT, "frames_per_gpu_per_step": B,
@@ -309,7 +717,9 @@ def main():
             return
         frames = synth_batch(64, WIDTH, HEIGHT, seed0=0, distinct=16 if WIDTH * HEIGHT < 1000000 else 4)
         threads = max(1, os.cpu_count() or 1)
-        FPT = 8            # frames per thread per step: long enough that thread start/join is noise, short enough for K steps in seconds
+        # frames per thread per step: ~1.5 s of work per step on one core, so that thread start / join and the slowest thread's tail are
+        # noise (8 frames per step read 27 % low against the continuous cpu_baseline leg in round 1)
+        FPT = max(8, int(round(128 * 307200.0 / (WIDTH * HEIGHT))))
         res = cpu_reference_run(None, frames, threads=threads, steps=W + K, frames_per_thread_step=FPT)
         st = res["step_times"][W:]
         fps = threads * FPT * K / sum(st)
@@ -322,6 +732,9 @@ def main():
         print(json.dumps(line))
         return
 
+    # B frames from B distinct seeds, generated by a process pool BEFORE CUDA is initialised in this process (the pool forks)
+    from tools.synth import synth_batch_distinct
+    frames = synth_batch_distinct(B, WIDTH, HEIGHT, seed0=1000 + B * rank, workers=max(1, min(32, (os.cpu_count() or 1) // max(world, 1))))
     import torch
     import torch.distributed as dist
     orbx = importlib.import_module("amos-slam_b200")
@@ -332,7 +745,6 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    frames = synth_batch(B, WIDTH, HEIGHT, seed0=1000 * rank, distinct=24 if WIDTH * HEIGHT < 1000000 else 8)
     ext = orbx.ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, device=local_rank)
     cap = ext.max_keypoints(HEIGHT, WIDTH)
     h_frames = torch.from_numpy(frames).pin_memory()

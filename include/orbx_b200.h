@@ -201,6 +201,11 @@ int orbx_matcher_create(float nnratio, int check_orientation, int device, orbx_m
 void orbx_matcher_destroy(orbx_matcher* m);
 void* orbx_matcher_stream(orbx_matcher* m);
 long long orbx_matcher_launch_count(const orbx_matcher* m);
+/* Per-stage device timing of the batched matcher calls (bench.py): see orbx_profile_enable.  Stages of
+ * orbx_search_for_initialization[_frames]_batch: grid build, window count, scan, window fill, resolve (nstages = 5);
+ * of orbx_compute_stereo_matches_batch[_device]: stereo match, median cut (nstages = 2). */
+int orbx_matcher_profile_enable(orbx_matcher* m, int on);
+int orbx_matcher_profile_collect(orbx_matcher* m, int nstages, double* stage_ms, int* ncalls);
 
 /* static int ORBmatcher::DescriptorDistance(const Mat& a, const Mat& b)   src/ORBmatcher.cc:1913-1933
  * n pairs: out[i] = popcount(a[i] xor b[i]) over 256 bits (device kernel; host pointers). */

@@ -99,3 +99,25 @@ def synth_labels(seed, width, height, blocks=5):
     centers_id = rng.integers(0, nclusters, blocks * blocks).astype(np.int32)
     rm = np.zeros(nclusters, np.int32); rm[rng.choice(nclusters, int(rng.integers(2, 5)), replace=False)] = 1
     return label, centers_id, rm
+
+
+def _synth_one(args):
+    seed, width, height = args
+    return synth_frame(seed, width, height)
+
+
+def synth_batch_distinct(n, width=640, height=480, seed0=1000, workers=None):
+    """n frames from n DISTINCT seeds seed0 .. seed0 + n - 1 ("batch of 1024 distinct seeds"), generated by a process pool
+    (call before CUDA is initialised: the pool forks)."""
+    import os
+    from concurrent.futures import ProcessPoolExecutor
+    workers = workers or max(1, min(os.cpu_count() or 1, 32))
+    out = np.empty((n, height, width), np.uint8)
+    if workers == 1 or n < 8:
+        for i in range(n):
+            out[i] = synth_frame(seed0 + i, width, height)
+        return out
+    with ProcessPoolExecutor(workers) as ex:
+        for i, f in enumerate(ex.map(_synth_one, [(seed0 + i, width, height) for i in range(n)], chunksize=max(1, n // (4 * workers)))):
+            out[i] = f
+    return out
