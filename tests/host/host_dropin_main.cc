@@ -12,6 +12,8 @@
 #include <cstdlib>
 #include <string>
 #include <vector>
+#include <chrono>
+#include <functional>
 
 using namespace ORB_SLAM2;
 namespace ORB_SLAM2 { void RegisterDeviceVocabulary(const ORBVocabulary* voc, const std::string& file); }   // amos-slam_b200/host/BoW_b200.cc
@@ -242,6 +244,26 @@ int main(int argc, char** argv) {
         for (size_t i = 0; i < m12.size(); ++i) put_i(m12[i] ? (int)(m12[i] - mp2.data()) : -1);
     }
     fclose(g_out); fclose(f);
+    // ---- per-call latency of the drop-in classes as C++ code sees them (everything the body does on the host included: flattening the
+    //      arguments, the C-ABI call with its copies, scattering the results back into the reference's containers)
+    {
+        ext.SetExportPyramid(false);
+        std::vector<cv::KeyPoint> kt; cv::Mat dt;
+        auto timeit = [&](const char* name, int reps, const std::function<void()>& fn) {
+            for (int i = 0; i < 5; ++i) fn();
+            const auto t0 = std::chrono::steady_clock::now();
+            for (int i = 0; i < reps; ++i) fn();
+            const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count() / reps;
+            printf("timing_us %s %.1f\n", name, us);
+        };
+        timeit("ORBextractor::operator()_640x480_1000", 200, [&] { ext(A, cv::Mat(), kt, dt); });
+        timeit("ORBmatcher::SearchForInitialization_host_frames", 200, [&] {
+            std::vector<cv::Point2f> pv(ka.size()); for (size_t i = 0; i < ka.size(); ++i) pv[i] = ka[i].pt;
+            std::vector<int> mm; ORBmatcher(0.9, true).SearchForInitialization(FA, FB, pv, mm, 100); });
+        timeit("ORBmatcher::SearchByProjection(Frame,MapPoints)_incl_flatten", 200, [&] {
+            FB.mvpMapPoints.assign(FB.N, (MapPoint*)NULL); ORBmatcher(0.8, true).SearchByProjection(FB, pts, 3.f); });
+        timeit("Frame::ComputeStereoMatches_2000x2000", 100, [&] { S.ComputeStereoMatches(); });
+    }
     printf("host drop-in ok: %zu / %zu keypoints, %d stereo keypoints\n", ka.size(), kb.size(), S.N);
     return 0;
 }
