@@ -22,7 +22,7 @@ LIB_PATH = os.path.join(HERE, "liborbx_b200.so")
 CSRC = os.path.join(HERE, "csrc")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177"]
-SOURCES = ["orbx_extractor.cu", "orbx_matcher.cu"]
+SOURCES = ["orbx_extractor.cu", "orbx_matcher.cu", "orbx_pool.cu"]
 
 KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
                      ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
@@ -101,6 +101,14 @@ def lib():
     L.orbx_extract_masked_batch_device.argtypes = [vp, vp, vp, ci, ci, ci, sz, sz, sz, sz, vp, vp, ci, vp, vp]
     L.orbx_extract_masked_batch_labels.argtypes = [vp, vp, vp, vp, ci, ci, ci, sz, sz, sz, sz, vp, vp, ci, vp, vp]
     L.orbx_extract_masked_batch_labels_device.argtypes = [vp, vp, vp, vp, ci, ci, ci, sz, sz, sz, sz, vp, vp, ci, vp, vp]
+    L.orbx_pool_shard_of.argtypes = [ci, ci, ci, C.POINTER(ci), C.POINTER(ci)]
+    L.orbx_pool_create.argtypes = [ci, cf, ci, ci, ci, ci, vp, ci, C.POINTER(vp)]
+    L.orbx_pool_destroy.argtypes = [vp]; L.orbx_pool_destroy.restype = None
+    L.orbx_pool_gpus.argtypes = [vp]; L.orbx_pool_streams_per_gpu.argtypes = [vp]; L.orbx_pool_device_of.argtypes = [vp, ci]
+    L.orbx_pool_frames_done.argtypes = [vp, ci, ci]; L.orbx_pool_frames_done.restype = C.c_longlong
+    L.orbx_pool_submit.argtypes = [vp, ci, vp, ci, ci, sz, vp, vp, ci, vp, C.POINTER(C.c_longlong)]
+    L.orbx_pool_submit_batch.argtypes = [vp, ci, vp, vp, vp, ci, ci, ci, sz, sz, sz, sz, vp, vp, ci, vp, vp, C.POINTER(C.c_longlong)]
+    L.orbx_pool_wait.argtypes = [vp, C.c_longlong]; L.orbx_pool_wait_all.argtypes = [vp]
     L.orbx_debug_level_candidates.argtypes = [vp, ci, ci, vp, ci, C.POINTER(ci)]
     L.orbx_debug_blurred_level.argtypes = [vp, ci, ci, vp, sz]
     L.orbx_debug_pyramid_level.argtypes = [vp, ci, ci, vp, sz]
@@ -375,6 +383,71 @@ class ORBextractor:
         out = np.zeros(cap, KP_DTYPE); n = C.c_int()
         _check(self._lib.orbx_debug_distribute(self._h, _ptr(cand), len(cand), minX, maxX, minY, maxY, N, _ptr(out), cap, C.byref(n)))
         return out[:n.value].copy()
+
+
+class ExtractorPool:
+    """orbx_pool: multi-sequence / multi-GPU driver (gpu = seq_id mod G, stream = (seq_id div G) mod S; one worker thread + extractor
+    handle per (gpu, stream)).  Buffers handed to submit* must stay alive until wait*()."""
+
+    def __init__(self, nfeatures=1000, scaleFactor=1.2, nlevels=8, iniThFAST=20, minThFAST=7, n_gpus=1, streams_per_gpu=2, devices=None):
+        self._lib = lib()
+        h = C.c_void_p()
+        dv = (C.c_int * n_gpus)(*devices) if devices is not None else None
+        _check(self._lib.orbx_pool_create(int(nfeatures), float(scaleFactor), int(nlevels), int(iniThFAST), int(minThFAST), int(n_gpus), dv, int(streams_per_gpu), C.byref(h)))
+        self._h = h; self.n_gpus = n_gpus; self.streams_per_gpu = streams_per_gpu; self._keep = {}
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.orbx_pool_destroy(self._h); self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def device_of(self, seq_id):
+        return self._lib.orbx_pool_device_of(self._h, int(seq_id))
+
+    def frames_done(self, gpu, stream):
+        return self._lib.orbx_pool_frames_done(self._h, int(gpu), int(stream))
+
+    def submit(self, seq_id, image, cap):
+        """One frame of sequence seq_id -> ticket; fetch with result(ticket)."""
+        img = np.ascontiguousarray(image, np.uint8)
+        kp = np.zeros(cap, KP_DTYPE); desc = np.zeros((cap, 32), np.uint8); n = np.zeros(1, np.int32); t = C.c_longlong()
+        _check(self._lib.orbx_pool_submit(self._h, int(seq_id), _ptr(img), img.shape[0], img.shape[1], img.strides[0], _ptr(kp), _ptr(desc), cap, _ptr(n), C.byref(t)))
+        self._keep[t.value] = (img, kp, desc, n, None)
+        return t.value
+
+    def submit_batch(self, seq_id, images, masks=None, labels=None, flagged=None, cap=None, out=None):
+        """B frames of sequence seq_id (same geometry) -> ticket.  out = (kp, desc, counts, culled) pre-allocated (pinned) arrays, optional."""
+        images = np.ascontiguousarray(images, np.uint8); B, rows, cols = images.shape
+        if out is None:
+            out = (np.zeros((B, cap), KP_DTYPE), np.zeros((B, cap, 32), np.uint8), np.zeros(B, np.int32), np.zeros(B, np.int32))
+        kp, desc, counts, culled = out
+        cap = kp.shape[1]
+        mk = None if masks is None else np.ascontiguousarray(masks, np.uint8)
+        lab = None; keep = None
+        if labels is not None:
+            l16 = np.ascontiguousarray(labels, np.uint16); fl = np.ascontiguousarray(flagged, np.uint8)
+            lab = LabelsC(_ptr(l16), cols, rows * cols, _ptr(fl), fl.shape[1]); keep = (l16, fl, lab)
+        t = C.c_longlong()
+        _check(self._lib.orbx_pool_submit_batch(self._h, int(seq_id), _ptr(images), _ptr(mk) if mk is not None else None, C.byref(lab) if lab is not None else None, B, rows, cols,
+                                                images.strides[1], images.strides[0], mk.strides[1] if mk is not None else 0, mk.strides[0] if mk is not None else 0,
+                                                _ptr(kp), _ptr(desc), cap, _ptr(counts), _ptr(culled), C.byref(t)))
+        self._keep[t.value] = (images, kp, desc, counts, culled, mk, keep)
+        return t.value
+
+    def result(self, ticket):
+        _check(self._lib.orbx_pool_wait(self._h, C.c_longlong(ticket)))
+        r = self._keep.pop(ticket)
+        if r[4] is None and len(r) == 5:          # single frame
+            n = int(r[3][0]); return r[1][:n].copy(), r[2][:n].copy()
+        return r[1], r[2], r[3], r[4]
+
+    def wait_all(self):
+        _check(self._lib.orbx_pool_wait_all(self._h)); self._keep.clear()
 
 
 from ._matcher import ORBmatcher, FrameView, Frame, Camera, ORBVocabulary  # noqa: E402,F401

@@ -86,55 +86,71 @@ k_gauss7(PyrView pv, const LevelGeom* __restrict__ levels, const BlurTile* __res
         if (fix && !slow && !(xa >= 0 && xa < gw && xb >= 0 && xb < gw)) slow = true;
     }
     const int rlast = y1 + 2;
+    // per-lane load mode, row-invariant: 0 = plain aligned word, 1 = nothing to load (word not needed, or rebuilt from the neighbours'
+    // loads by the shuffles below), 2 = reflected byte loads (levels narrower than the halo)
+    const int mode = (!edge_tile || (word_in && !slow)) ? 0 : ((needed && slow) ? 2 : 1);
+    // strips that do not touch the top / bottom edge of the level (warp-uniform) never reflect a row
+    const bool interior = y0 - 3 >= 0 && rlast <= gh - 1;
+    const bool tiny = gh < 4;                                            // warp-uniform: only then can a reflected row need a second reflection
+    const uint8_t* colp = img + x;                                       // halo lanes may point outside the row: dereferenced in mode 0 only
     auto load_row = [&](int r) -> uint32_t {
         int rr = min(r, rlast);                                          // the tail group re-reads the last row instead of running past it
-        if ((unsigned)rr >= (unsigned)gh) {                              // BORDER_REFLECT_101, closed form for |overshoot| <= 3 on any height >= 1
+        if (!interior) {                                                 // BORDER_REFLECT_101 of rows -3 .. -1 and gh .. gh + 2
             rr = rr < 0 ? -rr : rr; rr = rr >= gh ? 2 * gh - 2 - rr : rr;
-            rr = rr < 0 ? -rr : rr; rr = rr >= gh ? 2 * gh - 2 - rr : rr;
-            rr = max(rr, 0);
+            if (tiny) { rr = rr < 0 ? -rr : rr; rr = rr >= gh ? 2 * gh - 2 - rr : rr; rr = max(rr, 0); }
         }
-        const uint8_t* row = img + rr * pitch;                           // a frame's level is < 2^31 bytes
-        if (!edge_tile || word_in) {
-            if (!(edge_tile && slow)) return __ldg(reinterpret_cast<const uint32_t*>(row + x));
-        }
-        if (!needed || !slow) return 0u;
+        const int off = rr * pitch;                                      // a frame's level is < 2^31 bytes
+        if (mode == 0) return __ldg(reinterpret_cast<const uint32_t*>(colp + off));
+        if (mode == 1) return 0u;
+        const uint8_t* row = img + off;
         return (uint32_t)__ldg(row + rx[0]) | ((uint32_t)__ldg(row + rx[1]) << 8) | ((uint32_t)__ldg(row + rx[2]) << 16) | ((uint32_t)__ldg(row + rx[3]) << 24);
     };
-    uint8_t* dst = blur + (long long)b * blur_fstride + g.off + x;
+    uint8_t* dst = blur + (long long)b * blur_fstride + g.off + x + (long long)(y0 - 6) * gpitch;   // running pointer: output row of the next input row
     const uint32_t Q0 = 18u | (34u << 8) | (48u << 16) | (56u << 24);     // taps -3..0
     const uint32_t Q1 = 48u | (34u << 8) | (18u << 16);                   // taps +1..+3 (4th byte unused)
-    uint32_t hb[7][4];                                                    // ring of the horizontal sums of the last 7 input rows (<= 65280 each)
-    uint32_t pre[7];                                                      // ring of row words in flight
+    // Vertical pass on PAIRS of rows: the horizontal sums fit 16 bits (<= 65280), so row r is packed with row r-1 as it arrives
+    // (P = h[r-1] | h[r] << 16) and an output row is three 2-way integer dot products (IDP.2A: 16-bit sums x 8-bit taps) plus one multiply:
+    //   v(o) = (h[o-3], h[o-2]).(18, 34) + (h[o-1], h[o]).(48, 56) + (h[o+1], h[o+2]).(48, 34) + 18 h[o+3] + 32768
+    // -- 5 instructions per pixel instead of 7.  The ring holds the packed pairs of the last 6 input rows (static slots after unrolling).
+    const uint32_t WA = 18u | (34u << 8), WB = 48u | (56u << 8), WC = 48u | (34u << 8);
+    uint32_t P[6][4];
+    uint32_t hprev[4] = {0u, 0u, 0u, 0u};
+    uint32_t pre[6];                                                      // ring of row words in flight
 #pragma unroll
-    for (int j = 0; j < 7; ++j) { hb[j][0] = hb[j][1] = hb[j][2] = hb[j][3] = 0; pre[j] = load_row(y0 - 3 + j); }
-    const int ngroups = (y1 - y0 + 6 + 6) / 7;                            // input rows y0-3 .. y1+2 in groups of 7 (the tail group over-reads reflected rows)
+    for (int j = 0; j < 6; ++j) { P[j][0] = P[j][1] = P[j][2] = P[j][3] = 0; pre[j] = load_row(y0 - 3 + j); }
+    const int ngroups = (y1 - y0 + 6 + 5) / 6;                            // input rows y0-3 .. y1+2 in groups of 6 (the tail group over-reads clamped rows)
     for (int gi = 0; gi < ngroups; ++gi) {
-        const int r0 = y0 - 3 + gi * 7;
+        const int r0 = y0 - 3 + gi * 6;
 #pragma unroll
-        for (int j = 0; j < 7; ++j) {                                     // ring slot j is static after unrolling: no register moves
+        for (int j = 0; j < 6; ++j) {                                     // ring slot j is static after unrolling: no register moves
             const int r = r0 + j;
             uint32_t w1 = pre[j];
-            if (gi + 1 < ngroups) pre[j] = load_row(r + 7);
+            if (gi + 1 < ngroups) pre[j] = load_row(r + 6);
             if (edge_tile) {                                              // warp-uniform: rebuild the edge words from their neighbours' loads
                 const uint32_t wa = __shfl_sync(0xffffffffu, w1, srcA), wb = __shfl_sync(0xffffffffu, w1, srcB);
                 if (fix && !slow) w1 = __byte_perm(w1, __byte_perm(wa, wb, selG), selM);
             }
             const uint32_t w0 = __shfl_up_sync(0xffffffffu, w1, 1), w2 = __shfl_down_sync(0xffffffffu, w1, 1);
             // h(x+k) = sum_{i=0..6} q[i] * px(x+k-3+i): two 4-tap integer dot products on byte-aligned windows
-            hb[j][0] = __dp4a(__byte_perm(w0, w1, 0x4321), Q0, __dp4a(__byte_perm(w1, w2, 0x4321), Q1, 0u));
-            hb[j][1] = __dp4a(__byte_perm(w0, w1, 0x5432), Q0, __dp4a(__byte_perm(w1, w2, 0x5432), Q1, 0u));
-            hb[j][2] = __dp4a(__byte_perm(w0, w1, 0x6543), Q0, __dp4a(__byte_perm(w1, w2, 0x6543), Q1, 0u));
-            hb[j][3] = __dp4a(w1, Q0, __dp4a(w2, Q1, 0u));
+            uint32_t hh[4];
+            hh[0] = __dp4a(__byte_perm(w0, w1, 0x4321), Q0, __dp4a(__byte_perm(w1, w2, 0x4321), Q1, 0u));
+            hh[1] = __dp4a(__byte_perm(w0, w1, 0x5432), Q0, __dp4a(__byte_perm(w1, w2, 0x5432), Q1, 0u));
+            hh[2] = __dp4a(__byte_perm(w0, w1, 0x6543), Q0, __dp4a(__byte_perm(w1, w2, 0x6543), Q1, 0u));
+            hh[3] = __dp4a(w1, Q0, __dp4a(w2, Q1, 0u));
             const int o = r - 3;                                          // output row completed by this input row
             uint32_t v[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                v[k] = 18u * (hb[(j + 1) % 7][k] + hb[j][k]) + 34u * (hb[(j + 2) % 7][k] + hb[(j + 6) % 7][k]) +
-                       48u * (hb[(j + 3) % 7][k] + hb[(j + 5) % 7][k]) + (56u * hb[(j + 4) % 7][k] + 32768u);
+            for (int k = 0; k < 4; ++k) {
+                P[j][k] = __byte_perm(hprev[k], hh[k], 0x5410);           // rows (r-1, r)
+                hprev[k] = hh[k];
+                // rows (r-6, r-5) = slot j+1, (r-4, r-3) = slot j+3, (r-2, r-1) = slot j+5 (mod 6), row r alone
+                v[k] = __dp2a_lo(P[(j + 1) % 6][k], WA, __dp2a_lo(P[(j + 3) % 6][k], WB, __dp2a_lo(P[(j + 5) % 6][k], WC, 18u * hh[k] + 32768u)));
+            }
             // (v + 32768) >> 16 is byte 2 of each sum (v < 2^24)
             const uint32_t outw = __byte_perm(__byte_perm(v[0], v[1], 0x0062), __byte_perm(v[2], v[3], 0x0062), 0x5410);
             if (store && o >= y0 && o < y1)
-                *reinterpret_cast<uint32_t*>(dst + o * gpitch) = outw;   // bytes past the level width land in row padding
+                *reinterpret_cast<uint32_t*>(dst) = outw;                // bytes past the level width land in row padding
+            dst += gpitch;
         }
     }
 }
@@ -310,5 +326,19 @@ k_describe_given(const LevelGeom* __restrict__ levels, int nlevels, const KpOut*
     if (lane == 0) {
         if (level != 0) { kp.x = __fmul_rn(kp.x, g.scale); kp.y = __fmul_rn(kp.y, g.scale); }
         kp_out[i] = kp;
+    }
+}
+
+// single-frame result block [count | overflow flag | pad | keypoint slots | descriptor slots] for one download (orbx_extract)
+__global__ void __launch_bounds__(256)
+k_gather_result(const int* __restrict__ count, const int* __restrict__ overflow, const uint32_t* __restrict__ kp, int kp_words,
+                const uint32_t* __restrict__ desc, int desc_words, uint32_t* __restrict__ out) {
+    const int i = blockIdx.x * 256 * 4 + threadIdx.x;
+    if (i == 0) { out[0] = (uint32_t)count[0]; out[1] = (uint32_t)overflow[0]; out[2] = 0; out[3] = 0; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int j = i + k * 256;
+        if (j < kp_words) out[4 + j] = kp[j];
+        else if (j < kp_words + desc_words) out[4 + j] = desc[j - kp_words];
     }
 }

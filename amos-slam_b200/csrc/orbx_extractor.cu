@@ -87,6 +87,9 @@ struct orbx_extractor {
     const KpOut* lb_kp = nullptr; const uint8_t* lb_desc = nullptr; const int* lb_counts = nullptr; int lb_cap = 0, lb_B = 0;   // outputs of the last batched call (orbx_compute_stereo_matches_batch)
     const KpOut* last_kp = nullptr; const uint8_t* last_desc = nullptr; int last_n = -1;   // frame 0 of the last extract / describe (orbx_frame_assign)
     PyrView view{}; bool have_pyramid = false, blur_valid = false;
+    // single-frame operator(): the whole per-geometry chain (upload from a pinned staging frame, 7 resizes, FAST, quadtree, blur on the
+    // second stream, orientation + descriptors, result gather, download) captured once as a CUDA graph and replayed per call
+    cudaGraphExec_t graph1 = nullptr; int graph_launches = 0; uint8_t* h_in = nullptr; size_t h_in_cap = 0; const void* graph_sig[24] = {nullptr};
     // optional per-stage CUDA-event timing (bench.py's roofline): one event set per profiled call
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;     // ORBX_NSTAGES+1 events per call
@@ -238,6 +241,7 @@ static int build_plan(orbx_extractor* h, int rows, int cols) {
     // to the global-memory bitonic path inside the kernel
     { const long long want = (long long)rows * cols / 100; int k = 4096; if (want > 4096) k = (int)std::min<long long>(18432, (want + want / 4 + 2047) / 2048 * 2048); h->sort_smem_keys = k; }
     h->rows = rows; h->cols = cols; h->Bcap = 0; h->have_pyramid = false;
+    if (h->graph1) { cudaGraphExecDestroy(h->graph1); h->graph1 = nullptr; }       // the captured pointers / launch shapes belong to the old geometry
     return ORBX_OK;
 }
 
@@ -254,9 +258,11 @@ static int ensure_capacity(orbx_extractor* h, int B, int out_cap) {
             return ORBX_E_CUDA;
         CU_TRY(cudaMemsetAsync(h->d_overflow.p, 0, 16, h->stream));
         h->Bcap = B;
+        if (h->graph1) { cudaGraphExecDestroy(h->graph1); h->graph1 = nullptr; }   // buffers may have moved
     }
     if (out_cap > 0 && ((size_t)B * out_cap > h->d_kp_out.n)) {
         if (h->d_kp_out.ensure((size_t)B * out_cap) || h->d_desc_out.ensure((size_t)B * out_cap * 32)) return ORBX_E_CUDA;
+        if (h->graph1) { cudaGraphExecDestroy(h->graph1); h->graph1 = nullptr; }
     }
     return ORBX_OK;
 }
@@ -415,6 +421,83 @@ static int check_args(orbx_extractor* h, const void* image, int rows, int cols, 
     return ORBX_OK;
 }
 
+// operator()(image, mask, keypoints, descriptors) for ONE frame through a CUDA graph.  Tracking calls this once per frame, and the chain is
+// ~20 short dependent kernels: issued one by one the host's launch cost (~4 us each) is longer than most of the kernels, so the call was
+// launch-bound.  The graph is captured on first use per (geometry, buffer set) -- every pointer and launch shape in it is a function of
+// the plan -- and a call then costs: memcpy of the frame into the pinned staging frame, one cudaGraphLaunch, one synchronisation.
+static int extract_graph(orbx_extractor* h, const uint8_t* image, int rows, int cols, size_t step, orbx_keypoint* kp_out, uint8_t* desc_out, int cap, int* n_out, int icap) {
+    const int pitch = align_up(cols, 4);
+    const size_t fbytes = (size_t)pitch * rows;
+    const size_t kb = (size_t)icap * sizeof(KpOut), db = (size_t)icap * 32, blk = 16 + kb + db;
+    if (h->h_in_cap < fbytes) {
+        if (h->h_in) cudaFreeHost(h->h_in);
+        h->h_in = nullptr; h->h_in_cap = 0;
+        CU_TRY(cudaHostAlloc((void**)&h->h_in, fbytes, cudaHostAllocDefault));
+        h->h_in_cap = fbytes;
+        if (h->graph1) { cudaGraphExecDestroy(h->graph1); h->graph1 = nullptr; }
+    }
+    if (h->h_gather_cap < blk) {
+        if (h->h_gather) cudaFreeHost(h->h_gather);
+        h->h_gather = nullptr; h->h_gather_cap = 0;
+        CU_TRY(cudaHostAlloc((void**)&h->h_gather, blk, cudaHostAllocDefault));
+        h->h_gather_cap = blk;
+        if (h->graph1) { cudaGraphExecDestroy(h->graph1); h->graph1 = nullptr; }
+    }
+    if (h->d_gather.n < blk || h->d_l0.n < fbytes) {
+        if (h->d_gather.ensure(blk) || h->d_l0.ensure(fbytes)) return ORBX_E_CUDA;
+        if (h->graph1) { cudaGraphExecDestroy(h->graph1); h->graph1 = nullptr; }
+    }
+    // every buffer the captured nodes point at: any of them may have been re-allocated by another entry point since the capture
+    const void* sig[24] = {h->d_l0.p, h->d_pyr.p, h->d_blur.p, h->d_slots.p, h->d_ocand.p, h->d_spk.p, h->d_skey.p, h->d_cell_counts.p, h->d_ncand.p, h->d_kp_level.p,
+                           h->d_kp_count.p, h->d_counts.p, h->d_overflow.p, h->d_kp_out.p, h->d_desc_out.p, h->d_gather.p, h->h_gather, h->h_in, h->d_levels.p, h->d_cells.p,
+                           h->d_tiles.p, h->d_tabs.p, (const void*)(uintptr_t)pitch, (const void*)(uintptr_t)blk};
+    if (h->graph1 && std::memcmp(sig, h->graph_sig, sizeof(sig)) != 0) { cudaGraphExecDestroy(h->graph1); h->graph1 = nullptr; }
+    // stage the frame (the caller's buffer is pageable in general: a DMA straight from it would be a blocking, staged copy anyway)
+    if (step == (size_t)pitch) std::memcpy(h->h_in, image, fbytes - (size_t)(pitch - cols));
+    else for (int y = 0; y < rows; ++y) std::memcpy(h->h_in + (size_t)y * pitch, image + (size_t)y * step, (size_t)cols);
+    h->view.l0 = h->d_l0.p; h->view.l0_fstride = (long long)fbytes; h->view.l0_pitch = pitch;
+    h->view.pyr = h->d_pyr.p; h->view.pyr_fstride = h->pyr_fstride;
+    int rc = ORBX_OK;
+    if (!h->graph1) {
+        cudaGraph_t g = nullptr;
+        CU_TRY(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        const long long l0 = h->launches;
+        do {
+            if (cudaMemcpyAsync(h->d_l0.p, h->h_in, fbytes, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) { rc = ORBX_E_CUDA; break; }
+            h->cur = h->stream;
+            if ((rc = run_detect(h, 0, 1, true))) break;
+            if (cudaStreamWaitEvent(h->stream, h->ev_join, 0) != cudaSuccess) { rc = ORBX_E_CUDA; break; }
+            if ((rc = run_orient(h, 0, 1, true, h->d_kp_out.p, h->d_desc_out.p, icap, h->d_counts.p, nullptr))) break;
+            k_gather_result<<<(int)((kb + db + 16 + 4095) / 4096), 256, 0, h->stream>>>(h->d_counts.p, h->d_overflow.p, reinterpret_cast<const uint32_t*>(h->d_kp_out.p), (int)(kb / 4),
+                                                                                       reinterpret_cast<const uint32_t*>(h->d_desc_out.p), (int)(db / 4), reinterpret_cast<uint32_t*>(h->d_gather.p));
+            if (cudaGetLastError() != cudaSuccess) { rc = ORBX_E_CUDA; break; }
+            ++h->launches;
+            if (cudaMemcpyAsync(h->h_gather, h->d_gather.p, blk, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) { rc = ORBX_E_CUDA; break; }
+        } while (0);
+        h->graph_launches = (int)(h->launches - l0);
+        const cudaError_t ee = cudaStreamEndCapture(h->stream, &g);
+        if (rc || ee != cudaSuccess || !g) { if (g) cudaGraphDestroy(g); if (!rc) orbx_set_error(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ee)); return rc ? rc : ORBX_E_CUDA; }
+        const cudaError_t ei = cudaGraphInstantiate(&h->graph1, g, 0);
+        cudaGraphDestroy(g);
+        if (ei != cudaSuccess) { h->graph1 = nullptr; FAIL(ORBX_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ei)); }
+        std::memcpy(h->graph_sig, sig, sizeof(sig));
+        h->launches = l0;                                   // counted per replay below
+    }
+    CU_TRY(cudaGraphLaunch(h->graph1, h->stream));
+    h->launches += h->graph_launches;
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    h->lastB = 1; h->have_pyramid = true; h->blur_valid = true;
+    int n, ovf;
+    std::memcpy(&n, h->h_gather, 4); std::memcpy(&ovf, h->h_gather + 4, 4);
+    if (ovf) { CU_TRY(cudaMemsetAsync(h->d_overflow.p, 0, 16, h->stream)); FAIL(ORBX_E_OVERFLOW, "internal bound exceeded in the quadtree stage"); }
+    *n_out = n;
+    h->last_kp = h->d_kp_out.p; h->last_desc = h->d_desc_out.p; h->last_n = n;
+    if (n > cap) FAIL(ORBX_E_CAPACITY, "keypoint buffer too small");
+    std::memcpy(kp_out, h->h_gather + 16, (size_t)n * sizeof(KpOut));
+    std::memcpy(desc_out, h->h_gather + 16 + kb, (size_t)n * 32);
+    return ORBX_OK;
+}
+
 static int upload_constants() {
     // __constant__ tables are per-device module state; upload on every create (cheap, idempotent)
     char4 pt[8 * 32];
@@ -482,6 +565,8 @@ void orbx_destroy(orbx_extractor* h) {
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->ev_block) cudaEventDestroy(h->ev_block);
     h->d_gather.release(); if (h->h_gather) cudaFreeHost(h->h_gather);
+    if (h->graph1) cudaGraphExecDestroy(h->graph1);
+    if (h->h_in) cudaFreeHost(h->h_in);
     for (cudaEvent_t e : h->ev_h2d) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_done) cudaEventDestroy(e);
     h->d_l0.release();
@@ -733,6 +818,8 @@ int orbx_extract(orbx_extractor* h, const uint8_t* image, int rows, int cols, si
     if ((rc = build_plan(h, rows, cols))) return rc;
     const int icap = h->max_kp;
     if ((rc = ensure_capacity(h, 1, icap))) return rc;
+    static const bool use_graph = [] { const char* e = std::getenv("ORBX_GRAPH"); return !e || std::atoi(e) != 0; }();
+    if (use_graph && !h->profiling) return extract_graph(h, image, rows, cols, step, kp_out, desc_out, cap, n_out, icap);
     if ((rc = upload_level0(h, image, 1, rows, cols, step, 0))) return rc;
     if ((rc = run_detect(h, 0, 1, true))) return rc;                 // blur forked next to FAST / quadtree
     CU_TRY(cudaStreamWaitEvent(h->stream, h->ev_join, 0));

@@ -185,6 +185,34 @@ int orbx_profile_collect(orbx_extractor* h, double* stage_ms6, int* ncalls);
  * handle's stream and clears the flags, so one bad frame is reported once and later calls on the handle are unaffected */
 int orbx_check_overflow(orbx_extractor* h);
 
+/* ------------------------------------------------------------------------------------------------
+ * Multi-sequence / multi-GPU driver (BASELINE config 5): camera streams ("sequences") are pinned to workers by
+ *     gpu = seq_id mod n_gpus,   stream = (seq_id div n_gpus) mod streams_per_gpu
+ * Every worker is one host thread that owns one extractor handle (one CUDA stream, one resident pyramid) on its GPU and runs its
+ * jobs in submission order -- the reference's "one ORBextractor object per camera, each in its own thread" (src/Frame.cc:165-173)
+ * scaled out over the GPUs of one box.  No collective, no shared device state.  A single process drives all GPUs.
+ *   submit*       : asynchronous; returns a ticket.  Input and output buffers (host memory, pinned for full copy / compute overlap) must
+ *                   stay valid until the ticket has been waited for.  submit = operator()(image, mask, kps, desc) of one frame;
+ *                   submit_batch = orbx_extract_batch (masks == NULL) or orbx_extract_masked_batch_labels (labels may be NULL).
+ *   wait / wait_all: block until the job(s) finished; return the job's status (first failing status for wait_all).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct orbx_pool orbx_pool;
+int  orbx_pool_shard_of(int seq_id, int n_gpus, int streams_per_gpu, int* gpu, int* stream);     /* the mapping above, no device needed */
+int  orbx_pool_create(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST, int n_gpus, const int* devices /* NULL: 0 .. n_gpus-1 */,
+                      int streams_per_gpu, orbx_pool** out);
+void orbx_pool_destroy(orbx_pool* p);                                                            /* finishes the queued jobs first */
+int  orbx_pool_gpus(const orbx_pool* p);
+int  orbx_pool_streams_per_gpu(const orbx_pool* p);
+int  orbx_pool_device_of(const orbx_pool* p, int seq_id);                                        /* CUDA ordinal that serves this sequence */
+long long orbx_pool_frames_done(const orbx_pool* p, int gpu, int stream);                        /* frames finished by one worker so far */
+int  orbx_pool_submit(orbx_pool* p, int seq_id, const uint8_t* image, int rows, int cols, size_t step,
+                      orbx_keypoint* kp_out, uint8_t* desc_out, int cap, int* n_out, long long* ticket);
+int  orbx_pool_submit_batch(orbx_pool* p, int seq_id, const uint8_t* images, const uint8_t* masks, const orbx_labels* labels, int B, int rows, int cols,
+                            size_t step, size_t frame_stride, size_t mask_step, size_t mask_frame_stride,
+                            orbx_keypoint* kp_out, uint8_t* desc_out, int cap, int* counts_out, int* culled_out, long long* ticket);
+int  orbx_pool_wait(orbx_pool* p, long long ticket);
+int  orbx_pool_wait_all(orbx_pool* p);
+
 /* ================================================================================================
  * ORBmatcher  (include/ORBmatcher.h:57-215, src/ORBmatcher.cc)
  * ================================================================================================ */

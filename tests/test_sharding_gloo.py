@@ -53,3 +53,7 @@ def test_shard_helpers():
     assert sh.sequences_of_gpu(10, 1, 8) == [1, 9]
     with pytest.raises(ValueError):
         sh.shard_range(4, 2, 2)
+    # the pool's rule (C ABI, no device needed): gpu = seq mod G, stream = (seq div G) mod S -- every (gpu, stream) worker gets its share
+    assert [sh.worker_for_sequence(s, 4, 2) for s in range(9)] == [(0, 0), (1, 0), (2, 0), (3, 0), (0, 1), (1, 1), (2, 1), (3, 1), (0, 0)]
+    with pytest.raises(ValueError):
+        sh.worker_for_sequence(-1, 4, 2)
