@@ -26,6 +26,7 @@ struct LevelGeom {
     int kp_off, kp_cap;          // per-frame per-level keypoint slots
     float scale;                 // mvScaleFactor[level]
     float kp_size;               // (float)(int)(31 * scale)
+    int fast_bw, fast_bh;        // TMA box of this level's FAST cells (k_fast.cuh): bytes per patch row (multiple of 16), rows
 };
 
 // one FAST detection cell (ORBextractor.cc:1089-1157): ROI = [x0,x0+cw) x [y0,y0+ch) in level coords
@@ -34,6 +35,8 @@ struct CellDesc {
     short sx, sy;                // j*wCell, i*hCell  (shift applied at :1150-1151)
     short level, cap;            // cap = ceil(zw/2)*ceil(zh/2): max number of strict 3x3 local maxima
     int slot;                    // offset of the cell's candidate slots inside the frame's slot array
+    int geo;                     // k_fast.cuh stage A: zone word columns | rows per strip << 8 | strips << 16
+    int rcp;                     // 65536 / (zone word columns) + 1:  lane / columns = (lane * rcp) >> 16 for lane < 32
     int pad;
 };
 

@@ -10,6 +10,7 @@
 #include "orbx_common.cuh"
 #include "orbx_internal.h"
 #include "k_pyramid_fast.cuh"
+#include "k_fast.cuh"
 #include "k_octree.cuh"
 #include "k_describe.cuh"
 #include "k_cull.cuh"
@@ -71,7 +72,9 @@ struct orbx_extractor {
     int rows = 0, cols = 0;
     std::vector<LevelGeom> levels; std::vector<CellDesc> cells; std::vector<BlurTile> tiles;
     long long pyr_fstride = 0; int cand_per_frame = 0, kp_per_frame = 0, max_kp = 0;
-    int fast_smem_per_warp = 0, fast_patch_cap = 0, fast_s_cap = 0, tree_cap = 0, sort_smem_keys = 4096;
+    FastLayout fast_lay{}; int tree_cap = 0, sort_smem_keys = 4096;
+    DevBuf<CUtensorMap> d_tmaps; const void* tmaps_base = nullptr; int tmaps_B = 0;          // FAST tensor maps of levels >= 1 (by level), valid for (d_pyr.p, Bcap)
+    CUtensorMap map_l0; const void* map_l0_sig[4] = {nullptr};                                // level-0 map of the current view (pointer, frame stride, pitch, frames)
     DevBuf<LevelGeom> d_levels; DevBuf<CellDesc> d_cells; DevBuf<BlurTile> d_tiles; DevBuf<int> d_tabs;
     std::vector<ResizeTabs> resize_tabs;
 
@@ -121,7 +124,7 @@ static int build_plan(orbx_extractor* h, int rows, int cols) {
     const int L = h->nlevels;
     std::vector<LevelGeom> lv(L);
     std::vector<CellDesc> cells; std::vector<BlurTile> tiles;
-    long long off = 0; int cand_off = 0, kp_off = 0, patch_cap = 0, s_cap = 0, q_cap = 0, tree_cap = 0;
+    long long off = 0; int cand_off = 0, kp_off = 0, patch_cap = 0, s_cap = 0, wq_words = 1, zh_max = 1, tree_cap = 0;
     for (int l = 0; l < L; ++l) {
         LevelGeom& g = lv[l];
         std::memset(&g, 0, sizeof(g));
@@ -144,7 +147,7 @@ static int build_plan(orbx_extractor* h, int rows, int cols) {
         if (nCols <= 0 || nRows <= 0) nCols = nRows = 0;
         const int wCell = nCols ? (int)std::ceil(width / nCols) : 0, hCell = nRows ? (int)std::ceil(height / nRows) : 0;
         g.cell_begin = (int)cells.size(); g.slot_off = cand_off; g.cand_off = cand_off;
-        int slot = cand_off;
+        int slot = cand_off, bw_max = 0, ch_max = 0;
         for (int i = 0; i < nRows; i++) {
             const float iniY = (float)(g.minBY + i * hCell);
             float maxY = iniY + hCell + 6;
@@ -158,17 +161,28 @@ static int build_plan(orbx_extractor* h, int rows, int cols) {
                 CellDesc c; std::memset(&c, 0, sizeof(c));
                 c.x0 = (short)iniX; c.y0 = (short)iniY; c.cw = (short)((int)maxX - (int)iniX); c.ch = (short)((int)maxY - (int)iniY);
                 if (c.cw < 7 || c.ch < 7) continue;                                     // cv::FAST returns nothing
-                if (c.cw - 6 >= 64) FAIL(ORBX_E_INVALID, "unsupported cell width");
+                if (c.cw - 6 >= 64 || c.ch - 6 >= 64) FAIL(ORBX_E_INVALID, "unsupported cell size");
                 c.sx = (short)(j * wCell); c.sy = (short)(i * hCell); c.level = (short)l;
                 const int zw = c.cw - 6, zh = c.ch - 6;
                 c.cap = (short)(((zw + 1) / 2) * ((zh + 1) / 2));
                 c.slot = slot; slot += c.cap;
                 cells.push_back(c);
-                const int wpr = ((c.x0 + c.cw + 3) >> 2) - (c.x0 >> 2);
-                patch_cap = std::max(patch_cap, wpr * 4 * c.ch); s_cap = std::max(s_cap, ((zw + 2) * (zh + 2) + 3) & ~3); q_cap = std::max(q_cap, (2 * zw * zh + 3) & ~3);
+                // k_fast.cuh: zone word columns, row strips per warp, rows per strip
+                // (the patch starts at the 16-byte boundary left of x0 - 1: TMA's innermost coordinate must be 16-byte aligned)
+                const int pc0 = c.x0 + 3 - ((c.x0 - 1) & ~15), wi0 = pc0 >> 2, wi1 = (pc0 + zw - 1) >> 2;
+                const int nwz = wi1 - wi0 + 1, strips = 32 / nwz, rps = (zh + strips - 1) / strips;
+                cells.back().geo = nwz | (rps << 8) | (strips << 16); cells.back().rcp = 65536 / nwz + 1;
+                bw_max = std::max(bw_max, 4 * (wi1 + 2)); ch_max = std::max(ch_max, (int)c.ch);
+                s_cap = std::max(s_cap, (zw + 2) * (zh + 2)); wq_words = std::max(wq_words, nwz * zh); zh_max = std::max(zh_max, zh);
             }
         }
         g.cell_count = (int)cells.size() - g.cell_begin;
+        // TMA box of the level's cells: ROI from the 16-byte boundary on its left to the right neighbour of its last zone word
+        // -- as an ODD number of 16-byte units: the patch pitch is then an odd multiple of 4 banks, so that a column of the patch walks over 8
+        // different bank groups instead of 2 (pitch 64) and the ring gathers of vertically adjacent survivors do not collide
+        g.fast_bw = align_up(std::max(bw_max, 16), 16); { static const int odd = [] { const char* e = std::getenv("ORBX_FAST_ODD"); return e ? std::atoi(e) : 0; }(); if (odd && (g.fast_bw / 16) % 2 == 0) g.fast_bw += 16; }
+        g.fast_bh = std::max(ch_max, 1);
+        patch_cap = std::max(patch_cap, g.fast_bw * g.fast_bh);
         g.cand_cap = slot - cand_off; cand_off = slot;
         if (g.cand_cap >= (1 << 20)) FAIL(ORBX_E_INVALID, "level too large");
         // quadtree roots :719-722
@@ -234,8 +248,14 @@ static int build_plan(orbx_extractor* h, int rows, int cols) {
     h->pyr_fstride = (off + 255) / 256 * 256;
     h->cand_per_frame = cand_off; h->kp_per_frame = kp_off;
     h->max_kp = 0; for (int l = 0; l < L; ++l) h->max_kp += h->levels[l].kp_cap;
-    h->fast_patch_cap = align_up(patch_cap, 16); h->fast_s_cap = align_up(s_cap, 16);
-    h->fast_smem_per_warp = 2 * h->fast_patch_cap + h->fast_s_cap + align_up(q_cap, 16);     // [patch 0 | patch 1 | S | queue]
+    {   // [patch | S | wq | ring | clist | bm | mbarrier] per warp (k_fast.cuh)
+        FastLayout& f = h->fast_lay;
+        f.patch_cap = align_up(patch_cap, 128); f.s_cap = align_up(s_cap, 16); f.wq_cap = align_up(4 * wq_words, 16); f.bm_cap = align_up(8 * zh_max, 16);
+        static const int padx = [] { const char* e = std::getenv("ORBX_FAST_PAD"); return e ? std::atoi(e) : 0; }();
+        f.per_warp = align_up(f.patch_cap + f.s_cap + f.wq_cap + 2 * FAST_RING + 2 * FAST_CLIST + f.bm_cap + 16 + padx, 128);
+        if ((long long)f.per_warp * FAST_WARPS > 227 * 1024) FAIL(ORBX_E_INVALID, "FAST cells too large for shared memory");
+    }
+    h->tmaps_base = nullptr; h->map_l0_sig[0] = nullptr;
     h->tree_cap = tree_cap;
     // radix-sort capacity per (level, frame): ~1 candidate per 100 px of level 0 is generous for real images; larger levels fall back
     // to the global-memory bitonic path inside the kernel
@@ -279,6 +299,36 @@ static inline void prof_mark(orbx_extractor* h) {
 
 static int run_blur_range(orbx_extractor* h, int b0, int B);
 
+// Tensor maps of the FAST stage (k_fast.cuh).  Levels >= 1 live in d_pyr: one map per level in a device array, rebuilt when the pyramid
+// block moves.  Level 0 follows the current view (internal copy, pinned mirror or the caller's device frames) and travels as a kernel
+// parameter.  Must not be first called inside a stream capture (extract_graph prepares before capturing).
+static int fast_prepare(orbx_extractor* h) {
+    const int L = h->nlevels;
+    const long long frames = 1 << 16;                      // bound of the frame coordinate only; kernels index frames < B
+    if (h->tmaps_base != (const void*)h->d_pyr.p || !h->d_tmaps.p) {
+        std::vector<CUtensorMap> m((size_t)L);
+        std::memset(m.data(), 0, sizeof(CUtensorMap) * (size_t)L);
+        for (int l = 1; l < L; ++l) {
+            const LevelGeom& g = h->levels[l];
+            if (g.cell_count == 0) continue;
+            if (!orbx_tmap_image(&m[l], h->d_pyr.p + g.off, g.w, g.h, frames, g.pitch, h->pyr_fstride, g.fast_bw, g.fast_bh)) FAIL(ORBX_E_CUDA, "cuTensorMapEncodeTiled failed (pyramid level)");
+        }
+        if (h->d_tmaps.ensure((size_t)L)) return ORBX_E_CUDA;
+        CU_TRY(cudaMemcpyAsync(h->d_tmaps.p, m.data(), sizeof(CUtensorMap) * (size_t)L, cudaMemcpyHostToDevice, h->stream));
+        CU_TRY(cudaStreamSynchronize(h->stream));
+        h->tmaps_base = h->d_pyr.p;
+    }
+    const void* sig[4] = {h->view.l0, (const void*)(uintptr_t)h->view.l0_fstride, (const void*)(uintptr_t)h->view.l0_pitch, (const void*)(uintptr_t)(h->rows * 65536 + h->cols)};
+    if (std::memcmp(sig, h->map_l0_sig, sizeof(sig)) != 0) {
+        const LevelGeom& g = h->levels[0];
+        std::memset(&h->map_l0, 0, sizeof(h->map_l0));
+        if (g.cell_count && !orbx_tmap_image(&h->map_l0, h->view.l0, g.w, g.h, frames, h->view.l0_pitch, h->view.l0_fstride, g.fast_bw, g.fast_bh))
+            FAIL(ORBX_E_CUDA, "cuTensorMapEncodeTiled failed (level 0: frames must be 16-byte aligned in pointer, row step and frame stride)");
+        std::memcpy(h->map_l0_sig, sig, sizeof(sig));
+    }
+    return ORBX_OK;
+}
+
 // pyramid (levels >= 1) + FAST cells + quadtree; leaves per-level keypoints in d_kp_level / d_kp_count.
 // fork_blur: the blur only needs the pyramid, so it is launched on the second compute stream -- after FAST, which fills the GPU
 // by itself -- and runs next to the quadtree kernels (latency-bound: one serial warp per level, most SMs idle);
@@ -314,9 +364,10 @@ static int run_detect(orbx_extractor* h, int b0, int B, bool fork_blur = false) 
         const long long cells_total = (long long)ncells * B;
         const int cpw = cpw_env ? cpw_env : (cells_total >= 16LL * 2072 ? 4 : (cells_total >= 8LL * 2072 ? 2 : 1));
         dim3 grid((ncells + FAST_WARPS * cpw - 1) / (FAST_WARPS * cpw), B);
-        const int smem = h->fast_smem_per_warp * FAST_WARPS;
-        k_fast_cells<<<grid, FAST_WARPS * 32, smem, s>>>(view, h->d_levels.p, h->d_cells.p, ncells, h->cand_per_frame,
-                                                          h->fast_smem_per_warp, h->fast_patch_cap, h->fast_s_cap, h->iniThFAST, h->minThFAST, slots, cell_counts);
+        const int smem = h->fast_lay.per_warp * FAST_WARPS;
+        { const int rc = fast_prepare(h); if (rc) return rc; }
+        k_fast_cells<<<grid, FAST_WARPS * 32, smem, s>>>(h->map_l0, h->d_tmaps.p, b0, h->d_levels.p, h->d_cells.p, ncells, h->cand_per_frame,
+                                                          h->fast_lay, h->iniThFAST, h->minThFAST, slots, cell_counts);
         LAUNCH_CHECK();
     }
     prof_mark(h);
@@ -426,7 +477,7 @@ static int check_args(orbx_extractor* h, const void* image, int rows, int cols, 
 // launch-bound.  The graph is captured on first use per (geometry, buffer set) -- every pointer and launch shape in it is a function of
 // the plan -- and a call then costs: memcpy of the frame into the pinned staging frame, one cudaGraphLaunch, one synchronisation.
 static int extract_graph(orbx_extractor* h, const uint8_t* image, int rows, int cols, size_t step, orbx_keypoint* kp_out, uint8_t* desc_out, int cap, int* n_out, int icap) {
-    const int pitch = align_up(cols, 4);
+    const int pitch = align_up(cols, 16);                  // TMA: 16-byte row step
     const size_t fbytes = (size_t)pitch * rows;
     const size_t kb = (size_t)icap * sizeof(KpOut), db = (size_t)icap * 32, blk = 16 + kb + db;
     if (h->h_in_cap < fbytes) {
@@ -457,7 +508,7 @@ static int extract_graph(orbx_extractor* h, const uint8_t* image, int rows, int 
     else for (int y = 0; y < rows; ++y) std::memcpy(h->h_in + (size_t)y * pitch, image + (size_t)y * step, (size_t)cols);
     h->view.l0 = h->d_l0.p; h->view.l0_fstride = (long long)fbytes; h->view.l0_pitch = pitch;
     h->view.pyr = h->d_pyr.p; h->view.pyr_fstride = h->pyr_fstride;
-    int rc = ORBX_OK;
+    int rc = fast_prepare(h); if (rc) return rc;           // tensor maps are built outside the capture
     if (!h->graph1) {
         cudaGraph_t g = nullptr;
         CU_TRY(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
@@ -548,7 +599,7 @@ int orbx_create(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, in
     cudaFuncSetAttribute(k_octree_sort_t<SORT_THREADS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)octree_sort_smem_bytes(8192, SORT_THREADS_WIDE));
     cudaFuncSetAttribute(k_octree_tree, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_octree_tree_par, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ptree_smem_bytes(PTREE_MAXCAP, 4096));
-    cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     *out = h;
     return ORBX_OK;
 }
@@ -570,7 +621,7 @@ void orbx_destroy(orbx_extractor* h) {
     for (cudaEvent_t e : h->ev_h2d) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_done) cudaEventDestroy(e);
     h->d_l0.release();
-    h->d_levels.release(); h->d_cells.release(); h->d_tiles.release(); h->d_tabs.release();
+    h->d_tmaps.release(); h->d_levels.release(); h->d_cells.release(); h->d_tiles.release(); h->d_tabs.release();
     h->d_pyr.release(); h->d_blur.release(); h->d_slots.release(); h->d_ocand.release(); h->d_spk.release(); h->d_kp_level.release();
     h->d_skey.release(); h->d_cell_counts.release(); h->d_ncand.release(); h->d_kp_count.release(); h->d_counts.release();
     h->d_level_counts.release(); h->d_overflow.release(); h->d_kp_out.release(); h->d_desc_out.release();
@@ -633,7 +684,7 @@ int orbx_extract_batch_device(orbx_extractor* h, const uint8_t* d_images, int B,
     if (B <= 0 || !d_kp_out || !d_desc_out || !d_counts_out || cap <= 0) FAIL(ORBX_E_INVALID, "bad batch arguments");
     if ((rc = build_plan(h, rows, cols))) return rc;
     if ((rc = ensure_capacity(h, B, 0))) return rc;
-    if (((uintptr_t)d_images & 3) == 0 && (step & 3) == 0 && (frame_stride & 3) == 0) {
+    if (((uintptr_t)d_images & 15) == 0 && (step & 15) == 0 && (frame_stride & 15) == 0) {      // TMA reads level 0: 16-byte alignment
         h->view.l0 = d_images; h->view.l0_fstride = (long long)frame_stride; h->view.l0_pitch = (int)step;       // alias the caller's frames
     } else {
         const LevelGeom& g0 = h->levels[0];
@@ -683,7 +734,7 @@ static int host_batch_pipeline(orbx_extractor* h, const uint8_t* images, const u
     // level 0: mirror the host layout on the device when it is word-aligned and dense enough (one copy per chunk);
     // otherwise copy frame by frame into the pyramid block
     const bool dense = frame_stride >= step * (size_t)rows && frame_stride <= 2 * step * (size_t)rows;
-    const bool mirror = dense && (step & 3) == 0 && (frame_stride & 3) == 0;
+    const bool mirror = dense && (step & 15) == 0 && (frame_stride & 15) == 0;
     // rows that are not word-aligned (KITTI: 1241 px): still ONE dense copy per chunk over the bus -- a strided 2-D copy of 1241-byte rows
     // runs at a fraction of the link rate -- followed by a device-side re-pitch into the pyramid block
     const bool repitch = dense && !mirror;

@@ -138,8 +138,14 @@ extern "C" int orbx_extract_masked_batch_labels_device(orbx_extractor* h, const 
     if ((rc = build_plan(h, rows, cols))) return rc;
     if ((rc = ensure_capacity(h, B, 0))) return rc;
     if ((rc = ensure_closing(h, B, rows, cols))) return rc;
-    if (((uintptr_t)d_images & 3) || (step & 3) || (frame_stride & 3)) FAIL(ORBX_E_INVALID, "device frames must be 4-byte aligned (pointer, step, frame stride)");
-    h->view.l0 = d_images; h->view.l0_fstride = (long long)frame_stride; h->view.l0_pitch = (int)step;
+    if (((uintptr_t)d_images & 15) == 0 && (step & 15) == 0 && (frame_stride & 15) == 0) {      // TMA reads level 0: 16-byte alignment
+        h->view.l0 = d_images; h->view.l0_fstride = (long long)frame_stride; h->view.l0_pitch = (int)step;       // alias the caller's frames
+    } else {
+        const LevelGeom& g0 = h->levels[0];
+        for (int b = 0; b < B; ++b)
+            CU_TRY(cudaMemcpy2DAsync(h->d_pyr.p + (size_t)b * h->pyr_fstride + g0.off, g0.pitch, d_images + (size_t)b * frame_stride, step, cols, rows, cudaMemcpyDeviceToDevice, h->stream));
+        h->view.l0 = h->d_pyr.p + g0.off; h->view.l0_fstride = h->pyr_fstride; h->view.l0_pitch = g0.pitch;
+    }
     h->view.pyr = h->d_pyr.p; h->view.pyr_fstride = h->pyr_fstride;
     // masks: pack needs 32-byte row alignment; repack into our own pitched buffer unless the caller's layout already qualifies
     const uint8_t* mk = d_masks; long long mfs = (long long)mask_frame_stride; int mpitch = (int)mask_step;
