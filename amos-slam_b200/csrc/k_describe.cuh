@@ -2,6 +2,7 @@
 #pragma once
 #include "orbx_common.cuh"
 #include "det_math.cuh"
+#include "tma.cuh"
 #include <cuda_pipeline.h>
 
 // =================================================================================================
@@ -10,17 +11,22 @@
 // (SURVEY.md A.2):  q = [18,34,48,56,48,34,18]/256;  h = sum q*px (16-bit range, no rounding);
 // v = sum q*h (32-bit);  out = (v + 32768) >> 16.  Reflection is at the LEVEL edge (the reference
 // blurs a clone of the ROI).
-// One warp = one tile of 120 columns x BLUR_STRIP rows of one level of one frame (the tile list covers all
-// levels, so a single launch blurs the whole pyramid of the whole batch).  Each lane owns one aligned 32-bit
-// word (4 columns) per row; lanes 0 and 31 are halo lanes that only feed their neighbours.  Per input row a
-// lane takes the two neighbouring words by shuffle, forms its 4 horizontal sums with 8 integer dot products
-// (IDP.4A on PRMT-aligned byte windows), keeps the last 7 rows of them in registers and emits one output
-// word.  Words that touch the level edge are assembled from reflected byte loads (row-invariant columns).
-// The row loads run 7 rows ahead of the arithmetic (register ring), which is what keeps enough bytes in
-// flight per SM: the kernel has no shared memory and HBM traffic = read level + write level.
+// One warp = one tile of 128 columns x BLUR_STRIP rows of one level of one frame (the tile list covers all levels, so a single
+// launch blurs the whole pyramid of the whole batch).  The tile with its 3-px halo -- 160 bytes x (BLUR_STRIP + 6) rows, starting
+// 16 bytes left of the tile because TMA's innermost coordinate must be 16-byte aligned -- is fetched by ONE bulk tensor copy
+// (cp.async.bulk.tensor.3d over (x, y, frame)) and awaited on an mbarrier; elements outside the level arrive as zeros and the
+// BORDER_REFLECT_101 rows / columns are then written into the staged tile (edge tiles only).  After that the row loop has no
+// address arithmetic, no edge cases and no shuffles: per input row a lane reads three consecutive words of the staged row
+// (conflict-free), forms its 4 horizontal sums with 8 integer dot products (IDP.4A on PRMT-aligned byte windows), keeps the last
+// 6 packed row pairs in registers and emits one output word (previous form: 114 instructions per word and row, this one ~45;
+// profiles/r02b vs r02c).  HBM traffic = read level + write level (+ the halo rows, which L2 serves).
 // =================================================================================================
-#define BLUR_STRIP 64
-#define BLUR_TILE_W 120
+#define BLUR_STRIP 42
+#define BLUR_ROWS (BLUR_STRIP + 6)       // staged rows: a multiple of 6 (the row loop is unrolled over the 6 ring slots)
+#define BLUR_TILE_W 128
+#define BLUR_BOX_W 160                   // 16 bytes left of the tile + tile + 16 bytes right: 40 words per staged row
+#define BLUR_WARPS 4
+#define BLUR_SMEM_PER_WARP (BLUR_BOX_W * BLUR_ROWS + 128)
 struct BlurTile { short level, xc, strip, pad; };
 
 __device__ __noinline__ int reflect101(int p, int len) {
@@ -29,115 +35,77 @@ __device__ __noinline__ int reflect101(int p, int len) {
     return p;
 }
 
-__global__ void __launch_bounds__(128)
-k_gauss7(PyrView pv, const LevelGeom* __restrict__ levels, const BlurTile* __restrict__ tiles, int ntiles,
+__global__ void __launch_bounds__(BLUR_WARPS * 32)
+k_gauss7(const __grid_constant__ CUtensorMap map_l0, const CUtensorMap* __restrict__ maps, int b0,
+         const LevelGeom* __restrict__ levels, const BlurTile* __restrict__ tiles, int ntiles,
          uint8_t* __restrict__ blur, long long blur_fstride) {
-    const int lane = threadIdx.x & 31;
-    const int tile = blockIdx.x * 4 + (threadIdx.x >> 5);
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile = blockIdx.x * BLUR_WARPS + warp;
     if (tile >= ntiles) return;
+    uint8_t* sm = smem_raw + (size_t)warp * BLUR_SMEM_PER_WARP;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + BLUR_BOX_W * BLUR_ROWS);
     const BlurTile t = tiles[tile];
     const int b = blockIdx.y;
     const LevelGeom& g = levels[t.level];
-    const int gw = g.w, gh = g.h, gpitch = g.pitch;                  // keep the geometry in registers (no reloads in the row loop)
-    int pitch;
-    const uint8_t* img = level_ptr(pv, g, t.level, b, pitch);
-    const int x = t.xc * BLUR_TILE_W + (lane - 1) * 4;
+    const int gw = g.w, gh = g.h, gpitch = g.pitch;
+    const int x0 = t.xc * BLUR_TILE_W, bx0 = x0 - 16;               // tile / box origin (level columns)
     const int y0 = t.strip * BLUR_STRIP, y1 = min(y0 + BLUR_STRIP, gh);
-    const bool word_ok = x >= 0 && x + 3 < gw;                       // aligned word entirely inside the level
-    const bool word_in = x >= 0 && x < gw;                           // word starts inside the level (row pitches are multiples of 4: a partial word stays in its row)
-    const bool needed = x + 3 >= -3 && x <= gw + 2;                  // some neighbour reads this word
-    const bool store = lane >= 1 && lane <= 30 && x < gw;
-    // warp-uniform: does any lane of this tile (halo lanes included) touch the left / right level edge?
-    const bool edge_tile = t.xc == 0 || t.xc * BLUR_TILE_W + 30 * 4 + 3 >= gw;
-    // Edge words (BORDER_REFLECT_101 columns): the reflected source columns of a word are 4 consecutive columns in descending order,
-    // i.e. bytes of at most two aligned words that other lanes of this warp load anyway.  Row-invariant per lane: the two source
-    // lanes and two PRMT selectors (gather the reflected bytes; merge with the lane's own in-range bytes).  Lanes whose sources fall
-    // outside the warp (last tile with < 4 valid columns, levels narrower than the halo) fall back to reflected byte loads.
-    int srcA = lane, srcB = lane; uint32_t selG = 0x3210u, selM = 0x3210u; bool fix = false, slow = false;
-    int rx[4] = {0, 0, 0, 0};
-    if (edge_tile && needed && !word_ok) {
-        int ln[4], by[4]; bool own[4];
-        int lo = 64, hi = -1;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int c = x + j;
-            own[j] = c >= 0 && c < gw;
-            rx[j] = reflect101(c, gw);
-            const int rel = rx[j] - (t.xc * BLUR_TILE_W - 4);                // column offset from lane 0's word
-            ln[j] = rel >= 0 ? (rel >> 2) : -1; by[j] = rx[j] & 3;
-            if (!own[j]) { lo = min(lo, ln[j]); hi = max(hi, ln[j]); }
-        }
-        fix = true;
-        if (lo < 0 || hi > 31 || hi - lo > 1) slow = true;                   // sources not available as two neighbouring words of this warp
-        // the source words must themselves be plain loads (start inside the level)
-        if (!slow) {
-            srcA = lo; srcB = hi; selG = 0; selM = 0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t gsel = own[j] ? 0u : (uint32_t)((ln[j] == lo ? 0 : 4) + by[j]);
-                selG |= gsel << (4 * j);
-                selM |= (uint32_t)(own[j] ? j : 4 + j) << (4 * j);
-            }
-        }
+    const int nrows = y1 - y0 + 6;                                   // staged rows that are read: level rows y0 - 3 .. y1 + 2
+    if (lane == 0) {
+        mbar_init(bar, 1); mbar_fence_init();
+        mbar_expect_tx(bar, BLUR_BOX_W * BLUR_ROWS);
+        tma_load_3d(sm, t.level == 0 ? &map_l0 : maps + t.level, bx0, y0 - 3, b0 + b, bar);
     }
-    // a source lane must hold a genuinely loaded word: its x must start inside the level
-    {
-        const int xa = t.xc * BLUR_TILE_W + (srcA - 1) * 4, xb = t.xc * BLUR_TILE_W + (srcB - 1) * 4;
-        if (fix && !slow && !(xa >= 0 && xa < gw && xb >= 0 && xb < gw)) slow = true;
-    }
-    const int rlast = y1 + 2;
-    // per-lane load mode, row-invariant: 0 = plain aligned word, 1 = nothing to load (word not needed, or rebuilt from the neighbours'
-    // loads by the shuffles below), 2 = reflected byte loads (levels narrower than the halo)
-    const int mode = (!edge_tile || (word_in && !slow)) ? 0 : ((needed && slow) ? 2 : 1);
-    // strips that do not touch the top / bottom edge of the level (warp-uniform) never reflect a row
-    const bool interior = y0 - 3 >= 0 && rlast <= gh - 1;
-    const bool tiny = gh < 4;                                            // warp-uniform: only then can a reflected row need a second reflection
-    const uint8_t* colp = img + x;                                       // halo lanes may point outside the row: dereferenced in mode 0 only
-    auto load_row = [&](int r) -> uint32_t {
-        int rr = min(r, rlast);                                          // the tail group re-reads the last row instead of running past it
-        if (!interior) {                                                 // BORDER_REFLECT_101 of rows -3 .. -1 and gh .. gh + 2
-            rr = rr < 0 ? -rr : rr; rr = rr >= gh ? 2 * gh - 2 - rr : rr;
-            if (tiny) { rr = rr < 0 ? -rr : rr; rr = rr >= gh ? 2 * gh - 2 - rr : rr; rr = max(rr, 0); }
+    __syncwarp();
+    mbar_wait(bar, 0);
+    uint32_t* sm32 = reinterpret_cast<uint32_t*>(sm);
+    // ---- BORDER_REFLECT_101 (warp-uniform branches; interior tiles skip both) ----
+    if (y0 - 3 < 0 || y1 + 2 >= gh) {                               // rows above / below the level := their mirror rows (whole staged rows)
+        for (int i = 0; i < nrows; ++i) {
+            const int r = y0 - 3 + i;
+            if (r >= 0 && r < gh) continue;
+            const int si = reflect101(r, gh) - (y0 - 3);
+            for (int w = lane; w < BLUR_BOX_W / 4; w += 32) sm32[i * (BLUR_BOX_W / 4) + w] = sm32[si * (BLUR_BOX_W / 4) + w];
         }
-        const int off = rr * pitch;                                      // a frame's level is < 2^31 bytes
-        if (mode == 0) return __ldg(reinterpret_cast<const uint32_t*>(colp + off));
-        if (mode == 1) return 0u;
-        const uint8_t* row = img + off;
-        return (uint32_t)__ldg(row + rx[0]) | ((uint32_t)__ldg(row + rx[1]) << 8) | ((uint32_t)__ldg(row + rx[2]) << 16) | ((uint32_t)__ldg(row + rx[3]) << 24);
-    };
-    uint8_t* dst = blur + (long long)b * blur_fstride + g.off + x + (long long)(y0 - 6) * gpitch;   // running pointer: output row of the next input row
+        __syncwarp();
+    }
+    if (x0 == 0 || x0 + BLUR_TILE_W + 3 > gw) {                     // columns left / right of the level := their mirror columns
+        for (int k = lane; k < nrows * 6; k += 32) {
+            const int i = k / 6, q = k - i * 6;
+            const int c = q < 3 ? q - 3 : gw + q - 3;               // -3, -2, -1, gw, gw + 1, gw + 2
+            if (c >= bx0 && c < bx0 + BLUR_BOX_W && c >= x0 - 3 && c < x0 + BLUR_TILE_W + 3)
+                sm[i * BLUR_BOX_W + (c - bx0)] = sm[i * BLUR_BOX_W + (reflect101(c, gw) - bx0)];
+        }
+        __syncwarp();
+    }
+    // ---- row loop ----
+    const int x = x0 + 4 * lane;
+    const bool store = x < gw;
+    uint8_t* dst = blur + (long long)(b0 + b) * blur_fstride + g.off + x + (long long)(y0 - 6) * gpitch;   // running pointer: output row of the next input row
     const uint32_t Q0 = 18u | (34u << 8) | (48u << 16) | (56u << 24);     // taps -3..0
     const uint32_t Q1 = 48u | (34u << 8) | (18u << 16);                   // taps +1..+3 (4th byte unused)
     // Vertical pass on PAIRS of rows: the horizontal sums fit 16 bits (<= 65280), so row r is packed with row r-1 as it arrives
     // (P = h[r-1] | h[r] << 16) and an output row is three 2-way integer dot products (IDP.2A: 16-bit sums x 8-bit taps) plus one multiply:
     //   v(o) = (h[o-3], h[o-2]).(18, 34) + (h[o-1], h[o]).(48, 56) + (h[o+1], h[o+2]).(48, 34) + 18 h[o+3] + 32768
-    // -- 5 instructions per pixel instead of 7.  The ring holds the packed pairs of the last 6 input rows (static slots after unrolling).
+    // The ring holds the packed pairs of the last 6 input rows (static slots after unrolling).
     const uint32_t WA = 18u | (34u << 8), WB = 48u | (56u << 8), WC = 48u | (34u << 8);
     uint32_t P[6][4];
     uint32_t hprev[4] = {0u, 0u, 0u, 0u};
-    uint32_t pre[6];                                                      // ring of row words in flight
 #pragma unroll
-    for (int j = 0; j < 6; ++j) { P[j][0] = P[j][1] = P[j][2] = P[j][3] = 0; pre[j] = load_row(y0 - 3 + j); }
-    const int ngroups = (y1 - y0 + 6 + 5) / 6;                            // input rows y0-3 .. y1+2 in groups of 6 (the tail group over-reads clamped rows)
+    for (int j = 0; j < 6; ++j) { P[j][0] = P[j][1] = P[j][2] = P[j][3] = 0; }
+    const uint32_t* rowp = sm32 + 3 + lane;                               // words (x - 4, x, x + 4) of the staged row
+    const int ngroups = (nrows + 5) / 6;
     for (int gi = 0; gi < ngroups; ++gi) {
-        const int r0 = y0 - 3 + gi * 6;
 #pragma unroll
         for (int j = 0; j < 6; ++j) {                                     // ring slot j is static after unrolling: no register moves
-            const int r = r0 + j;
-            uint32_t w1 = pre[j];
-            if (gi + 1 < ngroups) pre[j] = load_row(r + 6);
-            if (edge_tile) {                                              // warp-uniform: rebuild the edge words from their neighbours' loads
-                const uint32_t wa = __shfl_sync(0xffffffffu, w1, srcA), wb = __shfl_sync(0xffffffffu, w1, srcB);
-                if (fix && !slow) w1 = __byte_perm(w1, __byte_perm(wa, wb, selG), selM);
-            }
-            const uint32_t w0 = __shfl_up_sync(0xffffffffu, w1, 1), w2 = __shfl_down_sync(0xffffffffu, w1, 1);
+            const uint32_t w0 = rowp[j * (BLUR_BOX_W / 4)], w1 = rowp[j * (BLUR_BOX_W / 4) + 1], w2 = rowp[j * (BLUR_BOX_W / 4) + 2];
             // h(x+k) = sum_{i=0..6} q[i] * px(x+k-3+i): two 4-tap integer dot products on byte-aligned windows
             uint32_t hh[4];
             hh[0] = __dp4a(__byte_perm(w0, w1, 0x4321), Q0, __dp4a(__byte_perm(w1, w2, 0x4321), Q1, 0u));
             hh[1] = __dp4a(__byte_perm(w0, w1, 0x5432), Q0, __dp4a(__byte_perm(w1, w2, 0x5432), Q1, 0u));
             hh[2] = __dp4a(__byte_perm(w0, w1, 0x6543), Q0, __dp4a(__byte_perm(w1, w2, 0x6543), Q1, 0u));
             hh[3] = __dp4a(w1, Q0, __dp4a(w2, Q1, 0u));
-            const int o = r - 3;                                          // output row completed by this input row
             uint32_t v[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -148,10 +116,12 @@ k_gauss7(PyrView pv, const LevelGeom* __restrict__ levels, const BlurTile* __res
             }
             // (v + 32768) >> 16 is byte 2 of each sum (v < 2^24)
             const uint32_t outw = __byte_perm(__byte_perm(v[0], v[1], 0x0062), __byte_perm(v[2], v[3], 0x0062), 0x5410);
-            if (store && o >= y0 && o < y1)
+            const int i = gi * 6 + j;                                     // staged row; completes output row y0 + i - 6
+            if (store && i >= 6 && i < nrows)
                 *reinterpret_cast<uint32_t*>(dst) = outw;                // bytes past the level width land in row padding
             dst += gpitch;
         }
+        rowp += 6 * (BLUR_BOX_W / 4);
     }
 }
 

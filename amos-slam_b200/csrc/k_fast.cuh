@@ -38,6 +38,7 @@ struct FastLayout { int patch_cap, s_cap, wq_cap, bm_cap, per_warp; };
 
 // exact byte-wise "d > T" (T <= 126) up to the final & 0x80808080: bit 7 of each byte of the result
 __device__ __forceinline__ uint32_t fast_gt(uint32_t d, uint32_t kc) { return ((d & 0x7F7F7F7Fu) + kc) | d; }
+__device__ __forceinline__ int max(int a, int b, int c) { return max(max(a, b), c); }
 
 __global__ void __launch_bounds__(FAST_WARPS * 32)
 k_fast_cells(const __grid_constant__ CUtensorMap map_l0, const CUtensorMap* __restrict__ maps, int b0,
@@ -218,8 +219,11 @@ k_fast_cells(const __grid_constant__ CUtensorMap map_l0, const CUtensorMap* __re
             if (k < cn) {
                 const int code = clist[k], y = code >> 6, x = code & 63;
                 const uint8_t* q = S + (y + 1) * sst + x + 1;
-                const int s = q[0];
-                mx = s > q[-1] && s > q[1] && s > q[-sst - 1] && s > q[-sst] && s > q[-sst + 1] && s > q[sst - 1] && s > q[sst] && s > q[sst + 1];
+                const uint8_t* qu = q - sst;
+                const uint8_t* qd = q + sst;
+                const int s = q[0];                                          // branch-free: all 8 neighbours, one 3-input max tree
+                const int nb = max(max(max((int)qu[-1], (int)qu[0], (int)qu[1]), (int)q[-1], (int)q[1]), max((int)qd[-1], (int)qd[0], (int)qd[1]));
+                mx = s > nb;
                 if (mx) atomicOr(&bm[2 * y + (x >> 5)], 1u << (x & 31));
             }
             nmax += __popc(__ballot_sync(0xffffffffu, mx));

@@ -74,7 +74,7 @@ struct orbx_extractor {
     long long pyr_fstride = 0; int cand_per_frame = 0, kp_per_frame = 0, max_kp = 0;
     FastLayout fast_lay{}; int tree_cap = 0, sort_smem_keys = 4096;
     DevBuf<CUtensorMap> d_tmaps; const void* tmaps_base = nullptr; int tmaps_B = 0;          // FAST tensor maps of levels >= 1 (by level), valid for (d_pyr.p, Bcap)
-    CUtensorMap map_l0; const void* map_l0_sig[4] = {nullptr};                                // level-0 map of the current view (pointer, frame stride, pitch, frames)
+    CUtensorMap map_l0, map_l0_blur; const void* map_l0_sig[4] = {nullptr};                                // level-0 map of the current view (pointer, frame stride, pitch, frames)
     DevBuf<LevelGeom> d_levels; DevBuf<CellDesc> d_cells; DevBuf<BlurTile> d_tiles; DevBuf<int> d_tabs;
     std::vector<ResizeTabs> resize_tabs;
 
@@ -299,22 +299,22 @@ static inline void prof_mark(orbx_extractor* h) {
 
 static int run_blur_range(orbx_extractor* h, int b0, int B);
 
-// Tensor maps of the FAST stage (k_fast.cuh).  Levels >= 1 live in d_pyr: one map per level in a device array, rebuilt when the pyramid
+// Tensor maps of the FAST and blur stages (k_fast.cuh, k_describe.cuh).  Levels >= 1 live in d_pyr: one map per level in a device array, rebuilt when the pyramid
 // block moves.  Level 0 follows the current view (internal copy, pinned mirror or the caller's device frames) and travels as a kernel
 // parameter.  Must not be first called inside a stream capture (extract_graph prepares before capturing).
 static int fast_prepare(orbx_extractor* h) {
     const int L = h->nlevels;
     const long long frames = 1 << 16;                      // bound of the frame coordinate only; kernels index frames < B
     if (h->tmaps_base != (const void*)h->d_pyr.p || !h->d_tmaps.p) {
-        std::vector<CUtensorMap> m((size_t)L);
-        std::memset(m.data(), 0, sizeof(CUtensorMap) * (size_t)L);
+        std::vector<CUtensorMap> m((size_t)2 * L);                       // [0, L): FAST cells, [L, 2L): blur tiles
+        std::memset(m.data(), 0, sizeof(CUtensorMap) * (size_t)2 * L);
         for (int l = 1; l < L; ++l) {
             const LevelGeom& g = h->levels[l];
-            if (g.cell_count == 0) continue;
-            if (!orbx_tmap_image(&m[l], h->d_pyr.p + g.off, g.w, g.h, frames, g.pitch, h->pyr_fstride, g.fast_bw, g.fast_bh)) FAIL(ORBX_E_CUDA, "cuTensorMapEncodeTiled failed (pyramid level)");
+            if (g.cell_count && !orbx_tmap_image(&m[l], h->d_pyr.p + g.off, g.w, g.h, frames, g.pitch, h->pyr_fstride, g.fast_bw, g.fast_bh)) FAIL(ORBX_E_CUDA, "cuTensorMapEncodeTiled failed (pyramid level)");
+            if (!orbx_tmap_image(&m[L + l], h->d_pyr.p + g.off, g.w, g.h, frames, g.pitch, h->pyr_fstride, BLUR_BOX_W, BLUR_ROWS)) FAIL(ORBX_E_CUDA, "cuTensorMapEncodeTiled failed (pyramid level, blur)");
         }
-        if (h->d_tmaps.ensure((size_t)L)) return ORBX_E_CUDA;
-        CU_TRY(cudaMemcpyAsync(h->d_tmaps.p, m.data(), sizeof(CUtensorMap) * (size_t)L, cudaMemcpyHostToDevice, h->stream));
+        if (h->d_tmaps.ensure((size_t)2 * L)) return ORBX_E_CUDA;
+        CU_TRY(cudaMemcpyAsync(h->d_tmaps.p, m.data(), sizeof(CUtensorMap) * (size_t)2 * L, cudaMemcpyHostToDevice, h->stream));
         CU_TRY(cudaStreamSynchronize(h->stream));
         h->tmaps_base = h->d_pyr.p;
     }
@@ -324,6 +324,7 @@ static int fast_prepare(orbx_extractor* h) {
         std::memset(&h->map_l0, 0, sizeof(h->map_l0));
         if (g.cell_count && !orbx_tmap_image(&h->map_l0, h->view.l0, g.w, g.h, frames, h->view.l0_pitch, h->view.l0_fstride, g.fast_bw, g.fast_bh))
             FAIL(ORBX_E_CUDA, "cuTensorMapEncodeTiled failed (level 0: frames must be 16-byte aligned in pointer, row step and frame stride)");
+        if (!orbx_tmap_image(&h->map_l0_blur, h->view.l0, g.w, g.h, frames, h->view.l0_pitch, h->view.l0_fstride, BLUR_BOX_W, BLUR_ROWS)) FAIL(ORBX_E_CUDA, "cuTensorMapEncodeTiled failed (level 0, blur)");
         std::memcpy(h->map_l0_sig, sig, sizeof(sig));
     }
     return ORBX_OK;
@@ -418,10 +419,9 @@ static int run_detect(orbx_extractor* h, int b0, int B, bool fork_blur = false) 
 // blur of frames [b0, b0+B).  The single-frame entry points (describe, debug taps) use the cached form below.
 static int run_blur_range(orbx_extractor* h, int b0, int B) {
     const int ntiles = (int)h->tiles.size();
-    PyrView view = h->view;
-    view.l0 += (long long)b0 * view.l0_fstride; view.pyr += (long long)b0 * view.pyr_fstride;
-    dim3 grid((ntiles + 3) / 4, B);
-    k_gauss7<<<grid, 128, 0, h->cur>>>(view, h->d_levels.p, h->d_tiles.p, ntiles, h->d_blur.p + (size_t)b0 * h->pyr_fstride, h->pyr_fstride);
+    { const int rc = fast_prepare(h); if (rc) return rc; }
+    dim3 grid((ntiles + BLUR_WARPS - 1) / BLUR_WARPS, B);
+    k_gauss7<<<grid, BLUR_WARPS * 32, BLUR_WARPS * BLUR_SMEM_PER_WARP, h->cur>>>(h->map_l0_blur, h->d_tmaps.p + h->nlevels, b0, h->d_levels.p, h->d_tiles.p, ntiles, h->d_blur.p, h->pyr_fstride);
     LAUNCH_CHECK();
     prof_mark(h);
     return ORBX_OK;
