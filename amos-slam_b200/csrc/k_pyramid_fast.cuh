@@ -1,7 +1,8 @@
-// k_pyramid_fast.cuh -- image pyramid (bilinear, fixed point) and per-cell FAST-9 detection kernels.
+// k_pyramid_fast.cuh -- image pyramid (bilinear resize, fixed point).  The FAST stage lives in k_fast.cuh.
 #pragma once
 #include "orbx_common.cuh"
 #include <cuda_pipeline.h>
+#include "tma.cuh"
 
 // =================================================================================================
 // K1  pyr_resize: level l from level l-1 (chained, /root/reference/src/ORBextractor.cc:1826-1886),
@@ -89,3 +90,77 @@ k_pyr_resize(const uint8_t* __restrict__ src, long long src_fstride, int spitch,
     *reinterpret_cast<uint32_t*>(dst + (long long)blockIdx.z * dst_fstride + (long long)y * dpitch + x) = out;
 }
 
+
+// =================================================================================================
+// K1t  pyr_resize, TMA-staged tile form (the one the batch and per-frame paths run; k_pyr_resize_w / k_pyr_resize above remain
+// for scale factors whose source tile does not fit a TMA box).  One warp = one tile of 128 destination columns x RESIZE_ROWS
+// destination rows; the source rectangle that tile reads (about 1.2x as wide and high at ORB's scale factor, widened to the
+// left to a 16-byte boundary) is fetched by ONE bulk tensor copy and awaited on an mbarrier.  Everything a lane needs about its 4
+// destination columns (first source column, PRMT selectors, horizontal weights) is loaded ONCE per tile instead of once per
+// row, and the horizontal pass of a source row is computed once and reused by the (up to two) destination rows that read it --
+// the previous per-thread form spent 155 instructions per 4 pixels, 110 of them on tables and addresses (profiles/r02b).
+// =================================================================================================
+#define RESIZE_ROWS 32
+#define RESIZE_WARPS 4
+
+__global__ void __launch_bounds__(RESIZE_WARPS * 32)
+k_pyr_resize_t(const __grid_constant__ CUtensorMap map_l0, const CUtensorMap* __restrict__ gmap, int b0, int sh,
+               uint8_t* __restrict__ dst, long long dst_fstride, int dpitch, int dw, int dh, ResizeTabs t, int bw, int bh) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int Y0 = (blockIdx.y * RESIZE_WARPS + warp) * RESIZE_ROWS;
+    if (Y0 >= dh) return;
+    const int per_warp = (bw * bh + 16 + 127) & ~127;
+    uint8_t* sm = smem_raw + (size_t)warp * per_warp;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + bw * bh);
+    const int gx0 = blockIdx.x * 32;                                  // first group of 4 destination columns of the tile
+    const int bx0 = __ldg(&t.xg[gx0].x) & ~15;                        // box origin: 16-byte boundary left of the tile's first source column
+    const int by0 = __ldg(t.yofs + Y0);
+    if (lane == 0) {
+        mbar_init(bar, 1); mbar_fence_init();
+        mbar_expect_tx(bar, (uint32_t)(bw * bh));
+        tma_load_3d(sm, gmap ? gmap : &map_l0, bx0, by0, b0 + (int)blockIdx.z, bar);
+    }
+    // per-lane column constants, loaded while the copy is in flight
+    const int gx = gx0 + lane, x = gx * 4;
+    const int2 e = __ldg(t.xg + gx);
+    const uint4 wq = __ldg(reinterpret_cast<const uint4*>(t.xw + x));          // 4 x (w0 | w1 << 16)
+    const int rel = e.x - bx0;
+    const int wi = rel >> 2, sh8 = (rel & 3) * 8;
+    const uint32_t s01 = (uint32_t)e.y & 0xFFFFu, s23 = (uint32_t)e.y >> 16;
+    const int wpr = bw >> 2;
+    const bool active = x < dpitch;                                   // tables are padded to the destination pitch
+    const bool store = x < dw;
+    __syncwarp();
+    mbar_wait(bar, 0);
+    const uint32_t* col = reinterpret_cast<const uint32_t*>(sm) + (active ? wi : 0);
+    // horizontal pass of one staged source row: 4 sums, already shifted (H >> 4)
+    auto hpass = [&](int row, uint32_t (&G)[4]) {
+        const uint32_t* r32 = col + row * wpr;
+        const uint32_t a0 = r32[0], a1 = r32[1], a2 = r32[2];
+        const uint32_t W0 = __funnelshift_r(a0, a1, sh8), W1 = __funnelshift_r(a1, a2, sh8);
+        const uint32_t X01 = __byte_perm(W0, W1, s01), X23 = __byte_perm(W0, W1, s23);     // (l0,r0,l1,r1), (l2,r2,l3,r3)
+        G[0] = __dp2a_lo(wq.x, X01, 0u) >> 4; G[1] = __dp2a_hi(wq.y, X01, 0u) >> 4;
+        G[2] = __dp2a_lo(wq.z, X23, 0u) >> 4; G[3] = __dp2a_hi(wq.w, X23, 0u) >> 4;
+    };
+    uint32_t G0[4], G1[4] = {0u, 0u, 0u, 0u};
+    int held = -1;                                                    // source row whose pass is in G1
+    uint8_t* drow = dst + (long long)(b0 + (int)blockIdx.z) * dst_fstride + (long long)Y0 * dpitch + x;
+    const int Y1 = min(Y0 + RESIZE_ROWS, dh);
+    for (int y = Y0; y < Y1; ++y) {
+        const int sy0 = __ldg(t.yofs + y), sy1 = min(sy0 + 1, sh - 1);
+        const short2 bwt = __ldg(t.yw + y);
+        if (sy0 == held) { G0[0] = G1[0]; G0[1] = G1[1]; G0[2] = G1[2]; G0[3] = G1[3]; }
+        else hpass(sy0 - by0, G0);
+        if (sy1 == sy0) { G1[0] = G0[0]; G1[1] = G0[1]; G1[2] = G0[2]; G1[3] = G0[3]; }
+        else hpass(sy1 - by0, G1);
+        held = sy1;
+        uint32_t v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            v[k] = (uint32_t)(((((int)bwt.x * (int)G0[k]) >> 16) + (((int)bwt.y * (int)G1[k]) >> 16) + 2) >> 2);
+        const uint32_t out = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
+        if (store) *reinterpret_cast<uint32_t*>(drow) = out;         // the (up to 3) bytes past dw land in row padding
+        drow += dpitch;
+    }
+}

@@ -74,9 +74,10 @@ struct orbx_extractor {
     long long pyr_fstride = 0; int cand_per_frame = 0, kp_per_frame = 0, max_kp = 0;
     FastLayout fast_lay{}; int tree_cap = 0, sort_smem_keys = 4096;
     DevBuf<CUtensorMap> d_tmaps; const void* tmaps_base = nullptr; int tmaps_B = 0;          // FAST tensor maps of levels >= 1 (by level), valid for (d_pyr.p, Bcap)
-    CUtensorMap map_l0, map_l0_blur; const void* map_l0_sig[4] = {nullptr};                                // level-0 map of the current view (pointer, frame stride, pitch, frames)
+    CUtensorMap map_l0, map_l0_blur, map_l0_resize; const void* map_l0_sig[4] = {nullptr};                                // level-0 map of the current view (pointer, frame stride, pitch, frames)
     DevBuf<LevelGeom> d_levels; DevBuf<CellDesc> d_cells; DevBuf<BlurTile> d_tiles; DevBuf<int> d_tabs;
     std::vector<ResizeTabs> resize_tabs;
+    std::vector<int> resize_bw, resize_bh;           // TMA box of the source tile per destination level (k_pyr_resize_t); 0 = use the per-thread kernels
 
     // ---- per-batch device state (the "stateful extractor": pyramid stays resident) ----
     int Bcap = 0, lastB = 0;
@@ -202,7 +203,7 @@ static int build_plan(orbx_extractor* h, int rows, int cols) {
     }
     if (tree_cap > 32000) FAIL(ORBX_E_INVALID, "too many features per level");
     // resize tables for levels >= 1
-    std::vector<int> tabs; std::vector<size_t> tab_off((size_t)L * 4, 0), xg_off(L, 0); std::vector<int> wide_ok(L, 0);
+    std::vector<int> tabs; std::vector<size_t> tab_off((size_t)L * 4, 0), xg_off(L, 0); std::vector<int> wide_ok(L, 0), rbw(L, 0), rbh(L, 0);
     for (int l = 1; l < L; ++l) {
         std::vector<int> xo, yo; std::vector<short> xw, yw;
         linear_coefs(lv[l - 1].w, lv[l].w, lv[l].pitch, xo, xw);
@@ -225,6 +226,20 @@ static int build_plan(orbx_extractor* h, int rows, int cols) {
             xg[2 * gx] = base; xg[2 * gx + 1] = (int)sel;
         }
         xg_off[l] = push(xg.data(), xg.size() * 4); wide_ok[l] = wide && (lv[l - 1].pitch % 4 == 0);
+        // k_pyr_resize_t: source rectangle of a 128 x RESIZE_ROWS destination tile, from the 16-byte boundary left of its first source column
+        int bwm = 0, bhm = 0;
+        for (int g0 = 0; g0 < ngroups; g0 += 32) {
+            const int bx0 = xg[2 * g0] & ~15;
+            for (int gx = g0; gx < std::min(g0 + 32, ngroups); ++gx) bwm = std::max(bwm, 4 * (((xg[2 * gx] - bx0) >> 2) + 3));
+        }
+        for (int y0 = 0; y0 < lv[l].h; y0 += RESIZE_ROWS) {
+            const int y1 = std::min(y0 + RESIZE_ROWS, lv[l].h) - 1;
+            bhm = std::max(bhm, std::min(yo[y1] + 1, lv[l - 1].h - 1) - yo[y0] + 1);
+        }
+        bwm = align_up(bwm, 16); if ((bwm / 16) % 2 == 0) bwm += 16;            // odd number of 16-byte units: rows of a column spread over the banks
+        const long long per_warp = ((long long)bwm * bhm + 16 + 127) / 128 * 128;
+        rbw[l] = rbh[l] = 0;
+        if (wide_ok[l] && bwm <= 256 && bhm <= 256 && per_warp * RESIZE_WARPS <= 100 * 1024) { rbw[l] = bwm; rbh[l] = bhm; }
     }
     if (h->d_levels.ensure(L)) return ORBX_E_CUDA;
     if (h->d_cells.ensure(cells.size())) return ORBX_E_CUDA;
@@ -244,7 +259,7 @@ static int build_plan(orbx_extractor* h, int rows, int cols) {
         h->resize_tabs[l].xg = reinterpret_cast<const int2*>(h->d_tabs.p + xg_off[l]);
         h->resize_tabs[l].wide = wide_ok[l];
     }
-    h->levels.swap(lv); h->cells.swap(cells); h->tiles.swap(tiles);
+    h->levels.swap(lv); h->cells.swap(cells); h->tiles.swap(tiles); h->resize_bw.swap(rbw); h->resize_bh.swap(rbh);
     h->pyr_fstride = (off + 255) / 256 * 256;
     h->cand_per_frame = cand_off; h->kp_per_frame = kp_off;
     h->max_kp = 0; for (int l = 0; l < L; ++l) h->max_kp += h->levels[l].kp_cap;
@@ -306,15 +321,17 @@ static int fast_prepare(orbx_extractor* h) {
     const int L = h->nlevels;
     const long long frames = 1 << 16;                      // bound of the frame coordinate only; kernels index frames < B
     if (h->tmaps_base != (const void*)h->d_pyr.p || !h->d_tmaps.p) {
-        std::vector<CUtensorMap> m((size_t)2 * L);                       // [0, L): FAST cells, [L, 2L): blur tiles
-        std::memset(m.data(), 0, sizeof(CUtensorMap) * (size_t)2 * L);
+        std::vector<CUtensorMap> m((size_t)3 * L);                       // [0, L): FAST cells, [L, 2L): blur tiles, [2L, 3L): resize source tiles (level l reads l - 1)
+        std::memset(m.data(), 0, sizeof(CUtensorMap) * (size_t)3 * L);
         for (int l = 1; l < L; ++l) {
             const LevelGeom& g = h->levels[l];
             if (g.cell_count && !orbx_tmap_image(&m[l], h->d_pyr.p + g.off, g.w, g.h, frames, g.pitch, h->pyr_fstride, g.fast_bw, g.fast_bh)) FAIL(ORBX_E_CUDA, "cuTensorMapEncodeTiled failed (pyramid level)");
             if (!orbx_tmap_image(&m[L + l], h->d_pyr.p + g.off, g.w, g.h, frames, g.pitch, h->pyr_fstride, BLUR_BOX_W, BLUR_ROWS)) FAIL(ORBX_E_CUDA, "cuTensorMapEncodeTiled failed (pyramid level, blur)");
+            if (l + 1 < L && h->resize_bw[l + 1] && !orbx_tmap_image(&m[2 * L + l + 1], h->d_pyr.p + g.off, g.w, g.h, frames, g.pitch, h->pyr_fstride, h->resize_bw[l + 1], h->resize_bh[l + 1]))
+                FAIL(ORBX_E_CUDA, "cuTensorMapEncodeTiled failed (pyramid level, resize)");
         }
-        if (h->d_tmaps.ensure((size_t)2 * L)) return ORBX_E_CUDA;
-        CU_TRY(cudaMemcpyAsync(h->d_tmaps.p, m.data(), sizeof(CUtensorMap) * (size_t)2 * L, cudaMemcpyHostToDevice, h->stream));
+        if (h->d_tmaps.ensure((size_t)3 * L)) return ORBX_E_CUDA;
+        CU_TRY(cudaMemcpyAsync(h->d_tmaps.p, m.data(), sizeof(CUtensorMap) * (size_t)3 * L, cudaMemcpyHostToDevice, h->stream));
         CU_TRY(cudaStreamSynchronize(h->stream));
         h->tmaps_base = h->d_pyr.p;
     }
@@ -325,6 +342,9 @@ static int fast_prepare(orbx_extractor* h) {
         if (g.cell_count && !orbx_tmap_image(&h->map_l0, h->view.l0, g.w, g.h, frames, h->view.l0_pitch, h->view.l0_fstride, g.fast_bw, g.fast_bh))
             FAIL(ORBX_E_CUDA, "cuTensorMapEncodeTiled failed (level 0: frames must be 16-byte aligned in pointer, row step and frame stride)");
         if (!orbx_tmap_image(&h->map_l0_blur, h->view.l0, g.w, g.h, frames, h->view.l0_pitch, h->view.l0_fstride, BLUR_BOX_W, BLUR_ROWS)) FAIL(ORBX_E_CUDA, "cuTensorMapEncodeTiled failed (level 0, blur)");
+        std::memset(&h->map_l0_resize, 0, sizeof(h->map_l0_resize));
+        if (L > 1 && h->resize_bw[1] && !orbx_tmap_image(&h->map_l0_resize, h->view.l0, g.w, g.h, frames, h->view.l0_pitch, h->view.l0_fstride, h->resize_bw[1], h->resize_bh[1]))
+            FAIL(ORBX_E_CUDA, "cuTensorMapEncodeTiled failed (level 0, resize)");
         std::memcpy(h->map_l0_sig, sig, sizeof(sig));
     }
     return ORBX_OK;
@@ -343,17 +363,26 @@ static int run_detect(orbx_extractor* h, int b0, int B, bool fork_blur = false) 
     uint32_t* slots = h->d_slots.p + (size_t)b0 * h->cand_per_frame;
     uint16_t* cell_counts = h->d_cell_counts.p + (size_t)b0 * h->cells.size();
     const size_t co = (size_t)b0 * h->cand_per_frame;
+    { const int rc = fast_prepare(h); if (rc) return rc; }
     prof_mark(h);
     for (int l = 1; l < L; ++l) {
         const LevelGeom& g = h->levels[l]; const LevelGeom& gp = h->levels[l - 1];
         const uint8_t* src; long long sfs; int sp;
         if (l == 1) { src = view.l0; sfs = view.l0_fstride; sp = view.l0_pitch; }
         else { src = pyr + gp.off; sfs = h->pyr_fstride; sp = gp.pitch; }
+        if (h->resize_bw[l]) {
+            const int bw = h->resize_bw[l], bh = h->resize_bh[l];
+            const int per_warp = (bw * bh + 16 + 127) / 128 * 128;
+            dim3 grid((g.w + 127) / 128, ((g.h + RESIZE_ROWS - 1) / RESIZE_ROWS + RESIZE_WARPS - 1) / RESIZE_WARPS, B);
+            k_pyr_resize_t<<<grid, RESIZE_WARPS * 32, per_warp * RESIZE_WARPS, s>>>(h->map_l0_resize, l == 1 ? nullptr : h->d_tmaps.p + 2 * L + l, b0, gp.h,
+                                                                                     h->d_pyr.p + g.off, h->pyr_fstride, g.pitch, g.w, g.h, h->resize_tabs[l], bw, bh);
+        } else {
         dim3 grid((g.w + 127) / 128, (g.h + 7) / 8, B), block(32, 8);
         if (h->resize_tabs[l].wide && (sp & 3) == 0)
             k_pyr_resize_w<<<grid, block, 0, s>>>(src, sfs, sp, gp.w, gp.h, pyr + g.off, h->pyr_fstride, g.pitch, g.w, g.h, h->resize_tabs[l]);
         else
             k_pyr_resize<<<grid, block, 0, s>>>(src, sfs, sp, gp.w, gp.h, pyr + g.off, h->pyr_fstride, g.pitch, g.w, g.h, h->resize_tabs[l]);
+        }
         LAUNCH_CHECK();
     }
     prof_mark(h);
@@ -600,6 +629,7 @@ int orbx_create(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, in
     cudaFuncSetAttribute(k_octree_tree, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_octree_tree_par, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ptree_smem_bytes(PTREE_MAXCAP, 4096));
     cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(k_pyr_resize_t, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     *out = h;
     return ORBX_OK;
 }
