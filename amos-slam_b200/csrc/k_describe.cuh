@@ -21,12 +21,13 @@
 // 6 packed row pairs in registers and emits one output word (previous form: 114 instructions per word and row, this one ~45;
 // profiles/r02b vs r02c).  HBM traffic = read level + write level (+ the halo rows, which L2 serves).
 // =================================================================================================
-#define BLUR_STRIP 42
-#define BLUR_ROWS (BLUR_STRIP + 6)       // staged rows: a multiple of 6 (the row loop is unrolled over the 6 ring slots)
+#define BLUR_STRIP 42                    // throughput form: 48 staged rows per tile
+#define BLUR_STRIP_SMALL 12              // latency form (a handful of frames): 18 staged rows per tile, 3.5x as many warps
 #define BLUR_TILE_W 128
 #define BLUR_BOX_W 160                   // 16 bytes left of the tile + tile + 16 bytes right: 40 words per staged row
 #define BLUR_WARPS 4
-#define BLUR_SMEM_PER_WARP (BLUR_BOX_W * BLUR_ROWS + 128)
+// staged rows = strip + 6: a multiple of 6 (the row loop is unrolled over the 6 ring slots)
+__host__ __device__ static inline int blur_smem_per_warp(int strip) { return (BLUR_BOX_W * (strip + 6) + 16 + 127) & ~127; }   // tile + mbarrier, 128-byte aligned (TMA destination)
 struct BlurTile { short level, xc, strip, pad; };
 
 __device__ __noinline__ int reflect101(int p, int len) {
@@ -37,24 +38,25 @@ __device__ __noinline__ int reflect101(int p, int len) {
 
 __global__ void __launch_bounds__(BLUR_WARPS * 32)
 k_gauss7(const __grid_constant__ CUtensorMap map_l0, const CUtensorMap* __restrict__ maps, int b0,
-         const LevelGeom* __restrict__ levels, const BlurTile* __restrict__ tiles, int ntiles,
+         const LevelGeom* __restrict__ levels, const BlurTile* __restrict__ tiles, int ntiles, int strip,
          uint8_t* __restrict__ blur, long long blur_fstride) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tile = blockIdx.x * BLUR_WARPS + warp;
     if (tile >= ntiles) return;
-    uint8_t* sm = smem_raw + (size_t)warp * BLUR_SMEM_PER_WARP;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + BLUR_BOX_W * BLUR_ROWS);
+    const int srows = strip + 6;
+    uint8_t* sm = smem_raw + (size_t)warp * blur_smem_per_warp(strip);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + BLUR_BOX_W * srows);
     const BlurTile t = tiles[tile];
     const int b = blockIdx.y;
     const LevelGeom& g = levels[t.level];
     const int gw = g.w, gh = g.h, gpitch = g.pitch;
     const int x0 = t.xc * BLUR_TILE_W, bx0 = x0 - 16;               // tile / box origin (level columns)
-    const int y0 = t.strip * BLUR_STRIP, y1 = min(y0 + BLUR_STRIP, gh);
+    const int y0 = t.strip * strip, y1 = min(y0 + strip, gh);
     const int nrows = y1 - y0 + 6;                                   // staged rows that are read: level rows y0 - 3 .. y1 + 2
     if (lane == 0) {
         mbar_init(bar, 1); mbar_fence_init();
-        mbar_expect_tx(bar, BLUR_BOX_W * BLUR_ROWS);
+        mbar_expect_tx(bar, (uint32_t)(BLUR_BOX_W * srows));
         tma_load_3d(sm, t.level == 0 ? &map_l0 : maps + t.level, bx0, y0 - 3, b0 + b, bar);
     }
     __syncwarp();

@@ -70,12 +70,12 @@ struct orbx_extractor {
 
     // ---- geometry plan for (rows, cols) ----
     int rows = 0, cols = 0;
-    std::vector<LevelGeom> levels; std::vector<CellDesc> cells; std::vector<BlurTile> tiles;
+    std::vector<LevelGeom> levels; std::vector<CellDesc> cells; std::vector<BlurTile> tiles, tiles_s;   // tiles_s: BLUR_STRIP_SMALL tiling
     long long pyr_fstride = 0; int cand_per_frame = 0, kp_per_frame = 0, max_kp = 0;
     FastLayout fast_lay{}; int tree_cap = 0, sort_smem_keys = 4096;
     DevBuf<CUtensorMap> d_tmaps; const void* tmaps_base = nullptr; int tmaps_B = 0;          // FAST tensor maps of levels >= 1 (by level), valid for (d_pyr.p, Bcap)
-    CUtensorMap map_l0, map_l0_blur, map_l0_resize; const void* map_l0_sig[4] = {nullptr};                                // level-0 map of the current view (pointer, frame stride, pitch, frames)
-    DevBuf<LevelGeom> d_levels; DevBuf<CellDesc> d_cells; DevBuf<BlurTile> d_tiles; DevBuf<int> d_tabs;
+    CUtensorMap map_l0, map_l0_blur, map_l0_blur_s, map_l0_resize; const void* map_l0_sig[4] = {nullptr};                                // level-0 map of the current view (pointer, frame stride, pitch, frames)
+    DevBuf<LevelGeom> d_levels; DevBuf<CellDesc> d_cells; DevBuf<BlurTile> d_tiles, d_tiles_s; DevBuf<int> d_tabs;
     std::vector<ResizeTabs> resize_tabs;
     std::vector<int> resize_bw, resize_bh;           // TMA box of the source tile per destination level (k_pyr_resize_t); 0 = use the per-thread kernels
 
@@ -93,7 +93,7 @@ struct orbx_extractor {
     PyrView view{}; bool have_pyramid = false, blur_valid = false;
     // single-frame operator(): the whole per-geometry chain (upload from a pinned staging frame, 7 resizes, FAST, quadtree, blur on the
     // second stream, orientation + descriptors, result gather, download) captured once as a CUDA graph and replayed per call
-    cudaGraphExec_t graph1 = nullptr; int graph_launches = 0; uint8_t* h_in = nullptr; size_t h_in_cap = 0; const void* graph_sig[24] = {nullptr};
+    cudaGraphExec_t graph1 = nullptr; int graph_launches = 0; uint8_t* h_in = nullptr; size_t h_in_cap = 0; const void* graph_sig[26] = {nullptr};
     // optional per-stage CUDA-event timing (bench.py's roofline): one event set per profiled call
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;     // ORBX_NSTAGES+1 events per call
@@ -124,7 +124,7 @@ static int build_plan(orbx_extractor* h, int rows, int cols) {
     if (h->rows == rows && h->cols == cols) return ORBX_OK;
     const int L = h->nlevels;
     std::vector<LevelGeom> lv(L);
-    std::vector<CellDesc> cells; std::vector<BlurTile> tiles;
+    std::vector<CellDesc> cells; std::vector<BlurTile> tiles, tiles_s;
     long long off = 0; int cand_off = 0, kp_off = 0, patch_cap = 0, s_cap = 0, wq_words = 1, zh_max = 1, tree_cap = 0;
     for (int l = 0; l < L; ++l) {
         LevelGeom& g = lv[l];
@@ -200,6 +200,8 @@ static int build_plan(orbx_extractor* h, int rows, int cols) {
         tree_cap = std::max(tree_cap, g.kp_cap + 8);
         for (int st = 0; st < (g.h + BLUR_STRIP - 1) / BLUR_STRIP; ++st)
             for (int xc = 0; xc < (g.w + BLUR_TILE_W - 1) / BLUR_TILE_W; ++xc) { BlurTile t; t.level = (short)l; t.xc = (short)xc; t.strip = (short)st; t.pad = 0; tiles.push_back(t); }
+        for (int st = 0; st < (g.h + BLUR_STRIP_SMALL - 1) / BLUR_STRIP_SMALL; ++st)
+            for (int xc = 0; xc < (g.w + BLUR_TILE_W - 1) / BLUR_TILE_W; ++xc) { BlurTile t; t.level = (short)l; t.xc = (short)xc; t.strip = (short)st; t.pad = 0; tiles_s.push_back(t); }
     }
     if (tree_cap > 32000) FAIL(ORBX_E_INVALID, "too many features per level");
     // resize tables for levels >= 1
@@ -243,11 +245,12 @@ static int build_plan(orbx_extractor* h, int rows, int cols) {
     }
     if (h->d_levels.ensure(L)) return ORBX_E_CUDA;
     if (h->d_cells.ensure(cells.size())) return ORBX_E_CUDA;
-    if (h->d_tiles.ensure(tiles.size())) return ORBX_E_CUDA;
+    if (h->d_tiles.ensure(tiles.size()) || h->d_tiles_s.ensure(tiles_s.size())) return ORBX_E_CUDA;
     if (h->d_tabs.ensure(std::max<size_t>(tabs.size(), 4))) return ORBX_E_CUDA;
     CU_TRY(cudaMemcpyAsync(h->d_levels.p, lv.data(), sizeof(LevelGeom) * L, cudaMemcpyHostToDevice, h->stream));
     CU_TRY(cudaMemcpyAsync(h->d_cells.p, cells.data(), sizeof(CellDesc) * cells.size(), cudaMemcpyHostToDevice, h->stream));
     CU_TRY(cudaMemcpyAsync(h->d_tiles.p, tiles.data(), sizeof(BlurTile) * tiles.size(), cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(cudaMemcpyAsync(h->d_tiles_s.p, tiles_s.data(), sizeof(BlurTile) * tiles_s.size(), cudaMemcpyHostToDevice, h->stream));
     if (!tabs.empty()) CU_TRY(cudaMemcpyAsync(h->d_tabs.p, tabs.data(), tabs.size() * 4, cudaMemcpyHostToDevice, h->stream));
     CU_TRY(cudaStreamSynchronize(h->stream));   // host vectors go out of scope below
     h->resize_tabs.assign(L, ResizeTabs());
@@ -259,7 +262,7 @@ static int build_plan(orbx_extractor* h, int rows, int cols) {
         h->resize_tabs[l].xg = reinterpret_cast<const int2*>(h->d_tabs.p + xg_off[l]);
         h->resize_tabs[l].wide = wide_ok[l];
     }
-    h->levels.swap(lv); h->cells.swap(cells); h->tiles.swap(tiles); h->resize_bw.swap(rbw); h->resize_bh.swap(rbh);
+    h->levels.swap(lv); h->cells.swap(cells); h->tiles.swap(tiles); h->tiles_s.swap(tiles_s); h->resize_bw.swap(rbw); h->resize_bh.swap(rbh);
     h->pyr_fstride = (off + 255) / 256 * 256;
     h->cand_per_frame = cand_off; h->kp_per_frame = kp_off;
     h->max_kp = 0; for (int l = 0; l < L; ++l) h->max_kp += h->levels[l].kp_cap;
@@ -321,17 +324,18 @@ static int fast_prepare(orbx_extractor* h) {
     const int L = h->nlevels;
     const long long frames = 1 << 16;                      // bound of the frame coordinate only; kernels index frames < B
     if (h->tmaps_base != (const void*)h->d_pyr.p || !h->d_tmaps.p) {
-        std::vector<CUtensorMap> m((size_t)3 * L);                       // [0, L): FAST cells, [L, 2L): blur tiles, [2L, 3L): resize source tiles (level l reads l - 1)
-        std::memset(m.data(), 0, sizeof(CUtensorMap) * (size_t)3 * L);
+        std::vector<CUtensorMap> m((size_t)4 * L);                       // [0, L): FAST cells, [L, 2L): blur tiles, [2L, 3L): resize source tiles (level l reads l - 1), [3L, 4L): small blur tiles
+        std::memset(m.data(), 0, sizeof(CUtensorMap) * (size_t)4 * L);
         for (int l = 1; l < L; ++l) {
             const LevelGeom& g = h->levels[l];
             if (g.cell_count && !orbx_tmap_image(&m[l], h->d_pyr.p + g.off, g.w, g.h, frames, g.pitch, h->pyr_fstride, g.fast_bw, g.fast_bh)) FAIL(ORBX_E_CUDA, "cuTensorMapEncodeTiled failed (pyramid level)");
-            if (!orbx_tmap_image(&m[L + l], h->d_pyr.p + g.off, g.w, g.h, frames, g.pitch, h->pyr_fstride, BLUR_BOX_W, BLUR_ROWS)) FAIL(ORBX_E_CUDA, "cuTensorMapEncodeTiled failed (pyramid level, blur)");
+            if (!orbx_tmap_image(&m[L + l], h->d_pyr.p + g.off, g.w, g.h, frames, g.pitch, h->pyr_fstride, BLUR_BOX_W, BLUR_STRIP + 6) ||
+                !orbx_tmap_image(&m[3 * L + l], h->d_pyr.p + g.off, g.w, g.h, frames, g.pitch, h->pyr_fstride, BLUR_BOX_W, BLUR_STRIP_SMALL + 6)) FAIL(ORBX_E_CUDA, "cuTensorMapEncodeTiled failed (pyramid level, blur)");
             if (l + 1 < L && h->resize_bw[l + 1] && !orbx_tmap_image(&m[2 * L + l + 1], h->d_pyr.p + g.off, g.w, g.h, frames, g.pitch, h->pyr_fstride, h->resize_bw[l + 1], h->resize_bh[l + 1]))
                 FAIL(ORBX_E_CUDA, "cuTensorMapEncodeTiled failed (pyramid level, resize)");
         }
-        if (h->d_tmaps.ensure((size_t)3 * L)) return ORBX_E_CUDA;
-        CU_TRY(cudaMemcpyAsync(h->d_tmaps.p, m.data(), sizeof(CUtensorMap) * (size_t)3 * L, cudaMemcpyHostToDevice, h->stream));
+        if (h->d_tmaps.ensure((size_t)4 * L)) return ORBX_E_CUDA;
+        CU_TRY(cudaMemcpyAsync(h->d_tmaps.p, m.data(), sizeof(CUtensorMap) * (size_t)4 * L, cudaMemcpyHostToDevice, h->stream));
         CU_TRY(cudaStreamSynchronize(h->stream));
         h->tmaps_base = h->d_pyr.p;
     }
@@ -341,7 +345,8 @@ static int fast_prepare(orbx_extractor* h) {
         std::memset(&h->map_l0, 0, sizeof(h->map_l0));
         if (g.cell_count && !orbx_tmap_image(&h->map_l0, h->view.l0, g.w, g.h, frames, h->view.l0_pitch, h->view.l0_fstride, g.fast_bw, g.fast_bh))
             FAIL(ORBX_E_CUDA, "cuTensorMapEncodeTiled failed (level 0: frames must be 16-byte aligned in pointer, row step and frame stride)");
-        if (!orbx_tmap_image(&h->map_l0_blur, h->view.l0, g.w, g.h, frames, h->view.l0_pitch, h->view.l0_fstride, BLUR_BOX_W, BLUR_ROWS)) FAIL(ORBX_E_CUDA, "cuTensorMapEncodeTiled failed (level 0, blur)");
+        if (!orbx_tmap_image(&h->map_l0_blur, h->view.l0, g.w, g.h, frames, h->view.l0_pitch, h->view.l0_fstride, BLUR_BOX_W, BLUR_STRIP + 6) ||
+            !orbx_tmap_image(&h->map_l0_blur_s, h->view.l0, g.w, g.h, frames, h->view.l0_pitch, h->view.l0_fstride, BLUR_BOX_W, BLUR_STRIP_SMALL + 6)) FAIL(ORBX_E_CUDA, "cuTensorMapEncodeTiled failed (level 0, blur)");
         std::memset(&h->map_l0_resize, 0, sizeof(h->map_l0_resize));
         if (L > 1 && h->resize_bw[1] && !orbx_tmap_image(&h->map_l0_resize, h->view.l0, g.w, g.h, frames, h->view.l0_pitch, h->view.l0_fstride, h->resize_bw[1], h->resize_bh[1]))
             FAIL(ORBX_E_CUDA, "cuTensorMapEncodeTiled failed (level 0, resize)");
@@ -370,7 +375,9 @@ static int run_detect(orbx_extractor* h, int b0, int B, bool fork_blur = false) 
         const uint8_t* src; long long sfs; int sp;
         if (l == 1) { src = view.l0; sfs = view.l0_fstride; sp = view.l0_pitch; }
         else { src = pyr + gp.off; sfs = h->pyr_fstride; sp = gp.pitch; }
-        if (h->resize_bw[l]) {
+        static const int rt_env = [] { const char* e = std::getenv("ORBX_RESIZE_TMA"); return e ? std::atoi(e) : -1; }();
+        const long long tile_warps = (long long)((g.w + 127) / 128) * ((g.h + RESIZE_ROWS - 1) / RESIZE_ROWS) * B;
+        if (h->resize_bw[l] && (rt_env >= 0 ? rt_env != 0 : tile_warps >= 2048)) {      // few tiles (a handful of frames): the per-thread form spreads them over more SMs
             const int bw = h->resize_bw[l], bh = h->resize_bh[l];
             const int per_warp = (bw * bh + 16 + 127) / 128 * 128;
             dim3 grid((g.w + 127) / 128, ((g.h + RESIZE_ROWS - 1) / RESIZE_ROWS + RESIZE_WARPS - 1) / RESIZE_WARPS, B);
@@ -447,10 +454,14 @@ static int run_detect(orbx_extractor* h, int b0, int B, bool fork_blur = false) 
 
 // blur of frames [b0, b0+B).  The single-frame entry points (describe, debug taps) use the cached form below.
 static int run_blur_range(orbx_extractor* h, int b0, int B) {
-    const int ntiles = (int)h->tiles.size();
     { const int rc = fast_prepare(h); if (rc) return rc; }
+    // a handful of frames: short strips, so that the few tiles there are spread over all SMs (latency form)
+    static const int small_env = [] { const char* e = std::getenv("ORBX_BLUR_SMALL"); return e ? std::atoi(e) : -1; }();
+    const bool small = small_env >= 0 ? small_env != 0 : (long long)h->tiles.size() * B < 4096;
+    const int ntiles = (int)(small ? h->tiles_s.size() : h->tiles.size()), strip = small ? BLUR_STRIP_SMALL : BLUR_STRIP;
     dim3 grid((ntiles + BLUR_WARPS - 1) / BLUR_WARPS, B);
-    k_gauss7<<<grid, BLUR_WARPS * 32, BLUR_WARPS * BLUR_SMEM_PER_WARP, h->cur>>>(h->map_l0_blur, h->d_tmaps.p + h->nlevels, b0, h->d_levels.p, h->d_tiles.p, ntiles, h->d_blur.p, h->pyr_fstride);
+    k_gauss7<<<grid, BLUR_WARPS * 32, BLUR_WARPS * blur_smem_per_warp(strip), h->cur>>>(small ? h->map_l0_blur_s : h->map_l0_blur, h->d_tmaps.p + (small ? 3 : 1) * h->nlevels, b0,
+        h->d_levels.p, small ? h->d_tiles_s.p : h->d_tiles.p, ntiles, strip, h->d_blur.p, h->pyr_fstride);
     LAUNCH_CHECK();
     prof_mark(h);
     return ORBX_OK;
@@ -527,17 +538,18 @@ static int extract_graph(orbx_extractor* h, const uint8_t* image, int rows, int 
         if (h->d_gather.ensure(blk) || h->d_l0.ensure(fbytes)) return ORBX_E_CUDA;
         if (h->graph1) { cudaGraphExecDestroy(h->graph1); h->graph1 = nullptr; }
     }
+    h->view.l0 = h->d_l0.p; h->view.l0_fstride = (long long)fbytes; h->view.l0_pitch = pitch;
+    h->view.pyr = h->d_pyr.p; h->view.pyr_fstride = h->pyr_fstride;
+    { const int rp = fast_prepare(h); if (rp) return rp; }    // tensor maps are built outside the capture
     // every buffer the captured nodes point at: any of them may have been re-allocated by another entry point since the capture
-    const void* sig[24] = {h->d_l0.p, h->d_pyr.p, h->d_blur.p, h->d_slots.p, h->d_ocand.p, h->d_spk.p, h->d_skey.p, h->d_cell_counts.p, h->d_ncand.p, h->d_kp_level.p,
+    const void* sig[26] = {h->d_tmaps.p, h->d_tiles_s.p, h->d_l0.p, h->d_pyr.p, h->d_blur.p, h->d_slots.p, h->d_ocand.p, h->d_spk.p, h->d_skey.p, h->d_cell_counts.p, h->d_ncand.p, h->d_kp_level.p,
                            h->d_kp_count.p, h->d_counts.p, h->d_overflow.p, h->d_kp_out.p, h->d_desc_out.p, h->d_gather.p, h->h_gather, h->h_in, h->d_levels.p, h->d_cells.p,
                            h->d_tiles.p, h->d_tabs.p, (const void*)(uintptr_t)pitch, (const void*)(uintptr_t)blk};
     if (h->graph1 && std::memcmp(sig, h->graph_sig, sizeof(sig)) != 0) { cudaGraphExecDestroy(h->graph1); h->graph1 = nullptr; }
     // stage the frame (the caller's buffer is pageable in general: a DMA straight from it would be a blocking, staged copy anyway)
     if (step == (size_t)pitch) std::memcpy(h->h_in, image, fbytes - (size_t)(pitch - cols));
     else for (int y = 0; y < rows; ++y) std::memcpy(h->h_in + (size_t)y * pitch, image + (size_t)y * step, (size_t)cols);
-    h->view.l0 = h->d_l0.p; h->view.l0_fstride = (long long)fbytes; h->view.l0_pitch = pitch;
-    h->view.pyr = h->d_pyr.p; h->view.pyr_fstride = h->pyr_fstride;
-    int rc = fast_prepare(h); if (rc) return rc;           // tensor maps are built outside the capture
+    int rc = ORBX_OK;
     if (!h->graph1) {
         cudaGraph_t g = nullptr;
         CU_TRY(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
@@ -651,7 +663,7 @@ void orbx_destroy(orbx_extractor* h) {
     for (cudaEvent_t e : h->ev_h2d) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_done) cudaEventDestroy(e);
     h->d_l0.release();
-    h->d_tmaps.release(); h->d_levels.release(); h->d_cells.release(); h->d_tiles.release(); h->d_tabs.release();
+    h->d_tmaps.release(); h->d_levels.release(); h->d_cells.release(); h->d_tiles.release(); h->d_tiles_s.release(); h->d_tabs.release();
     h->d_pyr.release(); h->d_blur.release(); h->d_slots.release(); h->d_ocand.release(); h->d_spk.release(); h->d_kp_level.release();
     h->d_skey.release(); h->d_cell_counts.release(); h->d_ncand.release(); h->d_kp_count.release(); h->d_counts.release();
     h->d_level_counts.release(); h->d_overflow.release(); h->d_kp_out.release(); h->d_desc_out.release();

@@ -966,7 +966,7 @@ def main():
     total_stage = sum(stage_ms.values())
     # DRAM traffic of the dominant kernel: dram__bytes_read.sum + dram__bytes_write.sum per frame from the committed ncu --set full
     # capture (profiles/traffic.json, written by tools/profile_digest.py), scaled to this launch's frame count
-    kernel_of = {"pyr_resize": "k_pyr_resize_w", "fast_cells": "k_fast_cells", "octree_sort": "k_octree_sort", "octree_tree": "k_octree_tree_par",
+    kernel_of = {"pyr_resize": "k_pyr_resize_t", "fast_cells": "k_fast_cells", "octree_sort": "k_octree_sort", "octree_tree": "k_octree_tree_par",
                  "gauss7": "k_gauss7", "orient_describe": "k_orient_describe"}
     traffic = None; ncu_note = None
     try:
