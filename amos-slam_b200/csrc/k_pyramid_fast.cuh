@@ -3,6 +3,7 @@
 #include "orbx_common.cuh"
 #include <cuda_pipeline.h>
 #include "tma.cuh"
+#include <cooperative_groups.h>
 
 // =================================================================================================
 // K1  pyr_resize: level l from level l-1 (chained, /root/reference/src/ORBextractor.cc:1826-1886),
@@ -162,5 +163,67 @@ k_pyr_resize_t(const __grid_constant__ CUtensorMap map_l0, const CUtensorMap* __
         const uint32_t out = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
         if (store) *reinterpret_cast<uint32_t*>(drow) = out;         // the (up to 3) bytes past dw land in row padding
         drow += dpitch;
+    }
+}
+
+// =================================================================================================
+// K1c  pyr_chain: all levels >= 1 of ONE frame in one launch, by one thread-block cluster of 8 CTAs (8192 threads).  The pyramid is a
+// chain (level l is resized from level l-1, /root/reference/src/ORBextractor.cc:1848), so a single frame costs 7 dependent launches
+// of a few microseconds each in the per-level forms -- launch-latency bound (31 us of the 118 us a 640 x 480 frame spends on the
+// device).  Here the dependency between levels is a cluster barrier (barrier.cluster arrive.release / wait.acquire, hardware-
+// supported on sm_90+) instead of a kernel boundary: the 8 CTAs of a cluster are co-scheduled on one GPC, write level l to global
+// memory (L2), synchronise, and read it back as the source of level l + 1.  Used for a handful of frames (one cluster per frame);
+// batches keep k_pyr_resize_t.  Arithmetic = k_pyr_resize_w's (word-load form), source reads bypass L1 (__ldcg): the lines were
+// written by other SMs during this launch.
+// =================================================================================================
+#define CHAIN_CTAS 8
+#define CHAIN_THREADS 1024
+struct ChainLevel { int sw, sh, spitch, dw, dh, dpitch; long long soff, doff; ResizeTabs t; };   // offsets inside one frame's pyramid block (level 1 reads the level-0 view)
+
+__global__ void __cluster_dims__(CHAIN_CTAS, 1, 1) __launch_bounds__(CHAIN_THREADS)
+k_pyr_chain(PyrView pv, int b0, const ChainLevel* __restrict__ lv, int L) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int b = b0 + (int)blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int gwarp = (int)blockIdx.x * (CHAIN_THREADS / 32) + (threadIdx.x >> 5), nwarps = CHAIN_CTAS * (CHAIN_THREADS / 32);
+    uint8_t* frame = pv.pyr + (long long)b * pv.pyr_fstride;
+    for (int l = 1; l < L; ++l) {
+        const ChainLevel c = lv[l];
+        const uint8_t* s = l == 1 ? pv.l0 + (long long)b * pv.l0_fstride : frame + c.soff;
+        const int spitch = l == 1 ? pv.l0_pitch : c.spitch;
+        uint8_t* d = frame + c.doff;
+        const int ngx = (c.dw + 3) >> 2, wc = (ngx + 31) >> 5, ntask = wc * c.dh;
+        const int wmax = (spitch >> 2) - 1;
+        for (int task = gwarp; task < ntask; task += nwarps) {
+            const int y = task / wc, gx = (task - y * wc) * 32 + lane;
+            if (gx < ngx) {
+                const int x = gx * 4;
+                const int sy0 = __ldg(c.t.yofs + y), sy1 = min(sy0 + 1, c.sh - 1);
+                const short2 bw = __ldg(c.t.yw + y);
+                const int2 e = __ldg(c.t.xg + gx);
+                const uint4 wq = __ldg(reinterpret_cast<const uint4*>(c.t.xw + x));
+                const int i0 = e.x >> 2, i1 = min(i0 + 1, wmax), i2 = min(i0 + 2, wmax);   // clamped words are never selected
+                const int sh8 = (e.x & 3) * 8;
+                const uint32_t s01 = (uint32_t)e.y & 0xFFFFu, s23 = (uint32_t)e.y >> 16;
+                int h[2][4];
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const uint32_t* row = reinterpret_cast<const uint32_t*>(s + (long long)(r ? sy1 : sy0) * spitch);
+                    const uint32_t a0 = __ldcg(row + i0), a1 = __ldcg(row + i1), a2 = __ldcg(row + i2);
+                    const uint32_t W0 = __funnelshift_r(a0, a1, sh8), W1 = __funnelshift_r(a1, a2, sh8);
+                    const uint32_t X01 = __byte_perm(W0, W1, s01), X23 = __byte_perm(W0, W1, s23);
+                    h[r][0] = (int)__dp2a_lo(wq.x, X01, 0u); h[r][1] = (int)__dp2a_hi(wq.y, X01, 0u);
+                    h[r][2] = (int)__dp2a_lo(wq.z, X23, 0u); h[r][3] = (int)__dp2a_hi(wq.w, X23, 0u);
+                }
+                uint32_t v[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    v[k] = (uint32_t)(((((int)bw.x * (h[0][k] >> 4)) >> 16) + (((int)bw.y * (h[1][k] >> 4)) >> 16) + 2) >> 2);
+                *reinterpret_cast<uint32_t*>(d + (long long)y * c.dpitch + x) = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
+            }
+        }
+        __threadfence();
+        cluster.sync();                                              // level l is complete and visible before any CTA of the cluster reads it
     }
 }

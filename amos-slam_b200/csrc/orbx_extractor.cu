@@ -77,6 +77,7 @@ struct orbx_extractor {
     CUtensorMap map_l0, map_l0_blur, map_l0_blur_s, map_l0_resize; const void* map_l0_sig[4] = {nullptr};                                // level-0 map of the current view (pointer, frame stride, pitch, frames)
     DevBuf<LevelGeom> d_levels; DevBuf<CellDesc> d_cells; DevBuf<BlurTile> d_tiles, d_tiles_s; DevBuf<int> d_tabs;
     std::vector<ResizeTabs> resize_tabs;
+    DevBuf<ChainLevel> d_chain; bool chain_ok = false;   // k_pyr_chain's level table (all levels in the word-load form)
     std::vector<int> resize_bw, resize_bh;           // TMA box of the source tile per destination level (k_pyr_resize_t); 0 = use the per-thread kernels
 
     // ---- per-batch device state (the "stateful extractor": pyramid stays resident) ----
@@ -93,7 +94,7 @@ struct orbx_extractor {
     PyrView view{}; bool have_pyramid = false, blur_valid = false;
     // single-frame operator(): the whole per-geometry chain (upload from a pinned staging frame, 7 resizes, FAST, quadtree, blur on the
     // second stream, orientation + descriptors, result gather, download) captured once as a CUDA graph and replayed per call
-    cudaGraphExec_t graph1 = nullptr; int graph_launches = 0; uint8_t* h_in = nullptr; size_t h_in_cap = 0; const void* graph_sig[26] = {nullptr};
+    cudaGraphExec_t graph1 = nullptr; int graph_launches = 0; uint8_t* h_in = nullptr; size_t h_in_cap = 0; const void* graph_sig[27] = {nullptr};
     // optional per-stage CUDA-event timing (bench.py's roofline): one event set per profiled call
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;     // ORBX_NSTAGES+1 events per call
@@ -262,6 +263,20 @@ static int build_plan(orbx_extractor* h, int rows, int cols) {
         h->resize_tabs[l].xg = reinterpret_cast<const int2*>(h->d_tabs.p + xg_off[l]);
         h->resize_tabs[l].wide = wide_ok[l];
     }
+    {   // k_pyr_chain: per-level geometry + tables in one device array
+        std::vector<ChainLevel> ch((size_t)L); std::memset(ch.data(), 0, sizeof(ChainLevel) * (size_t)L);
+        bool ok = L > 1;
+        for (int l = 1; l < L; ++l) {
+            ChainLevel& c = ch[l];
+            c.sw = lv[l - 1].w; c.sh = lv[l - 1].h; c.spitch = lv[l - 1].pitch; c.soff = lv[l - 1].off;
+            c.dw = lv[l].w; c.dh = lv[l].h; c.dpitch = lv[l].pitch; c.doff = lv[l].off; c.t = h->resize_tabs[l];
+            ok = ok && h->resize_tabs[l].wide;
+        }
+        if (h->d_chain.ensure((size_t)L)) return ORBX_E_CUDA;
+        CU_TRY(cudaMemcpyAsync(h->d_chain.p, ch.data(), sizeof(ChainLevel) * (size_t)L, cudaMemcpyHostToDevice, h->stream));
+        CU_TRY(cudaStreamSynchronize(h->stream));
+        h->chain_ok = ok;
+    }
     h->levels.swap(lv); h->cells.swap(cells); h->tiles.swap(tiles); h->tiles_s.swap(tiles_s); h->resize_bw.swap(rbw); h->resize_bh.swap(rbh);
     h->pyr_fstride = (off + 255) / 256 * 256;
     h->cand_per_frame = cand_off; h->kp_per_frame = kp_off;
@@ -370,7 +385,13 @@ static int run_detect(orbx_extractor* h, int b0, int B, bool fork_blur = false) 
     const size_t co = (size_t)b0 * h->cand_per_frame;
     { const int rc = fast_prepare(h); if (rc) return rc; }
     prof_mark(h);
-    for (int l = 1; l < L; ++l) {
+    static const int chain_env = [] { const char* e = std::getenv("ORBX_CHAIN"); return e ? std::atoi(e) : -1; }();
+    const bool chain = h->chain_ok && (h->view.l0_pitch & 3) == 0 && (chain_env > 0);
+    if (chain) {                                                     // a handful of frames: the whole chain in one launch, one 8-CTA cluster per frame
+        k_pyr_chain<<<dim3(CHAIN_CTAS, B), CHAIN_THREADS, 0, s>>>(h->view, b0, h->d_chain.p, L);
+        LAUNCH_CHECK();
+    }
+    for (int l = 1; l < L && !chain; ++l) {
         const LevelGeom& g = h->levels[l]; const LevelGeom& gp = h->levels[l - 1];
         const uint8_t* src; long long sfs; int sp;
         if (l == 1) { src = view.l0; sfs = view.l0_fstride; sp = view.l0_pitch; }
@@ -399,7 +420,7 @@ static int run_detect(orbx_extractor* h, int b0, int B, bool fork_blur = false) 
         // (4 cells per warp for throughput; a small batch would leave most SMs idle that way, so it gets one CTA per 4 cells: 148 SMs x 7 CTAs per wave)
         static const int cpw_env = [] { const char* e = std::getenv("ORBX_FAST_CPW"); int v = e ? std::atoi(e) : 0; return v < 0 ? 0 : v; }();
         const long long cells_total = (long long)ncells * B;
-        const int cpw = cpw_env ? cpw_env : (cells_total >= 16LL * 2072 ? 4 : (cells_total >= 8LL * 2072 ? 2 : 1));
+        const int cpw = cpw_env ? cpw_env : (cells_total >= 64LL * 2072 ? 8 : (cells_total >= 16LL * 2072 ? 4 : (cells_total >= 8LL * 2072 ? 2 : 1)));
         dim3 grid((ncells + FAST_WARPS * cpw - 1) / (FAST_WARPS * cpw), B);
         const int smem = h->fast_lay.per_warp * FAST_WARPS;
         { const int rc = fast_prepare(h); if (rc) return rc; }
@@ -542,7 +563,7 @@ static int extract_graph(orbx_extractor* h, const uint8_t* image, int rows, int 
     h->view.pyr = h->d_pyr.p; h->view.pyr_fstride = h->pyr_fstride;
     { const int rp = fast_prepare(h); if (rp) return rp; }    // tensor maps are built outside the capture
     // every buffer the captured nodes point at: any of them may have been re-allocated by another entry point since the capture
-    const void* sig[26] = {h->d_tmaps.p, h->d_tiles_s.p, h->d_l0.p, h->d_pyr.p, h->d_blur.p, h->d_slots.p, h->d_ocand.p, h->d_spk.p, h->d_skey.p, h->d_cell_counts.p, h->d_ncand.p, h->d_kp_level.p,
+    const void* sig[27] = {h->d_chain.p, h->d_tmaps.p, h->d_tiles_s.p, h->d_l0.p, h->d_pyr.p, h->d_blur.p, h->d_slots.p, h->d_ocand.p, h->d_spk.p, h->d_skey.p, h->d_cell_counts.p, h->d_ncand.p, h->d_kp_level.p,
                            h->d_kp_count.p, h->d_counts.p, h->d_overflow.p, h->d_kp_out.p, h->d_desc_out.p, h->d_gather.p, h->h_gather, h->h_in, h->d_levels.p, h->d_cells.p,
                            h->d_tiles.p, h->d_tabs.p, (const void*)(uintptr_t)pitch, (const void*)(uintptr_t)blk};
     if (h->graph1 && std::memcmp(sig, h->graph_sig, sizeof(sig)) != 0) { cudaGraphExecDestroy(h->graph1); h->graph1 = nullptr; }
@@ -663,7 +684,7 @@ void orbx_destroy(orbx_extractor* h) {
     for (cudaEvent_t e : h->ev_h2d) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_done) cudaEventDestroy(e);
     h->d_l0.release();
-    h->d_tmaps.release(); h->d_levels.release(); h->d_cells.release(); h->d_tiles.release(); h->d_tiles_s.release(); h->d_tabs.release();
+    h->d_chain.release(); h->d_tmaps.release(); h->d_levels.release(); h->d_cells.release(); h->d_tiles.release(); h->d_tiles_s.release(); h->d_tabs.release();
     h->d_pyr.release(); h->d_blur.release(); h->d_slots.release(); h->d_ocand.release(); h->d_spk.release(); h->d_kp_level.release();
     h->d_skey.release(); h->d_cell_counts.release(); h->d_ncand.release(); h->d_kp_count.release(); h->d_counts.release();
     h->d_level_counts.release(); h->d_overflow.release(); h->d_kp_out.release(); h->d_desc_out.release();
