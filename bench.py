@@ -650,6 +650,21 @@ def reference_pairs(args, defP):
     print(json.dumps(line))
 
 
+def spread_device(local_rank, world):
+    """Device of a rank when the box shows MORE GPUs than there are ranks: alternate between the lower and the upper half of the index
+    range instead of taking 0 .. world-1.  Boards group GPUs by PCIe switch in index order, and on this pool GPUs 0-3 share one host
+    uplink (4 GPUs: 116 GB/s together, profiles/r02d_h2d_matrix.jsonl) while 0,1,4,5 or 4-7 reach 4 x 55 GB/s -- the end-to-end figure
+    at N = 2 / 4 is bound by exactly that link.  With as many ranks as GPUs (or fewer visible devices) this is the identity."""
+    try:
+        import torch
+        n = torch.cuda.device_count()
+    except Exception:
+        return local_rank
+    if n <= world or n < 2 or local_rank // 2 >= n // 2:
+        return local_rank
+    return (local_rank % 2) * (n // 2) + local_rank // 2
+
+
 def bind_to_gpu_numa_node(index):
     """Pin this process to the CPUs that are local to GPU `index` (its PCIe root's NUMA node) BEFORE the pinned host buffers are
     allocated, so first-touch places them on the right socket: with 8 ranks feeding 8 GPUs, frames crossing the inter-socket link
@@ -697,6 +712,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-pointer leg (the line is then not a bench value)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); local_rank = int(os.environ.get("LOCAL_RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl != "reference":
+        local_rank = spread_device(local_rank, world)            # every use below is "the CUDA device of this rank"
     global WIDTH, HEIGHT, NFEAT, WORKLOAD, METRIC, MASKED
     if args.workload in PAIR_WORKLOADS:
         WIDTH, HEIGHT, NFEAT, defP, WORKLOAD, METRIC = PAIR_WORKLOADS[args.workload]
@@ -710,6 +727,7 @@ def main():
     N, K, W, B = args.gpus, args.steps, max(args.warmup, 0), (args.batch or defB)
     config = {"workload": WORKLOAD, "frame": [WIDTH, HEIGHT], "nfeatures": NFEAT, "frames_per_gpu_per_step": B,
               "parallelism": "frames sharded over %d GPU(s), no collective; %d extractor handles (streams) per GPU sharing the step's frames evenly" % (N, max(1, args.streams)),
+              "device_map": "rank r -> CUDA device %s" % ("r" if spread_device(1, world) == 1 else "(r % 2) * (visible / 2) + r // 2: ranks spread over both halves of the board (GPUs 0-3 share a host uplink)"),
               "l2_policy": "working set per step (%.0f MB of frames, ~%.1f GB of pyramid+scratch) exceeds the 126 MB L2" % (B * WIDTH * HEIGHT / 1e6, B * 6.3e-3 * WIDTH * HEIGHT / 307200.0)}
 
     if args.impl == "reference":

@@ -24,7 +24,7 @@ KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4
                      ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
 assert KP_DTYPE.itemsize == 28
 
-PORT_SOURCES = ["port/orb_port.cpp", "port/match_port.cpp", "port/bow_port.cpp"]
+PORT_SOURCES = ["port/orb_port.cpp", "port/match_port.cpp", "port/bow_port.cpp", "port/slic_port.cpp"]
 
 
 def build_port(force=False):
@@ -551,3 +551,31 @@ def distinctive_descriptors(kind, offsets, obs_desc, kf_of=None, kf_bad=None):
     f = lib.port_distinctive_descriptors; f.restype = None; f.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     f(n, off.ctypes.data, d.ctypes.data, best.ctypes.data)
     return best[:n]
+
+
+# ---- SLIC stage of `cluster` (src/cluster.cc): Lab image in (cv2.cvtColor is the input boundary), labels + centres out ----
+def slic(kind, lab, depth, length=5, m=10):
+    """labels (rows x cols float64, the reference's CV_64F labelMask) and centres (n x 7 int32: x, y, L, A, B, D, label)."""
+    lib = _lib(kind)
+    f = getattr(lib, kind + "_slic")
+    lab = np.ascontiguousarray(lab, np.uint8); depth = np.ascontiguousarray(depth, np.uint16)
+    rows, cols = depth.shape
+    assert lab.shape == (rows, cols, 3)
+    cap = ((rows + length - 1) // length) * ((cols + length - 1) // length)
+    labels = np.zeros((rows, cols), np.float64); centers = np.zeros((cap, 7), np.int32); n = C.c_int(0)
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+    rc = f(lab.ctypes.data, depth.ctypes.data, rows, cols, length, m, labels.ctypes.data, centers.ctypes.data, cap, C.byref(n))
+    assert rc == 0
+    return labels, centers[:n.value].copy()
+
+
+def slic_kmeans_ref(centers, seeds):
+    """k-means of the centres with explicit seed indices (canonical-seed contract): cluster id per centre."""
+    lib = _lib("ref")
+    centers = np.ascontiguousarray(centers, np.int32); seeds = np.ascontiguousarray(seeds, np.int32)
+    ids = np.zeros(len(centers), np.int32)
+    lib.ref_slic_kmeans.restype = C.c_int
+    lib.ref_slic_kmeans.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    assert lib.ref_slic_kmeans(centers.ctypes.data, len(centers), seeds.ctypes.data, len(seeds), ids.ctypes.data) == 0
+    return ids

@@ -42,15 +42,20 @@ typedef unsigned short ushort;
 
 #define CV_PI 3.1415926535897932384626433832795
 
-// ---- type codes (depth | (cn-1)<<3), single channel only ------------------------------------
+// ---- type codes (depth | (cn-1)<<3).  The ORB path is single channel; the SLIC stage (src/cluster.cc) adds 3-channel 8U / 64F --------
 enum { CV_8U = 0, CV_8S = 1, CV_16U = 2, CV_16S = 3, CV_32S = 4, CV_32F = 5, CV_64F = 6 };
 #define CV_8UC1 0
 #define CV_32FC1 5
 #define CV_64FC1 6
-static inline int cvl_elem_size(int type) {
+#define CV_16UC1 2
+#define CV_8UC3 (0 + (2 << 3))
+#define CV_64FC3 (6 + (2 << 3))
+static inline int cvl_channels(int type) { return ((type >> 3) & 63) + 1; }
+static inline int cvl_elem_size1(int type) {
     switch (type & 7) { case CV_8U: case CV_8S: return 1; case CV_16U: case CV_16S: return 2;
                         case CV_32S: case CV_32F: return 4; default: return 8; }
 }
+static inline int cvl_elem_size(int type) { return cvl_elem_size1(type) * cvl_channels(type); }
 
 enum { INTER_NEAREST = 0, INTER_LINEAR = 1 };
 enum { BORDER_CONSTANT = 0, BORDER_REPLICATE = 1, BORDER_REFLECT = 2, BORDER_WRAP = 3,
@@ -144,6 +149,7 @@ public:
     Mat() : rows(0), cols(0), data(nullptr), step(0), datastart(nullptr), dataend(nullptr), mtype(CV_8U) {}
     Mat(int r, int c, int type) : Mat() { create(r, c, type); }
     Mat(Size sz, int type) : Mat() { create(sz.height, sz.width, type); }
+    Mat(int r, int c, int type, const Scalar& s) : Mat() { create(r, c, type); for (int y = 0; y < rows; ++y) for (int x = 0; x < cols; ++x) for (int k = 0; k < channels(); ++k) setd(y, x * channels() + k, s.val[k]); }
     Mat(int r, int c, int type, void* ext, size_t _step = 0) : rows(r), cols(c), data((uchar*)ext), mtype(type) {
         step = _step ? _step : (size_t)c * cvl_elem_size(type);
         datastart = data; dataend = data + step * r;
@@ -170,9 +176,9 @@ public:
     void release() { buf.reset(); data = datastart = dataend = nullptr; rows = cols = 0; step = 0; }
     int type() const { return mtype; }
     int depth() const { return mtype & 7; }
-    int channels() const { return 1; }
+    int channels() const { return cvl_channels(mtype); }
     size_t elemSize() const { return (size_t)cvl_elem_size(mtype); }
-    size_t elemSize1() const { return elemSize(); }
+    size_t elemSize1() const { return (size_t)cvl_elem_size1(mtype); }
     size_t step1() const { return step / elemSize(); }
     bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
     bool isContinuous() const { return step == (size_t)cols * elemSize(); }
@@ -217,7 +223,7 @@ public:
     Mat(const MatExpr& e) : Mat() { *this = e; }
     Mat& operator=(const MatExpr& e) {
         create(e.rows, e.cols, e.type);      // no-op (keeps storage, incl. ROI views) when size/type already match
-        for (int y = 0; y < rows; ++y) for (int x = 0; x < cols; ++x) setd(y, x, e.eye ? (x == y ? e.fill : 0.0) : e.fill);
+        for (int y = 0; y < rows; ++y) for (int x = 0; x < cols * channels(); ++x) setd(y, x, e.eye ? (x == y ? e.fill : 0.0) : e.fill);
         return *this;
     }
 
@@ -736,6 +742,50 @@ static inline void cvl_morph(const Mat& src, Mat& dst, const Mat& kernel, bool i
 }
 static inline void dilate(InputArray src, OutputArray dst, InputArray kernel) { Mat s = src.getMat(), k = kernel.getMat(); dst.create(s.rows, s.cols, s.type()); Mat d = dst.getMat(); cvl_morph(s, d, k, true); }
 static inline void erode(InputArray src, OutputArray dst, InputArray kernel) { Mat s = src.getMat(), k = kernel.getMat(); dst.create(s.rows, s.cols, s.type()); Mat d = dst.getMat(); cvl_morph(s, d, k, false); }
+
+// ---- SLIC stage of the reference (src/cluster.cc:295-320): cvtColor(BGR2Lab) / Sobel(CV_64F, ksize 3) / addWeighted -----------------
+// cvtColor(COLOR_BGR2Lab) on 8-bit data is OpenCV's trilinear 33^3 LUT built with its own softfloat: NOT restated.  It is the input
+// boundary of the SLIC oracle: the harness computes the Lab image with the real OpenCV (cv2, fixtures under tests/golden/) and hands
+// it in through this hook; a call without a hook aborts rather than inventing numbers.
+enum { COLOR_BGR2Lab = 44 };
+typedef void (*cvl_bgr2lab_hook_t)(const Mat& bgr, Mat& lab);
+static inline cvl_bgr2lab_hook_t& cvl_bgr2lab_hook() { static thread_local cvl_bgr2lab_hook_t h = nullptr; return h; }
+static inline void cvtColor(InputArray src, OutputArray dst, int code) {
+    Mat s = src.getMat();
+    if (code != COLOR_BGR2Lab || !cvl_bgr2lab_hook()) { std::cerr << "cvlite::cvtColor: only COLOR_BGR2Lab through the harness hook\n"; std::abort(); }
+    dst.create(s.rows, s.cols, CV_8UC3);
+    Mat d = dst.getMat();
+    cvl_bgr2lab_hook()(s, d);
+}
+static inline int cvl_reflect101(int p, int len) { if (len == 1) return 0; while (p < 0 || p >= len) p = p < 0 ? -p : 2 * len - 2 - p; return p; }
+// cv::Sobel(src 8U, dst, CV_64F, dx, dy, 3): separable [-1 0 1] x [1 2 1], BORDER_REFLECT_101, every channel on its own; integers, exact in double
+static inline void Sobel(InputArray src_, OutputArray dst_, int ddepth, int dx, int dy, int ksize = 3, double scale = 1, double delta = 0, int border = BORDER_DEFAULT) {
+    Mat src = src_.getMat();
+    assert(ddepth == CV_64F && ksize == 3 && src.depth() == CV_8U && scale == 1 && delta == 0 && border == BORDER_DEFAULT && dx + dy == 1);
+    const int cn = src.channels();
+    dst_.create(src.rows, src.cols, CV_64F + ((cn - 1) << 3));
+    Mat dst = dst_.getMat();
+    static const int D[3] = {-1, 0, 1}, Sm[3] = {1, 2, 1};
+    const int* kx = dx ? D : Sm; const int* ky = dy ? D : Sm;
+    for (int y = 0; y < src.rows; ++y) for (int x = 0; x < src.cols; ++x) for (int c = 0; c < cn; ++c) {
+        int acc = 0;
+        for (int i = -1; i <= 1; ++i) { const uchar* row = src.ptr(cvl_reflect101(y + i, src.rows));
+            for (int j = -1; j <= 1; ++j) acc += ky[i + 1] * kx[j + 1] * (int)row[cvl_reflect101(x + j, src.cols) * cn + c]; }
+        dst.ptr<double>(y)[x * cn + c] = (double)acc;
+    }
+}
+// cv::addWeighted on CV_64F: dst = a*alpha + b*beta + gamma (OpenCV's scalar loop order)
+static inline void addWeighted(InputArray a_, double alpha, InputArray b_, double beta, double gamma, OutputArray dst_) {
+    Mat a = a_.getMat(), b = b_.getMat();
+    assert(a.type() == b.type() && a.depth() == CV_64F && a.rows == b.rows && a.cols == b.cols);
+    Mat out(a.rows, a.cols, a.type());
+    const int n = a.cols * a.channels();
+    for (int y = 0; y < a.rows; ++y) { const double* pa = a.ptr<double>(y); const double* pb = b.ptr<double>(y); double* po = out.ptr<double>(y);
+        for (int x = 0; x < n; ++x) po[x] = pa[x] * alpha + pb[x] * beta + gamma; }
+    dst_.create(a.rows, a.cols, a.type());
+    Mat d = dst_.getMat();
+    out.copyTo(d);
+}
 
 // ---- KeyPointsFilter::retainBest: only referenced from dead code (ComputeKeyPointsOld) ------
 struct KeyPointsFilter {

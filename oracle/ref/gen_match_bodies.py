@@ -11,6 +11,7 @@ output -- nothing is copied into the repository).  The functions are located by 
   src/KeyFrame.cc   : GetFeaturesInArea, IsInImage
   src/MapPoint.cc   : ComputeDistinctiveDescriptors
   Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h : transform(features, BowVector, FeatureVector, levelsup), transform(feature, ...)
+  src/cluster.cc    : clustering, updateCenter, initilizeCenters, fituneCenter, SLIC, initClusterAssment, loadDataSet, distEclud, kmeans
   src/Frame.cc      : AssignFeaturesToGrid, GetFeaturesInArea, PosInGrid, ComputeStereoMatches,
                       UndistortKeyPoints, ComputeImageBounds, ComputeStereoFromRGBD
 
@@ -92,7 +93,20 @@ b = extract("Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h", [
     "void TemplatedVocabulary<TDescriptor,F>::transform(const TDescriptor &feature, \n  WordId &word_id, WordValue &weight, NodeId *nid, int levelsup) const",
 ])
 b = b.replace("void TemplatedVocabulary<TDescriptor,F>::transform(", "template<class TDescriptor, class F>\nvoid TemplatedVocabulary<TDescriptor,F>::transform(")
+# SLIC stage of `cluster` (the k-means that follows seeds itself with rand(): canonical-seed contract, see oracle/ref/ref_slic_capi.cpp)
+sl = extract("src/cluster.cc", [
+    "int cluster::clustering(const cv::Mat &imageLAB,const cv::Mat &DepthImage, cv::Mat &DisMask, cv::Mat &labelMask,",
+    "int cluster::updateCenter(cv::Mat &imageLAB, cv::Mat &labelMask,cv::Mat const &Depth,std::vector<center> &centers, int len)",
+    "int cluster::initilizeCenters(cv::Mat &imageLAB,cv::Mat const &imagedepth, std::vector<center> &centers, int len)",
+    "int cluster::fituneCenter(cv::Mat &imageLAB, cv::Mat &sobelGradient, std::vector<center> &centers)",
+    "int cluster::SLIC(cv::Mat const &image,cv::Mat const &image_D, cv::Mat &resultLabel, std::vector<center> &centers, int len, int m)",
+    "void cluster::initClusterAssment()",
+    "void cluster::loadDataSet(vector<center> &centers)",
+    "double cluster::distEclud(center &v1 ,center &v2)",
+    "void cluster::kmeans()",
+])
 os.makedirs(out, exist_ok=True)
+open(os.path.join(out, "ref_slic_bodies.inc"), "w").write("// GENERATED from the reference sources by oracle/ref/gen_match_bodies.py -- do not commit\n" + sl)
 open(os.path.join(out, "ref_bow_bodies.inc"), "w").write("// GENERATED from the reference sources by oracle/ref/gen_match_bodies.py -- do not commit\n" + b)
 # the first ORBmatcher chunk (constants) ends at the ctor's closing brace because the ctor follows immediately
 open(os.path.join(out, "ref_match_bodies.inc"), "w").write("// GENERATED from the reference sources by oracle/ref/gen_match_bodies.py -- do not commit\n" + m + "\n" + f + "\n" + kf + "\n" + mp)
