@@ -22,7 +22,7 @@ LIB_PATH = os.path.join(HERE, "liborbx_b200.so")
 CSRC = os.path.join(HERE, "csrc")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177"]
-SOURCES = ["orbx_extractor.cu", "orbx_matcher.cu", "orbx_pool.cu"]
+SOURCES = ["orbx_extractor.cu", "orbx_matcher.cu", "orbx_pool.cu", "orbx_slic.cu"]
 
 KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
                      ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
@@ -101,6 +101,9 @@ def lib():
     L.orbx_extract_masked_batch_device.argtypes = [vp, vp, vp, ci, ci, ci, sz, sz, sz, sz, vp, vp, ci, vp, vp]
     L.orbx_extract_masked_batch_labels.argtypes = [vp, vp, vp, vp, ci, ci, ci, sz, sz, sz, sz, vp, vp, ci, vp, vp]
     L.orbx_extract_masked_batch_labels_device.argtypes = [vp, vp, vp, vp, ci, ci, ci, sz, sz, sz, sz, vp, vp, ci, vp, vp]
+    L.orbx_slic_create.argtypes = [ci, C.POINTER(vp)]
+    L.orbx_slic_destroy.argtypes = [vp]; L.orbx_slic_destroy.restype = None
+    L.orbx_slic_run.argtypes = [vp, vp, sz, vp, sz, ci, ci, ci, ci, ci, vp, sz, vp, sz, vp, ci, C.POINTER(ci)]
     L.orbx_pool_shard_of.argtypes = [ci, ci, ci, C.POINTER(ci), C.POINTER(ci)]
     L.orbx_pool_create.argtypes = [ci, cf, ci, ci, ci, ci, vp, ci, C.POINTER(vp)]
     L.orbx_pool_destroy.argtypes = [vp]; L.orbx_pool_destroy.restype = None
@@ -451,3 +454,40 @@ class ExtractorPool:
 
 
 from ._matcher import ORBmatcher, FrameView, Frame, Camera, ORBVocabulary  # noqa: E402,F401
+
+
+SLIC_CENTER_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("L", "<i4"), ("A", "<i4"), ("B", "<i4"), ("D", "<i4"), ("label", "<i4")])
+
+
+class cluster:
+    """SLIC stage of ORB_SLAM2::cluster (/root/reference/include/cluster.h:33-83, src/cluster.cc:295-344) on the GPU.
+
+    ``SLIC(lab, depth)`` takes the Lab image the reference obtains from cv::cvtColor(image, COLOR_BGR2Lab) (the conversion stays with
+    the caller's OpenCV) and returns (labelMask as float64, centres) exactly as the reference's SLIC() leaves them; ``labels16=True``
+    returns the labels as uint16 ids instead, the form ORBextractor.extract_masked_batch takes."""
+
+    def __init__(self, device=0, length=5, m=10, rounds=5):
+        self._lib = lib(); self._h = C.c_void_p()
+        self.len, self.m, self.rounds = int(length), int(m), int(rounds)
+        _check(self._lib.orbx_slic_create(int(device), C.byref(self._h)))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._lib.orbx_slic_destroy(self._h); self._h = None
+        except Exception:
+            pass
+
+    def SLIC(self, lab, depth, labels16=False):
+        lab = np.ascontiguousarray(lab, np.uint8); depth = np.ascontiguousarray(depth, np.uint16)
+        rows, cols = depth.shape
+        if lab.shape != (rows, cols, 3):
+            raise OrbxError(E_INVALID, "lab must be rows x cols x 3")
+        cap = (rows // self.len + 1) * (cols // self.len + 1)
+        centers = np.zeros(cap, SLIC_CENTER_DTYPE); n = C.c_int(0)
+        l64 = None if labels16 else np.zeros((rows, cols), np.float64)
+        l16 = np.zeros((rows, cols), np.uint16) if labels16 else None
+        _check(self._lib.orbx_slic_run(self._h, _ptr(lab), cols * 3, _ptr(depth), cols * 2, rows, cols, self.len, self.m, self.rounds,
+                                       _ptr(l64) if l64 is not None else None, cols * 8, _ptr(l16) if l16 is not None else None, cols * 2,
+                                       _ptr(centers), cap, C.byref(n)))
+        return (l16 if labels16 else l64), centers[:n.value].copy()

@@ -213,6 +213,26 @@ int  orbx_pool_submit_batch(orbx_pool* p, int seq_id, const uint8_t* images, con
 int  orbx_pool_wait(orbx_pool* p, long long ticket);
 int  orbx_pool_wait_all(orbx_pool* p);
 
+/* ------------------------------------------------------------------------------------------------
+ * SLIC super-pixels of `cluster` (src/cluster.cc:88-344): the label map MovingKeyPoints reads
+ * (src/ORBextractor.cc:1722-1736) and the centres the reference's k-means groups afterwards.
+ *   lab       rows x cols x 3, 8-bit: cv::cvtColor(image, COLOR_BGR2Lab) -- the conversion stays with the caller's OpenCV
+ *             (src/cluster.cc:305), everything after it (Sobel gradient, initilizeCenters, fituneCenter, `rounds` x clustering +
+ *             updateCenter) runs on the device and returns what the reference's SLIC() returns, bit for bit;
+ *   depth     rows x cols, 16-bit (imD); only feeds the centres' D field;
+ *   len, m    super-pixel size and compactness (the reference passes 5 and 10, :12-14), rounds = 5 (:330);
+ *   labels_out   rows x cols doubles = the reference's CV_64F labelMask (label = centre number from 1, 0 = never covered), may be NULL;
+ *   labels16_out the same as 16-bit ids -- the form orbx_extract_masked_batch_labels takes -- may be NULL (E_INVALID if > 65535 centres);
+ *   centers_out  n records {x, y, L, A, B, D, label} (struct center, include/cluster.h:22-31, without the k-means id), may be NULL.
+ * Steps are in BYTES.  *n_out = number of centres (also on E_CAPACITY).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct orbx_slic orbx_slic;
+typedef struct orbx_slic_center { int x, y, L, A, B, D, label; } orbx_slic_center;
+int  orbx_slic_create(int device, orbx_slic** out);
+void orbx_slic_destroy(orbx_slic* h);
+int  orbx_slic_run(orbx_slic* h, const uint8_t* lab, size_t lab_step, const uint16_t* depth, size_t depth_step, int rows, int cols, int len, int m, int rounds,
+                   double* labels_out, size_t labels_step, uint16_t* labels16_out, size_t labels16_step, orbx_slic_center* centers_out, int cap, int* n_out);
+
 /* ================================================================================================
  * ORBmatcher  (include/ORBmatcher.h:57-215, src/ORBmatcher.cc)
  * ================================================================================================ */

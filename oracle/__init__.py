@@ -579,3 +579,14 @@ def slic_kmeans_ref(centers, seeds):
     lib.ref_slic_kmeans.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
     assert lib.ref_slic_kmeans(centers.ctypes.data, len(centers), seeds.ctypes.data, len(seeds), ids.ctypes.data) == 0
     return ids
+
+
+def slic_gradient_ref(lab):
+    """cvlite's Sobel(CV_64F, 0/1, 1/0, 3) + addWeighted(0.5, 0.5) as the reference's SLIC() calls them."""
+    lib = _lib("ref")
+    lab = np.ascontiguousarray(lab, np.uint8)
+    out = np.zeros(lab.shape, np.float64)
+    lib.ref_slic_gradient.restype = C.c_int
+    lib.ref_slic_gradient.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    assert lib.ref_slic_gradient(lab.ctypes.data, lab.shape[0], lab.shape[1], out.ctypes.data) == 0
+    return out

@@ -45,6 +45,15 @@ int ref_slic(const uint8_t* lab, const uint16_t* depth, int rows, int cols, int 
     }
     return 0;
 }
+// the gradient image SLIC() builds (:308-312) through cvlite's Sobel / addWeighted: rows x cols x 3 doubles (pinned against cv2 by tests/test_oracle_slic.py)
+int ref_slic_gradient(const uint8_t* lab, int rows, int cols, double* out) {
+    cv::Mat imageLAB(rows, cols, CV_8UC3, (void*)lab), sx, sy, grad;
+    cv::Sobel(imageLAB, sx, CV_64F, 0, 1, 3);
+    cv::Sobel(imageLAB, sy, CV_64F, 1, 0, 3);
+    cv::addWeighted(sx, 0.5, sy, 0.5, 0, grad);
+    for (int y = 0; y < rows; ++y) std::memcpy(out + (size_t)y * cols * 3, grad.ptr<double>(y), sizeof(double) * cols * 3);
+    return 0;
+}
 // k-means of the super-pixel centres with explicit seeds (indices into centres, each with D > 0 as the reference's loop demands).
 // ids_out[i] = cluster index of centre i (what the reference stores into centers[label - 1].id, src/cluster.cc:20-27).
 int ref_slic_kmeans(const int* centers_in, int n, const int* seeds, int k, int* ids_out) {

@@ -89,7 +89,7 @@ def test_host_sources_parse_against_the_reference_headers(tmp_path):
     (inc / "Frame.h").write_text(fh)
     flags = ["g++", "-std=c++11", "-fsyntax-only", "-w", "-DORBX_B200", "-I" + str(inc), "-I" + HOST, "-I" + os.path.join(ROOT, "tests", "host", "realhdr"),
              "-I" + os.path.join(ROOT, "oracle", "shim"), "-I" + REFERENCE, "-I" + os.path.join(ROOT, "include")]
-    for src in ("ORBextractor.cc", "ORBmatcher_b200.cc", "Frame_b200.cc", "BoW_b200.cc"):
+    for src in ("ORBextractor.cc", "ORBmatcher_b200.cc", "Frame_b200.cc", "BoW_b200.cc", "cluster_b200.cc"):
         r = subprocess.run(flags + [os.path.join(HOST, src)], capture_output=True, text=True)
         assert r.returncode == 0, src + ":\n" + r.stderr[-3000:]
     # and the declarations the bodies implement are the reference's: ORBmatcher.h is used UNMODIFIED
