@@ -127,6 +127,7 @@ def lib():
         L.orbx_descriptor_distance.argtypes = [vp, vp, vp, ci, vp]
         L.orbx_search_for_initialization.argtypes = [vp, vp, vp, vp, vp, ci, C.POINTER(ci)]
         L.orbx_search_by_projection_frame.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp, vp, vp, vp, cf, ci, ci, cf, vp, C.POINTER(ci)]
+        L.orbx_search_by_projection_frame_pose.argtypes = [vp, vp, vp, ci, vp, vp, vp, vp, cf, cf, cf, cf, vp, vp, vp, vp, vp, cf, ci, ci, cf, vp, C.POINTER(ci), vp, vp, vp]
         L.orbx_search_by_projection_points.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp, vp, vp, cf, vp, C.POINTER(ci)]
         L.orbx_search_by_projection_keyframe.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp, vp, cf, ci, vp, C.POINTER(ci)]
         L.orbx_search_by_projection_keyframe_points.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp, cf, vp, C.POINTER(ci)]

@@ -307,6 +307,26 @@ class ORBmatcher:
         cm[cm == -2] = -1
         return nm.value, cm
 
+    # the same with the projection on the device: world points + pose of CurrentFrame instead of (u, v, 1/z)  (ORBmatcher.cc:1597-1623)
+    def SearchByProjectionFramePose(self, cur, world_xyz, has_point, Rcw, tcw, fx, fy, cx, cy, last_octave, last_angle, mp_desc, mp_observed, cur_occupied, th,
+                                    forward=False, backward=False, mbf=0.0, taps=False):
+        w = np.ascontiguousarray(world_xyz, np.float32).reshape(-1, 3); hp = _u8(has_point)
+        R = np.ascontiguousarray(Rcw, np.float32).reshape(9); t = np.ascontiguousarray(tcw, np.float32).reshape(3)
+        lo = np.ascontiguousarray(last_octave, np.int32); la = np.ascontiguousarray(last_angle, np.float32)
+        d, ob, oc = _u8(mp_desc), _u8(mp_observed), _u8(cur_occupied)
+        cm = np.zeros(len(cur.keys), np.int32); nm = C.c_int()
+        uv = np.zeros((len(w), 2), np.float32); iz = np.zeros(len(w), np.float32); va = np.zeros(len(w), np.uint8)
+        if isinstance(cur, Frame):
+            view, dev = None, cur._h
+        else:
+            v = cur.c(); view, dev = C.byref(v), None
+        self._check(self._lib.orbx_search_by_projection_frame_pose(self._h, view, dev, len(w), _p(w), _p(hp), _p(R), _p(t), float(fx), float(fy), float(cx), float(cy),
+                                                                   _p(lo), _p(la), _p(d), _p(ob), _p(oc), float(th), int(forward), int(backward), float(mbf), _p(cm), C.byref(nm),
+                                                                   _p(uv) if taps else None, _p(iz) if taps else None, _p(va) if taps else None))
+        self.last_raw_match = cm.copy()
+        cm[cm == -2] = -1
+        return (nm.value, cm, uv, iz, va) if taps else (nm.value, cm)
+
     # int SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const set<MapPoint*> &sAlreadyFound, const float th, const int ORBdist)
     def SearchByProjectionKeyFrame(self, cur, proj_uv, predicted_level, kf_angle, mp_desc, valid, cur_occupied, th, ORBdist):
         uv = np.ascontiguousarray(proj_uv, np.float32); lv = np.ascontiguousarray(predicted_level, np.int32); an = np.ascontiguousarray(kf_angle, np.float32)

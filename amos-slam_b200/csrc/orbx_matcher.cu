@@ -493,13 +493,41 @@ retry:
     return ORBX_OK;
 }
 
+// x3Dc = Rcw * x3Dw + tcw, invzc = 1.0 / z, (u, v) = (fx xc invzc + cx, fy yc invzc + cy)  (ORBmatcher.cc:1608-1623) for every feature of the
+// last frame that has a usable map point.  The product is evaluated as cv::gemm does for a 3 x 3 by 3 x 1 float matrix -- hand-unrolled
+// FLOAT arithmetic ((r0 x + r1 y) + r2 z), then + t (pinned against cv2.gemm of OpenCV 4.13 by the gemm_3x3_3x1_c fixtures under tests/golden) -- with every
+// operation individually rounded; 1.0 / z is the double division the reference's literal asks for, rounded to float.
+struct ProjPose { float R[9], t[3], fx, fy, cx, cy; };
+__global__ void k_project_frame(int n, const float* __restrict__ xyz, const uint8_t* __restrict__ has, ProjPose P, float min_x, float max_x, float min_y, float max_y,
+                                float* __restrict__ uv, float* __restrict__ iz, uint8_t* __restrict__ valid) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float u = 0.f, v = 0.f, invzc = 0.f; uint8_t ok = 0;
+    if (has[i]) {
+        const float x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+        const float xc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(P.R[0], x), __fmul_rn(P.R[1], y)), __fmul_rn(P.R[2], z)), P.t[0]);
+        const float yc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(P.R[3], x), __fmul_rn(P.R[4], y)), __fmul_rn(P.R[5], z)), P.t[1]);
+        const float zc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(P.R[6], x), __fmul_rn(P.R[7], y)), __fmul_rn(P.R[8], z)), P.t[2]);
+        invzc = __double2float_rn(__ddiv_rn(1.0, (double)zc));
+        if (!(invzc < 0)) {
+            u = __fadd_rn(__fmul_rn(__fmul_rn(P.fx, xc), invzc), P.cx);
+            v = __fadd_rn(__fmul_rn(__fmul_rn(P.fy, yc), invzc), P.cy);
+            ok = !(u < min_x || u > max_x || v < min_y || v > max_y);
+        }
+        if (!ok) { u = 0.f; v = 0.f; invzc = 0.f; }
+    }
+    uv[2 * i] = u; uv[2 * i + 1] = v; iz[i] = invzc; valid[i] = ok;
+}
+struct ProjPoseArgs { const float* world; const uint8_t* has; ProjPose P; float* uv_out; float* invz_out; uint8_t* valid_out; };
+
 static int search_proj_frame_impl(orbx_matcher* m, const FrameArg cur, int n_last, const float* proj_uv, const float* proj_invz,
                                     const int* last_octave, const float* last_angle, const uint8_t* mp_desc, const uint8_t* valid, const uint8_t* mp_observed,
                                     const uint8_t* cur_occupied, float th, int forward, int backward, float mbf, int* cur_match, int* nmatches,
-                                  int max_dist = M_TH_HIGH, int no_ur = 0, int check_ori = -1 /* -1: the matcher's own setting */) {
+                                  int max_dist = M_TH_HIGH, int no_ur = 0, int check_ori = -1 /* -1: the matcher's own setting */, const ProjPoseArgs* pose = nullptr) {
     if (!m || !nmatches) FAIL(ORBX_E_INVALID, "null argument");
     int rc;
     if ((rc = check_frame_arg(m, cur))) return rc;
+    if (pose) { if (n_last && (!pose->world || !pose->has)) FAIL(ORBX_E_INVALID, "bad arguments"); proj_uv = pose->world; proj_invz = pose->world; valid = pose->has; }   // (validated below as "present")
     if (n_last < 0 || n_last >= (1 << 20) || (n_last && (!proj_uv || !proj_invz || !last_octave || !last_angle || !mp_desc || !valid)) || (cur.n() && !cur_match))
         FAIL(ORBX_E_INVALID, "bad arguments");
     *nmatches = 0;
@@ -513,11 +541,20 @@ retry:
     FrameDev dc; uint32_t* skc;
     if ((rc = stage_frame(m, cur, dc, skc))) return rc;
     float *uv, *iz, *la; int* lo; uint8_t *dd, *va, *ob = nullptr, *oc = nullptr;
-    if ((rc = up(m, proj_uv, (size_t)n_last * 2, uv)) || (rc = up(m, proj_invz, (size_t)n_last, iz)) || (rc = up(m, last_angle, (size_t)n_last, la)) ||
-        (rc = up(m, last_octave, (size_t)n_last, lo)) || (rc = up(m, mp_desc, (size_t)n_last * 32, dd)) || (rc = up(m, valid, (size_t)n_last, va))) return rc;
+    float* wxyz = nullptr; uint8_t* whas = nullptr;
+    if (pose) {                                                       // the projection itself runs on the device: upload world points, not (u, v)
+        uv = m->arena.get<float>((size_t)n_last * 2 + 2); iz = m->arena.get<float>((size_t)n_last + 1); va = m->arena.get<uint8_t>((size_t)n_last + 16);
+        if (!uv || !iz || !va) FAIL(ORBX_E_CUDA, "matcher arena exhausted");
+        if ((rc = up(m, pose->world, (size_t)n_last * 3, wxyz)) || (rc = up(m, pose->has, (size_t)n_last, whas))) return rc;
+    } else if ((rc = up(m, proj_uv, (size_t)n_last * 2, uv)) || (rc = up(m, proj_invz, (size_t)n_last, iz)) || (rc = up(m, valid, (size_t)n_last, va))) return rc;
+    if ((rc = up(m, last_angle, (size_t)n_last, la)) || (rc = up(m, last_octave, (size_t)n_last, lo)) || (rc = up(m, mp_desc, (size_t)n_last * 32, dd))) return rc;
     if (mp_observed && (rc = up(m, mp_observed, (size_t)n_last, ob))) return rc;
     if (cur_occupied && (rc = up(m, cur_occupied, (size_t)nc, oc))) return rc;
     if ((rc = flush_uploads(m)) || (rc = grid_frame(m, cur, dc, skc))) return rc;
+    if (pose && n_last) {
+        k_project_frame<<<(n_last + 127) / 128, 128, 0, m->stream>>>(n_last, wxyz, whas, pose->P, dc.min_x, dc.max_x, dc.min_y, dc.max_y, uv, iz, va);
+        LAUNCH_CHECK();
+    }
     QueryParams P; std::memset(&P, 0, sizeof(P));
     P.mode = MODE_PROJ_FRAME; P.nq = n_last; P.q_desc = dd; P.q_xy = uv; P.q_invz = iz; P.q_octave = lo; P.q_valid = va; P.th = th; P.forward = forward; P.backward = backward; P.mbf = mbf; P.no_ur = no_ur;
     int *counts, *offsets; uint32_t* cand; uint2* pre;
@@ -534,6 +571,12 @@ retry:
     CAND_RETRY(total);
     std::memcpy(nmatches, g.host(o_n), 4);
     if (nc) std::memcpy(cur_match, g.host(o_cm), (size_t)nc * 4);
+    if (pose && n_last && (pose->uv_out || pose->invz_out || pose->valid_out)) {       // test / inspection taps of the device projection
+        if (pose->uv_out) CU_TRY(cudaMemcpyAsync(pose->uv_out, uv, (size_t)n_last * 8, cudaMemcpyDeviceToHost, m->stream));
+        if (pose->invz_out) CU_TRY(cudaMemcpyAsync(pose->invz_out, iz, (size_t)n_last * 4, cudaMemcpyDeviceToHost, m->stream));
+        if (pose->valid_out) CU_TRY(cudaMemcpyAsync(pose->valid_out, va, (size_t)n_last, cudaMemcpyDeviceToHost, m->stream));
+        CU_TRY(cudaStreamSynchronize(m->stream));
+    }
     return ORBX_OK;
 }
 
@@ -714,6 +757,19 @@ int orbx_search_by_projection_frame_dev(orbx_matcher* m, const orbx_frame* cur, 
                                         const uint8_t* cur_occupied, float th, int forward, int backward, float mbf, int* cur_match, int* nmatches) {
     if (!cur) FAIL(ORBX_E_INVALID, "null frame");
     return search_proj_frame_impl(m, FrameArg{nullptr, cur}, n_last, proj_uv, proj_invz, last_octave, last_angle, mp_desc, valid, mp_observed, cur_occupied, th, forward, backward, mbf, cur_match, nmatches);
+}
+int orbx_search_by_projection_frame_pose(orbx_matcher* m, const orbx_frame_view* cur, const orbx_frame* cur_dev, int n_last, const float* world_xyz, const uint8_t* has_point,
+                                         const float* Rcw, const float* tcw, float fx, float fy, float cx, float cy, const int* last_octave, const float* last_angle,
+                                         const uint8_t* mp_desc, const uint8_t* mp_observed, const uint8_t* cur_occupied, float th, int forward, int backward, float mbf,
+                                         int* cur_match, int* nmatches, float* proj_uv_out, float* proj_invz_out, uint8_t* valid_out) {
+    if ((cur == nullptr) == (cur_dev == nullptr)) FAIL(ORBX_E_INVALID, "exactly one of the frame view and the device frame must be given");
+    if (!Rcw || !tcw) FAIL(ORBX_E_INVALID, "null pose");
+    ProjPoseArgs a; a.world = world_xyz; a.has = has_point; a.uv_out = proj_uv_out; a.invz_out = proj_invz_out; a.valid_out = valid_out;
+    for (int i = 0; i < 9; ++i) a.P.R[i] = Rcw[i];
+    for (int i = 0; i < 3; ++i) a.P.t[i] = tcw[i];
+    a.P.fx = fx; a.P.fy = fy; a.P.cx = cx; a.P.cy = cy;
+    return search_proj_frame_impl(m, FrameArg{cur, cur_dev}, n_last, nullptr, nullptr, last_octave, last_angle, mp_desc, nullptr, mp_observed, cur_occupied, th, forward, backward, mbf,
+                                  cur_match, nmatches, M_TH_HIGH, 0, -1, &a);
 }
 // SearchByProjection(Frame&, KeyFrame*, const set<MapPoint*>&, th, ORBdist)  (ORBmatcher.cc:1731-1863) is the Frame x Frame search with the
 // level predicted from the distance, every claim blocking (mvpMapPoints[i2] != NULL), no uRight test, and ORBdist as the acceptance bound

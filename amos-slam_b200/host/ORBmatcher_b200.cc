@@ -151,7 +151,8 @@ int ORBmatcher::SearchByProjection(Frame &F, const std::vector<MapPoint*> &vpMap
 
 int ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono)
 {
-    // pose algebra stays on the host: it needs the MapPoint objects and is O(N) (:1580-1623)
+    // the pose of the two frames decides forward / backward once per call (:1580-1592); the per-point projection (:1597-1623) runs on the
+    // device from the flattened world positions -- with cv::gemm's float arithmetic, see orbx_search_by_projection_frame_pose
     const cv::Mat Rcw = CurrentFrame.mTcw.rowRange(0, 3).colRange(0, 3);
     const cv::Mat tcw = CurrentFrame.mTcw.rowRange(0, 3).col(3);
     const cv::Mat twc = -Rcw.t() * tcw;
@@ -160,41 +161,33 @@ int ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, 
     const cv::Mat tlc = Rlw * twc + tlw;
     const bool bForward = tlc.at<float>(2) > CurrentFrame.mb && !bMono;
     const bool bBackward = -tlc.at<float>(2) > CurrentFrame.mb && !bMono;
+    float R9[9], t3[3];
+    for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) R9[3 * r + c] = Rcw.at<float>(r, c); t3[r] = tcw.at<float>(r); }
 
     const int n = LastFrame.N;
-    std::vector<float> uv((size_t)n * 2, 0.f), invz(n, 0.f), angle(n, 0.f);
+    std::vector<float> world((size_t)n * 3, 0.f), angle(n, 0.f);
     std::vector<int> octave(n, 0);
-    std::vector<unsigned char> desc((size_t)n * 32, 0), valid(n, 0), obs(n, 0);
+    std::vector<unsigned char> desc((size_t)n * 32, 0), has(n, 0), obs(n, 0);
     for (int i = 0; i < n; ++i) {
         MapPoint* pMP = LastFrame.mvpMapPoints[i];
         if (!pMP || LastFrame.mvbOutlier[i]) continue;
-        const cv::Mat x3Dc = Rcw * pMP->GetWorldPos() + tcw;
-        const float xc = x3Dc.at<float>(0), yc = x3Dc.at<float>(1);
-        const float invzc = 1.0 / x3Dc.at<float>(2);
-        if (invzc < 0) continue;
-        const float u = CurrentFrame.fx * xc * invzc + CurrentFrame.cx;
-        const float v = CurrentFrame.fy * yc * invzc + CurrentFrame.cy;
-        if (u < CurrentFrame.mnMinX || u > CurrentFrame.mnMaxX || v < CurrentFrame.mnMinY || v > CurrentFrame.mnMaxY) continue;
-        uv[2 * i] = u; uv[2 * i + 1] = v; invz[i] = invzc;
+        const cv::Mat x3Dw = pMP->GetWorldPos();
+        world[3 * i] = x3Dw.at<float>(0); world[3 * i + 1] = x3Dw.at<float>(1); world[3 * i + 2] = x3Dw.at<float>(2);
         octave[i] = LastFrame.mvKeys[i].octave; angle[i] = LastFrame.mvKeysUn[i].angle;
         const cv::Mat d = pMP->GetDescriptor();
         std::memcpy(&desc[(size_t)i * 32], d.ptr(), 32);
         obs[i] = pMP->Observations() > 0;
-        valid[i] = 1;
+        has[i] = 1;
     }
     std::vector<unsigned char> occ = occupied_flags(CurrentFrame);
     std::vector<int> cmatch(CurrentFrame.N, -1);
     int nmatches = 0;
-    if (const orbx_frame* dc = device_of(CurrentFrame))
-        check(orbx_search_by_projection_frame_dev(t_matchers.get(mfNNratio, mbCheckOrientation), dc, n, uv.data(), invz.data(), octave.data(), angle.data(),
-                                                  desc.data(), valid.data(), obs.data(), occ.data(), th, bForward ? 1 : 0, bBackward ? 1 : 0, CurrentFrame.mbf,
-                                                  cmatch.data(), &nmatches), "orbx_search_by_projection_frame_dev");
-    else {
-        FrameFlat c(CurrentFrame);
-        check(orbx_search_by_projection_frame(t_matchers.get(mfNNratio, mbCheckOrientation), &c.v, n, uv.data(), invz.data(), octave.data(), angle.data(),
-                                              desc.data(), valid.data(), obs.data(), occ.data(), th, bForward ? 1 : 0, bBackward ? 1 : 0, CurrentFrame.mbf,
-                                              cmatch.data(), &nmatches), "orbx_search_by_projection_frame");
-    }
+    const orbx_frame* dc = device_of(CurrentFrame);
+    FrameFlat c(CurrentFrame);                                                           // (cheap when the device frame is used: only consulted if dc == NULL)
+    check(orbx_search_by_projection_frame_pose(t_matchers.get(mfNNratio, mbCheckOrientation), dc ? NULL : &c.v, dc, n, world.data(), has.data(), R9, t3,
+                                               CurrentFrame.fx, CurrentFrame.fy, CurrentFrame.cx, CurrentFrame.cy, octave.data(), angle.data(), desc.data(), obs.data(), occ.data(),
+                                               th, bForward ? 1 : 0, bBackward ? 1 : 0, CurrentFrame.mbf, cmatch.data(), &nmatches, NULL, NULL, NULL),
+          "orbx_search_by_projection_frame_pose");
     for (int j = 0; j < CurrentFrame.N; ++j) {
         if (cmatch[j] >= 0) CurrentFrame.mvpMapPoints[j] = LastFrame.mvpMapPoints[cmatch[j]];   // :1685
         else if (cmatch[j] == -2) CurrentFrame.mvpMapPoints[j] = static_cast<MapPoint*>(NULL); // :1719

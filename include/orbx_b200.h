@@ -307,6 +307,21 @@ int orbx_search_by_projection_frame(orbx_matcher* m, const orbx_frame_view* cur,
                                     const uint8_t* mp_observed, const uint8_t* cur_occupied, float th, int forward, int backward, float mbf,
                                     int* cur_match, int* nmatches);
 
+struct orbx_frame;   /* device-resident Frame, declared below */
+/* The same call with the projection itself on the device (src/ORBmatcher.cc:1597-1623): instead of (u, v, 1/z) the caller passes, per
+ * LastFrame feature i, has_point[i] != 0 iff mvpMapPoints[i] is set and not an outlier, and world_xyz + 3 i = pMP->GetWorldPos(); plus the
+ * pose of CurrentFrame (Rcw row-major 3 x 3, tcw) and its intrinsics.  x3Dc = Rcw * x3Dw + tcw is evaluated exactly as cv::gemm
+ * evaluates it for these sizes (float arithmetic, ((r0 x + r1 y) + r2 z) + t; pinned against cv2.gemm), invzc = 1.0 / z in double
+ * rounded to float, u = fx xc invzc + cx in float; points with invzc < 0 or outside [mnMinX, mnMaxX] x [mnMinY, mnMaxY] drop out.
+ * Exactly one of cur (host view) and cur_dev (device frame) is non-NULL.  proj_uv_out (2 n), proj_invz_out (n), valid_out (n) are
+ * optional taps of what the device computed (NULL in production). */
+int orbx_search_by_projection_frame_pose(orbx_matcher* m, const orbx_frame_view* cur, const struct orbx_frame* cur_dev, int n_last,
+                                         const float* world_xyz, const uint8_t* has_point, const float* Rcw, const float* tcw,
+                                         float fx, float fy, float cx, float cy, const int* last_octave, const float* last_angle,
+                                         const uint8_t* mp_desc, const uint8_t* mp_observed, const uint8_t* cur_occupied, float th,
+                                         int forward, int backward, float mbf, int* cur_match, int* nmatches,
+                                         float* proj_uv_out, float* proj_invz_out, uint8_t* valid_out);
+
 /* int ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>& vpMapPoints, float th)
  *   src/ORBmatcher.cc:70-175.  Per map point p (already filtered by mbTrackInView && !isBad(), :82-86):
  *     track_uv (mTrackProjX, mTrackProjY), track_ur (mTrackProjXR), track_level (mnTrackScaleLevel),

@@ -92,6 +92,7 @@ def _lib(kind):
         lib.cvl_c_blur7.restype = None; lib.cvl_c_blur7.argtypes = [_u8p, C.c_int, C.c_int, _u8p]
         lib.cvl_c_fast.restype = C.c_int; lib.cvl_c_fast.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, _kpp, C.c_int]
         lib.cvl_c_fast_smap.restype = None; lib.cvl_c_fast_smap.argtypes = [_u8p, C.c_int, C.c_int, _u8p]
+        lib.cvl_c_gemm.restype = None; lib.cvl_c_gemm.argtypes = [_f32p, C.c_int, C.c_int, _f32p, C.c_int, C.c_void_p, _f32p]
         lib.cvl_c_atan2.restype = None; lib.cvl_c_atan2.argtypes = [_f32p, _f32p, _f32p, C.c_int]
         lib.cvl_c_close31.restype = None; lib.cvl_c_close31.argtypes = [_u8p, C.c_int, C.c_int, _u8p]
         lib.cvl_c_ellipse31.restype = None; lib.cvl_c_ellipse31.argtypes = [_u8p]

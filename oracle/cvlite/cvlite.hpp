@@ -297,14 +297,28 @@ static inline Mat operator/(const Mat& a, double s) {
     return m;
 }
 static inline Mat operator-(const Mat& a) { return -1.0 * a; }
-// matrix product, float, accumulation in double then rounded (OpenCV gemm for tiny 32F matrices
-// accumulates in double: cv::gemm GEMMSingleMul<float,double>)
+// matrix product of 32F matrices as cv::gemm evaluates it (modules/core/src/matmul.simd.hpp), pinned against cv2.gemm by
+// tests/golden/cvlite_cv2.npz (gemm_*) -- the first version of this shim accumulated every product in double, which the real library
+// only does on its general path:
+//   * inner dimension 2..4 equal to the result's width or height (every pose product of the matcher bodies: 3x3 * 3x1, 3x3 * 3x3,
+//     4x4 * 4x4): hand-unrolled FLOAT arithmetic, ((a0 b0 + a1 b1) + a2 b2) + a3 b3, each operation rounded to float;
+//   * anything else (e.g. 1x3 * 3x1): GEMMSingleMul<float, double>, products and sum in double, one rounding to float.
+// A following "+ C" is fused by cv::MatExpr into the same gemm call: on the small path that is t * alpha + c * beta in double of two
+// floats = the float sum; on the general path the shim rounds twice where the library rounds once (no such call site in the bodies).
 static inline Mat operator*(const Mat& a, const Mat& b) {
     assert(a.cols == b.rows && a.type() == CV_32F && b.type() == CV_32F);
     Mat m(a.rows, b.cols, CV_32F);
+    const int len = a.cols;
+    const bool small = len >= 2 && len <= 4 && (len == m.cols || len == m.rows);
     for (int i = 0; i < a.rows; ++i) for (int j = 0; j < b.cols; ++j) {
-        double s = 0; for (int k = 0; k < a.cols; ++k) s += (double)a.at<float>(i, k) * (double)b.at<float>(k, j);
-        m.at<float>(i, j) = (float)s;
+        if (small) {
+            float t = a.at<float>(i, 0) * b.at<float>(0, j);
+            for (int k = 1; k < len; ++k) { const float p = a.at<float>(i, k) * b.at<float>(k, j); t = t + p; }
+            m.at<float>(i, j) = t;
+        } else {
+            double s = 0; for (int k = 0; k < len; ++k) s += (double)a.at<float>(i, k) * (double)b.at<float>(k, j);
+            m.at<float>(i, j) = (float)s;
+        }
     }
     return m;
 }

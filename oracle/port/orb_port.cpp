@@ -506,6 +506,13 @@ void cvl_c_fast_smap(const unsigned char* img, int w, int h, unsigned char* S) {
     std::memset(S, 0, (size_t)w * h);
     for (int y = 3; y < h - 3; ++y) for (int x = 3; x < w - 3; ++x) { int s = cv::cvl_fast_S(img + (size_t)y * w + x, (size_t)w); S[(size_t)y * w + x] = (unsigned char)std::max(s, 0); }
 }
+// D = A (ar x ac) * B (ac x bc) [+ C] through cvlite's Mat algebra (the expression the matcher bodies write: Rcw * x3Dw + tcw)
+void cvl_c_gemm(const float* a, int ar, int ac, const float* b, int bc, const float* c, float* d) {
+    cv::Mat A(ar, ac, cv::CV_32F, (void*)a), B(ac, bc, cv::CV_32F, (void*)b);
+    cv::Mat D = A * B;
+    if (c) { cv::Mat Cm(ar, bc, cv::CV_32F, (void*)c); D = D + Cm; }
+    for (int i = 0; i < ar; ++i) for (int j = 0; j < bc; ++j) d[i * bc + j] = D.at<float>(i, j);
+}
 void cvl_c_atan2(const float* y, const float* x, float* out, int n) { for (int i = 0; i < n; ++i) out[i] = cv::fastAtan2(y[i], x[i]); }
 void cvl_c_close31(const unsigned char* mask, int w, int h, unsigned char* out) {
     cv::Mat m(h, w, CV_8UC1, (void*)mask), d, c; cv::Mat k = cv::getStructuringElement(cv::MORPH_ELLIPSE, cv::Size(31, 31), cv::Point(15, 15));

@@ -45,6 +45,18 @@ g["ellipse31"] = k31
 m = synth_mask(1, 160, 120); m[:6, :9] = 255; m[50:53, 70:72] = 0
 g["mask"] = m
 g["mask_close"] = cv2.erode(cv2.dilate(m, k31), k31)
+# cv::gemm on small 32F matrices (the pose products of the matcher bodies, e.g. Rcw * x3Dw + tcw at src/ORBmatcher.cc:1608):
+# 3x3 * 3x1 (+ 3x1), 3x3 * 3x3, 4x4 * 4x4 (hand-unrolled float path), 1x3 * 3x1 and 5x5 * 5x1 (general path, double accumulation)
+def gemm_cases(seed=77, n=400):
+    r = np.random.default_rng(seed); out = {}
+    for name, (ar, ac, bc, withc) in {"3x3_3x1_c": (3, 3, 1, True), "3x3_3x1": (3, 3, 1, False), "3x3_3x3": (3, 3, 3, False), "4x4_4x4": (4, 4, 4, False),
+                                       "1x3_3x1": (1, 3, 1, False), "5x5_5x1": (5, 5, 1, False), "2x2_2x1_c": (2, 2, 1, True)}.items():
+        A = r.normal(0, 1, (n, ar, ac)).astype(np.float32); B = r.normal(0, 3, (n, ac, bc)).astype(np.float32); Cm = r.normal(0, 1, (n, ar, bc)).astype(np.float32)
+        D = np.stack([cv2.gemm(A[i], B[i], 1.0, Cm[i] if withc else None, 1.0 if withc else 0.0) for i in range(n)]).astype(np.float32).reshape(n, ar, bc)
+        out["gemm_%s_A" % name] = A; out["gemm_%s_B" % name] = B; out["gemm_%s_D" % name] = D
+        if withc: out["gemm_%s_C" % name] = Cm
+    return out
+g.update(gemm_cases())
 np.savez_compressed(os.path.join(HERE, "cvlite_cv2.npz"), **g)
 
 # ---------------- reference extractor ----------------

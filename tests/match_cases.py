@@ -40,6 +40,33 @@ def project(xyz):
     return np.stack([u, v], 1).astype(np.float32), invz
 
 
+def project_pose(xyz_w, Rcw, tcw, bounds):
+    """x3Dc = Rcw * x3Dw + tcw as cv::gemm evaluates it for 3 x 3 by 3 x 1 floats (((r0 x + r1 y) + r2 z) + t, every operation rounded
+    to float; pinned against cv2.gemm by tests/test_oracle_cvlite.py), then ORBmatcher.cc:1611-1623 in float32.  Returns uv, invz, valid."""
+    f = np.float32
+    R = np.asarray(Rcw, f).reshape(3, 3); t = np.asarray(tcw, f).reshape(3); X = np.asarray(xyz_w, f)
+    c = [(((R[r, 0] * X[:, 0]).astype(f) + (R[r, 1] * X[:, 1]).astype(f)).astype(f) + (R[r, 2] * X[:, 2]).astype(f)).astype(f) + t[r] for r in range(3)]
+    c = [v.astype(f) for v in c]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        invz = (1.0 / c[2].astype(np.float64)).astype(f)
+        u = ((f(FX) * c[0]).astype(f) * invz).astype(f) + f(CX)
+        v = ((f(FY) * c[1]).astype(f) * invz).astype(f) + f(CY)
+    minx, maxx, miny, maxy = bounds
+    valid = ~(invz < 0) & ~((u < minx) | (u > maxx) | (v < miny) | (v > maxy))
+    uv = np.stack([u, v], 1).astype(f); uv[~valid] = 0; invz = invz.copy(); invz[~valid] = 0
+    return uv, invz, valid.astype(np.uint8)
+
+
+def small_pose(seed=4):
+    """A camera motion of a few centimetres / half a degree (TrackWithMotionModel's situation): Rcw, tcw as float32."""
+    rng = np.random.default_rng(seed)
+    a = rng.normal(0, 0.008, 3)
+    K = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+    th = np.linalg.norm(a)
+    R = np.eye(3) + np.sin(th) / th * K + (1 - np.cos(th)) / th ** 2 * (K @ K)
+    return R.astype(np.float32), rng.normal(0, 0.03, 3).astype(np.float32)
+
+
 PROJ_FRAME_CASES = [(15.0, 1), (7.0, 0), (15.0, 0)]         # (th, bMono); TrackWithMotionModel uses 15 / 7 (Tracking.cc:1929-1944)
 PROJ_POINT_CASES = [1.0, 3.0, 5.0]                          # SearchLocalPoints th (Tracking.cc:2378-2389)
 

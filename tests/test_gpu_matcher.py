@@ -46,6 +46,29 @@ def test_search_by_projection_frame_and_points(orbx, case):
         assert nm == int(G["pp%d_nm" % i]) and np.array_equal(fm, G["pp%d_fm" % i])
 
 
+def test_search_by_projection_frame_pose_projects_on_the_device(orbx, case):
+    """The pose form (world points + Rcw, tcw in, projection on the device) must give what the (u, v, 1/z) form gives when the caller
+    projects with OpenCV's arithmetic: taps equal the float-path restatement bit for bit, matches equal the pre-projected call."""
+    pi = case["pi"]; ka = case["ka"]
+    Rcw, tcw = mc.small_pose()
+    Rf = Rcw.astype(np.float64); xyz_w = ((pi["xyz"].astype(np.float64) - tcw.astype(np.float64)) @ Rf).astype(np.float32)     # world points that land near pi["xyz"]
+    xyz_w[5::41, 2] = -xyz_w[5::41, 2]                                      # some behind the camera
+    xyz_w[7::53] *= 40                                                      # some far outside the image
+    for FBg in (case["FBu"], case["FB"]):
+        b = (0.0, 640.0, 0.0, 480.0)                                         # bounds of the undistorted 640 x 480 test frames (match_cases FrameView default)
+        uv, iz, va = mc.project_pose(xyz_w, Rcw, tcw, b)
+        va = (va & (pi["valid"] != 0)).astype(np.uint8); uv = uv.copy(); uv[va == 0] = 0; iz = iz.copy(); iz[va == 0] = 0
+        M = orbx.ORBmatcher(0.9, True)
+        for (th, fw, bw) in [(15.0, 0, 0), (7.0, 1, 0), (15.0, 0, 1)]:
+            nm, cm, guv, giz, gva = M.SearchByProjectionFramePose(FBg, xyz_w, pi["valid"], Rcw, tcw, mc.FX, mc.FY, mc.CX, mc.CY, ka["octave"], ka["angle"], case["da"],
+                                                                  pi["obs"], pi["occ"], th, fw, bw, 40.0, taps=True)
+            assert np.array_equal(gva, va) and np.array_equal(guv, uv) and np.array_equal(giz, iz)
+            nm2, cm2 = M.SearchByProjectionFrame(FBg, uv, iz, ka["octave"], ka["angle"], case["da"], va, pi["obs"], pi["occ"], th, fw, bw, 40.0)
+            assert nm == nm2 and np.array_equal(cm, cm2) and nm > 50
+    # the device-Frame form takes the same path
+    assert int(va.sum()) > 300 and int((pi["valid"] != 0).sum()) > int(va.sum())
+
+
 def test_projection_variants_vs_port(orbx, oracle, case):
     """forward / backward level ranges, no uRight, no observations, checkOri off."""
     pi = case["pi"]; ka = case["ka"]

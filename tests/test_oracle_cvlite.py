@@ -119,3 +119,35 @@ def test_det_sincos_is_glibc_sincosf(oracle):
     for a, b in ((s1, exact_s), (c1, exact_c)):
         ulp = np.abs(a.view(np.int32).astype(np.int64) - b.view(np.int32).astype(np.int64))
         assert ulp.max() <= 1
+
+
+def test_small_matrix_products_are_opencv_gemm(oracle):
+    """cv::Mat products of the matcher bodies (Rcw * x3Dw + tcw, src/ORBmatcher.cc:1608): cvlite's operator* / operator+ against
+    cv2.gemm of OpenCV 4.13 -- float arithmetic on the hand-unrolled 2..4 path, double accumulation on the general path."""
+    lib = oracle.port_lib()
+    names = sorted({k[5:-2] for k in G.files if k.startswith("gemm_") and k.endswith("_A")})
+    assert len(names) >= 7
+    for name in names:
+        A, B, D = G["gemm_%s_A" % name], G["gemm_%s_B" % name], G["gemm_%s_D" % name]
+        Cm = G["gemm_%s_C" % name] if ("gemm_%s_C" % name) in G.files else None
+        for i in range(len(A)):
+            out = np.zeros(D[i].shape, np.float32)
+            c = np.ascontiguousarray(Cm[i]) if Cm is not None else None
+            lib.cvl_c_gemm(np.ascontiguousarray(A[i]), A.shape[1], A.shape[2], np.ascontiguousarray(B[i]), B.shape[2], c.ctypes.data if c is not None else None, out)
+            assert np.array_equal(out, D[i]), (name, i)
+
+
+def test_numpy_projection_helper_is_opencv_gemm():
+    """tests/match_cases.project_pose (the expected values of the device projection) evaluates Rcw * x + tcw like cv2.gemm."""
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    import match_cases as mc
+    A, B, Cm, D = G["gemm_3x3_3x1_c_A"], G["gemm_3x3_3x1_c_B"], G["gemm_3x3_3x1_c_C"], G["gemm_3x3_3x1_c_D"]
+    f = np.float32
+    for i in range(len(A)):
+        R, X, t = A[i], B[i][:, 0][None, :], Cm[i][:, 0]
+        c = [((((R[r, 0] * X[:, 0]).astype(f) + (R[r, 1] * X[:, 1]).astype(f)).astype(f) + (R[r, 2] * X[:, 2]).astype(f)).astype(f) + t[r]).astype(f) for r in range(3)]
+        assert np.array_equal(np.array(c, f).reshape(3, 1), D[i]), i
+    # and project_pose uses exactly that expression: a point on the optical axis of an identity pose lands on the principal point
+    uv, iz, va = mc.project_pose(np.array([[0, 0, 2.0]], f), np.eye(3, dtype=f), np.zeros(3, f), (0, 640, 0, 480))
+    assert va[0] == 1 and uv[0, 0] == f(mc.CX) and uv[0, 1] == f(mc.CY) and iz[0] == f(0.5)
