@@ -117,6 +117,7 @@ def lib():
     L.orbx_debug_pyramid_level.argtypes = [vp, ci, ci, vp, sz]
     L.orbx_debug_distribute.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, vp, ci, C.POINTER(ci)]
     L.orbx_debug_sincos.argtypes = [vp, C.c_uint, ci, vp, vp]
+    L.orbx_debug_canary_check.argtypes = [C.POINTER(ci)]
     if hasattr(L, "orbx_matcher_create"):
         L.orbx_matcher_create.argtypes = [cf, ci, ci, C.POINTER(vp)]
         L.orbx_matcher_destroy.argtypes = [vp]; L.orbx_matcher_destroy.restype = None
@@ -492,3 +493,12 @@ class cluster:
                                        _ptr(l64) if l64 is not None else None, cols * 8, _ptr(l16) if l16 is not None else None, cols * 2,
                                        _ptr(centers), cap, C.byref(n)))
         return (l16 if labels16 else l64), centers[:n.value].copy()
+
+
+def debug_canary_check():
+    """(overwritten guard zones, buffers checked) -- only meaningful when the process was started with ORBX_CANARY=1 (test tap)."""
+    n = C.c_int(0)
+    bad = lib().orbx_debug_canary_check(C.byref(n))
+    if bad < 0:
+        _check(bad)
+    return bad, n.value

@@ -124,3 +124,24 @@ int orbx_debug_sincos(orbx_extractor* h, unsigned lo_bits, int n, float* sin_out
 }
 
 }  // extern "C"
+
+// Guard-zone check (ORBX_CANARY=1, see DevBuf in orbx_extractor.cu): returns the number of guarded device buffers whose 256-byte zones in
+// front of or behind the payload no longer hold the pattern (0 = clean), or a negative status.  *n_blocks = buffers checked.
+extern "C" int orbx_debug_canary_check(int* n_blocks) {
+    if (n_blocks) *n_blocks = 0;
+    if (!CanaryRegistry::on()) FAIL(ORBX_E_STATE, "ORBX_CANARY is not set: buffers carry no guard zones");
+    CU_TRY(cudaDeviceSynchronize());
+    std::vector<std::pair<uint8_t*, size_t>> blocks;
+    { std::lock_guard<std::mutex> lk(CanaryRegistry::get().mu); blocks = CanaryRegistry::get().blocks; }
+    int bad = 0;
+    std::vector<uint8_t> g(2 * ORBX_GUARD);
+    for (const auto& b : blocks) {
+        CU_TRY(cudaMemcpy(g.data(), b.first, ORBX_GUARD, cudaMemcpyDeviceToHost));
+        CU_TRY(cudaMemcpy(g.data() + ORBX_GUARD, b.first + ORBX_GUARD + b.second, ORBX_GUARD, cudaMemcpyDeviceToHost));
+        bool ok = true;
+        for (uint8_t v : g) ok = ok && v == 0xA5;
+        bad += !ok;
+    }
+    if (n_blocks) *n_blocks = (int)blocks.size();
+    return bad;
+}

@@ -25,6 +25,9 @@ int orbx_debug_distribute(orbx_extractor* h, const orbx_keypoint* cand, int ncan
  * evaluates it, for the n floats whose bit patterns are lo_bits, lo_bits + 1, ... */
 int orbx_debug_sincos(orbx_extractor* h, unsigned lo_bits, int n, float* sin_out, float* cos_out);
 
+/* ORBX_CANARY=1: every device buffer of the extractor handles carries 256 guard bytes on both sides; returns how many were overwritten. */
+int orbx_debug_canary_check(int* n_blocks);
+
 #ifdef __cplusplus
 }
 #endif

@@ -421,3 +421,35 @@ def test_masked_batch_with_label_map_vs_reference(orbx, oracle):
     _, _, counts_m, culled_m = E.extract_masked_batch(imgs, masks)
     assert (culled_m <= culled).all() and culled_m[B - 1] == 0 and culled_m.sum() < culled.sum()
     assert E.check_overflow() == 0
+
+
+@pytest.mark.gpu
+def test_no_kernel_writes_outside_its_buffers(tmp_path):
+    """Sanitizer substitute (compute-sanitizer is closed on this pool): with ORBX_CANARY=1 every device buffer of the extractor handles
+    carries 256 guard bytes on both sides; after single-frame, batched, two-stage and masked runs on several geometries -- including
+    widths that are not multiples of 4 / 16 and a tiny frame -- none of the guard zones may have changed."""
+    import subprocess, sys, textwrap
+    code = textwrap.dedent('''
+        import importlib, sys, numpy as np
+        sys.path.insert(0, %r)
+        from tools.synth import synth_frame, synth_batch, synth_mask
+        orbx = importlib.import_module("amos-slam_b200")
+        for (w, h, nf) in [(640, 480, 1000), (641, 479, 700), (1241, 376, 2000), (203, 147, 300), (96, 80, 100)]:
+            E = orbx.ORBextractor(nf, 1.2, 8, 20, 7)
+            A = synth_frame(3, w, h)
+            k, d = E(A)
+            kd, cd = E.detect(A)
+            m = synth_mask(1, w, h); lab = np.ones((h, w)); ids = np.zeros(1, np.int32); rm = np.zeros(1, np.int32)
+            kk, ck, _ = E.MovingKeyPoints(m, lab, ids, rm, kd, cd)
+            E.ProcessDesp(kk, ck)
+            fr = synth_batch(5, w, h, seed0=10)
+            E.extract_batch(fr)
+            E.extract_masked_batch(fr, np.stack([synth_mask(i, w, h) for i in range(5)]))
+        bad, n = orbx.debug_canary_check()
+        print("CANARY", bad, n)
+    ''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    env = dict(os.environ); env["ORBX_CANARY"] = "1"
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("CANARY")][-1].split()
+    assert int(line[1]) == 0 and int(line[2]) >= 20, line
