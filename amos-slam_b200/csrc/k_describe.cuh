@@ -132,7 +132,7 @@ k_gauss7(const __grid_constant__ CUtensorMap map_l0, const CUtensorMap* __restri
 // keypoint, lane = column u in [-15,15], loop over the 31 rows (coalesced 31-byte row reads), integer
 // moments reduced with shuffles, angle = fastAtan2((float)m01, (float)m10) in degrees.
 // =================================================================================================
-__device__ float4 g_pattern_t[8 * 32];   // rBRIEF pairs, transposed and already as floats: [bit k][byte i] = (x0,y0,x1,y1) of pair 8*i+k (no I2F in the loop)
+__device__ char4 g_pattern_t[8 * 32];    // rBRIEF pairs, transposed: [bit k][byte i] = (x0,y0,x1,y1) of pair 8*i+k
 
 // dot product of 4 unsigned bytes (pixels) with 4 signed bytes (weights)
 __device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {
@@ -200,20 +200,15 @@ __device__ __forceinline__ uint32_t brief_byte(const uint8_t* center, float a, f
     uint32_t val = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const float4 pt = g_pattern_t[k * 32 + lane];                     // coalesced (a lane-indexed __constant__ read would serialise 32-way)
-        const float x0 = pt.x, y0 = pt.y, x1 = pt.z, y1 = pt.w;
-        // center[cvRound(x*b + y*a)*step + cvRound(x*a - y*b)], unfused, round-half-even.  cvRound as "add 1.5 * 2^23, read the mantissa":
-        // exact round-half-even for |v| < 2^22 on the FMA pipe -- the conversion instructions (I2F / F2I) made the XU pipe the busiest
-        // one of this kernel (57 %, profiles/r02c)
-        const float RM = 12582912.0f;
-        const int r0 = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)), RM));
-        const int q0 = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)), RM));
-        const int r1 = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)), RM));
-        const int q1 = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)), RM));
-        // the rounded values still carry the bias of the rounding constant: removed in wrap-around arithmetic (the true offsets are small)
-        const uint32_t KB = 0x4B400000u * (uint32_t)(BRIEF_PS + 1);
-        const int t0 = c[(int)((uint32_t)r0 * BRIEF_PS + (uint32_t)q0 - KB)];
-        const int t1 = c[(int)((uint32_t)r1 * BRIEF_PS + (uint32_t)q1 - KB)];
+        const char4 pt = g_pattern_t[k * 32 + lane];                      // coalesced (a lane-indexed __constant__ read would serialise 32-way)
+        const float x0 = (float)pt.x, y0 = (float)pt.y, x1 = (float)pt.z, y1 = (float)pt.w;
+        // center[cvRound(x*b + y*a)*step + cvRound(x*a - y*b)], unfused, round-half-even
+        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+        const int q0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+        const int q1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+        const int t0 = c[r0 * BRIEF_PS + q0];
+        const int t1 = c[r1 * BRIEF_PS + q1];
         val |= (uint32_t)(t0 < t1) << k;
     }
     __syncwarp();

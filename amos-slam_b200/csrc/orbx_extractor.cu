@@ -643,10 +643,10 @@ static int extract_graph(orbx_extractor* h, const uint8_t* image, int rows, int 
 
 static int upload_constants() {
     // __constant__ tables are per-device module state; upload on every create (cheap, idempotent)
-    float4 pt[8 * 32];
+    char4 pt[8 * 32];
     for (int i = 0; i < 32; ++i) for (int k = 0; k < 8; ++k) {
         const signed char* p = k_brief_pattern_host + (size_t)(8 * i + k) * 4;
-        pt[k * 32 + i] = make_float4((float)p[0], (float)p[1], (float)p[2], (float)p[3]);
+        pt[k * 32 + i] = make_char4(p[0], p[1], p[2], p[3]);
     }
     CU_TRY(cudaMemcpyToSymbol(g_pattern_t, pt, sizeof(pt)));
     return ORBX_OK;

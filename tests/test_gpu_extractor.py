@@ -434,7 +434,7 @@ def test_no_kernel_writes_outside_its_buffers(tmp_path):
         sys.path.insert(0, %r)
         from tools.synth import synth_frame, synth_batch, synth_mask
         orbx = importlib.import_module("amos-slam_b200")
-        for (w, h, nf) in [(640, 480, 1000), (641, 479, 700), (1241, 376, 2000), (203, 147, 300), (96, 80, 100)]:
+        for (w, h, nf) in [(640, 480, 1000), (641, 479, 700), (1241, 376, 2000), (203, 147, 300), (120, 100, 100)]:
             E = orbx.ORBextractor(nf, 1.2, 8, 20, 7)
             A = synth_frame(3, w, h)
             k, d = E(A)
