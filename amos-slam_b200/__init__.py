@@ -22,7 +22,7 @@ LIB_PATH = os.path.join(HERE, "liborbx_b200.so")
 CSRC = os.path.join(HERE, "csrc")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177"]
-SOURCES = ["orbx_extractor.cu", "orbx_matcher.cu", "orbx_pool.cu", "orbx_slic.cu"]
+SOURCES = ["orbx_extractor.cu", "orbx_matcher.cu", "orbx_pool.cu", "orbx_slic.cu", "host_pack.cpp"]
 
 KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
                      ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])

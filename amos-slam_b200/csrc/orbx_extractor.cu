@@ -5,7 +5,10 @@
 // /root/reference/src/ORBextractor.cc).  There is no CPU path here: every stage is a CUDA kernel
 // (k_pyramid_fast.cuh, k_octree.cuh, k_describe.cuh, k_cull.cuh); the host only computes the small
 // per-geometry tables exactly as the reference's constructor / ComputePyramid / cell loop do.
+#include <memory>
 #include <mutex>
+#include <thread>
+#include <atomic>
 #include <utility>
 #include "../../include/orbx_b200.h"
 #include "../../include/orbx_b200_testtaps.h"
@@ -118,6 +121,7 @@ struct orbx_extractor {
     DevBuf<uint16_t> d_cell_counts;
     DevBuf<int> d_ncand, d_kp_count, d_counts, d_level_counts, d_overflow;
     DevBuf<KpOut> d_kp_out; DevBuf<uint8_t> d_desc_out; int out_cap = 0;
+    uint32_t* h_bits = nullptr; size_t h_bits_cap = 0;   // pinned staging of host-packed masks (host_pack.cpp), words
     DevBuf<uint8_t> d_gather; uint8_t* h_gather = nullptr; size_t h_gather_cap = 0;   // single-frame result block and its pinned landing buffer
     const KpOut* lb_kp = nullptr; const uint8_t* lb_desc = nullptr; const int* lb_counts = nullptr; int lb_cap = 0, lb_B = 0;   // outputs of the last batched call (orbx_compute_stereo_matches_batch)
     const KpOut* last_kp = nullptr; const uint8_t* last_desc = nullptr; int last_n = -1;   // frame 0 of the last extract / describe (orbx_frame_assign)
@@ -711,6 +715,7 @@ void orbx_destroy(orbx_extractor* h) {
     h->d_gather.release(); if (h->h_gather) cudaFreeHost(h->h_gather);
     if (h->graph1) cudaGraphExecDestroy(h->graph1);
     if (h->h_in) cudaFreeHost(h->h_in);
+    if (h->h_bits) cudaFreeHost(h->h_bits);
     for (cudaEvent_t e : h->ev_h2d) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_done) cudaEventDestroy(e);
     h->d_l0.release();
@@ -814,7 +819,8 @@ static int chunk_frames(const orbx_extractor* h, int B) {
 }
 
 static int run_masked_range(orbx_extractor* h, int b0, int nb, const uint8_t* d_masks, long long mfs, int mpitch, int rows, int cols, LabelView lv,
-                            KpOut* d_kp, uint8_t* d_desc, int cap, int* d_counts, int* d_culled);
+                            KpOut* d_kp, uint8_t* d_desc, int cap, int* d_counts, int* d_culled, bool prepacked = false);
+extern "C" void orbx_host_pack_mask(const uint8_t* mask, size_t step, int rows, int cols, uint32_t* bits);   // host_pack.cpp
 static int ensure_closing(orbx_extractor* h, int nframes, int rows, int cols);
 
 // masks == nullptr: operator()(image, mask, keypoints, descriptors) per frame; otherwise the two-stage Amos path with culling
@@ -843,9 +849,40 @@ static int host_batch_pipeline(orbx_extractor* h, const uint8_t* images, const u
     h->view.pyr = h->d_pyr.p; h->view.pyr_fstride = h->pyr_fstride;
     const int mpitch = align_up(cols, 128);
     const size_t mfs = (size_t)mpitch * rows;
+    // The masks only matter as "mask != 0" (src/ORBextractor.cc:1697-1724), and this call is bound by the host -> device link: pack them to
+    // 1 bit per pixel on the host (a few worker threads, frame by frame, ahead of the copies) and upload 1/8 of the bytes.  ORBX_HOST_PACK=0
+    // uploads the byte masks and packs on the device instead.
+    static const int pack_threads = [] { const char* e = std::getenv("ORBX_HOST_PACK"); int v = e ? std::atoi(e) : 6; return v < 0 ? 0 : (v > 16 ? 16 : v); }();
+    const bool hostpack = masks && pack_threads > 0;
+    const size_t bwords = (size_t)rows * ((cols + 31) / 32);
+    struct Packer {                                               // joins its threads on every exit path
+        std::vector<std::thread> th; std::atomic<int> next{0}; std::unique_ptr<std::atomic<unsigned char>[]> done; int B = 0;
+        ~Packer() { next.store(1 << 30); for (auto& t : th) if (t.joinable()) t.join(); }
+        void wait(int b0, int nb) { for (int b = b0; b < b0 + nb; ++b) while (!done[b].load(std::memory_order_acquire)) std::this_thread::yield(); }
+    } packer;
     if (masks) {
         if ((rc = ensure_closing(h, B, rows, cols))) return rc;
-        if (h->d_mask.ensure(mfs * B + 64) || h->d_culled.ensure(B)) return ORBX_E_CUDA;
+        if ((!hostpack && h->d_mask.ensure(mfs * B + 64)) || h->d_culled.ensure(B)) return ORBX_E_CUDA;
+    }
+    if (hostpack) {
+        if (h->h_bits_cap < bwords * B) {
+            if (h->h_bits) cudaFreeHost(h->h_bits);
+            h->h_bits = nullptr; h->h_bits_cap = 0;
+            CU_TRY(cudaHostAlloc((void**)&h->h_bits, bwords * B * 4, cudaHostAllocDefault));
+            h->h_bits_cap = bwords * B;
+        }
+        packer.B = B; packer.done.reset(new std::atomic<unsigned char>[B]);
+        for (int b = 0; b < B; ++b) packer.done[b].store(0);
+        uint32_t* hb = h->h_bits;
+        for (int t = 0; t < std::min(pack_threads, B); ++t)
+            packer.th.emplace_back([&packer, hb, masks, mask_step, mask_frame_stride, rows, cols, bwords] {
+                for (;;) {
+                    const int b = packer.next.fetch_add(1);
+                    if (b >= packer.B) break;
+                    orbx_host_pack_mask(masks + (size_t)b * mask_frame_stride, mask_step, rows, cols, hb + (size_t)b * bwords);
+                    packer.done[b].store(1, std::memory_order_release);
+                }
+            });
     }
     // super-pixel labels ride along with the masks: 16-bit ids in a dense device mirror (cols elements per row) + the per-frame flag tables
     const size_t lfs = (size_t)rows * cols;
@@ -867,7 +904,7 @@ static int host_batch_pipeline(orbx_extractor* h, const uint8_t* images, const u
     static const int nstreams = [] { const char* e = std::getenv("ORBX_HOST_STREAMS"); int v = e ? std::atoi(e) : 4; return v < 1 ? 1 : (v > 4 ? 4 : v); }();
     cudaStream_t cs[4] = {h->stream, h->s_alt, h->s_more[0], h->s_more[1]};
     for (int i = 1; i < nstreams; ++i) CU_TRY(cudaStreamWaitEvent(cs[i], h->ev_done[0], 0));
-    for (int c = 0; c < nchunks; ++c) {
+    auto issue_h2d = [&](int c) -> int {
         const int b0 = cb[c], nb = cb[c + 1] - b0;
         if (mirror || repitch) {
             const size_t bytes = (size_t)(nb - 1) * frame_stride + (size_t)(rows - 1) * step + cols;     // never reads past the last row of the last frame
@@ -884,7 +921,10 @@ static int host_batch_pipeline(orbx_extractor* h, const uint8_t* images, const u
                 CU_TRY(cudaMemcpy2DAsync(h->d_pyr.p + (size_t)b * h->pyr_fstride + g0.off, g0.pitch, images + (size_t)b * frame_stride, step,
                                          cols, rows, cudaMemcpyHostToDevice, h->s_h2d));
         }
-        if (masks) {
+        if (hostpack) {                                                                                    // 1 bit per pixel, packed by the worker threads above
+            packer.wait(b0, nb);
+            CU_TRY(cudaMemcpyAsync(h->d_bits0.p + (size_t)b0 * bwords, h->h_bits + (size_t)b0 * bwords, (size_t)nb * bwords * 4, cudaMemcpyHostToDevice, h->s_h2d));
+        } else if (masks) {
             if (mask_step == (size_t)mpitch && mask_frame_stride == mfs)                                  // dense and already pitched: one copy per chunk
                 CU_TRY(cudaMemcpyAsync(h->d_mask.p + (size_t)b0 * mfs, masks + (size_t)b0 * mask_frame_stride, (size_t)nb * mfs, cudaMemcpyHostToDevice, h->s_h2d));
             else
@@ -901,15 +941,16 @@ static int host_batch_pipeline(orbx_extractor* h, const uint8_t* images, const u
             CU_TRY(cudaMemcpyAsync(h->d_lflags.p + (size_t)b0 * labels->n_labels, labels->flagged + (size_t)b0 * labels->n_labels, (size_t)nb * labels->n_labels, cudaMemcpyHostToDevice, h->s_h2d));
         }
         CU_TRY(cudaEventRecord(h->ev_h2d[c], h->s_h2d));
-    }
-    for (int c = 0; c < nchunks; ++c) {
+        return ORBX_OK;
+    };
+    auto issue_compute = [&](int c) -> int {
         const int b0 = cb[c], nb = cb[c + 1] - b0;
         h->cur = cs[c % nstreams];
         CU_TRY(cudaStreamWaitEvent(h->cur, h->ev_h2d[c], 0));
         if (masks) {
             LabelView lv{nullptr, 0, 0, nullptr, 0};
             if (labels) lv = LabelView{h->d_label16.p + (size_t)b0 * lfs, (long long)lfs, cols, h->d_lflags.p + (size_t)b0 * labels->n_labels, labels->n_labels};
-            rc = run_masked_range(h, b0, nb, h->d_mask.p + (size_t)b0 * mfs, (long long)mfs, mpitch, rows, cols, lv, h->d_kp_out.p, h->d_desc_out.p, cap, h->d_counts.p, h->d_culled.p);
+            rc = run_masked_range(h, b0, nb, hostpack ? nullptr : h->d_mask.p + (size_t)b0 * mfs, (long long)mfs, mpitch, rows, cols, lv, h->d_kp_out.p, h->d_desc_out.p, cap, h->d_counts.p, h->d_culled.p, hostpack);
         }
         else {
             rc = run_detect(h, b0, nb);
@@ -925,6 +966,19 @@ static int host_batch_pipeline(orbx_extractor* h, const uint8_t* images, const u
         CU_TRY(cudaMemcpyAsync(desc_out + (size_t)b0 * cap * 32, h->d_desc_out.p + (size_t)b0 * cap * 32, (size_t)nb * cap * 32, cudaMemcpyDeviceToHost, h->s_d2h));
         CU_TRY(cudaMemcpyAsync(counts_out + b0, h->d_counts.p + b0, (size_t)nb * sizeof(int), cudaMemcpyDeviceToHost, h->s_d2h));
         if (masks && culled_out) CU_TRY(cudaMemcpyAsync(culled_out + b0, h->d_culled.p + b0, (size_t)nb * sizeof(int), cudaMemcpyDeviceToHost, h->s_d2h));
+        return ORBX_OK;
+    };
+    // Uploads run ahead of the kernels: all of them are queued first -- except when the masks are packed on the host, where an upload has to
+    // wait for its frames to be packed and the kernels of the chunk before it are queued meanwhile.
+    if (!hostpack) {
+        for (int c = 0; c < nchunks; ++c) if ((rc = issue_h2d(c))) return rc;
+        for (int c = 0; c < nchunks; ++c) if ((rc = issue_compute(c))) return rc;
+    } else {
+        if ((rc = issue_h2d(0))) return rc;
+        for (int c = 0; c < nchunks; ++c) {
+            if (c + 1 < nchunks && (rc = issue_h2d(c + 1))) return rc;
+            if ((rc = issue_compute(c))) return rc;
+        }
     }
     h->lastB = B; h->blur_valid = true;
     int ovf = 0;

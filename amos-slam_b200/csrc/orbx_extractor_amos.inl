@@ -12,13 +12,15 @@ static int upload_ellipse() {
 
 // bit-pack the masks of frames [b0, b0+nframes) (u8, pitch multiple of 32; d_mask points at frame b0) and close them on h->cur;
 // result: h->d_bits0 = (closing != 0), [B][rows][wpr].  The caller has sized d_bits0 / d_bits1 for the whole batch.
-static int run_closing(orbx_extractor* h, const uint8_t* d_mask, long long fstride, int pitch, int b0, int nframes, int rows, int cols) {
+static int run_closing(orbx_extractor* h, const uint8_t* d_mask, long long fstride, int pitch, int b0, int nframes, int rows, int cols, bool prepacked = false) {
     const int wpr = (cols + 31) / 32;
     cudaStream_t s = h->cur;
     uint32_t* a = h->d_bits0.p + (size_t)b0 * rows * wpr; uint32_t* b = h->d_bits1.p + (size_t)b0 * rows * wpr;
     dim3 grid((wpr + 63) / 64, rows, nframes);
-    k_mask_pack<<<grid, 64, 0, s>>>(d_mask, fstride, pitch, rows, cols, a, wpr);
-    LAUNCH_CHECK();
+    if (!prepacked) {                                             // (the host-pointer batch call uploads masks already packed, host_pack.cpp)
+        k_mask_pack<<<grid, 64, 0, s>>>(d_mask, fstride, pitch, rows, cols, a, wpr);
+        LAUNCH_CHECK();
+    }
     k_bin_dilate31<false><<<grid, 64, 0, s>>>(a, b, wpr, rows, cols);
     LAUNCH_CHECK();
     k_bin_dilate31<true><<<grid, 64, 0, s>>>(b, a, wpr, rows, cols);
@@ -108,10 +110,10 @@ extern "C" int orbx_cull(orbx_extractor* h, const uint8_t* mask, size_t mask_ste
 // Batched Amos path (BASELINE config 5): per frame  operator()(img, mask, vector<vector<KeyPoint>>&)  ->  MovingKeyPoints with the
 // dynamic mask and, when lv.labels is set, the super-pixel term  ->  ProcessDesp.  Frames [b0, b0+nb) on h->cur; d_masks points at frame b0's mask.
 static int run_masked_range(orbx_extractor* h, int b0, int nb, const uint8_t* d_masks, long long mfs, int mpitch, int rows, int cols, LabelView lv,
-                            KpOut* d_kp, uint8_t* d_desc, int cap, int* d_counts, int* d_culled) {
+                            KpOut* d_kp, uint8_t* d_desc, int cap, int* d_counts, int* d_culled, bool prepacked) {
     int rc;
     if ((rc = run_detect(h, b0, nb))) return rc;
-    if ((rc = run_closing(h, d_masks, mfs, mpitch, b0, nb, rows, cols))) return rc;
+    if ((rc = run_closing(h, d_masks, mfs, mpitch, b0, nb, rows, cols, prepacked))) return rc;
     if (d_culled) CU_TRY(cudaMemsetAsync(d_culled + b0, 0, (size_t)nb * sizeof(int), h->cur));
     const int wpr = (cols + 31) / 32;
     k_cull_levelkp<<<dim3(h->nlevels, nb), 32, 0, h->cur>>>(h->d_levels.p, h->nlevels, h->kp_per_frame, h->d_kp_level.p + (size_t)b0 * h->kp_per_frame,

@@ -725,6 +725,12 @@ def main():
         return
     WIDTH, HEIGHT, NFEAT, defB, MASKED, WORKLOAD, METRIC = WORKLOADS[args.workload]
     N, K, W, B = args.gpus, args.steps, max(args.warmup, 0), (args.batch or defB)
+    # masks travel packed (1 bit per pixel, packed by worker threads of the library inside the host-pointer call) unless ORBX_HOST_PACK=0;
+    # the default thread count leaves every feeding thread of every rank its share of the host cores
+    if MASKED and "ORBX_HOST_PACK" not in os.environ:
+        os.environ["ORBX_HOST_PACK"] = str(max(1, min(8, (os.cpu_count() or 8) // max(1, world * max(1, args.streams)) - 1)))
+    hostpack = MASKED and int(os.environ.get("ORBX_HOST_PACK", "0")) > 0
+    link_bytes_per_frame = WIDTH * HEIGHT + ((HEIGHT * ((WIDTH + 31) // 32) * 4) if hostpack else (WIDTH * HEIGHT if MASKED else 0))
     config = {"workload": WORKLOAD, "frame": [WIDTH, HEIGHT], "nfeatures": NFEAT, "frames_per_gpu_per_step": B,
               "parallelism": "frames sharded over %d GPU(s), no collective; %d extractor handles (streams) per GPU sharing the step's frames evenly" % (N, max(1, args.streams)),
               "device_map": "rank r -> CUDA device %s" % ("r" if spread_device(1, world) == 1 else "(r % 2) * (visible / 2) + r // 2: ranks spread over both halves of the board (GPUs 0-3 share a host uplink)"),
@@ -998,10 +1004,12 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": N, "steps": K, "warmup": max(W, 3),
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": config,
-            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(B * WIDTH * HEIGHT * (2 if MASKED else 1)), "d2h_bytes_per_step": int(B * cap * 60 + 4 * B + 4), "steps": Ke,
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(B * link_bytes_per_frame), "d2h_bytes_per_step": int(B * cap * 60 + 4 * B + 4), "steps": Ke,
+                    "host_input_bytes_per_step": int(B * WIDTH * HEIGHT * (2 if MASKED else 1)),
+                    "mask_transport": (("packed to 1 bit per pixel on the host by %s worker threads per handle (the masks only matter as != 0), 1/8 of the bytes on the link" % os.environ.get("ORBX_HOST_PACK")) if (MASKED and hostpack) else ("bytes" if MASKED else None)),
                     "streams_per_gpu": NS,
-                    "h2d_GBps_per_gpu": (e2e / N * WIDTH * HEIGHT * (2 if MASKED else 1) / 1e9) if e2e else None, "pcie_h2d_peak_GBps": pcie_h2d, "pcie_h2d_with_d2h_GBps": pcie_h2d_bi, "pcie_probe": "pinned 256 MiB H2D on two streams per GPU, all %d ranks concurrently, mean per GPU; _with_d2h: a third stream copies results device -> host at the e2e leg's 1:5 ratio" % world,
-                    "pcie_frac": (e2e / N * WIDTH * HEIGHT * (2 if MASKED else 1) / 1e9 / pcie_h2d_bi) if (e2e and pcie_h2d_bi) else None,   # against the probe WITH result traffic
+                    "h2d_GBps_per_gpu": (e2e / N * link_bytes_per_frame / 1e9) if e2e else None, "pcie_h2d_peak_GBps": pcie_h2d, "pcie_h2d_with_d2h_GBps": pcie_h2d_bi, "pcie_probe": "pinned 256 MiB H2D on two streams per GPU, all %d ranks concurrently, mean per GPU; _with_d2h: a third stream copies results device -> host at the e2e leg's 1:5 ratio" % world,
+                    "pcie_frac": (e2e / N * link_bytes_per_frame / 1e9 / pcie_h2d_bi) if (e2e and pcie_h2d_bi) else None,   # against the probe WITH result traffic
                     "note": "one host thread per extractor handle, each calling the synchronous host-pointer batch API on its share of the step's frames"},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
