@@ -227,3 +227,89 @@ k_pyr_chain(PyrView pv, int b0, const ChainLevel* __restrict__ lv, int L) {
         cluster.sync();                                              // level l is complete and visible before any CTA of the cluster reads it
     }
 }
+
+// =================================================================================================
+// K1p  pyr_tiles: the WHOLE pyramid of a frame in one launch without any synchronisation between CTAs.  The chain (level l from level
+// l-1) makes a single frame wait for 7 dependent launches (31 us of its 109 us on the device).  Here every CTA owns one rectangle of
+// every level (an equal split of each level over the CTA grid) and computes, level by level in shared memory, that rectangle plus the
+// few extra columns / rows of the level that its own rectangles further up need as sources -- recomputing the seam instead of waiting
+// for a neighbour.  A pixel is the same deterministic function of the level below whoever computes it, so the result is bit-identical
+// to the per-level kernels.  Level 0 is read from global memory once, every level is written once; only __syncthreads() between levels.
+// The regions are rectangles (the footprints are separable) precomputed by the host (build_plan): per level and CTA column / row the
+// needed range [n0, n1) and the owned range [o0, o1), in groups of 4 columns / in rows.  Arithmetic = k_pyr_resize_w's.
+// =================================================================================================
+#define TILEPYR_THREADS 512
+struct TilePyrLevel { int sw, sh, dw, dh, dpitch, spitch, sm_off, sm_pitch, tab_off, tab_rows, tab_groups; long long doff; ResizeTabs t; };   // tab_off: staged tables [yofs | yw | xg | xw]
+struct TilePyrPlan { const TilePyrLevel* lv; const int* xr; const int* yr; int L, nx, ny; };   // xr: [L][nx][4] = need0, need1, own0, own1 (groups); yr: [L][ny][4] (rows)
+
+__global__ void __launch_bounds__(TILEPYR_THREADS)
+k_pyr_tiles(PyrView pv, int b0, TilePyrPlan P) {
+    extern __shared__ __align__(16) uint8_t tp_sm[];
+    const int b = b0 + (int)blockIdx.z;
+    const uint8_t* l0 = pv.l0 + (long long)b * pv.l0_fstride;
+    uint8_t* frame = pv.pyr + (long long)b * pv.pyr_fstride;
+    // stage every level's slice of the resize tables in shared memory first, one warp per level: the loads of all levels are in flight
+    // together, so the chain below pays the global-memory latency once instead of once per level
+    {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (int l = 1 + warp; l < P.L; l += TILEPYR_THREADS / 32) {
+            const TilePyrLevel c = P.lv[l];
+            const int* xr = P.xr + ((size_t)l * P.nx + blockIdx.x) * 4;
+            const int* yr = P.yr + ((size_t)l * P.ny + blockIdx.y) * 4;
+            int* ty = reinterpret_cast<int*>(tp_sm + c.tab_off); short2* tw = reinterpret_cast<short2*>(ty + c.tab_rows);
+            int2* tg = reinterpret_cast<int2*>(tw + c.tab_rows); uint4* tq = reinterpret_cast<uint4*>(tg + c.tab_groups);
+            for (int t = lane; t < yr[1] - yr[0]; t += 32) { ty[t] = __ldg(c.t.yofs + yr[0] + t); tw[t] = __ldg(c.t.yw + yr[0] + t); }
+            for (int t = lane; t < xr[1] - xr[0]; t += 32) { tg[t] = __ldg(c.t.xg + xr[0] + t); tq[t] = __ldg(reinterpret_cast<const uint4*>(c.t.xw) + xr[0] + t); }
+        }
+        __syncthreads();
+    }
+    for (int l = 1; l < P.L; ++l) {
+        const TilePyrLevel c = P.lv[l];
+        const int* xr = P.xr + ((size_t)l * P.nx + blockIdx.x) * 4;
+        const int* yr = P.yr + ((size_t)l * P.ny + blockIdx.y) * 4;
+        const int gx0 = xr[0], gx1 = xr[1], ox0 = xr[2], ox1 = xr[3], y0 = yr[0], y1 = yr[1], oy0 = yr[2], oy1 = yr[3];
+        const int ngr = gx1 - gx0, n = ngr * (y1 - y0);
+        // source: level 0 in global memory (l = 1) or the region of level l-1 this CTA computed into shared memory
+        const int* sxr = P.xr + ((size_t)(l - 1) * P.nx + blockIdx.x) * 4;
+        const int* syr = P.yr + ((size_t)(l - 1) * P.ny + blockIdx.y) * 4;
+        const TilePyrLevel cs = P.lv[l - 1];
+        const uint8_t* sbase = l == 1 ? l0 : tp_sm + cs.sm_off;
+        const int spitch = l == 1 ? pv.l0_pitch : cs.sm_pitch;
+        const int sgx0 = l == 1 ? 0 : sxr[0], sy_org = l == 1 ? 0 : syr[0];
+        const int wlast = l == 1 ? (pv.l0_pitch >> 2) - 1 : (sxr[1] - sxr[0]) - 1;     // last source word that exists (clamped words are never selected)
+        uint8_t* dsm = tp_sm + c.sm_off;
+        uint8_t* dgl = frame + c.doff;
+        const int* ty = reinterpret_cast<const int*>(tp_sm + c.tab_off); const short2* tw = reinterpret_cast<const short2*>(ty + c.tab_rows);
+        const int2* tg = reinterpret_cast<const int2*>(tw + c.tab_rows); const uint4* tq = reinterpret_cast<const uint4*>(tg + c.tab_groups);
+        for (int t = threadIdx.x; t < n; t += TILEPYR_THREADS) {
+            const int ry = t / ngr, rg = t - ry * ngr;
+            const int y = y0 + ry, gx = gx0 + rg, x = gx * 4;
+            const int sy0 = ty[ry], sy1 = min(sy0 + 1, c.sh - 1);
+            const short2 bw = tw[ry];
+            const int2 e = tg[rg];
+            const uint4 wq = tq[rg];
+            const int i0 = (e.x >> 2) - sgx0, i1 = min(i0 + 1, wlast), i2 = min(i0 + 2, wlast);
+            const int sh8 = (e.x & 3) * 8;
+            const uint32_t s01 = (uint32_t)e.y & 0xFFFFu, s23 = (uint32_t)e.y >> 16;
+            int h[2][4];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const uint32_t* row = reinterpret_cast<const uint32_t*>(sbase + (long long)((r ? sy1 : sy0) - sy_org) * spitch);
+                const uint32_t a0 = row[i0], a1 = row[i1], a2 = row[i2];
+                const uint32_t W0 = __funnelshift_r(a0, a1, sh8), W1 = __funnelshift_r(a1, a2, sh8);
+                const uint32_t X01 = __byte_perm(W0, W1, s01), X23 = __byte_perm(W0, W1, s23);
+                h[r][0] = (int)__dp2a_lo(wq.x, X01, 0u); h[r][1] = (int)__dp2a_hi(wq.y, X01, 0u);
+                h[r][2] = (int)__dp2a_lo(wq.z, X23, 0u); h[r][3] = (int)__dp2a_hi(wq.w, X23, 0u);
+            }
+            uint32_t v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                v[k] = (uint32_t)(((((int)bw.x * (h[0][k] >> 4)) >> 16) + (((int)bw.y * (h[1][k] >> 4)) >> 16) + 2) >> 2);
+            const uint32_t out = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
+            *reinterpret_cast<uint32_t*>(dsm + ry * c.sm_pitch + 4 * rg) = out;
+            if (gx >= ox0 && gx < ox1 && y >= oy0 && y < oy1 && x < c.dw)
+                *reinterpret_cast<uint32_t*>(dgl + (long long)y * c.dpitch + x) = out;       // bytes past dw land in row padding
+        }
+        __syncthreads();
+    }
+}

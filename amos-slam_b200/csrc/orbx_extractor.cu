@@ -110,6 +110,7 @@ struct orbx_extractor {
     CUtensorMap map_l0, map_l0_blur, map_l0_blur_s, map_l0_resize; const void* map_l0_sig[4] = {nullptr};                                // level-0 map of the current view (pointer, frame stride, pitch, frames)
     DevBuf<LevelGeom> d_levels; DevBuf<CellDesc> d_cells; DevBuf<BlurTile> d_tiles, d_tiles_s; DevBuf<int> d_tabs;
     std::vector<ResizeTabs> resize_tabs;
+    DevBuf<TilePyrLevel> d_tp_lv; DevBuf<int> d_tp_xr, d_tp_yr; int tp_nx = 0, tp_ny = 0, tp_smem = 0; bool tp_ok = false;   // k_pyr_tiles plan
     DevBuf<ChainLevel> d_chain; bool chain_ok = false;   // k_pyr_chain's level table (all levels in the word-load form)
     std::vector<int> resize_bw, resize_bh;           // TMA box of the source tile per destination level (k_pyr_resize_t); 0 = use the per-thread kernels
 
@@ -128,7 +129,7 @@ struct orbx_extractor {
     PyrView view{}; bool have_pyramid = false, blur_valid = false;
     // single-frame operator(): the whole per-geometry chain (upload from a pinned staging frame, 7 resizes, FAST, quadtree, blur on the
     // second stream, orientation + descriptors, result gather, download) captured once as a CUDA graph and replayed per call
-    cudaGraphExec_t graph1 = nullptr; int graph_launches = 0; uint8_t* h_in = nullptr; size_t h_in_cap = 0; const void* graph_sig[27] = {nullptr};
+    cudaGraphExec_t graph1 = nullptr; int graph_launches = 0; uint8_t* h_in = nullptr; size_t h_in_cap = 0; const void* graph_sig[28] = {nullptr};
     // optional per-stage CUDA-event timing (bench.py's roofline): one event set per profiled call
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;     // ORBX_NSTAGES+1 events per call
@@ -311,6 +312,60 @@ static int build_plan(orbx_extractor* h, int rows, int cols) {
         CU_TRY(cudaStreamSynchronize(h->stream));
         h->chain_ok = ok;
     }
+    {   // k_pyr_tiles: one CTA per 64 x 64 rectangle of level 0; per level its owned rectangle and the (slightly larger) one it computes
+        const int TP = 64;
+        const int nx = (cols + TP - 1) / TP, ny = (rows + TP - 1) / TP;
+        bool ok = L > 1;
+        for (int l = 1; l < L; ++l) ok = ok && h->resize_tabs[l].wide;
+        std::vector<std::vector<int>> xo(L), yo(L);
+        for (int l = 1; l < L && ok; ++l) { std::vector<short> w; linear_coefs(lv[l - 1].w, lv[l].w, lv[l].pitch, xo[l], w); linear_coefs(lv[l - 1].h, lv[l].h, align_up(lv[l].h, 8), yo[l], w); }
+        std::vector<int> xr((size_t)L * nx * 4, 0), yr((size_t)L * ny * 4, 0);
+        auto X = [&](int l, int i) { return &xr[((size_t)l * nx + i) * 4]; };
+        auto Y = [&](int l, int j) { return &yr[((size_t)l * ny + j) * 4]; };
+        for (int l = 1; l < L && ok; ++l) {
+            const int G = (lv[l].w + 3) / 4;
+            for (int i = 0; i < nx; ++i) { int* r = X(l, i); r[2] = (int)((long long)i * G / nx); r[3] = (int)((long long)(i + 1) * G / nx); r[0] = r[2]; r[1] = r[3]; }
+            for (int j = 0; j < ny; ++j) { int* r = Y(l, j); r[2] = (int)((long long)j * lv[l].h / ny); r[3] = (int)((long long)(j + 1) * lv[l].h / ny); r[0] = r[2]; r[1] = r[3]; }
+        }
+        for (int l = L - 1; l >= 2 && ok; --l) {                      // what level l - 1 must hold for this CTA's region of level l
+            for (int i = 0; i < nx; ++i) {
+                const int* d = X(l, i); int* sr = X(l - 1, i);
+                if (d[1] > d[0]) {
+                    const int lo = xo[l][4 * d[0]] / 4, hi = std::min(xo[l][4 * d[1] - 1] + 1, lv[l - 1].w - 1) / 4 + 1;
+                    if (sr[1] > sr[0]) { sr[0] = std::min(sr[0], lo); sr[1] = std::max(sr[1], hi); } else { sr[0] = lo; sr[1] = hi; }
+                }
+            }
+            for (int j = 0; j < ny; ++j) {
+                const int* d = Y(l, j); int* sr = Y(l - 1, j);
+                if (d[1] > d[0]) {
+                    const int lo = yo[l][d[0]], hi = std::min(yo[l][d[1] - 1] + 1, lv[l - 1].h - 1) + 1;
+                    if (sr[1] > sr[0]) { sr[0] = std::min(sr[0], lo); sr[1] = std::max(sr[1], hi); } else { sr[0] = lo; sr[1] = hi; }
+                }
+            }
+        }
+        std::vector<TilePyrLevel> tl((size_t)L); std::memset(tl.data(), 0, sizeof(TilePyrLevel) * (size_t)L);
+        int off = 0;
+        for (int l = 1; l < L && ok; ++l) {
+            int gw = 0, gh = 0;
+            for (int i = 0; i < nx; ++i) gw = std::max(gw, X(l, i)[1] - X(l, i)[0]);
+            for (int j = 0; j < ny; ++j) gh = std::max(gh, Y(l, j)[1] - Y(l, j)[0]);
+            TilePyrLevel& c = tl[l];
+            c.sw = lv[l - 1].w; c.sh = lv[l - 1].h; c.dw = lv[l].w; c.dh = lv[l].h; c.dpitch = lv[l].pitch; c.spitch = lv[l - 1].pitch; c.doff = lv[l].off;
+            c.sm_off = off; c.sm_pitch = gw * 4; c.t = h->resize_tabs[l];
+            off += align_up(std::max(gw * 4 * gh, 16), 16);
+            c.tab_rows = align_up(std::max(gh, 1), 4); c.tab_groups = align_up(std::max(gw, 1), 2);      // keeps the int2 / uint4 slices aligned
+            c.tab_off = off; off += align_up(c.tab_rows * 8 + c.tab_groups * 24, 16);
+        }
+        ok = ok && off <= 200 * 1024;
+        if (ok) {
+            if (h->d_tp_lv.ensure((size_t)L) || h->d_tp_xr.ensure(xr.size()) || h->d_tp_yr.ensure(yr.size())) return ORBX_E_CUDA;
+            CU_TRY(cudaMemcpyAsync(h->d_tp_lv.p, tl.data(), sizeof(TilePyrLevel) * (size_t)L, cudaMemcpyHostToDevice, h->stream));
+            CU_TRY(cudaMemcpyAsync(h->d_tp_xr.p, xr.data(), xr.size() * 4, cudaMemcpyHostToDevice, h->stream));
+            CU_TRY(cudaMemcpyAsync(h->d_tp_yr.p, yr.data(), yr.size() * 4, cudaMemcpyHostToDevice, h->stream));
+            CU_TRY(cudaStreamSynchronize(h->stream));
+        }
+        h->tp_ok = ok; h->tp_nx = nx; h->tp_ny = ny; h->tp_smem = off;
+    }
     h->levels.swap(lv); h->cells.swap(cells); h->tiles.swap(tiles); h->tiles_s.swap(tiles_s); h->resize_bw.swap(rbw); h->resize_bh.swap(rbh);
     h->pyr_fstride = (off + 255) / 256 * 256;
     h->cand_per_frame = cand_off; h->kp_per_frame = kp_off;
@@ -421,11 +476,18 @@ static int run_detect(orbx_extractor* h, int b0, int B, bool fork_blur = false) 
     prof_mark(h);
     static const int chain_env = [] { const char* e = std::getenv("ORBX_CHAIN"); return e ? std::atoi(e) : -1; }();
     const bool chain = h->chain_ok && (h->view.l0_pitch & 3) == 0 && (chain_env > 0);
+    static const int tp_env = [] { const char* e = std::getenv("ORBX_TILEPYR"); return e ? std::atoi(e) : -1; }();
+    const bool tilepyr = !chain && h->tp_ok && (h->view.l0_pitch & 3) == 0 && (tp_env >= 0 ? tp_env != 0 : (long long)B * h->tp_nx * h->tp_ny <= 2048);
+    if (tilepyr) {                                                   // a handful of frames: the whole pyramid in ONE launch, seams recomputed instead of synchronised
+        TilePyrPlan P; P.lv = h->d_tp_lv.p; P.xr = h->d_tp_xr.p; P.yr = h->d_tp_yr.p; P.L = L; P.nx = h->tp_nx; P.ny = h->tp_ny;
+        k_pyr_tiles<<<dim3(h->tp_nx, h->tp_ny, B), TILEPYR_THREADS, h->tp_smem, s>>>(h->view, b0, P);
+        LAUNCH_CHECK();
+    }
     if (chain) {                                                     // a handful of frames: the whole chain in one launch, one 8-CTA cluster per frame
         k_pyr_chain<<<dim3(CHAIN_CTAS, B), CHAIN_THREADS, 0, s>>>(h->view, b0, h->d_chain.p, L);
         LAUNCH_CHECK();
     }
-    for (int l = 1; l < L && !chain; ++l) {
+    for (int l = 1; l < L && !chain && !tilepyr; ++l) {
         const LevelGeom& g = h->levels[l]; const LevelGeom& gp = h->levels[l - 1];
         const uint8_t* src; long long sfs; int sp;
         if (l == 1) { src = view.l0; sfs = view.l0_fstride; sp = view.l0_pitch; }
@@ -597,7 +659,7 @@ static int extract_graph(orbx_extractor* h, const uint8_t* image, int rows, int 
     h->view.pyr = h->d_pyr.p; h->view.pyr_fstride = h->pyr_fstride;
     { const int rp = fast_prepare(h); if (rp) return rp; }    // tensor maps are built outside the capture
     // every buffer the captured nodes point at: any of them may have been re-allocated by another entry point since the capture
-    const void* sig[27] = {h->d_chain.p, h->d_tmaps.p, h->d_tiles_s.p, h->d_l0.p, h->d_pyr.p, h->d_blur.p, h->d_slots.p, h->d_ocand.p, h->d_spk.p, h->d_skey.p, h->d_cell_counts.p, h->d_ncand.p, h->d_kp_level.p,
+    const void* sig[28] = {h->d_tp_lv.p, h->d_chain.p, h->d_tmaps.p, h->d_tiles_s.p, h->d_l0.p, h->d_pyr.p, h->d_blur.p, h->d_slots.p, h->d_ocand.p, h->d_spk.p, h->d_skey.p, h->d_cell_counts.p, h->d_ncand.p, h->d_kp_level.p,
                            h->d_kp_count.p, h->d_counts.p, h->d_overflow.p, h->d_kp_out.p, h->d_desc_out.p, h->d_gather.p, h->h_gather, h->h_in, h->d_levels.p, h->d_cells.p,
                            h->d_tiles.p, h->d_tabs.p, (const void*)(uintptr_t)pitch, (const void*)(uintptr_t)blk};
     if (h->graph1 && std::memcmp(sig, h->graph_sig, sizeof(sig)) != 0) { cudaGraphExecDestroy(h->graph1); h->graph1 = nullptr; }
@@ -697,6 +759,7 @@ int orbx_create(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, in
     cudaFuncSetAttribute(k_octree_tree_par, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ptree_smem_bytes(PTREE_MAXCAP, 4096));
     cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(k_pyr_resize_t, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(k_pyr_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     *out = h;
     return ORBX_OK;
 }
@@ -719,7 +782,7 @@ void orbx_destroy(orbx_extractor* h) {
     for (cudaEvent_t e : h->ev_h2d) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_done) cudaEventDestroy(e);
     h->d_l0.release();
-    h->d_chain.release(); h->d_tmaps.release(); h->d_levels.release(); h->d_cells.release(); h->d_tiles.release(); h->d_tiles_s.release(); h->d_tabs.release();
+    h->d_tp_lv.release(); h->d_tp_xr.release(); h->d_tp_yr.release(); h->d_chain.release(); h->d_tmaps.release(); h->d_levels.release(); h->d_cells.release(); h->d_tiles.release(); h->d_tiles_s.release(); h->d_tabs.release();
     h->d_pyr.release(); h->d_blur.release(); h->d_slots.release(); h->d_ocand.release(); h->d_spk.release(); h->d_kp_level.release();
     h->d_skey.release(); h->d_cell_counts.release(); h->d_ncand.release(); h->d_kp_count.release(); h->d_counts.release();
     h->d_level_counts.release(); h->d_overflow.release(); h->d_kp_out.release(); h->d_desc_out.release();
