@@ -453,3 +453,40 @@ def test_no_kernel_writes_outside_its_buffers(tmp_path):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("CANARY")][-1].split()
     assert int(line[1]) == 0 and int(line[2]) >= 20, line
+
+
+@pytest.mark.gpu
+def test_every_kernel_form_gives_the_same_result(tmp_path):
+    """The latency / throughput forms of the stages are chosen by batch size; every one of them must be bit-identical.  Each environment
+    below forces one form for BOTH a single frame and a small batch (resize: TMA tiles / per-thread / one-launch tile pyramid / 8-CTA
+    cluster chain; blur: long / short strips; FAST: 1 / 8 cells per warp; masks packed on the host / on the device) and the digest of all
+    outputs must equal the digest of the default run -- which the other tests pin to the reference."""
+    import subprocess, sys, textwrap, hashlib
+    code = textwrap.dedent('''
+        import importlib, sys, hashlib, numpy as np
+        sys.path.insert(0, %r)
+        from tools.synth import synth_frame, synth_batch, synth_mask
+        orbx = importlib.import_module("amos-slam_b200")
+        hsh = hashlib.sha256()
+        for (w, h, nf) in [(640, 480, 1000), (417, 301, 500)]:
+            E = orbx.ORBextractor(nf, 1.2, 8, 20, 7)
+            k, d = E(synth_frame(5, w, h)); hsh.update(k.tobytes()); hsh.update(d.tobytes())
+            fr = synth_batch(6, w, h, seed0=20)
+            kb, db, nb = E.extract_batch(fr)
+            for b in range(6): hsh.update(np.ascontiguousarray(kb[b][:nb[b]]).tobytes()); hsh.update(np.ascontiguousarray(db[b][:nb[b]]).tobytes())
+            out = E.extract_masked_batch(fr, np.stack([synth_mask(i, w, h) for i in range(6)]))
+            for b in range(6): hsh.update(np.ascontiguousarray(out[0][b][:out[2][b]]).tobytes()); hsh.update(np.ascontiguousarray(out[1][b][:out[2][b]]).tobytes()); hsh.update(bytes([int(out[3][b]) & 255]))
+        print("DIGEST", hsh.hexdigest())
+    ''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+    def run(extra):
+        env = dict(os.environ); env.update(extra)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode == 0, str(extra) + r.stdout[-1500:] + r.stderr[-3000:]
+        return [l for l in r.stdout.splitlines() if l.startswith("DIGEST")][-1]
+
+    base = run({})
+    for extra in ({"ORBX_TILEPYR": "0"}, {"ORBX_TILEPYR": "1"}, {"ORBX_TILEPYR": "0", "ORBX_RESIZE_TMA": "1"}, {"ORBX_TILEPYR": "0", "ORBX_RESIZE_TMA": "0"},
+                  {"ORBX_CHAIN": "1"}, {"ORBX_BLUR_SMALL": "0"}, {"ORBX_BLUR_SMALL": "1"}, {"ORBX_FAST_CPW": "1"}, {"ORBX_FAST_CPW": "8"},
+                  {"ORBX_HOST_PACK": "0"}, {"ORBX_HOST_PACK": "3"}, {"ORBX_GRAPH": "0"}):
+        assert run(extra) == base, extra
