@@ -728,7 +728,10 @@ def main():
     # masks travel packed (1 bit per pixel, packed by worker threads of the library inside the host-pointer call) unless ORBX_HOST_PACK=0;
     # the default thread count leaves every feeding thread of every rank its share of the host cores
     if MASKED and "ORBX_HOST_PACK" not in os.environ:
-        os.environ["ORBX_HOST_PACK"] = str(max(1, min(8, (os.cpu_count() or 8) // max(1, world * max(1, args.streams)) - 1)))
+        spare = (os.cpu_count() or 8) // max(1, world * max(1, args.streams)) - 1      # host cores per feeding thread, minus the feeder itself
+        # packing costs host cycles: with fewer than 3 spare cores per handle (8 ranks on a 32-vCPU box) the byte masks are faster
+        # (profiles/r02g: N = 8 packed 35.6 k vs bytes 45.7 k frames/s; N = 4 packed 41.4 k vs bytes 27.6 k)
+        os.environ["ORBX_HOST_PACK"] = str(min(8, spare)) if spare >= 3 else "0"
     hostpack = MASKED and int(os.environ.get("ORBX_HOST_PACK", "0")) > 0
     link_bytes_per_frame = WIDTH * HEIGHT + ((HEIGHT * ((WIDTH + 31) // 32) * 4) if hostpack else (WIDTH * HEIGHT if MASKED else 0))
     config = {"workload": WORKLOAD, "frame": [WIDTH, HEIGHT], "nfeatures": NFEAT, "frames_per_gpu_per_step": B,
