@@ -34,12 +34,18 @@
 #define FAST_CLIST 256         // corner list (entries)
 
 // per-warp shared memory: [patch | S | wq | ring | clist | bm | mbarrier]   (byte sizes; per_warp a multiple of 128)
-struct FastLayout { int patch_cap, s_cap, wq_cap, bm_cap, per_warp; };
+// CTA form (one cell per CTA, see below): [patch | S | bm | mbarrier + 2 ints] shared (cta_shared bytes), then [wq | ring | clist] per warp (cta_per_warp)
+struct FastLayout { int patch_cap, s_cap, wq_cap, bm_cap, per_warp, cta_shared, cta_per_warp; };
 
 // exact byte-wise "d > T" (T <= 126) up to the final & 0x80808080: bit 7 of each byte of the result
 __device__ __forceinline__ uint32_t fast_gt(uint32_t d, uint32_t kc) { return ((d & 0x7F7F7F7Fu) + kc) | d; }
 __device__ __forceinline__ int max(int a, int b, int c) { return max(max(a, b), c); }
 
+// CTA = false: throughput form, one WARP per cell (each warp walks several cells).  CTA = true: latency form for a handful of frames, one CTA per
+// cell: the four warps share the patch, the score map and the bitmap and split the zone's rows between them for the two expensive stages
+// (pre-test and score), so a cell takes a quarter of the dependent instruction chain (a lone warp per scheduler runs at ~25 cycles per
+// instruction: 29 us for the FAST stage of one 640 x 480 frame in the warp form).
+template <bool CTA>
 __global__ void __launch_bounds__(FAST_WARPS * 32)
 k_fast_cells(const __grid_constant__ CUtensorMap map_l0, const CUtensorMap* __restrict__ maps, int b0,
              const LevelGeom* __restrict__ levels, const CellDesc* __restrict__ cells, int ncells,
@@ -49,26 +55,30 @@ k_fast_cells(const __grid_constant__ CUtensorMap map_l0, const CUtensorMap* __re
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.y;
-    const int W = gridDim.x * FAST_WARPS;
-    int cell = blockIdx.x * FAST_WARPS + warp;
+    const int W = CTA ? (int)gridDim.x : (int)gridDim.x * FAST_WARPS;
+    int cell = CTA ? (int)blockIdx.x : (int)blockIdx.x * FAST_WARPS + warp;
     if (cell >= ncells) return;
-    uint8_t* smw = smem_raw + (size_t)warp * lay.per_warp;
+    uint8_t* smw = CTA ? smem_raw : smem_raw + (size_t)warp * lay.per_warp;
+    uint8_t* priv = CTA ? smem_raw + lay.cta_shared + (size_t)warp * lay.cta_per_warp : smw + lay.patch_cap + lay.s_cap;   // [wq | ring | clist]
     const uint8_t* patch = smw;                                             // patch column pc0 = zone x 0, patch row 3 = zone y 0
     uint8_t* S = smw + lay.patch_cap;                                       // score map of the zone with a 1-px zero ring, row stride sst
-    uint32_t* wq = reinterpret_cast<uint32_t*>(S + lay.s_cap);              // surviving words: flags (bits 7,15,23,31) | word column << 8 | zone row
-    uint16_t* ring = reinterpret_cast<uint16_t*>(S + lay.s_cap + lay.wq_cap);          // pixel codes y << 6 | x (zone coordinates)
+    uint32_t* wq = reinterpret_cast<uint32_t*>(priv);                       // surviving words: flags (bits 7,15,23,31) | word column << 8 | zone row
+    uint16_t* ring = reinterpret_cast<uint16_t*>(priv + lay.wq_cap);        // pixel codes y << 6 | x (zone coordinates)
     uint16_t* clist = ring + FAST_RING;                                     // corners
-    uint32_t* bm = reinterpret_cast<uint32_t*>(clist + FAST_CLIST);         // 64 bits per zone row: local maxima
+    uint32_t* bm = CTA ? reinterpret_cast<uint32_t*>(S + lay.s_cap) : reinterpret_cast<uint32_t*>(clist + FAST_CLIST);   // 64 bits per zone row: local maxima
     uint64_t* bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(bm) + lay.bm_cap);
+    int* sh_n = reinterpret_cast<int*>(bar + 1);                            // CTA form: the cell's candidate count, shared by the warps
     const uint32_t lt = (1u << lane) - 1u;
+    const int tid0 = CTA ? (int)threadIdx.x : lane, tstep = CTA ? FAST_WARPS * 32 : 32;
+    auto sync = [&]() { if (CTA) __syncthreads(); else __syncwarp(); };
 
-    for (int i = lane; i < (lay.s_cap >> 2); i += 32) reinterpret_cast<uint32_t*>(S)[i] = 0u;
-    for (int i = lane; i < (lay.bm_cap >> 2); i += 32) bm[i] = 0u;
-    if (lane == 0) { mbar_init(bar, 1); mbar_fence_init(); }
-    __syncwarp();
+    for (int i = tid0; i < (lay.s_cap >> 2); i += tstep) reinterpret_cast<uint32_t*>(S)[i] = 0u;
+    for (int i = tid0; i < (lay.bm_cap >> 2); i += tstep) bm[i] = 0u;
+    if (tid0 == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+    sync();
 
     auto issue = [&](const CellDesc& cd) {
-        if (lane == 0) {
+        if (tid0 == 0) {
             const LevelGeom& g = levels[cd.level];
             const CUtensorMap* m = cd.level == 0 ? &map_l0 : maps + cd.level;
             mbar_expect_tx(bar, (uint32_t)(g.fast_bw * g.fast_bh));
@@ -93,11 +103,13 @@ k_fast_cells(const __grid_constant__ CUtensorMap map_l0, const CUtensorMap* __re
     const int sst = zw + 2;
     // stage-A geometry (host-computed, build_plan): lane = (strip s, word column j of the patch words wi0 .. wi0 + nwz - 1 that hold zone pixels)
     const int wi0 = pc0 >> 2, xoff = pc0 & 3;
-    const int nwz = c.geo & 0xFF, rps = (c.geo >> 8) & 0xFF, strips = c.geo >> 16;
+    const int nwz = c.geo & 0xFF, strips = c.geo >> 16;
+    const int r_lo = CTA ? warp * zh / FAST_WARPS : 0, r_hi = CTA ? (warp + 1) * zh / FAST_WARPS : zh;   // zone rows of this warp
+    const int rps = CTA ? (r_hi - r_lo + strips - 1) / strips : (c.geo >> 8) & 0xFF;
     const int s_ = (lane * c.rcp) >> 16, j = lane - s_ * nwz;               // lane / nwz, lane % nwz
-    const bool owner = s_ < strips && s_ * rps < zh;
-    const int ys = owner ? s_ * rps : 0;
-    const int ye = owner ? min(ys + rps, zh) : 0;
+    const bool owner = s_ < strips && r_lo + s_ * rps < r_hi;
+    const int ys = owner ? r_lo + s_ * rps : 0;
+    const int ye = owner ? min(ys + rps, r_hi) : 0;
     // bytes of word j inside the zone: zone x = 4 j + k - xoff in [0, zw)
     const int kfirst = max(0, xoff - 4 * j), klast = min(3, zw - 1 + xoff - 4 * j);
     const uint32_t colmask = (0x80808080u << (8 * kfirst)) & (0x80808080u >> (8 * (3 - klast)));
@@ -207,6 +219,7 @@ k_fast_cells(const __grid_constant__ CUtensorMap map_l0, const CUtensorMap* __re
             __syncwarp();
         }
     }
+    if (CTA) __syncthreads();                                                // every warp's scores are in S before anybody looks at neighbours
     // the patch is dead unless this cell may need its second pass: let the next cell's copy start now
     const bool may_retry = pass == 0 && minTh != iniTh;
     if (!may_retry && !issued) { issue(cnext); issued = true; }
@@ -229,8 +242,8 @@ k_fast_cells(const __grid_constant__ CUtensorMap map_l0, const CUtensorMap* __re
             nmax += __popc(__ballot_sync(0xffffffffu, mx));
         }
     } else {                                                                 // very dense cell: walk the score map itself
-        for (int i = lane; i < zw * zh; i += 32) {
-            const int y = i / zw, x = i - y * zw;
+        for (int i = lane; i < zw * (r_hi - r_lo); i += 32) {
+            const int y = r_lo + i / zw, x = i % zw;
             const uint8_t* q = S + (y + 1) * sst + x + 1;
             const int s = q[0];
             if (s && s > q[-1] && s > q[1] && s > q[-sst - 1] && s > q[-sst] && s > q[-sst + 1] && s > q[sst - 1] && s > q[sst] && s > q[sst + 1]) {
@@ -240,10 +253,10 @@ k_fast_cells(const __grid_constant__ CUtensorMap map_l0, const CUtensorMap* __re
         }
         nmax = __any_sync(0xffffffffu, nmax != 0);
     }
-    __syncwarp();
-    if (may_retry && nmax > 0 && !issued) { issue(cnext); issued = true; }  // no second pass: the patch is dead
-    // ---- ordered emission: rows in raster order, one row per lane ----
-    if (nmax > 0) {
+    sync();
+    if (!CTA && may_retry && nmax > 0 && !issued) { issue(cnext); issued = true; }  // no second pass: the patch is dead
+    // ---- ordered emission: rows in raster order, one row per lane (CTA form: warp 0 emits for the cell, then shares the count) ----
+    if (CTA ? warp == 0 : nmax > 0) {
         for (int y0 = 0; y0 < zh; y0 += 32) {
             const int y = y0 + lane;
             uint32_t lo = 0, hi = 0;
@@ -263,17 +276,23 @@ k_fast_cells(const __grid_constant__ CUtensorMap map_l0, const CUtensorMap* __re
             }
         }
     }
+    if (CTA) {                                                               // all warps take the same decision
+        if (threadIdx.x == 0) sh_n[0] = n;
+        __syncthreads();
+        n = sh_n[0];
+    }
     if (n > 0 || !may_retry) {
-        __syncwarp();
+        sync();
         if (cn <= FAST_CLIST) { for (int k = lane; k < cn; k += 32) { const int code = clist[k]; S[((code >> 6) + 1) * sst + (code & 63) + 1] = 0; } }
-        else for (int i = lane; i < (lay.s_cap >> 2); i += 32) reinterpret_cast<uint32_t*>(S)[i] = 0u;
+        else if (!CTA) { for (int i = lane; i < (lay.s_cap >> 2); i += 32) reinterpret_cast<uint32_t*>(S)[i] = 0u; }
+        else { for (int i = lane; i < sst * (r_hi - r_lo); i += 32) S[(r_lo + 1) * sst + i] = 0; }      // this warp's rows of the score map
         break;                                                               // S is all zero again
     }
-    __syncwarp();                                                            // lists are rebuilt by the second pass (the scores already in S are a subset of its scores)
+    sync();                                                                  // lists are rebuilt by the second pass (the scores already in S are a subset of its scores)
     }
     if (!issued) issue(cnext);                                              // (a second pass that found nothing issues here)
-    if (lane == 0) cell_counts[(long long)b * ncells + cell] = (uint16_t)n;
+    if (tid0 == 0) cell_counts[(long long)b * ncells + cell] = (uint16_t)n;
     c = cnext;
-    __syncwarp();                                                            // S / lists are reused by the next cell
+    sync();                                                                  // S / lists are reused by the next cell
     }
 }

@@ -375,6 +375,7 @@ static int build_plan(orbx_extractor* h, int rows, int cols) {
         f.patch_cap = align_up(patch_cap, 128); f.s_cap = align_up(s_cap, 16); f.wq_cap = align_up(4 * wq_words, 16); f.bm_cap = align_up(8 * zh_max, 16);
         static const int padx = [] { const char* e = std::getenv("ORBX_FAST_PAD"); return e ? std::atoi(e) : 0; }();
         f.per_warp = align_up(f.patch_cap + f.s_cap + f.wq_cap + 2 * FAST_RING + 2 * FAST_CLIST + f.bm_cap + 16 + padx, 128);
+        f.cta_shared = align_up(f.patch_cap + f.s_cap + f.bm_cap + 32, 128); f.cta_per_warp = align_up(f.wq_cap + 2 * FAST_RING + 2 * FAST_CLIST, 16);
         if ((long long)f.per_warp * FAST_WARPS > 227 * 1024) FAIL(ORBX_E_INVALID, "FAST cells too large for shared memory");
     }
     h->tmaps_base = nullptr; h->map_l0_sig[0] = nullptr;
@@ -517,11 +518,18 @@ static int run_detect(orbx_extractor* h, int b0, int B, bool fork_blur = false) 
         static const int cpw_env = [] { const char* e = std::getenv("ORBX_FAST_CPW"); int v = e ? std::atoi(e) : 0; return v < 0 ? 0 : v; }();
         const long long cells_total = (long long)ncells * B;
         const int cpw = cpw_env ? cpw_env : (cells_total >= 64LL * 2072 ? 8 : (cells_total >= 16LL * 2072 ? 4 : (cells_total >= 8LL * 2072 ? 2 : 1)));
-        dim3 grid((ncells + FAST_WARPS * cpw - 1) / (FAST_WARPS * cpw), B);
-        const int smem = h->fast_lay.per_warp * FAST_WARPS;
         { const int rc = fast_prepare(h); if (rc) return rc; }
-        k_fast_cells<<<grid, FAST_WARPS * 32, smem, s>>>(h->map_l0, h->d_tmaps.p, b0, h->d_levels.p, h->d_cells.p, ncells, h->cand_per_frame,
-                                                          h->fast_lay, h->iniThFAST, h->minThFAST, slots, cell_counts);
+        static const int cta_env = [] { const char* e = std::getenv("ORBX_FAST_CTA"); return e ? std::atoi(e) : -1; }();
+        if (cta_env >= 0 ? cta_env != 0 : cells_total <= 4LL * 2072) {   // a handful of frames: one CTA per cell, its four warps split the zone's rows (latency form)
+            const int smem = h->fast_lay.cta_shared + FAST_WARPS * h->fast_lay.cta_per_warp;
+            k_fast_cells<true><<<dim3(ncells, B), FAST_WARPS * 32, smem, s>>>(h->map_l0, h->d_tmaps.p, b0, h->d_levels.p, h->d_cells.p, ncells, h->cand_per_frame,
+                                                                             h->fast_lay, h->iniThFAST, h->minThFAST, slots, cell_counts);
+        } else {
+            dim3 grid((ncells + FAST_WARPS * cpw - 1) / (FAST_WARPS * cpw), B);
+            const int smem = h->fast_lay.per_warp * FAST_WARPS;
+            k_fast_cells<false><<<grid, FAST_WARPS * 32, smem, s>>>(h->map_l0, h->d_tmaps.p, b0, h->d_levels.p, h->d_cells.p, ncells, h->cand_per_frame,
+                                                                     h->fast_lay, h->iniThFAST, h->minThFAST, slots, cell_counts);
+        }
         LAUNCH_CHECK();
     }
     prof_mark(h);
@@ -757,7 +765,8 @@ int orbx_create(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, in
     cudaFuncSetAttribute(k_octree_sort_t<SORT_THREADS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)octree_sort_smem_bytes(8192, SORT_THREADS_WIDE));
     cudaFuncSetAttribute(k_octree_tree, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_octree_tree_par, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ptree_smem_bytes(PTREE_MAXCAP, 4096));
-    cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(k_fast_cells<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(k_fast_cells<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(k_pyr_resize_t, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(k_pyr_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     *out = h;

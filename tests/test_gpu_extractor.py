@@ -459,7 +459,7 @@ def test_no_kernel_writes_outside_its_buffers(tmp_path):
 def test_every_kernel_form_gives_the_same_result(tmp_path):
     """The latency / throughput forms of the stages are chosen by batch size; every one of them must be bit-identical.  Each environment
     below forces one form for BOTH a single frame and a small batch (resize: TMA tiles / per-thread / one-launch tile pyramid / 8-CTA
-    cluster chain; blur: long / short strips; FAST: 1 / 8 cells per warp; masks packed on the host / on the device) and the digest of all
+    cluster chain; blur: long / short strips; FAST: 1 / 8 cells per warp, one CTA per cell; masks packed on the host / on the device) and the digest of all
     outputs must equal the digest of the default run -- which the other tests pin to the reference."""
     import subprocess, sys, textwrap, hashlib
     code = textwrap.dedent('''
@@ -487,6 +487,6 @@ def test_every_kernel_form_gives_the_same_result(tmp_path):
 
     base = run({})
     for extra in ({"ORBX_TILEPYR": "0"}, {"ORBX_TILEPYR": "1"}, {"ORBX_TILEPYR": "0", "ORBX_RESIZE_TMA": "1"}, {"ORBX_TILEPYR": "0", "ORBX_RESIZE_TMA": "0"},
-                  {"ORBX_CHAIN": "1"}, {"ORBX_BLUR_SMALL": "0"}, {"ORBX_BLUR_SMALL": "1"}, {"ORBX_FAST_CPW": "1"}, {"ORBX_FAST_CPW": "8"},
+                  {"ORBX_CHAIN": "1"}, {"ORBX_BLUR_SMALL": "0"}, {"ORBX_BLUR_SMALL": "1"}, {"ORBX_FAST_CPW": "1"}, {"ORBX_FAST_CPW": "8"}, {"ORBX_FAST_CTA": "0"}, {"ORBX_FAST_CTA": "1"},
                   {"ORBX_HOST_PACK": "0"}, {"ORBX_HOST_PACK": "3"}, {"ORBX_GRAPH": "0"}):
         assert run(extra) == base, extra
