@@ -20,7 +20,20 @@
 #include "orbx_common.cuh"
 
 // path code of a key; x,y are the integer coordinates relative to (minBorderX, minBorderY)
+// the x half (root << 26 | x decisions on the even bits) and the y half (y decisions on the odd bits) of the code depend on one coordinate each:
+// the host tabulates them per level (octree_code_tables below, same arithmetic), and a code is then two loads and an OR
+__host__ __device__ inline uint32_t octree_code_half(int v, int lo, int hi, int bit) {
+    uint32_t code = 0;
+    for (int d = 0; d < ORBX_MAXD; ++d) {
+        const int m = lo + ((hi - lo + 1) >> 1);
+        const uint32_t b = v >= m;
+        if (b) lo = m; else hi = m;
+        code |= b << (2 * (ORBX_MAXD - 1 - d) + bit);
+    }
+    return code;
+}
 __device__ __forceinline__ uint32_t octree_code(int x, int y, const LevelGeom& g) {
+    if (g.code_x) return g.code_x[min(x, g.code_nx - 1)] | g.code_y[min(y, g.code_ny - 1)];
     // root: vpIniNodes[kp.pt.x / hX]   (float division, truncation)        :766
     const int root = (int)__fdiv_rn((float)x, g.hX);
     // root geometry: UL.x = (int)(hX*i), UR.x = (int)(hX*(i+1)), y in [0, maxY-minY)   :741-745
@@ -38,6 +51,14 @@ __device__ __forceinline__ uint32_t octree_code(int x, int y, const LevelGeom& g
     }
     return code;
 }
+
+// phase stamps of the (level 0, frame 0) instance for tools/qt_stamps_probe.py; compiled in only with -DORBX_QT_STAMPS (a probe build, never the product library)
+#ifdef ORBX_QT_STAMPS
+__device__ long long g_qt_stamps[64];
+#define QT_STAMP(i) do { if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && (i) < 64) g_qt_stamps[(i)] = clock64(); } while (0)
+#else
+#define QT_STAMP(i) do { } while (0)
+#endif
 
 #define SORT_THREADS 256
 #define SORT_WARPS (SORT_THREADS / 32)
@@ -62,6 +83,7 @@ k_octree_sort_t(const LevelGeom* __restrict__ levels, const CellDesc* __restrict
     __shared__ int total_sm;
     const int level = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const LevelGeom& g = levels[level];
+    QT_STAMP(0);
     const uint16_t* counts = cell_counts + (long long)b * ncells + g.cell_begin;
     const uint32_t* slots = cand_slots + (long long)b * slots_per_frame;
     uint32_t* oc = ocand + (long long)b * cand_per_frame + g.cand_off;
@@ -88,6 +110,7 @@ k_octree_sort_t(const LevelGeom* __restrict__ levels, const CellDesc* __restrict
     }
     __syncthreads();
     const int n = total_sm;
+    QT_STAMP(1);
     if (n > g.cand_cap) { if (tid == 0) ncand[b * nlevels + level] = -1; return; }   // cannot happen (cap is the worst case)
     const bool radix = n <= smem_keys;
     uint32_t* keyA = reinterpret_cast<uint32_t*>(sort_sm);
@@ -102,6 +125,7 @@ k_octree_sort_t(const LevelGeom* __restrict__ levels, const CellDesc* __restrict
         for (int k = 0; k < cnt; ++k, ++pos) oc[pos] = src[k];
     }
     __syncthreads();
+    QT_STAMP(2);
     for (int i = tid; i < n; i += THREADS) {                        // ... the path codes are computed by all threads
         const uint32_t p = oc[i];
         const uint32_t code = octree_code((int)(p & 0xFFF), (int)((p >> 12) & 0xFFF), g);
@@ -109,6 +133,7 @@ k_octree_sort_t(const LevelGeom* __restrict__ levels, const CellDesc* __restrict
         else sk_g[i] = ((unsigned long long)code << 32) | (unsigned)i;
     }
     __syncthreads();
+    QT_STAMP(3);
 
     if (radix) {
         // ---- stable LSD radix sort on the path code, 8 bits per pass.  Digits below the depth at which a node is one
@@ -123,6 +148,7 @@ k_octree_sort_t(const LevelGeom* __restrict__ levels, const CellDesc* __restrict
         const int s0 = min(warp * seg, n), s1 = min(s0 + seg, n);
         const uint32_t lt = (1u << lane) - 1u;
         uint16_t* myhist = hist + warp * 256;
+        int qt_pass = 0; (void)qt_pass;
         for (int shift = low; shift < low + nbits; shift += 8) {
             for (int i = lane; i < 256; i += 32) myhist[i] = 0;
             __syncwarp();
@@ -173,12 +199,14 @@ k_octree_sort_t(const LevelGeom* __restrict__ levels, const CellDesc* __restrict
             __syncthreads();
             uint32_t* tk = keyA; keyA = keyB; keyB = tk;
             uint16_t* ti = idxA; idxA = idxB; idxB = ti;
+            QT_STAMP(4 + qt_pass); ++qt_pass;
         }
         for (int i = tid; i < n; i += THREADS) {
             const unsigned oi = idxA[i];
             sk_g[i] = ((unsigned long long)keyA[i] << 32) | oi;
             sp[i] = oc[oi];
         }
+        QT_STAMP(10);
         if (tid == 0) ncand[b * nlevels + level] = n;
         return;
     }
@@ -462,6 +490,7 @@ k_octree_tree_par(const LevelGeom* __restrict__ levels, int nlevels, int cand_pe
     __shared__ int s_ovf, s_rstar;
     const int level = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     const LevelGeom& g = levels[level];
+    QT_STAMP(16);
     const int n = ncand[b * nlevels + level];
     const unsigned long long* key = skey + (long long)b * cand_per_frame + g.cand_off;
     const uint32_t* pk = spk + (long long)b * cand_per_frame + g.cand_off;
@@ -483,6 +512,8 @@ k_octree_tree_par(const LevelGeom* __restrict__ levels, int nlevels, int cand_pe
     } else { ck = reinterpret_cast<const uint32_t*>(key) + 1; cs = 2; }
     if (tid == 0) s_ovf = 0;
     __syncthreads();
+    QT_STAMP(17);
+    int qt_round = 0; (void)qt_round;
 
     const int N = g.N;
     int cur = 0;                               // node buffer holding the current list, in list order
@@ -528,6 +559,7 @@ k_octree_tree_par(const LevelGeom* __restrict__ levels, int nlevels, int cand_pe
         if (b2[i] > b1[i]) { const int pos = sM[i] - 1; nlo[0][pos] = b1[i]; nhi[0][pos] = b2[i]; ncid[0][pos] = i; ndep[0][pos] = 0; }
     __syncthreads();
 
+    QT_STAMP(18);
     bool finish = false;
     while (!finish) {
         // ================= full pass =================
@@ -560,6 +592,7 @@ k_octree_tree_par(const LevelGeom* __restrict__ levels, int nlevels, int cand_pe
         }
         __syncthreads();
         cur = nx; count = newcount; nextCid += F; nv = Etot;
+        QT_STAMP(20 + qt_round); ++qt_round;
         const int nToExpand = Etot;
         if (count >= N || count == prevSize) { finish = true; break; }          // :907
         if (count + nToExpand * 3 > N) {                                          // :929
@@ -611,6 +644,7 @@ k_octree_tree_par(const LevelGeom* __restrict__ levels, int nlevels, int cand_pe
                 }
                 __syncthreads();
                 cur = nx; count = newcount; nextCid += F; nv = Etot;
+                QT_STAMP(20 + qt_round); ++qt_round;
                 if (count >= N || count == prevSize2) finish = true;               // :1009
             }
             break;
@@ -618,6 +652,7 @@ k_octree_tree_par(const LevelGeom* __restrict__ levels, int nlevels, int cand_pe
     }
     __syncthreads();
     const bool ovf = s_ovf != 0;
+    QT_STAMP(38);
 
     // ---- result: one keypoint per node in list order (:1018-1048): max response, first in the original order ----
     const int nout = min(count, g.kp_cap);
@@ -632,6 +667,7 @@ k_octree_tree_par(const LevelGeom* __restrict__ levels, int nlevels, int cand_pe
         }
         out[k] = bestp;
     }
+    QT_STAMP(39);
     if (tid == 0) {
         kp_count[b * nlevels + level] = nout;
         if (ovf || count > g.kp_cap) atomicOr(overflow, ORBX_OVF_TREE);

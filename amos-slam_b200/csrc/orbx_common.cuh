@@ -27,6 +27,9 @@ struct LevelGeom {
     float scale;                 // mvScaleFactor[level]
     float kp_size;               // (float)(int)(31 * scale)
     int fast_bw, fast_bh;        // TMA box of this level's FAST cells (k_fast.cuh): bytes per patch row (multiple of 16), rows
+    // quadtree path code of a candidate = code_x[x] | code_y[y] (k_octree.cuh: the x and y decisions of the 13 splits are independent, the root follows from x);
+    // device tables built by the host with the same float arithmetic, null = compute
+    const uint32_t* code_x; const uint32_t* code_y; int code_nx, code_ny;
 };
 
 // one FAST detection cell (ORBextractor.cc:1089-1157): ROI = [x0,x0+cw) x [y0,y0+ch) in level coords

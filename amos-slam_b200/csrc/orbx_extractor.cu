@@ -17,6 +17,7 @@
 #include "k_pyramid_fast.cuh"
 #include "k_fast.cuh"
 #include "k_octree.cuh"
+#include "k_octree_fused.cuh"
 #include "k_describe.cuh"
 #include "k_cull.cuh"
 #include "brief_pattern.inc"
@@ -106,6 +107,7 @@ struct orbx_extractor {
     std::vector<LevelGeom> levels; std::vector<CellDesc> cells; std::vector<BlurTile> tiles, tiles_s;   // tiles_s: BLUR_STRIP_SMALL tiling
     long long pyr_fstride = 0; int cand_per_frame = 0, kp_per_frame = 0, max_kp = 0;
     FastLayout fast_lay{}; int tree_cap = 0, sort_smem_keys = 4096;
+    QfPlan qf{}; bool qf_ok = false;                       // k_octree_fused.cuh: the one-launch quadtree of the latency form
     DevBuf<CUtensorMap> d_tmaps; const void* tmaps_base = nullptr; int tmaps_B = 0;          // FAST tensor maps of levels >= 1 (by level), valid for (d_pyr.p, Bcap)
     CUtensorMap map_l0, map_l0_blur, map_l0_blur_s, map_l0_resize; const void* map_l0_sig[4] = {nullptr};                                // level-0 map of the current view (pointer, frame stride, pitch, frames)
     DevBuf<LevelGeom> d_levels; DevBuf<CellDesc> d_cells; DevBuf<BlurTile> d_tiles, d_tiles_s; DevBuf<int> d_tabs;
@@ -117,7 +119,7 @@ struct orbx_extractor {
     // ---- per-batch device state (the "stateful extractor": pyramid stays resident) ----
     int Bcap = 0, lastB = 0;
     DevBuf<uint8_t> d_pyr, d_blur, d_l0;
-    DevBuf<uint32_t> d_slots, d_ocand, d_spk, d_kp_level;
+    DevBuf<uint32_t> d_slots, d_ocand, d_spk, d_kp_level, d_codetab;
     DevBuf<unsigned long long> d_skey;
     DevBuf<uint16_t> d_cell_counts;
     DevBuf<int> d_ncand, d_kp_count, d_counts, d_level_counts, d_overflow;
@@ -154,6 +156,18 @@ static void linear_coefs(int ssize, int dsize, int padded, std::vector<int>& ofs
         w[2 * d] = (short)cv_round_f((1.f - f) * 2048.f);
         w[2 * d + 1] = (short)cv_round_f(f * 2048.f);
     }
+}
+
+// path-code tables of one level (k_octree.cuh): nx entries for x, then ny entries for y, appended to `out`.  Same float arithmetic as octree_code
+// (IEEE single division / product, truncation), so a tabulated code equals the computed one.
+static void octree_code_tables(const LevelGeom& g, int nx, int ny, std::vector<uint32_t>& out) {
+    for (int x = 0; x < nx; ++x) {
+        const volatile float q = (float)x / g.hX;                              // vpIniNodes[kp.pt.x / hX]   ORBextractor.cc:766
+        const int root = (int)q;
+        const volatile float a = g.hX * (float)root, b = g.hX * (float)(root + 1);   // UL.x = (int)(hX*i), UR.x = (int)(hX*(i+1))   :741-745
+        out.push_back(((uint32_t)root << ORBX_ROOT_SHIFT) | octree_code_half(x, (int)a, (int)b, 0));
+    }
+    for (int y = 0; y < ny; ++y) out.push_back(octree_code_half(y, 0, g.maxBY - g.minBY, 1));
 }
 
 static int build_plan(orbx_extractor* h, int rows, int cols) {
@@ -279,6 +293,18 @@ static int build_plan(orbx_extractor* h, int rows, int cols) {
         rbw[l] = rbh[l] = 0;
         if (wide_ok[l] && bwm <= 256 && bhm <= 256 && per_warp * RESIZE_WARPS <= 100 * 1024) { rbw[l] = bwm; rbh[l] = bhm; }
     }
+    {   // quadtree path-code tables, one (x, y) pair per level
+        std::vector<uint32_t> ct; std::vector<size_t> at(L);
+        for (int l = 0; l < L; ++l) {
+            at[l] = ct.size();
+            lv[l].code_nx = std::max(lv[l].maxBX - lv[l].minBX, 1) + 8; lv[l].code_ny = std::max(lv[l].maxBY - lv[l].minBY, 1) + 8;
+            octree_code_tables(lv[l], lv[l].code_nx, lv[l].code_ny, ct);
+        }
+        if (h->d_codetab.ensure(ct.size())) return ORBX_E_CUDA;
+        CU_TRY(cudaMemcpyAsync(h->d_codetab.p, ct.data(), ct.size() * 4, cudaMemcpyHostToDevice, h->stream));
+        CU_TRY(cudaStreamSynchronize(h->stream));
+        for (int l = 0; l < L; ++l) { lv[l].code_x = h->d_codetab.p + at[l]; lv[l].code_y = lv[l].code_x + lv[l].code_nx; }
+    }
     if (h->d_levels.ensure(L)) return ORBX_E_CUDA;
     if (h->d_cells.ensure(cells.size())) return ORBX_E_CUDA;
     if (h->d_tiles.ensure(tiles.size()) || h->d_tiles_s.ensure(tiles_s.size())) return ORBX_E_CUDA;
@@ -383,6 +409,20 @@ static int build_plan(orbx_extractor* h, int rows, int cols) {
     // radix-sort capacity per (level, frame): ~1 candidate per 100 px of level 0 is generous for real images; larger levels fall back
     // to the global-memory bitonic path inside the kernel
     { const long long want = (long long)rows * cols / 100; int k = 4096; if (want > 4096) k = (int)std::min<long long>(18432, (want + want / 4 + 2047) / 2048 * 2048); h->sort_smem_keys = k; }
+    // one-launch quadtree of the latency form (k_octree_fused.cuh): node pool of the list's worst case (N + 3 nodes), the rest of the shared memory for keys.
+    // Frames above ~0.5 Mpx keep the two-kernel path: their level 0 can hold more candidates than the 16-bit radix counters of the fused kernel count.
+    {
+        int cellmax = 1, tabmax = 0;
+        for (int l = 0; l < L; ++l) { cellmax = std::max(cellmax, h->levels[l].cell_count); tabmax = std::max(tabmax, h->levels[l].code_nx + h->levels[l].code_ny); }
+        QfPlan q{}; q.pool_cap = std::max(1024, align_up(tree_cap, 32)); q.cell_cap = cellmax; q.tab_cap = align_up(tabmax, 4);
+        const size_t budget = 224 * 1024, fixed = qf_fixed_bytes(q.pool_cap, q.cell_cap, q.tab_cap);
+        h->qf_ok = q.pool_cap <= QF_MAXPOOL && fixed + 2048 * 16 <= budget && (long long)rows * cols <= 500000;
+        if (h->qf_ok) {
+            q.key_cap = (int)std::min<size_t>(8192, ((budget - fixed) / 16) & ~(size_t)31);
+            q.smem_bytes = (int)qf_smem_bytes(q);
+        }
+        h->qf = q;
+    }
     h->rows = rows; h->cols = cols; h->Bcap = 0; h->have_pyramid = false;
     if (h->graph1) { cudaGraphExecDestroy(h->graph1); h->graph1 = nullptr; }       // the captured pointers / launch shapes belong to the old geometry
     return ORBX_OK;
@@ -534,7 +574,15 @@ static int run_detect(orbx_extractor* h, int b0, int B, bool fork_blur = false) 
     }
     prof_mark(h);
     if (fork_blur) CU_TRY(cudaEventRecord(h->ev_fork, s));        // the blur may start once FAST is done ...
-    {
+    static const int qf_env = [] { const char* e = std::getenv("ORBX_QT_FUSED"); return e ? std::atoi(e) : -1; }();   // 0 / 1 force the two-kernel / one-kernel quadtree (A/B testing)
+    if (h->qf_ok && (qf_env >= 0 ? qf_env != 0 : B <= 4)) {
+        // a handful of frames (what Tracking calls): gather + path codes + sort + tree of a level in ONE launch, everything in shared memory
+        k_octree_fused<QF_THREADS><<<dim3(L, B), QF_THREADS, h->qf.smem_bytes, s>>>(h->d_levels.p, h->d_cells.p, ncells, h->cand_per_frame, h->cand_per_frame, h->kp_per_frame, L, h->qf,
+            slots, cell_counts, h->d_ocand.p + co, h->d_skey.p + co, h->d_spk.p + co, h->d_ncand.p + (size_t)b0 * L, h->d_kp_level.p + (size_t)b0 * h->kp_per_frame,
+            h->d_kp_count.p + (size_t)b0 * L, h->d_overflow.p);
+        LAUNCH_CHECK();
+        prof_mark(h); prof_mark(h);                                      // (the stage table keeps its sort / tree columns: the second one reads 0)
+    } else {
         dim3 grid(L, B);
         // a handful of frames: one CTA per level cannot fill the GPU anyway, so each CTA is made wide and the level-0 sort gets 4x the threads per pass
         static const int wide_env = [] { const char* e = std::getenv("ORBX_SORT_WIDE"); return e ? std::atoi(e) : -1; }();
@@ -765,6 +813,7 @@ int orbx_create(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, in
     cudaFuncSetAttribute(k_octree_sort_t<SORT_THREADS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)octree_sort_smem_bytes(8192, SORT_THREADS_WIDE));
     cudaFuncSetAttribute(k_octree_tree, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_octree_tree_par, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ptree_smem_bytes(PTREE_MAXCAP, 4096));
+    cudaFuncSetAttribute(k_octree_fused<QF_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     cudaFuncSetAttribute(k_fast_cells<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(k_fast_cells<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(k_pyr_resize_t, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
@@ -791,7 +840,7 @@ void orbx_destroy(orbx_extractor* h) {
     for (cudaEvent_t e : h->ev_h2d) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_done) cudaEventDestroy(e);
     h->d_l0.release();
-    h->d_tp_lv.release(); h->d_tp_xr.release(); h->d_tp_yr.release(); h->d_chain.release(); h->d_tmaps.release(); h->d_levels.release(); h->d_cells.release(); h->d_tiles.release(); h->d_tiles_s.release(); h->d_tabs.release();
+    h->d_tp_lv.release(); h->d_tp_xr.release(); h->d_tp_yr.release(); h->d_chain.release(); h->d_tmaps.release(); h->d_levels.release(); h->d_codetab.release(); h->d_cells.release(); h->d_tiles.release(); h->d_tiles_s.release(); h->d_tabs.release();
     h->d_pyr.release(); h->d_blur.release(); h->d_slots.release(); h->d_ocand.release(); h->d_spk.release(); h->d_kp_level.release();
     h->d_skey.release(); h->d_cell_counts.release(); h->d_ncand.release(); h->d_kp_count.release(); h->d_counts.release();
     h->d_level_counts.release(); h->d_overflow.release(); h->d_kp_out.release(); h->d_desc_out.release();
@@ -1267,3 +1316,13 @@ int orbx_internal_last_batch(orbx_extractor* h, OrbxBatchInfo* out) {
     out->scale = h->mvScaleFactor.data(); out->inv_scale = h->mvInvScaleFactor.data();
     return ORBX_OK;
 }
+
+#ifdef ORBX_QT_STAMPS
+// probe build only (tools/qt_stamps_probe.py): clock64 stamps of the quadtree kernels' phases, (level 0, frame 0) instance
+extern "C" int orbx_probe_qt_stamps(long long* out, int n) {
+    if (!out || n <= 0 || n > 64) FAIL(ORBX_E_INVALID, "bad arguments");
+    CU_TRY(cudaDeviceSynchronize());
+    CU_TRY(cudaMemcpyFromSymbol(out, g_qt_stamps, sizeof(long long) * (size_t)n));
+    return ORBX_OK;
+}
+#endif

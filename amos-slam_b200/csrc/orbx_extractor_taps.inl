@@ -33,11 +33,33 @@ extern "C" int orbx_debug_distribute(orbx_extractor* h, const orbx_keypoint* can
     if (dl.ensure(1) || dc.ensure(nc) || dcnt.ensure(nc) || dslots.ensure(ncand) || doc.ensure(ncand) || dspk.ensure(ncand) || dsk.ensure(ncand) ||
         dkp.ensure(g.kp_cap) || dn.ensure(1) || dkc.ensure(1) || h->d_overflow.ensure(4)) return ORBX_E_CUDA;
     cudaStream_t s = h->stream;
+    DevBuf<uint32_t> dtab; struct TabGuard { DevBuf<uint32_t>& t; ~TabGuard() { t.release(); } } tab_guard{dtab};
+    { const char* e = std::getenv("ORBX_QT_TABLES");                           // 1: path codes from tables (as the pipeline does), default: computed
+      if (e && std::atoi(e) != 0) {
+          std::vector<uint32_t> ct; g.code_nx = ORBX_MAX_DIM + 1; g.code_ny = ORBX_MAX_DIM + 1;
+          octree_code_tables(g, g.code_nx, g.code_ny, ct);
+          if (dtab.ensure(ct.size())) return ORBX_E_CUDA;
+          CU_TRY(cudaMemcpyAsync(dtab.p, ct.data(), ct.size() * 4, cudaMemcpyHostToDevice, s));
+          CU_TRY(cudaStreamSynchronize(s));
+          g.code_x = dtab.p; g.code_y = dtab.p + g.code_nx;
+      } }
     CU_TRY(cudaMemsetAsync(h->d_overflow.p, 0, 16, s));
     CU_TRY(cudaMemcpyAsync(dl.p, &g, sizeof(g), cudaMemcpyHostToDevice, s));
     CU_TRY(cudaMemcpyAsync(dc.p, cells.data(), sizeof(CellDesc) * nc, cudaMemcpyHostToDevice, s));
     CU_TRY(cudaMemcpyAsync(dcnt.p, counts.data(), 2 * nc, cudaMemcpyHostToDevice, s));
     CU_TRY(cudaMemcpyAsync(dslots.p, packed.data(), 4 * (size_t)ncand, cudaMemcpyHostToDevice, s));
+    // form: ORBX_QT_FUSED = 1 / 0 forces the one-launch kernel of the latency form / the sort + tree pair; default = what a single frame gets (read per call: tests switch it)
+    QfPlan q{}; q.pool_cap = std::max(1024, align_up(tcap, 32)); q.cell_cap = nc; q.tab_cap = 0;
+    const size_t qbudget = 224 * 1024, qfixed = qf_fixed_bytes(q.pool_cap, q.cell_cap, 0);
+    bool fused = q.pool_cap <= QF_MAXPOOL && qfixed + 2048 * 16 <= qbudget && ncand <= 65535;
+    { const char* e = std::getenv("ORBX_QT_FUSED"); if (e && std::atoi(e) == 0) fused = false; }
+    if (fused) {
+        q.key_cap = (int)std::min<size_t>(8192, ((qbudget - qfixed) / 16) & ~(size_t)31);
+        { const char* e = std::getenv("ORBX_QT_KEYCAP"); if (e && std::atoi(e) >= 32) q.key_cap = std::min(q.key_cap, std::atoi(e) & ~31); }   // small values exercise the global-scratch path
+        q.smem_bytes = (int)qf_smem_bytes(q);
+        k_octree_fused<QF_THREADS><<<dim3(1, 1), QF_THREADS, q.smem_bytes, s>>>(dl.p, dc.p, nc, ncand, ncand, g.kp_cap, 1, q, dslots.p, dcnt.p, doc.p, dsk.p, dspk.p, dn.p, dkp.p, dkc.p, h->d_overflow.p);
+        LAUNCH_CHECK();
+    } else {
     k_octree_sort_t<SORT_THREADS><<<dim3(1, 1), SORT_THREADS, octree_sort_smem_bytes(h->sort_smem_keys), s>>>(dl.p, dc.p, nc, ncand, ncand, 1, h->sort_smem_keys, dslots.p, dcnt.p, doc.p, dsk.p, dspk.p, dn.p);
     LAUNCH_CHECK();
     const int code_cap = 4096;
@@ -47,6 +69,7 @@ extern "C" int orbx_debug_distribute(orbx_extractor* h, const orbx_keypoint* can
     else
         k_octree_tree<<<dim3(1, 1), 32, tsm, s>>>(dl.p, 1, ncand, g.kp_cap, tcap, code_cap, dsk.p, dspk.p, dn.p, dkp.p, dkc.p, h->d_overflow.p);
     LAUNCH_CHECK();
+    }
     int n = 0, ovf = 0;
     std::vector<uint32_t> res(g.kp_cap);
     CU_TRY(cudaMemcpyAsync(&n, dkc.p, 4, cudaMemcpyDeviceToHost, s));

@@ -200,25 +200,42 @@ def test_batch_full_size_properties(orbx):
 def test_quadtree_stage_adversarial(orbx, oracle):
     """DistributeOctTree alone (device kernels) vs the reference's golden outputs and the port on adversarial sets."""
     E = orbx.ORBextractor(1000, 1.2, 8, 20, 7); P = oracle.Extractor("port", 1000, 1.2, 8, 20, 7)
+    # forms of the stage: the one-launch kernel of the latency form (default for a single frame), the same kernel with a key capacity so small
+    # that every set runs on its global-scratch path, the sort + tree pair of the batched path; path codes computed or read from the host's tables
+    forms = ({}, {"ORBX_QT_KEYCAP": "64"}, {"ORBX_QT_FUSED": "0"}, {"ORBX_QT_TABLES": "1"}, {"ORBX_QT_FUSED": "0", "ORBX_QT_TABLES": "1"})
+    def distribute(c, x0, x1, y0, y1, N):
+        outs = []
+        for f in forms:
+            os.environ.update(f)
+            try:
+                outs.append(E.debug_distribute(c, x0, x1, y0, y1, N))
+            finally:
+                for k in f: os.environ.pop(k, None)
+        for o in outs[1:]:
+            assert len(o) == len(outs[0]) and all(np.array_equal(o[f], outs[0][f]) for f in ("x", "y", "response"))
+        return outs[0]
     for k in [k for k in R.files if k.startswith("oct_") and k.endswith("_in")]:
         N = int(k.split("_")[-2])
-        out = E.debug_distribute(R[k], 16, 16 + 608, 16, 16 + 448, N)
+        out = distribute(R[k], 16, 16 + 608, 16, 16 + 448, N)
         ref = R[k[:-3] + "_out"]
         assert len(out) == len(ref) and all(np.array_equal(out[f], ref[f]) for f in ("x", "y", "response")), k
     rng = np.random.default_rng(9)
-    for trial in range(12):
+    for trial in range(36):
         W, H = int(rng.integers(80, 1900)), int(rng.integers(60, 1060))
         if not (0.5 <= W / H < 15.5):
             continue
-        n = int(rng.integers(1, 6000))
+        n = int(rng.integers(1, 6000 if trial % 4 else 30000))
         xs = rng.integers(3, W - 3, n); ys = rng.integers(3, H - 3, n)
         if trial % 3 == 0:                                                      # heavy clustering
             xs = np.clip(rng.normal(W * 0.3, 6, n), 3, W - 4).astype(int); ys = np.clip(rng.normal(H * 0.6, 5, n), 3, H - 4).astype(int)
+        if trial % 7 == 5:                                                      # a few tight pairs far apart: long chains of one-child divides
+            m = int(rng.integers(2, 40)); cx = rng.integers(8, W - 8, m); cy = rng.integers(8, H - 8, m)
+            xs = np.concatenate([cx, cx + rng.integers(1, 3, m)]); ys = np.concatenate([cy, cy + rng.integers(0, 2, m)])
         u = np.unique(np.stack([ys, xs], 1), axis=0); u = u[rng.permutation(len(u))]
         c = np.zeros(len(u), oracle.KP_DTYPE); c["x"] = u[:, 1]; c["y"] = u[:, 0]
         c["response"] = rng.integers(7, 40 if trial % 2 else 255, len(u)); c["size"] = 7; c["angle"] = -1; c["class_id"] = -1
-        N = int(rng.integers(1, 500))
-        out = E.debug_distribute(c, 16, 16 + W, 16, 16 + H, N); ref = P.distribute(c, 16, 16 + W, 16, 16 + H, N)
+        N = int(rng.integers(1, 500)) if trial % 5 else int(rng.integers(500, 1500))
+        out = distribute(c, 16, 16 + W, 16, 16 + H, N); ref = P.distribute(c, 16, 16 + W, 16, 16 + H, N)
         assert len(out) == len(ref) and all(np.array_equal(out[f], ref[f]) for f in ("x", "y", "response")), (trial, W, H, n, N)
 
 
@@ -459,7 +476,7 @@ def test_no_kernel_writes_outside_its_buffers(tmp_path):
 def test_every_kernel_form_gives_the_same_result(tmp_path):
     """The latency / throughput forms of the stages are chosen by batch size; every one of them must be bit-identical.  Each environment
     below forces one form for BOTH a single frame and a small batch (resize: TMA tiles / per-thread / one-launch tile pyramid / 8-CTA
-    cluster chain; blur: long / short strips; FAST: 1 / 8 cells per warp, one CTA per cell; masks packed on the host / on the device) and the digest of all
+    cluster chain; blur: long / short strips; FAST: 1 / 8 cells per warp, one CTA per cell; quadtree: sort + tree pair / one-launch kernel; masks packed on the host / on the device) and the digest of all
     outputs must equal the digest of the default run -- which the other tests pin to the reference."""
     import subprocess, sys, textwrap, hashlib
     code = textwrap.dedent('''
@@ -488,5 +505,5 @@ def test_every_kernel_form_gives_the_same_result(tmp_path):
     base = run({})
     for extra in ({"ORBX_TILEPYR": "0"}, {"ORBX_TILEPYR": "1"}, {"ORBX_TILEPYR": "0", "ORBX_RESIZE_TMA": "1"}, {"ORBX_TILEPYR": "0", "ORBX_RESIZE_TMA": "0"},
                   {"ORBX_CHAIN": "1"}, {"ORBX_BLUR_SMALL": "0"}, {"ORBX_BLUR_SMALL": "1"}, {"ORBX_FAST_CPW": "1"}, {"ORBX_FAST_CPW": "8"}, {"ORBX_FAST_CTA": "0"}, {"ORBX_FAST_CTA": "1"},
-                  {"ORBX_HOST_PACK": "0"}, {"ORBX_HOST_PACK": "3"}, {"ORBX_GRAPH": "0"}):
+                  {"ORBX_HOST_PACK": "0"}, {"ORBX_HOST_PACK": "3"}, {"ORBX_GRAPH": "0"}, {"ORBX_QT_FUSED": "0"}, {"ORBX_QT_FUSED": "1"}):
         assert run(extra) == base, extra
