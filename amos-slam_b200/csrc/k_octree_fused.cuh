@@ -1,7 +1,8 @@
 // k_octree_fused.cuh -- DistributeOctTree (/root/reference/src/ORBextractor.cc:635-1049) as ONE kernel, for the latency form (a handful
 // of frames: what Tracking calls once per frame).  One CTA per (level, frame); gather, path codes, radix sort and the tree all stay in
 // shared memory, so the chain  k_octree_sort -> skey / spk / ocand in HBM -> k_octree_tree_par  (two launches, ~130 block barriers,
-// 39 us for a 640 x 480 level 0 with its 2.5 k candidates) becomes one launch of ~12 us.
+// 39 us for a 640 x 480 level 0 with its 2.5 k candidates) becomes one launch of 17 us (phase times: tools/qt_stamps_probe.py).
+// The CTA is alone on its SM and bound by instruction issue there, so every phase is written for few instructions, not for few bytes.
 //
 // The tree is not replayed round by round any more.  With the keys sorted by path code (k_octree.cuh), let dd[i] be the first digit in
 // which key i differs from key i-1 (0 = different root, 1..13 = tree digit, dd[0] = dd[n] = 0).  Then:
@@ -31,11 +32,13 @@
 #define QF_BUCKETS (1 << QF_BUCKET_BITS)
 #define QF_BUCKET_MAX 48            // largest bucket the in-bucket ranking takes; above it the radix passes sort the level
 
+#define QF_MAXLEVELS 16
+struct QfLevels { LevelGeom lv[QF_MAXLEVELS]; };   // the level geometry travels as a kernel parameter: no dependent global load in front of the counts
 struct QfPlan { int key_cap, pool_cap, cell_cap, tab_cap, smem_bytes; };   // tab_cap: path-code table entries staged in shared memory (0 = read them from global memory)
 
-// shared-memory layout: [pool: lo hi (int) key rk (u64) clist order b1 b2 b3 gr (int) dep alive (u8), pool_cap each] [2 x hist] [cell_off cell_slot (int, cell_cap + 1 each)] [path-code tables (u32, tab_cap)]
+// shared-memory layout: [pool: rk (u64) lo hi (int) key (u32) clist order b1 b2 b3 gr (int) dep alive (u8), pool_cap each] [2 x hist] [cell_off cell_slot (int, cell_cap + 1 each)] [path-code tables (u32, tab_cap)]
 //                       [cand keyA keyB (u32, key_cap each)] [idxA idxB (u16, key_cap each)]
-__host__ __device__ inline size_t qf_pool_bytes(int pool_cap) { return (size_t)pool_cap * (4 + 4 + 8 + 8 + 6 * 4 + 1 + 1); }
+__host__ __device__ inline size_t qf_pool_bytes(int pool_cap) { return (size_t)pool_cap * (4 + 4 + 4 + 8 + 6 * 4 + 1 + 1); }
 __host__ __device__ inline size_t qf_fixed_bytes(int pool_cap, int cell_cap, int tab_cap) {
     return ((qf_pool_bytes(pool_cap) + 15) & ~(size_t)15) + 2 * 256 * QF_HS * 2 + (((size_t)(cell_cap + 1) * 8 + 15) & ~(size_t)15) + (((size_t)tab_cap * 4 + 15) & ~(size_t)15) + 256;
 }
@@ -61,12 +64,16 @@ __device__ __forceinline__ int qf_diff_digit(uint32_t a, uint32_t b) {
     return hb >= ORBX_ROOT_SHIFT ? 0 : ORBX_MAXD - (hb >> 1);
 }
 
-// list-order key of a node created at depth D by the full passes: ascending = list order inside the depth-D block
-__device__ __forceinline__ uint32_t qf_tkey(uint32_t code, int D) {
+// List-order key of a node, 32 bits, ascending = list order.  Blocks newest first: the largest-first rounds (round r: QF_LF_SPACE slots at
+// (13 - r) * QF_LF_SPACE), then the depth-D blocks of the full passes for D = Q down to 0 (4^D * 16 slots each: 4-bit root index + D digits).
+// Inside a full-pass block: prefix ^ xormask(D), the digits D, D-2, .. (and the root with digit 1) descending, the others ascending.
+#define QF_LF_SPACE (1u << 14)
+__device__ __forceinline__ uint32_t qf_tkey(uint32_t code, int D, int Q) {
     const uint32_t prefix = code >> (2 * (ORBX_MAXD - D));
-    const uint32_t low = D ? (0x33333333u & ((1u << (2 * D)) - 1u)) : 0u;          // digits D, D-2, .. descending
-    const uint32_t root = (D & 1) ? (0x3Fu << (2 * D)) : 0u;                        // the root index runs with digit 1
-    return prefix ^ (low | root);
+    const uint32_t low = D ? (0x33333333u & ((1u << (2 * D)) - 1u)) : 0u;
+    const uint32_t root = (D & 1) ? (0xFu << (2 * D)) : 0u;
+    const uint32_t base = 14u * QF_LF_SPACE + 16u * (((1u << (2 * (Q + 1))) - (1u << (2 * (D + 1)))) / 3u);   // blocks Q, Q-1, .., D+1 lie in front
+    return base + ((prefix ^ (low | root)) & ((16u << (2 * D)) - 1u));
 }
 
 struct QfShared {
@@ -131,6 +138,25 @@ __device__ __forceinline__ void qf_rank(const unsigned long long* key, int np, i
         if (e < np) {
             v = key[e];
             for (int f = g; f < np; f += G) r += key[f] < v;
+        }
+        for (int o = 1; o < G; o <<= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+        if (e < np && g == 0) order[r] = e;
+    }
+}
+
+// the same for 32-bit keys padded with 0xFFFFFFFF to a multiple of 4: four keys per load
+template <int THREADS>
+__device__ __forceinline__ void qf_rank32(const uint32_t* key, int np, int* order) {
+    int lg = 0;
+    while (lg < 5 && (np << (lg + 1)) <= THREADS) ++lg;
+    const int G = 1 << lg, n4 = (np + 3) >> 2;
+    const uint4* key4 = reinterpret_cast<const uint4*>(key);
+    for (int t = threadIdx.x; t < (((np << lg) + 31) & ~31); t += THREADS) {
+        const int e = t >> lg, g = t & (G - 1);
+        int r = 0;
+        if (e < np) {
+            const uint32_t v = key[e];
+            for (int f = g; f < n4; f += G) { const uint4 k = key4[f]; r += (k.x < v) + (k.y < v) + (k.z < v) + (k.w < v); }
         }
         for (int o = 1; o < G; o <<= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
         if (e < np && g == 0) order[r] = e;
@@ -286,11 +312,11 @@ __device__ __forceinline__ void qf_core(const LevelGeom& g, int n, int level, in
     uint8_t* dd = reinterpret_cast<uint8_t*>(keyB);                            // n + 1 entries (keyB is free now)
 
     // pool of node records (pool index = creation slot; the list order lives in nkey)
-    int* nlo = reinterpret_cast<int*>(pool_sm);
+    unsigned long long* rk = reinterpret_cast<unsigned long long*>(pool_sm);   // rank keys of the round (64 bits: size | list key); the final ranking reads them as u32
+    int* nlo = reinterpret_cast<int*>(rk + pool_cap);
     int* nhi = nlo + pool_cap;
-    unsigned long long* nkey = reinterpret_cast<unsigned long long*>(nhi + pool_cap);   // block age << 32 | key inside the block: ascending = list order
-    unsigned long long* rk = nkey + pool_cap;                                  // rank keys of the round
-    int* clist = reinterpret_cast<int*>(rk + pool_cap);                        // candidates of the current largest-first round / living nodes at the end (pool indices)
+    uint32_t* nkey = reinterpret_cast<uint32_t*>(nhi + pool_cap);              // list key (qf_tkey): ascending = list order
+    int* clist = reinterpret_cast<int*>(nkey + pool_cap);                      // candidates of the current largest-first round / living nodes at the end (pool indices)
     int* order = clist + pool_cap;                                             // element of rank r
     int* b1 = order + pool_cap; int* b2 = b1 + pool_cap; int* b3 = b2 + pool_cap;       // child boundaries of the candidate of rank r
     int* gr = b3 + pool_cap;                                                   // growth (children - 1) of rank r, then its inclusive prefix
@@ -301,7 +327,7 @@ __device__ __forceinline__ void qf_core(const LevelGeom& g, int n, int level, in
     // Warp w owns the positions [s0, s1); its own histogram row (wacc) later gives the rank of its first node without a second counting pass. ----
     const int seg = ((n + WARPS - 1) / WARPS + 31) & ~31;
     const int s0 = min(warp * seg, n), s1 = min(s0 + seg, n);
-    int* wacc = order;                                                          // [WARPS][32]: C counts of the values 0..15, S counts of 0..15 (pool_cap >= 1024)
+    int* wacc = order;                                                          // [WARPS][33]: C counts of the values 0..15, S counts of 0..15, one pad (pool_cap >= 1056)
     {
         uint32_t pc[4] = {0u, 0u, 0u, 0u}, ps[4] = {0u, 0u, 0u, 0u};            // 16 + 16 private 8-bit counters
         int acc = 0, pending = 0;
@@ -330,12 +356,13 @@ __device__ __forceinline__ void qf_core(const LevelGeom& g, int n, int level, in
             if (++pending == 7) flush();
         }
         if (pending) flush();
-        wacc[warp * 32 + lane] = acc;
+        wacc[warp * 33 + lane] = acc;
         if (tid == 0) dd[n] = 0;
         __syncthreads();
         if (tid < 32) {
             int t = 0;
-            for (int w = 0; w < WARPS; ++w) t += wacc[w * 32 + tid];
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) t += wacc[w * 33 + tid];
             int inc = t;                                                        // cumulative over the digit value inside each half-warp
 #pragma unroll
             for (int o = 1; o < 16; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o, 16); if ((lane & 15) >= o) inc += u; }
@@ -365,7 +392,7 @@ __device__ __forceinline__ void qf_core(const LevelGeom& g, int n, int level, in
         int base;
         {   // nodes in front of this warp's segment: lane l sums row l of the per-warp histograms up to Q
             int mine = 0;
-            if (lane < WARPS) for (int v = 0; v <= Q; ++v) mine += wacc[lane * 32 + v];
+            if (lane < WARPS) for (int v = 0; v <= Q; ++v) mine += wacc[lane * 33 + v];
             int inc = mine;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
@@ -388,7 +415,7 @@ __device__ __forceinline__ void qf_core(const LevelGeom& g, int n, int level, in
                 multi = hi - lo > 1;
                 const int D = multi ? Q : max((int)dd[lo], (int)dd[lo + 1]);
                 ndep[k] = (uint8_t)D; nalive[k] = 1;
-                nkey[k] = ((unsigned long long)(64 + Q - D) << 32) | qf_tkey(ck[lo], D);
+                nkey[k] = qf_tkey(ck[lo], D, Q);
             }
             if (lf) qf_append(multi, k, clist, &sh.counter[0]);
         }
@@ -405,12 +432,13 @@ __device__ __forceinline__ void qf_core(const LevelGeom& g, int n, int level, in
         // rank by (size desc, list order = newest first)
         for (int e = tid; e < np; e += THREADS) {
             const int k = clist[e];
-            rk[e] = ((unsigned long long)(0xFFFFFFu - (unsigned)(nhi[k] - nlo[k])) << 40) | (nkey[k] & 0xFFFFFFFFFFull);
+            rk[e] = ((unsigned long long)(0xFFFFFFu - (unsigned)(nhi[k] - nlo[k])) << 32) | nkey[k];
         }
         if (tid == 0) { sh.rstar = np - 1; sh.counter[(round + 1) & 1] = 0; }
         __syncthreads();
         qf_rank<THREADS>(rk, np, order);
         __syncthreads();
+        if (round == 0) QT_STAMP(24);
         // children of the candidate of rank r: boundaries c1..c3 (three interleaved lower bounds on the sorted codes), growth = non-empty children - 1
         for (int r = tid; r < np; r += THREADS) {
             const int k = clist[order[r]];
@@ -434,11 +462,13 @@ __device__ __forceinline__ void qf_core(const LevelGeom& g, int n, int level, in
             gr[r] = m - 1; b1[r] = c1; b2[r] = c2; b3[r] = c3;
         }
         __syncthreads();
+        if (round == 0) QT_STAMP(25);
         if (sh.ovf) { ovf = true; break; }
         qf_scan_array<THREADS>(gr, np, sh.wsum);
         for (int r = tid; r < np; r += THREADS)
             if (count + gr[r] >= N && (r == 0 || count + gr[r - 1] < N)) sh.rstar = r;   // first candidate after whose divide the list holds >= N nodes (:1003)
         __syncthreads();
+        if (round == 0) QT_STAMP(26);
         const int rstar = sh.rstar, P = rstar + 1, growth = gr[rstar];
         if (poolN + growth > pool_cap) { ovf = true; break; }                   // cannot happen: the list never holds more than N + 3 nodes
         int* cnt_next = &sh.counter[(round + 1) & 1];
@@ -462,7 +492,7 @@ __device__ __forceinline__ void qf_core(const LevelGeom& g, int n, int level, in
                     slot = first ? k : extra++;
                     first = false;
                     nlo[slot] = bnd[q]; nhi[slot] = bnd[q + 1]; ndep[slot] = (uint8_t)(dep + 1); nalive[slot] = 1;
-                    nkey[slot] = ((unsigned long long)(63 - round) << 32) | (unsigned)(((np - 1 - r) << 2) | (3 - q));   // reverse creation order
+                    nkey[slot] = (uint32_t)(13 - round) * QF_LF_SPACE + (uint32_t)(((np - 1 - r) << 2) | (3 - q));   // reverse creation order
                 }
                 qf_append(have && sz > 1, slot, clist, cnt_next);               // clist is dead since the barrier above: the next round's candidates go there
             }
@@ -485,10 +515,13 @@ __device__ __forceinline__ void qf_core(const LevelGeom& g, int n, int level, in
         for (int k0 = 0; k0 < poolN; k0 += THREADS) { const int k = k0 + tid; qf_append(k < poolN && nalive[k], k, clist, &sh.counter[2]); }
         __syncthreads();
         const int K = sh.counter[2];                                            // == count
-        for (int e = tid; e < K; e += THREADS) rk[e] = nkey[clist[e]];
+        uint32_t* rk32 = reinterpret_cast<uint32_t*>(rk);
+        for (int e = tid; e < ((K + 3) & ~3); e += THREADS) rk32[e] = e < K ? nkey[clist[e]] : 0xFFFFFFFFu;
         __syncthreads();
-        qf_rank<THREADS>(rk, K, order);
+        QT_STAMP(30);
+        qf_rank32<THREADS>(rk32, K, order);
         __syncthreads();
+        QT_STAMP(31);
         nout = min(K, g.kp_cap);
         if (K > g.kp_cap) ovf = true;
         for (int t0 = 0; t0 < nout * 8; t0 += THREADS) {                        // eight lanes per node
@@ -517,7 +550,7 @@ __device__ __forceinline__ void qf_core(const LevelGeom& g, int n, int level, in
 
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
-k_octree_fused(const LevelGeom* __restrict__ levels, const CellDesc* __restrict__ cells, int ncells, int slots_per_frame, int cand_per_frame,
+k_octree_fused(const __grid_constant__ QfLevels P, const CellDesc* __restrict__ cells, int ncells, int slots_per_frame, int cand_per_frame,
                int kp_per_frame, int nlevels, QfPlan plan,
                uint32_t* cand_slots,                    // [B][slots_per_frame] FAST candidates per cell slot (an oversized level reuses its slice as scratch once gathered)
                const uint16_t* __restrict__ cell_counts,
@@ -527,12 +560,9 @@ k_octree_fused(const LevelGeom* __restrict__ levels, const CellDesc* __restrict_
                int* __restrict__ ncand, uint32_t* __restrict__ kp_level, int* __restrict__ kp_count, int* __restrict__ overflow) {
     extern __shared__ __align__(16) uint8_t qf_sm[];
     __shared__ QfShared sh;
-    __shared__ LevelGeom gs;
     const int level = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     QT_STAMP(0);
-    if (tid < (int)(sizeof(LevelGeom) / 4)) reinterpret_cast<int*>(&gs)[tid] = reinterpret_cast<const int*>(levels + level)[tid];
-    __syncthreads();
-    const LevelGeom& g = gs;
+    const LevelGeom& g = P.lv[level];
     uint8_t* pool_sm = qf_sm;
     uint16_t* hist = reinterpret_cast<uint16_t*>(qf_sm + ((qf_pool_bytes(plan.pool_cap) + 15) & ~(size_t)15));
     int* cell_off = reinterpret_cast<int*>(hist + 2 * 256 * QF_HS);

@@ -107,7 +107,7 @@ struct orbx_extractor {
     std::vector<LevelGeom> levels; std::vector<CellDesc> cells; std::vector<BlurTile> tiles, tiles_s;   // tiles_s: BLUR_STRIP_SMALL tiling
     long long pyr_fstride = 0; int cand_per_frame = 0, kp_per_frame = 0, max_kp = 0;
     FastLayout fast_lay{}; int tree_cap = 0, sort_smem_keys = 4096;
-    QfPlan qf{}; bool qf_ok = false;                       // k_octree_fused.cuh: the one-launch quadtree of the latency form
+    QfPlan qf{}; QfLevels qf_levels{}; bool qf_ok = false;                       // k_octree_fused.cuh: the one-launch quadtree of the latency form
     DevBuf<CUtensorMap> d_tmaps; const void* tmaps_base = nullptr; int tmaps_B = 0;          // FAST tensor maps of levels >= 1 (by level), valid for (d_pyr.p, Bcap)
     CUtensorMap map_l0, map_l0_blur, map_l0_blur_s, map_l0_resize; const void* map_l0_sig[4] = {nullptr};                                // level-0 map of the current view (pointer, frame stride, pitch, frames)
     DevBuf<LevelGeom> d_levels; DevBuf<CellDesc> d_cells; DevBuf<BlurTile> d_tiles, d_tiles_s; DevBuf<int> d_tabs;
@@ -414,9 +414,10 @@ static int build_plan(orbx_extractor* h, int rows, int cols) {
     {
         int cellmax = 1, tabmax = 0;
         for (int l = 0; l < L; ++l) { cellmax = std::max(cellmax, h->levels[l].cell_count); tabmax = std::max(tabmax, h->levels[l].code_nx + h->levels[l].code_ny); }
-        QfPlan q{}; q.pool_cap = std::max(1024, align_up(tree_cap, 32)); q.cell_cap = cellmax; q.tab_cap = align_up(tabmax, 4);
+        QfPlan q{}; q.pool_cap = std::max(1056, align_up(tree_cap, 32)); q.cell_cap = cellmax; q.tab_cap = align_up(tabmax, 4);
         const size_t budget = 224 * 1024, fixed = qf_fixed_bytes(q.pool_cap, q.cell_cap, q.tab_cap);
-        h->qf_ok = q.pool_cap <= QF_MAXPOOL && fixed + 2048 * 16 <= budget && (long long)rows * cols <= 500000;
+        h->qf_ok = L <= QF_MAXLEVELS && q.pool_cap <= QF_MAXPOOL && fixed + 2048 * 16 <= budget && (long long)rows * cols <= 500000;
+        if (h->qf_ok) for (int l = 0; l < L; ++l) h->qf_levels.lv[l] = h->levels[l];
         if (h->qf_ok) {
             q.key_cap = (int)std::min<size_t>(8192, ((budget - fixed) / 16) & ~(size_t)31);
             q.smem_bytes = (int)qf_smem_bytes(q);
@@ -577,7 +578,7 @@ static int run_detect(orbx_extractor* h, int b0, int B, bool fork_blur = false) 
     static const int qf_env = [] { const char* e = std::getenv("ORBX_QT_FUSED"); return e ? std::atoi(e) : -1; }();   // 0 / 1 force the two-kernel / one-kernel quadtree (A/B testing)
     if (h->qf_ok && (qf_env >= 0 ? qf_env != 0 : B <= 4)) {
         // a handful of frames (what Tracking calls): gather + path codes + sort + tree of a level in ONE launch, everything in shared memory
-        k_octree_fused<QF_THREADS><<<dim3(L, B), QF_THREADS, h->qf.smem_bytes, s>>>(h->d_levels.p, h->d_cells.p, ncells, h->cand_per_frame, h->cand_per_frame, h->kp_per_frame, L, h->qf,
+        k_octree_fused<QF_THREADS><<<dim3(L, B), QF_THREADS, h->qf.smem_bytes, s>>>(h->qf_levels, h->d_cells.p, ncells, h->cand_per_frame, h->cand_per_frame, h->kp_per_frame, L, h->qf,
             slots, cell_counts, h->d_ocand.p + co, h->d_skey.p + co, h->d_spk.p + co, h->d_ncand.p + (size_t)b0 * L, h->d_kp_level.p + (size_t)b0 * h->kp_per_frame,
             h->d_kp_count.p + (size_t)b0 * L, h->d_overflow.p);
         LAUNCH_CHECK();

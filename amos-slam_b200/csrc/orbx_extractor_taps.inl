@@ -49,7 +49,7 @@ extern "C" int orbx_debug_distribute(orbx_extractor* h, const orbx_keypoint* can
     CU_TRY(cudaMemcpyAsync(dcnt.p, counts.data(), 2 * nc, cudaMemcpyHostToDevice, s));
     CU_TRY(cudaMemcpyAsync(dslots.p, packed.data(), 4 * (size_t)ncand, cudaMemcpyHostToDevice, s));
     // form: ORBX_QT_FUSED = 1 / 0 forces the one-launch kernel of the latency form / the sort + tree pair; default = what a single frame gets (read per call: tests switch it)
-    QfPlan q{}; q.pool_cap = std::max(1024, align_up(tcap, 32)); q.cell_cap = nc; q.tab_cap = 0;
+    QfPlan q{}; q.pool_cap = std::max(1056, align_up(tcap, 32)); q.cell_cap = nc; q.tab_cap = 0;
     const size_t qbudget = 224 * 1024, qfixed = qf_fixed_bytes(q.pool_cap, q.cell_cap, 0);
     bool fused = q.pool_cap <= QF_MAXPOOL && qfixed + 2048 * 16 <= qbudget && ncand <= 65535;
     { const char* e = std::getenv("ORBX_QT_FUSED"); if (e && std::atoi(e) == 0) fused = false; }
@@ -57,7 +57,8 @@ extern "C" int orbx_debug_distribute(orbx_extractor* h, const orbx_keypoint* can
         q.key_cap = (int)std::min<size_t>(8192, ((qbudget - qfixed) / 16) & ~(size_t)31);
         { const char* e = std::getenv("ORBX_QT_KEYCAP"); if (e && std::atoi(e) >= 32) q.key_cap = std::min(q.key_cap, std::atoi(e) & ~31); }   // small values exercise the global-scratch path
         q.smem_bytes = (int)qf_smem_bytes(q);
-        k_octree_fused<QF_THREADS><<<dim3(1, 1), QF_THREADS, q.smem_bytes, s>>>(dl.p, dc.p, nc, ncand, ncand, g.kp_cap, 1, q, dslots.p, dcnt.p, doc.p, dsk.p, dspk.p, dn.p, dkp.p, dkc.p, h->d_overflow.p);
+        QfLevels ql{}; ql.lv[0] = g;
+        k_octree_fused<QF_THREADS><<<dim3(1, 1), QF_THREADS, q.smem_bytes, s>>>(ql, dc.p, nc, ncand, ncand, g.kp_cap, 1, q, dslots.p, dcnt.p, doc.p, dsk.p, dspk.p, dn.p, dkp.p, dkc.p, h->d_overflow.p);
         LAUNCH_CHECK();
     } else {
     k_octree_sort_t<SORT_THREADS><<<dim3(1, 1), SORT_THREADS, octree_sort_smem_bytes(h->sort_smem_keys), s>>>(dl.p, dc.p, nc, ncand, ncand, 1, h->sort_smem_keys, dslots.p, dcnt.p, doc.p, dsk.p, dspk.p, dn.p);

@@ -32,8 +32,9 @@ if __name__ == "__main__":
         lv0 = int((kp["octave"] == 0).sum())
         fused = os.environ.get("ORBX_QT_FUSED", "1") != "0"
         if fused:
-            names = {0: "start", 1: "count scan", 3: "gather + codes", 16: "dd + histograms", 17: "nodes after the full passes", 39: "final order + select"}
-            idx = [0, 1, 3, 4, 5, 6, 7, 16, 17, 18, 19, 20, 21, 22, 23, 39]
+            names = {0: "start", 1: "count scan", 3: "gather + codes", 4: "bucket sort", 16: "dd + histograms", 17: "nodes after the full passes", 24: "  round 0: rank", 25: "  round 0: children",
+                     26: "  round 0: scan + cut", 18: "  round 0: emit", 30: "final: compact", 31: "final: rank", 39: "final: select"}
+            idx = [0, 1, 3, 4, 5, 6, 7, 16, 17, 24, 25, 26, 18, 19, 20, 21, 22, 23, 30, 31, 39]
         else:
             names = {0: "start", 1: "count scan", 2: "gather", 3: "codes", 10: "write-out", 16: "tree start", 17: "codes to smem", 18: "roots", 38: "loop end", 39: "select"}
             idx = list(range(0, 11)) + list(range(16, 40))
@@ -43,7 +44,7 @@ if __name__ == "__main__":
             if st[i] == 0 or st[i] < st[0]:
                 continue
             if fused:
-                lab = names.get(i, "radix pass %d" % (i - 4) if i < 16 else "largest-first round %d" % (i - 18))
+                lab = names.get(i, "radix pass %d" % (i - 5) if i < 16 else "largest-first round %d" % (i - 18))
             else:
                 lab = names.get(i, "radix pass %d" % (i - 4) if i < 10 else "round %d" % (i - 20))
             if prev is not None and i not in (0,) and not (i == 16 and not fused) and st[i] >= prev:
