@@ -25,24 +25,27 @@
 #pragma once
 #include "k_octree.cuh"
 
-#define QF_THREADS 1024
-#define QF_HS 40                    // u16 per digit row of the radix histogram: 32 warp counters + 8 padding (80 B rows: conflict-free 16-byte reads)
-#define QF_MAXPOOL 2048
 #define QF_BUCKET_BITS 11
 #define QF_BUCKETS (1 << QF_BUCKET_BITS)
 #define QF_BUCKET_MAX 48            // largest bucket the in-bucket ranking takes; above it the radix passes sort the level
+#define QF_THREADS 1024             // latency form: one wide CTA per level, alone on its SM
+#define QF_THREADS_BATCH 256        // batched form: lean CTAs, several per SM
+// u16 per digit row of the radix histogram: one counter per warp + 8 padding (1024 threads: 80 B rows, conflict-free 16-byte reads)
+__host__ __device__ constexpr int qf_hs(int threads) { return threads / 32 + 8; }
+#define QF_MAXPOOL 2048
 
 #define QF_MAXLEVELS 16
 struct QfLevels { LevelGeom lv[QF_MAXLEVELS]; };   // the level geometry travels as a kernel parameter: no dependent global load in front of the counts
-struct QfPlan { int key_cap, pool_cap, cell_cap, tab_cap, smem_bytes; };   // tab_cap: path-code table entries staged in shared memory (0 = read them from global memory)
+struct QfPlan { int key_cap, pool_cap, cell_cap, tab_cap, threads, smem_bytes; };   // tab_cap: path-code table entries staged in shared memory (0 = read them from global memory)
 
 // shared-memory layout: [pool: rk (u64) lo hi (int) key (u32) clist order b1 b2 b3 gr (int) dep alive (u8), pool_cap each] [2 x hist] [cell_off cell_slot (int, cell_cap + 1 each)] [path-code tables (u32, tab_cap)]
 //                       [cand keyA keyB (u32, key_cap each)] [idxA idxB (u16, key_cap each)]
 __host__ __device__ inline size_t qf_pool_bytes(int pool_cap) { return (size_t)pool_cap * (4 + 4 + 4 + 8 + 6 * 4 + 1 + 1); }
-__host__ __device__ inline size_t qf_fixed_bytes(int pool_cap, int cell_cap, int tab_cap) {
-    return ((qf_pool_bytes(pool_cap) + 15) & ~(size_t)15) + 2 * 256 * QF_HS * 2 + (((size_t)(cell_cap + 1) * 8 + 15) & ~(size_t)15) + (((size_t)tab_cap * 4 + 15) & ~(size_t)15) + 256;
+__host__ __device__ inline size_t qf_fixed_bytes(int pool_cap, int cell_cap, int tab_cap, int threads) {
+    const size_t hist = (size_t)2 * 256 * qf_hs(threads) * 2, buckets = (size_t)(QF_BUCKETS + 1) * 4;      // the bucket table overlays the radix histograms
+    return ((qf_pool_bytes(pool_cap) + 15) & ~(size_t)15) + (((hist > buckets ? hist : buckets) + 15) & ~(size_t)15) + (((size_t)(cell_cap + 1) * 8 + 15) & ~(size_t)15) + (((size_t)tab_cap * 4 + 15) & ~(size_t)15) + 256;
 }
-__host__ __device__ inline size_t qf_smem_bytes(const QfPlan& q) { return qf_fixed_bytes(q.pool_cap, q.cell_cap, q.tab_cap) + (size_t)q.key_cap * 16; }
+__host__ __device__ inline size_t qf_smem_bytes(const QfPlan& q) { return qf_fixed_bytes(q.pool_cap, q.cell_cap, q.tab_cap, q.threads) + (size_t)q.key_cap * 16; }
 
 // lanes with the same 8-bit digit as this one (among the active lanes)
 __device__ __forceinline__ uint32_t qf_peers(uint32_t d, bool act) {
@@ -169,7 +172,7 @@ __device__ __forceinline__ void qf_core(const LevelGeom& g, int n, int level, in
                                         uint32_t* cand, uint32_t* keyA, uint32_t* keyB, IdxT* idxA, IdxT* idxB,
                                         const uint32_t* __restrict__ slots, uint32_t* __restrict__ oc,
                                         uint32_t* __restrict__ kp_level, int* __restrict__ kp_count, int* __restrict__ overflow, QfShared& sh) {
-    constexpr int WARPS = THREADS / 32;
+    constexpr int WARPS = THREADS / 32, QF_HS = qf_hs(THREADS);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt = (1u << lane) - 1u;
 
@@ -273,9 +276,10 @@ __device__ __forceinline__ void qf_core(const LevelGeom& g, int n, int level, in
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
                 if (lane == 31) sh.wsum[warp] = inc;
-            } else {
+            } else if (THREADS > 256) {
                 for (int i = tid - 256; i < 128 * QF_HS; i += THREADS - 256) reinterpret_cast<uint32_t*>(hnext)[i] = 0u;
             }
+            if (THREADS <= 256) for (int i = tid; i < 128 * QF_HS; i += THREADS) reinterpret_cast<uint32_t*>(hnext)[i] = 0u;
             __syncthreads();
             if (tid < 256) {
                 int basew = 0;
@@ -565,10 +569,10 @@ k_octree_fused(const __grid_constant__ QfLevels P, const CellDesc* __restrict__ 
     const LevelGeom& g = P.lv[level];
     uint8_t* pool_sm = qf_sm;
     uint16_t* hist = reinterpret_cast<uint16_t*>(qf_sm + ((qf_pool_bytes(plan.pool_cap) + 15) & ~(size_t)15));
-    int* cell_off = reinterpret_cast<int*>(hist + 2 * 256 * QF_HS);
+    int* cell_off = reinterpret_cast<int*>(qf_sm + qf_fixed_bytes(plan.pool_cap, 0, 0, THREADS) - 256 - 16);
     int* cell_slot = cell_off + plan.cell_cap + 1;
-    uint32_t* tab_sm = reinterpret_cast<uint32_t*>(qf_sm + qf_fixed_bytes(plan.pool_cap, plan.cell_cap, 0) - 256);
-    uint8_t* keys_sm = qf_sm + qf_fixed_bytes(plan.pool_cap, plan.cell_cap, plan.tab_cap);
+    uint32_t* tab_sm = reinterpret_cast<uint32_t*>(qf_sm + qf_fixed_bytes(plan.pool_cap, plan.cell_cap, 0, THREADS) - 256);
+    uint8_t* keys_sm = qf_sm + qf_fixed_bytes(plan.pool_cap, plan.cell_cap, plan.tab_cap, THREADS);
     // path-code tables of the level: staged beside the counts when they fit (x entries, then y entries: contiguous in the level's global table)
     const uint32_t* tab = nullptr;
     if (g.code_x) {

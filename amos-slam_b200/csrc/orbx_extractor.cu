@@ -107,7 +107,7 @@ struct orbx_extractor {
     std::vector<LevelGeom> levels; std::vector<CellDesc> cells; std::vector<BlurTile> tiles, tiles_s;   // tiles_s: BLUR_STRIP_SMALL tiling
     long long pyr_fstride = 0; int cand_per_frame = 0, kp_per_frame = 0, max_kp = 0;
     FastLayout fast_lay{}; int tree_cap = 0, sort_smem_keys = 4096;
-    QfPlan qf{}; QfLevels qf_levels{}; bool qf_ok = false;                       // k_octree_fused.cuh: the one-launch quadtree of the latency form
+    QfPlan qf{}, qfb{}; QfLevels qf_levels{}; bool qf_ok = false, qfb_ok = false;                       // k_octree_fused.cuh: the one-launch quadtree of the latency form
     DevBuf<CUtensorMap> d_tmaps; const void* tmaps_base = nullptr; int tmaps_B = 0;          // FAST tensor maps of levels >= 1 (by level), valid for (d_pyr.p, Bcap)
     CUtensorMap map_l0, map_l0_blur, map_l0_blur_s, map_l0_resize; const void* map_l0_sig[4] = {nullptr};                                // level-0 map of the current view (pointer, frame stride, pitch, frames)
     DevBuf<LevelGeom> d_levels; DevBuf<CellDesc> d_cells; DevBuf<BlurTile> d_tiles, d_tiles_s; DevBuf<int> d_tabs;
@@ -414,8 +414,8 @@ static int build_plan(orbx_extractor* h, int rows, int cols) {
     {
         int cellmax = 1, tabmax = 0;
         for (int l = 0; l < L; ++l) { cellmax = std::max(cellmax, h->levels[l].cell_count); tabmax = std::max(tabmax, h->levels[l].code_nx + h->levels[l].code_ny); }
-        QfPlan q{}; q.pool_cap = std::max(1056, align_up(tree_cap, 32)); q.cell_cap = cellmax; q.tab_cap = align_up(tabmax, 4);
-        const size_t budget = 224 * 1024, fixed = qf_fixed_bytes(q.pool_cap, q.cell_cap, q.tab_cap);
+        QfPlan q{}; q.threads = QF_THREADS; q.pool_cap = std::max(1056, align_up(tree_cap, 32)); q.cell_cap = cellmax; q.tab_cap = align_up(tabmax, 4);
+        const size_t budget = 224 * 1024, fixed = qf_fixed_bytes(q.pool_cap, q.cell_cap, q.tab_cap, q.threads);
         h->qf_ok = L <= QF_MAXLEVELS && q.pool_cap <= QF_MAXPOOL && fixed + 2048 * 16 <= budget && (long long)rows * cols <= 500000;
         if (h->qf_ok) for (int l = 0; l < L; ++l) h->qf_levels.lv[l] = h->levels[l];
         if (h->qf_ok) {
@@ -423,6 +423,19 @@ static int build_plan(orbx_extractor* h, int rows, int cols) {
             q.smem_bytes = (int)qf_smem_bytes(q);
         }
         h->qf = q;
+        // batched form: lean CTAs (QF_THREADS_BATCH threads).  Measured on 1024 VGA frames (quadtree stage, ms): key_cap 4096 (2 CTAs per SM) 0.59 = the
+        // sort + tree pair, 2048 0.42, 1024 0.41, 512 without staged code tables 0.40: residency beats shared-memory keys (the global scratch of a level is
+        // L2-resident), so the batched form keeps only the small levels' keys in shared memory.
+        QfPlan qb{}; qb.threads = QF_THREADS_BATCH; qb.pool_cap = std::max(align_up(QF_THREADS_BATCH / 32 * 33, 32), align_up(tree_cap, 32)); qb.cell_cap = cellmax; qb.tab_cap = 0;
+        { static const int btab = [] { const char* e = std::getenv("ORBX_QT_BTAB"); return e ? std::atoi(e) : 0; }(); if (btab) qb.tab_cap = q.tab_cap; }
+        static const int bkeys = [] { const char* e = std::getenv("ORBX_QT_BKEYS"); return e ? std::atoi(e) : 0; }();
+        const size_t bbudget = 112 * 1024, bfixed = qf_fixed_bytes(qb.pool_cap, qb.cell_cap, qb.tab_cap, qb.threads);
+        h->qfb_ok = h->qf_ok && bfixed + 1024 * 16 <= bbudget;
+        if (h->qfb_ok) {
+            qb.key_cap = bkeys >= 256 ? (int)std::min<size_t>(bkeys & ~31, ((bbudget - bfixed) / 16) & ~(size_t)31) : 512;
+            qb.smem_bytes = (int)qf_smem_bytes(qb);
+        }
+        h->qfb = qb;
     }
     h->rows = rows; h->cols = cols; h->Bcap = 0; h->have_pyramid = false;
     if (h->graph1) { cudaGraphExecDestroy(h->graph1); h->graph1 = nullptr; }       // the captured pointers / launch shapes belong to the old geometry
@@ -575,14 +588,21 @@ static int run_detect(orbx_extractor* h, int b0, int B, bool fork_blur = false) 
     }
     prof_mark(h);
     if (fork_blur) CU_TRY(cudaEventRecord(h->ev_fork, s));        // the blur may start once FAST is done ...
-    static const int qf_env = [] { const char* e = std::getenv("ORBX_QT_FUSED"); return e ? std::atoi(e) : -1; }();   // 0 / 1 force the two-kernel / one-kernel quadtree (A/B testing)
-    if (h->qf_ok && (qf_env >= 0 ? qf_env != 0 : B <= 4)) {
+    static const int qf_env = [] { const char* e = std::getenv("ORBX_QT_FUSED"); return e ? std::atoi(e) : -1; }();
+    // ORBX_QT_FUSED: 0 = sort + tree pair, 1 = one-launch kernel in its wide (latency) form, 2 = in its lean (batched) form; default: by batch size
+    if (h->qfb_ok && (qf_env >= 0 ? qf_env == 2 : B > 4)) {
+        k_octree_fused<QF_THREADS_BATCH><<<dim3(L, B), QF_THREADS_BATCH, h->qfb.smem_bytes, s>>>(h->qf_levels, h->d_cells.p, ncells, h->cand_per_frame, h->cand_per_frame, h->kp_per_frame, L, h->qfb,
+            slots, cell_counts, h->d_ocand.p + co, h->d_skey.p + co, h->d_spk.p + co, h->d_ncand.p + (size_t)b0 * L, h->d_kp_level.p + (size_t)b0 * h->kp_per_frame,
+            h->d_kp_count.p + (size_t)b0 * L, h->d_overflow.p);
+        LAUNCH_CHECK();
+        prof_mark(h);                                                    // (the stage table keeps its sort / tree columns: the second one reads 0)
+    } else if (h->qf_ok && (qf_env >= 0 ? qf_env != 0 : B <= 4)) {
         // a handful of frames (what Tracking calls): gather + path codes + sort + tree of a level in ONE launch, everything in shared memory
         k_octree_fused<QF_THREADS><<<dim3(L, B), QF_THREADS, h->qf.smem_bytes, s>>>(h->qf_levels, h->d_cells.p, ncells, h->cand_per_frame, h->cand_per_frame, h->kp_per_frame, L, h->qf,
             slots, cell_counts, h->d_ocand.p + co, h->d_skey.p + co, h->d_spk.p + co, h->d_ncand.p + (size_t)b0 * L, h->d_kp_level.p + (size_t)b0 * h->kp_per_frame,
             h->d_kp_count.p + (size_t)b0 * L, h->d_overflow.p);
         LAUNCH_CHECK();
-        prof_mark(h); prof_mark(h);                                      // (the stage table keeps its sort / tree columns: the second one reads 0)
+        prof_mark(h);                                                    // (the stage table keeps its sort / tree columns: the second one reads 0)
     } else {
         dim3 grid(L, B);
         // a handful of frames: one CTA per level cannot fill the GPU anyway, so each CTA is made wide and the level-0 sort gets 4x the threads per pass
@@ -815,6 +835,7 @@ int orbx_create(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, in
     cudaFuncSetAttribute(k_octree_tree, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_octree_tree_par, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ptree_smem_bytes(PTREE_MAXCAP, 4096));
     cudaFuncSetAttribute(k_octree_fused<QF_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    cudaFuncSetAttribute(k_octree_fused<QF_THREADS_BATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     cudaFuncSetAttribute(k_fast_cells<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(k_fast_cells<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(k_pyr_resize_t, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);

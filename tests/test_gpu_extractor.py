@@ -505,5 +505,5 @@ def test_every_kernel_form_gives_the_same_result(tmp_path):
     base = run({})
     for extra in ({"ORBX_TILEPYR": "0"}, {"ORBX_TILEPYR": "1"}, {"ORBX_TILEPYR": "0", "ORBX_RESIZE_TMA": "1"}, {"ORBX_TILEPYR": "0", "ORBX_RESIZE_TMA": "0"},
                   {"ORBX_CHAIN": "1"}, {"ORBX_BLUR_SMALL": "0"}, {"ORBX_BLUR_SMALL": "1"}, {"ORBX_FAST_CPW": "1"}, {"ORBX_FAST_CPW": "8"}, {"ORBX_FAST_CTA": "0"}, {"ORBX_FAST_CTA": "1"},
-                  {"ORBX_HOST_PACK": "0"}, {"ORBX_HOST_PACK": "3"}, {"ORBX_GRAPH": "0"}, {"ORBX_QT_FUSED": "0"}, {"ORBX_QT_FUSED": "1"}):
+                  {"ORBX_HOST_PACK": "0"}, {"ORBX_HOST_PACK": "3"}, {"ORBX_GRAPH": "0"}, {"ORBX_QT_FUSED": "0"}, {"ORBX_QT_FUSED": "1"}, {"ORBX_QT_FUSED": "2"}, {"ORBX_QT_FUSED": "2", "ORBX_QT_BKEYS": "512"}):
         assert run(extra) == base, extra
