@@ -18,14 +18,12 @@ __global__ void k_border101(const uint8_t* __restrict__ src, int pitch, int w, i
 __constant__ int c_ell_dx[31];
 
 // -------------------------------------------------------------------------------------------------
-// closing = erode(dilate(mask, ellipse31), ellipse31)  (:1697-1704) is only ever tested for "!= 0" (:1734-1735).
+// closing = erode(dilate(mask, ellipse31), ellipse31)  (:1697-1704) is only ever tested for "!= 0" (:1734-1735), and only at keypoint positions.
 // With cv's default border (outside pixels ignored by both passes) that predicate depends only on the binary
 // image (mask != 0):  closing(p) != 0  <=>  every q in p+E has some r in q+E with mask(r) != 0.  So the masks
-// are bit-packed (1 bit per pixel, 32 pixels per word, LSB = leftmost) and both passes are binary dilations:
-//   D = dilate(M);   closing != 0  ==  ~dilate(~D)   (bits outside the image are 0 in M, ~D and ignored).
-// One thread per output word; per ellipse row it ORs the window of half-width dx over the (left, mid, right)
-// words with a doubling OR (two overlapping power-of-two windows).  The bit-planes are tiny (260 KB at 1080p)
-// and stay in L2; this replaces a 729-tap grey-scale max/min per pixel.
+// are bit-packed (1 bit per pixel, 32 pixels per word, LSB = leftmost), the dilation D = dilate(M) is one binary pass over the plane
+// (k_bin_dilate31: per ellipse row the window of half-width dx is OR-ed over the (left, mid, right) words with a doubling OR), and the
+// erosion is evaluated per keypoint (closing_nonzero_at).  This replaces two 729-tap grey-scale max / min passes per pixel.
 // -------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t swar_nz_byte(uint32_t x) { return (((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u; }
 __device__ __forceinline__ uint32_t nz_nibble(uint32_t w) { return (((swar_nz_byte(w) >> 7) * 0x00204081u) >> 21) & 0xFu; }   // 4 bytes -> 4 bits
@@ -53,45 +51,71 @@ __device__ __forceinline__ unsigned long long or_window(unsigned long long x, in
     return t | (t >> (n - p));
 }
 
-// out = dilate(COMPLEMENT ? ~in : in) with the 31x31 ellipse, complemented again if COMPLEMENT (i.e. an erosion)
-template <bool COMPLEMENT>
-__global__ void k_bin_dilate31(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int wpr, int rows, int cols) {
-    const int wx = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
-    if (wx >= wpr) return;
+// out = dilate(in) with the 31x31 ellipse.  One CTA per DIL_TW x DIL_TR tile of output words: the (DIL_TR + 30) x (DIL_TW + 2) input words it reads are staged
+// in shared memory once (the one-thread-per-word form read every input word 93 times through L2 and was bound by that: 147 us per 32 frames of 1080p).
+// Rows y-k and y+k share the half-width dx[15-k], and consecutive k often do too (15: k=0..3, 14: k=4..6, 13: k=7,8, ...): dilation distributes over OR,
+// so the rows of one half-width are OR-ed first and dilated horizontally once (10 window passes per output word instead of 31).
+#define DIL_TW 32
+#define DIL_TR 32
+__global__ void __launch_bounds__(256)
+k_bin_dilate31(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int wpr, int rows, int cols) {
+    __shared__ uint32_t sm[DIL_TR + 30][DIL_TW + 2];
+    const int wx0 = blockIdx.x * DIL_TW, y0 = blockIdx.y * DIL_TR, b = blockIdx.z;
     const uint32_t* plane = in + (long long)b * rows * wpr;
-    const int lastw = wpr - 1;
-    const uint32_t lastmask = (cols & 31) ? ((1u << (cols & 31)) - 1u) : 0xFFFFFFFFu;
-    // rows y-k and y+k share the half-width dx[15-k], and consecutive k often do too (15: k=0..3, 14: k=4..6, 13: k=7,8, ...):
-    // dilation distributes over OR, so the rows of one half-width are OR-ed first and dilated horizontally once (10 window
-    // passes per output word instead of 31)
-    uint32_t acc = 0, gL = 0, gM = 0, gR = 0;
-    int gd = c_ell_dx[0];                                            // half-width of the group being collected (k = 15 first)
-    auto flush = [&]() {
-        const unsigned long long A = ((unsigned long long)gM << 32) | gL, Bw = ((unsigned long long)gR << 32) | gM;
-        acc |= (uint32_t)(or_window(A >> (32 - gd), gd + 1) | or_window(Bw, gd + 1));
-        gL = gM = gR = 0;
-    };
-    auto add_row = [&](int yy) {
-        if (yy < 0 || yy >= rows) return;
-        const uint32_t* row = plane + (long long)yy * wpr;
-        uint32_t M = __ldg(row + wx), L = wx > 0 ? __ldg(row + wx - 1) : 0u, R = wx < lastw ? __ldg(row + wx + 1) : 0u;
-        if (COMPLEMENT) {
-            M = ~M; if (wx == lastw) M &= lastmask;
-            L = wx > 0 ? ~L : 0u;
-            R = wx < lastw ? ~R : 0u; if (wx + 1 == lastw) R &= lastmask;
-        }
-        gL |= L; gM |= M; gR |= R;
-    };
-    for (int k = 15; k >= 0; --k) {
-        const int d = c_ell_dx[15 - k];
-        if (d != gd) { flush(); gd = d; }
-        add_row(y - k);
-        if (k) add_row(y + k);
+    for (int i = threadIdx.x; i < (DIL_TR + 30) * (DIL_TW + 2); i += 256) {
+        const int r = i / (DIL_TW + 2), c = i - r * (DIL_TW + 2);
+        const int yy = y0 - 15 + r, wx = wx0 - 1 + c;
+        sm[r][c] = (yy >= 0 && yy < rows && wx >= 0 && wx < wpr) ? __ldg(plane + (long long)yy * wpr + wx) : 0u;    // (bits past `cols` are 0 in the packed mask)
     }
-    flush();
-    if (COMPLEMENT) { acc = ~acc; }
-    if (wx == lastw) acc &= lastmask;
-    out[((long long)b * rows + y) * wpr + wx] = acc;
+    __syncthreads();
+    const int tx = threadIdx.x & 31, wx = wx0 + tx;
+    if (wx >= wpr) return;
+    const uint32_t lastmask = (cols & 31) ? ((1u << (cols & 31)) - 1u) : 0xFFFFFFFFu;
+    for (int ty = threadIdx.x >> 5; ty < DIL_TR; ty += 8) {
+        const int y = y0 + ty;
+        if (y >= rows) break;
+        uint32_t acc = 0, gL = 0, gM = 0, gR = 0;
+        int gd = c_ell_dx[0];                                            // half-width of the group being collected (k = 15 first)
+#pragma unroll
+        for (int k = 15; k >= 0; --k) {
+            const int d = c_ell_dx[15 - k];
+            if (d != gd) {
+                const unsigned long long A = ((unsigned long long)gM << 32) | gL, Bw = ((unsigned long long)gR << 32) | gM;
+                acc |= (uint32_t)(or_window(A >> (32 - gd), gd + 1) | or_window(Bw, gd + 1));
+                gL = gM = gR = 0; gd = d;
+            }
+            const uint32_t* r0 = &sm[ty + 15 - k][tx];
+            gL |= r0[0]; gM |= r0[1]; gR |= r0[2];
+            if (k) { const uint32_t* r1 = &sm[ty + 15 + k][tx]; gL |= r1[0]; gM |= r1[1]; gR |= r1[2]; }
+        }
+        {
+            const unsigned long long A = ((unsigned long long)gM << 32) | gL, Bw = ((unsigned long long)gR << 32) | gM;
+            acc |= (uint32_t)(or_window(A >> (32 - gd), gd + 1) | or_window(Bw, gd + 1));
+        }
+        if (wx == wpr - 1) acc &= lastmask;
+        out[((long long)b * rows + y) * wpr + wx] = acc;
+    }
+}
+
+// closing(p) != 0 for ONE pixel, from D = dilate(mask != 0): the erosion is only ever consulted at keypoint positions (:1734-1735), so instead of eroding the
+// whole plane, every keypoint tests its own 31 ellipse rows: closing(p) != 0  <=>  D(q) = 1 for every q of p + E inside the image (cv's default border:
+// outside pixels are ignored by the erosion).
+__device__ __forceinline__ bool closing_nonzero_at(const uint32_t* __restrict__ D, int wpr, int rows, int cols, int px, int py) {
+    bool all = true;
+#pragma unroll 1
+    for (int k = -15; k <= 15; ++k) {
+        const int yy = py + k;
+        if (yy < 0 || yy >= rows) continue;
+        const int dx = c_ell_dx[15 + k];
+        const int x0 = max(px - dx, 0), x1 = min(px + dx, cols - 1);     // at most 31 pixels: two words
+        const uint32_t* row = D + (long long)yy * wpr;
+        const int w0 = x0 >> 5;
+        const unsigned long long lo = row[w0], hi = (w0 + 1 < wpr) ? row[w0 + 1] : 0u;
+        const unsigned long long v = ((hi << 32) | lo) >> (x0 & 31);
+        const unsigned long long need = (1ull << (x1 - x0 + 1)) - 1ull;
+        all = all && ((v & need) == need);
+    }
+    return all;
 }
 
 // Batched MovingKeyPoints on the per-level keypoint slots of the quadtree stage (:1718-1741): one warp per
@@ -104,12 +128,12 @@ struct LabelView { const uint16_t* labels; long long fstride; int pitch; const u
 
 __global__ void __launch_bounds__(32)
 k_cull_levelkp(const LevelGeom* __restrict__ levels, int nlevels, int kp_per_frame, uint32_t* __restrict__ kp_level, int* __restrict__ kp_count,
-               const uint32_t* __restrict__ closed, int wpr, int rows, int cols, LabelView lv, int* __restrict__ culled_count) {
+               const uint32_t* __restrict__ dilated, int wpr, int rows, int cols, LabelView lv, int* __restrict__ culled_count) {   // dilated = dilate(mask != 0), k_bin_dilate31
     const int level = blockIdx.x, b = blockIdx.y, lane = threadIdx.x;
     const LevelGeom& g = levels[level];
     uint32_t* kp = kp_level + (long long)b * kp_per_frame + g.kp_off;
     const int n = kp_count[b * nlevels + level];
-    const uint32_t* plane = closed + (long long)b * rows * wpr;
+    const uint32_t* plane = dilated + (long long)b * rows * wpr;
     const float scale = level ? g.scale : 1.0f;                          // :1712-1715
     int kept = 0;
     for (int k0 = 0; k0 < n; k0 += 32) {
@@ -121,7 +145,7 @@ k_cull_levelkp(const LevelGeom* __restrict__ levels, int nlevels, int kp_per_fra
             const int px = (int)__fmul_rn(x, scale), py = (int)__fmul_rn(y, scale);
             keep = true;
             if (px >= 0 && py >= 0 && px < cols && py < rows) {
-                keep = ((plane[(long long)py * wpr + (px >> 5)] >> (px & 31)) & 1u) == 0u;
+                keep = !closing_nonzero_at(plane, wpr, rows, cols, px, py);
                 if (keep && lv.labels) {
                     const int id = lv.labels[(long long)b * lv.fstride + (long long)py * lv.pitch + px];
                     if (id >= 1 && id <= lv.n_labels && lv.flagged[(long long)b * lv.n_labels + id - 1]) keep = false;
@@ -145,13 +169,13 @@ struct KpIn { float x, y, size, angle, response; int octave, class_id; };
 // p = (int)(pt * scale).  flags[i] = 1 => culled.  Out-of-range label / id indices (undefined behaviour
 // in the reference) are treated as "not flagged".
 __global__ void k_cull_flags(const KpIn* __restrict__ kp, const float* __restrict__ kp_scale, int n,
-                             const uint32_t* __restrict__ closed, int wpr, const uint8_t* __restrict__ rm_flag,
+                             const uint32_t* __restrict__ dilated, int wpr, const uint8_t* __restrict__ rm_flag,
                              int rows, int cols, uint8_t* __restrict__ flags) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float s = kp_scale[i];
     const int px = (int)__fmul_rn(kp[i].x, s), py = (int)__fmul_rn(kp[i].y, s);
     int flag = rm_flag[i];                                   // rm_vector[centers[label(p) - 1].id] == 1, looked up by the caller-side marshalling
-    if (px >= 0 && py >= 0 && px < cols && py < rows && ((closed[(size_t)py * wpr + (px >> 5)] >> (px & 31)) & 1u)) flag = 1;
+    if (px >= 0 && py >= 0 && px < cols && py < rows && closing_nonzero_at(dilated, wpr, rows, cols, px, py)) flag = 1;
     flags[i] = (uint8_t)flag;
 }

@@ -962,7 +962,7 @@ static int chunk_frames(const orbx_extractor* h, int B) {
 }
 
 static int run_masked_range(orbx_extractor* h, int b0, int nb, const uint8_t* d_masks, long long mfs, int mpitch, int rows, int cols, LabelView lv,
-                            KpOut* d_kp, uint8_t* d_desc, int cap, int* d_counts, int* d_culled, bool prepacked = false);
+                            KpOut* d_kp, uint8_t* d_desc, int cap, int* d_counts, int* d_culled, bool prepacked = false, bool fork = false);
 extern "C" void orbx_host_pack_mask(const uint8_t* mask, size_t step, int rows, int cols, uint32_t* bits);   // host_pack.cpp
 static int ensure_closing(orbx_extractor* h, int nframes, int rows, int cols);
 

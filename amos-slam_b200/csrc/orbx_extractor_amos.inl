@@ -11,7 +11,8 @@ static int upload_ellipse() {
 }
 
 // bit-pack the masks of frames [b0, b0+nframes) (u8, pitch multiple of 32; d_mask points at frame b0) and close them on h->cur;
-// result: h->d_bits0 = (closing != 0), [B][rows][wpr].  The caller has sized d_bits0 / d_bits1 for the whole batch.
+// result: h->d_bits1 = dilate(mask != 0), [B][rows][wpr] (the erosion half of the closing is evaluated per keypoint, k_cull.cuh).  The caller has sized
+// d_bits0 / d_bits1 for the whole batch.
 static int run_closing(orbx_extractor* h, const uint8_t* d_mask, long long fstride, int pitch, int b0, int nframes, int rows, int cols, bool prepacked = false) {
     const int wpr = (cols + 31) / 32;
     cudaStream_t s = h->cur;
@@ -21,9 +22,7 @@ static int run_closing(orbx_extractor* h, const uint8_t* d_mask, long long fstri
         k_mask_pack<<<grid, 64, 0, s>>>(d_mask, fstride, pitch, rows, cols, a, wpr);
         LAUNCH_CHECK();
     }
-    k_bin_dilate31<false><<<grid, 64, 0, s>>>(a, b, wpr, rows, cols);
-    LAUNCH_CHECK();
-    k_bin_dilate31<true><<<grid, 64, 0, s>>>(b, a, wpr, rows, cols);
+    k_bin_dilate31<<<dim3((wpr + DIL_TW - 1) / DIL_TW, (rows + DIL_TR - 1) / DIL_TR, nframes), 256, 0, s>>>(a, b, wpr, rows, cols);
     LAUNCH_CHECK();
     return ORBX_OK;
 }
@@ -52,7 +51,7 @@ extern "C" int orbx_cull(orbx_extractor* h, const uint8_t* mask, size_t mask_ste
         return ORBX_E_CUDA;
     cudaStream_t s = h->stream;
     CU_TRY(cudaMemcpy2DAsync(h->d_mask.p, pitch, mask, mask_step, cols, rows, cudaMemcpyHostToDevice, s));
-    // closing = erode(dilate(mask))   (:1697-1704), as two binary dilations on the bit-packed mask (k_cull.cuh)
+    // closing = erode(dilate(mask))   (:1697-1704): binary dilation of the bit-packed mask, erosion per keypoint (k_cull.cuh)
     if ((rc = ensure_closing(h, 1, rows, cols))) return rc;
     if ((rc = run_closing(h, h->d_mask.p, (long long)pitch * rows, pitch, 0, 1, rows, cols))) return rc;
     const int wpr = (cols + 31) / 32;
@@ -86,7 +85,7 @@ extern "C" int orbx_cull(orbx_extractor* h, const uint8_t* mask, size_t mask_ste
     } }
     CU_TRY(cudaMemcpyAsync(h->d_gather.p, h->h_gather, up_bytes, cudaMemcpyHostToDevice, s));
     uint8_t* d_flags = h->d_desc_tmp.p;
-    k_cull_flags<<<(n + 127) / 128, 128, 0, s>>>(reinterpret_cast<const KpIn*>(h->d_gather.p), reinterpret_cast<const float*>(h->d_gather.p + o_sc), n, h->d_bits0.p, wpr,
+    k_cull_flags<<<(n + 127) / 128, 128, 0, s>>>(reinterpret_cast<const KpIn*>(h->d_gather.p), reinterpret_cast<const float*>(h->d_gather.p + o_sc), n, h->d_bits1.p, wpr,
                                                   h->d_gather.p + o_rm, rows, cols, d_flags);
     LAUNCH_CHECK();
     // the flags land in the pinned block (the upload has been consumed by then: same stream)
@@ -110,17 +109,32 @@ extern "C" int orbx_cull(orbx_extractor* h, const uint8_t* mask, size_t mask_ste
 // Batched Amos path (BASELINE config 5): per frame  operator()(img, mask, vector<vector<KeyPoint>>&)  ->  MovingKeyPoints with the
 // dynamic mask and, when lv.labels is set, the super-pixel term  ->  ProcessDesp.  Frames [b0, b0+nb) on h->cur; d_masks points at frame b0's mask.
 static int run_masked_range(orbx_extractor* h, int b0, int nb, const uint8_t* d_masks, long long mfs, int mpitch, int rows, int cols, LabelView lv,
-                            KpOut* d_kp, uint8_t* d_desc, int cap, int* d_counts, int* d_culled, bool prepacked) {
+                            KpOut* d_kp, uint8_t* d_desc, int cap, int* d_counts, int* d_culled, bool prepacked, bool fork) {
     int rc;
+    // fork (device-batch call, one stream): the closing of the masks needs nothing from the detection and the blur only the pyramid, so both go to the second
+    // compute stream -- the closing beside resize / FAST, the blur beside the latency-bound quadtree -- and join in front of the culling.  (The host-pointer
+    // pipeline already overlaps its chunks over four streams and does not fork.)
+    fork = fork && !h->profiling && h->cur == h->stream;
+    if (fork) {
+        CU_TRY(cudaEventRecord(h->ev_fork, h->stream));
+        CU_TRY(cudaStreamWaitEvent(h->s_alt, h->ev_fork, 0));
+        h->cur = h->s_alt;
+        rc = run_closing(h, d_masks, mfs, mpitch, b0, nb, rows, cols, prepacked);
+        h->cur = h->stream;
+        if (rc) return rc;
+        if ((rc = run_detect(h, b0, nb, true))) return rc;                       // blur queued on s_alt behind the closing, after FAST (ev_fork); ev_join follows it
+        CU_TRY(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+    } else {
     if ((rc = run_detect(h, b0, nb))) return rc;
     if ((rc = run_closing(h, d_masks, mfs, mpitch, b0, nb, rows, cols, prepacked))) return rc;
+    }
     if (d_culled) CU_TRY(cudaMemsetAsync(d_culled + b0, 0, (size_t)nb * sizeof(int), h->cur));
     const int wpr = (cols + 31) / 32;
     k_cull_levelkp<<<dim3(h->nlevels, nb), 32, 0, h->cur>>>(h->d_levels.p, h->nlevels, h->kp_per_frame, h->d_kp_level.p + (size_t)b0 * h->kp_per_frame,
-                                                              h->d_kp_count.p + (size_t)b0 * h->nlevels, h->d_bits0.p + (size_t)b0 * rows * wpr, wpr, rows, cols,
+                                                              h->d_kp_count.p + (size_t)b0 * h->nlevels, h->d_bits1.p + (size_t)b0 * rows * wpr, wpr, rows, cols,
                                                               lv, d_culled ? d_culled + b0 : nullptr);      // lv points at frame b0's labels / flags
     LAUNCH_CHECK();
-    if ((rc = run_blur_range(h, b0, nb))) return rc;
+    if (!fork && (rc = run_blur_range(h, b0, nb))) return rc;
     return run_orient(h, b0, nb, true, d_kp, d_desc, cap, d_counts, nullptr);
 }
 
@@ -161,7 +175,7 @@ extern "C" int orbx_extract_masked_batch_labels_device(orbx_extractor* h, const 
     h->cur = h->stream;
     LabelView lv{nullptr, 0, 0, nullptr, 0};
     if (d_labels) lv = LabelView{d_labels->labels, (long long)d_labels->label_frame_stride, (int)d_labels->label_step, d_labels->flagged, d_labels->n_labels};
-    rc = run_masked_range(h, 0, B, mk, mfs, mpitch, rows, cols, lv, reinterpret_cast<KpOut*>(d_kp_out), d_desc_out, cap, d_counts_out, d_culled_out);
+    rc = run_masked_range(h, 0, B, mk, mfs, mpitch, rows, cols, lv, reinterpret_cast<KpOut*>(d_kp_out), d_desc_out, cap, d_counts_out, d_culled_out, false, true);
     if (!rc) { h->lastB = B; h->blur_valid = true; }
     return rc;
 }
