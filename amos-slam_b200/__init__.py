@@ -18,7 +18,7 @@ import sys
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "liborbx_b200.so")
+LIB_PATH = os.environ.get("ORBX_LIB_PATH") or os.path.join(HERE, "liborbx_b200.so")   # (ORBX_LIB_PATH: A/B builds of the same library while tuning a kernel)
 CSRC = os.path.join(HERE, "csrc")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177"]

@@ -27,7 +27,7 @@
 
 #define QF_BUCKET_BITS 11
 #define QF_BUCKETS (1 << QF_BUCKET_BITS)
-#define QF_BUCKET_MAX 48            // largest bucket the in-bucket ranking takes; above it the radix passes sort the level
+#define QF_BUCKET_MAX 48            // largest bucket the in-bucket ranking takes (n / 64 for large levels); above it the radix passes sort the level
 #define QF_THREADS 1024             // latency form: one wide CTA per level, alone on its SM
 #define QF_THREADS_BATCH 256        // batched form: lean CTAs, several per SM
 // u16 per digit row of the radix histogram: one counter per warp + 8 padding (1024 threads: 80 B rows, conflict-free 16-byte reads)
@@ -211,7 +211,7 @@ __device__ __forceinline__ void qf_core(const LevelGeom& g, int n, int level, in
 #pragma unroll
         for (int k = 0; k < PER; ++k) { const int bi = tid * PER + k; v[k] = bi < QF_BUCKETS ? bcnt[bi] : 0; mine += v[k]; big = max(big, v[k]); }
         big = __reduce_max_sync(0xffffffffu, big);
-        if (lane == 0 && big > QF_BUCKET_MAX) sh.counter[3] = 1;
+        if (lane == 0 && big > max(QF_BUCKET_MAX, n >> 6)) sh.counter[3] = 1;   // (large levels tolerate larger buckets: the ranking stays cheaper than four radix passes over global scratch)
         int total;
         int run = qf_block_scan<THREADS>(mine, sh.wsum, &total) - mine;
 #pragma unroll
@@ -242,6 +242,61 @@ __device__ __forceinline__ void qf_core(const LevelGeom& g, int n, int level, in
     QT_STAMP(4);
     // ---- stable LSD radix sort on the path code, 8 bits per pass; the digits below the depth at which a node is one pixel wide are
     // constant and skipped (k_octree.cuh).  Warp w owns a contiguous segment (stability), ranks inside a step come from ballots. ----
+    if (!sorted && sizeof(IdxT) == 4) {
+        // levels on global scratch can hold more than 65535 keys: the same passes with 32-bit counters (one histogram, zeroed per pass)
+        uint32_t* h32 = reinterpret_cast<uint32_t*>(hist);                     // [256][QF_HS]: exactly the bytes of the two 16-bit histograms
+        const int seg = ((n + WARPS - 1) / WARPS + 31) & ~31;
+        const int s0 = min(warp * seg, n), s1 = min(s0 + seg, n);
+        for (int shift = low; shift < low + nbits; shift += 8) {
+            for (int i = tid; i < 256 * QF_HS; i += THREADS) h32[i] = 0u;
+            __syncthreads();
+            for (int i0 = s0; i0 < s1; i0 += 32) {
+                const int i = i0 + lane;
+                const bool act = i < s1;
+                const uint32_t d = act ? ((keyA[i] >> shift) & 255u) : 0u;
+                const uint32_t peers = qf_peers(d, act);
+                if (act && (peers & lt) == 0u) h32[d * QF_HS + warp] += (uint32_t)__popc(peers);
+                __syncwarp();
+            }
+            __syncthreads();
+            int tot = 0, inc = 0;
+            if (tid < 256) {
+                uint32_t* row = h32 + tid * QF_HS;
+                for (int w = 0; w < WARPS; ++w) { const int c = (int)row[w]; row[w] = (uint32_t)tot; tot += c; }
+                inc = tot;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+                if (lane == 31) sh.wsum[warp] = inc;
+            }
+            __syncthreads();
+            if (tid < 256) {
+                int basew = 0;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) if (w < warp) basew += sh.wsum[w];
+                const uint32_t excl = (uint32_t)(basew + inc - tot);
+                uint32_t* row = h32 + tid * QF_HS;
+                for (int w = 0; w < WARPS; ++w) row[w] += excl;
+            }
+            __syncthreads();
+            for (int i0 = s0; i0 < s1; i0 += 32) {
+                const int i = i0 + lane;
+                const bool act = i < s1;
+                const uint32_t k = act ? keyA[i] : 0u;
+                const uint32_t d = (k >> shift) & 255u;
+                const uint32_t peers = qf_peers(d, act);
+                uint32_t dst = 0;
+                if (act) dst = h32[d * QF_HS + warp] + (uint32_t)__popc(peers & lt);
+                __syncwarp();
+                if (act && (peers & lt) == 0u) h32[d * QF_HS + warp] += (uint32_t)__popc(peers);
+                if (act) { keyB[dst] = k; idxB[dst] = idxA[i]; }
+                __syncwarp();
+            }
+            __syncthreads();
+            { uint32_t* t = keyA; keyA = keyB; keyB = t; }
+            { IdxT* t = idxA; idxA = idxB; idxB = t; }
+        }
+        sorted = true;
+    }
     if (!sorted) {
         for (int i = tid; i < 256 * QF_HS; i += THREADS) reinterpret_cast<uint32_t*>(hist)[i] = 0u;  // both radix histograms (2 x 256 x QF_HS u16; they overlay the bucket table)
         __syncthreads();
@@ -603,10 +658,10 @@ k_octree_fused(const __grid_constant__ QfLevels P, const CellDesc* __restrict__ 
                                    slots, oc, kp_level, kp_count, overflow, sh);
     } else {
         // oversized level: the same code on global scratch (the level's slices of skey = two u32 arrays, spk, and the cell slots themselves, which are dead once
-        // gathered; ocand doubles as the candidate array).  The radix histogram counts in 16 bits.
+        // gathered; ocand doubles as the candidate array).
         uint32_t* keyA = reinterpret_cast<uint32_t*>(skey + (long long)b * cand_per_frame + g.cand_off); uint32_t* keyB = keyA + g.cand_cap;
         uint32_t* idxA = spk + (long long)b * cand_per_frame + g.cand_off; uint32_t* idxB = cand_slots + (long long)b * slots_per_frame + g.slot_off;
-        if (n > 65535 || n > g.cand_cap) { if (tid == 0) { kp_count[b * nlevels + level] = 0; atomicOr(overflow, ORBX_OVF_SORT); } return; }
+        if (n >= (1 << 24) || n > g.cand_cap) { if (tid == 0) { kp_count[b * nlevels + level] = 0; atomicOr(overflow, ORBX_OVF_SORT); } return; }
         qf_core<uint32_t, THREADS>(g, n, level, b, nlevels, kp_per_frame, plan.pool_cap, pool_sm, hist, cell_off, cell_slot, tab, oc, keyA, keyB, idxA, idxB,
                                    slots, oc, kp_level, kp_count, overflow, sh);
     }

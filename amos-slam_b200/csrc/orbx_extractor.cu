@@ -409,14 +409,14 @@ static int build_plan(orbx_extractor* h, int rows, int cols) {
     // radix-sort capacity per (level, frame): ~1 candidate per 100 px of level 0 is generous for real images; larger levels fall back
     // to the global-memory bitonic path inside the kernel
     { const long long want = (long long)rows * cols / 100; int k = 4096; if (want > 4096) k = (int)std::min<long long>(18432, (want + want / 4 + 2047) / 2048 * 2048); h->sort_smem_keys = k; }
-    // one-launch quadtree of the latency form (k_octree_fused.cuh): node pool of the list's worst case (N + 3 nodes), the rest of the shared memory for keys.
-    // Frames above ~0.5 Mpx keep the two-kernel path: their level 0 can hold more candidates than the 16-bit radix counters of the fused kernel count.
+    // one-launch quadtree (k_octree_fused.cuh): node pool of the list's worst case (N + 3 nodes), the rest of the shared memory for keys; levels with more
+    // candidates than that run the same code on global scratch.
     {
         int cellmax = 1, tabmax = 0;
         for (int l = 0; l < L; ++l) { cellmax = std::max(cellmax, h->levels[l].cell_count); tabmax = std::max(tabmax, h->levels[l].code_nx + h->levels[l].code_ny); }
         QfPlan q{}; q.threads = QF_THREADS; q.pool_cap = std::max(1056, align_up(tree_cap, 32)); q.cell_cap = cellmax; q.tab_cap = align_up(tabmax, 4);
         const size_t budget = 224 * 1024, fixed = qf_fixed_bytes(q.pool_cap, q.cell_cap, q.tab_cap, q.threads);
-        h->qf_ok = L <= QF_MAXLEVELS && q.pool_cap <= QF_MAXPOOL && fixed + 2048 * 16 <= budget && (long long)rows * cols <= 500000;
+        h->qf_ok = L <= QF_MAXLEVELS && q.pool_cap <= QF_MAXPOOL && fixed + 2048 * 16 <= budget;
         if (h->qf_ok) for (int l = 0; l < L; ++l) h->qf_levels.lv[l] = h->levels[l];
         if (h->qf_ok) {
             q.key_cap = (int)std::min<size_t>(8192, ((budget - fixed) / 16) & ~(size_t)31);
@@ -590,13 +590,15 @@ static int run_detect(orbx_extractor* h, int b0, int B, bool fork_blur = false) 
     if (fork_blur) CU_TRY(cudaEventRecord(h->ev_fork, s));        // the blur may start once FAST is done ...
     static const int qf_env = [] { const char* e = std::getenv("ORBX_QT_FUSED"); return e ? std::atoi(e) : -1; }();
     // ORBX_QT_FUSED: 0 = sort + tree pair, 1 = one-launch kernel in its wide (latency) form, 2 = in its lean (batched) form; default: by batch size
-    if (h->qfb_ok && (qf_env >= 0 ? qf_env == 2 : B > 4)) {
+    // (a batch of large frames with few (level, frame) instances keeps the wide form: its big levels would crawl on 256 threads)
+    const bool wide_qt = B <= 4 || ((long long)h->rows * h->cols > 500000 && (long long)B * L <= 4 * 148);
+    if (h->qfb_ok && (qf_env >= 0 ? qf_env == 2 : !wide_qt)) {
         k_octree_fused<QF_THREADS_BATCH><<<dim3(L, B), QF_THREADS_BATCH, h->qfb.smem_bytes, s>>>(h->qf_levels, h->d_cells.p, ncells, h->cand_per_frame, h->cand_per_frame, h->kp_per_frame, L, h->qfb,
             slots, cell_counts, h->d_ocand.p + co, h->d_skey.p + co, h->d_spk.p + co, h->d_ncand.p + (size_t)b0 * L, h->d_kp_level.p + (size_t)b0 * h->kp_per_frame,
             h->d_kp_count.p + (size_t)b0 * L, h->d_overflow.p);
         LAUNCH_CHECK();
         prof_mark(h);                                                    // (the stage table keeps its sort / tree columns: the second one reads 0)
-    } else if (h->qf_ok && (qf_env >= 0 ? qf_env != 0 : B <= 4)) {
+    } else if (h->qf_ok && (qf_env >= 0 ? qf_env != 0 : wide_qt)) {
         // a handful of frames (what Tracking calls): gather + path codes + sort + tree of a level in ONE launch, everything in shared memory
         k_octree_fused<QF_THREADS><<<dim3(L, B), QF_THREADS, h->qf.smem_bytes, s>>>(h->qf_levels, h->d_cells.p, ncells, h->cand_per_frame, h->cand_per_frame, h->kp_per_frame, L, h->qf,
             slots, cell_counts, h->d_ocand.p + co, h->d_skey.p + co, h->d_spk.p + co, h->d_ncand.p + (size_t)b0 * L, h->d_kp_level.p + (size_t)b0 * h->kp_per_frame,

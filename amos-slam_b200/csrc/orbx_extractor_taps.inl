@@ -51,7 +51,7 @@ extern "C" int orbx_debug_distribute(orbx_extractor* h, const orbx_keypoint* can
     // form: ORBX_QT_FUSED = 1 / 0 forces the one-launch kernel of the latency form / the sort + tree pair; default = what a single frame gets (read per call: tests switch it)
     QfPlan q{}; q.threads = QF_THREADS; q.pool_cap = std::max(1056, align_up(tcap, 32)); q.cell_cap = nc; q.tab_cap = 0;
     const size_t qbudget = 224 * 1024, qfixed = qf_fixed_bytes(q.pool_cap, q.cell_cap, 0, q.threads);
-    bool fused = q.pool_cap <= QF_MAXPOOL && qfixed + 2048 * 16 <= qbudget && ncand <= 65535;
+    bool fused = q.pool_cap <= QF_MAXPOOL && qfixed + 2048 * 16 <= qbudget;
     { const char* e = std::getenv("ORBX_QT_FUSED"); if (e && std::atoi(e) == 0) fused = false; }
     if (fused) {
         q.key_cap = (int)std::min<size_t>(8192, ((qbudget - qfixed) / 16) & ~(size_t)31);
