@@ -642,6 +642,14 @@ retry:
     return ORBX_OK;
 }
 
+// capacity of the per-row candidate lists of one stereo pair (k_stereo_rows): a right keypoint of level l enters at most 2 * (2 * scale[l]) + 3 rows
+static size_t stereo_row_entries(const float* scale, int nlevels, int nr_max, int nRows) {
+    float smax = 1.f;
+    for (int l = 0; l < nlevels; ++l) smax = std::max(smax, scale[l]);
+    const double band = std::min<double>((double)nRows, 4.0 * (double)smax + 3.0);
+    return (size_t)std::max(nr_max, 1) * (size_t)std::ceil(band) + 32;
+}
+
 int orbx_compute_stereo_matches(orbx_matcher* m, orbx_extractor* left, orbx_extractor* right, const orbx_keypoint* keys_left, const uint8_t* desc_left, int nl,
                                 const orbx_keypoint* keys_right, const uint8_t* desc_right, int nr, float mb, float mbf, float* u_right, float* depth) {
     if (!m || !left || !right || nl < 0 || nr < 0 || nr >= (1 << 20) || (nl && (!keys_left || !desc_left || !u_right || !depth)) || (nr && (!keys_right || !desc_right)))
@@ -657,7 +665,11 @@ int orbx_compute_stereo_matches(orbx_matcher* m, orbx_extractor* left, orbx_extr
     for (int i = 0; i < nr; ++i) if (keys_right[i].octave < 0 || keys_right[i].octave >= L.nlevels) FAIL(ORBX_E_INVALID, "octave out of range");
     // both extractors' streams must have finished writing their pyramids
     CU_TRY(cudaStreamSynchronize(L.stream)); CU_TRY(cudaStreamSynchronize(R.stream));
-    const size_t need = pad((size_t)nl * 60) + pad((size_t)nr * 60) + 3 * pad((size_t)nl * 4) + 2 * pad((size_t)L.nlevels * 4) + pad((size_t)nl * 8 + 256) + 8192 + 64 * 256;
+    const int nRows = L.h[0];
+    if (nRows > STEREO_MAX_ROWS) FAIL(ORBX_E_INVALID, "image too high");
+    const size_t ent_cap = stereo_row_entries(L.scale, L.nlevels, nr, nRows);
+    const size_t need = pad((size_t)nl * 60) + pad((size_t)nr * 60) + 3 * pad((size_t)nl * 4) + 2 * pad((size_t)L.nlevels * 4) + pad((size_t)nl * 8 + 256) + 8192 + 64 * 256 +
+                        pad((size_t)(nRows + 1) * 4) + pad(ent_cap * 4);
     if ((rc = m->arena.reserve(need)) || (rc = m->uparena.reserve(need))) return rc;
     m->arena.reset(); m->uparena.reset();
     KpM *kl, *kr; uint8_t *dl, *dr; float *sc, *isc;
@@ -665,12 +677,15 @@ int orbx_compute_stereo_matches(orbx_matcher* m, orbx_extractor* left, orbx_extr
         (rc = up(m, desc_left, (size_t)nl * 32, dl)) || (rc = up(m, desc_right, (size_t)nr * 32, dr)) ||
         (rc = up(m, L.scale, (size_t)L.nlevels, sc)) || (rc = up(m, L.inv_scale, (size_t)L.nlevels, isc))) return rc;
     float* dur = m->arena.get<float>(nl); float* ddep = m->arena.get<float>(nl); int* sad = m->arena.get<int>(nl);
-    if (!dur || !ddep || !sad) FAIL(ORBX_E_CUDA, "matcher arena exhausted");
+    int* row_off = m->arena.get<int>((size_t)nRows + 1); int* entries = m->arena.get<int>(ent_cap);
+    if (!dur || !ddep || !sad || !row_off || !entries) FAIL(ORBX_E_CUDA, "matcher arena exhausted");
     if ((rc = flush_uploads(m))) return rc;
     StereoPyr PL, PR;
     for (int l = 0; l < L.nlevels; ++l) { PL.lv[l] = {L.ptr[l], L.pitch[l], L.w[l], L.h[l], 0}; PR.lv[l] = {R.ptr[l], R.pitch[l], R.w[l], R.h[l], 0}; }
     const StereoBatch single{nullptr, nullptr, 0};
-    k_stereo_match<<<(nl + 3) / 4, 128, 0, m->stream>>>(kl, dl, nl, kr, dr, nr, PL, PR, sc, isc, mb, mbf, dur, ddep, sad, single);
+    k_stereo_rows<<<1, 1024, 0, m->stream>>>(kr, nr, nRows, sc, row_off, entries, (int)ent_cap, single);
+    LAUNCH_CHECK();
+    k_stereo_match<<<(nl + 3) / 4, 128, 0, m->stream>>>(kl, dl, nl, kr, dr, nr, PL, PR, sc, isc, mb, mbf, dur, ddep, sad, single, row_off, entries, (int)ent_cap);
     LAUNCH_CHECK();
     k_stereo_median_cut<<<1, 1024, 0, m->stream>>>(nl, sad, dur, ddep, single);
     LAUNCH_CHECK();
@@ -695,7 +710,10 @@ static int stereo_batch_launch(orbx_matcher* m, orbx_extractor* left, orbx_extra
     if (!m->ev_left) { CU_TRY(cudaEventCreateWithFlags(&m->ev_left, cudaEventDisableTiming)); CU_TRY(cudaEventCreateWithFlags(&m->ev_right, cudaEventDisableTiming)); }
     CU_TRY(cudaEventRecord(m->ev_left, L.stream)); CU_TRY(cudaEventRecord(m->ev_right, R.stream));
     CU_TRY(cudaStreamWaitEvent(m->stream, m->ev_left, 0)); CU_TRY(cudaStreamWaitEvent(m->stream, m->ev_right, 0));
-    const size_t need = pad((size_t)B * cap * 4) + 8192;
+    const int nRows = L.h[0];
+    if (nRows > STEREO_MAX_ROWS) FAIL(ORBX_E_INVALID, "image too high");
+    const size_t ent_cap = stereo_row_entries(L.scale, L.nlevels, cap, nRows);
+    const size_t need = pad((size_t)B * cap * 4) + pad((size_t)B * (nRows + 1) * 4) + pad((size_t)B * ent_cap * 4) + 8192;
     if ((rc = m->arena.reserve(need))) return rc;
     m->arena.reset();
     // scale tables: a persistent device copy (the call is asynchronous, so nothing may travel through the per-call pinned mirror)
@@ -707,12 +725,16 @@ static int stereo_batch_launch(orbx_matcher* m, orbx_extractor* left, orbx_extra
     }
     const float* sc = m->stereo_scale; const float* isc = m->stereo_scale + L.nlevels;
     int* sad = m->arena.get<int>((size_t)B * cap);
-    if (!sad) FAIL(ORBX_E_CUDA, "matcher arena exhausted");
+    int* row_off = m->arena.get<int>((size_t)B * (nRows + 1)); int* entries = m->arena.get<int>((size_t)B * ent_cap);
+    if (!sad || !row_off || !entries) FAIL(ORBX_E_CUDA, "matcher arena exhausted");
     StereoPyr PL, PR;
     for (int l = 0; l < L.nlevels; ++l) { PL.lv[l] = {L.ptr[l], L.pitch[l], L.w[l], L.h[l], L.fstride[l]}; PR.lv[l] = {R.ptr[l], R.pitch[l], R.w[l], R.h[l], R.fstride[l]}; }
     const StereoBatch SB{L.counts, R.counts, cap};
     m->mark();
-    k_stereo_match<<<dim3((cap + 3) / 4, B), 128, 0, m->stream>>>(reinterpret_cast<const KpM*>(L.keys), L.desc, 0, reinterpret_cast<const KpM*>(R.keys), R.desc, 0, PL, PR, sc, isc, mb, mbf, d_ur, d_dep, sad, SB);
+    k_stereo_rows<<<B, 1024, 0, m->stream>>>(reinterpret_cast<const KpM*>(R.keys), 0, nRows, sc, row_off, entries, (int)ent_cap, SB);
+    LAUNCH_CHECK();
+    k_stereo_match<<<dim3((cap + 3) / 4, B), 128, 0, m->stream>>>(reinterpret_cast<const KpM*>(L.keys), L.desc, 0, reinterpret_cast<const KpM*>(R.keys), R.desc, 0, PL, PR, sc, isc, mb, mbf, d_ur, d_dep, sad, SB,
+                                                                   row_off, entries, (int)ent_cap);
     LAUNCH_CHECK();
     m->mark();
     k_stereo_median_cut<<<B, 1024, 0, m->stream>>>(0, sad, d_ur, d_dep, SB);
