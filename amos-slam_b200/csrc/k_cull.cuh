@@ -14,6 +14,26 @@ __global__ void k_border101(const uint8_t* __restrict__ src, int pitch, int w, i
     dst[(size_t)y * W + x] = src[(size_t)sy * pitch + sx];
 }
 
+// Frames whose rows are not 16-byte aligned (a 1241-px KITTI row) are re-pitched on the device before TMA reads them: ONE launch for the whole batch
+// (a cudaMemcpy2DAsync per frame cost ~4 us each: 0.25 ms per 64 KITTI frames, more than their FAST stage's share of a launch).  One thread per 4 destination
+// bytes; the source words are read aligned and funnel-shifted into place.
+__global__ void __launch_bounds__(256)
+k_repitch(const uint8_t* __restrict__ src, long long src_fstride, long long src_step, uint8_t* __restrict__ dst, long long dst_fstride, int dst_pitch, int cols, int rows) {
+    const int x4 = (blockIdx.x * 256 + threadIdx.x) * 4, y = blockIdx.y, b = blockIdx.z;
+    if (x4 >= cols) return;
+    const uint8_t* s = src + (long long)b * src_fstride + (long long)y * src_step + x4;
+    uint8_t* d = dst + (long long)b * dst_fstride + (long long)y * dst_pitch + x4;
+    if (x4 >= 4 && x4 + 8 <= cols) {                                         // both aligned words lie inside this row (never in front of / behind the caller's buffer)
+        const unsigned a = (unsigned)((uintptr_t)s & 3);
+        const uint32_t* sw = reinterpret_cast<const uint32_t*>(s - a);
+        const uint32_t w0 = __ldg(sw);
+        const uint32_t v = a ? __funnelshift_r(w0, __ldg(sw + 1), 8 * a) : w0;
+        *reinterpret_cast<uint32_t*>(d) = v;
+    } else {
+        for (int k = 0; k < 4 && x4 + k < cols; ++k) d[k] = s[k];
+    }
+}
+
 // half-widths of the 31x31 MORPH_ELLIPSE rows (cv::getStructuringElement), filled by the host
 __constant__ int c_ell_dx[31];
 

@@ -733,7 +733,7 @@ k_stereo_match(const KpM* __restrict__ kl, const uint8_t* __restrict__ dl, int n
     const int iL = blockIdx.x * 4 + (threadIdx.x >> 5);
     const int fb = blockIdx.y;
     if (SB.nl_arr) {
-        nl = min(SB.nl_arr[fb], SB.stride); nr = min(SB.nr_arr[fb], SB.stride);
+        nl = min(SB.nl_arr[fb], SB.stride);
         const size_t o = (size_t)fb * SB.stride;
         kl += o; kr += o; dl += o * 32; dr += o * 32; u_right += o; depth += o; sad_dist += o;
     }

@@ -476,6 +476,14 @@ static inline void prof_mark(orbx_extractor* h) {
 
 static int run_blur_range(orbx_extractor* h, int b0, int B);
 
+// re-pitch B frames on the device in one launch (k_cull.cuh); dst_pitch must be a multiple of 4
+static int repitch_frames(orbx_extractor* h, uint8_t* dst, long long dst_fstride, int dst_pitch, const uint8_t* src, long long src_fstride, long long src_step, int cols, int rows, int B, cudaStream_t s) {
+    if (B <= 0) return ORBX_OK;
+    k_repitch<<<dim3((cols + 1023) / 1024, rows, B), 256, 0, s>>>(src, src_fstride, src_step, dst, dst_fstride, dst_pitch, cols, rows);
+    LAUNCH_CHECK();
+    return ORBX_OK;
+}
+
 // Tensor maps of the FAST and blur stages (k_fast.cuh, k_describe.cuh).  Levels >= 1 live in d_pyr: one map per level in a device array, rebuilt when the pyramid
 // block moves.  Level 0 follows the current view (internal copy, pinned mirror or the caller's device frames) and travels as a kernel
 // parameter.  Must not be first called inside a stream capture (extract_graph prepares before capturing).
@@ -931,8 +939,7 @@ int orbx_extract_batch_device(orbx_extractor* h, const uint8_t* d_images, int B,
         h->view.l0 = d_images; h->view.l0_fstride = (long long)frame_stride; h->view.l0_pitch = (int)step;       // alias the caller's frames
     } else {
         const LevelGeom& g0 = h->levels[0];
-        for (int b = 0; b < B; ++b)
-            CU_TRY(cudaMemcpy2DAsync(h->d_pyr.p + (size_t)b * h->pyr_fstride + g0.off, g0.pitch, d_images + (size_t)b * frame_stride, step, cols, rows, cudaMemcpyDeviceToDevice, h->stream));
+        if ((rc = repitch_frames(h, h->d_pyr.p + g0.off, h->pyr_fstride, g0.pitch, d_images, (long long)frame_stride, (long long)step, cols, rows, B, h->stream))) return rc;
         h->view.l0 = h->d_pyr.p + g0.off; h->view.l0_fstride = h->pyr_fstride; h->view.l0_pitch = g0.pitch;
     }
     h->view.pyr = h->d_pyr.p; h->view.pyr_fstride = h->pyr_fstride;
@@ -1056,9 +1063,9 @@ static int host_batch_pipeline(orbx_extractor* h, const uint8_t* images, const u
             CU_TRY(cudaMemcpyAsync(h->d_l0.p + (size_t)b0 * frame_stride, images + (size_t)b0 * frame_stride, bytes, cudaMemcpyHostToDevice, h->s_h2d));
             if (repitch) {
                 const LevelGeom& g0 = h->levels[0];
-                for (int b = b0; b < b0 + nb; ++b)
-                    CU_TRY(cudaMemcpy2DAsync(h->d_pyr.p + (size_t)b * h->pyr_fstride + g0.off, g0.pitch, h->d_l0.p + (size_t)b * frame_stride, step,
-                                             cols, rows, cudaMemcpyDeviceToDevice, h->s_h2d));
+                const int rr = repitch_frames(h, h->d_pyr.p + (size_t)b0 * h->pyr_fstride + g0.off, h->pyr_fstride, g0.pitch, h->d_l0.p + (size_t)b0 * frame_stride, (long long)frame_stride, (long long)step,
+                                              cols, rows, nb, h->s_h2d);
+                if (rr) return rr;
             }
         } else {
             const LevelGeom& g0 = h->levels[0];

@@ -158,8 +158,7 @@ extern "C" int orbx_extract_masked_batch_labels_device(orbx_extractor* h, const 
         h->view.l0 = d_images; h->view.l0_fstride = (long long)frame_stride; h->view.l0_pitch = (int)step;       // alias the caller's frames
     } else {
         const LevelGeom& g0 = h->levels[0];
-        for (int b = 0; b < B; ++b)
-            CU_TRY(cudaMemcpy2DAsync(h->d_pyr.p + (size_t)b * h->pyr_fstride + g0.off, g0.pitch, d_images + (size_t)b * frame_stride, step, cols, rows, cudaMemcpyDeviceToDevice, h->stream));
+        if ((rc = repitch_frames(h, h->d_pyr.p + g0.off, h->pyr_fstride, g0.pitch, d_images, (long long)frame_stride, (long long)step, cols, rows, B, h->stream))) return rc;
         h->view.l0 = h->d_pyr.p + g0.off; h->view.l0_fstride = h->pyr_fstride; h->view.l0_pitch = g0.pitch;
     }
     h->view.pyr = h->d_pyr.p; h->view.pyr_fstride = h->pyr_fstride;
@@ -168,8 +167,7 @@ extern "C" int orbx_extract_masked_batch_labels_device(orbx_extractor* h, const 
     if (((uintptr_t)d_masks & 15) || (mask_step & 31) || (mask_frame_stride & 15) || mask_step < (size_t)align_up(cols, 32)) {
         mpitch = align_up(cols, 128); mfs = (long long)mpitch * rows;
         if (h->d_mask.ensure((size_t)mfs * B + 64)) return ORBX_E_CUDA;
-        for (int b = 0; b < B; ++b)
-            CU_TRY(cudaMemcpy2DAsync(h->d_mask.p + (size_t)b * mfs, mpitch, d_masks + (size_t)b * mask_frame_stride, mask_step, cols, rows, cudaMemcpyDeviceToDevice, h->stream));
+        if ((rc = repitch_frames(h, h->d_mask.p, mfs, mpitch, d_masks, (long long)mask_frame_stride, (long long)mask_step, cols, rows, B, h->stream))) return rc;
         mk = h->d_mask.p;
     }
     h->cur = h->stream;
