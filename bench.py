@@ -540,11 +540,17 @@ def bench_c4(args, rank, local_rank, world):
     ms = _timed_device_steps(torch, dist, world, stream, K, W, step_device)
     launches = EL.launch_count + ER.launch_count + M.launch_count - l0
     ur_dev = d_ur.cpu().numpy().copy()
-    # stage breakdown: extractor stages of the left handle (serialised pass) and the two matcher launches
-    EL.profile_enable(True); orbx._check(Lb.orbx_matcher_profile_enable(M._h, 1))
+    # stage breakdown: extractor stages of the left handle ALONE (serialised pass: with the right handle running beside it on its own stream the stage
+    # events of the left one absorb the other's kernels), x 2 for the two images; then the matcher launches of a whole step
+    torch.cuda.synchronize()
+    EL.profile_enable(True)
+    for _ in range(3):
+        EL.extract_batch_raw(dL.data_ptr(), B, HEIGHT, WIDTH, WIDTH, WIDTH * HEIGHT, dev[0][0].data_ptr(), dev[0][1].data_ptr(), cap, dev[0][2].data_ptr(), device=True)
+    torch.cuda.synchronize()
+    ext_ms, ncalls = EL.profile_collect(); EL.profile_enable(False)
+    orbx._check(Lb.orbx_matcher_profile_enable(M._h, 1))
     for _ in range(3):
         step_device()
-    ext_ms, ncalls = EL.profile_collect(); EL.profile_enable(False)
     st = (C.c_double * 2)(); nc = C.c_int()
     orbx._check(Lb.orbx_matcher_profile_collect(M._h, 2, st, C.byref(nc))); orbx._check(Lb.orbx_matcher_profile_enable(M._h, 0))
     stage_ms = {("extract_" + k): 2 * v / max(ncalls, 1) for k, v in ext_ms.items()}                     # x2: left and right image
@@ -575,7 +581,8 @@ def bench_c4(args, rank, local_rank, world):
     peak, peak_src = _peaks()
     n_cand = float(sum(len(EL.debug_level_candidates(0, l)) for l in range(NLEVELS)))
     sb = {("extract_" + k): 2 * v for k, v in stage_bytes(n_kp, n_cand).items()}
-    sb["stereo_match"] = 2 * n_kp * 60 + n_kp * n_kp * 28 / 32.0 + matched * 11 * 121 * 2; sb["stereo_median_cut"] = n_kp * 12
+    band = 4.0 * 1.2 ** 3 + 1.0                                                   # rows a right keypoint of a middle level enters (k_stereo_rows)
+    sb["stereo_match"] = 2 * n_kp * 60 + 2 * 4 * n_kp * band + n_kp * (n_kp * band / HEIGHT) * 28 + matched * (64 + 11 * 121 * 2); sb["stereo_median_cut"] = n_kp * 12
     dom = max(stage_ms, key=lambda k: stage_ms[k])
     nl = (NLEVELS - 1) if dom == "extract_pyr_resize" else 1
     achieved = sb[dom] * B / (stage_ms[dom] * 1e-3) / 1e9

@@ -507,3 +507,26 @@ def test_every_kernel_form_gives_the_same_result(tmp_path):
                   {"ORBX_CHAIN": "1"}, {"ORBX_BLUR_SMALL": "0"}, {"ORBX_BLUR_SMALL": "1"}, {"ORBX_FAST_CPW": "1"}, {"ORBX_FAST_CPW": "8"}, {"ORBX_FAST_CTA": "0"}, {"ORBX_FAST_CTA": "1"},
                   {"ORBX_HOST_PACK": "0"}, {"ORBX_HOST_PACK": "3"}, {"ORBX_GRAPH": "0"}, {"ORBX_QT_FUSED": "0"}, {"ORBX_QT_FUSED": "1"}, {"ORBX_QT_FUSED": "2"}, {"ORBX_QT_FUSED": "2", "ORBX_QT_BKEYS": "512"}):
         assert run(extra) == base, extra
+
+
+@pytest.mark.gpu
+def test_device_batch_with_unaligned_rows_and_base(orbx):
+    """Device-resident frames whose rows (331 px) and base pointer are not 16-byte aligned are re-pitched for TMA by one kernel per batch
+    (k_repitch: aligned word reads + funnel shift, byte path at both ends of a row): same result as the host-pointer call, for every base alignment."""
+    import torch
+    E = orbx.ORBextractor(500, 1.2, 8, 20, 7)
+    B, h, w = 5, 203, 331
+    fr = synth_batch(B, w, h, seed0=77)
+    kb, db, nb = E.extract_batch(fr)
+    cap = E.max_keypoints(h, w)
+    for off in (0, 1, 2, 3, 5):
+        buf = torch.full((B * h * w + 16,), 255, dtype=torch.uint8, device="cuda")
+        buf[off:off + B * h * w] = torch.from_numpy(fr.reshape(-1)).cuda()
+        kp = torch.zeros((B, cap, 28), dtype=torch.uint8, device="cuda"); ds = torch.zeros((B, cap, 32), dtype=torch.uint8, device="cuda"); cn = torch.zeros(B, dtype=torch.int32, device="cuda")
+        E.extract_batch_raw(buf.data_ptr() + off, B, h, w, w, w * h, kp.data_ptr(), ds.data_ptr(), cap, cn.data_ptr(), device=True)
+        torch.cuda.synchronize()
+        cnt = cn.cpu().numpy(); kph = kp.cpu().numpy(); dsh = ds.cpu().numpy()
+        assert np.array_equal(cnt, nb), off
+        for b in range(B):
+            assert np.array_equal(kph[b, :cnt[b]].reshape(-1), np.ascontiguousarray(kb[b][:nb[b]]).view(np.uint8).reshape(-1)), (off, b)
+            assert np.array_equal(dsh[b, :cnt[b]], db[b][:nb[b]]), (off, b)
