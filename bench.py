@@ -448,7 +448,9 @@ def bench_c2(args, rank, local_rank, world):
                        "l2_policy": "per-step working set is %.1f MB of keypoints + descriptors (< L2): the path is latency / issue bound, not HBM bound; every step re-reads the same resident frames" % (P * nkeys * 60 / 1e6)},
             "hamming_distances_per_s": value * ndist_pair,
             "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
-                    "note": "orbx_search_for_initialization_batch on host frame views: keypoints, descriptors and vbPrevMatched uploaded, matches / vbPrevMatched / counts downloaded, every step"},
+                    "note": "orbx_search_for_initialization_batch on host frame views: keypoints, descriptors and vbPrevMatched uploaded, matches / vbPrevMatched / counts downloaded, every step; "
+                            "bound by the host's memory bandwidth, not by the GPU or the link: the caller's pageable arrays (128 KB per pair) are staged into the pinned upload mirror by 8 threads and read again by the DMA "
+                            "(1 / 2 / 4 matcher handles on as many host threads measured 93 / 91 / 96 k pairs/s on the 16-vCPU box); frames kept on the device (orbx_frame_*) skip all of it: `value`"},
             "gpu_launches": int(launches), "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "kernel": {"grid_build": "k_grid_build_pairs", "window_count": "k_window_search_pairs<false>", "scan": "k_scan_counts_pairs", "window_fill": "k_window_search_pairs<true>",
                                                    "resolve": "k_resolve_init_pairs"}[dom],
