@@ -97,6 +97,7 @@ struct orbx_matcher {
     size_t cand_cap = 0;           // candidate entries the cand arena holds
     int cand_tries = 0;            // consecutive grow-and-repeat rounds of the current call (bounded)
     cudaEvent_t ev_left = nullptr, ev_right = nullptr;     // stereo batch: the matcher stream waits for both extractors' streams
+    cudaEvent_t ev_stereo = nullptr;                       // ... and the extractors' streams wait for the stereo kernels before they touch their pyramids again
     float* stereo_out = nullptr; size_t stereo_out_n = 0;  // device results of the host-pointer stereo batch call
     float* stereo_scale = nullptr; std::vector<float> stereo_scale_host;   // mvScaleFactor | mvInvScaleFactor of the extractors, persistent
     bool profiling = false; std::vector<cudaEvent_t> prof_events;          // per-stage events of the batched calls (bench.py's roofline)
@@ -305,6 +306,7 @@ void orbx_matcher_destroy(orbx_matcher* m) {
     if (m->stereo_out) cudaFree(m->stereo_out);
     if (m->stereo_scale) cudaFree(m->stereo_scale);
     if (m->ev_left) cudaEventDestroy(m->ev_left);
+    if (m->ev_stereo) cudaEventDestroy(m->ev_stereo);
     if (m->ev_right) cudaEventDestroy(m->ev_right);
     cudaStreamDestroy(m->stream);
     delete m;
@@ -708,6 +710,7 @@ static int stereo_batch_launch(orbx_matcher* m, orbx_extractor* left, orbx_extra
     if (L.device != m->device || R.device != m->device) FAIL(ORBX_E_INVALID, "extractors and matcher must live on the same device");
     if (L.nlevels != R.nlevels || L.B != B || R.B != B || L.cap != cap || R.cap != cap) FAIL(ORBX_E_INVALID, "left / right batches differ (levels, frames or keypoint capacity)");
     if (!m->ev_left) { CU_TRY(cudaEventCreateWithFlags(&m->ev_left, cudaEventDisableTiming)); CU_TRY(cudaEventCreateWithFlags(&m->ev_right, cudaEventDisableTiming)); }
+    if (!m->ev_stereo) CU_TRY(cudaEventCreateWithFlags(&m->ev_stereo, cudaEventDisableTiming));
     CU_TRY(cudaEventRecord(m->ev_left, L.stream)); CU_TRY(cudaEventRecord(m->ev_right, R.stream));
     CU_TRY(cudaStreamWaitEvent(m->stream, m->ev_left, 0)); CU_TRY(cudaStreamWaitEvent(m->stream, m->ev_right, 0));
     const int nRows = L.h[0];
@@ -740,6 +743,10 @@ static int stereo_batch_launch(orbx_matcher* m, orbx_extractor* left, orbx_extra
     k_stereo_median_cut<<<B, 1024, 0, m->stream>>>(0, sad, d_ur, d_dep, SB);
     LAUNCH_CHECK();
     m->mark();
+    // the kernels above read both extractors' pyramids, keypoints and descriptors: whatever is queued on the extractors next (their following batch) must not
+    // overwrite them before these kernels are done
+    CU_TRY(cudaEventRecord(m->ev_stereo, m->stream));
+    CU_TRY(cudaStreamWaitEvent(L.stream, m->ev_stereo, 0)); CU_TRY(cudaStreamWaitEvent(R.stream, m->ev_stereo, 0));
     return ORBX_OK;
 }
 int orbx_compute_stereo_matches_batch_device(orbx_matcher* m, orbx_extractor* left, orbx_extractor* right, int B, int cap, float mb, float mbf, float* d_u_right, float* d_depth) {

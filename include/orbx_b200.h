@@ -348,7 +348,8 @@ int orbx_compute_stereo_matches(orbx_matcher* m, orbx_extractor* left, orbx_extr
  * `left` with the B left images, on `right` with the B right images, same cap): both pyramids, keypoints, descriptors and counts are
  * still on the device, so nothing is uploaded.  Outputs are [B][cap] floats (pair b at + b * cap; entries past the pair's left keypoint
  * count are -1).  The host form is synchronous; the device form is asynchronous on orbx_matcher_stream(m), which first waits for the
- * work queued on both extractors' streams.  The stereo pair is the shard unit of BASELINE config 4. */
+ * work queued on both extractors' streams; in turn, work queued on either extractor AFTER this call waits for the stereo kernels (they read
+ * the extractors' pyramids and results).  The stereo pair is the shard unit of BASELINE config 4. */
 int orbx_compute_stereo_matches_batch(orbx_matcher* m, orbx_extractor* left, orbx_extractor* right, int B, int cap, float mb, float mbf,
                                       float* u_right, float* depth);
 int orbx_compute_stereo_matches_batch_device(orbx_matcher* m, orbx_extractor* left, orbx_extractor* right, int B, int cap, float mb, float mbf,

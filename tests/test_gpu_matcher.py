@@ -269,3 +269,15 @@ def test_compute_stereo_matches_batch(orbx):
     ur0, dep0 = m.ComputeStereoMatchesBatch(EL, ER, B, cap, 0.0, mc.BF_KITTI)
     assert np.array_equal(dur.cpu().numpy(), ur0) and np.array_equal(ddep.cpu().numpy(), dep0)
     assert np.array_equal(ur0[0][:cl[0]], G["stereo_ur"])
+    # the asynchronous form followed at once by the extractors' NEXT batch (different images, same buffers): the extractors' streams must wait for the stereo
+    # kernels, which are still reading their pyramids and results
+    dL2 = torch.flip(dL, dims=[0]).contiguous(); dR2 = torch.flip(dR, dims=[0]).contiguous()
+    for rep in range(4):
+        for E, d, o in ((EL, dL, outs[0]), (ER, dR, outs[1])):
+            E.extract_batch_raw(d.data_ptr(), B, 376, 1241, 1241, 1241 * 376, o[0].data_ptr(), o[1].data_ptr(), cap, o[2].data_ptr(), device=True)
+        dur.fill_(7.0); ddep.fill_(7.0)
+        orbx._check(m._lib.orbx_compute_stereo_matches_batch_device(m._h, EL._h, ER._h, B, cap, 0.0, mc.BF_KITTI, dur.data_ptr(), ddep.data_ptr()))
+        for E, d, o in ((EL, dL2, outs[0]), (ER, dR2, outs[1])):          # queued behind the stereo call without any host synchronisation
+            E.extract_batch_raw(d.data_ptr(), B, 376, 1241, 1241, 1241 * 376, o[0].data_ptr(), o[1].data_ptr(), cap, o[2].data_ptr(), device=True)
+        torch.cuda.synchronize()
+        assert np.array_equal(dur.cpu().numpy(), ur0) and np.array_equal(ddep.cpu().numpy(), dep0), rep
