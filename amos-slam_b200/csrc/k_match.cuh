@@ -797,16 +797,23 @@ k_stereo_match(const KpM* __restrict__ kl, const uint8_t* __restrict__ dl, int n
     const int cl = IL.ptr[(size_t)cy * IL.pitch + cxl];
     float vDists[11];
     int bestS = INT_MAX, bestinc = 0;
+    // the left patch does not move with the shift: its (up to) four pixels of this lane are read once, and so are the row offsets of the right patch
+    int aL[4]; const uint8_t* pR[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int p = lane + 32 * k;
+        const int dy = p / 11 - w, dx = p % 11 - w;
+        aL[k] = p < 121 ? (int)IL.ptr[(size_t)(cy + dy) * IL.pitch + cxl + dx] - cl : 0;
+        pR[k] = IR.ptr + (size_t)(cy + (p < 121 ? dy : 0)) * IR.pitch + cxr + (p < 121 ? dx : 0);
+    }
+    const uint8_t* pC = IR.ptr + (size_t)cy * IR.pitch + cxr;
 #pragma unroll 1
     for (int inc = -L; inc <= L; ++inc) {
-        const int cr = IR.ptr[(size_t)cy * IR.pitch + cxr + inc];
+        const int cr = pC[inc];
         int s = 0;
-        for (int p = lane; p < 121; p += 32) {
-            const int dy = p / 11 - w, dx = p % 11 - w;
-            const int a = (int)IL.ptr[(size_t)(cy + dy) * IL.pitch + cxl + dx] - cl;
-            const int b = (int)IR.ptr[(size_t)(cy + dy) * IR.pitch + cxr + inc + dx] - cr;
-            s += abs(a - b);
-        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (lane + 32 * k < 121) s += abs(aL[k] - ((int)pR[k][inc] - cr));
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         const float dist = (float)s;                                           // cv::norm(IL, IR, NORM_L1): exact integers
@@ -835,25 +842,43 @@ k_stereo_median_cut(int nl, const int* __restrict__ sad_dist, float* __restrict_
     if (SB.nl_arr) { nl = min(SB.nl_arr[blockIdx.x], SB.stride); const size_t o = (size_t)blockIdx.x * SB.stride; sad_dist += o; u_right += o; depth += o; }
     // the SAD values of the surviving matches are compacted into shared memory (order is irrelevant for a rank), so the rank
     // counting below reads broadcast shared words instead of re-walking the global array once per match
-    __shared__ int vals[STEREO_SMEM_VALS];
+    __shared__ __align__(16) int vals[STEREO_SMEM_VALS];
     __shared__ int total_sm, median_sm;
     const int tid = threadIdx.x;
     if (tid == 0) { total_sm = 0; median_sm = -1; }
     __syncthreads();
-    for (int i = tid; i < nl; i += 1024) {
-        const int d = sad_dist[i];
-        if (d != INT_MAX) { const int p = atomicAdd(&total_sm, 1); if (p < STEREO_SMEM_VALS) vals[p] = d; }
+    for (int i0 = 0; i0 < nl; i0 += 1024) {                                    // (one shared-memory atomic per warp, not per match)
+        const int i = i0 + tid;
+        const int d = i < nl ? sad_dist[i] : INT_MAX;
+        const uint32_t mk = __ballot_sync(0xffffffffu, d != INT_MAX);
+        int base = 0;
+        if (mk && (tid & 31) == __ffs(mk) - 1) base = atomicAdd(&total_sm, __popc(mk));
+        base = __shfl_sync(0xffffffffu, base, mk ? __ffs(mk) - 1 : 0);
+        if (d != INT_MAX) { const int p = base + __popc(mk & ((1u << (tid & 31)) - 1u)); if (p < STEREO_SMEM_VALS) vals[p] = d; }
     }
     __syncthreads();
     const int total = total_sm;
     if (total == 0) return;
     const int k = total / 2;                                                   // vDistIdx[size/2].first of the sorted list
-    if (total <= STEREO_SMEM_VALS) {
+    if (total <= STEREO_SMEM_VALS - 4) {
+        if (tid < 4 && (total & 3) && total + tid < ((total + 3) & ~3)) vals[total + tid] = INT_MAX;     // pad to a multiple of four: neither < nor <= any SAD value
+        __syncthreads();
+        const int4* v4 = reinterpret_cast<const int4*>(vals);
+        for (int i = tid; i < total; i += 1024) {
+            const int d = vals[i];
+            int less = 0, leq = 0;
+            for (int j = 0; j < (total + 3) >> 2; ++j) {
+                const int4 e = v4[j];
+                less += (e.x < d) + (e.y < d) + (e.z < d) + (e.w < d); leq += (e.x <= d) + (e.y <= d) + (e.z <= d) + (e.w <= d);
+            }
+            if (less <= k && k < leq) median_sm = d;                           // every qualifying thread writes the same value
+        }
+    } else if (total <= STEREO_SMEM_VALS) {
         for (int i = tid; i < total; i += 1024) {
             const int d = vals[i];
             int less = 0, leq = 0;
             for (int j = 0; j < total; ++j) { const int e = vals[j]; less += e < d; leq += e <= d; }
-            if (less <= k && k < leq) median_sm = d;                           // every qualifying thread writes the same value
+            if (less <= k && k < leq) median_sm = d;
         }
     } else {
         for (int i = tid; i < nl; i += 1024) {
