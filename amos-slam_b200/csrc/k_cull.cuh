@@ -62,6 +62,12 @@ __global__ void k_mask_pack(const uint8_t* __restrict__ mask, long long fstride,
     bits[((long long)b * rows + y) * wpr + wx] = w;
 }
 
+// half-width of the ellipse row at distance k from the centre row: round(sqrt(225 - k^2)) -- the values upload_ellipse() computes with OpenCV's formula and
+// checks against this table, which lets the dilation kernel unroll over the rows with every window width a compile-time constant
+__host__ __device__ constexpr int ell_dx(int k) {
+    return k <= 3 ? 15 : k <= 6 ? 14 : k <= 8 ? 13 : k == 9 ? 12 : k == 10 ? 11 : k == 11 ? 10 : k == 12 ? 9 : k == 13 ? 7 : k == 14 ? 5 : 0;
+}
+
 __device__ __forceinline__ unsigned long long or_window(unsigned long long x, int n) {   // OR of x >> k, k = 0..n-1, 1 <= n <= 16
     unsigned long long t = x; int p = 1;
     if (n >= 2) { t |= t >> 1; p = 2; }
@@ -95,22 +101,17 @@ k_bin_dilate31(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int 
         const int y = y0 + ty;
         if (y >= rows) break;
         uint32_t acc = 0, gL = 0, gM = 0, gR = 0;
-        int gd = c_ell_dx[0];                                            // half-width of the group being collected (k = 15 first)
 #pragma unroll
-        for (int k = 15; k >= 0; --k) {
-            const int d = c_ell_dx[15 - k];
-            if (d != gd) {
-                const unsigned long long A = ((unsigned long long)gM << 32) | gL, Bw = ((unsigned long long)gR << 32) | gM;
-                acc |= (uint32_t)(or_window(A >> (32 - gd), gd + 1) | or_window(Bw, gd + 1));
-                gL = gM = gR = 0; gd = d;
-            }
+        for (int k = 15; k >= 0; --k) {                                  // fully unrolled: ell_dx(k) and the group boundaries are compile-time constants
             const uint32_t* r0 = &sm[ty + 15 - k][tx];
             gL |= r0[0]; gM |= r0[1]; gR |= r0[2];
             if (k) { const uint32_t* r1 = &sm[ty + 15 + k][tx]; gL |= r1[0]; gM |= r1[1]; gR |= r1[2]; }
-        }
-        {
-            const unsigned long long A = ((unsigned long long)gM << 32) | gL, Bw = ((unsigned long long)gR << 32) | gM;
-            acc |= (uint32_t)(or_window(A >> (32 - gd), gd + 1) | or_window(Bw, gd + 1));
+            if (k == 0 || ell_dx(k - 1) != ell_dx(k)) {                  // last row pair of this half-width: dilate the collected rows horizontally once
+                const int gd = ell_dx(k);
+                const unsigned long long A = ((unsigned long long)gM << 32) | gL, Bw = ((unsigned long long)gR << 32) | gM;
+                acc |= (uint32_t)(or_window(A >> (32 - gd), gd + 1) | or_window(Bw, gd + 1));
+                gL = gM = gR = 0;
+            }
         }
         if (wx == wpr - 1) acc &= lastmask;
         out[((long long)b * rows + y) * wpr + wx] = acc;
@@ -121,19 +122,25 @@ k_bin_dilate31(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int 
 // whole plane, every keypoint tests its own 31 ellipse rows: closing(p) != 0  <=>  D(q) = 1 for every q of p + E inside the image (cv's default border:
 // outside pixels are ignored by the erosion).
 __device__ __forceinline__ bool closing_nonzero_at(const uint32_t* __restrict__ D, int wpr, int rows, int cols, int px, int py) {
+    // all 31 rows' words are fetched before any is tested (62 independent loads in flight: the plane is L2-resident, a row-by-row loop paid its latency 31 times)
+    uint32_t lo[31], hi[31];
+#pragma unroll
+    for (int k = -15; k <= 15; ++k) {
+        const int yy = min(max(py + k, 0), rows - 1);
+        const int dx = c_ell_dx[15 + k];
+        const int w0 = max(px - dx, 0) >> 5;
+        const uint32_t* row = D + (long long)yy * wpr;
+        lo[k + 15] = __ldg(row + w0); hi[k + 15] = (w0 + 1 < wpr) ? __ldg(row + w0 + 1) : 0u;
+    }
     bool all = true;
-#pragma unroll 1
+#pragma unroll
     for (int k = -15; k <= 15; ++k) {
         const int yy = py + k;
-        if (yy < 0 || yy >= rows) continue;
         const int dx = c_ell_dx[15 + k];
         const int x0 = max(px - dx, 0), x1 = min(px + dx, cols - 1);     // at most 31 pixels: two words
-        const uint32_t* row = D + (long long)yy * wpr;
-        const int w0 = x0 >> 5;
-        const unsigned long long lo = row[w0], hi = (w0 + 1 < wpr) ? row[w0 + 1] : 0u;
-        const unsigned long long v = ((hi << 32) | lo) >> (x0 & 31);
+        const unsigned long long v = (((unsigned long long)hi[k + 15] << 32) | lo[k + 15]) >> (x0 & 31);
         const unsigned long long need = (1ull << (x1 - x0 + 1)) - 1ull;
-        all = all && ((v & need) == need);
+        all = all && (yy < 0 || yy >= rows || (v & need) == need);
     }
     return all;
 }

@@ -5,7 +5,10 @@ static int upload_ellipse() {
     // cv::getStructuringElement(MORPH_ELLIPSE, 31x31): dx = cvRound(c * sqrt((r*r - dy*dy) * inv_r2))
     int dxs[31];
     const int r = 15, c = 15; const double inv_r2 = 1.0 / ((double)r * r);
-    for (int i = 0; i < 31; ++i) { const int dy = i - r; dxs[i] = (int)lrint(c * std::sqrt((r * r - dy * dy) * inv_r2)); }
+    for (int i = 0; i < 31; ++i) {
+        const int dy = i - r; dxs[i] = (int)lrint(c * std::sqrt((r * r - dy * dy) * inv_r2));
+        if (dxs[i] != ell_dx(dy < 0 ? -dy : dy)) FAIL(ORBX_E_STATE, "ellipse table differs from the compiled-in one");
+    }
     CU_TRY(cudaMemcpyToSymbol(c_ell_dx, dxs, sizeof(dxs)));
     return ORBX_OK;
 }
