@@ -8,6 +8,7 @@ timeout 900 bash tools/gpu_bench.sh $TAG "c2 c3 c4 c5"
 python tools/lat1_probe.py 2>&1 | grep -v Warn | tee $O/lat1_$TAG.txt
 python tools/qt_stamps_probe.py > $O/qt_stamps_$TAG.txt 2>&1; tail -n 16 $O/qt_stamps_$TAG.txt
 cat $O/host_dropin_timings.txt
+timeout 600 python tools/parity_report.py --frames 60 > $O/parity_$TAG.md 2> $O/parity_$TAG.err; echo "parity rc=$?"; grep -c "| 0 |" $O/parity_$TAG.md
 CMD="python bench.py --steps 1 --warmup 1 --batch 256 --streams 1 --no-cpu-baseline --no-e2e"
 $CMD > $O/plain_$TAG.log 2>&1 && \
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $O/launches_$TAG.csv $CMD > $O/ncu_l_$TAG.log 2>&1
