@@ -530,3 +530,20 @@ def test_device_batch_with_unaligned_rows_and_base(orbx):
         for b in range(B):
             assert np.array_equal(kph[b, :cnt[b]].reshape(-1), np.ascontiguousarray(kb[b][:nb[b]]).view(np.uint8).reshape(-1)), (off, b)
             assert np.array_equal(dsh[b, :cnt[b]], db[b][:nb[b]]), (off, b)
+
+
+@pytest.mark.gpu
+def test_large_feature_counts_and_sizes(orbx, oracle):
+    """Capacity edges of the quadtree stage: node pools above the default (6000 / 9500 features), the sort + tree fallback (12000 features: more nodes per level than
+    the one-launch kernel's pool), levels whose candidates exceed the shared-memory key capacity (1080p, 2200 x 1300), 12 levels, 3 levels -- single frame
+    (wide form) and a batch of 6 (lean form), against the oracle."""
+    for (w, h, nf, L, sf) in [(1241, 376, 6000, 8, 1.2), (1241, 376, 9500, 8, 1.2), (1241, 376, 12000, 8, 1.2), (1920, 1080, 9000, 8, 1.2), (640, 480, 4000, 12, 1.1),
+                              (2200, 1300, 2000, 8, 1.2), (333, 277, 800, 3, 1.5)]:
+        img = synth_frame(42, w, h)
+        E = orbx.ORBextractor(nf, sf, L, 20, 7); O = oracle.Extractor("port", nf, sf, L, 20, 7)
+        kg, dg = E(img); kr, dr = O.extract(img)
+        assert kp_equal(kg, kr) and np.array_equal(dg, dr), (w, h, nf, L)
+        kb, db, nb = E.extract_batch(np.stack([img] * 6))
+        for b in range(6):
+            assert nb[b] == len(kr) and kp_equal(kb[b][:nb[b]], kr) and np.array_equal(db[b][:nb[b]], dr), (w, h, nf, L, b)
+        assert E.check_overflow() == 0
