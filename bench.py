@@ -1046,7 +1046,7 @@ def main():
     total_stage = sum(stage_ms.values())
     # DRAM traffic of the dominant kernel: dram__bytes_read.sum + dram__bytes_write.sum per frame from the committed ncu --set full
     # capture (profiles/traffic.json, written by tools/profile_digest.py), scaled to this launch's frame count
-    kernel_of = {"pyr_resize": "k_pyr_resize_t", "fast_cells": "k_fast_cells", "octree_sort": "k_octree_sort", "octree_tree": "k_octree_tree_par",
+    kernel_of = {"pyr_resize": "k_pyr_resize_t", "fast_cells": "k_fast_cells", "octree_sort": "k_octree_fused", "octree_tree": "k_octree_tree_par",
                  "gauss7": "k_gauss7", "orient_describe": "k_orient_describe"}
     traffic = None; ncu_note = None
     try:
@@ -1073,6 +1073,7 @@ def main():
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes_per_launch, "ms_per_launch": dom_ms_per_launch,
                          "stage_ms_per_step": {k: v / max(ncalls, 1) for k, v in stage_ms.items()},
                          "stage_share": {k: (v / total_stage if total_stage else 0.0) for k, v in stage_ms.items()},
+                         "stage_note": "octree_sort = the whole quadtree stage (k_octree_fused: gather, sort and tree in one launch); octree_tree is non-zero only when the sort + tree pair runs (ORBX_QT_FUSED=0 or more than ~9000 features); on the masked path gauss7 includes the closing of the masks and the culling",
                          "whole_step_algorithmic_GBps": (2 * sum(level_pixels()) + 60 * n_kp) * B * K / (ms * 1e-3) / 1e9},
             "keypoints_per_frame": n_kp, "matcher": matcher_line, "host_affinity_rank0": numa}
     if N == 1 and not args.no_cpu_baseline:
