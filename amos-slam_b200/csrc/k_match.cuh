@@ -860,25 +860,38 @@ k_stereo_median_cut(int nl, const int* __restrict__ sad_dist, float* __restrict_
     const int total = total_sm;
     if (total == 0) return;
     const int k = total / 2;                                                   // vDistIdx[size/2].first of the sorted list
-    if (total <= STEREO_SMEM_VALS - 4) {
-        if (tid < 4 && (total & 3) && total + tid < ((total + 3) & ~3)) vals[total + tid] = INT_MAX;     // pad to a multiple of four: neither < nor <= any SAD value
-        __syncthreads();
-        const int4* v4 = reinterpret_cast<const int4*>(vals);
-        for (int i = tid; i < total; i += 1024) {
-            const int d = vals[i];
-            int less = 0, leq = 0;
-            for (int j = 0; j < (total + 3) >> 2; ++j) {
-                const int4 e = v4[j];
-                less += (e.x < d) + (e.y < d) + (e.z < d) + (e.w < d); leq += (e.x <= d) + (e.y <= d) + (e.z <= d) + (e.w <= d);
+    if (total <= STEREO_SMEM_VALS) {
+        // k-th smallest by a two-level radix select on the 16-bit SAD values (121 pixels x |difference| <= 510): histogram of the high byte, the bucket holding rank k,
+        // histogram of the low byte inside it -- linear in the number of matches (the rank counting it replaces compared every pair of matches)
+        __shared__ int hist[256];
+        __shared__ int sel_bucket, sel_rank;
+        int want = k, key_hi = 0;
+        for (int level = 0; level < 2; ++level) {
+            if (tid < 256) hist[tid] = 0;
+            __syncthreads();
+            for (int i = tid; i < total; i += 1024) {
+                const int d = min(vals[i], 0xFFFF);
+                if (level == 0) atomicAdd(&hist[d >> 8], 1);
+                else if ((d >> 8) == key_hi) atomicAdd(&hist[d & 255], 1);
             }
-            if (less <= k && k < leq) median_sm = d;                           // every qualifying thread writes the same value
-        }
-    } else if (total <= STEREO_SMEM_VALS) {
-        for (int i = tid; i < total; i += 1024) {
-            const int d = vals[i];
-            int less = 0, leq = 0;
-            for (int j = 0; j < total; ++j) { const int e = vals[j]; less += e < d; leq += e <= d; }
-            if (less <= k && k < leq) median_sm = d;
+            __syncthreads();
+            if (tid < 32) {                                                    // lane l owns buckets 8 l .. 8 l + 7
+                int c[8], mine = 0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) { c[q] = hist[8 * tid + q]; mine += c[q]; }
+                int incl = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (tid >= o) incl += t; }
+                int before = incl - mine;
+                if (before <= want && want < incl) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) { if (want >= before && want < before + c[q]) { sel_bucket = 8 * tid + q; sel_rank = want - before; } before += c[q]; }
+                }
+            }
+            __syncthreads();
+            if (level == 0) { key_hi = sel_bucket; want = sel_rank; }
+            else if (tid == 0) median_sm = (key_hi << 8) | sel_bucket;
+            __syncthreads();
         }
     } else {
         for (int i = tid; i < nl; i += 1024) {
