@@ -53,6 +53,51 @@ __device__ __forceinline__ void grid_build_body(const KpM* __restrict__ keys, in
     __shared__ uint32_t skeys_s[GRID_SMEM_KEYS];
     uint32_t* skeys = n <= GRID_SMEM_KEYS ? skeys_s : skeys_g;
     const int tid = threadIdx.x;
+    if (n <= GRID_SMEM_KEYS / 2) {
+        // Counting sort by cell (the usual case: a frame's ~1000-2000 keypoints): cell sizes by shared-memory atomics, exclusive scan = cell_start, an unordered fill
+        // through per-cell cursors, then every entry ranks itself among the handful of entries of its cell by keypoint index (the reference's push_back order).
+        // The bitonic sort below (~60 block barriers for 1000 keys) stays for larger sets.
+        __shared__ int cnt[GRID_CELLS + 2];
+        __shared__ int wsum[32];
+        uint32_t* cellof = skeys_s; uint32_t* tmp = skeys_s + GRID_SMEM_KEYS / 2;
+        const int lane = tid & 31, warp = tid >> 5;
+        for (int c = tid; c < GRID_CELLS + 2; c += 1024) cnt[c] = 0;
+        __syncthreads();
+        for (int i = tid; i < n; i += 1024) {
+            const int px = (int)roundf(__fmul_rn(__fsub_rn(keys[i].x, min_x), gw_inv));
+            const int py = (int)roundf(__fmul_rn(__fsub_rn(keys[i].y, min_y), gh_inv));
+            const int cell = (px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS) ? GRID_CELLS : px * GRID_ROWS + py;   // outside the grid: behind every cell
+            cellof[i] = (uint32_t)cell;
+            atomicAdd(&cnt[cell], 1);
+        }
+        __syncthreads();
+        // exclusive scan of cnt[0 .. GRID_CELLS]: every thread owns a run of cells
+        constexpr int PER = (GRID_CELLS + 1 + 1023) / 1024;
+        const int c0 = min(tid * PER, GRID_CELLS + 1), c1 = min(c0 + PER, GRID_CELLS + 1);
+        int mine = 0;
+        for (int c = c0; c < c1; ++c) mine += cnt[c];
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        int run = incl - mine;
+        for (int w = 0; w < warp; ++w) run += wsum[w];
+        for (int c = c0; c < c1; ++c) { const int v = cnt[c]; cnt[c] = run; cell_start[c] = run; run += v; }   // cnt becomes the fill cursor
+        __syncthreads();
+        for (int i = tid; i < n; i += 1024) tmp[atomicAdd(&cnt[cellof[i]], 1)] = (uint32_t)i;
+        __syncthreads();
+        for (int p = tid; p < n; p += 1024) {
+            const uint32_t i = tmp[p];
+            const int c = (int)cellof[i];
+            const int e1 = cnt[c];                                             // end of the cell's run (cursor after the fill)
+            int s0 = p; while (s0 > 0 && cellof[tmp[s0 - 1]] == (uint32_t)c) --s0;   // its start (runs are a few entries long)
+            int r = 0;
+            for (int q = s0; q < e1; ++q) r += tmp[q] < i;
+            entries[s0 + r] = (int)i;
+        }
+        return;
+    }
     for (int i = tid; i < n; i += 1024) {
         // posX = round((kp.pt.x - mnMinX) * mfGridElementWidthInv)   (roundf: half away from zero)
         const int px = (int)roundf(__fmul_rn(__fsub_rn(keys[i].x, min_x), gw_inv));
