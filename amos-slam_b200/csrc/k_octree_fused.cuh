@@ -1,8 +1,10 @@
-// k_octree_fused.cuh -- DistributeOctTree (/root/reference/src/ORBextractor.cc:635-1049) as ONE kernel, for the latency form (a handful
-// of frames: what Tracking calls once per frame).  One CTA per (level, frame); gather, path codes, radix sort and the tree all stay in
-// shared memory, so the chain  k_octree_sort -> skey / spk / ocand in HBM -> k_octree_tree_par  (two launches, ~130 block barriers,
-// 39 us for a 640 x 480 level 0 with its 2.5 k candidates) becomes one launch of 17 us (phase times: tools/qt_stamps_probe.py).
-// The CTA is alone on its SM and bound by instruction issue there, so every phase is written for few instructions, not for few bytes.
+// k_octree_fused.cuh -- DistributeOctTree (/root/reference/src/ORBextractor.cc:635-1049) as ONE kernel.  One CTA per (level, frame).
+//   * wide form (QF_THREADS, a handful of frames: what Tracking calls once per frame): gather, path codes, sort and the tree all stay in shared memory, so the chain
+//     k_octree_sort -> skey / spk / ocand in HBM -> k_octree_tree_par  (two launches, ~130 block barriers, 39 us for a 640 x 480 level 0 with its 2.5 k
+//     candidates) becomes one launch of 17 us (phase times: tools/qt_stamps_probe.py);
+//   * lean form (QF_THREADS_BATCH, batches): only small levels keep their keys in shared memory, the others run the same code on L2-resident global scratch -- more
+//     resident CTAs hide the latencies better than shared-memory keys do (0.59 -> 0.40 ms per 1024 VGA frames).
+// Levels with more candidates than the shared-memory key capacity of either form take the global-scratch path too (32-bit index and radix counters).
 //
 // The tree is not replayed round by round any more.  With the keys sorted by path code (k_octree.cuh), let dd[i] be the first digit in
 // which key i differs from key i-1 (0 = different root, 1..13 = tree digit, dd[0] = dd[n] = 0).  Then:
@@ -32,7 +34,7 @@
 #define QF_THREADS_BATCH 256        // batched form: lean CTAs, several per SM
 // u16 per digit row of the radix histogram: one counter per warp + 8 padding (1024 threads: 80 B rows, conflict-free 16-byte reads)
 __host__ __device__ constexpr int qf_hs(int threads) { return threads / 32 + 8; }
-#define QF_MAXPOOL 2048
+#define QF_MAXPOOL 2048             // node pool entries (N + 3 per level at most): more features per level than this fall back to the sort + tree pair
 
 #define QF_MAXLEVELS 16
 struct QfLevels { LevelGeom lv[QF_MAXLEVELS]; };   // the level geometry travels as a kernel parameter: no dependent global load in front of the counts
